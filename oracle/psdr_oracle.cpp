@@ -1,0 +1,1187 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the psdr-jit PathTracer hot path.
+//
+// A scalar C++ restatement of the reference algorithm (andyyankai/psdr-jit @ 50cc4f6), one
+// lane at a time, with forward-mode dual numbers standing in for Dr.Jit's AD.  It is pinned
+// against golden vectors produced by RUNNING the unmodified reference on a B200
+// (tools/ref_golden.py -> tests/golden/*.npz); tests/test_oracle_golden.py checks that.
+// Ray casting is brute force over all triangles (the reference uses OptiX).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load this library.  The product (psdr_jit_b200/) never does.
+//
+// Each function cites the reference file:line it follows.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "orc_math.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Discrete distribution (reference src/core/pmf.cpp:6-51, include/psdr/core/pmf.h:12-38)
+// ------------------------------------------------------------------------------------------
+// drjit::sum on the GPU = block tree reduction (ext/drjit/ext/drjit-core/resources/reduce.cuh:
+// 12-60): 1024 threads, thread t starts with data[t] + data[t+1024], then halving strides.
+static float drjit_sum(const std::vector<float> &x) {
+    size_t n = x.size();
+    std::vector<float> partial;
+    for (size_t base = 0; base < n || partial.empty(); base += 2048) {
+        float s[1024];
+        for (int t = 0; t < 1024; ++t) {
+            float v = 0.f;
+            size_t i = base + t;
+            if (i < n) {
+                v = v + x[i];
+                if (i + 1024 < n) v = v + x[i + 1024];
+            }
+            s[t] = v;
+        }
+        for (int stride = 512; stride >= 1; stride >>= 1)
+            for (int t = 0; t < stride; ++t) s[t] = s[t] + s[t + stride];
+        partial.push_back(s[0]);
+        if (n == 0) break;
+    }
+    if (partial.size() == 1) return partial[0];
+    return drjit_sum(partial);
+}
+
+struct Distrib {
+    int size = 0;
+    float sum = 0.f;
+    std::vector<float> pmf, cmf;
+    void init(const std::vector<float> &p) {
+        size = (int) p.size();
+        pmf = p;
+        sum = drjit_sum(p);
+        cmf.resize(p.size());
+        double acc = 0.0;  // pmf.h:19-25: double accumulation, rounded to float per entry
+        for (size_t i = 0; i < p.size(); ++i) {
+            acc += (double) p[i];
+            cmf[i] = (float) acc;
+        }
+    }
+    // drjit binary_search(0, size-1, cmf[i] < s)  (ext/drjit/include/drjit/util.h:172-217)
+    int search(float s) const {
+        int start = 0, end = size - 1;
+        int iterations = 0;
+        if (start < end) {
+            unsigned r = (unsigned) (end - start);
+            int lg = 0;
+            while (r >>= 1) ++lg;
+            iterations = lg + 1;
+        }
+        for (int i = 0; i < iterations; ++i) {
+            int middle = (start + end) >> 1;
+            bool cond = cmf[middle] < s;
+            if (cond) start = std::min(middle + 1, end);
+            else end = middle;
+        }
+        return start;
+    }
+    // pmf.cpp:18-28
+    std::pair<int, float> sample(float s) const {
+        if (size == 1) return {0, 1.f};
+        s *= sum;
+        int idx = search(s);
+        return {idx, pmf[idx] / sum};
+    }
+    // pmf.cpp:31-51 -- mutates the sample
+    std::pair<int, float> sample_reuse(float &s) const {
+        if (size == 1) return {0, 1.f};
+        s *= sum;
+        int idx = search(s);
+        if (idx > 0) s -= cmf[idx - 1];
+        float p = pmf[idx];
+        if (p > 0.f) s /= p;
+        s = std::min(std::max(s, 0.f), 1.f);
+        return {idx, p / sum};
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Scene description
+// ------------------------------------------------------------------------------------------
+template <class S> struct Tri {  // reference include/psdr/types.h:162-175
+    V3<S> p0, e1, e2, n0, n1, n2, fn;
+    S area;
+};
+
+struct Edge {  // reference src/shape/mesh.cpp:244-305 (m_edge_indices rows)
+    int v0, v1, f0, f1, v2;
+};
+
+struct Bsdf {
+    int type = 0;  // 0 diffuse
+    V3d reflectance;
+    bool two_side = false;
+};
+
+struct MeshRec {
+    std::vector<V3d> v_raw;
+    std::vector<int> f;  // 3*nf
+    std::vector<V2f> uv;
+    std::vector<int> fuv;
+    bool has_uv = false;
+    M4<Dual> to_world[3];  // left, raw, right
+    int bsdf = -1;
+    int emitter = -1;
+    bool use_face_normals = false, enable_edges = true;
+    // configured
+    std::vector<V3d> v_world;
+    std::vector<Tri<Dual>> tris;
+    std::vector<Edge> edges;
+    Distrib face_distrb;
+    float total_area = 0.f, inv_total_area = 0.f;
+    int face_offset = 0;
+};
+
+struct EmitterRec {
+    V3d radiance;
+    int mesh = -1;
+    float sampling_weight = 0.f;
+};
+
+struct PrimEdge {  // reference include/psdr/edge/edge.h:26-40
+    V2d p0, p1;
+    V2f normal;
+    float length;
+};
+
+struct SecEdge {  // edge.h:49-66
+    V3d p0, e1;
+    V3f n0, n1, p2;
+    bool is_boundary;
+};
+
+struct Camera {
+    float fov, near_, far_;
+    M4<Dual> to_world[3];
+    // configured (reference src/sensor/perspective.cpp:10-46)
+    M4<Dual> to_world_full, world_to_sample, sample_to_camera;
+    V3d pos, dir;
+    float inv_area;
+    std::vector<PrimEdge> edges;
+    Distrib edge_distrb;
+    bool enable_edges = false;
+};
+
+struct Scene {
+    int width = 128, height = 128, spp = 1, sppe = 0, sppse = 0;
+    std::vector<Bsdf> bsdfs;
+    std::vector<MeshRec> meshes;
+    std::vector<EmitterRec> emitters;
+    std::vector<Camera> cameras;
+    // configured
+    std::vector<Tri<Dual>> tris;
+    std::vector<int> tri_mesh;
+    std::vector<V2f> tri_uv;  // 3 per triangle
+    std::vector<SecEdge> sec_edges;
+    Distrib sec_edge_distrb, emitter_distrb;
+    bool configured = false;
+    std::string error;
+    // options
+    bool li_p_first = true;  // evaluation order of Li(ray_n) - Li(ray_p), integrator.cpp:185-186
+};
+
+// reference src/shape/mesh.cpp:23-62
+static void process_mesh(const std::vector<V3d> &vp, const std::vector<int> &f, std::vector<Tri<Dual>> &out) {
+    size_t nf = f.size() / 3, nv = vp.size();
+    out.resize(nf);
+    std::vector<V3d> vn(nv);
+    std::vector<Dual> vw(nv);
+    std::vector<V3d> fnorm(nf);
+    std::vector<Dual> farea(nf);
+    for (size_t i = 0; i < nf; ++i) {
+        Tri<Dual> &t = out[i];
+        t.p0 = vp[f[3 * i]];
+        t.e1 = vp[f[3 * i + 1]] - t.p0;
+        t.e2 = vp[f[3 * i + 2]] - t.p0;
+        fnorm[i] = cross(t.e1, t.e2);
+        farea[i] = norm(fnorm[i]);
+    }
+    // scatter_reduce order on the GPU is unspecified; accumulate in face order
+    for (int k = 0; k < 3; ++k)
+        for (size_t i = 0; i < nf; ++i) {
+            int vi = f[3 * i + k];
+            vn[vi] = vn[vi] + fnorm[i];
+            vw[vi] = vw[vi] + farea[i];
+        }
+    for (size_t i = 0; i < nv; ++i) vn[i] = normalize(vn[i] / vw[i]);
+    for (size_t i = 0; i < nf; ++i) {
+        Tri<Dual> &t = out[i];
+        t.n0 = vn[f[3 * i]];
+        t.n1 = vn[f[3 * i + 1]];
+        t.n2 = vn[f[3 * i + 2]];
+        t.fn = fnorm[i] / farea[i];
+        t.area = farea[i] * 0.5f;
+    }
+}
+
+// reference src/shape/mesh.cpp:244-305 (std::map keyed by (min,max) vertex id)
+static void build_edges(MeshRec &m) {
+    m.edges.clear();
+    if (!m.enable_edges) return;
+    std::map<std::pair<int, int>, std::vector<int>> edge_map;
+    size_t nf = m.f.size() / 3;
+    for (size_t fi = 0; fi < nf; ++fi)
+        for (int i = 0; i < 3; ++i) {
+            int i1 = m.f[3 * fi + i], i2 = m.f[3 * fi + (i + 1) % 3], i3 = m.f[3 * fi + (i + 2) % 3];
+            auto key = i1 < i2 ? std::make_pair(i1, i2) : std::make_pair(i2, i1);
+            if (edge_map.find(key) == edge_map.end()) edge_map[key].push_back(i3);
+            edge_map[key].push_back((int) fi);
+        }
+    for (auto &it : edge_map) {
+        Edge e;
+        e.v0 = it.first.first;
+        e.v1 = it.first.second;
+        e.f0 = it.second[1];
+        e.f1 = it.second.size() >= 3 ? it.second[2] : -1;
+        e.v2 = it.second[0];
+        m.edges.push_back(e);
+    }
+}
+
+static inline float rgb2luminance(V3f c) { return c.x * .2126f + c.y * .7152f + c.z * .0722f; }
+
+// reference include/psdr/core/transform.h:48-61
+static M4<float> perspective(float fov, float near_, float far_) {
+    float recip = 1.f / (far_ - near_);
+    float tn = std::tan(fov * .5f * (kPi / 180.f)), cot = 1.f / tn;
+    M4<float> t = M4<float>::identity();
+    t.m[0][0] = cot;
+    t.m[1][1] = cot;
+    t.m[2][2] = far_ * recip;
+    t.m[3][3] = 0.f;
+    t.m[2][3] = -near_ * far_ * recip;
+    t.m[3][2] = 1.f;
+    return t;
+}
+
+// reference src/shape/mesh.cpp:317-382
+static void configure_mesh(MeshRec &m) {
+    M4<Dual> tw = (m.to_world[0] * m.to_world[1]) * m.to_world[2];
+    m.v_world.resize(m.v_raw.size());
+    for (size_t i = 0; i < m.v_raw.size(); ++i) m.v_world[i] = transform_pos(tw, m.v_raw[i]);
+    process_mesh(m.v_world, m.f, m.tris);
+    std::vector<float> areas(m.tris.size());
+    for (size_t i = 0; i < m.tris.size(); ++i) areas[i] = m.tris[i].area.v;
+    m.total_area = drjit_sum(areas);
+    m.inv_total_area = 1.f / m.total_area;
+    m.face_distrb.init(areas);
+}
+
+// reference src/sensor/perspective.cpp:10-152
+static bool configure_camera(Scene &sc, Camera &cam, bool build_primary_edges) {
+    float aspect = (float) sc.width / (float) sc.height;
+    M4<float> sc_ = M4<float>::identity(), tr = M4<float>::identity();
+    sc_.m[0][0] = -0.5f;
+    sc_.m[1][1] = -0.5f * aspect;
+    tr.m[0][3] = -1.f;
+    tr.m[1][3] = -1.f / aspect;
+    M4<float> c2s = (sc_ * tr) * perspective(cam.fov, cam.near_, cam.far_);
+    M4<Dual> camera_to_sample = lift<Dual>(c2s);
+    cam.sample_to_camera = lift<Dual>(inverse(c2s));
+    cam.to_world_full = (cam.to_world[0] * cam.to_world[1]) * cam.to_world[2];
+    cam.world_to_sample = camera_to_sample * inverse(cam.to_world_full);
+    cam.pos = transform_pos(cam.to_world_full, V3d(Dual(0.f), Dual(0.f), Dual(0.f)));
+    cam.dir = transform_dir(cam.to_world_full, V3d(Dual(0.f), Dual(0.f), Dual(1.f)));
+    M4<float> s2c = val(cam.sample_to_camera);
+    V3f v00 = transform_pos(s2c, V3f(0.f, 0.f, 0.f)), v10 = transform_pos(s2c, V3f(1.f, 0.f, 0.f)),
+        v11 = transform_pos(s2c, V3f(1.f, 1.f, 0.f)), vc = transform_pos(s2c, V3f(.5f, .5f, 0.f));
+    cam.inv_area = (1.f / (norm(v00 - v10) * norm(v11 - v10))) * squared_norm(vc);
+
+    cam.edges.clear();
+    cam.enable_edges = false;
+    if (sc.sppe > 0 && build_primary_edges) {
+        for (auto &m : sc.meshes) {
+            if (!m.enable_edges) continue;
+            size_t before = cam.edges.size();
+            for (auto &e : m.edges) {
+                bool valid = e.f1 >= 0;
+                V3f camp = val(cam.pos);
+                V3f e0 = normalize(camp - val(m.tris[e.f0].p0));
+                V3f e1 = normalize(camp - (valid ? val(m.tris[e.f1].p0) : V3f(0.f, 0.f, 0.f)));
+                V3f n0 = val(m.tris[e.f0].fn);
+                V3f n1 = valid ? val(m.tris[e.f1].fn) : V3f(0.f, 0.f, 0.f);
+                bool uv_mask = false;
+                if (m.has_uv) {  // perspective.cpp:73-94
+                    int a[3] = {m.fuv[3 * e.f0], m.fuv[3 * e.f0 + 1], m.fuv[3 * e.f0 + 2]};
+                    int b[3] = {0, 0, 0};
+                    if (valid) { b[0] = m.fuv[3 * e.f1]; b[1] = m.fuv[3 * e.f1 + 1]; b[2] = m.fuv[3 * e.f1 + 2]; }
+                    int cut = 0;  // number of uv indices of face 0 that face 1 also uses
+                    for (int k = 0; k < 3; ++k)
+                        if (a[k] == b[0] || a[k] == b[1] || a[k] == b[2]) cut++;
+                    uv_mask = (cut != 2);
+                }
+                bool keep;
+                if (m.use_face_normals) {
+                    bool skip = valid && ((dot(e0, n0) < kEpsilon && dot(e1, n1) < kEpsilon) || (dot(n0, n1) > 1.f - kEpsilon));
+                    keep = !skip || (m.has_uv && uv_mask);
+                } else {
+                    bool active = !valid;
+                    active |= (dot(e0, n0) > kEpsilon) != (dot(e1, n1) > kEpsilon);
+                    keep = active || (m.has_uv && uv_mask);
+                }
+                if (!keep) continue;
+                PrimEdge pe;
+                V3d q0 = transform_pos(cam.world_to_sample, m.v_world[e.v0]);
+                V3d q1 = transform_pos(cam.world_to_sample, m.v_world[e.v1]);
+                pe.p0 = V2d(q0.x, q0.y);
+                pe.p1 = V2d(q1.x, q1.y);
+                V2f ev(q1.x.v - q0.x.v, q1.y.v - q0.y.v);
+                float len = norm(ev);
+                ev.x /= len;
+                ev.y /= len;
+                pe.normal = V2f(-ev.y, ev.x);
+                pe.length = len;
+                cam.edges.push_back(pe);
+            }
+            if (cam.edges.size() == before) {
+                sc.error = "PSDR_ASSERT(slices(info) > 0): a mesh produced no primary edges";
+                return false;
+            }
+        }
+        if (!cam.edges.empty()) {
+            std::vector<float> lens(cam.edges.size());
+            for (size_t i = 0; i < lens.size(); ++i) lens[i] = cam.edges[i].length;
+            cam.edge_distrb.init(lens);
+            cam.enable_edges = true;
+        }
+    }
+    return true;
+}
+
+// reference src/scene/scene.cpp:311-601
+static bool configure_scene(Scene &sc, const int *active, int nactive) {
+    sc.error.clear();
+    if (sc.meshes.empty()) { sc.error = "Missing meshes!"; return false; }
+    if (sc.cameras.empty()) { sc.error = "Missing sensor!"; return false; }
+    int off = 0;
+    for (auto &m : sc.meshes) {
+        build_edges(m);
+        configure_mesh(m);
+        m.face_offset = off;
+        off += (int) m.tris.size();
+    }
+    // sensors: primary edges only for the sensors named in `active` (scene.cpp:381-416)
+    for (size_t i = 0; i < sc.cameras.size(); ++i) {
+        bool act = false;
+        for (int k = 0; k < nactive; ++k) act |= (active[k] == (int) i);
+        if (!configure_camera(sc, sc.cameras[i], act)) return false;
+    }
+    // emitters (scene.cpp:489-515, src/emitter/area.cpp:9-14)
+    if (!sc.emitters.empty()) {
+        std::vector<float> w;
+        for (auto &e : sc.emitters) {
+            e.sampling_weight = sc.meshes[e.mesh].total_area * rgb2luminance(val(e.radiance));
+            w.push_back(e.sampling_weight);
+        }
+        sc.emitter_distrb.init(w);
+        float inv_total = 1.f / sc.emitter_distrb.sum;
+        for (auto &e : sc.emitters) e.sampling_weight *= inv_total;
+    }
+    // global triangle arrays (scene.cpp:529-542)
+    sc.tris.clear();
+    sc.tri_mesh.clear();
+    sc.tri_uv.clear();
+    for (size_t mi = 0; mi < sc.meshes.size(); ++mi) {
+        auto &m = sc.meshes[mi];
+        for (size_t i = 0; i < m.tris.size(); ++i) {
+            sc.tris.push_back(m.tris[i]);
+            sc.tri_mesh.push_back((int) mi);
+            for (int k = 0; k < 3; ++k) sc.tri_uv.push_back(m.has_uv ? m.uv[m.fuv[3 * i + k]] : V2f(0.f, 0.f));
+        }
+    }
+    // secondary edges (scene.cpp:547-571, mesh.cpp:353-369)
+    sc.sec_edges.clear();
+    if (sc.sppse > 0) {
+        for (auto &m : sc.meshes) {
+            if (!m.enable_edges) continue;
+            for (auto &e : m.edges) {
+                SecEdge s;
+                s.is_boundary = e.f1 < 0;
+                s.p0 = m.v_world[e.v0];
+                s.e1 = m.v_world[e.v1] - s.p0;
+                s.n0 = val(m.tris[e.f0].fn);
+                s.n1 = s.is_boundary ? V3f(0.f, 0.f, 0.f) : val(m.tris[e.f1].fn);
+                s.p2 = val(m.v_world[e.v2]);
+                sc.sec_edges.push_back(s);
+            }
+        }
+        std::vector<float> lens(sc.sec_edges.size());
+        for (size_t i = 0; i < lens.size(); ++i) lens[i] = norm(val(sc.sec_edges[i].e1));
+        if (lens.empty()) { sc.error = "DiscreteDistribution: empty distribution!"; return false; }
+        sc.sec_edge_distrb.init(lens);
+    }
+    sc.configured = true;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Ray casting: brute force closest hit in (RayEpsilon, 1e8); reference
+// src/scene/scene_optix.cpp:343-410 delegates this to OptiX.
+// ------------------------------------------------------------------------------------------
+struct Hit {
+    int tri = -1;
+    float u = 0.f, v = 0.f, t = 0.f;
+};
+
+// One fp32 Moeller-Trumbore test with a FIXED operation order (cross = mul,mul,sub; dot = fma
+// chain; IEEE divide).  The CUDA kernels use the same order so that hit ids and (u,v,t) agree
+// bit for bit with this oracle; it is also the formula of utils.h:82-93.
+static inline bool tri_test(const Tri<Dual> &T, V3f o, V3f d, float &u, float &v, float &t) {
+    V3f e1 = val(T.e1), e2 = val(T.e2), p0 = val(T.p0);
+    V3f h = cross(d, e2);
+    float a = dot(e1, h);
+    if (a == 0.f) return false;
+    float f = 1.f / a;
+    V3f s = o - p0;
+    u = f * dot(s, h);
+    if (!(u >= 0.f && u <= 1.f)) return false;
+    V3f q = cross(s, e1);
+    v = f * dot(d, q);
+    if (!(v >= 0.f && u + v <= 1.f)) return false;
+    t = f * dot(e2, q);
+    return true;
+}
+
+static Hit trace(const Scene &sc, V3f o, V3f d) {
+    Hit best;
+    if (std::isnan(o.x) || std::isnan(o.y) || std::isnan(o.z) || std::isnan(d.x) || std::isnan(d.y) || std::isnan(d.z))
+        return best;
+    float tbest = 1e8f;
+    for (size_t i = 0; i < sc.tris.size(); ++i) {
+        float u, v, t;
+        if (!tri_test(sc.tris[i], o, d, u, v, t)) continue;
+        if (t > kRayEpsilon && t < tbest) {  // ties: lowest triangle id wins (ascending scan, strict <)
+            tbest = t;
+            best.tri = (int) i;
+            best.u = u;
+            best.v = v;
+            best.t = t;
+        }
+    }
+    return best;
+}
+
+// reference include/psdr/core/frame.h:9-28 (Duff et al. ONB)
+template <class S> static void coordinate_system(V3<S> n, V3<S> &s, V3<S> &t) {
+    float sign = std::copysign(1.f, val(n.z));
+    S a = -rcp_(sign + n.z);
+    S b = n.x * n.y * a;
+    auto mulsign = [](S x, float z) { return std::signbit(z) ? -x : x; };
+    s = V3<S>(mulsign(sqr(n.x) * a, val(n.z)) + 1.f, mulsign(b, val(n.z)), mulsign(-n.x, val(n.z)));
+    t = V3<S>(b, sign + sqr(n.y) * a, -n.y);
+}
+
+template <class S> struct Its {  // reference include/psdr/core/intersection.h:23-60
+    bool valid = false;
+    int mesh = -1, tri = -1;
+    V3<S> p, n, wi, sh_s, sh_t, sh_n;
+    S t = S(0.f), J = S(1.f);
+    V2<S> uv;
+    float bu = 0.f, bv = 0.f;
+    V3<S> to_local(V3<S> v) const { return {dot(v, sh_s), dot(v, sh_t), dot(v, sh_n)}; }
+    V3<S> to_world(V3<S> v) const { return sh_s * v.x + sh_t * v.y + sh_n * v.z; }
+};
+
+template <class S> struct TriS {
+    V3<S> p0, e1, e2, n0, n1, n2, fn;
+    S area;
+};
+template <class S> static TriS<S> get_tri(const Scene &sc, int i);
+template <> TriS<Dual> get_tri<Dual>(const Scene &sc, int i) {
+    const Tri<Dual> &t = sc.tris[i];
+    return {t.p0, t.e1, t.e2, t.n0, t.n1, t.n2, t.fn, t.area};
+}
+template <> TriS<float> get_tri<float>(const Scene &sc, int i) {
+    const Tri<Dual> &t = sc.tris[i];
+    return {val(t.p0), val(t.e1), val(t.e2), val(t.n0), val(t.n1), val(t.n2), val(t.fn), t.area.v};
+}
+
+// reference include/psdr/utils.h:82-93
+template <class S> static void ray_intersect_triangle(V3<S> p0, V3<S> e1, V3<S> e2, V3<S> o, V3<S> d, S &u, S &v, S &t) {
+    V3<S> h = cross(d, e2);
+    S a = dot(e1, h);
+    S f = rcp_(a);
+    V3<S> s = o - p0;
+    u = f * dot(s, h);
+    V3<S> q = cross(s, e1);
+    v = f * dot(d, q);
+    t = f * dot(e2, q);
+}
+
+// reference src/scene/scene.cpp:612-806.  path_space=false with S=Dual is the solid-angle AD
+// formulation (analytic re-intersection); everything else is the material-form one.
+template <class S> static Its<S> ray_intersect(const Scene &sc, V3<S> o, V3<S> d, bool active, bool path_space,
+                                               int *out_tri = nullptr) {
+    Its<S> its;
+    if (out_tri) *out_tri = -1;
+    if (!active) return its;
+    Hit h = trace(sc, val(o), val(d));
+    if (h.tri < 0) return its;
+    if (out_tri) *out_tri = h.tri;
+    constexpr bool ad = std::is_same<S, Dual>::value;
+    TriS<S> T = get_tri<S>(sc, h.tri);
+    its.valid = true;
+    its.tri = h.tri;
+    its.mesh = sc.tri_mesh[h.tri];
+    its.n = T.fn;
+    const MeshRec &mesh = sc.meshes[its.mesh];
+    V2<S> uv0 = lift<S>(sc.tri_uv[3 * h.tri]), uv1 = lift<S>(sc.tri_uv[3 * h.tri + 1]), uv2 = lift<S>(sc.tri_uv[3 * h.tri + 2]);
+    V2<S> duv0 = uv1 - uv0, duv1 = uv2 - uv0;
+    S det = duv0.x * duv1.y - duv0.y * duv1.x;  // fmsub in the reference
+    bool valid_dp = val(det) != 0.f;
+    S inv_det = rcp_(det);
+    V3<S> sh_n, dir;
+    if (!ad || path_space) {
+        V2f uv(h.u, h.v);
+        sh_n = normalize(bilinear(T.n0, T.n1 - T.n0, T.n2 - T.n0, uv));
+        if (mesh.use_face_normals) sh_n = its.n;
+        its.p = bilinear(T.p0, T.e1, T.e2, uv);
+        dir = its.p - o;
+        its.t = norm(dir);
+        dir = dir / its.t;
+        its.uv = bilinear2(uv0, duv0, duv1, uv);
+        its.bu = h.u;
+        its.bv = h.v;
+        if (ad) its.J = T.area / detach(T.area);
+    } else {
+        S u, v, t;
+        ray_intersect_triangle(T.p0, T.e1, T.e2, o, d, u, v, t);
+        V2<S> uv(u, v);
+        sh_n = normalize(bilinear(T.n0, T.n1 - T.n0, T.n2 - T.n0, uv));
+        if (mesh.use_face_normals) sh_n = its.n;
+        its.p = V3<S>(fmadd(d.x, t, o.x), fmadd(d.y, t, o.y), fmadd(d.z, t, o.z));
+        its.t = t;
+        its.uv = bilinear2(uv0, duv0, duv1, uv);
+        its.bu = val(u);
+        its.bv = val(v);
+        dir = d;
+    }
+    its.sh_n = sh_n;
+    coordinate_system(sh_n, its.sh_s, its.sh_t);
+    if (valid_dp) {
+        V3<S> dp_du = (T.e1 * duv1.y - T.e2 * duv0.y) * inv_det;
+        its.sh_s = normalize(dp_du - sh_n * dot(sh_n, dp_du));
+        its.sh_t = cross(sh_n, its.sh_s);
+    }
+    its.wi = its.to_local(-dir);
+    return its;
+}
+
+// ---- BSDF (reference src/bsdf/diffuse.cpp:23-108) ----------------------------------------
+template <class S> static V3<S> refl_of(const Bsdf &b);
+template <> V3<Dual> refl_of<Dual>(const Bsdf &b) { return b.reflectance; }
+template <> V3<float> refl_of<float>(const Bsdf &b) { return val(b.reflectance); }
+
+template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
+    if (!active || !its.valid) return V3<S>(S(0.f));
+    const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
+    S wiz = its.wi.z;
+    if (b.two_side) {
+        if (std::signbit(val(wiz))) wo.z = -wo.z;
+        wiz = abs_(wiz);
+    }
+    if (!(val(wiz) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
+    V3<S> r = refl_of<S>(b);
+    return r * S(kInvPi) * wo.z;
+}
+
+template <class S> static float bsdf_pdf(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
+    if (!active || !its.valid) return 0.f;
+    const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
+    float wiz = val(its.wi.z), woz = val(wo.z);
+    if (b.two_side) {
+        if (std::signbit(wiz)) woz = -woz;
+        wiz = std::fabs(wiz);
+    }
+    if (!(wiz > 0.f && woz > 0.f)) return 0.f;
+    return kInvPi * woz;
+}
+
+struct BsdfSample {
+    V3f wo;
+    float pdf = 0.f, eta = 1.f;
+    bool valid = false;
+};
+
+// reference include/psdr/core/warp.h:15-63
+static V2f square_to_uniform_disk_concentric(V2f s) {
+    float x = std::fmaf(2.f, s.x, -1.f), y = std::fmaf(2.f, s.y, -1.f);
+    bool is_zero = (x == 0.f && y == 0.f), q13 = std::fabs(x) < std::fabs(y);
+    float r = q13 ? y : x, rp = q13 ? x : y;
+    // sincos(phi): |base phi| <= pi/4, evaluated with fixed polynomials (orc_math.h) so that the
+    // CUDA path can reproduce it bit for bit; quadrants 1/3 use sin(pi/2-x)=cos x.
+    float sn, cs;
+    sincos_quarter(.25f * kPi * rp / r, sn, cs);
+    if (is_zero) { sn = 0.f; cs = 1.f; }
+    if (q13 && !is_zero) std::swap(sn, cs);
+    return V2f(r * cs, r * sn);
+}
+
+template <class S> static BsdfSample bsdf_sample(const Scene &sc, const Its<S> &its, V3f sample, bool active) {
+    BsdfSample bs;
+    if (!its.valid) return bs;
+    const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
+    float wiz = val(its.wi.z);
+    if (b.two_side) wiz = std::fabs(wiz);
+    V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));  // tail<2>(sample)
+    float z = safe_sqrt(1.f - (std::fmaf(p.y, p.y, p.x * p.x)));
+    bs.wo = V3f(p.x, p.y, z);
+    bs.pdf = kInvPi * z;
+    bs.valid = active && (wiz > 0.f);
+    return bs;
+}
+
+// ---- emitters (reference src/emitter/area.cpp, src/shape/mesh.cpp:413-466) ---------------
+template <class S> static V3<S> radiance_of(const EmitterRec &e);
+template <> V3<Dual> radiance_of<Dual>(const EmitterRec &e) { return e.radiance; }
+template <> V3<float> radiance_of<float>(const EmitterRec &e) { return val(e.radiance); }
+
+template <class S> static bool is_emitter(const Scene &sc, const Its<S> &its) {
+    return its.valid && sc.meshes[its.mesh].emitter >= 0;
+}
+template <class S> static V3<S> Le(const Scene &sc, const Its<S> &its, bool active) {
+    if (!its.valid || sc.meshes[its.mesh].emitter < 0) return V3<S>(S(0.f));
+    if (!(active && val(its.wi.z) > 0.f)) return V3<S>(S(0.f));
+    return radiance_of<S>(sc.emitters[sc.meshes[its.mesh].emitter]);
+}
+
+template <class S> struct PosSample {
+    V3<S> p, n;
+    S J = S(1.f);
+    float pdf = 0.f;
+    bool valid = false;
+};
+
+// reference src/scene/scene.cpp:987-1013 + mesh.cpp:413-454
+template <class S> static PosSample<S> sample_emitter_position(const Scene &sc, V2f sample2) {
+    PosSample<S> ps;
+    int ei = 0;
+    float emitter_pdf = 1.f;
+    if (sc.emitters.size() != 1) {
+        auto r = sc.emitter_distrb.sample_reuse(sample2.y);
+        ei = r.first;
+        emitter_pdf = r.second;
+    }
+    const MeshRec &m = sc.meshes[sc.emitters[ei].mesh];
+    int fi = m.face_distrb.sample_reuse(sample2.x).first;
+    float t = safe_sqrt(1.f - sample2.x);
+    V2f st(1.f - t, t * sample2.y);
+    TriS<S> T = get_tri<S>(sc, m.face_offset + fi);
+    constexpr bool ad = std::is_same<S, Dual>::value;
+    if (ad) ps.J = T.area / detach(T.area);
+    ps.p = bilinear(T.p0, T.e1, T.e2, st);
+    ps.n = T.fn;
+    ps.pdf = m.inv_total_area;
+    if (sc.emitters.size() != 1) ps.pdf *= emitter_pdf;
+    ps.valid = true;
+    return ps;
+}
+
+// reference src/scene/scene.cpp:1016-1024, area.cpp:48-59, mesh.cpp:457-466
+template <class S> static float emitter_position_pdf(const Scene &sc, const Its<S> &its, bool active) {
+    if (!its.valid || !active) return 0.f;
+    int e = sc.meshes[its.mesh].emitter;
+    if (e < 0) return 0.f;
+    return sc.emitters[e].sampling_weight * sc.meshes[its.mesh].inv_total_area;
+}
+
+static inline float mis_weight(float a, float b) {
+    float w1 = a * a, w2 = b * b;
+    return w1 / (w1 + w2);
+}
+
+// ---- camera ------------------------------------------------------------------------------
+// reference src/sensor/perspective.cpp:160-178
+template <class S> static void sample_primary_ray(const Camera &cam, V2f s, V3<S> &o, V3<S> &d);
+template <> void sample_primary_ray<float>(const Camera &cam, V2f s, V3f &o, V3f &d) {
+    M4<float> s2c = val(cam.sample_to_camera), tw = val(cam.to_world_full);
+    V3f dc = normalize(transform_pos(s2c, V3f(s.x, s.y, 0.f)));
+    o = transform_pos(tw, V3f(0.f, 0.f, 0.f));
+    d = transform_dir(tw, dc);
+}
+template <> void sample_primary_ray<Dual>(const Camera &cam, V2f s, V3d &o, V3d &d) {
+    M4<float> s2c = val(cam.sample_to_camera);
+    V3f dc = normalize(transform_pos(s2c, V3f(s.x, s.y, 0.f)));
+    o = transform_pos(cam.to_world_full, V3d(Dual(0.f), Dual(0.f), Dual(0.f)));
+    d = transform_dir(cam.to_world_full, lift<Dual>(dc));
+}
+
+struct SensorDirect {
+    V2f q;
+    int pixel = -1;
+    float sensor_val = 0.f;
+    bool valid = false;
+};
+// reference src/sensor/perspective.cpp:181-197
+static SensorDirect sample_direct(const Scene &sc, const Camera &cam, V3f p) {
+    SensorDirect r;
+    V3f q = transform_pos(val(cam.world_to_sample), p);
+    r.q = V2f(q.x, q.y);
+    int ix = (int) std::floor(q.x * (float) sc.width), iy = (int) std::floor(q.y * (float) sc.height);
+    r.valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+    r.pixel = r.valid ? iy * sc.width + ix : -1;
+    V3f dir = p - val(cam.pos);
+    float dist2 = squared_norm(dir);
+    dir = dir / safe_sqrt(dist2);
+    float cosTheta = dot(val(cam.dir), dir);
+    float ic = 1.f / cosTheta;
+    r.sensor_val = (1.f / dist2) * (ic * ic * ic) * cam.inv_area;  // pow(rcp(cos),3)
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// PathTracer::__Li  (reference src/integrator/path.cpp:35-127)
+// ------------------------------------------------------------------------------------------
+template <class S>
+static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
+    constexpr bool ad = std::is_same<S, Dual>::value;
+    // primary hit: ray_intersect<ad> (path_space = false)
+    Its<S> its = ray_intersect<S>(sc, ro, rd, active, false);
+    active = active && its.valid;
+    V3<S> throughput(S(1.f));
+    V3<S> result = hide_emitters ? V3<S>(S(0.f)) : Le(sc, its, active);
+    for (int depth = 0; depth < max_depth; ++depth) {
+        // all lanes draw, masked or not (GCC evaluates next_2d's arguments right-to-left:
+        // y gets the first draw; sampler.h:19-21)
+        float s_y = rng.next_1d(), s_x = rng.next_1d();
+        float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();  // next_nd<3> = (d3,d2,d1)
+        if (!active) continue;
+        {   // ---- emitter sampling
+            PosSample<S> ps = sample_emitter_position<S>(sc, V2f(s_x, s_y));
+            bool active_direct = active && ps.valid && !is_emitter(sc, its);
+            V3<S> wod = ps.p - its.p;
+            S dist_sqr = squared_norm(wod);
+            S dist = safe_sqrt(dist_sqr);
+            wod = wod / dist;
+            Its<S> its1 = ray_intersect<S>(sc, its.p, wod, active_direct, ad);
+            active_direct = active_direct && its1.valid;
+            active_direct = active_direct && (val(its1.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its1);
+            S cos_val = dot(its1.n, -wod);
+            S G_val = abs_(cos_val) / dist_sqr;
+            V3<S> emitter_val = Le(sc, its1, active);
+            V3<S> wo_local = its.to_local(wod);
+            V3<S> bsdf_val2 = bsdf_eval(sc, its, wo_local, active_direct);
+            bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
+            float pdf1 = bsdf_pdf(sc, its, wo_local, active_direct) * val(G_val);
+            active_direct = active_direct && (pdf1 != 0.f);
+            float weight1 = mis_weight(ps.pdf, pdf1);
+            if (active_direct) result += throughput * emitter_val * bsdf_val2 * S(weight1);
+        }
+        {   // ---- BSDF sampling
+            BsdfSample bs = bsdf_sample(sc, its, V3f(s3_x, s3_y, s3_z), active);
+            V3<S> wdir = its.to_world(lift<S>(bs.wo));
+            Its<S> its1 = ray_intersect<S>(sc, its.p, wdir, active, ad);
+            active = active && bs.valid;
+            active = active && its1.valid;
+            V3<S> bsdf_val;
+            float pdf0;
+            if (ad) {
+                V3<S> wo = its1.p - its.p;
+                wo = wo / its1.t;
+                S cos_val = dot(its1.n, -wo);
+                S G_val = abs_(cos_val) / sqr(its1.t);
+                S J = its1.valid ? its1.J : S(1.f);
+                if (!its1.valid) G_val = S(1.f);
+                pdf0 = bs.pdf * val(G_val);
+                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                else bsdf_val = bsdf_eval(sc, its, its.to_local(wo), active) * (G_val * J / S(pdf0));
+            } else {
+                S cos_val = dot(its1.n, -wdir);
+                S G_val = abs_(cos_val) / sqr(its1.t);
+                pdf0 = bs.pdf * val(G_val);
+                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                else bsdf_val = bsdf_eval(sc, its, lift<S>(bs.wo), active) / S(bs.pdf);
+            }
+            float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, its1, active));
+            throughput *= bsdf_val;
+            if (active) result += Le(sc, its1, active) * throughput * S(weight2);
+            its = its1;
+        }
+    }
+    return result;
+}
+
+static inline bool finite3(float x) { return std::isfinite(x); }
+
+struct RenderArgs {
+    int sensor = 0, max_depth = 1, seed = 0;
+    bool hide_emitters = false;
+    int skip[3] = {0, 0, 0};  // draws already consumed per lane (seed = -1 continuation)
+};
+
+static void splat(float *img, int pix, int c, float v) {
+#pragma omp atomic
+    img[3 * pix + c] += v;
+}
+
+// reference src/integrator/integrator.cpp:104-136 (renderC: ad=false; renderD: ad=true)
+template <class S>
+static void render_interior(const Scene &sc, const RenderArgs &ra, float *img, float *dimg, const int *pix_id, int npix_sel,
+                            float *lane_out) {
+    const Camera &cam = sc.cameras[ra.sensor];
+    int64_t npix = pix_id ? npix_sel : (int64_t) sc.width * sc.height;
+    int64_t N = npix * sc.spp;
+    float inv_spp = sc.spp > 1 ? 1.f / (float) sc.spp : 1.f;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < N; ++i) {
+        int64_t idx = sc.spp > 1 ? i / sc.spp : i;
+        int pix = pix_id ? pix_id[idx] : (int) idx;
+        uint64_t seed_value = pix_id ? (uint64_t) ((int64_t) pix + ra.seed) : (uint64_t) (i + ra.seed);
+        Pcg32 rng = make_sampler(seed_value, (uint64_t) i);
+        for (int k = 0; k < ra.skip[0]; ++k) rng.next_1d();
+        float jy = rng.next_1d(), jx = rng.next_1d();
+        float sx = ((float) (pix % sc.width) + jx) / (float) sc.width;
+        float sy = ((float) (pix / sc.width) + jy) / (float) sc.height;
+        V3<S> o, d;
+        sample_primary_ray<S>(cam, V2f(sx, sy), o, d);
+        V3<S> v = Li<S>(sc, rng, o, d, true, ra.max_depth, ra.hide_emitters);
+        for (int c = 0; c < 3; ++c) {
+            float x = val(v[c]), dx = tan_(v[c]);
+            if (!std::isfinite(x)) { x = 0.f; dx = 0.f; }
+            if (lane_out) lane_out[3 * i + c] = x;
+            splat(img, (int) idx, c, x * inv_spp);   // sum then divide in the reference; see tests' tolerance
+            if (dimg) splat(dimg, (int) idx, c, dx * inv_spp);
+        }
+    }
+}
+
+// reference src/sensor/perspective.cpp:200-226 + src/integrator/integrator.cpp:179-198
+static void render_primary_edges(const Scene &sc, const RenderArgs &ra, float *dimg) {
+    const Camera &cam = sc.cameras[ra.sensor];
+    if (!cam.enable_edges || sc.sppe <= 0) return;
+    int64_t N = (int64_t) sc.width * sc.height * sc.sppe;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < N; ++i) {
+        Pcg32 rng = make_sampler((uint64_t) (i + ra.seed), (uint64_t) i);
+        for (int k = 0; k < ra.skip[1]; ++k) rng.next_1d();
+        float s1 = rng.next_1d();
+        auto r = cam.edge_distrb.sample_reuse(s1);
+        const PrimEdge &e = cam.edges[r.first];
+        float pdf = r.second / e.length;
+        V2d p_(fmadd(e.p0.x, Dual(1.0f - s1), e.p1.x * s1), fmadd(e.p0.y, Dual(1.0f - s1), e.p1.y * s1));
+        V2f p = val(p_);
+        Dual x_dot_n = dot(p_, lift<Dual>(e.normal));
+        int ix = (int) std::floor(p.x * (float) sc.width), iy = (int) std::floor(p.y * (float) sc.height);
+        bool valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+        int idx = valid ? iy * sc.width + ix : -1;
+        V3f op, dp, on, dn;
+        sample_primary_ray<float>(cam, V2f(p.x + kEdgeEpsilon * e.normal.x, p.y + kEdgeEpsilon * e.normal.y), op, dp);
+        sample_primary_ray<float>(cam, V2f(p.x - kEdgeEpsilon * e.normal.x, p.y - kEdgeEpsilon * e.normal.y), on, dn);
+        V3f Lp, Ln;
+        if (sc.li_p_first) {
+            Lp = Li<float>(sc, rng, op, dp, valid, ra.max_depth, ra.hide_emitters);
+            Ln = Li<float>(sc, rng, on, dn, valid, ra.max_depth, ra.hide_emitters);
+        } else {
+            Ln = Li<float>(sc, rng, on, dn, valid, ra.max_depth, ra.hide_emitters);
+            Lp = Li<float>(sc, rng, op, dp, valid, ra.max_depth, ra.hide_emitters);
+        }
+        if (!valid) continue;
+        for (int c = 0; c < 3; ++c) {
+            float dl = (Ln[c] - Lp[c]) / pdf;
+            Dual value = x_dot_n * Dual(dl);
+            if (!std::isfinite(value.v)) continue;   // masked(value, ~isfinite(value)) = 0
+            float t = value.d;
+            if (sc.sppe > 1) t /= (float) sc.sppe;
+            splat(dimg, idx, c, t);
+        }
+    }
+}
+
+// reference src/scene/scene.cpp:1027-1068
+struct BoundarySeg {
+    V3d p0;
+    V3f edge, edge2, p2, n;
+    float pdf = 0.f;
+    bool valid = false;
+};
+static int sign_eps(float x, float eps) { return x > eps ? 1 : (x < -eps ? -1 : 0); }
+
+static BoundarySeg sample_boundary_segment_direct(const Scene &sc, V3f sample3) {
+    BoundarySeg r;
+    float sample1 = sample3.x;
+    auto er = sc.sec_edge_distrb.sample_reuse(sample1);
+    const SecEdge &info = sc.sec_edges[er.first];
+    float pdf0 = er.second;
+    r.p0 = V3d(fmadd(info.e1.x, sample1, info.p0.x), fmadd(info.e1.y, sample1, info.p0.y), fmadd(info.e1.z, sample1, info.p0.z));
+    V3f e1 = val(info.e1);
+    r.edge = normalize(e1);
+    r.edge2 = info.p2 - val(info.p0);
+    V3f p0 = val(r.p0);
+    pdf0 /= norm(e1);
+    PosSample<float> ps2 = sample_emitter_position<float>(sc, V2f(sample3.y, sample3.z));
+    r.p2 = ps2.p;
+    r.n = ps2.n;
+    V3f e = r.p2 - p0;
+    float distSqr = squared_norm(e);
+    e = e / safe_sqrt(distSqr);
+    float cosTheta = dot(r.n, -e);
+    int sgn0 = sign_eps(dot(info.n0, e), kEdgeEpsilon), sgn1 = sign_eps(dot(info.n1, e), kEdgeEpsilon);
+    r.valid = (cosTheta > kEpsilon) && ((info.is_boundary && sgn0 != 0) || (!info.is_boundary && sgn0 * sgn1 < 0));
+    r.pdf = r.valid ? pdf0 * ps2.pdf * (distSqr / cosTheta) : 0.f;
+    return r;
+}
+
+static inline float sign1(float x) { return std::signbit(x) ? -1.f : 1.f; }  // drjit::sign
+
+// reference src/integrator/path.cpp:172-270; returns pixel (-1 = invalid), value0 (primal
+// boundary value, what the guiding pre-pass accumulates) and the tangent contribution.
+static int eval_secondary_edge(const Scene &sc, const Camera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
+    value0_out = V3f(0.f, 0.f, 0.f);
+    tangent_out = V3f(0.f, 0.f, 0.f);
+    BoundarySeg bss = sample_boundary_segment_direct(sc, sample3);
+    bool valid = bss.valid;
+    V3f _p0 = val(bss.p0), _p2 = bss.p2;
+    V3f _dir = normalize(_p2 - _p0);
+    int light_tri = -1;
+    Its<float> _its2 = ray_intersect<float>(sc, _p0, _dir, valid, false, &light_tri);
+    valid = valid && is_emitter(sc, _its2) && _its2.valid && norm(_its2.p - _p2) < kShadowEpsilon;
+    Its<float> _its1 = ray_intersect<float>(sc, _p0, -_dir, valid, false);
+    valid = valid && _its1.valid;
+    V3f _p1 = _its1.p;
+    SensorDirect sds = sample_direct(sc, cam, _p1);
+    valid = valid && sds.valid;
+    V3d co, cd;
+    sample_primary_ray<Dual>(cam, sds.q, co, cd);
+    Its<Dual> its1 = ray_intersect<Dual>(sc, co, cd, valid, false);
+    valid = valid && its1.valid && norm(val(its1.p) - _p1) < kShadowEpsilon;
+    valid = valid && its1.valid && sc.meshes[its1.mesh].bsdf >= 0;
+    if (!valid) return -1;
+
+    float dist = norm(_p2 - _p1), cos2 = std::fabs(dot(bss.n, -_dir));
+    V3f e = cross(bss.edge, _dir);
+    float sinphi = norm(e);
+    V3f proj = normalize(cross(e, bss.n));
+    float sinphi2 = norm(cross(_dir, proj));
+    float base_v = (_its1.t / dist) * (sinphi / sinphi2) * cos2;
+    valid = valid && (sinphi > kEpsilon) && (sinphi2 > kEpsilon);
+    if (!valid) return -1;
+
+    V3f d0 = -val(cd);
+    V3f d0_local = _its1.to_local(d0);
+    V3f bsdf_val = bsdf_eval<float>(sc, _its1, d0_local, valid);
+    float correction = std::fabs((_its1.wi.z * dot(d0, _its1.n)) / (d0_local.z * dot(_dir, _its1.n)));
+    bsdf_val = bsdf_val * correction;
+    V3f value0 = bsdf_val * Le(sc, _its2, valid) * (base_v * sds.sensor_val / bss.pdf);
+    value0_out = value0;
+
+    V3f n = normalize(cross(bss.n, proj));
+    value0 = value0 * (sign1(dot(e, bss.edge2)) * sign1(dot(e, n)));
+    const Tri<Dual> &T = sc.tris[light_tri];
+    V3d sdir = normalize(bss.p0 - its1.p);
+    Dual u, v, t;
+    ray_intersect_triangle<Dual>(T.p0, T.e1, T.e2, its1.p, sdir, u, v, t);
+    V3d u2 = bilinear(detach(T.p0), detach(T.e1), detach(T.e2), V2d(u, v));
+    Dual dn = dot(lift<Dual>(n), u2);
+    tangent_out = V3f(value0.x * dn.d, value0.y * dn.d, value0.z * dn.d);
+    if (getenv("ORC_DEBUG") && !(std::isfinite(tangent_out.x)))
+        fprintf(stderr, "sec-edge NaN: value0 %g %g %g dn %g %g base_v %g sensor %g pdf %g corr %g bsdf %g sinphi %g %g u %g %g v %g %g t %g %g\n", value0.x, value0.y, value0.z,
+                dn.v, dn.d, base_v, sds.sensor_val, bss.pdf, correction, bsdf_val.x, sinphi, sinphi2, u.v, u.d, v.v, v.d, t.v, t.d);
+    return sds.pixel;
+}
+
+// reference src/integrator/path.cpp:274-294 (no guiding distribution: pdf0 = 1)
+static void render_secondary_edges(const Scene &sc, const RenderArgs &ra, float *dimg) {
+    if (sc.sppse <= 0) return;
+    const Camera &cam = sc.cameras[ra.sensor];
+    int64_t N = (int64_t) sc.width * sc.height * sc.sppse;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < N; ++i) {
+        Pcg32 rng = make_sampler((uint64_t) (i + ra.seed), (uint64_t) i);
+        for (int k = 0; k < ra.skip[2]; ++k) rng.next_1d();
+        float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+        V3f value0, tangent;
+        int pix = eval_secondary_edge(sc, cam, V3f(d3, d2, d1), value0, tangent);
+        if (pix < 0) continue;
+        for (int c = 0; c < 3; ++c) {
+            float t = tangent[c];
+            // deviation: the reference leaves non-finite tangents in (its scrub is commented out,
+            // path.cpp:284); a shadow ray parallel to the emitter triangle gives 0*inf here.
+            if (!std::isfinite(t)) continue;
+            if (sc.sppse > 1) t /= (float) sc.sppse;
+            splat(dimg, pix, c, t);
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C API (ctypes)
+// ------------------------------------------------------------------------------------------
+static M4<Dual> load_m4(const float *v, const float *d) {
+    M4<Dual> m = M4<Dual>::identity();
+    if (v)
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) m.m[i][j] = Dual(v[4 * i + j], d ? d[4 * i + j] : 0.f);
+    return m;
+}
+
+extern "C" {
+
+void *orc_create(int width, int height, int spp, int sppe, int sppse) {
+    Scene *s = new Scene();
+    s->width = width; s->height = height; s->spp = spp; s->sppe = sppe; s->sppse = sppse;
+    return s;
+}
+void orc_destroy(void *h) { delete (Scene *) h; }
+const char *orc_error(void *h) { return ((Scene *) h)->error.c_str(); }
+void orc_set_li_order(void *h, int p_first) { ((Scene *) h)->li_p_first = p_first != 0; }
+
+int orc_add_diffuse(void *h, const float *refl, const float *d_refl, int two_side) {
+    Scene *s = (Scene *) h;
+    Bsdf b;
+    b.reflectance = V3d(Dual(refl[0], d_refl ? d_refl[0] : 0.f), Dual(refl[1], d_refl ? d_refl[1] : 0.f),
+                        Dual(refl[2], d_refl ? d_refl[2] : 0.f));
+    b.two_side = two_side != 0;
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+}
+
+// to_world / d_to_world: 3 consecutive row-major 4x4 (left, raw, right); NULL = identity / zero
+int orc_add_mesh(void *h, const float *v, const float *dv, int nv, const int *f, int nf, const float *uv, int nuv, const int *fuv,
+                 const float *to_world, const float *d_to_world, int bsdf, const float *radiance, const float *d_radiance,
+                 int use_face_normals, int enable_edges) {
+    Scene *s = (Scene *) h;
+    MeshRec m;
+    m.v_raw.resize(nv);
+    for (int i = 0; i < nv; ++i)
+        m.v_raw[i] = V3d(Dual(v[3 * i], dv ? dv[3 * i] : 0.f), Dual(v[3 * i + 1], dv ? dv[3 * i + 1] : 0.f),
+                         Dual(v[3 * i + 2], dv ? dv[3 * i + 2] : 0.f));
+    m.f.assign(f, f + 3 * nf);
+    m.has_uv = nuv > 0;
+    if (m.has_uv) {
+        m.uv.resize(nuv);
+        for (int i = 0; i < nuv; ++i) m.uv[i] = V2f(uv[2 * i], uv[2 * i + 1]);
+        m.fuv.assign(fuv, fuv + 3 * nf);
+    }
+    for (int k = 0; k < 3; ++k) m.to_world[k] = load_m4(to_world ? to_world + 16 * k : nullptr, d_to_world ? d_to_world + 16 * k : nullptr);
+    m.bsdf = bsdf;
+    m.use_face_normals = use_face_normals != 0;
+    m.enable_edges = enable_edges != 0;
+    if (radiance) {
+        EmitterRec e;
+        e.radiance = V3d(Dual(radiance[0], d_radiance ? d_radiance[0] : 0.f), Dual(radiance[1], d_radiance ? d_radiance[1] : 0.f),
+                         Dual(radiance[2], d_radiance ? d_radiance[2] : 0.f));
+        e.mesh = (int) s->meshes.size();
+        m.emitter = (int) s->emitters.size();
+        s->emitters.push_back(e);
+    }
+    s->meshes.push_back(m);
+    s->configured = false;
+    return (int) s->meshes.size() - 1;
+}
+
+int orc_add_camera(void *h, float fov, float near_, float far_, const float *to_world, const float *d_to_world) {
+    Scene *s = (Scene *) h;
+    Camera c;
+    c.fov = fov; c.near_ = near_; c.far_ = far_;
+    for (int k = 0; k < 3; ++k) c.to_world[k] = load_m4(to_world ? to_world + 16 * k : nullptr, d_to_world ? d_to_world + 16 * k : nullptr);
+    s->cameras.push_back(c);
+    s->configured = false;
+    return (int) s->cameras.size() - 1;
+}
+
+int orc_configure(void *h, const int *active, int nactive) { return configure_scene(*(Scene *) h, active, nactive) ? 0 : 1; }
+
+int orc_num_primary_edges(void *h, int sensor) { return (int) ((Scene *) h)->cameras[sensor].edges.size(); }
+int orc_num_secondary_edges(void *h) { return (int) ((Scene *) h)->sec_edges.size(); }
+int orc_num_mesh_edges(void *h, int mesh) { return (int) ((Scene *) h)->meshes[mesh].edges.size(); }
+// out: [4][ne] rows v0, v1, f0, f1 (what the reference's Mesh.edge_indices() returns)
+void orc_mesh_edges(void *h, int mesh, int *out) {
+    auto &E = ((Scene *) h)->meshes[mesh].edges;
+    size_t n = E.size();
+    for (size_t i = 0; i < n; ++i) { out[i] = E[i].v0; out[n + i] = E[i].v1; out[2 * n + i] = E[i].f0; out[3 * n + i] = E[i].f1; }
+}
+
+// mode 0 = renderC, 1 = renderD.  terms: bit0 interior, bit1 primary edges, bit2 secondary edges.
+// img/dimg: [npix*3] (zeroed here).  pix_id may be NULL.  lane_out may be NULL ([N0*3] primal lane values).
+int orc_render(void *h, int sensor, int max_depth, int seed, int mode, int terms, int hide_emitters, const int *skip,
+               const int *pix_id, int npix_sel, float *img, float *dimg, float *lane_out) {
+    Scene &sc = *(Scene *) h;
+    if (!sc.configured) { sc.error = "Input scene must be configured!"; return 1; }
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) { sc.error = "Invalid sensor id!"; return 1; }
+    if (pix_id && seed < 0) { sc.error = "While using batch rendering, seed must be set!"; return 1; }
+    RenderArgs ra;
+    ra.sensor = sensor; ra.max_depth = max_depth; ra.seed = seed; ra.hide_emitters = hide_emitters != 0;
+    if (skip) for (int k = 0; k < 3; ++k) ra.skip[k] = skip[k];
+    int64_t npix = pix_id ? npix_sel : (int64_t) sc.width * sc.height;
+    std::fill(img, img + 3 * npix, 0.f);
+    if (dimg) std::fill(dimg, dimg + 3 * npix, 0.f);
+    if (sc.spp > 0 && (terms & 1)) {
+        if (mode == 0) render_interior<float>(sc, ra, img, nullptr, pix_id, npix_sel, lane_out);
+        else render_interior<Dual>(sc, ra, img, dimg, pix_id, npix_sel, lane_out);
+    }
+    if (mode == 1 && dimg) {
+        if ((terms & 2) && sc.sppe > 0) render_primary_edges(sc, ra, dimg);
+        if ((terms & 4) && sc.sppse > 0) render_secondary_edges(sc, ra, dimg);
+    }
+    return 0;
+}
+
+// Sampler tap: out[ndraws][n] = successive next_1d() of a sampler seeded with arange(n)+seed
+void orc_sampler_draws(int64_t seed, int n, int ndraws, float *out) {
+    for (int i = 0; i < n; ++i) {
+        Pcg32 r = make_sampler((uint64_t) (i + seed), (uint64_t) i);
+        for (int k = 0; k < ndraws; ++k) out[(size_t) k * n + i] = r.next_1d();
+    }
+}
+
+// DiscreteDistribution tap (pmf.cpp:18-28)
+void orc_pmf_sample(const float *pmf, int n, const float *samples, int m, int *idx, float *p, float *sum) {
+    Distrib d;
+    d.init(std::vector<float>(pmf, pmf + n));
+    *sum = d.sum;
+    for (int i = 0; i < m; ++i) {
+        auto r = d.sample(samples[i]);
+        idx[i] = r.first;
+        p[i] = r.second;
+    }
+}
+
+// AOV tap = what FieldExtractionIntegrator returns at spp=1 (reference src/integrator/field.cpp:47-121):
+// per lane: mesh id+1, tri id, position, depth t, geometric normal, shading normal, uv.  out: [N][14]
+void orc_aov(void *h, int sensor, int seed, float *out) {
+    Scene &sc = *(Scene *) h;
+    const Camera &cam = sc.cameras[sensor];
+    int64_t N = (int64_t) sc.width * sc.height * sc.spp;
+#pragma omp parallel for
+    for (int64_t i = 0; i < N; ++i) {
+        int64_t idx = sc.spp > 1 ? i / sc.spp : i;
+        Pcg32 rng = make_sampler((uint64_t) (i + seed), (uint64_t) i);
+        float jy = rng.next_1d(), jx = rng.next_1d();
+        float sx = ((float) (idx % sc.width) + jx) / (float) sc.width, sy = ((float) (idx / sc.width) + jy) / (float) sc.height;
+        V3f o, d;
+        sample_primary_ray<float>(cam, V2f(sx, sy), o, d);
+        Its<float> its = ray_intersect<float>(sc, o, d, true, false);
+        float *r = out + 14 * i;
+        for (int k = 0; k < 14; ++k) r[k] = 0.f;
+        if (!its.valid) { r[1] = -1.f; continue; }
+        r[0] = (float) (its.mesh + 1); r[1] = (float) its.tri;
+        r[2] = its.p.x; r[3] = its.p.y; r[4] = its.p.z; r[5] = its.t;
+        r[6] = its.n.x; r[7] = its.n.y; r[8] = its.n.z;
+        r[9] = its.sh_n.x; r[10] = its.sh_n.y; r[11] = its.sh_n.z; r[12] = its.uv.x; r[13] = its.uv.y;
+    }
+}
+
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of the CPU oracle (oracle/psdr_oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (psdr_jit_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_f = C.POINTER(C.c_float)
+_i = C.POINTER(C.c_int)
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libpsdr_oracle.so")
+    srcs = [os.path.join(_HERE, n) for n in ("psdr_oracle.cpp", "orc_math.h")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int] * 5
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_error.restype = C.c_char_p
+        L.orc_error.argtypes = [C.c_void_p]
+        L.orc_set_li_order.argtypes = [C.c_void_p, C.c_int]
+        L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
+        L.orc_add_mesh.argtypes = [C.c_void_p, _f, _f, C.c_int, _i, C.c_int, _f, C.c_int, _i, _f, _f, C.c_int, _f, _f, C.c_int, C.c_int]
+        L.orc_add_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f, _f]
+        L.orc_configure.argtypes = [C.c_void_p, _i, C.c_int]
+        L.orc_num_primary_edges.argtypes = [C.c_void_p, C.c_int]
+        L.orc_num_secondary_edges.argtypes = [C.c_void_p]
+        L.orc_num_mesh_edges.argtypes = [C.c_void_p, C.c_int]
+        L.orc_mesh_edges.argtypes = [C.c_void_p, C.c_int, _i]
+        L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i, _i, C.c_int, _f, _f, _f]
+        L.orc_sampler_draws.argtypes = [C.c_int64, C.c_int, C.c_int, _f]
+        L.orc_pmf_sample.argtypes = [_f, C.c_int, _f, C.c_int, _i, _f, _f]
+        L.orc_aov.argtypes = [C.c_void_p, C.c_int, C.c_int, _f]
+        L.orc_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(_f)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(_i)
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    return a if shape is None else a.reshape(shape)
+
+
+def _mats(m):
+    """3x(4x4): (left, raw, right); accepts a single 4x4 (= raw) or a dict."""
+    out = np.tile(np.eye(4, dtype=np.float32), (3, 1, 1))
+    if m is None:
+        return out
+    if isinstance(m, dict):
+        for k, name in enumerate(("left", "raw", "right")):
+            if name in m and m[name] is not None:
+                out[k] = np.asarray(m[name], dtype=np.float32)
+        return out
+    out[1] = np.asarray(m, dtype=np.float32)
+    return out
+
+
+def _dmats(m):
+    out = np.zeros((3, 4, 4), dtype=np.float32)
+    if m is None:
+        return None
+    if isinstance(m, dict):
+        for k, name in enumerate(("left", "raw", "right")):
+            if name in m and m[name] is not None:
+                out[k] = np.asarray(m[name], dtype=np.float32)
+        return out
+    out[1] = np.asarray(m, dtype=np.float32)
+    return out
+
+
+class OracleScene:
+    def __init__(self, width, height, spp, sppe=0, sppse=0):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_create(width, height, spp, sppe, sppse))
+        self.width, self.height, self.spp, self.sppe, self.sppse = width, height, spp, sppe, sppse
+        self._keep = []
+        self.bsdf_ids = {}
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def add_diffuse(self, name, refl, d_refl=None, two_side=False):
+        r, dr = _f32(refl), _f32(d_refl)
+        idx = self.L.orc_add_diffuse(self.h, _fp(r), _fp(dr), int(two_side))
+        self.bsdf_ids[name] = idx
+        return idx
+
+    def add_mesh(self, v, f, bsdf, uv=None, fuv=None, to_world=None, d_to_world=None, dv=None, radiance=None,
+                 d_radiance=None, use_face_normals=False, enable_edges=True):
+        v = _f32(v, (-1, 3))
+        f = np.ascontiguousarray(np.asarray(f, dtype=np.int32).reshape(-1, 3))
+        dv = _f32(dv, (-1, 3))
+        uv_ = _f32(uv, (-1, 2)) if uv is not None else None
+        fuv_ = np.ascontiguousarray(np.asarray(fuv, dtype=np.int32).reshape(-1, 3)) if fuv is not None else None
+        tw, dtw = _mats(to_world), _dmats(d_to_world)
+        rad, drad = _f32(radiance), _f32(d_radiance)
+        b = self.bsdf_ids[bsdf] if isinstance(bsdf, str) else int(bsdf)
+        return self.L.orc_add_mesh(self.h, _fp(v), _fp(dv), len(v), _ip(f), len(f), _fp(uv_), 0 if uv_ is None else len(uv_),
+                                   _ip(fuv_), _fp(tw), _fp(dtw), b, _fp(rad), _fp(drad), int(use_face_normals), int(enable_edges))
+
+    def add_camera(self, fov, near, far, to_world, d_to_world=None):
+        tw, dtw = _mats(to_world), _dmats(d_to_world)
+        return self.L.orc_add_camera(self.h, fov, near, far, _fp(tw), _fp(dtw))
+
+    def configure(self, active=(0,)):
+        a = np.asarray(list(active), dtype=np.int32)
+        rc = self.L.orc_configure(self.h, _ip(a), len(a))
+        if rc:
+            raise RuntimeError(self.L.orc_error(self.h).decode())
+
+    def set_li_order(self, p_first=True):
+        self.L.orc_set_li_order(self.h, int(p_first))
+
+    def num_primary_edges(self, sensor=0):
+        return self.L.orc_num_primary_edges(self.h, sensor)
+
+    def num_secondary_edges(self):
+        return self.L.orc_num_secondary_edges(self.h)
+
+    def mesh_edges(self, mesh):
+        n = self.L.orc_num_mesh_edges(self.h, mesh)
+        out = np.zeros((4, n), dtype=np.int32)
+        self.L.orc_mesh_edges(self.h, mesh, _ip(out))
+        return out
+
+    def render(self, depth, seed=0, mode=1, terms=7, sensor=0, hide_emitters=False, skip=None, pix_id=None, lane_out=False):
+        if pix_id is not None:
+            pix = np.ascontiguousarray(np.asarray(pix_id, dtype=np.int32))
+            npix = len(pix)
+        else:
+            pix, npix = None, self.width * self.height
+        img = np.zeros((npix, 3), dtype=np.float32)
+        dimg = np.zeros((npix, 3), dtype=np.float32) if mode == 1 else None
+        lanes = np.zeros((npix * self.spp, 3), dtype=np.float32) if lane_out else None
+        sk = None if skip is None else np.asarray(skip, dtype=np.int32)
+        rc = self.L.orc_render(self.h, sensor, depth, seed, mode, terms, int(hide_emitters), _ip(sk), _ip(pix),
+                               0 if pix is None else npix, _fp(img), _fp(dimg), _fp(lanes))
+        if rc:
+            raise RuntimeError(self.L.orc_error(self.h).decode())
+        if lane_out:
+            return img, dimg, lanes
+        return (img, dimg) if mode == 1 else img
+
+    def aov(self, sensor=0, seed=0):
+        out = np.zeros((self.width * self.height * self.spp, 14), dtype=np.float32)
+        self.L.orc_aov(self.h, sensor, seed, _fp(out))
+        return out
+
+
+def sampler_draws(seed, n, ndraws):
+    out = np.zeros((ndraws, n), dtype=np.float32)
+    lib().orc_sampler_draws(seed, n, ndraws, _fp(out))
+    return out
+
+
+def pmf_sample(pmf, samples):
+    pmf, samples = _f32(pmf), _f32(samples)
+    idx = np.zeros(len(samples), dtype=np.int32)
+    p = np.zeros(len(samples), dtype=np.float32)
+    s = np.zeros(1, dtype=np.float32)
+    lib().orc_pmf_sample(_fp(pmf), len(pmf), _fp(samples), len(samples), _ip(idx), _fp(p), _fp(s))
+    return idx, p, float(s[0])
+
+
+def num_threads():
+    return lib().orc_num_threads()
