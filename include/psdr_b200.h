@@ -1,0 +1,136 @@
+/* psdr_b200.h -- C ABI of the B200-native path-space differentiable path tracer.
+ *
+ * Drop-in boundary for the integrator path of andyyankai/psdr-jit.  The reference has no FFI seam
+ * of its own: its boundary is the pybind11 module surface in src/psdr.cpp, so every entry point
+ * below names the reference binding it stands in for.  Plain pointers and sizes only; no C++ or
+ * torch types; no exception crosses this boundary (functions return 0 on success, non-zero on
+ * error, psdr_last_error() gives the message -- the reference throws psdr_jit::Exception,
+ * include/misc/Exception.h:7-40, which pybind11 turns into RuntimeError).
+ *
+ * Threading: re-entrant per scene handle, not thread-safe on one handle.  Render calls are
+ * asynchronous on the given CUDA stream (pass NULL for the default stream) and never synchronise;
+ * the *_host variants copy through pinned staging and return when the host buffers are filled.
+ */
+#ifndef PSDR_B200_H
+#define PSDR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psdr_scene psdr_scene;
+
+/* Parameter kinds for psdr_scene_set_param / psdr_scene_set_tangent.  They are the fields the
+ * reference exposes through Scene.param_map objects (src/psdr.cpp:314-339,344-347,279-284,357-370). */
+enum {
+    PSDR_MESH_VERTICES = 0,        /* Mesh.vertex_positions (object space), n = 3*num_vertices, xyz interleaved */
+    PSDR_MESH_TO_WORLD_LEFT = 1,   /* Mesh.to_world_left  = Mesh.set_transform(mat, set_left=True), 16 floats row-major */
+    PSDR_MESH_TO_WORLD_RAW = 2,    /* Mesh.to_world */
+    PSDR_MESH_TO_WORLD_RIGHT = 3,  /* Mesh.to_world_right */
+    PSDR_SENSOR_TO_WORLD_LEFT = 4, /* Sensor.to_world_left = Sensor.set_transform */
+    PSDR_SENSOR_TO_WORLD_RAW = 5,  /* Sensor.to_world */
+    PSDR_SENSOR_TO_WORLD_RIGHT = 6,
+    PSDR_BSDF_REFLECTANCE = 7,     /* DiffuseBSDF.reflectance (1x1 bitmap), 3 floats */
+    PSDR_EMITTER_RADIANCE = 8      /* AreaLight.radiance, 3 floats */
+};
+
+/* What psdr_scene_query() can return. */
+enum {
+    PSDR_Q_NUM_MESHES = 0,          /* Scene.num_meshes */
+    PSDR_Q_NUM_SENSORS = 1,         /* Scene.num_sensors */
+    PSDR_Q_NUM_EMITTERS = 2,        /* Scene.get_num_emitters() */
+    PSDR_Q_NUM_TRIANGLES = 3,
+    PSDR_Q_NUM_PRIMARY_EDGES = 4,   /* index = sensor; "(n) primary edges initialized" (scene.cpp:425-431) */
+    PSDR_Q_NUM_SECONDARY_EDGES = 5, /* "n secondary edges initialized" (scene.cpp:563-567) */
+    PSDR_Q_NUM_MESH_EDGES = 6,      /* index = mesh; columns of Mesh.edge_indices() */
+    PSDR_Q_NUM_MESH_VERTICES = 7,
+    PSDR_Q_NUM_MESH_FACES = 8,
+    PSDR_Q_IS_CONFIGURED = 9,
+    PSDR_Q_USES_BVH = 10
+};
+
+/* Terms of renderD (bit mask). */
+enum { PSDR_TERM_INTERIOR = 1, PSDR_TERM_PRIMARY_EDGES = 2, PSDR_TERM_SECONDARY_EDGES = 4, PSDR_TERM_ALL = 7 };
+
+const char *psdr_last_error(void);
+int psdr_version(void);
+/* Number of this library's kernel launches so far in the calling process (bench.py's gpu_launches). */
+long long psdr_kernel_launch_count(void);
+
+/* Scene() -- src/psdr.cpp:393, src/scene/scene.cpp:49-57.  `device` = CUDA ordinal. */
+psdr_scene *psdr_scene_create(int device);
+/* Scene::~Scene -- src/scene/scene.cpp:60-71 */
+void psdr_scene_destroy(psdr_scene *s);
+
+/* Scene.opts (RenderOption, src/psdr.cpp:125-144, include/psdr/types.h:217-228) */
+int psdr_scene_set_options(psdr_scene *s, int width, int height, int spp, int sppe, int sppse, int log_level);
+/* Scene.seed -- src/psdr.cpp:411 (used by configure() when it seeds the samplers) */
+int psdr_scene_set_seed(psdr_scene *s, long long seed);
+/* New (the reference is single-GPU): this process renders lanes [rank/world, (rank+1)/world) of
+ * every term into a full-frame buffer; the caller sums the buffers over ranks (NCCL all-reduce). */
+int psdr_scene_set_shard(psdr_scene *s, int rank, int world);
+/* -1 = automatic (BVH2 above 64 triangles), 0 = brute force, 1 = BVH2 */
+int psdr_scene_set_accel(psdr_scene *s, int mode);
+
+/* Scene.add_BSDF(DiffuseBSDF([r,g,b]), name, twoSide) -- src/psdr.cpp:401, src/scene/scene.cpp:148-247.
+ * Returns the BSDF index (>= 0) or -1. */
+int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float reflectance[3], int two_side);
+
+/* Scene.add_Mesh(mesh, bsdf_id, emitter) with mesh = Mesh.load_raw(v, f, uv, f_uv) -- src/psdr.cpp:399-400,
+ * src/scene/scene.cpp:249-309, src/shape/mesh.cpp:74-162.  v: nv*3 floats (object space), f: nf*3 ints,
+ * uv: nuv*2 floats or NULL, fuv: nf*3 ints or NULL, to_world: 16 floats row-major or NULL (identity),
+ * radiance: 3 floats (makes the mesh an AreaLight, src/emitter/area.cpp) or NULL.
+ * Returns the mesh index (>= 0) or -1 ("Unknown BSDF id: ..."). */
+int psdr_scene_add_mesh(psdr_scene *s, const float *v, int nv, const int *f, int nf, const float *uv, int nuv, const int *fuv,
+                        const float *to_world, const char *bsdf_id, const float *radiance, int use_face_normals, int enable_edges);
+
+/* Scene.add_Sensor(PerspectiveCamera(fov, near, far)) with sensor.to_world -- src/psdr.cpp:365-375,396 */
+int psdr_scene_add_perspective(psdr_scene *s, float fov_x, float near_clip, float far_clip, const float *to_world);
+
+/* Writes through Scene.param_map[...] (README.md:87-90): new primal value of a parameter ... */
+int psdr_scene_set_param(psdr_scene *s, int kind, int index, const float *value, int n);
+/* ... and its forward-mode tangent d(param)/dP (what drjit.set_grad + forward_to propagate in the
+ * reference, README.md:102-104).  Tangents persist until cleared. */
+int psdr_scene_set_tangent(psdr_scene *s, int kind, int index, const float *tangent, int n);
+int psdr_scene_clear_tangents(psdr_scene *s);
+
+/* Scene.configure(active_sensor=[...]) -- src/psdr.cpp:409, src/scene/scene.cpp:311-601 */
+int psdr_scene_configure(psdr_scene *s, const int *active_sensors, int n_active);
+double psdr_scene_last_configure_ms(psdr_scene *s);
+
+int psdr_scene_query(psdr_scene *s, int what, int index);
+/* Mesh.edge_indices() -- src/psdr.cpp:338: out = 4 rows (v0, v1, face0, face1) of n_edges ints */
+int psdr_scene_mesh_edges(psdr_scene *s, int mesh, int *out);
+
+/* PathTracer(max_depth).renderC(scene, sensor_id, seed, batch_pix) -- src/psdr.cpp:419-420,431-434,
+ * src/integrator/integrator.cpp:12-48.  seed = -1 continues the sampler streams.  pix_id (device, may be
+ * NULL) = batch_pix pixel list of length npix; img (device) = float32[npix or W*H][3]. */
+int psdr_render_c(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, const int *pix_id, int npix,
+                  float *img, void *cuda_stream);
+
+/* PathTracer.renderD(...) followed by drjit.forward_to(img) -- src/integrator/integrator.cpp:51-100,179-198,
+ * src/integrator/path.cpp:172-294, README.md:96-104: primal image and the forward-mode derivative image
+ * for the tangents set with psdr_scene_set_tangent.  terms = PSDR_TERM_* mask.  reference_scaling != 0
+ * reproduces the reference binary's output, whose interior and secondary-edge tangents come out
+ * exactly 2x the finite-difference-correct value ("derivative scaling"). */
+int psdr_render_d(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                  const int *pix_id, int npix, float *img, float *dimg, void *cuda_stream);
+
+/* Same calls with HOST output buffers (pageable or pinned): device work + device->host copies,
+ * returns after the buffers are filled. */
+int psdr_render_c_host(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, const int *pix_id_host, int npix,
+                       float *img_host);
+int psdr_render_d_host(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                       const int *pix_id_host, int npix, float *img_host, float *dimg_host);
+
+/* FieldExtractionIntegrator taps (src/integrator/field.cpp:47-121) at the scene's spp: per lane 14 floats
+ * (mesh id + 1, triangle id, position xyz, distance, geometric normal xyz, shading normal xyz, 0, 0). */
+int psdr_render_aov(psdr_scene *s, int sensor, long long seed, float *out, void *cuda_stream);
+
+/* Sampler.seed / next_1d (src/psdr.cpp:181-185): out[ndraws][n], host memory, computed on the host. */
+int psdr_sampler_draws(long long seed, int n, int ndraws, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSDR_B200_H */

@@ -1,0 +1,558 @@
+"""psdr_jit_b200 -- B200-native drop-in for the integrator path of psdr_jit.
+
+The Python surface mirrors the reference module (reference src/psdr.cpp:100-441):
+``Scene``, ``RenderOption``, ``PerspectiveCamera``, ``DiffuseBSDF``, ``AreaLight``, ``Mesh``,
+``PathTracer(max_depth).renderC / renderD``, ``Scene.param_map``.  Arrays are numpy / torch instead
+of ``drjit.cuda(.ad)`` types; results are torch CUDA tensors.  All numerics run in the C++/CUDA
+library behind the C ABI of ``include/psdr_b200.h`` -- this file is host-side plumbing only.
+
+Differences a reference user has to know (DESIGN.md has the rationale):
+  * forward-mode derivatives: set tangents on the parameter objects (``d_*`` fields or the
+    ``tangent=`` argument of ``set_transform``) and call ``renderD``; the derivative image is
+    returned by ``renderD_fwd`` / kept in ``integrator.grad_image`` (the reference needs
+    ``drjit.set_grad(P, 1); drjit.forward_to(img); drjit.grad(img)``).
+  * ``PathTracer.reference_tangent_scaling = True`` reproduces the reference binary's scaling of the
+    interior and secondary-edge tangents (2x); the default is the finite-difference-correct value.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib, scenes  # noqa: F401
+
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "AreaLight", "Mesh", "PathTracer", "Sampler",
+           "Integrator", "Object", "scenes", "kernel_launch_count"]
+
+
+def _f32(a, shape=None) -> np.ndarray:
+    if hasattr(a, "detach"):   # torch tensor
+        a = a.detach().cpu().numpy()
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+    return a if shape is None else a.reshape(shape)
+
+
+def _mat4(m) -> np.ndarray:
+    if m is None:
+        return np.eye(4, dtype=np.float32)
+    m = _f32(m)
+    if m.shape != (4, 4):
+        raise RuntimeError("expected a 4x4 matrix")
+    return m.copy()
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(_lib.P_F)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(_lib.P_I)
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().psdr_kernel_launch_count())
+
+
+class Object:
+    """reference include/psdr/object.h"""
+    id = ""
+
+    def type_name(self) -> str:
+        return type(self).__name__
+
+    def __repr__(self) -> str:
+        return "%s[id=%s]" % (type(self).__name__, self.id)
+
+
+class RenderOption:
+    """reference include/psdr/types.h:217-228"""
+
+    def __init__(self, width: int = 128, height: int = 128, spp: int = 1, sppe: Optional[int] = None, sppse: Optional[int] = None):
+        n_given = 3 + (sppe is not None) + (sppse is not None)
+        self.width, self.height, self.spp = width, height, spp
+        if n_given == 3 and (width, height, spp) == (128, 128, 1):
+            self.sppe, self.sppse = 0, 0            # RenderOption()
+        else:
+            self.sppe = spp if sppe is None else sppe
+            self.sppse = self.sppe if sppse is None else sppse
+        self.log_level = 1
+
+    def __repr__(self):
+        return "[width: %d, height: %d, spp: %d, sppe: %d, sppse: %d, log_level: %d]" % (
+            self.width, self.height, self.spp, self.sppe, self.sppse, self.log_level)
+
+
+class _Transformable(Object):
+    """to_world = to_world_left * to_world * to_world_right (reference mesh.h:25-41, sensor.h:34-48)."""
+
+    def __init__(self):
+        self.to_world = np.eye(4, dtype=np.float32)
+        self.to_world_left = np.eye(4, dtype=np.float32)
+        self.to_world_right = np.eye(4, dtype=np.float32)
+        self.d_to_world = np.zeros((4, 4), dtype=np.float32)
+        self.d_to_world_left = np.zeros((4, 4), dtype=np.float32)
+        self.d_to_world_right = np.zeros((4, 4), dtype=np.float32)
+
+    def set_transform(self, mat, set_left: bool = True, tangent=None):
+        t = np.zeros((4, 4), dtype=np.float32) if tangent is None else _f32(tangent, (4, 4)).copy()
+        if set_left:
+            self.to_world_left, self.d_to_world_left = _mat4(mat), t
+        else:
+            self.to_world_right, self.d_to_world_right = _mat4(mat), t
+
+    def append_transform(self, mat, append_left: bool = True):
+        m = _mat4(mat)
+        if append_left:
+            self.d_to_world_left = m @ self.d_to_world_left
+            self.to_world_left = m @ self.to_world_left
+        else:
+            self.d_to_world_right = self.d_to_world_right @ m
+            self.to_world_right = self.to_world_right @ m
+
+    def _copy_transform_from(self, other: "_Transformable"):
+        for n in ("to_world", "to_world_left", "to_world_right", "d_to_world", "d_to_world_left", "d_to_world_right"):
+            setattr(self, n, np.array(getattr(other, n), dtype=np.float32))
+
+
+class PerspectiveCamera(_Transformable):
+    """reference src/psdr.cpp:365-375, src/sensor/perspective.cpp"""
+
+    def __init__(self, fov: float, near: float, far: float, *intrinsics):
+        super().__init__()
+        if intrinsics:
+            raise NotImplementedError("PerspectiveCamera(fx, fy, cx, cy, near, far) is outside the north-star path")
+        self.fov, self.near, self.far = float(fov), float(near), float(far)
+
+    def _clone(self):
+        c = PerspectiveCamera(self.fov, self.near, self.far)
+        c._copy_transform_from(self)
+        return c
+
+
+class BSDF(Object):
+    twoSide = False
+
+    def anisotropic(self) -> bool:
+        return False
+
+
+class DiffuseBSDF(BSDF):
+    """reference src/psdr.cpp:279-284, src/bsdf/diffuse.cpp (1x1 reflectance bitmap)."""
+
+    def __init__(self, reflectance=None):
+        if isinstance(reflectance, str):
+            raise NotImplementedError("textured DiffuseBSDF(path) is outside the round-1 path")
+        self.reflectance = np.full(3, 0.5, dtype=np.float32) if reflectance is None else _f32(reflectance, (3,)).copy()
+        self.d_reflectance = np.zeros(3, dtype=np.float32)
+
+    def _clone(self):
+        b = DiffuseBSDF(self.reflectance)
+        b.d_reflectance = self.d_reflectance.copy()
+        b.twoSide = self.twoSide
+        return b
+
+
+class Emitter(Object):
+    pass
+
+
+class AreaLight(Emitter):
+    """reference src/psdr.cpp:344-347, src/emitter/area.cpp"""
+
+    def __init__(self, radiance, mesh=None):
+        self.radiance = _f32(radiance, (3,)).copy()
+        self.d_radiance = np.zeros(3, dtype=np.float32)
+
+
+def _load_obj(path: str):
+    """Minimal OBJ reader: v / vt / f, polygons fan-triangulated (a,b,c),(a,c,d),..."""
+    v, vt, f, ft = [], [], [], []
+    with open(path) as fh:
+        for line in fh:
+            tok = line.split()
+            if not tok or tok[0].startswith("#"):
+                continue
+            if tok[0] == "v":
+                v.append([float(x) for x in tok[1:4]])
+            elif tok[0] == "vt":
+                vt.append([float(x) for x in tok[1:3]])
+            elif tok[0] == "f":
+                vi, ti = [], []
+                for c in tok[1:]:
+                    parts = c.split("/")
+                    a = int(parts[0])
+                    vi.append(a - 1 if a > 0 else len(v) + a)
+                    if len(parts) > 1 and parts[1]:
+                        b = int(parts[1])
+                        ti.append(b - 1 if b > 0 else len(vt) + b)
+                for k in range(1, len(vi) - 1):
+                    f.append([vi[0], vi[k], vi[k + 1]])
+                    if len(ti) == len(vi):
+                        ft.append([ti[0], ti[k], ti[k + 1]])
+    has_uv = len(vt) > 0 and len(ft) == len(f)
+    return (np.asarray(v, np.float32), np.asarray(f, np.int32), np.asarray(vt, np.float32) if has_uv else None,
+            np.asarray(ft, np.int32) if has_uv else None)
+
+
+class Mesh(_Transformable):
+    """reference src/psdr.cpp:314-339, src/shape/mesh.cpp"""
+
+    def __init__(self):
+        super().__init__()
+        self.vertex_positions = np.zeros((0, 3), dtype=np.float32)
+        self.d_vertex_positions = None
+        self.face_indices = np.zeros((0, 3), dtype=np.int32)
+        self.vertex_uv = None
+        self.face_uv_indices = None
+        self.use_face_normal = False
+        self.enable_edges = True
+        self.bsdf = None
+        self._scene = None
+        self._index = -1
+
+    num_vertices = property(lambda self: len(self.vertex_positions))
+    num_faces = property(lambda self: len(self.face_indices))
+
+    def load_raw(self, v, f, uv=None, f_uv=None, verbose: bool = False):
+        self.vertex_positions = _f32(v).reshape(-1, 3).copy()
+        self.face_indices = np.ascontiguousarray(np.asarray(f, dtype=np.int32).reshape(-1, 3))
+        if uv is not None and len(uv) > 0:
+            self.vertex_uv = _f32(uv).reshape(-1, 2).copy()
+            self.face_uv_indices = np.ascontiguousarray(np.asarray(f_uv, dtype=np.int32).reshape(-1, 3))
+        else:
+            self.vertex_uv, self.face_uv_indices = None, None
+        self.d_vertex_positions = None
+
+    def load(self, filename: str, verbose: bool = False):
+        v, f, uv, fuv = _load_obj(filename)
+        if len(f) == 0:
+            raise RuntimeError("Failed to load OBJ from: " + filename)
+        self.load_raw(v, f, uv, fuv, verbose)
+
+    def edge_indices(self):
+        if self._scene is None or self._scene._h is None:
+            raise RuntimeError("edge_indices() needs a mesh that was added to a configured scene")
+        L = _lib.load()
+        n = L.psdr_scene_query(self._scene._h, _lib.Q_NUM_MESH_EDGES, self._index)
+        out = np.zeros((4, n), dtype=np.int32)
+        _lib.check(L.psdr_scene_mesh_edges(self._scene._h, self._index, _ip(out)))
+        return out
+
+    def _clone(self):
+        m = Mesh()
+        m._copy_transform_from(self)
+        m.vertex_positions = self.vertex_positions.copy()
+        m.d_vertex_positions = None if self.d_vertex_positions is None else _f32(self.d_vertex_positions).reshape(-1, 3).copy()
+        m.face_indices = self.face_indices.copy()
+        m.vertex_uv = None if self.vertex_uv is None else self.vertex_uv.copy()
+        m.face_uv_indices = None if self.face_uv_indices is None else self.face_uv_indices.copy()
+        m.use_face_normal, m.enable_edges = self.use_face_normal, self.enable_edges
+        return m
+
+
+class Sampler:
+    """reference src/psdr.cpp:181-185 -- host-side view of the PCG32 streams the kernels use."""
+
+    def __init__(self):
+        self._seed, self._n, self._k = None, 0, 0
+
+    def seed(self, seed_value):
+        sv = np.asarray(seed_value, dtype=np.int64).ravel()
+        if len(sv) == 0 or not np.array_equal(sv - sv[0], np.arange(len(sv))):
+            raise NotImplementedError("only seeds of the form arange(n) + s are supported")
+        self._seed, self._n, self._k = int(sv[0]), len(sv), 0
+
+    def _draw(self, n):
+        if self._seed is None:
+            raise RuntimeError("Sampler::seed() must be invoked before using this sampler!")
+        out = np.zeros((self._k + n, self._n), dtype=np.float32)
+        _lib.check(_lib.load().psdr_sampler_draws(self._seed, self._n, self._k + n, _fp(out)))
+        self._k += n
+        return out[-n:]
+
+    def next_1d(self):
+        return self._draw(1)[0]
+
+    def next_2d(self):
+        d = self._draw(2)
+        return np.stack([d[1], d[0]])   # y receives the first draw (sampler.h:19-21, GCC argument order)
+
+
+class Scene(Object):
+    """reference src/psdr.cpp:393-414, src/scene/scene.cpp"""
+
+    def __init__(self, device: Optional[int] = None):
+        self.opts = RenderOption()
+        self.seed = 0
+        self.param_map: Dict[str, Object] = {}
+        self._sensors: List[PerspectiveCamera] = []
+        self._bsdfs: List[BSDF] = []
+        self._meshes: List[Mesh] = []
+        self._emitters: List[AreaLight] = []
+        self._mesh_emitter: List[int] = []
+        self._h = None
+        self._pushed = [0, 0, 0]   # bsdfs, meshes, sensors already in the native scene
+        self._device = device
+        self._shard = (0, 1)
+        self._accel = -1
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.load().psdr_scene_destroy(self._h)
+        except Exception:
+            pass
+
+    num_sensors = property(lambda self: len(self._sensors))
+    num_meshes = property(lambda self: len(self._meshes))
+
+    def get_num_emitters(self) -> int:
+        return len(self._emitters)
+
+    def _register(self, kind: str, arr: Sequence[Object]):
+        for i, o in enumerate(arr):
+            self.param_map["%s[%d]" % (kind, i)] = o
+            if o.id:
+                self.param_map["%s[id=%s]" % (kind, o.id)] = o
+
+    def add_Sensor(self, sensor: PerspectiveCamera):
+        if not isinstance(sensor, PerspectiveCamera):
+            raise RuntimeError("Unknown sensor type!")
+        self._sensors.append(sensor._clone())
+        self._register("Sensor", self._sensors)
+
+    def add_BSDF(self, bsdf: BSDF, name: str, twoSide: bool = False):
+        if not isinstance(bsdf, DiffuseBSDF):
+            raise RuntimeError("Unknown BSDF type!")
+        if ("BSDF[id=%s]" % name) in self.param_map:
+            raise RuntimeError("Duplicate BSDF id: " + name)
+        b = bsdf._clone()
+        b.id = name
+        b.twoSide = bool(twoSide)
+        self._bsdfs.append(b)
+        self._register("BSDF", self._bsdfs)
+
+    def add_Mesh(self, mesh_or_path, *args):
+        """add_Mesh(path, to_world, bsdf_id, emitter) or add_Mesh(mesh, bsdf_id, emitter=None)"""
+        if isinstance(mesh_or_path, Mesh):
+            bsdf_id = args[0]
+            emitter = args[1] if len(args) > 1 else None
+            mesh = mesh_or_path._clone()
+        else:
+            to_world, bsdf_id = args[0], args[1]
+            emitter = args[2] if len(args) > 2 else None
+            mesh = Mesh()
+            mesh.load(mesh_or_path)
+            mesh.to_world = _mat4(to_world)
+        if ("BSDF[id=%s]" % bsdf_id) not in self.param_map:
+            raise RuntimeError("Unknown BSDF id: " + str(bsdf_id))
+        mesh.bsdf = bsdf_id
+        mesh._scene, mesh._index = self, len(self._meshes)
+        if emitter is not None:
+            if not isinstance(emitter, AreaLight):
+                raise RuntimeError("Unknown emitter type!")
+            e = AreaLight(emitter.radiance)
+            e.d_radiance = emitter.d_radiance.copy()
+            self._mesh_emitter.append(len(self._emitters))
+            self._emitters.append(e)
+            self._register("Emitter", self._emitters)
+        else:
+            self._mesh_emitter.append(-1)
+        self._meshes.append(mesh)
+        self._register("Mesh", self._meshes)
+
+    # -- multi-GPU / acceleration knobs (new; the reference is single-GPU OptiX)
+    def set_shard(self, rank: int, world: int):
+        self._shard = (int(rank), int(world))
+        if self._h is not None:
+            _lib.check(_lib.load().psdr_scene_set_shard(self._h, rank, world))
+
+    def set_accel(self, mode: int):
+        self._accel = int(mode)
+        if self._h is not None:
+            _lib.check(_lib.load().psdr_scene_set_accel(self._h, self._accel))
+
+    def _native(self):
+        L = _lib.load()
+        if self._h is None:
+            dev = self._device
+            if dev is None:
+                try:
+                    import torch
+                    dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+                except Exception:
+                    dev = 0
+            h = L.psdr_scene_create(int(dev))
+            if not h:
+                raise RuntimeError(L.psdr_last_error().decode())
+            self._h = C.c_void_p(h)
+            _lib.check(L.psdr_scene_set_shard(self._h, *self._shard))
+            _lib.check(L.psdr_scene_set_accel(self._h, self._accel))
+        return L
+
+    def configure(self, active_sensor: Sequence[int] = ()):
+        """Scene.configure (reference src/scene/scene.cpp:311-601): pushes every parameter (and
+        tangent) to the native scene, which rebuilds triangle records, distributions, edges and BVH."""
+        if not self._meshes:
+            raise RuntimeError("Missing meshes!")
+        if not self._sensors:
+            raise RuntimeError("Missing sensor!")
+        L = self._native()
+        o = self.opts
+        _lib.check(L.psdr_scene_set_options(self._h, o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level))
+        _lib.check(L.psdr_scene_set_seed(self._h, int(self.seed)))
+        for b in self._bsdfs[self._pushed[0]:]:
+            if L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(_f32(b.reflectance)), int(b.twoSide)) < 0:
+                raise RuntimeError(L.psdr_last_error().decode())
+        self._pushed[0] = len(self._bsdfs)
+        for i in range(self._pushed[1], len(self._meshes)):
+            m = self._meshes[i]
+            v, f = _f32(m.vertex_positions).reshape(-1, 3), np.ascontiguousarray(m.face_indices, dtype=np.int32)
+            uv = None if m.vertex_uv is None else _f32(m.vertex_uv).reshape(-1, 2)
+            fuv = None if m.face_uv_indices is None else np.ascontiguousarray(m.face_uv_indices, dtype=np.int32)
+            e = self._mesh_emitter[i]
+            rad = None if e < 0 else _f32(self._emitters[e].radiance)
+            if L.psdr_scene_add_mesh(self._h, _fp(v), len(v), _ip(f), len(f), _fp(uv), 0 if uv is None else len(uv), _ip(fuv),
+                                     _fp(_mat4(m.to_world)), m.bsdf.encode(), _fp(rad), int(m.use_face_normal), int(m.enable_edges)) < 0:
+                raise RuntimeError(L.psdr_last_error().decode())
+        self._pushed[1] = len(self._meshes)
+        for s in self._sensors[self._pushed[2]:]:
+            if L.psdr_scene_add_perspective(self._h, s.fov, s.near, s.far, _fp(_mat4(s.to_world))) < 0:
+                raise RuntimeError(L.psdr_last_error().decode())
+        self._pushed[2] = len(self._sensors)
+
+        def push(kind, idx, value, tangent):
+            value = _f32(value).ravel()
+            _lib.check(L.psdr_scene_set_param(self._h, kind, idx, _fp(value), value.size))
+            t = np.zeros_like(value) if tangent is None else _f32(tangent).ravel()
+            _lib.check(L.psdr_scene_set_tangent(self._h, kind, idx, _fp(t), t.size))
+
+        for i, m in enumerate(self._meshes):
+            push(_lib.MESH_VERTICES, i, m.vertex_positions, m.d_vertex_positions)
+            push(_lib.MESH_TO_WORLD_LEFT, i, m.to_world_left, m.d_to_world_left)
+            push(_lib.MESH_TO_WORLD_RAW, i, m.to_world, m.d_to_world)
+            push(_lib.MESH_TO_WORLD_RIGHT, i, m.to_world_right, m.d_to_world_right)
+        for i, s in enumerate(self._sensors):
+            push(_lib.SENSOR_TO_WORLD_LEFT, i, s.to_world_left, s.d_to_world_left)
+            push(_lib.SENSOR_TO_WORLD_RAW, i, s.to_world, s.d_to_world)
+            push(_lib.SENSOR_TO_WORLD_RIGHT, i, s.to_world_right, s.d_to_world_right)
+        for i, b in enumerate(self._bsdfs):
+            push(_lib.BSDF_REFLECTANCE, i, b.reflectance, b.d_reflectance)
+        for i, e in enumerate(self._emitters):
+            push(_lib.EMITTER_RADIANCE, i, e.radiance, e.d_radiance)
+        act = np.asarray(list(active_sensor), dtype=np.int32)
+        _lib.check(L.psdr_scene_configure(self._h, _ip(act), len(act)))
+        if o.log_level > 0 and o.sppe > 0:
+            print("(%s) primary edges initialized." % ", ".join(str(self.num_primary_edges(i)) for i in range(len(self._sensors))))
+        if o.log_level > 0 and o.sppse > 0:
+            print("%d secondary edges initialized." % self.num_secondary_edges())
+
+    def is_ready(self) -> bool:
+        return self._h is not None and _lib.load().psdr_scene_query(self._h, _lib.Q_IS_CONFIGURED, 0) == 1
+
+    def num_primary_edges(self, sensor: int = 0) -> int:
+        return _lib.load().psdr_scene_query(self._h, _lib.Q_NUM_PRIMARY_EDGES, sensor)
+
+    def num_secondary_edges(self) -> int:
+        return _lib.load().psdr_scene_query(self._h, _lib.Q_NUM_SECONDARY_EDGES, 0)
+
+    def last_configure_ms(self) -> float:
+        return float(_lib.load().psdr_scene_last_configure_ms(self._h))
+
+
+class Integrator(Object):
+    """reference src/psdr.cpp:419-421, src/integrator/integrator.cpp"""
+    max_depth = 1
+    hide_emitters = False
+    reference_tangent_scaling = False
+    grad_image = None
+
+    def _check(self, scene: Scene):
+        if scene._h is None or not scene.is_ready():
+            raise RuntimeError("Input scene must be configured!")
+
+    @staticmethod
+    def _torch():
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("psdr_jit_b200 needs a CUDA device (no CPU fallback)")
+        return torch
+
+    def _pix(self, torch, batch_pix, device):
+        if batch_pix is None or (np.isscalar(batch_pix) and int(batch_pix) == -1):
+            return None
+        if hasattr(batch_pix, "to"):
+            return batch_pix.to(device=device, dtype=torch.int32).contiguous()
+        return torch.as_tensor(np.asarray(batch_pix, dtype=np.int32), device=device)
+
+    def renderC(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        """Primal image, float32[H*W, 3] on the GPU (reference Integrator::renderC)."""
+        self._check(scene)
+        torch = self._torch()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pix = self._pix(torch, batch_pix, dev)
+        n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
+        img = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.load().psdr_render_c(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters),
+                                             None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel(),
+                                             img.data_ptr(), st))
+        return img
+
+    def renderD_fwd(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL):
+        """(image, forward-mode derivative image) for the tangents configured on the scene."""
+        self._check(scene)
+        torch = self._torch()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pix = self._pix(torch, batch_pix, dev)
+        n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
+        img = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        dimg = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.load().psdr_render_d(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms),
+                                             int(self.reference_tangent_scaling), None if pix is None else pix.data_ptr(),
+                                             0 if pix is None else pix.numel(), img.data_ptr(), dimg.data_ptr(), st))
+        return img, dimg
+
+    def renderD(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        """reference Integrator::renderD; the derivative image is kept in ``self.grad_image``."""
+        img, self.grad_image = self.renderD_fwd(scene, sensor_id, seed, batch_pix)
+        return img
+
+    # host-buffer entry points (numpy in/out; used for the end-to-end measurement)
+    def renderC_host(self, scene: Scene, sensor_id: int = 0, seed: int = -1, out: Optional[np.ndarray] = None):
+        self._check(scene)
+        n = scene.opts.width * scene.opts.height
+        img = np.empty((n, 3), dtype=np.float32) if out is None else out
+        _lib.check(_lib.load().psdr_render_c_host(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), None, 0, _fp(img)))
+        return img
+
+    def renderD_host(self, scene: Scene, sensor_id: int = 0, seed: int = -1, terms: int = _lib.TERM_ALL, out=None, dout=None):
+        self._check(scene)
+        n = scene.opts.width * scene.opts.height
+        img = np.empty((n, 3), dtype=np.float32) if out is None else out
+        dimg = np.empty((n, 3), dtype=np.float32) if dout is None else dout
+        _lib.check(_lib.load().psdr_render_d_host(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms),
+                                                  int(self.reference_tangent_scaling), None, 0, _fp(img), _fp(dimg)))
+        return img, dimg
+
+    def render_aov(self, scene: Scene, sensor_id: int = 0, seed: int = 0):
+        self._check(scene)
+        torch = self._torch()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        n = scene.opts.width * scene.opts.height * max(scene.opts.spp, 1)
+        out = torch.empty((n, 14), dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().psdr_render_aov(scene._h, sensor_id, int(seed), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return out
+
+
+class PathTracer(Integrator):
+    """reference src/psdr.cpp:431-434, src/integrator/path.cpp"""
+
+    def __init__(self, max_depth: int = 1):
+        if max_depth < 0:
+            raise RuntimeError("max_depth >= 0")
+        self.max_depth = int(max_depth)
+        self.hide_emitters = False

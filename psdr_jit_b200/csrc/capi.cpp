@@ -1,0 +1,461 @@
+// C ABI of libpsdr_b200.so (declared in include/psdr_b200.h).  Translates handles + plain buffers
+// into the host Scene (scene.h) and the kernel launchers (kernels.h); converts every C++ exception
+// into an error code + psdr_last_error().
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/psdr_b200.h"
+#include "kernels.h"
+#include "scene.h"
+
+using namespace psdr;
+
+struct psdr_scene {
+    Scene sc;
+    // staging for the *_host entry points
+    float *d_img = nullptr, *d_dimg = nullptr;
+    int *d_pix = nullptr;
+    size_t img_cap = 0, pix_cap = 0;
+    cudaStream_t stream = nullptr;
+    ~psdr_scene() {
+        if (d_img) cudaFree(d_img);
+        if (d_dimg) cudaFree(d_dimg);
+        if (d_pix) cudaFree(d_pix);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static thread_local std::string g_error;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const std::string &msg) {
+    g_error = msg;
+    return 1;
+}
+#define PSDR_TRY try {
+#define PSDR_CATCH                                                  \
+    }                                                               \
+    catch (const std::exception &e) { return fail(e.what()); }      \
+    catch (...) { return fail("unknown error"); }
+
+static void cuda_ok(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+static M4<Dual> mat_from(const float *v, const M4<Dual> *keep_tangent = nullptr) {
+    M4<Dual> m = M4<Dual>::identity();
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            m.m[i][j].v = v ? v[4 * i + j] : (i == j ? 1.f : 0.f);
+            m.m[i][j].d = keep_tangent ? keep_tangent->m[i][j].d : 0.f;
+        }
+    return m;
+}
+
+extern "C" {
+
+const char *psdr_last_error(void) { return g_error.c_str(); }
+int psdr_version(void) { return 100; }
+long long psdr_kernel_launch_count(void) { return g_launches.load(); }
+
+psdr_scene *psdr_scene_create(int device) {
+    try {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0) {
+            g_error = std::string("psdr_b200 needs a CUDA device (no CPU fallback): ") + cudaGetErrorString(e);
+            return nullptr;
+        }
+        if (device < 0 || device >= count) {
+            g_error = "invalid CUDA device ordinal";
+            return nullptr;
+        }
+        psdr_scene *s = new psdr_scene();
+        s->sc.device = device;
+        return s;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return nullptr;
+    }
+}
+
+void psdr_scene_destroy(psdr_scene *s) { delete s; }
+
+int psdr_scene_set_options(psdr_scene *s, int width, int height, int spp, int sppe, int sppse, int log_level) {
+    if (!s) return fail("null scene");
+    if (width <= 0 || height <= 0 || spp < 0 || sppe < 0 || sppse < 0) return fail("invalid render options");
+    Scene &sc = s->sc;
+    if (sc.width != width || sc.height != height || sc.spp != spp || sc.sppe != sppe || sc.sppse != sppse) sc.configured = false;
+    sc.width = width; sc.height = height; sc.spp = spp; sc.sppe = sppe; sc.sppse = sppse; sc.log_level = log_level;
+    return 0;
+}
+
+int psdr_scene_set_seed(psdr_scene *s, long long seed) {
+    if (!s) return fail("null scene");
+    s->sc.seed = seed;
+    return 0;
+}
+
+int psdr_scene_set_shard(psdr_scene *s, int rank, int world) {
+    if (!s) return fail("null scene");
+    if (world < 1 || rank < 0 || rank >= world) return fail("invalid shard");
+    s->sc.rank = rank;
+    s->sc.world = world;
+    return 0;
+}
+
+int psdr_scene_set_accel(psdr_scene *s, int mode) {
+    if (!s) return fail("null scene");
+    s->sc.force_bvh = mode;
+    s->sc.configured = false;
+    return 0;
+}
+
+int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float reflectance[3], int two_side) {
+    if (!s || !id || !reflectance) { fail("null argument"); return -1; }
+    Scene &sc = s->sc;
+    if (sc.find_bsdf(id) >= 0) { fail(std::string("Duplicate BSDF id: ") + id); return -1; }
+    HBsdf b;
+    b.id = id;
+    b.type = 0;
+    b.reflectance = V3d(Dual(reflectance[0]), Dual(reflectance[1]), Dual(reflectance[2]));
+    b.two_side = two_side != 0;
+    sc.bsdfs.push_back(b);
+    sc.configured = false;
+    return (int) sc.bsdfs.size() - 1;
+}
+
+int psdr_scene_add_mesh(psdr_scene *s, const float *v, int nv, const int *f, int nf, const float *uv, int nuv, const int *fuv,
+                        const float *to_world, const char *bsdf_id, const float *radiance, int use_face_normals, int enable_edges) {
+    if (!s || !v || !f || !bsdf_id || nv <= 0 || nf <= 0) { fail("invalid mesh arguments"); return -1; }
+    Scene &sc = s->sc;
+    const int bi = sc.find_bsdf(bsdf_id);
+    if (bi < 0) { fail(std::string("Unknown BSDF id: ") + bsdf_id); return -1; }
+    for (int i = 0; i < 3 * nf; ++i)
+        if (f[i] < 0 || f[i] >= nv) { fail("face index out of range"); return -1; }
+    HMesh m;
+    m.v_raw.resize(nv);
+    for (int i = 0; i < nv; ++i) m.v_raw[i] = V3d(Dual(v[3 * i]), Dual(v[3 * i + 1]), Dual(v[3 * i + 2]));
+    m.f.assign(f, f + 3 * nf);
+    m.has_uv = uv != nullptr && nuv > 0 && fuv != nullptr;
+    if (m.has_uv) {
+        m.uv.resize(nuv);
+        for (int i = 0; i < nuv; ++i) m.uv[i] = V2f(uv[2 * i], uv[2 * i + 1]);
+        m.fuv.assign(fuv, fuv + 3 * nf);
+        for (int i = 0; i < 3 * nf; ++i)
+            if (fuv[i] < 0 || fuv[i] >= nuv) { fail("uv index out of range"); return -1; }
+    }
+    m.to_world[0] = M4<Dual>::identity();
+    m.to_world[1] = mat_from(to_world);
+    m.to_world[2] = M4<Dual>::identity();
+    m.bsdf = bi;
+    m.use_face_normals = use_face_normals != 0;
+    m.enable_edges = enable_edges != 0;
+    if (radiance) {
+        HEmitter e;
+        e.radiance = V3d(Dual(radiance[0]), Dual(radiance[1]), Dual(radiance[2]));
+        e.mesh = (int) sc.meshes.size();
+        m.emitter = (int) sc.emitters.size();
+        sc.emitters.push_back(e);
+    }
+    sc.meshes.push_back(std::move(m));
+    sc.configured = false;
+    return (int) sc.meshes.size() - 1;
+}
+
+int psdr_scene_add_perspective(psdr_scene *s, float fov_x, float near_clip, float far_clip, const float *to_world) {
+    if (!s) { fail("null scene"); return -1; }
+    HCamera c;
+    c.fov = fov_x;
+    c.near_ = near_clip;
+    c.far_ = far_clip;
+    c.to_world[0] = M4<Dual>::identity();
+    c.to_world[1] = mat_from(to_world);
+    c.to_world[2] = M4<Dual>::identity();
+    s->sc.cameras.push_back(c);
+    s->sc.configured = false;
+    return (int) s->sc.cameras.size() - 1;
+}
+
+static int set_param_impl(psdr_scene *s, int kind, int index, const float *data, int n, bool tangent) {
+    if (!s || !data) return fail("null argument");
+    Scene &sc = s->sc;
+    auto put = [&](Dual &x, float val_) { if (tangent) x.d = val_; else x.v = val_; };
+    switch (kind) {
+        case PSDR_MESH_VERTICES: {
+            if (index < 0 || index >= (int) sc.meshes.size()) return fail("invalid mesh index");
+            HMesh &m = sc.meshes[index];
+            if (n != 3 * (int) m.v_raw.size()) return fail("vertex buffer size mismatch");
+            for (size_t i = 0; i < m.v_raw.size(); ++i) { put(m.v_raw[i].x, data[3 * i]); put(m.v_raw[i].y, data[3 * i + 1]); put(m.v_raw[i].z, data[3 * i + 2]); }
+            break;
+        }
+        case PSDR_MESH_TO_WORLD_LEFT: case PSDR_MESH_TO_WORLD_RAW: case PSDR_MESH_TO_WORLD_RIGHT: {
+            if (index < 0 || index >= (int) sc.meshes.size()) return fail("invalid mesh index");
+            if (n != 16) return fail("a transform is 16 floats");
+            M4<Dual> &M = sc.meshes[index].to_world[kind - PSDR_MESH_TO_WORLD_LEFT];
+            for (int i = 0; i < 16; ++i) put(M.m[i / 4][i % 4], data[i]);
+            break;
+        }
+        case PSDR_SENSOR_TO_WORLD_LEFT: case PSDR_SENSOR_TO_WORLD_RAW: case PSDR_SENSOR_TO_WORLD_RIGHT: {
+            if (index < 0 || index >= (int) sc.cameras.size()) return fail("Invalid sensor id!");
+            if (n != 16) return fail("a transform is 16 floats");
+            M4<Dual> &M = sc.cameras[index].to_world[kind - PSDR_SENSOR_TO_WORLD_LEFT];
+            for (int i = 0; i < 16; ++i) put(M.m[i / 4][i % 4], data[i]);
+            break;
+        }
+        case PSDR_BSDF_REFLECTANCE: {
+            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            if (n != 3) return fail("reflectance is 3 floats");
+            put(sc.bsdfs[index].reflectance.x, data[0]); put(sc.bsdfs[index].reflectance.y, data[1]); put(sc.bsdfs[index].reflectance.z, data[2]);
+            break;
+        }
+        case PSDR_EMITTER_RADIANCE: {
+            if (index < 0 || index >= (int) sc.emitters.size()) return fail("invalid emitter index");
+            if (n != 3) return fail("radiance is 3 floats");
+            put(sc.emitters[index].radiance.x, data[0]); put(sc.emitters[index].radiance.y, data[1]); put(sc.emitters[index].radiance.z, data[2]);
+            break;
+        }
+        default: return fail("unknown parameter kind");
+    }
+    sc.configured = false;   // as in the reference, configure() must follow a parameter change
+    return 0;
+}
+
+int psdr_scene_set_param(psdr_scene *s, int kind, int index, const float *value, int n) { return set_param_impl(s, kind, index, value, n, false); }
+int psdr_scene_set_tangent(psdr_scene *s, int kind, int index, const float *tangent, int n) { return set_param_impl(s, kind, index, tangent, n, true); }
+
+int psdr_scene_clear_tangents(psdr_scene *s) {
+    if (!s) return fail("null scene");
+    Scene &sc = s->sc;
+    for (HMesh &m : sc.meshes) {
+        for (V3d &p : m.v_raw) p = detach(p);
+        for (auto &M : m.to_world)
+            for (int i = 0; i < 16; ++i) M.m[i / 4][i % 4].d = 0.f;
+    }
+    for (HCamera &c : sc.cameras)
+        for (auto &M : c.to_world)
+            for (int i = 0; i < 16; ++i) M.m[i / 4][i % 4].d = 0.f;
+    for (HBsdf &b : sc.bsdfs) b.reflectance = detach(b.reflectance);
+    for (HEmitter &e : sc.emitters) e.radiance = detach(e.radiance);
+    sc.configured = false;
+    return 0;
+}
+
+int psdr_scene_configure(psdr_scene *s, const int *active_sensors, int n_active) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    s->sc.configure(active_sensors, n_active);
+    return 0;
+    PSDR_CATCH
+}
+
+double psdr_scene_last_configure_ms(psdr_scene *s) { return s ? s->sc.last_configure_ms : 0.0; }
+
+int psdr_scene_query(psdr_scene *s, int what, int index) {
+    if (!s) { fail("null scene"); return -1; }
+    const Scene &sc = s->sc;
+    switch (what) {
+        case PSDR_Q_NUM_MESHES: return (int) sc.meshes.size();
+        case PSDR_Q_NUM_SENSORS: return (int) sc.cameras.size();
+        case PSDR_Q_NUM_EMITTERS: return (int) sc.emitters.size();
+        case PSDR_Q_NUM_TRIANGLES: { int n = 0; for (auto &m : sc.meshes) n += (int) m.f.size() / 3; return n; }
+        case PSDR_Q_NUM_PRIMARY_EDGES: return (index >= 0 && index < (int) sc.cameras.size()) ? (int) sc.cameras[index].edges.size() : -1;
+        case PSDR_Q_NUM_SECONDARY_EDGES: return (int) sc.sec_edges.size();
+        case PSDR_Q_NUM_MESH_EDGES: return (index >= 0 && index < (int) sc.meshes.size()) ? (int) sc.meshes[index].edges.size() : -1;
+        case PSDR_Q_NUM_MESH_VERTICES: return (index >= 0 && index < (int) sc.meshes.size()) ? (int) sc.meshes[index].v_raw.size() : -1;
+        case PSDR_Q_NUM_MESH_FACES: return (index >= 0 && index < (int) sc.meshes.size()) ? (int) sc.meshes[index].f.size() / 3 : -1;
+        case PSDR_Q_IS_CONFIGURED: return sc.configured ? 1 : 0;
+        case PSDR_Q_USES_BVH: return sc.dscene.use_bvh;
+        default: fail("unknown query"); return -1;
+    }
+}
+
+int psdr_scene_mesh_edges(psdr_scene *s, int mesh, int *out) {
+    if (!s || !out) return fail("null argument");
+    if (mesh < 0 || mesh >= (int) s->sc.meshes.size()) return fail("invalid mesh index");
+    const auto &E = s->sc.meshes[mesh].edges;
+    const size_t n = E.size();
+    for (size_t i = 0; i < n; ++i) { out[i] = E[i].v0; out[n + i] = E[i].v1; out[2 * n + i] = E[i].f0; out[3 * n + i] = E[i].f1; }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// render
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Shard { long long begin, end; };
+Shard shard_of(long long n, int rank, int world) {
+    auto cut = [&](int r) { long long c = n * r / world; return r == world ? n : c / 32 * 32; };
+    return {cut(rank), cut(rank + 1)};
+}
+
+// Integrator::renderC / renderD front matter (integrator.cpp:12-31, 51-73): argument checks and
+// sampler (re)seeding; returns the per-sampler (seed, skip) pair of this call.
+void begin_render(Scene &sc, int sensor, long long seed, const int *pix_id, bool ad, int terms, int max_depth, RenderParams rp[3]) {
+    if (pix_id && seed == -1) throw std::runtime_error("While using batch rendering, seed must be set!");
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    if (max_depth < 0) throw std::runtime_error("max_depth >= 0");
+    const int per[3] = {sc.spp, ad ? sc.sppe : 0, ad ? sc.sppse : 0};
+    const unsigned long long draws[3] = {2ull + 5ull * max_depth, 1ull + 10ull * max_depth, 3ull};
+    for (int k = 0; k < 3; ++k) {
+        if (per[k] <= 0) continue;
+        SamplerState &st = sc.samplers[k];
+        if (seed != -1) { st.seed = seed; st.consumed = 0; st.ready = true; }
+        if (!st.ready) throw std::runtime_error("Sampler::seed() must be invoked before using this sampler!");
+        rp[k].seed = st.seed;
+        rp[k].skip = st.consumed;
+        if (terms & (1 << k)) st.consumed += draws[k];
+    }
+}
+
+int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, bool ad, int terms, int reference_scaling,
+                const int *pix_id, int npix_sel, float *img, float *dimg, cudaStream_t st) {
+    Scene &sc = s->sc;
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    RenderParams rp[3];
+    for (auto &r : rp) {
+        r = RenderParams{};
+        r.max_depth = max_depth;
+        r.hide_emitters = hide_emitters;
+        r.pix_id = nullptr;
+        r.tangent_scale = 1.f;
+    }
+    begin_render(sc, sensor, seed, pix_id, ad, terms, max_depth, rp);
+    const long long npix_full = (long long) sc.width * sc.height;
+    const long long npix = pix_id ? npix_sel : npix_full;
+    if (pix_id && npix_sel <= 0) throw std::runtime_error("empty pixel batch");
+    if (npix * (long long) std::max(sc.spp, 1) > 2147483647LL) throw std::runtime_error("num_samples <= std::numeric_limits<int>::max()");
+    if (!img) throw std::runtime_error("null image buffer");
+    if (ad && !dimg) throw std::runtime_error("null derivative image buffer");
+    const DCamera &cam = sc.dcameras[sensor];
+    cuda_ok(cudaMemsetAsync(img, 0, sizeof(float) * 3 * npix, st), "memset(img)");
+    if (ad) cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
+    if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
+        const Shard sh = shard_of(npix * sc.spp, sc.rank, sc.world);
+        rp[0].lane_begin = sh.begin; rp[0].lane_end = sh.end;
+        rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
+        rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
+        cuda_ok(launch_interior(sc.dscene, cam, rp[0], ad, img, dimg, st), "interior kernel");
+        g_launches++;
+    }
+    if (ad && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
+        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+        const Shard sh = shard_of(npix_full * sc.sppe, sc.rank, sc.world);
+        rp[1].lane_begin = sh.begin; rp[1].lane_end = sh.end;
+        cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, st), "primary-edge kernel");
+        g_launches++;
+    }
+    if (ad && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
+        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+        const Shard sh = shard_of(npix_full * sc.sppse, sc.rank, sc.world);
+        rp[2].lane_begin = sh.begin; rp[2].lane_end = sh.end;
+        rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
+        cuda_ok(launch_secondary_edges(sc.dscene, cam, rp[2], dimg, st), "secondary-edge kernel");
+        g_launches++;
+    }
+    return 0;
+}
+
+void ensure_staging(psdr_scene *s, size_t npix, size_t npix_ids) {
+    cuda_ok(cudaSetDevice(s->sc.device), "cudaSetDevice");
+    if (!s->stream) cuda_ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (npix > s->img_cap) {
+        if (s->d_img) cudaFree(s->d_img);
+        if (s->d_dimg) cudaFree(s->d_dimg);
+        cuda_ok(cudaMalloc(&s->d_img, sizeof(float) * 3 * npix), "cudaMalloc(img)");
+        cuda_ok(cudaMalloc(&s->d_dimg, sizeof(float) * 3 * npix), "cudaMalloc(dimg)");
+        s->img_cap = npix;
+    }
+    if (npix_ids > s->pix_cap) {
+        if (s->d_pix) cudaFree(s->d_pix);
+        cuda_ok(cudaMalloc(&s->d_pix, sizeof(int) * npix_ids), "cudaMalloc(pix)");
+        s->pix_cap = npix_ids;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int psdr_render_c(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, const int *pix_id, int npix, float *img,
+                  void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    return render_impl(s, sensor, max_depth, seed, hide_emitters, false, PSDR_TERM_INTERIOR, 0, pix_id, npix, img, nullptr, (cudaStream_t) cuda_stream);
+    PSDR_CATCH
+}
+
+int psdr_render_d(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                  const int *pix_id, int npix, float *img, float *dimg, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    return render_impl(s, sensor, max_depth, seed, hide_emitters, true, terms, reference_scaling, pix_id, npix, img, dimg, (cudaStream_t) cuda_stream);
+    PSDR_CATCH
+}
+
+int psdr_render_c_host(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, const int *pix_id_host, int npix,
+                       float *img_host) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    const size_t n = pix_id_host ? (size_t) npix : (size_t) s->sc.width * s->sc.height;
+    ensure_staging(s, n, pix_id_host ? n : 0);
+    if (pix_id_host) cuda_ok(cudaMemcpyAsync(s->d_pix, pix_id_host, sizeof(int) * n, cudaMemcpyHostToDevice, s->stream), "H2D(pix)");
+    render_impl(s, sensor, max_depth, seed, hide_emitters, false, PSDR_TERM_INTERIOR, 0, pix_id_host ? s->d_pix : nullptr, npix, s->d_img, nullptr, s->stream);
+    cuda_ok(cudaMemcpyAsync(img_host, s->d_img, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream), "D2H(img)");
+    cuda_ok(cudaStreamSynchronize(s->stream), "stream sync");
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_render_d_host(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                       const int *pix_id_host, int npix, float *img_host, float *dimg_host) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    const size_t n = pix_id_host ? (size_t) npix : (size_t) s->sc.width * s->sc.height;
+    ensure_staging(s, n, pix_id_host ? n : 0);
+    if (pix_id_host) cuda_ok(cudaMemcpyAsync(s->d_pix, pix_id_host, sizeof(int) * n, cudaMemcpyHostToDevice, s->stream), "H2D(pix)");
+    render_impl(s, sensor, max_depth, seed, hide_emitters, true, terms, reference_scaling, pix_id_host ? s->d_pix : nullptr, npix, s->d_img, s->d_dimg, s->stream);
+    cuda_ok(cudaMemcpyAsync(img_host, s->d_img, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream), "D2H(img)");
+    cuda_ok(cudaMemcpyAsync(dimg_host, s->d_dimg, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream), "D2H(dimg)");
+    cuda_ok(cudaStreamSynchronize(s->stream), "stream sync");
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_render_aov(psdr_scene *s, int sensor, long long seed, float *out, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    RenderParams rp{};
+    rp.seed = seed < 0 ? 0 : seed;
+    rp.lane_begin = 0;
+    rp.lane_end = (long long) sc.width * sc.height * std::max(sc.spp, 1);
+    cuda_ok(launch_aov(sc.dscene, sc.dcameras[sensor], rp, out, (cudaStream_t) cuda_stream), "aov kernel");
+    g_launches++;
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_sampler_draws(long long seed, int n, int ndraws, float *out) {
+    if (!out || n < 0 || ndraws < 0) return fail("invalid arguments");
+    for (int i = 0; i < n; ++i) {
+        Pcg32 r;
+        r.seed((unsigned long long) (i + seed), (unsigned long long) i);
+        for (int k = 0; k < ndraws; ++k) out[(size_t) k * n + i] = r.next_1d();
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,609 @@
+// Device-side path-space integrand: intersection records, Diffuse BSDF, area-light sampling,
+// the PathTracer radiance estimator (interior term) and the secondary-edge boundary estimator.
+// Everything is templated on the scalar S: float = primal (renderC and the detached Li calls of the
+// edge terms), Dual = value + forward tangent (renderD interior term; what the reference gets from
+// Dr.Jit's AD with detach() at the same places).  One thread = one lane of the reference wavefront.
+#pragma once
+#include "dscene.h"
+#include "pmath.h"
+
+namespace psdr {
+
+struct Hit {
+    int tri;
+    float u, v, t;
+};
+
+template <class S> struct TriRec {
+    V3<S> p0, e1, e2;
+    S area;
+    int mesh;
+};
+template <class S> struct ShadeRec {
+    V3<S> n0, n1, n2, fn;
+};
+
+__device__ __forceinline__ V3f f3(float4 a) { return V3f(a.x, a.y, a.z); }
+
+template <class S> __device__ __forceinline__ TriRec<S> load_tri(const DScene &sc, int i);
+template <> __device__ __forceinline__ TriRec<float> load_tri<float>(const DScene &sc, int i) {
+    const float4 a = __ldg(sc.geo + 3 * i), b = __ldg(sc.geo + 3 * i + 1), c = __ldg(sc.geo + 3 * i + 2);
+    TriRec<float> t;
+    t.p0 = V3f(a.x, a.y, a.z);
+    t.e1 = V3f(a.w, b.x, b.y);
+    t.e2 = V3f(b.z, b.w, c.x);
+    t.area = c.y;
+    t.mesh = __float_as_int(c.z);
+    return t;
+}
+template <> __device__ __forceinline__ TriRec<Dual> load_tri<Dual>(const DScene &sc, int i) {
+    const float4 a = __ldg(sc.geo + 3 * i), b = __ldg(sc.geo + 3 * i + 1), c = __ldg(sc.geo + 3 * i + 2);
+    const float4 da = __ldg(sc.dgeo + 3 * i), db = __ldg(sc.dgeo + 3 * i + 1), dc = __ldg(sc.dgeo + 3 * i + 2);
+    TriRec<Dual> t;
+    t.p0 = V3d(Dual(a.x, da.x), Dual(a.y, da.y), Dual(a.z, da.z));
+    t.e1 = V3d(Dual(a.w, da.w), Dual(b.x, db.x), Dual(b.y, db.y));
+    t.e2 = V3d(Dual(b.z, db.z), Dual(b.w, db.w), Dual(c.x, dc.x));
+    t.area = Dual(c.y, dc.y);
+    t.mesh = __float_as_int(c.z);
+    return t;
+}
+template <class S> __device__ __forceinline__ ShadeRec<S> load_shade(const DScene &sc, int i);
+template <> __device__ __forceinline__ ShadeRec<float> load_shade<float>(const DScene &sc, int i) {
+    const float4 a = __ldg(sc.shade + 3 * i), b = __ldg(sc.shade + 3 * i + 1), c = __ldg(sc.shade + 3 * i + 2);
+    ShadeRec<float> s;
+    s.n0 = V3f(a.x, a.y, a.z);
+    s.n1 = V3f(a.w, b.x, b.y);
+    s.n2 = V3f(b.z, b.w, c.x);
+    s.fn = V3f(c.y, c.z, c.w);
+    return s;
+}
+template <> __device__ __forceinline__ ShadeRec<Dual> load_shade<Dual>(const DScene &sc, int i) {
+    const float4 a = __ldg(sc.shade + 3 * i), b = __ldg(sc.shade + 3 * i + 1), c = __ldg(sc.shade + 3 * i + 2);
+    const float4 da = __ldg(sc.dshade + 3 * i), db = __ldg(sc.dshade + 3 * i + 1), dc = __ldg(sc.dshade + 3 * i + 2);
+    ShadeRec<Dual> s;
+    s.n0 = V3d(Dual(a.x, da.x), Dual(a.y, da.y), Dual(a.z, da.z));
+    s.n1 = V3d(Dual(a.w, da.w), Dual(b.x, db.x), Dual(b.y, db.y));
+    s.n2 = V3d(Dual(b.z, db.z), Dual(b.w, db.w), Dual(c.x, dc.x));
+    s.fn = V3d(Dual(c.y, dc.y), Dual(c.z, dc.z), Dual(c.w, dc.w));
+    return s;
+}
+
+// ---- closest hit in (RayEpsilon, 1e8): replaces OptiX (reference src/scene/scene_optix.cpp:343-410)
+// Moeller-Trumbore with a fixed operation order; ties resolve to the lowest triangle id.
+__device__ __forceinline__ void tri_test(const DScene &sc, int id, V3f o, V3f d, Hit &best) {
+    const float4 a = __ldg(sc.geo + 3 * id), b = __ldg(sc.geo + 3 * id + 1);
+    const float e2z = __ldg(&sc.geo[3 * id + 2].x);
+    const V3f p0(a.x, a.y, a.z), e1(a.w, b.x, b.y), e2(b.z, b.w, e2z);
+    const V3f h = cross(d, e2);
+    const float det = dot(e1, h);
+    if (det == 0.f) return;
+    const float f = 1.f / det;
+    const V3f s = o - p0;
+    const float u = f * dot(s, h);
+    if (!(u >= 0.f && u <= 1.f)) return;
+    const V3f q = cross(s, e1);
+    const float v = f * dot(d, q);
+    if (!(v >= 0.f && u + v <= 1.f)) return;
+    const float t = f * dot(e2, q);
+    if (t > kRayEpsilon && t < kTraceTMax && (t < best.t || (t == best.t && id < best.tri))) {
+        best.tri = id;
+        best.u = u;
+        best.v = v;
+        best.t = t;
+    }
+}
+
+__device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
+    Hit best;
+    best.tri = 0x7fffffff;
+    best.u = best.v = 0.f;
+    best.t = kTraceTMax;
+    if (isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z)) {
+        best.tri = -1;
+        return best;
+    }
+    if (!sc.use_bvh) {
+        for (int i = 0; i < sc.n_tris; ++i) tri_test(sc, i, o, d, best);
+    } else {
+        const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
+        int stack[48];
+        int sp = 0;
+        int node = 0;
+        while (true) {
+            const DBvhNode *nd = sc.nodes + node;
+            const float4 n0 = __ldg(reinterpret_cast<const float4 *>(nd)), n1 = __ldg(reinterpret_cast<const float4 *>(nd) + 1);
+            const int ia = __float_as_int(n0.w), ib = __float_as_int(n1.w);
+            // slab test; fminf/fmaxf drop the NaNs of 0*inf
+            const float tx0 = (n0.x - o.x) * ix, tx1 = (n1.x - o.x) * ix;
+            const float ty0 = (n0.y - o.y) * iy, ty1 = (n1.y - o.y) * iy;
+            const float tz0 = (n0.z - o.z) * iz, tz1 = (n1.z - o.z) * iz;
+            const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.f));
+            const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best.t));
+            bool descend = false;
+            if (tn <= tf * 1.0000005f + 1e-6f) {
+                if (ib < 0) {
+                    const int first = ia, cnt = -ib;
+                    for (int k = 0; k < cnt; ++k) tri_test(sc, __ldg(sc.tri_order + first + k), o, d, best);
+                } else {
+                    if (sp < 47) stack[sp++] = ib;
+                    node = ia;
+                    descend = true;
+                }
+            }
+            if (!descend) {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        }
+    }
+    if (best.tri == 0x7fffffff) best.tri = -1;
+    return best;
+}
+
+// reference include/psdr/core/frame.h:9-28 (Duff et al.)
+template <class S> __device__ __forceinline__ void coordinate_system(V3<S> n, V3<S> &s, V3<S> &t) {
+    const bool neg = signbit_(val(n.z));
+    const float sign = neg ? -1.f : 1.f;
+    const S a = -rcp_(sign + n.z);
+    const S b = n.x * n.y * a;
+    const S sx = sqr(n.x) * a;
+    s = V3<S>((neg ? -sx : sx) + 1.f, neg ? -b : b, neg ? n.x : -n.x);
+    t = V3<S>(b, sign + sqr(n.y) * a, -n.y);
+}
+
+template <class S> struct Its {   // reference include/psdr/core/intersection.h:23-60
+    bool valid;
+    int mesh, tri;
+    V3<S> p, n, wi, sh_s, sh_t, sh_n;
+    S t, J;
+    __device__ __forceinline__ V3<S> to_local(V3<S> v) const { return V3<S>(dot(v, sh_s), dot(v, sh_t), dot(v, sh_n)); }
+    __device__ __forceinline__ V3<S> to_world(V3<S> v) const { return sh_s * v.x + sh_t * v.y + sh_n * v.z; }
+};
+
+// reference include/psdr/utils.h:82-93
+template <class S>
+__device__ __forceinline__ void ray_intersect_triangle(V3<S> p0, V3<S> e1, V3<S> e2, V3<S> o, V3<S> d, S &u, S &v, S &t) {
+    const V3<S> h = cross(d, e2);
+    const S a = dot(e1, h);
+    const S f = rcp_(a);
+    const V3<S> s = o - p0;
+    u = f * dot(s, h);
+    const V3<S> q = cross(s, e1);
+    v = f * dot(d, q);
+    t = f * dot(e2, q);
+}
+
+template <class S> struct IsDual { static constexpr bool value = false; };
+template <> struct IsDual<Dual> { static constexpr bool value = true; };
+
+// Scene::ray_intersect<ad, path_space> (reference src/scene/scene.cpp:612-806).  The material-form
+// ("path-space") variant pins the hit to the triangle by detached barycentrics; the solid-angle
+// variant (S = Dual, path_space = false: primary hits) re-intersects analytically.
+template <class S>
+__device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S> d, bool active, bool path_space, int *out_tri = nullptr) {
+    constexpr bool ad = IsDual<S>::value;
+    Its<S> its;
+    its.valid = false;
+    its.mesh = -1;
+    its.tri = -1;
+    its.t = S(0.f);
+    its.J = S(1.f);
+    if (out_tri) *out_tri = -1;
+    if (!active) return its;
+    const Hit h = trace(sc, val(o), val(d));
+    if (h.tri < 0) return its;
+    if (out_tri) *out_tri = h.tri;
+    const TriRec<S> T = load_tri<S>(sc, h.tri);
+    const ShadeRec<S> N = load_shade<S>(sc, h.tri);
+    its.valid = true;
+    its.tri = h.tri;
+    its.mesh = T.mesh;
+    its.n = N.fn;
+    const DMesh mesh = sc.meshes[T.mesh];
+    V3<S> sh_n, dir;
+    if (!ad || path_space) {
+        const V2f uv(h.u, h.v);
+        sh_n = normalize(bilinear(N.n0, N.n1 - N.n0, N.n2 - N.n0, uv));
+        its.p = bilinear(T.p0, T.e1, T.e2, uv);
+        dir = its.p - o;
+        its.t = norm(dir);
+        dir = dir / its.t;
+        if (ad) its.J = T.area / detach(T.area);
+    } else {
+        S u, v, t;
+        ray_intersect_triangle(T.p0, T.e1, T.e2, o, d, u, v, t);
+        const V2<S> uv(u, v);
+        sh_n = normalize(bilinear(N.n0, N.n1 - N.n0, N.n2 - N.n0, uv));
+        its.p = V3<S>(fmadd(d.x, t, o.x), fmadd(d.y, t, o.y), fmadd(d.z, t, o.z));
+        its.t = t;
+        dir = d;
+    }
+    if (mesh.flags & 1) sh_n = its.n;
+    its.sh_n = sh_n;
+    coordinate_system(sh_n, its.sh_s, its.sh_t);
+    if (mesh.flags & 2) {   // uv-derived tangent frame (scene.cpp:716-728, 757-765)
+        const float2 t0 = __ldg(sc.uv + 3 * h.tri), t1 = __ldg(sc.uv + 3 * h.tri + 1), t2 = __ldg(sc.uv + 3 * h.tri + 2);
+        const float du0x = t1.x - t0.x, du0y = t1.y - t0.y, du1x = t2.x - t0.x, du1y = t2.y - t0.y;
+        const float det = du0x * du1y - du0y * du1x;
+        if (det != 0.f) {
+            const float inv_det = 1.f / det;
+            const V3<S> dp_du = (T.e1 * S(du1y) - T.e2 * S(du0y)) * S(inv_det);
+            its.sh_s = normalize(dp_du - sh_n * dot(sh_n, dp_du));
+            its.sh_t = cross(sh_n, its.sh_s);
+        }
+    }
+    its.wi = its.to_local(-dir);
+    return its;
+}
+
+// ---- Diffuse BSDF (reference src/bsdf/diffuse.cpp:23-108) ------------------------------------
+template <class S> __device__ __forceinline__ V3<S> bsdf_reflectance(const DBsdf &b);
+template <> __device__ __forceinline__ V3f bsdf_reflectance<float>(const DBsdf &b) { return V3f(b.refl[0], b.refl[1], b.refl[2]); }
+template <> __device__ __forceinline__ V3d bsdf_reflectance<Dual>(const DBsdf &b) {
+    return V3d(Dual(b.refl[0], b.d_refl[0]), Dual(b.refl[1], b.d_refl[1]), Dual(b.refl[2], b.d_refl[2]));
+}
+
+template <class S> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
+    if (!active || !its.valid) return V3<S>(S(0.f));
+    const int bi = sc.meshes[its.mesh].bsdf;
+    if (bi < 0) return V3<S>(S(0.f));
+    const DBsdf &b = sc.bsdfs[bi];
+    S wiz = its.wi.z;
+    if (b.two_side) {
+        if (signbit_(val(wiz))) wo.z = -wo.z;
+        wiz = abs_(wiz);
+    }
+    if (!(val(wiz) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
+    return bsdf_reflectance<S>(b) * S(kInvPi) * wo.z;
+}
+
+template <class S> __device__ __forceinline__ float bsdf_pdf(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
+    if (!active || !its.valid) return 0.f;
+    const int bi = sc.meshes[its.mesh].bsdf;
+    if (bi < 0) return 0.f;
+    float wiz = val(its.wi.z), woz = val(wo.z);
+    if (sc.bsdfs[bi].two_side) {
+        if (signbit_(wiz)) woz = -woz;
+        wiz = fabsf(wiz);
+    }
+    if (!(wiz > 0.f && woz > 0.f)) return 0.f;
+    return kInvPi * woz;
+}
+
+struct BsdfSample {
+    V3f wo;
+    float pdf;
+    bool valid;
+};
+
+// concentric disk map (reference include/psdr/core/warp.h:15-63) with polynomial sincos
+__device__ __forceinline__ V2f square_to_uniform_disk_concentric(V2f s) {
+    const float x = fmaf(2.f, s.x, -1.f), y = fmaf(2.f, s.y, -1.f);
+    const bool is_zero = (x == 0.f && y == 0.f), q13 = fabsf(x) < fabsf(y);
+    const float r = q13 ? y : x, rp = q13 ? x : y;
+    float sn, cs;
+    sincos_quarter(.25f * kPi * rp / r, sn, cs);
+    if (is_zero) { sn = 0.f; cs = 1.f; }
+    if (q13 && !is_zero) { const float tmp = sn; sn = cs; cs = tmp; }
+    return V2f(r * cs, r * sn);
+}
+
+template <class S> __device__ __forceinline__ BsdfSample bsdf_sample(const DScene &sc, const Its<S> &its, V3f sample, bool active) {
+    BsdfSample bs;
+    bs.wo = V3f(0.f, 0.f, 0.f);
+    bs.pdf = 0.f;
+    bs.valid = false;
+    if (!its.valid) return bs;
+    const int bi = sc.meshes[its.mesh].bsdf;
+    if (bi < 0) return bs;
+    float wiz = val(its.wi.z);
+    if (sc.bsdfs[bi].two_side) wiz = fabsf(wiz);
+    const V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));
+    const float z = safe_sqrt(1.f - fmaf(p.y, p.y, p.x * p.x));
+    bs.wo = V3f(p.x, p.y, z);
+    bs.pdf = kInvPi * z;
+    bs.valid = active && (wiz > 0.f);
+    return bs;
+}
+
+// ---- emitters (reference src/emitter/area.cpp, src/shape/mesh.cpp:413-466) --------------------
+template <class S> __device__ __forceinline__ V3<S> emitter_radiance(const DEmitter &e);
+template <> __device__ __forceinline__ V3f emitter_radiance<float>(const DEmitter &e) { return V3f(e.radiance[0], e.radiance[1], e.radiance[2]); }
+template <> __device__ __forceinline__ V3d emitter_radiance<Dual>(const DEmitter &e) {
+    return V3d(Dual(e.radiance[0], e.d_radiance[0]), Dual(e.radiance[1], e.d_radiance[1]), Dual(e.radiance[2], e.d_radiance[2]));
+}
+template <class S> __device__ __forceinline__ bool is_emitter(const DScene &sc, const Its<S> &its) {
+    return its.valid && sc.meshes[its.mesh].emitter >= 0;
+}
+template <class S> __device__ __forceinline__ V3<S> Le(const DScene &sc, const Its<S> &its, bool active) {
+    if (!its.valid) return V3<S>(S(0.f));
+    const int e = sc.meshes[its.mesh].emitter;
+    if (e < 0 || !(active && val(its.wi.z) > 0.f)) return V3<S>(S(0.f));
+    return emitter_radiance<S>(sc.emitters[e]);
+}
+
+// DiscreteDistribution::sample_reuse (reference src/core/pmf.cpp:31-51): binary search of the
+// unnormalised fp32 CDF, sample re-stretched to [0,1]
+__device__ __forceinline__ int sample_reuse(const float *pmf, const float *cmf, int size, float sum, float &s, float &prob) {
+    if (size == 1) { prob = 1.f; return 0; }
+    s *= sum;
+    int start = 0, end = size - 1;
+    const int iterations = 32 - __clz(end - start);   // log2i(end-start)+1, end-start >= 1
+    for (int i = 0; i < iterations; ++i) {
+        const int middle = (start + end) >> 1;
+        if (__ldg(cmf + middle) < s) start = min(middle + 1, end);
+        else end = middle;
+    }
+    const int idx = start;
+    if (idx > 0) s -= __ldg(cmf + idx - 1);
+    const float p = __ldg(pmf + idx);
+    if (p > 0.f) s /= p;
+    s = fminf(fmaxf(s, 0.f), 1.f);
+    prob = p / sum;
+    return idx;
+}
+
+template <class S> struct PosSample {
+    V3<S> p, n;
+    S J;
+    float pdf;
+};
+
+// Scene::sample_emitter_position (reference src/scene/scene.cpp:987-1013) -> Mesh::sample_position
+template <class S> __device__ __forceinline__ PosSample<S> sample_emitter_position(const DScene &sc, V2f sample2) {
+    PosSample<S> ps;
+    int ei = 0;
+    float emitter_pdf = 1.f;
+    if (sc.n_emitters != 1) ei = sample_reuse(sc.emitter_pmf, sc.emitter_cmf, sc.n_emitters, sc.emitter_sum, sample2.y, emitter_pdf);
+    const DEmitter &em = sc.emitters[ei];
+    float dummy;
+    const int fi = sample_reuse(sc.face_pmf + em.distrb_offset, sc.face_cmf + em.distrb_offset, em.nfaces, em.face_sum, sample2.x, dummy);
+    const float t = safe_sqrt(1.f - sample2.x);
+    const V2f st(1.f - t, t * sample2.y);
+    const TriRec<S> T = load_tri<S>(sc, em.face_offset + fi);
+    ps.J = S(1.f);
+    if (IsDual<S>::value) ps.J = T.area / detach(T.area);
+    ps.p = bilinear(T.p0, T.e1, T.e2, st);
+    const float4 c = __ldg(sc.shade + 3 * (em.face_offset + fi) + 2);
+    if (IsDual<S>::value) {
+        const float4 dc = __ldg(sc.dshade + 3 * (em.face_offset + fi) + 2);
+        ps.n = Lift<S>::v3(V3f(c.y, c.z, c.w), V3f(dc.y, dc.z, dc.w));
+    } else {
+        ps.n = Lift<S>::v3(V3f(c.y, c.z, c.w), V3f(0.f, 0.f, 0.f));
+    }
+    ps.pdf = em.inv_total_area;
+    if (sc.n_emitters != 1) ps.pdf *= emitter_pdf;
+    return ps;
+}
+
+template <class S> __device__ __forceinline__ float emitter_position_pdf(const DScene &sc, const Its<S> &its, bool active) {
+    if (!its.valid || !active) return 0.f;
+    const int e = sc.meshes[its.mesh].emitter;
+    if (e < 0) return 0.f;
+    return sc.emitters[e].sampling_weight * sc.emitters[e].inv_total_area;
+}
+
+__device__ __forceinline__ float mis_weight(float a, float b) {
+    const float w1 = a * a, w2 = b * b;
+    return w1 / (w1 + w2);
+}
+
+// ---- camera (reference src/sensor/perspective.cpp:160-197) ------------------------------------
+__device__ __forceinline__ V3f xform_pos(const float *M, V3f p) {
+    float t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = fmaf(M[4 * i + 2], p.z, fmaf(M[4 * i + 1], p.y, M[4 * i] * p.x)) + M[4 * i + 3];
+    return V3f(t[0] / t[3], t[1] / t[3], t[2] / t[3]);
+}
+__device__ __forceinline__ V3f xform_dir(const float *M, V3f p) {
+    return V3f(fmaf(M[2], p.z, fmaf(M[1], p.y, M[0] * p.x)), fmaf(M[6], p.z, fmaf(M[5], p.y, M[4] * p.x)),
+               fmaf(M[10], p.z, fmaf(M[9], p.y, M[8] * p.x)));
+}
+__device__ __forceinline__ V3d xform_pos_d(const float *M, const float *dM, V3d p) {
+    Dual t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const Dual a(M[4 * i], dM[4 * i]), b(M[4 * i + 1], dM[4 * i + 1]), c(M[4 * i + 2], dM[4 * i + 2]), w(M[4 * i + 3], dM[4 * i + 3]);
+        t[i] = fmadd(c, p.z, fmadd(b, p.y, a * p.x)) + w;
+    }
+    return V3d(t[0] / t[3], t[1] / t[3], t[2] / t[3]);
+}
+__device__ __forceinline__ V3d xform_dir_d(const float *M, const float *dM, V3d p) {
+    Dual t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const Dual a(M[4 * i], dM[4 * i]), b(M[4 * i + 1], dM[4 * i + 1]), c(M[4 * i + 2], dM[4 * i + 2]);
+        t[i] = fmadd(c, p.z, fmadd(b, p.y, a * p.x));
+    }
+    return V3d(t[0], t[1], t[2]);
+}
+
+template <class S> __device__ __forceinline__ void sample_primary_ray(const DCamera &cam, V2f s, V3<S> &o, V3<S> &d);
+template <> __device__ __forceinline__ void sample_primary_ray<float>(const DCamera &cam, V2f s, V3f &o, V3f &d) {
+    const V3f dc = normalize(xform_pos(cam.sample_to_camera, V3f(s.x, s.y, 0.f)));
+    o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f));
+    d = xform_dir(cam.to_world, dc);
+}
+template <> __device__ __forceinline__ void sample_primary_ray<Dual>(const DCamera &cam, V2f s, V3d &o, V3d &d) {
+    const V3f dc = normalize(xform_pos(cam.sample_to_camera, V3f(s.x, s.y, 0.f)));   // detached direction
+    o = xform_pos_d(cam.to_world, cam.d_to_world, V3d(Dual(0.f), Dual(0.f), Dual(0.f)));
+    d = xform_dir_d(cam.to_world, cam.d_to_world, lift3<Dual>(dc));
+}
+
+// ---- PathTracer::__Li (reference src/integrator/path.cpp:35-127) ------------------------------
+// NEE + BSDF sampling with the power heuristic, fixed max_depth, no Russian roulette.  Every lane
+// draws 5 numbers per bounce whether it is alive or not, so draw k of a lane is a closed-form
+// function of (seed, lane, k).
+template <class S>
+__device__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
+    constexpr bool ad = IsDual<S>::value;
+    Its<S> its = ray_intersect<S>(sc, ro, rd, active, false);
+    active = active && its.valid;
+    V3<S> throughput(S(1.f));
+    V3<S> result = hide_emitters ? V3<S>(S(0.f)) : Le(sc, its, active);
+    for (int depth = 0; depth < max_depth; ++depth) {
+        if (!active) {   // dead lanes only burn their draws
+            rng.advance(5ull * (unsigned long long) (max_depth - depth));
+            break;
+        }
+        const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
+        const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
+        {   // ---- emitter sampling
+            const PosSample<S> ps = sample_emitter_position<S>(sc, V2f(s_x, s_y));
+            bool active_direct = active && !is_emitter(sc, its);
+            V3<S> wod = ps.p - its.p;
+            const S dist_sqr = squared_norm(wod);
+            const S dist = safe_sqrt(dist_sqr);
+            wod = wod / dist;
+            const Its<S> its1 = ray_intersect<S>(sc, its.p, wod, active_direct, ad);
+            active_direct = active_direct && its1.valid;
+            active_direct = active_direct && (val(its1.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its1);
+            if (active_direct) {
+                const S cos_val = dot(its1.n, -wod);
+                const S G_val = abs_(cos_val) / dist_sqr;
+                const V3<S> emitter_val = Le(sc, its1, active);
+                const V3<S> wo_local = its.to_local(wod);
+                V3<S> bsdf_val2 = bsdf_eval(sc, its, wo_local, active_direct);
+                bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
+                const float pdf1 = bsdf_pdf(sc, its, wo_local, active_direct) * val(G_val);
+                if (pdf1 != 0.f) {
+                    const float weight1 = mis_weight(ps.pdf, pdf1);
+                    result = result + throughput * emitter_val * bsdf_val2 * S(weight1);
+                }
+            }
+        }
+        {   // ---- BSDF sampling
+            const BsdfSample bs = bsdf_sample(sc, its, V3f(s3_x, s3_y, s3_z), active);
+            const V3<S> wdir = its.to_world(lift3<S>(bs.wo));
+            const Its<S> its1 = ray_intersect<S>(sc, its.p, wdir, active, ad);
+            active = active && bs.valid && its1.valid;
+            if (!active) continue;
+            V3<S> bsdf_val;
+            float pdf0;
+            if (ad) {
+                V3<S> wo = its1.p - its.p;
+                wo = wo / its1.t;
+                const S cos_val = dot(its1.n, -wo);
+                const S G_val = abs_(cos_val) / sqr(its1.t);
+                pdf0 = bs.pdf * val(G_val);
+                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                else bsdf_val = bsdf_eval(sc, its, its.to_local(wo), active) * (G_val * its1.J / S(pdf0));
+            } else {
+                const S cos_val = dot(its1.n, -wdir);
+                const S G_val = abs_(cos_val) / sqr(its1.t);
+                pdf0 = bs.pdf * val(G_val);
+                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                else bsdf_val = bsdf_eval(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
+            }
+            const float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, its1, active));
+            throughput = throughput * bsdf_val;
+            result = result + Le(sc, its1, active) * throughput * S(weight2);
+            its = its1;
+        }
+    }
+    return result;
+}
+
+// ---- secondary (shadow) edges: reference src/scene/scene.cpp:1027-1068, src/integrator/path.cpp:172-270
+struct SensorDirect {
+    V2f q;
+    int pixel;
+    float sensor_val;
+    bool valid;
+};
+__device__ __forceinline__ SensorDirect sample_direct(const DScene &sc, const DCamera &cam, V3f p) {
+    SensorDirect r;
+    const V3f q = xform_pos(cam.world_to_sample, p);
+    r.q = V2f(q.x, q.y);
+    const int ix = (int) floorf(q.x * (float) sc.width), iy = (int) floorf(q.y * (float) sc.height);
+    r.valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+    r.pixel = r.valid ? iy * sc.width + ix : -1;
+    V3f dir = p - V3f(cam.pos[0], cam.pos[1], cam.pos[2]);
+    const float dist2 = squared_norm(dir);
+    dir = dir / safe_sqrt(dist2);
+    const float cosTheta = dot(V3f(cam.dir[0], cam.dir[1], cam.dir[2]), dir);
+    const float ic = 1.f / cosTheta;
+    r.sensor_val = (1.f / dist2) * (ic * ic * ic) * cam.inv_area;
+    return r;
+}
+
+__device__ __forceinline__ int sign_eps(float x, float eps) { return x > eps ? 1 : (x < -eps ? -1 : 0); }
+__device__ __forceinline__ float sign1(float x) { return signbit_(x) ? -1.f : 1.f; }
+
+// returns the pixel (-1: no contribution); value0 = primal boundary value (guiding pre-pass),
+// tangent = d/dP of the zero-primal estimator.
+__device__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
+    value0_out = V3f(0.f, 0.f, 0.f);
+    tangent_out = V3f(0.f, 0.f, 0.f);
+    // -- sample_boundary_segment_direct
+    float sample1 = sample3.x, pdf0;
+    const int ei = sample_reuse(sc.sec_pmf, sc.sec_cmf, sc.n_sec_edges, sc.sec_sum, sample1, pdf0);
+    const float4 q0 = __ldg(sc.sec_edges + 6 * ei), q1 = __ldg(sc.sec_edges + 6 * ei + 1), q2 = __ldg(sc.sec_edges + 6 * ei + 2),
+                 q3 = __ldg(sc.sec_edges + 6 * ei + 3), q4 = __ldg(sc.sec_edges + 6 * ei + 4), q5 = __ldg(sc.sec_edges + 6 * ei + 5);
+    const V3d ep0(Dual(q0.x, q1.z), Dual(q0.y, q1.w), Dual(q0.z, q2.x));
+    const V3d ee1(Dual(q0.w, q2.y), Dual(q1.x, q2.z), Dual(q1.y, q2.w));
+    const V3f n0(q3.x, q3.y, q3.z), n1(q3.w, q4.x, q4.y), ep2(q4.z, q4.w, q5.x);
+    const bool is_boundary = q5.y != 0.f;
+    const V3d bp0(fmadd(ee1.x, sample1, ep0.x), fmadd(ee1.y, sample1, ep0.y), fmadd(ee1.z, sample1, ep0.z));
+    const V3f e1v = val(ee1);
+    const V3f edge = normalize(e1v);
+    const V3f edge2 = ep2 - val(ep0);
+    const V3f _p0 = val(bp0);
+    pdf0 /= norm(e1v);
+    const PosSample<float> ps2 = sample_emitter_position<float>(sc, V2f(sample3.y, sample3.z));
+    const V3f _p2 = ps2.p, bn = ps2.n;
+    V3f e = _p2 - _p0;
+    const float distSqr = squared_norm(e);
+    e = e / safe_sqrt(distSqr);
+    const float cosTheta = dot(bn, -e);
+    const int sgn0 = sign_eps(dot(n0, e), kEdgeEpsilon), sgn1 = sign_eps(dot(n1, e), kEdgeEpsilon);
+    bool valid = (cosTheta > kEpsilon) && ((is_boundary && sgn0 != 0) || (!is_boundary && sgn0 * sgn1 < 0));
+    if (!valid) return -1;
+    const float bss_pdf = pdf0 * ps2.pdf * (distSqr / cosTheta);
+    // -- eval_secondary_edge
+    const V3f _dir = normalize(_p2 - _p0);
+    int light_tri = -1;
+    const Its<float> _its2 = ray_intersect<float>(sc, _p0, _dir, valid, false, &light_tri);
+    valid = valid && is_emitter(sc, _its2) && _its2.valid && norm(_its2.p - _p2) < kShadowEpsilon;
+    if (!valid) return -1;
+    const Its<float> _its1 = ray_intersect<float>(sc, _p0, -_dir, valid, false);
+    valid = valid && _its1.valid;
+    if (!valid) return -1;
+    const V3f _p1 = _its1.p;
+    const SensorDirect sds = sample_direct(sc, cam, _p1);
+    valid = valid && sds.valid;
+    if (!valid) return -1;
+    V3d co, cd;
+    sample_primary_ray<Dual>(cam, sds.q, co, cd);
+    const Its<Dual> its1 = ray_intersect<Dual>(sc, co, cd, valid, false);
+    valid = valid && its1.valid && norm(val(its1.p) - _p1) < kShadowEpsilon;
+    valid = valid && its1.valid && sc.meshes[its1.mesh].bsdf >= 0;
+    if (!valid) return -1;
+    const float dist = norm(_p2 - _p1), cos2 = fabsf(dot(bn, -_dir));
+    const V3f ec = cross(edge, _dir);
+    const float sinphi = norm(ec);
+    const V3f proj = normalize(cross(ec, bn));
+    const float sinphi2 = norm(cross(_dir, proj));
+    const float base_v = (_its1.t / dist) * (sinphi / sinphi2) * cos2;
+    valid = valid && (sinphi > kEpsilon) && (sinphi2 > kEpsilon);
+    if (!valid) return -1;
+    const V3f d0 = -val(cd);
+    const V3f d0_local = _its1.to_local(d0);
+    V3f bsdf_val = bsdf_eval<float>(sc, _its1, d0_local, valid);
+    const float correction = fabsf((_its1.wi.z * dot(d0, _its1.n)) / (d0_local.z * dot(_dir, _its1.n)));
+    bsdf_val = bsdf_val * correction;
+    V3f value0 = bsdf_val * Le(sc, _its2, valid) * (base_v * sds.sensor_val / bss_pdf);
+    value0_out = value0;
+    const V3f n = normalize(cross(bn, proj));
+    value0 = value0 * (sign1(dot(ec, edge2)) * sign1(dot(ec, n)));
+    const TriRec<Dual> T = load_tri<Dual>(sc, light_tri);
+    const V3d sdir = normalize(bp0 - its1.p);
+    Dual u, v, t;
+    ray_intersect_triangle<Dual>(T.p0, T.e1, T.e2, its1.p, sdir, u, v, t);
+    const V3d u2 = bilinear(detach(T.p0), detach(T.e1), detach(T.e2), V2d(u, v));
+    const Dual dn = dot(lift3<Dual>(n), u2);
+    tangent_out = V3f(value0.x * dn.d, value0.y * dn.d, value0.z * dn.d);
+    return sds.pixel;
+}
+
+}  // namespace psdr

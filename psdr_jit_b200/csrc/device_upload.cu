@@ -1,0 +1,225 @@
+// Packs the configured host scene into the float4 tables of dscene.h and uploads them.
+// All tables of one scene live in ONE device allocation (a few KB for a Cornell box, ~1 MB for a
+// 5k-triangle mesh), refreshed by a single cudaMemcpyAsync per configure() from pinned staging.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "scene.h"
+
+namespace psdr {
+
+struct DeviceBuffers {
+    void *dev = nullptr;
+    void *host = nullptr;     // pinned staging
+    size_t capacity = 0;
+    ~DeviceBuffers() {
+        if (dev) cudaFree(dev);
+        if (host) cudaFreeHost(host);
+    }
+};
+
+static void check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+Scene::~Scene() { delete dev; }
+
+namespace {
+struct Packer {
+    std::vector<unsigned char> bytes;
+    template <class T> size_t add(const std::vector<T> &v) {
+        size_t off = (bytes.size() + 255) / 256 * 256;
+        bytes.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
+        if (!v.empty()) std::memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+        return off;
+    }
+};
+inline float as_float(int i) {
+    float f;
+    std::memcpy(&f, &i, 4);
+    return f;
+}
+}  // namespace
+
+void upload_scene(Scene &sc) {
+    check(cudaSetDevice(sc.device), "cudaSetDevice");
+    std::vector<float4> geo, shade, dgeo, dshade, sec, pe_a, pe_da, pe_b;
+    std::vector<float2> uv;
+    std::vector<DMesh> dmeshes;
+    std::vector<DEmitter> demit;
+    std::vector<DBsdf> dbsdf;
+    std::vector<float> face_pmf, face_cmf, em_pmf, em_cmf, sec_pmf, sec_cmf, pe_pmf, pe_cmf;
+    std::vector<HTri> all_tris;
+
+    for (size_t mi = 0; mi < sc.meshes.size(); ++mi) {
+        const HMesh &m = sc.meshes[mi];
+        DMesh dm;
+        dm.bsdf = m.bsdf;
+        dm.emitter = m.emitter;
+        dm.flags = (m.use_face_normals ? 1 : 0) | (m.has_uv ? 2 : 0);
+        dm.face_offset = m.face_offset;
+        dmeshes.push_back(dm);
+        for (size_t i = 0; i < m.tris.size(); ++i) {
+            const HTri &t = m.tris[i];
+            all_tris.push_back(t);
+            geo.push_back(make_float4(t.p0.x.v, t.p0.y.v, t.p0.z.v, t.e1.x.v));
+            geo.push_back(make_float4(t.e1.y.v, t.e1.z.v, t.e2.x.v, t.e2.y.v));
+            geo.push_back(make_float4(t.e2.z.v, t.area.v, as_float((int) mi), 0.f));
+            dgeo.push_back(make_float4(t.p0.x.d, t.p0.y.d, t.p0.z.d, t.e1.x.d));
+            dgeo.push_back(make_float4(t.e1.y.d, t.e1.z.d, t.e2.x.d, t.e2.y.d));
+            dgeo.push_back(make_float4(t.e2.z.d, t.area.d, 0.f, 0.f));
+            shade.push_back(make_float4(t.n0.x.v, t.n0.y.v, t.n0.z.v, t.n1.x.v));
+            shade.push_back(make_float4(t.n1.y.v, t.n1.z.v, t.n2.x.v, t.n2.y.v));
+            shade.push_back(make_float4(t.n2.z.v, t.fn.x.v, t.fn.y.v, t.fn.z.v));
+            dshade.push_back(make_float4(t.n0.x.d, t.n0.y.d, t.n0.z.d, t.n1.x.d));
+            dshade.push_back(make_float4(t.n1.y.d, t.n1.z.d, t.n2.x.d, t.n2.y.d));
+            dshade.push_back(make_float4(t.n2.z.d, t.fn.x.d, t.fn.y.d, t.fn.z.d));
+            for (int k = 0; k < 3; ++k) {
+                const V2f c = m.has_uv ? m.uv[m.fuv[3 * i + k]] : V2f(0.f, 0.f);
+                uv.push_back(make_float2(c.x, c.y));
+            }
+        }
+    }
+    for (const HBsdf &b : sc.bsdfs) {
+        DBsdf d;
+        d.refl[0] = b.reflectance.x.v; d.refl[1] = b.reflectance.y.v; d.refl[2] = b.reflectance.z.v;
+        d.d_refl[0] = b.reflectance.x.d; d.d_refl[1] = b.reflectance.y.d; d.d_refl[2] = b.reflectance.z.d;
+        d.type = b.type;
+        d.two_side = b.two_side ? 1 : 0;
+        dbsdf.push_back(d);
+    }
+    for (const HEmitter &e : sc.emitters) {
+        const HMesh &m = sc.meshes[e.mesh];
+        DEmitter d{};
+        d.radiance[0] = e.radiance.x.v; d.radiance[1] = e.radiance.y.v; d.radiance[2] = e.radiance.z.v;
+        d.d_radiance[0] = e.radiance.x.d; d.d_radiance[1] = e.radiance.y.d; d.d_radiance[2] = e.radiance.z.d;
+        d.mesh = e.mesh;
+        d.sampling_weight = e.sampling_weight;
+        d.face_offset = m.face_offset;
+        d.nfaces = (int) m.tris.size();
+        d.inv_total_area = m.inv_total_area;
+        d.distrb_offset = (int) face_pmf.size();
+        d.face_sum = m.face_distrb.sum;
+        d.emitter_pmf = e.raw_weight;
+        face_pmf.insert(face_pmf.end(), m.face_distrb.pmf.begin(), m.face_distrb.pmf.end());
+        face_cmf.insert(face_cmf.end(), m.face_distrb.cmf.begin(), m.face_distrb.cmf.end());
+        demit.push_back(d);
+    }
+    if (!sc.emitters.empty()) { em_pmf = sc.emitter_distrb.pmf; em_cmf = sc.emitter_distrb.cmf; }
+    for (const HSecEdge &s : sc.sec_edges) {
+        sec.push_back(make_float4(s.p0.x.v, s.p0.y.v, s.p0.z.v, s.e1.x.v));
+        sec.push_back(make_float4(s.e1.y.v, s.e1.z.v, s.p0.x.d, s.p0.y.d));
+        sec.push_back(make_float4(s.p0.z.d, s.e1.x.d, s.e1.y.d, s.e1.z.d));
+        sec.push_back(make_float4(s.n0.x, s.n0.y, s.n0.z, s.n1.x));
+        sec.push_back(make_float4(s.n1.y, s.n1.z, s.p2.x, s.p2.y));
+        sec.push_back(make_float4(s.p2.z, s.is_boundary ? 1.f : 0.f, 0.f, 0.f));
+    }
+    if (!sc.sec_edges.empty()) { sec_pmf = sc.sec_edge_distrb.pmf; sec_cmf = sc.sec_edge_distrb.cmf; }
+
+    std::vector<size_t> cam_edge_first(sc.cameras.size());
+    for (size_t ci = 0; ci < sc.cameras.size(); ++ci) {
+        const HCamera &c = sc.cameras[ci];
+        cam_edge_first[ci] = pe_a.size();
+        for (const HPrimEdge &e : c.edges) {
+            pe_a.push_back(make_float4(e.p0.x.v, e.p0.y.v, e.p1.x.v, e.p1.y.v));
+            pe_da.push_back(make_float4(e.p0.x.d, e.p0.y.d, e.p1.x.d, e.p1.y.d));
+            pe_b.push_back(make_float4(e.normal.x, e.normal.y, e.length, 0.f));
+        }
+        if (!c.edges.empty()) {
+            pe_pmf.insert(pe_pmf.end(), c.edge_distrb.pmf.begin(), c.edge_distrb.pmf.end());
+            pe_cmf.insert(pe_cmf.end(), c.edge_distrb.cmf.begin(), c.edge_distrb.cmf.end());
+        }
+    }
+
+    std::vector<DBvhNode> nodes;
+    std::vector<int> order;
+    const int ntris = (int) all_tris.size();
+    const bool use_bvh = sc.force_bvh < 0 ? ntris > 64 : sc.force_bvh != 0;
+    if (use_bvh) build_bvh(all_tris, nodes, order, 4);
+
+    Packer pk;
+    const size_t o_geo = pk.add(geo), o_shade = pk.add(shade), o_dgeo = pk.add(dgeo), o_dshade = pk.add(dshade), o_uv = pk.add(uv),
+                 o_mesh = pk.add(dmeshes), o_emit = pk.add(demit), o_bsdf = pk.add(dbsdf), o_fp = pk.add(face_pmf), o_fc = pk.add(face_cmf),
+                 o_ep = pk.add(em_pmf), o_ec = pk.add(em_cmf), o_sec = pk.add(sec), o_sp = pk.add(sec_pmf), o_scm = pk.add(sec_cmf),
+                 o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
+                 o_nodes = pk.add(nodes), o_order = pk.add(order);
+
+    if (!sc.dev) sc.dev = new DeviceBuffers();
+    DeviceBuffers &db = *sc.dev;
+    if (pk.bytes.size() > db.capacity) {
+        if (db.dev) cudaFree(db.dev);
+        if (db.host) cudaFreeHost(db.host);
+        db.capacity = pk.bytes.size() * 2;
+        check(cudaMalloc(&db.dev, db.capacity), "cudaMalloc(scene tables)");
+        check(cudaMallocHost(&db.host, db.capacity), "cudaMallocHost(scene staging)");
+    }
+    // the previous tables may still be read by kernels in flight on other streams
+    check(cudaDeviceSynchronize(), "cudaDeviceSynchronize(before table refresh)");
+    std::memcpy(db.host, pk.bytes.data(), pk.bytes.size());
+    check(cudaMemcpy(db.dev, db.host, pk.bytes.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene tables)");
+    const unsigned char *base = (const unsigned char *) db.dev;
+
+    DScene &d = sc.dscene;
+    d = DScene{};
+    d.width = sc.width; d.height = sc.height; d.spp = sc.spp; d.sppe = sc.sppe; d.sppse = sc.sppse;
+    d.n_tris = ntris;
+    d.n_meshes = (int) sc.meshes.size();
+    d.n_emitters = (int) sc.emitters.size();
+    d.n_bsdfs = (int) sc.bsdfs.size();
+    d.n_sec_edges = (int) sc.sec_edges.size();
+    d.n_nodes = (int) nodes.size();
+    d.use_bvh = use_bvh ? 1 : 0;
+    d.geo = (const float4 *) (base + o_geo);
+    d.shade = (const float4 *) (base + o_shade);
+    d.dgeo = (const float4 *) (base + o_dgeo);
+    d.dshade = (const float4 *) (base + o_dshade);
+    d.uv = (const float2 *) (base + o_uv);
+    d.meshes = (const DMesh *) (base + o_mesh);
+    d.emitters = (const DEmitter *) (base + o_emit);
+    d.bsdfs = (const DBsdf *) (base + o_bsdf);
+    d.face_pmf = (const float *) (base + o_fp);
+    d.face_cmf = (const float *) (base + o_fc);
+    d.emitter_pmf = (const float *) (base + o_ep);
+    d.emitter_cmf = (const float *) (base + o_ec);
+    d.emitter_sum = sc.emitters.empty() ? 0.f : sc.emitter_distrb.sum;
+    d.sec_edges = (const float4 *) (base + o_sec);
+    d.sec_pmf = (const float *) (base + o_sp);
+    d.sec_cmf = (const float *) (base + o_scm);
+    d.sec_sum = sc.sec_edges.empty() ? 0.f : sc.sec_edge_distrb.sum;
+    d.nodes = (const DBvhNode *) (base + o_nodes);
+    d.tri_order = (const int *) (base + o_order);
+
+    sc.dcameras.assign(sc.cameras.size(), DCamera{});
+    size_t pmf_off = 0;
+    for (size_t ci = 0; ci < sc.cameras.size(); ++ci) {
+        const HCamera &c = sc.cameras[ci];
+        DCamera &dc = sc.dcameras[ci];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                dc.sample_to_camera[4 * i + j] = c.sample_to_camera.m[i][j];
+                dc.to_world[4 * i + j] = c.to_world_full.m[i][j].v;
+                dc.d_to_world[4 * i + j] = c.to_world_full.m[i][j].d;
+                dc.world_to_sample[4 * i + j] = c.world_to_sample.m[i][j].v;
+                dc.d_world_to_sample[4 * i + j] = c.world_to_sample.m[i][j].d;
+            }
+        dc.pos[0] = c.pos.x.v; dc.pos[1] = c.pos.y.v; dc.pos[2] = c.pos.z.v;
+        dc.d_pos[0] = c.pos.x.d; dc.d_pos[1] = c.pos.y.d; dc.d_pos[2] = c.pos.z.d;
+        dc.dir[0] = c.dir.x.v; dc.dir[1] = c.dir.y.v; dc.dir[2] = c.dir.z.v;
+        dc.d_dir[0] = c.dir.x.d; dc.d_dir[1] = c.dir.y.d; dc.d_dir[2] = c.dir.z.d;
+        dc.inv_area = c.inv_area;
+        dc.n_edges = (int) c.edges.size();
+        dc.edge_sum = c.edges.empty() ? 0.f : c.edge_distrb.sum;
+        dc.pe_a = (const float4 *) (base + o_pa) + cam_edge_first[ci];
+        dc.pe_da = (const float4 *) (base + o_pda) + cam_edge_first[ci];
+        dc.pe_b = (const float4 *) (base + o_pb) + cam_edge_first[ci];
+        dc.pe_pmf = (const float *) (base + o_pp) + pmf_off;
+        dc.pe_cmf = (const float *) (base + o_pc) + pmf_off;
+        pmf_off += c.edges.size();
+    }
+}
+
+}  // namespace psdr

@@ -1,0 +1,97 @@
+// Device-side scene tables read by the sm_100a kernels (all read-only during a render call).
+// Layout: float4-packed structure-of-arrays so that one triangle's geometry is three 16-byte
+// loads; everything a Cornell-box-class scene needs is a few KB and stays L1/L2 resident,
+// bigger meshes stream through L2 (126 MB) -- HBM is touched once per call.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace psdr {
+
+// triangle i: geo[3i+0] = (p0.x,p0.y,p0.z,e1.x) geo[3i+1] = (e1.y,e1.z,e2.x,e2.y)
+//             geo[3i+2] = (e2.z, face_area, int_as_float(mesh_id), 0)
+//             shade[3i+0] = (n0.xyz, n1.x) shade[3i+1] = (n1.yz, n2.xy) shade[3i+2] = (n2.z, fn.xyz)
+// dgeo/dshade: the forward-mode tangents in the same layout (dgeo[3i+2].z/.w unused).
+// uv[3i+k] = texture coordinate of corner k (zeros for meshes without UVs)
+struct DBvhNode {        // 32 B
+    float lo[3];
+    int a;               // inner: left child;  leaf: first index into tri_order
+    float hi[3];
+    int b;               // inner: right child; leaf: -(count)
+};
+
+struct DMesh {
+    int bsdf;            // index into bsdf tables, -1 = none
+    int emitter;         // index into emitter table, -1 = none
+    int flags;           // bit0 use_face_normals, bit1 has_uv
+    int face_offset;
+};
+
+struct DEmitter {
+    float radiance[3];
+    float d_radiance[3];
+    int mesh;
+    float sampling_weight;   // normalised: weight * rcp(sum of weights)
+    int face_offset;         // global id of the mesh's first triangle
+    int nfaces;
+    float inv_total_area;
+    int distrb_offset;       // into face_pmf / face_cmf
+    float face_sum;          // drjit-style fp32 sum of the face areas
+    float emitter_pmf;       // unnormalised selection weight (area*luminance)
+    float pad0, pad1;
+};
+
+struct DBsdf {
+    float refl[3];
+    float d_refl[3];
+    int type;                // 0 diffuse
+    int two_side;
+};
+
+struct DCamera {
+    float sample_to_camera[16];
+    float to_world[16], d_to_world[16];
+    float world_to_sample[16], d_world_to_sample[16];
+    float pos[3], d_pos[3], dir[3], d_dir[3];
+    float inv_area;
+    int n_edges;             // primary edges (0 = none / not an active sensor)
+    float edge_sum;
+    int pad;
+    // primary edges: pe_a = (p0.x,p0.y,p1.x,p1.y), pe_da = tangents, pe_b = (nx,ny,len,0)
+    const float4 *pe_a, *pe_da, *pe_b;
+    const float *pe_pmf, *pe_cmf;
+};
+
+struct DScene {
+    int width, height, spp, sppe, sppse;
+    int n_tris, n_meshes, n_emitters, n_bsdfs, n_sec_edges, n_nodes;
+    int use_bvh;             // 0: brute force over all triangles (tiny scenes)
+    const float4 *geo, *shade, *dgeo, *dshade;
+    const float2 *uv;
+    const DMesh *meshes;
+    const DEmitter *emitters;
+    const DBsdf *bsdfs;
+    const float *face_pmf, *face_cmf;          // concatenated per-emitter face distributions
+    const float *emitter_pmf, *emitter_cmf;    // emitter selection (size n_emitters)
+    float emitter_sum;
+    // secondary edges: 6 float4 per edge:
+    //  [0]=(p0.xyz,e1.x) [1]=(e1.yz, dp0.xy) [2]=(dp0.z, de1.xyz) [3]=(n0.xyz, n1.x) [4]=(n1.yz, p2.xy) [5]=(p2.z, boundary,0,0)
+    const float4 *sec_edges;
+    const float *sec_pmf, *sec_cmf;
+    float sec_sum;
+    const DBvhNode *nodes;
+    const int *tri_order;
+};
+
+struct RenderParams {
+    int max_depth;
+    int hide_emitters;
+    long long seed;          // >= 0
+    unsigned long long skip; // draws already consumed per lane of this sampler (seed = -1 continuation)
+    long long lane_begin, lane_end;   // lane range rendered by this call (multi-GPU sharding)
+    const int *pix_id;       // batch mode: pixel list (device), else nullptr
+    int npix;                // number of output pixels (W*H or len(pix_id))
+    float tangent_scale;     // 1, or 2 to reproduce the reference's forward-mode scaling
+};
+
+}  // namespace psdr

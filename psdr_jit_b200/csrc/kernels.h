@@ -1,0 +1,12 @@
+// Host-callable launchers of the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dscene.h"
+
+namespace psdr {
+cudaError_t launch_interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st);
+cudaError_t launch_primary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);
+cudaError_t launch_secondary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);
+cudaError_t launch_aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st);
+}  // namespace psdr

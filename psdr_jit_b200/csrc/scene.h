@@ -1,0 +1,121 @@
+// Host-side scene graph of the B200 path tracer: owns the objects a user adds through the C ABI
+// (mirroring psdr_jit.Scene: reference src/scene/scene.cpp), evaluates `configure()` in fp32 +
+// forward-mode duals on the host, builds the BVH2 and uploads float4-packed tables (dscene.h).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dscene.h"
+#include "pmath.h"
+
+namespace psdr {
+
+struct Distrib {   // reference src/core/pmf.cpp:6-15, include/psdr/core/pmf.h:12-38
+    int size = 0;
+    float sum = 0.f;
+    std::vector<float> pmf, cmf;
+    void init(const std::vector<float> &p);
+};
+
+struct HTri {
+    V3d p0, e1, e2, n0, n1, n2, fn;
+    Dual area;
+};
+
+struct HEdge {
+    int v0, v1, f0, f1, v2;
+};
+
+struct HBsdf {
+    std::string id;
+    int type = 0;
+    V3d reflectance;
+    bool two_side = false;
+};
+
+struct HMesh {
+    std::vector<V3d> v_raw;
+    std::vector<int> f, fuv;
+    std::vector<V2f> uv;
+    bool has_uv = false;
+    M4<Dual> to_world[3];   // left, raw, right
+    int bsdf = -1, emitter = -1;
+    bool use_face_normals = false, enable_edges = true;
+    bool edges_dirty = true;
+    // configured
+    std::vector<V3d> v_world;
+    std::vector<HTri> tris;
+    std::vector<HEdge> edges;
+    Distrib face_distrb;
+    float total_area = 0.f, inv_total_area = 0.f;
+    int face_offset = 0;
+};
+
+struct HEmitter {
+    V3d radiance;
+    int mesh = -1;
+    float sampling_weight = 0.f, raw_weight = 0.f;
+};
+
+struct HPrimEdge {
+    V2d p0, p1;
+    V2f normal;
+    float length;
+};
+
+struct HCamera {
+    float fov = 60.f, near_ = 1e-6f, far_ = 1e7f;
+    M4<Dual> to_world[3];
+    M4<Dual> to_world_full, world_to_sample;
+    M4<float> sample_to_camera;
+    V3d pos, dir;
+    float inv_area = 0.f;
+    std::vector<HPrimEdge> edges;
+    Distrib edge_distrb;
+};
+
+struct HSecEdge {
+    V3d p0, e1;
+    V3f n0, n1, p2;
+    bool is_boundary;
+};
+
+struct DeviceBuffers;  // owns every cudaMalloc'ed table
+
+struct SamplerState {   // reference Sampler (src/core/sampler.cpp): stateless on the device --
+    bool ready = false; // a stream is (seed, lane) + number of draws consumed so far
+    long long sample_count = 0;
+    long long seed = 0;
+    unsigned long long consumed = 0;
+};
+
+struct Scene {
+    int width = 128, height = 128, spp = 1, sppe = 0, sppse = 0, log_level = 1;  // RenderOption defaults (types.h:217-228)
+    long long seed = 0;
+    std::vector<HBsdf> bsdfs;
+    std::vector<HMesh> meshes;
+    std::vector<HEmitter> emitters;
+    std::vector<HCamera> cameras;
+    std::vector<HSecEdge> sec_edges;
+    Distrib sec_edge_distrb, emitter_distrb;
+    SamplerState samplers[3];
+    bool configured = false;
+    int device = 0;
+    int rank = 0, world = 1;   // lane-range sharding across GPUs
+    int force_bvh = -1;        // -1 auto, 0 brute force, 1 bvh
+    DeviceBuffers *dev = nullptr;
+    DScene dscene{};
+    std::vector<DCamera> dcameras;
+    double last_configure_ms = 0.0;
+
+    Scene();
+    ~Scene();
+    int find_bsdf(const std::string &id) const;
+    void configure(const int *active, int nactive);   // throws std::runtime_error
+};
+
+// BVH2 over world-space triangles (binned SAH); nodes/order are what DScene points to.
+void build_bvh(const std::vector<HTri> &tris, std::vector<DBvhNode> &nodes, std::vector<int> &order, int leaf_size);
+
+}  // namespace psdr

@@ -45,3 +45,49 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
     sc.add_camera(cam["fov"], cam["near"], cam["far"], {"raw": cam["to_world"]})
     sc.configure(active)
     return sc
+
+
+def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, accel=-1,
+                  shard=None, two_side=False, d_radiance=None, d_reflectance=None, d_cam_left=None, log_level=0):
+    """The same scene through the product's psdr_jit-style Python surface."""
+    import psdr_jit_b200 as psdr
+    cam = cam or scenes.CBOX_CAMERA
+    sc = psdr.Scene()
+    o = sc.opts
+    o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level = w, h, spp, sppe, sppse, log_level
+    sensor = psdr.PerspectiveCamera(cam["fov"], cam["near"], cam["far"])
+    sensor.to_world = cam["to_world"]
+    sc.add_Sensor(sensor)
+    for name, refl in scenes.CBOX_BSDFS:
+        sc.add_BSDF(psdr.DiffuseBSDF(refl), name, twoSide=two_side)
+    for i, m in enumerate(meshes):
+        mesh = psdr.Mesh()
+        mesh.load_raw(m.v, m.f, m.uv, m.fuv)
+        mesh.to_world = m.to_world
+        sc.add_Mesh(mesh, m.bsdf, psdr.AreaLight(m.emitter) if m.emitter is not None else None)
+    if move_mesh is not None:
+        sc.param_map["Mesh[%d]" % move_mesh].set_transform(np.eye(4, dtype=np.float32), tangent=translation_tangent(axis_scale))
+    if d_radiance is not None:
+        sc.param_map["Emitter[0]"].d_radiance = np.asarray(d_radiance, dtype=np.float32)
+    if d_reflectance is not None:
+        name, d = d_reflectance
+        sc.param_map["BSDF[id=%s]" % name].d_reflectance = np.asarray(d, dtype=np.float32)
+    if d_cam_left is not None:
+        sc.param_map["Sensor[0]"].set_transform(np.eye(4, dtype=np.float32), tangent=d_cam_left)
+    sc.set_accel(accel)
+    if shard is not None:
+        sc.set_shard(*shard)
+    sc.configure()
+    sc.configure(list(active))
+    return sc
+
+
+def compare_stats(a, b, flip_rel=1e-3):
+    """rel-L2, number of pixels whose max channel error exceeds flip_rel*max|b|, rel-L2 without them."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = np.abs(a - b).max(axis=1)
+    bad = d > flip_rel * max(np.abs(b).max(), 1e-12)
+    a2 = a.copy()
+    a2[bad] = b[bad]
+    return rel_l2(a, b), int(bad.sum()), rel_l2(a2, b)
