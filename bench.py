@@ -1,0 +1,397 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for the PathTracer.renderD hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): Cornell box 512x512, spp = sppe = sppse = 32, PathTracer(3)
+renderD, DiffuseBSDF; the differentiated parameter is the scalar P of the README
+(`Mesh[0].set_transform(translate(100 P, 0, 0))`), the derivative image is the forward-mode one.
+A step = one renderD call (interior + primary-edge + secondary-edge kernels) producing the image and
+the derivative image, seed = step index.  metric = Msamples/s = W*H*(spp+sppe+sppse) / seconds.
+
+  value  -- device time (CUDA events on the launch stream), scene tables already resident in HBM;
+            an L2 flush (256 MiB memset) runs between timed steps, outside the events.
+  e2e    -- the same through the host-buffer C-ABI call a drop-in user makes each optimisation
+            iteration: set the parameter, Scene.configure() (host tables -> pinned staging -> H2D),
+            psdr_render_d_host (kernels + D2H of image and derivative image); wall clock.
+  N > 1  -- strong scaling: every term is sharded by lane range over the ranks, partial full-frame
+            images are summed with one NCCL all-reduce inside the timed region.
+
+--impl reference runs the UNMODIFIED reference (baseline/_ref, Dr.Jit + OptiX on the same GPU)
+through its own Python API on the same config; if it cannot load, the CPU oracle port
+(oracle/, OpenMP) is timed on a bounded sample instead and the line says so.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 512
+SPP = SPPE = SPPSE = 32
+DEPTH = 3
+METRIC = "Msamples/s renderD Cornell 512^2 spp=32 sppe=32 sppse=32 depth=3 (image + forward derivative image)"
+RAYS_PER_LANE = (1 + 2 * DEPTH, 2 * (1 + 2 * DEPTH), 3)       # interior, primary-edge, secondary-edge
+BYTES_PER_RAY = 88                                               # ray 28 B + hit 16 B, written and read once
+
+
+def algorithmic_bytes(term: int, lanes: int) -> int:
+    """SURVEY.md section 8(d) wavefront figure for ONE kernel launch of `term` over `lanes` lanes."""
+    if term == 1:      # interior, forward-mode: image + derivative image splats (24 B/lane)
+        return lanes * (BYTES_PER_RAY * RAYS_PER_LANE[0] + 24)
+    if term == 2:
+        return lanes * (BYTES_PER_RAY * RAYS_PER_LANE[1] + 12)
+    return lanes * (BYTES_PER_RAY * RAYS_PER_LANE[2] + 12)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(psdr, rank: int, world: int, w=W, h=H, spp=SPP, sppe=SPPE, sppse=SPPSE):
+    import numpy as np
+    from psdr_jit_b200 import scenes
+    sc = psdr.Scene()
+    o = sc.opts
+    o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level = w, h, spp, sppe, sppse, 0
+    cam = scenes.CBOX_CAMERA
+    sensor = psdr.PerspectiveCamera(cam["fov"], cam["near"], cam["far"])
+    sensor.to_world = cam["to_world"]
+    sc.add_Sensor(sensor)
+    for name, refl in scenes.CBOX_BSDFS:
+        sc.add_BSDF(psdr.DiffuseBSDF(refl), name)
+    for m in scenes.cbox_meshes():
+        mesh = psdr.Mesh()
+        mesh.load_raw(m.v, m.f, m.uv, m.fuv)
+        mesh.to_world = m.to_world
+        sc.add_Mesh(mesh, m.bsdf, psdr.AreaLight(m.emitter) if m.emitter is not None else None)
+    tangent = np.zeros((4, 4), dtype=np.float32)
+    tangent[0, 3] = 100.0                                    # d/dP translate(100 P, 0, 0)
+    sc.param_map["Mesh[0]"].set_transform(np.eye(4, dtype=np.float32), tangent=tangent)
+    sc.set_shard(rank, world)
+    sc.configure()
+    sc.configure([0])
+    return sc, tangent
+
+
+def cpu_oracle_rate(size: int, spp: int):
+    """The CPU oracle port (OpenMP, all host threads) on a bounded sample of the same workload."""
+    from oracle import psdr_oracle
+    from tests.common import build_oracle, scenes
+    psdr_oracle.build()
+    osc = build_oracle(scenes.cbox_meshes(), size, size, spp, spp, spp, move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+    t0 = time.perf_counter()
+    osc.render(DEPTH, seed=0, mode=1, terms=7)
+    dt = time.perf_counter() - t0
+    n = size * size * 3 * spp
+    return n / dt / 1e6, psdr_oracle.num_threads(), "cbox %dx%d spp=sppe=sppse=%d depth=%d renderD (%.2f Msamples, %.1f s)" % (
+        size, size, spp, DEPTH, n / 1e6, dt)
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import psdr_jit_b200 as psdr
+    from psdr_jit_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.load()
+    sc, tangent = build_scene(psdr, rank, world)
+    integ = psdr.PathTracer(DEPTH)
+    _lib.check(L.psdr_scene_enable_timing(sc._h, 1))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
+    n_samples = W * H * (SPP + SPPE + SPPSE)
+    st = torch.cuda.current_stream()
+
+    def step(seed):
+        img, dimg = integ.renderD_fwd(sc, 0, seed=seed)
+        if world > 1:
+            buf = torch.stack((img, dimg))
+            dist.all_reduce(buf)
+            img, dimg = buf[0], buf[1]
+        return img, dimg
+
+    for it in range(args.warmup):
+        step(it)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = psdr.kernel_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = {1: [], 2: [], 4: []}
+    for it in range(args.steps):
+        flush.fill_(it & 255)                                  # L2 flush, outside the timed events
+        ev[it][0].record(st)
+        step(args.warmup + it)
+        ev[it][1].record(st)
+        # reading the per-kernel events waits for this step; the next step's start event comes after
+        for term in (1, 2, 4):
+            kernel_ms[term].append(L.psdr_scene_kernel_ms(sc._h, term))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = psdr.kernel_launch_count() - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end to end through the host-buffer C ABI: parameter update + configure + render + D2H
+    himg = np.empty((W * H, 3), dtype=np.float32)
+    hdimg = np.empty((W * H, 3), dtype=np.float32)
+    try:
+        torch.cuda.cudart().cudaHostRegister(himg.ctypes.data, himg.nbytes, 0)
+        torch.cuda.cudart().cudaHostRegister(hdimg.ctypes.data, hdimg.nbytes, 0)
+    except Exception:
+        pass
+    mesh0 = sc.param_map["Mesh[0]"]
+
+    def e2e_step(seed):
+        mesh0.set_transform(np.eye(4, dtype=np.float32), tangent=tangent)
+        sc.configure([0])
+        integ.renderD_host(sc, 0, seed=seed, out=himg, dout=hdimg)
+        if world > 1:
+            buf = torch.from_numpy(np.stack((himg, hdimg))).to(dev)
+            dist.all_reduce(buf)
+            buf = buf.cpu()
+        return float(himg[0, 0])
+
+    for it in range(max(1, args.warmup)):
+        e2e_step(it)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        e2e_step(args.warmup + it)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = int(L.psdr_scene_query(sc._h, _lib.Q_UPLOAD_BYTES, 0))
+    d2h = himg.nbytes + hdimg.nbytes
+
+    if rank == 0:
+        # dominant kernel = largest mean device time
+        means = {k: (sum(v) / len(v) if v and min(v) >= 0 else -1.0) for k, v in kernel_ms.items()}
+        dom = max(means, key=lambda k: means[k])
+        lanes = W * H * {1: SPP, 2: SPPE, 4: SPPSE}[dom] // world
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = algorithmic_bytes(dom, lanes) / (means[dom] * 1e-3) / 1e9 if means[dom] > 0 else None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_oracle_rate(256, 32)
+            cpu = {"value": round(v, 4), "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample}
+        out = {
+            "metric": METRIC, "value": round(n_samples * args.steps / (total_ms * 1e-3) / 1e6, 3), "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cbox 512x512 spp=32 sppe=32 sppse=32 PathTracer(3) renderD DiffuseBSDF (BASELINE configs[1])",
+                       "l2": "256 MiB memset between timed steps (flush, outside the events)",
+                       "sharding": "lane ranges of every term over %d rank(s); partial images summed by one NCCL all-reduce" % world
+                       if world > 1 else "single GPU", "seed": "step index", "param": "Mesh[0] translate(100 P,0,0), forward tangent"},
+            "clocks": clk,
+            "e2e": {"value": round(n_samples * args.steps / e2e_s / 1e6, 3), "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
+                    "path": "set_transform + Scene.configure + psdr_render_d_host (pinned host image buffers)"},
+            "gpu_launches": int(launches),
+            "kernel_ms": {"interior": round(means[1], 4), "primary_edges": round(means[2], 4), "secondary_edges": round(means[4], 4)},
+            "roofline": {"bound": "hbm", "kernel": {1: "interior_kernel<Dual>", 2: "primary_edge_kernel", 4: "secondary_edge_kernel"}[dom],
+                         "achieved": None if ach is None else round(ach, 1), "peak": peak, "unit": "GB/s",
+                         "frac": None if ach is None else round(ach / peak, 4), "traffic": load_traffic(dom),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
+                         "note": "achieved = SURVEY 8(d) wavefront bytes (88 B/ray + splats) / CUDA-event kernel time; the fused kernel keeps "
+                                 "rays and hits in registers, so DRAM traffic is far below the algorithmic figure and frac may exceed 1"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic(term: int):
+    """dram bytes per launch of the kernel from the committed ncu capture (profiles/), else null."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d.get({1: "interior", 2: "primary_edges", 4: "secondary_edges"}[term])
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int, local_rank: int):
+    if rank != 0:
+        return
+    n_samples = W * H * (SPP + SPPE + SPPSE)
+    base = {"impl": "reference", "metric": METRIC, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    err = None
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    try:
+        if not os.path.isdir(os.path.join(ref_dir, "psdr_jit")):
+            raise RuntimeError("baseline/_ref is not installed")
+        sys.path.insert(0, ref_dir)
+        import numpy as np
+        import drjit
+        import psdr_jit as ref
+        from drjit.cuda import Matrix4f as Matrix4fC
+        from drjit.cuda.ad import Float as FloatD, Matrix4f as Matrix4fD
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("scenes", os.path.join(ROOT, "psdr_jit_b200", "scenes.py"))
+        scenes = importlib.util.module_from_spec(spec)
+        sys.modules["scenes"] = scenes
+        spec.loader.exec_module(scenes)
+        objdir = os.path.join(ROOT, "gpurun_out", "ref_obj")
+        os.makedirs(objdir, exist_ok=True)
+        mat = lambda m: [[float(m[i][j]) for j in range(4)] for i in range(4)]   # noqa: E731
+        sc = ref.Scene()
+        o = sc.opts
+        o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level = W, H, SPP, SPPE, SPPSE, 0
+        cam = scenes.CBOX_CAMERA
+        sensor = ref.PerspectiveCamera(cam["fov"], cam["near"], cam["far"])
+        sensor.to_world = Matrix4fD(mat(cam["to_world"]))
+        sc.add_Sensor(sensor)
+        for name, refl in scenes.CBOX_BSDFS:
+            sc.add_BSDF(ref.DiffuseBSDF([float(x) for x in refl]), name)
+        for i, m in enumerate(scenes.cbox_meshes()):
+            path = os.path.join(objdir, "m%d_%s.obj" % (i, m.name))
+            scenes.write_obj(m, path)
+            em = ref.AreaLight([float(x) for x in m.emitter]) if m.emitter is not None else None
+            sc.add_Mesh(path, Matrix4fC(mat(m.to_world)), m.bsdf, em)
+        integ = ref.PathTracer(DEPTH)
+
+        def step(seed):
+            P = FloatD(0.)
+            drjit.enable_grad(P)
+            sc.param_map["Mesh[0]"].set_transform(Matrix4fD([[1., 0., 0., P * 100.], [0., 1., 0., 0.], [0., 0., 1., 0.], [0., 0., 0., 1.]]))
+            sc.configure()
+            sc.configure([0])
+            img = integ.renderD(sc, 0, seed=seed)
+            drjit.eval(img)
+            drjit.set_grad(P, 1.0)
+            drjit.forward_to(img)
+            g = drjit.grad(img)
+            drjit.eval(g)
+            drjit.sync_thread()
+            return float(np.asarray(img.numpy()).ravel()[0]) + float(np.asarray(g.numpy()).ravel()[0])
+
+        for it in range(max(1, args.warmup)):
+            step(it)
+        t0 = time.perf_counter()
+        for it in range(args.steps):
+            step(args.warmup + it)
+        dt = time.perf_counter() - t0
+        v = n_samples * args.steps / dt / 1e6
+        base.update({"value": round(v, 4), "ms_per_step": round(dt / args.steps * 1e3, 3),
+                     "config": {"workload": "cbox 512x512 spp=32 sppe=32 sppse=32 PathTracer(3) renderD DiffuseBSDF (BASELINE configs[1])",
+                                "path": "unmodified reference (Dr.Jit 0.4.6 + OptiX) on the same GPU: set_transform, configure, renderD, "
+                                        "forward_to, grad, numpy readback; wall clock"},
+                     "cpu_baseline": {"value": round(v, 4), "unit": "Msamples/s", "cores": 1, "kind": "reference",
+                                      "sample": "the full workload on the GPU (the reference has no CPU back-end: include/psdr/types.h:19-26)"},
+                     "e2e": {"value": round(v, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base), flush=True)
+        return
+    except Exception as e:  # the reference cannot run here -> CPU oracle port on a bounded sample
+        err = "%s: %s" % (type(e).__name__, e)
+    vals = []
+    cores, sample = 1, ""
+    for _ in range(max(1, min(args.steps, 3))):
+        v, cores, sample = cpu_oracle_rate(256, 32)
+        vals.append(v)
+    v = sum(vals) / len(vals)
+    base.update({"value": round(v, 4), "ms_per_step": round(n_samples / (v * 1e6) * 1e3, 3),
+                 "config": {"workload": "cbox 512x512 spp=32 sppe=32 sppse=32 PathTracer(3) renderD DiffuseBSDF (BASELINE configs[1])",
+                            "path": "CPU oracle port (oracle/psdr_oracle.cpp, OpenMP); reference GPU path unavailable: " + err},
+                 "cpu_baseline": {"value": round(v, 4), "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+                 "e2e": {"value": round(v, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,7 +46,8 @@ enum {
     PSDR_Q_NUM_MESH_VERTICES = 7,
     PSDR_Q_NUM_MESH_FACES = 8,
     PSDR_Q_IS_CONFIGURED = 9,
-    PSDR_Q_USES_BVH = 10
+    PSDR_Q_USES_BVH = 10,
+    PSDR_Q_UPLOAD_BYTES = 11        /* bytes of device tables the last configure() copied host->device */
 };
 
 /* Terms of renderD (bit mask). */
@@ -97,6 +98,13 @@ int psdr_scene_clear_tangents(psdr_scene *s);
 /* Scene.configure(active_sensor=[...]) -- src/psdr.cpp:409, src/scene/scene.cpp:311-601 */
 int psdr_scene_configure(psdr_scene *s, const int *active_sensors, int n_active);
 double psdr_scene_last_configure_ms(psdr_scene *s);
+
+/* New (measurement): with timing on, every render call brackets each of its kernels with CUDA events
+ * on the launch stream (the reference only prints std::chrono wall time, integrator.cpp:14,40-45).
+ * psdr_scene_kernel_ms waits for the events of the LAST render call and returns the device time of
+ * the kernel of `term` (one of PSDR_TERM_INTERIOR / _PRIMARY_EDGES / _SECONDARY_EDGES), or -1. */
+int psdr_scene_enable_timing(psdr_scene *s, int on);
+double psdr_scene_kernel_ms(psdr_scene *s, int term);
 
 int psdr_scene_query(psdr_scene *s, int what, int index);
 /* Mesh.edge_indices() -- src/psdr.cpp:338: out = 4 rows (v0, v1, face0, face1) of n_edges ints */

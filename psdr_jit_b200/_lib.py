@@ -20,7 +20,7 @@ MESH_VERTICES, MESH_TO_WORLD_LEFT, MESH_TO_WORLD_RAW, MESH_TO_WORLD_RIGHT = 0, 1
 SENSOR_TO_WORLD_LEFT, SENSOR_TO_WORLD_RAW, SENSOR_TO_WORLD_RIGHT = 4, 5, 6
 BSDF_REFLECTANCE, EMITTER_RADIANCE = 7, 8
 Q_NUM_MESHES, Q_NUM_SENSORS, Q_NUM_EMITTERS, Q_NUM_TRIANGLES, Q_NUM_PRIMARY_EDGES, Q_NUM_SECONDARY_EDGES = 0, 1, 2, 3, 4, 5
-Q_NUM_MESH_EDGES, Q_NUM_MESH_VERTICES, Q_NUM_MESH_FACES, Q_IS_CONFIGURED, Q_USES_BVH = 6, 7, 8, 9, 10
+Q_NUM_MESH_EDGES, Q_NUM_MESH_VERTICES, Q_NUM_MESH_FACES, Q_IS_CONFIGURED, Q_USES_BVH, Q_UPLOAD_BYTES = 6, 7, 8, 9, 10, 11
 TERM_INTERIOR, TERM_PRIMARY_EDGES, TERM_SECONDARY_EDGES, TERM_ALL = 1, 2, 4, 7
 
 EXPORTS = [
@@ -29,7 +29,7 @@ EXPORTS = [
     "psdr_scene_add_bsdf_diffuse", "psdr_scene_add_mesh", "psdr_scene_add_perspective", "psdr_scene_set_param",
     "psdr_scene_set_tangent", "psdr_scene_clear_tangents", "psdr_scene_configure", "psdr_scene_last_configure_ms",
     "psdr_scene_query", "psdr_scene_mesh_edges", "psdr_render_c", "psdr_render_d", "psdr_render_c_host",
-    "psdr_render_d_host", "psdr_render_aov", "psdr_sampler_draws",
+    "psdr_render_d_host", "psdr_render_aov", "psdr_sampler_draws", "psdr_scene_enable_timing", "psdr_scene_kernel_ms",
 ]
 
 
@@ -63,6 +63,9 @@ def load():
     L.psdr_scene_last_configure_ms.restype = C.c_double
     L.psdr_scene_last_configure_ms.argtypes = [vp]
     L.psdr_scene_query.argtypes = [vp, i, i]
+    L.psdr_scene_enable_timing.argtypes = [vp, i]
+    L.psdr_scene_kernel_ms.restype = C.c_double
+    L.psdr_scene_kernel_ms.argtypes = [vp, i]
     L.psdr_scene_mesh_edges.argtypes = [vp, i, P_I]
     L.psdr_render_c.argtypes = [vp, i, i, ll, i, vp, i, vp, vp]
     L.psdr_render_d.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp, vp, vp]

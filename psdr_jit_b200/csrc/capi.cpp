@@ -22,7 +22,14 @@ struct psdr_scene {
     int *d_pix = nullptr;
     size_t img_cap = 0, pix_cap = 0;
     cudaStream_t stream = nullptr;
+    // optional per-kernel timing (psdr_scene_enable_timing)
+    bool timing = false;
+    cudaEvent_t ev[3][2] = {};
+    bool ev_used[3] = {false, false, false};
     ~psdr_scene() {
+        for (auto &p : ev)
+            for (auto &e : p)
+                if (e) cudaEventDestroy(e);
         if (d_img) cudaFree(d_img);
         if (d_dimg) cudaFree(d_dimg);
         if (d_pix) cudaFree(d_pix);
@@ -256,6 +263,28 @@ int psdr_scene_configure(psdr_scene *s, const int *active_sensors, int n_active)
 
 double psdr_scene_last_configure_ms(psdr_scene *s) { return s ? s->sc.last_configure_ms : 0.0; }
 
+int psdr_scene_enable_timing(psdr_scene *s, int on) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    s->timing = on != 0;
+    if (s->timing && !s->ev[0][0]) {
+        cuda_ok(cudaSetDevice(s->sc.device), "cudaSetDevice");
+        for (auto &p : s->ev)
+            for (auto &e : p) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
+    }
+    return 0;
+    PSDR_CATCH
+}
+
+double psdr_scene_kernel_ms(psdr_scene *s, int term) {
+    if (!s || !s->timing) return -1.0;
+    const int k = term == PSDR_TERM_INTERIOR ? 0 : term == PSDR_TERM_PRIMARY_EDGES ? 1 : term == PSDR_TERM_SECONDARY_EDGES ? 2 : -1;
+    if (k < 0 || !s->ev_used[k]) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(s->ev[k][1]) != cudaSuccess || cudaEventElapsedTime(&ms, s->ev[k][0], s->ev[k][1]) != cudaSuccess) return -1.0;
+    return (double) ms;
+}
+
 int psdr_scene_query(psdr_scene *s, int what, int index) {
     if (!s) { fail("null scene"); return -1; }
     const Scene &sc = s->sc;
@@ -271,6 +300,7 @@ int psdr_scene_query(psdr_scene *s, int what, int index) {
         case PSDR_Q_NUM_MESH_FACES: return (index >= 0 && index < (int) sc.meshes.size()) ? (int) sc.meshes[index].f.size() / 3 : -1;
         case PSDR_Q_IS_CONFIGURED: return sc.configured ? 1 : 0;
         case PSDR_Q_USES_BVH: return sc.dscene.use_bvh;
+        case PSDR_Q_UPLOAD_BYTES: return (int) sc.upload_bytes;
         default: fail("unknown query"); return -1;
     }
 }
@@ -317,6 +347,12 @@ void begin_render(Scene &sc, int sensor, long long seed, const int *pix_id, bool
     }
 }
 
+void tick(psdr_scene *s, int k, int which, cudaStream_t st) {
+    if (!s->timing) return;
+    cuda_ok(cudaEventRecord(s->ev[k][which], st), "cudaEventRecord");
+    if (which) s->ev_used[k] = true;
+}
+
 int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, bool ad, int terms, int reference_scaling,
                 const int *pix_id, int npix_sel, float *img, float *dimg, cudaStream_t st) {
     Scene &sc = s->sc;
@@ -330,6 +366,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         r.tangent_scale = 1.f;
     }
     begin_render(sc, sensor, seed, pix_id, ad, terms, max_depth, rp);
+    s->ev_used[0] = s->ev_used[1] = s->ev_used[2] = false;
     const long long npix_full = (long long) sc.width * sc.height;
     const long long npix = pix_id ? npix_sel : npix_full;
     if (pix_id && npix_sel <= 0) throw std::runtime_error("empty pixel batch");
@@ -344,14 +381,18 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         rp[0].lane_begin = sh.begin; rp[0].lane_end = sh.end;
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
         rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
+        tick(s, 0, 0, st);
         cuda_ok(launch_interior(sc.dscene, cam, rp[0], ad, img, dimg, st), "interior kernel");
+        tick(s, 0, 1, st);
         g_launches++;
     }
     if (ad && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
         if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
         const Shard sh = shard_of(npix_full * sc.sppe, sc.rank, sc.world);
         rp[1].lane_begin = sh.begin; rp[1].lane_end = sh.end;
+        tick(s, 1, 0, st);
         cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, st), "primary-edge kernel");
+        tick(s, 1, 1, st);
         g_launches++;
     }
     if (ad && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
@@ -359,7 +400,9 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         const Shard sh = shard_of(npix_full * sc.sppse, sc.rank, sc.world);
         rp[2].lane_begin = sh.begin; rp[2].lane_end = sh.end;
         rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
+        tick(s, 2, 0, st);
         cuda_ok(launch_secondary_edges(sc.dscene, cam, rp[2], dimg, st), "secondary-edge kernel");
+        tick(s, 2, 1, st);
         g_launches++;
     }
     return 0;

@@ -161,6 +161,7 @@ void upload_scene(Scene &sc) {
     check(cudaDeviceSynchronize(), "cudaDeviceSynchronize(before table refresh)");
     std::memcpy(db.host, pk.bytes.data(), pk.bytes.size());
     check(cudaMemcpy(db.dev, db.host, pk.bytes.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene tables)");
+    sc.upload_bytes = pk.bytes.size();
     const unsigned char *base = (const unsigned char *) db.dev;
 
     DScene &d = sc.dscene;

@@ -108,6 +108,7 @@ struct Scene {
     DScene dscene{};
     std::vector<DCamera> dcameras;
     double last_configure_ms = 0.0;
+    size_t upload_bytes = 0;
 
     Scene();
     ~Scene();
