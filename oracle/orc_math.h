@@ -133,6 +133,10 @@ template <class S> inline S squared_norm(V3<S> a) { return dot(a, a); }
 template <class S> inline S norm(V3<S> a) { return sqrt_(dot(a, a)); }
 template <class S> inline S norm(V2<S> a) { return sqrt_(dot(a, a)); }
 template <class S> inline V3<S> normalize(V3<S> a) { return a / norm(a); }
+// fused multiply-subtract cross product (Dr.Jit's cross() emits fmsub); used by the triangle tests
+inline V3<float> cross_fms(V3<float> a, V3<float> b) {
+    return V3<float>(std::fmaf(a.y, b.z, -(a.z * b.y)), std::fmaf(a.z, b.x, -(a.x * b.z)), std::fmaf(a.x, b.y, -(a.y * b.x)));
+}
 template <class S> inline V3<S> cross(V3<S> a, V3<S> b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }

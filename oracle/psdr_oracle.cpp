@@ -436,22 +436,27 @@ struct Hit {
     float u = 0.f, v = 0.f, t = 0.f;
 };
 
-// One fp32 Moeller-Trumbore test with a FIXED operation order (cross = mul,mul,sub; dot = fma
-// chain; IEEE divide).  The CUDA kernels use the same order so that hit ids and (u,v,t) agree
-// bit for bit with this oracle; it is also the formula of utils.h:82-93.
+// One fp32 Moeller-Trumbore test with a FIXED operation order (cross = fused multiply-subtract, dot =
+// fma chain).  The inside test runs on the sign-normalised numerators (0 <= u, 0 <= v, u + v <= 1
+// without a division); only then the IEEE divide.  OptiX's own arithmetic is closed source, so this
+// is the repo's definition of the closest hit; the CUDA kernels use the same order so that hit ids
+// and (u,v,t) agree bit for bit with this oracle.  Formula: utils.h:82-93.
 static inline bool tri_test(const Tri<Dual> &T, V3f o, V3f d, float &u, float &v, float &t) {
     V3f e1 = val(T.e1), e2 = val(T.e2), p0 = val(T.p0);
-    V3f h = cross(d, e2);
-    float a = dot(e1, h);
-    if (a == 0.f) return false;
-    float f = 1.f / a;
+    V3f h = cross_fms(d, e2);
+    float det = dot(e1, h);
     V3f s = o - p0;
-    u = f * dot(s, h);
-    if (!(u >= 0.f && u <= 1.f)) return false;
-    V3f q = cross(s, e1);
-    v = f * dot(d, q);
-    if (!(v >= 0.f && u + v <= 1.f)) return false;
-    t = f * dot(e2, q);
+    float un = dot(s, h);
+    V3f q = cross_fms(s, e1);
+    float vn = dot(d, q);
+    float tn = dot(e2, q);
+    float adet = std::fabs(det);
+    float us = det < 0.f ? -un : un, vs = det < 0.f ? -vn : vn;
+    if (!(us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f)) return false;
+    float f = 1.f / det;
+    t = f * tn;
+    u = f * un;
+    v = f * vn;
     return true;
 }
 

@@ -69,31 +69,34 @@ template <> __device__ __forceinline__ ShadeRec<Dual> load_shade<Dual>(const DSc
 }
 
 // ---- closest hit in (RayEpsilon, 1e8): replaces OptiX (reference src/scene/scene_optix.cpp:343-410)
-// Moeller-Trumbore with a fixed operation order; ties resolve to the lowest triangle id.
-__device__ __forceinline__ void tri_test(const DScene &sc, int id, V3f o, V3f d, Hit &best) {
-    const float4 a = __ldg(sc.geo + 3 * id), b = __ldg(sc.geo + 3 * id + 1);
-    const float e2z = __ldg(&sc.geo[3 * id + 2].x);
-    const V3f p0(a.x, a.y, a.z), e1(a.w, b.x, b.y), e2(b.z, b.w, e2z);
-    const V3f h = cross(d, e2);
+// Moeller-Trumbore numerators with a fixed operation order (cross = fused multiply-subtract, dot =
+// fma chain), inside test on the sign-normalised numerators (0 <= u, 0 <= v, u + v <= 1 without a
+// division); the IEEE division only happens for the 1-3 triangles a ray line actually pierces.
+// Branch-free up to that point, so incoherent rays of a warp do not diverge in the scan.
+// Ties resolve to the lowest triangle id.
+__device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, V3f d, Hit &best) {
+    const V3f h = cross_fms(d, e2);
     const float det = dot(e1, h);
-    if (det == 0.f) return;
-    const float f = 1.f / det;
     const V3f s = o - p0;
-    const float u = f * dot(s, h);
-    if (!(u >= 0.f && u <= 1.f)) return;
-    const V3f q = cross(s, e1);
-    const float v = f * dot(d, q);
-    if (!(v >= 0.f && u + v <= 1.f)) return;
-    const float t = f * dot(e2, q);
-    if (t > kRayEpsilon && t < kTraceTMax && (t < best.t || (t == best.t && id < best.tri))) {
-        best.tri = id;
-        best.u = u;
-        best.v = v;
-        best.t = t;
+    const float un = dot(s, h);
+    const V3f q = cross_fms(s, e1);
+    const float vn = dot(d, q);
+    const float tn = dot(e2, q);
+    const float adet = fabsf(det);
+    const float us = det < 0.f ? -un : un, vs = det < 0.f ? -vn : vn;
+    if (us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f) {
+        const float f = 1.f / det;
+        const float t = f * tn;
+        if (t > kRayEpsilon && t < kTraceTMax && (t < best.t || (t == best.t && id < best.tri))) {
+            best.tri = id;
+            best.u = f * un;
+            best.v = f * vn;
+            best.t = t;
+        }
     }
 }
 
-__device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
+template <bool kBvh> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
     Hit best;
     best.tri = 0x7fffffff;
     best.u = best.v = 0.f;
@@ -102,8 +105,15 @@ __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
         best.tri = -1;
         return best;
     }
-    if (!sc.use_bvh) {
-        for (int i = 0; i < sc.n_tris; ++i) tri_test(sc, i, o, d, best);
+    if (!kBvh) {
+        // tiny scenes: the triangle table rides in the kernel parameters (constant bank), the scan index
+        // is warp-uniform, so the operands come through the uniform datapath -- no LSU traffic at all
+#pragma unroll 4
+        for (int i = 0; i < sc.n_tris; ++i) {
+            const float4 a = sc.bg_a[i], b = sc.bg_b[i];
+            const float c = sc.bg_c[i];
+            tri_test(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), i, o, d, best);
+        }
     } else {
         const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
         int stack[48];
@@ -123,7 +133,12 @@ __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
             if (tn <= tf * 1.0000005f + 1e-6f) {
                 if (ib < 0) {
                     const int first = ia, cnt = -ib;
-                    for (int k = 0; k < cnt; ++k) tri_test(sc, __ldg(sc.tri_order + first + k), o, d, best);
+                    for (int k = 0; k < cnt; ++k) {
+                        const int id = __ldg(sc.tri_order + first + k);
+                        const float4 a = __ldg(sc.geo + 3 * id), b = __ldg(sc.geo + 3 * id + 1);
+                        const float c = __ldg(&sc.geo[3 * id + 2].x);
+                        tri_test(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), id, o, d, best);
+                    }
                 } else {
                     if (sp < 47) stack[sp++] = ib;
                     node = ia;
@@ -179,7 +194,7 @@ template <> struct IsDual<Dual> { static constexpr bool value = true; };
 // Scene::ray_intersect<ad, path_space> (reference src/scene/scene.cpp:612-806).  The material-form
 // ("path-space") variant pins the hit to the triangle by detached barycentrics; the solid-angle
 // variant (S = Dual, path_space = false: primary hits) re-intersects analytically.
-template <class S>
+template <class S, bool kBvh>
 __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S> d, bool active, bool path_space, int *out_tri = nullptr) {
     constexpr bool ad = IsDual<S>::value;
     Its<S> its;
@@ -190,7 +205,7 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
     its.J = S(1.f);
     if (out_tri) *out_tri = -1;
     if (!active) return its;
-    const Hit h = trace(sc, val(o), val(d));
+    const Hit h = trace<kBvh>(sc, val(o), val(d));
     if (h.tri < 0) return its;
     if (out_tri) *out_tri = h.tri;
     const TriRec<S> T = load_tri<S>(sc, h.tri);
@@ -434,34 +449,77 @@ template <> __device__ __forceinline__ void sample_primary_ray<Dual>(const DCame
 // NEE + BSDF sampling with the power heuristic, fixed max_depth, no Russian roulette.  Every lane
 // draws 5 numbers per bounce whether it is alive or not, so draw k of a lane is a closed-form
 // function of (seed, lane, k).
-template <class S>
-__device__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
+// The reference unrolls "primary hit; for each bounce {NEE; BSDF ray}" into one megakernel; here the
+// same arithmetic is rolled into ONE loop whose iteration is {main ray (camera ray or the BSDF ray of
+// the previous bounce) -> vertex; NEE shadow ray}, so the kernel holds exactly two copies of the
+// closest-hit scan and stays inside the instruction cache (profiles/r01a: the unrolled form stalled
+// 49 % of the cycles on instruction fetch).
+template <class S, bool kBvh>
+__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
     constexpr bool ad = IsDual<S>::value;
-    Its<S> its = ray_intersect<S>(sc, ro, rd, active, false);
-    active = active && its.valid;
-    V3<S> throughput(S(1.f));
-    V3<S> result = hide_emitters ? V3<S>(S(0.f)) : Le(sc, its, active);
-    for (int depth = 0; depth < max_depth; ++depth) {
+    V3<S> throughput(S(1.f)), result(S(0.f));
+    Its<S> its;
+    its.valid = false;
+    BsdfSample bs;
+    bs.wo = V3f(0.f, 0.f, 1.f);
+    bs.pdf = 1.f;
+    bs.valid = true;
+    V3<S> ray_o = ro, ray_d = rd;
+#pragma unroll 1
+    for (int depth = -1; depth < max_depth; ++depth) {
+        // ---- main ray: primary hit (solid-angle form under AD) or the BSDF-sampled ray (path-space form)
+        const Its<S> its1 = ray_intersect<S, kBvh>(sc, ray_o, ray_d, active, ad && depth >= 0);
+        if (depth < 0) {
+            active = active && its1.valid;
+            if (!hide_emitters) result = Le(sc, its1, active);
+        } else {
+            active = active && bs.valid && its1.valid;
+            if (active) {
+                V3<S> bsdf_val;
+                float pdf0;
+                if (ad) {
+                    V3<S> wo = its1.p - its.p;
+                    wo = wo / its1.t;
+                    const S cos_val = dot(its1.n, -wo);
+                    const S G_val = abs_(cos_val) / sqr(its1.t);
+                    pdf0 = bs.pdf * val(G_val);
+                    if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                    else bsdf_val = bsdf_eval(sc, its, its.to_local(wo), active) * (G_val * its1.J / S(pdf0));
+                } else {
+                    const S cos_val = dot(its1.n, -ray_d);
+                    const S G_val = abs_(cos_val) / sqr(its1.t);
+                    pdf0 = bs.pdf * val(G_val);
+                    if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                    else bsdf_val = bsdf_eval(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
+                }
+                const float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, its1, active));
+                throughput = throughput * bsdf_val;
+                result = result + Le(sc, its1, active) * throughput * S(weight2);
+            }
+        }
+        const int bounces_left = max_depth - depth - 1;
         if (!active) {   // dead lanes only burn their draws
-            rng.advance(5ull * (unsigned long long) (max_depth - depth));
+            if (bounces_left > 0) rng.advance(5ull * (unsigned long long) bounces_left);
             break;
         }
+        if (bounces_left <= 0) break;
+        its = its1;
         const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
         const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
         {   // ---- emitter sampling
             const PosSample<S> ps = sample_emitter_position<S>(sc, V2f(s_x, s_y));
-            bool active_direct = active && !is_emitter(sc, its);
+            bool active_direct = !is_emitter(sc, its);
             V3<S> wod = ps.p - its.p;
             const S dist_sqr = squared_norm(wod);
             const S dist = safe_sqrt(dist_sqr);
             wod = wod / dist;
-            const Its<S> its1 = ray_intersect<S>(sc, its.p, wod, active_direct, ad);
-            active_direct = active_direct && its1.valid;
-            active_direct = active_direct && (val(its1.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its1);
+            const Its<S> its2 = ray_intersect<S, kBvh>(sc, its.p, wod, active_direct, ad);
+            active_direct = active_direct && its2.valid;
+            active_direct = active_direct && (val(its2.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its2);
             if (active_direct) {
-                const S cos_val = dot(its1.n, -wod);
+                const S cos_val = dot(its2.n, -wod);
                 const S G_val = abs_(cos_val) / dist_sqr;
-                const V3<S> emitter_val = Le(sc, its1, active);
+                const V3<S> emitter_val = Le(sc, its2, true);
                 const V3<S> wo_local = its.to_local(wod);
                 V3<S> bsdf_val2 = bsdf_eval(sc, its, wo_local, active_direct);
                 bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
@@ -472,34 +530,10 @@ __device__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool activ
                 }
             }
         }
-        {   // ---- BSDF sampling
-            const BsdfSample bs = bsdf_sample(sc, its, V3f(s3_x, s3_y, s3_z), active);
-            const V3<S> wdir = its.to_world(lift3<S>(bs.wo));
-            const Its<S> its1 = ray_intersect<S>(sc, its.p, wdir, active, ad);
-            active = active && bs.valid && its1.valid;
-            if (!active) continue;
-            V3<S> bsdf_val;
-            float pdf0;
-            if (ad) {
-                V3<S> wo = its1.p - its.p;
-                wo = wo / its1.t;
-                const S cos_val = dot(its1.n, -wo);
-                const S G_val = abs_(cos_val) / sqr(its1.t);
-                pdf0 = bs.pdf * val(G_val);
-                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
-                else bsdf_val = bsdf_eval(sc, its, its.to_local(wo), active) * (G_val * its1.J / S(pdf0));
-            } else {
-                const S cos_val = dot(its1.n, -wdir);
-                const S G_val = abs_(cos_val) / sqr(its1.t);
-                pdf0 = bs.pdf * val(G_val);
-                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
-                else bsdf_val = bsdf_eval(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
-            }
-            const float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, its1, active));
-            throughput = throughput * bsdf_val;
-            result = result + Le(sc, its1, active) * throughput * S(weight2);
-            its = its1;
-        }
+        // ---- BSDF sampling: the ray is traced at the top of the next iteration
+        bs = bsdf_sample(sc, its, V3f(s3_x, s3_y, s3_z), true);
+        ray_o = its.p;
+        ray_d = its.to_world(lift3<S>(bs.wo));
     }
     return result;
 }
@@ -532,7 +566,8 @@ __device__ __forceinline__ float sign1(float x) { return signbit_(x) ? -1.f : 1.
 
 // returns the pixel (-1: no contribution); value0 = primal boundary value (guiding pre-pass),
 // tangent = d/dP of the zero-primal estimator.
-__device__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
+template <bool kBvh>
+__device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
     value0_out = V3f(0.f, 0.f, 0.f);
     tangent_out = V3f(0.f, 0.f, 0.f);
     // -- sample_boundary_segment_direct
@@ -563,10 +598,10 @@ __device__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sam
     // -- eval_secondary_edge
     const V3f _dir = normalize(_p2 - _p0);
     int light_tri = -1;
-    const Its<float> _its2 = ray_intersect<float>(sc, _p0, _dir, valid, false, &light_tri);
+    const Its<float> _its2 = ray_intersect<float, kBvh>(sc, _p0, _dir, valid, false, &light_tri);
     valid = valid && is_emitter(sc, _its2) && _its2.valid && norm(_its2.p - _p2) < kShadowEpsilon;
     if (!valid) return -1;
-    const Its<float> _its1 = ray_intersect<float>(sc, _p0, -_dir, valid, false);
+    const Its<float> _its1 = ray_intersect<float, kBvh>(sc, _p0, -_dir, valid, false);
     valid = valid && _its1.valid;
     if (!valid) return -1;
     const V3f _p1 = _its1.p;
@@ -575,7 +610,7 @@ __device__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sam
     if (!valid) return -1;
     V3d co, cd;
     sample_primary_ray<Dual>(cam, sds.q, co, cd);
-    const Its<Dual> its1 = ray_intersect<Dual>(sc, co, cd, valid, false);
+    const Its<Dual> its1 = ray_intersect<Dual, kBvh>(sc, co, cd, valid, false);
     valid = valid && its1.valid && norm(val(its1.p) - _p1) < kShadowEpsilon;
     valid = valid && its1.valid && sc.meshes[its1.mesh].bsdf >= 0;
     if (!valid) return -1;

@@ -138,7 +138,7 @@ void upload_scene(Scene &sc) {
     std::vector<DBvhNode> nodes;
     std::vector<int> order;
     const int ntris = (int) all_tris.size();
-    const bool use_bvh = sc.force_bvh < 0 ? ntris > 64 : sc.force_bvh != 0;
+    const bool use_bvh = ntris > kMaxBruteTris || (sc.force_bvh < 0 ? false : sc.force_bvh != 0);
     if (use_bvh) build_bvh(all_tris, nodes, order, 4);
 
     Packer pk;
@@ -193,6 +193,12 @@ void upload_scene(Scene &sc) {
     d.sec_sum = sc.sec_edges.empty() ? 0.f : sc.sec_edge_distrb.sum;
     d.nodes = (const DBvhNode *) (base + o_nodes);
     d.tri_order = (const int *) (base + o_order);
+    if (!use_bvh)
+        for (int i = 0; i < ntris; ++i) {
+            d.bg_a[i] = geo[3 * i];
+            d.bg_b[i] = geo[3 * i + 1];
+            d.bg_c[i] = geo[3 * i + 2].x;
+        }
 
     sc.dcameras.assign(sc.cameras.size(), DCamera{});
     size_t pmf_off = 0;

@@ -13,6 +13,8 @@ namespace psdr {
 //             shade[3i+0] = (n0.xyz, n1.x) shade[3i+1] = (n1.yz, n2.xy) shade[3i+2] = (n2.z, fn.xyz)
 // dgeo/dshade: the forward-mode tangents in the same layout (dgeo[3i+2].z/.w unused).
 // uv[3i+k] = texture coordinate of corner k (zeros for meshes without UVs)
+constexpr int kMaxBruteTris = 64;
+
 struct DBvhNode {        // 32 B
     float lo[3];
     int a;               // inner: left child;  leaf: first index into tri_order
@@ -81,6 +83,11 @@ struct DScene {
     float sec_sum;
     const DBvhNode *nodes;
     const int *tri_order;
+    // brute-force mode (n_tris <= kMaxBruteTris): the triangle geometry again, by value -- it travels in
+    // the kernel parameters and is read through the constant bank / uniform datapath.
+    // bg_a = (p0.xyz, e1.x), bg_b = (e1.yz, e2.xy), bg_c = e2.z
+    float4 bg_a[kMaxBruteTris], bg_b[kMaxBruteTris];
+    float bg_c[kMaxBruteTris];
 };
 
 struct RenderParams {

@@ -37,7 +37,7 @@ __device__ __forceinline__ void splat_runs(float *img, int pix, float r, float g
 __device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; }
 
 // ---- interior term: Integrator::__render / __render_batch ------------------------------------
-template <class S>
+template <class S, bool kBvh>
 __global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                            const __grid_constant__ RenderParams rp, float *__restrict__ img,
                                                            float *__restrict__ dimg) {
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant_
             const float sy = ((float) (pix / sc.width) + jy) / (float) sc.height;
             V3<S> o, d;
             sample_primary_ray<S>(cam, V2f(sx, sy), o, d);
-            v = Li<S>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0);
+            v = Li<S, kBvh>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0);
         }
         float r = val(v.x), g = val(v.y), b = val(v.z), dr = tang(v.x), dg = tang(v.y), db = tang(v.z);
         // masked(value, ~isfinite(value)) = 0 zeroes value and tangent (integrator.cpp:126)
@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant_
 }
 
 // ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges
+template <bool kBvh>
 __global__ void __launch_bounds__(kBlock) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
@@ -95,13 +96,18 @@ __global__ void __launch_bounds__(kBlock) primary_edge_kernel(const __grid_const
         const Dual x_dot_n = dot(V2d(px, py), V2d(Dual(bq.x), Dual(bq.y)));
         const int ix = (int) floorf(px.v * (float) sc.width), iy = (int) floorf(py.v * (float) sc.height);
         const bool valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
-        V3f op, dp, on, dn;
-        sample_primary_ray<float>(cam, V2f(px.v + kEdgeEpsilon * bq.x, py.v + kEdgeEpsilon * bq.y), op, dp);
-        sample_primary_ray<float>(cam, V2f(px.v - kEdgeEpsilon * bq.x, py.v - kEdgeEpsilon * bq.y), on, dn);
         // Li(ray_n) - Li(ray_p): the reference binary evaluates Li(ray_p) first (verified on the
-        // running reference, tests/golden/renderD_*: primary-only images)
-        const V3f Lp = Li<float>(sc, rng, op, dp, valid, rp.max_depth, rp.hide_emitters != 0);
-        const V3f Ln = Li<float>(sc, rng, on, dn, valid, rp.max_depth, rp.hide_emitters != 0);
+        // running reference, tests/golden/renderD_*: primary-only images).  One rolled loop over the two
+        // sides keeps a single copy of Li in the kernel.
+        V3f Lside[2];
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
+            V3f ro, rd;
+            sample_primary_ray<float>(cam, V2f(px.v + sg * bq.x, py.v + sg * bq.y), ro, rd);
+            Lside[side] = Li<float, kBvh>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
+        }
+        const V3f Lp = Lside[0], Ln = Lside[1];
         if (!valid) continue;
         const int pix = iy * sc.width + ix;
         const float dl[3] = {(Ln.x - Lp.x) / pdf, (Ln.y - Lp.y) / pdf, (Ln.z - Lp.z) / pdf};
@@ -116,6 +122,7 @@ __global__ void __launch_bounds__(kBlock) primary_edge_kernel(const __grid_const
 }
 
 // ---- secondary (shadow) edges: PathTracer::render_secondary_edges -----------------------------
+template <bool kBvh>
 __global__ void __launch_bounds__(kBlock) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                  const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(kBlock) secondary_edge_kernel(const __grid_con
         if (rp.skip) rng.advance(rp.skip);
         const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
         V3f value0, tangent;
-        const int pix = eval_secondary_edge(sc, cam, V3f(d3, d2, d1), value0, tangent);
+        const int pix = eval_secondary_edge<kBvh>(sc, cam, V3f(d3, d2, d1), value0, tangent);
         if (pix < 0) continue;
         const float t[3] = {tangent.x, tangent.y, tangent.z};
 #pragma unroll
@@ -136,6 +143,7 @@ __global__ void __launch_bounds__(kBlock) secondary_edge_kernel(const __grid_con
 }
 
 // ---- AOV tap: what the reference's FieldExtractionIntegrator exposes (src/integrator/field.cpp:47-121)
+template <bool kBvh>
 __global__ void __launch_bounds__(kBlock) aov_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                       const __grid_constant__ RenderParams rp, float *__restrict__ out) {
     const long long stride = (long long) gridDim.x * kBlock;
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(kBlock) aov_kernel(const __grid_constant__ DSc
         const float sx = ((float) (idx % sc.width) + jx) / (float) sc.width, sy = ((float) (idx / sc.width) + jy) / (float) sc.height;
         V3f o, d;
         sample_primary_ray<float>(cam, V2f(sx, sy), o, d);
-        const Its<float> its = ray_intersect<float>(sc, o, d, true, false);
+        const Its<float> its = ray_intersect<float, kBvh>(sc, o, d, true, false);
         float *r = out + 14 * i;
         for (int k = 0; k < 14; ++k) r[k] = 0.f;
         if (!its.valid) { r[1] = -1.f; continue; }
@@ -175,26 +183,35 @@ static int grid_for(long long lanes, int blocks_per_sm) {
 cudaError_t launch_interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st) {
     const long long lanes = rp.lane_end - rp.lane_begin;
     if (lanes <= 0) return cudaSuccess;
-    if (ad) interior_kernel<Dual><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
-    else interior_kernel<float><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+    const int grid = grid_for(lanes, 8);
+    if (ad) {
+        if (sc.use_bvh) interior_kernel<Dual, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        else interior_kernel<Dual, false><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+    } else {
+        if (sc.use_bvh) interior_kernel<float, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        else interior_kernel<float, false><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_primary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) {
     const long long lanes = rp.lane_end - rp.lane_begin;
     if (lanes <= 0 || cam.n_edges <= 0) return cudaSuccess;
-    primary_edge_kernel<<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
+    if (sc.use_bvh) primary_edge_kernel<true><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
+    else primary_edge_kernel<false><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
     return cudaGetLastError();
 }
 cudaError_t launch_secondary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) {
     const long long lanes = rp.lane_end - rp.lane_begin;
     if (lanes <= 0 || sc.n_sec_edges <= 0) return cudaSuccess;
-    secondary_edge_kernel<<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
+    if (sc.use_bvh) secondary_edge_kernel<true><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
+    else secondary_edge_kernel<false><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
     return cudaGetLastError();
 }
 cudaError_t launch_aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st) {
     const long long lanes = rp.lane_end - rp.lane_begin;
     if (lanes <= 0) return cudaSuccess;
-    aov_kernel<<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, out);
+    if (sc.use_bvh) aov_kernel<true><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, out);
+    else aov_kernel<false><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, out);
     return cudaGetLastError();
 }
 

@@ -127,6 +127,11 @@ template <class S> PSDR_HD V3<S> normalize(V3<S> a) { return a / norm(a); }
 template <class S> PSDR_HD V3<S> cross(V3<S> a, V3<S> b) {
     return V3<S>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
+// cross product with one rounding less per component (fused multiply-subtract, what Dr.Jit's cross()
+// emits: ext/drjit/include/drjit/array_router.h fmsub) -- used by the triangle tests
+PSDR_HD V3f cross_fms(V3f a, V3f b) {
+    return V3f(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
 PSDR_HD V3f detach(V3f a) { return a; }
 PSDR_HD V3d detach(V3d a) { return V3d(detach(a.x), detach(a.y), detach(a.z)); }
 PSDR_HD V3f val(V3f a) { return a; }
