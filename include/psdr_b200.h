@@ -120,9 +120,28 @@ int psdr_render_c(psdr_scene *s, int sensor, int max_depth, long long seed, int 
  * src/integrator/path.cpp:172-294, README.md:96-104: primal image and the forward-mode derivative image
  * for the tangents set with psdr_scene_set_tangent.  terms = PSDR_TERM_* mask.  reference_scaling != 0
  * reproduces the reference binary's output, whose interior and secondary-edge tangents come out
- * exactly 2x the finite-difference-correct value ("derivative scaling"). */
+ * exactly 2x the finite-difference-correct value ("derivative scaling").  dimg = NULL: only
+ * the primal image of renderD (the zero-primal edge kernels are skipped, their sampler streams still
+ * advance) -- the forward half of an autograd step whose backward half is psdr_render_vjp. */
 int psdr_render_d(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
                   const int *pix_id, int npix, float *img, float *dimg, void *cuda_stream);
+
+/* Reverse mode of renderD -- what drjit.backward(loss(img)) computes in the reference (README.md:96-104,
+ * the AD graph recorded by src/integrator/integrator.cpp:51-100 and src/integrator/path.cpp): given the
+ * cotangent image d_img = d(loss)/d(img) (device, float32[npix][3]) the adjoint kernels replay the paths of
+ * the forward call (same sensor / max_depth / seed / terms) and accumulate d(loss)/d(parameter) for EVERY
+ * parameter reachable through Scene.param_map.  Synchronises the stream (the gradients are returned on
+ * the host).  The sampler streams are left exactly as they were before the call.  reference_scaling as in
+ * psdr_render_d. */
+int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                    const int *pix_id, int npix, const float *d_img, void *cuda_stream);
+/* Gradient of parameter (kind, index) from the last psdr_render_vjp, same shapes as psdr_scene_set_param;
+ * host buffer.  drjit.grad(param) in the reference. */
+int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n);
+/* Sampler streams (reference Sampler state, src/core/sampler.cpp): state[2k] = seed, state[2k+1] = draws
+ * consumed per lane of sampler k (0 interior, 1 primary edges, 2 secondary edges); seed < 0 = not seeded. */
+int psdr_scene_get_sampler_state(psdr_scene *s, long long state[6]);
+int psdr_scene_set_sampler_state(psdr_scene *s, const long long state[6]);
 
 /* Same calls with HOST output buffers (pageable or pinned): device work + device->host copies,
  * returns after the buffers are filled. */

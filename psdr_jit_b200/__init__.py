@@ -97,10 +97,11 @@ class _Transformable(Object):
 
     def set_transform(self, mat, set_left: bool = True, tangent=None):
         t = np.zeros((4, 4), dtype=np.float32) if tangent is None else _f32(tangent, (4, 4)).copy()
+        m = mat if hasattr(mat, "requires_grad") else _mat4(mat)     # torch tensors stay live for autograd
         if set_left:
-            self.to_world_left, self.d_to_world_left = _mat4(mat), t
+            self.to_world_left, self.d_to_world_left = m, t
         else:
-            self.to_world_right, self.d_to_world_right = _mat4(mat), t
+            self.to_world_right, self.d_to_world_right = m, t
 
     def append_transform(self, mat, append_left: bool = True):
         m = _mat4(mat)
@@ -449,6 +450,52 @@ class Scene(Object):
         if o.log_level > 0 and o.sppse > 0:
             print("%d secondary edges initialized." % self.num_secondary_edges())
 
+    # -- reverse mode -------------------------------------------------------------------------
+    _GRAD_FIELDS = {"Mesh": (("vertex_positions", _lib.MESH_VERTICES), ("to_world_left", _lib.MESH_TO_WORLD_LEFT),
+                             ("to_world", _lib.MESH_TO_WORLD_RAW), ("to_world_right", _lib.MESH_TO_WORLD_RIGHT)),
+                    "Sensor": (("to_world_left", _lib.SENSOR_TO_WORLD_LEFT), ("to_world", _lib.SENSOR_TO_WORLD_RAW),
+                               ("to_world_right", _lib.SENSOR_TO_WORLD_RIGHT)),
+                    "BSDF": (("reflectance", _lib.BSDF_REFLECTANCE),),
+                    "Emitter": (("radiance", _lib.EMITTER_RADIANCE),)}
+
+    def _objects(self):
+        return (("Mesh", self._meshes), ("Sensor", self._sensors), ("BSDF", self._bsdfs), ("Emitter", self._emitters))
+
+    def _grad_leaves(self):
+        """[(tensor, kind, index)] for every parameter field that is a torch tensor requiring grad."""
+        out = []
+        for kind_name, objs in self._objects():
+            for i, o in enumerate(objs):
+                for field, kind in self._GRAD_FIELDS[kind_name]:
+                    t = getattr(o, field, None)
+                    if hasattr(t, "requires_grad") and t.requires_grad:
+                        out.append((t, kind, i))
+        return out
+
+    def grad_of(self, name: str, field: str) -> np.ndarray:
+        """Gradient of the last adjoint pass for ``scene.param_map[name].<field>`` (drjit.grad in the reference)."""
+        obj = self.param_map[name]
+        for kind_name, objs in self._objects():
+            for i, o in enumerate(objs):
+                if o is obj:
+                    for f, kind in self._GRAD_FIELDS[kind_name]:
+                        if f == field:
+                            return self._read_grad(kind, i, np.asarray(_f32(getattr(o, f))).shape)
+        raise RuntimeError("no differentiable field %s on %s" % (field, name))
+
+    def _read_grad(self, kind: int, index: int, shape) -> np.ndarray:
+        out = np.zeros(int(np.prod(shape)), dtype=np.float32)
+        _lib.check(_lib.load().psdr_scene_get_grad(self._h, kind, index, _fp(out), out.size))
+        return out.reshape(shape)
+
+    def _sampler_state(self):
+        st = (C.c_longlong * 6)()
+        _lib.check(_lib.load().psdr_scene_get_sampler_state(self._h, st))
+        return st
+
+    def _set_sampler_state(self, st):
+        _lib.check(_lib.load().psdr_scene_set_sampler_state(self._h, st))
+
     def is_ready(self) -> bool:
         return self._h is not None and _lib.load().psdr_scene_query(self._h, _lib.Q_IS_CONFIGURED, 0) == 1
 
@@ -517,9 +564,44 @@ class Integrator(Object):
         return img, dimg
 
     def renderD(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
-        """reference Integrator::renderD; the derivative image is kept in ``self.grad_image``."""
+        """reference Integrator::renderD.  If any parameter reachable through ``scene.param_map`` is a torch
+        tensor with ``requires_grad`` the returned image carries an autograd node whose backward runs the
+        adjoint kernels (``psdr_render_vjp``) -- ``loss(img).backward()`` then fills ``param.grad`` like
+        ``drjit.backward`` does in the reference.  Otherwise: primal image, and the forward-mode derivative
+        image for the configured tangents is kept in ``self.grad_image``."""
+        leaves = scene._grad_leaves()
+        if leaves:
+            return _render_d_autograd(self, scene, sensor_id, int(seed), batch_pix, leaves)
         img, self.grad_image = self.renderD_fwd(scene, sensor_id, seed, batch_pix)
         return img
+
+    def renderD_primal(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        """Image of renderD without any derivative (psdr_render_d with dimg = NULL)."""
+        self._check(scene)
+        torch = self._torch()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pix = self._pix(torch, batch_pix, dev)
+        n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
+        img = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().psdr_render_d(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), _lib.TERM_ALL,
+                                             0, None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel(),
+                                             img.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+        return img
+
+    def render_vjp(self, scene: Scene, d_img, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL):
+        """Adjoint pass: accumulates d<d_img, img>/d(parameter) for every parameter; read them with
+        ``scene.grad_of(name, field)``.  Replays the sample streams of a forward call with the same seed."""
+        self._check(scene)
+        torch = self._torch()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        pix = self._pix(torch, batch_pix, dev)
+        d_img = torch.as_tensor(d_img, dtype=torch.float32, device=dev).contiguous()
+        n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
+        if d_img.numel() != 3 * n:
+            raise RuntimeError("cotangent image must have %d x 3 entries" % n)
+        _lib.check(_lib.load().psdr_render_vjp(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms),
+                                               int(self.reference_tangent_scaling), None if pix is None else pix.data_ptr(),
+                                               0 if pix is None else pix.numel(), d_img.data_ptr(), torch.cuda.current_stream().cuda_stream))
 
     # host-buffer entry points (numpy in/out; used for the end-to-end measurement)
     def renderC_host(self, scene: Scene, sensor_id: int = 0, seed: int = -1, out: Optional[np.ndarray] = None):
@@ -556,3 +638,36 @@ class PathTracer(Integrator):
             raise RuntimeError("max_depth >= 0")
         self.max_depth = int(max_depth)
         self.hide_emitters = False
+
+
+def _render_d_autograd(integ: Integrator, scene: Scene, sensor_id: int, seed: int, batch_pix, leaves):
+    import torch
+
+    class _RenderD(torch.autograd.Function):
+        """forward = primal kernels of renderD; backward = adjoint kernels + host chain (psdr_render_vjp)."""
+
+        @staticmethod
+        def forward(ctx, *tensors):
+            ctx.state0 = scene._sampler_state()
+            img = integ.renderD_primal(scene, sensor_id, seed, batch_pix)
+            ctx.state1 = scene._sampler_state()
+            return img
+
+        @staticmethod
+        def backward(ctx, d_img):
+            if seed == -1:                    # replay the streams the forward call consumed
+                scene._set_sampler_state(ctx.state0)
+            integ.render_vjp(scene, d_img, sensor_id, seed, batch_pix)
+            scene._set_sampler_state(ctx.state1)
+            grads = []
+            for t, kind, index in leaves:
+                g = scene._read_grad(kind, index, tuple(t.shape))
+                g = torch.from_numpy(g).to(device=t.device, dtype=t.dtype)
+                if torch.distributed.is_available() and torch.distributed.is_initialized() and scene._shard[1] > 1:
+                    g = g.cuda() if torch.distributed.get_backend() == "nccl" else g
+                    torch.distributed.all_reduce(g)          # lane shards -> sum of the partial gradients
+                    g = g.to(t.device)
+                grads.append(g)
+            return tuple(grads)
+
+    return _RenderD.apply(*[t for t, _, _ in leaves])

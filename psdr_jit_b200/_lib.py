@@ -30,6 +30,7 @@ EXPORTS = [
     "psdr_scene_set_tangent", "psdr_scene_clear_tangents", "psdr_scene_configure", "psdr_scene_last_configure_ms",
     "psdr_scene_query", "psdr_scene_mesh_edges", "psdr_render_c", "psdr_render_d", "psdr_render_c_host",
     "psdr_render_d_host", "psdr_render_aov", "psdr_sampler_draws", "psdr_scene_enable_timing", "psdr_scene_kernel_ms",
+    "psdr_render_vjp", "psdr_scene_get_grad", "psdr_scene_get_sampler_state", "psdr_scene_set_sampler_state",
 ]
 
 
@@ -73,6 +74,10 @@ def load():
     L.psdr_render_d_host.argtypes = [vp, i, i, ll, i, i, i, P_I, i, P_F, P_F]
     L.psdr_render_aov.argtypes = [vp, i, ll, vp, vp]
     L.psdr_sampler_draws.argtypes = [ll, i, i, P_F]
+    L.psdr_render_vjp.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp, vp]
+    L.psdr_scene_get_grad.argtypes = [vp, i, i, P_F, i]
+    L.psdr_scene_get_sampler_state.argtypes = [vp, C.POINTER(ll)]
+    L.psdr_scene_set_sampler_state.argtypes = [vp, C.POINTER(ll)]
     _LIB = L
     return L
 

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpsdr_b200.so")
-SOURCES = ["capi.cpp", "scene.cpp", "device_upload.cu", "kernels.cu"]
-HEADERS = ["pmath.h", "dscene.h", "scene.h", "kernels.h", "device_path.cuh", os.path.join("..", "..", "include", "psdr_b200.h")]
+SOURCES = ["capi.cpp", "scene.cpp", "scene_grad.cpp", "device_upload.cu", "kernels.cu", "kernels_vjp.cu"]
+HEADERS = ["pmath.h", "dscene.h", "scene.h", "kernels.h", "device_path.cuh", "adjoint.cuh", "grad_layout.h", os.path.join("..", "..", "include", "psdr_b200.h")]
 
 
 def nvcc_path() -> str:

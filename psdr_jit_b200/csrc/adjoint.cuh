@@ -1,0 +1,440 @@
+// Reverse-mode (adjoint / VJP) of the path-space estimators: "radiative backprop with path replay".
+//
+// The reference obtains d(loss)/d(parameters) from Dr.Jit's AD graph, which materialises every
+// intermediate of Li as an N-lane array in HBM.  Here a lane
+//   1. replays its path with the primal code (Li<float, kBvh, /*kAD=*/true>) and records only what cannot be
+//      recomputed cheaply: the vertices (triangle id + detached barycentrics), the light samples and the
+//      detached pdfs / MIS weights / throughputs -- a few dozen words in registers or local memory;
+//   2. sweeps the bounces backwards: with the suffix radiance known, every bounce is a product of a few
+//      differentiable geometric factors whose adjoints are written out by hand below;
+//   3. scatters the adjoints of the triangle records / materials / camera with atomics -- into a
+//      shared-memory copy of the gradient table when it fits, flushed once per block, else into HBM.
+//
+// What carries derivatives is exactly SURVEY.md A.9: triangle records of every hit (p, face normal, shading
+// normal, area Jacobian), light-sample position/area, BSDF and emitter parameters, the camera matrix.
+// Sampling decisions, pdfs and MIS weights are detached.
+#pragma once
+#include "device_path.cuh"
+#include "grad_layout.h"
+
+namespace psdr {
+
+// Accumulator: either the block's shared-memory copy of [lo, hi) of the table or the global table.
+struct GradAcc {
+    float *g;         // global table
+    float *s;         // shared copy (nullptr = none)
+    int lo, hi;
+    __device__ __forceinline__ void add(int idx, float v) const {
+        if (v == 0.f || !isfinite(v)) return;
+        if (s && idx >= lo && idx < hi) atomicAdd(s + (idx - lo), v);
+        else atomicAdd(g + idx, v);
+    }
+    __device__ __forceinline__ void add3(int idx, V3f v) const { add(idx, v.x); add(idx + 1, v.y); add(idx + 2, v.z); }
+};
+
+__device__ __forceinline__ GradAcc grad_acc_begin(const GradLayout &gl, float *smem, int lo, int hi, bool use_smem) {
+    GradAcc a;
+    a.g = gl.base;
+    a.s = use_smem ? smem : nullptr;
+    a.lo = lo;
+    a.hi = hi;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < hi - lo; i += blockDim.x) smem[i] = 0.f;
+        __syncthreads();
+    }
+    return a;
+}
+__device__ __forceinline__ void grad_acc_end(const GradAcc &a) {
+    if (!a.s) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.hi - a.lo; i += blockDim.x) {
+        const float v = a.s[i];
+        if (v != 0.f) atomicAdd(a.g + a.lo + i, v);
+    }
+}
+
+// ---- what the primal replay records -------------------------------------------------------------
+template <int kD> struct PathRecord {
+    int nv, nsh;                        // vertices found; vertices that were shaded (NEE + BSDF sample)
+    int vtri[kD + 1];
+    float vu[kD + 1], vv[kD + 1];
+    V3f T[kD];                          // throughput in front of bounce k
+    unsigned char nee_ok[kD], bnc_ok[kD], bnc_nz[kD];
+    int ltri[kD], htri[kD];
+    float la[kD], lb[kD], lpdf[kD], w1[kD], pdf0[kD], w2[kD];
+    __device__ __forceinline__ void reset() {
+        nv = nsh = 0;
+#pragma unroll
+        for (int k = 0; k < kD; ++k) nee_ok[k] = bnc_ok[k] = bnc_nz[k] = 0;
+    }
+    __device__ __forceinline__ void vertex(int k, int tri, float u, float v) {
+        if (k <= kD) { vtri[k] = tri; vu[k] = u; vv[k] = v; nv = k + 1; }
+    }
+    __device__ __forceinline__ void throughput(int k, V3f t) {
+        if (k < kD) { T[k] = t; nsh = k + 1; }
+    }
+    __device__ __forceinline__ void bounce(int k, bool nonzero, float p0, float w) {
+        if (k < kD) { bnc_ok[k] = 1; bnc_nz[k] = nonzero ? 1 : 0; pdf0[k] = p0; w2[k] = w; }
+    }
+    __device__ __forceinline__ void nee(int k, bool ok, int lt, V2f st, int ht, float pdf, float w) {
+        if (k < kD) { nee_ok[k] = ok ? 1 : 0; ltri[k] = lt; la[k] = st.x; lb[k] = st.y; htri[k] = ht; lpdf[k] = pdf; w1[k] = w; }
+    }
+};
+
+// ---- isotropic BSDF as a function of the three cosines (what the adjoint differentiates) ---------
+// ci = cos(wi, sh_n), co = cos(wo, sh_n), cio = dot(wi, wo).  Diffuse: reference src/bsdf/diffuse.cpp:23-55.
+template <class S> __device__ __forceinline__ V3<S> bsdf_iso(const DBsdf &b, S ci, S co, S cio) {
+    if (b.two_side) {
+        if (signbit_(val(ci))) co = -co;
+        ci = abs_(ci);
+    }
+    if (!(val(ci) > 0.f && val(co) > 0.f)) return V3<S>(S(0.f));
+    return V3<S>(S(b.refl[0]), S(b.refl[1]), S(b.refl[2])) * S(kInvPi) * co;
+}
+
+struct BsdfJet {        // value and partials of sum_c W_c f_c
+    V3f f;
+    float d_ci, d_co, d_cio;
+};
+__device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, float ci, float co, float cio, V3f W) {
+    BsdfJet j;
+    const V3d a = bsdf_iso<Dual>(b, Dual(ci, 1.f), Dual(co), Dual(cio));
+    const V3d c = bsdf_iso<Dual>(b, Dual(ci), Dual(co, 1.f), Dual(cio));
+    const V3d e = bsdf_iso<Dual>(b, Dual(ci), Dual(co), Dual(cio, 1.f));
+    j.f = val(a);
+    j.d_ci = W.x * a.x.d + W.y * a.y.d + W.z * a.z.d;
+    j.d_co = W.x * c.x.d + W.y * c.y.d + W.z * c.z.d;
+    j.d_cio = W.x * e.x.d + W.y * e.y.d + W.z * e.z.d;
+    return j;
+}
+// d(sum_c W_c f_c * scale)/d(params): Diffuse reflectance
+__device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, float ci, float co,
+                                                V3f W, float scale) {
+    if (b.two_side) {
+        if (signbit_(ci)) co = -co;
+        ci = fabsf(ci);
+    }
+    if (!(ci > 0.f && co > 0.f)) return;
+    const float k = kInvPi * co * scale;
+    acc.add3(gl.off_bsdf + 4 * bi, V3f(W.x * k, W.y * k, W.z * k));
+}
+
+// ---- geometry of a recorded vertex ---------------------------------------------------------------
+struct VtxGeo {
+    V3f p, fn, shn, m;      // position, face normal, shading normal, un-normalised interpolated normal
+    float minv;             // 1 / |m|
+    float area, u, v;
+    int tri, mesh, bsdf, emitter;
+    bool face_normals;
+};
+__device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
+    VtxGeo g;
+    const TriRec<float> T = load_tri<float>(sc, tri);
+    const ShadeRec<float> N = load_shade<float>(sc, tri);
+    const DMesh mesh = sc.meshes[T.mesh];
+    g.tri = tri;
+    g.mesh = T.mesh;
+    g.bsdf = mesh.bsdf;
+    g.emitter = mesh.emitter;
+    g.face_normals = (mesh.flags & 1) != 0;
+    g.u = u;
+    g.v = v;
+    g.p = bilinear(T.p0, T.e1, T.e2, V2f(u, v));
+    g.fn = N.fn;
+    g.area = T.area;
+    g.m = bilinear(N.n0, N.n1 - N.n0, N.n2 - N.n0, V2f(u, v));
+    g.minv = 1.f / norm(g.m);
+    g.shn = g.face_normals ? g.fn : g.m * g.minv;
+    return g;
+}
+
+struct VtxAdj {
+    V3f p, shn, fn;
+    float area;
+};
+
+// adjoint of v -> (w = v / |v|, t = |v|):  v_bar = (w_bar - w <w, w_bar>)/t + t_bar w
+__device__ __forceinline__ V3f unit_adj(V3f w, float t, V3f w_bar, float t_bar) {
+    const float k = dot(w, w_bar);
+    return (w_bar - w * k) * (1.f / t) + w * t_bar;
+}
+
+// scatter the adjoint of a vertex pinned to its triangle: p = p0 + u e1 + v e2, sh_n = normalize(n0 + u (n1-n0) + v (n2-n0))
+__device__ __forceinline__ void scatter_shading_normal(const GradAcc &acc, const VtxGeo &g, V3f shn_bar, V3f &m_bar_out) {
+    m_bar_out = V3f(0.f, 0.f, 0.f);
+    const int b = kGradTri * g.tri;
+    if (g.face_normals) {
+        acc.add3(b + 19, shn_bar);
+        return;
+    }
+    const V3f m_bar = (shn_bar - g.shn * dot(g.shn, shn_bar)) * g.minv;
+    acc.add3(b + 10, m_bar * (1.f - g.u - g.v));
+    acc.add3(b + 13, m_bar * g.u);
+    acc.add3(b + 16, m_bar * g.v);
+    m_bar_out = m_bar;
+}
+__device__ __forceinline__ void scatter_pinned_vertex(const GradAcc &acc, const VtxGeo &g, const VtxAdj &a) {
+    const int b = kGradTri * g.tri;
+    acc.add3(b, a.p);
+    acc.add3(b + 3, a.p * g.u);
+    acc.add3(b + 6, a.p * g.v);
+    acc.add3(b + 19, a.fn);
+    acc.add(b + 9, a.area);
+    V3f unused;
+    scatter_shading_normal(acc, g, a.shn, unused);
+}
+
+// adjoint of (u, v, t) = ray_intersect_triangle(p0, e1, e2, o, d)  [o + t d = p0 + u e1 + v e2]:
+// with A = [e1 e2 -d], A dx = do - dp0 - u de1 - v de2 + t dd  =>  r_bar = A^{-T} x_bar.
+__device__ __forceinline__ V3f isect_adj(V3f e1, V3f e2, V3f d, float u_bar, float v_bar, float t_bar) {
+    const V3f nd = -d;
+    const V3f c0 = cross(e2, nd), c1 = cross(nd, e1), c2 = cross(e1, e2);
+    const float det = dot(e1, c0);
+    return (c0 * u_bar + c1 * v_bar + c2 * t_bar) * (1.f / det);
+}
+// scatter r_bar of isect_adj into the triangle's geometry; returns nothing for o/d (the caller owns them)
+__device__ __forceinline__ void scatter_isect_tri(const GradAcc &acc, int tri, float u, float v, V3f r_bar) {
+    const int b = kGradTri * tri;
+    acc.add3(b, -r_bar);
+    acc.add3(b + 3, r_bar * (-u));
+    acc.add3(b + 6, r_bar * (-v));
+}
+// camera ray o = to_world * (0,0,0,1), d = to_world[:3,:3] * d_cam
+__device__ __forceinline__ void scatter_camera_ray(const GradAcc &acc, const GradLayout &gl, V3f dc, V3f o_bar, V3f d_bar) {
+    const int b = gl.off_cam;
+    const float ob[3] = {o_bar.x, o_bar.y, o_bar.z}, db[3] = {d_bar.x, d_bar.y, d_bar.z}, c[3] = {dc.x, dc.y, dc.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        acc.add(b + 4 * i + 3, ob[i]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc.add(b + 4 * i + j, db[i] * c[j]);
+    }
+}
+
+// One scattering event x -> y seen from x: C = sum_c W_c f_c(ci, co, cio) * |cos_y| / t^2 * J_y * scale
+// (scale = detached 1/pdf * MIS weight).  Accumulates the adjoints of x (p, sh_n), of the previous point
+// (through wi) and returns those of y.
+struct EventAdj {
+    V3f py, ny;       // d/d p_y, d/d n_y (face normal at y)
+    float area_y;     // d/d area_y
+    V3f wi_bar;       // adjoint of the unit direction wi at x (caller maps it to the previous point / camera)
+    V3f f;            // BSDF value (rgb)
+    float geo;        // |cos_y| / t^2 * scale  (J = 1 in the primal)
+};
+__device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const GradLayout &gl, const DScene &sc, const VtxGeo &x, V3f wi,
+                                                  V3f py, V3f ny, float area_y, V3f W, float scale, VtxAdj &xa) {
+    EventAdj r;
+    r.py = r.ny = r.wi_bar = V3f(0.f, 0.f, 0.f);
+    r.area_y = 0.f;
+    r.f = V3f(0.f, 0.f, 0.f);
+    r.geo = 0.f;
+    if (x.bsdf < 0) return r;
+    const DBsdf &b = sc.bsdfs[x.bsdf];
+    const V3f vec = py - x.p;
+    const float t = norm(vec);
+    const V3f wo = vec / t;
+    const float cy = -dot(ny, wo);
+    const float G = fabsf(cy) / (t * t);
+    const float ci = dot(wi, x.shn), co = dot(wo, x.shn), cio = dot(wi, wo);
+    const BsdfJet j = bsdf_jet(b, ci, co, cio, W);
+    r.f = j.f;
+    r.geo = G * scale;
+    const float phi = W.x * j.f.x + W.y * j.f.y + W.z * j.f.z;          // sum_c W_c f_c
+    // C = phi * G * J * scale
+    const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
+    bsdf_param_grad(acc, gl, x.bsdf, b, ci, co, W, G * scale);
+    const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
+    const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) / (t * t);
+    const float t_bar = G_bar * (-2.f * fabsf(cy) / (t * t * t));
+    V3f wo_bar = ny * (-cy_bar) + x.shn * co_bar + wi * cio_bar;
+    r.ny = wo * (-cy_bar);
+    r.wi_bar = wo * cio_bar + x.shn * ci_bar;
+    xa.shn = xa.shn + wo * co_bar + wi * ci_bar;
+    const V3f vec_bar = unit_adj(wo, t, wo_bar, t_bar);
+    r.py = vec_bar;
+    xa.p = xa.p - vec_bar;
+    r.area_y = J_bar / area_y;
+    return r;
+}
+
+// ---- reverse sweep of one interior path --------------------------------------------------------------
+// g = d(loss)/d(lane value) (rgb, already divided by spp).  o/d/dc = camera ray (world origin, world
+// direction, camera-space direction).
+template <int kD>
+__device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout &gl, const GradAcc &acc, const PathRecord<kD> &R, V3f o, V3f d,
+                                             V3f dc, V3f g, bool hide_emitters) {
+    if (R.nv <= 0) return;
+    // vertex 0: solid-angle form -- (u, v, t) are functions of the triangle and the camera ray
+    const TriRec<float> T0 = load_tri<float>(sc, R.vtri[0]);
+    float u0, v0, t0;
+    ray_intersect_triangle<float>(T0.p0, T0.e1, T0.e2, o, d, u0, v0, t0);
+    VtxGeo cur = vertex_geo(sc, R.vtri[0], u0, v0);
+    cur.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
+    // Le at the primary hit
+    if (!hide_emitters && cur.emitter >= 0 && dot(-d, cur.shn) > 0.f) acc.add3(gl.off_emit + 4 * cur.emitter, g);
+    if (R.nsh <= 0) return;
+
+    // geometry of every vertex (recomputed from the tables; no tracing)
+    VtxGeo vg[kD + 1];
+    VtxAdj va[kD + 1];
+    vg[0] = cur;
+#pragma unroll
+    for (int k = 0; k <= kD; ++k) {
+        if (k > 0 && k < R.nv) vg[k] = vertex_geo(sc, R.vtri[k], R.vu[k], R.vv[k]);
+        va[k].p = va[k].shn = va[k].fn = V3f(0.f, 0.f, 0.f);
+        va[k].area = 0.f;
+    }
+    V3f o_bar(0.f, 0.f, 0.f), d_bar(0.f, 0.f, 0.f);
+    V3f Lnext(0.f, 0.f, 0.f);     // R_{k+1}: radiance gathered after vertex k+1 (without E_{k+1})
+#pragma unroll
+    for (int kk = 0; kk < kD; ++kk) {
+        const int k = R.nsh - 1 - kk;
+        if (k < 0) break;
+        const VtxGeo &x = vg[k];
+        const V3f A = g * R.T[k];
+        float tprev = 1.f;
+        V3f wi;
+        if (k == 0) wi = -d;
+        else {
+            const V3f vp = vg[k - 1].p - x.p;
+            tprev = norm(vp);
+            wi = vp / tprev;
+        }
+        V3f wi_bar(0.f, 0.f, 0.f);
+        V3f Rk(0.f, 0.f, 0.f);
+        // ---- BSDF bounce k -> vertex k+1
+        if (R.bnc_ok[k] && k + 1 < R.nv) {
+            const VtxGeo &y = vg[k + 1];
+            const V3f wo = normalize(y.p - x.p);
+            V3f E(0.f, 0.f, 0.f);
+            const bool y_emits = y.emitter >= 0 && dot(-wo, y.shn) > 0.f;
+            if (y_emits) {
+                const DEmitter &em = sc.emitters[y.emitter];
+                E = V3f(em.radiance[0], em.radiance[1], em.radiance[2]) * R.w2[k];
+            }
+            const V3f Ltot = E + Lnext;
+            if (R.bnc_nz[k]) {
+                const float scale = 1.f / R.pdf0[k];
+                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, y.p, y.fn, y.area, A * Ltot, scale, va[k]);
+                va[k + 1].p = va[k + 1].p + ev.py;
+                va[k + 1].fn = va[k + 1].fn + ev.ny;
+                va[k + 1].area += ev.area_y;
+                wi_bar = wi_bar + ev.wi_bar;
+                const V3f fb = ev.f * ev.geo;
+                if (y_emits) acc.add3(gl.off_emit + 4 * y.emitter, A * fb * R.w2[k]);
+                Rk = Rk + fb * Ltot;
+            }
+        }
+        // ---- emitter sampling at vertex k
+        if (R.nee_ok[k]) {
+            const TriRec<float> TL = load_tri<float>(sc, R.ltri[k]);
+            const V3f py = bilinear(TL.p0, TL.e1, TL.e2, V2f(R.la[k], R.lb[k]));
+            const float4 c = __ldg(sc.shade + 3 * R.htri[k] + 2);
+            const V3f ny(c.y, c.z, c.w);
+            const int emi = sc.meshes[__float_as_int(__ldg(&sc.geo[3 * R.htri[k] + 2].z))].emitter;
+            if (emi >= 0) {
+                const DEmitter &em = sc.emitters[emi];
+                const V3f Le(em.radiance[0], em.radiance[1], em.radiance[2]);
+                const float scale = R.w1[k] / R.lpdf[k];
+                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, py, ny, TL.area, A * Le, scale, va[k]);
+                wi_bar = wi_bar + ev.wi_bar;
+                const int lb = kGradTri * R.ltri[k];
+                acc.add3(lb, ev.py);
+                acc.add3(lb + 3, ev.py * R.la[k]);
+                acc.add3(lb + 6, ev.py * R.lb[k]);
+                acc.add(lb + 9, ev.area_y);
+                acc.add3(kGradTri * R.htri[k] + 19, ev.ny);
+                const V3f c_rgb = ev.f * ev.geo;
+                acc.add3(gl.off_emit + 4 * emi, A * c_rgb);
+                Rk = Rk + Le * c_rgb;
+            }
+        }
+        // ---- wi at vertex k: through the previous vertex, or the camera ray direction
+        if (k == 0) d_bar = d_bar - wi_bar;
+        else {
+            const V3f vp_bar = unit_adj(wi, tprev, wi_bar, 0.f);
+            va[k - 1].p = va[k - 1].p + vp_bar;
+            va[k].p = va[k].p - vp_bar;
+        }
+        Lnext = Rk;
+    }
+    // ---- scatter the vertex adjoints
+#pragma unroll
+    for (int k = 1; k <= kD; ++k)
+        if (k < R.nv) scatter_pinned_vertex(acc, vg[k], va[k]);
+    {   // vertex 0: p = o + t d, sh_n from the differentiable (u, v)
+        const VtxGeo &x = vg[0];
+        const int b = kGradTri * x.tri;
+        acc.add3(b + 19, va[0].fn);
+        acc.add(b + 9, va[0].area);
+        V3f m_bar;
+        scatter_shading_normal(acc, x, va[0].shn, m_bar);
+        const ShadeRec<float> N = load_shade<float>(sc, x.tri);
+        const float u_bar = dot(N.n1 - N.n0, m_bar), v_bar = dot(N.n2 - N.n0, m_bar);
+        o_bar = o_bar + va[0].p;
+        d_bar = d_bar + va[0].p * t0;
+        const float t_bar = dot(d, va[0].p);
+        const V3f r_bar = isect_adj(T0.e1, T0.e2, d, u_bar, v_bar, t_bar);
+        scatter_isect_tri(acc, x.tri, u0, v0, r_bar);
+        o_bar = o_bar + r_bar;
+        d_bar = d_bar + r_bar * t0;
+        scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
+    }
+}
+
+// ---- secondary-edge estimator, reverse mode (forward code: device_path.cuh eval_secondary_edge) ---------
+// tangent = value0 * d<n, u2>, u2 = point on the (detached) emitter triangle at the differentiable
+// barycentrics of the ray its1.p -> bp0 (reference src/integrator/path.cpp:252-265).
+struct SecEdgeAdjoint {
+    static constexpr bool enabled = true;
+    const float *d_img;     // cotangent image
+    float scale;            // tangent_scale / sppse
+    GradLayout gl;
+    GradAcc acc;
+    template <bool kBvh>
+    __device__ __forceinline__ void tail(const DScene &sc, const DCamera &cam, int pixel, V3f value0, V3f n, int edge, float s, V3d bp0d,
+                                         int light_tri, const Its<Dual> &its1, V3f cd, V2f q) const {
+        const SecEdgeAdjoint *adj = this;
+    const float *gp = adj->d_img + 3 * pixel;
+    float w = 0.f;
+    {
+        const float gv[3] = {__ldg(gp), __ldg(gp + 1), __ldg(gp + 2)}, v0[3] = {value0.x, value0.y, value0.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (isfinite(v0[c])) w += gv[c] * v0[c];
+    }
+    w *= adj->scale;
+    if (w == 0.f || !isfinite(w)) return;
+    const GradAcc &acc = adj->acc;
+    const TriRec<float> TL = load_tri<float>(sc, light_tri);
+    const V3f p1 = val(its1.p), bp0 = val(bp0d);
+    const V3f vec = bp0 - p1;
+    const float len = norm(vec);
+    const V3f sdir = vec / len;
+    float u, v, t;
+    ray_intersect_triangle<float>(TL.p0, TL.e1, TL.e2, p1, sdir, u, v, t);
+    const float u_bar = w * dot(n, TL.e1), v_bar = w * dot(n, TL.e2);
+    const V3f r_bar = isect_adj(TL.e1, TL.e2, sdir, u_bar, v_bar, 0.f);
+    scatter_isect_tri(acc, light_tri, u, v, r_bar);
+    V3f p1_bar = r_bar;                      // origin of the ray
+    const V3f sdir_bar = r_bar * t;
+    const V3f vec_bar = unit_adj(sdir, len, sdir_bar, 0.f);
+    p1_bar = p1_bar - vec_bar;
+    const int eb = adj->gl.off_se + 6 * edge;   // bp0 = edge.p0 + s * edge.e1
+    acc.add3(eb, vec_bar);
+    acc.add3(eb + 3, vec_bar * s);
+    // its1.p = o + t1 d: camera ray re-intersected with the triangle under p1 (solid-angle form)
+    const TriRec<float> TP = load_tri<float>(sc, its1.tri);
+    const float t1 = val(its1.t);
+    V3f o_bar = p1_bar, d_bar = p1_bar * t1;
+    const float t1_bar = dot(cd, p1_bar);
+    const V3f r1 = isect_adj(TP.e1, TP.e2, cd, 0.f, 0.f, t1_bar);
+    scatter_isect_tri(acc, its1.tri, its1.bu, its1.bv, r1);
+    o_bar = o_bar + r1;
+    d_bar = d_bar + r1 * t1;
+    const V3f dc = normalize(xform_pos(cam.sample_to_camera, V3f(q.x, q.y, 0.f)));
+    scatter_camera_ray(acc, adj->gl, dc, o_bar, d_bar);
+    }
+};
+
+}  // namespace psdr

@@ -22,6 +22,9 @@ struct psdr_scene {
     int *d_pix = nullptr;
     size_t img_cap = 0, pix_cap = 0;
     cudaStream_t stream = nullptr;
+    // reverse mode: device gradient table + pinned host copy
+    float *d_grad = nullptr, *h_grad = nullptr;
+    size_t grad_cap = 0;
     // optional per-kernel timing (psdr_scene_enable_timing)
     bool timing = false;
     cudaEvent_t ev[3][2] = {};
@@ -33,6 +36,8 @@ struct psdr_scene {
         if (d_img) cudaFree(d_img);
         if (d_dimg) cudaFree(d_dimg);
         if (d_pix) cudaFree(d_pix);
+        if (d_grad) cudaFree(d_grad);
+        if (h_grad) cudaFreeHost(h_grad);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -372,10 +377,10 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
     if (pix_id && npix_sel <= 0) throw std::runtime_error("empty pixel batch");
     if (npix * (long long) std::max(sc.spp, 1) > 2147483647LL) throw std::runtime_error("num_samples <= std::numeric_limits<int>::max()");
     if (!img) throw std::runtime_error("null image buffer");
-    if (ad && !dimg) throw std::runtime_error("null derivative image buffer");
+    const bool primal_only = ad && !dimg;   // renderD's image without the forward-mode derivative image
     const DCamera &cam = sc.dcameras[sensor];
     cuda_ok(cudaMemsetAsync(img, 0, sizeof(float) * 3 * npix, st), "memset(img)");
-    if (ad) cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
+    if (ad && dimg) cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
     if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
         const Shard sh = shard_of(npix * sc.spp, sc.rank, sc.world);
         rp[0].lane_begin = sh.begin; rp[0].lane_end = sh.end;
@@ -386,7 +391,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         tick(s, 0, 1, st);
         g_launches++;
     }
-    if (ad && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
+    if (ad && !primal_only && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
         if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
         const Shard sh = shard_of(npix_full * sc.sppe, sc.rank, sc.world);
         rp[1].lane_begin = sh.begin; rp[1].lane_end = sh.end;
@@ -395,7 +400,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         tick(s, 1, 1, st);
         g_launches++;
     }
-    if (ad && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
+    if (ad && !primal_only && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
         if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
         const Shard sh = shard_of(npix_full * sc.sppse, sc.rank, sc.world);
         rp[2].lane_begin = sh.begin; rp[2].lane_end = sh.end;
@@ -443,6 +448,124 @@ int psdr_render_d(psdr_scene *s, int sensor, int max_depth, long long seed, int 
     PSDR_TRY
     return render_impl(s, sensor, max_depth, seed, hide_emitters, true, terms, reference_scaling, pix_id, npix, img, dimg, (cudaStream_t) cuda_stream);
     PSDR_CATCH
+}
+
+int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                    const int *pix_id, int npix_sel, const float *d_img, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    cudaStream_t st = (cudaStream_t) cuda_stream;
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    if (!d_img) throw std::runtime_error("null cotangent image");
+    if (max_depth > 8) throw std::runtime_error("the adjoint supports max_depth <= 8");
+    RenderParams rp[3];
+    for (auto &r : rp) {
+        r = RenderParams{};
+        r.max_depth = max_depth;
+        r.hide_emitters = hide_emitters;
+        r.tangent_scale = 1.f;
+    }
+    SamplerState saved[3] = {sc.samplers[0], sc.samplers[1], sc.samplers[2]};
+    begin_render(sc, sensor, seed, pix_id, true, terms, max_depth, rp);
+    for (int k = 0; k < 3; ++k) sc.samplers[k] = saved[k];    // a replay does not consume the streams
+    const long long npix_full = (long long) sc.width * sc.height;
+    const long long npix = pix_id ? npix_sel : npix_full;
+    if (pix_id && npix_sel <= 0) throw std::runtime_error("empty pixel batch");
+    const DCamera &cam = sc.dcameras[sensor];
+    GradLayout gl = sc.grad_layout(sensor);
+    if ((size_t) gl.total > s->grad_cap) {
+        if (s->d_grad) cudaFree(s->d_grad);
+        if (s->h_grad) cudaFreeHost(s->h_grad);
+        s->grad_cap = (size_t) gl.total * 2;
+        cuda_ok(cudaMalloc(&s->d_grad, sizeof(float) * s->grad_cap), "cudaMalloc(grad table)");
+        cuda_ok(cudaMallocHost(&s->h_grad, sizeof(float) * s->grad_cap), "cudaMallocHost(grad table)");
+    }
+    gl.base = s->d_grad;
+    cuda_ok(cudaMemsetAsync(s->d_grad, 0, sizeof(float) * gl.total, st), "memset(grad table)");
+    s->ev_used[0] = s->ev_used[1] = s->ev_used[2] = false;
+    if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
+        const Shard sh = shard_of(npix * sc.spp, sc.rank, sc.world);
+        rp[0].lane_begin = sh.begin; rp[0].lane_end = sh.end;
+        rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
+        rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
+        tick(s, 0, 0, st);
+        cuda_ok(launch_interior_vjp(sc.dscene, cam, rp[0], gl, d_img, st), "interior adjoint kernel");
+        tick(s, 0, 1, st);
+        g_launches++;
+    }
+    if (sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
+        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+        const Shard sh = shard_of(npix_full * sc.sppe, sc.rank, sc.world);
+        rp[1].lane_begin = sh.begin; rp[1].lane_end = sh.end;
+        tick(s, 1, 0, st);
+        cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp[1], gl, d_img, st), "primary-edge adjoint kernel");
+        tick(s, 1, 1, st);
+        g_launches++;
+    }
+    if (sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
+        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+        const Shard sh = shard_of(npix_full * sc.sppse, sc.rank, sc.world);
+        rp[2].lane_begin = sh.begin; rp[2].lane_end = sh.end;
+        rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
+        tick(s, 2, 0, st);
+        cuda_ok(launch_secondary_edges_vjp(sc.dscene, cam, rp[2], gl, d_img, st), "secondary-edge adjoint kernel");
+        tick(s, 2, 1, st);
+        g_launches++;
+    }
+    cuda_ok(cudaMemcpyAsync(s->h_grad, s->d_grad, sizeof(float) * gl.total, cudaMemcpyDeviceToHost, st), "D2H(grad table)");
+    cuda_ok(cudaStreamSynchronize(st), "stream sync");
+    sc.backprop(s->h_grad, gl, sensor);
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
+    if (!s || !out) return fail("null argument");
+    const Scene &sc = s->sc;
+    const ParamGrads &g = sc.grads;
+    if (!g.valid) return fail("no gradients: call psdr_render_vjp first");
+    auto copy = [&](const double *src, int count) {
+        if (n != count) return fail("gradient buffer size mismatch");
+        for (int i = 0; i < count; ++i) out[i] = (float) src[i];
+        return 0;
+    };
+    switch (kind) {
+        case PSDR_MESH_VERTICES:
+            if (index < 0 || index >= (int) g.meshes.size()) return fail("invalid mesh index");
+            return copy(g.meshes[index].v.data(), (int) g.meshes[index].v.size());
+        case PSDR_MESH_TO_WORLD_LEFT: case PSDR_MESH_TO_WORLD_RAW: case PSDR_MESH_TO_WORLD_RIGHT:
+            if (index < 0 || index >= (int) g.meshes.size()) return fail("invalid mesh index");
+            return copy(g.meshes[index].to_world[kind - PSDR_MESH_TO_WORLD_LEFT], 16);
+        case PSDR_SENSOR_TO_WORLD_LEFT: case PSDR_SENSOR_TO_WORLD_RAW: case PSDR_SENSOR_TO_WORLD_RIGHT:
+            if (index < 0 || index >= (int) g.cameras.size()) return fail("Invalid sensor id!");
+            return copy(g.cameras[index].to_world[kind - PSDR_SENSOR_TO_WORLD_LEFT], 16);
+        case PSDR_BSDF_REFLECTANCE:
+            if (index < 0 || 3 * index + 3 > (int) g.bsdf_refl.size()) return fail("invalid BSDF index");
+            return copy(g.bsdf_refl.data() + 3 * index, 3);
+        case PSDR_EMITTER_RADIANCE:
+            if (index < 0 || 3 * index + 3 > (int) g.emitter_rad.size()) return fail("invalid emitter index");
+            return copy(g.emitter_rad.data() + 3 * index, 3);
+        default: return fail("unknown parameter kind");
+    }
+}
+
+int psdr_scene_get_sampler_state(psdr_scene *s, long long state[6]) {
+    if (!s || !state) return fail("null argument");
+    for (int k = 0; k < 3; ++k) {
+        state[2 * k] = s->sc.samplers[k].ready ? s->sc.samplers[k].seed : -1;
+        state[2 * k + 1] = (long long) s->sc.samplers[k].consumed;
+    }
+    return 0;
+}
+int psdr_scene_set_sampler_state(psdr_scene *s, const long long state[6]) {
+    if (!s || !state) return fail("null argument");
+    for (int k = 0; k < 3; ++k) {
+        s->sc.samplers[k].ready = state[2 * k] >= 0;
+        s->sc.samplers[k].seed = state[2 * k] >= 0 ? state[2 * k] : 0;
+        s->sc.samplers[k].consumed = (unsigned long long) state[2 * k + 1];
+    }
+    return 0;
 }
 
 int psdr_render_c_host(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, const int *pix_id_host, int npix,

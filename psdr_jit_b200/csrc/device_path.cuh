@@ -171,6 +171,7 @@ template <class S> struct Its {   // reference include/psdr/core/intersection.h:
     int mesh, tri;
     V3<S> p, n, wi, sh_s, sh_t, sh_n;
     S t, J;
+    float bu, bv;   // detached barycentrics of the hit (p = p0 + bu e1 + bv e2)
     __device__ __forceinline__ V3<S> to_local(V3<S> v) const { return V3<S>(dot(v, sh_s), dot(v, sh_t), dot(v, sh_n)); }
     __device__ __forceinline__ V3<S> to_world(V3<S> v) const { return sh_s * v.x + sh_t * v.y + sh_n * v.z; }
 };
@@ -194,15 +195,18 @@ template <> struct IsDual<Dual> { static constexpr bool value = true; };
 // Scene::ray_intersect<ad, path_space> (reference src/scene/scene.cpp:612-806).  The material-form
 // ("path-space") variant pins the hit to the triangle by detached barycentrics; the solid-angle
 // variant (S = Dual, path_space = false: primary hits) re-intersects analytically.
-template <class S, bool kBvh>
+// kAD selects the formulas of the reference's ad=true instantiation; it defaults to "S carries a
+// tangent", the adjoint's primal replay uses <float, kBvh, true> to walk the same path as renderD.
+template <class S, bool kBvh, bool kAD = IsDual<S>::value>
 __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S> d, bool active, bool path_space, int *out_tri = nullptr) {
-    constexpr bool ad = IsDual<S>::value;
+    constexpr bool ad = kAD;
     Its<S> its;
     its.valid = false;
     its.mesh = -1;
     its.tri = -1;
     its.t = S(0.f);
     its.J = S(1.f);
+    its.bu = its.bv = 0.f;
     if (out_tri) *out_tri = -1;
     if (!active) return its;
     const Hit h = trace<kBvh>(sc, val(o), val(d));
@@ -224,6 +228,8 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
         its.t = norm(dir);
         dir = dir / its.t;
         if (ad) its.J = T.area / detach(T.area);
+        its.bu = h.u;
+        its.bv = h.v;
     } else {
         S u, v, t;
         ray_intersect_triangle(T.p0, T.e1, T.e2, o, d, u, v, t);
@@ -232,6 +238,8 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
         its.p = V3<S>(fmadd(d.x, t, o.x), fmadd(d.y, t, o.y), fmadd(d.z, t, o.z));
         its.t = t;
         dir = d;
+        its.bu = val(u);
+        its.bv = val(v);
     }
     if (mesh.flags & 1) sh_n = its.n;
     its.sh_n = sh_n;
@@ -362,6 +370,8 @@ template <class S> struct PosSample {
     V3<S> p, n;
     S J;
     float pdf;
+    int tri;     // global id of the sampled emitter triangle
+    V2f st;      // barycentrics of the sample on it
 };
 
 // Scene::sample_emitter_position (reference src/scene/scene.cpp:987-1013) -> Mesh::sample_position
@@ -376,6 +386,8 @@ template <class S> __device__ __forceinline__ PosSample<S> sample_emitter_positi
     const float t = safe_sqrt(1.f - sample2.x);
     const V2f st(1.f - t, t * sample2.y);
     const TriRec<S> T = load_tri<S>(sc, em.face_offset + fi);
+    ps.tri = em.face_offset + fi;
+    ps.st = st;
     ps.J = S(1.f);
     if (IsDual<S>::value) ps.J = T.area / detach(T.area);
     ps.p = bilinear(T.p0, T.e1, T.e2, st);
@@ -454,9 +466,19 @@ template <> __device__ __forceinline__ void sample_primary_ray<Dual>(const DCame
 // the previous bounce) -> vertex; NEE shadow ray}, so the kernel holds exactly two copies of the
 // closest-hit scan and stays inside the instruction cache (profiles/r01a: the unrolled form stalled
 // 49 % of the cycles on instruction fetch).
-template <class S, bool kBvh>
-__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
-    constexpr bool ad = IsDual<S>::value;
+// Rec = recorder policy: the adjoint's primal replay passes a PathRecord (adjoint.cuh) that keeps what the
+// reverse sweep needs (vertices, light samples, detached pdfs/MIS weights, throughputs); NoRecord
+// compiles to nothing.
+struct NoRecord {
+    __device__ __forceinline__ void vertex(int, int, float, float) {}
+    __device__ __forceinline__ void throughput(int, V3f) {}
+    __device__ __forceinline__ void bounce(int, bool, float, float) {}
+    __device__ __forceinline__ void nee(int, bool, int, V2f, int, float, float) {}
+};
+
+template <class S, bool kBvh, bool kAD, class Rec>
+__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, Rec &R) {
+    constexpr bool ad = kAD;
     V3<S> throughput(S(1.f)), result(S(0.f));
     Its<S> its;
     its.valid = false;
@@ -468,7 +490,8 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
 #pragma unroll 1
     for (int depth = -1; depth < max_depth; ++depth) {
         // ---- main ray: primary hit (solid-angle form under AD) or the BSDF-sampled ray (path-space form)
-        const Its<S> its1 = ray_intersect<S, kBvh>(sc, ray_o, ray_d, active, ad && depth >= 0);
+        const Its<S> its1 = ray_intersect<S, kBvh, kAD>(sc, ray_o, ray_d, active, ad && depth >= 0);
+        if (its1.valid) R.vertex(depth + 1, its1.tri, its1.bu, its1.bv);
         if (depth < 0) {
             active = active && its1.valid;
             if (!hide_emitters) result = Le(sc, its1, active);
@@ -493,6 +516,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
                     else bsdf_val = bsdf_eval(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
                 }
                 const float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, its1, active));
+                R.bounce(depth, val(its1.t) >= kEpsilon, pdf0, weight2);
                 throughput = throughput * bsdf_val;
                 result = result + Le(sc, its1, active) * throughput * S(weight2);
             }
@@ -504,6 +528,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
         }
         if (bounces_left <= 0) break;
         its = its1;
+        R.throughput(depth + 1, val(throughput));
         const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
         const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
         {   // ---- emitter sampling
@@ -513,7 +538,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
             const S dist_sqr = squared_norm(wod);
             const S dist = safe_sqrt(dist_sqr);
             wod = wod / dist;
-            const Its<S> its2 = ray_intersect<S, kBvh>(sc, its.p, wod, active_direct, ad);
+            const Its<S> its2 = ray_intersect<S, kBvh, kAD>(sc, its.p, wod, active_direct, ad);
             active_direct = active_direct && its2.valid;
             active_direct = active_direct && (val(its2.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its2);
             if (active_direct) {
@@ -526,6 +551,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
                 const float pdf1 = bsdf_pdf(sc, its, wo_local, active_direct) * val(G_val);
                 if (pdf1 != 0.f) {
                     const float weight1 = mis_weight(ps.pdf, pdf1);
+                    R.nee(depth + 1, val(its2.wi.z) > 0.f, ps.tri, ps.st, its2.tri, ps.pdf, weight1);
                     result = result + throughput * emitter_val * bsdf_val2 * S(weight1);
                 }
             }
@@ -536,6 +562,12 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
         ray_d = its.to_world(lift3<S>(bs.wo));
     }
     return result;
+}
+
+template <class S, bool kBvh>
+__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
+    NoRecord rec;
+    return Li<S, kBvh, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec);
 }
 
 // ---- secondary (shadow) edges: reference src/scene/scene.cpp:1027-1068, src/integrator/path.cpp:172-270
@@ -566,8 +598,17 @@ __device__ __forceinline__ float sign1(float x) { return signbit_(x) ? -1.f : 1.
 
 // returns the pixel (-1: no contribution); value0 = primal boundary value (guiding pre-pass),
 // tangent = d/dP of the zero-primal estimator.
-template <bool kBvh>
-__device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
+// Adj = reverse-mode policy of the secondary-edge estimator: NoSecAdjoint (forward mode) or
+// SecEdgeAdjoint (adjoint.cuh), whose tail() scatters the gradients instead of forming the tangent.
+struct NoSecAdjoint {
+    static constexpr bool enabled = false;
+    template <bool kBvh>
+    __device__ __forceinline__ void tail(const DScene &, const DCamera &, int, V3f, V3f, int, float, V3d, int, const Its<Dual> &, V3f, V2f) const {}
+};
+
+template <bool kBvh, class Adj>
+__device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out,
+                                                   const Adj &adj) {
     value0_out = V3f(0.f, 0.f, 0.f);
     tangent_out = V3f(0.f, 0.f, 0.f);
     // -- sample_boundary_segment_direct
@@ -631,6 +672,10 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     value0_out = value0;
     const V3f n = normalize(cross(bn, proj));
     value0 = value0 * (sign1(dot(ec, edge2)) * sign1(dot(ec, n)));
+    if (Adj::enabled) {
+        adj.template tail<kBvh>(sc, cam, sds.pixel, value0, n, ei, sample1, bp0, light_tri, its1, val(cd), sds.q);
+        return sds.pixel;
+    }
     const TriRec<Dual> T = load_tri<Dual>(sc, light_tri);
     const V3d sdir = normalize(bp0 - its1.p);
     Dual u, v, t;
@@ -639,6 +684,11 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     const Dual dn = dot(lift3<Dual>(n), u2);
     tangent_out = V3f(value0.x * dn.d, value0.y * dn.d, value0.z * dn.d);
     return sds.pixel;
+}
+
+template <bool kBvh>
+__device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
+    return eval_secondary_edge<kBvh, NoSecAdjoint>(sc, cam, sample3, value0_out, tangent_out, NoSecAdjoint());
 }
 
 }  // namespace psdr

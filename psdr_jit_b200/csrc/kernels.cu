@@ -37,7 +37,9 @@ __device__ __forceinline__ void splat_runs(float *img, int pix, float r, float g
 __device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; }
 
 // ---- interior term: Integrator::__render / __render_batch ------------------------------------
-template <class S, bool kBvh>
+// kAD = use the formulas of the reference's renderD instantiation (the primary hit re-intersected
+// analytically, scene.cpp:772-801) -- <float, kBvh, true> is the primal image of renderD.
+template <class S, bool kBvh, bool kAD>
 __global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                            const __grid_constant__ RenderParams rp, float *__restrict__ img,
                                                            float *__restrict__ dimg) {
@@ -62,7 +64,8 @@ __global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant_
             const float sy = ((float) (pix / sc.width) + jy) / (float) sc.height;
             V3<S> o, d;
             sample_primary_ray<S>(cam, V2f(sx, sy), o, d);
-            v = Li<S, kBvh>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0);
+            NoRecord rec;
+            v = Li<S, kBvh, kAD, NoRecord>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, rec);
         }
         float r = val(v.x), g = val(v.y), b = val(v.z), dr = tang(v.x), dg = tang(v.y), db = tang(v.z);
         // masked(value, ~isfinite(value)) = 0 zeroes value and tangent (integrator.cpp:126)
@@ -184,12 +187,15 @@ cudaError_t launch_interior(const DScene &sc, const DCamera &cam, const RenderPa
     const long long lanes = rp.lane_end - rp.lane_begin;
     if (lanes <= 0) return cudaSuccess;
     const int grid = grid_for(lanes, 8);
-    if (ad) {
-        if (sc.use_bvh) interior_kernel<Dual, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
-        else interior_kernel<Dual, false><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+    if (ad && dimg) {
+        if (sc.use_bvh) interior_kernel<Dual, true, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        else interior_kernel<Dual, false, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+    } else if (ad) {   // primal image of renderD (the adjoint pass supplies the derivatives later)
+        if (sc.use_bvh) interior_kernel<float, true, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        else interior_kernel<float, false, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
     } else {
-        if (sc.use_bvh) interior_kernel<float, true><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
-        else interior_kernel<float, false><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        if (sc.use_bvh) interior_kernel<float, true, false><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        else interior_kernel<float, false, false><<<grid, kBlock, 0, st>>>(sc, cam, rp, img, dimg);
     }
     return cudaGetLastError();
 }

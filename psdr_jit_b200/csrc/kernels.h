@@ -3,10 +3,16 @@
 #include <cuda_runtime.h>
 
 #include "dscene.h"
+#include "grad_layout.h"
 
 namespace psdr {
 cudaError_t launch_interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st);
 cudaError_t launch_primary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);
 cudaError_t launch_secondary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);
 cudaError_t launch_aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st);
+
+// reverse mode (kernels_vjp.cu); GradLayout = adjoint.cuh
+cudaError_t launch_interior_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st);
+cudaError_t launch_primary_edges_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st);
+cudaError_t launch_secondary_edges_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st);
 }  // namespace psdr

@@ -200,6 +200,7 @@ static void configure_camera(const Scene &sc, HCamera &cam, bool with_primary_ed
     trn.m[1][3] = -1.f / aspect;
     const M4<float> c2s = (scl * trn) * perspective_matrix(cam.fov, cam.near_, cam.far_);
     cam.sample_to_camera = invert(c2s);
+    cam.camera_to_sample = c2s;
     cam.to_world_full = (cam.to_world[0] * cam.to_world[1]) * cam.to_world[2];
     {   // "Sensor transformation should not involve scaling!" (sensor.cpp:12-13)
         const M4<float> t = lower(cam.to_world_full);
@@ -252,6 +253,9 @@ static void configure_camera(const Scene &sc, HCamera &cam, bool with_primary_ed
             const V3d q1 = transform_pos(cam.world_to_sample, m.v_world[e.v1]);
             pe.p0 = V2d(q0.x, q0.y);
             pe.p1 = V2d(q1.x, q1.y);
+            pe.mesh = (int) (&m - &sc.meshes[0]);
+            pe.v0 = e.v0;
+            pe.v1 = e.v1;
             V2f dir2(q1.x.v - q0.x.v, q1.y.v - q0.y.v);
             const float len = norm(dir2);
             dir2.x /= len;
@@ -454,6 +458,9 @@ void Scene::configure(const int *active, int nactive) {
             if (!m.enable_edges) continue;
             for (const HEdge &e : m.edges) {
                 HSecEdge s;
+                s.mesh = (int) (&m - &meshes[0]);
+                s.v0 = e.v0;
+                s.v1 = e.v1;
                 s.is_boundary = e.f1 < 0;
                 s.p0 = m.v_world[e.v0];
                 s.e1 = m.v_world[e.v1] - s.p0;

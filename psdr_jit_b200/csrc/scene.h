@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "dscene.h"
+#include "grad_layout.h"
 #include "pmath.h"
 
 namespace psdr {
@@ -62,13 +63,14 @@ struct HPrimEdge {
     V2d p0, p1;
     V2f normal;
     float length;
+    int mesh, v0, v1;   // where the endpoints come from (reverse mode)
 };
 
 struct HCamera {
     float fov = 60.f, near_ = 1e-6f, far_ = 1e7f;
     M4<Dual> to_world[3];
     M4<Dual> to_world_full, world_to_sample;
-    M4<float> sample_to_camera;
+    M4<float> sample_to_camera, camera_to_sample;
     V3d pos, dir;
     float inv_area = 0.f;
     std::vector<HPrimEdge> edges;
@@ -79,6 +81,17 @@ struct HSecEdge {
     V3d p0, e1;
     V3f n0, n1, p2;
     bool is_boundary;
+    int mesh, v0, v1;
+};
+
+// Gradients of one scalar loss with respect to every parameter (filled by Scene::backprop).
+struct ParamGrads {
+    struct MeshG { std::vector<double> v; double to_world[3][16]; };
+    struct CamG { double to_world[3][16]; };
+    std::vector<MeshG> meshes;
+    std::vector<CamG> cameras;
+    std::vector<double> bsdf_refl, emitter_rad;   // 3 per object
+    bool valid = false;
 };
 
 struct DeviceBuffers;  // owns every cudaMalloc'ed table
@@ -109,6 +122,12 @@ struct Scene {
     std::vector<DCamera> dcameras;
     double last_configure_ms = 0.0;
     size_t upload_bytes = 0;
+    ParamGrads grads;
+
+    // reverse mode: table layout for `sensor` (base = nullptr) and the host chain
+    // table gradients -> world vertices -> raw vertices / to_world / camera matrices (scene_grad.cpp)
+    GradLayout grad_layout(int sensor) const;
+    void backprop(const float *table, const GradLayout &gl, int sensor);
 
     Scene();
     ~Scene();

@@ -1,0 +1,134 @@
+"""GPU tests of the reverse pass (psdr_render_vjp): the adjoint kernels + host chain must be the exact
+transpose of the forward-mode pass (which is pinned against the oracle and the reference):
+<w, J v> == <J^T w, v> for random tangents v over every parameter kind and random cotangent images w."""
+import numpy as np
+import pytest
+
+from tests.common import build_product, scenes, sphere_meshes
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene_with_tangents(psdr, meshes, w, h, spps, rng, what):
+    sc = build_product(meshes, w, h, *spps)
+    tang = {}
+    if "mesh_left" in what:
+        t = np.zeros((4, 4), np.float32)
+        t[:3, 3] = rng.normal(size=3) * 30
+        t[:3, :3] = rng.normal(size=(3, 3)) * 0.05
+        for name in ("Mesh[0]", "Mesh[1]"):
+            sc.param_map[name].d_to_world_left = t.copy()
+            tang[(name, "to_world_left")] = t.copy()
+    if "mesh_raw" in what:
+        t = np.zeros((4, 4), np.float32)
+        t[:3, 3] = rng.normal(size=3) * 10
+        sc.param_map["Mesh[2]"].d_to_world = t
+        tang[("Mesh[2]", "to_world")] = t
+    if "vertices" in what:
+        for name in ("Mesh[2]", "Mesh[0]", "Mesh[%d]" % (len(meshes) - 1)):
+            m = sc.param_map[name]
+            t = (rng.normal(size=m.vertex_positions.shape) * 3).astype(np.float32)
+            m.d_vertex_positions = t
+            tang[(name, "vertex_positions")] = t
+    if "materials" in what:
+        sc.param_map["BSDF[id=white]"].d_reflectance = np.array([0.3, -0.2, 0.1], np.float32)
+        tang[("BSDF[id=white]", "reflectance")] = sc.param_map["BSDF[id=white]"].d_reflectance
+        sc.param_map["BSDF[id=red]"].d_reflectance = np.array([0.1, 0.2, -0.3], np.float32)
+        tang[("BSDF[id=red]", "reflectance")] = sc.param_map["BSDF[id=red]"].d_reflectance
+        sc.param_map["Emitter[0]"].d_radiance = np.array([1.0, -2.0, 3.0], np.float32)
+        tang[("Emitter[0]", "radiance")] = sc.param_map["Emitter[0]"].d_radiance
+    if "camera" in what:
+        t = np.zeros((4, 4), np.float32)
+        t[:3, 3] = rng.normal(size=3) * 5
+        sc.param_map["Sensor[0]"].d_to_world_left = t
+        tang[("Sensor[0]", "to_world_left")] = t
+    sc.configure()
+    sc.configure([0])
+    return sc, tang
+
+
+CASES = [
+    ("materials", 1, 3, "cbox"), ("mesh_left", 1, 3, "cbox"), ("vertices", 1, 2, "cbox"), ("camera", 1, 3, "cbox"),
+    ("mesh_left", 2, 2, "cbox"), ("vertices", 2, 2, "sphere"), ("camera", 2, 2, "cbox"),
+    ("mesh_left", 4, 2, "cbox"), ("vertices", 4, 2, "sphere"), ("camera", 4, 2, "cbox"), ("mesh_raw", 4, 2, "cbox"),
+    ("mesh_left vertices materials camera mesh_raw", 7, 3, "sphere"),
+]
+
+
+@pytest.mark.parametrize("what,terms,depth,scene", CASES)
+def test_vjp_is_transpose_of_jvp(what, terms, depth, scene):
+    import torch
+    import psdr_jit_b200 as psdr
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(("%s/%d" % (what, terms)).encode()))
+    meshes = scenes.cbox_meshes() if scene == "cbox" else sphere_meshes()
+    w = h = 64
+    spps = (8 if terms & 1 else 0, 8 if terms & 2 else 0, 8 if terms & 4 else 0)
+    sc, tang = _scene_with_tangents(psdr, meshes, w, h, spps, rng, what.split())
+    integ = psdr.PathTracer(depth)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=3, terms=terms)
+    cot = torch.as_tensor(rng.normal(size=(w * h, 3)).astype(np.float32), device=img.device)
+    lhs = float((cot.double() * dimg.double()).sum())
+    integ.render_vjp(sc, cot, 0, seed=3, terms=terms)
+    rhs, parts = 0.0, {}
+    for (name, field), t in tang.items():
+        g = sc.grad_of(name, field)
+        parts[(name, field)] = float((g.astype(np.float64) * t.astype(np.float64)).sum())
+        rhs += parts[(name, field)]
+    scale = float(torch.linalg.norm(cot.double()) * torch.linalg.norm(dimg.double()))
+    assert scale > 0 and abs(lhs) > 1e-6 * scale, (lhs, scale)
+    assert abs(lhs - rhs) < 2e-4 * max(abs(lhs), 1e-3 * scale), (lhs, rhs, parts)
+
+
+def test_autograd_backward_matches_forward_mode():
+    """renderD returns an image with an autograd node; d loss / dP through it equals <dloss/dimg, dimg/dP>."""
+    import torch
+    import psdr_jit_b200 as psdr
+    meshes = scenes.cbox_meshes()
+    w = h = 64
+    sc = build_product(meshes, w, h, 8, 8, 8, move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+    integ = psdr.PathTracer(2)
+    img_f, dimg = integ.renderD_fwd(sc, 0, seed=5)
+    target = torch.full_like(img_f, 0.25)
+    dl_dimg = 2.0 * (img_f - target) / img_f.numel()
+    expect = float((dl_dimg.double() * dimg.double()).sum())
+
+    sc2 = build_product(meshes, w, h, 8, 8, 8)
+    P = torch.zeros((), dtype=torch.float32, requires_grad=True)
+    M = torch.eye(4).clone()
+    M[0, 3] = P * 100.0
+    sc2.param_map["Mesh[0]"].set_transform(M)
+    R = torch.tensor([20.0, 20.0, 8.0], requires_grad=True)
+    sc2.param_map["Emitter[0]"].radiance = R
+    sc2.configure()
+    sc2.configure([0])
+    img = integ.renderD(sc2, 0, seed=5)
+    assert img.requires_grad
+    loss = ((img - target) ** 2).mean()
+    loss.backward()
+    assert abs(float(P.grad) - expect) < 2e-4 * abs(expect), (float(P.grad), expect)
+    # d loss / d radiance: the image is linear in the radiance (interior term only, detached elsewhere)
+    sc3 = build_product(meshes, w, h, 8, 0, 0, d_radiance=(1.0, 0.0, 0.0))
+    a, da = integ.renderD_fwd(sc3, 0, seed=5, terms=1)
+    assert abs(float(R.grad[0]) - float((dl_dimg.double() * da.double()).sum())) < 2e-4 * abs(float(R.grad[0]))
+    # the primal of the autograd path is the primal of renderD
+    assert float((img.detach() - img_f).abs().max()) < 1e-6
+
+
+def test_vjp_replays_continued_sampler_streams():
+    """seed = -1: backward replays the draws its forward call consumed and leaves the streams advanced."""
+    import torch
+    import psdr_jit_b200 as psdr
+    sc = build_product(scenes.cbox_meshes(), 48, 48, 4, 4, 4)
+    R = torch.tensor([20.0, 20.0, 8.0], requires_grad=True)
+    sc.param_map["Emitter[0]"].radiance = R
+    sc.configure()
+    sc.configure([0])
+    integ = psdr.PathTracer(2)
+    integ.renderD_primal(sc, 0, seed=11)
+    img = integ.renderD(sc, 0, seed=-1)
+    st_after = list(sc._sampler_state())
+    img.sum().backward()
+    assert list(sc._sampler_state()) == st_after
+    # image is linear in the radiance: <grad, R> == sum(img)
+    assert abs(float((R.grad * R.detach()).sum()) - float(img.detach().sum())) < 1e-4 * float(img.detach().sum())
