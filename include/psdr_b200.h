@@ -30,8 +30,10 @@ enum {
     PSDR_SENSOR_TO_WORLD_LEFT = 4, /* Sensor.to_world_left = Sensor.set_transform */
     PSDR_SENSOR_TO_WORLD_RAW = 5,  /* Sensor.to_world */
     PSDR_SENSOR_TO_WORLD_RIGHT = 6,
-    PSDR_BSDF_REFLECTANCE = 7,     /* DiffuseBSDF.reflectance (1x1 bitmap), 3 floats */
-    PSDR_EMITTER_RADIANCE = 8      /* AreaLight.radiance, 3 floats */
+    PSDR_BSDF_REFLECTANCE = 7,     /* DiffuseBSDF.reflectance / MicrofacetBSDF.diffuseReflectance (1x1 bitmap), 3 floats */
+    PSDR_EMITTER_RADIANCE = 8,     /* AreaLight.radiance, 3 floats */
+    PSDR_BSDF_SPECULAR = 9,        /* MicrofacetBSDF.specularReflectance (1x1 bitmap), 3 floats */
+    PSDR_BSDF_ROUGHNESS = 10       /* MicrofacetBSDF.roughness (1x1 bitmap), 1 float */
 };
 
 /* What psdr_scene_query() can return. */
@@ -47,7 +49,8 @@ enum {
     PSDR_Q_NUM_MESH_FACES = 8,
     PSDR_Q_IS_CONFIGURED = 9,
     PSDR_Q_USES_BVH = 10,
-    PSDR_Q_UPLOAD_BYTES = 11        /* bytes of device tables the last configure() copied host->device */
+    PSDR_Q_UPLOAD_BYTES = 11,       /* bytes of device tables the last configure() copied host->device */
+    PSDR_Q_GUIDING_CELLS = 12       /* index = sensor; cells of its secondary-edge guiding grid (0 = none) */
 };
 
 /* Terms of renderD (bit mask). */
@@ -76,6 +79,11 @@ int psdr_scene_set_accel(psdr_scene *s, int mode);
 /* Scene.add_BSDF(DiffuseBSDF([r,g,b]), name, twoSide) -- src/psdr.cpp:401, src/scene/scene.cpp:148-247.
  * Returns the BSDF index (>= 0) or -1. */
 int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float reflectance[3], int two_side);
+
+/* Scene.add_BSDF(MicrofacetBSDF([spec], [diff], roughness), name, twoSide) -- src/psdr.cpp:298-304,
+ * include/psdr/bsdf/microfacet.h:12 (argument order: specular, diffuse, roughness), src/bsdf/microfacet.cpp. */
+int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float specular[3], const float diffuse[3], float roughness,
+                                   int two_side);
 
 /* Scene.add_Mesh(mesh, bsdf_id, emitter) with mesh = Mesh.load_raw(v, f, uv, f_uv) -- src/psdr.cpp:399-400,
  * src/scene/scene.cpp:249-309, src/shape/mesh.cpp:74-162.  v: nv*3 floats (object space), f: nf*3 ints,
@@ -142,6 +150,16 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n);
  * consumed per lane of sampler k (0 interior, 1 primary edges, 2 secondary edges); seed < 0 = not seeded. */
 int psdr_scene_get_sampler_state(psdr_scene *s, long long state[6]);
 int psdr_scene_set_sampler_state(psdr_scene *s, const long long state[6]);
+
+/* PathTracer.preprocess_secondary_edges(scene, sensor_id, [rx, ry, rz, n], nrounds, seed) -- src/psdr.cpp:431-434,
+ * src/integrator/path.cpp:130-168: builds the guiding grid (rx*ry*rz cells, n samples per cell and round) of the
+ * secondary-edge sampler for `sensor` and enables it.  The grid belongs to the scene handle and survives
+ * configure(); psdr_scene_set_guiding switches its use on/off (the reference keeps it in the integrator object).
+ * Synchronises the stream. */
+int psdr_preprocess_secondary_edges(psdr_scene *s, int sensor, const int reso[4], int nrounds, long long seed, void *cuda_stream);
+int psdr_scene_set_guiding(psdr_scene *s, int sensor, int enabled);
+/* Mass per cell of the last pre-pass (host buffer, rx*ry*rz floats). */
+int psdr_scene_guiding_mass(psdr_scene *s, int sensor, float *out, int n);
 
 /* Same calls with HOST output buffers (pageable or pinned): device work + device->host copies,
  * returns after the buffers are filled. */

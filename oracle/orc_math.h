@@ -73,6 +73,11 @@ inline float abs_(float x) { return std::fabs(x); }
 inline Dual abs_(Dual x) { return Dual(std::fabs(x.v), std::signbit(x.v) ? -x.d : x.d); }
 inline float rcp_(float x) { return 1.f / x; }
 inline Dual rcp_(Dual x) { return 1.f / x; }
+inline float exp2_(float x) { return std::exp2(x); }
+inline Dual exp2_(Dual x) {
+    float e = std::exp2(x.v);
+    return Dual(e, 0.69314718055994530942f * e * x.d);
+}
 inline float sqr(float x) { return x * x; }
 inline Dual sqr(Dual x) { return x * x; }
 // fmadd(a,b,c) = a*b+c with a single rounding on the value (drjit emits fma.rn.ftz)

@@ -121,8 +121,10 @@ struct Edge {  // reference src/shape/mesh.cpp:244-305 (m_edge_indices rows)
 };
 
 struct Bsdf {
-    int type = 0;  // 0 diffuse
-    V3d reflectance;
+    int type = 0;  // 0 Diffuse, 1 Microfacet
+    V3d reflectance;  // Diffuse reflectance / Microfacet diffuseReflectance
+    V3d specular;     // Microfacet specularReflectance
+    Dual roughness;   // Microfacet roughness
     bool two_side = false;
 };
 
@@ -173,6 +175,10 @@ struct Camera {
     std::vector<PrimEdge> edges;
     Distrib edge_distrb;
     bool enable_edges = false;
+    // secondary-edge guiding: HyperCubeDistribution<3> (reference src/core/cube_distrb.cpp:9-64)
+    bool guided = false;
+    int greso[3] = {0, 0, 0};
+    Distrib guide;
 };
 
 struct Scene {
@@ -590,9 +596,68 @@ template <class S> static V3<S> refl_of(const Bsdf &b);
 template <> V3<Dual> refl_of<Dual>(const Bsdf &b) { return b.reflectance; }
 template <> V3<float> refl_of<float>(const Bsdf &b) { return val(b.reflectance); }
 
+template <class S> static V3<S> spec_of(const Bsdf &b);
+template <> V3<Dual> spec_of<Dual>(const Bsdf &b) { return b.specular; }
+template <> V3<float> spec_of<float>(const Bsdf &b) { return val(b.specular); }
+template <class S> static S rough_of(const Bsdf &b);
+template <> Dual rough_of<Dual>(const Bsdf &b) { return b.roughness; }
+template <> float rough_of<float>(const Bsdf &b) { return b.roughness.v; }
+
+// GGXDistribution::eval (reference src/bsdf/ggx.cpp:13-33), alpha_u = alpha_v
+template <class S> static S ggx_eval(S alpha, V3<S> m) {
+    S alpha_uv = alpha * alpha;
+    S t = sqr(m.x / alpha) + sqr(m.y / alpha) + sqr(m.z);
+    S result = rcp_(S(kPi) * alpha_uv * sqr(t));
+    return (val(result) * val(m.z) > 1e-20f) ? result : S(0.f);
+}
+// GGXDistribution::smith_g1 (ggx.cpp:82-96)
+template <class S> static S ggx_smith_g1(S alpha, V3<S> v, V3<S> m) {
+    S xy_alpha_2 = sqr(alpha * v.x) + sqr(alpha * v.y);
+    S tan_theta_alpha_2 = xy_alpha_2 / sqr(v.z);
+    S result = S(2.f) / (S(1.f) + sqrt_(S(1.f) + tan_theta_alpha_2));
+    if (val(xy_alpha_2) == 0.f) result = S(1.f);
+    if (val(dot(v, m)) * val(v.z) <= 0.f) result = S(0.f);
+    return result;
+}
+// Microfacet::__eval (reference src/bsdf/microfacet.cpp:22-68)
+template <class S> static V3<S> microfacet_eval(const Bsdf &b, V3<S> wi, V3<S> wo) {
+    if (b.two_side) {
+        if (std::signbit(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    S cos_nv = wi.z, cos_nl = wo.z;
+    if (!(val(cos_nv) > 0.f && val(cos_nl) > 0.f)) return V3<S>(S(0.f));
+    V3<S> diffuse = refl_of<S>(b) * S(kInvPi);
+    V3<S> H = normalize(wi + wo);
+    S cos_vh = dot(H, wi);
+    V3<S> F0 = spec_of<S>(b);
+    S alpha = sqr(rough_of<S>(b));
+    S ggx = ggx_eval<S>(alpha, H);
+    S coeff = cos_vh * (S(-5.55473f) * cos_vh - S(6.8316f));
+    S e = exp2_(coeff);
+    V3<S> fresnel = F0 + (V3<S>(S(1.f)) - F0) * e;
+    S smithG = ggx_smith_g1<S>(alpha, wi, H) * ggx_smith_g1<S>(alpha, wo, H);
+    V3<S> numerator = fresnel * (ggx * smithG);
+    S denominator = S(4.f) * cos_nl * cos_nv;
+    V3<S> specular = numerator / (denominator + S(1e-6f));
+    return (diffuse + specular) * cos_nl;
+}
+// Microfacet::__pdf (microfacet.cpp:108-133), detached
+static float microfacet_pdf(const Bsdf &b, V3f wi, V3f wo) {
+    if (b.two_side) {
+        if (std::signbit(wi.z)) wo.z = -wo.z;
+        wi.z = std::fabs(wi.z);
+    }
+    V3f m = normalize(wo + wi);
+    if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
+    float alpha = sqr(b.roughness.v);
+    return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
+}
+
 template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return V3<S>(S(0.f));
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
+    if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (std::signbit(val(wiz))) wo.z = -wo.z;
@@ -606,6 +671,7 @@ template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3
 template <class S> static float bsdf_pdf(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return 0.f;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
+    if (b.type == 1) return microfacet_pdf(b, val(its.wi), val(wo));
     float wiz = val(its.wi.z), woz = val(wo.z);
     if (b.two_side) {
         if (std::signbit(wiz)) woz = -woz;
@@ -635,10 +701,43 @@ static V2f square_to_uniform_disk_concentric(V2f s) {
     return V2f(r * cs, r * sn);
 }
 
+// GGXDistribution::sample_visible_11 (reference src/bsdf/ggx.cpp:99-109)
+static V2f ggx_sample_visible_11(float cos_theta_i, V2f sample) {
+    V2f p = square_to_uniform_disk_concentric(sample);
+    float s = .5f * (1.f + cos_theta_i);
+    float a = safe_sqrt(1.f - sqr(p.x));
+    p.y = std::fmaf(p.y, s, std::fmaf(-a, s, a));  // drjit lerp(a, b, t) = fmadd(b, t, fnmadd(a, t, a))
+    float x = p.x, y = p.y, z = safe_sqrt(1.f - std::fmaf(p.y, p.y, p.x * p.x));
+    float sin_theta_i = safe_sqrt(1.f - sqr(cos_theta_i));
+    float norm = 1.f / std::fmaf(sin_theta_i, y, cos_theta_i * z);
+    return V2f(std::fmaf(cos_theta_i, y, -(sin_theta_i * z)) * norm, x * norm);
+}
+// Microfacet::__sample (microfacet.cpp:80-98) + GGXDistribution::sample (ggx.cpp:36-79); sin/cos phi: frame.h:104-122
+static BsdfSample microfacet_sample(const Bsdf &b, V3f wi, V3f sample, bool active) {
+    BsdfSample bs;
+    if (b.two_side) wi.z = std::fabs(wi.z);
+    float alpha = sqr(b.roughness.v);
+    V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
+    float sin_theta_2 = std::fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / std::sqrt(sin_theta_2);
+    bool pole = std::fabs(sin_theta_2) <= 4.f * kEpsilon;
+    float sin_phi = pole ? 0.f : std::fmin(std::fmax(wi_p.y * inv_sin_theta, -1.f), 1.f);
+    float cos_phi = pole ? 1.f : std::fmin(std::fmax(wi_p.x * inv_sin_theta, -1.f), 1.f);
+    V2f slope = ggx_sample_visible_11(wi_p.z, V2f(sample.x, sample.y));
+    slope = V2f(std::fmaf(cos_phi, slope.x, -(sin_phi * slope.y)) * alpha, std::fmaf(sin_phi, slope.x, cos_phi * slope.y) * alpha);
+    V3f m = normalize(V3f(-slope.x, -slope.y, 1.f));
+    float m_pdf = ggx_smith_g1<float>(alpha, wi, m) * std::fabs(dot(wi, m)) * ggx_eval<float>(alpha, m) / std::fabs(wi.z);
+    float k = 2.f * dot(wi, m);
+    bs.wo = V3f(std::fmaf(m.x, k, -wi.x), std::fmaf(m.y, k, -wi.y), std::fmaf(m.z, k, -wi.z));
+    bs.pdf = m_pdf / (4.f * dot(bs.wo, m));
+    bs.valid = active && (wi.z > 0.f) && (bs.pdf != 0.f) && (bs.wo.z > 0.f);
+    return bs;
+}
+
 template <class S> static BsdfSample bsdf_sample(const Scene &sc, const Its<S> &its, V3f sample, bool active) {
     BsdfSample bs;
     if (!its.valid) return bs;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
+    if (b.type == 1) return microfacet_sample(b, val(its.wi), sample, active);
     float wiz = val(its.wi.z);
     if (b.two_side) wiz = std::fabs(wiz);
     V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));  // tail<2>(sample)
@@ -998,6 +1097,20 @@ static int eval_secondary_edge(const Scene &sc, const Camera &cam, V3f sample3, 
 }
 
 // reference src/integrator/path.cpp:274-294 (no guiding distribution: pdf0 = 1)
+// HyperCubeDistribution<3>::sample_reuse (reference src/core/cube_distrb.cpp:41-48): the cell is chosen with
+// the LAST sample dimension, the sample becomes (cell + sample) * unit, pdf = pmf * num_cells
+static float guide_sample_reuse(const Camera &cam, V3f &s) {
+    auto r = cam.guide.sample_reuse(s.z);
+    int idx = r.first;
+    int c0 = idx / (cam.greso[1] * cam.greso[2]);
+    int rem = idx - c0 * (cam.greso[1] * cam.greso[2]);
+    int c1 = rem / cam.greso[2], c2 = rem - c1 * cam.greso[2];
+    s.x = (s.x + (float) c0) * (1.f / (float) cam.greso[0]);
+    s.y = (s.y + (float) c1) * (1.f / (float) cam.greso[1]);
+    s.z = (s.z + (float) c2) * (1.f / (float) cam.greso[2]);
+    return r.second * (float) (cam.greso[0] * cam.greso[1] * cam.greso[2]);
+}
+
 static void render_secondary_edges(const Scene &sc, const RenderArgs &ra, float *dimg) {
     if (sc.sppse <= 0) return;
     const Camera &cam = sc.cameras[ra.sensor];
@@ -1007,11 +1120,15 @@ static void render_secondary_edges(const Scene &sc, const RenderArgs &ra, float 
         Pcg32 rng = make_sampler((uint64_t) (i + ra.seed), (uint64_t) i);
         for (int k = 0; k < ra.skip[2]; ++k) rng.next_1d();
         float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+        V3f sample3(d3, d2, d1);
+        float pdf0 = 1.f;
+        if (cam.guided) pdf0 = guide_sample_reuse(cam, sample3);   // path.cpp:279-281
         V3f value0, tangent;
-        int pix = eval_secondary_edge(sc, cam, V3f(d3, d2, d1), value0, tangent);
+        int pix = eval_secondary_edge(sc, cam, sample3, value0, tangent);
         if (pix < 0) continue;
         for (int c = 0; c < 3; ++c) {
             float t = tangent[c];
+            if (pdf0 > kEpsilon) t /= pdf0;                          // masked(value, pdf0 > Epsilon) /= pdf0
             // deviation: the reference leaves non-finite tangents in (its scrub is commented out,
             // path.cpp:284); a shadow ray parallel to the emitter triangle gives 0*inf here.
             if (!std::isfinite(t)) continue;
@@ -1050,6 +1167,19 @@ int orc_add_diffuse(void *h, const float *refl, const float *d_refl, int two_sid
     Bsdf b;
     b.reflectance = V3d(Dual(refl[0], d_refl ? d_refl[0] : 0.f), Dual(refl[1], d_refl ? d_refl[1] : 0.f),
                         Dual(refl[2], d_refl ? d_refl[2] : 0.f));
+    b.two_side = two_side != 0;
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+}
+
+// MicrofacetBSDF(specular, diffuse, roughness); d = [d_spec(3), d_diff(3), d_rough(1)] or NULL
+int orc_add_microfacet(void *h, const float *spec, const float *diff, float rough, const float *d, int two_side) {
+    Scene *s = (Scene *) h;
+    Bsdf b;
+    b.type = 1;
+    b.specular = V3d(Dual(spec[0], d ? d[0] : 0.f), Dual(spec[1], d ? d[1] : 0.f), Dual(spec[2], d ? d[2] : 0.f));
+    b.reflectance = V3d(Dual(diff[0], d ? d[3] : 0.f), Dual(diff[1], d ? d[4] : 0.f), Dual(diff[2], d ? d[5] : 0.f));
+    b.roughness = Dual(rough, d ? d[6] : 0.f);
     b.two_side = two_side != 0;
     s->bsdfs.push_back(b);
     return (int) s->bsdfs.size() - 1;
@@ -1133,6 +1263,55 @@ int orc_render(void *h, int sensor, int max_depth, int seed, int mode, int terms
         if ((terms & 2) && sc.sppe > 0) render_primary_edges(sc, ra, dimg);
         if ((terms & 4) && sc.sppse > 0) render_secondary_edges(sc, ra, dimg);
     }
+    return 0;
+}
+
+// PathTracer::preprocess_secondary_edges (reference src/integrator/path.cpp:130-168)
+int orc_preprocess_secondary_edges(void *h, int sensor, const int *reso, int nrounds, int seed, float *mass_out) {
+    Scene &sc = *(Scene *) h;
+    if (!sc.configured) { sc.error = "Scene needs to be configured!"; return 1; }
+    Camera &cam = sc.cameras[sensor];
+    const int ncells = reso[0] * reso[1] * reso[2];
+    const int64_t N = (int64_t) ncells * reso[3];
+    std::vector<double> acc(ncells, 0.0);
+    std::vector<float> mass(ncells, 0.f);
+    cam.guided = false;
+    (void) N;
+    (void) acc;
+    // one cell at a time, its samples in lane order: a fixed summation order (the reference's
+    // scatter_reduce order is unspecified)
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int cell = 0; cell < ncells; ++cell) {
+        int c0 = cell / (reso[1] * reso[2]);
+        int rem = cell - c0 * (reso[1] * reso[2]);
+        int c1 = rem / reso[2], c2 = rem - c1 * reso[2];
+        float total = 0.f;
+        for (int j = 0; j < nrounds; ++j)
+            for (int k2 = 0; k2 < reso[3]; ++k2) {
+                int64_t i = (int64_t) cell * reso[3] + k2;
+                Pcg32 rng = make_sampler((uint64_t) (i + seed), (uint64_t) i);
+                for (int k = 0; k < 3 * j; ++k) rng.next_1d();
+                float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+                V3f s3(((float) c0 + d3) * (1.f / (float) reso[0]), ((float) c1 + d2) * (1.f / (float) reso[1]),
+                       ((float) c2 + d1) * (1.f / (float) reso[2]));
+                V3f value0, tangent;
+                eval_secondary_edge(sc, cam, s3, value0, tangent);
+                float m = 0.f;
+                for (int c = 0; c < 3; ++c) {
+                    float v = value0[c];
+                    if (!std::isfinite(v)) v = 0.f;
+                    if (reso[3] > 1) v /= (float) reso[3];
+                    m = c == 0 ? v : std::fmax(m, v);
+                }
+                total += m;
+            }
+        mass[cell] = total;
+    }
+    if (nrounds > 1) for (float &m : mass) m /= (float) nrounds;
+    cam.greso[0] = reso[0]; cam.greso[1] = reso[1]; cam.greso[2] = reso[2];
+    cam.guide.init(mass);
+    cam.guided = true;
+    if (mass_out) std::copy(mass.begin(), mass.end(), mass_out);
     return 0;
 }
 

@@ -38,6 +38,7 @@ def lib():
         L.orc_error.argtypes = [C.c_void_p]
         L.orc_set_li_order.argtypes = [C.c_void_p, C.c_int]
         L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
+        L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
         L.orc_add_mesh.argtypes = [C.c_void_p, _f, _f, C.c_int, _i, C.c_int, _f, C.c_int, _i, _f, _f, C.c_int, _f, _f, C.c_int, C.c_int]
         L.orc_add_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f, _f]
         L.orc_configure.argtypes = [C.c_void_p, _i, C.c_int]
@@ -46,6 +47,7 @@ def lib():
         L.orc_num_mesh_edges.argtypes = [C.c_void_p, C.c_int]
         L.orc_mesh_edges.argtypes = [C.c_void_p, C.c_int, _i]
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i, _i, C.c_int, _f, _f, _f]
+        L.orc_preprocess_secondary_edges.argtypes = [C.c_void_p, C.c_int, _i, C.c_int, C.c_int, _f]
         L.orc_sampler_draws.argtypes = [C.c_int64, C.c_int, C.c_int, _f]
         L.orc_pmf_sample.argtypes = [_f, C.c_int, _f, C.c_int, _i, _f, _f]
         L.orc_aov.argtypes = [C.c_void_p, C.c_int, C.c_int, _f]
@@ -116,6 +118,13 @@ class OracleScene:
         self.bsdf_ids[name] = idx
         return idx
 
+    def add_microfacet(self, name, spec, diff, rough, d=None, two_side=False):
+        """d = (d_spec[3], d_diff[3], d_rough) flattened to 7 floats, or None"""
+        sp, df, dd = _f32(spec), _f32(diff), _f32(d)
+        idx = self.L.orc_add_microfacet(self.h, _fp(sp), _fp(df), float(rough), _fp(dd), int(two_side))
+        self.bsdf_ids[name] = idx
+        return idx
+
     def add_mesh(self, v, f, bsdf, uv=None, fuv=None, to_world=None, d_to_world=None, dv=None, radiance=None,
                  d_radiance=None, use_face_normals=False, enable_edges=True):
         v = _f32(v, (-1, 3))
@@ -171,6 +180,14 @@ class OracleScene:
         if lane_out:
             return img, dimg, lanes
         return (img, dimg) if mode == 1 else img
+
+    def preprocess_secondary_edges(self, sensor, reso, nrounds=1, seed=0):
+        r = np.asarray(reso, dtype=np.int32)
+        mass = np.zeros(int(r[0]) * int(r[1]) * int(r[2]), dtype=np.float32)
+        rc = self.L.orc_preprocess_secondary_edges(self.h, sensor, _ip(r), nrounds, seed, _fp(mass))
+        if rc:
+            raise RuntimeError(self.L.orc_error(self.h).decode())
+        return mass
 
     def aov(self, sensor=0, seed=0):
         out = np.zeros((self.width * self.height * self.spp, 14), dtype=np.float32)

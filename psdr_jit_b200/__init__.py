@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib, scenes  # noqa: F401
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "AreaLight", "Mesh", "PathTracer", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "Mesh", "PathTracer", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
@@ -151,6 +151,27 @@ class DiffuseBSDF(BSDF):
     def _clone(self):
         b = DiffuseBSDF(self.reflectance)
         b.d_reflectance = self.d_reflectance.copy()
+        b.twoSide = self.twoSide
+        return b
+
+
+class MicrofacetBSDF(BSDF):
+    """reference src/psdr.cpp:298-304, src/bsdf/microfacet.cpp.  Argument order as in the reference:
+    (specular, diffuse, roughness) (include/psdr/bsdf/microfacet.h:12); 1x1 bitmaps."""
+
+    def __init__(self, specular=None, diffuse=None, roughness=None):
+        self.specularReflectance = np.full(3, 0.04, dtype=np.float32) if specular is None else _f32(specular, (3,)).copy()
+        self.diffuseReflectance = np.full(3, 0.5, dtype=np.float32) if diffuse is None else _f32(diffuse, (3,)).copy()
+        self.roughness = np.float32(0.8) if roughness is None else (roughness if hasattr(roughness, "requires_grad") else np.float32(roughness))
+        self.d_specularReflectance = np.zeros(3, dtype=np.float32)
+        self.d_diffuseReflectance = np.zeros(3, dtype=np.float32)
+        self.d_roughness = np.float32(0.0)
+
+    def _clone(self):
+        b = MicrofacetBSDF(self.specularReflectance, self.diffuseReflectance, self.roughness)
+        b.d_specularReflectance = _f32(self.d_specularReflectance, (3,)).copy()
+        b.d_diffuseReflectance = _f32(self.d_diffuseReflectance, (3,)).copy()
+        b.d_roughness = np.float32(self.d_roughness)
         b.twoSide = self.twoSide
         return b
 
@@ -325,7 +346,7 @@ class Scene(Object):
         self._register("Sensor", self._sensors)
 
     def add_BSDF(self, bsdf: BSDF, name: str, twoSide: bool = False):
-        if not isinstance(bsdf, DiffuseBSDF):
+        if not isinstance(bsdf, (DiffuseBSDF, MicrofacetBSDF)):
             raise RuntimeError("Unknown BSDF type!")
         if ("BSDF[id=%s]" % name) in self.param_map:
             raise RuntimeError("Duplicate BSDF id: " + name)
@@ -405,7 +426,12 @@ class Scene(Object):
         _lib.check(L.psdr_scene_set_options(self._h, o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level))
         _lib.check(L.psdr_scene_set_seed(self._h, int(self.seed)))
         for b in self._bsdfs[self._pushed[0]:]:
-            if L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(_f32(b.reflectance)), int(b.twoSide)) < 0:
+            if isinstance(b, MicrofacetBSDF):
+                rc = L.psdr_scene_add_bsdf_microfacet(self._h, b.id.encode(), _fp(_f32(b.specularReflectance)), _fp(_f32(b.diffuseReflectance)),
+                                                      float(_f32(b.roughness).ravel()[0]), int(b.twoSide))
+            else:
+                rc = L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(_f32(b.reflectance)), int(b.twoSide))
+            if rc < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[0] = len(self._bsdfs)
         for i in range(self._pushed[1], len(self._meshes)):
@@ -440,7 +466,12 @@ class Scene(Object):
             push(_lib.SENSOR_TO_WORLD_RAW, i, s.to_world, s.d_to_world)
             push(_lib.SENSOR_TO_WORLD_RIGHT, i, s.to_world_right, s.d_to_world_right)
         for i, b in enumerate(self._bsdfs):
-            push(_lib.BSDF_REFLECTANCE, i, b.reflectance, b.d_reflectance)
+            if isinstance(b, MicrofacetBSDF):
+                push(_lib.BSDF_REFLECTANCE, i, b.diffuseReflectance, b.d_diffuseReflectance)
+                push(_lib.BSDF_SPECULAR, i, b.specularReflectance, b.d_specularReflectance)
+                push(_lib.BSDF_ROUGHNESS, i, np.reshape(_f32(b.roughness), (1,)), np.reshape(_f32(b.d_roughness), (1,)))
+            else:
+                push(_lib.BSDF_REFLECTANCE, i, b.reflectance, b.d_reflectance)
         for i, e in enumerate(self._emitters):
             push(_lib.EMITTER_RADIANCE, i, e.radiance, e.d_radiance)
         act = np.asarray(list(active_sensor), dtype=np.int32)
@@ -455,7 +486,8 @@ class Scene(Object):
                              ("to_world", _lib.MESH_TO_WORLD_RAW), ("to_world_right", _lib.MESH_TO_WORLD_RIGHT)),
                     "Sensor": (("to_world_left", _lib.SENSOR_TO_WORLD_LEFT), ("to_world", _lib.SENSOR_TO_WORLD_RAW),
                                ("to_world_right", _lib.SENSOR_TO_WORLD_RIGHT)),
-                    "BSDF": (("reflectance", _lib.BSDF_REFLECTANCE),),
+                    "BSDF": (("reflectance", _lib.BSDF_REFLECTANCE), ("diffuseReflectance", _lib.BSDF_REFLECTANCE),
+                             ("specularReflectance", _lib.BSDF_SPECULAR), ("roughness", _lib.BSDF_ROUGHNESS)),
                     "Emitter": (("radiance", _lib.EMITTER_RADIANCE),)}
 
     def _objects(self):
@@ -638,6 +670,33 @@ class PathTracer(Integrator):
             raise RuntimeError("max_depth >= 0")
         self.max_depth = int(max_depth)
         self.hide_emitters = False
+        self._guided = set()          # (id(scene), sensor) pairs this integrator has a guiding grid for
+
+    def preprocess_secondary_edges(self, scene: Scene, sensor_id: int, reso, nrounds: int = 1, seed: int = 0):
+        """reference PathTracer::preprocess_secondary_edges (src/integrator/path.cpp:130-168)."""
+        if nrounds <= 0:
+            raise RuntimeError("nrounds > 0")
+        if scene._h is None or not scene.is_ready():
+            raise RuntimeError("Scene needs to be configured!")
+        torch = self._torch()
+        r = np.asarray(list(reso), dtype=np.int32)
+        if r.shape != (4,):
+            raise RuntimeError("reso = [rx, ry, rz, samples per cell]")
+        _lib.check(_lib.load().psdr_preprocess_secondary_edges(scene._h, sensor_id, _ip(r), int(nrounds), int(seed),
+                                                               torch.cuda.current_stream().cuda_stream))
+        self._guided.add((id(scene), sensor_id))
+
+    def guiding_mass(self, scene: Scene, sensor_id: int = 0):
+        L = _lib.load()
+        n = L.psdr_scene_query(scene._h, _lib.Q_GUIDING_CELLS, sensor_id)
+        out = np.zeros(max(n, 0), dtype=np.float32)
+        _lib.check(L.psdr_scene_guiding_mass(scene._h, sensor_id, _fp(out), out.size))
+        return out
+
+    def _check(self, scene: Scene):
+        super()._check(scene)
+        for i in range(scene.num_sensors):      # the grid belongs to the integrator in the reference
+            _lib.check(_lib.load().psdr_scene_set_guiding(scene._h, i, int((id(scene), i) in getattr(self, "_guided", ()))))
 
 
 def _render_d_autograd(integ: Integrator, scene: Scene, sensor_id: int, seed: int, batch_pix, leaves):

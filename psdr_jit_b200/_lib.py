@@ -18,19 +18,19 @@ P_I = C.POINTER(C.c_int)
 # parameter kinds / queries / terms (include/psdr_b200.h)
 MESH_VERTICES, MESH_TO_WORLD_LEFT, MESH_TO_WORLD_RAW, MESH_TO_WORLD_RIGHT = 0, 1, 2, 3
 SENSOR_TO_WORLD_LEFT, SENSOR_TO_WORLD_RAW, SENSOR_TO_WORLD_RIGHT = 4, 5, 6
-BSDF_REFLECTANCE, EMITTER_RADIANCE = 7, 8
+BSDF_REFLECTANCE, EMITTER_RADIANCE, BSDF_SPECULAR, BSDF_ROUGHNESS = 7, 8, 9, 10
 Q_NUM_MESHES, Q_NUM_SENSORS, Q_NUM_EMITTERS, Q_NUM_TRIANGLES, Q_NUM_PRIMARY_EDGES, Q_NUM_SECONDARY_EDGES = 0, 1, 2, 3, 4, 5
-Q_NUM_MESH_EDGES, Q_NUM_MESH_VERTICES, Q_NUM_MESH_FACES, Q_IS_CONFIGURED, Q_USES_BVH, Q_UPLOAD_BYTES = 6, 7, 8, 9, 10, 11
+Q_NUM_MESH_EDGES, Q_NUM_MESH_VERTICES, Q_NUM_MESH_FACES, Q_IS_CONFIGURED, Q_USES_BVH, Q_UPLOAD_BYTES, Q_GUIDING_CELLS = 6, 7, 8, 9, 10, 11, 12
 TERM_INTERIOR, TERM_PRIMARY_EDGES, TERM_SECONDARY_EDGES, TERM_ALL = 1, 2, 4, 7
 
 EXPORTS = [
     "psdr_last_error", "psdr_version", "psdr_kernel_launch_count", "psdr_scene_create", "psdr_scene_destroy",
     "psdr_scene_set_options", "psdr_scene_set_seed", "psdr_scene_set_shard", "psdr_scene_set_accel",
-    "psdr_scene_add_bsdf_diffuse", "psdr_scene_add_mesh", "psdr_scene_add_perspective", "psdr_scene_set_param",
+    "psdr_scene_add_bsdf_diffuse", "psdr_scene_add_bsdf_microfacet", "psdr_scene_add_mesh", "psdr_scene_add_perspective", "psdr_scene_set_param",
     "psdr_scene_set_tangent", "psdr_scene_clear_tangents", "psdr_scene_configure", "psdr_scene_last_configure_ms",
     "psdr_scene_query", "psdr_scene_mesh_edges", "psdr_render_c", "psdr_render_d", "psdr_render_c_host",
     "psdr_render_d_host", "psdr_render_aov", "psdr_sampler_draws", "psdr_scene_enable_timing", "psdr_scene_kernel_ms",
-    "psdr_render_vjp", "psdr_scene_get_grad", "psdr_scene_get_sampler_state", "psdr_scene_set_sampler_state",
+    "psdr_preprocess_secondary_edges", "psdr_scene_set_guiding", "psdr_scene_guiding_mass", "psdr_render_vjp", "psdr_scene_get_grad", "psdr_scene_get_sampler_state", "psdr_scene_set_sampler_state",
 ]
 
 
@@ -55,6 +55,7 @@ def load():
     L.psdr_scene_set_shard.argtypes = [vp, i, i]
     L.psdr_scene_set_accel.argtypes = [vp, i]
     L.psdr_scene_add_bsdf_diffuse.argtypes = [vp, C.c_char_p, P_F, i]
+    L.psdr_scene_add_bsdf_microfacet.argtypes = [vp, C.c_char_p, P_F, P_F, f, i]
     L.psdr_scene_add_mesh.argtypes = [vp, P_F, i, P_I, i, P_F, i, P_I, P_F, C.c_char_p, P_F, i, i]
     L.psdr_scene_add_perspective.argtypes = [vp, f, f, f, P_F]
     L.psdr_scene_set_param.argtypes = [vp, i, i, P_F, i]
@@ -74,6 +75,9 @@ def load():
     L.psdr_render_d_host.argtypes = [vp, i, i, ll, i, i, i, P_I, i, P_F, P_F]
     L.psdr_render_aov.argtypes = [vp, i, ll, vp, vp]
     L.psdr_sampler_draws.argtypes = [ll, i, i, P_F]
+    L.psdr_preprocess_secondary_edges.argtypes = [vp, i, P_I, i, ll, vp]
+    L.psdr_scene_set_guiding.argtypes = [vp, i, i]
+    L.psdr_scene_guiding_mass.argtypes = [vp, i, P_F, i]
     L.psdr_render_vjp.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp, vp]
     L.psdr_scene_get_grad.argtypes = [vp, i, i, P_F, i]
     L.psdr_scene_get_sampler_state.argtypes = [vp, C.POINTER(ll)]

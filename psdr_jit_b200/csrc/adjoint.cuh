@@ -82,14 +82,56 @@ template <int kD> struct PathRecord {
 };
 
 // ---- isotropic BSDF as a function of the three cosines (what the adjoint differentiates) ---------
-// ci = cos(wi, sh_n), co = cos(wo, sh_n), cio = dot(wi, wo).  Diffuse: reference src/bsdf/diffuse.cpp:23-55.
-template <class S> __device__ __forceinline__ V3<S> bsdf_iso(const DBsdf &b, S ci, S co, S cio) {
+// ci = cos(wi, sh_n), co = cos(wo, sh_n), cio = dot(wi, wo).  Diffuse: reference src/bsdf/diffuse.cpp:23-55;
+// Microfacet: src/bsdf/microfacet.cpp:22-68 + src/bsdf/ggx.cpp rewritten in frame-invariant quantities
+// (|wi + wo|^2 = 2 + 2 cio, H.z = (ci + co)/|wi + wo|, <wi,H> = <wo,H> = (1 + cio)/|wi + wo|).
+template <class S> struct BsdfP {
+    int type, two_side;
+    V3<S> diff, spec;
+    S rough;
+};
+template <class S> __device__ __forceinline__ BsdfP<S> bsdf_params(const DBsdf &b) {
+    BsdfP<S> p;
+    p.type = b.type;
+    p.two_side = b.two_side;
+    p.diff = V3<S>(S(b.refl[0]), S(b.refl[1]), S(b.refl[2]));
+    p.spec = V3<S>(S(b.spec[0]), S(b.spec[1]), S(b.spec[2]));
+    p.rough = S(b.rough);
+    return p;
+}
+template <class S> __device__ __forceinline__ S iso_smith_g1(S alpha, S vz, S vdoth) {
+    const S s2 = S(1.f) - sqr(vz);
+    const S xy_alpha_2 = sqr(alpha) * (val(s2) > 0.f ? s2 : S(0.f));
+    S result = S(2.f) / (S(1.f) + sqrt_(S(1.f) + xy_alpha_2 / sqr(vz)));
+    if (val(xy_alpha_2) == 0.f) result = S(1.f);
+    if (val(vdoth) * val(vz) <= 0.f) result = S(0.f);
+    return result;
+}
+// specular lobe without the Fresnel colour: D * G / (4 ci co + 1e-6), and the Fresnel blend weight e
+template <class S> __device__ __forceinline__ void iso_specular(S rough, S ci, S co, S cio, S &dg, S &e) {
+    const S alpha = sqr(rough);
+    const S L = sqrt_(S(2.f) + S(2.f) * cio);
+    const S hz = (ci + co) / L, vh = (S(1.f) + cio) / L;
+    const S s2 = S(1.f) - sqr(hz);
+    const S t = (val(s2) > 0.f ? s2 : S(0.f)) / sqr(alpha) + sqr(hz);
+    S ggx = rcp_(S(kPi) * sqr(alpha) * sqr(t));
+    if (!(val(ggx) * val(hz) > 1e-20f)) ggx = S(0.f);
+    e = exp2_(vh * (S(-5.55473f) * vh - S(6.8316f)));
+    dg = ggx * iso_smith_g1<S>(alpha, ci, vh) * iso_smith_g1<S>(alpha, co, vh) / (S(4.f) * co * ci + S(1e-6f));
+}
+template <class S> __device__ __forceinline__ V3<S> bsdf_iso(const BsdfP<S> &b, S ci, S co, S cio) {
     if (b.two_side) {
         if (signbit_(val(ci))) co = -co;
         ci = abs_(ci);
     }
     if (!(val(ci) > 0.f && val(co) > 0.f)) return V3<S>(S(0.f));
-    return V3<S>(S(b.refl[0]), S(b.refl[1]), S(b.refl[2])) * S(kInvPi) * co;
+    if (b.type == 1) {
+        S dg, e;
+        iso_specular<S>(b.rough, ci, co, cio, dg, e);
+        const V3<S> fresnel = b.spec + (V3<S>(S(1.f)) - b.spec) * e;
+        return (b.diff * S(kInvPi) + fresnel * dg) * co;
+    }
+    return b.diff * S(kInvPi) * co;
 }
 
 struct BsdfJet {        // value and partials of sum_c W_c f_c
@@ -98,25 +140,45 @@ struct BsdfJet {        // value and partials of sum_c W_c f_c
 };
 __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, float ci, float co, float cio, V3f W) {
     BsdfJet j;
-    const V3d a = bsdf_iso<Dual>(b, Dual(ci, 1.f), Dual(co), Dual(cio));
-    const V3d c = bsdf_iso<Dual>(b, Dual(ci), Dual(co, 1.f), Dual(cio));
-    const V3d e = bsdf_iso<Dual>(b, Dual(ci), Dual(co), Dual(cio, 1.f));
+    const BsdfP<Dual> p = bsdf_params<Dual>(b);
+    const V3d a = bsdf_iso<Dual>(p, Dual(ci, 1.f), Dual(co), Dual(cio));
+    const V3d c = bsdf_iso<Dual>(p, Dual(ci), Dual(co, 1.f), Dual(cio));
     j.f = val(a);
     j.d_ci = W.x * a.x.d + W.y * a.y.d + W.z * a.z.d;
     j.d_co = W.x * c.x.d + W.y * c.y.d + W.z * c.z.d;
-    j.d_cio = W.x * e.x.d + W.y * e.y.d + W.z * e.z.d;
+    j.d_cio = 0.f;
+    if (b.type == 1) {
+        const V3d e = bsdf_iso<Dual>(p, Dual(ci), Dual(co), Dual(cio, 1.f));
+        j.d_cio = W.x * e.x.d + W.y * e.y.d + W.z * e.z.d;
+    }
     return j;
 }
-// d(sum_c W_c f_c * scale)/d(params): Diffuse reflectance
+// d(sum_c W_c f_c * scale)/d(params): reflectance (Diffuse / Microfacet diffuse), Microfacet specular + roughness
 __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, float ci, float co,
-                                                V3f W, float scale) {
+                                                float cio, V3f W, float scale) {
     if (b.two_side) {
         if (signbit_(ci)) co = -co;
         ci = fabsf(ci);
     }
     if (!(ci > 0.f && co > 0.f)) return;
+    const int base = gl.off_bsdf + kGradBsdf * bi;
     const float k = kInvPi * co * scale;
-    acc.add3(gl.off_bsdf + 4 * bi, V3f(W.x * k, W.y * k, W.z * k));
+    acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));
+    if (b.type == 1) {
+        Dual dg, e;
+        iso_specular<Dual>(Dual(b.rough, 1.f), Dual(ci), Dual(co), Dual(cio), dg, e);
+        // f_spec,c = (F0_c + (1 - F0_c) e) dg co
+        const float ks = (1.f - e.v) * dg.v * co * scale;
+        acc.add3(base + 4, V3f(W.x * ks, W.y * ks, W.z * ks));
+        float gr = 0.f;
+        const float F0[3] = {b.spec[0], b.spec[1], b.spec[2]}, Wc[3] = {W.x, W.y, W.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const Dual fr = Dual(F0[c]) + Dual(1.f - F0[c]) * e;
+            gr += Wc[c] * (fr * dg).d;
+        }
+        acc.add(base + 3, gr * co * scale);
+    }
 }
 
 // ---- geometry of a recorded vertex ---------------------------------------------------------------
@@ -242,7 +304,7 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const float phi = W.x * j.f.x + W.y * j.f.y + W.z * j.f.z;          // sum_c W_c f_c
     // C = phi * G * J * scale
     const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
-    bsdf_param_grad(acc, gl, x.bsdf, b, ci, co, W, G * scale);
+    bsdf_param_grad(acc, gl, x.bsdf, b, ci, co, cio, W, G * scale);
     const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
     const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) / (t * t);
     const float t_bar = G_bar * (-2.f * fabsf(cy) / (t * t * t));

@@ -142,6 +142,23 @@ int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float refle
     return (int) sc.bsdfs.size() - 1;
 }
 
+int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float specular[3], const float diffuse[3], float roughness,
+                                   int two_side) {
+    if (!s || !id || !specular || !diffuse) { fail("null argument"); return -1; }
+    Scene &sc = s->sc;
+    if (sc.find_bsdf(id) >= 0) { fail(std::string("Duplicate BSDF id: ") + id); return -1; }
+    HBsdf b;
+    b.id = id;
+    b.type = 1;
+    b.reflectance = V3d(Dual(diffuse[0]), Dual(diffuse[1]), Dual(diffuse[2]));
+    b.specular = V3d(Dual(specular[0]), Dual(specular[1]), Dual(specular[2]));
+    b.roughness = Dual(roughness);
+    b.two_side = two_side != 0;
+    sc.bsdfs.push_back(b);
+    sc.configured = false;
+    return (int) sc.bsdfs.size() - 1;
+}
+
 int psdr_scene_add_mesh(psdr_scene *s, const float *v, int nv, const int *f, int nf, const float *uv, int nuv, const int *fuv,
                         const float *to_world, const char *bsdf_id, const float *radiance, int use_face_normals, int enable_edges) {
     if (!s || !v || !f || !bsdf_id || nv <= 0 || nf <= 0) { fail("invalid mesh arguments"); return -1; }
@@ -226,6 +243,18 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
             put(sc.bsdfs[index].reflectance.x, data[0]); put(sc.bsdfs[index].reflectance.y, data[1]); put(sc.bsdfs[index].reflectance.z, data[2]);
             break;
         }
+        case PSDR_BSDF_SPECULAR: {
+            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            if (n != 3) return fail("specular reflectance is 3 floats");
+            put(sc.bsdfs[index].specular.x, data[0]); put(sc.bsdfs[index].specular.y, data[1]); put(sc.bsdfs[index].specular.z, data[2]);
+            break;
+        }
+        case PSDR_BSDF_ROUGHNESS: {
+            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            if (n != 1) return fail("roughness is 1 float");
+            put(sc.bsdfs[index].roughness, data[0]);
+            break;
+        }
         case PSDR_EMITTER_RADIANCE: {
             if (index < 0 || index >= (int) sc.emitters.size()) return fail("invalid emitter index");
             if (n != 3) return fail("radiance is 3 floats");
@@ -252,7 +281,7 @@ int psdr_scene_clear_tangents(psdr_scene *s) {
     for (HCamera &c : sc.cameras)
         for (auto &M : c.to_world)
             for (int i = 0; i < 16; ++i) M.m[i / 4][i % 4].d = 0.f;
-    for (HBsdf &b : sc.bsdfs) b.reflectance = detach(b.reflectance);
+    for (HBsdf &b : sc.bsdfs) { b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
     for (HEmitter &e : sc.emitters) e.radiance = detach(e.radiance);
     sc.configured = false;
     return 0;
@@ -306,6 +335,8 @@ int psdr_scene_query(psdr_scene *s, int what, int index) {
         case PSDR_Q_IS_CONFIGURED: return sc.configured ? 1 : 0;
         case PSDR_Q_USES_BVH: return sc.dscene.use_bvh;
         case PSDR_Q_UPLOAD_BYTES: return (int) sc.upload_bytes;
+        case PSDR_Q_GUIDING_CELLS:
+            return (index >= 0 && index < (int) sc.cameras.size() && sc.cameras[index].guide_ready) ? (int) sc.cameras[index].guide.pmf.size() : 0;
         default: fail("unknown query"); return -1;
     }
 }
@@ -543,6 +574,12 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
         case PSDR_BSDF_REFLECTANCE:
             if (index < 0 || 3 * index + 3 > (int) g.bsdf_refl.size()) return fail("invalid BSDF index");
             return copy(g.bsdf_refl.data() + 3 * index, 3);
+        case PSDR_BSDF_SPECULAR:
+            if (index < 0 || 3 * index + 3 > (int) g.bsdf_spec.size()) return fail("invalid BSDF index");
+            return copy(g.bsdf_spec.data() + 3 * index, 3);
+        case PSDR_BSDF_ROUGHNESS:
+            if (index < 0 || index >= (int) g.bsdf_rough.size()) return fail("invalid BSDF index");
+            return copy(g.bsdf_rough.data() + index, 1);
         case PSDR_EMITTER_RADIANCE:
             if (index < 0 || 3 * index + 3 > (int) g.emitter_rad.size()) return fail("invalid emitter index");
             return copy(g.emitter_rad.data() + 3 * index, 3);
@@ -565,6 +602,64 @@ int psdr_scene_set_sampler_state(psdr_scene *s, const long long state[6]) {
         s->sc.samplers[k].seed = state[2 * k] >= 0 ? state[2 * k] : 0;
         s->sc.samplers[k].consumed = (unsigned long long) state[2 * k + 1];
     }
+    return 0;
+}
+
+int psdr_preprocess_secondary_edges(psdr_scene *s, int sensor, const int reso[4], int nrounds, long long seed, void *cuda_stream) {
+    if (!s || !reso) return fail("null argument");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    cudaStream_t st = (cudaStream_t) cuda_stream;
+    if (nrounds <= 0) throw std::runtime_error("nrounds > 0");
+    if (!sc.configured) throw std::runtime_error("Scene needs to be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    if (reso[0] <= 0 || reso[1] <= 0 || reso[2] <= 0 || reso[3] <= 0) throw std::runtime_error("invalid guiding resolution");
+    const long long cells = (long long) reso[0] * reso[1] * reso[2];
+    if (cells * reso[3] > 2147483647LL) throw std::runtime_error("num_samples <= std::numeric_limits<int>::max()");
+    if (sc.dscene.n_sec_edges <= 0) throw std::runtime_error("no secondary edges (sppse must be > 0 at configure)");
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    float *d_mass = nullptr;
+    cuda_ok(cudaMalloc(&d_mass, sizeof(float) * cells), "cudaMalloc(guiding mass)");
+    std::vector<float> mass((size_t) cells);
+    DCamera cam = sc.dcameras[sensor];
+    cam.guided = 0;                                  // the pre-pass samples the unit cube directly
+    cudaError_t e = launch_guiding(sc.dscene, cam, reso, nrounds, seed, d_mass, st);
+    g_launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mass.data(), d_mass, sizeof(float) * cells, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_mass);
+    cuda_ok(e, "guiding pre-pass");
+    if (nrounds > 1) for (float &m : mass) m /= (float) nrounds;
+    HCamera &hc = sc.cameras[sensor];
+    hc.guide.init(mass);
+    for (int k = 0; k < 3; ++k) hc.greso[k] = reso[k];
+    hc.guide_ready = true;
+    hc.guide_enabled = true;
+    sc.refresh_tables();                             // re-upload so that the kernels see the grid
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_scene_set_guiding(psdr_scene *s, int sensor, int enabled) {
+    if (!s) return fail("null scene");
+    Scene &sc = s->sc;
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) return fail("Invalid sensor id!");
+    HCamera &hc = sc.cameras[sensor];
+    const bool on = enabled != 0 && hc.guide_ready;
+    if (on != hc.guide_enabled) {
+        hc.guide_enabled = on;
+        if (sensor < (int) sc.dcameras.size()) sc.dcameras[sensor].guided = on ? 1 : 0;
+    }
+    return 0;
+}
+
+int psdr_scene_guiding_mass(psdr_scene *s, int sensor, float *out, int n) {
+    if (!s || !out) return fail("null argument");
+    const Scene &sc = s->sc;
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) return fail("Invalid sensor id!");
+    const HCamera &hc = sc.cameras[sensor];
+    if (!hc.guide_ready || n != (int) hc.guide.pmf.size()) return fail("no guiding grid of that size");
+    std::memcpy(out, hc.guide.pmf.data(), sizeof(float) * n);
     return 0;
 }
 

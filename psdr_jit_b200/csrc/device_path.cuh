@@ -266,11 +266,62 @@ template <> __device__ __forceinline__ V3d bsdf_reflectance<Dual>(const DBsdf &b
     return V3d(Dual(b.refl[0], b.d_refl[0]), Dual(b.refl[1], b.d_refl[1]), Dual(b.refl[2], b.d_refl[2]));
 }
 
+template <class S> __device__ __forceinline__ V3<S> bsdf_specular(const DBsdf &b);
+template <> __device__ __forceinline__ V3f bsdf_specular<float>(const DBsdf &b) { return V3f(b.spec[0], b.spec[1], b.spec[2]); }
+template <> __device__ __forceinline__ V3d bsdf_specular<Dual>(const DBsdf &b) {
+    return V3d(Dual(b.spec[0], b.d_spec[0]), Dual(b.spec[1], b.d_spec[1]), Dual(b.spec[2], b.d_spec[2]));
+}
+template <class S> __device__ __forceinline__ S bsdf_roughness(const DBsdf &b);
+template <> __device__ __forceinline__ float bsdf_roughness<float>(const DBsdf &b) { return b.rough; }
+template <> __device__ __forceinline__ Dual bsdf_roughness<Dual>(const DBsdf &b) { return Dual(b.rough, b.d_rough); }
+
+// ---- GGX (reference src/bsdf/ggx.cpp:13-109), isotropic: alpha_u = alpha_v = alpha ---------------
+template <class S> __device__ __forceinline__ S ggx_eval(S alpha, V3<S> m) {
+    const S alpha_uv = alpha * alpha;
+    const S t = sqr(m.x / alpha) + sqr(m.y / alpha) + sqr(m.z);
+    const S result = rcp_(S(kPi) * alpha_uv * sqr(t));
+    return (val(result) * val(m.z) > 1e-20f) ? result : S(0.f);
+}
+template <class S> __device__ __forceinline__ S ggx_smith_g1(S alpha, V3<S> v, V3<S> m) {
+    const S xy_alpha_2 = sqr(alpha * v.x) + sqr(alpha * v.y);
+    const S tan_theta_alpha_2 = xy_alpha_2 / sqr(v.z);
+    S result = S(2.f) / (S(1.f) + sqrt_(S(1.f) + tan_theta_alpha_2));
+    if (val(xy_alpha_2) == 0.f) result = S(1.f);
+    if (val(dot(v, m)) * val(v.z) <= 0.f) result = S(0.f);
+    return result;
+}
+
+// Microfacet::__eval (reference src/bsdf/microfacet.cpp:22-68): Lambert + GGX specular with the
+// Schlick-Gaussian Fresnel fit; wi, wo in the shading frame
+template <class S> __device__ __forceinline__ V3<S> microfacet_eval(const DBsdf &b, V3<S> wi, V3<S> wo) {
+    if (b.two_side) {
+        if (signbit_(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    const S cos_nv = wi.z, cos_nl = wo.z;
+    if (!(val(cos_nv) > 0.f && val(cos_nl) > 0.f)) return V3<S>(S(0.f));
+    const V3<S> diffuse = bsdf_reflectance<S>(b) * S(kInvPi);
+    const V3<S> H = normalize(wi + wo);
+    const S cos_vh = dot(H, wi);
+    const V3<S> F0 = bsdf_specular<S>(b);
+    const S alpha = sqr(bsdf_roughness<S>(b));
+    const S ggx = ggx_eval<S>(alpha, H);
+    const S coeff = cos_vh * (S(-5.55473f) * cos_vh - S(6.8316f));
+    const S e = exp2_(coeff);
+    const V3<S> fresnel = F0 + (V3<S>(S(1.f)) - F0) * e;
+    const S smithG = ggx_smith_g1<S>(alpha, wi, H) * ggx_smith_g1<S>(alpha, wo, H);
+    const V3<S> numerator = fresnel * (ggx * smithG);
+    const S denominator = S(4.f) * cos_nl * cos_nv;
+    const V3<S> specular = numerator / (denominator + S(1e-6f));
+    return (diffuse + specular) * cos_nl;
+}
+
 template <class S> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return V3<S>(S(0.f));
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return V3<S>(S(0.f));
     const DBsdf &b = sc.bsdfs[bi];
+    if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (signbit_(val(wiz))) wo.z = -wo.z;
@@ -280,10 +331,23 @@ template <class S> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, 
     return bsdf_reflectance<S>(b) * S(kInvPi) * wo.z;
 }
 
+// Microfacet::__pdf (reference src/bsdf/microfacet.cpp:108-133), detached
+__device__ __forceinline__ float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo) {
+    if (b.two_side) {
+        if (signbit_(wi.z)) wo.z = -wo.z;
+        wi.z = fabsf(wi.z);
+    }
+    const V3f m = normalize(wo + wi);
+    if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
+    const float alpha = sqr(b.rough);
+    return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
+}
+
 template <class S> __device__ __forceinline__ float bsdf_pdf(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return 0.f;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return 0.f;
+    if (sc.bsdfs[bi].type == 1) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo));
     float wiz = val(its.wi.z), woz = val(wo.z);
     if (sc.bsdfs[bi].two_side) {
         if (signbit_(wiz)) woz = -woz;
@@ -311,6 +375,39 @@ __device__ __forceinline__ V2f square_to_uniform_disk_concentric(V2f s) {
     return V2f(r * cs, r * sn);
 }
 
+// GGXDistribution::sample_visible_11 (reference src/bsdf/ggx.cpp:99-109)
+__device__ __forceinline__ V2f ggx_sample_visible_11(float cos_theta_i, V2f sample) {
+    V2f p = square_to_uniform_disk_concentric(sample);
+    const float s = .5f * (1.f + cos_theta_i);
+    const float a = safe_sqrt(1.f - sqr(p.x));
+    p.y = fmaf(p.y, s, fmaf(-a, s, a));                       // lerp(a, p.y, s)
+    const float x = p.x, y = p.y, z = safe_sqrt(1.f - fmaf(p.y, p.y, p.x * p.x));
+    const float sin_theta_i = safe_sqrt(1.f - sqr(cos_theta_i));
+    const float norm = 1.f / fmaf(sin_theta_i, y, cos_theta_i * z);
+    return V2f(fmaf(cos_theta_i, y, -(sin_theta_i * z)) * norm, x * norm);
+}
+
+// Microfacet::__sample (reference src/bsdf/microfacet.cpp:80-98) + GGXDistribution::sample (ggx.cpp:36-79)
+__device__ __forceinline__ BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sample, bool active) {
+    BsdfSample bs;
+    if (b.two_side) wi.z = fabsf(wi.z);
+    const float alpha = sqr(b.rough);
+    const V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
+    const float sin_theta_2 = fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / sqrtf(sin_theta_2);
+    const bool pole = fabsf(sin_theta_2) <= 4.f * kEpsilon;
+    const float sin_phi = pole ? 0.f : fminf(fmaxf(wi_p.y * inv_sin_theta, -1.f), 1.f);
+    const float cos_phi = pole ? 1.f : fminf(fmaxf(wi_p.x * inv_sin_theta, -1.f), 1.f);
+    V2f slope = ggx_sample_visible_11(wi_p.z, V2f(sample.x, sample.y));
+    slope = V2f(fmaf(cos_phi, slope.x, -(sin_phi * slope.y)) * alpha, fmaf(sin_phi, slope.x, cos_phi * slope.y) * alpha);
+    const V3f m = normalize(V3f(-slope.x, -slope.y, 1.f));
+    const float m_pdf = ggx_smith_g1<float>(alpha, wi, m) * fabsf(dot(wi, m)) * ggx_eval<float>(alpha, m) / fabsf(wi.z);
+    const float k = 2.f * dot(wi, m);
+    bs.wo = V3f(fmaf(m.x, k, -wi.x), fmaf(m.y, k, -wi.y), fmaf(m.z, k, -wi.z));
+    bs.pdf = m_pdf / (4.f * dot(bs.wo, m));
+    bs.valid = active && (wi.z > 0.f) && (bs.pdf != 0.f) && (bs.wo.z > 0.f);
+    return bs;
+}
+
 template <class S> __device__ __forceinline__ BsdfSample bsdf_sample(const DScene &sc, const Its<S> &its, V3f sample, bool active) {
     BsdfSample bs;
     bs.wo = V3f(0.f, 0.f, 0.f);
@@ -319,6 +416,7 @@ template <class S> __device__ __forceinline__ BsdfSample bsdf_sample(const DScen
     if (!its.valid) return bs;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return bs;
+    if (sc.bsdfs[bi].type == 1) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active);
     float wiz = val(its.wi.z);
     if (sc.bsdfs[bi].two_side) wiz = fabsf(wiz);
     const V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));
@@ -684,6 +782,20 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     const Dual dn = dot(lift3<Dual>(n), u2);
     tangent_out = V3f(value0.x * dn.d, value0.y * dn.d, value0.z * dn.d);
     return sds.pixel;
+}
+
+// HyperCubeDistribution<3>::sample_reuse (reference src/core/cube_distrb.cpp:41-48): the cell is picked with the
+// LAST sample dimension; the sample becomes (cell + sample) * unit; returns pdf = pmf * num_cells
+__device__ __forceinline__ float guide_sample_reuse(const DCamera &cam, V3f &s) {
+    const int ncells = cam.greso[0] * cam.greso[1] * cam.greso[2];
+    float prob;
+    const int idx = sample_reuse(cam.guide_pmf, cam.guide_cmf, ncells, cam.guide_sum, s.z, prob);
+    const int r12 = cam.greso[1] * cam.greso[2];
+    const int c0 = idx / r12, rem = idx - c0 * r12, c1 = rem / cam.greso[2], c2 = rem - c1 * cam.greso[2];
+    s.x = (s.x + (float) c0) * (1.f / (float) cam.greso[0]);
+    s.y = (s.y + (float) c1) * (1.f / (float) cam.greso[1]);
+    s.z = (s.z + (float) c2) * (1.f / (float) cam.greso[2]);
+    return prob * (float) ncells;
 }
 
 template <bool kBvh>

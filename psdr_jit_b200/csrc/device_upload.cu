@@ -85,11 +85,15 @@ void upload_scene(Scene &sc) {
         }
     }
     for (const HBsdf &b : sc.bsdfs) {
-        DBsdf d;
+        DBsdf d{};
         d.refl[0] = b.reflectance.x.v; d.refl[1] = b.reflectance.y.v; d.refl[2] = b.reflectance.z.v;
         d.d_refl[0] = b.reflectance.x.d; d.d_refl[1] = b.reflectance.y.d; d.d_refl[2] = b.reflectance.z.d;
         d.type = b.type;
         d.two_side = b.two_side ? 1 : 0;
+        d.spec[0] = b.specular.x.v; d.spec[1] = b.specular.y.v; d.spec[2] = b.specular.z.v;
+        d.d_spec[0] = b.specular.x.d; d.d_spec[1] = b.specular.y.d; d.d_spec[2] = b.specular.z.d;
+        d.rough = b.roughness.v;
+        d.d_rough = b.roughness.d;
         dbsdf.push_back(d);
     }
     for (const HEmitter &e : sc.emitters) {
@@ -135,6 +139,17 @@ void upload_scene(Scene &sc) {
         }
     }
 
+    std::vector<float> g_pmf, g_cmf;
+    std::vector<size_t> cam_guide_first(sc.cameras.size(), 0);
+    for (size_t ci = 0; ci < sc.cameras.size(); ++ci) {
+        const HCamera &c = sc.cameras[ci];
+        cam_guide_first[ci] = g_pmf.size();
+        if (c.guide_ready) {
+            g_pmf.insert(g_pmf.end(), c.guide.pmf.begin(), c.guide.pmf.end());
+            g_cmf.insert(g_cmf.end(), c.guide.cmf.begin(), c.guide.cmf.end());
+        }
+    }
+
     std::vector<DBvhNode> nodes;
     std::vector<int> order;
     const int ntris = (int) all_tris.size();
@@ -146,7 +161,7 @@ void upload_scene(Scene &sc) {
                  o_mesh = pk.add(dmeshes), o_emit = pk.add(demit), o_bsdf = pk.add(dbsdf), o_fp = pk.add(face_pmf), o_fc = pk.add(face_cmf),
                  o_ep = pk.add(em_pmf), o_ec = pk.add(em_cmf), o_sec = pk.add(sec), o_sp = pk.add(sec_pmf), o_scm = pk.add(sec_cmf),
                  o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
-                 o_nodes = pk.add(nodes), o_order = pk.add(order);
+                 o_nodes = pk.add(nodes), o_order = pk.add(order), o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf);
 
     if (!sc.dev) sc.dev = new DeviceBuffers();
     DeviceBuffers &db = *sc.dev;
@@ -226,6 +241,11 @@ void upload_scene(Scene &sc) {
         dc.pe_pmf = (const float *) (base + o_pp) + pmf_off;
         dc.pe_cmf = (const float *) (base + o_pc) + pmf_off;
         pmf_off += c.edges.size();
+        dc.guided = (c.guide_ready && c.guide_enabled) ? 1 : 0;
+        for (int k = 0; k < 3; ++k) dc.greso[k] = c.greso[k];
+        dc.guide_sum = c.guide_ready ? c.guide.sum : 0.f;
+        dc.guide_pmf = (const float *) (base + o_gp) + cam_guide_first[ci];
+        dc.guide_cmf = (const float *) (base + o_gc) + cam_guide_first[ci];
     }
 }
 

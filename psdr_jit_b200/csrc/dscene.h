@@ -44,10 +44,13 @@ struct DEmitter {
 };
 
 struct DBsdf {
-    float refl[3];
+    float refl[3];           // Diffuse: reflectance; Microfacet: diffuseReflectance
     float d_refl[3];
-    int type;                // 0 diffuse
+    int type;                // 0 Diffuse, 1 Microfacet
     int two_side;
+    float spec[3];           // Microfacet: specularReflectance (F0)
+    float d_spec[3];
+    float rough, d_rough;    // Microfacet: roughness (alpha = roughness^2)
 };
 
 struct DCamera {
@@ -62,6 +65,11 @@ struct DCamera {
     // primary edges: pe_a = (p0.x,p0.y,p1.x,p1.y), pe_da = tangents, pe_b = (nx,ny,len,0)
     const float4 *pe_a, *pe_da, *pe_b;
     const float *pe_pmf, *pe_cmf;
+    // secondary-edge guiding grid (HyperCubeDistribution<3>, reference src/core/cube_distrb.cpp:9-64)
+    int guided;              // 0 = sample3 is used as drawn
+    int greso[3];
+    float guide_sum;
+    const float *guide_pmf, *guide_cmf;
 };
 
 struct DScene {

@@ -135,13 +135,53 @@ __global__ void __launch_bounds__(kBlock) secondary_edge_kernel(const __grid_con
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
         const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+        V3f sample3(d3, d2, d1);
+        float pdf0 = 1.f;
+        if (cam.guided) pdf0 = guide_sample_reuse(cam, sample3);     // path.cpp:279-281
         V3f value0, tangent;
-        const int pix = eval_secondary_edge<kBvh>(sc, cam, V3f(d3, d2, d1), value0, tangent);
+        const int pix = eval_secondary_edge<kBvh>(sc, cam, sample3, value0, tangent);
         if (pix < 0) continue;
-        const float t[3] = {tangent.x, tangent.y, tangent.z};
+        float t[3] = {tangent.x, tangent.y, tangent.z};
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
+            if (pdf0 > kEpsilon) t[c] = t[c] / pdf0;                 // masked(value, pdf0 > Epsilon) /= pdf0
             if (isfinite(t[c]) && t[c] != 0.f) atomicAdd(dimg + 3 * pix + c, t[c] * scale);
+        }
+
+    }
+}
+
+// ---- guiding pre-pass: PathTracer::preprocess_secondary_edges (reference src/integrator/path.cpp:130-168)
+// One thread per grid cell walks that cell's reso[3] x nrounds samples in lane order (a fixed summation
+// order; the reference's scatter_reduce order is unspecified) and writes mass[cell].
+template <bool kBvh>
+__global__ void __launch_bounds__(kBlock) guiding_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, int r0, int r1, int r2,
+                                                          int r3, int nrounds, long long seed, float *__restrict__ mass) {
+    const int ncells = r0 * r1 * r2;
+    for (int cell = blockIdx.x * kBlock + threadIdx.x; cell < ncells; cell += gridDim.x * kBlock) {
+        const int c0 = cell / (r1 * r2), rem = cell - c0 * (r1 * r2), c1 = rem / r2, c2 = rem - c1 * r2;
+        float total = 0.f;
+        for (int j = 0; j < nrounds; ++j)
+            for (int k = 0; k < r3; ++k) {
+                const long long i = (long long) cell * r3 + k;
+                Pcg32 rng;
+                rng.seed((unsigned long long) (i + seed), (unsigned long long) i);
+                if (j) rng.advance(3ull * (unsigned long long) j);
+                const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+                const V3f s3(((float) c0 + d3) * (1.f / (float) r0), ((float) c1 + d2) * (1.f / (float) r1), ((float) c2 + d1) * (1.f / (float) r2));
+                V3f value0, tangent;
+                eval_secondary_edge<kBvh>(sc, cam, s3, value0, tangent);
+                const float v[3] = {value0.x, value0.y, value0.z};
+                float m = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float x = isfinite(v[c]) ? v[c] : 0.f;
+                    if (r3 > 1) x /= (float) r3;
+                    m = c == 0 ? x : fmaxf(m, x);
+                }
+                total += m;
+            }
+        mass[cell] = total;
     }
 }
 
@@ -211,6 +251,14 @@ cudaError_t launch_secondary_edges(const DScene &sc, const DCamera &cam, const R
     if (lanes <= 0 || sc.n_sec_edges <= 0) return cudaSuccess;
     if (sc.use_bvh) secondary_edge_kernel<true><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
     else secondary_edge_kernel<false><<<grid_for(lanes, 8), kBlock, 0, st>>>(sc, cam, rp, dimg);
+    return cudaGetLastError();
+}
+cudaError_t launch_guiding(const DScene &sc, const DCamera &cam, const int reso[4], int nrounds, long long seed, float *mass, cudaStream_t st) {
+    const long long cells = (long long) reso[0] * reso[1] * reso[2];
+    if (cells <= 0) return cudaSuccess;
+    const int grid = grid_for(cells, 8);
+    if (sc.use_bvh) guiding_kernel<true><<<grid, kBlock, 0, st>>>(sc, cam, reso[0], reso[1], reso[2], reso[3], nrounds, seed, mass);
+    else guiding_kernel<false><<<grid, kBlock, 0, st>>>(sc, cam, reso[0], reso[1], reso[2], reso[3], nrounds, seed, mass);
     return cudaGetLastError();
 }
 cudaError_t launch_aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st) {

@@ -112,8 +112,14 @@ __global__ void __launch_bounds__(kBlockV) secondary_edge_vjp_kernel(const __gri
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
         const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+        V3f sample3(d3, d2, d1);
+        SecEdgeAdjoint a2 = adj;
+        if (cam.guided) {
+            const float pdf0 = guide_sample_reuse(cam, sample3);
+            if (pdf0 > kEpsilon) a2.scale = adj.scale / pdf0;
+        }
         V3f value0, tangent;
-        eval_secondary_edge<kBvh, SecEdgeAdjoint>(sc, cam, V3f(d3, d2, d1), value0, tangent, adj);
+        eval_secondary_edge<kBvh, SecEdgeAdjoint>(sc, cam, sample3, value0, tangent, a2);
     }
     grad_acc_end(adj.acc);
 }

@@ -74,6 +74,11 @@ PSDR_HD float abs_(float x) { return fabsf(x); }
 PSDR_HD Dual abs_(Dual x) { return Dual(fabsf(x.v), signbit_(x.v) ? -x.d : x.d); }
 PSDR_HD float rcp_(float x) { return 1.f / x; }
 PSDR_HD Dual rcp_(Dual x) { return 1.f / x; }
+PSDR_HD float exp2_(float x) { return exp2f(x); }
+PSDR_HD Dual exp2_(Dual x) {
+    const float e = exp2f(x.v);
+    return Dual(e, 0.69314718055994530942f * e * x.d);
+}
 PSDR_HD float sqr(float x) { return x * x; }
 PSDR_HD Dual sqr(Dual x) { return x * x; }
 PSDR_HD float fmadd(float a, float b, float c) { return fmaf(a, b, c); }

@@ -479,4 +479,9 @@ void Scene::configure(const int *active, int nactive) {
     last_configure_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
 }
 
+void Scene::refresh_tables() {
+    if (!configured) throw std::runtime_error("Scene needs to be configured!");
+    upload_scene(*this);
+}
+
 }  // namespace psdr

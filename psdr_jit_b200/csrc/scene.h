@@ -30,8 +30,10 @@ struct HEdge {
 
 struct HBsdf {
     std::string id;
-    int type = 0;
-    V3d reflectance;
+    int type = 0;             // 0 Diffuse, 1 Microfacet
+    V3d reflectance;          // Diffuse reflectance / Microfacet diffuseReflectance
+    V3d specular;             // Microfacet specularReflectance
+    Dual roughness;           // Microfacet roughness
     bool two_side = false;
 };
 
@@ -75,6 +77,10 @@ struct HCamera {
     float inv_area = 0.f;
     std::vector<HPrimEdge> edges;
     Distrib edge_distrb;
+    // secondary-edge guiding (PathTracer::preprocess_secondary_edges); survives configure()
+    bool guide_ready = false, guide_enabled = false;
+    int greso[3] = {0, 0, 0};
+    Distrib guide;
 };
 
 struct HSecEdge {
@@ -90,7 +96,8 @@ struct ParamGrads {
     struct CamG { double to_world[3][16]; };
     std::vector<MeshG> meshes;
     std::vector<CamG> cameras;
-    std::vector<double> bsdf_refl, emitter_rad;   // 3 per object
+    std::vector<double> bsdf_refl, emitter_rad, bsdf_spec;   // 3 per object
+    std::vector<double> bsdf_rough;                          // 1 per BSDF
     bool valid = false;
 };
 
@@ -133,6 +140,7 @@ struct Scene {
     ~Scene();
     int find_bsdf(const std::string &id) const;
     void configure(const int *active, int nactive);   // throws std::runtime_error
+    void refresh_tables();                             // re-pack + upload the device tables of a configured scene
 };
 
 // BVH2 over world-space triangles (binned SAH); nodes/order are what DScene points to.

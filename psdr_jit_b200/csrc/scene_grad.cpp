@@ -119,7 +119,7 @@ GradLayout Scene::grad_layout(int sensor) const {
     for (const HMesh &m : meshes) ntris += (int) m.tris.size();
     gl.base = nullptr;
     gl.off_bsdf = kGradTri * ntris;
-    gl.off_emit = gl.off_bsdf + 4 * (int) bsdfs.size();
+    gl.off_emit = gl.off_bsdf + kGradBsdf * (int) bsdfs.size();
     gl.off_cam = gl.off_emit + 4 * (int) emitters.size();
     gl.off_pe = gl.off_cam + kGradCam;
     const int npe = (sensor >= 0 && sensor < (int) cameras.size()) ? (int) cameras[sensor].edges.size() : 0;
@@ -229,8 +229,15 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
         }
         split_product(m.to_world, gtw, out.to_world);
     }
-    for (size_t i = 0; i < bsdfs.size(); ++i)
-        for (int c = 0; c < 3; ++c) grads.bsdf_refl[3 * i + c] = table[gl.off_bsdf + 4 * i + c];
+    grads.bsdf_spec.assign(3 * bsdfs.size(), 0.0);
+    grads.bsdf_rough.assign(bsdfs.size(), 0.0);
+    for (size_t i = 0; i < bsdfs.size(); ++i) {
+        for (int c = 0; c < 3; ++c) {
+            grads.bsdf_refl[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + c];
+            grads.bsdf_spec[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + 4 + c];
+        }
+        grads.bsdf_rough[i] = table[gl.off_bsdf + kGradBsdf * i + 3];
+    }
     for (size_t i = 0; i < emitters.size(); ++i)
         for (int c = 0; c < 3; ++c) grads.emitter_rad[3 * i + c] = table[gl.off_emit + 4 * i + c];
     grads.valid = true;

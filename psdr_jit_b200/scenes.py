@@ -119,6 +119,17 @@ CBOX_BSDFS = [
     ("red", (0.90, 0.20, 0.20)),
 ]
 
+# The same scene with MicrofacetBSDF(specular, diffuse, roughness) materials (BASELINE config 3 uses
+# ([.2,.9,.9], [.01,.01,.01], 0.3) on every non-light mesh; the walls get a rougher, more diffuse one so that
+# both lobes matter).  Entries with 3 fields are Microfacet, with 1 field Diffuse.
+CBOX_MF_BSDFS = [
+    ("light", (0.0, 0.0, 0.0)),
+    ("cat", ((0.2, 0.9, 0.9), (0.01, 0.01, 0.01), 0.3)),
+    ("white", ((0.04, 0.04, 0.04), (0.7, 0.7, 0.7), 0.5)),
+    ("green", ((0.1, 0.3, 0.1), (0.10, 0.60, 0.10), 0.4)),
+    ("red", ((0.3, 0.1, 0.1), (0.60, 0.10, 0.10), 0.6)),
+]
+
 CBOX_CAMERA = dict(fov=60.0, near=1e-6, far=1e7, to_world=translate(278.0, 273.0, -800.0))
 
 

@@ -29,14 +29,22 @@ def translation_tangent(axis_scale):
     return d
 
 
-def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None):
+def is_microfacet(params):
+    return len(params) == 3 and hasattr(params[0], "__len__")
+
+
+def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, bsdfs=None, d_bsdf=None):
     """Scene = scenes.* meshes + CBOX bsdfs + camera; derivative parameter P translates mesh
     `move_mesh` by P*axis_scale through to_world_left (reference README.md:87-90)."""
     from oracle.psdr_oracle import OracleScene
     cam = cam or scenes.CBOX_CAMERA
     sc = OracleScene(w, h, spp, sppe, sppse)
-    for name, refl in scenes.CBOX_BSDFS:
-        sc.add_diffuse(name, refl)
+    for name, params in (bsdfs or scenes.CBOX_BSDFS):
+        d = d_bsdf.get(name) if d_bsdf else None
+        if is_microfacet(params):
+            sc.add_microfacet(name, params[0], params[1], params[2], d=d)
+        else:
+            sc.add_diffuse(name, params, d_refl=d)
     for i, m in enumerate(meshes):
         dtw = None
         if move_mesh is not None and i == move_mesh:
@@ -48,7 +56,7 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
 
 
 def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, accel=-1,
-                  shard=None, two_side=False, d_radiance=None, d_reflectance=None, d_cam_left=None, log_level=0):
+                  shard=None, two_side=False, d_radiance=None, d_reflectance=None, d_cam_left=None, log_level=0, bsdfs=None, d_bsdf=None):
     """The same scene through the product's psdr_jit-style Python surface."""
     import psdr_jit_b200 as psdr
     cam = cam or scenes.CBOX_CAMERA
@@ -58,8 +66,17 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
     sensor = psdr.PerspectiveCamera(cam["fov"], cam["near"], cam["far"])
     sensor.to_world = cam["to_world"]
     sc.add_Sensor(sensor)
-    for name, refl in scenes.CBOX_BSDFS:
-        sc.add_BSDF(psdr.DiffuseBSDF(refl), name, twoSide=two_side)
+    for name, params in (bsdfs or scenes.CBOX_BSDFS):
+        d = d_bsdf.get(name) if d_bsdf else None
+        if is_microfacet(params):
+            b = psdr.MicrofacetBSDF(params[0], params[1], params[2])
+            if d is not None:
+                b.d_specularReflectance, b.d_diffuseReflectance, b.d_roughness = np.float32(d[0:3]), np.float32(d[3:6]), np.float32(d[6])
+        else:
+            b = psdr.DiffuseBSDF(params)
+            if d is not None:
+                b.d_reflectance = np.float32(d)
+        sc.add_BSDF(b, name, twoSide=two_side)
     for i, m in enumerate(meshes):
         mesh = psdr.Mesh()
         mesh.load_raw(m.v, m.f, m.uv, m.fuv)

@@ -200,3 +200,42 @@ def test_python_surface_host_logic():
         psdr.PathTracer(1).renderC(sc, 0, seed=0)
     with pytest.raises(RuntimeError, match="Missing meshes"):
         psdr.Scene().configure()
+
+
+def test_microfacet_vs_reference(oracle):
+    """MicrofacetBSDF (microfacet.cpp, ggx.cpp): renderC and every term of renderD against the running reference."""
+    g = np.load(GOLDEN + "/mf_renderC.npz")
+    for depth, seed in ((1, 0), (3, 3)):
+        img = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS).render(depth, seed=seed, mode=0)
+        r, nbad, r_ex = compare_stats(img, g["img_d%d_seed%d" % (depth, seed)], flip_rel=2e-5)
+        assert r < 2e-3 and nbad <= 40 and r_ex < 2e-5, (depth, r, nbad, r_ex)
+    g = np.load(GOLDEN + "/mf_renderD_128_s4_d2_smallbox.npz")
+    for term, spps, scale in (("interior", (4, 0, 0), 2.0), ("primary", (0, 4, 0), 1.0), ("secondary", (0, 0, 4), 2.0)):
+        osc = build_oracle(scenes.cbox_meshes(), 128, 128, *spps, move_mesh=1, axis_scale=(0.0, 30.0, 50.0), bsdfs=scenes.CBOX_MF_BSDFS)
+        img, dimg = osc.render(2, seed=5, mode=1, terms=7)
+        if spps[0]:
+            r, nbad, r_ex = compare_stats(img, g["img_" + term])
+            assert nbad <= 120 and r_ex < 1e-3, (term, r, nbad, r_ex)
+        r, nbad, r_ex = compare_stats(dimg * scale, g["grad_" + term])
+        assert nbad <= 0.02 * len(dimg) and r_ex < 1e-3, (term, r, nbad, r_ex)
+
+
+def test_guided_secondary_edges_vs_reference(oracle):
+    """HyperCubeDistribution3f semantics pinned on the cases that do not depend on the Monte-Carlo mass values:
+    a 1-cell grid is the identity, a grid whose mass sits in a cell without moving edges yields exactly zero.
+    Grids whose result depends on the mass values are chaotic in the reference itself (the pre-pass keeps a
+    sample only if two fp32 reconstructions of the same point agree to 1e-3 while their typical distance is
+    3e-4) -- for those only the order of magnitude is compared."""
+    g = np.load(GOLDEN + "/guided_probe.npz")
+    kw = dict(move_mesh=8, axis_scale=(40.0, 20.0, 0.0))
+
+    def run(reso, seed):
+        osc = build_oracle(sphere_meshes(), 128, 128, 0, 0, 8, **kw)
+        osc.preprocess_secondary_edges(0, reso, 1, seed)
+        return osc.render(2, seed=1, mode=1, terms=4)[1] * 2.0      # reference tangent scaling
+    r, nbad, r_ex = compare_stats(run([1, 1, 1, 8], 0), g["g111"])
+    assert nbad <= 100 and r_ex < 3e-4, (r, nbad, r_ex)
+    assert np.abs(g["g311"]).max() == 0.0 and np.abs(run([3, 1, 1, 64], 3)).max() == 0.0
+    for name, reso in (("g211", [2, 1, 1, 64]), ("g112", [1, 1, 2, 64]), ("g222", [2, 2, 2, 64])):
+        a, b = np.abs(run(reso, 0)).sum(), np.abs(g[name]).sum()
+        assert 0.6 < a / b < 1.6, (name, a, b)

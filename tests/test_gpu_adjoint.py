@@ -10,8 +10,19 @@ pytestmark = pytest.mark.gpu
 
 
 def _scene_with_tangents(psdr, meshes, w, h, spps, rng, what):
-    sc = build_product(meshes, w, h, *spps)
+    mf = "microfacet" in what
+    sc = build_product(meshes, w, h, *spps, bsdfs=scenes.CBOX_MF_BSDFS if mf else None)
     tang = {}
+    if mf:
+        for name in ("BSDF[id=cat]", "BSDF[id=white]", "BSDF[id=red]"):
+            b = sc.param_map[name]
+            b.d_specularReflectance = (rng.normal(size=3) * 0.1).astype(np.float32)
+            b.d_diffuseReflectance = (rng.normal(size=3) * 0.1).astype(np.float32)
+            b.d_roughness = np.float32(rng.normal() * 0.1)
+            tang[(name, "specularReflectance")] = b.d_specularReflectance
+            tang[(name, "diffuseReflectance")] = b.d_diffuseReflectance
+            tang[(name, "roughness")] = np.reshape(b.d_roughness, (1,))
+        what = [x for x in what if x != "materials"]
     if "mesh_left" in what:
         t = np.zeros((4, 4), np.float32)
         t[:3, 3] = rng.normal(size=3) * 30
@@ -52,6 +63,8 @@ CASES = [
     ("mesh_left", 2, 2, "cbox"), ("vertices", 2, 2, "sphere"), ("camera", 2, 2, "cbox"),
     ("mesh_left", 4, 2, "cbox"), ("vertices", 4, 2, "sphere"), ("camera", 4, 2, "cbox"), ("mesh_raw", 4, 2, "cbox"),
     ("mesh_left vertices materials camera mesh_raw", 7, 3, "sphere"),
+    ("microfacet", 1, 3, "cbox"), ("microfacet mesh_left vertices camera", 1, 2, "cbox"),
+    ("microfacet mesh_left vertices camera", 7, 2, "sphere"),
 ]
 
 
@@ -72,12 +85,43 @@ def test_vjp_is_transpose_of_jvp(what, terms, depth, scene):
     integ.render_vjp(sc, cot, 0, seed=3, terms=terms)
     rhs, parts = 0.0, {}
     for (name, field), t in tang.items():
-        g = sc.grad_of(name, field)
+        g = sc.grad_of(name, field).reshape(np.shape(t))
         parts[(name, field)] = float((g.astype(np.float64) * t.astype(np.float64)).sum())
         rhs += parts[(name, field)]
     scale = float(torch.linalg.norm(cot.double()) * torch.linalg.norm(dimg.double()))
-    assert scale > 0 and abs(lhs) > 1e-6 * scale, (lhs, scale)
-    assert abs(lhs - rhs) < 2e-4 * max(abs(lhs), 1e-3 * scale), (lhs, rhs, parts)
+    mag = max(abs(lhs), sum(abs(v) for v in parts.values()))      # the per-parameter terms may cancel
+    assert scale > 0 and mag > 1e-6 * scale, (lhs, scale)
+    assert abs(lhs - rhs) < 2e-4 * max(mag, 1e-3 * scale), (lhs, rhs, parts)
+
+
+def test_vjp_per_parameter_microfacet():
+    """one JVP per material parameter against the matching entry of a single VJP"""
+    import torch
+    import psdr_jit_b200 as psdr
+    rng = np.random.default_rng(11)
+    w = h = 48
+    sc = build_product(scenes.cbox_meshes(), w, h, 16, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS)
+    integ = psdr.PathTracer(3)
+    cot = torch.as_tensor(rng.normal(size=(w * h, 3)).astype(np.float32), device="cuda")
+    integ.render_vjp(sc, cot, 0, seed=2, terms=1)
+    grads = {(n, f): sc.grad_of(n, f).ravel().copy() for n in ("BSDF[id=cat]", "BSDF[id=white]")
+             for f in ("specularReflectance", "diffuseReflectance", "roughness")}
+    for (n, f), g in grads.items():
+        for k in range(len(g)):
+            sc2 = build_product(scenes.cbox_meshes(), w, h, 16, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS)
+            b = sc2.param_map[n]
+            if f == "roughness":
+                b.d_roughness = np.float32(1.0)
+            else:
+                t = np.zeros(3, np.float32)
+                t[k] = 1.0
+                setattr(b, "d_" + f, t)
+            sc2.configure()
+            sc2.configure([0])
+            dimg = integ.renderD_fwd(sc2, 0, seed=2, terms=1)[1]
+            lhs = float((cot.double() * dimg.double()).sum())
+            ref = float(torch.linalg.norm(cot.double()) * torch.linalg.norm(dimg.double()))
+            assert abs(lhs - float(g[k])) < 3e-4 * max(abs(lhs), 1e-2 * ref), (n, f, k, lhs, float(g[k]))
 
 
 def test_autograd_backward_matches_forward_mode():
@@ -132,3 +176,18 @@ def test_vjp_replays_continued_sampler_streams():
     assert list(sc._sampler_state()) == st_after
     # image is linear in the radiance: <grad, R> == sum(img)
     assert abs(float((R.grad * R.detach()).sum()) - float(img.detach().sum())) < 1e-4 * float(img.detach().sum())
+
+
+def test_vjp_of_guided_secondary_edges():
+    import torch
+    import psdr_jit_b200 as psdr
+    rng = np.random.default_rng(5)
+    sc, tang = _scene_with_tangents(psdr, sphere_meshes(), 64, 64, (0, 0, 8), rng, ["mesh_left", "vertices", "camera"])
+    integ = psdr.PathTracer(2)
+    integ.preprocess_secondary_edges(sc, 0, [100, 4, 4, 8], 1, 0)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=3, terms=4)
+    cot = torch.as_tensor(rng.normal(size=(64 * 64, 3)).astype(np.float32), device=img.device)
+    lhs = float((cot.double() * dimg.double()).sum())
+    integ.render_vjp(sc, cot, 0, seed=3, terms=4)
+    rhs = sum(float((sc.grad_of(n, f).astype(np.float64) * t.astype(np.float64)).sum()) for (n, f), t in tang.items())
+    assert abs(lhs) > 0 and abs(lhs - rhs) < 2e-4 * abs(lhs), (lhs, rhs)

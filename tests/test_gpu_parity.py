@@ -250,3 +250,97 @@ def test_full_size_properties_cfg2():
     r, nbad, r_ex = compare_stats(dimg3.cpu().numpy(), g["grad"], flip_rel=2e-5)
     print("cfg2 derivative image vs reference: rel-L2 %.3e, %d/%d pixels off, rel-L2 of the rest %.3e" % (r, nbad, len(img3), r_ex))
     assert nbad < 0.25 * len(img3) and r_ex < 1e-3, (r, nbad, r_ex)
+
+
+# ---- MicrofacetBSDF (reference src/bsdf/microfacet.cpp, src/bsdf/ggx.cpp) --------------------------------
+MF_TANGENT = {"cat": np.array([0.1, -0.2, 0.05, 0.02, 0.01, -0.01, 0.2], np.float32),
+              "white": np.array([0.01, 0.02, 0.03, -0.1, 0.1, 0.05, -0.3], np.float32)}
+
+
+@pytest.mark.parametrize("depth,spp,seed", [(1, 2, 0), (3, 4, 3), (6, 1, 2)])
+def test_microfacet_renderC_vs_oracle(oracle, depth, spp, seed):
+    psdr = _psdr()
+    ref = build_oracle(scenes.cbox_meshes(), 128, 128, spp, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS).render(depth, seed=seed, mode=0)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, spp, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS)
+    got = psdr.PathTracer(depth).renderC(sc, 0, seed=seed).cpu().numpy()
+    assert np.isfinite(got).all() and rel_l2(got, ref) < TOL
+
+
+@pytest.mark.parametrize("terms", [1, 2, 4, 7])
+def test_microfacet_renderD_vs_oracle(oracle, terms):
+    """geometry tangent (small box) + material tangents (specular, diffuse, roughness of two BSDFs)"""
+    psdr = _psdr()
+    spps = (4 if terms & 1 else 0, 4 if terms & 2 else 0, 4 if terms & 4 else 0)
+    kw = dict(move_mesh=1, axis_scale=(0.0, 30.0, 50.0), bsdfs=scenes.CBOX_MF_BSDFS, d_bsdf=MF_TANGENT)
+    img_ref, dimg_ref = build_oracle(scenes.cbox_meshes(), 128, 128, *spps, **kw).render(2, seed=5, mode=1, terms=7)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, *spps, **kw)
+    img, dimg = psdr.PathTracer(2).renderD_fwd(sc, 0, seed=5)
+    if terms & 1:
+        assert rel_l2(img.cpu().numpy(), img_ref) < TOL
+    assert np.abs(dimg_ref).max() > 0
+    assert rel_l2(dimg.cpu().numpy(), dimg_ref) < TOL
+
+
+def test_microfacet_two_sided_vs_oracle(oracle):
+    from oracle.psdr_oracle import OracleScene
+    psdr = _psdr()
+    osc = OracleScene(64, 64, 4, 0, 0)
+    for name, p in scenes.CBOX_MF_BSDFS:
+        if len(p) == 3 and hasattr(p[0], "__len__"):
+            osc.add_microfacet(name, p[0], p[1], p[2], two_side=True)
+        else:
+            osc.add_diffuse(name, p, two_side=True)
+    for m in scenes.cbox_meshes():
+        osc.add_mesh(m.v, m.f, m.bsdf, uv=m.uv, fuv=m.fuv, to_world={"raw": m.to_world}, radiance=m.emitter)
+    c = scenes.CBOX_CAMERA
+    osc.add_camera(c["fov"], c["near"], c["far"], {"raw": c["to_world"]})
+    osc.configure((0,))
+    ref = osc.render(3, seed=1, mode=0)
+    sc = build_product(scenes.cbox_meshes(), 64, 64, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, two_side=True)
+    got = psdr.PathTracer(3).renderC(sc, 0, seed=1).cpu().numpy()
+    assert rel_l2(got, ref) < TOL
+
+
+# ---- guided secondary-edge sampling (reference src/integrator/path.cpp:130-168, src/core/cube_distrb.cpp) ----
+@pytest.mark.parametrize("reso,nrounds,pseed", [([200, 4, 4, 8], 1, 0), ([64, 8, 8, 4], 2, 7)])
+def test_guided_secondary_edges_vs_oracle(oracle, reso, nrounds, pseed):
+    psdr = _psdr()
+    kw = dict(move_mesh=8, axis_scale=(40.0, 20.0, 0.0))
+    osc = build_oracle(sphere_meshes(), 128, 128, 0, 0, 8, **kw)
+    mass_ref = osc.preprocess_secondary_edges(0, reso, nrounds, pseed)
+    _, dimg_ref = osc.render(2, seed=1, mode=1, terms=4)
+    sc = build_product(sphere_meshes(), 128, 128, 0, 0, 8, **kw)
+    integ = psdr.PathTracer(2)
+    plain = integ.renderD_fwd(sc, 0, seed=1)[1].cpu().numpy()
+    integ.preprocess_secondary_edges(sc, 0, reso, nrounds, pseed)
+    mass = integ.guiding_mass(sc, 0)
+    assert mass.shape == mass_ref.shape and mass_ref.sum() > 0
+    np.testing.assert_allclose(mass, mass_ref, rtol=2e-5, atol=1e-9)
+    dimg = integ.renderD_fwd(sc, 0, seed=1)[1].cpu().numpy()
+    assert rel_l2(dimg, dimg_ref) < TOL
+    assert rel_l2(dimg, plain) > 1e-2                      # guiding changed the samples
+    # the grid survives configure() and belongs to this integrator only
+    sc.configure([0])
+    assert rel_l2(integ.renderD_fwd(sc, 0, seed=1)[1].cpu().numpy(), dimg_ref) < TOL
+    assert rel_l2(psdr.PathTracer(2).renderD_fwd(sc, 0, seed=1)[1].cpu().numpy(), plain) < 1e-6
+    with pytest.raises(RuntimeError, match="nrounds > 0"):
+        integ.preprocess_secondary_edges(sc, 0, reso, 0)
+
+
+def test_microfacet_vs_reference_golden():
+    psdr = _psdr()
+    g = np.load(GOLDEN + "/mf_renderC.npz")
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS)
+    for depth, seed in ((1, 0), (3, 3)):
+        got = psdr.PathTracer(depth).renderC(sc, 0, seed=seed).cpu().numpy()
+        r, nbad, r_ex = compare_stats(got, g["img_d%d_seed%d" % (depth, seed)], flip_rel=2e-5)
+        assert r < 2e-3 and nbad <= 40 and r_ex < 2e-5, (depth, r, nbad, r_ex)
+    g = np.load(GOLDEN + "/mf_renderD_128_s4_d2_smallbox.npz")
+    integ = psdr.PathTracer(2)
+    integ.reference_tangent_scaling = True
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 4, 4, move_mesh=1, axis_scale=(0.0, 30.0, 50.0), bsdfs=scenes.CBOX_MF_BSDFS)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=5)
+    r, nbad, r_ex = compare_stats(img.cpu().numpy(), g["img_all"])
+    assert nbad <= 120 and r_ex < 1e-3, (r, nbad, r_ex)
+    r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["grad_all"])
+    assert nbad <= 0.06 * len(dimg) and r_ex < 5e-3, (r, nbad, r_ex)
