@@ -33,7 +33,10 @@ enum {
     PSDR_BSDF_REFLECTANCE = 7,     /* DiffuseBSDF.reflectance / MicrofacetBSDF.diffuseReflectance (1x1 bitmap), 3 floats */
     PSDR_EMITTER_RADIANCE = 8,     /* AreaLight.radiance, 3 floats */
     PSDR_BSDF_SPECULAR = 9,        /* MicrofacetBSDF.specularReflectance (1x1 bitmap), 3 floats */
-    PSDR_BSDF_ROUGHNESS = 10       /* MicrofacetBSDF.roughness (1x1 bitmap), 1 float */
+    PSDR_BSDF_ROUGHNESS = 10,      /* MicrofacetBSDF.roughness (1x1 bitmap), 1 float */
+    PSDR_ENVMAP_RADIANCE = 11,     /* EnvironmentMap.radiance (lat-long Bitmap3fD), 3*w*h floats, rgb interleaved, index ignored */
+    PSDR_ENVMAP_SCALE = 12,        /* EnvironmentMap.scale, 1 float */
+    PSDR_ENVMAP_TO_WORLD_LEFT = 13 /* EnvironmentMap.set_transform(mat), 16 floats */
 };
 
 /* What psdr_scene_query() can return. */
@@ -92,6 +95,12 @@ int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float sp
  * Returns the mesh index (>= 0) or -1 ("Unknown BSDF id: ..."). */
 int psdr_scene_add_mesh(psdr_scene *s, const float *v, int nv, const int *f, int nf, const float *uv, int nuv, const int *fuv,
                         const float *to_world, const char *bsdf_id, const float *radiance, int use_face_normals, int enable_edges);
+
+/* Scene.add_EnvironmentMap(envmap) with envmap.radiance = Bitmap3fD(w, h, data), envmap.scale, envmap.to_world
+ * -- src/psdr.cpp:349-355,397-398, src/scene/scene.cpp:85-105, src/emitter/envmap.cpp.  radiance: h*w*3 floats
+ * (row-major, pixel = y*w + x).  configure() appends the 12-triangle bounding mesh (scene.cpp:435-485).
+ * Returns the emitter index or -1 ("A scene is only allowed to have one envmap!"). */
+int psdr_scene_add_envmap(psdr_scene *s, const float *radiance, int w, int h, const float *to_world, float scale);
 
 /* Scene.add_Sensor(PerspectiveCamera(fov, near, far)) with sensor.to_world -- src/psdr.cpp:365-375,396 */
 int psdr_scene_add_perspective(psdr_scene *s, float fov_x, float near_clip, float far_clip, const float *to_world);

@@ -148,9 +148,24 @@ struct MeshRec {
 };
 
 struct EmitterRec {
+    int type = 0;  // 0 AreaLight, 1 EnvironmentMap
     V3d radiance;
     int mesh = -1;
     float sampling_weight = 0.f;
+};
+
+// EnvironmentMap (reference src/emitter/envmap.cpp, include/psdr/emitter/envmap.h)
+struct Envmap {
+    bool present = false, has_bounds = false;
+    int emitter = -1, mesh = -1;
+    int w = 0, h = 0;
+    std::vector<float> data, ddata;  // rgb interleaved; forward tangents (may be empty)
+    Dual scale = Dual(1.f);
+    M4<Dual> to_world[2];            // left, raw
+    M4<Dual> to_world_full, from_world;
+    V3f lower, upper;
+    int cw = 0, ch = 0;
+    Distrib cell;
 };
 
 struct PrimEdge {  // reference include/psdr/edge/edge.h:26-40
@@ -187,6 +202,7 @@ struct Scene {
     std::vector<MeshRec> meshes;
     std::vector<EmitterRec> emitters;
     std::vector<Camera> cameras;
+    Envmap env;
     // configured
     std::vector<Tri<Dual>> tris;
     std::vector<int> tri_mesh;
@@ -368,6 +384,104 @@ static bool configure_camera(Scene &sc, Camera &cam, bool build_primary_edges) {
 }
 
 // reference src/scene/scene.cpp:311-601
+// ---- EnvironmentMap ---------------------------------------------------------------------------
+// Bitmap<3>::eval, envmap mode, no uv transform (reference src/core/bitmap.cpp:46-131)
+template <class S> static V3<S> texel(const Envmap &e, int i);
+template <> V3<float> texel<float>(const Envmap &e, int i) { return V3f(e.data[3 * i], e.data[3 * i + 1], e.data[3 * i + 2]); }
+template <> V3<Dual> texel<Dual>(const Envmap &e, int i) {
+    if (e.ddata.empty()) return lift<Dual>(V3f(e.data[3 * i], e.data[3 * i + 1], e.data[3 * i + 2]));
+    return V3d(Dual(e.data[3 * i], e.ddata[3 * i]), Dual(e.data[3 * i + 1], e.ddata[3 * i + 1]), Dual(e.data[3 * i + 2], e.ddata[3 * i + 2]));
+}
+template <class S> static V3<S> envmap_bitmap_eval(const Envmap &e, V2<S> uv) {
+    const int w = e.w, h = e.h;
+    uv = V2<S>((uv.x - 0.5f) + 0.5f, (uv.y - 0.5f) + 0.5f);
+    uv.x = uv.x - (float) (0.5 / (double) w);
+    uv = V2<S>(uv.x - floor_(uv.x), uv.y - floor_(uv.y));
+    uv.x = uv.x * (float) w;
+    uv.y = uv.y * (float) (h - 1);
+    int px = (int) std::floor(val(uv.x)), py = (int) std::floor(val(uv.y));
+    S w1x = uv.x - (float) px, w1y = uv.y - (float) py;
+    S w0x = 1.0f - w1x, w0y = 1.0f - w1y;
+    int yw = std::min(py, h - 2) * w, xp1 = (px + 1) % w, last = w * h - 1;
+    int i00 = std::min(yw + px, last), i10 = std::min(yw + xp1, last), i01 = std::min(yw + px + w, last), i11 = std::min(yw + xp1 + w, last);
+    V3<S> v00 = texel<S>(e, i00), v10 = texel<S>(e, i10), v01 = texel<S>(e, i01), v11 = texel<S>(e, i11);
+    V3<S> v0(fmadd(w0x, v00.x, w1x * v10.x), fmadd(w0x, v00.y, w1x * v10.y), fmadd(w0x, v00.z, w1x * v10.z));
+    V3<S> v1(fmadd(w0x, v01.x, w1x * v11.x), fmadd(w0x, v01.y, w1x * v11.y), fmadd(w0x, v01.z, w1x * v11.z));
+    return V3<S>(fmadd(w0y, v0.x, w1y * v1.x), fmadd(w0y, v0.y, w1y * v1.y), fmadd(w0y, v0.z, w1y * v1.z));
+}
+template <class S> static V2<S> dir_to_uv(V3<S> v) {  // envmap.cpp:66-67
+    V2<S> uv(atan2_(v.x, -v.z) * 0.15915494309189533577f, safe_acos_(v.y) * kInvPi);
+    return V2<S>(uv.x - floor_(uv.x), uv.y - floor_(uv.y));
+}
+template <class S> static M4<S> mat_as(const M4<Dual> &m);
+template <> M4<Dual> mat_as<Dual>(const M4<Dual> &m) { return m; }
+template <> M4<float> mat_as<float>(const M4<Dual> &m) { return val(m); }
+template <class S> static S scale_of(const Envmap &e);
+template <> Dual scale_of<Dual>(const Envmap &e) { return e.scale; }
+template <> float scale_of<float>(const Envmap &e) { return e.scale.v; }
+// EnvironmentMap::eval_direction (envmap.cpp:56-73)
+template <class S> static V3<S> env_eval_direction(const Envmap &e, V3<S> wi) {
+    V3<S> v = transform_dir(mat_as<S>(e.from_world), wi);
+    V3<S> r = envmap_bitmap_eval<S>(e, dir_to_uv<S>(v));
+    return r * scale_of<S>(e);
+}
+
+static void configure_mesh(MeshRec &m);
+// scene.cpp:355-368,435-485 (bounding box fixed at the first configure) + envmap.cpp:17-41 (cell masses)
+static bool configure_envmap(Scene &sc) {
+    Envmap &env = sc.env;
+    if (!env.present) return true;
+    if (env.w < 2 || env.h < 2) { sc.error = "src/emitter/envmap.cpp (21): width > 1 && height > 1"; return false; }
+    env.to_world_full = env.to_world[0] * env.to_world[1];
+    env.from_world = inverse(env.to_world_full);
+    if (!env.has_bounds) {
+        V3f lo(3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f), hi(1.175494351e-38f, 1.175494351e-38f, 1.175494351e-38f);
+        auto grow = [&](V3f p) {
+            lo = V3f(std::fmin(lo.x, p.x), std::fmin(lo.y, p.y), std::fmin(lo.z, p.z));
+            hi = V3f(std::fmax(hi.x, p.x), std::fmax(hi.y, p.y), std::fmax(hi.z, p.z));
+        };
+        for (auto &m : sc.meshes) for (auto &p : m.v_world) grow(val(p));
+        for (auto &c : sc.cameras) grow(val(c.pos));
+        float margin = std::fmin(std::fmin((hi.x - lo.x) * 0.05f, (hi.y - lo.y) * 0.05f), (hi.z - lo.z) * 0.05f);
+        env.lower = V3f(lo.x - margin, lo.y - margin, lo.z - margin);
+        env.upper = V3f(hi.x + margin, hi.y + margin, hi.z + margin);
+        static const int face_data[3][12] = {{0, 0, 1, 1, 2, 2, 0, 0, 0, 0, 4, 4}, {1, 3, 5, 7, 3, 7, 5, 4, 2, 6, 7, 6}, {3, 2, 7, 3, 7, 6, 1, 5, 6, 4, 5, 7}};
+        MeshRec b;
+        for (int i = 0; i < 8; ++i) {
+            float c[3];
+            for (int j = 0; j < 3; ++j) c[j] = (i & (1 << j)) ? env.upper[j] : env.lower[j];
+            b.v_raw.push_back(V3d(Dual(c[0]), Dual(c[1]), Dual(c[2])));
+        }
+        for (int k = 0; k < 12; ++k) for (int r = 0; r < 3; ++r) b.f.push_back(face_data[r][k]);
+        for (auto &M : b.to_world) M = M4<Dual>::identity();
+        b.use_face_normals = true;
+        b.enable_edges = false;
+        b.bsdf = -1;
+        b.emitter = env.emitter;
+        configure_mesh(b);
+        b.face_offset = 0;
+        for (auto &m : sc.meshes) b.face_offset += (int) m.tris.size();
+        env.mesh = (int) sc.meshes.size();
+        sc.emitters[env.emitter].mesh = env.mesh;
+        sc.meshes.push_back(b);
+        env.has_bounds = true;
+    }
+    env.cw = (env.w - 1) << 1;
+    env.ch = (env.h - 1) << 1;
+    size_t ncells = (size_t) env.cw * env.ch;
+    std::vector<float> mass(ncells);
+    float ux = 1.f / (float) env.cw, uy = 1.f / (float) env.ch, dtheta = kPi / (float) env.ch;
+    for (size_t idx = 0; idx < ncells; ++idx) {
+        int cx = (int) (idx / env.ch), cy = (int) (idx % env.ch);
+        V3f v = envmap_bitmap_eval<float>(env, V2f(((float) cx + .5f) * ux, ((float) cy + .5f) * uy));
+        float sn, cs;
+        sincos_full(((float) cy + .5f) * dtheta, sn, cs);
+        mass[idx] = rgb2luminance(v) * sn;
+    }
+    env.cell.init(mass);
+    return true;
+}
+
 static bool configure_scene(Scene &sc, const int *active, int nactive) {
     sc.error.clear();
     if (sc.meshes.empty()) { sc.error = "Missing meshes!"; return false; }
@@ -385,13 +499,17 @@ static bool configure_scene(Scene &sc, const int *active, int nactive) {
         for (int k = 0; k < nactive; ++k) act |= (active[k] == (int) i);
         if (!configure_camera(sc, sc.cameras[i], act)) return false;
     }
-    // emitters (scene.cpp:489-515, src/emitter/area.cpp:9-14)
+    if (!configure_envmap(sc)) return false;
+    // emitters (scene.cpp:489-515, src/emitter/area.cpp:9-14); the envmap's weight = sum of the others
     if (!sc.emitters.empty()) {
         std::vector<float> w;
+        double total = 0.0;
         for (auto &e : sc.emitters) {
-            e.sampling_weight = sc.meshes[e.mesh].total_area * rgb2luminance(val(e.radiance));
-            w.push_back(e.sampling_weight);
+            e.sampling_weight = e.type == 1 ? 0.f : sc.meshes[e.mesh].total_area * rgb2luminance(val(e.radiance));
+            total += e.sampling_weight;
         }
+        for (auto &e : sc.emitters) if (e.type == 1) e.sampling_weight = (float) total;
+        for (auto &e : sc.emitters) w.push_back(e.sampling_weight);
         sc.emitter_distrb.init(w);
         float inv_total = 1.f / sc.emitter_distrb.sum;
         for (auto &e : sc.emitters) e.sampling_weight *= inv_total;
@@ -656,6 +774,7 @@ static float microfacet_pdf(const Bsdf &b, V3f wi, V3f wo) {
 
 template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return V3<S>(S(0.f));
+    if (sc.meshes[its.mesh].bsdf < 0) return V3<S>(S(0.f));   // bsdf == nullptr (envmap bounding mesh): a Dr.Jit vcall on null yields 0
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
     if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo);
     S wiz = its.wi.z;
@@ -670,6 +789,7 @@ template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3
 
 template <class S> static float bsdf_pdf(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return 0.f;
+    if (sc.meshes[its.mesh].bsdf < 0) return 0.f;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
     if (b.type == 1) return microfacet_pdf(b, val(its.wi), val(wo));
     float wiz = val(its.wi.z), woz = val(wo.z);
@@ -736,6 +856,7 @@ static BsdfSample microfacet_sample(const Bsdf &b, V3f wi, V3f sample, bool acti
 template <class S> static BsdfSample bsdf_sample(const Scene &sc, const Its<S> &its, V3f sample, bool active) {
     BsdfSample bs;
     if (!its.valid) return bs;
+    if (sc.meshes[its.mesh].bsdf < 0) return bs;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
     if (b.type == 1) return microfacet_sample(b, val(its.wi), sample, active);
     float wiz = val(its.wi.z);
@@ -758,6 +879,10 @@ template <class S> static bool is_emitter(const Scene &sc, const Its<S> &its) {
 }
 template <class S> static V3<S> Le(const Scene &sc, const Its<S> &its, bool active) {
     if (!its.valid || sc.meshes[its.mesh].emitter < 0) return V3<S>(S(0.f));
+    if (sc.emitters[sc.meshes[its.mesh].emitter].type == 1) {  // EnvironmentMap::eval (envmap.cpp:44-53)
+        if (!active) return V3<S>(S(0.f));
+        return env_eval_direction<S>(sc.env, -its.to_world(its.wi));
+    }
     if (!(active && val(its.wi.z) > 0.f)) return V3<S>(S(0.f));
     return radiance_of<S>(sc.emitters[sc.meshes[its.mesh].emitter]);
 }
@@ -770,7 +895,49 @@ template <class S> struct PosSample {
 };
 
 // reference src/scene/scene.cpp:987-1013 + mesh.cpp:413-454
-template <class S> static PosSample<S> sample_emitter_position(const Scene &sc, V2f sample2) {
+// EnvironmentMap::sample_direction + __sample_position (envmap.cpp:86-129), ray_intersect_scene_aabb (utils.h:144-164)
+static void env_sample_position(const Envmap &e, V3f ref_p, V2f sample2, V3f &p, V3f &n, float &pdf_out) {
+    int ncells = e.cw * e.ch;
+    auto r = e.cell.sample_reuse(sample2.y);
+    int idx = r.first, cx = idx / e.ch, cy = idx - cx * e.ch;
+    float u = (sample2.x + (float) cx) * (1.f / (float) e.cw), v = (sample2.y + (float) cy) * (1.f / (float) e.ch);
+    float pdf = r.second * (float) ncells;
+    float st, ct, sp, cp;
+    sincos_full(v * kPi, st, ct);
+    sincos_full(u * (2.f * kPi), sp, cp);
+    V3f d(sp * st, ct, -(cp * st));
+    float inv_sin_theta = 1.f / std::sqrt(std::fmax(sqr(d.x) + sqr(d.z), sqr(kEpsilon)));
+    if (pdf > kEpsilon) pdf *= inv_sin_theta * (.5f / sqr(kPi));
+    d = transform_dir(val(e.to_world_full), d);
+    float t = 0.f;
+    int axis = 0;
+    for (int i = 0; i < 3; ++i) {
+        float t1 = (e.lower[i] - ref_p[i]) / d[i], t2 = (e.upper[i] - ref_p[i]) / d[i];
+        float tm = std::fmax(t1, t2);
+        if (i == 0 || tm < t) { t = tm; axis = i; }
+    }
+    float nn[3] = {0.f, 0.f, 0.f};
+    nn[axis] = std::signbit(d[axis]) ? 1.f : -1.f;
+    n = V3f(nn[0], nn[1], nn[2]);
+    float G = dot(n, -d) * (1.f / sqr(t));
+    p = V3f(std::fmaf(d.x, t, ref_p.x), std::fmaf(d.y, t, ref_p.y), std::fmaf(d.z, t, ref_p.z));
+    pdf_out = pdf * G;
+}
+// EnvironmentMap::__sample_position_pdf (envmap.cpp:142-162) + HyperCubeDistribution::pdf (cube_distrb.cpp:51-63)
+template <class S> static float env_position_pdf(const Envmap &e, V3f ref_p, const Its<S> &its) {
+    V3f d = val(its.p) - ref_p;
+    float dist2 = squared_norm(d);
+    d = d / safe_sqrt(dist2);
+    float G = std::fabs(dot(d, val(its.n))) / dist2;
+    d = transform_dir(val(e.from_world), d);
+    float factor = G * (1.f / std::sqrt(std::fmax(sqr(d.x) + sqr(d.z), sqr(kEpsilon)))) * (.5f / sqr(kPi));
+    V2f uv = dir_to_uv<float>(d);
+    int ix = (int) std::floor(uv.x * (float) e.cw), iy = (int) std::floor(uv.y * (float) e.ch);
+    if (!(ix >= 0 && ix < e.cw && iy >= 0 && iy < e.ch)) return 0.f;
+    return (e.cell.pmf[ix * e.ch + iy] / e.cell.sum) * (float) (e.cw * e.ch) * factor;
+}
+
+template <class S> static PosSample<S> sample_emitter_position(const Scene &sc, V3f ref_p, V2f sample2) {
     PosSample<S> ps;
     int ei = 0;
     float emitter_pdf = 1.f;
@@ -778,6 +945,17 @@ template <class S> static PosSample<S> sample_emitter_position(const Scene &sc, 
         auto r = sc.emitter_distrb.sample_reuse(sample2.y);
         ei = r.first;
         emitter_pdf = r.second;
+    }
+    if (sc.emitters[ei].type == 1) {
+        V3f p, n;
+        float pdf;
+        env_sample_position(sc.env, ref_p, sample2, p, n, pdf);
+        ps.p = lift<S>(p);
+        ps.n = lift<S>(n);
+        ps.pdf = pdf;
+        if (sc.emitters.size() != 1) ps.pdf *= emitter_pdf;
+        ps.valid = true;
+        return ps;
     }
     const MeshRec &m = sc.meshes[sc.emitters[ei].mesh];
     int fi = m.face_distrb.sample_reuse(sample2.x).first;
@@ -795,10 +973,11 @@ template <class S> static PosSample<S> sample_emitter_position(const Scene &sc, 
 }
 
 // reference src/scene/scene.cpp:1016-1024, area.cpp:48-59, mesh.cpp:457-466
-template <class S> static float emitter_position_pdf(const Scene &sc, const Its<S> &its, bool active) {
+template <class S> static float emitter_position_pdf(const Scene &sc, V3f ref_p, const Its<S> &its, bool active) {
     if (!its.valid || !active) return 0.f;
     int e = sc.meshes[its.mesh].emitter;
     if (e < 0) return 0.f;
+    if (sc.emitters[e].type == 1) return env_position_pdf<S>(sc.env, ref_p, its);
     return sc.emitters[e].sampling_weight * sc.meshes[its.mesh].inv_total_area;
 }
 
@@ -864,7 +1043,7 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
         float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();  // next_nd<3> = (d3,d2,d1)
         if (!active) continue;
         {   // ---- emitter sampling
-            PosSample<S> ps = sample_emitter_position<S>(sc, V2f(s_x, s_y));
+            PosSample<S> ps = sample_emitter_position<S>(sc, val(its.p), V2f(s_x, s_y));
             bool active_direct = active && ps.valid && !is_emitter(sc, its);
             V3<S> wod = ps.p - its.p;
             S dist_sqr = squared_norm(wod);
@@ -909,7 +1088,7 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
                 if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
                 else bsdf_val = bsdf_eval(sc, its, lift<S>(bs.wo), active) / S(bs.pdf);
             }
-            float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, its1, active));
+            float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, val(its.p), its1, active));
             throughput *= bsdf_val;
             if (active) result += Le(sc, its1, active) * throughput * S(weight2);
             its = its1;
@@ -1025,7 +1204,7 @@ static BoundarySeg sample_boundary_segment_direct(const Scene &sc, V3f sample3) 
     r.edge2 = info.p2 - val(info.p0);
     V3f p0 = val(r.p0);
     pdf0 /= norm(e1);
-    PosSample<float> ps2 = sample_emitter_position<float>(sc, V2f(sample3.y, sample3.z));
+    PosSample<float> ps2 = sample_emitter_position<float>(sc, p0, V2f(sample3.y, sample3.z));
     r.p2 = ps2.p;
     r.n = ps2.n;
     V3f e = r.p2 - p0;
@@ -1183,6 +1362,24 @@ int orc_add_microfacet(void *h, const float *spec, const float *diff, float roug
     b.two_side = two_side != 0;
     s->bsdfs.push_back(b);
     return (int) s->bsdfs.size() - 1;
+}
+
+// EnvironmentMap: radiance [h*w*3], optional tangents; to_world = (left, raw) 2x16 floats or NULL; returns emitter index
+int orc_add_envmap(void *h, const float *data, const float *ddata, int w, int hh, const float *to_world, const float *d_to_world,
+                   float scale, float d_scale) {
+    Scene *s = (Scene *) h;
+    Envmap &e = s->env;
+    e.present = true;
+    e.w = w; e.h = hh;
+    e.data.assign(data, data + (size_t) 3 * w * hh);
+    if (ddata) e.ddata.assign(ddata, ddata + (size_t) 3 * w * hh);
+    e.scale = Dual(scale, d_scale);
+    for (int k = 0; k < 2; ++k) e.to_world[k] = load_m4(to_world ? to_world + 16 * k : nullptr, d_to_world ? d_to_world + 16 * k : nullptr);
+    EmitterRec em;
+    em.type = 1;
+    e.emitter = (int) s->emitters.size();
+    s->emitters.push_back(em);
+    return e.emitter;
 }
 
 // to_world / d_to_world: 3 consecutive row-major 4x4 (left, raw, right); NULL = identity / zero

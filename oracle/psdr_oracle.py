@@ -39,6 +39,7 @@ def lib():
         L.orc_set_li_order.argtypes = [C.c_void_p, C.c_int]
         L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
         L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
+        L.orc_add_envmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int, _f, _f, C.c_float, C.c_float]
         L.orc_add_mesh.argtypes = [C.c_void_p, _f, _f, C.c_int, _i, C.c_int, _f, C.c_int, _i, _f, _f, C.c_int, _f, _f, C.c_int, C.c_int]
         L.orc_add_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f, _f]
         L.orc_configure.argtypes = [C.c_void_p, _i, C.c_int]
@@ -124,6 +125,18 @@ class OracleScene:
         idx = self.L.orc_add_microfacet(self.h, _fp(sp), _fp(df), float(rough), _fp(dd), int(two_side))
         self.bsdf_ids[name] = idx
         return idx
+
+    def add_envmap(self, data, w, h, to_world=None, scale=1.0, d_data=None, d_to_world_left=None, d_scale=0.0):
+        """data: [h*w, 3]; to_world = raw 4x4 (left = identity); d_to_world_left = tangent of the left factor"""
+        dat, dd = _f32(data).reshape(-1), (None if d_data is None else _f32(d_data).reshape(-1))
+        tw = np.tile(np.eye(4, dtype=np.float32), (2, 1, 1))
+        if to_world is not None:
+            tw[1] = np.asarray(to_world, dtype=np.float32)
+        dtw = None
+        if d_to_world_left is not None:
+            dtw = np.zeros((2, 4, 4), dtype=np.float32)
+            dtw[0] = np.asarray(d_to_world_left, dtype=np.float32)
+        return self.L.orc_add_envmap(self.h, _fp(dat), _fp(dd), int(w), int(h), _fp(tw), _fp(dtw), float(scale), float(d_scale))
 
     def add_mesh(self, v, f, bsdf, uv=None, fuv=None, to_world=None, d_to_world=None, dv=None, radiance=None,
                  d_radiance=None, use_face_normals=False, enable_edges=True):

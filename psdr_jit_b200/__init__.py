@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib, scenes  # noqa: F401
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "Mesh", "PathTracer", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Mesh", "PathTracer", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
@@ -180,6 +180,48 @@ class Emitter(Object):
     pass
 
 
+class Bitmap3fD:
+    """reference src/psdr.cpp:195-219 (Bitmap3fD): w x h RGB bitmap, data = [h*w, 3] row-major (pixel = y*w + x)."""
+
+    def __init__(self, width: int = 1, height: int = 1, data=None):
+        self.resolution = (int(width), int(height))
+        if data is None:
+            data = np.zeros((width * height, 3), dtype=np.float32)
+        self.data = data if hasattr(data, "requires_grad") else _f32(data).reshape(-1, 3).copy()
+        self.d_data = None
+        n = int(np.prod(self.data.shape))
+        if n != 3 * width * height:
+            raise RuntimeError("Bitmap: invalid data size!")
+
+
+class EnvironmentMap(Emitter):
+    """reference src/psdr.cpp:349-355, src/emitter/envmap.cpp.  ``radiance`` is a lat-long Bitmap3fD; EXR loading
+    (EnvironmentMap(path)) is I/O outside this path -- build the bitmap from an array instead."""
+
+    def __init__(self, radiance: Optional[Bitmap3fD] = None):
+        if isinstance(radiance, str):
+            raise NotImplementedError("EnvironmentMap(path): EXR loading is outside the hot path; pass a Bitmap3fD")
+        self.radiance = radiance if radiance is not None else Bitmap3fD(2, 2, np.ones((4, 3), np.float32))
+        self.scale = np.float32(1.0)
+        self.d_scale = np.float32(0.0)
+        self.to_world = np.eye(4, dtype=np.float32)           # read-only in the reference (to_world_raw)
+        self.to_world_left = np.eye(4, dtype=np.float32)
+        self.d_to_world_left = np.zeros((4, 4), dtype=np.float32)
+
+    def set_transform(self, mat, tangent=None):
+        self.to_world_left = mat if hasattr(mat, "requires_grad") else _mat4(mat)
+        self.d_to_world_left = np.zeros((4, 4), np.float32) if tangent is None else _f32(tangent, (4, 4)).copy()
+
+    def _clone(self):
+        e = EnvironmentMap(Bitmap3fD(self.radiance.resolution[0], self.radiance.resolution[1], self.radiance.data))
+        e.radiance.d_data = None if self.radiance.d_data is None else _f32(self.radiance.d_data).reshape(-1, 3).copy()
+        e.scale, e.d_scale = self.scale, self.d_scale
+        e.to_world = _mat4(self.to_world)
+        e.to_world_left = self.to_world_left if hasattr(self.to_world_left, "requires_grad") else _mat4(self.to_world_left)
+        e.d_to_world_left = _f32(self.d_to_world_left, (4, 4)).copy()
+        return e
+
+
 class AreaLight(Emitter):
     """reference src/psdr.cpp:344-347, src/emitter/area.cpp"""
 
@@ -315,7 +357,9 @@ class Scene(Object):
         self._emitters: List[AreaLight] = []
         self._mesh_emitter: List[int] = []
         self._h = None
-        self._pushed = [0, 0, 0]   # bsdfs, meshes, sensors already in the native scene
+        self._pushed = [0, 0, 0]   # bsdfs, creation events (meshes / envmap), sensors already in the native scene
+        self._events = []          # ("mesh", i) / ("env", emitter index) in add_* order = native emitter order
+        self._env = None
         self._device = device
         self._shard = (0, 1)
         self._accel = -1
@@ -356,6 +400,19 @@ class Scene(Object):
         self._bsdfs.append(b)
         self._register("BSDF", self._bsdfs)
 
+    def add_EnvironmentMap(self, envmap, to_world=None, scale: float = 1.0):
+        """add_EnvironmentMap(EnvironmentMap) (reference src/scene/scene.cpp:97-105); the (path, to_world, scale)
+        overload needs an EXR reader and is not part of this path."""
+        if self._env is not None:
+            raise RuntimeError("A scene is only allowed to have one envmap!")
+        if not isinstance(envmap, EnvironmentMap):
+            raise NotImplementedError("add_EnvironmentMap(path, ...): EXR loading is outside the hot path")
+        e = envmap._clone()
+        self._env = e
+        self._events.append(("env", len(self._emitters)))
+        self._emitters.append(e)
+        self._register("Emitter", self._emitters)
+
     def add_Mesh(self, mesh_or_path, *args):
         """add_Mesh(path, to_world, bsdf_id, emitter) or add_Mesh(mesh, bsdf_id, emitter=None)"""
         if isinstance(mesh_or_path, Mesh):
@@ -372,6 +429,7 @@ class Scene(Object):
             raise RuntimeError("Unknown BSDF id: " + str(bsdf_id))
         mesh.bsdf = bsdf_id
         mesh._scene, mesh._index = self, len(self._meshes)
+        self._events.append(("mesh", len(self._meshes)))
         if emitter is not None:
             if not isinstance(emitter, AreaLight):
                 raise RuntimeError("Unknown emitter type!")
@@ -434,7 +492,13 @@ class Scene(Object):
             if rc < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[0] = len(self._bsdfs)
-        for i in range(self._pushed[1], len(self._meshes)):
+        for kind, i in self._events[self._pushed[1]:]:
+            if kind == "env":
+                e = self._env
+                w, h = e.radiance.resolution
+                if L.psdr_scene_add_envmap(self._h, _fp(_f32(e.radiance.data).reshape(-1)), w, h, _fp(_mat4(e.to_world)), float(_f32(e.scale).ravel()[0])) < 0:
+                    raise RuntimeError(L.psdr_last_error().decode())
+                continue
             m = self._meshes[i]
             v, f = _f32(m.vertex_positions).reshape(-1, 3), np.ascontiguousarray(m.face_indices, dtype=np.int32)
             uv = None if m.vertex_uv is None else _f32(m.vertex_uv).reshape(-1, 2)
@@ -444,7 +508,7 @@ class Scene(Object):
             if L.psdr_scene_add_mesh(self._h, _fp(v), len(v), _ip(f), len(f), _fp(uv), 0 if uv is None else len(uv), _ip(fuv),
                                      _fp(_mat4(m.to_world)), m.bsdf.encode(), _fp(rad), int(m.use_face_normal), int(m.enable_edges)) < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
-        self._pushed[1] = len(self._meshes)
+        self._pushed[1] = len(self._events)
         for s in self._sensors[self._pushed[2]:]:
             if L.psdr_scene_add_perspective(self._h, s.fov, s.near, s.far, _fp(_mat4(s.to_world))) < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
@@ -473,7 +537,12 @@ class Scene(Object):
             else:
                 push(_lib.BSDF_REFLECTANCE, i, b.reflectance, b.d_reflectance)
         for i, e in enumerate(self._emitters):
-            push(_lib.EMITTER_RADIANCE, i, e.radiance, e.d_radiance)
+            if isinstance(e, EnvironmentMap):
+                push(_lib.ENVMAP_RADIANCE, i, e.radiance.data, e.radiance.d_data)
+                push(_lib.ENVMAP_SCALE, i, np.reshape(_f32(e.scale), (1,)), np.reshape(_f32(e.d_scale), (1,)))
+                push(_lib.ENVMAP_TO_WORLD_LEFT, i, e.to_world_left, e.d_to_world_left)
+            else:
+                push(_lib.EMITTER_RADIANCE, i, e.radiance, e.d_radiance)
         act = np.asarray(list(active_sensor), dtype=np.int32)
         _lib.check(L.psdr_scene_configure(self._h, _ip(act), len(act)))
         if o.log_level > 0 and o.sppe > 0:
@@ -488,7 +557,20 @@ class Scene(Object):
                                ("to_world_right", _lib.SENSOR_TO_WORLD_RIGHT)),
                     "BSDF": (("reflectance", _lib.BSDF_REFLECTANCE), ("diffuseReflectance", _lib.BSDF_REFLECTANCE),
                              ("specularReflectance", _lib.BSDF_SPECULAR), ("roughness", _lib.BSDF_ROUGHNESS)),
-                    "Emitter": (("radiance", _lib.EMITTER_RADIANCE),)}
+                    "Emitter": (("radiance", _lib.EMITTER_RADIANCE),),
+                    "EnvironmentMap": (("radiance.data", _lib.ENVMAP_RADIANCE), ("scale", _lib.ENVMAP_SCALE),
+                                       ("to_world_left", _lib.ENVMAP_TO_WORLD_LEFT))}
+
+    @staticmethod
+    def _field(o, dotted):
+        for part in dotted.split("."):
+            o = getattr(o, part, None)
+            if o is None:
+                return None
+        return o
+
+    def _fields_of(self, kind_name, o):
+        return self._GRAD_FIELDS["EnvironmentMap" if isinstance(o, EnvironmentMap) else kind_name]
 
     def _objects(self):
         return (("Mesh", self._meshes), ("Sensor", self._sensors), ("BSDF", self._bsdfs), ("Emitter", self._emitters))
@@ -498,8 +580,8 @@ class Scene(Object):
         out = []
         for kind_name, objs in self._objects():
             for i, o in enumerate(objs):
-                for field, kind in self._GRAD_FIELDS[kind_name]:
-                    t = getattr(o, field, None)
+                for field, kind in self._fields_of(kind_name, o):
+                    t = self._field(o, field)
                     if hasattr(t, "requires_grad") and t.requires_grad:
                         out.append((t, kind, i))
         return out
@@ -510,9 +592,9 @@ class Scene(Object):
         for kind_name, objs in self._objects():
             for i, o in enumerate(objs):
                 if o is obj:
-                    for f, kind in self._GRAD_FIELDS[kind_name]:
+                    for f, kind in self._fields_of(kind_name, o):
                         if f == field:
-                            return self._read_grad(kind, i, np.asarray(_f32(getattr(o, f))).shape)
+                            return self._read_grad(kind, i, np.asarray(_f32(self._field(o, f))).shape)
         raise RuntimeError("no differentiable field %s on %s" % (field, name))
 
     def _read_grad(self, kind: int, index: int, shape) -> np.ndarray:

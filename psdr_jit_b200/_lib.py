@@ -19,6 +19,7 @@ P_I = C.POINTER(C.c_int)
 MESH_VERTICES, MESH_TO_WORLD_LEFT, MESH_TO_WORLD_RAW, MESH_TO_WORLD_RIGHT = 0, 1, 2, 3
 SENSOR_TO_WORLD_LEFT, SENSOR_TO_WORLD_RAW, SENSOR_TO_WORLD_RIGHT = 4, 5, 6
 BSDF_REFLECTANCE, EMITTER_RADIANCE, BSDF_SPECULAR, BSDF_ROUGHNESS = 7, 8, 9, 10
+ENVMAP_RADIANCE, ENVMAP_SCALE, ENVMAP_TO_WORLD_LEFT = 11, 12, 13
 Q_NUM_MESHES, Q_NUM_SENSORS, Q_NUM_EMITTERS, Q_NUM_TRIANGLES, Q_NUM_PRIMARY_EDGES, Q_NUM_SECONDARY_EDGES = 0, 1, 2, 3, 4, 5
 Q_NUM_MESH_EDGES, Q_NUM_MESH_VERTICES, Q_NUM_MESH_FACES, Q_IS_CONFIGURED, Q_USES_BVH, Q_UPLOAD_BYTES, Q_GUIDING_CELLS = 6, 7, 8, 9, 10, 11, 12
 TERM_INTERIOR, TERM_PRIMARY_EDGES, TERM_SECONDARY_EDGES, TERM_ALL = 1, 2, 4, 7
@@ -26,7 +27,7 @@ TERM_INTERIOR, TERM_PRIMARY_EDGES, TERM_SECONDARY_EDGES, TERM_ALL = 1, 2, 4, 7
 EXPORTS = [
     "psdr_last_error", "psdr_version", "psdr_kernel_launch_count", "psdr_scene_create", "psdr_scene_destroy",
     "psdr_scene_set_options", "psdr_scene_set_seed", "psdr_scene_set_shard", "psdr_scene_set_accel",
-    "psdr_scene_add_bsdf_diffuse", "psdr_scene_add_bsdf_microfacet", "psdr_scene_add_mesh", "psdr_scene_add_perspective", "psdr_scene_set_param",
+    "psdr_scene_add_bsdf_diffuse", "psdr_scene_add_bsdf_microfacet", "psdr_scene_add_envmap", "psdr_scene_add_mesh", "psdr_scene_add_perspective", "psdr_scene_set_param",
     "psdr_scene_set_tangent", "psdr_scene_clear_tangents", "psdr_scene_configure", "psdr_scene_last_configure_ms",
     "psdr_scene_query", "psdr_scene_mesh_edges", "psdr_render_c", "psdr_render_d", "psdr_render_c_host",
     "psdr_render_d_host", "psdr_render_aov", "psdr_sampler_draws", "psdr_scene_enable_timing", "psdr_scene_kernel_ms",
@@ -56,6 +57,7 @@ def load():
     L.psdr_scene_set_accel.argtypes = [vp, i]
     L.psdr_scene_add_bsdf_diffuse.argtypes = [vp, C.c_char_p, P_F, i]
     L.psdr_scene_add_bsdf_microfacet.argtypes = [vp, C.c_char_p, P_F, P_F, f, i]
+    L.psdr_scene_add_envmap.argtypes = [vp, P_F, i, i, P_F, f]
     L.psdr_scene_add_mesh.argtypes = [vp, P_F, i, P_I, i, P_F, i, P_I, P_F, C.c_char_p, P_F, i, i]
     L.psdr_scene_add_perspective.argtypes = [vp, f, f, f, P_F]
     L.psdr_scene_set_param.argtypes = [vp, i, i, P_F, i]

@@ -61,7 +61,7 @@ template <int kD> struct PathRecord {
     V3f T[kD];                          // throughput in front of bounce k
     unsigned char nee_ok[kD], bnc_ok[kD], bnc_nz[kD];
     int ltri[kD], htri[kD];
-    float la[kD], lb[kD], lpdf[kD], w1[kD], pdf0[kD], w2[kD];
+    float la[kD], lb[kD], lc[kD], lpdf[kD], w1[kD], pdf0[kD], w2[kD];   // (la, lb) = barycentrics, or (la, lb, lc) = envmap position if ltri < 0
     __device__ __forceinline__ void reset() {
         nv = nsh = 0;
 #pragma unroll
@@ -76,8 +76,11 @@ template <int kD> struct PathRecord {
     __device__ __forceinline__ void bounce(int k, bool nonzero, float p0, float w) {
         if (k < kD) { bnc_ok[k] = 1; bnc_nz[k] = nonzero ? 1 : 0; pdf0[k] = p0; w2[k] = w; }
     }
-    __device__ __forceinline__ void nee(int k, bool ok, int lt, V2f st, int ht, float pdf, float w) {
-        if (k < kD) { nee_ok[k] = ok ? 1 : 0; ltri[k] = lt; la[k] = st.x; lb[k] = st.y; htri[k] = ht; lpdf[k] = pdf; w1[k] = w; }
+    __device__ __forceinline__ void nee(int k, bool ok, int lt, V2f st, V3f p, int ht, float pdf, float w) {
+        if (k < kD) {
+            nee_ok[k] = ok ? 1 : 0; ltri[k] = lt; htri[k] = ht; lpdf[k] = pdf; w1[k] = w;
+            if (lt >= 0) { la[k] = st.x; lb[k] = st.y; lc[k] = 0.f; } else { la[k] = p.x; lb[k] = p.y; lc[k] = p.z; }
+        }
     }
 };
 
@@ -273,6 +276,42 @@ __device__ __forceinline__ void scatter_camera_ray(const GradAcc &acc, const Gra
     }
 }
 
+// Environment-map radiance along `dir` weighted by Wc (contribution = sum_c Wc_c Le_c(dir)): scatters the
+// gradients of the texels, the scale and the from_world rotation, returns d contribution / d dir and Le.
+__device__ __forceinline__ V3f env_le_adjoint(const GradAcc &acc, const GradLayout &gl, const DEnv &env, V3f dir, V3f Wc, V3f &Le_out) {
+    EnvTexelTaps tp;
+    const V3f v = mul3x3<float>(env.from_world, nullptr, dir);
+    const V3f tex = bitmap_eval_envmap<float>(env.data, nullptr, env.w, env.h, envmap_dir_to_uv<float>(v), &tp);
+    Le_out = tex * env.scale;
+    const float wsum = Wc.x + Wc.y + Wc.z;
+    if (wsum == 0.f && Wc.x == 0.f && Wc.y == 0.f) return V3f(0.f, 0.f, 0.f);
+    const int base = gl.off_env;
+    acc.add(base, Wc.x * tex.x + Wc.y * tex.y + Wc.z * tex.z);                 // d scale
+    const int idx[4] = {tp.i00, tp.i10, tp.i01, tp.i11};
+    const float bw[4] = {tp.w0y * tp.w0x, tp.w0y * tp.w1x, tp.w1y * tp.w0x, tp.w1y * tp.w1x};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc.add3(base + kGradEnvHead + 3 * idx[k], Wc * (env.scale * bw[k]));
+    // direction: three dual evaluations in the map's local frame (parameter tangents switched off)
+    V3f v_bar;
+    {
+        float gb[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const V3d vd(Dual(v.x, a == 0 ? 1.f : 0.f), Dual(v.y, a == 1 ? 1.f : 0.f), Dual(v.z, a == 2 ? 1.f : 0.f));
+            const V3d r = bitmap_eval_envmap<Dual>(env.data, nullptr, env.w, env.h, envmap_dir_to_uv<Dual>(vd));
+            gb[a] = (Wc.x * r.x.d + Wc.y * r.y.d + Wc.z * r.z.d) * env.scale;
+        }
+        v_bar = V3f(gb[0], gb[1], gb[2]);
+    }
+    const float vb[3] = {v_bar.x, v_bar.y, v_bar.z}, dd[3] = {dir.x, dir.y, dir.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc.add(base + 1 + 3 * i + j, vb[i] * dd[j]);      // v = F dir
+    const float *F = env.from_world;
+    return V3f(F[0] * vb[0] + F[3] * vb[1] + F[6] * vb[2], F[1] * vb[0] + F[4] * vb[1] + F[7] * vb[2], F[2] * vb[0] + F[5] * vb[1] + F[8] * vb[2]);
+}
+
 // One scattering event x -> y seen from x: C = sum_c W_c f_c(ci, co, cio) * |cos_y| / t^2 * J_y * scale
 // (scale = detached 1/pdf * MIS weight).  Accumulates the adjoints of x (p, sh_n), of the previous point
 // (through wi) and returns those of y.
@@ -283,8 +322,10 @@ struct EventAdj {
     V3f f;            // BSDF value (rgb)
     float geo;        // |cos_y| / t^2 * scale  (J = 1 in the primal)
 };
+// wo_extra(f * geo) lets the caller add d(contribution)/d(wo) coming from a direction-dependent emitter (envmap).
+template <class F>
 __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const GradLayout &gl, const DScene &sc, const VtxGeo &x, V3f wi,
-                                                  V3f py, V3f ny, float area_y, V3f W, float scale, VtxAdj &xa) {
+                                                  V3f py, V3f ny, float area_y, V3f W, float scale, VtxAdj &xa, F wo_extra) {
     EventAdj r;
     r.py = r.ny = r.wi_bar = V3f(0.f, 0.f, 0.f);
     r.area_y = 0.f;
@@ -309,13 +350,14 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) / (t * t);
     const float t_bar = G_bar * (-2.f * fabsf(cy) / (t * t * t));
     V3f wo_bar = ny * (-cy_bar) + x.shn * co_bar + wi * cio_bar;
+    wo_bar = wo_bar + wo_extra(wo, j.f * (G * scale));
     r.ny = wo * (-cy_bar);
     r.wi_bar = wo * cio_bar + x.shn * ci_bar;
     xa.shn = xa.shn + wo * co_bar + wi * ci_bar;
     const V3f vec_bar = unit_adj(wo, t, wo_bar, t_bar);
     r.py = vec_bar;
     xa.p = xa.p - vec_bar;
-    r.area_y = J_bar / area_y;
+    r.area_y = area_y > 0.f ? J_bar / area_y : 0.f;
     return r;
 }
 
@@ -332,8 +374,15 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     ray_intersect_triangle<float>(T0.p0, T0.e1, T0.e2, o, d, u0, v0, t0);
     VtxGeo cur = vertex_geo(sc, R.vtri[0], u0, v0);
     cur.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
+    V3f o_bar(0.f, 0.f, 0.f), d_bar(0.f, 0.f, 0.f);
     // Le at the primary hit
-    if (!hide_emitters && cur.emitter >= 0 && dot(-d, cur.shn) > 0.f) acc.add3(gl.off_emit + 4 * cur.emitter, g);
+    if (!hide_emitters && cur.emitter >= 0) {
+        if (sc.emitters[cur.emitter].type == 1) {
+            V3f le;
+            d_bar = d_bar + env_le_adjoint(acc, gl, sc.env, d, g, le);
+            if (R.nsh <= 0) scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
+        } else if (dot(-d, cur.shn) > 0.f) acc.add3(gl.off_emit + 4 * cur.emitter, g);
+    }
     if (R.nsh <= 0) return;
 
     // geometry of every vertex (recomputed from the tables; no tracing)
@@ -346,7 +395,6 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         va[k].p = va[k].shn = va[k].fn = V3f(0.f, 0.f, 0.f);
         va[k].area = 0.f;
     }
-    V3f o_bar(0.f, 0.f, 0.f), d_bar(0.f, 0.f, 0.f);
     V3f Lnext(0.f, 0.f, 0.f);     // R_{k+1}: radiance gathered after vertex k+1 (without E_{k+1})
 #pragma unroll
     for (int kk = 0; kk < kD; ++kk) {
@@ -369,26 +417,54 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
             const VtxGeo &y = vg[k + 1];
             const V3f wo = normalize(y.p - x.p);
             V3f E(0.f, 0.f, 0.f);
-            const bool y_emits = y.emitter >= 0 && dot(-wo, y.shn) > 0.f;
-            if (y_emits) {
+            const bool y_env = y.emitter >= 0 && sc.emitters[y.emitter].type == 1;
+            const bool y_emits = y.emitter >= 0 && (y_env || dot(-wo, y.shn) > 0.f);
+            if (y_env) {
+                const V2f uv = envmap_dir_to_uv<float>(mul3x3<float>(sc.env.from_world, nullptr, wo));
+                E = bitmap_eval_envmap<float>(sc.env.data, nullptr, sc.env.w, sc.env.h, uv) * (sc.env.scale * R.w2[k]);
+            } else if (y_emits) {
                 const DEmitter &em = sc.emitters[y.emitter];
                 E = V3f(em.radiance[0], em.radiance[1], em.radiance[2]) * R.w2[k];
             }
             const V3f Ltot = E + Lnext;
             if (R.bnc_nz[k]) {
                 const float scale = 1.f / R.pdf0[k];
-                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, y.p, y.fn, y.area, A * Ltot, scale, va[k]);
+                const float w2k = R.w2[k];
+                // a direction-dependent emitter at y adds d(E)/d(wo) and the texel / scale gradients
+                auto extra = [&](V3f wo_, V3f fgeo) {
+                    if (!y_env) return V3f(0.f, 0.f, 0.f);
+                    V3f le;
+                    return env_le_adjoint(acc, gl, sc.env, wo_, A * fgeo * w2k, le);
+                };
+                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, y.p, y.fn, y.area, A * Ltot, scale, va[k], extra);
                 va[k + 1].p = va[k + 1].p + ev.py;
                 va[k + 1].fn = va[k + 1].fn + ev.ny;
                 va[k + 1].area += ev.area_y;
                 wi_bar = wi_bar + ev.wi_bar;
                 const V3f fb = ev.f * ev.geo;
-                if (y_emits) acc.add3(gl.off_emit + 4 * y.emitter, A * fb * R.w2[k]);
+                if (y_emits && !y_env) acc.add3(gl.off_emit + 4 * y.emitter, A * fb * R.w2[k]);
                 Rk = Rk + fb * Ltot;
             }
         }
         // ---- emitter sampling at vertex k
-        if (R.nee_ok[k]) {
+        if (R.nee_ok[k] && R.ltri[k] < 0) {
+            // environment-map sample: the position on the bounding box is detached (envmap.cpp:95-101), J = 1;
+            // derivatives flow through the direction (x.p) into the radiance lookup and the geometric term
+            const V3f py(R.la[k], R.lb[k], R.lc[k]);
+            const float4 c = __ldg(sc.shade + 3 * R.htri[k] + 2);
+            const V3f ny(c.y, c.z, c.w);
+            const V3f wod = normalize(py - x.p);
+            const V2f uv = envmap_dir_to_uv<float>(mul3x3<float>(sc.env.from_world, nullptr, wod));
+            const V3f Le = bitmap_eval_envmap<float>(sc.env.data, nullptr, sc.env.w, sc.env.h, uv) * sc.env.scale;
+            const float scale = R.w1[k] / R.lpdf[k];
+            auto extra = [&](V3f wo_, V3f fgeo) {
+                V3f le;
+                return env_le_adjoint(acc, gl, sc.env, wo_, A * fgeo, le);
+            };
+            const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, py, ny, 0.f, A * Le, scale, va[k], extra);
+            wi_bar = wi_bar + ev.wi_bar;
+            Rk = Rk + Le * (ev.f * ev.geo);
+        } else if (R.nee_ok[k]) {
             const TriRec<float> TL = load_tri<float>(sc, R.ltri[k]);
             const V3f py = bilinear(TL.p0, TL.e1, TL.e2, V2f(R.la[k], R.lb[k]));
             const float4 c = __ldg(sc.shade + 3 * R.htri[k] + 2);
@@ -398,7 +474,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
                 const DEmitter &em = sc.emitters[emi];
                 const V3f Le(em.radiance[0], em.radiance[1], em.radiance[2]);
                 const float scale = R.w1[k] / R.lpdf[k];
-                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, py, ny, TL.area, A * Le, scale, va[k]);
+                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, py, ny, TL.area, A * Le, scale, va[k], [](V3f, V3f) { return V3f(0.f, 0.f, 0.f); });
                 wi_bar = wi_bar + ev.wi_bar;
                 const int lb = kGradTri * R.ltri[k];
                 acc.add3(lb, ev.py);

@@ -197,6 +197,28 @@ int psdr_scene_add_mesh(psdr_scene *s, const float *v, int nv, const int *f, int
     return (int) sc.meshes.size() - 1;
 }
 
+int psdr_scene_add_envmap(psdr_scene *s, const float *radiance, int w, int h, const float *to_world, float scale) {
+    if (!s || !radiance) { fail("null argument"); return -1; }
+    Scene &sc = s->sc;
+    if (sc.env.present) { fail("A scene is only allowed to have one envmap!"); return -1; }
+    if (w < 2 || h < 2) { fail("Bitmap: invalid resolution!"); return -1; }
+    HEnvmap &e = sc.env;
+    e.present = true;
+    e.w = w; e.h = h;
+    e.data.assign(radiance, radiance + (size_t) 3 * w * h);
+    e.ddata.clear();
+    e.scale = Dual(scale);
+    e.to_world[0] = M4<Dual>::identity();
+    e.to_world[1] = mat_from(to_world);
+    HEmitter em;
+    em.type = 1;
+    em.mesh = -1;
+    e.emitter = (int) sc.emitters.size();
+    sc.emitters.push_back(em);
+    sc.configured = false;
+    return e.emitter;
+}
+
 int psdr_scene_add_perspective(psdr_scene *s, float fov_x, float near_clip, float far_clip, const float *to_world) {
     if (!s) { fail("null scene"); return -1; }
     HCamera c;
@@ -255,8 +277,31 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
             put(sc.bsdfs[index].roughness, data[0]);
             break;
         }
+        case PSDR_ENVMAP_RADIANCE: {
+            if (!sc.env.present) return fail("the scene has no environment map");
+            if (n != 3 * sc.env.w * sc.env.h) return fail("envmap radiance size mismatch");
+            if (tangent) {
+                bool any = false;
+                for (int i = 0; i < n; ++i) any |= data[i] != 0.f;
+                if (any) sc.env.ddata.assign(data, data + n); else sc.env.ddata.clear();
+            } else sc.env.data.assign(data, data + n);
+            break;
+        }
+        case PSDR_ENVMAP_SCALE: {
+            if (!sc.env.present) return fail("the scene has no environment map");
+            if (n != 1) return fail("scale is 1 float");
+            put(sc.env.scale, data[0]);
+            break;
+        }
+        case PSDR_ENVMAP_TO_WORLD_LEFT: {
+            if (!sc.env.present) return fail("the scene has no environment map");
+            if (n != 16) return fail("a transform is 16 floats");
+            for (int i = 0; i < 16; ++i) put(sc.env.to_world[0].m[i / 4][i % 4], data[i]);
+            break;
+        }
         case PSDR_EMITTER_RADIANCE: {
             if (index < 0 || index >= (int) sc.emitters.size()) return fail("invalid emitter index");
+            if (sc.emitters[index].type != 0) return fail("not an AreaLight");
             if (n != 3) return fail("radiance is 3 floats");
             put(sc.emitters[index].radiance.x, data[0]); put(sc.emitters[index].radiance.y, data[1]); put(sc.emitters[index].radiance.z, data[2]);
             break;
@@ -283,6 +328,9 @@ int psdr_scene_clear_tangents(psdr_scene *s) {
             for (int i = 0; i < 16; ++i) M.m[i / 4][i % 4].d = 0.f;
     for (HBsdf &b : sc.bsdfs) { b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
     for (HEmitter &e : sc.emitters) e.radiance = detach(e.radiance);
+    sc.env.ddata.clear();
+    sc.env.scale = detach(sc.env.scale);
+    for (int i = 0; i < 16; ++i) sc.env.to_world[0].m[i / 4][i % 4].d = 0.f;
     sc.configured = false;
     return 0;
 }
@@ -574,6 +622,12 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
         case PSDR_BSDF_REFLECTANCE:
             if (index < 0 || 3 * index + 3 > (int) g.bsdf_refl.size()) return fail("invalid BSDF index");
             return copy(g.bsdf_refl.data() + 3 * index, 3);
+        case PSDR_ENVMAP_RADIANCE:
+            if (n != (int) g.env_radiance.size()) return fail("gradient buffer size mismatch");
+            std::memcpy(out, g.env_radiance.data(), sizeof(float) * n);
+            return 0;
+        case PSDR_ENVMAP_SCALE: return copy(&g.env_scale, 1);
+        case PSDR_ENVMAP_TO_WORLD_LEFT: return copy(g.env_to_world_left, 16);
         case PSDR_BSDF_SPECULAR:
             if (index < 0 || 3 * index + 3 > (int) g.bsdf_spec.size()) return fail("invalid BSDF index");
             return copy(g.bsdf_spec.data() + 3 * index, 3);

@@ -6,6 +6,7 @@
 #pragma once
 #include "dscene.h"
 #include "pmath.h"
+#include "texture.h"
 
 namespace psdr {
 
@@ -436,10 +437,22 @@ template <> __device__ __forceinline__ V3d emitter_radiance<Dual>(const DEmitter
 template <class S> __device__ __forceinline__ bool is_emitter(const DScene &sc, const Its<S> &its) {
     return its.valid && sc.meshes[its.mesh].emitter >= 0;
 }
+// EnvironmentMap::eval_direction (reference src/emitter/envmap.cpp:56-73)
+template <class S> __device__ __forceinline__ V3<S> env_eval_direction(const DEnv &e, V3<S> wi, EnvTexelTaps *taps = nullptr) {
+    const V3<S> v = mul3x3<S>(e.from_world, e.d_from_world, wi);
+    const V2<S> uv = envmap_dir_to_uv<S>(v);
+    const V3<S> r = bitmap_eval_envmap<S>(e.data, IsDual<S>::value ? e.ddata : nullptr, e.w, e.h, uv, taps);
+    return r * Lift<S>::s(e.scale, e.d_scale);
+}
 template <class S> __device__ __forceinline__ V3<S> Le(const DScene &sc, const Its<S> &its, bool active) {
     if (!its.valid) return V3<S>(S(0.f));
     const int e = sc.meshes[its.mesh].emitter;
-    if (e < 0 || !(active && val(its.wi.z) > 0.f)) return V3<S>(S(0.f));
+    if (e < 0) return V3<S>(S(0.f));
+    if (sc.emitters[e].type == 1) {   // EnvironmentMap::eval: radiance arriving along -wi, no cosine test
+        if (!active) return V3<S>(S(0.f));
+        return env_eval_direction<S>(sc.env, -its.to_world(its.wi));
+    }
+    if (!(active && val(its.wi.z) > 0.f)) return V3<S>(S(0.f));
     return emitter_radiance<S>(sc.emitters[e]);
 }
 
@@ -472,13 +485,75 @@ template <class S> struct PosSample {
     V2f st;      // barycentrics of the sample on it
 };
 
-// Scene::sample_emitter_position (reference src/scene/scene.cpp:987-1013) -> Mesh::sample_position
-template <class S> __device__ __forceinline__ PosSample<S> sample_emitter_position(const DScene &sc, V2f sample2) {
+// EnvironmentMap::sample_direction + __sample_position (reference src/emitter/envmap.cpp:86-129) and
+// ray_intersect_scene_aabb (include/psdr/utils.h:144-164): a direction drawn from the cell distribution,
+// turned into the point where it leaves the scene bounding box.  Everything is detached.
+__device__ __forceinline__ void env_sample_position(const DEnv &e, V3f ref_p, V2f sample2, V3f &p, V3f &n, float &pdf_out) {
+    const int ncells = e.cw * e.ch;
+    float prob;
+    const int idx = sample_reuse(e.cell_pmf, e.cell_cmf, ncells, e.cell_sum, sample2.y, prob);   // HyperCube<2>: last dimension
+    const int cx = idx / e.ch, cy = idx - cx * e.ch;
+    const float u = (sample2.x + (float) cx) * (1.f / (float) e.cw), v = (sample2.y + (float) cy) * (1.f / (float) e.ch);
+    float pdf = prob * (float) ncells;
+    float st, ct, sp, cp;
+    sincos_full(v * kPi, st, ct);
+    sincos_full(u * (2.f * kPi), sp, cp);
+    V3f d(sp * st, ct, -(cp * st));                                   // sphdir(theta, phi) -> (y, z, -x)
+    const float inv_sin_theta = 1.f / sqrtf(fmaxf(sqr(d.x) + sqr(d.z), sqr(kEpsilon)));
+    if (pdf > kEpsilon) pdf *= inv_sin_theta * (.5f / sqr(kPi));
+    d = mul3x3<float>(e.to_world, nullptr, d);
+    const float dd[3] = {d.x, d.y, d.z}, oo[3] = {ref_p.x, ref_p.y, ref_p.z};
+    float t = 0.f;
+    int axis = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float t1 = (e.lower[i] - oo[i]) / dd[i], t2 = (e.upper[i] - oo[i]) / dd[i];
+        const float tm = fmaxf(t1, t2);
+        if (i == 0 || tm < t) { t = tm; axis = i; }
+    }
+    float nn[3] = {0.f, 0.f, 0.f};
+    nn[axis] = signbit_(dd[axis]) ? 1.f : -1.f;                       // -sign(d[axis])
+    n = V3f(nn[0], nn[1], nn[2]);
+    const float G = dot(n, -d) * (1.f / sqr(t));
+    p = V3f(fmaf(d.x, t, ref_p.x), fmaf(d.y, t, ref_p.y), fmaf(d.z, t, ref_p.z));
+    pdf_out = pdf * G;
+}
+
+// EnvironmentMap::__sample_position_pdf (reference src/emitter/envmap.cpp:142-162) + HyperCubeDistribution::pdf
+template <class S> __device__ __forceinline__ float env_position_pdf(const DEnv &e, V3f ref_p, const Its<S> &its) {
+    V3f d = val(its.p) - ref_p;
+    const float dist2 = squared_norm(d);
+    d = d / safe_sqrt(dist2);
+    const float G = fabsf(dot(d, val(its.n))) / dist2;
+    d = mul3x3<float>(e.from_world, nullptr, d);
+    const float factor = G * (1.f / sqrtf(fmaxf(sqr(d.x) + sqr(d.z), sqr(kEpsilon)))) * (.5f / sqr(kPi));
+    const V2f uv = envmap_dir_to_uv<float>(d);
+    const int ix = (int) floorf(uv.x * (float) e.cw), iy = (int) floorf(uv.y * (float) e.ch);
+    if (!(ix >= 0 && ix < e.cw && iy >= 0 && iy < e.ch)) return 0.f;
+    const int idx = ix * e.ch + iy;
+    return (__ldg(e.cell_pmf + idx) / e.cell_sum) * (float) (e.cw * e.ch) * factor;
+}
+
+// Scene::sample_emitter_position (reference src/scene/scene.cpp:987-1013) -> Mesh::sample_position / EnvironmentMap
+template <class S> __device__ __forceinline__ PosSample<S> sample_emitter_position(const DScene &sc, V3f ref_p, V2f sample2) {
     PosSample<S> ps;
     int ei = 0;
     float emitter_pdf = 1.f;
     if (sc.n_emitters != 1) ei = sample_reuse(sc.emitter_pmf, sc.emitter_cmf, sc.n_emitters, sc.emitter_sum, sample2.y, emitter_pdf);
     const DEmitter &em = sc.emitters[ei];
+    if (em.type == 1) {
+        V3f p, n;
+        float pdf;
+        env_sample_position(sc.env, ref_p, sample2, p, n, pdf);
+        ps.p = lift3<S>(p);
+        ps.n = lift3<S>(n);
+        ps.J = S(1.f);
+        ps.pdf = pdf;
+        if (sc.n_emitters != 1) ps.pdf *= emitter_pdf;
+        ps.tri = -1;
+        ps.st = V2f(0.f, 0.f);
+        return ps;
+    }
     float dummy;
     const int fi = sample_reuse(sc.face_pmf + em.distrb_offset, sc.face_cmf + em.distrb_offset, em.nfaces, em.face_sum, sample2.x, dummy);
     const float t = safe_sqrt(1.f - sample2.x);
@@ -501,10 +576,11 @@ template <class S> __device__ __forceinline__ PosSample<S> sample_emitter_positi
     return ps;
 }
 
-template <class S> __device__ __forceinline__ float emitter_position_pdf(const DScene &sc, const Its<S> &its, bool active) {
+template <class S> __device__ __forceinline__ float emitter_position_pdf(const DScene &sc, V3f ref_p, const Its<S> &its, bool active) {
     if (!its.valid || !active) return 0.f;
     const int e = sc.meshes[its.mesh].emitter;
     if (e < 0) return 0.f;
+    if (sc.emitters[e].type == 1) return env_position_pdf<S>(sc.env, ref_p, its);
     return sc.emitters[e].sampling_weight * sc.emitters[e].inv_total_area;
 }
 
@@ -571,7 +647,7 @@ struct NoRecord {
     __device__ __forceinline__ void vertex(int, int, float, float) {}
     __device__ __forceinline__ void throughput(int, V3f) {}
     __device__ __forceinline__ void bounce(int, bool, float, float) {}
-    __device__ __forceinline__ void nee(int, bool, int, V2f, int, float, float) {}
+    __device__ __forceinline__ void nee(int, bool, int, V2f, V3f, int, float, float) {}
 };
 
 template <class S, bool kBvh, bool kAD, class Rec>
@@ -613,7 +689,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
                     if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
                     else bsdf_val = bsdf_eval(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
                 }
-                const float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, its1, active));
+                const float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, val(its.p), its1, active));
                 R.bounce(depth, val(its1.t) >= kEpsilon, pdf0, weight2);
                 throughput = throughput * bsdf_val;
                 result = result + Le(sc, its1, active) * throughput * S(weight2);
@@ -630,7 +706,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
         const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
         const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
         {   // ---- emitter sampling
-            const PosSample<S> ps = sample_emitter_position<S>(sc, V2f(s_x, s_y));
+            const PosSample<S> ps = sample_emitter_position<S>(sc, val(its.p), V2f(s_x, s_y));
             bool active_direct = !is_emitter(sc, its);
             V3<S> wod = ps.p - its.p;
             const S dist_sqr = squared_norm(wod);
@@ -649,7 +725,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
                 const float pdf1 = bsdf_pdf(sc, its, wo_local, active_direct) * val(G_val);
                 if (pdf1 != 0.f) {
                     const float weight1 = mis_weight(ps.pdf, pdf1);
-                    R.nee(depth + 1, val(its2.wi.z) > 0.f, ps.tri, ps.st, its2.tri, ps.pdf, weight1);
+                    R.nee(depth + 1, ps.tri < 0 || val(its2.wi.z) > 0.f, ps.tri, ps.st, val(ps.p), its2.tri, ps.pdf, weight1);
                     result = result + throughput * emitter_val * bsdf_val2 * S(weight1);
                 }
             }
@@ -724,7 +800,7 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     const V3f edge2 = ep2 - val(ep0);
     const V3f _p0 = val(bp0);
     pdf0 /= norm(e1v);
-    const PosSample<float> ps2 = sample_emitter_position<float>(sc, V2f(sample3.y, sample3.z));
+    const PosSample<float> ps2 = sample_emitter_position<float>(sc, _p0, V2f(sample3.y, sample3.z));
     const V3f _p2 = ps2.p, bn = ps2.n;
     V3f e = _p2 - _p0;
     const float distSqr = squared_norm(e);

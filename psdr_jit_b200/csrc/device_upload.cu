@@ -97,6 +97,15 @@ void upload_scene(Scene &sc) {
         dbsdf.push_back(d);
     }
     for (const HEmitter &e : sc.emitters) {
+        if (e.type == 1) {   // EnvironmentMap: everything lives in DEnv
+            DEmitter d{};
+            d.type = 1;
+            d.mesh = e.mesh;
+            d.sampling_weight = e.sampling_weight;
+            d.emitter_pmf = e.raw_weight;
+            demit.push_back(d);
+            continue;
+        }
         const HMesh &m = sc.meshes[e.mesh];
         DEmitter d{};
         d.radiance[0] = e.radiance.x.v; d.radiance[1] = e.radiance.y.v; d.radiance[2] = e.radiance.z.v;
@@ -161,7 +170,8 @@ void upload_scene(Scene &sc) {
                  o_mesh = pk.add(dmeshes), o_emit = pk.add(demit), o_bsdf = pk.add(dbsdf), o_fp = pk.add(face_pmf), o_fc = pk.add(face_cmf),
                  o_ep = pk.add(em_pmf), o_ec = pk.add(em_cmf), o_sec = pk.add(sec), o_sp = pk.add(sec_pmf), o_scm = pk.add(sec_cmf),
                  o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
-                 o_nodes = pk.add(nodes), o_order = pk.add(order), o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf);
+                 o_nodes = pk.add(nodes), o_order = pk.add(order), o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf),
+                 o_env = pk.add(sc.env.data), o_denv = pk.add(sc.env.ddata), o_cp = pk.add(sc.env.cell.pmf), o_cc = pk.add(sc.env.cell.cmf);
 
     if (!sc.dev) sc.dev = new DeviceBuffers();
     DeviceBuffers &db = *sc.dev;
@@ -214,6 +224,29 @@ void upload_scene(Scene &sc) {
             d.bg_b[i] = geo[3 * i + 1];
             d.bg_c[i] = geo[3 * i + 2].x;
         }
+
+    d.env = DEnv{};
+    if (sc.env.present) {
+        const HEnvmap &e = sc.env;
+        DEnv &de = d.env;
+        de.present = 1;
+        de.emitter = e.emitter;
+        de.w = e.w; de.h = e.h;
+        de.data = (const float *) (base + o_env);
+        de.ddata = e.ddata.empty() ? nullptr : (const float *) (base + o_denv);
+        de.scale = e.scale.v; de.d_scale = e.scale.d;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                de.to_world[3 * i + j] = e.to_world_full.m[i][j].v; de.d_to_world[3 * i + j] = e.to_world_full.m[i][j].d;
+                de.from_world[3 * i + j] = e.from_world.m[i][j].v; de.d_from_world[3 * i + j] = e.from_world.m[i][j].d;
+            }
+        de.lower[0] = e.lower.x; de.lower[1] = e.lower.y; de.lower[2] = e.lower.z;
+        de.upper[0] = e.upper.x; de.upper[1] = e.upper.y; de.upper[2] = e.upper.z;
+        de.cw = e.cw; de.ch = e.ch;
+        de.cell_sum = e.cell.sum;
+        de.cell_pmf = (const float *) (base + o_cp);
+        de.cell_cmf = (const float *) (base + o_cc);
+    }
 
     sc.dcameras.assign(sc.cameras.size(), DCamera{});
     size_t pmf_off = 0;

@@ -30,6 +30,8 @@ struct DMesh {
 };
 
 struct DEmitter {
+    int type;                // 0 AreaLight, 1 EnvironmentMap (fields below unused, see DEnv)
+    int pad_;
     float radiance[3];
     float d_radiance[3];
     int mesh;
@@ -41,6 +43,20 @@ struct DEmitter {
     float face_sum;          // drjit-style fp32 sum of the face areas
     float emitter_pmf;       // unnormalised selection weight (area*luminance)
     float pad0, pad1;
+};
+
+// EnvironmentMap tables (reference src/emitter/envmap.cpp)
+struct DEnv {
+    int present, emitter;
+    int w, h;                          // radiance bitmap (lat-long)
+    const float *data, *ddata;         // rgb interleaved [h][w][3] + forward tangents
+    float scale, d_scale;
+    float to_world[9], d_to_world[9];  // 3x3 direction transforms, row-major
+    float from_world[9], d_from_world[9];
+    float lower[3], upper[3];          // scene bounding box the "positions" live on
+    int cw, ch;                        // cell grid 2(w-1) x 2(h-1)
+    float cell_sum;
+    const float *cell_pmf, *cell_cmf;
 };
 
 struct DBsdf {
@@ -91,6 +107,7 @@ struct DScene {
     float sec_sum;
     const DBvhNode *nodes;
     const int *tri_order;
+    DEnv env;
     // brute-force mode (n_tris <= kMaxBruteTris): the triangle geometry again, by value -- it travels in
     // the kernel parameters and is read through the constant bank / uniform datapath.
     // bg_a = (p0.xyz, e1.x), bg_b = (e1.yz, e2.xy), bg_c = e2.z

@@ -7,6 +7,7 @@ namespace psdr {
 constexpr int kGradTri = 24;
 constexpr int kGradCam = 40;
 constexpr int kGradBsdf = 8;
+constexpr int kGradEnvHead = 16;
 struct GradLayout {
     float *base;      // global table (device)
     int off_bsdf;     // kGradBsdf floats per BSDF: 0..2 d reflectance (diffuse) | 3 d roughness | 4..6 d specular
@@ -14,6 +15,7 @@ struct GradLayout {
     int off_cam;      // 40 floats: 0..15 d to_world | 16..31 d world_to_sample | 32..34 d pos | 35..37 d dir
     int off_pe;       // 4 floats per primary edge of the rendered sensor (d p0.xy, d p1.xy)
     int off_se;       // 6 floats per secondary edge (d p0, d e1)
+    int off_env;      // environment map: 0 d scale | 1..9 d from_world (3x3) | 16.. d texels (3*w*h); == total if none
     int total;
 };
 

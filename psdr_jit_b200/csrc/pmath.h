@@ -96,6 +96,62 @@ PSDR_HD void sincos_quarter(float x, float &sn, float &cs) {
     cs = fmaf(pc * z, z, fmaf(-0.5f, z, 1.f));
 }
 
+
+// ---- elementary functions with a fixed operation order, shared bit for bit by host and device code
+// (library sincosf/atan2f/acosf differ in the last ulp between glibc and libdevice, and the environment
+// map turns them into discrete cell / texel choices).  Polynomials: Cephes single precision.
+PSDR_HD void sincos_full(float x, float &sn, float &cs) {   // any |x| < ~1e4
+    const float kf = rintf(x * 0.63661977236758134308f);    // x / (pi/2)
+    const int k = (int) kf;
+    float r = fmaf(-kf, 1.5703125f, x);                      // Cody-Waite, pi/2 split in three
+    r = fmaf(-kf, 4.837512969970703125e-4f, r);
+    r = fmaf(-kf, 7.54978995489188216e-8f, r);
+    float s, c;
+    sincos_quarter(r, s, c);
+    switch (k & 3) {
+        case 0: sn = s; cs = c; break;
+        case 1: sn = c; cs = -s; break;
+        case 2: sn = -s; cs = -c; break;
+        default: sn = -c; cs = s; break;
+    }
+}
+PSDR_HD float atan_pos(float x) {   // x >= 0
+    float y = 0.f;
+    if (x > 2.414213562373095f) { y = 1.5707963267948966f; x = -1.f / x; }
+    else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = (x - 1.f) / (x + 1.f); }
+    const float z = x * x;
+    const float p = fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f);
+    return y + fmaf(p * z, x, x);
+}
+PSDR_HD float atan2_(float y, float x) {
+    if (x == 0.f && y == 0.f) return 0.f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a = ax >= ay ? atan_pos(ay / ax) : 1.5707963267948966f - atan_pos(ax / ay);
+    if (x < 0.f) a = 3.14159265358979323846f - a;
+    return y < 0.f ? -a : a;
+}
+PSDR_HD float asin_small(float x) {   // |x| <= 0.5
+    const float z = x * x;
+    const float p = fmaf(fmaf(fmaf(fmaf(4.2163199048e-2f, z, 2.4181311049e-2f), z, 4.5470025998e-2f), z, 7.4953002686e-2f), z, 1.6666752422e-1f);
+    return fmaf(p * z, x, x);
+}
+PSDR_HD float safe_acos_(float x) {   // drjit safe_acos: clamps to [-1, 1]
+    x = fminf(fmaxf(x, -1.f), 1.f);
+    if (x < -0.5f) return 3.14159265358979323846f - 2.f * asin_small(sqrtf(0.5f * (1.f + x)));
+    if (x > 0.5f) return 2.f * asin_small(sqrtf(0.5f * (1.f - x)));
+    return 1.5707963267948966f - asin_small(x);
+}
+PSDR_HD Dual atan2_(Dual y, Dual x) {
+    const float r2 = x.v * x.v + y.v * y.v;
+    return Dual(atan2_(y.v, x.v), r2 > 0.f ? (x.v * y.d - y.v * x.d) / r2 : 0.f);
+}
+PSDR_HD Dual safe_acos_(Dual x) {
+    const float s = 1.f - x.v * x.v;
+    return Dual(safe_acos_(x.v), s > 0.f ? -x.d / sqrtf(s) : 0.f);
+}
+PSDR_HD float floor_(float x) { return floorf(x); }
+PSDR_HD Dual floor_(Dual x) { return Dual(floorf(x.v), 0.f); }
+
 template <class S> struct V2 {
     S x, y;
     PSDR_HD V2() : x(S(0.f)), y(S(0.f)) {}

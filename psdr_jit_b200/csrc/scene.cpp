@@ -3,6 +3,7 @@
 // primary/secondary edge lists and the BVH2.  Follows reference src/scene/scene.cpp:311-601,
 // src/shape/mesh.cpp:23-62,244-382, src/sensor/perspective.cpp:10-152, src/emitter/area.cpp:9-14.
 #include "scene.h"
+#include "texture.h"
 
 #include <algorithm>
 #include <chrono>
@@ -410,6 +411,71 @@ void build_bvh(const std::vector<HTri> &tris, std::vector<DBvhNode> &nodes, std:
 // ---------------------------------------------------------------------------------------------
 void upload_scene(Scene &sc);   // device_upload.cu
 
+// EnvironmentMap part of Scene::configure (reference src/scene/scene.cpp:355-368,384-416,435-485 and
+// src/emitter/envmap.cpp:17-41).  Runs after the meshes and sensors are configured.
+static void configure_envmap(Scene &sc, bool plain_configure) {
+    HEnvmap &env = sc.env;
+    if (!env.present) return;
+    if (env.w < 2 || env.h < 2) throw std::runtime_error("src/emitter/envmap.cpp (21): width > 1 && height > 1");
+    env.to_world_full = env.to_world[0] * env.to_world[1];
+    env.from_world = invert(env.to_world_full);
+    if (!env.has_bounds) {
+        // scene AABB over mesh vertices and camera positions; the reference initialises the upper corner with
+        // numeric_limits<float>::min() (the smallest POSITIVE float), kept
+        V3f lo(3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f), hi(1.175494351e-38f, 1.175494351e-38f, 1.175494351e-38f);
+        auto grow = [&](V3f p) {
+            lo = V3f(std::fmin(lo.x, p.x), std::fmin(lo.y, p.y), std::fmin(lo.z, p.z));
+            hi = V3f(std::fmax(hi.x, p.x), std::fmax(hi.y, p.y), std::fmax(hi.z, p.z));
+        };
+        for (const HMesh &m : sc.meshes)
+            for (const V3d &p : m.v_world) grow(val(p));
+        (void) plain_configure;
+        for (const HCamera &c : sc.cameras) grow(val(c.pos));
+        const float margin = std::fmin(std::fmin((hi.x - lo.x) * 0.05f, (hi.y - lo.y) * 0.05f), (hi.z - lo.z) * 0.05f);
+        env.lower = V3f(lo.x - margin, lo.y - margin, lo.z - margin);
+        env.upper = V3f(hi.x + margin, hi.y + margin, hi.z + margin);
+        // bounding mesh: 8 corners, 12 triangles, face normals, no edges, no BSDF, emitter = the envmap
+        static const int face_data[3][12] = {{0, 0, 1, 1, 2, 2, 0, 0, 0, 0, 4, 4}, {1, 3, 5, 7, 3, 7, 5, 4, 2, 6, 7, 6}, {3, 2, 7, 3, 7, 6, 1, 5, 6, 4, 5, 7}};
+        HMesh b;
+        const float lo3[3] = {env.lower.x, env.lower.y, env.lower.z}, hi3[3] = {env.upper.x, env.upper.y, env.upper.z};
+        for (int i = 0; i < 8; ++i) {
+            float c[3];
+            for (int j = 0; j < 3; ++j) c[j] = (i & (1 << j)) ? hi3[j] : lo3[j];
+            b.v_raw.push_back(V3d(Dual(c[0]), Dual(c[1]), Dual(c[2])));
+        }
+        for (int k = 0; k < 12; ++k)
+            for (int r = 0; r < 3; ++r) b.f.push_back(face_data[r][k]);
+        for (auto &M : b.to_world) M = M4<Dual>::identity();
+        b.use_face_normals = true;
+        b.enable_edges = false;
+        b.bsdf = -1;
+        b.emitter = env.emitter;
+        b.is_bound_mesh = true;
+        configure_mesh(b);
+        b.face_offset = 0;
+        for (const HMesh &m : sc.meshes) b.face_offset += (int) m.tris.size();
+        env.mesh = (int) sc.meshes.size();
+        sc.emitters[env.emitter].mesh = env.mesh;
+        sc.meshes.push_back(std::move(b));
+        env.has_bounds = true;
+    }
+    // cell distribution: luminance * sin(theta) at the centres of 2(w-1) x 2(h-1) cells, x-major
+    env.cw = (env.w - 1) << 1;
+    env.ch = (env.h - 1) << 1;
+    const size_t ncells = (size_t) env.cw * env.ch;
+    std::vector<float> mass(ncells);
+    const float ux = 1.f / (float) env.cw, uy = 1.f / (float) env.ch, dtheta = kPi / (float) env.ch;
+    for (size_t idx = 0; idx < ncells; ++idx) {
+        const int cx = (int) (idx / env.ch), cy = (int) (idx % env.ch);
+        const V2f uv(((float) cx + .5f) * ux, ((float) cy + .5f) * uy);
+        const V3f v = bitmap_eval_envmap<float>(env.data.data(), nullptr, env.w, env.h, uv);
+        float sn, cs;
+        sincos_full(((float) cy + .5f) * dtheta, sn, cs);
+        mass[idx] = luminance(v) * sn;
+    }
+    env.cell.init(mass);
+}
+
 void Scene::configure(const int *active, int nactive) {
     const auto t0 = std::chrono::high_resolution_clock::now();
     configured = false;
@@ -442,12 +508,17 @@ void Scene::configure(const int *active, int nactive) {
         }
         configure_camera(*this, cameras[i], act);
     }
+    configure_envmap(*this, nactive == 0);
     if (!emitters.empty()) {
         std::vector<float> w;
+        double total_weight = 0.0;          // scene.cpp:489-503: the envmap's weight is the sum of the others
         for (HEmitter &e : emitters) {
-            e.raw_weight = meshes[e.mesh].total_area * luminance(val(e.radiance));
-            w.push_back(e.raw_weight);
+            e.raw_weight = e.type == 1 ? 0.f : meshes[e.mesh].total_area * luminance(val(e.radiance));
+            total_weight += e.raw_weight;
         }
+        for (HEmitter &e : emitters)
+            if (e.type == 1) e.raw_weight = (float) total_weight;
+        for (HEmitter &e : emitters) w.push_back(e.raw_weight);
         emitter_distrb.init(w);
         const float inv_total = 1.f / emitter_distrb.sum;
         for (HEmitter &e : emitters) e.sampling_weight = e.raw_weight * inv_total;

@@ -46,6 +46,7 @@ struct HMesh {
     int bsdf = -1, emitter = -1;
     bool use_face_normals = false, enable_edges = true;
     bool edges_dirty = true;
+    bool is_bound_mesh = false;   // the envmap's bounding box (appended by configure)
     // configured
     std::vector<V3d> v_world;
     std::vector<HTri> tris;
@@ -56,9 +57,27 @@ struct HMesh {
 };
 
 struct HEmitter {
+    int type = 0;             // 0 AreaLight, 1 EnvironmentMap
     V3d radiance;
     int mesh = -1;
     float sampling_weight = 0.f, raw_weight = 0.f;
+};
+
+// EnvironmentMap (reference src/emitter/envmap.cpp, include/psdr/emitter/envmap.h): lat-long radiance bitmap,
+// scale, to_world = left * raw; `cell` = HyperCubeDistribution2f over 2(w-1) x 2(h-1) cells (x-major)
+struct HEnvmap {
+    bool present = false;
+    int emitter = -1, mesh = -1;      // index into emitters / the bounding mesh (appended by configure)
+    int w = 0, h = 0;
+    std::vector<float> data, ddata;   // rgb interleaved, row-major (pixel = y*w + x); forward tangents
+    Dual scale = Dual(1.f);
+    M4<Dual> to_world[2];             // left, raw
+    // configured
+    M4<Dual> to_world_full, from_world;
+    bool has_bounds = false;          // the bounding box is fixed by the first configure() (scene.cpp:435)
+    V3f lower, upper;
+    int cw = 0, ch = 0;
+    Distrib cell;
 };
 
 struct HPrimEdge {
@@ -98,6 +117,8 @@ struct ParamGrads {
     std::vector<CamG> cameras;
     std::vector<double> bsdf_refl, emitter_rad, bsdf_spec;   // 3 per object
     std::vector<double> bsdf_rough;                          // 1 per BSDF
+    std::vector<float> env_radiance;                         // 3*w*h
+    double env_scale = 0.0, env_to_world_left[16] = {};
     bool valid = false;
 };
 
@@ -118,6 +139,7 @@ struct Scene {
     std::vector<HEmitter> emitters;
     std::vector<HCamera> cameras;
     std::vector<HSecEdge> sec_edges;
+    HEnvmap env;
     Distrib sec_edge_distrb, emitter_distrb;
     SamplerState samplers[3];
     bool configured = false;

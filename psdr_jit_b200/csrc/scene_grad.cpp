@@ -124,7 +124,8 @@ GradLayout Scene::grad_layout(int sensor) const {
     gl.off_pe = gl.off_cam + kGradCam;
     const int npe = (sensor >= 0 && sensor < (int) cameras.size()) ? (int) cameras[sensor].edges.size() : 0;
     gl.off_se = gl.off_pe + 4 * npe;
-    gl.total = gl.off_se + 6 * (int) sec_edges.size();
+    gl.off_env = gl.off_se + 6 * (int) sec_edges.size();
+    gl.total = gl.off_env + (env.present ? kGradEnvHead + 3 * env.w * env.h : 0);
     return gl;
 }
 
@@ -240,6 +241,25 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
     }
     for (size_t i = 0; i < emitters.size(); ++i)
         for (int c = 0; c < 3; ++c) grads.emitter_rad[3 * i + c] = table[gl.off_emit + 4 * i + c];
+    grads.env_radiance.clear();
+    grads.env_scale = 0.0;
+    std::memset(grads.env_to_world_left, 0, sizeof(grads.env_to_world_left));
+    if (env.present && gl.total > gl.off_env) {
+        const float *g = table + gl.off_env;
+        grads.env_scale = g[0];
+        grads.env_radiance.assign(g + kGradEnvHead, g + kGradEnvHead + (size_t) 3 * env.w * env.h);
+        // from_world = inverse(to_world_full), to_world_full = left * raw
+        Mat gF = zero();
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) gF.m[i][j] = g[1 + 3 * i + j];
+        const Mat F = mat_of(env.from_world), FT = transpose(F);
+        const Mat t = mul(mul(FT, gF), FT);
+        Mat gM = zero();
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) gM.m[i][j] = -t.m[i][j];
+        const Mat gL = mul(gM, transpose(mat_of(env.to_world[1])));
+        for (int i = 0; i < 16; ++i) grads.env_to_world_left[i] = gL.m[i / 4][i % 4];
+    }
     grads.valid = true;
 }
 

@@ -33,7 +33,17 @@ def is_microfacet(params):
     return len(params) == 3 and hasattr(params[0], "__len__")
 
 
-def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, bsdfs=None, d_bsdf=None):
+def test_envmap(w=32, h=16, seed=0):
+    """synthetic lat-long environment map (BASELINE config 3 recipe: rng.random**4 * 4), [h*w, 3]"""
+    rng = np.random.default_rng(seed)
+    return (rng.random((h * w, 3), dtype=np.float32) ** 4 * 4).astype(np.float32)
+
+
+test_envmap.__test__ = False
+
+
+def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, bsdfs=None, d_bsdf=None,
+                 envmap=None):
     """Scene = scenes.* meshes + CBOX bsdfs + camera; derivative parameter P translates mesh
     `move_mesh` by P*axis_scale through to_world_left (reference README.md:87-90)."""
     from oracle.psdr_oracle import OracleScene
@@ -45,6 +55,9 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
             sc.add_microfacet(name, params[0], params[1], params[2], d=d)
         else:
             sc.add_diffuse(name, params, d_refl=d)
+    if envmap is not None:      # dict(data, w, h, scale, to_world, d_data, d_scale, d_to_world_left); added before the meshes
+        sc.add_envmap(envmap["data"], envmap["w"], envmap["h"], to_world=envmap.get("to_world"), scale=envmap.get("scale", 1.0),
+                      d_data=envmap.get("d_data"), d_to_world_left=envmap.get("d_to_world_left"), d_scale=envmap.get("d_scale", 0.0))
     for i, m in enumerate(meshes):
         dtw = None
         if move_mesh is not None and i == move_mesh:
@@ -56,7 +69,8 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
 
 
 def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, accel=-1,
-                  shard=None, two_side=False, d_radiance=None, d_reflectance=None, d_cam_left=None, log_level=0, bsdfs=None, d_bsdf=None):
+                  shard=None, two_side=False, d_radiance=None, d_reflectance=None, d_cam_left=None, log_level=0, bsdfs=None, d_bsdf=None,
+                  envmap=None):
     """The same scene through the product's psdr_jit-style Python surface."""
     import psdr_jit_b200 as psdr
     cam = cam or scenes.CBOX_CAMERA
@@ -77,6 +91,17 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
             if d is not None:
                 b.d_reflectance = np.float32(d)
         sc.add_BSDF(b, name, twoSide=two_side)
+    if envmap is not None:
+        env = psdr.EnvironmentMap(psdr.Bitmap3fD(envmap["w"], envmap["h"], envmap["data"]))
+        env.scale = np.float32(envmap.get("scale", 1.0))
+        env.d_scale = np.float32(envmap.get("d_scale", 0.0))
+        if envmap.get("to_world") is not None:
+            env.to_world = np.asarray(envmap["to_world"], dtype=np.float32)
+        if envmap.get("d_data") is not None:
+            env.radiance.d_data = np.asarray(envmap["d_data"], dtype=np.float32)
+        if envmap.get("d_to_world_left") is not None:
+            env.set_transform(np.eye(4, dtype=np.float32), tangent=envmap["d_to_world_left"])
+        sc.add_EnvironmentMap(env)
     for i, m in enumerate(meshes):
         mesh = psdr.Mesh()
         mesh.load_raw(m.v, m.f, m.uv, m.fuv)
@@ -85,7 +110,7 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
     if move_mesh is not None:
         sc.param_map["Mesh[%d]" % move_mesh].set_transform(np.eye(4, dtype=np.float32), tangent=translation_tangent(axis_scale))
     if d_radiance is not None:
-        sc.param_map["Emitter[0]"].d_radiance = np.asarray(d_radiance, dtype=np.float32)
+        sc.param_map["Emitter[%d]" % (1 if envmap is not None else 0)].d_radiance = np.asarray(d_radiance, dtype=np.float32)
     if d_reflectance is not None:
         name, d = d_reflectance
         sc.param_map["BSDF[id=%s]" % name].d_reflectance = np.asarray(d, dtype=np.float32)

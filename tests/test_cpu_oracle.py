@@ -239,3 +239,28 @@ def test_guided_secondary_edges_vs_reference(oracle):
     for name, reso in (("g211", [2, 1, 1, 64]), ("g112", [1, 1, 2, 64]), ("g222", [2, 2, 2, 64])):
         a, b = np.abs(run(reso, 0)).sum(), np.abs(g[name]).sum()
         assert 0.6 < a / b < 1.6, (name, a, b)
+
+
+def _golden_env():
+    from tests.common import test_envmap
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    return dict(data=test_envmap(32, 16), w=32, h=16, scale=1.5,
+                to_world=np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]], np.float32))
+
+
+def test_envmap_vs_reference(oracle):
+    """EnvironmentMap (envmap.cpp, bitmap.cpp envmap mode, bounding mesh + emitter weights of scene.cpp:435-515):
+    two emitters (envmap first, area light second), Diffuse and Microfacet materials, against the running reference."""
+    g = np.load(GOLDEN + "/env_renderC.npz")
+    for tag, bs in (("diffuse", None), ("mf", scenes.CBOX_MF_BSDFS)):
+        for depth, seed in ((1, 0), (3, 3)):
+            img = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bs, envmap=_golden_env()).render(depth, seed=seed, mode=0)
+            r, nbad, r_ex = compare_stats(img, g["img_%s_d%d_seed%d" % (tag, depth, seed)], flip_rel=2e-5)
+            assert r < 1e-2 and nbad <= 60 and r_ex < 2e-5, (tag, depth, r, nbad, r_ex)
+    g = np.load(GOLDEN + "/env_renderD_128_s4_d3_smallbox.npz")
+    kw = dict(move_mesh=1, axis_scale=(0.0, 30.0, 50.0), bsdfs=scenes.CBOX_MF_BSDFS, envmap=_golden_env())
+    img, d = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, **kw).render(3, seed=5, mode=1, terms=7)
+    r, nbad, r_ex = compare_stats(img, g["img_interior"], flip_rel=2e-5)
+    assert nbad <= 0.03 * len(img) and r_ex < 1e-4, (r, nbad, r_ex)
+    r, nbad, r_ex = compare_stats(d * 2.0, g["grad_interior"], flip_rel=2e-5)      # reference tangent scaling
+    assert nbad <= 0.05 * len(img) and r_ex < 2e-4, (r, nbad, r_ex)

@@ -11,8 +11,24 @@ pytestmark = pytest.mark.gpu
 
 def _scene_with_tangents(psdr, meshes, w, h, spps, rng, what):
     mf = "microfacet" in what
-    sc = build_product(meshes, w, h, *spps, bsdfs=scenes.CBOX_MF_BSDFS if mf else None)
+    envmap = None
+    if "envmap" in what:
+        from tests.common import test_envmap
+        envmap = dict(data=test_envmap(32, 16), w=32, h=16, scale=1.5,
+                      to_world=np.array([[0.8, 0, 0.6, 0], [0, 1, 0, 0], [-0.6, 0, 0.8, 0], [0, 0, 0, 1]], np.float32))
+    sc = build_product(meshes, w, h, *spps, bsdfs=scenes.CBOX_MF_BSDFS if mf else None, envmap=envmap)
     tang = {}
+    if envmap is not None:
+        e = sc.param_map["Emitter[0]"]
+        e.radiance.d_data = rng.normal(size=(16 * 32, 3)).astype(np.float32)
+        e.d_scale = np.float32(0.7)
+        t = np.zeros((4, 4), np.float32)
+        t[:3, :3] = rng.normal(size=(3, 3)) * 0.3
+        e.d_to_world_left = t
+        tang[("Emitter[0]", "radiance.data")] = e.radiance.d_data
+        tang[("Emitter[0]", "scale")] = np.reshape(e.d_scale, (1,))
+        tang[("Emitter[0]", "to_world_left")] = t
+        what = [x for x in what if x != "envmap"]
     if mf:
         for name in ("BSDF[id=cat]", "BSDF[id=white]", "BSDF[id=red]"):
             b = sc.param_map[name]
@@ -65,6 +81,7 @@ CASES = [
     ("mesh_left vertices materials camera mesh_raw", 7, 3, "sphere"),
     ("microfacet", 1, 3, "cbox"), ("microfacet mesh_left vertices camera", 1, 2, "cbox"),
     ("microfacet mesh_left vertices camera", 7, 2, "sphere"),
+    ("envmap", 1, 2, "cbox"), ("envmap microfacet", 1, 3, "cbox"), ("envmap microfacet mesh_left vertices camera", 7, 3, "cbox"),
 ]
 
 

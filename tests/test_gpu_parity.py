@@ -344,3 +344,65 @@ def test_microfacet_vs_reference_golden():
     assert nbad <= 120 and r_ex < 1e-3, (r, nbad, r_ex)
     r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["grad_all"])
     assert nbad <= 0.06 * len(dimg) and r_ex < 5e-3, (r, nbad, r_ex)
+
+
+# ---- EnvironmentMap (reference src/emitter/envmap.cpp, src/core/bitmap.cpp envmap mode, scene.cpp:435-515) -----
+def _env(rot=None, **kw):
+    from tests.common import test_envmap
+    e = dict(data=test_envmap(32, 16), w=32, h=16, scale=1.5)
+    if rot is not None:
+        c, s_ = np.cos(rot), np.sin(rot)
+        e["to_world"] = np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]], np.float32)
+    e.update(kw)
+    return e
+
+
+@pytest.mark.parametrize("depth,spp,seed,bs", [(1, 2, 0, "diffuse"), (3, 4, 3, "mf"), (6, 1, 2, "mf")])
+def test_envmap_renderC_vs_oracle(oracle, depth, spp, seed, bs):
+    psdr = _psdr()
+    bsdfs = scenes.CBOX_MF_BSDFS if bs == "mf" else None
+    env = _env(rot=0.7)
+    ref = build_oracle(scenes.cbox_meshes(), 128, 128, spp, 0, 0, bsdfs=bsdfs, envmap=env).render(depth, seed=seed, mode=0)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, spp, 0, 0, bsdfs=bsdfs, envmap=env)
+    assert sc.get_num_emitters() == 2
+    got = psdr.PathTracer(depth).renderC(sc, 0, seed=seed).cpu().numpy()
+    assert np.isfinite(got).all() and rel_l2(got, ref) < TOL
+
+
+@pytest.mark.parametrize("terms", [1, 7])
+def test_envmap_renderD_vs_oracle(oracle, terms):
+    """tangents: small box translation, envmap texels, envmap scale, envmap rotation, camera"""
+    psdr = _psdr()
+    rng = np.random.default_rng(3)
+    d_left = np.zeros((4, 4), np.float32)
+    d_left[0, 2], d_left[2, 0] = 1.0, -1.0                      # d/dangle of a rotation about y at angle 0
+    env = _env(rot=0.7, d_data=rng.normal(size=(16 * 32, 3)).astype(np.float32), d_scale=0.5, d_to_world_left=d_left)
+    spps = (4 if terms & 1 else 0, 4 if terms & 2 else 0, 4 if terms & 4 else 0)
+    kw = dict(move_mesh=1, axis_scale=(0.0, 30.0, 50.0), bsdfs=scenes.CBOX_MF_BSDFS, envmap=env)
+    img_ref, dimg_ref = build_oracle(scenes.cbox_meshes(), 128, 128, *spps, **kw).render(3, seed=5, mode=1, terms=7)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, *spps, **kw)
+    img, dimg = psdr.PathTracer(3).renderD_fwd(sc, 0, seed=5)
+    assert rel_l2(img.cpu().numpy(), img_ref) < TOL
+    assert np.abs(dimg_ref).max() > 0 and rel_l2(dimg.cpu().numpy(), dimg_ref) < TOL
+
+
+def test_envmap_vs_reference_golden():
+    psdr = _psdr()
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    from tests.common import test_envmap
+    env = dict(data=test_envmap(32, 16), w=32, h=16, scale=1.5,
+               to_world=np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]], np.float32))
+    g = np.load(GOLDEN + "/env_renderC.npz")
+    for tag, bs in (("diffuse", None), ("mf", scenes.CBOX_MF_BSDFS)):
+        sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bs, envmap=env)
+        for depth, seed in ((1, 0), (3, 3)):
+            got = psdr.PathTracer(depth).renderC(sc, 0, seed=seed).cpu().numpy()
+            r, nbad, r_ex = compare_stats(got, g["img_%s_d%d_seed%d" % (tag, depth, seed)], flip_rel=2e-5)
+            assert r < 1e-2 and nbad <= 60 and r_ex < 2e-5, (tag, depth, r, nbad, r_ex)
+    g = np.load(GOLDEN + "/env_renderD_128_s4_d3_smallbox.npz")
+    integ = psdr.PathTracer(3)
+    integ.reference_tangent_scaling = True
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 4, 4, move_mesh=1, axis_scale=(0.0, 30.0, 50.0), bsdfs=scenes.CBOX_MF_BSDFS, envmap=env)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=5)
+    r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["grad_all"], flip_rel=2e-5)
+    assert nbad <= 0.08 * len(dimg) and r_ex < 1e-3, (r, nbad, r_ex)
