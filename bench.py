@@ -117,6 +117,7 @@ def build_scene(psdr, rank: int, world: int, w=W, h=H, spp=SPP, sppe=SPPE, sppse
     tangent[0, 3] = 100.0                                    # d/dP translate(100 P, 0, 0)
     sc.param_map["Mesh[0]"].set_transform(np.eye(4, dtype=np.float32), tangent=tangent)
     sc.set_shard(rank, world)
+    sc.set_accel(int(os.environ.get("PSDR_ACCEL", "-1")))     # -1 auto, 0 brute-force scan, 1 BVH2 (experiments)
     sc.configure()
     sc.configure([0])
     return sc, tangent

@@ -20,22 +20,38 @@
 namespace psdr {
 
 // Accumulator: either the block's shared-memory copy of [lo, hi) of the table or the global table.
+// The atomic itself lives in ONE non-inlined function per translation unit: inlined, the ~300 scatter sites of
+// the adjoint made up half of the kernel's instructions (generic-address atomics expand to ~45 SASS
+// instructions each) and the kernel stalled on instruction fetch (profiles/r01e).
+static __device__ __noinline__ void grad_add3_impl(unsigned smem_addr, float *g, int lo, int hi, int idx, float x, float y, float z) {
+    const float v[3] = {x, y, z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (v[c] == 0.f || !isfinite(v[c])) continue;
+        const int i = idx + c;
+        if (smem_addr && i >= lo && i < hi) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_addr + 4u * (unsigned) (i - lo)), "f"(v[c]) : "memory");
+        else atomicAdd(g + i, v[c]);
+    }
+}
+static __device__ __noinline__ void grad_add1_impl(unsigned smem_addr, float *g, int lo, int hi, int idx, float v) {
+    if (v == 0.f || !isfinite(v)) return;
+    if (smem_addr && idx >= lo && idx < hi) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_addr + 4u * (unsigned) (idx - lo)), "f"(v) : "memory");
+    else atomicAdd(g + idx, v);
+}
 struct GradAcc {
     float *g;         // global table
     float *s;         // shared copy (nullptr = none)
+    unsigned s_addr;  // its shared-window address (0 = none)
     int lo, hi;
-    __device__ __forceinline__ void add(int idx, float v) const {
-        if (v == 0.f || !isfinite(v)) return;
-        if (s && idx >= lo && idx < hi) atomicAdd(s + (idx - lo), v);
-        else atomicAdd(g + idx, v);
-    }
-    __device__ __forceinline__ void add3(int idx, V3f v) const { add(idx, v.x); add(idx + 1, v.y); add(idx + 2, v.z); }
+    __device__ __forceinline__ void add(int idx, float v) const { grad_add1_impl(s_addr, g, lo, hi, idx, v); }
+    __device__ __forceinline__ void add3(int idx, V3f v) const { grad_add3_impl(s_addr, g, lo, hi, idx, v.x, v.y, v.z); }
 };
 
 __device__ __forceinline__ GradAcc grad_acc_begin(const GradLayout &gl, float *smem, int lo, int hi, bool use_smem) {
     GradAcc a;
     a.g = gl.base;
     a.s = use_smem ? smem : nullptr;
+    a.s_addr = use_smem ? (unsigned) __cvta_generic_to_shared(smem) : 0u;
     a.lo = lo;
     a.hi = hi;
     if (use_smem) {
@@ -122,13 +138,13 @@ template <class S> __device__ __forceinline__ void iso_specular(S rough, S ci, S
     e = exp2_(vh * (S(-5.55473f) * vh - S(6.8316f)));
     dg = ggx * iso_smith_g1<S>(alpha, ci, vh) * iso_smith_g1<S>(alpha, co, vh) / (S(4.f) * co * ci + S(1e-6f));
 }
-template <class S> __device__ __forceinline__ V3<S> bsdf_iso(const BsdfP<S> &b, S ci, S co, S cio) {
+template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_iso(const BsdfP<S> &b, S ci, S co, S cio) {
     if (b.two_side) {
         if (signbit_(val(ci))) co = -co;
         ci = abs_(ci);
     }
     if (!(val(ci) > 0.f && val(co) > 0.f)) return V3<S>(S(0.f));
-    if (b.type == 1) {
+    if ((kCfg & kCfgFull) && b.type == 1) {
         S dg, e;
         iso_specular<S>(b.rough, ci, co, cio, dg, e);
         const V3<S> fresnel = b.spec + (V3<S>(S(1.f)) - b.spec) * e;
@@ -141,23 +157,23 @@ struct BsdfJet {        // value and partials of sum_c W_c f_c
     V3f f;
     float d_ci, d_co, d_cio;
 };
-__device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, float ci, float co, float cio, V3f W) {
+template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, float ci, float co, float cio, V3f W) {
     BsdfJet j;
     const BsdfP<Dual> p = bsdf_params<Dual>(b);
-    const V3d a = bsdf_iso<Dual>(p, Dual(ci, 1.f), Dual(co), Dual(cio));
-    const V3d c = bsdf_iso<Dual>(p, Dual(ci), Dual(co, 1.f), Dual(cio));
+    const V3d a = bsdf_iso<Dual, kCfg>(p, Dual(ci, 1.f), Dual(co), Dual(cio));
+    const V3d c = bsdf_iso<Dual, kCfg>(p, Dual(ci), Dual(co, 1.f), Dual(cio));
     j.f = val(a);
     j.d_ci = W.x * a.x.d + W.y * a.y.d + W.z * a.z.d;
     j.d_co = W.x * c.x.d + W.y * c.y.d + W.z * c.z.d;
     j.d_cio = 0.f;
-    if (b.type == 1) {
-        const V3d e = bsdf_iso<Dual>(p, Dual(ci), Dual(co), Dual(cio, 1.f));
+    if ((kCfg & kCfgFull) && b.type == 1) {
+        const V3d e = bsdf_iso<Dual, kCfg>(p, Dual(ci), Dual(co), Dual(cio, 1.f));
         j.d_cio = W.x * e.x.d + W.y * e.y.d + W.z * e.z.d;
     }
     return j;
 }
 // d(sum_c W_c f_c * scale)/d(params): reflectance (Diffuse / Microfacet diffuse), Microfacet specular + roughness
-__device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, float ci, float co,
+template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, float ci, float co,
                                                 float cio, V3f W, float scale) {
     if (b.two_side) {
         if (signbit_(ci)) co = -co;
@@ -167,7 +183,7 @@ __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLa
     const int base = gl.off_bsdf + kGradBsdf * bi;
     const float k = kInvPi * co * scale;
     acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));
-    if (b.type == 1) {
+    if ((kCfg & kCfgFull) && b.type == 1) {
         Dual dg, e;
         iso_specular<Dual>(Dual(b.rough, 1.f), Dual(ci), Dual(co), Dual(cio), dg, e);
         // f_spec,c = (F0_c + (1 - F0_c) e) dg co
@@ -278,7 +294,7 @@ __device__ __forceinline__ void scatter_camera_ray(const GradAcc &acc, const Gra
 
 // Environment-map radiance along `dir` weighted by Wc (contribution = sum_c Wc_c Le_c(dir)): scatters the
 // gradients of the texels, the scale and the from_world rotation, returns d contribution / d dir and Le.
-__device__ __forceinline__ V3f env_le_adjoint(const GradAcc &acc, const GradLayout &gl, const DEnv &env, V3f dir, V3f Wc, V3f &Le_out) {
+static __device__ __noinline__ V3f env_le_adjoint(const GradAcc &acc, const GradLayout &gl, const DEnv &env, V3f dir, V3f Wc, V3f &Le_out) {
     EnvTexelTaps tp;
     const V3f v = mul3x3<float>(env.from_world, nullptr, dir);
     const V3f tex = bitmap_eval_envmap<float>(env.data, nullptr, env.w, env.h, envmap_dir_to_uv<float>(v), &tp);
@@ -323,7 +339,7 @@ struct EventAdj {
     float geo;        // |cos_y| / t^2 * scale  (J = 1 in the primal)
 };
 // wo_extra(f * geo) lets the caller add d(contribution)/d(wo) coming from a direction-dependent emitter (envmap).
-template <class F>
+template <int kCfg, class F>
 __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const GradLayout &gl, const DScene &sc, const VtxGeo &x, V3f wi,
                                                   V3f py, V3f ny, float area_y, V3f W, float scale, VtxAdj &xa, F wo_extra) {
     EventAdj r;
@@ -339,13 +355,13 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const float cy = -dot(ny, wo);
     const float G = fabsf(cy) / (t * t);
     const float ci = dot(wi, x.shn), co = dot(wo, x.shn), cio = dot(wi, wo);
-    const BsdfJet j = bsdf_jet(b, ci, co, cio, W);
+    const BsdfJet j = bsdf_jet<kCfg>(b, ci, co, cio, W);
     r.f = j.f;
     r.geo = G * scale;
     const float phi = W.x * j.f.x + W.y * j.f.y + W.z * j.f.z;          // sum_c W_c f_c
     // C = phi * G * J * scale
     const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
-    bsdf_param_grad(acc, gl, x.bsdf, b, ci, co, cio, W, G * scale);
+    bsdf_param_grad<kCfg>(acc, gl, x.bsdf, b, ci, co, cio, W, G * scale);
     const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
     const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) / (t * t);
     const float t_bar = G_bar * (-2.f * fabsf(cy) / (t * t * t));
@@ -363,50 +379,50 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
 
 // ---- reverse sweep of one interior path --------------------------------------------------------------
 // g = d(loss)/d(lane value) (rgb, already divided by spp).  o/d/dc = camera ray (world origin, world
-// direction, camera-space direction).
-template <int kD>
+// direction, camera-space direction).  The loop runs k = nsh-1 .. 0 with a rolling window of three vertices
+// (previous, x = vertex k, y = vertex k+1) held in registers; a vertex's adjoint is complete -- and scattered
+// -- one iteration after it was x.
+template <int kD, int kCfg>
 __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout &gl, const GradAcc &acc, const PathRecord<kD> &R, V3f o, V3f d,
                                              V3f dc, V3f g, bool hide_emitters) {
+    constexpr bool kFull = (kCfg & kCfgFull) != 0;
     if (R.nv <= 0) return;
     // vertex 0: solid-angle form -- (u, v, t) are functions of the triangle and the camera ray
     const TriRec<float> T0 = load_tri<float>(sc, R.vtri[0]);
     float u0, v0, t0;
     ray_intersect_triangle<float>(T0.p0, T0.e1, T0.e2, o, d, u0, v0, t0);
-    VtxGeo cur = vertex_geo(sc, R.vtri[0], u0, v0);
-    cur.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
+    VtxGeo v0geo = vertex_geo(sc, R.vtri[0], u0, v0);
+    v0geo.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
     V3f o_bar(0.f, 0.f, 0.f), d_bar(0.f, 0.f, 0.f);
     // Le at the primary hit
-    if (!hide_emitters && cur.emitter >= 0) {
-        if (sc.emitters[cur.emitter].type == 1) {
+    if (!hide_emitters && v0geo.emitter >= 0) {
+        if (kFull && sc.emitters[v0geo.emitter].type == 1) {
             V3f le;
             d_bar = d_bar + env_le_adjoint(acc, gl, sc.env, d, g, le);
             if (R.nsh <= 0) scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
-        } else if (dot(-d, cur.shn) > 0.f) acc.add3(gl.off_emit + 4 * cur.emitter, g);
+        } else if (dot(-d, v0geo.shn) > 0.f) acc.add3(gl.off_emit + 4 * v0geo.emitter, g);
     }
     if (R.nsh <= 0) return;
 
-    // geometry of every vertex (recomputed from the tables; no tracing)
-    VtxGeo vg[kD + 1];
-    VtxAdj va[kD + 1];
-    vg[0] = cur;
-#pragma unroll
-    for (int k = 0; k <= kD; ++k) {
-        if (k > 0 && k < R.nv) vg[k] = vertex_geo(sc, R.vtri[k], R.vu[k], R.vv[k]);
-        va[k].p = va[k].shn = va[k].fn = V3f(0.f, 0.f, 0.f);
-        va[k].area = 0.f;
-    }
+    const VtxAdj zero_adj = {V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), 0.f};
+    const int ktop = R.nsh - 1;
+    auto geo_of = [&](int k) { return k == 0 ? v0geo : vertex_geo(sc, R.vtri[k], R.vu[k], R.vv[k]); };
+    VtxGeo y = (ktop + 1 < R.nv) ? geo_of(ktop + 1) : v0geo;      // only read when the bounce exists
+    VtxGeo x = geo_of(ktop);
+    VtxAdj ya = zero_adj, xa = zero_adj, pa = zero_adj;
     V3f Lnext(0.f, 0.f, 0.f);     // R_{k+1}: radiance gathered after vertex k+1 (without E_{k+1})
-#pragma unroll
+    // every lane of the warp executes iteration kk together, whatever its own k is
+#pragma unroll 1
     for (int kk = 0; kk < kD; ++kk) {
-        const int k = R.nsh - 1 - kk;
+        const int k = ktop - kk;
         if (k < 0) break;
-        const VtxGeo &x = vg[k];
+        VtxGeo prev = k > 0 ? geo_of(k - 1) : v0geo;
         const V3f A = g * R.T[k];
         float tprev = 1.f;
         V3f wi;
         if (k == 0) wi = -d;
         else {
-            const V3f vp = vg[k - 1].p - x.p;
+            const V3f vp = prev.p - x.p;
             tprev = norm(vp);
             wi = vp / tprev;
         }
@@ -414,10 +430,9 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         V3f Rk(0.f, 0.f, 0.f);
         // ---- BSDF bounce k -> vertex k+1
         if (R.bnc_ok[k] && k + 1 < R.nv) {
-            const VtxGeo &y = vg[k + 1];
             const V3f wo = normalize(y.p - x.p);
             V3f E(0.f, 0.f, 0.f);
-            const bool y_env = y.emitter >= 0 && sc.emitters[y.emitter].type == 1;
+            const bool y_env = kFull && y.emitter >= 0 && sc.emitters[y.emitter].type == 1;
             const bool y_emits = y.emitter >= 0 && (y_env || dot(-wo, y.shn) > 0.f);
             if (y_env) {
                 const V2f uv = envmap_dir_to_uv<float>(mul3x3<float>(sc.env.from_world, nullptr, wo));
@@ -436,10 +451,10 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
                     V3f le;
                     return env_le_adjoint(acc, gl, sc.env, wo_, A * fgeo * w2k, le);
                 };
-                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, y.p, y.fn, y.area, A * Ltot, scale, va[k], extra);
-                va[k + 1].p = va[k + 1].p + ev.py;
-                va[k + 1].fn = va[k + 1].fn + ev.ny;
-                va[k + 1].area += ev.area_y;
+                const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, x, wi, y.p, y.fn, y.area, A * Ltot, scale, xa, extra);
+                ya.p = ya.p + ev.py;
+                ya.fn = ya.fn + ev.ny;
+                ya.area += ev.area_y;
                 wi_bar = wi_bar + ev.wi_bar;
                 const V3f fb = ev.f * ev.geo;
                 if (y_emits && !y_env) acc.add3(gl.off_emit + 4 * y.emitter, A * fb * R.w2[k]);
@@ -447,7 +462,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
             }
         }
         // ---- emitter sampling at vertex k
-        if (R.nee_ok[k] && R.ltri[k] < 0) {
+        if (kFull && R.nee_ok[k] && R.ltri[k] < 0) {
             // environment-map sample: the position on the bounding box is detached (envmap.cpp:95-101), J = 1;
             // derivatives flow through the direction (x.p) into the radiance lookup and the geometric term
             const V3f py(R.la[k], R.lb[k], R.lc[k]);
@@ -461,7 +476,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
                 V3f le;
                 return env_le_adjoint(acc, gl, sc.env, wo_, A * fgeo, le);
             };
-            const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, py, ny, 0.f, A * Le, scale, va[k], extra);
+            const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, x, wi, py, ny, 0.f, A * Le, scale, xa, extra);
             wi_bar = wi_bar + ev.wi_bar;
             Rk = Rk + Le * (ev.f * ev.geo);
         } else if (R.nee_ok[k]) {
@@ -474,7 +489,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
                 const DEmitter &em = sc.emitters[emi];
                 const V3f Le(em.radiance[0], em.radiance[1], em.radiance[2]);
                 const float scale = R.w1[k] / R.lpdf[k];
-                const EventAdj ev = event_adjoint(acc, gl, sc, x, wi, py, ny, TL.area, A * Le, scale, va[k], [](V3f, V3f) { return V3f(0.f, 0.f, 0.f); });
+                const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, x, wi, py, ny, TL.area, A * Le, scale, xa, [](V3f, V3f) { return V3f(0.f, 0.f, 0.f); });
                 wi_bar = wi_bar + ev.wi_bar;
                 const int lb = kGradTri * R.ltri[k];
                 acc.add3(lb, ev.py);
@@ -491,29 +506,31 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         if (k == 0) d_bar = d_bar - wi_bar;
         else {
             const V3f vp_bar = unit_adj(wi, tprev, wi_bar, 0.f);
-            va[k - 1].p = va[k - 1].p + vp_bar;
-            va[k].p = va[k].p - vp_bar;
+            pa.p = pa.p + vp_bar;
+            xa.p = xa.p - vp_bar;
         }
         Lnext = Rk;
+        // vertex k+1 has received everything: scatter it, then slide the window down
+        if (k + 1 < R.nv) scatter_pinned_vertex(acc, y, ya);
+        y = x; ya = xa;
+        x = prev; xa = pa;
+        pa = zero_adj;
     }
-    // ---- scatter the vertex adjoints
-#pragma unroll
-    for (int k = 1; k <= kD; ++k)
-        if (k < R.nv) scatter_pinned_vertex(acc, vg[k], va[k]);
-    {   // vertex 0: p = o + t d, sh_n from the differentiable (u, v)
-        const VtxGeo &x = vg[0];
-        const int b = kGradTri * x.tri;
-        acc.add3(b + 19, va[0].fn);
-        acc.add(b + 9, va[0].area);
+    {   // vertex 0 (now in y / ya): p = o + t d, sh_n from the differentiable (u, v)
+        const VtxGeo &x0 = y;
+        const VtxAdj &a0 = ya;
+        const int b = kGradTri * x0.tri;
+        acc.add3(b + 19, a0.fn);
+        acc.add(b + 9, a0.area);
         V3f m_bar;
-        scatter_shading_normal(acc, x, va[0].shn, m_bar);
-        const ShadeRec<float> N = load_shade<float>(sc, x.tri);
+        scatter_shading_normal(acc, x0, a0.shn, m_bar);
+        const ShadeRec<float> N = load_shade<float>(sc, x0.tri);
         const float u_bar = dot(N.n1 - N.n0, m_bar), v_bar = dot(N.n2 - N.n0, m_bar);
-        o_bar = o_bar + va[0].p;
-        d_bar = d_bar + va[0].p * t0;
-        const float t_bar = dot(d, va[0].p);
+        o_bar = o_bar + a0.p;
+        d_bar = d_bar + a0.p * t0;
+        const float t_bar = dot(d, a0.p);
         const V3f r_bar = isect_adj(T0.e1, T0.e2, d, u_bar, v_bar, t_bar);
-        scatter_isect_tri(acc, x.tri, u0, v0, r_bar);
+        scatter_isect_tri(acc, x0.tri, u0, v0, r_bar);
         o_bar = o_bar + r_bar;
         d_bar = d_bar + r_bar * t0;
         scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
@@ -529,7 +546,7 @@ struct SecEdgeAdjoint {
     float scale;            // tangent_scale / sppse
     GradLayout gl;
     GradAcc acc;
-    template <bool kBvh>
+    template <int kCfg>
     __device__ __forceinline__ void tail(const DScene &sc, const DCamera &cam, int pixel, V3f value0, V3f n, int edge, float s, V3d bp0d,
                                          int light_tri, const Its<Dual> &its1, V3f cd, V2f q) const {
         const SecEdgeAdjoint *adj = this;

@@ -10,6 +10,10 @@
 
 namespace psdr {
 
+// kernel configuration bits (template parameter kCfg): which code a kernel instantiation contains
+constexpr int kCfgBvh = 1;    // BVH2 traversal instead of the parameter-space triangle scan
+constexpr int kCfgFull = 2;   // MicrofacetBSDF + EnvironmentMap code paths (otherwise Diffuse + AreaLight only)
+
 struct Hit {
     int tri;
     float u, v, t;
@@ -97,7 +101,7 @@ __device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, 
     }
 }
 
-template <bool kBvh> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
+template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
     Hit best;
     best.tri = 0x7fffffff;
     best.u = best.v = 0.f;
@@ -106,6 +110,7 @@ template <bool kBvh> __device__ __forceinline__ Hit trace(const DScene &sc, V3f 
         best.tri = -1;
         return best;
     }
+    constexpr bool kBvh = (kCfg & kCfgBvh) != 0;
     if (!kBvh) {
         // tiny scenes: the triangle table rides in the kernel parameters (constant bank), the scan index
         // is warp-uniform, so the operands come through the uniform datapath -- no LSU traffic at all
@@ -198,7 +203,7 @@ template <> struct IsDual<Dual> { static constexpr bool value = true; };
 // variant (S = Dual, path_space = false: primary hits) re-intersects analytically.
 // kAD selects the formulas of the reference's ad=true instantiation; it defaults to "S carries a
 // tangent", the adjoint's primal replay uses <float, kBvh, true> to walk the same path as renderD.
-template <class S, bool kBvh, bool kAD = IsDual<S>::value>
+template <class S, int kCfg, bool kAD = IsDual<S>::value>
 __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S> d, bool active, bool path_space, int *out_tri = nullptr) {
     constexpr bool ad = kAD;
     Its<S> its;
@@ -210,7 +215,7 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
     its.bu = its.bv = 0.f;
     if (out_tri) *out_tri = -1;
     if (!active) return its;
-    const Hit h = trace<kBvh>(sc, val(o), val(d));
+    const Hit h = trace<kCfg>(sc, val(o), val(d));
     if (h.tri < 0) return its;
     if (out_tri) *out_tri = h.tri;
     const TriRec<S> T = load_tri<S>(sc, h.tri);
@@ -317,12 +322,12 @@ template <class S> __device__ __forceinline__ V3<S> microfacet_eval(const DBsdf 
     return (diffuse + specular) * cos_nl;
 }
 
-template <class S> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
+template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return V3<S>(S(0.f));
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return V3<S>(S(0.f));
     const DBsdf &b = sc.bsdfs[bi];
-    if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo);
+    if ((kCfg & kCfgFull) && b.type == 1) return microfacet_eval<S>(b, its.wi, wo);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (signbit_(val(wiz))) wo.z = -wo.z;
@@ -344,11 +349,11 @@ __device__ __forceinline__ float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo) 
     return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
 }
 
-template <class S> __device__ __forceinline__ float bsdf_pdf(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
+template <class S, int kCfg> __device__ __forceinline__ float bsdf_pdf(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return 0.f;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return 0.f;
-    if (sc.bsdfs[bi].type == 1) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo));
+    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo));
     float wiz = val(its.wi.z), woz = val(wo.z);
     if (sc.bsdfs[bi].two_side) {
         if (signbit_(wiz)) woz = -woz;
@@ -409,7 +414,7 @@ __device__ __forceinline__ BsdfSample microfacet_sample(const DBsdf &b, V3f wi, 
     return bs;
 }
 
-template <class S> __device__ __forceinline__ BsdfSample bsdf_sample(const DScene &sc, const Its<S> &its, V3f sample, bool active) {
+template <class S, int kCfg> __device__ __forceinline__ BsdfSample bsdf_sample(const DScene &sc, const Its<S> &its, V3f sample, bool active) {
     BsdfSample bs;
     bs.wo = V3f(0.f, 0.f, 0.f);
     bs.pdf = 0.f;
@@ -417,7 +422,7 @@ template <class S> __device__ __forceinline__ BsdfSample bsdf_sample(const DScen
     if (!its.valid) return bs;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return bs;
-    if (sc.bsdfs[bi].type == 1) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active);
+    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active);
     float wiz = val(its.wi.z);
     if (sc.bsdfs[bi].two_side) wiz = fabsf(wiz);
     const V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));
@@ -444,11 +449,11 @@ template <class S> __device__ __forceinline__ V3<S> env_eval_direction(const DEn
     const V3<S> r = bitmap_eval_envmap<S>(e.data, IsDual<S>::value ? e.ddata : nullptr, e.w, e.h, uv, taps);
     return r * Lift<S>::s(e.scale, e.d_scale);
 }
-template <class S> __device__ __forceinline__ V3<S> Le(const DScene &sc, const Its<S> &its, bool active) {
+template <class S, int kCfg> __device__ __forceinline__ V3<S> Le(const DScene &sc, const Its<S> &its, bool active) {
     if (!its.valid) return V3<S>(S(0.f));
     const int e = sc.meshes[its.mesh].emitter;
     if (e < 0) return V3<S>(S(0.f));
-    if (sc.emitters[e].type == 1) {   // EnvironmentMap::eval: radiance arriving along -wi, no cosine test
+    if ((kCfg & kCfgFull) && sc.emitters[e].type == 1) {   // EnvironmentMap::eval: radiance arriving along -wi, no cosine test
         if (!active) return V3<S>(S(0.f));
         return env_eval_direction<S>(sc.env, -its.to_world(its.wi));
     }
@@ -535,13 +540,13 @@ template <class S> __device__ __forceinline__ float env_position_pdf(const DEnv 
 }
 
 // Scene::sample_emitter_position (reference src/scene/scene.cpp:987-1013) -> Mesh::sample_position / EnvironmentMap
-template <class S> __device__ __forceinline__ PosSample<S> sample_emitter_position(const DScene &sc, V3f ref_p, V2f sample2) {
+template <class S, int kCfg> __device__ __forceinline__ PosSample<S> sample_emitter_position(const DScene &sc, V3f ref_p, V2f sample2) {
     PosSample<S> ps;
     int ei = 0;
     float emitter_pdf = 1.f;
     if (sc.n_emitters != 1) ei = sample_reuse(sc.emitter_pmf, sc.emitter_cmf, sc.n_emitters, sc.emitter_sum, sample2.y, emitter_pdf);
     const DEmitter &em = sc.emitters[ei];
-    if (em.type == 1) {
+    if ((kCfg & kCfgFull) && em.type == 1) {
         V3f p, n;
         float pdf;
         env_sample_position(sc.env, ref_p, sample2, p, n, pdf);
@@ -576,11 +581,11 @@ template <class S> __device__ __forceinline__ PosSample<S> sample_emitter_positi
     return ps;
 }
 
-template <class S> __device__ __forceinline__ float emitter_position_pdf(const DScene &sc, V3f ref_p, const Its<S> &its, bool active) {
+template <class S, int kCfg> __device__ __forceinline__ float emitter_position_pdf(const DScene &sc, V3f ref_p, const Its<S> &its, bool active) {
     if (!its.valid || !active) return 0.f;
     const int e = sc.meshes[its.mesh].emitter;
     if (e < 0) return 0.f;
-    if (sc.emitters[e].type == 1) return env_position_pdf<S>(sc.env, ref_p, its);
+    if ((kCfg & kCfgFull) && sc.emitters[e].type == 1) return env_position_pdf<S>(sc.env, ref_p, its);
     return sc.emitters[e].sampling_weight * sc.emitters[e].inv_total_area;
 }
 
@@ -650,7 +655,7 @@ struct NoRecord {
     __device__ __forceinline__ void nee(int, bool, int, V2f, V3f, int, float, float) {}
 };
 
-template <class S, bool kBvh, bool kAD, class Rec>
+template <class S, int kCfg, bool kAD, class Rec>
 __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, Rec &R) {
     constexpr bool ad = kAD;
     V3<S> throughput(S(1.f)), result(S(0.f));
@@ -664,11 +669,11 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
 #pragma unroll 1
     for (int depth = -1; depth < max_depth; ++depth) {
         // ---- main ray: primary hit (solid-angle form under AD) or the BSDF-sampled ray (path-space form)
-        const Its<S> its1 = ray_intersect<S, kBvh, kAD>(sc, ray_o, ray_d, active, ad && depth >= 0);
+        const Its<S> its1 = ray_intersect<S, kCfg, kAD>(sc, ray_o, ray_d, active, ad && depth >= 0);
         if (its1.valid) R.vertex(depth + 1, its1.tri, its1.bu, its1.bv);
         if (depth < 0) {
             active = active && its1.valid;
-            if (!hide_emitters) result = Le(sc, its1, active);
+            if (!hide_emitters) result = Le<S, kCfg>(sc, its1, active);
         } else {
             active = active && bs.valid && its1.valid;
             if (active) {
@@ -681,18 +686,18 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
                     const S G_val = abs_(cos_val) / sqr(its1.t);
                     pdf0 = bs.pdf * val(G_val);
                     if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
-                    else bsdf_val = bsdf_eval(sc, its, its.to_local(wo), active) * (G_val * its1.J / S(pdf0));
+                    else bsdf_val = bsdf_eval<S, kCfg>(sc, its, its.to_local(wo), active) * (G_val * its1.J / S(pdf0));
                 } else {
                     const S cos_val = dot(its1.n, -ray_d);
                     const S G_val = abs_(cos_val) / sqr(its1.t);
                     pdf0 = bs.pdf * val(G_val);
                     if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
-                    else bsdf_val = bsdf_eval(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
+                    else bsdf_val = bsdf_eval<S, kCfg>(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
                 }
-                const float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, val(its.p), its1, active));
+                const float weight2 = mis_weight(pdf0, emitter_position_pdf<S, kCfg>(sc, val(its.p), its1, active));
                 R.bounce(depth, val(its1.t) >= kEpsilon, pdf0, weight2);
                 throughput = throughput * bsdf_val;
-                result = result + Le(sc, its1, active) * throughput * S(weight2);
+                result = result + Le<S, kCfg>(sc, its1, active) * throughput * S(weight2);
             }
         }
         const int bounces_left = max_depth - depth - 1;
@@ -706,23 +711,23 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
         const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
         const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
         {   // ---- emitter sampling
-            const PosSample<S> ps = sample_emitter_position<S>(sc, val(its.p), V2f(s_x, s_y));
+            const PosSample<S> ps = sample_emitter_position<S, kCfg>(sc, val(its.p), V2f(s_x, s_y));
             bool active_direct = !is_emitter(sc, its);
             V3<S> wod = ps.p - its.p;
             const S dist_sqr = squared_norm(wod);
             const S dist = safe_sqrt(dist_sqr);
             wod = wod / dist;
-            const Its<S> its2 = ray_intersect<S, kBvh, kAD>(sc, its.p, wod, active_direct, ad);
+            const Its<S> its2 = ray_intersect<S, kCfg, kAD>(sc, its.p, wod, active_direct, ad);
             active_direct = active_direct && its2.valid;
             active_direct = active_direct && (val(its2.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its2);
             if (active_direct) {
                 const S cos_val = dot(its2.n, -wod);
                 const S G_val = abs_(cos_val) / dist_sqr;
-                const V3<S> emitter_val = Le(sc, its2, true);
+                const V3<S> emitter_val = Le<S, kCfg>(sc, its2, true);
                 const V3<S> wo_local = its.to_local(wod);
-                V3<S> bsdf_val2 = bsdf_eval(sc, its, wo_local, active_direct);
+                V3<S> bsdf_val2 = bsdf_eval<S, kCfg>(sc, its, wo_local, active_direct);
                 bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
-                const float pdf1 = bsdf_pdf(sc, its, wo_local, active_direct) * val(G_val);
+                const float pdf1 = bsdf_pdf<S, kCfg>(sc, its, wo_local, active_direct) * val(G_val);
                 if (pdf1 != 0.f) {
                     const float weight1 = mis_weight(ps.pdf, pdf1);
                     R.nee(depth + 1, ps.tri < 0 || val(its2.wi.z) > 0.f, ps.tri, ps.st, val(ps.p), its2.tri, ps.pdf, weight1);
@@ -731,17 +736,17 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
             }
         }
         // ---- BSDF sampling: the ray is traced at the top of the next iteration
-        bs = bsdf_sample(sc, its, V3f(s3_x, s3_y, s3_z), true);
+        bs = bsdf_sample<S, kCfg>(sc, its, V3f(s3_x, s3_y, s3_z), true);
         ray_o = its.p;
         ray_d = its.to_world(lift3<S>(bs.wo));
     }
     return result;
 }
 
-template <class S, bool kBvh>
+template <class S, int kCfg>
 __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
     NoRecord rec;
-    return Li<S, kBvh, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec);
+    return Li<S, kCfg, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec);
 }
 
 // ---- secondary (shadow) edges: reference src/scene/scene.cpp:1027-1068, src/integrator/path.cpp:172-270
@@ -776,11 +781,11 @@ __device__ __forceinline__ float sign1(float x) { return signbit_(x) ? -1.f : 1.
 // SecEdgeAdjoint (adjoint.cuh), whose tail() scatters the gradients instead of forming the tangent.
 struct NoSecAdjoint {
     static constexpr bool enabled = false;
-    template <bool kBvh>
+    template <int kCfg>
     __device__ __forceinline__ void tail(const DScene &, const DCamera &, int, V3f, V3f, int, float, V3d, int, const Its<Dual> &, V3f, V2f) const {}
 };
 
-template <bool kBvh, class Adj>
+template <int kCfg, class Adj>
 __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out,
                                                    const Adj &adj) {
     value0_out = V3f(0.f, 0.f, 0.f);
@@ -800,7 +805,7 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     const V3f edge2 = ep2 - val(ep0);
     const V3f _p0 = val(bp0);
     pdf0 /= norm(e1v);
-    const PosSample<float> ps2 = sample_emitter_position<float>(sc, _p0, V2f(sample3.y, sample3.z));
+    const PosSample<float> ps2 = sample_emitter_position<float, kCfg>(sc, _p0, V2f(sample3.y, sample3.z));
     const V3f _p2 = ps2.p, bn = ps2.n;
     V3f e = _p2 - _p0;
     const float distSqr = squared_norm(e);
@@ -813,10 +818,10 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     // -- eval_secondary_edge
     const V3f _dir = normalize(_p2 - _p0);
     int light_tri = -1;
-    const Its<float> _its2 = ray_intersect<float, kBvh>(sc, _p0, _dir, valid, false, &light_tri);
+    const Its<float> _its2 = ray_intersect<float, kCfg>(sc, _p0, _dir, valid, false, &light_tri);
     valid = valid && is_emitter(sc, _its2) && _its2.valid && norm(_its2.p - _p2) < kShadowEpsilon;
     if (!valid) return -1;
-    const Its<float> _its1 = ray_intersect<float, kBvh>(sc, _p0, -_dir, valid, false);
+    const Its<float> _its1 = ray_intersect<float, kCfg>(sc, _p0, -_dir, valid, false);
     valid = valid && _its1.valid;
     if (!valid) return -1;
     const V3f _p1 = _its1.p;
@@ -825,7 +830,7 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     if (!valid) return -1;
     V3d co, cd;
     sample_primary_ray<Dual>(cam, sds.q, co, cd);
-    const Its<Dual> its1 = ray_intersect<Dual, kBvh>(sc, co, cd, valid, false);
+    const Its<Dual> its1 = ray_intersect<Dual, kCfg>(sc, co, cd, valid, false);
     valid = valid && its1.valid && norm(val(its1.p) - _p1) < kShadowEpsilon;
     valid = valid && its1.valid && sc.meshes[its1.mesh].bsdf >= 0;
     if (!valid) return -1;
@@ -839,15 +844,15 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     if (!valid) return -1;
     const V3f d0 = -val(cd);
     const V3f d0_local = _its1.to_local(d0);
-    V3f bsdf_val = bsdf_eval<float>(sc, _its1, d0_local, valid);
+    V3f bsdf_val = bsdf_eval<float, kCfg>(sc, _its1, d0_local, valid);
     const float correction = fabsf((_its1.wi.z * dot(d0, _its1.n)) / (d0_local.z * dot(_dir, _its1.n)));
     bsdf_val = bsdf_val * correction;
-    V3f value0 = bsdf_val * Le(sc, _its2, valid) * (base_v * sds.sensor_val / bss_pdf);
+    V3f value0 = bsdf_val * Le<float, kCfg>(sc, _its2, valid) * (base_v * sds.sensor_val / bss_pdf);
     value0_out = value0;
     const V3f n = normalize(cross(bn, proj));
     value0 = value0 * (sign1(dot(ec, edge2)) * sign1(dot(ec, n)));
     if (Adj::enabled) {
-        adj.template tail<kBvh>(sc, cam, sds.pixel, value0, n, ei, sample1, bp0, light_tri, its1, val(cd), sds.q);
+        adj.template tail<kCfg>(sc, cam, sds.pixel, value0, n, ei, sample1, bp0, light_tri, its1, val(cd), sds.q);
         return sds.pixel;
     }
     const TriRec<Dual> T = load_tri<Dual>(sc, light_tri);
@@ -874,9 +879,9 @@ __device__ __forceinline__ float guide_sample_reuse(const DCamera &cam, V3f &s) 
     return prob * (float) ncells;
 }
 
-template <bool kBvh>
+template <int kCfg>
 __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
-    return eval_secondary_edge<kBvh, NoSecAdjoint>(sc, cam, sample3, value0_out, tangent_out, NoSecAdjoint());
+    return eval_secondary_edge<kCfg, NoSecAdjoint>(sc, cam, sample3, value0_out, tangent_out, NoSecAdjoint());
 }
 
 }  // namespace psdr

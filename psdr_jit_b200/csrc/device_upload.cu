@@ -199,6 +199,8 @@ void upload_scene(Scene &sc) {
     d.n_sec_edges = (int) sc.sec_edges.size();
     d.n_nodes = (int) nodes.size();
     d.use_bvh = use_bvh ? 1 : 0;
+    d.full_features = sc.env.present ? 1 : 0;
+    for (const HBsdf &b : sc.bsdfs) d.full_features |= (b.type != 0) ? 1 : 0;
     d.geo = (const float4 *) (base + o_geo);
     d.shade = (const float4 *) (base + o_shade);
     d.dgeo = (const float4 *) (base + o_dgeo);

@@ -92,6 +92,7 @@ struct DScene {
     int width, height, spp, sppe, sppse;
     int n_tris, n_meshes, n_emitters, n_bsdfs, n_sec_edges, n_nodes;
     int use_bvh;             // 0: brute force over all triangles (tiny scenes)
+    int full_features;       // 1: some BSDF is a Microfacet or an EnvironmentMap exists (selects the kernel variant)
     const float4 *geo, *shade, *dgeo, *dshade;
     const float2 *uv;
     const DMesh *meshes;
@@ -123,6 +124,7 @@ struct RenderParams {
     long long lane_begin, lane_end;   // lane range rendered by this call (multi-GPU sharding)
     const int *pix_id;       // batch mode: pixel list (device), else nullptr
     int npix;                // number of output pixels (W*H or len(pix_id))
+    int smem_grad;           // adjoint kernels: 1 = accumulate into a shared-memory copy of the gradient table
     float tangent_scale;     // 1, or 2 to reproduce the reference's forward-mode scaling
 };
 

@@ -1,0 +1,18 @@
+// Forward kernels (interior / primary-edge / secondary-edge / guiding / AOV) of configuration 1
+// (bit 0: BVH2 traversal, bit 1: Microfacet + EnvironmentMap code).  See kernels_impl.cuh.
+#include "kernels_impl.cuh"
+#include "launch_decl.h"
+
+namespace psdr {
+namespace fwd1 {
+cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st) {
+    return ForwardLaunch<1>::interior(sc, cam, rp, ad, img, dimg, st);
+}
+cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) { return ForwardLaunch<1>::primary(sc, cam, rp, dimg, st); }
+cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) { return ForwardLaunch<1>::secondary(sc, cam, rp, dimg, st); }
+cudaError_t guiding(const DScene &sc, const DCamera &cam, const int reso[4], int nrounds, long long seed, float *mass, cudaStream_t st) {
+    return ForwardLaunch<1>::guiding(sc, cam, reso, nrounds, seed, mass, st);
+}
+cudaError_t aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st) { return ForwardLaunch<1>::aov(sc, cam, rp, out, st); }
+}  // namespace fwd1
+}  // namespace psdr

@@ -6,6 +6,7 @@
 #include "grad_layout.h"
 
 namespace psdr {
+int scene_cfg(const DScene &sc);
 cudaError_t launch_interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st);
 cudaError_t launch_primary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);
 cudaError_t launch_secondary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);

@@ -1,0 +1,282 @@
+// sm_100a kernels of the PathTracer hot path (reference src/integrator/integrator.cpp:104-198,
+// src/integrator/path.cpp:35-294).  One fused kernel per term: a lane generates its camera ray /
+// edge sample from a counter-based PCG32 stream, walks the whole path in registers (closest-hit
+// queries against the L1/L2-resident triangle tables) and splats into the image.  Nothing but the
+// final image (and derivative image) goes to HBM.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_path.cuh"
+#include "kernels.h"
+
+namespace psdr {
+
+constexpr int kBlock = 128;
+
+// Reduce values over runs of consecutive lanes that share a pixel (lanes are pixel-major, so a
+// warp holds at most a few contiguous runs; with spp a multiple of 32 it is one run) and issue one
+// atomicAdd per run and channel.  Reference: scatter_reduce(Add) in integrator.cpp:128.
+__device__ __forceinline__ void splat_runs(float *img, int pix, float r, float g, float b, bool valid) {
+    const unsigned lane = threadIdx.x & 31u;
+    const int key = valid ? pix : -1;
+    if (!valid) { r = g = b = 0.f; }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int k2 = __shfl_down_sync(0xffffffffu, key, off);
+        const float r2 = __shfl_down_sync(0xffffffffu, r, off), g2 = __shfl_down_sync(0xffffffffu, g, off),
+                    b2 = __shfl_down_sync(0xffffffffu, b, off);
+        if (lane + off < 32 && k2 == key) { r += r2; g += g2; b += b2; }
+    }
+    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    if (valid && (lane == 0 || kprev != key)) {
+        atomicAdd(img + 3 * pix, r);
+        atomicAdd(img + 3 * pix + 1, g);
+        atomicAdd(img + 3 * pix + 2, b);
+    }
+}
+
+__device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; }
+
+// ---- interior term: Integrator::__render / __render_batch ------------------------------------
+// kAD = use the formulas of the reference's renderD instantiation (the primary hit re-intersected
+// analytically, scene.cpp:772-801) -- <float, kBvh, true> is the primal image of renderD.
+template <class S, int kCfg, bool kAD>
+__global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+                                                           const __grid_constant__ RenderParams rp, float *__restrict__ img,
+                                                           float *__restrict__ dimg) {
+    const long long stride = (long long) gridDim.x * kBlock;
+    const long long span = rp.lane_end - rp.lane_begin;
+    const long long span_pad = (span + 31) / 32 * 32;   // keep warps converged for the shuffles
+    const float inv_spp = sc.spp > 1 ? 1.f / (float) sc.spp : 1.f;
+    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
+        const long long i = rp.lane_begin + j;
+        const bool live = j < span;
+        int idx = 0;
+        V3<S> v(S(0.f));
+        if (live) {
+            idx = (int) (sc.spp > 1 ? i / sc.spp : i);
+            const int pix = rp.pix_id ? __ldg(rp.pix_id + idx) : idx;
+            const unsigned long long seed_value = rp.pix_id ? (unsigned long long) ((long long) pix + rp.seed) : (unsigned long long) (i + rp.seed);
+            Pcg32 rng;
+            rng.seed(seed_value, (unsigned long long) i);
+            if (rp.skip) rng.advance(rp.skip);
+            const float jy = rng.next_1d(), jx = rng.next_1d();
+            const float sx = ((float) (pix % sc.width) + jx) / (float) sc.width;
+            const float sy = ((float) (pix / sc.width) + jy) / (float) sc.height;
+            V3<S> o, d;
+            sample_primary_ray<S>(cam, V2f(sx, sy), o, d);
+            NoRecord rec;
+            v = Li<S, kCfg, kAD, NoRecord>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, rec);
+        }
+        float r = val(v.x), g = val(v.y), b = val(v.z), dr = tang(v.x), dg = tang(v.y), db = tang(v.z);
+        // masked(value, ~isfinite(value)) = 0 zeroes value and tangent (integrator.cpp:126)
+        if (!isfinite(r)) { r = 0.f; dr = 0.f; }
+        if (!isfinite(g)) { g = 0.f; dg = 0.f; }
+        if (!isfinite(b)) { b = 0.f; db = 0.f; }
+        splat_runs(img, idx, r * inv_spp, g * inv_spp, b * inv_spp, live);
+        if (IsDual<S>::value) {
+            const float ts = rp.tangent_scale * inv_spp;
+            splat_runs(dimg, idx, scrub(dr) * ts, scrub(dg) * ts, scrub(db) * ts, live);
+        }
+    }
+}
+
+// ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges
+template <int kCfg>
+__global__ void __launch_bounds__(kBlock) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+                                                               const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
+    const long long stride = (long long) gridDim.x * kBlock;
+    const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
+        Pcg32 rng;
+        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+        if (rp.skip) rng.advance(rp.skip);
+        float s1 = rng.next_1d(), prob;
+        const int ei = sample_reuse(cam.pe_pmf, cam.pe_cmf, cam.n_edges, cam.edge_sum, s1, prob);
+        const float4 a = __ldg(cam.pe_a + ei), da = __ldg(cam.pe_da + ei), bq = __ldg(cam.pe_b + ei);
+        const float pdf = prob / bq.z;
+        const float w0 = 1.0f - s1;
+        const Dual px = fmadd(Dual(a.x, da.x), Dual(w0), Dual(a.z, da.z) * s1), py = fmadd(Dual(a.y, da.y), Dual(w0), Dual(a.w, da.w) * s1);
+        const Dual x_dot_n = dot(V2d(px, py), V2d(Dual(bq.x), Dual(bq.y)));
+        const int ix = (int) floorf(px.v * (float) sc.width), iy = (int) floorf(py.v * (float) sc.height);
+        const bool valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+        // Li(ray_n) - Li(ray_p): the reference binary evaluates Li(ray_p) first (verified on the
+        // running reference, tests/golden/renderD_*: primary-only images).  One rolled loop over the two
+        // sides keeps a single copy of Li in the kernel.
+        V3f Lside[2];
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            __syncwarp(live_mask);
+            const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
+            V3f ro, rd;
+            sample_primary_ray<float>(cam, V2f(px.v + sg * bq.x, py.v + sg * bq.y), ro, rd);
+            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
+        }
+        const V3f Lp = Lside[0], Ln = Lside[1];
+        if (!valid) continue;
+        const int pix = iy * sc.width + ix;
+        const float dl[3] = {(Ln.x - Lp.x) / pdf, (Ln.y - Lp.y) / pdf, (Ln.z - Lp.z) / pdf};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float primal = x_dot_n.v * dl[c];
+            if (!isfinite(primal)) continue;
+            const float t = x_dot_n.d * dl[c] * inv_sppe;
+            if (t != 0.f && isfinite(t)) atomicAdd(dimg + 3 * pix + c, t);
+        }
+    }
+}
+
+// ---- secondary (shadow) edges: PathTracer::render_secondary_edges -----------------------------
+template <int kCfg>
+__global__ void __launch_bounds__(kBlock) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+                                                                 const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
+    const long long stride = (long long) gridDim.x * kBlock;
+    const float scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
+        Pcg32 rng;
+        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+        if (rp.skip) rng.advance(rp.skip);
+        const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+        V3f sample3(d3, d2, d1);
+        float pdf0 = 1.f;
+        if (cam.guided) pdf0 = guide_sample_reuse(cam, sample3);     // path.cpp:279-281
+        V3f value0, tangent;
+        const int pix = eval_secondary_edge<kCfg>(sc, cam, sample3, value0, tangent);
+        if (pix < 0) continue;
+        float t[3] = {tangent.x, tangent.y, tangent.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (pdf0 > kEpsilon) t[c] = t[c] / pdf0;                 // masked(value, pdf0 > Epsilon) /= pdf0
+            if (isfinite(t[c]) && t[c] != 0.f) atomicAdd(dimg + 3 * pix + c, t[c] * scale);
+        }
+
+    }
+}
+
+// ---- guiding pre-pass: PathTracer::preprocess_secondary_edges (reference src/integrator/path.cpp:130-168)
+// One thread per grid cell walks that cell's reso[3] x nrounds samples in lane order (a fixed summation
+// order; the reference's scatter_reduce order is unspecified) and writes mass[cell].
+template <int kCfg>
+__global__ void __launch_bounds__(kBlock) guiding_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, int r0, int r1, int r2,
+                                                          int r3, int nrounds, long long seed, float *__restrict__ mass) {
+    const int ncells = r0 * r1 * r2;
+    for (int cell = blockIdx.x * kBlock + threadIdx.x; cell < ncells; cell += gridDim.x * kBlock) {
+        const int c0 = cell / (r1 * r2), rem = cell - c0 * (r1 * r2), c1 = rem / r2, c2 = rem - c1 * r2;
+        float total = 0.f;
+        for (int j = 0; j < nrounds; ++j)
+            for (int k = 0; k < r3; ++k) {
+                const long long i = (long long) cell * r3 + k;
+                Pcg32 rng;
+                rng.seed((unsigned long long) (i + seed), (unsigned long long) i);
+                if (j) rng.advance(3ull * (unsigned long long) j);
+                const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+                const V3f s3(((float) c0 + d3) * (1.f / (float) r0), ((float) c1 + d2) * (1.f / (float) r1), ((float) c2 + d1) * (1.f / (float) r2));
+                V3f value0, tangent;
+                eval_secondary_edge<kCfg>(sc, cam, s3, value0, tangent);
+                const float v[3] = {value0.x, value0.y, value0.z};
+                float m = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float x = isfinite(v[c]) ? v[c] : 0.f;
+                    if (r3 > 1) x /= (float) r3;
+                    m = c == 0 ? x : fmaxf(m, x);
+                }
+                total += m;
+            }
+        mass[cell] = total;
+    }
+}
+
+// ---- AOV tap: what the reference's FieldExtractionIntegrator exposes (src/integrator/field.cpp:47-121)
+template <int kCfg>
+__global__ void __launch_bounds__(kBlock) aov_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+                                                      const __grid_constant__ RenderParams rp, float *__restrict__ out) {
+    const long long stride = (long long) gridDim.x * kBlock;
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
+        const int idx = (int) (sc.spp > 1 ? i / sc.spp : i);
+        Pcg32 rng;
+        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+        const float jy = rng.next_1d(), jx = rng.next_1d();
+        const float sx = ((float) (idx % sc.width) + jx) / (float) sc.width, sy = ((float) (idx / sc.width) + jy) / (float) sc.height;
+        V3f o, d;
+        sample_primary_ray<float>(cam, V2f(sx, sy), o, d);
+        const Its<float> its = ray_intersect<float, kCfg>(sc, o, d, true, false);
+        float *r = out + 14 * i;
+        for (int k = 0; k < 14; ++k) r[k] = 0.f;
+        if (!its.valid) { r[1] = -1.f; continue; }
+        r[0] = (float) (its.mesh + 1); r[1] = (float) its.tri;
+        r[2] = its.p.x; r[3] = its.p.y; r[4] = its.p.z; r[5] = its.t;
+        r[6] = its.n.x; r[7] = its.n.y; r[8] = its.n.z;
+        r[9] = its.sh_n.x; r[10] = its.sh_n.y; r[11] = its.sh_n.z;
+    }
+}
+
+// ---- per-configuration launchers: one explicit instantiation of ForwardLaunch<kCfg> per translation unit
+// (kern_cfg*.cu) so that the four kernel families compile in parallel ----------------------------------------
+// Persistent grid = exactly the number of CTAs that are resident at once (occupancy API x SM count): a larger
+// grid runs in more than one wave and the last, partially filled wave costs as much as a full one.
+template <class K> inline int persistent_grid(K kernel, int block, size_t smem, long long lanes) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long need = (lanes + block - 1) / block, cap = (long long) sms * per_sm;
+    return (int) (need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+template <int kCfg> struct ForwardLaunch {
+    static cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st) {
+        const long long n = rp.lane_end - rp.lane_begin;
+        if (ad && dimg) interior_kernel<Dual, kCfg, true><<<persistent_grid(interior_kernel<Dual, kCfg, true>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        else if (ad)    // primal image of renderD
+            interior_kernel<float, kCfg, true><<<persistent_grid(interior_kernel<float, kCfg, true>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        else interior_kernel<float, kCfg, false><<<persistent_grid(interior_kernel<float, kCfg, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        return cudaGetLastError();
+    }
+    static cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) {
+        primary_edge_kernel<kCfg><<<persistent_grid(primary_edge_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, dimg);
+        return cudaGetLastError();
+    }
+    static cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) {
+        secondary_edge_kernel<kCfg><<<persistent_grid(secondary_edge_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, dimg);
+        return cudaGetLastError();
+    }
+    static cudaError_t guiding(const DScene &sc, const DCamera &cam, const int reso[4], int nrounds, long long seed, float *mass, cudaStream_t st) {
+        const long long cells = (long long) reso[0] * reso[1] * reso[2];
+        guiding_kernel<kCfg><<<persistent_grid(guiding_kernel<kCfg>, kBlock, 0, cells), kBlock, 0, st>>>(sc, cam, reso[0], reso[1], reso[2], reso[3], nrounds, seed, mass);
+        return cudaGetLastError();
+    }
+    static cudaError_t aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st) {
+        aov_kernel<kCfg><<<persistent_grid(aov_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, out);
+        return cudaGetLastError();
+    }
+};
+
+}  // namespace psdr

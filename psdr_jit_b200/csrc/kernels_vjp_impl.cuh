@@ -2,6 +2,7 @@
 // reference: AD-graph traversal kernels scattering into triangle-record / texel / radiance gradient
 // arrays).  One fused kernel per term, same lane -> random-stream mapping as the
 // forward kernels (kernels.cu), so a backward call with the forward call's seed replays the same paths.
+#pragma once
 #include <cuda_runtime.h>
 
 #include "adjoint.cuh"
@@ -11,15 +12,24 @@ namespace psdr {
 
 constexpr int kBlockV = 128;
 
-template <bool kBvh, int kD, bool kSmem>
-__global__ void __launch_bounds__(kBlockV) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+template <int kCfg, int kD>
+__global__ void __launch_bounds__(kBlockV, 4) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                 const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                 const float *__restrict__ d_img) {
     extern __shared__ float smem[];
-    const GradAcc acc = grad_acc_begin(gl, smem, 0, gl.off_pe, kSmem);
+    const GradAcc acc = grad_acc_begin(gl, smem, 0, gl.off_pe, rp.smem_grad != 0);
     const long long stride = (long long) gridDim.x * kBlockV;
     const float inv_spp = (sc.spp > 1 ? 1.f / (float) sc.spp : 1.f) * rp.tangent_scale;
-    for (long long i = rp.lane_begin + (long long) blockIdx.x * kBlockV + threadIdx.x; i < rp.lane_end; i += stride) {
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
         const int idx = (int) (sc.spp > 1 ? i / sc.spp : i);
         const int pix = rp.pix_id ? __ldg(rp.pix_id + idx) : idx;
         const unsigned long long seed_value = rp.pix_id ? (unsigned long long) ((long long) pix + rp.seed) : (unsigned long long) (i + rp.seed);
@@ -33,27 +43,37 @@ __global__ void __launch_bounds__(kBlockV) interior_vjp_kernel(const __grid_cons
         const V3f o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f)), d = xform_dir(cam.to_world, dc);
         PathRecord<kD> R;
         R.reset();
-        const V3f v = Li<float, kBvh, true, PathRecord<kD>>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, R);
+        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, R);
         // cotangent of this lane's value; channels the forward pass scrubbed (non-finite) carry none
         V3f g(__ldg(d_img + 3 * idx) * inv_spp, __ldg(d_img + 3 * idx + 1) * inv_spp, __ldg(d_img + 3 * idx + 2) * inv_spp);
         if (!isfinite(v.x)) g.x = 0.f;
         if (!isfinite(v.y)) g.y = 0.f;
         if (!isfinite(v.z)) g.z = 0.f;
+        __syncwarp(live_mask);
         if (g.x == 0.f && g.y == 0.f && g.z == 0.f) continue;
-        path_adjoint<kD>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0);
+        path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0);
     }
     grad_acc_end(acc);
 }
 
-template <bool kBvh, bool kSmem>
+template <int kCfg>
 __global__ void __launch_bounds__(kBlockV) primary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                     const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                     const float *__restrict__ d_img) {
     extern __shared__ float smem[];
-    const GradAcc acc = grad_acc_begin(gl, smem, gl.off_pe, gl.off_se, kSmem);
+    const GradAcc acc = grad_acc_begin(gl, smem, gl.off_pe, gl.off_se, rp.smem_grad != 0);
     const long long stride = (long long) gridDim.x * kBlockV;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
-    for (long long i = rp.lane_begin + (long long) blockIdx.x * kBlockV + threadIdx.x; i < rp.lane_end; i += stride) {
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
@@ -69,10 +89,11 @@ __global__ void __launch_bounds__(kBlockV) primary_edge_vjp_kernel(const __grid_
         V3f Lside[2];
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
+            __syncwarp(live_mask);
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px + sg * bq.x, py + sg * bq.y), ro, rd);
-            Lside[side] = Li<float, kBvh>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
+            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
         }
         if (!valid) continue;
         const int pix = iy * sc.width + ix;
@@ -96,18 +117,27 @@ __global__ void __launch_bounds__(kBlockV) primary_edge_vjp_kernel(const __grid_
     grad_acc_end(acc);
 }
 
-template <bool kBvh, bool kSmem>
+template <int kCfg>
 __global__ void __launch_bounds__(kBlockV) secondary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                       const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                       const float *__restrict__ d_img) {
     extern __shared__ float smem[];
     SecEdgeAdjoint adj;
-    adj.acc = grad_acc_begin(gl, smem, 0, gl.total, kSmem);
+    adj.acc = grad_acc_begin(gl, smem, 0, gl.off_env, rp.smem_grad != 0);
     adj.gl = gl;
     adj.d_img = d_img;
     adj.scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
     const long long stride = (long long) gridDim.x * kBlockV;
-    for (long long i = rp.lane_begin + (long long) blockIdx.x * kBlockV + threadIdx.x; i < rp.lane_end; i += stride) {
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
@@ -119,78 +149,46 @@ __global__ void __launch_bounds__(kBlockV) secondary_edge_vjp_kernel(const __gri
             if (pdf0 > kEpsilon) a2.scale = adj.scale / pdf0;
         }
         V3f value0, tangent;
-        eval_secondary_edge<kBvh, SecEdgeAdjoint>(sc, cam, sample3, value0, tangent, a2);
+        eval_secondary_edge<kCfg, SecEdgeAdjoint>(sc, cam, sample3, value0, tangent, a2);
     }
     grad_acc_end(adj.acc);
 }
 
-// ---- launchers -------------------------------------------------------------------------------
-static int g_sms = 0;
-static int vjp_grid(long long lanes, int blocks_per_sm) {
-    if (g_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms <= 0) g_sms = 148;
-    }
-    const long long need = (lanes + kBlockV - 1) / kBlockV, cap = (long long) g_sms * blocks_per_sm;
+// ---- per-configuration launchers (one translation unit per configuration: vjp_cfg*.cu) -----------------
+template <class K> inline int vjp_grid(K kernel, size_t smem, long long lanes) {   // resident CTAs only (see kernels_impl.cuh)
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockV, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long need = (lanes + kBlockV - 1) / kBlockV, cap = (long long) sms * per_sm;
     return (int) (need < cap ? (need > 0 ? need : 1) : cap);
 }
 constexpr int kSmemGradMaxFloats = 12 * 1024;   // 48 KB: no opt-in needed
 
-template <class K> static cudaError_t launch_k(K kern, int grid, size_t smem, cudaStream_t st, const DScene &sc, const DCamera &cam,
-                                               const RenderParams &rp, const GradLayout &gl, const float *d_img) {
-    kern<<<grid, kBlockV, smem, st>>>(sc, cam, rp, gl, d_img);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_interior_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img,
-                                cudaStream_t st) {
-    const long long lanes = rp.lane_end - rp.lane_begin;
-    if (lanes <= 0) return cudaSuccess;
-    const int n = gl.off_pe;
-    const bool sm = n <= kSmemGradMaxFloats;
-    const size_t bytes = sm ? sizeof(float) * n : 0;
-    const int grid = vjp_grid(lanes, 4);
-    const bool deep = rp.max_depth > 4;
-    if (rp.max_depth > 8) return cudaErrorInvalidValue;
-#define PSDR_LAUNCH_I(BVH, D, SM) return launch_k(interior_vjp_kernel<BVH, D, SM>, grid, bytes, st, sc, cam, rp, gl, d_img)
-    if (sc.use_bvh) {
-        if (deep) { if (sm) PSDR_LAUNCH_I(true, 8, true); else PSDR_LAUNCH_I(true, 8, false); }
-        else { if (sm) PSDR_LAUNCH_I(true, 4, true); else PSDR_LAUNCH_I(true, 4, false); }
-    } else {
-        if (deep) { if (sm) PSDR_LAUNCH_I(false, 8, true); else PSDR_LAUNCH_I(false, 8, false); }
-        else { if (sm) PSDR_LAUNCH_I(false, 4, true); else PSDR_LAUNCH_I(false, 4, false); }
+template <int kCfg> struct AdjointLaunch {
+    static cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
+        RenderParams rq = rp;
+        rq.smem_grad = gl.off_pe <= kSmemGradMaxFloats ? 1 : 0;
+        const size_t bytes = rq.smem_grad ? sizeof(float) * gl.off_pe : 0;
+        const long long n = rp.lane_end - rp.lane_begin;
+        if (rp.max_depth > 4) interior_vjp_kernel<kCfg, 8><<<vjp_grid(interior_vjp_kernel<kCfg, 8>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+        else interior_vjp_kernel<kCfg, 4><<<vjp_grid(interior_vjp_kernel<kCfg, 4>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+        return cudaGetLastError();
     }
-#undef PSDR_LAUNCH_I
-}
-
-cudaError_t launch_primary_edges_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img,
-                                     cudaStream_t st) {
-    const long long lanes = rp.lane_end - rp.lane_begin;
-    if (lanes <= 0 || cam.n_edges <= 0) return cudaSuccess;
-    const int n = gl.off_se - gl.off_pe;
-    const bool sm = n <= kSmemGradMaxFloats;
-    const size_t bytes = sm ? sizeof(float) * n : 0;
-    const int grid = vjp_grid(lanes, 8);
-    if (sc.use_bvh) return sm ? launch_k(primary_edge_vjp_kernel<true, true>, grid, bytes, st, sc, cam, rp, gl, d_img)
-                              : launch_k(primary_edge_vjp_kernel<true, false>, grid, bytes, st, sc, cam, rp, gl, d_img);
-    return sm ? launch_k(primary_edge_vjp_kernel<false, true>, grid, bytes, st, sc, cam, rp, gl, d_img)
-              : launch_k(primary_edge_vjp_kernel<false, false>, grid, bytes, st, sc, cam, rp, gl, d_img);
-}
-
-cudaError_t launch_secondary_edges_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img,
-                                       cudaStream_t st) {
-    const long long lanes = rp.lane_end - rp.lane_begin;
-    if (lanes <= 0 || sc.n_sec_edges <= 0) return cudaSuccess;
-    const int n = gl.total;
-    const bool sm = n <= kSmemGradMaxFloats;
-    const size_t bytes = sm ? sizeof(float) * n : 0;
-    const int grid = vjp_grid(lanes, 8);
-    if (sc.use_bvh) return sm ? launch_k(secondary_edge_vjp_kernel<true, true>, grid, bytes, st, sc, cam, rp, gl, d_img)
-                              : launch_k(secondary_edge_vjp_kernel<true, false>, grid, bytes, st, sc, cam, rp, gl, d_img);
-    return sm ? launch_k(secondary_edge_vjp_kernel<false, true>, grid, bytes, st, sc, cam, rp, gl, d_img)
-              : launch_k(secondary_edge_vjp_kernel<false, false>, grid, bytes, st, sc, cam, rp, gl, d_img);
-}
+    static cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
+        RenderParams rq = rp;
+        const int n = gl.off_se - gl.off_pe;
+        rq.smem_grad = n <= kSmemGradMaxFloats ? 1 : 0;
+        primary_edge_vjp_kernel<kCfg><<<vjp_grid(primary_edge_vjp_kernel<kCfg>, rq.smem_grad ? sizeof(float) * n : 0, rp.lane_end - rp.lane_begin), kBlockV, rq.smem_grad ? sizeof(float) * n : 0, st>>>(sc, cam, rq, gl, d_img);
+        return cudaGetLastError();
+    }
+    static cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
+        RenderParams rq = rp;
+        const int n = gl.off_env;            // everything but the envmap texels
+        rq.smem_grad = n <= kSmemGradMaxFloats ? 1 : 0;
+        secondary_edge_vjp_kernel<kCfg><<<vjp_grid(secondary_edge_vjp_kernel<kCfg>, rq.smem_grad ? sizeof(float) * n : 0, rp.lane_end - rp.lane_begin), kBlockV, rq.smem_grad ? sizeof(float) * n : 0, st>>>(sc, cam, rq, gl, d_img);
+        return cudaGetLastError();
+    }
+};
 
 }  // namespace psdr
