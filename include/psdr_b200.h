@@ -88,6 +88,12 @@ int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float refle
 int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float specular[3], const float diffuse[3], float roughness,
                                    int two_side);
 
+/* DiffuseBSDF.reflectance / MicrofacetBSDF.diffuseReflectance = Bitmap3fD(w, h, data) with more than one texel
+ * (src/psdr.cpp:209-219, src/core/bitmap.cpp:46-131): declares the texture resolution of BSDF `index`; afterwards
+ * PSDR_BSDF_REFLECTANCE takes / returns 3*w*h floats (rgb interleaved, pixel = y*w + x).  w = h = 1 switches back
+ * to the constant. */
+int psdr_scene_set_bsdf_texture(psdr_scene *s, int index, int w, int h);
+
 /* Scene.add_Mesh(mesh, bsdf_id, emitter) with mesh = Mesh.load_raw(v, f, uv, f_uv) -- src/psdr.cpp:399-400,
  * src/scene/scene.cpp:249-309, src/shape/mesh.cpp:74-162.  v: nv*3 floats (object space), f: nf*3 ints,
  * uv: nuv*2 floats or NULL, fuv: nf*3 ints or NULL, to_world: 16 floats row-major or NULL (identity),

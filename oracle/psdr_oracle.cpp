@@ -126,6 +126,9 @@ struct Bsdf {
     V3d specular;     // Microfacet specularReflectance
     Dual roughness;   // Microfacet roughness
     bool two_side = false;
+    // reflectance / diffuseReflectance texture (Bitmap3fD with > 1 texel): rgb interleaved, pixel = y*w + x
+    int tex_w = 0, tex_h = 0;
+    std::vector<float> tex, dtex;
 };
 
 struct MeshRec {
@@ -710,9 +713,34 @@ template <class S> static Its<S> ray_intersect(const Scene &sc, V3<S> o, V3<S> d
 }
 
 // ---- BSDF (reference src/bsdf/diffuse.cpp:23-108) ----------------------------------------
-template <class S> static V3<S> refl_of(const Bsdf &b);
-template <> V3<Dual> refl_of<Dual>(const Bsdf &b) { return b.reflectance; }
-template <> V3<float> refl_of<float>(const Bsdf &b) { return val(b.reflectance); }
+template <class S> static V3<S> refl_const(const Bsdf &b);
+template <> V3<Dual> refl_const<Dual>(const Bsdf &b) { return b.reflectance; }
+template <> V3<float> refl_const<float>(const Bsdf &b) { return val(b.reflectance); }
+template <class S> static V3<S> bsdf_texel(const Bsdf &b, int i);
+template <> V3<float> bsdf_texel<float>(const Bsdf &b, int i) { return V3f(b.tex[3 * i], b.tex[3 * i + 1], b.tex[3 * i + 2]); }
+template <> V3<Dual> bsdf_texel<Dual>(const Bsdf &b, int i) {
+    if (b.dtex.empty()) return lift<Dual>(V3f(b.tex[3 * i], b.tex[3 * i + 1], b.tex[3 * i + 2]));
+    return V3d(Dual(b.tex[3 * i], b.dtex[3 * i]), Dual(b.tex[3 * i + 1], b.dtex[3 * i + 1]), Dual(b.tex[3 * i + 2], b.dtex[3 * i + 2]));
+}
+// Bitmap3fD::eval(uv) (reference src/core/bitmap.cpp:46-131): flip_v = true, no uv transform, wrap, bilinear
+template <class S> static V3<S> refl_of(const Bsdf &b, V2<S> uv) {
+    if (b.tex_w <= 0) return refl_const<S>(b);
+    const int w = b.tex_w, h = b.tex_h;
+    uv = V2<S>((uv.x - 0.5f) + 0.5f, -((uv.y - 0.5f) + 0.5f));
+    uv = V2<S>(uv.x - floor_(uv.x), uv.y - floor_(uv.y));
+    uv.x = uv.x * (float) (w - 1);
+    uv.y = uv.y * (float) (h - 1);
+    int px = (int) std::floor(val(uv.x)), py = (int) std::floor(val(uv.y));
+    S w1x = uv.x - (float) px, w1y = uv.y - (float) py;
+    S w0x = 1.0f - w1x, w0y = 1.0f - w1y;
+    px = std::min(px, w - 2);
+    py = std::min(py, h - 2);
+    int i00 = py * w + px;
+    V3<S> v00 = bsdf_texel<S>(b, i00), v10 = bsdf_texel<S>(b, i00 + 1), v01 = bsdf_texel<S>(b, i00 + w), v11 = bsdf_texel<S>(b, i00 + w + 1);
+    V3<S> v0(fmadd(w0x, v00.x, w1x * v10.x), fmadd(w0x, v00.y, w1x * v10.y), fmadd(w0x, v00.z, w1x * v10.z));
+    V3<S> v1(fmadd(w0x, v01.x, w1x * v11.x), fmadd(w0x, v01.y, w1x * v11.y), fmadd(w0x, v01.z, w1x * v11.z));
+    return V3<S>(fmadd(w0y, v0.x, w1y * v1.x), fmadd(w0y, v0.y, w1y * v1.y), fmadd(w0y, v0.z, w1y * v1.z));
+}
 
 template <class S> static V3<S> spec_of(const Bsdf &b);
 template <> V3<Dual> spec_of<Dual>(const Bsdf &b) { return b.specular; }
@@ -738,14 +766,14 @@ template <class S> static S ggx_smith_g1(S alpha, V3<S> v, V3<S> m) {
     return result;
 }
 // Microfacet::__eval (reference src/bsdf/microfacet.cpp:22-68)
-template <class S> static V3<S> microfacet_eval(const Bsdf &b, V3<S> wi, V3<S> wo) {
+template <class S> static V3<S> microfacet_eval(const Bsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
     if (b.two_side) {
         if (std::signbit(val(wi.z))) wo.z = -wo.z;
         wi.z = abs_(wi.z);
     }
     S cos_nv = wi.z, cos_nl = wo.z;
     if (!(val(cos_nv) > 0.f && val(cos_nl) > 0.f)) return V3<S>(S(0.f));
-    V3<S> diffuse = refl_of<S>(b) * S(kInvPi);
+    V3<S> diffuse = refl_of<S>(b, uv) * S(kInvPi);
     V3<S> H = normalize(wi + wo);
     S cos_vh = dot(H, wi);
     V3<S> F0 = spec_of<S>(b);
@@ -776,14 +804,14 @@ template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3
     if (!active || !its.valid) return V3<S>(S(0.f));
     if (sc.meshes[its.mesh].bsdf < 0) return V3<S>(S(0.f));   // bsdf == nullptr (envmap bounding mesh): a Dr.Jit vcall on null yields 0
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo);
+    if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo, its.uv);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (std::signbit(val(wiz))) wo.z = -wo.z;
         wiz = abs_(wiz);
     }
     if (!(val(wiz) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
-    V3<S> r = refl_of<S>(b);
+    V3<S> r = refl_of<S>(b, its.uv);
     return r * S(kInvPi) * wo.z;
 }
 
@@ -1349,6 +1377,16 @@ int orc_add_diffuse(void *h, const float *refl, const float *d_refl, int two_sid
     b.two_side = two_side != 0;
     s->bsdfs.push_back(b);
     return (int) s->bsdfs.size() - 1;
+}
+
+// Bitmap3fD texture for the reflectance / diffuseReflectance of BSDF `bsdf` (data [h*w*3], optional tangents)
+int orc_set_bsdf_texture(void *h, int bsdf, int w, int hh, const float *data, const float *ddata) {
+    Scene *s = (Scene *) h;
+    Bsdf &b = s->bsdfs[bsdf];
+    b.tex_w = w; b.tex_h = hh;
+    b.tex.assign(data, data + (size_t) 3 * w * hh);
+    if (ddata) b.dtex.assign(ddata, ddata + (size_t) 3 * w * hh); else b.dtex.clear();
+    return 0;
 }
 
 // MicrofacetBSDF(specular, diffuse, roughness); d = [d_spec(3), d_diff(3), d_rough(1)] or NULL

@@ -40,6 +40,7 @@ def lib():
         L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
         L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
         L.orc_add_envmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int, _f, _f, C.c_float, C.c_float]
+        L.orc_set_bsdf_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f, _f]
         L.orc_add_mesh.argtypes = [C.c_void_p, _f, _f, C.c_int, _i, C.c_int, _f, C.c_int, _i, _f, _f, C.c_int, _f, _f, C.c_int, C.c_int]
         L.orc_add_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f, _f]
         L.orc_configure.argtypes = [C.c_void_p, _i, C.c_int]
@@ -125,6 +126,10 @@ class OracleScene:
         idx = self.L.orc_add_microfacet(self.h, _fp(sp), _fp(df), float(rough), _fp(dd), int(two_side))
         self.bsdf_ids[name] = idx
         return idx
+
+    def set_bsdf_texture(self, name, data, w, h, d_data=None):
+        dat, dd = _f32(data).reshape(-1), (None if d_data is None else _f32(d_data).reshape(-1))
+        return self.L.orc_set_bsdf_texture(self.h, self.bsdf_ids[name], int(w), int(h), _fp(dat), _fp(dd))
 
     def add_envmap(self, data, w, h, to_world=None, scale=1.0, d_data=None, d_to_world_left=None, d_scale=0.0):
         """data: [h*w, 3]; to_world = raw 4x4 (left = identity); d_to_world_left = tangent of the left factor"""

@@ -144,13 +144,21 @@ class DiffuseBSDF(BSDF):
 
     def __init__(self, reflectance=None):
         if isinstance(reflectance, str):
-            raise NotImplementedError("textured DiffuseBSDF(path) is outside the round-1 path")
-        self.reflectance = np.full(3, 0.5, dtype=np.float32) if reflectance is None else _f32(reflectance, (3,)).copy()
+            raise NotImplementedError("DiffuseBSDF(path): EXR loading is outside the hot path; pass a Bitmap3fD")
+        if isinstance(reflectance, Bitmap3fD):          # textured reflectance (src/psdr.cpp:282)
+            self.reflectance = reflectance
+        else:
+            self.reflectance = np.full(3, 0.5, dtype=np.float32) if reflectance is None else _f32(reflectance, (3,)).copy()
         self.d_reflectance = np.zeros(3, dtype=np.float32)
 
     def _clone(self):
-        b = DiffuseBSDF(self.reflectance)
-        b.d_reflectance = self.d_reflectance.copy()
+        r = self.reflectance
+        if isinstance(r, Bitmap3fD):
+            c = Bitmap3fD(r.resolution[0], r.resolution[1], r.data)
+            c.d_data = None if r.d_data is None else _f32(r.d_data).reshape(-1, 3).copy()
+            r = c
+        b = DiffuseBSDF(r)
+        b.d_reflectance = _f32(self.d_reflectance).copy()
         b.twoSide = self.twoSide
         return b
 
@@ -161,16 +169,24 @@ class MicrofacetBSDF(BSDF):
 
     def __init__(self, specular=None, diffuse=None, roughness=None):
         self.specularReflectance = np.full(3, 0.04, dtype=np.float32) if specular is None else _f32(specular, (3,)).copy()
-        self.diffuseReflectance = np.full(3, 0.5, dtype=np.float32) if diffuse is None else _f32(diffuse, (3,)).copy()
+        if isinstance(diffuse, Bitmap3fD):
+            self.diffuseReflectance = diffuse
+        else:
+            self.diffuseReflectance = np.full(3, 0.5, dtype=np.float32) if diffuse is None else _f32(diffuse, (3,)).copy()
         self.roughness = np.float32(0.8) if roughness is None else (roughness if hasattr(roughness, "requires_grad") else np.float32(roughness))
         self.d_specularReflectance = np.zeros(3, dtype=np.float32)
         self.d_diffuseReflectance = np.zeros(3, dtype=np.float32)
         self.d_roughness = np.float32(0.0)
 
     def _clone(self):
-        b = MicrofacetBSDF(self.specularReflectance, self.diffuseReflectance, self.roughness)
+        d = self.diffuseReflectance
+        if isinstance(d, Bitmap3fD):
+            c = Bitmap3fD(d.resolution[0], d.resolution[1], d.data)
+            c.d_data = None if d.d_data is None else _f32(d.d_data).reshape(-1, 3).copy()
+            d = c
+        b = MicrofacetBSDF(self.specularReflectance, d, self.roughness)
         b.d_specularReflectance = _f32(self.d_specularReflectance, (3,)).copy()
-        b.d_diffuseReflectance = _f32(self.d_diffuseReflectance, (3,)).copy()
+        b.d_diffuseReflectance = _f32(self.d_diffuseReflectance).copy()
         b.d_roughness = np.float32(self.d_roughness)
         b.twoSide = self.twoSide
         return b
@@ -485,10 +501,12 @@ class Scene(Object):
         _lib.check(L.psdr_scene_set_seed(self._h, int(self.seed)))
         for b in self._bsdfs[self._pushed[0]:]:
             if isinstance(b, MicrofacetBSDF):
-                rc = L.psdr_scene_add_bsdf_microfacet(self._h, b.id.encode(), _fp(_f32(b.specularReflectance)), _fp(_f32(b.diffuseReflectance)),
+                d0 = np.full(3, 0.5, np.float32) if isinstance(b.diffuseReflectance, Bitmap3fD) else _f32(b.diffuseReflectance)
+                rc = L.psdr_scene_add_bsdf_microfacet(self._h, b.id.encode(), _fp(_f32(b.specularReflectance)), _fp(d0),
                                                       float(_f32(b.roughness).ravel()[0]), int(b.twoSide))
             else:
-                rc = L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(_f32(b.reflectance)), int(b.twoSide))
+                r0 = np.full(3, 0.5, np.float32) if isinstance(b.reflectance, Bitmap3fD) else _f32(b.reflectance)
+                rc = L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(r0), int(b.twoSide))
             if rc < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[0] = len(self._bsdfs)
@@ -529,13 +547,21 @@ class Scene(Object):
             push(_lib.SENSOR_TO_WORLD_LEFT, i, s.to_world_left, s.d_to_world_left)
             push(_lib.SENSOR_TO_WORLD_RAW, i, s.to_world, s.d_to_world)
             push(_lib.SENSOR_TO_WORLD_RIGHT, i, s.to_world_right, s.d_to_world_right)
+        def push_reflectance(i, r, d_const):
+            if isinstance(r, Bitmap3fD) and r.resolution[0] * r.resolution[1] > 1:
+                _lib.check(L.psdr_scene_set_bsdf_texture(self._h, i, r.resolution[0], r.resolution[1]))
+                push(_lib.BSDF_REFLECTANCE, i, r.data, r.d_data)
+            else:
+                _lib.check(L.psdr_scene_set_bsdf_texture(self._h, i, 1, 1))
+                push(_lib.BSDF_REFLECTANCE, i, r.data if isinstance(r, Bitmap3fD) else r, d_const)
+
         for i, b in enumerate(self._bsdfs):
             if isinstance(b, MicrofacetBSDF):
-                push(_lib.BSDF_REFLECTANCE, i, b.diffuseReflectance, b.d_diffuseReflectance)
+                push_reflectance(i, b.diffuseReflectance, b.d_diffuseReflectance)
                 push(_lib.BSDF_SPECULAR, i, b.specularReflectance, b.d_specularReflectance)
                 push(_lib.BSDF_ROUGHNESS, i, np.reshape(_f32(b.roughness), (1,)), np.reshape(_f32(b.d_roughness), (1,)))
             else:
-                push(_lib.BSDF_REFLECTANCE, i, b.reflectance, b.d_reflectance)
+                push_reflectance(i, b.reflectance, b.d_reflectance)
         for i, e in enumerate(self._emitters):
             if isinstance(e, EnvironmentMap):
                 push(_lib.ENVMAP_RADIANCE, i, e.radiance.data, e.radiance.d_data)
@@ -556,6 +582,7 @@ class Scene(Object):
                     "Sensor": (("to_world_left", _lib.SENSOR_TO_WORLD_LEFT), ("to_world", _lib.SENSOR_TO_WORLD_RAW),
                                ("to_world_right", _lib.SENSOR_TO_WORLD_RIGHT)),
                     "BSDF": (("reflectance", _lib.BSDF_REFLECTANCE), ("diffuseReflectance", _lib.BSDF_REFLECTANCE),
+                             ("reflectance.data", _lib.BSDF_REFLECTANCE), ("diffuseReflectance.data", _lib.BSDF_REFLECTANCE),
                              ("specularReflectance", _lib.BSDF_SPECULAR), ("roughness", _lib.BSDF_ROUGHNESS)),
                     "Emitter": (("radiance", _lib.EMITTER_RADIANCE),),
                     "EnvironmentMap": (("radiance.data", _lib.ENVMAP_RADIANCE), ("scale", _lib.ENVMAP_SCALE),

@@ -109,11 +109,11 @@ template <class S> struct BsdfP {
     V3<S> diff, spec;
     S rough;
 };
-template <class S> __device__ __forceinline__ BsdfP<S> bsdf_params(const DBsdf &b) {
+template <class S> __device__ __forceinline__ BsdfP<S> bsdf_params(const DBsdf &b, V3f refl) {
     BsdfP<S> p;
     p.type = b.type;
     p.two_side = b.two_side;
-    p.diff = V3<S>(S(b.refl[0]), S(b.refl[1]), S(b.refl[2]));
+    p.diff = V3<S>(S(refl.x), S(refl.y), S(refl.z));
     p.spec = V3<S>(S(b.spec[0]), S(b.spec[1]), S(b.spec[2]));
     p.rough = S(b.rough);
     return p;
@@ -157,9 +157,9 @@ struct BsdfJet {        // value and partials of sum_c W_c f_c
     V3f f;
     float d_ci, d_co, d_cio;
 };
-template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, float ci, float co, float cio, V3f W) {
+template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, V3f refl, float ci, float co, float cio, V3f W) {
     BsdfJet j;
-    const BsdfP<Dual> p = bsdf_params<Dual>(b);
+    const BsdfP<Dual> p = bsdf_params<Dual>(b, refl);
     const V3d a = bsdf_iso<Dual, kCfg>(p, Dual(ci, 1.f), Dual(co), Dual(cio));
     const V3d c = bsdf_iso<Dual, kCfg>(p, Dual(ci), Dual(co, 1.f), Dual(cio));
     j.f = val(a);
@@ -173,8 +173,9 @@ template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, 
     return j;
 }
 // d(sum_c W_c f_c * scale)/d(params): reflectance (Diffuse / Microfacet diffuse), Microfacet specular + roughness
+// uv_bar: d(contribution)/d(texture coordinate) through a textured reflectance (used at the primary hit only)
 template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, float ci, float co,
-                                                float cio, V3f W, float scale) {
+                                                float cio, V3f W, float scale, V2f uv, V2f &uv_bar) {
     if (b.two_side) {
         if (signbit_(ci)) co = -co;
         ci = fabsf(ci);
@@ -182,7 +183,19 @@ template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAc
     if (!(ci > 0.f && co > 0.f)) return;
     const int base = gl.off_bsdf + kGradBsdf * bi;
     const float k = kInvPi * co * scale;
-    acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));
+    if ((kCfg & kCfgFull) && b.tex_w > 0) {   // textured reflectance: the four taps, and the lookup's uv derivative
+        EnvTexelTaps tp;
+        bitmap_eval_uv<float>(b.tex, nullptr, b.tex_w, b.tex_h, uv, &tp);
+        const int idx[4] = {tp.i00, tp.i10, tp.i01, tp.i11};
+        const float bw[4] = {tp.w0y * tp.w0x, tp.w0y * tp.w1x, tp.w1y * tp.w0x, tp.w1y * tp.w1x};
+        const int tbase = gl.total + b.tex_goff;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc.add3(tbase + 3 * idx[t], W * (k * bw[t]));
+        const V3d ru = bitmap_eval_uv<Dual>(b.tex, nullptr, b.tex_w, b.tex_h, V2d(Dual(uv.x, 1.f), Dual(uv.y)));
+        const V3d rv = bitmap_eval_uv<Dual>(b.tex, nullptr, b.tex_w, b.tex_h, V2d(Dual(uv.x), Dual(uv.y, 1.f)));
+        uv_bar.x += k * (W.x * ru.x.d + W.y * ru.y.d + W.z * ru.z.d);
+        uv_bar.y += k * (W.x * rv.x.d + W.y * rv.y.d + W.z * rv.z.d);
+    } else acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));
     if ((kCfg & kCfgFull) && b.type == 1) {
         Dual dg, e;
         iso_specular<Dual>(Dual(b.rough, 1.f), Dual(ci), Dual(co), Dual(cio), dg, e);
@@ -207,6 +220,8 @@ struct VtxGeo {
     float area, u, v;
     int tri, mesh, bsdf, emitter;
     bool face_normals;
+    V2f uv, duv0, duv1;     // texture coordinate and its edge differences (uv = uv0 + u duv0 + v duv1)
+    V3f refl;               // reflectance / diffuseReflectance of the BSDF at uv
 };
 __device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
     VtxGeo g;
@@ -226,12 +241,25 @@ __device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u,
     g.m = bilinear(N.n0, N.n1 - N.n0, N.n2 - N.n0, V2f(u, v));
     g.minv = 1.f / norm(g.m);
     g.shn = g.face_normals ? g.fn : g.m * g.minv;
+    g.uv = g.duv0 = g.duv1 = V2f(0.f, 0.f);
+    if (mesh.flags & 2) {
+        const float2 t0 = __ldg(sc.uv + 3 * tri), t1 = __ldg(sc.uv + 3 * tri + 1), t2 = __ldg(sc.uv + 3 * tri + 2);
+        g.duv0 = V2f(t1.x - t0.x, t1.y - t0.y);
+        g.duv1 = V2f(t2.x - t0.x, t2.y - t0.y);
+        g.uv = V2f(fmaf(g.duv0.x, u, fmaf(g.duv1.x, v, t0.x)), fmaf(g.duv0.y, u, fmaf(g.duv1.y, v, t0.y)));
+    }
+    g.refl = V3f(0.f, 0.f, 0.f);
+    if (g.bsdf >= 0) {
+        const DBsdf &b = sc.bsdfs[g.bsdf];
+        g.refl = b.tex_w > 0 ? bitmap_eval_uv<float>(b.tex, nullptr, b.tex_w, b.tex_h, g.uv) : V3f(b.refl[0], b.refl[1], b.refl[2]);
+    }
     return g;
 }
 
 struct VtxAdj {
     V3f p, shn, fn;
     float area;
+    V2f uv;
 };
 
 // adjoint of v -> (w = v / |v|, t = |v|):  v_bar = (w_bar - w <w, w_bar>)/t + t_bar w
@@ -355,13 +383,13 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const float cy = -dot(ny, wo);
     const float G = fabsf(cy) / (t * t);
     const float ci = dot(wi, x.shn), co = dot(wo, x.shn), cio = dot(wi, wo);
-    const BsdfJet j = bsdf_jet<kCfg>(b, ci, co, cio, W);
+    const BsdfJet j = bsdf_jet<kCfg>(b, x.refl, ci, co, cio, W);
     r.f = j.f;
     r.geo = G * scale;
     const float phi = W.x * j.f.x + W.y * j.f.y + W.z * j.f.z;          // sum_c W_c f_c
     // C = phi * G * J * scale
     const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
-    bsdf_param_grad<kCfg>(acc, gl, x.bsdf, b, ci, co, cio, W, G * scale);
+    bsdf_param_grad<kCfg>(acc, gl, x.bsdf, b, ci, co, cio, W, G * scale, x.uv, xa.uv);
     const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
     const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) / (t * t);
     const float t_bar = G_bar * (-2.f * fabsf(cy) / (t * t * t));
@@ -404,7 +432,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     }
     if (R.nsh <= 0) return;
 
-    const VtxAdj zero_adj = {V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), 0.f};
+    const VtxAdj zero_adj = {V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), 0.f, V2f(0.f, 0.f)};
     const int ktop = R.nsh - 1;
     auto geo_of = [&](int k) { return k == 0 ? v0geo : vertex_geo(sc, R.vtri[k], R.vu[k], R.vv[k]); };
     VtxGeo y = (ktop + 1 < R.nv) ? geo_of(ktop + 1) : v0geo;      // only read when the bounce exists
@@ -525,7 +553,8 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         V3f m_bar;
         scatter_shading_normal(acc, x0, a0.shn, m_bar);
         const ShadeRec<float> N = load_shade<float>(sc, x0.tri);
-        const float u_bar = dot(N.n1 - N.n0, m_bar), v_bar = dot(N.n2 - N.n0, m_bar);
+        // uv = uv0 + u duv0 + v duv1 is differentiable at the primary hit (scene.cpp:785-788)
+        const float u_bar = dot(N.n1 - N.n0, m_bar) + dot(x0.duv0, a0.uv), v_bar = dot(N.n2 - N.n0, m_bar) + dot(x0.duv1, a0.uv);
         o_bar = o_bar + a0.p;
         d_bar = d_bar + a0.p * t0;
         const float t_bar = dot(d, a0.p);

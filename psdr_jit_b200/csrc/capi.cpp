@@ -159,6 +159,22 @@ int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float sp
     return (int) sc.bsdfs.size() - 1;
 }
 
+int psdr_scene_set_bsdf_texture(psdr_scene *s, int index, int w, int h) {
+    if (!s) return fail("null scene");
+    Scene &sc = s->sc;
+    if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+    if (w < 1 || h < 1 || (w * h > 1 && (w < 2 || h < 2))) return fail("Bitmap: invalid resolution!");
+    HBsdf &b = sc.bsdfs[index];
+    if (w * h == 1) { b.tex_w = b.tex_h = 0; b.tex.clear(); b.dtex.clear(); }
+    else if (b.tex_w != w || b.tex_h != h) {
+        b.tex_w = w; b.tex_h = h;
+        b.tex.assign((size_t) 3 * w * h, 0.5f);
+        b.dtex.clear();
+    }
+    sc.configured = false;
+    return 0;
+}
+
 int psdr_scene_add_mesh(psdr_scene *s, const float *v, int nv, const int *f, int nf, const float *uv, int nuv, const int *fuv,
                         const float *to_world, const char *bsdf_id, const float *radiance, int use_face_normals, int enable_edges) {
     if (!s || !v || !f || !bsdf_id || nv <= 0 || nf <= 0) { fail("invalid mesh arguments"); return -1; }
@@ -261,6 +277,16 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
         }
         case PSDR_BSDF_REFLECTANCE: {
             if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            if (sc.bsdfs[index].tex_w > 0) {   // textured
+                HBsdf &b = sc.bsdfs[index];
+                if (n != 3 * b.tex_w * b.tex_h) return fail("texture size mismatch");
+                if (tangent) {
+                    bool any = false;
+                    for (int i = 0; i < n; ++i) any |= data[i] != 0.f;
+                    if (any) b.dtex.assign(data, data + n); else b.dtex.clear();
+                } else b.tex.assign(data, data + n);
+                break;
+            }
             if (n != 3) return fail("reflectance is 3 floats");
             put(sc.bsdfs[index].reflectance.x, data[0]); put(sc.bsdfs[index].reflectance.y, data[1]); put(sc.bsdfs[index].reflectance.z, data[2]);
             break;
@@ -326,7 +352,7 @@ int psdr_scene_clear_tangents(psdr_scene *s) {
     for (HCamera &c : sc.cameras)
         for (auto &M : c.to_world)
             for (int i = 0; i < 16; ++i) M.m[i / 4][i % 4].d = 0.f;
-    for (HBsdf &b : sc.bsdfs) { b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
+    for (HBsdf &b : sc.bsdfs) { b.dtex.clear(); b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
     for (HEmitter &e : sc.emitters) e.radiance = detach(e.radiance);
     sc.env.ddata.clear();
     sc.env.scale = detach(sc.env.scale);
@@ -621,6 +647,11 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
             return copy(g.cameras[index].to_world[kind - PSDR_SENSOR_TO_WORLD_LEFT], 16);
         case PSDR_BSDF_REFLECTANCE:
             if (index < 0 || 3 * index + 3 > (int) g.bsdf_refl.size()) return fail("invalid BSDF index");
+            if (index < (int) g.bsdf_tex.size() && !g.bsdf_tex[index].empty()) {
+                if (n != (int) g.bsdf_tex[index].size()) return fail("gradient buffer size mismatch");
+                std::memcpy(out, g.bsdf_tex[index].data(), sizeof(float) * n);
+                return 0;
+            }
             return copy(g.bsdf_refl.data() + 3 * index, 3);
         case PSDR_ENVMAP_RADIANCE:
             if (n != (int) g.env_radiance.size()) return fail("gradient buffer size mismatch");

@@ -178,6 +178,7 @@ template <class S> struct Its {   // reference include/psdr/core/intersection.h:
     V3<S> p, n, wi, sh_s, sh_t, sh_n;
     S t, J;
     float bu, bv;   // detached barycentrics of the hit (p = p0 + bu e1 + bv e2)
+    V2<S> uv;       // texture coordinate (differentiable at the primary hit of renderD, scene.cpp:755-788)
     __device__ __forceinline__ V3<S> to_local(V3<S> v) const { return V3<S>(dot(v, sh_s), dot(v, sh_t), dot(v, sh_n)); }
     __device__ __forceinline__ V3<S> to_world(V3<S> v) const { return sh_s * v.x + sh_t * v.y + sh_n * v.z; }
 };
@@ -226,8 +227,11 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
     its.n = N.fn;
     const DMesh mesh = sc.meshes[T.mesh];
     V3<S> sh_n, dir;
+    S bary_u(0.f), bary_v(0.f);
     if (!ad || path_space) {
         const V2f uv(h.u, h.v);
+        bary_u = S(h.u);
+        bary_v = S(h.v);
         sh_n = normalize(bilinear(N.n0, N.n1 - N.n0, N.n2 - N.n0, uv));
         its.p = bilinear(T.p0, T.e1, T.e2, uv);
         dir = its.p - o;
@@ -240,6 +244,8 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
         S u, v, t;
         ray_intersect_triangle(T.p0, T.e1, T.e2, o, d, u, v, t);
         const V2<S> uv(u, v);
+        bary_u = u;
+        bary_v = v;
         sh_n = normalize(bilinear(N.n0, N.n1 - N.n0, N.n2 - N.n0, uv));
         its.p = V3<S>(fmadd(d.x, t, o.x), fmadd(d.y, t, o.y), fmadd(d.z, t, o.z));
         its.t = t;
@@ -250,9 +256,11 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
     if (mesh.flags & 1) sh_n = its.n;
     its.sh_n = sh_n;
     coordinate_system(sh_n, its.sh_s, its.sh_t);
+    its.uv = V2<S>(S(0.f), S(0.f));
     if (mesh.flags & 2) {   // uv-derived tangent frame (scene.cpp:716-728, 757-765)
         const float2 t0 = __ldg(sc.uv + 3 * h.tri), t1 = __ldg(sc.uv + 3 * h.tri + 1), t2 = __ldg(sc.uv + 3 * h.tri + 2);
         const float du0x = t1.x - t0.x, du0y = t1.y - t0.y, du1x = t2.x - t0.x, du1y = t2.y - t0.y;
+        its.uv = V2<S>(fmadd(S(du0x), bary_u, fmadd(S(du1x), bary_v, S(t0.x))), fmadd(S(du0y), bary_u, fmadd(S(du1y), bary_v, S(t0.y))));
         const float det = du0x * du1y - du0y * du1x;
         if (det != 0.f) {
             const float inv_det = 1.f / det;
@@ -266,10 +274,16 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
 }
 
 // ---- Diffuse BSDF (reference src/bsdf/diffuse.cpp:23-108) ------------------------------------
-template <class S> __device__ __forceinline__ V3<S> bsdf_reflectance(const DBsdf &b);
-template <> __device__ __forceinline__ V3f bsdf_reflectance<float>(const DBsdf &b) { return V3f(b.refl[0], b.refl[1], b.refl[2]); }
-template <> __device__ __forceinline__ V3d bsdf_reflectance<Dual>(const DBsdf &b) {
+template <class S> __device__ __forceinline__ V3<S> bsdf_reflectance_const(const DBsdf &b);
+template <> __device__ __forceinline__ V3f bsdf_reflectance_const<float>(const DBsdf &b) { return V3f(b.refl[0], b.refl[1], b.refl[2]); }
+template <> __device__ __forceinline__ V3d bsdf_reflectance_const<Dual>(const DBsdf &b) {
     return V3d(Dual(b.refl[0], b.d_refl[0]), Dual(b.refl[1], b.d_refl[1]), Dual(b.refl[2], b.d_refl[2]));
+}
+// Bitmap3fD::eval(its.uv): 1x1 -> the constant, else bilinear texture lookup (reference src/core/bitmap.cpp:46-131);
+// textures belong to the "full" kernel family
+template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_reflectance(const DBsdf &b, V2<S> uv) {
+    if ((kCfg & kCfgFull) && b.tex_w > 0) return bitmap_eval_uv<S>(b.tex, IsDual<S>::value ? b.dtex : nullptr, b.tex_w, b.tex_h, uv);
+    return bsdf_reflectance_const<S>(b);
 }
 
 template <class S> __device__ __forceinline__ V3<S> bsdf_specular(const DBsdf &b);
@@ -299,14 +313,14 @@ template <class S> __device__ __forceinline__ S ggx_smith_g1(S alpha, V3<S> v, V
 
 // Microfacet::__eval (reference src/bsdf/microfacet.cpp:22-68): Lambert + GGX specular with the
 // Schlick-Gaussian Fresnel fit; wi, wo in the shading frame
-template <class S> __device__ __forceinline__ V3<S> microfacet_eval(const DBsdf &b, V3<S> wi, V3<S> wo) {
+template <class S, int kCfg> __device__ __forceinline__ V3<S> microfacet_eval(const DBsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
     if (b.two_side) {
         if (signbit_(val(wi.z))) wo.z = -wo.z;
         wi.z = abs_(wi.z);
     }
     const S cos_nv = wi.z, cos_nl = wo.z;
     if (!(val(cos_nv) > 0.f && val(cos_nl) > 0.f)) return V3<S>(S(0.f));
-    const V3<S> diffuse = bsdf_reflectance<S>(b) * S(kInvPi);
+    const V3<S> diffuse = bsdf_reflectance<S, kCfg>(b, uv) * S(kInvPi);
     const V3<S> H = normalize(wi + wo);
     const S cos_vh = dot(H, wi);
     const V3<S> F0 = bsdf_specular<S>(b);
@@ -327,14 +341,14 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DS
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return V3<S>(S(0.f));
     const DBsdf &b = sc.bsdfs[bi];
-    if ((kCfg & kCfgFull) && b.type == 1) return microfacet_eval<S>(b, its.wi, wo);
+    if ((kCfg & kCfgFull) && b.type == 1) return microfacet_eval<S, kCfg>(b, its.wi, wo, its.uv);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (signbit_(val(wiz))) wo.z = -wo.z;
         wiz = abs_(wiz);
     }
     if (!(val(wiz) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
-    return bsdf_reflectance<S>(b) * S(kInvPi) * wo.z;
+    return bsdf_reflectance<S, kCfg>(b, its.uv) * S(kInvPi) * wo.z;
 }
 
 // Microfacet::__pdf (reference src/bsdf/microfacet.cpp:108-133), detached

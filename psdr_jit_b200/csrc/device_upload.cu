@@ -172,6 +172,12 @@ void upload_scene(Scene &sc) {
                  o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
                  o_nodes = pk.add(nodes), o_order = pk.add(order), o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf),
                  o_env = pk.add(sc.env.data), o_denv = pk.add(sc.env.ddata), o_cp = pk.add(sc.env.cell.pmf), o_cc = pk.add(sc.env.cell.cmf);
+    std::vector<size_t> o_tex(sc.bsdfs.size(), 0), o_dtex(sc.bsdfs.size(), 0);
+    for (size_t i = 0; i < sc.bsdfs.size(); ++i)
+        if (sc.bsdfs[i].tex_w > 0) {
+            o_tex[i] = pk.add(sc.bsdfs[i].tex);
+            o_dtex[i] = pk.add(sc.bsdfs[i].dtex);
+        }
 
     if (!sc.dev) sc.dev = new DeviceBuffers();
     DeviceBuffers &db = *sc.dev;
@@ -184,6 +190,19 @@ void upload_scene(Scene &sc) {
     }
     // the previous tables may still be read by kernels in flight on other streams
     check(cudaDeviceSynchronize(), "cudaDeviceSynchronize(before table refresh)");
+    // texture pointers of the BSDF records can only be filled in once the allocation is known
+    for (size_t i = 0; i < sc.bsdfs.size(); ++i) {
+        DBsdf *rec = reinterpret_cast<DBsdf *>(pk.bytes.data() + o_bsdf) + i;
+        rec->tex_w = rec->tex_h = 0;
+        rec->tex = rec->dtex = nullptr;
+        rec->tex_goff = sc.texture_grad_offset((int) i);   // relative to the end of the gradient table
+        if (sc.bsdfs[i].tex_w > 0) {
+            rec->tex_w = sc.bsdfs[i].tex_w;
+            rec->tex_h = sc.bsdfs[i].tex_h;
+            rec->tex = (const float *) ((const unsigned char *) db.dev + o_tex[i]);
+            rec->dtex = sc.bsdfs[i].dtex.empty() ? nullptr : (const float *) ((const unsigned char *) db.dev + o_dtex[i]);
+        }
+    }
     std::memcpy(db.host, pk.bytes.data(), pk.bytes.size());
     check(cudaMemcpy(db.dev, db.host, pk.bytes.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene tables)");
     sc.upload_bytes = pk.bytes.size();
@@ -200,7 +219,7 @@ void upload_scene(Scene &sc) {
     d.n_nodes = (int) nodes.size();
     d.use_bvh = use_bvh ? 1 : 0;
     d.full_features = sc.env.present ? 1 : 0;
-    for (const HBsdf &b : sc.bsdfs) d.full_features |= (b.type != 0) ? 1 : 0;
+    for (const HBsdf &b : sc.bsdfs) d.full_features |= (b.type != 0 || b.tex_w > 0) ? 1 : 0;
     d.geo = (const float4 *) (base + o_geo);
     d.shade = (const float4 *) (base + o_shade);
     d.dgeo = (const float4 *) (base + o_dgeo);

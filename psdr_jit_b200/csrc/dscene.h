@@ -67,6 +67,11 @@ struct DBsdf {
     float spec[3];           // Microfacet: specularReflectance (F0)
     float d_spec[3];
     float rough, d_rough;    // Microfacet: roughness (alpha = roughness^2)
+    // reflectance / diffuseReflectance as a w x h texture (Bitmap3fD); tex_w * tex_h == 0: the constant refl[]
+    int tex_w, tex_h;
+    const float *tex, *dtex;
+    int tex_goff;            // offset of the texel gradients in the adjoint's gradient table
+    int pad_;
 };
 
 struct DCamera {

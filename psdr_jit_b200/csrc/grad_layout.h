@@ -15,6 +15,7 @@ struct GradLayout {
     int off_cam;      // 40 floats: 0..15 d to_world | 16..31 d world_to_sample | 32..34 d pos | 35..37 d dir
     int off_pe;       // 4 floats per primary edge of the rendered sensor (d p0.xy, d p1.xy)
     int off_se;       // 6 floats per secondary edge (d p0, d e1)
+    // (texel gradients of textured BSDFs follow the environment map block; their offsets are in DBsdf::tex_goff)
     int off_env;      // environment map: 0 d scale | 1..9 d from_world (3x3) | 16.. d texels (3*w*h); == total if none
     int total;
 };

@@ -35,6 +35,9 @@ struct HBsdf {
     V3d specular;             // Microfacet specularReflectance
     Dual roughness;           // Microfacet roughness
     bool two_side = false;
+    // reflectance / diffuseReflectance texture (Bitmap3fD with more than one texel): rgb interleaved, pixel = y*w + x
+    int tex_w = 0, tex_h = 0;
+    std::vector<float> tex, dtex;
 };
 
 struct HMesh {
@@ -118,6 +121,7 @@ struct ParamGrads {
     std::vector<double> bsdf_refl, emitter_rad, bsdf_spec;   // 3 per object
     std::vector<double> bsdf_rough;                          // 1 per BSDF
     std::vector<float> env_radiance;                         // 3*w*h
+    std::vector<std::vector<float>> bsdf_tex;                // per textured BSDF: 3*w*h
     double env_scale = 0.0, env_to_world_left[16] = {};
     bool valid = false;
 };
@@ -156,6 +160,7 @@ struct Scene {
     // reverse mode: table layout for `sensor` (base = nullptr) and the host chain
     // table gradients -> world vertices -> raw vertices / to_world / camera matrices (scene_grad.cpp)
     GradLayout grad_layout(int sensor) const;
+    int texture_grad_offset(int bsdf) const;   // relative to GradLayout::total (negative)
     void backprop(const float *table, const GradLayout &gl, int sensor);
 
     Scene();

@@ -49,6 +49,30 @@ template <class S> PSDR_HD V3<S> bitmap_eval_envmap(const float *data, const flo
     return V3<S>(fmadd(w0y, v0.x, w1y * v1.x), fmadd(w0y, v0.y, w1y * v1.y), fmadd(w0y, v0.z, w1y * v1.z));
 }
 
+// Bitmap<3>::eval for surface textures (flip_v = true, envmap_mode = false; rotation 0, scale 1, translation 0):
+// reference src/core/bitmap.cpp:60-131.  uv wraps, bilinear over (w-1) x (h-1) cells.
+template <class S> PSDR_HD V3<S> bitmap_eval_uv(const float *data, const float *ddata, int w, int h, V2<S> uv, EnvTexelTaps *taps = nullptr) {
+    uv = V2<S>((uv.x - 0.5f) + 0.5f, -((uv.y - 0.5f) + 0.5f));           // rotation by 0 about the centre, then flip v
+    uv = V2<S>(uv.x - floor_(uv.x), uv.y - floor_(uv.y));
+    uv.x = uv.x * (float) (w - 1);
+    uv.y = uv.y * (float) (h - 1);
+    int px = (int) floorf(val(uv.x)), py = (int) floorf(val(uv.y));
+    const S w1x = uv.x - (float) px, w1y = uv.y - (float) py;
+    const S w0x = 1.0f - w1x, w0y = 1.0f - w1y;
+    px = px < w - 2 ? px : w - 2;
+    py = py < h - 2 ? py : h - 2;
+    const int i00 = py * w + px, i10 = i00 + 1, i01 = i00 + w, i11 = i01 + 1;
+    if (taps) {
+        taps->i00 = i00; taps->i10 = i10; taps->i01 = i01; taps->i11 = i11;
+        taps->w0x = val(w0x); taps->w1x = val(w1x); taps->w0y = val(w0y); taps->w1y = val(w1y);
+    }
+    const V3<S> v00 = TexelLoad<S>::get(data, ddata, i00), v10 = TexelLoad<S>::get(data, ddata, i10),
+                v01 = TexelLoad<S>::get(data, ddata, i01), v11 = TexelLoad<S>::get(data, ddata, i11);
+    const V3<S> v0(fmadd(w0x, v00.x, w1x * v10.x), fmadd(w0x, v00.y, w1x * v10.y), fmadd(w0x, v00.z, w1x * v10.z));
+    const V3<S> v1(fmadd(w0x, v01.x, w1x * v11.x), fmadd(w0x, v01.y, w1x * v11.y), fmadd(w0x, v01.z, w1x * v11.z));
+    return V3<S>(fmadd(w0y, v0.x, w1y * v1.x), fmadd(w0y, v0.y, w1y * v1.y), fmadd(w0y, v0.z, w1y * v1.z));
+}
+
 // lat-long uv of a direction in the map's local frame (envmap.cpp:66-67)
 template <class S> PSDR_HD V2<S> envmap_dir_to_uv(V3<S> v) {
     V2<S> uv(atan2_(v.x, -v.z) * 0.15915494309189533577f, safe_acos_(v.y) * kInvPi);

@@ -43,7 +43,7 @@ test_envmap.__test__ = False
 
 
 def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, bsdfs=None, d_bsdf=None,
-                 envmap=None):
+                 envmap=None, textures=None):
     """Scene = scenes.* meshes + CBOX bsdfs + camera; derivative parameter P translates mesh
     `move_mesh` by P*axis_scale through to_world_left (reference README.md:87-90)."""
     from oracle.psdr_oracle import OracleScene
@@ -55,6 +55,9 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
             sc.add_microfacet(name, params[0], params[1], params[2], d=d)
         else:
             sc.add_diffuse(name, params, d_refl=d)
+        if textures and name in textures:      # (data [h*w,3], w, h, d_data or None) on the reflectance / diffuseReflectance slot
+            t = textures[name]
+            sc.set_bsdf_texture(name, t[0], t[1], t[2], t[3] if len(t) > 3 else None)
     if envmap is not None:      # dict(data, w, h, scale, to_world, d_data, d_scale, d_to_world_left); added before the meshes
         sc.add_envmap(envmap["data"], envmap["w"], envmap["h"], to_world=envmap.get("to_world"), scale=envmap.get("scale", 1.0),
                       d_data=envmap.get("d_data"), d_to_world_left=envmap.get("d_to_world_left"), d_scale=envmap.get("d_scale", 0.0))
@@ -70,7 +73,7 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
 
 def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, accel=-1,
                   shard=None, two_side=False, d_radiance=None, d_reflectance=None, d_cam_left=None, log_level=0, bsdfs=None, d_bsdf=None,
-                  envmap=None):
+                  envmap=None, textures=None):
     """The same scene through the product's psdr_jit-style Python surface."""
     import psdr_jit_b200 as psdr
     cam = cam or scenes.CBOX_CAMERA
@@ -90,6 +93,15 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
             b = psdr.DiffuseBSDF(params)
             if d is not None:
                 b.d_reflectance = np.float32(d)
+        if textures and name in textures:
+            t = textures[name]
+            bm = psdr.Bitmap3fD(t[1], t[2], t[0])
+            if len(t) > 3 and t[3] is not None:
+                bm.d_data = np.asarray(t[3], dtype=np.float32)
+            if is_microfacet(params):
+                b.diffuseReflectance = bm
+            else:
+                b.reflectance = bm
         sc.add_BSDF(b, name, twoSide=two_side)
     if envmap is not None:
         env = psdr.EnvironmentMap(psdr.Bitmap3fD(envmap["w"], envmap["h"], envmap["data"]))

@@ -264,3 +264,37 @@ def test_envmap_vs_reference(oracle):
     assert nbad <= 0.03 * len(img) and r_ex < 1e-4, (r, nbad, r_ex)
     r, nbad, r_ex = compare_stats(d * 2.0, g["grad_interior"], flip_rel=2e-5)      # reference tangent scaling
     assert nbad <= 0.05 * len(img) and r_ex < 2e-4, (r, nbad, r_ex)
+
+
+def _golden_textures(seed=4):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, (w, h) in (("white", (8, 6)), ("cat", (5, 7))):
+        out[name] = (rng.random((h * w, 3), dtype=np.float32) * 0.8 + 0.1, w, h, None)
+        rng.normal(size=(h * w, 3))
+    return out
+
+
+def test_textured_reflectance_vs_reference(oracle):
+    """Bitmap3fD::eval with more than one texel (bitmap.cpp:46-131) on the meshes with UVs, and the derivative
+    through the texture coordinate of the primary hit (camera translation), against the running reference."""
+    from oracle.psdr_oracle import OracleScene
+    g = np.load(GOLDEN + "/tex_render.npz")
+    img = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, textures=_golden_textures()).render(3, seed=3, mode=0)
+    r, nbad, r_ex = compare_stats(img, g["img_d3_seed3"], flip_rel=2e-5)
+    assert nbad <= 60 and r_ex < 1e-6, (r, nbad, r_ex)
+    osc = OracleScene(128, 128, 4, 0, 0)
+    tex = _golden_textures()
+    for name, refl in scenes.CBOX_BSDFS:
+        osc.add_diffuse(name, refl)
+        if name in tex:
+            osc.set_bsdf_texture(name, *tex[name])
+    for m in scenes.cbox_meshes():
+        osc.add_mesh(m.v, m.f, m.bsdf, uv=m.uv, fuv=m.fuv, to_world={"raw": m.to_world}, radiance=m.emitter)
+    c = scenes.CBOX_CAMERA
+    from tests.common import translation_tangent
+    osc.add_camera(c["fov"], c["near"], c["far"], {"raw": c["to_world"]}, d_to_world={"left": translation_tangent((3.0, -2.0, 1.0))})
+    osc.configure((0,))
+    i, d = osc.render(2, seed=6, mode=1, terms=1)
+    r, nbad, r_ex = compare_stats(d * 2.0, g["grad_cam"], flip_rel=2e-5)
+    assert nbad <= 0.02 * len(d) and r_ex < 2e-4, (r, nbad, r_ex)

@@ -406,3 +406,51 @@ def test_envmap_vs_reference_golden():
     img, dimg = integ.renderD_fwd(sc, 0, seed=5)
     r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["grad_all"], flip_rel=2e-5)
     assert nbad <= 0.08 * len(dimg) and r_ex < 1e-3, (r, nbad, r_ex)
+
+
+# ---- textured reflectance: Bitmap3fD::eval (reference src/core/bitmap.cpp:46-131) --------------------------
+def _textures(with_tangent=False, seed=4):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, (w, h) in (("white", (8, 6)), ("cat", (5, 7))):
+        data = rng.random((h * w, 3), dtype=np.float32) * 0.8 + 0.1
+        out[name] = (data, w, h, rng.normal(size=(h * w, 3)).astype(np.float32) * 0.2 if with_tangent else None)
+    return out
+
+
+@pytest.mark.parametrize("bs", ["diffuse", "mf"])
+def test_textured_bsdf_renderC_vs_oracle(oracle, bs):
+    psdr = _psdr()
+    bsdfs = scenes.CBOX_MF_BSDFS if bs == "mf" else None
+    ref = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bsdfs, textures=_textures()).render(3, seed=3, mode=0)
+    plain = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bsdfs).render(3, seed=3, mode=0)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bsdfs, textures=_textures())
+    got = psdr.PathTracer(3).renderC(sc, 0, seed=3).cpu().numpy()
+    assert rel_l2(got, ref) < TOL
+    assert rel_l2(ref, plain) > 1e-2           # the textures are visible
+
+
+@pytest.mark.parametrize("terms", [1, 7])
+def test_textured_bsdf_renderD_vs_oracle(oracle, terms):
+    """tangents: texels, camera translation (moves uv at the primary hit), large-box translation"""
+    psdr = _psdr()
+    spps = (4 if terms & 1 else 0, 4 if terms & 2 else 0, 4 if terms & 4 else 0)
+    from oracle.psdr_oracle import OracleScene
+    tex = _textures(with_tangent=True)
+    cam_t = translation_tangent((3.0, -2.0, 1.0))
+    osc = OracleScene(128, 128, *spps)
+    for name, refl in scenes.CBOX_BSDFS:
+        osc.add_diffuse(name, refl)
+        if name in tex:
+            osc.set_bsdf_texture(name, *tex[name])
+    for i, m in enumerate(scenes.cbox_meshes()):
+        osc.add_mesh(m.v, m.f, m.bsdf, uv=m.uv, fuv=m.fuv, to_world={"raw": m.to_world}, radiance=m.emitter,
+                     d_to_world={"left": translation_tangent((10.0, 0.0, 20.0))} if i == 2 else None)
+    c = scenes.CBOX_CAMERA
+    osc.add_camera(c["fov"], c["near"], c["far"], {"raw": c["to_world"]}, d_to_world={"left": cam_t})
+    osc.configure((0,))
+    img_ref, dimg_ref = osc.render(2, seed=6, mode=1, terms=7)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, *spps, move_mesh=2, axis_scale=(10.0, 0.0, 20.0), textures=tex, d_cam_left=cam_t)
+    img, dimg = psdr.PathTracer(2).renderD_fwd(sc, 0, seed=6)
+    assert rel_l2(img.cpu().numpy(), img_ref) < TOL
+    assert np.abs(dimg_ref).max() > 0 and rel_l2(dimg.cpu().numpy(), dimg_ref) < TOL
