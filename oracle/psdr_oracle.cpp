@@ -563,46 +563,42 @@ struct Hit {
     float u = 0.f, v = 0.f, t = 0.f;
 };
 
-// One fp32 Moeller-Trumbore test with a FIXED operation order (cross = fused multiply-subtract, dot =
-// fma chain).  The inside test runs on the sign-normalised numerators (0 <= u, 0 <= v, u + v <= 1
-// without a division); only then the IEEE divide.  OptiX's own arithmetic is closed source, so this
-// is the repo's definition of the closest hit; the CUDA kernels use the same order so that hit ids
-// and (u,v,t) agree bit for bit with this oracle.  Formula: utils.h:82-93.
-static inline bool tri_test(const Tri<Dual> &T, V3f o, V3f d, float &u, float &v, float &t) {
-    V3f e1 = val(T.e1), e2 = val(T.e2), p0 = val(T.p0);
-    V3f h = cross_fms(d, e2);
-    float det = dot(e1, h);
-    V3f s = o - p0;
-    float un = dot(s, h);
-    V3f q = cross_fms(s, e1);
-    float vn = dot(d, q);
-    float tn = dot(e2, q);
-    float adet = std::fabs(det);
-    float us = det < 0.f ? -un : un, vs = det < 0.f ? -vn : vn;
-    if (!(us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f)) return false;
-    float f = 1.f / det;
-    t = f * tn;
-    u = f * un;
-    v = f * vn;
-    return true;
-}
-
+// fp32 Moeller-Trumbore numerators with a FIXED operation order (cross = fused multiply-subtract, dot = fma
+// chain).  A candidate is accepted on the numerators alone: inside test on the sign-normalised numerators,
+// t in (RayEpsilon, 1e8) and "closer than the best so far" by cross-multiplication (t1 < t2 <=> tn1 |det2| <
+// tn2 |det1|); the IEEE divide happens once, for the winner.  OptiX's own arithmetic is closed source, so this is
+// the repo's definition of the closest hit; the CUDA kernels use the same order so that hit ids and (u,v,t) agree
+// bit for bit with this oracle.  Ascending scan, strict comparison: ties keep the lowest triangle id.
 static Hit trace(const Scene &sc, V3f o, V3f d) {
     Hit best;
     if (std::isnan(o.x) || std::isnan(o.y) || std::isnan(o.z) || std::isnan(d.x) || std::isnan(d.y) || std::isnan(d.z))
         return best;
-    float tbest = 1e8f;
+    float b_ts = 1e8f, b_adet = 1.f, b_tn = 0.f, b_det = 0.f, b_un = 0.f, b_vn = 0.f;
+    int b_tri = -1;
     for (size_t i = 0; i < sc.tris.size(); ++i) {
-        float u, v, t;
-        if (!tri_test(sc.tris[i], o, d, u, v, t)) continue;
-        if (t > kRayEpsilon && t < tbest) {  // ties: lowest triangle id wins (ascending scan, strict <)
-            tbest = t;
-            best.tri = (int) i;
-            best.u = u;
-            best.v = v;
-            best.t = t;
-        }
+        const Tri<Dual> &T = sc.tris[i];
+        V3f e1 = val(T.e1), e2 = val(T.e2), p0 = val(T.p0);
+        V3f h = cross_fms(d, e2);
+        float det = dot(e1, h);
+        V3f s = o - p0;
+        float un = dot(s, h);
+        V3f q = cross_fms(s, e1);
+        float vn = dot(d, q);
+        float tn = dot(e2, q);
+        float adet = std::fabs(det);
+        bool neg = det < 0.f;
+        float us = neg ? -un : un, vs = neg ? -vn : vn, ts = neg ? -tn : tn;
+        bool ok = us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f && ts > kRayEpsilon * adet && ts < 1e8f * adet &&
+                  ts * b_adet < b_ts * adet;
+        if (!ok) continue;
+        b_ts = ts; b_adet = adet; b_tn = tn; b_det = det; b_un = un; b_vn = vn; b_tri = (int) i;
     }
+    if (b_tri < 0) return best;
+    float f = 1.f / b_det;
+    best.tri = b_tri;
+    best.t = f * b_tn;
+    best.u = f * b_un;
+    best.v = f * b_vn;
     return best;
 }
 

@@ -74,12 +74,26 @@ template <> __device__ __forceinline__ ShadeRec<Dual> load_shade<Dual>(const DSc
 }
 
 // ---- closest hit in (RayEpsilon, 1e8): replaces OptiX (reference src/scene/scene_optix.cpp:343-410)
-// Moeller-Trumbore numerators with a fixed operation order (cross = fused multiply-subtract, dot =
-// fma chain), inside test on the sign-normalised numerators (0 <= u, 0 <= v, u + v <= 1 without a
-// division); the IEEE division only happens for the 1-3 triangles a ray line actually pierces.
-// Branch-free up to that point, so incoherent rays of a warp do not diverge in the scan.
-// Ties resolve to the lowest triangle id.
-__device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, V3f d, Hit &best) {
+// Moeller-Trumbore numerators with a fixed operation order (cross = fused multiply-subtract, dot = fma chain).
+// Everything a candidate has to pass -- inside test on the sign-normalised numerators, t in (eps, tmax), closer
+// than the best so far -- is decided on the NUMERATORS by cross-multiplication (t1 < t2  <=>  tn1 |det2| < tn2 |det1|),
+// so the scan is branch-free: the best candidate is carried as (tn, det, un, vn, id) with predicated moves and
+// the one IEEE division per ray happens after the scan.  With a division per pierced triangle inside the loop the
+// 1-3 lanes of a warp that pierce the current triangle ran ~20 instructions alone while 30 lanes waited
+// (profiles/r01e: 17 of 32 lanes active in kernels whose paths were all alive).  Ties resolve to the lowest id.
+struct HitCand {
+    float ts, adet;        // sign-normalised t numerator and |det| of the best candidate (t = ts / adet)
+    float tn, det, un, vn;
+    int tri;
+};
+__device__ __forceinline__ void hit_init(HitCand &b) {
+    b.ts = kTraceTMax;
+    b.adet = 1.f;
+    b.tn = b.det = b.un = b.vn = 0.f;
+    b.tri = -1;
+}
+template <bool kOrdered>   // kOrdered: candidates arrive in ascending id (strict "closer" keeps the lowest id on ties)
+__device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, V3f d, HitCand &b) {
     const V3f h = cross_fms(d, e2);
     const float det = dot(e1, h);
     const V3f s = o - p0;
@@ -88,28 +102,37 @@ __device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, 
     const float vn = dot(d, q);
     const float tn = dot(e2, q);
     const float adet = fabsf(det);
-    const float us = det < 0.f ? -un : un, vs = det < 0.f ? -vn : vn;
-    if (us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f) {
-        const float f = 1.f / det;
-        const float t = f * tn;
-        if (t > kRayEpsilon && t < kTraceTMax && (t < best.t || (t == best.t && id < best.tri))) {
-            best.tri = id;
-            best.u = f * un;
-            best.v = f * vn;
-            best.t = t;
-        }
+    const bool neg = det < 0.f;
+    const float us = neg ? -un : un, vs = neg ? -vn : vn, ts = neg ? -tn : tn;
+    const float lhs = ts * b.adet, rhs = b.ts * adet;
+    const bool closer = kOrdered ? (lhs < rhs) : (lhs < rhs || (lhs == rhs && id < b.tri));
+    const bool ok = us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f && ts > kRayEpsilon * adet && ts < kTraceTMax * adet && closer;
+    b.ts = ok ? ts : b.ts;
+    b.adet = ok ? adet : b.adet;
+    b.tn = ok ? tn : b.tn;
+    b.det = ok ? det : b.det;
+    b.un = ok ? un : b.un;
+    b.vn = ok ? vn : b.vn;
+    b.tri = ok ? id : b.tri;
+}
+__device__ __forceinline__ Hit hit_finish(const HitCand &b) {
+    Hit h;
+    h.tri = b.tri;
+    h.u = h.v = 0.f;
+    h.t = kTraceTMax;
+    if (b.tri >= 0) {
+        const float f = 1.f / b.det;
+        h.t = f * b.tn;
+        h.u = f * b.un;
+        h.v = f * b.vn;
     }
+    return h;
 }
 
 template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
-    Hit best;
-    best.tri = 0x7fffffff;
-    best.u = best.v = 0.f;
-    best.t = kTraceTMax;
-    if (isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z)) {
-        best.tri = -1;
-        return best;
-    }
+    HitCand best;
+    hit_init(best);
+    if (isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z)) return hit_finish(best);
     constexpr bool kBvh = (kCfg & kCfgBvh) != 0;
     if (!kBvh) {
         // tiny scenes: the triangle table rides in the kernel parameters (constant bank), the scan index
@@ -118,13 +141,14 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
         for (int i = 0; i < sc.n_tris; ++i) {
             const float4 a = sc.bg_a[i], b = sc.bg_b[i];
             const float c = sc.bg_c[i];
-            tri_test(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), i, o, d, best);
+            tri_test<true>(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), i, o, d, best);
         }
     } else {
         const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
         int stack[48];
         int sp = 0;
         int node = 0;
+        float best_t = kTraceTMax;          // conservative bound for the box pruning only
         while (true) {
             const DBvhNode *nd = sc.nodes + node;
             const float4 n0 = __ldg(reinterpret_cast<const float4 *>(nd)), n1 = __ldg(reinterpret_cast<const float4 *>(nd) + 1);
@@ -134,7 +158,7 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
             const float ty0 = (n0.y - o.y) * iy, ty1 = (n1.y - o.y) * iy;
             const float tz0 = (n0.z - o.z) * iz, tz1 = (n1.z - o.z) * iz;
             const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.f));
-            const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best.t));
+            const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_t));
             bool descend = false;
             if (tn <= tf * 1.0000005f + 1e-6f) {
                 if (ib < 0) {
@@ -143,8 +167,9 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
                         const int id = __ldg(sc.tri_order + first + k);
                         const float4 a = __ldg(sc.geo + 3 * id), b = __ldg(sc.geo + 3 * id + 1);
                         const float c = __ldg(&sc.geo[3 * id + 2].x);
-                        tri_test(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), id, o, d, best);
+                        tri_test<false>(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), id, o, d, best);
                     }
+                    best_t = best.ts / best.adet * 1.000001f;
                 } else {
                     if (sp < 47) stack[sp++] = ib;
                     node = ia;
@@ -157,8 +182,7 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
             }
         }
     }
-    if (best.tri == 0x7fffffff) best.tri = -1;
-    return best;
+    return hit_finish(best);
 }
 
 // reference include/psdr/core/frame.h:9-28 (Duff et al.)
@@ -669,92 +693,118 @@ struct NoRecord {
     __device__ __forceinline__ void nee(int, bool, int, V2f, V3f, int, float, float) {}
 };
 
+// The loop body is exposed as a state machine (li_begin / li_step) so that the persistent kernels can let every
+// lane walk its OWN sequence of paths: a lane whose path ends starts its next one in the same warp iteration
+// instead of idling until the slowest lane of the warp is done ("lane regeneration").
+template <class S> struct LiState {
+    V3<S> throughput, result, ray_o, ray_d;
+    Its<S> its;
+    BsdfSample bs;
+    int depth;
+    bool active;
+};
+
+template <class S> __device__ __forceinline__ void li_begin(LiState<S> &st, V3<S> ro, V3<S> rd, bool active) {
+    st.throughput = V3<S>(S(1.f));
+    st.result = V3<S>(S(0.f));
+    st.its.valid = false;
+    st.bs.wo = V3f(0.f, 0.f, 1.f);
+    st.bs.pdf = 1.f;
+    st.bs.valid = true;
+    st.ray_o = ro;
+    st.ray_d = rd;
+    st.depth = -1;
+    st.active = active;
+}
+
+// one iteration {main ray -> vertex, NEE shadow ray, BSDF sample}; returns true when the path is finished
+template <class S, int kCfg, bool kAD, class Rec>
+__device__ __forceinline__ bool li_step(const DScene &sc, Pcg32 &rng, LiState<S> &st, int max_depth, bool hide_emitters, Rec &R) {
+    constexpr bool ad = kAD;
+    const int depth = st.depth;
+    Its<S> &its = st.its;
+    // ---- main ray: primary hit (solid-angle form under AD) or the BSDF-sampled ray (path-space form)
+    const Its<S> its1 = ray_intersect<S, kCfg, kAD>(sc, st.ray_o, st.ray_d, st.active, ad && depth >= 0);
+    if (its1.valid) R.vertex(depth + 1, its1.tri, its1.bu, its1.bv);
+    if (depth < 0) {
+        st.active = st.active && its1.valid;
+        if (!hide_emitters) st.result = Le<S, kCfg>(sc, its1, st.active);
+    } else {
+        st.active = st.active && st.bs.valid && its1.valid;
+        if (st.active) {
+            V3<S> bsdf_val;
+            float pdf0;
+            if (ad) {
+                V3<S> wo = its1.p - its.p;
+                wo = wo / its1.t;
+                const S cos_val = dot(its1.n, -wo);
+                const S G_val = abs_(cos_val) / sqr(its1.t);
+                pdf0 = st.bs.pdf * val(G_val);
+                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                else bsdf_val = bsdf_eval<S, kCfg>(sc, its, its.to_local(wo), st.active) * (G_val * its1.J / S(pdf0));
+            } else {
+                const S cos_val = dot(its1.n, -st.ray_d);
+                const S G_val = abs_(cos_val) / sqr(its1.t);
+                pdf0 = st.bs.pdf * val(G_val);
+                if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
+                else bsdf_val = bsdf_eval<S, kCfg>(sc, its, lift3<S>(st.bs.wo), st.active) / S(st.bs.pdf);
+            }
+            const float weight2 = mis_weight(pdf0, emitter_position_pdf<S, kCfg>(sc, val(its.p), its1, st.active));
+            R.bounce(depth, val(its1.t) >= kEpsilon, pdf0, weight2);
+            st.throughput = st.throughput * bsdf_val;
+            st.result = st.result + Le<S, kCfg>(sc, its1, st.active) * st.throughput * S(weight2);
+        }
+    }
+    const int bounces_left = max_depth - depth - 1;
+    if (!st.active) {   // dead lanes only burn their draws
+        if (bounces_left > 0) rng.advance(5ull * (unsigned long long) bounces_left);
+        return true;
+    }
+    if (bounces_left <= 0) return true;
+    its = its1;
+    R.throughput(depth + 1, val(st.throughput));
+    const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
+    const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
+    {   // ---- emitter sampling
+        const PosSample<S> ps = sample_emitter_position<S, kCfg>(sc, val(its.p), V2f(s_x, s_y));
+        bool active_direct = !is_emitter(sc, its);
+        V3<S> wod = ps.p - its.p;
+        const S dist_sqr = squared_norm(wod);
+        const S dist = safe_sqrt(dist_sqr);
+        wod = wod / dist;
+        const Its<S> its2 = ray_intersect<S, kCfg, kAD>(sc, its.p, wod, active_direct, ad);
+        active_direct = active_direct && its2.valid;
+        active_direct = active_direct && (val(its2.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its2);
+        if (active_direct) {
+            const S cos_val = dot(its2.n, -wod);
+            const S G_val = abs_(cos_val) / dist_sqr;
+            const V3<S> emitter_val = Le<S, kCfg>(sc, its2, true);
+            const V3<S> wo_local = its.to_local(wod);
+            V3<S> bsdf_val2 = bsdf_eval<S, kCfg>(sc, its, wo_local, active_direct);
+            bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
+            const float pdf1 = bsdf_pdf<S, kCfg>(sc, its, wo_local, active_direct) * val(G_val);
+            if (pdf1 != 0.f) {
+                const float weight1 = mis_weight(ps.pdf, pdf1);
+                R.nee(depth + 1, ps.tri < 0 || val(its2.wi.z) > 0.f, ps.tri, ps.st, val(ps.p), its2.tri, ps.pdf, weight1);
+                st.result = st.result + st.throughput * emitter_val * bsdf_val2 * S(weight1);
+            }
+        }
+    }
+    // ---- BSDF sampling: the ray is traced by the next step
+    st.bs = bsdf_sample<S, kCfg>(sc, its, V3f(s3_x, s3_y, s3_z), true);
+    st.ray_o = its.p;
+    st.ray_d = its.to_world(lift3<S>(st.bs.wo));
+    st.depth = depth + 1;
+    return false;
+}
+
 template <class S, int kCfg, bool kAD, class Rec>
 __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, Rec &R) {
-    constexpr bool ad = kAD;
-    V3<S> throughput(S(1.f)), result(S(0.f));
-    Its<S> its;
-    its.valid = false;
-    BsdfSample bs;
-    bs.wo = V3f(0.f, 0.f, 1.f);
-    bs.pdf = 1.f;
-    bs.valid = true;
-    V3<S> ray_o = ro, ray_d = rd;
+    LiState<S> st;
+    li_begin<S>(st, ro, rd, active);
 #pragma unroll 1
-    for (int depth = -1; depth < max_depth; ++depth) {
-        // ---- main ray: primary hit (solid-angle form under AD) or the BSDF-sampled ray (path-space form)
-        const Its<S> its1 = ray_intersect<S, kCfg, kAD>(sc, ray_o, ray_d, active, ad && depth >= 0);
-        if (its1.valid) R.vertex(depth + 1, its1.tri, its1.bu, its1.bv);
-        if (depth < 0) {
-            active = active && its1.valid;
-            if (!hide_emitters) result = Le<S, kCfg>(sc, its1, active);
-        } else {
-            active = active && bs.valid && its1.valid;
-            if (active) {
-                V3<S> bsdf_val;
-                float pdf0;
-                if (ad) {
-                    V3<S> wo = its1.p - its.p;
-                    wo = wo / its1.t;
-                    const S cos_val = dot(its1.n, -wo);
-                    const S G_val = abs_(cos_val) / sqr(its1.t);
-                    pdf0 = bs.pdf * val(G_val);
-                    if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
-                    else bsdf_val = bsdf_eval<S, kCfg>(sc, its, its.to_local(wo), active) * (G_val * its1.J / S(pdf0));
-                } else {
-                    const S cos_val = dot(its1.n, -ray_d);
-                    const S G_val = abs_(cos_val) / sqr(its1.t);
-                    pdf0 = bs.pdf * val(G_val);
-                    if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
-                    else bsdf_val = bsdf_eval<S, kCfg>(sc, its, lift3<S>(bs.wo), active) / S(bs.pdf);
-                }
-                const float weight2 = mis_weight(pdf0, emitter_position_pdf<S, kCfg>(sc, val(its.p), its1, active));
-                R.bounce(depth, val(its1.t) >= kEpsilon, pdf0, weight2);
-                throughput = throughput * bsdf_val;
-                result = result + Le<S, kCfg>(sc, its1, active) * throughput * S(weight2);
-            }
-        }
-        const int bounces_left = max_depth - depth - 1;
-        if (!active) {   // dead lanes only burn their draws
-            if (bounces_left > 0) rng.advance(5ull * (unsigned long long) bounces_left);
-            break;
-        }
-        if (bounces_left <= 0) break;
-        its = its1;
-        R.throughput(depth + 1, val(throughput));
-        const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
-        const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
-        {   // ---- emitter sampling
-            const PosSample<S> ps = sample_emitter_position<S, kCfg>(sc, val(its.p), V2f(s_x, s_y));
-            bool active_direct = !is_emitter(sc, its);
-            V3<S> wod = ps.p - its.p;
-            const S dist_sqr = squared_norm(wod);
-            const S dist = safe_sqrt(dist_sqr);
-            wod = wod / dist;
-            const Its<S> its2 = ray_intersect<S, kCfg, kAD>(sc, its.p, wod, active_direct, ad);
-            active_direct = active_direct && its2.valid;
-            active_direct = active_direct && (val(its2.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its2);
-            if (active_direct) {
-                const S cos_val = dot(its2.n, -wod);
-                const S G_val = abs_(cos_val) / dist_sqr;
-                const V3<S> emitter_val = Le<S, kCfg>(sc, its2, true);
-                const V3<S> wo_local = its.to_local(wod);
-                V3<S> bsdf_val2 = bsdf_eval<S, kCfg>(sc, its, wo_local, active_direct);
-                bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
-                const float pdf1 = bsdf_pdf<S, kCfg>(sc, its, wo_local, active_direct) * val(G_val);
-                if (pdf1 != 0.f) {
-                    const float weight1 = mis_weight(ps.pdf, pdf1);
-                    R.nee(depth + 1, ps.tri < 0 || val(its2.wi.z) > 0.f, ps.tri, ps.st, val(ps.p), its2.tri, ps.pdf, weight1);
-                    result = result + throughput * emitter_val * bsdf_val2 * S(weight1);
-                }
-            }
-        }
-        // ---- BSDF sampling: the ray is traced at the top of the next iteration
-        bs = bsdf_sample<S, kCfg>(sc, its, V3f(s3_x, s3_y, s3_z), true);
-        ray_o = its.p;
-        ray_d = its.to_world(lift3<S>(bs.wo));
-    }
-    return result;
+    while (!li_step<S, kCfg, kAD, Rec>(sc, rng, st, max_depth, hide_emitters, R)) {}
+    return st.result;
 }
 
 template <class S, int kCfg>

@@ -81,100 +81,58 @@ __global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant_
     }
 }
 
-// ---- warp-level lane compaction ----------------------------------------------------------------------
-// Boundary samples are cheap to reject (an edge sample that projects outside the image, a boundary segment that
-// is not a silhouette) but expensive to evaluate (up to 14 closest-hit queries).  Each warp therefore filters
-// candidate lanes with `accept(i)` (ballot + prefix ranks into a 64-entry shared-memory queue) and only runs
-// `process(have, i)` on full batches of 32 accepted lanes; the reference evaluates rejected lanes masked.
-// Lane -> random stream is a function of the lane index, so the regrouping does not change any sample.
-template <int kWarps, class Accept, class Process>
-__device__ __forceinline__ void compacted_lanes(const RenderParams &rp, Accept accept, Process process) {
-    __shared__ unsigned queue[kWarps][64];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const long long stride = (long long) gridDim.x * blockDim.x;
-    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
-    long long jbase = (long long) blockIdx.x * blockDim.x + (threadIdx.x & ~31u);     // warp-uniform
-    int qn = 0;                                                                          // warp-uniform
-    while (true) {
-        while (qn < 32 && jbase < span_pad) {
-            const long long j = jbase + lane;
-            const bool ok = j < span && accept(rp.lane_begin + j);
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) queue[warp][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned) j;
-            qn += __popc(m);
-            jbase += stride;
-            __syncwarp();
-        }
-        if (qn == 0) break;
-        const int take = qn < 32 ? qn : 32;
-        const bool have = (int) lane < take;
-        const unsigned jj = have ? queue[warp][qn - take + lane] : 0u;
-        qn -= take;
-        __syncwarp();
-        process(have, rp.lane_begin + (long long) jj);
-    }
-}
-
 // ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges
-struct PrimaryEdgeSample {
-    Pcg32 rng;
-    int ei, pix;
-    float s1, pdf;
-    Dual px, py, x_dot_n;
-    float4 bq;
-    bool valid;
-};
-__device__ __forceinline__ PrimaryEdgeSample sample_primary_edge(const DScene &sc, const DCamera &cam, const RenderParams &rp, long long i) {
-    PrimaryEdgeSample e;
-    e.rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
-    if (rp.skip) e.rng.advance(rp.skip);
-    float prob;
-    e.s1 = e.rng.next_1d();
-    e.ei = sample_reuse(cam.pe_pmf, cam.pe_cmf, cam.n_edges, cam.edge_sum, e.s1, prob);
-    const float4 a = __ldg(cam.pe_a + e.ei), da = __ldg(cam.pe_da + e.ei);
-    e.bq = __ldg(cam.pe_b + e.ei);
-    e.pdf = prob / e.bq.z;
-    const float w0 = 1.0f - e.s1;
-    e.px = fmadd(Dual(a.x, da.x), Dual(w0), Dual(a.z, da.z) * e.s1);
-    e.py = fmadd(Dual(a.y, da.y), Dual(w0), Dual(a.w, da.w) * e.s1);
-    e.x_dot_n = dot(V2d(e.px, e.py), V2d(Dual(e.bq.x), Dual(e.bq.y)));
-    const int ix = (int) floorf(e.px.v * (float) sc.width), iy = (int) floorf(e.py.v * (float) sc.height);
-    e.valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
-    e.pix = iy * sc.width + ix;
-    return e;
-}
-
 template <int kCfg>
 __global__ void __launch_bounds__(kBlock) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
+    const long long stride = (long long) gridDim.x * kBlock;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
-    compacted_lanes<kBlock / 32>(
-        rp, [&](long long i) { return sample_primary_edge(sc, cam, rp, i).valid; },
-        [&](bool have, long long i) {
-            PrimaryEdgeSample e = sample_primary_edge(sc, cam, rp, i);
-            // Li(ray_n) - Li(ray_p): the reference binary evaluates Li(ray_p) first (verified on the
-            // running reference, tests/golden/renderD_*: primary-only images).  One rolled loop over the two
-            // sides keeps a single copy of Li in the kernel.
-            V3f Lside[2];
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
+        Pcg32 rng;
+        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+        if (rp.skip) rng.advance(rp.skip);
+        float s1 = rng.next_1d(), prob;
+        const int ei = sample_reuse(cam.pe_pmf, cam.pe_cmf, cam.n_edges, cam.edge_sum, s1, prob);
+        const float4 a = __ldg(cam.pe_a + ei), da = __ldg(cam.pe_da + ei), bq = __ldg(cam.pe_b + ei);
+        const float pdf = prob / bq.z;
+        const float w0 = 1.0f - s1;
+        const Dual px = fmadd(Dual(a.x, da.x), Dual(w0), Dual(a.z, da.z) * s1), py = fmadd(Dual(a.y, da.y), Dual(w0), Dual(a.w, da.w) * s1);
+        const Dual x_dot_n = dot(V2d(px, py), V2d(Dual(bq.x), Dual(bq.y)));
+        const int ix = (int) floorf(px.v * (float) sc.width), iy = (int) floorf(py.v * (float) sc.height);
+        const bool valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+        // Li(ray_n) - Li(ray_p): the reference binary evaluates Li(ray_p) first (verified on the
+        // running reference, tests/golden/renderD_*: primary-only images).  One rolled loop over the two
+        // sides keeps a single copy of Li in the kernel.
+        V3f Lside[2];
 #pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-                __syncwarp();
-                const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
-                V3f ro, rd;
-                sample_primary_ray<float>(cam, V2f(e.px.v + sg * e.bq.x, e.py.v + sg * e.bq.y), ro, rd);
-                Lside[side] = Li<float, kCfg>(sc, e.rng, ro, rd, have, rp.max_depth, rp.hide_emitters != 0);
-            }
-            if (!have) return;
-            const V3f Lp = Lside[0], Ln = Lside[1];
-            const float dl[3] = {(Ln.x - Lp.x) / e.pdf, (Ln.y - Lp.y) / e.pdf, (Ln.z - Lp.z) / e.pdf};
+        for (int side = 0; side < 2; ++side) {
+            __syncwarp(live_mask);
+            const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
+            V3f ro, rd;
+            sample_primary_ray<float>(cam, V2f(px.v + sg * bq.x, py.v + sg * bq.y), ro, rd);
+            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
+        }
+        const V3f Lp = Lside[0], Ln = Lside[1];
+        if (!valid) continue;
+        const int pix = iy * sc.width + ix;
+        const float dl[3] = {(Ln.x - Lp.x) / pdf, (Ln.y - Lp.y) / pdf, (Ln.z - Lp.z) / pdf};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float primal = e.x_dot_n.v * dl[c];
-                if (!isfinite(primal)) continue;
-                const float t = e.x_dot_n.d * dl[c] * inv_sppe;
-                if (t != 0.f && isfinite(t)) atomicAdd(dimg + 3 * e.pix + c, t);
-            }
-        });
+        for (int c = 0; c < 3; ++c) {
+            const float primal = x_dot_n.v * dl[c];
+            if (!isfinite(primal)) continue;
+            const float t = x_dot_n.d * dl[c] * inv_sppe;
+            if (t != 0.f && isfinite(t)) atomicAdd(dimg + 3 * pix + c, t);
+        }
+    }
 }
 
 // ---- secondary (shadow) edges: PathTracer::render_secondary_edges -----------------------------

@@ -7,7 +7,6 @@
 
 #include "adjoint.cuh"
 #include "kernels.h"
-#include "kernels_impl.cuh"
 
 namespace psdr {
 
@@ -63,39 +62,58 @@ __global__ void __launch_bounds__(kBlockV) primary_edge_vjp_kernel(const __grid_
                                                                     const float *__restrict__ d_img) {
     extern __shared__ float smem[];
     const GradAcc acc = grad_acc_begin(gl, smem, gl.off_pe, gl.off_se, rp.smem_grad != 0);
+    const long long stride = (long long) gridDim.x * kBlockV;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
-    compacted_lanes<kBlockV / 32>(
-        rp, [&](long long i) { return sample_primary_edge(sc, cam, rp, i).valid; },
-        [&](bool have, long long i) {
-            PrimaryEdgeSample e = sample_primary_edge(sc, cam, rp, i);
-            V3f Lside[2];
+    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
+    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
+    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
+        if (j >= span) continue;
+        const long long i = rp.lane_begin + j;
+        (void) live_mask;
+        Pcg32 rng;
+        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+        if (rp.skip) rng.advance(rp.skip);
+        float s1 = rng.next_1d(), prob;
+        const int ei = sample_reuse(cam.pe_pmf, cam.pe_cmf, cam.n_edges, cam.edge_sum, s1, prob);
+        const float4 a = __ldg(cam.pe_a + ei), bq = __ldg(cam.pe_b + ei);
+        const float pdf = prob / bq.z;
+        const float w0 = 1.0f - s1;
+        const float px = fmaf(a.x, w0, a.z * s1), py = fmaf(a.y, w0, a.w * s1);
+        const float x_dot_n = fmaf(py, bq.y, px * bq.x);
+        const int ix = (int) floorf(px * (float) sc.width), iy = (int) floorf(py * (float) sc.height);
+        const bool valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+        V3f Lside[2];
 #pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-                __syncwarp();
-                const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
-                V3f ro, rd;
-                sample_primary_ray<float>(cam, V2f(e.px.v + sg * e.bq.x, e.py.v + sg * e.bq.y), ro, rd);
-                Lside[side] = Li<float, kCfg>(sc, e.rng, ro, rd, have, rp.max_depth, rp.hide_emitters != 0);
-            }
-            if (!have) return;
-            const float dl[3] = {(Lside[1].x - Lside[0].x) / e.pdf, (Lside[1].y - Lside[0].y) / e.pdf, (Lside[1].z - Lside[0].z) / e.pdf};
-            float gsum = 0.f;
+        for (int side = 0; side < 2; ++side) {
+            __syncwarp(live_mask);
+            const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
+            V3f ro, rd;
+            sample_primary_ray<float>(cam, V2f(px + sg * bq.x, py + sg * bq.y), ro, rd);
+            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
+        }
+        if (!valid) continue;
+        const int pix = iy * sc.width + ix;
+        const float dl[3] = {(Lside[1].x - Lside[0].x) / pdf, (Lside[1].y - Lside[0].y) / pdf, (Lside[1].z - Lside[0].z) / pdf};
+        float gsum = 0.f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float primal = e.x_dot_n.v * dl[c];
-                if (!isfinite(primal)) continue;
-                gsum += __ldg(d_img + 3 * e.pix + c) * dl[c];
-            }
-            gsum *= inv_sppe;
-            if (gsum == 0.f || !isfinite(gsum)) return;
-            // x_dot_n = <lerp(p0, p1, s), n>
-            const float w0 = 1.0f - e.s1;
-            const int b = gl.off_pe + 4 * e.ei;
-            acc.add(b, gsum * w0 * e.bq.x);
-            acc.add(b + 1, gsum * w0 * e.bq.y);
-            acc.add(b + 2, gsum * e.s1 * e.bq.x);
-            acc.add(b + 3, gsum * e.s1 * e.bq.y);
-        });
+        for (int c = 0; c < 3; ++c) {
+            const float primal = x_dot_n * dl[c];
+            if (!isfinite(primal)) continue;
+            gsum += __ldg(d_img + 3 * pix + c) * dl[c];
+        }
+        gsum *= inv_sppe;
+        if (gsum == 0.f || !isfinite(gsum)) continue;
+        // x_dot_n = <lerp(p0, p1, s), n>
+        const int b = gl.off_pe + 4 * ei;
+        acc.add(b, gsum * w0 * bq.x);
+        acc.add(b + 1, gsum * w0 * bq.y);
+        acc.add(b + 2, gsum * s1 * bq.x);
+        acc.add(b + 3, gsum * s1 * bq.y);
+    }
     grad_acc_end(acc);
 }
 
