@@ -29,8 +29,8 @@ if [ "$SKIP_NCU" != "1" ]; then
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
   tail -2 $OUT/ncu_full.log
   ncu -i $REP.ncu-rep --page raw --csv > $OUT/raw.csv 2>/dev/null
-  for k in interior_kernel primary_edge_kernel secondary_edge_kernel interior_vjp_kernel primary_edge_vjp_kernel; do
-    ncu -i $REP.ncu-rep --page source --csv --print-source sass -k regex:"$k<" > $OUT/sass_$k.csv 2>/dev/null
+  for k in interior_kernel primary_edge_kernel secondary_edge_kernel interior_vjp_kernel; do
+    ncu -i $REP.ncu-rep --page source --csv --print-source sass -k regex:"$k" > $OUT/sass_$k.csv 2>/dev/null
   done
   ls -la $OUT
 fi
