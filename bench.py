@@ -282,7 +282,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         ach = algorithmic_bytes(dom, lanes) / (means[dom] * 1e-3) / 1e9 if means[dom] > 0 else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_oracle_rate(256, 32)
+            v, cores, sample = cpu_oracle_rate(512, 32)
             cpu = {"value": round(v, 4), "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample}
         out = {
             "metric": METRIC, "value": round(n_samples * args.steps / (total_ms * 1e-3) / 1e6, 3), "unit": "Msamples/s",
@@ -399,7 +399,7 @@ def run_reference(args, rank: int, world: int, local_rank: int):
     vals = []
     cores, sample = 1, ""
     for _ in range(max(1, min(args.steps, 3))):
-        v, cores, sample = cpu_oracle_rate(256, 32)
+        v, cores, sample = cpu_oracle_rate(512, 32)
         vals.append(v)
     v = sum(vals) / len(vals)
     base.update({"value": round(v, 4), "ms_per_step": round(n_samples / (v * 1e6) * 1e3, 3),
