@@ -41,7 +41,7 @@ __device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; 
 // kAD = use the formulas of the reference's renderD instantiation (the primary hit re-intersected
 // analytically, scene.cpp:772-801) -- <float, kBvh, true> is the primal image of renderD.
 template <class S, int kCfg, bool kAD>
-__global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? 5 : 6)) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                            const __grid_constant__ RenderParams rp, float *__restrict__ img,
                                                            float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kBlock) interior_kernel(const __grid_constant_
 
 // ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges
 template <int kCfg>
-__global__ void __launch_bounds__(kBlock) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlock, 8) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kBlock) primary_edge_kernel(const __grid_const
 
 // ---- secondary (shadow) edges: PathTracer::render_secondary_edges -----------------------------
 template <int kCfg>
-__global__ void __launch_bounds__(kBlock) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlock, 8) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                  const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
     const float scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);

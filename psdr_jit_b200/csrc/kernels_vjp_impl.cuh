@@ -13,7 +13,7 @@ namespace psdr {
 constexpr int kBlockV = 128;
 
 template <int kCfg, int kD>
-__global__ void __launch_bounds__(kBlockV, 4) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                 const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                 const float *__restrict__ d_img) {
     extern __shared__ float smem[];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kBlockV, 4) interior_vjp_kernel(const __grid_c
 }
 
 template <int kCfg>
-__global__ void __launch_bounds__(kBlockV) primary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                     const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                     const float *__restrict__ d_img) {
     extern __shared__ float smem[];
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kBlockV) primary_edge_vjp_kernel(const __grid_
 }
 
 template <int kCfg>
-__global__ void __launch_bounds__(kBlockV) secondary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlockV, 6) secondary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                       const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                       const float *__restrict__ d_img) {
     extern __shared__ float smem[];
