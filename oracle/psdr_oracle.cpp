@@ -588,8 +588,8 @@ static Hit trace(const Scene &sc, V3f o, V3f d) {
         float adet = std::fabs(det);
         bool neg = det < 0.f;
         float us = neg ? -un : un, vs = neg ? -vn : vn, ts = neg ? -tn : tn;
-        bool ok = us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f && ts > kRayEpsilon * adet && ts < 1e8f * adet &&
-                  ts * b_adet < b_ts * adet;
+        bool ok = us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f && ts > kRayEpsilon * adet &&
+                  ts * b_adet < b_ts * adet;   // b_ts starts at 1e8 (b_adet = 1): closer also means t < 1e8
         if (!ok) continue;
         b_ts = ts; b_adet = adet; b_tn = tn; b_det = det; b_un = un; b_vn = vn; b_tri = (int) i;
     }

@@ -412,7 +412,7 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
 // -- one iteration after it was x.
 template <int kD, int kCfg>
 __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout &gl, const GradAcc &acc, const PathRecord<kD> &R, V3f o, V3f d,
-                                             V3f dc, V3f g, bool hide_emitters) {
+                                             V3f dc, V3f g, bool hide_emitters, unsigned sweep_mask) {
     constexpr bool kFull = (kCfg & kCfgFull) != 0;
     if (R.nv <= 0) return;
     // vertex 0: solid-angle form -- (u, v, t) are functions of the triangle and the camera ray
@@ -439,11 +439,16 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     VtxGeo x = geo_of(ktop);
     VtxAdj ya = zero_adj, xa = zero_adj, pa = zero_adj;
     V3f Lnext(0.f, 0.f, 0.f);     // R_{k+1}: radiance gathered after vertex k+1 (without E_{k+1})
-    // every lane of the warp executes iteration kk together, whatever its own k is
+    // every lane of sweep_mask (the lanes of this warp that have a sweep to run: the caller's ballot) executes
+    // iteration kk together, whatever its own k is; the barrier is what makes that true -- the body's branches
+    // leave through different back edges and without it the lanes drift apart and run the sweep a few at a time
+    // (profiles/r01g: 2.9 of 32 lanes active here)
+    const int iters = __reduce_max_sync(sweep_mask, R.nsh);
 #pragma unroll 1
-    for (int kk = 0; kk < kD; ++kk) {
+    for (int kk = 0; kk < iters; ++kk) {
+        __syncwarp(sweep_mask);
         const int k = ktop - kk;
-        if (k < 0) break;
+        if (k < 0) continue;
         VtxGeo prev = k > 0 ? geo_of(k - 1) : v0geo;
         const V3f A = g * R.T[k];
         float tprev = 1.f;

@@ -83,66 +83,149 @@ template <> __device__ __forceinline__ ShadeRec<Dual> load_shade<Dual>(const DSc
 // (profiles/r01e: 17 of 32 lanes active in kernels whose paths were all alive).  Ties resolve to the lowest id.
 struct HitCand {
     float ts, adet;        // sign-normalised t numerator and |det| of the best candidate (t = ts / adet)
-    float tn, det, un, vn;
     int tri;
 };
 __device__ __forceinline__ void hit_init(HitCand &b) {
-    b.ts = kTraceTMax;
+    b.ts = kTraceTMax;     // "closer than the best" therefore also means t < kTraceTMax
     b.adet = 1.f;
-    b.tn = b.det = b.un = b.vn = 0.f;
     b.tri = -1;
 }
-template <bool kOrdered>   // kOrdered: candidates arrive in ascending id (strict "closer" keeps the lowest id on ties)
-__device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, V3f d, HitCand &b) {
+// the four numerators of one triangle (scalar form: BVH leaves, and the winner of a scan)
+struct TriNum {
+    float tn, det, un, vn;
+};
+__device__ __forceinline__ TriNum tri_numerators(V3f p0, V3f e1, V3f e2, V3f o, V3f d) {
+    TriNum r;
     const V3f h = cross_fms(d, e2);
-    const float det = dot(e1, h);
+    r.det = dot(e1, h);
     const V3f s = o - p0;
-    const float un = dot(s, h);
+    r.un = dot(s, h);
     const V3f q = cross_fms(s, e1);
-    const float vn = dot(d, q);
-    const float tn = dot(e2, q);
+    r.vn = dot(d, q);
+    r.tn = dot(e2, q);
+    return r;
+}
+// acceptance of one candidate on its numerators
+template <bool kOrdered>   // kOrdered: candidates arrive in ascending id (strict "closer" keeps the lowest id on ties)
+__device__ __forceinline__ void hit_consider(float tn, float det, float un, float vn, int id, HitCand &b) {
     const float adet = fabsf(det);
     const bool neg = det < 0.f;
     const float us = neg ? -un : un, vs = neg ? -vn : vn, ts = neg ? -tn : tn;
     const float lhs = ts * b.adet, rhs = b.ts * adet;
     const bool closer = kOrdered ? (lhs < rhs) : (lhs < rhs || (lhs == rhs && id < b.tri));
-    const bool ok = us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f && ts > kRayEpsilon * adet && ts < kTraceTMax * adet && closer;
+    const bool ok = us >= 0.f && vs >= 0.f && us + vs <= adet && adet > 0.f && ts > kRayEpsilon * adet && closer;
     b.ts = ok ? ts : b.ts;
     b.adet = ok ? adet : b.adet;
-    b.tn = ok ? tn : b.tn;
-    b.det = ok ? det : b.det;
-    b.un = ok ? un : b.un;
-    b.vn = ok ? vn : b.vn;
     b.tri = ok ? id : b.tri;
 }
-__device__ __forceinline__ Hit hit_finish(const HitCand &b) {
+template <bool kOrdered>
+__device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, V3f d, HitCand &b) {
+    const TriNum n = tri_numerators(p0, e1, e2, o, d);
+    hit_consider<kOrdered>(n.tn, n.det, n.un, n.vn, id, b);
+}
+// the winner's numerators are recomputed (same operations, same bits) and divided once
+__device__ __forceinline__ Hit hit_finish(const HitCand &b, V3f p0, V3f e1, V3f e2, V3f o, V3f d) {
     Hit h;
     h.tri = b.tri;
     h.u = h.v = 0.f;
     h.t = kTraceTMax;
     if (b.tri >= 0) {
-        const float f = 1.f / b.det;
-        h.t = f * b.tn;
-        h.u = f * b.un;
-        h.v = f * b.vn;
+        const TriNum n = tri_numerators(p0, e1, e2, o, d);
+        const float f = 1.f / n.det;
+        h.t = f * n.tn;
+        h.u = f * n.un;
+        h.v = f * n.vn;
     }
     return h;
+}
+
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): one instruction, two IEEE round-to-nearest results --
+// the brute-force scan tests triangles (2j, 2j+1) in the two halves, so its 27 multiply/add/fma per triangle
+// cost 27 issue slots per PAIR; the results are bit-identical to the scalar forms above.
+struct F2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ F2 f2_dup(float x) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r.v) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void f2_split(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_sub(F2 a, F2 b) {
+    F2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+struct V3p {
+    F2 x, y, z;
+};
+__device__ __forceinline__ F2 dot(V3p a, V3p b) { return f2_fma(a.z, b.z, f2_fma(a.y, b.y, f2_mul(a.x, b.x))); }
+// cross_fms(a, b) with the subtrahend's sign carried by an operand: fma(a.y, b.z, -(a.z * b.y)) = fma(a.y, b.z, na.z * b.y)
+__device__ __forceinline__ V3p cross_fms_na(V3p a, V3p na, V3p b) {
+    V3p r;
+    r.x = f2_fma(a.y, b.z, f2_mul(na.z, b.y));
+    r.y = f2_fma(a.z, b.x, f2_mul(na.x, b.z));
+    r.z = f2_fma(a.x, b.y, f2_mul(na.y, b.x));
+    return r;
+}
+__device__ __forceinline__ V3p cross_fms_nb(V3p a, V3p b, V3p nb) {
+    V3p r;
+    r.x = f2_fma(a.y, b.z, f2_mul(a.z, nb.y));
+    r.y = f2_fma(a.z, b.x, f2_mul(a.x, nb.z));
+    r.z = f2_fma(a.x, b.y, f2_mul(a.y, nb.x));
+    return r;
 }
 
 template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
     HitCand best;
     hit_init(best);
-    if (isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z)) return hit_finish(best);
+    Hit miss;
+    miss.tri = -1;
+    miss.u = miss.v = 0.f;
+    miss.t = kTraceTMax;
+    if (isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z)) return miss;
     constexpr bool kBvh = (kCfg & kCfgBvh) != 0;
     if (!kBvh) {
-        // tiny scenes: the triangle table rides in the kernel parameters (constant bank), the scan index
-        // is warp-uniform, so the operands come through the uniform datapath -- no LSU traffic at all
-#pragma unroll 4
-        for (int i = 0; i < sc.n_tris; ++i) {
-            const float4 a = sc.bg_a[i], b = sc.bg_b[i];
-            const float c = sc.bg_c[i];
-            tri_test<true>(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), i, o, d, best);
+        // tiny scenes: the triangle table rides in the kernel parameters (constant bank) and the scan index is
+        // warp-uniform, so the operands arrive by LDC.64 with no LSU traffic; two triangles per packed operation
+        V3p O, D, ND;
+        O.x = f2_dup(o.x); O.y = f2_dup(o.y); O.z = f2_dup(o.z);
+        D.x = f2_dup(d.x); D.y = f2_dup(d.y); D.z = f2_dup(d.z);
+        ND.x = f2_dup(-d.x); ND.y = f2_dup(-d.y); ND.z = f2_dup(-d.z);
+        const int n_pairs = (sc.n_tris + 1) >> 1;
+#pragma unroll 2
+        for (int j = 0; j < n_pairs; ++j) {
+            const unsigned long long *w = sc.bg_pair + kBrutePairWords * j;
+            V3p P0, E1, E2, NE1;
+            P0.x.v = w[0]; P0.y.v = w[1]; P0.z.v = w[2];
+            E1.x.v = w[3]; E1.y.v = w[4]; E1.z.v = w[5];
+            E2.x.v = w[6]; E2.y.v = w[7]; E2.z.v = w[8];
+            NE1.x.v = w[9]; NE1.y.v = w[10]; NE1.z.v = w[11];
+            const V3p h = cross_fms_na(D, ND, E2);
+            const F2 det = dot(E1, h);
+            V3p S;
+            S.x = f2_sub(O.x, P0.x); S.y = f2_sub(O.y, P0.y); S.z = f2_sub(O.z, P0.z);
+            const F2 un = dot(S, h);
+            const V3p q = cross_fms_nb(S, E1, NE1);
+            const F2 vn = dot(D, q), tn = dot(E2, q);
+            float tn0, tn1, det0, det1, un0, un1, vn0, vn1;
+            f2_split(tn, tn0, tn1); f2_split(det, det0, det1); f2_split(un, un0, un1); f2_split(vn, vn0, vn1);
+            hit_consider<true>(tn0, det0, un0, vn0, 2 * j, best);
+            hit_consider<true>(tn1, det1, un1, vn1, 2 * j + 1, best);
         }
+        if (best.tri < 0) return miss;
+        const float *f = reinterpret_cast<const float *>(sc.bg_pair) + 2 * kBrutePairWords * (best.tri >> 1) + (best.tri & 1);
+        return hit_finish(best, V3f(f[0], f[2], f[4]), V3f(f[6], f[8], f[10]), V3f(f[12], f[14], f[16]), o, d);
     } else {
         const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
         int stack[48];
@@ -181,8 +264,11 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
                 node = stack[--sp];
             }
         }
+        if (best.tri < 0) return miss;
+        const float4 a = __ldg(sc.geo + 3 * best.tri), b = __ldg(sc.geo + 3 * best.tri + 1);
+        const float c = __ldg(&sc.geo[3 * best.tri + 2].x);
+        return hit_finish(best, V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), o, d);
     }
-    return hit_finish(best);
 }
 
 // reference include/psdr/core/frame.h:9-28 (Duff et al.)

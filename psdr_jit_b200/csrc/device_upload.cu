@@ -239,12 +239,17 @@ void upload_scene(Scene &sc) {
     d.sec_sum = sc.sec_edges.empty() ? 0.f : sc.sec_edge_distrb.sum;
     d.nodes = (const DBvhNode *) (base + o_nodes);
     d.tri_order = (const int *) (base + o_order);
-    if (!use_bvh)
+    if (!use_bvh) {
+        // (even, odd) triangle of a pair -> (low, high) half of each 64-bit word
+        float *w = reinterpret_cast<float *>(d.bg_pair);
+        std::memset(d.bg_pair, 0, sizeof(d.bg_pair));
         for (int i = 0; i < ntris; ++i) {
-            d.bg_a[i] = geo[3 * i];
-            d.bg_b[i] = geo[3 * i + 1];
-            d.bg_c[i] = geo[3 * i + 2].x;
+            const float4 a = geo[3 * i], b = geo[3 * i + 1];
+            const float c = geo[3 * i + 2].x;
+            const float comp[kBrutePairWords] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c, -a.w, -b.x, -b.y};
+            for (int k = 0; k < kBrutePairWords; ++k) w[2 * (kBrutePairWords * (i >> 1) + k) + (i & 1)] = comp[k];
         }
+    }
 
     d.env = DEnv{};
     if (sc.env.present) {

@@ -14,6 +14,7 @@ namespace psdr {
 // dgeo/dshade: the forward-mode tangents in the same layout (dgeo[3i+2].z/.w unused).
 // uv[3i+k] = texture coordinate of corner k (zeros for meshes without UVs)
 constexpr int kMaxBruteTris = 64;
+constexpr int kBrutePairWords = 12;   // 64-bit words per triangle pair in DScene::bg_pair
 
 struct DBvhNode {        // 32 B
     float lo[3];
@@ -115,10 +116,11 @@ struct DScene {
     const int *tri_order;
     DEnv env;
     // brute-force mode (n_tris <= kMaxBruteTris): the triangle geometry again, by value -- it travels in
-    // the kernel parameters and is read through the constant bank / uniform datapath.
-    // bg_a = (p0.xyz, e1.x), bg_b = (e1.yz, e2.xy), bg_c = e2.z
-    float4 bg_a[kMaxBruteTris], bg_b[kMaxBruteTris];
-    float bg_c[kMaxBruteTris];
+    // the kernel parameters and is read through the constant bank (LDC.64), two triangles at a time: entry
+    // [12 j + c] holds component c of triangles (2j, 2j+1) as the two halves of one 64-bit word, c = p0.xyz,
+    // e1.xyz, e2.xyz, -e1.xyz, the operand layout of the packed fp32x2 closest-hit scan (device_path.cuh).
+    // An odd count is padded with an all-zero triangle (det = 0: never accepted).
+    unsigned long long bg_pair[kMaxBruteTris / 2 * kBrutePairWords];
 };
 
 struct RenderParams {

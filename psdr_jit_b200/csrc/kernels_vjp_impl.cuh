@@ -29,7 +29,6 @@ __global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_c
         const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
         if (j >= span) continue;
         const long long i = rp.lane_begin + j;
-        (void) live_mask;
         const int idx = (int) (sc.spp > 1 ? i / sc.spp : i);
         const int pix = rp.pix_id ? __ldg(rp.pix_id + idx) : idx;
         const unsigned long long seed_value = rp.pix_id ? (unsigned long long) ((long long) pix + rp.seed) : (unsigned long long) (i + rp.seed);
@@ -50,8 +49,10 @@ __global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_c
         if (!isfinite(v.y)) g.y = 0.f;
         if (!isfinite(v.z)) g.z = 0.f;
         __syncwarp(live_mask);
-        if (g.x == 0.f && g.y == 0.f && g.z == 0.f) continue;
-        path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0);
+        const bool has_cotangent = !(g.x == 0.f && g.y == 0.f && g.z == 0.f);
+        const unsigned sweep_mask = __ballot_sync(live_mask, has_cotangent && R.nv > 0 && R.nsh > 0);
+        if (!has_cotangent) continue;
+        path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, sweep_mask);
     }
     grad_acc_end(acc);
 }
@@ -73,7 +74,6 @@ __global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __gr
         const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
         if (j >= span) continue;
         const long long i = rp.lane_begin + j;
-        (void) live_mask;
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(kBlockV, 6) secondary_edge_vjp_kernel(const __
         const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
         if (j >= span) continue;
         const long long i = rp.lane_begin + j;
-        (void) live_mask;
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
