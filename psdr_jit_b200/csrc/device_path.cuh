@@ -118,6 +118,14 @@ __device__ __forceinline__ void hit_consider(float tn, float det, float un, floa
     b.adet = ok ? adet : b.adet;
     b.tri = ok ? id : b.tri;
 }
+// the same acceptance for the ordered brute-force scan, on operands the packed code has already normalised
+__device__ __forceinline__ void hit_consider_ordered(float us, float vs, float sum, float ts, float adet, float eps_adet, int id, HitCand &b) {
+    const float lhs = ts * b.adet, rhs = b.ts * adet;
+    const bool ok = us >= 0.f && vs >= 0.f && sum <= adet && ts > eps_adet && lhs < rhs;
+    b.ts = ok ? ts : b.ts;
+    b.adet = ok ? adet : b.adet;
+    b.tri = ok ? id : b.tri;
+}
 template <bool kOrdered>
 __device__ __forceinline__ void tri_test(V3f p0, V3f e1, V3f e2, int id, V3f o, V3f d, HitCand &b) {
     const TriNum n = tri_numerators(p0, e1, e2, o, d);
@@ -150,10 +158,20 @@ __device__ __forceinline__ F2 f2_dup(float x) {
     asm("mov.b64 %0, {%1, %1};" : "=l"(r.v) : "f"(x));
     return r;
 }
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
 __device__ __forceinline__ void f2_split(F2 a, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
 __device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
     F2 r;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
     return r;
 }
 __device__ __forceinline__ F2 f2_sub(F2 a, F2 b) {
@@ -218,10 +236,19 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
             const F2 un = dot(S, h);
             const V3p q = cross_fms_nb(S, E1, NE1);
             const F2 vn = dot(D, q), tn = dot(E2, q);
-            float tn0, tn1, det0, det1, un0, un1, vn0, vn1;
-            f2_split(tn, tn0, tn1); f2_split(det, det0, det1); f2_split(un, un0, un1); f2_split(vn, vn0, vn1);
-            hit_consider<true>(tn0, det0, un0, vn0, 2 * j, best);
-            hit_consider<true>(tn1, det1, un1, vn1, 2 * j + 1, best);
+            // sign normalisation by an exact packed multiply with copysign(1, det); a zero determinant cannot pass:
+            // its rhs below is 0 and lhs >= 0, so "adet > 0" is implied by the strict "closer" of the ordered scan
+            float det0, det1;
+            f2_split(det, det0, det1);
+            const F2 SG = f2_pack(__int_as_float((__float_as_int(det0) & 0x80000000) | 0x3f800000),
+                                  __int_as_float((__float_as_int(det1) & 0x80000000) | 0x3f800000));
+            const F2 US = f2_mul(un, SG), VS = f2_mul(vn, SG), TS = f2_mul(tn, SG), AD = f2_mul(det, SG);
+            const F2 SUM = f2_add(US, VS), EPS = f2_mul(AD, f2_dup(kRayEpsilon));
+            float us0, us1, vs0, vs1, ts0, ts1, ad0, ad1, sum0, sum1, eps0, eps1;
+            f2_split(US, us0, us1); f2_split(VS, vs0, vs1); f2_split(TS, ts0, ts1);
+            f2_split(AD, ad0, ad1); f2_split(SUM, sum0, sum1); f2_split(EPS, eps0, eps1);
+            hit_consider_ordered(us0, vs0, sum0, ts0, ad0, eps0, 2 * j, best);
+            hit_consider_ordered(us1, vs1, sum1, ts1, ad1, eps1, 2 * j + 1, best);
         }
         if (best.tri < 0) return miss;
         const float *f = reinterpret_cast<const float *>(sc.bg_pair) + 2 * kBrutePairWords * (best.tri >> 1) + (best.tri & 1);

@@ -9,6 +9,20 @@
 #include "device_path.cuh"
 #include "kernels.h"
 
+// resident CTAs per SM each kernel is compiled for (register cap = 65536 / (128 * n)); tuned on cfg 2, B200
+#ifndef PSDR_LB_INTERIOR
+#define PSDR_LB_INTERIOR 6
+#endif
+#ifndef PSDR_LB_INTERIOR_DUAL
+#define PSDR_LB_INTERIOR_DUAL 6
+#endif
+#ifndef PSDR_LB_PRIMARY
+#define PSDR_LB_PRIMARY 8
+#endif
+#ifndef PSDR_LB_SECONDARY
+#define PSDR_LB_SECONDARY 8
+#endif
+
 namespace psdr {
 
 constexpr int kBlock = 128;
@@ -41,7 +55,7 @@ __device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; 
 // kAD = use the formulas of the reference's renderD instantiation (the primary hit re-intersected
 // analytically, scene.cpp:772-801) -- <float, kBvh, true> is the primal image of renderD.
 template <class S, int kCfg, bool kAD>
-__global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? 5 : 6)) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? PSDR_LB_INTERIOR_DUAL : PSDR_LB_INTERIOR)) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                            const __grid_constant__ RenderParams rp, float *__restrict__ img,
                                                            float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
@@ -83,7 +97,7 @@ __global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? 5 : 6)) interior_k
 
 // ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges
 template <int kCfg>
-__global__ void __launch_bounds__(kBlock, 8) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
@@ -137,7 +151,7 @@ __global__ void __launch_bounds__(kBlock, 8) primary_edge_kernel(const __grid_co
 
 // ---- secondary (shadow) edges: PathTracer::render_secondary_edges -----------------------------
 template <int kCfg>
-__global__ void __launch_bounds__(kBlock, 8) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlock, PSDR_LB_SECONDARY) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                  const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
     const long long stride = (long long) gridDim.x * kBlock;
     const float scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
