@@ -23,20 +23,51 @@ namespace psdr {
 // The atomic itself lives in ONE non-inlined function per translation unit: inlined, the ~300 scatter sites of
 // the adjoint made up half of the kernel's instructions (generic-address atomics expand to ~45 SASS
 // instructions each) and the kernel stalled on instruction fetch (profiles/r01e).
-static __device__ __noinline__ void grad_add3_impl(unsigned smem_addr, float *g, int lo, int hi, int idx, float x, float y, float z) {
-    const float v[3] = {x, y, z};
+// Shared-memory float adds are compare-and-swap loops on sm_100 (ATOMS.CAST.SPIN): a k-way address conflict inside
+// the warp costs k rounds, and the 32 lanes of a warp are the 32 samples of ONE pixel -- camera, emitter, BSDF and
+// primary-triangle entries conflict 32 ways.  So the lanes that arrive together first check (MATCH.ALL) whether
+// they all target the same entry; if so their values are summed with shuffles and one lane issues one add.
+// Mixed targets fall back to one predicated add per lane.  No data-dependent early return: lanes that leave a
+// non-inlined function in separate groups are not re-merged before the end of the caller's enclosing region.
+__device__ __forceinline__ void grad_red(unsigned m, unsigned smem_addr, float *g, int lo, int hi, int i, float v) {
+    float val = (v != 0.f && isfinite(v)) ? v : 0.f;
+    int same = 0;
+    __match_all_sync(m, i, &same);
+    bool mine = true;
+    if (same && (m & (m - 1u)) != 0u) {            // uniform over m: every lane targets entry i
+        if (m == 0xffffffffu) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        if (v[c] == 0.f || !isfinite(v[c])) continue;
-        const int i = idx + c;
-        if (smem_addr && i >= lo && i < hi) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_addr + 4u * (unsigned) (i - lo)), "f"(v[c]) : "memory");
-        else atomicAdd(g + i, v[c]);
+            for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+        } else {
+            float sum = 0.f;
+            for (unsigned r = m; r; r &= r - 1u) sum += __shfl_sync(m, val, __ffs((int) r) - 1);
+            val = sum;
+        }
+        mine = (threadIdx.x & 31) == __ffs((int) m) - 1;
     }
+    const bool ok = mine && val != 0.f && isfinite(val);
+    const bool in = smem_addr != 0u && i >= lo && i < hi;
+    const int to_shared = ok && in, to_global = ok && !in;
+    asm volatile(
+        "{\n\t.reg .pred ps, pg;\n\t"
+        "setp.ne.s32 ps, %0, 0;\n\t"
+        "setp.ne.s32 pg, %1, 0;\n\t"
+        "@ps red.shared.add.f32 [%2], %4;\n\t"
+        "@pg red.global.add.f32 [%3], %4;\n\t}"
+        ::"r"(to_shared), "r"(to_global), "r"(smem_addr + 4u * (unsigned) (i - lo)), "l"(g + i), "f"(val)
+        : "memory");
+}
+static __device__ __noinline__ void grad_add3_impl(unsigned smem_addr, float *g, int lo, int hi, int idx, float x, float y, float z) {
+    const unsigned m = __activemask();
+    grad_red(m, smem_addr, g, lo, hi, idx, x);
+    grad_red(m, smem_addr, g, lo, hi, idx + 1, y);
+    grad_red(m, smem_addr, g, lo, hi, idx + 2, z);
+    __syncwarp(m);
 }
 static __device__ __noinline__ void grad_add1_impl(unsigned smem_addr, float *g, int lo, int hi, int idx, float v) {
-    if (v == 0.f || !isfinite(v)) return;
-    if (smem_addr && idx >= lo && idx < hi) asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_addr + 4u * (unsigned) (idx - lo)), "f"(v) : "memory");
-    else atomicAdd(g + idx, v);
+    const unsigned m = __activemask();
+    grad_red(m, smem_addr, g, lo, hi, idx, v);
+    __syncwarp(m);
 }
 struct GradAcc {
     float *g;         // global table
@@ -412,43 +443,52 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
 // -- one iteration after it was x.
 template <int kD, int kCfg>
 __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout &gl, const GradAcc &acc, const PathRecord<kD> &R, V3f o, V3f d,
-                                             V3f dc, V3f g, bool hide_emitters, unsigned sweep_mask) {
+                                             V3f dc, V3f g, bool hide_emitters, bool enabled) {
+    // Called by ALL 32 lanes of the warp from warp-uniform control flow (`enabled` = this lane has a path and a
+    // cotangent).  The sweep loop below therefore sits at the top level, runs the warp's maximum trip count and
+    // re-converges with a full-mask barrier every iteration; everything lane-specific hangs off plain `if`s.
+    // (A barrier over a lane subset inside divergent code becomes a collective wait in SASS that lets the
+    // groups through one by one without merging them -- profiles/r01g: 3 of 32 lanes active in the sweep.)
     constexpr bool kFull = (kCfg & kCfgFull) != 0;
-    if (R.nv <= 0) return;
+    const bool has_v0 = enabled && R.nv > 0;
+    const bool sweep = has_v0 && R.nsh > 0;
     // vertex 0: solid-angle form -- (u, v, t) are functions of the triangle and the camera ray
-    const TriRec<float> T0 = load_tri<float>(sc, R.vtri[0]);
-    float u0, v0, t0;
-    ray_intersect_triangle<float>(T0.p0, T0.e1, T0.e2, o, d, u0, v0, t0);
-    VtxGeo v0geo = vertex_geo(sc, R.vtri[0], u0, v0);
-    v0geo.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
+    TriRec<float> T0;
+    float u0 = 0.f, v0 = 0.f, t0 = 0.f;
+    VtxGeo v0geo;
     V3f o_bar(0.f, 0.f, 0.f), d_bar(0.f, 0.f, 0.f);
-    // Le at the primary hit
-    if (!hide_emitters && v0geo.emitter >= 0) {
-        if (kFull && sc.emitters[v0geo.emitter].type == 1) {
-            V3f le;
-            d_bar = d_bar + env_le_adjoint(acc, gl, sc.env, d, g, le);
-            if (R.nsh <= 0) scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
-        } else if (dot(-d, v0geo.shn) > 0.f) acc.add3(gl.off_emit + 4 * v0geo.emitter, g);
+    if (has_v0) {
+        T0 = load_tri<float>(sc, R.vtri[0]);
+        ray_intersect_triangle<float>(T0.p0, T0.e1, T0.e2, o, d, u0, v0, t0);
+        v0geo = vertex_geo(sc, R.vtri[0], u0, v0);
+        v0geo.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
+        // Le at the primary hit
+        if (!hide_emitters && v0geo.emitter >= 0) {
+            if (kFull && sc.emitters[v0geo.emitter].type == 1) {
+                V3f le;
+                d_bar = d_bar + env_le_adjoint(acc, gl, sc.env, d, g, le);
+                if (R.nsh <= 0) scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
+            } else if (dot(-d, v0geo.shn) > 0.f) acc.add3(gl.off_emit + 4 * v0geo.emitter, g);
+        }
     }
-    if (R.nsh <= 0) return;
 
     const VtxAdj zero_adj = {V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), 0.f, V2f(0.f, 0.f)};
     const int ktop = R.nsh - 1;
     auto geo_of = [&](int k) { return k == 0 ? v0geo : vertex_geo(sc, R.vtri[k], R.vu[k], R.vv[k]); };
-    VtxGeo y = (ktop + 1 < R.nv) ? geo_of(ktop + 1) : v0geo;      // only read when the bounce exists
-    VtxGeo x = geo_of(ktop);
+    VtxGeo y = v0geo, x = v0geo;
+    if (sweep) {
+        if (ktop + 1 < R.nv) y = geo_of(ktop + 1);      // only read when the bounce exists
+        x = geo_of(ktop);
+    }
     VtxAdj ya = zero_adj, xa = zero_adj, pa = zero_adj;
     V3f Lnext(0.f, 0.f, 0.f);     // R_{k+1}: radiance gathered after vertex k+1 (without E_{k+1})
-    // every lane of sweep_mask (the lanes of this warp that have a sweep to run: the caller's ballot) executes
-    // iteration kk together, whatever its own k is; the barrier is what makes that true -- the body's branches
-    // leave through different back edges and without it the lanes drift apart and run the sweep a few at a time
-    // (profiles/r01g: 2.9 of 32 lanes active here)
-    const int iters = __reduce_max_sync(sweep_mask, R.nsh);
+    // every lane executes iteration kk together, whatever its own k is
+    const int iters = __reduce_max_sync(0xffffffffu, sweep ? R.nsh : 0);
 #pragma unroll 1
     for (int kk = 0; kk < iters; ++kk) {
-        __syncwarp(sweep_mask);
+        __syncwarp();
         const int k = ktop - kk;
-        if (k < 0) continue;
+        if (sweep && k >= 0) {
         VtxGeo prev = k > 0 ? geo_of(k - 1) : v0geo;
         const V3f A = g * R.T[k];
         float tprev = 1.f;
@@ -548,8 +588,9 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         y = x; ya = xa;
         x = prev; xa = pa;
         pa = zero_adj;
+        }
     }
-    {   // vertex 0 (now in y / ya): p = o + t d, sh_n from the differentiable (u, v)
+    if (sweep) {   // vertex 0 (now in y / ya): p = o + t d, sh_n from the differentiable (u, v)
         const VtxGeo &x0 = y;
         const VtxAdj &a0 = ya;
         const int b = kGradTri * x0.tri;

@@ -25,10 +25,12 @@ __global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_c
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
     for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
+        // the whole body is warp-uniform control flow: lanes past the end of the span ride along inactive (the
+        // span is padded to 32), so the barriers here and inside path_adjoint are full-mask barriers at the top
+        // level -- the only form that really re-converges the warp (see path_adjoint)
         __syncwarp();
-        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
-        if (j >= span) continue;
-        const long long i = rp.lane_begin + j;
+        const bool live = j < span;
+        const long long i = rp.lane_begin + (live ? j : 0);
         const int idx = (int) (sc.spp > 1 ? i / sc.spp : i);
         const int pix = rp.pix_id ? __ldg(rp.pix_id + idx) : idx;
         const unsigned long long seed_value = rp.pix_id ? (unsigned long long) ((long long) pix + rp.seed) : (unsigned long long) (i + rp.seed);
@@ -42,17 +44,15 @@ __global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_c
         const V3f o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f)), d = xform_dir(cam.to_world, dc);
         PathRecord<kD> R;
         R.reset();
-        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, R);
+        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, R);
         // cotangent of this lane's value; channels the forward pass scrubbed (non-finite) carry none
         V3f g(__ldg(d_img + 3 * idx) * inv_spp, __ldg(d_img + 3 * idx + 1) * inv_spp, __ldg(d_img + 3 * idx + 2) * inv_spp);
         if (!isfinite(v.x)) g.x = 0.f;
         if (!isfinite(v.y)) g.y = 0.f;
         if (!isfinite(v.z)) g.z = 0.f;
-        __syncwarp(live_mask);
         const bool has_cotangent = !(g.x == 0.f && g.y == 0.f && g.z == 0.f);
-        const unsigned sweep_mask = __ballot_sync(live_mask, has_cotangent && R.nv > 0 && R.nsh > 0);
-        if (!has_cotangent) continue;
-        path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, sweep_mask);
+        __syncwarp();
+        path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, live && has_cotangent);
     }
     grad_acc_end(acc);
 }
