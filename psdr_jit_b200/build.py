@@ -21,11 +21,24 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = LIB + ".stamp"
+
+
+def source_digest() -> str:
+    """Content hash of every source and header (file times do not survive a copy to another machine)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_digest()
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:
@@ -58,6 +71,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     subprocess.check_call([nvcc_path(), "-shared", "-o", LIB, "-ccbin", host_cxx] + objs)
+    with open(STAMP, "w") as fh:
+        fh.write(source_digest() + "\n")
     return LIB
 
 
