@@ -501,78 +501,94 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         }
         V3f wi_bar(0.f, 0.f, 0.f);
         V3f Rk(0.f, 0.f, 0.f);
-        // ---- BSDF bounce k -> vertex k+1
-        if (R.bnc_ok[k] && k + 1 < R.nv) {
-            const V3f wo = normalize(y.p - x.p);
-            V3f E(0.f, 0.f, 0.f);
-            const bool y_env = kFull && y.emitter >= 0 && sc.emitters[y.emitter].type == 1;
-            const bool y_emits = y.emitter >= 0 && (y_env || dot(-wo, y.shn) > 0.f);
-            if (y_env) {
-                const V2f uv = envmap_dir_to_uv<float>(mul3x3<float>(sc.env.from_world, nullptr, wo));
-                E = bitmap_eval_envmap<float>(sc.env.data, nullptr, sc.env.w, sc.env.h, uv) * (sc.env.scale * R.w2[k]);
-            } else if (y_emits) {
-                const DEmitter &em = sc.emitters[y.emitter];
-                E = V3f(em.radiance[0], em.radiance[1], em.radiance[2]) * R.w2[k];
+        // The two events of vertex k -- e = 0: BSDF bounce to vertex k+1, e = 1: emitter sampling -- run through ONE
+        // copy of event_adjoint (a rolled loop): three inlined copies made the kernel 3x the instruction cache.
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+            // mode 0: nothing; 1: bounce; 2: area-light sample; 3: environment-map sample
+            int mode = 0;
+            V3f py, ny, W, envW(0.f, 0.f, 0.f), Ltot(0.f, 0.f, 0.f), Le(0.f, 0.f, 0.f);
+            float area_y = 0.f, scale = 0.f;
+            bool y_emits = false, y_env = false;
+            int emi = -1;
+            if (e == 0) {
+                if (R.bnc_ok[k] && k + 1 < R.nv) {
+                    const V3f wo = normalize(y.p - x.p);
+                    V3f E(0.f, 0.f, 0.f);
+                    y_env = kFull && y.emitter >= 0 && sc.emitters[y.emitter].type == 1;
+                    y_emits = y.emitter >= 0 && (y_env || dot(-wo, y.shn) > 0.f);
+                    if (y_env) {
+                        const V2f uv = envmap_dir_to_uv<float>(mul3x3<float>(sc.env.from_world, nullptr, wo));
+                        E = bitmap_eval_envmap<float>(sc.env.data, nullptr, sc.env.w, sc.env.h, uv) * (sc.env.scale * R.w2[k]);
+                    } else if (y_emits) {
+                        const DEmitter &em = sc.emitters[y.emitter];
+                        E = V3f(em.radiance[0], em.radiance[1], em.radiance[2]) * R.w2[k];
+                    }
+                    Ltot = E + Lnext;
+                    if (R.bnc_nz[k]) {
+                        mode = 1;
+                        py = y.p; ny = y.fn; area_y = y.area;
+                        W = A * Ltot;
+                        scale = 1.f / R.pdf0[k];
+                        // a direction-dependent emitter at y adds d(E)/d(wo) and the texel / scale gradients
+                        if (y_env) envW = A * R.w2[k];
+                    }
+                }
+            } else if (R.nee_ok[k]) {
+                const float4 c = __ldg(sc.shade + 3 * R.htri[k] + 2);
+                ny = V3f(c.y, c.z, c.w);
+                scale = R.w1[k] / R.lpdf[k];
+                if (kFull && R.ltri[k] < 0) {
+                    // environment-map sample: the position on the bounding box is detached (envmap.cpp:95-101), J = 1;
+                    // derivatives flow through the direction (x.p) into the radiance lookup and the geometric term
+                    py = V3f(R.la[k], R.lb[k], R.lc[k]);
+                    const V3f wod = normalize(py - x.p);
+                    const V2f uv = envmap_dir_to_uv<float>(mul3x3<float>(sc.env.from_world, nullptr, wod));
+                    Le = bitmap_eval_envmap<float>(sc.env.data, nullptr, sc.env.w, sc.env.h, uv) * sc.env.scale;
+                    mode = 3;
+                    envW = A;
+                    W = A * Le;
+                } else {
+                    const TriRec<float> TL = load_tri<float>(sc, R.ltri[k]);
+                    py = bilinear(TL.p0, TL.e1, TL.e2, V2f(R.la[k], R.lb[k]));
+                    area_y = TL.area;
+                    emi = sc.meshes[__float_as_int(__ldg(&sc.geo[3 * R.htri[k] + 2].z))].emitter;
+                    if (emi >= 0) {
+                        const DEmitter &em = sc.emitters[emi];
+                        Le = V3f(em.radiance[0], em.radiance[1], em.radiance[2]);
+                        mode = 2;
+                        W = A * Le;
+                    }
+                }
             }
-            const V3f Ltot = E + Lnext;
-            if (R.bnc_nz[k]) {
-                const float scale = 1.f / R.pdf0[k];
-                const float w2k = R.w2[k];
-                // a direction-dependent emitter at y adds d(E)/d(wo) and the texel / scale gradients
+            if (mode != 0) {
+                const bool with_env = kFull && (mode == 3 || (mode == 1 && y_env));
                 auto extra = [&](V3f wo_, V3f fgeo) {
-                    if (!y_env) return V3f(0.f, 0.f, 0.f);
+                    if (!with_env) return V3f(0.f, 0.f, 0.f);
                     V3f le;
-                    return env_le_adjoint(acc, gl, sc.env, wo_, A * fgeo * w2k, le);
+                    return env_le_adjoint(acc, gl, sc.env, wo_, envW * fgeo, le);
                 };
-                const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, x, wi, y.p, y.fn, y.area, A * Ltot, scale, xa, extra);
-                ya.p = ya.p + ev.py;
-                ya.fn = ya.fn + ev.ny;
-                ya.area += ev.area_y;
+                const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, x, wi, py, ny, area_y, W, scale, xa, extra);
                 wi_bar = wi_bar + ev.wi_bar;
                 const V3f fb = ev.f * ev.geo;
-                if (y_emits && !y_env) acc.add3(gl.off_emit + 4 * y.emitter, A * fb * R.w2[k]);
-                Rk = Rk + fb * Ltot;
-            }
-        }
-        // ---- emitter sampling at vertex k
-        if (kFull && R.nee_ok[k] && R.ltri[k] < 0) {
-            // environment-map sample: the position on the bounding box is detached (envmap.cpp:95-101), J = 1;
-            // derivatives flow through the direction (x.p) into the radiance lookup and the geometric term
-            const V3f py(R.la[k], R.lb[k], R.lc[k]);
-            const float4 c = __ldg(sc.shade + 3 * R.htri[k] + 2);
-            const V3f ny(c.y, c.z, c.w);
-            const V3f wod = normalize(py - x.p);
-            const V2f uv = envmap_dir_to_uv<float>(mul3x3<float>(sc.env.from_world, nullptr, wod));
-            const V3f Le = bitmap_eval_envmap<float>(sc.env.data, nullptr, sc.env.w, sc.env.h, uv) * sc.env.scale;
-            const float scale = R.w1[k] / R.lpdf[k];
-            auto extra = [&](V3f wo_, V3f fgeo) {
-                V3f le;
-                return env_le_adjoint(acc, gl, sc.env, wo_, A * fgeo, le);
-            };
-            const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, x, wi, py, ny, 0.f, A * Le, scale, xa, extra);
-            wi_bar = wi_bar + ev.wi_bar;
-            Rk = Rk + Le * (ev.f * ev.geo);
-        } else if (R.nee_ok[k]) {
-            const TriRec<float> TL = load_tri<float>(sc, R.ltri[k]);
-            const V3f py = bilinear(TL.p0, TL.e1, TL.e2, V2f(R.la[k], R.lb[k]));
-            const float4 c = __ldg(sc.shade + 3 * R.htri[k] + 2);
-            const V3f ny(c.y, c.z, c.w);
-            const int emi = sc.meshes[__float_as_int(__ldg(&sc.geo[3 * R.htri[k] + 2].z))].emitter;
-            if (emi >= 0) {
-                const DEmitter &em = sc.emitters[emi];
-                const V3f Le(em.radiance[0], em.radiance[1], em.radiance[2]);
-                const float scale = R.w1[k] / R.lpdf[k];
-                const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, x, wi, py, ny, TL.area, A * Le, scale, xa, [](V3f, V3f) { return V3f(0.f, 0.f, 0.f); });
-                wi_bar = wi_bar + ev.wi_bar;
-                const int lb = kGradTri * R.ltri[k];
-                acc.add3(lb, ev.py);
-                acc.add3(lb + 3, ev.py * R.la[k]);
-                acc.add3(lb + 6, ev.py * R.lb[k]);
-                acc.add(lb + 9, ev.area_y);
-                acc.add3(kGradTri * R.htri[k] + 19, ev.ny);
-                const V3f c_rgb = ev.f * ev.geo;
-                acc.add3(gl.off_emit + 4 * emi, A * c_rgb);
-                Rk = Rk + Le * c_rgb;
+                if (mode == 1) {
+                    ya.p = ya.p + ev.py;
+                    ya.fn = ya.fn + ev.ny;
+                    ya.area += ev.area_y;
+                    if (y_emits && !y_env) acc.add3(gl.off_emit + 4 * y.emitter, A * fb * R.w2[k]);
+                    Rk = Rk + fb * Ltot;
+                } else {
+                    if (mode == 2) {
+                        const int lb = kGradTri * R.ltri[k];
+                        acc.add3(lb, ev.py);
+                        acc.add3(lb + 3, ev.py * R.la[k]);
+                        acc.add3(lb + 6, ev.py * R.lb[k]);
+                        acc.add(lb + 9, ev.area_y);
+                        acc.add3(kGradTri * R.htri[k] + 19, ev.ny);
+                        acc.add3(gl.off_emit + 4 * emi, A * fb);
+                    }
+                    Rk = Rk + Le * fb;
+                }
             }
         }
         // ---- wi at vertex k: through the previous vertex, or the camera ray direction
