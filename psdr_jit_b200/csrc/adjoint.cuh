@@ -29,10 +29,10 @@ namespace psdr {
 // they all target the same entry; if so their values are summed with shuffles and one lane issues one add.
 // Mixed targets fall back to one predicated add per lane.  No data-dependent early return: lanes that leave a
 // non-inlined function in separate groups are not re-merged before the end of the caller's enclosing region.
-__device__ __forceinline__ void grad_red(unsigned m, unsigned smem_addr, float *g, int lo, int hi, int i, float v) {
+__device__ __forceinline__ void grad_red(unsigned m, bool aggregate, unsigned smem_addr, float *g, int lo, int hi, int i, float v) {
     float val = (v != 0.f && isfinite(v)) ? v : 0.f;
     int same = 0;
-    __match_all_sync(m, i, &same);
+    if (aggregate) __match_all_sync(m, i, &same);      // (kernel-wide constant: the edge kernels' lanes sit on different edges)
     bool mine = true;
     if (same && (m & (m - 1u)) != 0u) {            // uniform over m: every lane targets entry i
         if (m == 0xffffffffu) {
@@ -57,16 +57,16 @@ __device__ __forceinline__ void grad_red(unsigned m, unsigned smem_addr, float *
         ::"r"(to_shared), "r"(to_global), "r"(smem_addr + 4u * (unsigned) (i - lo)), "l"(g + i), "f"(val)
         : "memory");
 }
-static __device__ __noinline__ void grad_add3_impl(unsigned smem_addr, float *g, int lo, int hi, int idx, float x, float y, float z) {
+static __device__ __noinline__ void grad_add3_impl(bool aggregate, unsigned smem_addr, float *g, int lo, int hi, int idx, float x, float y, float z) {
     const unsigned m = __activemask();
-    grad_red(m, smem_addr, g, lo, hi, idx, x);
-    grad_red(m, smem_addr, g, lo, hi, idx + 1, y);
-    grad_red(m, smem_addr, g, lo, hi, idx + 2, z);
+    grad_red(m, aggregate, smem_addr, g, lo, hi, idx, x);
+    grad_red(m, aggregate, smem_addr, g, lo, hi, idx + 1, y);
+    grad_red(m, aggregate, smem_addr, g, lo, hi, idx + 2, z);
     __syncwarp(m);
 }
-static __device__ __noinline__ void grad_add1_impl(unsigned smem_addr, float *g, int lo, int hi, int idx, float v) {
+static __device__ __noinline__ void grad_add1_impl(bool aggregate, unsigned smem_addr, float *g, int lo, int hi, int idx, float v) {
     const unsigned m = __activemask();
-    grad_red(m, smem_addr, g, lo, hi, idx, v);
+    grad_red(m, aggregate, smem_addr, g, lo, hi, idx, v);
     __syncwarp(m);
 }
 struct GradAcc {
@@ -74,12 +74,14 @@ struct GradAcc {
     float *s;         // shared copy (nullptr = none)
     unsigned s_addr;  // its shared-window address (0 = none)
     int lo, hi;
-    __device__ __forceinline__ void add(int idx, float v) const { grad_add1_impl(s_addr, g, lo, hi, idx, v); }
-    __device__ __forceinline__ void add3(int idx, V3f v) const { grad_add3_impl(s_addr, g, lo, hi, idx, v.x, v.y, v.z); }
+    bool aggregate;   // sum across the lanes that target the same entry before adding (interior kernel: one pixel per warp)
+    __device__ __forceinline__ void add(int idx, float v) const { grad_add1_impl(aggregate, s_addr, g, lo, hi, idx, v); }
+    __device__ __forceinline__ void add3(int idx, V3f v) const { grad_add3_impl(aggregate, s_addr, g, lo, hi, idx, v.x, v.y, v.z); }
 };
 
-__device__ __forceinline__ GradAcc grad_acc_begin(const GradLayout &gl, float *smem, int lo, int hi, bool use_smem) {
+__device__ __forceinline__ GradAcc grad_acc_begin(const GradLayout &gl, float *smem, int lo, int hi, bool use_smem, bool aggregate) {
     GradAcc a;
+    a.aggregate = aggregate;
     a.g = gl.base;
     a.s = use_smem ? smem : nullptr;
     a.s_addr = use_smem ? (unsigned) __cvta_generic_to_shared(smem) : 0u;
