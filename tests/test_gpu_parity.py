@@ -129,6 +129,30 @@ def test_brute_force_and_bvh_agree(oracle):
     assert rel_l2(out[0][1], out[1][1]) < 1e-5
 
 
+@pytest.mark.parametrize("extra", [1, 3])
+def test_odd_triangle_count_in_the_paired_scan(oracle, extra):
+    """The brute-force scan tests triangles two at a time (dscene.h bg_pair): an odd count is padded with a
+    zero triangle that must never be hit, and the last real triangle must still be found."""
+    psdr = _psdr()
+    from psdr_jit_b200.scenes import MeshData
+    v = np.array([[150, 330, 200], [400, 330, 200], [275, 330, 420], [150, 120, 420], [400, 120, 420]], np.float32)
+    f = np.array([[0, 1, 2], [2, 3, 4], [0, 2, 3]][:extra], np.int32)
+    fin = MeshData(name="fin", v=v, f=f, bsdf="white")
+    meshes = scenes.cbox_meshes() + [fin]
+    assert sum(len(m.f) for m in meshes) % 2 == 1
+    osc = build_oracle(meshes, 96, 96, 2, 2, 2, move_mesh=8, axis_scale=(30.0, 10.0, 0.0))
+    img_ref, dimg_ref = osc.render(3, seed=2, mode=1, terms=7)
+    sc = build_product(meshes, 96, 96, 2, 2, 2, move_mesh=8, axis_scale=(30.0, 10.0, 0.0))
+    integ = psdr.PathTracer(3)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=2)
+    assert rel_l2(img.cpu().numpy(), img_ref) < TOL
+    assert rel_l2(dimg.cpu().numpy(), dimg_ref) < TOL
+    ref = build_oracle(meshes, 96, 96, 1, 0, 0).aov()
+    got = psdr.PathTracer(1).render_aov(build_product(meshes, 96, 96, 1, 0, 0), 0, seed=0).cpu().numpy()
+    assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, 1], ref[:, 1])     # mesh and triangle ids
+    assert (got[:, 0] == 8).any()           # the fin (the last, unpaired triangles) is visible
+
+
 def test_seed_continuation_matches_oracle_skip(oracle):
     """seed=-1 continues the sampler streams (reference integrator.cpp:23,60)."""
     psdr = _psdr()
