@@ -179,9 +179,16 @@ template <class S> inline V3<S> operator-(V3<S> a) { return {-a.x, -a.y, -a.z}; 
 template <class S> inline V3<S> operator*(V3<S> a, V3<S> b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
 template <class S> inline V3<S> operator*(V3<S> a, S b) { return {a.x * b, a.y * b, a.z * b}; }
 template <class S> inline V3<S> operator*(S b, V3<S> a) { return {a.x * b, a.y * b, a.z * b}; }
-template <class S> inline V3<S> operator/(V3<S> a, S b) { return {a.x / b, a.y / b, a.z / b}; }
+// vector / scalar = vector * (1 / scalar) (Dr.Jit's array / scalar); same spelling as psdr_jit_b200/csrc/pmath.h
+template <class S> inline V3<S> operator/(V3<S> a, S b) {
+    const S r = S(1.f) / b;
+    return {a.x * r, a.y * r, a.z * r};
+}
 inline V3d operator*(V3d a, float b) { return {a.x * b, a.y * b, a.z * b}; }
-inline V3d operator/(V3d a, float b) { return {a.x / b, a.y / b, a.z / b}; }
+inline V3d operator/(V3d a, float b) {
+    const float r = 1.f / b;
+    return {a.x * r, a.y * r, a.z * r};
+}
 template <class S> inline V3<S> &operator+=(V3<S> &a, V3<S> b) { a = a + b; return a; }
 template <class S> inline V3<S> &operator*=(V3<S> &a, V3<S> b) { a = a * b; return a; }
 template <class S> inline V2<S> operator+(V2<S> a, V2<S> b) { return {a.x + b.x, a.y + b.y}; }

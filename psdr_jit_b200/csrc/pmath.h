@@ -173,9 +173,17 @@ template <class S> PSDR_HD V3<S> operator-(V3<S> a, V3<S> b) { return V3<S>(a.x 
 template <class S> PSDR_HD V3<S> operator-(V3<S> a) { return V3<S>(-a.x, -a.y, -a.z); }
 template <class S> PSDR_HD V3<S> operator*(V3<S> a, V3<S> b) { return V3<S>(a.x * b.x, a.y * b.y, a.z * b.z); }
 template <class S> PSDR_HD V3<S> operator*(V3<S> a, S b) { return V3<S>(a.x * b, a.y * b, a.z * b); }
-template <class S> PSDR_HD V3<S> operator/(V3<S> a, S b) { return V3<S>(a.x / b, a.y / b, a.z / b); }
+// vector / scalar = vector * (1 / scalar): one IEEE division instead of three (Dr.Jit's array / scalar does the same);
+// the oracle (oracle/orc_math.h) spells it identically
+template <class S> PSDR_HD V3<S> operator/(V3<S> a, S b) {
+    const S r = S(1.f) / b;
+    return V3<S>(a.x * r, a.y * r, a.z * r);
+}
 PSDR_HD V3d operator*(V3d a, float b) { return V3d(a.x * b, a.y * b, a.z * b); }
-PSDR_HD V3d operator/(V3d a, float b) { return V3d(a.x / b, a.y / b, a.z / b); }
+PSDR_HD V3d operator/(V3d a, float b) {
+    const float r = 1.f / b;
+    return V3d(a.x * r, a.y * r, a.z * r);
+}
 template <class S> PSDR_HD V2<S> operator+(V2<S> a, V2<S> b) { return V2<S>(a.x + b.x, a.y + b.y); }
 template <class S> PSDR_HD V2<S> operator-(V2<S> a, V2<S> b) { return V2<S>(a.x - b.x, a.y - b.y); }
 
