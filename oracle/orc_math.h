@@ -295,7 +295,7 @@ template <class S> inline M4<S> inverse(const M4<S> &a) {
 template <class S> inline V3<S> transform_pos(const M4<S> &M, V3<S> p) {
     S t[4];
     for (int i = 0; i < 4; ++i) t[i] = fmadd(M.m[i][2], p.z, fmadd(M.m[i][1], p.y, M.m[i][0] * p.x)) + M.m[i][3];
-    return {t[0] / t[3], t[1] / t[3], t[2] / t[3]};
+    return V3<S>{t[0], t[1], t[2]} / t[3];      // one reciprocal (vector / scalar)
 }
 template <class S> inline V3<S> transform_dir(const M4<S> &M, V3<S> p) {
     S t[3];

@@ -1196,8 +1196,9 @@ static void render_primary_edges(const Scene &sc, const RenderArgs &ra, float *d
             Lp = Li<float>(sc, rng, op, dp, valid, ra.max_depth, ra.hide_emitters);
         }
         if (!valid) continue;
+        const float inv_pdf = 1.f / pdf;      // (Ln - Lp) / pdf as a Spectrum / scalar: one reciprocal
         for (int c = 0; c < 3; ++c) {
-            float dl = (Ln[c] - Lp[c]) / pdf;
+            float dl = (Ln[c] - Lp[c]) * inv_pdf;
             Dual value = x_dot_n * Dual(dl);
             if (!std::isfinite(value.v)) continue;   // masked(value, ~isfinite(value)) = 0
             float t = value.d;

@@ -750,7 +750,7 @@ __device__ __forceinline__ V3f xform_pos(const float *M, V3f p) {
     float t[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) t[i] = fmaf(M[4 * i + 2], p.z, fmaf(M[4 * i + 1], p.y, M[4 * i] * p.x)) + M[4 * i + 3];
-    return V3f(t[0] / t[3], t[1] / t[3], t[2] / t[3]);
+    return V3f(t[0], t[1], t[2]) / t[3];
 }
 __device__ __forceinline__ V3f xform_dir(const float *M, V3f p) {
     return V3f(fmaf(M[2], p.z, fmaf(M[1], p.y, M[0] * p.x)), fmaf(M[6], p.z, fmaf(M[5], p.y, M[4] * p.x)),
@@ -763,7 +763,7 @@ __device__ __forceinline__ V3d xform_pos_d(const float *M, const float *dM, V3d 
         const Dual a(M[4 * i], dM[4 * i]), b(M[4 * i + 1], dM[4 * i + 1]), c(M[4 * i + 2], dM[4 * i + 2]), w(M[4 * i + 3], dM[4 * i + 3]);
         t[i] = fmadd(c, p.z, fmadd(b, p.y, a * p.x)) + w;
     }
-    return V3d(t[0] / t[3], t[1] / t[3], t[2] / t[3]);
+    return V3d(t[0], t[1], t[2]) / t[3];
 }
 __device__ __forceinline__ V3d xform_dir_d(const float *M, const float *dM, V3d p) {
     Dual t[3];

@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(c
         const V3f Lp = Lside[0], Ln = Lside[1];
         if (!valid) continue;
         const int pix = iy * sc.width + ix;
-        const float dl[3] = {(Ln.x - Lp.x) / pdf, (Ln.y - Lp.y) / pdf, (Ln.z - Lp.z) / pdf};
+        const float inv_pdf = 1.f / pdf;
+        const float dl[3] = {(Ln.x - Lp.x) * inv_pdf, (Ln.y - Lp.y) * inv_pdf, (Ln.z - Lp.z) * inv_pdf};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float primal = x_dot_n.v * dl[c];

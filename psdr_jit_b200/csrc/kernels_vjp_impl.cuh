@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __gr
         }
         if (!valid) continue;
         const int pix = iy * sc.width + ix;
-        const float dl[3] = {(Lside[1].x - Lside[0].x) / pdf, (Lside[1].y - Lside[0].y) / pdf, (Lside[1].z - Lside[0].z) / pdf};
+        const float inv_pdf = 1.f / pdf;
+        const float dl[3] = {(Lside[1].x - Lside[0].x) * inv_pdf, (Lside[1].y - Lside[0].y) * inv_pdf, (Lside[1].z - Lside[0].z) * inv_pdf};
         float gsum = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {

@@ -69,7 +69,13 @@ PSDR_HD Dual safe_sqrt(Dual x) {
     float sg = sqrtf(fmaxf(x.v, kFltEps));
     return Dual(s, x.d / (2.f * sg));
 }
-PSDR_HD bool signbit_(float x) { return (x < 0.f) || (x == 0.f && 1.f / x < 0.f); }
+PSDR_HD bool signbit_(float x) {      // std::signbit (the sign bit itself: -0.f counts as negative)
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(x) < 0;
+#else
+    return std::signbit(x);
+#endif
+}
 PSDR_HD float abs_(float x) { return fabsf(x); }
 PSDR_HD Dual abs_(Dual x) { return Dual(fabsf(x.v), signbit_(x.v) ? -x.d : x.d); }
 PSDR_HD float rcp_(float x) { return 1.f / x; }
@@ -254,7 +260,7 @@ template <class S> PSDR_HD M4<S> operator*(const M4<S> &a, const M4<S> &b) {
 template <class S> PSDR_HD V3<S> transform_pos(const M4<S> &M, V3<S> p) {
     S t[4];
     for (int i = 0; i < 4; ++i) t[i] = fmadd(M.m[i][2], p.z, fmadd(M.m[i][1], p.y, M.m[i][0] * p.x)) + M.m[i][3];
-    return V3<S>(t[0] / t[3], t[1] / t[3], t[2] / t[3]);
+    return V3<S>(t[0], t[1], t[2]) / t[3];      // one reciprocal (vector / scalar)
 }
 template <class S> PSDR_HD V3<S> transform_dir(const M4<S> &M, V3<S> p) {
     S t[3];
