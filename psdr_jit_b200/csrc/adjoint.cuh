@@ -57,11 +57,47 @@ __device__ __forceinline__ void grad_red(unsigned m, bool aggregate, unsigned sm
         ::"r"(to_shared), "r"(to_global), "r"(smem_addr + 4u * (unsigned) (i - lo)), "l"(g + i), "f"(val)
         : "memory");
 }
+// three consecutive entries (a vector): one MATCH on the base index, the three sums interleaved
 static __device__ __noinline__ void grad_add3_impl(bool aggregate, unsigned smem_addr, float *g, int lo, int hi, int idx, float x, float y, float z) {
     const unsigned m = __activemask();
-    grad_red(m, aggregate, smem_addr, g, lo, hi, idx, x);
-    grad_red(m, aggregate, smem_addr, g, lo, hi, idx + 1, y);
-    grad_red(m, aggregate, smem_addr, g, lo, hi, idx + 2, z);
+    float v0 = (x != 0.f && isfinite(x)) ? x : 0.f, v1 = (y != 0.f && isfinite(y)) ? y : 0.f, v2 = (z != 0.f && isfinite(z)) ? z : 0.f;
+    bool mine = true;
+    int same = 0;
+    if (aggregate) __match_all_sync(m, idx, &same);
+    if (same && (m & (m - 1u)) != 0u) {            // uniform over m: every lane targets the same three entries
+        if (m == 0xffffffffu) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, d);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, d);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, d);
+            }
+        } else {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+            for (unsigned r = m; r; r &= r - 1u) {
+                const int src = __ffs((int) r) - 1;
+                s0 += __shfl_sync(m, v0, src);
+                s1 += __shfl_sync(m, v1, src);
+                s2 += __shfl_sync(m, v2, src);
+            }
+            v0 = s0; v1 = s1; v2 = s2;
+        }
+        mine = (threadIdx.x & 31) == __ffs((int) m) - 1;
+    }
+    // a vector never straddles the shared window (its bounds are record-aligned section offsets of grad_layout.h)
+    const bool in = smem_addr != 0u && idx >= lo && idx + 2 < hi;
+    const int s0 = mine && in && v0 != 0.f && isfinite(v0), s1 = mine && in && v1 != 0.f && isfinite(v1), s2 = mine && in && v2 != 0.f && isfinite(v2);
+    const int g0 = mine && !in && v0 != 0.f && isfinite(v0), g1 = mine && !in && v1 != 0.f && isfinite(v1), g2 = mine && !in && v2 != 0.f && isfinite(v2);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.s32 p, %0, 0;\n\t@p red.shared.add.f32 [%6], %8;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t@p red.shared.add.f32 [%6+4], %9;\n\t"
+        "setp.ne.s32 p, %2, 0;\n\t@p red.shared.add.f32 [%6+8], %10;\n\t"
+        "setp.ne.s32 p, %3, 0;\n\t@p red.global.add.f32 [%7], %8;\n\t"
+        "setp.ne.s32 p, %4, 0;\n\t@p red.global.add.f32 [%7+4], %9;\n\t"
+        "setp.ne.s32 p, %5, 0;\n\t@p red.global.add.f32 [%7+8], %10;\n\t}"
+        ::"r"(s0), "r"(s1), "r"(s2), "r"(g0), "r"(g1), "r"(g2), "r"(smem_addr + 4u * (unsigned) (idx - lo)), "l"(g + idx), "f"(v0), "f"(v1), "f"(v2)
+        : "memory");
     __syncwarp(m);
 }
 static __device__ __noinline__ void grad_add1_impl(bool aggregate, unsigned smem_addr, float *g, int lo, int hi, int idx, float v) {
@@ -345,12 +381,15 @@ __device__ __forceinline__ void scatter_isect_tri(const GradAcc &acc, int tri, f
 __device__ __forceinline__ void scatter_camera_ray(const GradAcc &acc, const GradLayout &gl, V3f dc, V3f o_bar, V3f d_bar) {
     const int b = gl.off_cam;
     const float ob[3] = {o_bar.x, o_bar.y, o_bar.z}, db[3] = {d_bar.x, d_bar.y, d_bar.z}, c[3] = {dc.x, dc.y, dc.z};
+    float f[12];      // rows 0..2 of d to_world: (d_bar_i * dc, o_bar_i); twelve consecutive entries = four vector adds
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        acc.add(b + 4 * i + 3, ob[i]);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc.add(b + 4 * i + j, db[i] * c[j]);
+        for (int j = 0; j < 3; ++j) f[4 * i + j] = db[i] * c[j];
+        f[4 * i + 3] = ob[i];
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc.add3(b + 3 * k, V3f(f[3 * k], f[3 * k + 1], f[3 * k + 2]));
 }
 
 // Environment-map radiance along `dir` weighted by Wc (contribution = sum_c Wc_c Le_c(dir)): scatters the
@@ -382,9 +421,7 @@ static __device__ __noinline__ V3f env_le_adjoint(const GradAcc &acc, const Grad
     }
     const float vb[3] = {v_bar.x, v_bar.y, v_bar.z}, dd[3] = {dir.x, dir.y, dir.z};
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) acc.add(base + 1 + 3 * i + j, vb[i] * dd[j]);      // v = F dir
+    for (int i = 0; i < 3; ++i) acc.add3(base + 1 + 3 * i, V3f(vb[i] * dd[0], vb[i] * dd[1], vb[i] * dd[2]));      // v = F dir
     const float *F = env.from_world;
     return V3f(F[0] * vb[0] + F[3] * vb[1] + F[6] * vb[2], F[1] * vb[0] + F[4] * vb[1] + F[7] * vb[2], F[2] * vb[0] + F[5] * vb[1] + F[8] * vb[2]);
 }
