@@ -976,26 +976,48 @@ struct NoSecAdjoint {
     __device__ __forceinline__ void tail(const DScene &, const DCamera &, int, V3f, V3f, int, float, V3d, int, const Its<Dual> &, V3f, V2f) const {}
 };
 
-template <int kCfg, class Adj>
-__device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out,
-                                                   const Adj &adj) {
-    value0_out = V3f(0.f, 0.f, 0.f);
-    tangent_out = V3f(0.f, 0.f, 0.f);
-    // -- sample_boundary_segment_direct
-    float sample1 = sample3.x, pdf0;
-    const int ei = sample_reuse(sc.sec_pmf, sc.sec_cmf, sc.n_sec_edges, sc.sec_sum, sample1, pdf0);
+// The estimator runs in two stages so that a kernel can batch the survivors of the first one: stage 0 (edge and
+// light-point sample, the orientation test: no ray) passes ~30 % of the samples, stage 1 (three closest-hit scans)
+// is where the time goes.  A candidate carries what stage 1 cannot recompute from (edge, position on it).
+struct SecCand {
+    int ei;              // secondary edge
+    float sample1;       // position on it (re-stretched first sample)
+    V3f p2, bn;          // sampled light point and its normal
+    float bss_pdf;
+};
+struct SecEdgeGeo {      // the sampled boundary point with its tangent, and the edge frame
+    V3d bp0;
+    V3f edge, edge2;
+};
+__device__ __forceinline__ SecEdgeGeo sec_edge_geo(const DScene &sc, int ei, float sample1, V3f &n0, V3f &n1, bool &is_boundary, float &e1_norm) {
     const float4 q0 = __ldg(sc.sec_edges + 6 * ei), q1 = __ldg(sc.sec_edges + 6 * ei + 1), q2 = __ldg(sc.sec_edges + 6 * ei + 2),
                  q3 = __ldg(sc.sec_edges + 6 * ei + 3), q4 = __ldg(sc.sec_edges + 6 * ei + 4), q5 = __ldg(sc.sec_edges + 6 * ei + 5);
     const V3d ep0(Dual(q0.x, q1.z), Dual(q0.y, q1.w), Dual(q0.z, q2.x));
     const V3d ee1(Dual(q0.w, q2.y), Dual(q1.x, q2.z), Dual(q1.y, q2.w));
-    const V3f n0(q3.x, q3.y, q3.z), n1(q3.w, q4.x, q4.y), ep2(q4.z, q4.w, q5.x);
-    const bool is_boundary = q5.y != 0.f;
-    const V3d bp0(fmadd(ee1.x, sample1, ep0.x), fmadd(ee1.y, sample1, ep0.y), fmadd(ee1.z, sample1, ep0.z));
+    n0 = V3f(q3.x, q3.y, q3.z);
+    n1 = V3f(q3.w, q4.x, q4.y);
+    const V3f ep2(q4.z, q4.w, q5.x);
+    is_boundary = q5.y != 0.f;
+    SecEdgeGeo g;
+    g.bp0 = V3d(fmadd(ee1.x, sample1, ep0.x), fmadd(ee1.y, sample1, ep0.y), fmadd(ee1.z, sample1, ep0.z));
     const V3f e1v = val(ee1);
-    const V3f edge = normalize(e1v);
-    const V3f edge2 = ep2 - val(ep0);
-    const V3f _p0 = val(bp0);
-    pdf0 /= norm(e1v);
+    g.edge = normalize(e1v);
+    g.edge2 = ep2 - val(ep0);
+    e1_norm = norm(e1v);
+    return g;
+}
+
+// -- sample_boundary_segment_direct
+template <int kCfg>
+__device__ __forceinline__ bool sec_edge_stage0(const DScene &sc, V3f sample3, SecCand &c) {
+    float sample1 = sample3.x, pdf0;
+    const int ei = sample_reuse(sc.sec_pmf, sc.sec_cmf, sc.n_sec_edges, sc.sec_sum, sample1, pdf0);
+    V3f n0, n1;
+    bool is_boundary;
+    float e1_norm;
+    const SecEdgeGeo g = sec_edge_geo(sc, ei, sample1, n0, n1, is_boundary, e1_norm);
+    const V3f _p0 = val(g.bp0);
+    pdf0 /= e1_norm;
     const PosSample<float> ps2 = sample_emitter_position<float, kCfg>(sc, _p0, V2f(sample3.y, sample3.z));
     const V3f _p2 = ps2.p, bn = ps2.n;
     V3f e = _p2 - _p0;
@@ -1003,10 +1025,31 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     e = e / safe_sqrt(distSqr);
     const float cosTheta = dot(bn, -e);
     const int sgn0 = sign_eps(dot(n0, e), kEdgeEpsilon), sgn1 = sign_eps(dot(n1, e), kEdgeEpsilon);
-    bool valid = (cosTheta > kEpsilon) && ((is_boundary && sgn0 != 0) || (!is_boundary && sgn0 * sgn1 < 0));
-    if (!valid) return -1;
-    const float bss_pdf = pdf0 * ps2.pdf * (distSqr / cosTheta);
-    // -- eval_secondary_edge
+    const bool valid = (cosTheta > kEpsilon) && ((is_boundary && sgn0 != 0) || (!is_boundary && sgn0 * sgn1 < 0));
+    c.ei = ei;
+    c.sample1 = sample1;
+    c.p2 = _p2;
+    c.bn = bn;
+    c.bss_pdf = pdf0 * ps2.pdf * (distSqr / cosTheta);
+    return valid;
+}
+
+// -- eval_secondary_edge
+template <int kCfg, class Adj>
+__device__ __forceinline__ int sec_edge_stage1(const DScene &sc, const DCamera &cam, const SecCand &c, V3f &value0_out, V3f &tangent_out,
+                                               const Adj &adj) {
+    value0_out = V3f(0.f, 0.f, 0.f);
+    tangent_out = V3f(0.f, 0.f, 0.f);
+    const int ei = c.ei;
+    const float sample1 = c.sample1;
+    V3f n0_, n1_;
+    bool is_boundary_;
+    float e1_norm_;
+    const SecEdgeGeo g = sec_edge_geo(sc, ei, sample1, n0_, n1_, is_boundary_, e1_norm_);
+    const V3d bp0 = g.bp0;
+    const V3f edge = g.edge, edge2 = g.edge2, _p0 = val(g.bp0), _p2 = c.p2, bn = c.bn;
+    const float bss_pdf = c.bss_pdf;
+    bool valid = true;
     const V3f _dir = normalize(_p2 - _p0);
     int light_tri = -1;
     const Its<float> _its2 = ray_intersect<float, kCfg>(sc, _p0, _dir, valid, false, &light_tri);
@@ -1055,6 +1098,16 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
     tangent_out = V3f(value0.x * dn.d, value0.y * dn.d, value0.z * dn.d);
     return sds.pixel;
 }
+// both stages back to back (guiding pre-pass: one thread per grid cell)
+template <int kCfg, class Adj>
+__device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out,
+                                                   const Adj &adj) {
+    value0_out = V3f(0.f, 0.f, 0.f);
+    tangent_out = V3f(0.f, 0.f, 0.f);
+    SecCand c;
+    if (!sec_edge_stage0<kCfg>(sc, sample3, c)) return -1;
+    return sec_edge_stage1<kCfg, Adj>(sc, cam, c, value0_out, tangent_out, adj);
+}
 
 // HyperCubeDistribution<3>::sample_reuse (reference src/core/cube_distrb.cpp:41-48): the cell is picked with the
 // LAST sample dimension; the sample becomes (cell + sample) * unit; returns pdf = pmf * num_cells
@@ -1073,6 +1126,54 @@ __device__ __forceinline__ float guide_sample_reuse(const DCamera &cam, V3f &s) 
 template <int kCfg>
 __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCamera &cam, V3f sample3, V3f &value0_out, V3f &tangent_out) {
     return eval_secondary_edge<kCfg, NoSecAdjoint>(sc, cam, sample3, value0_out, tangent_out, NoSecAdjoint());
+}
+
+// ---- batches of stage-0 survivors (used by the forward and the adjoint secondary-edge kernels; see kernels_impl.cuh)
+constexpr int kSecFillRounds = 8;
+struct SecSample {      // what the fill loop hands to stage 1
+    SecCand cand;
+    float pdf0;         // guiding pdf (1 without guiding)
+};
+template <int kCfg>
+__device__ __forceinline__ bool sec_edge_draw(const DScene &sc, const DCamera &cam, const RenderParams &rp, long long j, SecSample &out) {
+    const long long i = rp.lane_begin + j;
+    Pcg32 rng;
+    rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+    if (rp.skip) rng.advance(rp.skip);
+    const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
+    V3f sample3(d3, d2, d1);
+    out.pdf0 = 1.f;
+    if (cam.guided) out.pdf0 = guide_sample_reuse(cam, sample3);     // path.cpp:279-281
+    return sec_edge_stage0<kCfg>(sc, sample3, out.cand);
+}
+// warp-uniform batch loop; `body(sample)` is called by the lanes that hold a candidate
+template <int kCfg, class F>
+__device__ __forceinline__ void sec_edge_batches(const DScene &sc, const DCamera &cam, const RenderParams &rp, int block, F body) {
+    const long long span = rp.lane_end - rp.lane_begin;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long n_warps = (long long) gridDim.x * (block / 32), warp = (long long) blockIdx.x * (block / 32) + (threadIdx.x >> 5);
+    const long long per = ((span + n_warps - 1) / n_warps + 31) / 32 * 32;      // slice of this warp
+    long long next = warp * per;
+    const long long end = next + per < span ? next + per : span;
+    while (true) {
+        __syncwarp();
+        bool have = false;
+        SecSample smp;
+        for (int round = 0; round < kSecFillRounds; ++round) {
+            const unsigned need = __ballot_sync(0xffffffffu, !have);
+            if (need == 0u || next >= end) break;
+            if (!have) {
+                const long long j = next + __popc(need & ((1u << lane) - 1u));
+                if (j < end) have = sec_edge_draw<kCfg>(sc, cam, rp, j, smp);
+            }
+            next += __popc(need);
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (next >= end) break;
+            continue;
+        }
+        if (have) body(smp);
+    }
 }
 
 }  // namespace psdr

@@ -128,29 +128,13 @@ __global__ void __launch_bounds__(kBlockV, 6) secondary_edge_vjp_kernel(const __
     adj.gl = gl;
     adj.d_img = d_img;
     adj.scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
-    const long long stride = (long long) gridDim.x * kBlockV;
-    // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
-    // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
-    // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
-    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
-    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
-        __syncwarp();
-        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
-        if (j >= span) continue;
-        const long long i = rp.lane_begin + j;
-        Pcg32 rng;
-        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
-        if (rp.skip) rng.advance(rp.skip);
-        const float d1 = rng.next_1d(), d2 = rng.next_1d(), d3 = rng.next_1d();
-        V3f sample3(d3, d2, d1);
+    // batches of stage-0 survivors, as in the forward kernel (kernels_impl.cuh sec_edge_batches)
+    sec_edge_batches<kCfg>(sc, cam, rp, kBlockV, [&](const SecSample &smp) {
         SecEdgeAdjoint a2 = adj;
-        if (cam.guided) {
-            const float pdf0 = guide_sample_reuse(cam, sample3);
-            if (pdf0 > kEpsilon) a2.scale = adj.scale / pdf0;
-        }
+        if (cam.guided && smp.pdf0 > kEpsilon) a2.scale = adj.scale / smp.pdf0;
         V3f value0, tangent;
-        eval_secondary_edge<kCfg, SecEdgeAdjoint>(sc, cam, sample3, value0, tangent, a2);
-    }
+        sec_edge_stage1<kCfg, SecEdgeAdjoint>(sc, cam, smp.cand, value0, tangent, a2);
+    });
     grad_acc_end(adj.acc);
 }
 
