@@ -1129,7 +1129,10 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
 }
 
 // ---- batches of stage-0 survivors (used by the forward and the adjoint secondary-edge kernels; see kernels_impl.cuh)
-constexpr int kSecFillRounds = 8;
+#ifndef PSDR_SEC_FILL_ROUNDS
+#define PSDR_SEC_FILL_ROUNDS 4
+#endif
+constexpr int kSecFillRounds = PSDR_SEC_FILL_ROUNDS;   // cap on the fill loop (tools/gpu_lb_sweep.sh)
 struct SecSample {      // what the fill loop hands to stage 1
     SecCand cand;
     float pdf0;         // guiding pdf (1 without guiding)
