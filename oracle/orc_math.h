@@ -39,9 +39,10 @@ inline Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
 inline Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
 inline Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
 inline Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+// tangent * (1 / denominator): same spelling as psdr_jit_b200/csrc/pmath.h (see the note there)
 inline Dual operator/(Dual a, Dual b) {
     float q = a.v / b.v;
-    return Dual(q, (a.d - q * b.d) / b.v);
+    return Dual(q, (a.d - q * b.d) * (1.f / b.v));
 }
 inline Dual &operator+=(Dual &a, Dual b) { a = a + b; return a; }
 inline Dual &operator-=(Dual &a, Dual b) { a = a - b; return a; }
@@ -53,13 +54,13 @@ inline Dual operator-(Dual a, float b) { return Dual(a.v - b, a.d); }
 inline Dual operator-(float a, Dual b) { return Dual(a - b.v, -b.d); }
 inline Dual operator*(Dual a, float b) { return Dual(a.v * b, a.d * b); }
 inline Dual operator*(float a, Dual b) { return Dual(a * b.v, a * b.d); }
-inline Dual operator/(Dual a, float b) { return Dual(a.v / b, a.d / b); }
+inline Dual operator/(Dual a, float b) { return Dual(a.v / b, a.d * (1.f / b)); }
 inline Dual operator/(float a, Dual b) { return Dual(a) / b; }
 
 inline float sqrt_(float x) { return std::sqrt(x); }
 inline Dual sqrt_(Dual x) {
     float s = std::sqrt(x.v);
-    return Dual(s, x.d / (2.f * s));
+    return Dual(s, x.d * (1.f / (2.f * s)));
 }
 // drjit safe_sqrt (ext/drjit/include/drjit/array_router.h:1987): sqrt(max(a,0)); the
 // derivative is taken at max(a, eps).
@@ -67,7 +68,7 @@ inline float safe_sqrt(float x) { return std::sqrt(std::fmax(x, 0.f)); }
 inline Dual safe_sqrt(Dual x) {
     float s = std::sqrt(std::fmax(x.v, 0.f));
     float sg = std::sqrt(std::fmax(x.v, std::numeric_limits<float>::epsilon()));
-    return Dual(s, x.d / (2.f * sg));
+    return Dual(s, x.d * (1.f / (2.f * sg)));
 }
 inline float abs_(float x) { return std::fabs(x); }
 inline Dual abs_(Dual x) { return Dual(std::fabs(x.v), std::signbit(x.v) ? -x.d : x.d); }

@@ -42,9 +42,12 @@ PSDR_HD Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
 PSDR_HD Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
 PSDR_HD Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
 PSDR_HD Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+// The tangent is multiplied by the reciprocal of the denominator instead of divided: tangents are exactly 0 for
+// everything the derivative parameter does not move, and div.rn.f32 with a zero numerator takes its out-of-line
+// slow path (FCHK) every time; 1 / (a normal number) never does.  The oracle spells it identically.
 PSDR_HD Dual operator/(Dual a, Dual b) {
     float q = a.v / b.v;
-    return Dual(q, (a.d - q * b.d) / b.v);
+    return Dual(q, (a.d - q * b.d) * (1.f / b.v));
 }
 PSDR_HD Dual operator+(Dual a, float b) { return Dual(a.v + b, a.d); }
 PSDR_HD Dual operator+(float a, Dual b) { return Dual(a + b.v, b.d); }
@@ -52,7 +55,7 @@ PSDR_HD Dual operator-(Dual a, float b) { return Dual(a.v - b, a.d); }
 PSDR_HD Dual operator-(float a, Dual b) { return Dual(a - b.v, -b.d); }
 PSDR_HD Dual operator*(Dual a, float b) { return Dual(a.v * b, a.d * b); }
 PSDR_HD Dual operator*(float a, Dual b) { return Dual(a * b.v, a * b.d); }
-PSDR_HD Dual operator/(Dual a, float b) { return Dual(a.v / b, a.d / b); }
+PSDR_HD Dual operator/(Dual a, float b) { return Dual(a.v / b, a.d * (1.f / b)); }
 PSDR_HD Dual operator/(float a, Dual b) { return Dual(a) / b; }
 PSDR_HD Dual &operator+=(Dual &a, Dual b) { a = a + b; return a; }
 PSDR_HD Dual &operator*=(Dual &a, Dual b) { a = a * b; return a; }
@@ -60,14 +63,14 @@ PSDR_HD Dual &operator*=(Dual &a, Dual b) { a = a * b; return a; }
 PSDR_HD float sqrt_(float x) { return sqrtf(x); }
 PSDR_HD Dual sqrt_(Dual x) {
     float s = sqrtf(x.v);
-    return Dual(s, x.d / (2.f * s));
+    return Dual(s, x.d * (1.f / (2.f * s)));
 }
 // drjit safe_sqrt: sqrt(max(a,0)), derivative taken at max(a, eps)
 PSDR_HD float safe_sqrt(float x) { return sqrtf(fmaxf(x, 0.f)); }
 PSDR_HD Dual safe_sqrt(Dual x) {
     float s = sqrtf(fmaxf(x.v, 0.f));
     float sg = sqrtf(fmaxf(x.v, kFltEps));
-    return Dual(s, x.d / (2.f * sg));
+    return Dual(s, x.d * (1.f / (2.f * sg)));
 }
 PSDR_HD bool signbit_(float x) {      // std::signbit (the sign bit itself: -0.f counts as negative)
 #if defined(__CUDA_ARCH__)
