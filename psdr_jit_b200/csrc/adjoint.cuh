@@ -461,8 +461,10 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
     bsdf_param_grad<kCfg>(acc, gl, x.bsdf, b, ci, co, cio, W, G * scale, x.uv, xa.uv);
     const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
-    const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) / (t * t);
-    const float t_bar = G_bar * (-2.f * fabsf(cy) / (t * t * t));
+    // adjoints are often exactly 0 (W = 0): multiply by reciprocals, a zero numerator sends div.rn.f32 down its slow path
+    const float inv_t = 1.f / t, inv_t2 = 1.f / (t * t);
+    const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) * inv_t2;
+    const float t_bar = G_bar * (-2.f * fabsf(cy) * (inv_t2 * inv_t));
     V3f wo_bar = ny * (-cy_bar) + x.shn * co_bar + wi * cio_bar;
     wo_bar = wo_bar + wo_extra(wo, j.f * (G * scale));
     r.ny = wo * (-cy_bar);
@@ -471,7 +473,7 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const V3f vec_bar = unit_adj(wo, t, wo_bar, t_bar);
     r.py = vec_bar;
     xa.p = xa.p - vec_bar;
-    r.area_y = area_y > 0.f ? J_bar / area_y : 0.f;
+    r.area_y = area_y > 0.f ? J_bar * (1.f / area_y) : 0.f;
     return r;
 }
 
