@@ -141,6 +141,29 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert np.array_equal(out, g["draws_seed7"])
 
 
+def test_library_staleness_is_decided_by_content_not_by_file_times():
+    """The built library travels to other machines by copy (file times do not survive): build.is_stale() compares a
+    hash of the sources with the stamp written next to the library."""
+    from psdr_jit_b200 import build
+    build.build_native()
+    assert os.path.exists(build.STAMP) and not build.is_stale()
+    src = os.path.join(build.CSRC, build.SOURCES[0])
+    st = os.stat(src)
+    try:
+        os.utime(src, None)                     # newer than the library: still not stale
+        assert not build.is_stale()
+        with open(build.STAMP) as fh:
+            good = fh.read()
+        with open(build.STAMP, "w") as fh:
+            fh.write("0" * 64 + "\n")
+        assert build.is_stale()
+        with open(build.STAMP, "w") as fh:
+            fh.write(good)
+        assert not build.is_stale()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+
+
 def test_product_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under psdr_jit_b200/ may reference it."""
     pkg = os.path.join(ROOT, "psdr_jit_b200")
