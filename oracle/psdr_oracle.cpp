@@ -210,6 +210,8 @@ struct Scene {
     std::vector<Tri<Dual>> tris;
     std::vector<int> tri_mesh;
     std::vector<V2f> tri_uv;  // 3 per triangle
+    // per triangle PAIR (2j, 2j+1): padded bounding box, centre / half extent (scenes of <= 64 triangles; see trace())
+    std::vector<float> cull_c, cull_h;
     std::vector<SecEdge> sec_edges;
     Distrib sec_edge_distrb, emitter_distrb;
     bool configured = false;
@@ -217,6 +219,58 @@ struct Scene {
     // options
     bool li_p_first = true;  // evaluation order of Li(ray_n) - Li(ray_p), integrator.cpp:185-186
 };
+
+// The product's closest-hit query (psdr_jit_b200/csrc/device_path.cuh trace<brute>, the replacement of OptiX) tests a
+// triangle pair only if the ray passes the pair's padded bounding box; that slab test is part of the DEFINITION of the
+// closest hit in scenes of <= 64 triangles, so it is restated here operation by operation (boxes: device_upload.cu).
+static void build_cull_boxes(Scene &sc) {
+    sc.cull_c.clear();
+    sc.cull_h.clear();
+    const int ntris = (int) sc.tris.size();
+    if (ntris > 64) return;
+    const int npairs = (ntris + 1) / 2;
+    std::vector<float> blo((size_t) 3 * npairs, 1e30f), bhi((size_t) 3 * npairs, -1e30f);
+    float slo[3] = {1e30f, 1e30f, 1e30f}, shi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int i = 0; i < ntris; ++i) {
+        const V3f p0 = val(sc.tris[i].p0), e1 = val(sc.tris[i].e1), e2 = val(sc.tris[i].e2);
+        const float P[3] = {p0.x, p0.y, p0.z}, A[3] = {e1.x, e1.y, e1.z}, B[3] = {e2.x, e2.y, e2.z};
+        for (int k = 0; k < 3; ++k) {
+            const float v[3] = {P[k], P[k] + A[k], P[k] + B[k]};
+            for (float x : v) {
+                blo[3 * (i >> 1) + k] = std::fmin(blo[3 * (i >> 1) + k], x);
+                bhi[3 * (i >> 1) + k] = std::fmax(bhi[3 * (i >> 1) + k], x);
+                slo[k] = std::fmin(slo[k], x);
+                shi[k] = std::fmax(shi[k], x);
+            }
+        }
+    }
+    float ext = 0.f;
+    for (int k = 0; k < 3; ++k) ext = std::fmax(ext, shi[k] - slo[k]);
+    const float pad_fat = 2.5e-4f * ext, pad_flat = 2.5e-7f * ext, flat_below = 1e-5f * ext;
+    sc.cull_c.resize((size_t) 3 * npairs);
+    sc.cull_h.resize((size_t) 3 * npairs);
+    for (int j = 0; j < npairs; ++j)
+        for (int k = 0; k < 3; ++k) {
+            const float lo = blo[3 * j + k], hi = bhi[3 * j + k];
+            const float half = 0.5f * (hi - lo);
+            sc.cull_c[3 * j + k] = 0.5f * (lo + hi);
+            sc.cull_h[3 * j + k] = half + (half < flat_below ? pad_flat : pad_fat);
+        }
+}
+static bool cull_box_hit(const Scene &sc, int pair, V3f o, V3f d) {
+    const float O[3] = {o.x, o.y, o.z}, D[3] = {d.x, d.y, d.z};
+    float mn[3], fr[3];
+    for (int k = 0; k < 3; ++k) {
+        const float inv = 1.f / D[k];
+        const float dx = sc.cull_c[3 * pair + k] - O[k];
+        const float th = sc.cull_h[3 * pair + k] * std::fabs(inv);
+        fr[k] = std::fmaf(dx, inv, th);
+        mn[k] = std::fmaf(dx, -inv, th);       // = -(near)
+    }
+    const float tn = -std::fmin(std::fmin(std::fmin(mn[0], mn[1]), mn[2]), -kRayEpsilon);   // fmin / fmax drop NaNs
+    const float tf = std::fmin(std::fmin(fr[0], fr[1]), fr[2]);
+    return tn <= tf;
+}
 
 // reference src/shape/mesh.cpp:23-62
 static void process_mesh(const std::vector<V3d> &vp, const std::vector<int> &f, std::vector<Tri<Dual>> &out) {
@@ -529,6 +583,7 @@ static bool configure_scene(Scene &sc, const int *active, int nactive) {
             for (int k = 0; k < 3; ++k) sc.tri_uv.push_back(m.has_uv ? m.uv[m.fuv[3 * i + k]] : V2f(0.f, 0.f));
         }
     }
+    build_cull_boxes(sc);
     // secondary edges (scene.cpp:547-571, mesh.cpp:353-369)
     sc.sec_edges.clear();
     if (sc.sppse > 0) {
@@ -575,7 +630,11 @@ static Hit trace(const Scene &sc, V3f o, V3f d) {
         return best;
     float b_ts = 1e8f, b_adet = 1.f, b_tn = 0.f, b_det = 0.f, b_un = 0.f, b_vn = 0.f;
     int b_tri = -1;
+    const bool cull = !sc.cull_c.empty();
+    bool pair_ok = true;
     for (size_t i = 0; i < sc.tris.size(); ++i) {
+        if (cull && (i & 1) == 0) pair_ok = cull_box_hit(sc, (int) (i >> 1), o, d);
+        if (!pair_ok) continue;
         const Tri<Dual> &T = sc.tris[i];
         V3f e1 = val(T.e1), e2 = val(T.e2), p0 = val(T.p0);
         V3f h = cross_fms(d, e2);

@@ -3,6 +3,7 @@
 // 5k-triangle mesh), refreshed by a single cudaMemcpyAsync per configure() from pinned staging.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -246,9 +247,44 @@ void upload_scene(Scene &sc) {
         for (int i = 0; i < ntris; ++i) {
             const float4 a = geo[3 * i], b = geo[3 * i + 1];
             const float c = geo[3 * i + 2].x;
-            const float comp[kBrutePairWords] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c, -a.w, -b.x, -b.y};
+            const float comp[kBrutePairWords] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c};
             for (int k = 0; k < kBrutePairWords; ++k) w[2 * (kBrutePairWords * (i >> 1) + k) + (i & 1)] = comp[k];
         }
+        // Cull boxes, one per pair.  Part of the closest-hit DEFINITION (the oracle builds the same boxes with the
+        // same fp32 operations): vertices are p0, p0+e1, p0+e2 of the stored records; the box is padded on every
+        // axis so that any hit Moeller-Trumbore accepts lies inside it -- by 2.5e-4 of the scene extent on axes where
+        // the pair has thickness (fp32 noise of the barycentric test moves accepted hits sideways by far less), by
+        // 2.5e-7 of it on an axis where the pair is flat (the hit lies on the pair's plane by construction; the small
+        // pad keeps rays that leave a flat quad from testing that quad again unless they graze it).
+        const int npairs = (ntris + 1) / 2;
+        float slo[3] = {1e30f, 1e30f, 1e30f}, shi[3] = {-1e30f, -1e30f, -1e30f};
+        std::vector<float> blo((size_t) 3 * npairs, 1e30f), bhi((size_t) 3 * npairs, -1e30f);
+        for (int i = 0; i < ntris; ++i) {
+            const float4 a = geo[3 * i], b = geo[3 * i + 1];
+            const float c = geo[3 * i + 2].x;
+            const float p0[3] = {a.x, a.y, a.z}, e1[3] = {a.w, b.x, b.y}, e2[3] = {b.z, b.w, c};
+            for (int k = 0; k < 3; ++k) {
+                const float v[3] = {p0[k], p0[k] + e1[k], p0[k] + e2[k]};
+                for (float x : v) {
+                    blo[3 * (i >> 1) + k] = std::fmin(blo[3 * (i >> 1) + k], x);
+                    bhi[3 * (i >> 1) + k] = std::fmax(bhi[3 * (i >> 1) + k], x);
+                    slo[k] = std::fmin(slo[k], x);
+                    shi[k] = std::fmax(shi[k], x);
+                }
+            }
+        }
+        float ext = 0.f;
+        for (int k = 0; k < 3; ++k) ext = std::fmax(ext, shi[k] - slo[k]);
+        const float pad_fat = 2.5e-4f * ext, pad_flat = 2.5e-7f * ext, flat_below = 1e-5f * ext;
+        float *bw = reinterpret_cast<float *>(d.bg_box);
+        std::memset(d.bg_box, 0, sizeof(d.bg_box));
+        for (int j = 0; j < npairs; ++j)
+            for (int k = 0; k < 3; ++k) {
+                const float lo = blo[3 * j + k], hi = bhi[3 * j + k];
+                const float half = 0.5f * (hi - lo);
+                bw[2 * (kBruteBoxWords * (j >> 1) + k) + (j & 1)] = 0.5f * (lo + hi);
+                bw[2 * (kBruteBoxWords * (j >> 1) + 3 + k) + (j & 1)] = half + (half < flat_below ? pad_flat : pad_fat);
+            }
     }
 
     d.env = DEnv{};

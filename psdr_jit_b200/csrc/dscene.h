@@ -14,7 +14,10 @@ namespace psdr {
 // dgeo/dshade: the forward-mode tangents in the same layout (dgeo[3i+2].z/.w unused).
 // uv[3i+k] = texture coordinate of corner k (zeros for meshes without UVs)
 constexpr int kMaxBruteTris = 64;
-constexpr int kBrutePairWords = 12;   // 64-bit words per triangle pair in DScene::bg_pair
+constexpr int kBrutePairWords = 9;    // 64-bit words per triangle pair in DScene::bg_pair
+constexpr int kBruteSmemStride = 5;   // 16-byte units per pair in the kernels' shared-memory copy (9 words + 1 pad:
+                                      // an odd unit stride keeps the 8 lanes of a 128-bit load phase on distinct banks)
+constexpr int kBruteBoxWords = 6;     // 64-bit words per PAIR of cull boxes in DScene::bg_box
 
 struct DBvhNode {        // 32 B
     float lo[3];
@@ -116,11 +119,15 @@ struct DScene {
     const int *tri_order;
     DEnv env;
     // brute-force mode (n_tris <= kMaxBruteTris): the triangle geometry again, by value -- it travels in
-    // the kernel parameters and is read through the constant bank (LDC.64), two triangles at a time: entry
-    // [12 j + c] holds component c of triangles (2j, 2j+1) as the two halves of one 64-bit word, c = p0.xyz,
-    // e1.xyz, e2.xyz, -e1.xyz, the operand layout of the packed fp32x2 closest-hit scan (device_path.cuh).
+    // the kernel parameters, two triangles at a time: entry [9 j + c] holds component c of triangles (2j, 2j+1)
+    // as the two halves of one 64-bit word, c = p0.xyz, e1.xyz, e2.xyz, the operand layout of the packed fp32x2
+    // closest-hit test (device_path.cuh); every CTA copies it to shared memory once (brute_init).
     // An odd count is padded with an all-zero triangle (det = 0: never accepted).
     unsigned long long bg_pair[kMaxBruteTris / 2 * kBrutePairWords];
+    // one padded bounding box per triangle pair, two boxes per 64-bit word (boxes 2k, 2k+1 in the low / high
+    // half): entry [6 k + c], c = centre.xyz, half-extent.xyz.  A ray tests a pair only if it passes that pair's
+    // slab test (trace<brute>, stage 1); read warp-uniformly through the constant bank.
+    unsigned long long bg_box[kMaxBruteTris / 4 * kBruteBoxWords];
 };
 
 struct RenderParams {

@@ -58,6 +58,7 @@ template <class S, int kCfg, bool kAD>
 __global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? PSDR_LB_INTERIOR_DUAL : PSDR_LB_INTERIOR)) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                            const __grid_constant__ RenderParams rp, float *__restrict__ img,
                                                            float *__restrict__ dimg) {
+    brute_init<kCfg>(sc, kBlock);
     const long long stride = (long long) gridDim.x * kBlock;
     const long long span = rp.lane_end - rp.lane_begin;
     const long long span_pad = (span + 31) / 32 * 32;   // keep warps converged for the shuffles
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? PSDR_LB_INTERIOR_D
 template <int kCfg>
 __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
+    brute_init<kCfg>(sc, kBlock);
     const long long stride = (long long) gridDim.x * kBlock;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
     // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(c
 template <int kCfg>
 __global__ void __launch_bounds__(kBlock, PSDR_LB_SECONDARY) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                  const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
+    brute_init<kCfg>(sc, kBlock);
     const float scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
     sec_edge_batches<kCfg>(sc, cam, rp, kBlock, [&](const SecSample &smp) {
         V3f value0, tangent;
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_SECONDARY) secondary_edge_kern
 template <int kCfg>
 __global__ void __launch_bounds__(kBlock) guiding_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, int r0, int r1, int r2,
                                                           int r3, int nrounds, long long seed, float *__restrict__ mass) {
+    brute_init<kCfg>(sc, kBlock);
     const int ncells = r0 * r1 * r2;
     for (int cell = blockIdx.x * kBlock + threadIdx.x; cell < ncells; cell += gridDim.x * kBlock) {
         const int c0 = cell / (r1 * r2), rem = cell - c0 * (r1 * r2), c1 = rem / r2, c2 = rem - c1 * r2;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(kBlock) guiding_kernel(const __grid_constant__
 template <int kCfg>
 __global__ void __launch_bounds__(kBlock) aov_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                       const __grid_constant__ RenderParams rp, float *__restrict__ out) {
+    brute_init<kCfg>(sc, kBlock);
     const long long stride = (long long) gridDim.x * kBlock;
     // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's

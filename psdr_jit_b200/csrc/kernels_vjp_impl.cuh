@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_c
                                                                 const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                 const float *__restrict__ d_img) {
     extern __shared__ float smem[];
+    brute_init<kCfg>(sc, kBlockV);
     const GradAcc acc = grad_acc_begin(gl, smem, 0, gl.off_pe, rp.smem_grad != 0, true);
     const long long stride = (long long) gridDim.x * kBlockV;
     const float inv_spp = (sc.spp > 1 ? 1.f / (float) sc.spp : 1.f) * rp.tangent_scale;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __gr
                                                                     const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                     const float *__restrict__ d_img) {
     extern __shared__ float smem[];
+    brute_init<kCfg>(sc, kBlockV);
     const GradAcc acc = grad_acc_begin(gl, smem, gl.off_pe, gl.off_se, rp.smem_grad != 0, false);
     const long long stride = (long long) gridDim.x * kBlockV;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(kBlockV, 6) secondary_edge_vjp_kernel(const __
                                                                       const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                       const float *__restrict__ d_img) {
     extern __shared__ float smem[];
+    brute_init<kCfg>(sc, kBlockV);
     SecEdgeAdjoint adj;
     adj.acc = grad_acc_begin(gl, smem, 0, gl.off_env, rp.smem_grad != 0, false);
     adj.gl = gl;
