@@ -168,11 +168,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     st = torch.cuda.current_stream()
 
     def step(seed):
-        img, dimg = integ.renderD_fwd(sc, 0, seed=seed)
+        img, dimg = integ.renderD_fwd(sc, 0, seed=seed)       # views of ONE [2, npix, 3] buffer
         if world > 1:
-            buf = torch.stack((img, dimg))
-            dist.all_reduce(buf)
-            img, dimg = buf[0], buf[1]
+            dist.all_reduce(integ.last_buffer)                # in place: image + derivative image in one message
         return img, dimg
 
     step(0)                                                    # seed = 0 once, then the streams continue (seed = -1)
@@ -214,6 +212,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         def vjp_step(seed):
             img = integ.renderD_primal(sc, 0, seed=seed)
+            if world > 1:
+                dist.all_reduce(img)                         # the loss needs the full image on every rank
             integ.render_vjp(sc, cot, 0, seed=seed)          # synchronises: gradients come back on the host
             return img
 
@@ -239,7 +239,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         vjp = {"value": round(n_samples * args.steps / (vms * 1e-3) / 1e6, 3), "unit": "Msamples/s", "ms_per_step": round(vms / args.steps, 4),
                "kernel_ms": {"interior_adjoint": round(sum(vk[1]) / len(vk[1]), 4), "primary_edges_adjoint": round(sum(vk[2]) / len(vk[2]), 4),
                              "secondary_edges_adjoint": round(sum(vk[4]) / len(vk[4]), 4)},
-               "step": "renderD primal image + psdr_render_vjp (adjoint kernels, D2H of the gradient table, host chain to all parameters)"}
+               "step": "renderD primal image + adjoint kernels + " + ("ONE NCCL all-reduce of the flat device gradient table + " if world > 1 else "") +
+                       "D2H of the table + host chain to all parameters"}
 
     # ---- end to end through the host-buffer C ABI: parameter update + configure + render + D2H
     himg = np.empty((W * H, 3), dtype=np.float32)
@@ -257,12 +258,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         mesh0.set_transform(np.eye(4, dtype=np.float32), tangent=tangent)
         sc.configure([0])
         if world > 1:
-            # N ranks: each renders its lane shard on the device, ONE NCCL all-reduce sums the partial images
-            # (psdr_jit_b200.dist.all_reduce_images), one D2H into pinned host memory
-            img, dimg = integ.renderD_fwd(sc, 0, seed=seed)
-            img, dimg = psdr_dist.all_reduce_images(img, dimg)
-            pinned[0].copy_(img, non_blocking=True)
-            pinned[1].copy_(dimg, non_blocking=True)
+            # N ranks: each renders its lane shard on the device, ONE NCCL reduce sums the partial images on rank 0
+            # (psdr_jit_b200.dist.all_reduce_images), one D2H into pinned host memory there
+            integ.renderD_fwd(sc, 0, seed=seed)
+            psdr_dist.all_reduce_images(integ.last_buffer, dst=0)      # the result is needed on the host of rank 0 only
+            if rank == 0:
+                pinned.copy_(integ.last_buffer, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return float(pinned[0, 0, 0])
         integ.renderD_host(sc, 0, seed=seed, out=himg, dout=hdimg)
@@ -313,7 +314,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": round(n_samples * args.steps / e2e_s / 1e6, 3), "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
                     "path": ("set_transform + Scene.configure + psdr_render_d_host (pinned host image buffers)" if world == 1 else
-                             "set_transform + Scene.configure + renderD_fwd on each rank's lane shard + one NCCL all-reduce + D2H into pinned host memory")},
+                             "set_transform + Scene.configure + renderD_fwd on each rank's lane shard + one NCCL reduce to rank 0 + one D2H into pinned host memory there")},
             "gpu_launches": int(launches),
             "kernel_ms": {"interior": round(means[1], 4), "primary_edges": round(means[2], 4), "secondary_edges": round(means[4], 4)},
             "roofline": {"bound": "hbm", "kernel": {1: "interior_kernel<Dual>", 2: "primary_edge_kernel", 4: "secondary_edge_kernel"}[dom],

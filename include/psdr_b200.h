@@ -73,8 +73,10 @@ void psdr_scene_destroy(psdr_scene *s);
 int psdr_scene_set_options(psdr_scene *s, int width, int height, int spp, int sppe, int sppse, int log_level);
 /* Scene.seed -- src/psdr.cpp:411 (used by configure() when it seeds the samplers) */
 int psdr_scene_set_seed(psdr_scene *s, long long seed);
-/* New (the reference is single-GPU): this process renders lanes [rank/world, (rank+1)/world) of
- * every term into a full-frame buffer; the caller sums the buffers over ranks (NCCL all-reduce). */
+/* New (the reference is single-GPU): the lanes of every term are dealt to the ranks round-robin in blocks of
+ * 32; this process renders blocks rank, rank + world, ... into a full-frame buffer and the caller sums the
+ * buffers over ranks (one NCCL all-reduce).  In reverse mode the caller sums the gradient TABLES
+ * (psdr_render_vjp_device) over ranks before psdr_scene_backprop_table. */
 int psdr_scene_set_shard(psdr_scene *s, int rank, int world);
 /* -1 = automatic (BVH2 above 64 triangles), 0 = brute force, 1 = BVH2 */
 int psdr_scene_set_accel(psdr_scene *s, int mode);
@@ -158,6 +160,15 @@ int psdr_render_d(psdr_scene *s, int sensor, int max_depth, long long seed, int 
  * psdr_render_d. */
 int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
                     const int *pix_id, int npix, const float *d_img, void *cuda_stream);
+/* The same in two halves, for multi-GPU runs ("one ncclAllReduce over the flat parameter-gradient
+ * buffer"): psdr_render_vjp_device launches the adjoint kernels into a CALLER-owned device table of
+ * psdr_grad_table_size(s, sensor) floats (zeroed by the call; asynchronous, no synchronisation); the caller
+ * all-reduces the table over ranks on the same stream; psdr_scene_backprop_table copies it to the host and runs
+ * the host reverse chain of configure() (drjit.backward through Scene::configure in the reference). */
+int psdr_grad_table_size(psdr_scene *s, int sensor);
+int psdr_render_vjp_device(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                           const int *pix_id, int npix, const float *d_img, float *grad_table, int n_table, void *cuda_stream);
+int psdr_scene_backprop_table(psdr_scene *s, int sensor, const float *grad_table, int n_table, void *cuda_stream);
 /* Gradient of parameter (kind, index) from the last psdr_render_vjp, same shapes as psdr_scene_set_param;
  * host buffer.  drjit.grad(param) in the reference. */
 int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n);

@@ -618,6 +618,39 @@ struct Hit {
     float u = 0.f, v = 0.f, t = 0.f;
 };
 
+// Decision margins of one path (tools/ref_parity.py: which lanes can flip against OptiX and why).  Every closest-hit
+// query and every shadow test of the path lowers the minimum of its class:
+//   [0] shadow: |t - (dist - ShadowEpsilon)| of an emitter hit by a next-event ray (path.cpp:58), world units
+//   [1] border: |min(u, v, 1-u-v)| of any triangle whose plane is crossed no farther than the winner (the ray passes
+//       that close, in barycentric units, to an edge where the closest triangle changes)
+//   [2] self:   |t - RayEpsilon| / RayEpsilon of a triangle pierced near the tmin threshold (self-intersection)
+//   [3] tie:    (t2 - t1) / t1 between the winner and the runner-up
+struct LaneDiag {
+    float m[4] = {1e30f, 1e30f, 1e30f, 1e30f};
+};
+static thread_local LaneDiag *g_diag = nullptr;
+
+static void trace_margins(const Scene &sc, V3f o, V3f d, int best_tri, float best_t) {
+    LaneDiag &D = *g_diag;
+    for (size_t i = 0; i < sc.tris.size(); ++i) {
+        const Tri<Dual> &T = sc.tris[i];
+        V3f e1 = val(T.e1), e2 = val(T.e2), p0 = val(T.p0);
+        V3f h = cross_fms(d, e2);
+        float det = dot(e1, h);
+        if (det == 0.f) continue;
+        V3f s = o - p0;
+        float f = 1.f / det;
+        float u = f * dot(s, h);
+        V3f q = cross_fms(s, e1);
+        float v = f * dot(d, q), t = f * dot(e2, q);
+        float m = std::fmin(std::fmin(u, v), 1.f - u - v);
+        bool no_farther = best_tri < 0 ? (t > 0.5f * kRayEpsilon) : (t > 0.5f * kRayEpsilon && t <= best_t * 1.001f);
+        if (no_farther) D.m[1] = std::fmin(D.m[1], std::fabs(m));
+        if (m > -1e-3f && t < 4.f * kRayEpsilon && t > -2.f * kRayEpsilon) D.m[2] = std::fmin(D.m[2], std::fabs(t - kRayEpsilon) / kRayEpsilon);
+        if (best_tri >= 0 && (int) i != best_tri && m >= 0.f && t > kRayEpsilon) D.m[3] = std::fmin(D.m[3], (t - best_t) / best_t);
+    }
+}
+
 // fp32 Moeller-Trumbore numerators with a FIXED operation order (cross = fused multiply-subtract, dot = fma
 // chain).  A candidate is accepted on the numerators alone: inside test on the sign-normalised numerators,
 // t in (RayEpsilon, 1e8) and "closer than the best so far" by cross-multiplication (t1 < t2 <=> tn1 |det2| <
@@ -652,12 +685,16 @@ static Hit trace(const Scene &sc, V3f o, V3f d) {
         if (!ok) continue;
         b_ts = ts; b_adet = adet; b_tn = tn; b_det = det; b_un = un; b_vn = vn; b_tri = (int) i;
     }
-    if (b_tri < 0) return best;
+    if (b_tri < 0) {
+        if (g_diag) trace_margins(sc, o, d, -1, 0.f);
+        return best;
+    }
     float f = 1.f / b_det;
     best.tri = b_tri;
     best.t = f * b_tn;
     best.u = f * b_un;
     best.v = f * b_vn;
+    if (g_diag) trace_margins(sc, o, d, best.tri, best.t);
     return best;
 }
 
@@ -1134,6 +1171,8 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
             wod = wod / dist;
             Its<S> its1 = ray_intersect<S>(sc, its.p, wod, active_direct, ad);
             active_direct = active_direct && its1.valid;
+            if (g_diag && active_direct && is_emitter(sc, its1))
+                g_diag->m[0] = std::fmin(g_diag->m[0], std::fabs(val(its1.t) - (val(dist) - kShadowEpsilon)));
             active_direct = active_direct && (val(its1.t) > val(dist) - kShadowEpsilon) && is_emitter(sc, its1);
             S cos_val = dot(its1.n, -wod);
             S G_val = abs_(cos_val) / dist_sqr;
@@ -1196,13 +1235,15 @@ static void splat(float *img, int pix, int c, float v) {
 // reference src/integrator/integrator.cpp:104-136 (renderC: ad=false; renderD: ad=true)
 template <class S>
 static void render_interior(const Scene &sc, const RenderArgs &ra, float *img, float *dimg, const int *pix_id, int npix_sel,
-                            float *lane_out) {
+                            float *lane_out, float *diag_out = nullptr) {
     const Camera &cam = sc.cameras[ra.sensor];
     int64_t npix = pix_id ? npix_sel : (int64_t) sc.width * sc.height;
     int64_t N = npix * sc.spp;
     float inv_spp = sc.spp > 1 ? 1.f / (float) sc.spp : 1.f;
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t i = 0; i < N; ++i) {
+        LaneDiag diag;
+        g_diag = diag_out ? &diag : nullptr;
         int64_t idx = sc.spp > 1 ? i / sc.spp : i;
         int pix = pix_id ? pix_id[idx] : (int) idx;
         uint64_t seed_value = pix_id ? (uint64_t) ((int64_t) pix + ra.seed) : (uint64_t) (i + ra.seed);
@@ -1221,6 +1262,8 @@ static void render_interior(const Scene &sc, const RenderArgs &ra, float *img, f
             splat(img, (int) idx, c, x * inv_spp);   // sum then divide in the reference; see tests' tolerance
             if (dimg) splat(dimg, (int) idx, c, dx * inv_spp);
         }
+        if (diag_out) for (int k = 0; k < 4; ++k) diag_out[4 * i + k] = diag.m[k];
+        g_diag = nullptr;
     }
 }
 
@@ -1554,6 +1597,21 @@ int orc_render(void *h, int sensor, int max_depth, int seed, int mode, int terms
         if ((terms & 2) && sc.sppe > 0) render_primary_edges(sc, ra, dimg);
         if ((terms & 4) && sc.sppse > 0) render_secondary_edges(sc, ra, dimg);
     }
+    return 0;
+}
+
+// interior term only, with the decision margins of every lane: diag_out [N0][4] (see LaneDiag)
+int orc_render_diag(void *h, int sensor, int max_depth, int seed, int mode, const int *skip, float *img, float *lane_out, float *diag_out) {
+    Scene &sc = *(Scene *) h;
+    if (!sc.configured) { sc.error = "Input scene must be configured!"; return 1; }
+    RenderArgs ra;
+    ra.sensor = sensor; ra.max_depth = max_depth; ra.seed = seed;
+    if (skip) for (int k = 0; k < 3; ++k) ra.skip[k] = skip[k];
+    int64_t npix = (int64_t) sc.width * sc.height;
+    std::fill(img, img + 3 * npix, 0.f);
+    std::vector<float> dimg((size_t) 3 * npix, 0.f);
+    if (mode == 0) render_interior<float>(sc, ra, img, nullptr, nullptr, 0, lane_out, diag_out);
+    else render_interior<Dual>(sc, ra, img, dimg.data(), nullptr, 0, lane_out, diag_out);
     return 0;
 }
 

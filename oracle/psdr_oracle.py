@@ -49,6 +49,7 @@ def lib():
         L.orc_num_mesh_edges.argtypes = [C.c_void_p, C.c_int]
         L.orc_mesh_edges.argtypes = [C.c_void_p, C.c_int, _i]
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i, _i, C.c_int, _f, _f, _f]
+        L.orc_render_diag.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _i, _f, _f, _f]
         L.orc_preprocess_secondary_edges.argtypes = [C.c_void_p, C.c_int, _i, C.c_int, C.c_int, _f]
         L.orc_sampler_draws.argtypes = [C.c_int64, C.c_int, C.c_int, _f]
         L.orc_pmf_sample.argtypes = [_f, C.c_int, _f, C.c_int, _i, _f, _f]
@@ -198,6 +199,18 @@ class OracleScene:
         if lane_out:
             return img, dimg, lanes
         return (img, dimg) if mode == 1 else img
+
+    def render_diag(self, depth, seed=0, mode=0, sensor=0, skip=None):
+        """interior term + per-lane decision margins [N0, 4] = (shadow, border, self, tie); see LaneDiag in psdr_oracle.cpp"""
+        n = self.width * self.height
+        img = np.zeros((n, 3), dtype=np.float32)
+        lanes = np.zeros((n * self.spp, 3), dtype=np.float32)
+        diag = np.zeros((n * self.spp, 4), dtype=np.float32)
+        sk = None if skip is None else np.asarray(skip, dtype=np.int32)
+        rc = self.L.orc_render_diag(self.h, sensor, depth, seed, mode, _ip(sk), _fp(img), _fp(lanes), _fp(diag))
+        if rc:
+            raise RuntimeError(self.L.orc_error(self.h).decode())
+        return img, lanes, diag
 
     def preprocess_secondary_edges(self, sensor, reso, nrounds=1, seed=0):
         r = np.asarray(reso, dtype=np.int32)

@@ -69,14 +69,16 @@ class Object:
 class RenderOption:
     """reference include/psdr/types.h:217-228"""
 
-    def __init__(self, width: int = 128, height: int = 128, spp: int = 1, sppe: Optional[int] = None, sppse: Optional[int] = None):
-        n_given = 3 + (sppe is not None) + (sppse is not None)
-        self.width, self.height, self.spp = width, height, spp
-        if n_given == 3 and (width, height, spp) == (128, 128, 1):
-            self.sppe, self.sppse = 0, 0            # RenderOption()
-        else:
-            self.sppe = spp if sppe is None else sppe
-            self.sppse = self.sppe if sppse is None else sppse
+    def __init__(self, *args):
+        """RenderOption() | (w, h, spp) | (w, h, spp, sppe) | (w, h, spp, sppe, sppse); the 3-argument form sets
+        sppe = sppse = spp, the default constructor leaves both boundary terms off (types.h:218-221)."""
+        if len(args) not in (0, 3, 4, 5):
+            raise TypeError("RenderOption(): expected 0, 3, 4 or 5 arguments")
+        self.width, self.height, self.spp, self.sppe, self.sppse = 128, 128, 1, 0, 0
+        if args:
+            self.width, self.height, self.spp = int(args[0]), int(args[1]), int(args[2])
+            self.sppe = int(args[3]) if len(args) > 3 else self.spp
+            self.sppse = int(args[4]) if len(args) > 4 else self.sppe
         self.log_level = 1
 
     def __repr__(self):
@@ -470,16 +472,19 @@ class Scene(Object):
         if self._h is not None:
             _lib.check(_lib.load().psdr_scene_set_accel(self._h, self._accel))
 
+    def _device_index(self) -> int:
+        if self._device is None:
+            try:
+                import torch
+                self._device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+            except Exception:
+                self._device = 0
+        return int(self._device)
+
     def _native(self):
         L = _lib.load()
         if self._h is None:
-            dev = self._device
-            if dev is None:
-                try:
-                    import torch
-                    dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
-                except Exception:
-                    dev = 0
+            dev = self._device_index()
             h = L.psdr_scene_create(int(dev))
             if not h:
                 raise RuntimeError(L.psdr_last_error().decode())
@@ -668,6 +673,13 @@ class Integrator(Object):
             raise RuntimeError("psdr_jit_b200 needs a CUDA device (no CPU fallback)")
         return torch
 
+    @staticmethod
+    def _dev_stream(torch, scene):
+        """Outputs live on the SCENE's device and launches go to torch's current stream of that device (the native
+        side does cudaSetDevice(scene device); a stream of another device would be an invalid handle)."""
+        dev = torch.device("cuda", scene._device_index())
+        return dev, torch.cuda.current_stream(dev).cuda_stream
+
     def _pix(self, torch, batch_pix, device):
         if batch_pix is None or (np.isscalar(batch_pix) and int(batch_pix) == -1):
             return None
@@ -679,11 +691,10 @@ class Integrator(Object):
         """Primal image, float32[H*W, 3] on the GPU (reference Integrator::renderC)."""
         self._check(scene)
         torch = self._torch()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev, st = self._dev_stream(torch, scene)
         pix = self._pix(torch, batch_pix, dev)
         n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
         img = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        st = torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.load().psdr_render_c(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters),
                                              None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel(),
                                              img.data_ptr(), st))
@@ -693,15 +704,16 @@ class Integrator(Object):
         """(image, forward-mode derivative image) for the tangents configured on the scene."""
         self._check(scene)
         torch = self._torch()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev, st = self._dev_stream(torch, scene)
         pix = self._pix(torch, batch_pix, dev)
         n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
-        img = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        dimg = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        st = torch.cuda.current_stream().cuda_stream
+        # ONE [2, n, 3] buffer: the multi-GPU path sums image and derivative image with a single all-reduce of it
+        buf = torch.empty((2, n, 3), dtype=torch.float32, device=dev)
+        img, dimg = buf[0], buf[1]
         _lib.check(_lib.load().psdr_render_d(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms),
                                              int(self.reference_tangent_scaling), None if pix is None else pix.data_ptr(),
                                              0 if pix is None else pix.numel(), img.data_ptr(), dimg.data_ptr(), st))
+        self.last_buffer = buf
         return img, dimg
 
     def renderD(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
@@ -720,29 +732,64 @@ class Integrator(Object):
         """Image of renderD without any derivative (psdr_render_d with dimg = NULL)."""
         self._check(scene)
         torch = self._torch()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev, st = self._dev_stream(torch, scene)
         pix = self._pix(torch, batch_pix, dev)
         n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
         img = torch.empty((n, 3), dtype=torch.float32, device=dev)
         _lib.check(_lib.load().psdr_render_d(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), _lib.TERM_ALL,
                                              0, None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel(),
-                                             img.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
+                                             img.data_ptr(), None, st))
         return img
 
-    def render_vjp(self, scene: Scene, d_img, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL):
+    def render_vjp(self, scene: Scene, d_img, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL, group=None):
         """Adjoint pass: accumulates d<d_img, img>/d(parameter) for every parameter; read them with
-        ``scene.grad_of(name, field)``.  Replays the sample streams of a forward call with the same seed."""
+        ``scene.grad_of(name, field)``.  Replays the sample streams of a forward call with the same seed.
+        With a sharded scene (``set_shard(rank, world > 1)``) and an initialised process group the flat device
+        gradient table is summed over the ranks with ONE all-reduce (NCCL) before it is copied to the host, so every
+        rank ends up with the full gradients (``d_img`` must be the same, complete cotangent image on every rank)."""
         self._check(scene)
         torch = self._torch()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev, st = self._dev_stream(torch, scene)
         pix = self._pix(torch, batch_pix, dev)
         d_img = torch.as_tensor(d_img, dtype=torch.float32, device=dev).contiguous()
         n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
         if d_img.numel() != 3 * n:
             raise RuntimeError("cotangent image must have %d x 3 entries" % n)
-        _lib.check(_lib.load().psdr_render_vjp(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms),
-                                               int(self.reference_tangent_scaling), None if pix is None else pix.data_ptr(),
-                                               0 if pix is None else pix.numel(), d_img.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        L = _lib.load()
+        args = (scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms), int(self.reference_tangent_scaling),
+                None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel(), d_img.data_ptr())
+        if scene._shard[1] > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            nt = L.psdr_grad_table_size(scene._h, sensor_id)
+            if nt < 0:
+                raise RuntimeError(L.psdr_last_error().decode())
+            table = torch.empty(nt, dtype=torch.float32, device=dev)
+            _lib.check(L.psdr_render_vjp_device(*args, table.data_ptr(), nt, st))
+            torch.distributed.all_reduce(table, group=group)          # the single gradient all-reduce (SURVEY.md 8e)
+            _lib.check(L.psdr_scene_backprop_table(scene._h, sensor_id, table.data_ptr(), nt, st))
+        else:
+            _lib.check(L.psdr_render_vjp(*args, st))
+
+    def render_vjp_table(self, scene: Scene, d_img, sensor_id: int = 0, seed: int = -1, terms: int = _lib.TERM_ALL):
+        """The adjoint kernels only: this rank's flat device gradient table (psdr_render_vjp_device), a torch tensor.
+        Tables of lane shards add up to the table of the whole frame; ``backprop_table`` finishes the pass."""
+        self._check(scene)
+        torch = self._torch()
+        dev, st = self._dev_stream(torch, scene)
+        d_img = torch.as_tensor(d_img, dtype=torch.float32, device=dev).contiguous()
+        L = _lib.load()
+        nt = L.psdr_grad_table_size(scene._h, sensor_id)
+        if nt < 0:
+            raise RuntimeError(L.psdr_last_error().decode())
+        table = torch.empty(nt, dtype=torch.float32, device=dev)
+        _lib.check(L.psdr_render_vjp_device(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms),
+                                            int(self.reference_tangent_scaling), None, 0, d_img.data_ptr(), table.data_ptr(), nt, st))
+        return table
+
+    def backprop_table(self, scene: Scene, table, sensor_id: int = 0):
+        """Host reverse chain of configure() for a (summed) gradient table; afterwards ``scene.grad_of`` reads gradients."""
+        torch = self._torch()
+        _, st = self._dev_stream(torch, scene)
+        _lib.check(_lib.load().psdr_scene_backprop_table(scene._h, sensor_id, table.data_ptr(), table.numel(), st))
 
     # host-buffer entry points (numpy in/out; used for the end-to-end measurement)
     def renderC_host(self, scene: Scene, sensor_id: int = 0, seed: int = -1, out: Optional[np.ndarray] = None):
@@ -764,10 +811,10 @@ class Integrator(Object):
     def render_aov(self, scene: Scene, sensor_id: int = 0, seed: int = 0):
         self._check(scene)
         torch = self._torch()
-        dev = torch.device("cuda", torch.cuda.current_device())
+        dev, st = self._dev_stream(torch, scene)
         n = scene.opts.width * scene.opts.height * max(scene.opts.spp, 1)
         out = torch.empty((n, 14), dtype=torch.float32, device=dev)
-        _lib.check(_lib.load().psdr_render_aov(scene._h, sensor_id, int(seed), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        _lib.check(_lib.load().psdr_render_aov(scene._h, sensor_id, int(seed), out.data_ptr(), st))
         return out
 
 
@@ -792,7 +839,7 @@ class PathTracer(Integrator):
         if r.shape != (4,):
             raise RuntimeError("reso = [rx, ry, rz, samples per cell]")
         _lib.check(_lib.load().psdr_preprocess_secondary_edges(scene._h, sensor_id, _ip(r), int(nrounds), int(seed),
-                                                               torch.cuda.current_stream().cuda_stream))
+                                                               self._dev_stream(torch, scene)[1]))
         self._guided.add((id(scene), sensor_id))
 
     def guiding_mass(self, scene: Scene, sensor_id: int = 0):
@@ -818,24 +865,23 @@ def _render_d_autograd(integ: Integrator, scene: Scene, sensor_id: int, seed: in
         def forward(ctx, *tensors):
             ctx.state0 = scene._sampler_state()
             img = integ.renderD_primal(scene, sensor_id, seed, batch_pix)
-            ctx.state1 = scene._sampler_state()
+            if scene._shard[1] > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+                # every rank rendered its lane shard into a full-frame buffer: a loss must see the SUM (a nonlinear
+                # loss of a partial image has the wrong cotangent, different on every rank)
+                torch.distributed.all_reduce(img)
             return img
 
         @staticmethod
         def backward(ctx, d_img):
-            if seed == -1:                    # replay the streams the forward call consumed
-                scene._set_sampler_state(ctx.state0)
-            integ.render_vjp(scene, d_img, sensor_id, seed, batch_pix)
-            scene._set_sampler_state(ctx.state1)
+            now = scene._sampler_state()            # the streams as they are when backward starts (other renders may
+            if seed == -1:                          # have consumed draws since this node's forward)
+                scene._set_sampler_state(ctx.state0)     # replay the streams the forward call consumed
+            integ.render_vjp(scene, d_img, sensor_id, seed, batch_pix)     # sharded: one all-reduce of the gradient table
+            scene._set_sampler_state(now)
             grads = []
             for t, kind, index in leaves:
                 g = scene._read_grad(kind, index, tuple(t.shape))
-                g = torch.from_numpy(g).to(device=t.device, dtype=t.dtype)
-                if torch.distributed.is_available() and torch.distributed.is_initialized() and scene._shard[1] > 1:
-                    g = g.cuda() if torch.distributed.get_backend() == "nccl" else g
-                    torch.distributed.all_reduce(g)          # lane shards -> sum of the partial gradients
-                    g = g.to(t.device)
-                grads.append(g)
+                grads.append(torch.from_numpy(g).to(device=t.device, dtype=t.dtype))
             return tuple(grads)
 
     return _RenderD.apply(*[t for t, _, _ in leaves])

@@ -31,7 +31,7 @@ EXPORTS = [
     "psdr_scene_set_tangent", "psdr_scene_clear_tangents", "psdr_scene_configure", "psdr_scene_last_configure_ms",
     "psdr_scene_query", "psdr_scene_mesh_edges", "psdr_render_c", "psdr_render_d", "psdr_render_c_host",
     "psdr_render_d_host", "psdr_render_aov", "psdr_sampler_draws", "psdr_scene_enable_timing", "psdr_scene_kernel_ms",
-    "psdr_preprocess_secondary_edges", "psdr_scene_set_guiding", "psdr_scene_guiding_mass", "psdr_render_vjp", "psdr_scene_get_grad", "psdr_scene_get_sampler_state", "psdr_scene_set_sampler_state",
+    "psdr_preprocess_secondary_edges", "psdr_scene_set_guiding", "psdr_scene_guiding_mass", "psdr_render_vjp", "psdr_grad_table_size", "psdr_render_vjp_device", "psdr_scene_backprop_table", "psdr_scene_get_grad", "psdr_scene_get_sampler_state", "psdr_scene_set_sampler_state",
 ]
 
 
@@ -82,6 +82,9 @@ def load():
     L.psdr_scene_set_guiding.argtypes = [vp, i, i]
     L.psdr_scene_guiding_mass.argtypes = [vp, i, P_F, i]
     L.psdr_render_vjp.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp, vp]
+    L.psdr_grad_table_size.argtypes = [vp, i]
+    L.psdr_render_vjp_device.argtypes = [vp, i, i, ll, i, i, i, vp, i, vp, vp, i, vp]
+    L.psdr_scene_backprop_table.argtypes = [vp, i, vp, i, vp]
     L.psdr_scene_get_grad.argtypes = [vp, i, i, P_F, i]
     L.psdr_scene_get_sampler_state.argtypes = [vp, C.POINTER(ll)]
     L.psdr_scene_set_sampler_state.argtypes = [vp, C.POINTER(ll)]

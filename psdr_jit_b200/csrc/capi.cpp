@@ -431,10 +431,15 @@ int psdr_scene_mesh_edges(psdr_scene *s, int mesh, int *out) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-struct Shard { long long begin, end; };
-Shard shard_of(long long n, int rank, int world) {
-    auto cut = [&](int r) { long long c = n * r / world; return r == world ? n : c / 32 * 32; };
-    return {cut(rank), cut(rank + 1)};
+// Block-cyclic deal of 32-lane blocks (dscene.h RenderParams): fills the sharding fields for a term of n lanes
+void set_shard(RenderParams &rp, long long n, int rank, int world) {
+    const long long blocks = (n + 31) / 32;
+    const long long owned = blocks > rank ? (blocks - rank + world - 1) / world : 0;
+    rp.lane_begin = 0;
+    rp.lane_end = world == 1 ? n : owned * 32;
+    rp.n_lanes = n;
+    rp.shard_rank = rank;
+    rp.shard_world = world;
 }
 
 // Integrator::renderC / renderD front matter (integrator.cpp:12-31, 51-73): argument checks and
@@ -487,8 +492,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
     cuda_ok(cudaMemsetAsync(img, 0, sizeof(float) * 3 * npix, st), "memset(img)");
     if (ad && dimg) cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
     if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
-        const Shard sh = shard_of(npix * sc.spp, sc.rank, sc.world);
-        rp[0].lane_begin = sh.begin; rp[0].lane_end = sh.end;
+        set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
         rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
         tick(s, 0, 0, st);
@@ -498,8 +502,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
     }
     if (ad && !primal_only && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
         if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
-        const Shard sh = shard_of(npix_full * sc.sppe, sc.rank, sc.world);
-        rp[1].lane_begin = sh.begin; rp[1].lane_end = sh.end;
+        set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
         tick(s, 1, 0, st);
         cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, st), "primary-edge kernel");
         tick(s, 1, 1, st);
@@ -507,8 +510,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
     }
     if (ad && !primal_only && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
         if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
-        const Shard sh = shard_of(npix_full * sc.sppse, sc.rank, sc.world);
-        rp[2].lane_begin = sh.begin; rp[2].lane_end = sh.end;
+        set_shard(rp[2], npix_full * sc.sppse, sc.rank, sc.world);
         rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
         tick(s, 2, 0, st);
         cuda_ok(launch_secondary_edges(sc.dscene, cam, rp[2], dimg, st), "secondary-edge kernel");
@@ -555,12 +557,10 @@ int psdr_render_d(psdr_scene *s, int sensor, int max_depth, long long seed, int 
     PSDR_CATCH
 }
 
-int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
-                    const int *pix_id, int npix_sel, const float *d_img, void *cuda_stream) {
-    if (!s) return fail("null scene");
-    PSDR_TRY
+// adjoint kernels of all requested terms into a device gradient table (zeroed here); asynchronous on `st`
+static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                       const int *pix_id, int npix_sel, const float *d_img, float *table, cudaStream_t st) {
     Scene &sc = s->sc;
-    cudaStream_t st = (cudaStream_t) cuda_stream;
     cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
     if (!d_img) throw std::runtime_error("null cotangent image");
     if (max_depth > 8) throw std::runtime_error("the adjoint supports max_depth <= 8");
@@ -579,19 +579,11 @@ int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, in
     if (pix_id && npix_sel <= 0) throw std::runtime_error("empty pixel batch");
     const DCamera &cam = sc.dcameras[sensor];
     GradLayout gl = sc.grad_layout(sensor);
-    if ((size_t) gl.total > s->grad_cap) {
-        if (s->d_grad) cudaFree(s->d_grad);
-        if (s->h_grad) cudaFreeHost(s->h_grad);
-        s->grad_cap = (size_t) gl.total * 2;
-        cuda_ok(cudaMalloc(&s->d_grad, sizeof(float) * s->grad_cap), "cudaMalloc(grad table)");
-        cuda_ok(cudaMallocHost(&s->h_grad, sizeof(float) * s->grad_cap), "cudaMallocHost(grad table)");
-    }
-    gl.base = s->d_grad;
-    cuda_ok(cudaMemsetAsync(s->d_grad, 0, sizeof(float) * gl.total, st), "memset(grad table)");
+    gl.base = table;
+    cuda_ok(cudaMemsetAsync(table, 0, sizeof(float) * gl.total, st), "memset(grad table)");
     s->ev_used[0] = s->ev_used[1] = s->ev_used[2] = false;
     if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
-        const Shard sh = shard_of(npix * sc.spp, sc.rank, sc.world);
-        rp[0].lane_begin = sh.begin; rp[0].lane_end = sh.end;
+        set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
         rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
         tick(s, 0, 0, st);
@@ -601,8 +593,7 @@ int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, in
     }
     if (sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
         if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
-        const Shard sh = shard_of(npix_full * sc.sppe, sc.rank, sc.world);
-        rp[1].lane_begin = sh.begin; rp[1].lane_end = sh.end;
+        set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
         tick(s, 1, 0, st);
         cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp[1], gl, d_img, st), "primary-edge adjoint kernel");
         tick(s, 1, 1, st);
@@ -610,17 +601,79 @@ int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, in
     }
     if (sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
         if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
-        const Shard sh = shard_of(npix_full * sc.sppse, sc.rank, sc.world);
-        rp[2].lane_begin = sh.begin; rp[2].lane_end = sh.end;
+        set_shard(rp[2], npix_full * sc.sppse, sc.rank, sc.world);
         rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
         tick(s, 2, 0, st);
         cuda_ok(launch_secondary_edges_vjp(sc.dscene, cam, rp[2], gl, d_img, st), "secondary-edge adjoint kernel");
         tick(s, 2, 1, st);
         g_launches++;
     }
-    cuda_ok(cudaMemcpyAsync(s->h_grad, s->d_grad, sizeof(float) * gl.total, cudaMemcpyDeviceToHost, st), "D2H(grad table)");
+}
+
+static void ensure_grad_table(psdr_scene *s, size_t total) {
+    if (total <= s->grad_cap) return;
+    if (s->d_grad) cudaFree(s->d_grad);
+    if (s->h_grad) cudaFreeHost(s->h_grad);
+    s->grad_cap = total * 2;
+    cuda_ok(cudaMalloc(&s->d_grad, sizeof(float) * s->grad_cap), "cudaMalloc(grad table)");
+    cuda_ok(cudaMallocHost(&s->h_grad, sizeof(float) * s->grad_cap), "cudaMallocHost(grad table)");
+}
+
+// D2H of a device gradient table + the host reverse chain of configure()
+static void vjp_finish(psdr_scene *s, int sensor, const float *table, cudaStream_t st) {
+    Scene &sc = s->sc;
+    GradLayout gl = sc.grad_layout(sensor);
+    ensure_grad_table(s, (size_t) gl.total);
+    cuda_ok(cudaMemcpyAsync(s->h_grad, table, sizeof(float) * gl.total, cudaMemcpyDeviceToHost, st), "D2H(grad table)");
     cuda_ok(cudaStreamSynchronize(st), "stream sync");
     sc.backprop(s->h_grad, gl, sensor);
+}
+
+int psdr_render_vjp(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                    const int *pix_id, int npix_sel, const float *d_img, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    ensure_grad_table(s, (size_t) sc.grad_layout(sensor).total);
+    vjp_launch(s, sensor, max_depth, seed, hide_emitters, terms, reference_scaling, pix_id, npix_sel, d_img, s->d_grad, (cudaStream_t) cuda_stream);
+    vjp_finish(s, sensor, s->d_grad, (cudaStream_t) cuda_stream);
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_grad_table_size(psdr_scene *s, int sensor) {
+    if (!s) { fail("null scene"); return -1; }
+    Scene &sc = s->sc;
+    if (!sc.configured) { fail("Input scene must be configured!"); return -1; }
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) { fail("Invalid sensor id!"); return -1; }
+    return sc.grad_layout(sensor).total;
+}
+
+int psdr_render_vjp_device(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, int terms, int reference_scaling,
+                           const int *pix_id, int npix_sel, const float *d_img, float *grad_table, int n_table, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    if (!grad_table || n_table != sc.grad_layout(sensor).total) throw std::runtime_error("gradient table size mismatch (psdr_grad_table_size)");
+    vjp_launch(s, sensor, max_depth, seed, hide_emitters, terms, reference_scaling, pix_id, npix_sel, d_img, grad_table, (cudaStream_t) cuda_stream);
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_scene_backprop_table(psdr_scene *s, int sensor, const float *grad_table, int n_table, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    if (!grad_table || n_table != sc.grad_layout(sensor).total) throw std::runtime_error("gradient table size mismatch (psdr_grad_table_size)");
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    vjp_finish(s, sensor, grad_table, (cudaStream_t) cuda_stream);
     return 0;
     PSDR_CATCH
 }
@@ -786,8 +839,7 @@ int psdr_render_aov(psdr_scene *s, int sensor, long long seed, float *out, void 
     cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
     RenderParams rp{};
     rp.seed = seed < 0 ? 0 : seed;
-    rp.lane_begin = 0;
-    rp.lane_end = (long long) sc.width * sc.height * std::max(sc.spp, 1);
+    set_shard(rp, (long long) sc.width * sc.height * std::max(sc.spp, 1), 0, 1);
     cuda_ok(launch_aov(sc.dscene, sc.dcameras[sensor], rp, out, (cudaStream_t) cuda_stream), "aov kernel");
     g_launches++;
     return 0;

@@ -19,6 +19,11 @@ struct Hit {
     float u, v, t;
 };
 
+// local lane index of this rank -> global lane index of the term (RenderParams: block-cyclic deal of 32-lane blocks)
+__device__ __forceinline__ long long global_lane(const RenderParams &rp, long long j) {
+    return rp.shard_world <= 1 ? rp.lane_begin + j : (((j >> 5) * rp.shard_world + rp.shard_rank) << 5) + (j & 31);
+}
+
 template <class S> struct TriRec {
     V3<S> p0, e1, e2;
     S area;
@@ -1211,7 +1216,8 @@ struct SecSample {      // what the fill loop hands to stage 1
 };
 template <int kCfg>
 __device__ __forceinline__ bool sec_edge_draw(const DScene &sc, const DCamera &cam, const RenderParams &rp, long long j, SecSample &out) {
-    const long long i = rp.lane_begin + j;
+    const long long i = global_lane(rp, j);
+    if (i >= rp.n_lanes) return false;
     Pcg32 rng;
     rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
     if (rp.skip) rng.advance(rp.skip);

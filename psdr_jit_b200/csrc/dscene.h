@@ -135,7 +135,13 @@ struct RenderParams {
     int hide_emitters;
     long long seed;          // >= 0
     unsigned long long skip; // draws already consumed per lane of this sampler (seed = -1 continuation)
-    long long lane_begin, lane_end;   // lane range rendered by this call (multi-GPU sharding)
+    long long lane_begin, lane_end;   // LOCAL lane index range of this call: [0, 32 * owned blocks)
+    // multi-GPU sharding: the lanes of a term are dealt to the ranks in blocks of 32 (one warp; one pixel at spp = 32),
+    // round-robin -- local lane j is global lane ((j / 32) * shard_world + shard_rank) * 32 + j % 32; lanes >= n_lanes
+    // (the tail of the last block) are dead.  Contiguous ranges gave the rank that owns the empty top rows of the
+    // image a quarter of the interior work of the others.
+    long long n_lanes;
+    int shard_rank, shard_world;
     const int *pix_id;       // batch mode: pixel list (device), else nullptr
     int npix;                // number of output pixels (W*H or len(pix_id))
     int smem_grad;           // adjoint kernels: 1 = accumulate into a shared-memory copy of the gradient table

@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? PSDR_LB_INTERIOR_D
     const long long span_pad = (span + 31) / 32 * 32;   // keep warps converged for the shuffles
     const float inv_spp = sc.spp > 1 ? 1.f / (float) sc.spp : 1.f;
     for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
-        const long long i = rp.lane_begin + j;
-        const bool live = j < span;
+        const long long i = global_lane(rp, j);
+        const bool live = j < span && i < rp.n_lanes;
         int idx = 0;
         V3<S> v(S(0.f));
         if (live) {
@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(c
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
     for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
         __syncwarp();
-        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
-        if (j >= span) continue;
-        const long long i = rp.lane_begin + j;
-        (void) live_mask;
+        const long long i = global_lane(rp, j);
+        const bool live = j < span && i < rp.n_lanes;
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        if (!live) continue;
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
@@ -223,10 +223,8 @@ __global__ void __launch_bounds__(kBlock) aov_kernel(const __grid_constant__ DSc
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
     for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
         __syncwarp();
-        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
-        if (j >= span) continue;
-        const long long i = rp.lane_begin + j;
-        (void) live_mask;
+        const long long i = global_lane(rp, j);
+        if (!(j < span && i < rp.n_lanes)) continue;
         const int idx = (int) (sc.spp > 1 ? i / sc.spp : i);
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);

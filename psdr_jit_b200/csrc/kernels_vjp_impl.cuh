@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_c
         // span is padded to 32), so the barriers here and inside path_adjoint are full-mask barriers at the top
         // level -- the only form that really re-converges the warp (see path_adjoint)
         __syncwarp();
-        const bool live = j < span;
-        const long long i = rp.lane_begin + (live ? j : 0);
+        const long long gi = global_lane(rp, j);
+        const bool live = j < span && gi < rp.n_lanes;
+        const long long i = live ? gi : 0;
         const int idx = (int) (sc.spp > 1 ? i / sc.spp : i);
         const int pix = rp.pix_id ? __ldg(rp.pix_id + idx) : idx;
         const unsigned long long seed_value = rp.pix_id ? (unsigned long long) ((long long) pix + rp.seed) : (unsigned long long) (i + rp.seed);
@@ -73,9 +74,10 @@ __global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __gr
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
     for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
         __syncwarp();
-        const unsigned live_mask = __ballot_sync(0xffffffffu, j < span);
-        if (j >= span) continue;
-        const long long i = rp.lane_begin + j;
+        const long long i = global_lane(rp, j);
+        const bool live = j < span && i < rp.n_lanes;
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        if (!live) continue;
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);

@@ -1,4 +1,4 @@
-"""world_size-2 gloo test of the multi-GPU host logic: lane-range shards of every term,
+"""world_size-2 gloo test of the multi-GPU host logic: block-cyclic lane shards of every term,
 accumulated into private full-frame images and summed with ONE all-reduce, reproduce the full image."""
 import os
 import socket
@@ -20,20 +20,20 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from psdr_jit_b200.dist import all_reduce_images, shard_range
+    from psdr_jit_b200.dist import all_reduce_images, shard_lanes
     from tests.common import build_oracle, scenes
     w = h = 32
     spp = 4
     osc = build_oracle(scenes.cbox_meshes(), w, h, spp, 0, 0, move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
     img, dimg, lanes = osc.render(2, seed=3, mode=1, terms=1, lane_out=True)
-    b, e = shard_range(w * h * spp, rank, world)
+    mine = shard_lanes(w * h * spp, rank, world)
     part = np.zeros((w * h, 3), dtype=np.float64)
-    np.add.at(part, np.arange(b, e) // spp, lanes[b:e].astype(np.float64) / spp)
+    np.add.at(part, mine // spp, lanes[mine].astype(np.float64) / spp)
     t = torch.from_numpy(part)
     t2 = torch.full((5,), float(rank + 1), dtype=torch.float64)
     (tot, tot2) = all_reduce_images(t, t2)
     if rank == 0:
-        q.put((float(np.abs(tot.numpy() - img).max()), float(np.abs(img).max()), tot2.tolist(), (b, e)))
+        q.put((float(np.abs(tot.numpy() - img).max()), float(np.abs(img).max()), tot2.tolist(), (int(mine[0]), int(mine[32]), len(mine))))
     dist.destroy_process_group()
 
 
@@ -51,16 +51,19 @@ def test_lane_shards_allreduce_to_full_image(oracle):
         assert p.exitcode == 0
     assert err < 1e-5 * mx
     assert tot2 == [3.0] * 5
-    assert rng == (0, 2048)
+    assert rng == (0, 64, 2048)
 
 
-def test_shard_range_properties():
-    from psdr_jit_b200.dist import shard_range
-    for n in (0, 31, 32, 1000, 8388608, 12345677):
+def test_shard_lanes_properties():
+    from psdr_jit_b200.dist import shard_lanes
+    for n in (0, 31, 32, 1000, 65536, 123457):
         for world in (1, 2, 3, 8):
-            cuts = [shard_range(n, r, world) for r in range(world)]
-            assert cuts[0][0] == 0 and cuts[-1][1] == n
-            for a, b in zip(cuts, cuts[1:]):
-                assert a[1] == b[0] and a[1] % 32 == 0
+            parts = [shard_lanes(n, r, world) for r in range(world)]
+            allv = np.sort(np.concatenate(parts)) if n else np.zeros(0, np.int64)
+            assert np.array_equal(allv, np.arange(n))                     # a partition of the lanes
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 32                           # balanced to one block
+            for r, p in enumerate(parts):
+                assert np.all((p // 32) % world == r)                      # block b belongs to rank b % world
     with pytest.raises(ValueError):
-        shard_range(10, 2, 2)
+        shard_lanes(10, 2, 2)
