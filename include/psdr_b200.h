@@ -36,8 +36,17 @@ enum {
     PSDR_BSDF_ROUGHNESS = 10,      /* MicrofacetBSDF.roughness (1x1 bitmap), 1 float */
     PSDR_ENVMAP_RADIANCE = 11,     /* EnvironmentMap.radiance (lat-long Bitmap3fD), 3*w*h floats, rgb interleaved, index ignored */
     PSDR_ENVMAP_SCALE = 12,        /* EnvironmentMap.scale, 1 float */
-    PSDR_ENVMAP_TO_WORLD_LEFT = 13 /* EnvironmentMap.set_transform(mat), 16 floats */
+    PSDR_ENVMAP_TO_WORLD_LEFT = 13,/* EnvironmentMap.set_transform(mat), 16 floats */
+    /* Bitmap.scale / .rotate / .translate (src/psdr.cpp:204-206,217-219; the uv transform of src/core/bitmap.cpp:64-72)
+     * of a BSDF's texture slots: 4 floats (scale, rotate, translate.x, translate.y); forward-mode tangents supported,
+     * no reverse-mode gradient */
+    PSDR_BSDF_REFLECTANCE_UV = 14,
+    PSDR_BSDF_SPECULAR_UV = 15,
+    PSDR_BSDF_ROUGHNESS_UV = 16
 };
+
+/* Texture slots of a BSDF (psdr_scene_set_bsdf_texture_slot). */
+enum { PSDR_TEX_REFLECTANCE = 0, PSDR_TEX_SPECULAR = 1, PSDR_TEX_ROUGHNESS = 2 };
 
 /* What psdr_scene_query() can return. */
 enum {
@@ -78,6 +87,11 @@ int psdr_scene_set_seed(psdr_scene *s, long long seed);
  * buffers over ranks (one NCCL all-reduce).  In reverse mode the caller sums the gradient TABLES
  * (psdr_render_vjp_device) over ranks before psdr_scene_backprop_table. */
 int psdr_scene_set_shard(psdr_scene *s, int rank, int world);
+/* New.  on != 0: the analytic re-intersection of the primary hit in renderD (src/scene/scene.cpp:772-801,
+ * include/psdr/utils.h:82-93) takes its reciprocal with rcp.approx.ftz.f32, the instruction Dr.Jit emits for rcp()
+ * (drjit-core cuda_eval.cpp:638-640), instead of the correctly rounded 1/x.  Everything else stays IEEE.  Reproduces the
+ * reference's self-shadowing statistics on faces lit at grazing angles (DESIGN.md "parity"); off by default. */
+int psdr_scene_set_reference_arithmetic(psdr_scene *s, int on);
 /* -1 = automatic (BVH2 above 64 triangles), 0 = brute force, 1 = BVH2 */
 int psdr_scene_set_accel(psdr_scene *s, int mode);
 
@@ -95,6 +109,11 @@ int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float sp
  * PSDR_BSDF_REFLECTANCE takes / returns 3*w*h floats (rgb interleaved, pixel = y*w + x).  w = h = 1 switches back
  * to the constant. */
 int psdr_scene_set_bsdf_texture(psdr_scene *s, int index, int w, int h);
+/* The same for any of the three bitmaps of a BSDF: slot PSDR_TEX_REFLECTANCE (Bitmap3fD reflectance / diffuseReflectance),
+ * PSDR_TEX_SPECULAR (Bitmap3fD specularReflectance) or PSDR_TEX_ROUGHNESS (Bitmap1fD roughness) -- MicrofacetBSDF(Bitmap3fD,
+ * Bitmap3fD, Bitmap1fD), src/psdr.cpp:301, include/psdr/bsdf/microfacet.h:17,33-35.  Afterwards PSDR_BSDF_SPECULAR takes /
+ * returns 3*w*h floats and PSDR_BSDF_ROUGHNESS w*h floats. */
+int psdr_scene_set_bsdf_texture_slot(psdr_scene *s, int index, int slot, int w, int h);
 
 /* Scene.add_Mesh(mesh, bsdf_id, emitter) with mesh = Mesh.load_raw(v, f, uv, f_uv) -- src/psdr.cpp:399-400,
  * src/scene/scene.cpp:249-309, src/shape/mesh.cpp:74-162.  v: nv*3 floats (object space), f: nf*3 ints,

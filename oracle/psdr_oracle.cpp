@@ -126,9 +126,15 @@ struct Bsdf {
     V3d specular;     // Microfacet specularReflectance
     Dual roughness;   // Microfacet roughness
     bool two_side = false;
-    // reflectance / diffuseReflectance texture (Bitmap3fD with > 1 texel): rgb interleaved, pixel = y*w + x
-    int tex_w = 0, tex_h = 0;
-    std::vector<float> tex, dtex;
+    // bitmap slots with more than one texel (channels interleaved, pixel = y*w + x): 0 reflectance / diffuseReflectance
+    // (Bitmap3fD), 1 specularReflectance (Bitmap3fD), 2 roughness (Bitmap1fD); each with the bitmap's uv transform
+    // (reference include/psdr/core/bitmap.h:36-38)
+    struct Tex {
+        int w = 0, h = 0, ch = 3;
+        std::vector<float> data, ddata;
+        Dual scale = Dual(1.f), rot = Dual(0.f), tx = Dual(0.f), ty = Dual(0.f);
+    };
+    Tex tex[3];
 };
 
 struct MeshRec {
@@ -808,18 +814,35 @@ template <class S> static Its<S> ray_intersect(const Scene &sc, V3<S> o, V3<S> d
 template <class S> static V3<S> refl_const(const Bsdf &b);
 template <> V3<Dual> refl_const<Dual>(const Bsdf &b) { return b.reflectance; }
 template <> V3<float> refl_const<float>(const Bsdf &b) { return val(b.reflectance); }
-template <class S> static V3<S> bsdf_texel(const Bsdf &b, int i);
-template <> V3<float> bsdf_texel<float>(const Bsdf &b, int i) { return V3f(b.tex[3 * i], b.tex[3 * i + 1], b.tex[3 * i + 2]); }
-template <> V3<Dual> bsdf_texel<Dual>(const Bsdf &b, int i) {
-    if (b.dtex.empty()) return lift<Dual>(V3f(b.tex[3 * i], b.tex[3 * i + 1], b.tex[3 * i + 2]));
-    return V3d(Dual(b.tex[3 * i], b.dtex[3 * i]), Dual(b.tex[3 * i + 1], b.dtex[3 * i + 1]), Dual(b.tex[3 * i + 2], b.dtex[3 * i + 2]));
+template <class S> static S lift_d(Dual x);
+template <> float lift_d<float>(Dual x) { return x.v; }
+template <> Dual lift_d<Dual>(Dual x) { return x; }
+template <class S> static V3<S> tex_texel(const Bsdf::Tex &t, int i) {
+    V3<S> r(S(0.f));
+    for (int c = 0; c < t.ch; ++c) {
+        Dual x(t.data[t.ch * i + c], t.ddata.empty() ? 0.f : t.ddata[t.ch * i + c]);
+        (c == 0 ? r.x : c == 1 ? r.y : r.z) = lift_d<S>(x);
+    }
+    return r;
 }
-// Bitmap3fD::eval(uv) (reference src/core/bitmap.cpp:46-131): flip_v = true, no uv transform, wrap, bilinear
-template <class S> static V3<S> refl_of(const Bsdf &b, V2<S> uv) {
-    if (b.tex_w <= 0) return refl_const<S>(b);
-    const int w = b.tex_w, h = b.tex_h;
-    uv = V2<S>((uv.x - 0.5f) + 0.5f, -((uv.y - 0.5f) + 0.5f));
-    uv = V2<S>(uv.x - floor_(uv.x), uv.y - floor_(uv.y));
+// Bitmap<channels>::eval(uv) (reference src/core/bitmap.cpp:46-131): rotate about the centre, flip_v = true, scale about
+// the centre, translate, wrap, bilinear.  cos / sin of the rotation are evaluated once in fp32 (std::cos / std::sin)
+template <class S> static V3<S> tex_eval(const Bsdf::Tex &t, V2<S> uv) {
+    const int w = t.w, h = t.h;
+    const float crv = std::cos(t.rot.v), srv = std::sin(t.rot.v);
+    const S cr = lift_d<S>(Dual(crv, -srv * t.rot.d)), sr = lift_d<S>(Dual(srv, crv * t.rot.d)), sc = lift_d<S>(t.scale);
+    const S ux = uv.x - 0.5f, uy = uv.y - 0.5f;
+    S rx = ux * cr + uy * sr, ry = -ux * sr + uy * cr;
+    rx = rx + 0.5f;
+    ry = -(ry + 0.5f);
+    rx = rx * sc;
+    ry = ry * sc;
+    const S off = sc * 0.5f + (-0.5f);
+    rx = rx - off;
+    ry = ry + off;
+    rx = rx + lift_d<S>(t.tx);
+    ry = ry + lift_d<S>(t.ty);
+    uv = V2<S>(rx - floor_(rx), ry - floor_(ry));
     uv.x = uv.x * (float) (w - 1);
     uv.y = uv.y * (float) (h - 1);
     int px = (int) std::floor(val(uv.x)), py = (int) std::floor(val(uv.y));
@@ -828,18 +851,21 @@ template <class S> static V3<S> refl_of(const Bsdf &b, V2<S> uv) {
     px = std::min(px, w - 2);
     py = std::min(py, h - 2);
     int i00 = py * w + px;
-    V3<S> v00 = bsdf_texel<S>(b, i00), v10 = bsdf_texel<S>(b, i00 + 1), v01 = bsdf_texel<S>(b, i00 + w), v11 = bsdf_texel<S>(b, i00 + w + 1);
+    V3<S> v00 = tex_texel<S>(t, i00), v10 = tex_texel<S>(t, i00 + 1), v01 = tex_texel<S>(t, i00 + w), v11 = tex_texel<S>(t, i00 + w + 1);
     V3<S> v0(fmadd(w0x, v00.x, w1x * v10.x), fmadd(w0x, v00.y, w1x * v10.y), fmadd(w0x, v00.z, w1x * v10.z));
     V3<S> v1(fmadd(w0x, v01.x, w1x * v11.x), fmadd(w0x, v01.y, w1x * v11.y), fmadd(w0x, v01.z, w1x * v11.z));
     return V3<S>(fmadd(w0y, v0.x, w1y * v1.x), fmadd(w0y, v0.y, w1y * v1.y), fmadd(w0y, v0.z, w1y * v1.z));
 }
+template <class S> static V3<S> refl_of(const Bsdf &b, V2<S> uv) {
+    if (b.tex[0].w <= 0) return refl_const<S>(b);
+    return tex_eval<S>(b.tex[0], uv);
+}
 
-template <class S> static V3<S> spec_of(const Bsdf &b);
-template <> V3<Dual> spec_of<Dual>(const Bsdf &b) { return b.specular; }
-template <> V3<float> spec_of<float>(const Bsdf &b) { return val(b.specular); }
-template <class S> static S rough_of(const Bsdf &b);
-template <> Dual rough_of<Dual>(const Bsdf &b) { return b.roughness; }
-template <> float rough_of<float>(const Bsdf &b) { return b.roughness.v; }
+template <class S> static V3<S> spec_const(const Bsdf &b);
+template <> V3<Dual> spec_const<Dual>(const Bsdf &b) { return b.specular; }
+template <> V3<float> spec_const<float>(const Bsdf &b) { return val(b.specular); }
+template <class S> static V3<S> spec_of(const Bsdf &b, V2<S> uv) { return b.tex[1].w > 0 ? tex_eval<S>(b.tex[1], uv) : spec_const<S>(b); }
+template <class S> static S rough_of(const Bsdf &b, V2<S> uv) { return b.tex[2].w > 0 ? tex_eval<S>(b.tex[2], uv).x : lift_d<S>(b.roughness); }
 
 // GGXDistribution::eval (reference src/bsdf/ggx.cpp:13-33), alpha_u = alpha_v
 template <class S> static S ggx_eval(S alpha, V3<S> m) {
@@ -868,8 +894,8 @@ template <class S> static V3<S> microfacet_eval(const Bsdf &b, V3<S> wi, V3<S> w
     V3<S> diffuse = refl_of<S>(b, uv) * S(kInvPi);
     V3<S> H = normalize(wi + wo);
     S cos_vh = dot(H, wi);
-    V3<S> F0 = spec_of<S>(b);
-    S alpha = sqr(rough_of<S>(b));
+    V3<S> F0 = spec_of<S>(b, uv);
+    S alpha = sqr(rough_of<S>(b, uv));
     S ggx = ggx_eval<S>(alpha, H);
     S coeff = cos_vh * (S(-5.55473f) * cos_vh - S(6.8316f));
     S e = exp2_(coeff);
@@ -881,14 +907,14 @@ template <class S> static V3<S> microfacet_eval(const Bsdf &b, V3<S> wi, V3<S> w
     return (diffuse + specular) * cos_nl;
 }
 // Microfacet::__pdf (microfacet.cpp:108-133), detached
-static float microfacet_pdf(const Bsdf &b, V3f wi, V3f wo) {
+static float microfacet_pdf(const Bsdf &b, V3f wi, V3f wo, V2f uv) {
     if (b.two_side) {
         if (std::signbit(wi.z)) wo.z = -wo.z;
         wi.z = std::fabs(wi.z);
     }
     V3f m = normalize(wo + wi);
     if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
-    float alpha = sqr(b.roughness.v);
+    float alpha = sqr(rough_of<float>(b, uv));
     return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
 }
 
@@ -911,7 +937,7 @@ template <class S> static float bsdf_pdf(const Scene &sc, const Its<S> &its, V3<
     if (!active || !its.valid) return 0.f;
     if (sc.meshes[its.mesh].bsdf < 0) return 0.f;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type == 1) return microfacet_pdf(b, val(its.wi), val(wo));
+    if (b.type == 1) return microfacet_pdf(b, val(its.wi), val(wo), val(its.uv));
     float wiz = val(its.wi.z), woz = val(wo.z);
     if (b.two_side) {
         if (std::signbit(wiz)) woz = -woz;
@@ -953,10 +979,10 @@ static V2f ggx_sample_visible_11(float cos_theta_i, V2f sample) {
     return V2f(std::fmaf(cos_theta_i, y, -(sin_theta_i * z)) * norm, x * norm);
 }
 // Microfacet::__sample (microfacet.cpp:80-98) + GGXDistribution::sample (ggx.cpp:36-79); sin/cos phi: frame.h:104-122
-static BsdfSample microfacet_sample(const Bsdf &b, V3f wi, V3f sample, bool active) {
+static BsdfSample microfacet_sample(const Bsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
     BsdfSample bs;
     if (b.two_side) wi.z = std::fabs(wi.z);
-    float alpha = sqr(b.roughness.v);
+    float alpha = sqr(rough_of<float>(b, uv));
     V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
     float sin_theta_2 = std::fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / std::sqrt(sin_theta_2);
     bool pole = std::fabs(sin_theta_2) <= 4.f * kEpsilon;
@@ -978,7 +1004,7 @@ template <class S> static BsdfSample bsdf_sample(const Scene &sc, const Its<S> &
     if (!its.valid) return bs;
     if (sc.meshes[its.mesh].bsdf < 0) return bs;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type == 1) return microfacet_sample(b, val(its.wi), sample, active);
+    if (b.type == 1) return microfacet_sample(b, val(its.wi), sample, active, val(its.uv));
     float wiz = val(its.wi.z);
     if (b.two_side) wiz = std::fabs(wiz);
     V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));  // tail<2>(sample)
@@ -1478,14 +1504,23 @@ int orc_add_diffuse(void *h, const float *refl, const float *d_refl, int two_sid
     return (int) s->bsdfs.size() - 1;
 }
 
-// Bitmap3fD texture for the reflectance / diffuseReflectance of BSDF `bsdf` (data [h*w*3], optional tangents)
-int orc_set_bsdf_texture(void *h, int bsdf, int w, int hh, const float *data, const float *ddata) {
+// Bitmap texture for slot `slot` of BSDF `bsdf` (0 reflectance / diffuseReflectance, 1 specularReflectance, 2 roughness):
+// data [h*w*channels], optional tangents; xform = (scale, rotate, tx, ty), d_xform its tangent (NULL: identity / zero)
+int orc_set_bsdf_texture_slot(void *h, int bsdf, int slot, int w, int hh, const float *data, const float *ddata, const float *xform,
+                              const float *d_xform) {
     Scene *s = (Scene *) h;
-    Bsdf &b = s->bsdfs[bsdf];
-    b.tex_w = w; b.tex_h = hh;
-    b.tex.assign(data, data + (size_t) 3 * w * hh);
-    if (ddata) b.dtex.assign(ddata, ddata + (size_t) 3 * w * hh); else b.dtex.clear();
+    Bsdf::Tex &t = s->bsdfs[bsdf].tex[slot];
+    t.ch = slot == 2 ? 1 : 3;
+    t.w = w; t.h = hh;
+    t.data.assign(data, data + (size_t) t.ch * w * hh);
+    if (ddata) t.ddata.assign(ddata, ddata + (size_t) t.ch * w * hh); else t.ddata.clear();
+    const float id[4] = {1.f, 0.f, 0.f, 0.f}, z[4] = {0.f, 0.f, 0.f, 0.f};
+    const float *x = xform ? xform : id, *dx = d_xform ? d_xform : z;
+    t.scale = Dual(x[0], dx[0]); t.rot = Dual(x[1], dx[1]); t.tx = Dual(x[2], dx[2]); t.ty = Dual(x[3], dx[3]);
     return 0;
+}
+int orc_set_bsdf_texture(void *h, int bsdf, int w, int hh, const float *data, const float *ddata) {
+    return orc_set_bsdf_texture_slot(h, bsdf, 0, w, hh, data, ddata, nullptr, nullptr);
 }
 
 // MicrofacetBSDF(specular, diffuse, roughness); d = [d_spec(3), d_diff(3), d_rough(1)] or NULL

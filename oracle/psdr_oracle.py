@@ -41,6 +41,7 @@ def lib():
         L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
         L.orc_add_envmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int, _f, _f, C.c_float, C.c_float]
         L.orc_set_bsdf_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f, _f]
+        L.orc_set_bsdf_texture_slot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f, _f, _f, _f]
         L.orc_add_mesh.argtypes = [C.c_void_p, _f, _f, C.c_int, _i, C.c_int, _f, C.c_int, _i, _f, _f, C.c_int, _f, _f, C.c_int, C.c_int]
         L.orc_add_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f, _f]
         L.orc_configure.argtypes = [C.c_void_p, _i, C.c_int]
@@ -128,9 +129,12 @@ class OracleScene:
         self.bsdf_ids[name] = idx
         return idx
 
-    def set_bsdf_texture(self, name, data, w, h, d_data=None):
+    def set_bsdf_texture(self, name, data, w, h, d_data=None, slot=0, xform=None, d_xform=None):
+        """slot 0 reflectance / diffuseReflectance, 1 specularReflectance, 2 roughness (1 channel);
+        xform = (scale, rotate, translate.x, translate.y) of the bitmap's uv transform, d_xform its tangent"""
         dat, dd = _f32(data).reshape(-1), (None if d_data is None else _f32(d_data).reshape(-1))
-        return self.L.orc_set_bsdf_texture(self.h, self.bsdf_ids[name], int(w), int(h), _fp(dat), _fp(dd))
+        xf, dxf = (None if xform is None else _f32(xform, (4,))), (None if d_xform is None else _f32(d_xform, (4,)))
+        return self.L.orc_set_bsdf_texture_slot(self.h, self.bsdf_ids[name], int(slot), int(w), int(h), _fp(dat), _fp(dd), _fp(xf), _fp(dxf))
 
     def add_envmap(self, data, w, h, to_world=None, scale=1.0, d_data=None, d_to_world_left=None, d_scale=0.0):
         """data: [h*w, 3]; to_world = raw 4x4 (left = identity); d_to_world_left = tangent of the left factor"""

@@ -23,13 +23,17 @@ import numpy as np
 
 from . import _lib, scenes  # noqa: F401
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Mesh", "PathTracer", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
 def _f32(a, shape=None) -> np.ndarray:
-    if hasattr(a, "detach"):   # torch tensor
+    if hasattr(a, "__psdr_value__"):   # Dr.Jit stand-in types (psdr_jit_b200.compat)
+        a = a.__psdr_value__()
+    elif hasattr(a, "detach"):   # torch tensor
         a = a.detach().cpu().numpy()
+    if shape is not None and np.ndim(a) == 0:      # DiffuseBSDF(0.5): a scalar fills the vector
+        a = np.full(shape, a, dtype=np.float32)
     a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
     return a if shape is None else a.reshape(shape)
 
@@ -98,6 +102,9 @@ class _Transformable(Object):
         self.d_to_world_right = np.zeros((4, 4), dtype=np.float32)
 
     def set_transform(self, mat, set_left: bool = True, tangent=None):
+        # a matrix whose entries depend on AD leaves (Dr.Jit stand-in): remember d(matrix)/d(leaf) for forward_to
+        if hasattr(mat, "__psdr_tangents__"):
+            self.__dict__.setdefault("_leaf_tangents", {})["to_world_left" if set_left else "to_world_right"] = mat.__psdr_tangents__()
         t = np.zeros((4, 4), dtype=np.float32) if tangent is None else _f32(tangent, (4, 4)).copy()
         m = mat if hasattr(mat, "requires_grad") else _mat4(mat)     # torch tensors stay live for autograd
         if set_left:
@@ -116,7 +123,7 @@ class _Transformable(Object):
 
     def _copy_transform_from(self, other: "_Transformable"):
         for n in ("to_world", "to_world_left", "to_world_right", "d_to_world", "d_to_world_left", "d_to_world_right"):
-            setattr(self, n, np.array(getattr(other, n), dtype=np.float32))
+            setattr(self, n, _f32(getattr(other, n), (4, 4)).copy())
 
 
 class PerspectiveCamera(_Transformable):
@@ -156,9 +163,7 @@ class DiffuseBSDF(BSDF):
     def _clone(self):
         r = self.reflectance
         if isinstance(r, Bitmap3fD):
-            c = Bitmap3fD(r.resolution[0], r.resolution[1], r.data)
-            c.d_data = None if r.d_data is None else _f32(r.d_data).reshape(-1, 3).copy()
-            r = c
+            r = r._clone()
         b = DiffuseBSDF(r)
         b.d_reflectance = _f32(self.d_reflectance).copy()
         b.twoSide = self.twoSide
@@ -167,26 +172,29 @@ class DiffuseBSDF(BSDF):
 
 class MicrofacetBSDF(BSDF):
     """reference src/psdr.cpp:298-304, src/bsdf/microfacet.cpp.  Argument order as in the reference:
-    (specular, diffuse, roughness) (include/psdr/bsdf/microfacet.h:12); 1x1 bitmaps."""
+    (specular, diffuse, roughness) (include/psdr/bsdf/microfacet.h:12); each slot is a constant (1x1 bitmap) or a
+    texture: Bitmap3fD, Bitmap3fD, Bitmap1fD (microfacet.h:17)."""
 
     def __init__(self, specular=None, diffuse=None, roughness=None):
-        self.specularReflectance = np.full(3, 0.04, dtype=np.float32) if specular is None else _f32(specular, (3,)).copy()
+        if isinstance(specular, Bitmap3fD):
+            self.specularReflectance = specular
+        else:
+            self.specularReflectance = np.full(3, 0.04, dtype=np.float32) if specular is None else _f32(specular, (3,)).copy()
         if isinstance(diffuse, Bitmap3fD):
             self.diffuseReflectance = diffuse
         else:
             self.diffuseReflectance = np.full(3, 0.5, dtype=np.float32) if diffuse is None else _f32(diffuse, (3,)).copy()
-        self.roughness = np.float32(0.8) if roughness is None else (roughness if hasattr(roughness, "requires_grad") else np.float32(roughness))
+        if isinstance(roughness, Bitmap1fD):
+            self.roughness = roughness
+        else:
+            self.roughness = np.float32(0.8) if roughness is None else (roughness if hasattr(roughness, "requires_grad") else np.float32(roughness))
         self.d_specularReflectance = np.zeros(3, dtype=np.float32)
         self.d_diffuseReflectance = np.zeros(3, dtype=np.float32)
         self.d_roughness = np.float32(0.0)
 
     def _clone(self):
-        d = self.diffuseReflectance
-        if isinstance(d, Bitmap3fD):
-            c = Bitmap3fD(d.resolution[0], d.resolution[1], d.data)
-            c.d_data = None if d.d_data is None else _f32(d.d_data).reshape(-1, 3).copy()
-            d = c
-        b = MicrofacetBSDF(self.specularReflectance, d, self.roughness)
+        cl = lambda x: x._clone() if isinstance(x, _Bitmap) else x      # noqa: E731
+        b = MicrofacetBSDF(cl(self.specularReflectance), cl(self.diffuseReflectance), cl(self.roughness))
         b.d_specularReflectance = _f32(self.d_specularReflectance, (3,)).copy()
         b.d_diffuseReflectance = _f32(self.d_diffuseReflectance).copy()
         b.d_roughness = np.float32(self.d_roughness)
@@ -198,18 +206,50 @@ class Emitter(Object):
     pass
 
 
-class Bitmap3fD:
-    """reference src/psdr.cpp:195-219 (Bitmap3fD): w x h RGB bitmap, data = [h*w, 3] row-major (pixel = y*w + x)."""
+class _Bitmap:
+    """reference src/psdr.cpp:195-219 (Bitmap1fD / Bitmap3fD): w x h bitmap, data = [h*w, channels] row-major
+    (pixel = y*w + x), plus the uv transform applied by eval (src/core/bitmap.cpp:64-72): ``scale``, ``rotate``
+    (radians, about the centre), ``translate`` (2 floats); ``d_*`` = forward-mode tangents."""
+    channels = 3
 
     def __init__(self, width: int = 1, height: int = 1, data=None):
+        c = self.channels
+        if np.isscalar(width) and data is None and not isinstance(width, (int, np.integer)):   # Bitmap(value)
+            width, data = 1, np.full((1, c), float(width), np.float32)
         self.resolution = (int(width), int(height))
         if data is None:
-            data = np.zeros((width * height, 3), dtype=np.float32)
-        self.data = data if hasattr(data, "requires_grad") else _f32(data).reshape(-1, 3).copy()
+            data = np.zeros((self.resolution[0] * self.resolution[1], c), dtype=np.float32)
+        self.data = data if hasattr(data, "requires_grad") else _f32(data).reshape(-1, c).copy()
         self.d_data = None
         n = int(np.prod(self.data.shape))
-        if n != 3 * width * height:
+        if n != c * self.resolution[0] * self.resolution[1]:
             raise RuntimeError("Bitmap: invalid data size!")
+        self.scale, self.rotate, self.translate = np.float32(1.0), np.float32(0.0), np.zeros(2, np.float32)
+        self.d_scale, self.d_rotate, self.d_translate = np.float32(0.0), np.float32(0.0), np.zeros(2, np.float32)
+
+    def _clone(self):
+        c = type(self)(self.resolution[0], self.resolution[1], self.data)
+        c.d_data = None if self.d_data is None else _f32(self.d_data).reshape(-1, self.channels).copy()
+        for n in ("scale", "rotate", "d_scale", "d_rotate"):
+            setattr(c, n, np.float32(getattr(self, n)))
+        c.translate, c.d_translate = _f32(self.translate, (2,)).copy(), _f32(self.d_translate, (2,)).copy()
+        return c
+
+    def _uv(self, tangent: bool):
+        if tangent:
+            return np.array([self.d_scale, self.d_rotate, self.d_translate[0], self.d_translate[1]], np.float32)
+        return np.array([self.scale, self.rotate, self.translate[0], self.translate[1]], np.float32)
+
+    def _textured(self) -> bool:
+        return self.resolution[0] * self.resolution[1] > 1
+
+
+class Bitmap3fD(_Bitmap):
+    channels = 3
+
+
+class Bitmap1fD(_Bitmap):
+    channels = 1
 
 
 class EnvironmentMap(Emitter):
@@ -231,8 +271,7 @@ class EnvironmentMap(Emitter):
         self.d_to_world_left = np.zeros((4, 4), np.float32) if tangent is None else _f32(tangent, (4, 4)).copy()
 
     def _clone(self):
-        e = EnvironmentMap(Bitmap3fD(self.radiance.resolution[0], self.radiance.resolution[1], self.radiance.data))
-        e.radiance.d_data = None if self.radiance.d_data is None else _f32(self.radiance.d_data).reshape(-1, 3).copy()
+        e = EnvironmentMap(self.radiance._clone())
         e.scale, e.d_scale = self.scale, self.d_scale
         e.to_world = _mat4(self.to_world)
         e.to_world_left = self.to_world_left if hasattr(self.to_world_left, "requires_grad") else _mat4(self.to_world_left)
@@ -381,6 +420,7 @@ class Scene(Object):
         self._device = device
         self._shard = (0, 1)
         self._accel = -1
+        self.reference_arithmetic = False     # Dr.Jit's approximate rcp in renderD's analytic primary hit (psdr_b200.h)
 
     def __del__(self):
         try:
@@ -504,11 +544,13 @@ class Scene(Object):
         o = self.opts
         _lib.check(L.psdr_scene_set_options(self._h, o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level))
         _lib.check(L.psdr_scene_set_seed(self._h, int(self.seed)))
+        _lib.check(L.psdr_scene_set_reference_arithmetic(self._h, int(bool(self.reference_arithmetic))))
         for b in self._bsdfs[self._pushed[0]:]:
             if isinstance(b, MicrofacetBSDF):
-                d0 = np.full(3, 0.5, np.float32) if isinstance(b.diffuseReflectance, Bitmap3fD) else _f32(b.diffuseReflectance)
-                rc = L.psdr_scene_add_bsdf_microfacet(self._h, b.id.encode(), _fp(_f32(b.specularReflectance)), _fp(d0),
-                                                      float(_f32(b.roughness).ravel()[0]), int(b.twoSide))
+                d0 = np.full(3, 0.5, np.float32) if isinstance(b.diffuseReflectance, _Bitmap) else _f32(b.diffuseReflectance)
+                s0 = np.full(3, 0.04, np.float32) if isinstance(b.specularReflectance, _Bitmap) else _f32(b.specularReflectance)
+                r0 = 0.8 if isinstance(b.roughness, _Bitmap) else float(_f32(b.roughness).ravel()[0])
+                rc = L.psdr_scene_add_bsdf_microfacet(self._h, b.id.encode(), _fp(s0), _fp(d0), r0, int(b.twoSide))
             else:
                 r0 = np.full(3, 0.5, np.float32) if isinstance(b.reflectance, Bitmap3fD) else _f32(b.reflectance)
                 rc = L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(r0), int(b.twoSide))
@@ -552,21 +594,23 @@ class Scene(Object):
             push(_lib.SENSOR_TO_WORLD_LEFT, i, s.to_world_left, s.d_to_world_left)
             push(_lib.SENSOR_TO_WORLD_RAW, i, s.to_world, s.d_to_world)
             push(_lib.SENSOR_TO_WORLD_RIGHT, i, s.to_world_right, s.d_to_world_right)
-        def push_reflectance(i, r, d_const):
-            if isinstance(r, Bitmap3fD) and r.resolution[0] * r.resolution[1] > 1:
-                _lib.check(L.psdr_scene_set_bsdf_texture(self._h, i, r.resolution[0], r.resolution[1]))
-                push(_lib.BSDF_REFLECTANCE, i, r.data, r.d_data)
+        def push_slot(i, slot, kind, r, d_const):
+            """one bitmap slot of a BSDF: texture (texels + uv transform) or constant"""
+            if isinstance(r, _Bitmap) and r._textured():
+                _lib.check(L.psdr_scene_set_bsdf_texture_slot(self._h, i, slot, r.resolution[0], r.resolution[1]))
+                push(kind, i, r.data, r.d_data)
+                push(_lib.BSDF_REFLECTANCE_UV + slot, i, r._uv(False), r._uv(True))
             else:
-                _lib.check(L.psdr_scene_set_bsdf_texture(self._h, i, 1, 1))
-                push(_lib.BSDF_REFLECTANCE, i, r.data if isinstance(r, Bitmap3fD) else r, d_const)
+                _lib.check(L.psdr_scene_set_bsdf_texture_slot(self._h, i, slot, 1, 1))
+                push(kind, i, r.data if isinstance(r, _Bitmap) else np.reshape(_f32(r), (-1,)), np.reshape(_f32(d_const), (-1,)))
 
         for i, b in enumerate(self._bsdfs):
             if isinstance(b, MicrofacetBSDF):
-                push_reflectance(i, b.diffuseReflectance, b.d_diffuseReflectance)
-                push(_lib.BSDF_SPECULAR, i, b.specularReflectance, b.d_specularReflectance)
-                push(_lib.BSDF_ROUGHNESS, i, np.reshape(_f32(b.roughness), (1,)), np.reshape(_f32(b.d_roughness), (1,)))
+                push_slot(i, _lib.TEX_REFLECTANCE, _lib.BSDF_REFLECTANCE, b.diffuseReflectance, b.d_diffuseReflectance)
+                push_slot(i, _lib.TEX_SPECULAR, _lib.BSDF_SPECULAR, b.specularReflectance, b.d_specularReflectance)
+                push_slot(i, _lib.TEX_ROUGHNESS, _lib.BSDF_ROUGHNESS, b.roughness, b.d_roughness)
             else:
-                push_reflectance(i, b.reflectance, b.d_reflectance)
+                push_slot(i, _lib.TEX_REFLECTANCE, _lib.BSDF_REFLECTANCE, b.reflectance, b.d_reflectance)
         for i, e in enumerate(self._emitters):
             if isinstance(e, EnvironmentMap):
                 push(_lib.ENVMAP_RADIANCE, i, e.radiance.data, e.radiance.d_data)
@@ -575,6 +619,7 @@ class Scene(Object):
             else:
                 push(_lib.EMITTER_RADIANCE, i, e.radiance, e.d_radiance)
         act = np.asarray(list(active_sensor), dtype=np.int32)
+        self._last_active = [int(a) for a in act]
         _lib.check(L.psdr_scene_configure(self._h, _ip(act), len(act)))
         if o.log_level > 0 and o.sppe > 0:
             print("(%s) primary edges initialized." % ", ".join(str(self.num_primary_edges(i)) for i in range(len(self._sensors))))
@@ -588,7 +633,8 @@ class Scene(Object):
                                ("to_world_right", _lib.SENSOR_TO_WORLD_RIGHT)),
                     "BSDF": (("reflectance", _lib.BSDF_REFLECTANCE), ("diffuseReflectance", _lib.BSDF_REFLECTANCE),
                              ("reflectance.data", _lib.BSDF_REFLECTANCE), ("diffuseReflectance.data", _lib.BSDF_REFLECTANCE),
-                             ("specularReflectance", _lib.BSDF_SPECULAR), ("roughness", _lib.BSDF_ROUGHNESS)),
+                             ("specularReflectance", _lib.BSDF_SPECULAR), ("roughness", _lib.BSDF_ROUGHNESS),
+                             ("specularReflectance.data", _lib.BSDF_SPECULAR), ("roughness.data", _lib.BSDF_ROUGHNESS)),
                     "Emitter": (("radiance", _lib.EMITTER_RADIANCE),),
                     "EnvironmentMap": (("radiance.data", _lib.ENVMAP_RADIANCE), ("scale", _lib.ENVMAP_SCALE),
                                        ("to_world_left", _lib.ENVMAP_TO_WORLD_LEFT))}

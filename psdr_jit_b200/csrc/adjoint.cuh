@@ -178,13 +178,17 @@ template <class S> struct BsdfP {
     V3<S> diff, spec;
     S rough;
 };
-template <class S> __device__ __forceinline__ BsdfP<S> bsdf_params(const DBsdf &b, V3f refl) {
+struct BsdfVals {       // the three parameter slots of a BSDF evaluated at a vertex (constants or texture lookups)
+    V3f refl, spec;
+    float rough;
+};
+template <class S> __device__ __forceinline__ BsdfP<S> bsdf_params(const DBsdf &b, const BsdfVals &v) {
     BsdfP<S> p;
     p.type = b.type;
     p.two_side = b.two_side;
-    p.diff = V3<S>(S(refl.x), S(refl.y), S(refl.z));
-    p.spec = V3<S>(S(b.spec[0]), S(b.spec[1]), S(b.spec[2]));
-    p.rough = S(b.rough);
+    p.diff = V3<S>(S(v.refl.x), S(v.refl.y), S(v.refl.z));
+    p.spec = V3<S>(S(v.spec.x), S(v.spec.y), S(v.spec.z));
+    p.rough = S(v.rough);
     return p;
 }
 template <class S> __device__ __forceinline__ S iso_smith_g1(S alpha, S vz, S vdoth) {
@@ -226,9 +230,9 @@ struct BsdfJet {        // value and partials of sum_c W_c f_c
     V3f f;
     float d_ci, d_co, d_cio;
 };
-template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, V3f refl, float ci, float co, float cio, V3f W) {
+template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, const BsdfVals &bv, float ci, float co, float cio, V3f W) {
     BsdfJet j;
-    const BsdfP<Dual> p = bsdf_params<Dual>(b, refl);
+    const BsdfP<Dual> p = bsdf_params<Dual>(b, bv);
     const V3d a = bsdf_iso<Dual, kCfg>(p, Dual(ci, 1.f), Dual(co), Dual(cio));
     const V3d c = bsdf_iso<Dual, kCfg>(p, Dual(ci), Dual(co, 1.f), Dual(cio));
     j.f = val(a);
@@ -241,10 +245,29 @@ template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, 
     }
     return j;
 }
-// d(sum_c W_c f_c * scale)/d(params): reflectance (Diffuse / Microfacet diffuse), Microfacet specular + roughness
-// uv_bar: d(contribution)/d(texture coordinate) through a textured reflectance (used at the primary hit only)
-template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, float ci, float co,
-                                                float cio, V3f W, float scale, V2f uv, V2f &uv_bar) {
+// texel gradients of one texture slot: value_bar (rgb, or x for 1 channel) scattered through the four bilinear taps, and
+// the lookup's uv derivative added to uv_bar
+__device__ __forceinline__ void tex_slot_grad(const GradAcc &acc, const GradLayout &gl, const DTex &t, V2f uv, V3f value_bar, V2f &uv_bar) {
+    EnvTexelTaps tp;
+    tex_eval_uv<float>(t, false, uv, &tp);
+    const int idx[4] = {tp.i00, tp.i10, tp.i01, tp.i11};
+    const float bw[4] = {tp.w0y * tp.w0x, tp.w0y * tp.w1x, tp.w1y * tp.w0x, tp.w1y * tp.w1x};
+    const int tbase = gl.total + t.goff;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (t.ch == 1) acc.add(tbase + idx[k], value_bar.x * bw[k]);
+        else acc.add3(tbase + 3 * idx[k], value_bar * bw[k]);
+    }
+    const V3d ru = tex_eval_uv<Dual>(t, false, V2d(Dual(uv.x, 1.f), Dual(uv.y)));
+    const V3d rv = tex_eval_uv<Dual>(t, false, V2d(Dual(uv.x), Dual(uv.y, 1.f)));
+    uv_bar.x += value_bar.x * ru.x.d + value_bar.y * ru.y.d + value_bar.z * ru.z.d;
+    uv_bar.y += value_bar.x * rv.x.d + value_bar.y * rv.y.d + value_bar.z * rv.z.d;
+}
+// d(sum_c W_c f_c * scale)/d(params): reflectance (Diffuse / Microfacet diffuse), Microfacet specular + roughness;
+// constants go to the BSDF block of the table, textured slots to their texel blocks.
+// uv_bar: d(contribution)/d(texture coordinate) through textured slots (used at the primary hit only)
+template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, const BsdfVals &bv,
+                                                float ci, float co, float cio, V3f W, float scale, V2f uv, V2f &uv_bar) {
     if (b.two_side) {
         if (signbit_(ci)) co = -co;
         ci = fabsf(ci);
@@ -252,33 +275,24 @@ template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAc
     if (!(ci > 0.f && co > 0.f)) return;
     const int base = gl.off_bsdf + kGradBsdf * bi;
     const float k = kInvPi * co * scale;
-    if ((kCfg & kCfgFull) && b.tex_w > 0) {   // textured reflectance: the four taps, and the lookup's uv derivative
-        EnvTexelTaps tp;
-        bitmap_eval_uv<float>(b.tex, nullptr, b.tex_w, b.tex_h, uv, &tp);
-        const int idx[4] = {tp.i00, tp.i10, tp.i01, tp.i11};
-        const float bw[4] = {tp.w0y * tp.w0x, tp.w0y * tp.w1x, tp.w1y * tp.w0x, tp.w1y * tp.w1x};
-        const int tbase = gl.total + b.tex_goff;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) acc.add3(tbase + 3 * idx[t], W * (k * bw[t]));
-        const V3d ru = bitmap_eval_uv<Dual>(b.tex, nullptr, b.tex_w, b.tex_h, V2d(Dual(uv.x, 1.f), Dual(uv.y)));
-        const V3d rv = bitmap_eval_uv<Dual>(b.tex, nullptr, b.tex_w, b.tex_h, V2d(Dual(uv.x), Dual(uv.y, 1.f)));
-        uv_bar.x += k * (W.x * ru.x.d + W.y * ru.y.d + W.z * ru.z.d);
-        uv_bar.y += k * (W.x * rv.x.d + W.y * rv.y.d + W.z * rv.z.d);
-    } else acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));
+    if ((kCfg & kCfgFull) && b.tex[0].w > 0) tex_slot_grad(acc, gl, b.tex[0], uv, W * k, uv_bar);
+    else acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));
     if ((kCfg & kCfgFull) && b.type == 1) {
         Dual dg, e;
-        iso_specular<Dual>(Dual(b.rough, 1.f), Dual(ci), Dual(co), Dual(cio), dg, e);
+        iso_specular<Dual>(Dual(bv.rough, 1.f), Dual(ci), Dual(co), Dual(cio), dg, e);
         // f_spec,c = (F0_c + (1 - F0_c) e) dg co
         const float ks = (1.f - e.v) * dg.v * co * scale;
-        acc.add3(base + 4, V3f(W.x * ks, W.y * ks, W.z * ks));
+        if (b.tex[1].w > 0) tex_slot_grad(acc, gl, b.tex[1], uv, W * ks, uv_bar);
+        else acc.add3(base + 4, V3f(W.x * ks, W.y * ks, W.z * ks));
         float gr = 0.f;
-        const float F0[3] = {b.spec[0], b.spec[1], b.spec[2]}, Wc[3] = {W.x, W.y, W.z};
+        const float F0[3] = {bv.spec.x, bv.spec.y, bv.spec.z}, Wc[3] = {W.x, W.y, W.z};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const Dual fr = Dual(F0[c]) + Dual(1.f - F0[c]) * e;
             gr += Wc[c] * (fr * dg).d;
         }
-        acc.add(base + 3, gr * co * scale);
+        if (b.tex[2].w > 0) tex_slot_grad(acc, gl, b.tex[2], uv, V3f(gr * co * scale, 0.f, 0.f), uv_bar);
+        else acc.add(base + 3, gr * co * scale);
     }
 }
 
@@ -290,7 +304,7 @@ struct VtxGeo {
     int tri, mesh, bsdf, emitter;
     bool face_normals;
     V2f uv, duv0, duv1;     // texture coordinate and its edge differences (uv = uv0 + u duv0 + v duv1)
-    V3f refl;               // reflectance / diffuseReflectance of the BSDF at uv
+    BsdfVals bv;            // reflectance / diffuseReflectance, specularReflectance, roughness of the BSDF at uv
 };
 __device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
     VtxGeo g;
@@ -317,10 +331,13 @@ __device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u,
         g.duv1 = V2f(t2.x - t0.x, t2.y - t0.y);
         g.uv = V2f(fmaf(g.duv0.x, u, fmaf(g.duv1.x, v, t0.x)), fmaf(g.duv0.y, u, fmaf(g.duv1.y, v, t0.y)));
     }
-    g.refl = V3f(0.f, 0.f, 0.f);
+    g.bv.refl = g.bv.spec = V3f(0.f, 0.f, 0.f);
+    g.bv.rough = 0.f;
     if (g.bsdf >= 0) {
         const DBsdf &b = sc.bsdfs[g.bsdf];
-        g.refl = b.tex_w > 0 ? bitmap_eval_uv<float>(b.tex, nullptr, b.tex_w, b.tex_h, g.uv) : V3f(b.refl[0], b.refl[1], b.refl[2]);
+        g.bv.refl = b.tex[0].w > 0 ? tex_eval_uv<float>(b.tex[0], false, g.uv) : V3f(b.refl[0], b.refl[1], b.refl[2]);
+        g.bv.spec = b.tex[1].w > 0 ? tex_eval_uv<float>(b.tex[1], false, g.uv) : V3f(b.spec[0], b.spec[1], b.spec[2]);
+        g.bv.rough = b.tex[2].w > 0 ? tex_eval_uv<float>(b.tex[2], false, g.uv).x : b.rough;
     }
     return g;
 }
@@ -453,13 +470,13 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const float cy = -dot(ny, wo);
     const float G = fabsf(cy) / (t * t);
     const float ci = dot(wi, x.shn), co = dot(wo, x.shn), cio = dot(wi, wo);
-    const BsdfJet j = bsdf_jet<kCfg>(b, x.refl, ci, co, cio, W);
+    const BsdfJet j = bsdf_jet<kCfg>(b, x.bv, ci, co, cio, W);
     r.f = j.f;
     r.geo = G * scale;
     const float phi = W.x * j.f.x + W.y * j.f.y + W.z * j.f.z;          // sum_c W_c f_c
     // C = phi * G * J * scale
     const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
-    bsdf_param_grad<kCfg>(acc, gl, x.bsdf, b, ci, co, cio, W, G * scale, x.uv, xa.uv);
+    bsdf_param_grad<kCfg>(acc, gl, x.bsdf, b, x.bv, ci, co, cio, W, G * scale, x.uv, xa.uv);
     const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
     // adjoints are often exactly 0 (W = 0): multiply by reciprocals, a zero numerator sends div.rn.f32 down its slow path
     const float inv_t = 1.f / t, inv_t2 = 1.f / (t * t);

@@ -128,6 +128,13 @@ int psdr_scene_set_accel(psdr_scene *s, int mode) {
     return 0;
 }
 
+int psdr_scene_set_reference_arithmetic(psdr_scene *s, int on) {
+    if (!s) return fail("null scene");
+    s->sc.ref_rcp = on != 0;
+    s->sc.configured = false;
+    return 0;
+}
+
 int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float reflectance[3], int two_side) {
     if (!s || !id || !reflectance) { fail("null argument"); return -1; }
     Scene &sc = s->sc;
@@ -159,21 +166,24 @@ int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float sp
     return (int) sc.bsdfs.size() - 1;
 }
 
-int psdr_scene_set_bsdf_texture(psdr_scene *s, int index, int w, int h) {
+int psdr_scene_set_bsdf_texture_slot(psdr_scene *s, int index, int slot, int w, int h) {
     if (!s) return fail("null scene");
     Scene &sc = s->sc;
     if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+    if (slot < 0 || slot > 2) return fail("invalid texture slot");
+    if (slot > 0 && sc.bsdfs[index].type != 1) return fail("specular / roughness textures need a MicrofacetBSDF");
     if (w < 1 || h < 1 || (w * h > 1 && (w < 2 || h < 2))) return fail("Bitmap: invalid resolution!");
-    HBsdf &b = sc.bsdfs[index];
-    if (w * h == 1) { b.tex_w = b.tex_h = 0; b.tex.clear(); b.dtex.clear(); }
-    else if (b.tex_w != w || b.tex_h != h) {
-        b.tex_w = w; b.tex_h = h;
-        b.tex.assign((size_t) 3 * w * h, 0.5f);
-        b.dtex.clear();
+    HBsdf::Tex &t = sc.bsdfs[index].tex[slot];
+    if (w * h == 1) { t.w = t.h = 0; t.data.clear(); t.ddata.clear(); }
+    else if (t.w != w || t.h != h) {
+        t.w = w; t.h = h;
+        t.data.assign((size_t) HBsdf::tex_channels(slot) * w * h, 0.5f);
+        t.ddata.clear();
     }
     sc.configured = false;
     return 0;
 }
+int psdr_scene_set_bsdf_texture(psdr_scene *s, int index, int w, int h) { return psdr_scene_set_bsdf_texture_slot(s, index, PSDR_TEX_REFLECTANCE, w, h); }
 
 int psdr_scene_add_mesh(psdr_scene *s, const float *v, int nv, const int *f, int nf, const float *uv, int nuv, const int *fuv,
                         const float *to_world, const char *bsdf_id, const float *radiance, int use_face_normals, int enable_edges) {
@@ -253,6 +263,17 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
     if (!s || !data) return fail("null argument");
     Scene &sc = s->sc;
     auto put = [&](Dual &x, float val_) { if (tangent) x.d = val_; else x.v = val_; };
+    // texel data (or its tangent) of a textured slot; returns -1 if the slot holds a constant
+    auto put_texels = [&](HBsdf::Tex &t, int channels) -> int {
+        if (t.w <= 0) return -1;
+        if (n != channels * t.w * t.h) return fail("texture size mismatch");
+        if (tangent) {
+            bool any = false;
+            for (int i = 0; i < n; ++i) any |= data[i] != 0.f;
+            if (any) t.ddata.assign(data, data + n); else t.ddata.clear();
+        } else t.data.assign(data, data + n);
+        return 0;
+    };
     switch (kind) {
         case PSDR_MESH_VERTICES: {
             if (index < 0 || index >= (int) sc.meshes.size()) return fail("invalid mesh index");
@@ -277,30 +298,36 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
         }
         case PSDR_BSDF_REFLECTANCE: {
             if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
-            if (sc.bsdfs[index].tex_w > 0) {   // textured
-                HBsdf &b = sc.bsdfs[index];
-                if (n != 3 * b.tex_w * b.tex_h) return fail("texture size mismatch");
-                if (tangent) {
-                    bool any = false;
-                    for (int i = 0; i < n; ++i) any |= data[i] != 0.f;
-                    if (any) b.dtex.assign(data, data + n); else b.dtex.clear();
-                } else b.tex.assign(data, data + n);
-                break;
-            }
+            const int rc = put_texels(sc.bsdfs[index].tex[0], 3);
+            if (rc > 0) return rc;
+            if (rc == 0) break;
             if (n != 3) return fail("reflectance is 3 floats");
             put(sc.bsdfs[index].reflectance.x, data[0]); put(sc.bsdfs[index].reflectance.y, data[1]); put(sc.bsdfs[index].reflectance.z, data[2]);
             break;
         }
         case PSDR_BSDF_SPECULAR: {
             if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            const int rc = put_texels(sc.bsdfs[index].tex[1], 3);
+            if (rc > 0) return rc;
+            if (rc == 0) break;
             if (n != 3) return fail("specular reflectance is 3 floats");
             put(sc.bsdfs[index].specular.x, data[0]); put(sc.bsdfs[index].specular.y, data[1]); put(sc.bsdfs[index].specular.z, data[2]);
             break;
         }
         case PSDR_BSDF_ROUGHNESS: {
             if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            const int rc = put_texels(sc.bsdfs[index].tex[2], 1);
+            if (rc > 0) return rc;
+            if (rc == 0) break;
             if (n != 1) return fail("roughness is 1 float");
             put(sc.bsdfs[index].roughness, data[0]);
+            break;
+        }
+        case PSDR_BSDF_REFLECTANCE_UV: case PSDR_BSDF_SPECULAR_UV: case PSDR_BSDF_ROUGHNESS_UV: {
+            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            if (n != 4) return fail("a uv transform is 4 floats (scale, rotate, translate.x, translate.y)");
+            HBsdf::Tex &t = sc.bsdfs[index].tex[kind - PSDR_BSDF_REFLECTANCE_UV];
+            put(t.scale, data[0]); put(t.rot, data[1]); put(t.tx, data[2]); put(t.ty, data[3]);
             break;
         }
         case PSDR_ENVMAP_RADIANCE: {
@@ -352,7 +379,9 @@ int psdr_scene_clear_tangents(psdr_scene *s) {
     for (HCamera &c : sc.cameras)
         for (auto &M : c.to_world)
             for (int i = 0; i < 16; ++i) M.m[i / 4][i % 4].d = 0.f;
-    for (HBsdf &b : sc.bsdfs) { b.dtex.clear(); b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
+    for (HBsdf &b : sc.bsdfs) {
+        for (HBsdf::Tex &t : b.tex) { t.ddata.clear(); t.scale = detach(t.scale); t.rot = detach(t.rot); t.tx = detach(t.tx); t.ty = detach(t.ty); }
+        b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
     for (HEmitter &e : sc.emitters) e.radiance = detach(e.radiance);
     sc.env.ddata.clear();
     sc.env.scale = detach(sc.env.scale);
@@ -688,6 +717,11 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
         for (int i = 0; i < count; ++i) out[i] = (float) src[i];
         return 0;
     };
+    auto copy_tex = [&](const std::vector<float> &src) {
+        if (n != (int) src.size()) return fail("gradient buffer size mismatch");
+        std::memcpy(out, src.data(), sizeof(float) * n);
+        return 0;
+    };
     switch (kind) {
         case PSDR_MESH_VERTICES:
             if (index < 0 || index >= (int) g.meshes.size()) return fail("invalid mesh index");
@@ -700,11 +734,7 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
             return copy(g.cameras[index].to_world[kind - PSDR_SENSOR_TO_WORLD_LEFT], 16);
         case PSDR_BSDF_REFLECTANCE:
             if (index < 0 || 3 * index + 3 > (int) g.bsdf_refl.size()) return fail("invalid BSDF index");
-            if (index < (int) g.bsdf_tex.size() && !g.bsdf_tex[index].empty()) {
-                if (n != (int) g.bsdf_tex[index].size()) return fail("gradient buffer size mismatch");
-                std::memcpy(out, g.bsdf_tex[index].data(), sizeof(float) * n);
-                return 0;
-            }
+            if (index < (int) g.bsdf_tex[0].size() && !g.bsdf_tex[0][index].empty()) return copy_tex(g.bsdf_tex[0][index]);
             return copy(g.bsdf_refl.data() + 3 * index, 3);
         case PSDR_ENVMAP_RADIANCE:
             if (n != (int) g.env_radiance.size()) return fail("gradient buffer size mismatch");
@@ -714,9 +744,11 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
         case PSDR_ENVMAP_TO_WORLD_LEFT: return copy(g.env_to_world_left, 16);
         case PSDR_BSDF_SPECULAR:
             if (index < 0 || 3 * index + 3 > (int) g.bsdf_spec.size()) return fail("invalid BSDF index");
+            if (index < (int) g.bsdf_tex[1].size() && !g.bsdf_tex[1][index].empty()) return copy_tex(g.bsdf_tex[1][index]);
             return copy(g.bsdf_spec.data() + 3 * index, 3);
         case PSDR_BSDF_ROUGHNESS:
             if (index < 0 || index >= (int) g.bsdf_rough.size()) return fail("invalid BSDF index");
+            if (index < (int) g.bsdf_tex[2].size() && !g.bsdf_tex[2][index].empty()) return copy_tex(g.bsdf_tex[2][index]);
             return copy(g.bsdf_rough.data() + index, 1);
         case PSDR_EMITTER_RADIANCE:
             if (index < 0 || 3 * index + 3 > (int) g.emitter_rad.size()) return fail("invalid emitter index");

@@ -398,11 +398,26 @@ template <class S> struct Its {   // reference include/psdr/core/intersection.h:
 };
 
 // reference include/psdr/utils.h:82-93
+// rcp() as Dr.Jit emits it for CUDA floats: rcp.approx.ftz.f32 (ext/drjit/ext/drjit-core/src/cuda_eval.cpp:638-640),
+// within 1 ulp of 1/x but not correctly rounded.  Used only on request (DScene::ref_rcp): the primary hit of renderD is
+// reconstructed as o + t d, and on faces lit at grazing angles the share of next-event rays that re-intersect the face
+// itself depends on which side of the surface that rounding leaves the point (DESIGN.md "parity").
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_sel(float a, bool approx) { return approx ? rcp_approx(a) : 1.f / a; }
+__device__ __forceinline__ Dual rcp_sel(Dual a, bool approx) {
+    if (!approx) return rcp_(a);
+    const float r = rcp_approx(a.v);
+    return Dual(r, -a.d * r * r);
+}
 template <class S>
-__device__ __forceinline__ void ray_intersect_triangle(V3<S> p0, V3<S> e1, V3<S> e2, V3<S> o, V3<S> d, S &u, S &v, S &t) {
+__device__ __forceinline__ void ray_intersect_triangle(V3<S> p0, V3<S> e1, V3<S> e2, V3<S> o, V3<S> d, S &u, S &v, S &t, bool approx_rcp = false) {
     const V3<S> h = cross(d, e2);
     const S a = dot(e1, h);
-    const S f = rcp_(a);
+    const S f = rcp_sel(a, approx_rcp);
     const V3<S> s = o - p0;
     u = f * dot(s, h);
     const V3<S> q = cross(s, e1);
@@ -456,7 +471,7 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
         its.bv = h.v;
     } else {
         S u, v, t;
-        ray_intersect_triangle(T.p0, T.e1, T.e2, o, d, u, v, t);
+        ray_intersect_triangle(T.p0, T.e1, T.e2, o, d, u, v, t, sc.ref_rcp != 0);
         const V2<S> uv(u, v);
         bary_u = u;
         bary_v = v;
@@ -493,21 +508,29 @@ template <> __device__ __forceinline__ V3f bsdf_reflectance_const<float>(const D
 template <> __device__ __forceinline__ V3d bsdf_reflectance_const<Dual>(const DBsdf &b) {
     return V3d(Dual(b.refl[0], b.d_refl[0]), Dual(b.refl[1], b.d_refl[1]), Dual(b.refl[2], b.d_refl[2]));
 }
-// Bitmap3fD::eval(its.uv): 1x1 -> the constant, else bilinear texture lookup (reference src/core/bitmap.cpp:46-131);
+// Bitmap::eval(its.uv): 1x1 -> the constant, else transformed bilinear texture lookup (reference src/core/bitmap.cpp:46-131);
 // textures belong to the "full" kernel family
 template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_reflectance(const DBsdf &b, V2<S> uv) {
-    if ((kCfg & kCfgFull) && b.tex_w > 0) return bitmap_eval_uv<S>(b.tex, IsDual<S>::value ? b.dtex : nullptr, b.tex_w, b.tex_h, uv);
+    if ((kCfg & kCfgFull) && b.tex[0].w > 0) return tex_eval_uv<S>(b.tex[0], IsDual<S>::value, uv);
     return bsdf_reflectance_const<S>(b);
 }
 
-template <class S> __device__ __forceinline__ V3<S> bsdf_specular(const DBsdf &b);
-template <> __device__ __forceinline__ V3f bsdf_specular<float>(const DBsdf &b) { return V3f(b.spec[0], b.spec[1], b.spec[2]); }
-template <> __device__ __forceinline__ V3d bsdf_specular<Dual>(const DBsdf &b) {
+template <class S> __device__ __forceinline__ V3<S> bsdf_specular_const(const DBsdf &b);
+template <> __device__ __forceinline__ V3f bsdf_specular_const<float>(const DBsdf &b) { return V3f(b.spec[0], b.spec[1], b.spec[2]); }
+template <> __device__ __forceinline__ V3d bsdf_specular_const<Dual>(const DBsdf &b) {
     return V3d(Dual(b.spec[0], b.d_spec[0]), Dual(b.spec[1], b.d_spec[1]), Dual(b.spec[2], b.d_spec[2]));
 }
-template <class S> __device__ __forceinline__ S bsdf_roughness(const DBsdf &b);
-template <> __device__ __forceinline__ float bsdf_roughness<float>(const DBsdf &b) { return b.rough; }
-template <> __device__ __forceinline__ Dual bsdf_roughness<Dual>(const DBsdf &b) { return Dual(b.rough, b.d_rough); }
+template <class S> __device__ __forceinline__ V3<S> bsdf_specular(const DBsdf &b, V2<S> uv) {     // Microfacet: full family only
+    if (b.tex[1].w > 0) return tex_eval_uv<S>(b.tex[1], IsDual<S>::value, uv);
+    return bsdf_specular_const<S>(b);
+}
+template <class S> __device__ __forceinline__ S bsdf_roughness_const(const DBsdf &b);
+template <> __device__ __forceinline__ float bsdf_roughness_const<float>(const DBsdf &b) { return b.rough; }
+template <> __device__ __forceinline__ Dual bsdf_roughness_const<Dual>(const DBsdf &b) { return Dual(b.rough, b.d_rough); }
+template <class S> __device__ __forceinline__ S bsdf_roughness(const DBsdf &b, V2<S> uv) {
+    if (b.tex[2].w > 0) return tex_eval_uv<S>(b.tex[2], IsDual<S>::value, uv).x;
+    return bsdf_roughness_const<S>(b);
+}
 
 // ---- GGX (reference src/bsdf/ggx.cpp:13-109), isotropic: alpha_u = alpha_v = alpha ---------------
 template <class S> __device__ __forceinline__ S ggx_eval(S alpha, V3<S> m) {
@@ -537,8 +560,8 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> microfacet_eval(co
     const V3<S> diffuse = bsdf_reflectance<S, kCfg>(b, uv) * S(kInvPi);
     const V3<S> H = normalize(wi + wo);
     const S cos_vh = dot(H, wi);
-    const V3<S> F0 = bsdf_specular<S>(b);
-    const S alpha = sqr(bsdf_roughness<S>(b));
+    const V3<S> F0 = bsdf_specular<S>(b, uv);
+    const S alpha = sqr(bsdf_roughness<S>(b, uv));
     const S ggx = ggx_eval<S>(alpha, H);
     const S coeff = cos_vh * (S(-5.55473f) * cos_vh - S(6.8316f));
     const S e = exp2_(coeff);
@@ -566,14 +589,14 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DS
 }
 
 // Microfacet::__pdf (reference src/bsdf/microfacet.cpp:108-133), detached
-__device__ __forceinline__ float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo) {
+__device__ __forceinline__ float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo, V2f uv) {
     if (b.two_side) {
         if (signbit_(wi.z)) wo.z = -wo.z;
         wi.z = fabsf(wi.z);
     }
     const V3f m = normalize(wo + wi);
     if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
-    const float alpha = sqr(b.rough);
+    const float alpha = sqr(bsdf_roughness<float>(b, uv));
     return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
 }
 
@@ -581,7 +604,7 @@ template <class S, int kCfg> __device__ __forceinline__ float bsdf_pdf(const DSc
     if (!active || !its.valid) return 0.f;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return 0.f;
-    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo));
+    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo), val(its.uv));
     float wiz = val(its.wi.z), woz = val(wo.z);
     if (sc.bsdfs[bi].two_side) {
         if (signbit_(wiz)) woz = -woz;
@@ -622,10 +645,10 @@ __device__ __forceinline__ V2f ggx_sample_visible_11(float cos_theta_i, V2f samp
 }
 
 // Microfacet::__sample (reference src/bsdf/microfacet.cpp:80-98) + GGXDistribution::sample (ggx.cpp:36-79)
-__device__ __forceinline__ BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sample, bool active) {
+__device__ __forceinline__ BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
     BsdfSample bs;
     if (b.two_side) wi.z = fabsf(wi.z);
-    const float alpha = sqr(b.rough);
+    const float alpha = sqr(bsdf_roughness<float>(b, uv));
     const V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
     const float sin_theta_2 = fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / sqrtf(sin_theta_2);
     const bool pole = fabsf(sin_theta_2) <= 4.f * kEpsilon;
@@ -650,7 +673,7 @@ template <class S, int kCfg> __device__ __forceinline__ BsdfSample bsdf_sample(c
     if (!its.valid) return bs;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return bs;
-    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active);
+    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active, val(its.uv));
     float wiz = val(its.wi.z);
     if (sc.bsdfs[bi].two_side) wiz = fabsf(wiz);
     const V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));

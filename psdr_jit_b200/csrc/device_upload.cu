@@ -173,11 +173,11 @@ void upload_scene(Scene &sc) {
                  o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
                  o_nodes = pk.add(nodes), o_order = pk.add(order), o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf),
                  o_env = pk.add(sc.env.data), o_denv = pk.add(sc.env.ddata), o_cp = pk.add(sc.env.cell.pmf), o_cc = pk.add(sc.env.cell.cmf);
-    std::vector<size_t> o_tex(sc.bsdfs.size(), 0), o_dtex(sc.bsdfs.size(), 0);
+    std::vector<size_t> o_tex(3 * sc.bsdfs.size(), 0), o_dtex(3 * sc.bsdfs.size(), 0);
     for (size_t i = 0; i < sc.bsdfs.size(); ++i)
-        if (sc.bsdfs[i].tex_w > 0) {
-            o_tex[i] = pk.add(sc.bsdfs[i].tex);
-            o_dtex[i] = pk.add(sc.bsdfs[i].dtex);
+        for (int k = 0; k < 3; ++k) if (sc.bsdfs[i].tex[k].w > 0) {
+            o_tex[3 * i + k] = pk.add(sc.bsdfs[i].tex[k].data);
+            o_dtex[3 * i + k] = pk.add(sc.bsdfs[i].tex[k].ddata);
         }
 
     if (!sc.dev) sc.dev = new DeviceBuffers();
@@ -194,14 +194,23 @@ void upload_scene(Scene &sc) {
     // texture pointers of the BSDF records can only be filled in once the allocation is known
     for (size_t i = 0; i < sc.bsdfs.size(); ++i) {
         DBsdf *rec = reinterpret_cast<DBsdf *>(pk.bytes.data() + o_bsdf) + i;
-        rec->tex_w = rec->tex_h = 0;
-        rec->tex = rec->dtex = nullptr;
-        rec->tex_goff = sc.texture_grad_offset((int) i);   // relative to the end of the gradient table
-        if (sc.bsdfs[i].tex_w > 0) {
-            rec->tex_w = sc.bsdfs[i].tex_w;
-            rec->tex_h = sc.bsdfs[i].tex_h;
-            rec->tex = (const float *) ((const unsigned char *) db.dev + o_tex[i]);
-            rec->dtex = sc.bsdfs[i].dtex.empty() ? nullptr : (const float *) ((const unsigned char *) db.dev + o_dtex[i]);
+        for (int k = 0; k < 3; ++k) {
+            const HBsdf::Tex &t = sc.bsdfs[i].tex[k];
+            DTex &dt = rec->tex[k];
+            dt = DTex{};
+            dt.ch = HBsdf::tex_channels(k);
+            dt.goff = sc.texture_grad_offset((int) i, k);   // relative to the end of the gradient table
+            // cos / sin of the rotation on the host (the reference evaluates them per lookup on the device)
+            const float cr = std::cos(t.rot.v), sr = std::sin(t.rot.v);
+            dt.cr = cr; dt.sr = sr; dt.d_cr = -sr * t.rot.d; dt.d_sr = cr * t.rot.d;
+            dt.scale = t.scale.v; dt.d_scale = t.scale.d;
+            dt.tx = t.tx.v; dt.d_tx = t.tx.d; dt.ty = t.ty.v; dt.d_ty = t.ty.d;
+            if (t.w > 0) {
+                dt.w = t.w;
+                dt.h = t.h;
+                dt.data = (const float *) ((const unsigned char *) db.dev + o_tex[3 * i + k]);
+                dt.ddata = t.ddata.empty() ? nullptr : (const float *) ((const unsigned char *) db.dev + o_dtex[3 * i + k]);
+            }
         }
     }
     std::memcpy(db.host, pk.bytes.data(), pk.bytes.size());
@@ -219,8 +228,9 @@ void upload_scene(Scene &sc) {
     d.n_sec_edges = (int) sc.sec_edges.size();
     d.n_nodes = (int) nodes.size();
     d.use_bvh = use_bvh ? 1 : 0;
+    d.ref_rcp = sc.ref_rcp ? 1 : 0;
     d.full_features = sc.env.present ? 1 : 0;
-    for (const HBsdf &b : sc.bsdfs) d.full_features |= (b.type != 0 || b.tex_w > 0) ? 1 : 0;
+    for (const HBsdf &b : sc.bsdfs) d.full_features |= (b.type != 0 || b.tex[0].w > 0 || b.tex[1].w > 0 || b.tex[2].w > 0) ? 1 : 0;
     d.geo = (const float4 *) (base + o_geo);
     d.shade = (const float4 *) (base + o_shade);
     d.dgeo = (const float4 *) (base + o_dgeo);

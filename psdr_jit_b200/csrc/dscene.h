@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "texture.h"
+
 namespace psdr {
 
 // triangle i: geo[3i+0] = (p0.x,p0.y,p0.z,e1.x) geo[3i+1] = (e1.y,e1.z,e2.x,e2.y)
@@ -71,11 +73,9 @@ struct DBsdf {
     float spec[3];           // Microfacet: specularReflectance (F0)
     float d_spec[3];
     float rough, d_rough;    // Microfacet: roughness (alpha = roughness^2)
-    // reflectance / diffuseReflectance as a w x h texture (Bitmap3fD); tex_w * tex_h == 0: the constant refl[]
-    int tex_w, tex_h;
-    const float *tex, *dtex;
-    int tex_goff;            // offset of the texel gradients in the adjoint's gradient table
-    int pad_;
+    // texture slots (texture.h DTex): 0 reflectance / diffuseReflectance (Bitmap3fD), 1 specularReflectance (Bitmap3fD),
+    // 2 roughness (Bitmap1fD); w * h == 0: the constant above
+    DTex tex[3];
 };
 
 struct DCamera {
@@ -101,6 +101,7 @@ struct DScene {
     int width, height, spp, sppe, sppse;
     int n_tris, n_meshes, n_emitters, n_bsdfs, n_sec_edges, n_nodes;
     int use_bvh;             // 0: brute force over all triangles (tiny scenes)
+    int ref_rcp;             // 1: the analytic primary hit of renderD uses Dr.Jit's approximate rcp (device_path.cuh rcp_approx)
     int full_features;       // 1: some BSDF is a Microfacet or an EnvironmentMap exists (selects the kernel variant)
     const float4 *geo, *shade, *dgeo, *dshade;
     const float2 *uv;

@@ -35,9 +35,16 @@ struct HBsdf {
     V3d specular;             // Microfacet specularReflectance
     Dual roughness;           // Microfacet roughness
     bool two_side = false;
-    // reflectance / diffuseReflectance texture (Bitmap3fD with more than one texel): rgb interleaved, pixel = y*w + x
-    int tex_w = 0, tex_h = 0;
-    std::vector<float> tex, dtex;
+    // texture slots (Bitmap with more than one texel; channels interleaved, pixel = y*w + x):
+    // 0 reflectance / diffuseReflectance (3 channels), 1 specularReflectance (3), 2 roughness (1);
+    // each with the bitmap's uv transform (reference include/psdr/core/bitmap.h:36-38: m_scale, m_rot, m_trans)
+    struct Tex {
+        int w = 0, h = 0;
+        std::vector<float> data, ddata;
+        Dual scale = Dual(1.f), rot = Dual(0.f), tx = Dual(0.f), ty = Dual(0.f);
+    };
+    Tex tex[3];
+    static int tex_channels(int slot) { return slot == 2 ? 1 : 3; }
 };
 
 struct HMesh {
@@ -121,7 +128,7 @@ struct ParamGrads {
     std::vector<double> bsdf_refl, emitter_rad, bsdf_spec;   // 3 per object
     std::vector<double> bsdf_rough;                          // 1 per BSDF
     std::vector<float> env_radiance;                         // 3*w*h
-    std::vector<std::vector<float>> bsdf_tex;                // per textured BSDF: 3*w*h
+    std::vector<std::vector<float>> bsdf_tex[3];             // per BSDF and texture slot: channels*w*h (empty: not textured)
     double env_scale = 0.0, env_to_world_left[16] = {};
     bool valid = false;
 };
@@ -150,6 +157,7 @@ struct Scene {
     int device = 0;
     int rank = 0, world = 1;   // lane-range sharding across GPUs
     int force_bvh = -1;        // -1 auto, 0 brute force, 1 bvh
+    bool ref_rcp = false;      // reference arithmetic for the analytic primary hit (psdr_scene_set_reference_arithmetic)
     DeviceBuffers *dev = nullptr;
     DScene dscene{};
     std::vector<DCamera> dcameras;
@@ -160,7 +168,7 @@ struct Scene {
     // reverse mode: table layout for `sensor` (base = nullptr) and the host chain
     // table gradients -> world vertices -> raw vertices / to_world / camera matrices (scene_grad.cpp)
     GradLayout grad_layout(int sensor) const;
-    int texture_grad_offset(int bsdf) const;   // relative to GradLayout::total (negative)
+    int texture_grad_offset(int bsdf, int slot) const;   // relative to GradLayout::total (negative)
     void backprop(const float *table, const GradLayout &gl, int sensor);
 
     Scene();

@@ -113,15 +113,12 @@ void transform_pos_adj(const Mat &M, D3 p, D3 gq, D3 &gp, Mat &gM) {
 
 }  // namespace
 
-int Scene::texture_grad_offset(int bsdf) const {
-    int off = kGradTri * 0;
-    int ntris = 0;
-    for (const HMesh &m : meshes) ntris += (int) m.tris.size();
-    (void) off;
-    // tail of the table: [.. secondary edges | envmap block | textures of BSDF 0, 1, ...]; the sensor-dependent
-    // primary-edge block sits before, so the offset is taken relative to the END of the table
+int Scene::texture_grad_offset(int bsdf, int slot) const {
+    // tail of the table: [.. secondary edges | envmap block | textures of BSDF 0 (slots 0, 1, 2), BSDF 1, ...]; the
+    // sensor-dependent primary-edge block sits before, so the offset is taken relative to the END of the table
     int back = 0;
-    for (int i = (int) bsdfs.size() - 1; i >= bsdf; --i) back += 3 * bsdfs[i].tex_w * bsdfs[i].tex_h;
+    for (int i = (int) bsdfs.size() - 1; i >= bsdf; --i)
+        for (int k = 2; k >= (i == bsdf ? slot : 0); --k) back += HBsdf::tex_channels(k) * bsdfs[i].tex[k].w * bsdfs[i].tex[k].h;
     return -back;   // negative: relative to GradLayout::total
 }
 
@@ -138,7 +135,8 @@ GradLayout Scene::grad_layout(int sensor) const {
     gl.off_se = gl.off_pe + 4 * npe;
     gl.off_env = gl.off_se + 6 * (int) sec_edges.size();
     gl.total = gl.off_env + (env.present ? kGradEnvHead + 3 * env.w * env.h : 0);
-    for (const HBsdf &b : bsdfs) gl.total += 3 * b.tex_w * b.tex_h;      // same order as texture_grad_offset()
+    for (const HBsdf &b : bsdfs)
+        for (int k = 0; k < 3; ++k) gl.total += HBsdf::tex_channels(k) * b.tex[k].w * b.tex[k].h;      // same order as texture_grad_offset()
     return gl;
 }
 
@@ -243,12 +241,14 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
         }
         split_product(m.to_world, gtw, out.to_world);
     }
-    grads.bsdf_tex.assign(bsdfs.size(), std::vector<float>());
-    for (size_t i = 0; i < bsdfs.size(); ++i)
-        if (bsdfs[i].tex_w > 0) {
-            const float *g = table + gl.total + texture_grad_offset((int) i);
-            grads.bsdf_tex[i].assign(g, g + (size_t) 3 * bsdfs[i].tex_w * bsdfs[i].tex_h);
-        }
+    for (int k = 0; k < 3; ++k) {
+        grads.bsdf_tex[k].assign(bsdfs.size(), std::vector<float>());
+        for (size_t i = 0; i < bsdfs.size(); ++i)
+            if (bsdfs[i].tex[k].w > 0) {
+                const float *g = table + gl.total + texture_grad_offset((int) i, k);
+                grads.bsdf_tex[k][i].assign(g, g + (size_t) HBsdf::tex_channels(k) * bsdfs[i].tex[k].w * bsdfs[i].tex[k].h);
+            }
+    }
     grads.bsdf_spec.assign(3 * bsdfs.size(), 0.0);
     grads.bsdf_rough.assign(bsdfs.size(), 0.0);
     for (size_t i = 0; i < bsdfs.size(); ++i) {

@@ -49,11 +49,44 @@ template <class S> PSDR_HD V3<S> bitmap_eval_envmap(const float *data, const flo
     return V3<S>(fmadd(w0y, v0.x, w1y * v1.x), fmadd(w0y, v0.y, w1y * v1.y), fmadd(w0y, v0.z, w1y * v1.z));
 }
 
-// Bitmap<3>::eval for surface textures (flip_v = true, envmap_mode = false; rotation 0, scale 1, translation 0):
-// reference src/core/bitmap.cpp:60-131.  uv wraps, bilinear over (w-1) x (h-1) cells.
-template <class S> PSDR_HD V3<S> bitmap_eval_uv(const float *data, const float *ddata, int w, int h, V2<S> uv, EnvTexelTaps *taps = nullptr) {
-    uv = V2<S>((uv.x - 0.5f) + 0.5f, -((uv.y - 0.5f) + 0.5f));           // rotation by 0 about the centre, then flip v
-    uv = V2<S>(uv.x - floor_(uv.x), uv.y - floor_(uv.y));
+// A surface texture slot of a BSDF (reference Bitmap<1|3>, src/core/bitmap.cpp): w x h texels of `ch` channels
+// (interleaved, pixel = y*w + x) and the uv transform rotate / scale / translate (bitmap.cpp:64-72) with forward tangents.
+// w * h == 0: the slot holds a constant (1x1 bitmap) and the BSDF record's scalar fields are used instead.
+struct DTex {
+    int w, h;
+    const float *data, *ddata;
+    float cr, sr, d_cr, d_sr;        // cos / sin of m_rot and their tangents
+    float scale, d_scale;
+    float tx, ty, d_tx, d_ty;
+    int goff;                        // offset of the texel gradients, relative to the END of the adjoint's gradient table
+    int ch;                          // 1 or 3
+};
+
+template <class S> struct Lift2 {
+    static PSDR_HD S s(float v, float) { return S(v); }
+};
+template <> struct Lift2<Dual> {
+    static PSDR_HD Dual s(float v, float d) { return Dual(v, d); }
+};
+
+// Bitmap<channels>::eval for surface textures (flip_v = true, envmap_mode = false): reference src/core/bitmap.cpp:60-131.
+// uv is rotated about the centre, flipped, scaled about the centre, translated, wrapped; bilinear over (w-1) x (h-1) cells.
+// Returns rgb for 3-channel data, (x, 0, 0) for 1-channel data.
+template <class S> PSDR_HD V3<S> tex_eval_uv(const DTex &t, bool with_texel_tangents, V2<S> uv, EnvTexelTaps *taps = nullptr) {
+    const S cr = Lift2<S>::s(t.cr, t.d_cr), sr = Lift2<S>::s(t.sr, t.d_sr), sc = Lift2<S>::s(t.scale, t.d_scale);
+    const S ux = uv.x - 0.5f, uy = uv.y - 0.5f;
+    S rx = ux * cr + uy * sr, ry = -ux * sr + uy * cr;
+    rx = rx + 0.5f;
+    ry = -(ry + 0.5f);                                                    // flip v
+    rx = rx * sc;
+    ry = ry * sc;
+    const S off = sc * 0.5f + (-0.5f);                                    // -.5 + scale / 2
+    rx = rx - off;
+    ry = ry + off;
+    rx = rx + Lift2<S>::s(t.tx, t.d_tx);
+    ry = ry + Lift2<S>::s(t.ty, t.d_ty);
+    uv = V2<S>(rx - floor_(rx), ry - floor_(ry));
+    const int w = t.w, h = t.h;
     uv.x = uv.x * (float) (w - 1);
     uv.y = uv.y * (float) (h - 1);
     int px = (int) floorf(val(uv.x)), py = (int) floorf(val(uv.y));
@@ -66,8 +99,15 @@ template <class S> PSDR_HD V3<S> bitmap_eval_uv(const float *data, const float *
         taps->i00 = i00; taps->i10 = i10; taps->i01 = i01; taps->i11 = i11;
         taps->w0x = val(w0x); taps->w1x = val(w1x); taps->w0y = val(w0y); taps->w1y = val(w1y);
     }
-    const V3<S> v00 = TexelLoad<S>::get(data, ddata, i00), v10 = TexelLoad<S>::get(data, ddata, i10),
-                v01 = TexelLoad<S>::get(data, ddata, i01), v11 = TexelLoad<S>::get(data, ddata, i11);
+    const float *dd = with_texel_tangents ? t.ddata : nullptr;
+    if (t.ch == 1) {
+        auto get = [&](int i) { return (dd ? Lift2<S>::s(t.data[i], dd[i]) : S(t.data[i])); };
+        const S v00 = get(i00), v10 = get(i10), v01 = get(i01), v11 = get(i11);
+        const S v0 = fmadd(w0x, v00, w1x * v10), v1 = fmadd(w0x, v01, w1x * v11);
+        return V3<S>(fmadd(w0y, v0, w1y * v1), S(0.f), S(0.f));
+    }
+    const V3<S> v00 = TexelLoad<S>::get(t.data, dd, i00), v10 = TexelLoad<S>::get(t.data, dd, i10),
+                v01 = TexelLoad<S>::get(t.data, dd, i01), v11 = TexelLoad<S>::get(t.data, dd, i11);
     const V3<S> v0(fmadd(w0x, v00.x, w1x * v10.x), fmadd(w0x, v00.y, w1x * v10.y), fmadd(w0x, v00.z, w1x * v10.z));
     const V3<S> v1(fmadd(w0x, v01.x, w1x * v11.x), fmadd(w0x, v01.y, w1x * v11.y), fmadd(w0x, v01.z, w1x * v11.z));
     return V3<S>(fmadd(w0y, v0.x, w1y * v1.x), fmadd(w0y, v0.y, w1y * v1.y), fmadd(w0y, v0.z, w1y * v1.z));

@@ -42,6 +42,16 @@ def test_envmap(w=32, h=16, seed=0):
 test_envmap.__test__ = False
 
 
+def tex_slots(t):
+    """textures[name] -> {slot: dict(data, w, h, d_data, xform, d_xform)}.  The short form (data, w, h[, d_data]) is slot 0
+    (reflectance / diffuseReflectance) without a uv transform; the long form is a dict keyed by slot (0, 1 specular,
+    2 roughness) or slot name."""
+    names = {"reflectance": 0, "diffuse": 0, "specular": 1, "roughness": 2}
+    if isinstance(t, dict):
+        return {names.get(k, k): v for k, v in t.items()}
+    return {0: dict(data=t[0], w=t[1], h=t[2], d_data=t[3] if len(t) > 3 else None)}
+
+
 def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None, active=(0,), cam=None, bsdfs=None, d_bsdf=None,
                  envmap=None, textures=None):
     """Scene = scenes.* meshes + CBOX bsdfs + camera; derivative parameter P translates mesh
@@ -55,9 +65,9 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
             sc.add_microfacet(name, params[0], params[1], params[2], d=d)
         else:
             sc.add_diffuse(name, params, d_refl=d)
-        if textures and name in textures:      # (data [h*w,3], w, h, d_data or None) on the reflectance / diffuseReflectance slot
-            t = textures[name]
-            sc.set_bsdf_texture(name, t[0], t[1], t[2], t[3] if len(t) > 3 else None)
+        if textures and name in textures:
+            for slot, t in tex_slots(textures[name]).items():
+                sc.set_bsdf_texture(name, t["data"], t["w"], t["h"], t.get("d_data"), slot=slot, xform=t.get("xform"), d_xform=t.get("d_xform"))
     if envmap is not None:      # dict(data, w, h, scale, to_world, d_data, d_scale, d_to_world_left); added before the meshes
         sc.add_envmap(envmap["data"], envmap["w"], envmap["h"], to_world=envmap.get("to_world"), scale=envmap.get("scale", 1.0),
                       d_data=envmap.get("d_data"), d_to_world_left=envmap.get("d_to_world_left"), d_scale=envmap.get("d_scale", 0.0))
@@ -94,14 +104,18 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
             if d is not None:
                 b.d_reflectance = np.float32(d)
         if textures and name in textures:
-            t = textures[name]
-            bm = psdr.Bitmap3fD(t[1], t[2], t[0])
-            if len(t) > 3 and t[3] is not None:
-                bm.d_data = np.asarray(t[3], dtype=np.float32)
-            if is_microfacet(params):
-                b.diffuseReflectance = bm
-            else:
-                b.reflectance = bm
+            for slot, t in tex_slots(textures[name]).items():
+                bm = (psdr.Bitmap1fD if slot == 2 else psdr.Bitmap3fD)(t["w"], t["h"], t["data"])
+                if t.get("d_data") is not None:
+                    bm.d_data = np.asarray(t["d_data"], dtype=np.float32)
+                if t.get("xform") is not None:
+                    bm.scale, bm.rotate, bm.translate = np.float32(t["xform"][0]), np.float32(t["xform"][1]), np.float32(t["xform"][2:4])
+                if t.get("d_xform") is not None:
+                    bm.d_scale, bm.d_rotate, bm.d_translate = np.float32(t["d_xform"][0]), np.float32(t["d_xform"][1]), np.float32(t["d_xform"][2:4])
+                if not is_microfacet(params):
+                    b.reflectance = bm
+                else:
+                    setattr(b, ("diffuseReflectance", "specularReflectance", "roughness")[slot], bm)
         sc.add_BSDF(b, name, twoSide=two_side)
     if envmap is not None:
         env = psdr.EnvironmentMap(psdr.Bitmap3fD(envmap["w"], envmap["h"], envmap["data"]))

@@ -321,3 +321,20 @@ def test_textured_reflectance_vs_reference(oracle):
     i, d = osc.render(2, seed=6, mode=1, terms=1)
     r, nbad, r_ex = compare_stats(d * 2.0, g["grad_cam"], flip_rel=2e-5)
     assert nbad <= 0.02 * len(d) and r_ex < 2e-4, (r, nbad, r_ex)
+
+
+def test_oracle_texture_slots_vs_reference_golden(oracle):
+    """Oracle vs the running reference for MicrofacetBSDF(Bitmap3fD, Bitmap3fD, Bitmap1fD) with the bitmaps' uv
+    transforms (tests/golden/tex_slots.npz, tools/ref_golden5.py)."""
+    from tests.common import compare_stats
+    from tests.test_gpu_parity import _slot_textures
+    g = np.load(os.path.join(GOLDEN, "tex_slots.npz"))
+    got = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, textures=_slot_textures()).render(3, seed=5, mode=0)
+    r, nbad, r_ex = compare_stats(got, g["img_d3_seed5"], flip_rel=1e-4)
+    assert nbad < 60 and r_ex < 3e-5, (r, nbad, r_ex)                  # 25 pixels hold a flipped lane, the rest agrees to 1.2e-5
+    texd = _slot_textures(with_tangent=True, texel_tangents=False)
+    img, d = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, textures=texd).render(2, seed=8, mode=1, terms=1)
+    r, nbad, r_ex = compare_stats(img, g["img_uv"], flip_rel=1e-4)
+    assert nbad < 300 and r_ex < 1e-4, (r, nbad, r_ex)
+    r, nbad, r_ex = compare_stats(2 * d, g["grad_uv"], flip_rel=1e-3)  # the reference's 2x interior scaling (DESIGN.md)
+    assert nbad < 250 and r_ex < 5e-3, (r, nbad, r_ex)

@@ -21,8 +21,22 @@ def _scene_with_tangents(psdr, meshes, w, h, spps, rng, what):
         trng = np.random.default_rng(9)
         textures = {n: (trng.random((hh * ww, 3), dtype=np.float32) * 0.8 + 0.1, ww, hh, trng.normal(size=(hh * ww, 3)).astype(np.float32) * 0.2)
                     for n, (ww, hh) in (("white", (8, 6)), ("cat", (5, 7)))}
+    slot_tex = None
+    if "slots" in what:        # all three bitmap slots of the Microfacet BSDFs textured, with uv transforms (no transform tangents)
+        from tests.test_gpu_parity import _slot_textures
+        slot_tex = _slot_textures(with_tangent=True)
+        for n in slot_tex:
+            for k in slot_tex[n]:
+                slot_tex[n][k].pop("d_xform", None)
+        textures, mf = slot_tex, True
     sc = build_product(meshes, w, h, *spps, bsdfs=scenes.CBOX_MF_BSDFS if mf else None, envmap=envmap, textures=textures)
     tang = {}
+    if slot_tex is not None:
+        for n in slot_tex:
+            for k, field in ((0, "diffuseReflectance.data"), (1, "specularReflectance.data"), (2, "roughness.data")):
+                tang[("BSDF[id=%s]" % n, field)] = slot_tex[n][k]["d_data"]
+        what = [x for x in what if x != "slots"]
+        textures = None
     if textures is not None:
         for n in textures:
             tang[("BSDF[id=%s]" % n, "diffuseReflectance.data" if mf else "reflectance.data")] = textures[n][3]
@@ -39,7 +53,7 @@ def _scene_with_tangents(psdr, meshes, w, h, spps, rng, what):
         tang[("Emitter[0]", "to_world_left")] = t
         what = [x for x in what if x != "envmap"]
     if mf:
-        for name in ("BSDF[id=cat]", "BSDF[id=white]", "BSDF[id=red]"):
+        for name in (("BSDF[id=red]", "BSDF[id=green]") if slot_tex is not None else ("BSDF[id=cat]", "BSDF[id=white]", "BSDF[id=red]")):
             b = sc.param_map[name]
             b.d_specularReflectance = (rng.normal(size=3) * 0.1).astype(np.float32)
             b.d_diffuseReflectance = (rng.normal(size=3) * 0.1).astype(np.float32)
@@ -92,6 +106,7 @@ CASES = [
     ("microfacet", 1, 3, "cbox"), ("microfacet mesh_left vertices camera", 1, 2, "cbox"),
     ("microfacet mesh_left vertices camera", 7, 2, "sphere"),
     ("textures", 1, 2, "cbox"), ("textures camera mesh_left", 7, 2, "cbox"), ("textures microfacet camera", 1, 3, "cbox"),
+    ("slots", 1, 2, "cbox"), ("slots camera mesh_left", 7, 3, "cbox"),
     ("envmap", 1, 2, "cbox"), ("envmap microfacet", 1, 3, "cbox"), ("envmap microfacet mesh_left vertices camera", 7, 3, "cbox"),
 ]
 
@@ -119,7 +134,7 @@ def test_vjp_is_transpose_of_jvp(what, terms, depth, scene):
     scale = float(torch.linalg.norm(cot.double()) * torch.linalg.norm(dimg.double()))
     mag = max(abs(lhs), sum(abs(v) for v in parts.values()))      # the per-parameter terms may cancel
     assert scale > 0 and mag > 1e-6 * scale, (lhs, scale)
-    tol = 5e-4 if "microfacet" in what else 2e-4        # GGX roughness derivatives are spiky: more fp32 cancellation
+    tol = 5e-4 if ("microfacet" in what or "slots" in what) else 2e-4        # GGX roughness derivatives are spiky: more fp32 cancellation
     assert abs(lhs - rhs) < tol * max(mag, 1e-3 * scale), (lhs, rhs, parts)
 
 

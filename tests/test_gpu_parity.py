@@ -261,19 +261,82 @@ def test_full_size_properties_cfg2():
     sc_r = build_product(scenes.cbox_meshes(), 512, 512, 32, 0, 0, d_radiance=(20.0, 20.0, 8.0))
     a, da = integ.renderD_fwd(sc_r, 0, seed=0, terms=1)
     assert rel_l2(da.cpu().numpy(), a.cpu().numpy()) < 1e-5
-    # against the running reference (golden, reference scaling)
+    # against the running reference (golden, reference scaling), BASELINE config 2 at full size, seed 0.
+    # What round 2's census (tools/ref_parity.py, profiles/r02c_parity_summary.json) established about the residual:
+    #  * lanes whose discrete decisions differ (OptiX vs our closest hit) are sparse, zero-mean noise -- except on the tall
+    #    box's side face (triangles 22 / 23), where renderD's primary hit o + t d lands on one or the other side of the face
+    #    depending on how the reciprocal in ray_intersect_triangle is rounded and grazing next-event rays re-intersect the
+    #    face: +1.5 % mean radiance with IEEE division, -0.4 % with Dr.Jit's rcp.approx (Scene.reference_arithmetic);
+    #  * the reference's one-call derivative image contradicts the sum of its own three terms in the BLUE channel of the
+    #    ~30 pixels on the luminaire's silhouette (rel-L2 0.25; red / green agree bit for bit), so the gradient is anchored
+    #    on the reference's terms rendered one at a time (cfg2_512_grad_terms.npz).
     g = np.load(GOLDEN + "/cfg2_512_s32_d3_light.npz")
+    gt = np.load(GOLDEN + "/cfg2_512_grad_terms.npz")
+    face = gt["face22"]
     integ.reference_tangent_scaling = True
     img3, dimg3 = integ.renderD_fwd(sc, 0, seed=0)
-    # Lanes whose discrete decisions differ (OptiX vs our closest hit on grazing / self-shadowing rays,
-    # e.g. the tall box's side face: DESIGN.md "parity") move a pixel by >= ~1/spp of a path's value;
-    # every other pixel must agree to float rounding.
-    r, nbad, r_ex = compare_stats(img3.cpu().numpy(), g["img"], flip_rel=2e-5)
-    print("cfg2 image vs reference: rel-L2 %.3e, %d/%d pixels with a flipped lane, rel-L2 of the rest %.3e" % (r, nbad, len(img3), r_ex))
-    assert r < 4e-3 and nbad < 0.05 * len(img3) and r_ex < 1e-4, (r, nbad, r_ex)
-    r, nbad, r_ex = compare_stats(dimg3.cpu().numpy(), g["grad"], flip_rel=2e-5)
-    print("cfg2 derivative image vs reference: rel-L2 %.3e, %d/%d pixels off, rel-L2 of the rest %.3e" % (r, nbad, len(img3), r_ex))
-    assert nbad < 0.25 * len(img3) and r_ex < 1e-3, (r, nbad, r_ex)
+    img3, dimg3 = img3.cpu().numpy(), dimg3.cpu().numpy()
+    r, nbad, r_ex = compare_stats(img3, g["img"], flip_rel=2e-5)
+    bias = float((img3[face].astype(np.float64) - g["img"][face]).sum() / g["img"][face].astype(np.float64).sum())
+    print("cfg2 image vs reference: rel-L2 %.3e, %d/%d pixels with a flipped lane, rel-L2 of the rest %.3e, face 22/23 bias %+.4f"
+          % (r, nbad, len(img3), r_ex, bias))
+    assert r < 3e-3 and nbad < 0.035 * len(img3) and r_ex < 3e-5, (r, nbad, r_ex)     # measured: 2.29e-3, 8241 pixels, 1.3e-5
+    assert 0.005 < bias < 0.03, bias                                                  # measured: +1.66 %
+    assert rel_l2(dimg3, g["grad"]) > 0.1                                             # the reference's one-call blue channel (0.23)
+    assert rel_l2(g["grad"], gt["grad_terms"]) > 0.1                                  # ... contradicts its own terms (0.25)
+    rg, nbadg, rg_ex = compare_stats(dimg3, gt["grad_terms"], flip_rel=1e-3)
+    print("cfg2 derivative image vs the reference's terms: rel-L2 %.3e, %d pixels off by > 1e-3 of the maximum, rel-L2 of the rest %.3e"
+          % (rg, nbadg, rg_ex))
+    assert rg < 1e-3 and nbadg <= 8, (rg, nbadg)                                      # measured: 5.7e-4, 2 pixels
+    # Dr.Jit's approximate reciprocal at the analytic primary hit moves the face bias to the other side of zero
+    sc.reference_arithmetic = True
+    sc.configure([0])
+    img4 = integ.renderD_fwd(sc, 0, seed=0)[0].cpu().numpy()
+    bias4 = float((img4[face].astype(np.float64) - g["img"][face]).sum() / g["img"][face].astype(np.float64).sum())
+    print("   with Scene.reference_arithmetic: rel-L2 %.3e, face 22/23 bias %+.4f" % (rel_l2(img4, g["img"]), bias4))
+    assert abs(bias4) < 0.01 and rel_l2(img4, g["img"]) < r, bias4                   # measured: -0.38 %, 2.06e-3
+
+
+def test_unbiased_against_reference_seed_mean():
+    """Is the residual against the reference a bias or zero-mean noise of flipped lanes?  64 consecutive renderD calls
+    (seed 0, then continuing streams) at 128 x 128, spp = sppe = sppse = 32, depth 3, on both sides
+    (tools/ref_parity.py -> tests/golden/seedmean_128.npz); means compared."""
+    psdr = _psdr()
+    g = np.load(GOLDEN + "/seedmean_128.npz")
+    n, face = int(g["calls"]), g["face22"]
+    integ = psdr.PathTracer(3)
+    integ.reference_tangent_scaling = True
+    res = {}
+    for tag, ra in (("ieee", False), ("refarith", True)):
+        sc = build_product(scenes.cbox_meshes(), 128, 128, 32, 32, 32, move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+        sc.reference_arithmetic = ra
+        sc.configure([0])
+        acc_i = acc_g = first_i = first_g = None
+        for k in range(n):
+            img, dimg = integ.renderD_fwd(sc, 0, seed=0 if k == 0 else -1)
+            if k == 0:
+                first_i, first_g = img.cpu().numpy(), dimg.cpu().numpy()
+                acc_i, acc_g = img.double(), dimg.double()
+            else:
+                acc_i += img
+                acc_g += dimg
+        res[tag] = (first_i, first_g, (acc_i / n).cpu().numpy(), (acc_g / n).cpu().numpy())
+    f_i, f_g, m_i, m_g = res["ieee"]
+    one = rel_l2(f_i[~face], g["first_img"][~face])
+    mean = rel_l2(m_i[~face], g["mean_img"][~face])
+    bias = float((m_i[face].astype(np.float64) - g["mean_img"][face]).sum() / g["mean_img"][face].astype(np.float64).sum())
+    print("image off face 22/23: rel-L2 1 call %.2e -> %d-call mean %.2e; on the face: mean bias %+.4f" % (one, n, mean, bias))
+    assert mean < 1.5e-4 and mean < one / 2.5, (one, mean)            # measured 3.9e-4 -> 9.9e-5: noise, falls with the call count
+    assert 0.005 < bias < 0.025, bias                                 # measured +1.46 %: the rounding artifact described above
+    m_ra = res["refarith"][2]
+    bias_ra = float((m_ra[face].astype(np.float64) - g["mean_img"][face]).sum() / g["mean_img"][face].astype(np.float64).sum())
+    print("   with Scene.reference_arithmetic: whole image rel-L2 %.2e, face bias %+.4f" % (rel_l2(m_ra, g["mean_img"]), bias_ra))
+    assert rel_l2(m_ra, g["mean_img"]) < 4e-4 and abs(bias_ra) < 0.008           # measured 2.4e-4, -0.40 %
+    # derivative image: against the reference's three terms rendered one at a time (its one-call result contradicts them)
+    assert rel_l2(g["mean_grad"], g["mean_grad_terms"]) > 0.03                   # measured 0.070
+    r1, rm = rel_l2(f_g, g["first_grad_terms"]), rel_l2(m_g, g["mean_grad_terms"])
+    print("derivative image vs the reference's terms: rel-L2 1 call %.2e -> %d-call mean %.2e" % (r1, n, rm))
+    assert rm < 6e-4 and r1 < 1e-3, (r1, rm)                                     # measured 6.9e-4 -> 4.3e-4
 
 
 # ---- MicrofacetBSDF (reference src/bsdf/microfacet.cpp, src/bsdf/ggx.cpp) --------------------------------
@@ -478,3 +541,78 @@ def test_textured_bsdf_renderD_vs_oracle(oracle, terms):
     img, dimg = psdr.PathTracer(2).renderD_fwd(sc, 0, seed=6)
     assert rel_l2(img.cpu().numpy(), img_ref) < TOL
     assert np.abs(dimg_ref).max() > 0 and rel_l2(dimg.cpu().numpy(), dimg_ref) < TOL
+
+
+# ---- all three bitmap slots of a MicrofacetBSDF + the bitmaps' uv transform (reference src/core/bitmap.cpp:64-72,
+#      include/psdr/bsdf/microfacet.h:17,33-35) ------------------------------------------------------------------
+def _slot_textures(with_tangent=False, with_xform=True, texel_tangents=True):
+    """texel data from ONE stream (tools/ref_golden5.py draws the same); tangents from a second one"""
+    rng, trng = np.random.default_rng(21), np.random.default_rng(22)
+    out = {}
+    for name, dims in (("cat", ((7, 5), (4, 6), (5, 5))), ("white", ((6, 4), (3, 3), (8, 2)))):
+        slots = {}
+        for slot, (w, h) in enumerate(dims):
+            ch = 1 if slot == 2 else 3
+            lo, hi = ((0.05, 0.9), (0.02, 0.6), (0.15, 0.7))[slot]
+            t = dict(data=(rng.random((h * w, ch), dtype=np.float32) * (hi - lo) + lo), w=w, h=h)
+            if with_tangent and texel_tangents:
+                t["d_data"] = trng.normal(size=(h * w, ch)).astype(np.float32) * 0.1
+            if with_xform:
+                t["xform"] = np.array([1.0 + 0.4 * slot, 0.3 - 0.25 * slot, 0.11 * (slot + 1), -0.07 * slot], np.float32)
+                if with_tangent:
+                    t["d_xform"] = np.array([0.2, -0.3, 0.05, 0.1], np.float32) * (slot + 1)
+            slots[slot] = t
+        out[name] = slots
+    return out
+
+
+def test_texture_slots_and_uv_transform_renderC_vs_oracle(oracle):
+    psdr = _psdr()
+    tex = _slot_textures()
+    ref = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, textures=tex).render(3, seed=5, mode=0)
+    no_xf = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, textures=_slot_textures(with_xform=False)).render(3, seed=5, mode=0)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, textures=tex)
+    got = psdr.PathTracer(3).renderC(sc, 0, seed=5).cpu().numpy()
+    assert rel_l2(got, ref) < TOL
+    assert rel_l2(ref, no_xf) > 1e-3            # the uv transforms are visible
+
+
+@pytest.mark.parametrize("terms", [1, 7])
+def test_texture_slots_and_uv_transform_renderD_vs_oracle(oracle, terms):
+    """tangents: texels of all three slots, the uv transforms (scale, rotate, translate), large-box translation"""
+    psdr = _psdr()
+    spps = (4 if terms & 1 else 0, 4 if terms & 2 else 0, 4 if terms & 4 else 0)
+    tex = _slot_textures(with_tangent=True)
+    kw = dict(move_mesh=2, axis_scale=(10.0, 0.0, 20.0), bsdfs=scenes.CBOX_MF_BSDFS, textures=tex)
+    img_ref, dimg_ref = build_oracle(scenes.cbox_meshes(), 128, 128, *spps, **kw).render(2, seed=8, mode=1, terms=7)
+    sc = build_product(scenes.cbox_meshes(), 128, 128, *spps, **kw)
+    img, dimg = psdr.PathTracer(2).renderD_fwd(sc, 0, seed=8)
+    assert rel_l2(img.cpu().numpy(), img_ref) < TOL
+    assert np.abs(dimg_ref).max() > 0 and rel_l2(dimg.cpu().numpy(), dimg_ref) < TOL
+
+
+def test_texture_slots_vs_reference_golden():
+    """MicrofacetBSDF(Bitmap3fD, Bitmap3fD, Bitmap1fD) with uv transforms against the running reference
+    (tools/ref_golden5.py -> tests/golden/tex_slots.npz): primal image, derivative w.r.t. the six uv transforms,
+    derivative w.r.t. a translation of the textured large box."""
+    psdr = _psdr()
+    g = np.load(GOLDEN + "/tex_slots.npz")
+    tex = _slot_textures()
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, textures=tex)
+    got = psdr.PathTracer(3).renderC(sc, 0, seed=5).cpu().numpy()
+    r, nbad, r_ex = compare_stats(got, g["img_d3_seed5"], flip_rel=1e-4)
+    print("texture slots renderC vs reference: rel-L2 %.3e, %d pixels with a flipped lane, rest %.3e" % (r, nbad, r_ex))
+    assert nbad < 0.03 * len(got) and r_ex < 2e-5, (r, nbad, r_ex)
+    texd = _slot_textures(with_tangent=True, texel_tangents=False)
+    integ = psdr.PathTracer(2)
+    integ.reference_tangent_scaling = True
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=scenes.CBOX_MF_BSDFS, textures=texd)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=8)
+    r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["grad_uv"], flip_rel=1e-3)
+    print("d/d(uv transforms) vs reference: rel-L2 %.3e, %d pixels off, rest %.3e" % (r, nbad, r_ex))
+    assert nbad < 0.03 * len(got) and r_ex < 5e-3 and r < 6e-2, (r, nbad, r_ex)        # CPU oracle vs this golden: 2.6e-2, 105 px, 1.7e-3
+    sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 4, 4, bsdfs=scenes.CBOX_MF_BSDFS, textures=tex, move_mesh=2, axis_scale=(10.0, 0.0, 20.0))
+    img, dimg = integ.renderD_fwd(sc, 0, seed=8)
+    r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["grad_box"], flip_rel=1e-3)
+    print("d/d(box translation) vs reference: rel-L2 %.3e, %d pixels off, rest %.3e" % (r, nbad, r_ex))
+    assert nbad < 0.03 * len(got) and r_ex < 1.5e-2 and r < 0.1, (r, nbad, r_ex)        # CPU oracle vs this golden: 5.2e-2, 129 px, 5.7e-3

@@ -1,0 +1,107 @@
+"""The reference's own "Example of Diff rendering" (reference README.md:45-107) executed VERBATIM against the `psdr_jit`
+module this repo ships (psdr_jit/__init__.py -> psdr_jit_b200 -> C ABI -> sm_100a kernels), with the Dr.Jit stand-in of
+psdr_jit_b200.compat when Dr.Jit is not installed.  Only the environment is prepared: the OBJ files the example loads are
+written where it expects them and cv2 (image writing) is replaced by a recorder."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from tests.common import build_product, rel_l2, scenes
+
+pytestmark = pytest.mark.gpu
+
+# reference README.md:45-107, unchanged
+README_EXAMPLE = '''
+import cv2
+import sys
+import torch
+
+import psdr_jit as psdr
+import drjit
+from drjit.cuda.ad import Float as FloatD, Matrix4f as Matrix4fD
+from drjit.cuda import Float as FloatC, Matrix4f as Matrix4fC
+
+sc = psdr.Scene()
+sc.opts.spp = 32 # Interior Term
+sc.opts.sppe = 32 # Primary Edge
+sc.opts.sppse = 32 # Secondary Edge
+sc.opts.height = 512
+sc.opts.width = 512
+
+integrator = psdr.PathTracer(3)	
+
+
+sensor = psdr.PerspectiveCamera(60, 0.000001, 10000000.)
+to_world = Matrix4fD([[1.,0.,0.,208.],
+                     [0.,1.,0.,273.],
+                     [0.,0.,1.,-800.],
+                     [0.,0.,0.,1.],])
+sensor.to_world = to_world
+sc.add_Sensor(sensor)
+
+sc.add_BSDF(psdr.DiffuseBSDF([0.0, 0.0, 0.0]), "light")
+sc.add_BSDF(psdr.DiffuseBSDF(), "cat")
+sc.add_BSDF(psdr.DiffuseBSDF([0.95, 0.95, 0.95]), "white")
+sc.add_BSDF(psdr.DiffuseBSDF([0.20, 0.90, 0.20]), "green")
+sc.add_BSDF(psdr.DiffuseBSDF([0.90, 0.20, 0.20]), "red")
+
+sc.add_Mesh("./data/objects/cbox/cbox_luminaire.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,-0.5],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "light", psdr.AreaLight([20.0, 20.0, 8.0]))
+sc.add_Mesh("./data/objects/cbox/cbox_smallbox.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "cat", None)
+sc.add_Mesh("./data/objects/cbox/cbox_largebox.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "cat", None)
+sc.add_Mesh("./data/objects/cbox/cbox_floor.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "white", None)
+sc.add_Mesh("./data/objects/cbox/cbox_ceiling.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "white", None)
+sc.add_Mesh("./data/objects/cbox/cbox_back.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "white", None)
+sc.add_Mesh("./data/objects/cbox/cbox_greenwall.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "green", None)
+sc.add_Mesh("./data/objects/cbox/cbox_redwall.obj", Matrix4fC([[1.,0.,0.,0.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.]]), "red", None)
+
+P = FloatD(0.)
+drjit.enable_grad(P)
+
+sc.param_map["Mesh[0]"].set_transform(Matrix4fD([[1.,0.,0.,P*100.],[0.,1.,0.,0.],[0.,0.,1.,0.],[0.,0.,0.,1.],]))
+
+
+sc.configure()
+sc.configure([0])
+
+img = integrator.renderD(sc, 0)
+org_img = img.numpy().reshape((sc.opts.width, sc.opts.height, 3))
+output = cv2.cvtColor(org_img, cv2.COLOR_RGB2BGR)
+cv2.imwrite("psdr_jit_forward.exr", output)
+
+
+drjit.set_grad(P, 1.0)
+drjit.forward_to(img)
+diff_img = drjit.grad(img)
+diff_img = diff_img.numpy().reshape((sc.opts.width, sc.opts.height, 3))
+output = cv2.cvtColor(diff_img, cv2.COLOR_RGB2BGR)
+cv2.imwrite("psdr_jit_diff_debug.exr", output)
+'''
+
+
+def test_reference_readme_example_runs_verbatim(tmp_path, monkeypatch):
+    scenes.write_cbox_objs(str(tmp_path / "data" / "objects" / "cbox"))
+    written = {}
+    fake_cv2 = types.ModuleType("cv2")
+    fake_cv2.COLOR_RGB2BGR = 4
+    fake_cv2.cvtColor = lambda a, code: np.ascontiguousarray(a[..., ::-1])
+    fake_cv2.imwrite = lambda name, a: written.__setitem__(name, np.array(a)) or True
+    monkeypatch.setitem(sys.modules, "cv2", fake_cv2)
+    monkeypatch.chdir(tmp_path)
+    ns = {"__name__": "readme_example"}
+    exec(compile(README_EXAMPLE, "reference README.md:45-107", "exec"), ns)
+    assert set(written) == {"psdr_jit_forward.exr", "psdr_jit_diff_debug.exr"}
+    img = written["psdr_jit_forward.exr"][..., ::-1].reshape(-1, 3)
+    dimg = written["psdr_jit_diff_debug.exr"][..., ::-1].reshape(-1, 3)
+    # the same scene through this repo's native surface (explicit forward-mode tangent, seed 0 = the freshly seeded streams)
+    import psdr_jit_b200 as psdr
+    cam = dict(scenes.CBOX_CAMERA)
+    cam["to_world"] = scenes.translate(208.0, 273.0, -800.0)
+    sc = build_product(scenes.cbox_meshes(), 512, 512, 32, 32, 32, move_mesh=0, axis_scale=(100.0, 0.0, 0.0), cam=cam)
+    ref_img, ref_dimg = psdr.PathTracer(3).renderD_fwd(sc, 0, seed=0)
+    assert np.isfinite(img).all() and img.max() > 1.0 and np.abs(dimg).max() > 1.0
+    assert rel_l2(img, ref_img.cpu().numpy()) < 1e-6
+    assert rel_l2(dimg, ref_dimg.cpu().numpy()) < 1e-4
+    assert ns["sc"].num_meshes == 8 and ns["sc"].param_map["Mesh[0]"] is not None

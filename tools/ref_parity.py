@@ -19,8 +19,13 @@ B. flip census (which lanes differ, and why?)
    lane with decision margins (oracle/psdr_oracle.cpp LaneDiag): flipped lanes are classified by the margin class that
    is critical for them and compared with the margin distribution of all lanes.
 
+   Every experiment renders the reference four ways -- all three terms in one renderD call, and each term alone (the
+   pattern of tutorials/Forward_AD_envmap.ipynb cells 6/10/12): round 2 found that the reference's one-call derivative
+   image DISAGREES WITH THE SUM OF ITS OWN TERMS in the blue channel at the luminaire's silhouette pixels (red and
+   green agree bit for bit), so the sum of the separately rendered terms is the consistent gradient anchor.
+
 Outputs: gpurun_out/parity/summary.json, seedmean_128.npz (committed as tests/golden/seedmean_128.npz),
-census_flips.npz.
+cfg2_512_grad_terms.npz, census_flips.npz.
 """
 import json
 import os
@@ -37,8 +42,13 @@ DEPTH = 3
 SEEDMEAN = [(128, 64), (512, 16)]          # (resolution, number of calls)
 CENSUS_RES, CENSUS_CALLS = 512, 4
 AXIS = (100.0, 0.0, 0.0)
+COUNTS = (1, 2, 4, 8, 16, 32, 64)
+# all three terms in one renderD call, and each term alone (the pattern of tutorials/Forward_AD_envmap.ipynb cells 6/10/12)
+VARIANTS = {"all": (32, 32, 32), "int": (32, 0, 0), "pri": (0, 32, 0), "sec": (0, 0, 32)}
 if os.environ.get("PARITY_SMALL"):          # dry run of the plumbing
     SEEDMEAN, CENSUS_RES, CENSUS_CALLS = [(32, 4)], 32, 2
+if os.environ.get("PARITY_SKIP_CENSUS"):
+    CENSUS_CALLS = 0
 
 
 def T(x, y, z):
@@ -99,22 +109,23 @@ def side_ref():
 
     times = {}
     for res, n in SEEDMEAN:
-        sc = build(res, res, 32, 32, 32)
-        acc_i = np.zeros((res * res, 3), np.float64)
-        acc_g = np.zeros((res * res, 3), np.float64)
-        t0 = time.time()
-        for k in range(n):
-            img, g = render_d(sc, 0 if k == 0 else -1)
-            acc_i += img
-            acc_g += g
-            if k == 0:
-                np.save(os.path.join(TMP, "ref_sm%d_first_img.npy" % res), img)
-                np.save(os.path.join(TMP, "ref_sm%d_first_grad.npy" % res), g)
-            if (k + 1) in (1, 2, 4, 8, 16, 32, 64):
-                np.save(os.path.join(TMP, "ref_sm%d_mean%d_img.npy" % (res, k + 1)), (acc_i / (k + 1)).astype(np.float32))
-                np.save(os.path.join(TMP, "ref_sm%d_mean%d_grad.npy" % (res, k + 1)), (acc_g / (k + 1)).astype(np.float32))
-        times["seedmean_%d" % res] = time.time() - t0
-        print("ref seedmean", res, n, "calls", times["seedmean_%d" % res], "s", flush=True)
+        for vname, (a, b, c) in VARIANTS.items():
+            sc = build(res, res, a, b, c)
+            acc_i = np.zeros((res * res, 3), np.float64)
+            acc_g = np.zeros((res * res, 3), np.float64)
+            t0 = time.time()
+            for k in range(n):
+                img, g = render_d(sc, 0 if k == 0 else -1)
+                acc_i += img
+                acc_g += g
+                if k == 0:
+                    np.save(os.path.join(TMP, "ref_sm%d_%s_first_img.npy" % (res, vname)), img)
+                    np.save(os.path.join(TMP, "ref_sm%d_%s_first_grad.npy" % (res, vname)), g)
+                if (k + 1) in COUNTS:
+                    np.save(os.path.join(TMP, "ref_sm%d_%s_mean%d_img.npy" % (res, vname, k + 1)), (acc_i / (k + 1)).astype(np.float32))
+                    np.save(os.path.join(TMP, "ref_sm%d_%s_mean%d_grad.npy" % (res, vname, k + 1)), (acc_g / (k + 1)).astype(np.float32))
+            times["seedmean_%d_%s" % (res, vname)] = time.time() - t0
+            print("ref seedmean", res, vname, n, "calls", times["seedmean_%d_%s" % (res, vname)], "s", flush=True)
     # census: spp 1, interior term only
     res = CENSUS_RES
     sc = build(res, res, 1, 0, 0)
@@ -141,21 +152,32 @@ def side_ours():
     from tests.common import build_product, scenes
     integ = psdr.PathTracer(DEPTH)
     integ.reference_tangent_scaling = True
-    for res, n in SEEDMEAN:
-        sc = build_product(scenes.cbox_meshes(), res, res, 32, 32, 32, move_mesh=0, axis_scale=AXIS)
-        acc_i = torch.zeros((res * res, 3), dtype=torch.float64, device="cuda")
-        acc_g = torch.zeros_like(acc_i)
-        for k in range(n):
+    # ours: IEEE arithmetic (the default, bit-comparable with the CPU oracle); oursra: Scene.reference_arithmetic
+    # (approximate rcp at the analytic primary hit only); oursfa: the whole library compiled with Dr.Jit-like approximate
+    # division / sqrt (PSDR_REFERENCE_ARITHMETIC=1, psdr_jit_b200/build.py variant "refarith")
+    full_approx = os.environ.get("PSDR_REFERENCE_ARITHMETIC") == "1"
+    for tag, ref_arith in ((("oursfa", True),) if full_approx else (("ours", False), ("oursra", True))):
+        for res, n in SEEDMEAN:
+            sc = build_product(scenes.cbox_meshes(), res, res, 32, 32, 32, move_mesh=0, axis_scale=AXIS)
+            sc.reference_arithmetic = ref_arith
             sc.configure([0])
-            img, g = integ.renderD_fwd(sc, 0, seed=0 if k == 0 else -1)
-            acc_i += img
-            acc_g += g
-            if k == 0:
-                np.save(os.path.join(TMP, "ours_sm%d_first_img.npy" % res), img.cpu().numpy())
-                np.save(os.path.join(TMP, "ours_sm%d_first_grad.npy" % res), g.cpu().numpy())
-            if (k + 1) in (1, 2, 4, 8, 16, 32, 64):
-                np.save(os.path.join(TMP, "ours_sm%d_mean%d_img.npy" % (res, k + 1)), (acc_i / (k + 1)).float().cpu().numpy())
-                np.save(os.path.join(TMP, "ours_sm%d_mean%d_grad.npy" % (res, k + 1)), (acc_g / (k + 1)).float().cpu().numpy())
+            acc_i = torch.zeros((res * res, 3), dtype=torch.float64, device="cuda")
+            acc_g = torch.zeros_like(acc_i)
+            for k in range(n):
+                sc.configure([0])
+                img, g = integ.renderD_fwd(sc, 0, seed=0 if k == 0 else -1)
+                acc_i += img
+                acc_g += g
+                if (k + 1) in COUNTS:
+                    np.save(os.path.join(TMP, "%s_sm%d_mean%d_img.npy" % (tag, res, k + 1)), (acc_i / (k + 1)).float().cpu().numpy())
+                    np.save(os.path.join(TMP, "%s_sm%d_mean%d_grad.npy" % (tag, res, k + 1)), (acc_g / (k + 1)).float().cpu().numpy())
+    if full_approx:
+        return
+    # primary-hit triangle ids (which pixels look at the tall box's side face, triangles 22 / 23)
+    for res, n in SEEDMEAN:
+        sc = build_product(scenes.cbox_meshes(), res, res, 16, 0, 0, move_mesh=0, axis_scale=AXIS)
+        tri = psdr.PathTracer(1).render_aov(sc, 0, seed=0).cpu().numpy()[:, 1].astype(np.int32).reshape(res * res, 16)
+        np.save(os.path.join(TMP, "ours_sm%d_face22.npy" % res), np.isin(tri, [22, 23]).any(axis=1))
     res = CENSUS_RES
     sc = build_product(scenes.cbox_meshes(), res, res, 1, 0, 0, move_mesh=0, axis_scale=AXIS)
     for k in range(CENSUS_CALLS):
@@ -179,23 +201,38 @@ def analyze():
     ld = lambda n: np.load(os.path.join(TMP, n))   # noqa: E731
     for res, n in SEEDMEAN:
         rows = []
-        for k in (1, 2, 4, 8, 16, 32, 64):
+        face = ld("ours_sm%d_face22.npy" % res)
+        for k in COUNTS:
             if k > n:
                 break
-            ri, rg = ld("ref_sm%d_mean%d_img.npy" % (res, k)), ld("ref_sm%d_mean%d_grad.npy" % (res, k))
-            oi, og = ld("ours_sm%d_mean%d_img.npy" % (res, k)), ld("ours_sm%d_mean%d_grad.npy" % (res, k))
-            di = np.abs(oi - ri).max(axis=1)
-            dg = np.abs(og - rg).max(axis=1)
-            rows.append({"calls": k, "rel_l2_img": rel_l2(oi, ri), "rel_l2_grad": rel_l2(og, rg),
-                         "pixels_img_gt_1e-3": int((di > 1e-3 * np.abs(ri).max()).sum()),
-                         "pixels_grad_gt_1e-3": int((dg > 1e-3 * np.abs(rg).max()).sum())})
-            print("seedmean", res, rows[-1], flush=True)
+            R = {v: (ld("ref_sm%d_%s_mean%d_img.npy" % (res, v, k)), ld("ref_sm%d_%s_mean%d_grad.npy" % (res, v, k))) for v in VARIANTS}
+            ri, rg = R["all"]
+            rg_terms = R["int"][1] + R["pri"][1] + R["sec"][1]         # the reference's terms rendered one at a time, summed
+            row = {"calls": k, "reference_all_vs_its_own_terms_rel_l2_grad": rel_l2(rg, rg_terms),
+                   "reference_all_vs_its_own_interior_rel_l2_img": rel_l2(ri, R["int"][0])}
+            for tag in ("ours", "oursra", "oursfa"):
+                if not os.path.exists(os.path.join(TMP, "%s_sm%d_mean%d_img.npy" % (tag, res, k))):
+                    continue
+                oi, og = ld("%s_sm%d_mean%d_img.npy" % (tag, res, k)), ld("%s_sm%d_mean%d_grad.npy" % (tag, res, k))
+                dg = np.abs(og - rg_terms).max(axis=1)
+                row[tag] = {"rel_l2_img": rel_l2(oi, ri), "rel_l2_img_off_face22": rel_l2(oi[~face], ri[~face]),
+                            "face22_mean_bias": float((oi[face].astype(np.float64) - ri[face]).sum() / ri[face].astype(np.float64).sum()),
+                            "rel_l2_grad_vs_all": rel_l2(og, rg), "rel_l2_grad_vs_terms": rel_l2(og, rg_terms),
+                            "pixels_grad_vs_terms_gt_1e-3": int((dg > 1e-3 * np.abs(rg_terms).max()).sum())}
+            rows.append(row)
+            print("seedmean", res, json.dumps(row), flush=True)
         S["seedmean"][str(res)] = rows
+        S["seedmean"]["face22_pixels_%d" % res] = int(face.sum())
         if res == 128:
             np.savez_compressed(os.path.join(OUT, "seedmean_128.npz"),
-                                first_img=ld("ref_sm128_first_img.npy"), first_grad=ld("ref_sm128_first_grad.npy"),
-                                mean_img=ld("ref_sm128_mean%d_img.npy" % n), mean_grad=ld("ref_sm128_mean%d_grad.npy" % n),
-                                calls=np.int32(n), depth=np.int32(DEPTH), spp=np.int32(32), axis=np.float32(AXIS))
+                                first_img=ld("ref_sm128_all_first_img.npy"), first_grad=ld("ref_sm128_all_first_grad.npy"),
+                                first_grad_terms=ld("ref_sm128_int_first_grad.npy") + ld("ref_sm128_pri_first_grad.npy") + ld("ref_sm128_sec_first_grad.npy"),
+                                mean_img=ld("ref_sm128_all_mean%d_img.npy" % n), mean_grad=ld("ref_sm128_all_mean%d_grad.npy" % n),
+                                mean_grad_terms=ld("ref_sm128_int_mean%d_grad.npy" % n) + ld("ref_sm128_pri_mean%d_grad.npy" % n) + ld("ref_sm128_sec_mean%d_grad.npy" % n),
+                                face22=face, calls=np.int32(n), depth=np.int32(DEPTH), spp=np.int32(32), axis=np.float32(AXIS))
+        if res == 512:      # the consistent full-size gradient anchor: the reference's three terms of call 1, summed
+            g = ld("ref_sm512_int_first_grad.npy") + ld("ref_sm512_pri_first_grad.npy") + ld("ref_sm512_sec_first_grad.npy")
+            np.savez_compressed(os.path.join(OUT, "cfg2_512_grad_terms.npz"), grad_terms=g.astype(np.float16 if False else np.float32), face22=face)
     # ---- census
     from tests.common import build_oracle, scenes
     res = CENSUS_RES
@@ -203,6 +240,8 @@ def analyze():
     names = ("shadow", "border", "self", "tie")
     flips_out = {}
     for mode, tag, draws in ((0, "C", 2 + 5 * DEPTH), (1, "D", 2 + 5 * DEPTH)):
+        if CENSUS_CALLS == 0:
+            break
         tot = {"lanes": 0, "flipped": 0, "ours_vs_oracle_flipped": 0}
         diag_all, flip_all, ids = [], [], []
         for k in range(CENSUS_CALLS):
@@ -243,7 +282,8 @@ def analyze():
         flips_out["ids_" + tag] = np.concatenate(ids).astype(np.int64)
         flips_out["diag_" + tag] = diag[flipped]
         print("census", tag, json.dumps(tot)[:1500], flush=True)
-    np.savez_compressed(os.path.join(OUT, "census_flips.npz"), **flips_out)
+    if flips_out:
+        np.savez_compressed(os.path.join(OUT, "census_flips.npz"), **flips_out)
     try:
         S["ref_times_s"] = json.load(open(os.path.join(TMP, "ref_times.json")))
     except Exception:
@@ -261,6 +301,10 @@ if __name__ == "__main__":
             print("side", side, "rc", rc, "%.1f s" % (time.time() - t0), flush=True)
             if rc:
                 sys.exit(rc)
+        env = dict(os.environ, PSDR_REFERENCE_ARITHMETIC="1")
+        t0 = time.time()
+        rc = subprocess.call([sys.executable, os.path.abspath(__file__), "ours"], env=env)
+        print("side oursfa rc", rc, "%.1f s" % (time.time() - t0), flush=True)
         analyze()
     elif what == "ref":
         side_ref()
