@@ -87,6 +87,12 @@ int psdr_scene_set_seed(psdr_scene *s, long long seed);
  * buffers over ranks (one NCCL all-reduce).  In reverse mode the caller sums the gradient TABLES
  * (psdr_render_vjp_device) over ranks before psdr_scene_backprop_table. */
 int psdr_scene_set_shard(psdr_scene *s, int rank, int world);
+/* Which Li the following render calls evaluate.  PSDR_INTEGRATOR_PATH: PathTracer(max_depth) (src/integrator/path.cpp:35-127).
+ * PSDR_INTEGRATOR_DIRECT: Direct(mis) (src/psdr.cpp:436-439, src/integrator/direct.cpp:35-131): one bounce (call the render
+ * entry points with max_depth = 1); mis = 2 both strategies with the power heuristic (= PathTracer(1)), mis = 0 emitter
+ * sampling only, mis = 1 BSDF sampling only.  The sample streams consume only the draws the mode uses. */
+enum { PSDR_INTEGRATOR_PATH = 0, PSDR_INTEGRATOR_DIRECT = 1 };
+int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis);
 /* New.  on != 0: the analytic re-intersection of the primary hit in renderD (src/scene/scene.cpp:772-801,
  * include/psdr/utils.h:82-93) takes its reciprocal with rcp.approx.ftz.f32, the instruction Dr.Jit emits for rcp()
  * (drjit-core cuda_eval.cpp:638-640), instead of the correctly rounded 1/x.  Everything else stays IEEE.  Reproduces the
@@ -214,7 +220,7 @@ int psdr_render_d_host(psdr_scene *s, int sensor, int max_depth, long long seed,
                        const int *pix_id_host, int npix, float *img_host, float *dimg_host);
 
 /* FieldExtractionIntegrator taps (src/integrator/field.cpp:47-121) at the scene's spp: per lane 14 floats
- * (mesh id + 1, triangle id, position xyz, distance, geometric normal xyz, shading normal xyz, 0, 0). */
+ * (mesh id + 1, triangle id, position xyz, distance, geometric normal xyz, shading normal xyz, uv). */
 int psdr_render_aov(psdr_scene *s, int sensor, long long seed, float *out, void *cuda_stream);
 
 /* Sampler.seed / next_1d (src/psdr.cpp:181-185): out[ndraws][n], host memory, computed on the host. */

@@ -224,6 +224,7 @@ struct Scene {
     std::string error;
     // options
     bool li_p_first = true;  // evaluation order of Li(ray_n) - Li(ray_p), integrator.cpp:185-186
+    int mis = 2;             // 2: PathTracer / Direct(2); 0 / 1: Direct(0) / Direct(1) (reference src/integrator/direct.cpp)
 };
 
 // The product's closest-hit query (psdr_jit_b200/csrc/device_path.cuh trace<brute>, the replacement of OptiX) tests a
@@ -1185,10 +1186,13 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
     for (int depth = 0; depth < max_depth; ++depth) {
         // all lanes draw, masked or not (GCC evaluates next_2d's arguments right-to-left:
         // y gets the first draw; sampler.h:19-21)
-        float s_y = rng.next_1d(), s_x = rng.next_1d();
-        float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();  // next_nd<3> = (d3,d2,d1)
+        // DirectIntegrator's one-strategy modes draw only what they use (direct.cpp:47,84-91)
+        const int mis = sc.mis;
+        float s_y = 0.f, s_x = 0.f, s3_z = 0.f, s3_y = 0.f, s3_x = 0.f;
+        if (mis != 1) { s_y = rng.next_1d(); s_x = rng.next_1d(); }
+        if (mis != 0) { s3_z = rng.next_1d(); s3_y = rng.next_1d(); s3_x = rng.next_1d(); }  // next_nd<3> = (d3,d2,d1)
         if (!active) continue;
-        {   // ---- emitter sampling
+        if (mis != 1) {   // ---- emitter sampling
             PosSample<S> ps = sample_emitter_position<S>(sc, val(its.p), V2f(s_x, s_y));
             bool active_direct = active && ps.valid && !is_emitter(sc, its);
             V3<S> wod = ps.p - its.p;
@@ -1208,10 +1212,10 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
             bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
             float pdf1 = bsdf_pdf(sc, its, wo_local, active_direct) * val(G_val);
             active_direct = active_direct && (pdf1 != 0.f);
-            float weight1 = mis_weight(ps.pdf, pdf1);
+            float weight1 = mis == 0 ? 1.f : mis_weight(ps.pdf, pdf1);
             if (active_direct) result += throughput * emitter_val * bsdf_val2 * S(weight1);
         }
-        {   // ---- BSDF sampling
+        if (mis != 0) {   // ---- BSDF sampling
             BsdfSample bs = bsdf_sample(sc, its, V3f(s3_x, s3_y, s3_z), active);
             V3<S> wdir = its.to_world(lift<S>(bs.wo));
             Its<S> its1 = ray_intersect<S>(sc, its.p, wdir, active, ad);
@@ -1236,7 +1240,7 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
                 if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
                 else bsdf_val = bsdf_eval(sc, its, lift<S>(bs.wo), active) / S(bs.pdf);
             }
-            float weight2 = mis_weight(pdf0, emitter_position_pdf(sc, val(its.p), its1, active));
+            float weight2 = mis == 1 ? 1.f : mis_weight(pdf0, emitter_position_pdf(sc, val(its.p), its1, active));
             throughput *= bsdf_val;
             if (active) result += Le(sc, its1, active) * throughput * S(weight2);
             its = its1;
@@ -1493,6 +1497,7 @@ void *orc_create(int width, int height, int spp, int sppe, int sppse) {
 void orc_destroy(void *h) { delete (Scene *) h; }
 const char *orc_error(void *h) { return ((Scene *) h)->error.c_str(); }
 void orc_set_li_order(void *h, int p_first) { ((Scene *) h)->li_p_first = p_first != 0; }
+void orc_set_mis(void *h, int mis) { ((Scene *) h)->mis = mis; }
 
 int orc_add_diffuse(void *h, const float *refl, const float *d_refl, int two_side) {
     Scene *s = (Scene *) h;

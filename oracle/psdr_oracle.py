@@ -37,6 +37,7 @@ def lib():
         L.orc_error.restype = C.c_char_p
         L.orc_error.argtypes = [C.c_void_p]
         L.orc_set_li_order.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_mis.argtypes = [C.c_void_p, C.c_int]
         L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
         L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
         L.orc_add_envmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int, _f, _f, C.c_float, C.c_float]
@@ -170,6 +171,10 @@ class OracleScene:
         rc = self.L.orc_configure(self.h, _ip(a), len(a))
         if rc:
             raise RuntimeError(self.L.orc_error(self.h).decode())
+
+    def set_mis(self, mis=2):
+        """2: PathTracer / Direct(2); 0 / 1: Direct(0) / Direct(1) -- render with depth 1"""
+        self.L.orc_set_mis(self.h, int(mis))
 
     def set_li_order(self, p_first=True):
         self.L.orc_set_li_order(self.h, int(p_first))

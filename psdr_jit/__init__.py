@@ -88,3 +88,12 @@ class _IntegratorMixin:
 
 class PathTracer(_IntegratorMixin, _b.PathTracer):
     pass
+
+
+class Direct(_IntegratorMixin, _b.Direct):
+    pass
+
+
+class FieldExtractionIntegrator(_b.FieldExtractionIntegrator):
+    def renderC(self, scene, sensor_id=0, seed=-1, batch_pix=-1):
+        return ArrayXf(super().renderC(scene, sensor_id, seed, batch_pix))

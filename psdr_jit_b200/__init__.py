@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib, scenes  # noqa: F401
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
@@ -708,9 +708,12 @@ class Integrator(Object):
     reference_tangent_scaling = False
     grad_image = None
 
+    _kind, _mis = 0, 2      # PSDR_INTEGRATOR_PATH; Direct overrides
+
     def _check(self, scene: Scene):
         if scene._h is None or not scene.is_ready():
             raise RuntimeError("Input scene must be configured!")
+        _lib.check(_lib.load().psdr_scene_set_integrator(scene._h, self._kind, self._mis))
 
     @staticmethod
     def _torch():
@@ -899,6 +902,49 @@ class PathTracer(Integrator):
         super()._check(scene)
         for i in range(scene.num_sensors):      # the grid belongs to the integrator in the reference
             _lib.check(_lib.load().psdr_scene_set_guiding(scene._h, i, int((id(scene), i) in getattr(self, "_guided", ()))))
+
+
+class Direct(PathTracer):
+    """reference src/psdr.cpp:436-439, src/integrator/direct.cpp: direct illumination, one bounce.  mis = 2: emitter and
+    BSDF sampling combined with the power heuristic, 0: emitter sampling only, 1: BSDF sampling only."""
+
+    def __init__(self, mis: int = 2):
+        if not 0 <= int(mis) <= 2:
+            raise RuntimeError("mis >= 0 && mis <= 2")
+        super().__init__(1)
+        self._kind, self._mis = 1, int(mis)
+
+
+DirectIntegrator = Direct
+
+
+class FieldExtractionIntegrator(Integrator):
+    """reference src/psdr.cpp:423-425, src/integrator/field.cpp: the value of an intersection field at the primary hit,
+    averaged over the pixel's samples.  Fields: silhouette, position, depth, geoNormal, shNormal, uv, segmentation
+    (mesh index; the reference reports the id parsed from the mesh's name), optionally "<field> <mesh index>" to keep
+    one object only.  renderC only (the derivative of a field image is not part of this path)."""
+    FIELDS = ("segmentation", "silhouette", "position", "depth", "geoNormal", "shNormal", "uv")
+
+    def __init__(self, field: str):
+        tok = field.split()
+        if not tok or tok[0] not in self.FIELDS + ("bsdf",):
+            raise RuntimeError("Unsupported field: " + (tok[0] if tok else ""))
+        if tok[0] == "bsdf":
+            raise NotImplementedError("FieldExtractionIntegrator('bsdf') is not implemented")
+        self.field, self.object = tok[0], (tok[1] if len(tok) > 1 else "")
+        self.max_depth = 0
+
+    def renderC(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        torch = self._torch()
+        spp = max(scene.opts.spp, 1)
+        a = self.render_aov(scene, sensor_id, 0 if seed < 0 else seed).view(-1, spp, 14)
+        valid = a[:, :, 0] > 0
+        if self.object:
+            valid = valid & (a[:, :, 0] == float(int(self.object) + 1))
+        f = {"segmentation": a[:, :, 0:1].expand(-1, -1, 3) - 1.0, "silhouette": torch.ones_like(a[:, :, 2:5]), "position": a[:, :, 2:5],
+             "depth": a[:, :, 5:6].expand(-1, -1, 3), "geoNormal": a[:, :, 6:9], "shNormal": a[:, :, 9:12],
+             "uv": torch.cat((a[:, :, 12:14], torch.zeros_like(a[:, :, 0:1])), dim=2)}[self.field]
+        return (f * valid.unsqueeze(-1)).sum(dim=1) / float(spp)
 
 
 def _render_d_autograd(integ: Integrator, scene: Scene, sensor_id: int, seed: int, batch_pix, leaves):

@@ -28,7 +28,7 @@ TERM_INTERIOR, TERM_PRIMARY_EDGES, TERM_SECONDARY_EDGES, TERM_ALL = 1, 2, 4, 7
 
 EXPORTS = [
     "psdr_last_error", "psdr_version", "psdr_kernel_launch_count", "psdr_scene_create", "psdr_scene_destroy",
-    "psdr_scene_set_options", "psdr_scene_set_seed", "psdr_scene_set_shard", "psdr_scene_set_accel", "psdr_scene_set_reference_arithmetic",
+    "psdr_scene_set_options", "psdr_scene_set_seed", "psdr_scene_set_shard", "psdr_scene_set_accel", "psdr_scene_set_reference_arithmetic", "psdr_scene_set_integrator",
     "psdr_scene_add_bsdf_diffuse", "psdr_scene_add_bsdf_microfacet", "psdr_scene_add_envmap", "psdr_scene_set_bsdf_texture", "psdr_scene_set_bsdf_texture_slot", "psdr_scene_add_mesh", "psdr_scene_add_perspective", "psdr_scene_set_param",
     "psdr_scene_set_tangent", "psdr_scene_clear_tangents", "psdr_scene_configure", "psdr_scene_last_configure_ms",
     "psdr_scene_query", "psdr_scene_mesh_edges", "psdr_render_c", "psdr_render_d", "psdr_render_c_host",
@@ -59,6 +59,7 @@ def load():
     L.psdr_scene_set_shard.argtypes = [vp, i, i]
     L.psdr_scene_set_accel.argtypes = [vp, i]
     L.psdr_scene_set_reference_arithmetic.argtypes = [vp, i]
+    L.psdr_scene_set_integrator.argtypes = [vp, i, i]
     L.psdr_scene_add_bsdf_diffuse.argtypes = [vp, C.c_char_p, P_F, i]
     L.psdr_scene_add_bsdf_microfacet.argtypes = [vp, C.c_char_p, P_F, P_F, f, i]
     L.psdr_scene_add_envmap.argtypes = [vp, P_F, i, i, P_F, f]

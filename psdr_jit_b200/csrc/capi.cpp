@@ -128,6 +128,14 @@ int psdr_scene_set_accel(psdr_scene *s, int mode) {
     return 0;
 }
 
+int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis) {
+    if (!s) return fail("null scene");
+    if (kind != PSDR_INTEGRATOR_PATH && kind != PSDR_INTEGRATOR_DIRECT) return fail("unknown integrator kind");
+    if (kind == PSDR_INTEGRATOR_DIRECT && (mis < 0 || mis > 2)) return fail("mis >= 0 && mis <= 2");
+    s->sc.integrator_mis = kind == PSDR_INTEGRATOR_DIRECT ? mis : 2;
+    return 0;
+}
+
 int psdr_scene_set_reference_arithmetic(psdr_scene *s, int on) {
     if (!s) return fail("null scene");
     s->sc.ref_rcp = on != 0;
@@ -474,12 +482,15 @@ void set_shard(RenderParams &rp, long long n, int rank, int world) {
 // Integrator::renderC / renderD front matter (integrator.cpp:12-31, 51-73): argument checks and
 // sampler (re)seeding; returns the per-sampler (seed, skip) pair of this call.
 void begin_render(Scene &sc, int sensor, long long seed, const int *pix_id, bool ad, int terms, int max_depth, RenderParams rp[3]) {
+    const int mis = sc.integrator_mis;
+    const unsigned long long per_bounce = mis == 0 ? 2ull : mis == 1 ? 3ull : 5ull;      // draws per bounce (device_path.cuh li_step)
+    for (int k = 0; k < 3; ++k) rp[k].mis = mis;
     if (pix_id && seed == -1) throw std::runtime_error("While using batch rendering, seed must be set!");
     if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
     if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
     if (max_depth < 0) throw std::runtime_error("max_depth >= 0");
     const int per[3] = {sc.spp, ad ? sc.sppe : 0, ad ? sc.sppse : 0};
-    const unsigned long long draws[3] = {2ull + 5ull * max_depth, 1ull + 10ull * max_depth, 3ull};
+    const unsigned long long draws[3] = {2ull + per_bounce * max_depth, 1ull + 2ull * per_bounce * max_depth, 3ull};
     for (int k = 0; k < 3; ++k) {
         if (per[k] <= 0) continue;
         SamplerState &st = sc.samplers[k];

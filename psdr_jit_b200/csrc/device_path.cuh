@@ -932,7 +932,7 @@ template <class S> __device__ __forceinline__ void li_begin(LiState<S> &st, V3<S
 
 // one iteration {main ray -> vertex, NEE shadow ray, BSDF sample}; returns true when the path is finished
 template <class S, int kCfg, bool kAD, class Rec>
-__device__ __forceinline__ bool li_step(const DScene &sc, Pcg32 &rng, LiState<S> &st, int max_depth, bool hide_emitters, Rec &R) {
+__device__ __forceinline__ bool li_step(const DScene &sc, Pcg32 &rng, LiState<S> &st, int max_depth, bool hide_emitters, Rec &R, int mis = 2) {
     constexpr bool ad = kAD;
     const int depth = st.depth;
     Its<S> &its = st.its;
@@ -962,23 +962,28 @@ __device__ __forceinline__ bool li_step(const DScene &sc, Pcg32 &rng, LiState<S>
                 if (val(its1.t) < kEpsilon) bsdf_val = V3<S>(S(0.f));
                 else bsdf_val = bsdf_eval<S, kCfg>(sc, its, lift3<S>(st.bs.wo), st.active) / S(st.bs.pdf);
             }
-            const float weight2 = mis_weight(pdf0, emitter_position_pdf<S, kCfg>(sc, val(its.p), its1, st.active));
+            // DirectIntegrator(mis = 1): BSDF sampling only, weight 1 (reference src/integrator/direct.cpp:121-124)
+            const float weight2 = mis == 1 ? 1.f : mis_weight(pdf0, emitter_position_pdf<S, kCfg>(sc, val(its.p), its1, st.active));
             R.bounce(depth, val(its1.t) >= kEpsilon, pdf0, weight2);
             st.throughput = st.throughput * bsdf_val;
             st.result = st.result + Le<S, kCfg>(sc, its1, st.active) * st.throughput * S(weight2);
         }
     }
     const int bounces_left = max_depth - depth - 1;
+    // draws per bounce: next_2d (emitter sampling) + next_nd<3> (BSDF sampling); the Direct integrator's one-strategy
+    // modes draw only what they use (mis = 0: emitter sampling only, mis = 1: BSDF sampling only; direct.cpp:47,84-91)
+    const unsigned long long per_bounce = mis == 0 ? 2ull : mis == 1 ? 3ull : 5ull;
     if (!st.active) {   // dead lanes only burn their draws
-        if (bounces_left > 0) rng.advance(5ull * (unsigned long long) bounces_left);
+        if (bounces_left > 0) rng.advance(per_bounce * (unsigned long long) bounces_left);
         return true;
     }
     if (bounces_left <= 0) return true;
     its = its1;
     R.throughput(depth + 1, val(st.throughput));
-    const float s_y = rng.next_1d(), s_x = rng.next_1d();                              // next_2d: y first
-    const float s3_z = rng.next_1d(), s3_y = rng.next_1d(), s3_x = rng.next_1d();      // next_nd<3> = (d3,d2,d1)
-    {   // ---- emitter sampling
+    float s_y = 0.f, s_x = 0.f, s3_z = 0.f, s3_y = 0.f, s3_x = 0.f;
+    if (mis != 1) { s_y = rng.next_1d(); s_x = rng.next_1d(); }                        // next_2d: y first
+    if (mis != 0) { s3_z = rng.next_1d(); s3_y = rng.next_1d(); s3_x = rng.next_1d(); }   // next_nd<3> = (d3,d2,d1)
+    if (mis != 1) {   // ---- emitter sampling
         const PosSample<S> ps = sample_emitter_position<S, kCfg>(sc, val(its.p), V2f(s_x, s_y));
         bool active_direct = !is_emitter(sc, its);
         V3<S> wod = ps.p - its.p;
@@ -997,12 +1002,13 @@ __device__ __forceinline__ bool li_step(const DScene &sc, Pcg32 &rng, LiState<S>
             bsdf_val2 = bsdf_val2 * (G_val * ps.J / S(ps.pdf));
             const float pdf1 = bsdf_pdf<S, kCfg>(sc, its, wo_local, active_direct) * val(G_val);
             if (pdf1 != 0.f) {
-                const float weight1 = mis_weight(ps.pdf, pdf1);
+                const float weight1 = mis == 0 ? 1.f : mis_weight(ps.pdf, pdf1);
                 R.nee(depth + 1, ps.tri < 0 || val(its2.wi.z) > 0.f, ps.tri, ps.st, val(ps.p), its2.tri, ps.pdf, weight1);
                 st.result = st.result + st.throughput * emitter_val * bsdf_val2 * S(weight1);
             }
         }
     }
+    if (mis == 0) return true;      // emitter sampling only: no BSDF-sampled ray
     // ---- BSDF sampling: the ray is traced by the next step
     st.bs = bsdf_sample<S, kCfg>(sc, its, V3f(s3_x, s3_y, s3_z), true);
     st.ray_o = its.p;
@@ -1017,27 +1023,27 @@ __device__ __forceinline__ bool li_step(const DScene &sc, Pcg32 &rng, LiState<S>
 // the plain loop (`lanes` = 0) and re-converge at the caller's barrier, which measured 2-7 % faster for them.
 template <class S, int kCfg, bool kAD, class Rec>
 __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, Rec &R,
-                                    unsigned lanes = 0u) {
+                                    unsigned lanes = 0u, int mis = 2) {
     LiState<S> st;
     li_begin<S>(st, ro, rd, active);
     if (lanes != 0u) {
         bool done = false;
 #pragma unroll 1
         while (true) {
-            if (!done) done = li_step<S, kCfg, kAD, Rec>(sc, rng, st, max_depth, hide_emitters, R);
+            if (!done) done = li_step<S, kCfg, kAD, Rec>(sc, rng, st, max_depth, hide_emitters, R, mis);
             if (__all_sync(lanes, done)) break;
         }
     } else {
 #pragma unroll 1
-        while (!li_step<S, kCfg, kAD, Rec>(sc, rng, st, max_depth, hide_emitters, R)) {}
+        while (!li_step<S, kCfg, kAD, Rec>(sc, rng, st, max_depth, hide_emitters, R, mis)) {}
     }
     return st.result;
 }
 
 template <class S, int kCfg>
-__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters) {
+__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, int mis = 2) {
     NoRecord rec;
-    return Li<S, kCfg, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec);
+    return Li<S, kCfg, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec, 0u, mis);
 }
 
 // ---- secondary (shadow) edges: reference src/scene/scene.cpp:1027-1068, src/integrator/path.cpp:172-270

@@ -134,6 +134,7 @@ struct DScene {
 struct RenderParams {
     int max_depth;
     int hide_emitters;
+    int mis;                 // 2: PathTracer / Direct(2) (both strategies, power heuristic); 0 / 1: Direct(0) / Direct(1)
     long long seed;          // >= 0
     unsigned long long skip; // draws already consumed per lane of this sampler (seed = -1 continuation)
     long long lane_begin, lane_end;   // LOCAL lane index range of this call: [0, 32 * owned blocks)

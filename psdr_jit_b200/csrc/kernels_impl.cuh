@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? PSDR_LB_INTERIOR_D
             V3<S> o, d;
             sample_primary_ray<S>(cam, V2f(sx, sy), o, d);
             NoRecord rec;
-            v = Li<S, kCfg, kAD, NoRecord>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, rec);
+            v = Li<S, kCfg, kAD, NoRecord>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, rec, 0u, rp.mis);
         }
         float r = val(v.x), g = val(v.y), b = val(v.z), dr = tang(v.x), dg = tang(v.y), db = tang(v.z);
         // masked(value, ~isfinite(value)) = 0 zeroes value and tangent (integrator.cpp:126)
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(c
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px.v + sg * bq.x, py.v + sg * bq.y), ro, rd);
-            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
+            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis);
         }
         const V3f Lp = Lside[0], Ln = Lside[1];
         if (!valid) continue;
@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(kBlock) aov_kernel(const __grid_constant__ DSc
         r[2] = its.p.x; r[3] = its.p.y; r[4] = its.p.z; r[5] = its.t;
         r[6] = its.n.x; r[7] = its.n.y; r[8] = its.n.z;
         r[9] = its.sh_n.x; r[10] = its.sh_n.y; r[11] = its.sh_n.z;
+        r[12] = its.uv.x; r[13] = its.uv.y;
     }
 }
 

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_c
         const V3f o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f)), d = xform_dir(cam.to_world, dc);
         PathRecord<kD> R;
         R.reset();
-        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, R, 0xffffffffu);
+        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, R, 0xffffffffu, rp.mis);
         // cotangent of this lane's value; channels the forward pass scrubbed (non-finite) carry none
         V3f g(__ldg(d_img + 3 * idx) * inv_spp, __ldg(d_img + 3 * idx + 1) * inv_spp, __ldg(d_img + 3 * idx + 2) * inv_spp);
         if (!isfinite(v.x)) g.x = 0.f;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __gr
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px + sg * bq.x, py + sg * bq.y), ro, rd);
-            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0);
+            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis);
         }
         if (!valid) continue;
         const int pix = iy * sc.width + ix;

@@ -157,6 +157,7 @@ struct Scene {
     int device = 0;
     int rank = 0, world = 1;   // lane-range sharding across GPUs
     int force_bvh = -1;        // -1 auto, 0 brute force, 1 bvh
+    int integrator_mis = 2;    // 2 PathTracer / Direct(2); 0, 1: Direct(0), Direct(1) (psdr_scene_set_integrator)
     bool ref_rcp = false;      // reference arithmetic for the analytic primary hit (psdr_scene_set_reference_arithmetic)
     DeviceBuffers *dev = nullptr;
     DScene dscene{};

@@ -262,3 +262,19 @@ def test_shard_vjp_tables_sum_to_full_vjp():
     integ.backprop_table(parts[0], acc, 0)
     g_sum = parts[0].grad_of("Mesh[0]", "to_world_left")
     assert np.abs(g_sum - g_full).max() < 2e-4 * max(np.abs(g_full).max(), 1e-12)
+
+
+@pytest.mark.parametrize("mis", [0, 1])
+def test_direct_integrator_vjp_is_transpose_of_jvp(mis):
+    import torch
+    import psdr_jit_b200 as psdr
+    rng = np.random.default_rng(31 + mis)
+    sc, tang = _scene_with_tangents(psdr, scenes.cbox_meshes(), 64, 64, (8, 8, 8), rng, "mesh_left vertices materials camera".split())
+    integ = psdr.Direct(mis)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=3)
+    cot = torch.as_tensor(rng.normal(size=(64 * 64, 3)).astype(np.float32), device=img.device)
+    lhs = float((cot.double() * dimg.double()).sum())
+    integ.render_vjp(sc, cot, 0, seed=3)
+    parts = [float((sc.grad_of(n, f).reshape(np.shape(t)).astype(np.float64) * t.astype(np.float64)).sum()) for (n, f), t in tang.items()]
+    mag = max(abs(lhs), sum(abs(v) for v in parts))
+    assert abs(lhs - sum(parts)) < 2e-4 * mag, (lhs, sum(parts))

@@ -2,6 +2,8 @@
 against the CPU oracle on identical seeded inputs, and against golden vectors produced by the
 unmodified reference.  Tolerance: rel-L2 < 1e-4 (BASELINE.json north_star) for radiance and the
 forward-mode derivative image; hit ids bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -616,3 +618,62 @@ def test_texture_slots_vs_reference_golden():
     r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["grad_box"], flip_rel=1e-3)
     print("d/d(box translation) vs reference: rel-L2 %.3e, %d pixels off, rest %.3e" % (r, nbad, r_ex))
     assert nbad < 0.03 * len(got) and r_ex < 1.5e-2 and r < 0.1, (r, nbad, r_ex)        # CPU oracle vs this golden: 5.2e-2, 129 px, 5.7e-3
+
+
+# ---- Direct integrator (reference src/integrator/direct.cpp) and field extraction (src/integrator/field.cpp) ----------
+@pytest.mark.parametrize("mis", [0, 1, 2])
+def test_direct_integrator_vs_oracle(oracle, mis):
+    psdr = _psdr()
+    kw = dict(move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+    osc = build_oracle(scenes.cbox_meshes(), 96, 96, 4, 4, 4, **kw)
+    osc.set_mis(mis)
+    ref_c = osc.render(1, seed=4, mode=0)
+    ref_i, ref_d = osc.render(1, seed=4, mode=1, terms=7)
+    sc = build_product(scenes.cbox_meshes(), 96, 96, 4, 4, 4, **kw)
+    integ = psdr.Direct(mis)
+    assert rel_l2(integ.renderC(sc, 0, seed=4).cpu().numpy(), ref_c) < TOL
+    img, dimg = integ.renderD_fwd(sc, 0, seed=4)
+    assert rel_l2(img.cpu().numpy(), ref_i) < TOL and rel_l2(dimg.cpu().numpy(), ref_d) < TOL
+    # continuation of the streams consumes the mode's own number of draws
+    img2, _ = integ.renderD_fwd(sc, 0, seed=-1)
+    draws = {0: 2, 1: 3, 2: 5}[mis]
+    ref2, _ = osc.render(1, seed=4, mode=1, terms=7, skip=[2 + draws, 1 + 2 * draws, 3])
+    assert rel_l2(img2.cpu().numpy(), ref2) < TOL
+    if mis == 2:      # Direct(2) is PathTracer(1)
+        assert rel_l2(psdr.PathTracer(1).renderC(sc, 0, seed=4).cpu().numpy(), ref_c) < TOL
+
+
+def test_direct_integrator_vs_reference_golden():
+    psdr = _psdr()
+    path = GOLDEN + "/direct.npz"
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/direct.npz not generated yet (tools/ref_golden6.py)")
+    g = np.load(path)
+    kw = dict(move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+    for mis in (0, 1, 2):
+        sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 4, 4, **kw)
+        integ = psdr.Direct(mis)
+        integ.reference_tangent_scaling = True
+        r, nbad, r_ex = compare_stats(integ.renderC(sc, 0, seed=0).cpu().numpy(), g["imgC_mis%d" % mis], flip_rel=2e-5)
+        print("Direct(%d) renderC vs reference: rel-L2 %.3e, %d pixels with a flipped lane, rest %.3e" % (mis, r, nbad, r_ex))
+        assert nbad < 0.03 * 128 * 128 and r_ex < 2e-5, (mis, r, nbad, r_ex)
+        img, dimg = integ.renderD_fwd(sc, 0, seed=0, terms=1)
+        r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["gradD_int_mis%d" % mis], flip_rel=1e-3)
+        print("Direct(%d) interior derivative vs reference: rel-L2 %.3e, %d pixels off, rest %.3e" % (mis, r, nbad, r_ex))
+        assert nbad < 0.03 * 128 * 128 and r_ex < 1e-3, (mis, r, nbad, r_ex)
+
+
+def test_field_extraction_integrator(oracle):
+    psdr = _psdr()
+    sc = build_product(scenes.cbox_meshes(), 64, 64, 4, 0, 0)
+    aov = build_oracle(scenes.cbox_meshes(), 64, 64, 4, 0, 0).aov(0, seed=0).reshape(64 * 64, 4, 14)
+    valid = (aov[:, :, 0] > 0)[..., None]
+    for field, cols in (("position", slice(2, 5)), ("geoNormal", slice(6, 9)), ("shNormal", slice(9, 12))):
+        got = psdr.FieldExtractionIntegrator(field).renderC(sc, 0, seed=0).cpu().numpy()
+        assert rel_l2(got, (aov[:, :, cols] * valid).sum(1) / 4.0) < 1e-6, field
+    depth = psdr.FieldExtractionIntegrator("depth").renderC(sc, 0, seed=0).cpu().numpy()
+    assert rel_l2(depth[:, 0], (aov[:, :, 5] * valid[..., 0]).sum(1) / 4.0) < 1e-6
+    sil = psdr.FieldExtractionIntegrator("silhouette 1").renderC(sc, 0, seed=0).cpu().numpy()       # the small box only
+    assert rel_l2(sil[:, 0], (aov[:, :, 0] == 2.0).sum(1) / 4.0) < 1e-6 and 0 < sil.sum() < 3 * 64 * 64
+    with pytest.raises(RuntimeError, match="Unsupported field"):
+        psdr.FieldExtractionIntegrator("albedo")

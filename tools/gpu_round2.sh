@@ -44,4 +44,15 @@ ncu)
     ncu -i $REP.ncu-rep --page source --csv --print-source sass -k regex:"$k" > $OUT/sass_$k.csv 2>/dev/null
   done
   ls -la $OUT ;;
+ncuvjp)
+  echo "== ncu full capture of the adjoint kernels"
+  REP=/tmp/profv_$TAG
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'vjp_kernel' -s 9 -c 3 -f -o $REP \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_vjp.log 2>&1
+  tail -2 $OUT/ncu_vjp.log
+  ncu -i $REP.ncu-rep --page raw --csv > $OUT/raw_vjp.csv 2>/dev/null
+  for k in interior_vjp_kernel primary_edge_vjp_kernel secondary_edge_vjp_kernel; do
+    ncu -i $REP.ncu-rep --page source --csv --print-source sass -k regex:"$k" > $OUT/sass_$k.csv 2>/dev/null
+  done
+  ls -la $OUT ;;
 esac; done
