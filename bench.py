@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- the driver's measurement contract for the PathTracer.renderD hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1]): Cornell box 512x512, spp = sppe = sppse = 32, PathTracer(3)
@@ -439,6 +439,269 @@ def run_reference(args, rank: int, world: int, local_rank: int):
     print(json.dumps(base), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# The other BASELINE.json workloads (--config 1 | 3 | 4 | 5; psdr_jit_b200/bench_scenes.py): same JSON contract.
+def run_ours_config(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import psdr_jit_b200 as psdr
+    from psdr_jit_b200 import _lib, bench_scenes
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.load()
+    wl = bench_scenes.workload(args.config)
+    per_sensor = args.config == 5                        # one sensor per GPU: replicas, no image collective
+    sc = bench_scenes.build_ours(psdr, wl, 0 if per_sensor else rank, 1 if per_sensor else world)
+    integ = psdr.PathTracer(wl["depth"])
+    prep_ms = None
+    if wl["guiding"]:
+        t0 = time.perf_counter()
+        integ.preprocess_secondary_edges(sc, 0, wl["guiding"], 1)
+        torch.cuda.synchronize()
+        prep_ms = (time.perf_counter() - t0) * 1e3
+    _lib.check(L.psdr_scene_enable_timing(sc._h, 1))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    mine = [k for k in wl["sensors"] if (k % world == rank or not per_sensor)]
+    n_samples = wl["samples_per_call"] * len(wl["sensors"])
+    st = torch.cuda.current_stream()
+
+    def step(seed):
+        for k in mine:
+            if wl["mode"] == "renderC":
+                img = integ.renderC(sc, k, seed=seed)
+                if world > 1 and not per_sensor:
+                    dist.all_reduce(img)
+            else:
+                integ.renderD_fwd(sc, k, seed=seed)
+                if world > 1 and not per_sensor:
+                    dist.all_reduce(integ.last_buffer)
+
+    step(0)
+    for it in range(args.warmup):
+        step(-1)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = psdr.kernel_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = {1: [], 2: [], 4: []}
+    for it in range(args.steps):
+        flush.fill_(it & 255)
+        ev[it][0].record(st)
+        step(-1)
+        ev[it][1].record(st)
+        for term in (1, 2, 4):
+            kernel_ms[term].append(L.psdr_scene_kernel_ms(sc._h, term))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = psdr.kernel_launch_count() - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    # end to end: parameter update + configure (H2D of the tables) + render + D2H into host buffers
+    npix = wl["w"] * wl["h"]
+    himg, hdimg = np.empty((npix, 3), np.float32), np.empty((npix, 3), np.float32)
+    mesh = sc.param_map["Mesh[%d]" % wl["moving"]]
+    tangent = bench_scenes.tangent_matrix()
+    pinned = torch.empty((2, npix, 3), dtype=torch.float32, pin_memory=True)
+
+    def e2e_step(seed):
+        if wl["mode"] == "renderD":
+            mesh.set_transform(np.eye(4, dtype=np.float32), tangent=tangent)
+        sc.configure(wl["sensors"])
+        for k in mine:
+            if world > 1 and not per_sensor:
+                if wl["mode"] == "renderC":
+                    buf = integ.renderC(sc, k, seed=seed)
+                else:
+                    integ.renderD_fwd(sc, k, seed=seed)
+                    buf = integ.last_buffer
+                dist.reduce(buf, dst=0)
+                if rank == 0:
+                    pinned.view(-1)[:buf.numel()].copy_(buf.view(-1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            elif wl["mode"] == "renderC":
+                integ.renderC_host(sc, k, seed=seed, out=himg)
+            else:
+                integ.renderD_host(sc, k, seed=seed, out=himg, dout=hdimg)
+        return float(himg[0, 0])
+
+    e2e_steps = max(1, min(args.steps, 10))
+    e2e_step(0)
+    e2e_step(-1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for it in range(e2e_steps):
+        e2e_step(-1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    if rank == 0:
+        means = {k: (sum(v) / len(v) if v and min(v) >= 0 else -1.0) for k, v in kernel_ms.items()}
+        dom = max(means, key=lambda k: means[k])
+        lanes = npix * {1: wl["spp"], 2: wl["sppe"], 4: wl["sppse"]}[dom] // (1 if per_sensor else world)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = bench_scenes.algorithmic_bytes(wl, dom, lanes) / (means[dom] * 1e-3) / 1e9 if means[dom] > 0 else None
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_oracle_rate_config(args.config)
+        out = {
+            "metric": "Msamples/s %s" % wl["name"], "value": round(n_samples * args.steps / (total_ms * 1e-3) / 1e6, 3), "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak" if False else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(wl, world, "device buffers (value); parameter update + Scene.configure + host-buffer render (e2e)"),
+            "clocks": clk,
+            "e2e": {"value": round(n_samples * e2e_steps / e2e_s / 1e6, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(L.psdr_scene_query(sc._h, _lib.Q_UPLOAD_BYTES, 0)),
+                    "d2h_bytes_per_step": int(himg.nbytes * (2 if wl["mode"] == "renderD" else 1) * len(wl["sensors"])), "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4)},
+            "gpu_launches": int(launches),
+            "kernel_ms": {"interior": round(means[1], 4), "primary_edges": round(means[2], 4), "secondary_edges": round(means[4], 4)},
+            "configure_ms": round(sc.last_configure_ms(), 3), "guiding_prepass_ms": None if prep_ms is None else round(prep_ms, 2),
+            "uses_bvh": bool(L.psdr_scene_query(sc._h, _lib.Q_USES_BVH, 0)),
+            "roofline": {"bound": "hbm", "kernel": {1: "interior_kernel", 2: "primary_edge_kernel", 4: "secondary_edge_kernel"}[dom],
+                         "achieved": None if ach is None else round(ach, 1), "peak": peak, "unit": "GB/s", "frac": None if ach is None else round(ach / peak, 4),
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def config_dict(wl, world, path):
+    return {"workload": wl["name"], "l2": "256 MiB memset between timed steps (flush, outside the events)",
+            "sharding": ("one sensor per rank (replicas)" if wl["cfg"] == 5 else "interleaved 32-lane blocks over %d rank(s), one NCCL all-reduce" % world)
+            if world > 1 else "single GPU",
+            "seed": "seed=0 on the first call, then seed=-1 (continuing sampler streams, reference README.md:96)",
+            "param": "Mesh[%d] translate(100 P,0,0), forward tangent" % wl["moving"], "path": path}
+
+
+def cpu_oracle_rate_config(cfg: int):
+    """CPU oracle port on a bounded sample of workload `cfg` (a reported baseline, not the target)."""
+    from oracle import psdr_oracle
+    from psdr_jit_b200 import bench_scenes
+    from tests.common import build_oracle
+    psdr_oracle.build()
+    size, spp = {1: (128, 1), 3: (512, 32), 4: (128, 4), 5: (512, 16)}[cfg]
+    wl = bench_scenes.workload(cfg)
+    env = None
+    if wl["envmap"] is not None:
+        env = dict(data=wl["envmap"][0], w=wl["envmap"][1], h=wl["envmap"][2])
+    osc = build_oracle(wl["meshes"], size, size, spp, 0, spp if wl["sppse"] else 0, move_mesh=wl["moving"], axis_scale=(100.0, 0.0, 0.0),
+                       bsdfs=wl["bsdfs"], envmap=env, cam=wl["cams"][0])
+    t0 = time.perf_counter()
+    osc.render(wl["depth"], seed=0, mode=0 if wl["mode"] == "renderC" else 1, terms=7)
+    dt = time.perf_counter() - t0
+    n = size * size * spp * (2 if wl["sppse"] else 1)
+    return {"value": round(n / dt / 1e6, 4), "unit": "Msamples/s", "cores": psdr_oracle.num_threads(), "kind": "port",
+            "sample": "workload %d at %dx%d spp=%d (%.3f Msamples, %.1f s; unguided)" % (cfg, size, size, spp, n / 1e6, dt)}
+
+
+def run_reference_config(args, rank: int, world: int):
+    """--impl reference for configs 1, 3, 4, 5: the unmodified reference on a bounded sample of the workload (spp scaled
+    down where the full workload would not fit its AD graph in memory), steady state (first call excluded)."""
+    if rank != 0:
+        return
+    from psdr_jit_b200 import bench_scenes as _bs_unused  # noqa: F401  (numpy-only module; keeps import errors early)
+    scale = {1: 1.0, 3: 1.0 / 16.0, 4: 0.5, 5: 1.0}[args.config]
+    base = {"impl": "reference", "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    try:
+        sys.path.insert(0, ref_dir)
+        import numpy as np
+        import drjit
+        import psdr_jit as ref
+        import importlib.util
+        for name in ("scenes", "bench_scenes"):          # load the numpy-only modules without importing this repo's package (torch, CUDA library)
+            spec = importlib.util.spec_from_file_location("psdr_jit_b200." + name, os.path.join(ROOT, "psdr_jit_b200", name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["psdr_jit_b200." + name] = mod
+            if name == "scenes":
+                pkg = type(sys)("psdr_jit_b200")
+                pkg.__path__ = []
+                pkg.scenes = mod
+                sys.modules["psdr_jit_b200"] = pkg
+            spec.loader.exec_module(mod)
+        bs = sys.modules["psdr_jit_b200.bench_scenes"]
+        full = bs.workload(args.config)
+        wl = bs.workload(args.config, scale)
+        sc, set_param = bs.build_reference(ref, drjit, wl, os.path.join(ROOT, "gpurun_out", "ref_obj"))
+        integ = ref.PathTracer(wl["depth"])
+        if wl["guiding"]:
+            set_param()
+            integ.preprocess_secondary_edges(sc, 0, wl["guiding"], 1)
+
+        def step(first):
+            acc = 0.0
+            for k in wl["sensors"]:
+                if wl["mode"] == "renderC":
+                    if first:
+                        sc.configure()
+                        sc.configure(wl["sensors"])
+                    img = integ.renderC(sc, k, seed=0) if first else integ.renderC(sc, k)
+                    drjit.eval(img)
+                    drjit.sync_thread()
+                    acc += float(np.asarray(img.numpy()).ravel()[0])
+                else:
+                    P = set_param()
+                    img = integ.renderD(sc, k, seed=0) if first else integ.renderD(sc, k)
+                    drjit.eval(img)
+                    drjit.set_grad(P, 1.0)
+                    drjit.forward_to(img)
+                    g = drjit.grad(img)
+                    drjit.eval(g)
+                    drjit.sync_thread()
+                    acc += float(np.asarray(img.numpy()).ravel()[0]) + float(np.asarray(g.numpy()).ravel()[0])
+            return acc
+
+        t0 = time.perf_counter()
+        step(True)
+        cold_ms = (time.perf_counter() - t0) * 1e3
+        for it in range(max(1, args.warmup)):
+            step(False)
+        t0 = time.perf_counter()
+        for it in range(args.steps):
+            step(False)
+        dt = time.perf_counter() - t0
+        n = wl["samples_per_call"] * len(wl["sensors"])
+        v = n * args.steps / dt / 1e6
+        base.update({"metric": "Msamples/s %s" % full["name"], "value": round(v, 4), "ms_per_step": round(dt / args.steps * 1e3, 3),
+                     "cold_ms_first_step": round(cold_ms, 1),
+                     "config": config_dict(full, 1, "unmodified reference (Dr.Jit + OptiX) on the same GPU, steady state; sample: %s" % wl["name"]),
+                     "cpu_baseline": {"value": round(v, 4), "unit": "Msamples/s", "cores": 1, "kind": "reference",
+                                      "sample": "%s on the GPU (the reference has no CPU back-end)" % wl["name"]},
+                     "e2e": {"value": round(v, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    except Exception as e:
+        base.update({"unavailable": "%s: %s" % (type(e).__name__, e)})
+    print(json.dumps(base), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -447,13 +710,19 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vjp", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json workload (2 = the headline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    if args.impl == "reference":
+    if args.config != 2:
+        if args.impl == "reference":
+            run_reference_config(args, rank, world)
+        else:
+            run_ours_config(args, rank, world, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)

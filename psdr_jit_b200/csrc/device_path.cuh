@@ -247,9 +247,12 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
     miss.tri = -1;
     miss.u = miss.v = 0.f;
     miss.t = kTraceTMax;
-    if (isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z)) return miss;
     constexpr bool kBvh = (kCfg & kCfgBvh) != 0;
+    const bool nan_ray = isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z);
+    if (kBvh && nan_ray) return miss;
     if (!kBvh) {
+        // the lanes that trace together (converged on entry); nothing below returns before the warp-level reduction
+        const unsigned lanes = __activemask();
         const int n_pairs = (sc.n_tris + 1) >> 1;
         V3p O;
         O.x = f2_dup(o.x); O.y = f2_dup(o.y); O.z = f2_dup(o.z);
@@ -287,13 +290,20 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
             mask &= pass;
         }
 #endif
-        if (mask == 0u) return miss;
+        if (nan_ray) mask = 0u;
         V3p D, ND;
         D.x = f2_dup(d.x); D.y = f2_dup(d.y); D.z = f2_dup(d.z);
         ND.x = f2_dup(-d.x); ND.y = f2_dup(-d.y); ND.z = f2_dup(-d.z);
         const ulonglong2 *tab = brute_table();
         const F2 EPSV = f2_dup(kRayEpsilon);
-        while (mask) {
+        // Every lane runs the loop as often as the lane with the most candidates: the trip count is the same register
+        // value in all lanes, so the loop branch never diverges and the lanes stay converged through it.  (A plain
+        // `while (mask)` left the lanes split by trip count for the rest of the caller wherever ptxas placed no
+        // reconvergence point behind the loop: 5.7 of 27 lanes in the secondary-edge adjoint, profiles/r02e.)
+        const int n_it = __reduce_max_sync(lanes, __popc(mask));
+#pragma unroll 1
+        for (int it = 0; it < n_it; ++it) {
+            if (mask == 0u) continue;
             const int j = __ffs(mask) - 1;
             mask &= mask - 1u;
             const ulonglong2 *w = tab + kBruteSmemStride * j;
