@@ -287,34 +287,7 @@ class AreaLight(Emitter):
         self.d_radiance = np.zeros(3, dtype=np.float32)
 
 
-def _load_obj(path: str):
-    """Minimal OBJ reader: v / vt / f, polygons fan-triangulated (a,b,c),(a,c,d),..."""
-    v, vt, f, ft = [], [], [], []
-    with open(path) as fh:
-        for line in fh:
-            tok = line.split()
-            if not tok or tok[0].startswith("#"):
-                continue
-            if tok[0] == "v":
-                v.append([float(x) for x in tok[1:4]])
-            elif tok[0] == "vt":
-                vt.append([float(x) for x in tok[1:3]])
-            elif tok[0] == "f":
-                vi, ti = [], []
-                for c in tok[1:]:
-                    parts = c.split("/")
-                    a = int(parts[0])
-                    vi.append(a - 1 if a > 0 else len(v) + a)
-                    if len(parts) > 1 and parts[1]:
-                        b = int(parts[1])
-                        ti.append(b - 1 if b > 0 else len(vt) + b)
-                for k in range(1, len(vi) - 1):
-                    f.append([vi[0], vi[k], vi[k + 1]])
-                    if len(ti) == len(vi):
-                        ft.append([ti[0], ti[k], ti[k + 1]])
-    has_uv = len(vt) > 0 and len(ft) == len(f)
-    return (np.asarray(v, np.float32), np.asarray(f, np.int32), np.asarray(vt, np.float32) if has_uv else None,
-            np.asarray(ft, np.int32) if has_uv else None)
+_load_obj = scenes.load_obj
 
 
 class Mesh(_Transformable):

@@ -27,11 +27,6 @@ BUNNY_TO_WORLD = np.array([[2.5, 0, 0, 278.0], [0, 2.5, 0, 102.5], [0, 0, 2.5, 2
 MF_CFG3 = ((0.2, 0.9, 0.9), (0.01, 0.01, 0.01), 0.3)
 
 
-def _load_obj(path):
-    from . import _load_obj as lo
-    return lo(path)
-
-
 def ring_cameras(n: int = 8) -> List[dict]:
     cams = []
     for k in range(n):
@@ -60,7 +55,7 @@ def workload(cfg: int, scale: float = 1.0) -> Dict:
     elif cfg == 4:
         ms = [m for m in scenes.cbox_meshes() if m.name not in ("smallbox", "largebox")]
         if os.path.exists(BUNNY):
-            v, f, _, _ = _load_obj(BUNNY)
+            v, f, _, _ = scenes.load_obj(BUNNY)
             bunny = scenes.MeshData(name="bunny", v=v, f=f, to_world=BUNNY_TO_WORLD.copy(), bsdf="cat")
             what = "bunny_low.obj (%d faces)" % len(f)
         else:       # the data file did not travel: a stand-in of the same size (icosphere level 4, 5 120 faces)

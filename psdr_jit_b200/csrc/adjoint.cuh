@@ -17,6 +17,10 @@
 #include "device_path.cuh"
 #include "grad_layout.h"
 
+#ifndef PSDR_AGG_PARTIAL
+#define PSDR_AGG_PARTIAL 1      // 0: lanes aggregate their adds only when the whole warp arrives together
+#endif
+
 namespace psdr {
 
 // Accumulator: either the block's shared-memory copy of [lo, hi) of the table or the global table.
@@ -32,7 +36,7 @@ namespace psdr {
 __device__ __forceinline__ void grad_red(unsigned m, bool aggregate, unsigned smem_addr, float *g, int lo, int hi, int i, float v) {
     float val = (v != 0.f && isfinite(v)) ? v : 0.f;
     int same = 0;
-    if (aggregate) __match_all_sync(m, i, &same);      // (kernel-wide constant: the edge kernels' lanes sit on different edges)
+    if (aggregate && (PSDR_AGG_PARTIAL || m == 0xffffffffu)) __match_all_sync(m, i, &same);      // (kernel-wide constant: the edge kernels' lanes sit on different edges)
     bool mine = true;
     if (same && (m & (m - 1u)) != 0u) {            // uniform over m: every lane targets entry i
         if (m == 0xffffffffu) {
@@ -63,7 +67,7 @@ static __device__ __noinline__ void grad_add3_impl(bool aggregate, unsigned smem
     float v0 = (x != 0.f && isfinite(x)) ? x : 0.f, v1 = (y != 0.f && isfinite(y)) ? y : 0.f, v2 = (z != 0.f && isfinite(z)) ? z : 0.f;
     bool mine = true;
     int same = 0;
-    if (aggregate) __match_all_sync(m, idx, &same);
+    if (aggregate && (PSDR_AGG_PARTIAL || m == 0xffffffffu)) __match_all_sync(m, idx, &same);
     if (same && (m & (m - 1u)) != 0u) {            // uniform over m: every lane targets the same three entries
         if (m == 0xffffffffu) {
 #pragma unroll
@@ -306,7 +310,14 @@ struct VtxGeo {
     V2f uv, duv0, duv1;     // texture coordinate and its edge differences (uv = uv0 + u duv0 + v duv1)
     BsdfVals bv;            // reflectance / diffuseReflectance, specularReflectance, roughness of the BSDF at uv
 };
+#ifndef PSDR_VJP_GEO_NOINLINE
+#define PSDR_VJP_GEO_NOINLINE 0
+#endif
+#if PSDR_VJP_GEO_NOINLINE
+static __device__ __noinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
+#else
 __device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
+#endif
     VtxGeo g;
     const TriRec<float> T = load_tri<float>(sc, tri);
     const ShadeRec<float> N = load_shade<float>(sc, tri);

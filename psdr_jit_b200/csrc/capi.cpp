@@ -344,8 +344,12 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
             if (tangent) {
                 bool any = false;
                 for (int i = 0; i < n; ++i) any |= data[i] != 0.f;
+                if (any || !sc.env.ddata.empty()) sc.env.ddata_version++;
                 if (any) sc.env.ddata.assign(data, data + n); else sc.env.ddata.clear();
-            } else sc.env.data.assign(data, data + n);
+            } else if (sc.env.data.size() != (size_t) n || std::memcmp(sc.env.data.data(), data, sizeof(float) * n) != 0) {
+                sc.env.data.assign(data, data + n);
+                sc.env.data_version++;       // the cell table and the device copy follow (scene.cpp configure_envmap, device_upload.cu)
+            }
             break;
         }
         case PSDR_ENVMAP_SCALE: {
@@ -391,6 +395,7 @@ int psdr_scene_clear_tangents(psdr_scene *s) {
         for (HBsdf::Tex &t : b.tex) { t.ddata.clear(); t.scale = detach(t.scale); t.rot = detach(t.rot); t.tx = detach(t.tx); t.ty = detach(t.ty); }
         b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
     for (HEmitter &e : sc.emitters) e.radiance = detach(e.radiance);
+    if (!sc.env.ddata.empty()) sc.env.ddata_version++;
     sc.env.ddata.clear();
     sc.env.scale = detach(sc.env.scale);
     for (int i = 0; i < 16; ++i) sc.env.to_world[0].m[i / 4][i % 4].d = 0.f;

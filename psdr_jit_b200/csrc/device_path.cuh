@@ -13,6 +13,7 @@ namespace psdr {
 // kernel configuration bits (template parameter kCfg): which code a kernel instantiation contains
 constexpr int kCfgBvh = 1;    // BVH2 traversal instead of the parameter-space triangle scan
 constexpr int kCfgFull = 2;   // MicrofacetBSDF + EnvironmentMap code paths (otherwise Diffuse + AreaLight only)
+constexpr int kCfgUniformScan = 4;   // brute-force scan: warp-uniform trip count in the per-lane candidate loop (see trace())
 
 struct Hit {
     int tri;
@@ -240,7 +241,14 @@ template <int kCfg> __device__ __forceinline__ void brute_init(const DScene &sc,
 //   the strict "closer" keep the lowest triangle id on ties, as a full ascending scan would.
 // The box test is part of the definition of the closest hit (the CPU checker used by the tests applies the identical
 // test), so hit ids agree bit for bit whether or not a pad was generous enough.
+#ifndef PSDR_TRACE_NOINLINE
+#define PSDR_TRACE_NOINLINE 0   // 1: one out-of-line copy of the closest-hit query per kernel (instruction-cache experiments)
+#endif
+#if PSDR_TRACE_NOINLINE
+template <int kCfg> __device__ __noinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
+#else
 template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o, V3f d) {
+#endif
     HitCand best;
     hit_init(best);
     Hit miss;
@@ -248,11 +256,12 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
     miss.u = miss.v = 0.f;
     miss.t = kTraceTMax;
     constexpr bool kBvh = (kCfg & kCfgBvh) != 0;
+    constexpr bool kUniform = (kCfg & kCfgUniformScan) != 0;
     const bool nan_ray = isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(d.x) || isnan(d.y) || isnan(d.z);
-    if (kBvh && nan_ray) return miss;
+    if ((kBvh || !kUniform) && nan_ray) return miss;
     if (!kBvh) {
-        // the lanes that trace together (converged on entry); nothing below returns before the warp-level reduction
-        const unsigned lanes = __activemask();
+        // kUniform: the lanes that trace together (converged on entry); nothing below returns before the warp-level reduction
+        const unsigned lanes = kUniform ? __activemask() : 0u;
         const int n_pairs = (sc.n_tris + 1) >> 1;
         V3p O;
         O.x = f2_dup(o.x); O.y = f2_dup(o.y); O.z = f2_dup(o.z);
@@ -290,20 +299,23 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
             mask &= pass;
         }
 #endif
-        if (nan_ray) mask = 0u;
+        if (kUniform && nan_ray) mask = 0u;
+        if (!kUniform && mask == 0u) return miss;
         V3p D, ND;
         D.x = f2_dup(d.x); D.y = f2_dup(d.y); D.z = f2_dup(d.z);
         ND.x = f2_dup(-d.x); ND.y = f2_dup(-d.y); ND.z = f2_dup(-d.z);
         const ulonglong2 *tab = brute_table();
         const F2 EPSV = f2_dup(kRayEpsilon);
-        // Every lane runs the loop as often as the lane with the most candidates: the trip count is the same register
-        // value in all lanes, so the loop branch never diverges and the lanes stay converged through it.  (A plain
-        // `while (mask)` left the lanes split by trip count for the rest of the caller wherever ptxas placed no
-        // reconvergence point behind the loop: 5.7 of 27 lanes in the secondary-edge adjoint, profiles/r02e.)
-        const int n_it = __reduce_max_sync(lanes, __popc(mask));
+        // kUniform: every lane runs the loop as often as the lane with the most candidates -- the trip count is the same
+        // register value in all lanes, so the loop branch never diverges and the lanes stay converged through it.  A plain
+        // `while (mask)` leaves the lanes split by trip count for the rest of the caller wherever ptxas places no
+        // reconvergence point behind the loop: the secondary-edge adjoint ran its second and third trace with 5.7 of 27
+        // lanes (profiles/r02e; 3.6 -> 1.7 ms with the uniform loop).  The forward kernels and the other adjoints do
+        // reconverge behind the plain loop and lose 8 % to the extra vote, so the choice is per kernel (kCfgUniformScan).
+        const int n_it = kUniform ? __reduce_max_sync(lanes, __popc(mask)) : 0;
 #pragma unroll 1
-        for (int it = 0; it < n_it; ++it) {
-            if (mask == 0u) continue;
+        for (int it = 0; kUniform ? it < n_it : mask != 0u; ++it) {
+            if (kUniform && mask == 0u) continue;
             const int j = __ffs(mask) - 1;
             mask &= mask - 1u;
             const ulonglong2 *w = tab + kBruteSmemStride * j;

@@ -17,9 +17,15 @@ struct DeviceBuffers {
     void *dev = nullptr;
     void *host = nullptr;     // pinned staging
     size_t capacity = 0;
+    // the environment map's big tables (texels, texel tangents, cell pmf / cdf: 22 MB for a 1024 x 512 map) live in their
+    // own allocation and are re-uploaded only when their versions change (HEnvmap::data_version / ddata_version)
+    void *big = nullptr;
+    size_t big_capacity = 0, big_off[4] = {0, 0, 0, 0};
+    unsigned big_data_version = 0, big_ddata_version = 0;
     ~DeviceBuffers() {
         if (dev) cudaFree(dev);
         if (host) cudaFreeHost(host);
+        if (big) cudaFree(big);
     }
 };
 
@@ -172,7 +178,8 @@ void upload_scene(Scene &sc) {
                  o_ep = pk.add(em_pmf), o_ec = pk.add(em_cmf), o_sec = pk.add(sec), o_sp = pk.add(sec_pmf), o_scm = pk.add(sec_cmf),
                  o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
                  o_nodes = pk.add(nodes), o_order = pk.add(order), o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf),
-                 o_env = pk.add(sc.env.data), o_denv = pk.add(sc.env.ddata), o_cp = pk.add(sc.env.cell.pmf), o_cc = pk.add(sc.env.cell.cmf);
+                 o_small_end = 0;
+    (void) o_small_end;
     std::vector<size_t> o_tex(3 * sc.bsdfs.size(), 0), o_dtex(3 * sc.bsdfs.size(), 0);
     for (size_t i = 0; i < sc.bsdfs.size(); ++i)
         for (int k = 0; k < 3; ++k) if (sc.bsdfs[i].tex[k].w > 0) {
@@ -191,6 +198,29 @@ void upload_scene(Scene &sc) {
     }
     // the previous tables may still be read by kernels in flight on other streams
     check(cudaDeviceSynchronize(), "cudaDeviceSynchronize(before table refresh)");
+    size_t big_uploaded = 0;
+    if (sc.env.present) {
+        const HEnvmap &e = sc.env;
+        const std::vector<float> *tabs[4] = {&e.data, &e.ddata, &e.cell.pmf, &e.cell.cmf};
+        size_t need = 0, off[4];
+        for (int k = 0; k < 4; ++k) { off[k] = need; need += (std::max<size_t>(tabs[k]->size() * sizeof(float), 16) + 255) / 256 * 256; }
+        const bool realloc = need > db.big_capacity;
+        if (realloc) {
+            if (db.big) cudaFree(db.big);
+            db.big_capacity = need;
+            check(cudaMalloc(&db.big, db.big_capacity), "cudaMalloc(envmap tables)");
+        }
+        const bool data_changed = realloc || db.big_data_version != e.data_version || std::memcmp(off, db.big_off, sizeof(off)) != 0;
+        const bool ddata_changed = data_changed || db.big_ddata_version != e.ddata_version;
+        for (int k = 0; k < 4; ++k) {
+            if (!(k == 1 ? ddata_changed : data_changed) || tabs[k]->empty()) continue;
+            check(cudaMemcpy((unsigned char *) db.big + off[k], tabs[k]->data(), tabs[k]->size() * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(envmap tables)");
+            big_uploaded += tabs[k]->size() * sizeof(float);
+        }
+        std::memcpy(db.big_off, off, sizeof(off));
+        db.big_data_version = e.data_version;
+        db.big_ddata_version = e.ddata_version;
+    }
     // texture pointers of the BSDF records can only be filled in once the allocation is known
     for (size_t i = 0; i < sc.bsdfs.size(); ++i) {
         DBsdf *rec = reinterpret_cast<DBsdf *>(pk.bytes.data() + o_bsdf) + i;
@@ -215,7 +245,7 @@ void upload_scene(Scene &sc) {
     }
     std::memcpy(db.host, pk.bytes.data(), pk.bytes.size());
     check(cudaMemcpy(db.dev, db.host, pk.bytes.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene tables)");
-    sc.upload_bytes = pk.bytes.size();
+    sc.upload_bytes = pk.bytes.size() + big_uploaded;
     const unsigned char *base = (const unsigned char *) db.dev;
 
     DScene &d = sc.dscene;
@@ -304,8 +334,9 @@ void upload_scene(Scene &sc) {
         de.present = 1;
         de.emitter = e.emitter;
         de.w = e.w; de.h = e.h;
-        de.data = (const float *) (base + o_env);
-        de.ddata = e.ddata.empty() ? nullptr : (const float *) (base + o_denv);
+        const unsigned char *big = (const unsigned char *) db.big;
+        de.data = (const float *) (big + db.big_off[0]);
+        de.ddata = e.ddata.empty() ? nullptr : (const float *) (big + db.big_off[1]);
         de.scale = e.scale.v; de.d_scale = e.scale.d;
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) {
@@ -316,8 +347,8 @@ void upload_scene(Scene &sc) {
         de.upper[0] = e.upper.x; de.upper[1] = e.upper.y; de.upper[2] = e.upper.z;
         de.cw = e.cw; de.ch = e.ch;
         de.cell_sum = e.cell.sum;
-        de.cell_pmf = (const float *) (base + o_cp);
-        de.cell_cmf = (const float *) (base + o_cc);
+        de.cell_pmf = (const float *) (big + db.big_off[2]);
+        de.cell_cmf = (const float *) (big + db.big_off[3]);
     }
 
     sc.dcameras.assign(sc.cameras.size(), DCamera{});

@@ -11,9 +11,12 @@
 namespace psdr {
 
 constexpr int kBlockV = 128;
+#ifndef PSDR_LB_IVJP
+#define PSDR_LB_IVJP 5          // resident CTAs per SM the interior adjoint is compiled for (96 registers)
+#endif
 
 template <int kCfg, int kD>
-__global__ void __launch_bounds__(kBlockV, 5) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+__global__ void __launch_bounds__(kBlockV, PSDR_LB_IVJP) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                 const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                 const float *__restrict__ d_img) {
     extern __shared__ float smem[];
@@ -133,12 +136,14 @@ __global__ void __launch_bounds__(kBlockV, 6) secondary_edge_vjp_kernel(const __
     adj.gl = gl;
     adj.d_img = d_img;
     adj.scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
-    // batches of stage-0 survivors, as in the forward kernel (kernels_impl.cuh sec_edge_batches)
-    sec_edge_batches<kCfg>(sc, cam, rp, kBlockV, [&](const SecSample &smp) {
+    // batches of stage-0 survivors, as in the forward kernel (kernels_impl.cuh sec_edge_batches); this kernel needs the
+    // warp-uniform scan loop to keep its lanes together across the three traces of stage 1 (device_path.cuh trace())
+    constexpr int kC = kCfg | kCfgUniformScan;
+    sec_edge_batches<kC>(sc, cam, rp, kBlockV, [&](const SecSample &smp) {
         SecEdgeAdjoint a2 = adj;
         if (cam.guided && smp.pdf0 > kEpsilon) a2.scale = adj.scale / smp.pdf0;
         V3f value0, tangent;
-        sec_edge_stage1<kCfg, SecEdgeAdjoint>(sc, cam, smp.cand, value0, tangent, a2);
+        sec_edge_stage1<kC, SecEdgeAdjoint>(sc, cam, smp.cand, value0, tangent, a2);
     });
     grad_acc_end(adj.acc);
 }

@@ -2,6 +2,8 @@
 // triangle records (+ forward-mode tangents), light/edge distributions, camera matrices, the
 // primary/secondary edge lists and the BVH2.  Follows reference src/scene/scene.cpp:311-601,
 // src/shape/mesh.cpp:23-62,244-382, src/sensor/perspective.cpp:10-152, src/emitter/area.cpp:9-14.
+#include <thread>
+
 #include "scene.h"
 #include "texture.h"
 
@@ -459,21 +461,35 @@ static void configure_envmap(Scene &sc, bool plain_configure) {
         sc.meshes.push_back(std::move(b));
         env.has_bounds = true;
     }
-    // cell distribution: luminance * sin(theta) at the centres of 2(w-1) x 2(h-1) cells, x-major
+    // cell distribution: luminance * sin(theta) at the centres of 2(w-1) x 2(h-1) cells, x-major.  Depends on the texels
+    // only: rebuilt when they changed (2 M cells for a 1024 x 512 map: 107 ms single-threaded in round 1), the cell loop
+    // split over the host cores (cells are independent, so the result does not depend on the split)
+    if (env.cell_built == env.data_version && env.cw == ((env.w - 1) << 1) && env.ch == ((env.h - 1) << 1)) return;
     env.cw = (env.w - 1) << 1;
     env.ch = (env.h - 1) << 1;
     const size_t ncells = (size_t) env.cw * env.ch;
     std::vector<float> mass(ncells);
     const float ux = 1.f / (float) env.cw, uy = 1.f / (float) env.ch, dtheta = kPi / (float) env.ch;
-    for (size_t idx = 0; idx < ncells; ++idx) {
-        const int cx = (int) (idx / env.ch), cy = (int) (idx % env.ch);
-        const V2f uv(((float) cx + .5f) * ux, ((float) cy + .5f) * uy);
-        const V3f v = bitmap_eval_envmap<float>(env.data.data(), nullptr, env.w, env.h, uv);
-        float sn, cs;
-        sincos_full(((float) cy + .5f) * dtheta, sn, cs);
-        mass[idx] = luminance(v) * sn;
+    auto fill = [&](size_t lo, size_t hi) {
+        for (size_t idx = lo; idx < hi; ++idx) {
+            const int cx = (int) (idx / env.ch), cy = (int) (idx % env.ch);
+            const V2f uv(((float) cx + .5f) * ux, ((float) cy + .5f) * uy);
+            const V3f v = bitmap_eval_envmap<float>(env.data.data(), nullptr, env.w, env.h, uv);
+            float sn, cs;
+            sincos_full(((float) cy + .5f) * dtheta, sn, cs);
+            mass[idx] = luminance(v) * sn;
+        }
+    };
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = ncells < (1u << 16) ? 1 : std::min<size_t>(hw ? hw : 4, 32);
+    if (nthreads <= 1) fill(0, ncells);
+    else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nthreads; ++t) pool.emplace_back(fill, ncells * t / nthreads, ncells * (t + 1) / nthreads);
+        for (auto &th : pool) th.join();
     }
     env.cell.init(mass);
+    env.cell_built = env.data_version;
 }
 
 void Scene::configure(const int *active, int nactive) {

@@ -88,6 +88,10 @@ struct HEnvmap {
     V3f lower, upper;
     int cw = 0, ch = 0;
     Distrib cell;
+    // versions: data_version changes with every write of the radiance texels (psdr_scene_set_param), ddata_version with
+    // their tangents; the cell table is rebuilt and the big device tables re-uploaded only when they differ from the
+    // *_built / *_uploaded copies (an optimisation loop that only moves geometry pays neither)
+    unsigned data_version = 1, ddata_version = 1, cell_built = 0;
 };
 
 struct HPrimEdge {

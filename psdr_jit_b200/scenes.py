@@ -133,6 +133,21 @@ CBOX_MF_BSDFS = [
 CBOX_CAMERA = dict(fov=60.0, near=1e-6, far=1e7, to_world=translate(278.0, 273.0, -800.0))
 
 
+def scaled_cbox(scale: float):
+    """The Cornell box shrunk by `scale` (vertices, the luminaire's offset and the camera position).  At scale 0.01 the
+    coordinates are ~5 and fp32 reconstruction errors (~1e-6) sit three orders below the reference's fixed epsilons
+    (RayEpsilon = ShadowEpsilon = 1e-3), so epsilon-band decisions that flip between implementations at full scale
+    (DESIGN.md "parity") are excluded by construction.  Returns (meshes, camera)."""
+    ms = cbox_meshes()
+    for m in ms:
+        m.v = (m.v.astype(np.float64) * scale).astype(F32)
+        m.to_world = m.to_world.copy()
+        m.to_world[:3, 3] *= F32(scale)
+    cam = dict(CBOX_CAMERA)
+    cam["to_world"] = translate(278.0 * scale, 273.0 * scale, -800.0 * scale)
+    return ms, cam
+
+
 def icosphere(subdiv: int, radius: float, center) -> MeshData:
     """A closed smooth-shaded sphere (used for curved-silhouette test scenes)."""
     t = (1.0 + 5.0 ** 0.5) / 2.0
@@ -160,6 +175,36 @@ def icosphere(subdiv: int, radius: float, center) -> MeshData:
         f = nf
     vv = np.asarray(v) * radius + np.asarray(center, dtype=np.float64)
     return _m("sphere", vv.astype(F32), f, "cat")
+
+
+def load_obj(path: str):
+    """Minimal OBJ reader: v / vt / f, polygons fan-triangulated (a,b,c),(a,c,d),..."""
+    v, vt, f, ft = [], [], [], []
+    with open(path) as fh:
+        for line in fh:
+            tok = line.split()
+            if not tok or tok[0].startswith("#"):
+                continue
+            if tok[0] == "v":
+                v.append([float(x) for x in tok[1:4]])
+            elif tok[0] == "vt":
+                vt.append([float(x) for x in tok[1:3]])
+            elif tok[0] == "f":
+                vi, ti = [], []
+                for c in tok[1:]:
+                    parts = c.split("/")
+                    a = int(parts[0])
+                    vi.append(a - 1 if a > 0 else len(v) + a)
+                    if len(parts) > 1 and parts[1]:
+                        b = int(parts[1])
+                        ti.append(b - 1 if b > 0 else len(vt) + b)
+                for k in range(1, len(vi) - 1):
+                    f.append([vi[0], vi[k], vi[k + 1]])
+                    if len(ti) == len(vi):
+                        ft.append([ti[0], ti[k], ti[k + 1]])
+    has_uv = len(vt) > 0 and len(ft) == len(f)
+    return (np.asarray(v, np.float32), np.asarray(f, np.int32), np.asarray(vt, np.float32) if has_uv else None,
+            np.asarray(ft, np.int32) if has_uv else None)
 
 
 def write_obj(mesh: MeshData, path: str) -> None:

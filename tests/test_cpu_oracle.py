@@ -338,3 +338,16 @@ def test_oracle_texture_slots_vs_reference_golden(oracle):
     assert nbad < 300 and r_ex < 1e-4, (r, nbad, r_ex)
     r, nbad, r_ex = compare_stats(2 * d, g["grad_uv"], flip_rel=1e-3)  # the reference's 2x interior scaling
     assert nbad < 250 and r_ex < 5e-3, (r, nbad, r_ex)
+
+
+def test_oracle_direct_integrator_vs_reference_golden(oracle):
+    """Direct(mis) (tests/golden/direct.npz): the reference binary returns 2x the radiance and 2x the interior derivative."""
+    g = np.load(os.path.join(GOLDEN, "direct.npz"))
+    osc = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+    for mis in (0, 1, 2):
+        osc.set_mis(mis)
+        r, nbad, r_ex = compare_stats(2.0 * osc.render(1, seed=0, mode=0), g["imgC_mis%d" % mis], flip_rel=2e-5)
+        assert nbad < 250 and r_ex < 1e-5, (mis, r, nbad, r_ex)
+        img, d = osc.render(1, seed=0, mode=1, terms=1)
+        r, nbad, r_ex = compare_stats(2.0 * d, g["gradD_int_mis%d" % mis], flip_rel=1e-3)
+        assert nbad < 250 and r_ex < 1e-4, (mis, r, nbad, r_ex)

@@ -644,23 +644,25 @@ def test_direct_integrator_vs_oracle(oracle, mis):
 
 
 def test_direct_integrator_vs_reference_golden():
+    """psdr.Direct(mis) against the running reference (tools/ref_golden6.py -> tests/golden/direct.npz).  The reference
+    binary's Direct integrator returns exactly TWICE the radiance PathTracer(1) returns for the same samples (a directly
+    visible (20, 20, 8) luminaire reads (40, 40, 16)); the factor is applied to the golden here, the product returns the
+    radiance.  Its interior derivative image carries the same 2x as PathTracer's (reference_tangent_scaling)."""
     psdr = _psdr()
-    path = GOLDEN + "/direct.npz"
-    if not os.path.exists(path):
-        pytest.skip("tests/golden/direct.npz not generated yet (tools/ref_golden6.py)")
-    g = np.load(path)
+    g = np.load(GOLDEN + "/direct.npz")
     kw = dict(move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+    assert np.allclose(g["imgC_mis2"].max(axis=0), [40.0, 40.0, 16.0])
     for mis in (0, 1, 2):
-        sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 4, 4, **kw)
+        sc = build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, **kw)
         integ = psdr.Direct(mis)
         integ.reference_tangent_scaling = True
-        r, nbad, r_ex = compare_stats(integ.renderC(sc, 0, seed=0).cpu().numpy(), g["imgC_mis%d" % mis], flip_rel=2e-5)
+        r, nbad, r_ex = compare_stats(2.0 * integ.renderC(sc, 0, seed=0).cpu().numpy(), g["imgC_mis%d" % mis], flip_rel=2e-5)
         print("Direct(%d) renderC vs reference: rel-L2 %.3e, %d pixels with a flipped lane, rest %.3e" % (mis, r, nbad, r_ex))
-        assert nbad < 0.03 * 128 * 128 and r_ex < 2e-5, (mis, r, nbad, r_ex)
+        assert nbad < 0.02 * 128 * 128 and r_ex < 2e-5, (mis, r, nbad, r_ex)               # CPU oracle vs this golden: <= 108 pixels, 3e-6
         img, dimg = integ.renderD_fwd(sc, 0, seed=0, terms=1)
         r, nbad, r_ex = compare_stats(dimg.cpu().numpy(), g["gradD_int_mis%d" % mis], flip_rel=1e-3)
         print("Direct(%d) interior derivative vs reference: rel-L2 %.3e, %d pixels off, rest %.3e" % (mis, r, nbad, r_ex))
-        assert nbad < 0.03 * 128 * 128 and r_ex < 1e-3, (mis, r, nbad, r_ex)
+        assert nbad < 0.02 * 128 * 128 and r_ex < 2e-4, (mis, r, nbad, r_ex)               # CPU oracle: 0 / 5e-7 (mis 1), 5e-5 (mis 0, 2)
 
 
 def test_field_extraction_integrator(oracle):
