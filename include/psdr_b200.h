@@ -62,7 +62,9 @@ enum {
     PSDR_Q_IS_CONFIGURED = 9,
     PSDR_Q_USES_BVH = 10,
     PSDR_Q_UPLOAD_BYTES = 11,       /* bytes of device tables the last configure() copied host->device */
-    PSDR_Q_GUIDING_CELLS = 12       /* index = sensor; cells of its secondary-edge guiding grid (0 = none) */
+    PSDR_Q_GUIDING_CELLS = 12,      /* index = sensor; cells of its secondary-edge guiding grid (0 = none) */
+    PSDR_Q_BVH_BUILDS = 13,         /* host BVH topology builds so far (first configure, or after the set of meshes changed) */
+    PSDR_Q_BVH_REFITS = 14          /* GPU BVH refits so far (every configure of a scene above 64 triangles) */
 };
 
 /* Terms of renderD (bit mask). */
@@ -98,7 +100,9 @@ int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis);
  * (drjit-core cuda_eval.cpp:638-640), instead of the correctly rounded 1/x.  Everything else stays IEEE.  Reproduces the
  * reference's self-shadowing statistics on faces lit at grazing angles (DESIGN.md "parity"); off by default. */
 int psdr_scene_set_reference_arithmetic(psdr_scene *s, int on);
-/* -1 = automatic (BVH2 above 64 triangles), 0 = brute force, 1 = BVH2 */
+/* -1 = automatic (BVH2 above 64 triangles), 0 = brute force, 1 = BVH2.  Replaces the OptiX GAS build of
+ * Scene_OptiX::configure (src/scene/scene_optix.cpp:254-333): the BVH topology is built once (host, binned SAH) and every
+ * later configure() refits boxes and leaf blocks on the GPU; calling this function forces a fresh topology build. */
 int psdr_scene_set_accel(psdr_scene *s, int mode);
 
 /* Scene.add_BSDF(DiffuseBSDF([r,g,b]), name, twoSide) -- src/psdr.cpp:401, src/scene/scene.cpp:148-247.

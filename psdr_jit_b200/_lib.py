@@ -24,6 +24,7 @@ BSDF_REFLECTANCE_UV, BSDF_SPECULAR_UV, BSDF_ROUGHNESS_UV = 14, 15, 16
 TEX_REFLECTANCE, TEX_SPECULAR, TEX_ROUGHNESS = 0, 1, 2
 Q_NUM_MESHES, Q_NUM_SENSORS, Q_NUM_EMITTERS, Q_NUM_TRIANGLES, Q_NUM_PRIMARY_EDGES, Q_NUM_SECONDARY_EDGES = 0, 1, 2, 3, 4, 5
 Q_NUM_MESH_EDGES, Q_NUM_MESH_VERTICES, Q_NUM_MESH_FACES, Q_IS_CONFIGURED, Q_USES_BVH, Q_UPLOAD_BYTES, Q_GUIDING_CELLS = 6, 7, 8, 9, 10, 11, 12
+Q_BVH_BUILDS, Q_BVH_REFITS = 13, 14
 TERM_INTERIOR, TERM_PRIMARY_EDGES, TERM_SECONDARY_EDGES, TERM_ALL = 1, 2, 4, 7
 
 EXPORTS = [

@@ -311,7 +311,7 @@ struct VtxGeo {
     BsdfVals bv;            // reflectance / diffuseReflectance, specularReflectance, roughness of the BSDF at uv
 };
 #ifndef PSDR_VJP_GEO_NOINLINE
-#define PSDR_VJP_GEO_NOINLINE 0
+#define PSDR_VJP_GEO_NOINLINE 1     // out-of-line vertex_geo: interior adjoint 8.92 -> 8.63 ms (profiles/r02g vjp sweep)
 #endif
 #if PSDR_VJP_GEO_NOINLINE
 static __device__ __noinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {

@@ -124,6 +124,7 @@ int psdr_scene_set_shard(psdr_scene *s, int rank, int world) {
 int psdr_scene_set_accel(psdr_scene *s, int mode) {
     if (!s) return fail("null scene");
     s->sc.force_bvh = mode;
+    s->sc.bvh_rebuild = true;      // also: rebuild the BVH topology (not only refit it) at the next configure
     s->sc.configured = false;
     return 0;
 }
@@ -451,6 +452,8 @@ int psdr_scene_query(psdr_scene *s, int what, int index) {
         case PSDR_Q_IS_CONFIGURED: return sc.configured ? 1 : 0;
         case PSDR_Q_USES_BVH: return sc.dscene.use_bvh;
         case PSDR_Q_UPLOAD_BYTES: return (int) sc.upload_bytes;
+        case PSDR_Q_BVH_BUILDS: return sc.bvh_builds;
+        case PSDR_Q_BVH_REFITS: return sc.bvh_refits;
         case PSDR_Q_GUIDING_CELLS:
             return (index >= 0 && index < (int) sc.cameras.size() && sc.cameras[index].guide_ready) ? (int) sc.cameras[index].guide.pmf.size() : 0;
         default: fail("unknown query"); return -1;

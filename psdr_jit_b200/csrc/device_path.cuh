@@ -353,42 +353,63 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
         const float *f = reinterpret_cast<const float *>(tab + kBruteSmemStride * (best.tri >> 1)) + (best.tri & 1);
         return hit_finish(best, V3f(f[0], f[2], f[4]), V3f(f[6], f[8], f[10]), V3f(f[12], f[14], f[16]), o, d);
     } else {
+        // BVH2 with both child boxes in the parent record and near-child-first descent: the nearer subtree usually yields a
+        // hit that prunes the farther one.  Leaves (<= 4 triangles, stored contiguously in traversal order) are tested as
+        // soon as their box is hit.  The slab test is conservative (padded boxes, slack on the comparison), candidates
+        // pass the same numerator test as the brute-force scan and ties go to the lowest id whatever the visiting order.
         const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
-        int stack[48];
+        int stack[32];
         int sp = 0;
         int node = 0;
         float best_t = kTraceTMax;          // conservative bound for the box pruning only
+        auto leaf = [&](int c) {
+            const int code = ~c, first = code >> 3, cnt = code & 7;
+            for (int k = 0; k < cnt; ++k) {
+                const float4 a = __ldg(sc.leaf_tri + 3 * (first + k)), b = __ldg(sc.leaf_tri + 3 * (first + k) + 1), c2 = __ldg(sc.leaf_tri + 3 * (first + k) + 2);
+                tri_test<false>(V3f(a.x, a.y, a.z), V3f(b.x, b.y, b.z), V3f(c2.x, c2.y, c2.z), __float_as_int(a.w), o, d, best);
+            }
+            best_t = best.ts / best.adet * 1.000001f;
+        };
         while (true) {
-            const DBvhNode *nd = sc.nodes + node;
-            const float4 n0 = __ldg(reinterpret_cast<const float4 *>(nd)), n1 = __ldg(reinterpret_cast<const float4 *>(nd) + 1);
-            const int ia = __float_as_int(n0.w), ib = __float_as_int(n1.w);
-            // slab test; fminf/fmaxf drop the NaNs of 0*inf
-            const float tx0 = (n0.x - o.x) * ix, tx1 = (n1.x - o.x) * ix;
-            const float ty0 = (n0.y - o.y) * iy, ty1 = (n1.y - o.y) * iy;
-            const float tz0 = (n0.z - o.z) * iz, tz1 = (n1.z - o.z) * iz;
-            const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.f));
-            const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), best_t));
-            bool descend = false;
-            if (tn <= tf * 1.0000005f + 1e-6f) {
-                if (ib < 0) {
-                    const int first = ia, cnt = -ib;
-                    for (int k = 0; k < cnt; ++k) {
-                        const int id = __ldg(sc.tri_order + first + k);
-                        const float4 a = __ldg(sc.geo + 3 * id), b = __ldg(sc.geo + 3 * id + 1);
-                        const float c = __ldg(&sc.geo[3 * id + 2].x);
-                        tri_test<false>(V3f(a.x, a.y, a.z), V3f(a.w, b.x, b.y), V3f(b.z, b.w, c), id, o, d, best);
-                    }
-                    best_t = best.ts / best.adet * 1.000001f;
-                } else {
-                    if (sp < 47) stack[sp++] = ib;
-                    node = ia;
-                    descend = true;
-                }
+            const float4 *nd = reinterpret_cast<const float4 *>(sc.nodes2 + node);
+            const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
+            const int4 lk = __ldg(reinterpret_cast<const int4 *>(nd + 3));
+            // slab tests; fminf/fmaxf drop the NaNs of 0*inf
+            float tn[2], tf[2];
+            {
+                const float x0 = (n0.x - o.x) * ix, x1 = (n0.w - o.x) * ix, y0 = (n0.y - o.y) * iy, y1 = (n1.x - o.y) * iy;
+                const float z0 = (n0.z - o.z) * iz, z1 = (n1.y - o.z) * iz;
+                tn[0] = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                tf[0] = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best_t));
             }
-            if (!descend) {
+            {
+                const float x0 = (n1.z - o.x) * ix, x1 = (n2.y - o.x) * ix, y0 = (n1.w - o.y) * iy, y1 = (n2.z - o.y) * iy;
+                const float z0 = (n2.x - o.z) * iz, z1 = (n2.w - o.z) * iz;
+                tn[1] = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                tf[1] = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best_t));
+            }
+            bool h0 = tn[0] <= tf[0] * 1.0000005f + 1e-6f, h1 = tn[1] <= tf[1] * 1.0000005f + 1e-6f;
+            int c0 = lk.x, c1 = lk.y;
+            if (h0 && h1 && tn[1] < tn[0]) {      // nearer child first
+                const int t = c0; c0 = c1; c1 = t;
+                const float q = tn[0]; tn[0] = tn[1]; tn[1] = q;
+            } else if (!h0) { c0 = c1; tn[0] = tn[1]; h0 = h1; h1 = false; }
+            // c0 = the (nearer) hit child if h0, c1 = the other hit child if h1
+            int next = -1;
+            if (h0) {
+                if (c0 < 0) leaf(c0);
+                else next = c0;
+            }
+            if (h1 && tn[1] <= best_t) {          // the nearer leaf may have pruned it
+                if (c1 < 0) leaf(c1);
+                else if (next < 0) next = c1;
+                else if (sp < 31) stack[sp++] = c1;
+            }
+            if (next < 0) {
                 if (sp == 0) break;
-                node = stack[--sp];
+                next = stack[--sp];
             }
+            node = next;
         }
         if (best.tri < 0) return miss;
         const float4 a = __ldg(sc.geo + 3 * best.tri), b = __ldg(sc.geo + 3 * best.tri + 1);

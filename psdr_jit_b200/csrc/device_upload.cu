@@ -22,12 +22,66 @@ struct DeviceBuffers {
     void *big = nullptr;
     size_t big_capacity = 0, big_off[4] = {0, 0, 0, 0};
     unsigned big_data_version = 0, big_ddata_version = 0;
+    // BVH (scenes above 64 triangles): the TOPOLOGY (node links, leaf slots -> triangle ids) is built on the host (binned
+    // SAH) when the set of meshes / face counts changes and stays on the device; every configure() after that only
+    // refits the boxes and refreshes the leaf triangle blocks ON THE GPU from the freshly uploaded triangle table
+    // (bvh_refit_kernel below) -- the reference rebuilds its OptiX GAS on every configure (scene_optix.cpp:254-333).
+    void *bvh = nullptr;
+    size_t bvh_capacity = 0;
+    std::vector<int> bvh_key;          // face count per mesh the topology was built for
+    int n_nodes2 = 0, n_slots = 0, n_leaves = 0;
+    float bvh_pad = 0.f;
+    size_t off_nodes2 = 0, off_leaf_tri = 0, off_slot_tri = 0, off_leaf_list = 0, off_ready = 0;
     ~DeviceBuffers() {
         if (dev) cudaFree(dev);
         if (host) cudaFreeHost(host);
         if (big) cudaFree(big);
+        if (bvh) cudaFree(bvh);
     }
 };
+
+// ---- GPU refit of the BVH ----------------------------------------------------------------------------------------
+// One thread per leaf: copy the leaf's triangles from the triangle table into its contiguous slots, bound them, write
+// the box into the parent's child slot and walk up; the second thread to arrive at a node (atomic counter) unions the
+// two child boxes and continues, so every box is final before it is read (Karras-style bottom-up pass).
+struct BvhLeaf {
+    int node, slot, first, count;     // parent node, which child of it (0 / 1), first leaf slot, triangles
+};
+__global__ void bvh_refit_kernel(DBvhNode2 *nodes, float4 *leaf_tri, const int *slot_tri, const BvhLeaf *leaves, int n_leaves,
+                                 const float4 *geo, int *ready, float pad) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_leaves) return;
+    const BvhLeaf L = leaves[li];
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int k = 0; k < L.count; ++k) {
+        const int id = slot_tri[L.first + k];
+        const float4 a = geo[3 * id], b = geo[3 * id + 1], c = geo[3 * id + 2];
+        const float p0[3] = {a.x, a.y, a.z}, e1[3] = {a.w, b.x, b.y}, e2[3] = {b.z, b.w, c.x};
+        leaf_tri[3 * (L.first + k)] = make_float4(a.x, a.y, a.z, __int_as_float(id));
+        leaf_tri[3 * (L.first + k) + 1] = make_float4(a.w, b.x, b.y, 0.f);
+        leaf_tri[3 * (L.first + k) + 2] = make_float4(b.z, b.w, c.x, 0.f);
+        for (int ax = 0; ax < 3; ++ax) {
+            const float v1 = p0[ax] + e1[ax], v2 = p0[ax] + e2[ax];
+            lo[ax] = fminf(lo[ax], fminf(p0[ax], fminf(v1, v2)));
+            hi[ax] = fmaxf(hi[ax], fmaxf(p0[ax], fmaxf(v1, v2)));
+        }
+    }
+    for (int ax = 0; ax < 3; ++ax) { lo[ax] -= pad; hi[ax] += pad; }
+    int node = L.node, slot = L.slot;
+    while (node >= 0) {
+        float *f = nodes[node].f + 6 * slot;
+        for (int ax = 0; ax < 3; ++ax) { f[ax] = lo[ax]; f[3 + ax] = hi[ax]; }
+        __threadfence();
+        if (atomicAdd(ready + node, 1) == 0) return;      // the sibling subtree is not finished: its thread continues
+        const float *g = nodes[node].f + 6 * (1 - slot);  // written before the sibling's fence + atomic
+        for (int ax = 0; ax < 3; ++ax) {
+            lo[ax] = fminf(lo[ax], ((volatile const float *) g)[ax]);
+            hi[ax] = fmaxf(hi[ax], ((volatile const float *) g)[3 + ax]);
+        }
+        slot = nodes[node].pslot;
+        node = nodes[node].parent;
+    }
+}
 
 static void check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
@@ -166,18 +220,15 @@ void upload_scene(Scene &sc) {
         }
     }
 
-    std::vector<DBvhNode> nodes;
-    std::vector<int> order;
     const int ntris = (int) all_tris.size();
     const bool use_bvh = ntris > kMaxBruteTris || (sc.force_bvh < 0 ? false : sc.force_bvh != 0);
-    if (use_bvh) build_bvh(all_tris, nodes, order, 4);
 
     Packer pk;
     const size_t o_geo = pk.add(geo), o_shade = pk.add(shade), o_dgeo = pk.add(dgeo), o_dshade = pk.add(dshade), o_uv = pk.add(uv),
                  o_mesh = pk.add(dmeshes), o_emit = pk.add(demit), o_bsdf = pk.add(dbsdf), o_fp = pk.add(face_pmf), o_fc = pk.add(face_cmf),
                  o_ep = pk.add(em_pmf), o_ec = pk.add(em_cmf), o_sec = pk.add(sec), o_sp = pk.add(sec_pmf), o_scm = pk.add(sec_cmf),
                  o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
-                 o_nodes = pk.add(nodes), o_order = pk.add(order), o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf),
+                 o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf),
                  o_small_end = 0;
     (void) o_small_end;
     std::vector<size_t> o_tex(3 * sc.bsdfs.size(), 0), o_dtex(3 * sc.bsdfs.size(), 0);
@@ -246,6 +297,78 @@ void upload_scene(Scene &sc) {
     std::memcpy(db.host, pk.bytes.data(), pk.bytes.size());
     check(cudaMemcpy(db.dev, db.host, pk.bytes.size(), cudaMemcpyHostToDevice), "cudaMemcpy(scene tables)");
     sc.upload_bytes = pk.bytes.size() + big_uploaded;
+    if (use_bvh) {
+        std::vector<int> key;
+        for (const HMesh &m : sc.meshes) key.push_back((int) m.tris.size());
+        if (key != db.bvh_key || sc.bvh_rebuild) {
+            // ---- topology: host binned-SAH build, converted to the wide-fetch layout
+            std::vector<DBvhNode> nodes;
+            std::vector<int> order;
+            build_bvh(all_tris, nodes, order, 4);
+            if (nodes.empty() || nodes[0].b < 0) throw std::runtime_error("BVH mode needs more than one leaf");
+            std::vector<int> inner_index(nodes.size(), -1);
+            int n_inner = 0;
+            for (size_t i = 0; i < nodes.size(); ++i)
+                if (nodes[i].b >= 0) inner_index[i] = n_inner++;
+            std::vector<DBvhNode2> n2((size_t) n_inner);
+            std::vector<BvhLeaf> leaves;
+            for (size_t i = 0; i < nodes.size(); ++i) {
+                if (nodes[i].b < 0) continue;
+                DBvhNode2 &nd = n2[inner_index[i]];
+                if (i == 0) { nd.parent = -1; nd.pslot = 0; }
+                const int ch[2] = {nodes[i].a, nodes[i].b};
+                for (int k = 0; k < 2; ++k) {
+                    const DBvhNode &c = nodes[ch[k]];
+                    for (int ax = 0; ax < 3; ++ax) { nd.f[6 * k + ax] = c.lo[ax]; nd.f[6 * k + 3 + ax] = c.hi[ax]; }
+                    int link;
+                    if (c.b < 0) {      // leaf: first slot = position in `order`, count = -b
+                        if (-c.b > 7) throw std::runtime_error("BVH leaf too large");
+                        link = ~((c.a << 3) | (-c.b));
+                        leaves.push_back(BvhLeaf{inner_index[i], k, c.a, -c.b});
+                    } else {
+                        link = inner_index[ch[k]];
+                        n2[link].parent = inner_index[i];
+                        n2[link].pslot = k;
+                    }
+                    (k == 0 ? nd.c0 : nd.c1) = link;
+                }
+            }
+            const float dx = nodes[0].hi[0] - nodes[0].lo[0], dy = nodes[0].hi[1] - nodes[0].lo[1], dz = nodes[0].hi[2] - nodes[0].lo[2];
+            db.bvh_pad = 2e-5f * std::sqrt(dx * dx + dy * dy + dz * dz) + 1e-6f;     // as build_bvh pads (boxes above include it twice at most)
+            db.n_nodes2 = n_inner;
+            db.n_slots = (int) order.size();
+            db.n_leaves = (int) leaves.size();
+            auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+            db.off_nodes2 = 0;
+            db.off_leaf_tri = align(sizeof(DBvhNode2) * n2.size());
+            db.off_slot_tri = db.off_leaf_tri + align(sizeof(float4) * 3 * order.size());
+            db.off_leaf_list = db.off_slot_tri + align(sizeof(int) * order.size());
+            db.off_ready = db.off_leaf_list + align(sizeof(BvhLeaf) * leaves.size());
+            const size_t need = db.off_ready + align(sizeof(int) * n2.size());
+            if (need > db.bvh_capacity) {
+                if (db.bvh) cudaFree(db.bvh);
+                db.bvh_capacity = need;
+                check(cudaMalloc(&db.bvh, need), "cudaMalloc(BVH)");
+            }
+            unsigned char *bv = (unsigned char *) db.bvh;
+            check(cudaMemcpy(bv + db.off_nodes2, n2.data(), sizeof(DBvhNode2) * n2.size(), cudaMemcpyHostToDevice), "cudaMemcpy(BVH nodes)");
+            check(cudaMemcpy(bv + db.off_slot_tri, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice), "cudaMemcpy(BVH slots)");
+            check(cudaMemcpy(bv + db.off_leaf_list, leaves.data(), sizeof(BvhLeaf) * leaves.size(), cudaMemcpyHostToDevice), "cudaMemcpy(BVH leaves)");
+            db.bvh_key = key;
+            sc.bvh_rebuild = false;
+            sc.upload_bytes += sizeof(DBvhNode2) * n2.size() + sizeof(int) * order.size() + sizeof(BvhLeaf) * leaves.size();
+            sc.bvh_builds++;
+        }
+        // ---- boxes + leaf triangle blocks: always refit on the GPU from the triangle table just uploaded
+        unsigned char *bv = (unsigned char *) db.bvh;
+        check(cudaMemsetAsync(bv + db.off_ready, 0, sizeof(int) * db.n_nodes2, 0), "memset(BVH counters)");
+        bvh_refit_kernel<<<(db.n_leaves + 127) / 128, 128>>>((DBvhNode2 *) (bv + db.off_nodes2), (float4 *) (bv + db.off_leaf_tri),
+                                                             (const int *) (bv + db.off_slot_tri), (const BvhLeaf *) (bv + db.off_leaf_list), db.n_leaves,
+                                                             (const float4 *) ((const unsigned char *) db.dev + o_geo), (int *) (bv + db.off_ready), db.bvh_pad);
+        check(cudaGetLastError(), "bvh_refit_kernel");
+        check(cudaDeviceSynchronize(), "bvh_refit_kernel");
+        sc.bvh_refits++;
+    }
     const unsigned char *base = (const unsigned char *) db.dev;
 
     DScene &d = sc.dscene;
@@ -256,7 +379,7 @@ void upload_scene(Scene &sc) {
     d.n_emitters = (int) sc.emitters.size();
     d.n_bsdfs = (int) sc.bsdfs.size();
     d.n_sec_edges = (int) sc.sec_edges.size();
-    d.n_nodes = (int) nodes.size();
+    d.n_nodes = use_bvh ? db.n_nodes2 : 0;
     d.use_bvh = use_bvh ? 1 : 0;
     d.ref_rcp = sc.ref_rcp ? 1 : 0;
     d.full_features = sc.env.present ? 1 : 0;
@@ -278,8 +401,8 @@ void upload_scene(Scene &sc) {
     d.sec_pmf = (const float *) (base + o_sp);
     d.sec_cmf = (const float *) (base + o_scm);
     d.sec_sum = sc.sec_edges.empty() ? 0.f : sc.sec_edge_distrb.sum;
-    d.nodes = (const DBvhNode *) (base + o_nodes);
-    d.tri_order = (const int *) (base + o_order);
+    d.nodes2 = use_bvh ? (const DBvhNode2 *) ((const unsigned char *) db.bvh + db.off_nodes2) : nullptr;
+    d.leaf_tri = use_bvh ? (const float4 *) ((const unsigned char *) db.bvh + db.off_leaf_tri) : nullptr;
     if (!use_bvh) {
         // (even, odd) triangle of a pair -> (low, high) half of each 64-bit word
         float *w = reinterpret_cast<float *>(d.bg_pair);

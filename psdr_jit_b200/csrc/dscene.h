@@ -28,6 +28,15 @@ struct DBvhNode {        // 32 B
     int b;               // inner: right child; leaf: -(count)
 };
 
+// Traversal node: BOTH children's boxes and links in one 64-byte record (four 16-byte loads), so a visit decides both
+// children without touching them; leaves are not nodes -- a leaf child is a run of slots in DScene::leaf_tri.
+//   box0 = (f[0..2], f[3..5]), box1 = (f[6..8], f[9..11]);  c0 / c1 >= 0: inner node index, < 0: leaf ~((first_slot << 3) | count)
+//   parent / pslot: where this node's own box lives (refit walks up), parent < 0 for the root
+struct DBvhNode2 {
+    float f[12];
+    int c0, c1, parent, pslot;
+};
+
 struct DMesh {
     int bsdf;            // index into bsdf tables, -1 = none
     int emitter;         // index into emitter table, -1 = none
@@ -116,8 +125,8 @@ struct DScene {
     const float4 *sec_edges;
     const float *sec_pmf, *sec_cmf;
     float sec_sum;
-    const DBvhNode *nodes;
-    const int *tri_order;
+    const DBvhNode2 *nodes2;                   // BVH mode: wide-fetch BVH2 (device_upload.cu builds / refits it)
+    const float4 *leaf_tri;                    // 3 float4 per leaf slot: (p0.xyz, int_as_float(triangle id)), (e1.xyz, 0), (e2.xyz, 0)
     DEnv env;
     // brute-force mode (n_tris <= kMaxBruteTris): the triangle geometry again, by value -- it travels in
     // the kernel parameters, two triangles at a time: entry [9 j + c] holds component c of triangles (2j, 2j+1)
