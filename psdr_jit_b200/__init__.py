@@ -17,11 +17,13 @@ Differences a reference user has to know (DESIGN.md has the rationale):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
 from . import _lib, scenes  # noqa: F401
+from . import loader as _loader
 
 __all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
@@ -152,8 +154,8 @@ class DiffuseBSDF(BSDF):
     """reference src/psdr.cpp:279-284, src/bsdf/diffuse.cpp (1x1 reflectance bitmap)."""
 
     def __init__(self, reflectance=None):
-        if isinstance(reflectance, str):
-            raise NotImplementedError("DiffuseBSDF(path): EXR loading is outside the hot path; pass a Bitmap3fD")
+        if isinstance(reflectance, str):                # DiffuseBSDF(file_name): src/psdr.cpp:281
+            reflectance = Bitmap3fD(reflectance)
         if isinstance(reflectance, Bitmap3fD):          # textured reflectance (src/psdr.cpp:282)
             self.reflectance = reflectance
         else:
@@ -212,8 +214,13 @@ class _Bitmap:
     (radians, about the centre), ``translate`` (2 floats); ``d_*`` = forward-mode tangents."""
     channels = 3
 
-    def __init__(self, width: int = 1, height: int = 1, data=None):
+    def __init__(self, width=1, height: int = 1, data=None):
         c = self.channels
+        if isinstance(width, str):                     # Bitmap(file_name): src/core/bitmap.cpp:16-19
+            w, h, rgb = _loader.load_exr(width)
+            width, height, data = w, h, (rgb[:, :1] if c == 1 else rgb)
+        elif data is None and not np.isscalar(width) and np.ndim(width) == 1 and len(width) == c:   # Bitmap3fD([r, g, b])
+            width, data = 1, _f32(width, (1, c))
         if np.isscalar(width) and data is None and not isinstance(width, (int, np.integer)):   # Bitmap(value)
             width, data = 1, np.full((1, c), float(width), np.float32)
         self.resolution = (int(width), int(height))
@@ -234,6 +241,10 @@ class _Bitmap:
             setattr(c, n, np.float32(getattr(self, n)))
         c.translate, c.d_translate = _f32(self.translate, (2,)).copy(), _f32(self.d_translate, (2,)).copy()
         return c
+
+    def load_openexr(self, file_name: str):
+        w, h, rgb = _loader.load_exr(file_name)
+        self.resolution, self.data, self.d_data = (w, h), (rgb[:, :1].copy() if self.channels == 1 else rgb), None
 
     def _uv(self, tangent: bool):
         if tangent:
@@ -257,8 +268,8 @@ class EnvironmentMap(Emitter):
     (EnvironmentMap(path)) is I/O outside this path -- build the bitmap from an array instead."""
 
     def __init__(self, radiance: Optional[Bitmap3fD] = None):
-        if isinstance(radiance, str):
-            raise NotImplementedError("EnvironmentMap(path): EXR loading is outside the hot path; pass a Bitmap3fD")
+        if isinstance(radiance, str):                   # EnvironmentMap(file_name): include/psdr/emitter/envmap.h:14-16
+            radiance = Bitmap3fD(radiance)
         self.radiance = radiance if radiance is not None else Bitmap3fD(2, 2, np.ones((4, 3), np.float32))
         self.scale = np.float32(1.0)
         self.d_scale = np.float32(0.0)
@@ -325,6 +336,17 @@ class Mesh(_Transformable):
             raise RuntimeError("Failed to load OBJ from: " + filename)
         self.load_raw(v, f, uv, fuv, verbose)
 
+    def dump(self, fname: str, raw: bool = False):
+        """reference Mesh::dump (src/shape/mesh.cpp:469-554): OBJ with per-vertex normals unless face normals are used.
+        raw = False writes the object-space vertices, raw = True the world-space ones (the reference's flag naming)."""
+        v = self.vertex_positions
+        if raw:
+            tw = _f32(self.to_world_left, (4, 4)) @ _f32(self.to_world, (4, 4)) @ _f32(self.to_world_right, (4, 4))
+            v = (np.c_[_f32(v).reshape(-1, 3), np.ones(len(v), np.float32)] @ tw.T)[:, :3].astype(np.float32)
+        m = self._clone()
+        m.vertex_positions = _f32(v).reshape(-1, 3)
+        _loader.dump_obj(m, fname, None if self.use_face_normal else _loader.vertex_normals(m.vertex_positions, m.face_indices))
+
     def edge_indices(self):
         if self._scene is None or self._scene._h is None:
             raise RuntimeError("edge_indices() needs a mesh that was added to a configured scene")
@@ -343,6 +365,7 @@ class Mesh(_Transformable):
         m.vertex_uv = None if self.vertex_uv is None else self.vertex_uv.copy()
         m.face_uv_indices = None if self.face_uv_indices is None else self.face_uv_indices.copy()
         m.use_face_normal, m.enable_edges = self.use_face_normal, self.enable_edges
+        m.id = self.id
         return m
 
 
@@ -436,8 +459,12 @@ class Scene(Object):
         overload needs an EXR reader and is not part of this path."""
         if self._env is not None:
             raise RuntimeError("A scene is only allowed to have one envmap!")
+        if isinstance(envmap, str):                     # add_EnvironmentMap(fname, to_world, scale): scene.cpp:85-95
+            envmap = EnvironmentMap(envmap)
+            envmap.to_world = _mat4(to_world)
+            envmap.scale = np.float32(scale)
         if not isinstance(envmap, EnvironmentMap):
-            raise NotImplementedError("add_EnvironmentMap(path, ...): EXR loading is outside the hot path")
+            raise RuntimeError("Unknown emitter type!")
         e = envmap._clone()
         self._env = e
         self._events.append(("env", len(self._emitters)))
@@ -473,6 +500,27 @@ class Scene(Object):
             self._mesh_emitter.append(-1)
         self._meshes.append(mesh)
         self._register("Mesh", self._meshes)
+
+    def load_file(self, file_name: str, auto_configure: bool = True):
+        """reference Scene::load_file (src/psdr.cpp:407, src/scene/scene_loader.cpp): Mitsuba-style XML scene"""
+        import xml.etree.ElementTree as ET
+        try:
+            root = ET.parse(file_name).getroot()
+        except Exception:
+            raise RuntimeError("XML parsing failed")
+        _loader.load_scene_xml(self, root, os.path.dirname(os.path.abspath(file_name)))
+        if auto_configure:
+            self.configure()
+
+    def load_string(self, scene_xml: str, auto_configure: bool = True):
+        import xml.etree.ElementTree as ET
+        try:
+            root = ET.fromstring(scene_xml)
+        except Exception:
+            raise RuntimeError("XML parsing failed")
+        _loader.load_scene_xml(self, root, os.getcwd())
+        if auto_configure:
+            self.configure()
 
     # -- multi-GPU / acceleration knobs (new; the reference is single-GPU OptiX)
     def set_shard(self, rank: int, world: int):

@@ -105,3 +105,27 @@ def test_reference_readme_example_runs_verbatim(tmp_path, monkeypatch):
     assert rel_l2(img, ref_img.cpu().numpy()) < 1e-6
     assert rel_l2(dimg, ref_dimg.cpu().numpy()) < 1e-4
     assert ns["sc"].num_meshes == 8 and ns["sc"].param_map["Mesh[0]"] is not None
+
+
+def test_xml_scene_renders_like_the_hand_built_scene(tmp_path):
+    """Scene.load_file (reference src/scene/scene_loader.cpp) -> the same image as the scene assembled through add_*."""
+    import psdr_jit_b200 as psdr
+    paths = scenes.write_cbox_objs(str(tmp_path))
+    shapes = ""
+    for m, p in zip(scenes.cbox_meshes(), paths):
+        em = '<emitter type="area"><rgb name="radiance" value="20,20,8"/></emitter>' if m.emitter is not None else ""
+        tr = '<transform name="to_world"><translate y="-0.5"/></transform>' if m.name == "luminaire" else ""
+        shapes += '<shape type="obj"><string name="filename" value="%s"/><ref id="%s"/>%s%s</shape>\n' % (os.path.basename(p), m.bsdf, tr, em)
+    bsdfs = "".join('<bsdf type="diffuse" id="%s"><rgb name="reflectance" value="%g,%g,%g"/></bsdf>\n' % ((n,) + tuple(r)) for n, r in scenes.CBOX_BSDFS)
+    xml = ('<scene><sensor type="perspective"><float name="fov" value="60"/><float name="near_clip" value="1e-6"/><float name="far_clip" value="1e7"/>'
+           '<transform name="to_world"><translate x="278" y="273" z="-800"/></transform><sampler type="independent"><integer name="sample_count" value="4"/></sampler>'
+           '<film type="hdrfilm"><integer name="width" value="96"/><integer name="height" value="96"/></film></sensor>\n' + bsdfs + shapes + '</scene>')
+    (tmp_path / "cbox.xml").write_text(xml)
+    sc = psdr.Scene()
+    sc.opts.log_level = 0
+    sc.load_file(str(tmp_path / "cbox.xml"))
+    sc.opts.log_level = 0
+    sc.configure([0])
+    got = psdr.PathTracer(3).renderC(sc, 0, seed=1).cpu().numpy()
+    ref = psdr.PathTracer(3).renderC(build_product(scenes.cbox_meshes(), 96, 96, 4, 0, 0), 0, seed=1).cpu().numpy()
+    assert rel_l2(got, ref) < 1e-6
