@@ -600,11 +600,33 @@ class Scene(Object):
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[2] = len(self._sensors)
 
-        def push(kind, idx, value, tangent):
+        sent = self.__dict__.setdefault("_sent", {})      # what the native scene already holds: (kind, index, is_tangent) -> key
+
+        def key_of(a):
+            """cheap identity of a parameter value: bytes for small arrays, (object, in-place version) for torch tensors,
+            a checksum for mid-sized numpy arrays; None = always push"""
+            if hasattr(a, "_version") and hasattr(a, "data_ptr"):
+                return ("t", id(a), a._version, tuple(a.shape))
+            if a.size <= 64:
+                return a.tobytes()
+            if a.nbytes <= (1 << 20):
+                import zlib
+                return ("c", a.shape, zlib.crc32(a))
+            return None
+
+        def push1(kind, idx, value, is_tangent, fn):
+            raw = value
             value = _f32(value).ravel()
-            _lib.check(L.psdr_scene_set_param(self._h, kind, idx, _fp(value), value.size))
-            t = np.zeros_like(value) if tangent is None else _f32(tangent).ravel()
-            _lib.check(L.psdr_scene_set_tangent(self._h, kind, idx, _fp(t), t.size))
+            k = key_of(raw if hasattr(raw, "_version") else value)
+            if k is not None and sent.get((kind, idx, is_tangent)) == k:
+                return                                   # unchanged since the last configure: nothing to send
+            _lib.check(fn(self._h, kind, idx, _fp(value), value.size))
+            sent[(kind, idx, is_tangent)] = k
+
+        def push(kind, idx, value, tangent):
+            push1(kind, idx, value, False, L.psdr_scene_set_param)
+            n = int(np.prod(np.shape(_f32(value)))) if tangent is None else 0
+            push1(kind, idx, np.zeros(n, np.float32) if tangent is None else tangent, True, L.psdr_scene_set_tangent)
 
         for i, m in enumerate(self._meshes):
             push(_lib.MESH_VERTICES, i, m.vertex_positions, m.d_vertex_positions)
@@ -617,6 +639,11 @@ class Scene(Object):
             push(_lib.SENSOR_TO_WORLD_RIGHT, i, s.to_world_right, s.d_to_world_right)
         def push_slot(i, slot, kind, r, d_const):
             """one bitmap slot of a BSDF: texture (texels + uv transform) or constant"""
+            res = tuple(r.resolution) if isinstance(r, _Bitmap) and r._textured() else (1, 1)
+            if sent.get(("slot", i, slot)) != res:       # the native side re-allocates the slot: forget what it held
+                sent[("slot", i, slot)] = res
+                sent.pop((kind, i, False), None)
+                sent.pop((kind, i, True), None)
             if isinstance(r, _Bitmap) and r._textured():
                 _lib.check(L.psdr_scene_set_bsdf_texture_slot(self._h, i, slot, r.resolution[0], r.resolution[1]))
                 push(kind, i, r.data, r.d_data)
