@@ -312,42 +312,53 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
         // reconvergence point behind the loop: the secondary-edge adjoint ran its second and third trace with 5.7 of 27
         // lanes (profiles/r02e; 3.6 -> 1.7 ms with the uniform loop).  The forward kernels and the other adjoints do
         // reconverge behind the plain loop and lose 8 % to the extra vote, so the choice is per kernel (kCfgUniformScan).
-        const int n_it = kUniform ? __reduce_max_sync(lanes, __popc(mask)) : 0;
+        auto test_pair = [&](int j) {
+                const ulonglong2 *w = tab + kBruteSmemStride * j;
+                const ulonglong2 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                V3p P0, E1, E2, S, NS;
+                P0.x.v = w0.x; P0.y.v = w0.y; P0.z.v = w1.x;
+                E1.x.v = w1.y; E1.y.v = w2.x; E1.z.v = w2.y;
+                E2.x.v = w3.x; E2.y.v = w3.y; E2.z.v = w4.x;
+                const V3p h = cross_fms_na(D, ND, E2);
+                const F2 det = dot(E1, h);
+                S.x = f2_sub(O.x, P0.x); S.y = f2_sub(O.y, P0.y); S.z = f2_sub(O.z, P0.z);
+                NS.x = f2_sub(P0.x, O.x); NS.y = f2_sub(P0.y, O.y); NS.z = f2_sub(P0.z, O.z);   // = -S exactly
+                const F2 un = dot(S, h);
+                // cross_fms(S, E1): fma(S.y, E1.z, -(S.z * E1.y)) with the sign carried by -S (exact)
+                V3p q;
+                q.x = f2_fma(S.y, E1.z, f2_mul(NS.z, E1.y));
+                q.y = f2_fma(S.z, E1.x, f2_mul(NS.x, E1.z));
+                q.z = f2_fma(S.x, E1.y, f2_mul(NS.y, E1.x));
+                const F2 vn = dot(D, q), tn = dot(E2, q);
+                // sign normalisation by an exact packed multiply with copysign(1, det); a zero determinant cannot pass:
+                // its rhs below is 0 and lhs >= 0, so "adet > 0" is implied by the strict "closer" of the ordered scan
+                float det0, det1;
+                f2_split(det, det0, det1);
+                const F2 SG = f2_pack(__int_as_float((__float_as_int(det0) & 0x80000000) | 0x3f800000),
+                                      __int_as_float((__float_as_int(det1) & 0x80000000) | 0x3f800000));
+                const F2 US = f2_mul(un, SG), VS = f2_mul(vn, SG), TS = f2_mul(tn, SG), AD = f2_mul(det, SG);
+                const F2 SUM = f2_add(US, VS), EPS = f2_mul(AD, EPSV);
+                float us0, us1, vs0, vs1, ts0, ts1, ad0, ad1, sum0, sum1, eps0, eps1;
+                f2_split(US, us0, us1); f2_split(VS, vs0, vs1); f2_split(TS, ts0, ts1);
+                f2_split(AD, ad0, ad1); f2_split(SUM, sum0, sum1); f2_split(EPS, eps0, eps1);
+                hit_consider_ordered(us0, vs0, sum0, ts0, ad0, eps0, 2 * j, best);
+                hit_consider_ordered(us1, vs1, sum1, ts1, ad1, eps1, 2 * j + 1, best);
+        };
+        if (kUniform) {
+            const int n_it = __reduce_max_sync(lanes, __popc(mask));
 #pragma unroll 1
-        for (int it = 0; kUniform ? it < n_it : mask != 0u; ++it) {
-            if (kUniform && mask == 0u) continue;
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            const ulonglong2 *w = tab + kBruteSmemStride * j;
-            const ulonglong2 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-            V3p P0, E1, E2, S, NS;
-            P0.x.v = w0.x; P0.y.v = w0.y; P0.z.v = w1.x;
-            E1.x.v = w1.y; E1.y.v = w2.x; E1.z.v = w2.y;
-            E2.x.v = w3.x; E2.y.v = w3.y; E2.z.v = w4.x;
-            const V3p h = cross_fms_na(D, ND, E2);
-            const F2 det = dot(E1, h);
-            S.x = f2_sub(O.x, P0.x); S.y = f2_sub(O.y, P0.y); S.z = f2_sub(O.z, P0.z);
-            NS.x = f2_sub(P0.x, O.x); NS.y = f2_sub(P0.y, O.y); NS.z = f2_sub(P0.z, O.z);   // = -S exactly
-            const F2 un = dot(S, h);
-            // cross_fms(S, E1): fma(S.y, E1.z, -(S.z * E1.y)) with the sign carried by -S (exact)
-            V3p q;
-            q.x = f2_fma(S.y, E1.z, f2_mul(NS.z, E1.y));
-            q.y = f2_fma(S.z, E1.x, f2_mul(NS.x, E1.z));
-            q.z = f2_fma(S.x, E1.y, f2_mul(NS.y, E1.x));
-            const F2 vn = dot(D, q), tn = dot(E2, q);
-            // sign normalisation by an exact packed multiply with copysign(1, det); a zero determinant cannot pass:
-            // its rhs below is 0 and lhs >= 0, so "adet > 0" is implied by the strict "closer" of the ordered scan
-            float det0, det1;
-            f2_split(det, det0, det1);
-            const F2 SG = f2_pack(__int_as_float((__float_as_int(det0) & 0x80000000) | 0x3f800000),
-                                  __int_as_float((__float_as_int(det1) & 0x80000000) | 0x3f800000));
-            const F2 US = f2_mul(un, SG), VS = f2_mul(vn, SG), TS = f2_mul(tn, SG), AD = f2_mul(det, SG);
-            const F2 SUM = f2_add(US, VS), EPS = f2_mul(AD, EPSV);
-            float us0, us1, vs0, vs1, ts0, ts1, ad0, ad1, sum0, sum1, eps0, eps1;
-            f2_split(US, us0, us1); f2_split(VS, vs0, vs1); f2_split(TS, ts0, ts1);
-            f2_split(AD, ad0, ad1); f2_split(SUM, sum0, sum1); f2_split(EPS, eps0, eps1);
-            hit_consider_ordered(us0, vs0, sum0, ts0, ad0, eps0, 2 * j, best);
-            hit_consider_ordered(us1, vs1, sum1, ts1, ad1, eps1, 2 * j + 1, best);
+            for (int it = 0; it < n_it; ++it) {
+                if (mask == 0u) continue;
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                test_pair(j);
+            }
+        } else {
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                test_pair(j);
+            }
         }
         if (best.tri < 0) return miss;
         const float *f = reinterpret_cast<const float *>(tab + kBruteSmemStride * (best.tri >> 1)) + (best.tri & 1);
