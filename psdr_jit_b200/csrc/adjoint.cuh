@@ -521,6 +521,17 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     constexpr bool kFull = (kCfg & kCfgFull) != 0;
     const bool has_v0 = enabled && R.nv > 0;
     const bool sweep = has_v0 && R.nsh > 0;
+    // Emitter-radiance gradients are summed per lane in registers and scattered ONCE, from the warp-uniform epilogue:
+    // every event of every lane of the warp adds to the same few entries (one emitter in most scenes), and inside the
+    // divergent event code that was a same-target add with a partial lane mask -- the slow path of grad_add3_impl
+    // (a serial loop of variable-lane shuffles: 9 % of the kernel's instructions, profiles/r02e).
+    int em_idx = -1;
+    V3f em_acc(0.f, 0.f, 0.f);
+    auto add_emitter = [&](int e, V3f v) {
+        if (em_idx < 0) em_idx = e;
+        if (e == em_idx) em_acc = em_acc + V3f(isfinite(v.x) ? v.x : 0.f, isfinite(v.y) ? v.y : 0.f, isfinite(v.z) ? v.z : 0.f);
+        else acc.add3(gl.off_emit + 4 * e, v);           // a second emitter on the same path: rare, scattered directly
+    };
     // vertex 0: solid-angle form -- (u, v, t) are functions of the triangle and the camera ray
     TriRec<float> T0;
     float u0 = 0.f, v0 = 0.f, t0 = 0.f;
@@ -537,7 +548,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
                 V3f le;
                 d_bar = d_bar + env_le_adjoint(acc, gl, sc.env, d, g, le);
                 if (R.nsh <= 0) scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
-            } else if (dot(-d, v0geo.shn) > 0.f) acc.add3(gl.off_emit + 4 * v0geo.emitter, g);
+            } else if (dot(-d, v0geo.shn) > 0.f) add_emitter(v0geo.emitter, g);
         }
     }
 
@@ -644,7 +655,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
                     ya.p = ya.p + ev.py;
                     ya.fn = ya.fn + ev.ny;
                     ya.area += ev.area_y;
-                    if (y_emits && !y_env) acc.add3(gl.off_emit + 4 * y.emitter, A * fb * R.w2[k]);
+                    if (y_emits && !y_env) add_emitter(y.emitter, A * fb * R.w2[k]);
                     Rk = Rk + fb * Ltot;
                 } else {
                     if (mode == 2) {
@@ -654,7 +665,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
                         acc.add3(lb + 6, ev.py * R.lb[k]);
                         acc.add(lb + 9, ev.area_y);
                         acc.add3(kGradTri * R.htri[k] + 19, ev.ny);
-                        acc.add3(gl.off_emit + 4 * emi, A * fb);
+                        add_emitter(emi, A * fb);
                     }
                     Rk = Rk + Le * fb;
                 }
@@ -675,25 +686,54 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         pa = zero_adj;
         }
     }
-    if (sweep) {   // vertex 0 (now in y / ya): p = o + t d, sh_n from the differentiable (u, v)
-        const VtxGeo &x0 = y;
-        const VtxAdj &a0 = ya;
-        const int b = kGradTri * x0.tri;
+    // ---- epilogue, executed by ALL 32 lanes (lanes without a path carry zeros): vertex 0 (now in y / ya: p = o + t d,
+    // sh_n from the differentiable (u, v)), the camera ray and the emitter accumulator.  The 32 lanes are the samples of
+    // one pixel, so these adds mostly share their target: with the whole warp present they take the 5-step butterfly
+    // of grad_add3_impl instead of its partial-mask loop.
+    __syncwarp();
+    const unsigned sw = __ballot_sync(0xffffffffu, sweep);
+    const unsigned ew = __ballot_sync(0xffffffffu, em_idx >= 0);
+    if (sw != 0u) {
+        const int leader = __ffs((int) sw) - 1;
+        const int tri_l = __shfl_sync(0xffffffffu, y.tri, leader);
+        const bool fnrm_l = __shfl_sync(0xffffffffu, (int) y.face_normals, leader) != 0;
+        const int tri = sweep ? y.tri : tri_l;                  // idle lanes adopt the leader's target and add zeros
+        const bool face_normals = sweep ? y.face_normals : fnrm_l;
+        const VtxAdj a0 = sweep ? ya : zero_adj;
+        const int b = kGradTri * tri;
         acc.add3(b + 19, a0.fn);
         acc.add(b + 9, a0.area);
-        V3f m_bar;
-        scatter_shading_normal(acc, x0, a0.shn, m_bar);
-        const ShadeRec<float> N = load_shade<float>(sc, x0.tri);
-        // uv = uv0 + u duv0 + v duv1 is differentiable at the primary hit (scene.cpp:785-788)
-        const float u_bar = dot(N.n1 - N.n0, m_bar) + dot(x0.duv0, a0.uv), v_bar = dot(N.n2 - N.n0, m_bar) + dot(x0.duv1, a0.uv);
-        o_bar = o_bar + a0.p;
-        d_bar = d_bar + a0.p * t0;
-        const float t_bar = dot(d, a0.p);
-        const V3f r_bar = isect_adj(T0.e1, T0.e2, d, u_bar, v_bar, t_bar);
-        scatter_isect_tri(acc, x0.tri, u0, v0, r_bar);
-        o_bar = o_bar + r_bar;
-        d_bar = d_bar + r_bar * t0;
-        scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
+        V3f m_bar(0.f, 0.f, 0.f);
+        if (face_normals) acc.add3(b + 19, a0.shn);             // scatter_shading_normal, with the branch on a per-lane flag that
+        else {                                                  // is uniform whenever the lanes share the triangle
+            const float gu = sweep ? y.u : 0.f, gv = sweep ? y.v : 0.f, minv = sweep ? y.minv : 0.f;
+            const V3f shn = sweep ? y.shn : V3f(0.f, 0.f, 0.f);
+            m_bar = (a0.shn - shn * dot(shn, a0.shn)) * minv;
+            acc.add3(b + 10, m_bar * (1.f - gu - gv));
+            acc.add3(b + 13, m_bar * gu);
+            acc.add3(b + 16, m_bar * gv);
+        }
+        V3f r_bar(0.f, 0.f, 0.f);
+        if (sweep) {
+            const ShadeRec<float> N = load_shade<float>(sc, y.tri);
+            // uv = uv0 + u duv0 + v duv1 is differentiable at the primary hit (scene.cpp:785-788)
+            const float u_bar = dot(N.n1 - N.n0, m_bar) + dot(y.duv0, a0.uv), v_bar = dot(N.n2 - N.n0, m_bar) + dot(y.duv1, a0.uv);
+            o_bar = o_bar + a0.p;
+            d_bar = d_bar + a0.p * t0;
+            const float t_bar = dot(d, a0.p);
+            r_bar = isect_adj(T0.e1, T0.e2, d, u_bar, v_bar, t_bar);
+            o_bar = o_bar + r_bar;
+            d_bar = d_bar + r_bar * t0;
+        }
+        acc.add3(b, -r_bar);                                    // scatter_isect_tri
+        acc.add3(b + 3, r_bar * (-(sweep ? u0 : 0.f)));
+        acc.add3(b + 6, r_bar * (-(sweep ? v0 : 0.f)));
+        scatter_camera_ray(acc, gl, dc, sweep ? o_bar : V3f(0.f, 0.f, 0.f), sweep ? d_bar : V3f(0.f, 0.f, 0.f));
+    }
+    if (ew != 0u) {
+        const int leader = __ffs((int) ew) - 1;
+        const int e_l = __shfl_sync(0xffffffffu, em_idx, leader);
+        acc.add3(gl.off_emit + 4 * (em_idx >= 0 ? em_idx : e_l), em_acc);
     }
 }
 
