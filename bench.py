@@ -43,11 +43,13 @@ RAYS_PER_LANE = (1 + 2 * DEPTH, 2 * (1 + 2 * DEPTH), 3)       # interior, primar
 BYTES_PER_RAY = 88                                               # ray 28 B + hit 16 B, written and read once
 
 
-def bench_config(world: int, path: str) -> dict:
+def bench_config(world: int, path: str, peer: bool = False) -> dict:
     """The `config` object of the JSON line: identical keys (and workload string) in both arms."""
     return {"workload": "cbox 512x512 spp=32 sppe=32 sppse=32 PathTracer(3) renderD DiffuseBSDF (BASELINE configs[1])",
             "l2": "256 MiB memset between timed steps (flush, outside the events)",
-            "sharding": ("interleaved 32-lane blocks of every term over %d rank(s); partial images summed by one NCCL all-reduce" % world)
+            "sharding": ("interleaved 32-lane blocks of every term over %d rank(s); " % world +
+                         ("the kernels add into every rank's replica through the NVLS multicast address (multimem.red), one device barrier per step"
+                          if peer else "partial images summed by one NCCL all-reduce"))
             if world > 1 else "single GPU",
             "seed": "seed=0 on the first call, then seed=-1 (continuing sampler streams, reference README.md:96)",
             "param": "Mesh[0] translate(100 P,0,0), forward tangent", "path": path}
@@ -162,6 +164,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     L = _lib.load()
     sc, tangent = build_scene(psdr, rank, world)
     integ = psdr.PathTracer(DEPTH)
+    # N > 1: the reduction over ranks is fused into the term kernels (multimem.red through the NVSwitch into every rank's
+    # replica, psdr_jit_b200/dist.py PeerBuffers); without NVLS multicast on the node: one NCCL all-reduce per step
+    peer = world > 1 and not args.no_peer and sc.enable_peer_reduction()
     _lib.check(L.psdr_scene_enable_timing(sc._h, 1))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
     n_samples = W * H * (SPP + SPPE + SPPSE)
@@ -169,7 +174,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     def step(seed):
         img, dimg = integ.renderD_fwd(sc, 0, seed=seed)       # views of ONE [2, npix, 3] buffer
-        if world > 1:
+        if world > 1 and not integ.last_reduced:
             dist.all_reduce(integ.last_buffer)                # in place: image + derivative image in one message
         return img, dimg
 
@@ -216,7 +221,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         def vjp_step(seed):
             img = integ.renderD_primal(sc, 0, seed=seed)
-            if world > 1:
+            if world > 1 and not integ.last_reduced:
                 dist.all_reduce(img)                         # the loss needs the full image on every rank
             integ.render_vjp(sc, cot, 0, seed=seed)          # synchronises: gradients come back on the host
             return img
@@ -243,7 +248,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         vjp = {"value": round(n_samples * args.steps / (vms * 1e-3) / 1e6, 3), "unit": "Msamples/s", "ms_per_step": round(vms / args.steps, 4),
                "kernel_ms": {"interior_adjoint": round(sum(vk[1]) / len(vk[1]), 4), "primary_edges_adjoint": round(sum(vk[2]) / len(vk[2]), 4),
                              "secondary_edges_adjoint": round(sum(vk[4]) / len(vk[4]), 4)},
-               "step": "renderD primal image + adjoint kernels + " + ("ONE NCCL all-reduce of the flat device gradient table + " if world > 1 else "") +
+               "step": "renderD primal image + adjoint kernels + " + (("gradient table summed inside the adjoint kernels (multimem.red) + " if peer else "ONE NCCL all-reduce of the flat device gradient table + ") if world > 1 else "") +
                        "D2H of the table + host chain to all parameters"}
 
     # ---- end to end through the host-buffer C ABI: parameter update + configure + render + D2H
@@ -265,7 +270,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             # N ranks: each renders its lane shard on the device, ONE NCCL reduce sums the partial images on rank 0
             # (psdr_jit_b200.dist.all_reduce_images), one D2H into pinned host memory there
             integ.renderD_fwd(sc, 0, seed=seed)
-            psdr_dist.all_reduce_images(integ.last_buffer, dst=0)      # the result is needed on the host of rank 0 only
+            if not integ.last_reduced:
+                psdr_dist.all_reduce_images(integ.last_buffer, dst=0)      # the result is needed on the host of rank 0 only
             if rank == 0:
                 pinned.copy_(integ.last_buffer, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -313,12 +319,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "metric": METRIC, "value": round(n_samples * args.steps / (total_ms * 1e-3) / 1e6, 3), "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": bench_config(world, "psdr_render_d on device buffers (value); set_transform + Scene.configure + psdr_render_d_host (e2e)"),
+            "config": bench_config(world, "psdr_render_d on device buffers (value); set_transform + Scene.configure + psdr_render_d_host (e2e)", peer),
             "clocks": clk,
             "e2e": {"value": round(n_samples * args.steps / e2e_s / 1e6, 3), "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
                     "path": ("set_transform + Scene.configure + psdr_render_d_host (pinned host image buffers)" if world == 1 else
-                             "set_transform + Scene.configure + renderD_fwd on each rank's lane shard + one NCCL reduce to rank 0 + one D2H into pinned host memory there")},
+                             "set_transform + Scene.configure + renderD_fwd on each rank's lane shard + " +
+                             ("in-kernel multimem.red into every rank's replica" if peer else "one NCCL reduce to rank 0") + " + one D2H into pinned host memory on rank 0")},
             "gpu_launches": int(launches),
             "kernel_ms": {"interior": round(means[1], 4), "primary_edges": round(means[2], 4), "secondary_edges": round(means[4], 4)},
             "roofline": {"bound": "hbm", "kernel": {1: "interior_kernel<Dual>", 2: "primary_edge_kernel", 4: "secondary_edge_kernel"}[dom],
@@ -461,6 +468,7 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
     per_sensor = args.config == 5                        # one sensor per GPU: replicas, no image collective
     sc = bench_scenes.build_ours(psdr, wl, 0 if per_sensor else rank, 1 if per_sensor else world)
     integ = psdr.PathTracer(wl["depth"])
+    peer = world > 1 and not per_sensor and not args.no_peer and sc.enable_peer_reduction()     # fused NVLink reduction (run_ours)
     prep_ms = None
     if wl["guiding"]:
         t0 = time.perf_counter()
@@ -477,11 +485,11 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
         for k in mine:
             if wl["mode"] == "renderC":
                 img = integ.renderC(sc, k, seed=seed)
-                if world > 1 and not per_sensor:
+                if world > 1 and not per_sensor and not integ.last_reduced:
                     dist.all_reduce(img)
             else:
                 integ.renderD_fwd(sc, k, seed=seed)
-                if world > 1 and not per_sensor:
+                if world > 1 and not per_sensor and not integ.last_reduced:
                     dist.all_reduce(integ.last_buffer)
 
     step(0)
@@ -536,7 +544,8 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
                 else:
                     integ.renderD_fwd(sc, k, seed=seed)
                     buf = integ.last_buffer
-                dist.reduce(buf, dst=0)
+                if not integ.last_reduced:
+                    dist.reduce(buf, dst=0)
                 if rank == 0:
                     pinned.view(-1)[:buf.numel()].copy_(buf.view(-1), non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -582,7 +591,7 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
             "metric": "Msamples/s %s" % wl["name"], "value": round(n_samples * args.steps / (total_ms * 1e-3) / 1e6, 3), "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak" if False else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(wl, world, "device buffers (value); parameter update + Scene.configure + host-buffer render (e2e)"),
+            "config": config_dict(wl, world, "device buffers (value); parameter update + Scene.configure + host-buffer render (e2e)", peer),
             "clocks": clk,
             "e2e": {"value": round(n_samples * e2e_steps / e2e_s / 1e6, 3), "unit": "Msamples/s", "h2d_bytes_per_step": int(L.psdr_scene_query(sc._h, _lib.Q_UPLOAD_BYTES, 0)),
                     "d2h_bytes_per_step": int(himg.nbytes * (2 if wl["mode"] == "renderD" else 1) * len(wl["sensors"])), "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4)},
@@ -600,9 +609,9 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
-def config_dict(wl, world, path):
+def config_dict(wl, world, path, peer=False):
     return {"workload": wl["name"], "l2": "256 MiB memset between timed steps (flush, outside the events)",
-            "sharding": ("one sensor per rank (replicas)" if wl["cfg"] == 5 else "interleaved 32-lane blocks over %d rank(s), one NCCL all-reduce" % world)
+            "sharding": ("one sensor per rank (replicas)" if wl["cfg"] == 5 else "interleaved 32-lane blocks over %d rank(s), " % world + ("reduction fused into the kernels (multimem.red)" if peer else "one NCCL all-reduce"))
             if world > 1 else "single GPU",
             "seed": "seed=0 on the first call, then seed=-1 (continuing sampler streams, reference README.md:96)",
             "param": "Mesh[%d] translate(100 P,0,0), forward tangent" % wl["moving"], "path": path}
@@ -717,6 +726,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vjp", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="N > 1: sum the partial images with NCCL instead of the fused multimem.red path")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json workload (2 = the headline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

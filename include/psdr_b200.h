@@ -64,7 +64,9 @@ enum {
     PSDR_Q_UPLOAD_BYTES = 11,       /* bytes of device tables the last configure() copied host->device */
     PSDR_Q_GUIDING_CELLS = 12,      /* index = sensor; cells of its secondary-edge guiding grid (0 = none) */
     PSDR_Q_BVH_BUILDS = 13,         /* host BVH topology builds so far (first configure, or after the set of meshes changed) */
-    PSDR_Q_BVH_REFITS = 14          /* GPU BVH refits so far (every configure of a scene above 64 triangles) */
+    PSDR_Q_BVH_REFITS = 14,         /* GPU BVH refits so far (every configure of a scene above 64 triangles) */
+    PSDR_Q_GRAD_TABLE_MULTICAST = 15 /* index = sensor; 1 = psdr_render_vjp_device may target a multicast table
+                                      * (psdr_scene_set_output_multicast): the table fits the kernels' shared-memory copy */
 };
 
 /* Terms of renderD (bit mask). */
@@ -95,6 +97,19 @@ int psdr_scene_set_shard(psdr_scene *s, int rank, int world);
  * sampling only, mis = 1 BSDF sampling only.  The sample streams consume only the draws the mode uses. */
 enum { PSDR_INTEGRATOR_PATH = 0, PSDR_INTEGRATOR_DIRECT = 1 };
 int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis);
+/* Multi-GPU output fusion (new: SURVEY.md 8e).  on = 1: the img / dimg pointers of psdr_render_c / psdr_render_d and the
+ * grad_table pointer of psdr_render_vjp_device are NVLS MULTICAST addresses of a buffer that every rank of the node has
+ * mapped (cuMulticast* / torch symmetric memory).  The term kernels then accumulate with multimem.red: the NVSwitch adds
+ * every contribution into the replica of every GPU, so the complete image (or gradient table) is present on all ranks
+ * when the kernels of all ranks have finished -- no all-reduce pass.  The calls do NOT zero the buffer in this mode: the
+ * caller zeroes every replica and synchronises the ranks before, and synchronises them again before reading
+ * (psdr_jit_b200/dist.py PeerBuffers does both with one device-side barrier per step). */
+int psdr_scene_set_output_multicast(psdr_scene *s, int on);
+/* CTA shape of the term kernels (process-wide; new).  Every term kernel exists in two shapes: large CTAs (one or two
+ * per SM) with block barriers that keep the warps of an SM in the same stretch of code, and 128-thread CTAs for launches
+ * too small to fill the large shape.  0 = choose by launch size (default), 1 = always 128 threads, 2 = always large.
+ * Results do not depend on the shape (a lane's value is a function of its global index and the seed). */
+int psdr_set_cta_policy(int policy);
 /* New.  on != 0: the analytic re-intersection of the primary hit in renderD (src/scene/scene.cpp:772-801,
  * include/psdr/utils.h:82-93) takes its reciprocal with rcp.approx.ftz.f32, the instruction Dr.Jit emits for rcp()
  * (drjit-core cuda_eval.cpp:638-640), instead of the correctly rounded 1/x.  Everything else stays IEEE.  Reproduces the

@@ -61,6 +61,12 @@ def kernel_launch_count() -> int:
     return int(_lib.load().psdr_kernel_launch_count())
 
 
+def set_cta_policy(policy: int = 0):
+    """CTA shape of the term kernels: 0 = by launch size, 1 = 128-thread CTAs, 2 = large CTAs with block barriers
+    (include/psdr_b200.h psdr_set_cta_policy).  Results do not depend on it."""
+    _lib.check(_lib.load().psdr_set_cta_policy(int(policy)))
+
+
 class Object:
     """reference include/psdr/object.h"""
     id = ""
@@ -415,6 +421,8 @@ class Scene(Object):
         self._env = None
         self._device = device
         self._shard = (0, 1)
+        self._peer_group = None    # process group of the fused NVLink reduction (enable_peer_reduction)
+        self._peer_bufs = {}
         self._accel = -1
         self.reference_arithmetic = False     # Dr.Jit's approximate rcp in renderD's analytic primary hit (psdr_b200.h)
 
@@ -527,6 +535,39 @@ class Scene(Object):
         self._shard = (int(rank), int(world))
         if self._h is not None:
             _lib.check(_lib.load().psdr_scene_set_shard(self._h, rank, world))
+
+    def enable_peer_reduction(self, group=None, strict: bool = False) -> bool:
+        """Fuse the multi-GPU image / gradient reduction INTO the term kernels: on a sharded scene (set_shard) the kernels
+        of every rank accumulate through an NVLS multicast address (multimem.red over NVLink / NVSwitch; dist.PeerBuffers),
+        so renderC / renderD_fwd / renderD_primal / render_vjp return the complete result on every rank with no
+        all-reduce.  Returns False (and leaves the NCCL path in place) when the node has no multicast support."""
+        import torch.distributed as dist
+        from . import dist as _dist
+        if self._shard[1] <= 1 or not dist.is_initialized():
+            if strict:
+                raise RuntimeError("enable_peer_reduction needs a sharded scene and an initialised process group")
+            return False
+        try:
+            import torch
+            probe = _dist.PeerBuffers(32, torch.device("cuda", self._device_index()), group)
+        except Exception:
+            if strict:
+                raise
+            return False
+        self._peer_group = group if group is not None else dist.group.WORLD
+        self._peer_bufs = {("probe", 32): probe}
+        return True
+
+    def _peer(self, key: str, numel: int):
+        """PeerBuffers for outputs of `numel` floats, or None when the fused reduction is off."""
+        if self._peer_group is None or self._shard[1] <= 1:
+            return None
+        pb = self._peer_bufs.get((key, numel))
+        if pb is None:
+            import torch
+            from . import dist as _dist
+            pb = self._peer_bufs[(key, numel)] = _dist.PeerBuffers(numel, torch.device("cuda", self._device_index()), self._peer_group)
+        return pb
 
     def set_accel(self, mode: int):
         self._accel = int(mode)
@@ -784,6 +825,21 @@ class Integrator(Object):
             return batch_pix.to(device=device, dtype=torch.int32).contiguous()
         return torch.as_tensor(np.asarray(batch_pix, dtype=np.int32), device=device)
 
+    last_reduced = False     # the last render already holds the sum over the ranks (fused NVLink reduction)
+
+    @staticmethod
+    def _multicast(scene, pb, launch):
+        """Run `launch(base address)` with the scene's outputs switched to the multicast address of `pb`, then barrier
+        and fetch the summed buffer (dist.PeerBuffers)."""
+        L = _lib.load()
+        base, _ = pb.target()
+        _lib.check(L.psdr_scene_set_output_multicast(scene._h, 1))
+        try:
+            launch(base)
+        finally:
+            _lib.check(L.psdr_scene_set_output_multicast(scene._h, 0))
+        return pb.finish()
+
     def renderC(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
         """Primal image, float32[H*W, 3] on the GPU (reference Integrator::renderC)."""
         self._check(scene)
@@ -791,10 +847,15 @@ class Integrator(Object):
         dev, st = self._dev_stream(torch, scene)
         pix = self._pix(torch, batch_pix, dev)
         n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
+        L = _lib.load()
+        args = (scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters),
+                None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel())
+        pb = scene._peer("img", 3 * n)
+        self.last_reduced = pb is not None
+        if pb is not None:
+            return self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_c(*args, base, st))).view(n, 3)
         img = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        _lib.check(_lib.load().psdr_render_c(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters),
-                                             None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel(),
-                                             img.data_ptr(), st))
+        _lib.check(L.psdr_render_c(*args, img.data_ptr(), st))
         return img
 
     def renderD_fwd(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL):
@@ -804,14 +865,19 @@ class Integrator(Object):
         dev, st = self._dev_stream(torch, scene)
         pix = self._pix(torch, batch_pix, dev)
         n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
-        # ONE [2, n, 3] buffer: the multi-GPU path sums image and derivative image with a single all-reduce of it
-        buf = torch.empty((2, n, 3), dtype=torch.float32, device=dev)
-        img, dimg = buf[0], buf[1]
-        _lib.check(_lib.load().psdr_render_d(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms),
-                                             int(self.reference_tangent_scaling), None if pix is None else pix.data_ptr(),
-                                             0 if pix is None else pix.numel(), img.data_ptr(), dimg.data_ptr(), st))
+        L = _lib.load()
+        args = (scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms), int(self.reference_tangent_scaling),
+                None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel())
+        pb = scene._peer("img2", 6 * n)
+        self.last_reduced = pb is not None
+        if pb is not None:      # fused reduction: the kernels of all ranks add straight into every rank's replica
+            buf = self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_d(*args, base, base + 12 * n, st))).view(2, n, 3)
+        else:
+            # ONE [2, n, 3] buffer: the NCCL path sums image and derivative image with a single all-reduce of it
+            buf = torch.empty((2, n, 3), dtype=torch.float32, device=dev)
+            _lib.check(L.psdr_render_d(*args, buf[0].data_ptr(), buf[1].data_ptr(), st))
         self.last_buffer = buf
-        return img, dimg
+        return buf[0], buf[1]
 
     def renderD(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
         """reference Integrator::renderD.  If any parameter reachable through ``scene.param_map`` is a torch
@@ -832,10 +898,15 @@ class Integrator(Object):
         dev, st = self._dev_stream(torch, scene)
         pix = self._pix(torch, batch_pix, dev)
         n = scene.opts.width * scene.opts.height if pix is None else pix.numel()
+        L = _lib.load()
+        args = (scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), _lib.TERM_ALL, 0,
+                None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel())
+        pb = scene._peer("img", 3 * n)
+        self.last_reduced = pb is not None
+        if pb is not None:
+            return self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_d(*args, base, None, st))).view(n, 3)
         img = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        _lib.check(_lib.load().psdr_render_d(scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), _lib.TERM_ALL,
-                                             0, None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel(),
-                                             img.data_ptr(), None, st))
+        _lib.check(L.psdr_render_d(*args, img.data_ptr(), None, st))
         return img
 
     def render_vjp(self, scene: Scene, d_img, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL, group=None):
@@ -859,9 +930,13 @@ class Integrator(Object):
             nt = L.psdr_grad_table_size(scene._h, sensor_id)
             if nt < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
-            table = torch.empty(nt, dtype=torch.float32, device=dev)
-            _lib.check(L.psdr_render_vjp_device(*args, table.data_ptr(), nt, st))
-            torch.distributed.all_reduce(table, group=group)          # the single gradient all-reduce
+            pb = scene._peer("table", nt) if L.psdr_scene_query(scene._h, _lib.Q_GRAD_TABLE_MULTICAST, sensor_id) == 1 else None
+            if pb is not None:      # the adjoint kernels of all ranks add into every rank's table (multimem.red)
+                table = self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_vjp_device(*args, base, nt, st)))
+            else:
+                table = torch.empty(nt, dtype=torch.float32, device=dev)
+                _lib.check(L.psdr_render_vjp_device(*args, table.data_ptr(), nt, st))
+                torch.distributed.all_reduce(table, group=group)          # the single gradient all-reduce
             _lib.check(L.psdr_scene_backprop_table(scene._h, sensor_id, table.data_ptr(), nt, st))
         else:
             _lib.check(L.psdr_render_vjp(*args, st))
@@ -1005,7 +1080,7 @@ def _render_d_autograd(integ: Integrator, scene: Scene, sensor_id: int, seed: in
         def forward(ctx, *tensors):
             ctx.state0 = scene._sampler_state()
             img = integ.renderD_primal(scene, sensor_id, seed, batch_pix)
-            if scene._shard[1] > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            if not integ.last_reduced and scene._shard[1] > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
                 # every rank rendered its lane shard into a full-frame buffer: a loss must see the SUM (a nonlinear
                 # loss of a partial image has the wrong cotangent, different on every rank)
                 torch.distributed.all_reduce(img)

@@ -115,13 +115,16 @@ struct GradAcc {
     unsigned s_addr;  // its shared-window address (0 = none)
     int lo, hi;
     bool aggregate;   // sum across the lanes that target the same entry before adding (interior kernel: one pixel per warp)
+    int mc;           // 1 = g is an NVLS multicast address (RenderParams::out_multicast): the shared copy is flushed with
+                      // multimem.red (out_add); only tables that fit the shared window run in this mode (capi.cpp vjp_launch)
     __device__ __forceinline__ void add(int idx, float v) const { grad_add1_impl(aggregate, s_addr, g, lo, hi, idx, v); }
     __device__ __forceinline__ void add3(int idx, V3f v) const { grad_add3_impl(aggregate, s_addr, g, lo, hi, idx, v.x, v.y, v.z); }
 };
 
-__device__ __forceinline__ GradAcc grad_acc_begin(const GradLayout &gl, float *smem, int lo, int hi, bool use_smem, bool aggregate) {
+__device__ __forceinline__ GradAcc grad_acc_begin(const GradLayout &gl, float *smem, int lo, int hi, bool use_smem, bool aggregate, int mc = 0) {
     GradAcc a;
     a.aggregate = aggregate;
+    a.mc = mc;
     a.g = gl.base;
     a.s = use_smem ? smem : nullptr;
     a.s_addr = use_smem ? (unsigned) __cvta_generic_to_shared(smem) : 0u;
@@ -138,7 +141,7 @@ __device__ __forceinline__ void grad_acc_end(const GradAcc &a) {
     __syncthreads();
     for (int i = threadIdx.x; i < a.hi - a.lo; i += blockDim.x) {
         const float v = a.s[i];
-        if (v != 0.f) atomicAdd(a.g + a.lo + i, v);
+        if (v != 0.f) out_add(a.g + a.lo + i, v, a.mc);
     }
 }
 
@@ -565,8 +568,13 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     // every lane executes iteration kk together, whatever its own k is
     const int iters = __reduce_max_sync(0xffffffffu, sweep ? R.nsh : 0);
 #pragma unroll 1
-    for (int kk = 0; kk < iters; ++kk) {
+    for (int kk = 0;; ++kk) {
+#if defined(PSDR_VJP_PHASE_SYNC) && PSDR_VJP_PHASE_SYNC >= 3
+        if (!__syncthreads_or(kk < iters)) break;      // CTA-uniform trip count (called by every thread of the CTA)
+#else
+        if (kk >= iters) break;
         __syncwarp();
+#endif
         const int k = ktop - kk;
         if (sweep && k >= 0) {
         VtxGeo prev = k > 0 ? geo_of(k - 1) : v0geo;

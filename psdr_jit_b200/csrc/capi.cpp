@@ -44,6 +44,7 @@ struct psdr_scene {
 
 static thread_local std::string g_error;
 static std::atomic<long long> g_launches{0};
+namespace psdr { int g_cta_policy = 0; }      // psdr_set_cta_policy; read by the launchers (kernels_impl.cuh use_big_cta)
 
 static int fail(const std::string &msg) {
     g_error = msg;
@@ -134,6 +135,18 @@ int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis) {
     if (kind != PSDR_INTEGRATOR_PATH && kind != PSDR_INTEGRATOR_DIRECT) return fail("unknown integrator kind");
     if (kind == PSDR_INTEGRATOR_DIRECT && (mis < 0 || mis > 2)) return fail("mis >= 0 && mis <= 2");
     s->sc.integrator_mis = kind == PSDR_INTEGRATOR_DIRECT ? mis : 2;
+    return 0;
+}
+
+int psdr_set_cta_policy(int policy) {
+    if (policy < 0 || policy > 2) return fail("policy >= 0 && policy <= 2");
+    psdr::g_cta_policy = policy;
+    return 0;
+}
+
+int psdr_scene_set_output_multicast(psdr_scene *s, int on) {
+    if (!s) return fail("null scene");
+    s->sc.out_multicast = on != 0;
     return 0;
 }
 
@@ -454,6 +467,11 @@ int psdr_scene_query(psdr_scene *s, int what, int index) {
         case PSDR_Q_UPLOAD_BYTES: return (int) sc.upload_bytes;
         case PSDR_Q_BVH_BUILDS: return sc.bvh_builds;
         case PSDR_Q_BVH_REFITS: return sc.bvh_refits;
+        case PSDR_Q_GRAD_TABLE_MULTICAST: {
+            if (index < 0 || index >= (int) sc.cameras.size()) { fail("sensor index out of range"); return -1; }
+            const GradLayout gl = sc.grad_layout(index);
+            return grad_table_multicast_ok(gl) ? 1 : 0;
+        }
         case PSDR_Q_GUIDING_CELLS:
             return (index >= 0 && index < (int) sc.cameras.size() && sc.cameras[index].guide_ready) ? (int) sc.cameras[index].guide.pmf.size() : 0;
         default: fail("unknown query"); return -1;
@@ -537,8 +555,12 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
     if (!img) throw std::runtime_error("null image buffer");
     const bool primal_only = ad && !dimg;   // renderD's image without the forward-mode derivative image
     const DCamera &cam = sc.dcameras[sensor];
-    cuda_ok(cudaMemsetAsync(img, 0, sizeof(float) * 3 * npix, st), "memset(img)");
-    if (ad && dimg) cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
+    // multicast outputs: the caller zeroed every rank's replica (and synchronised the ranks) before this call
+    for (auto &r : rp) r.out_multicast = sc.out_multicast ? 1 : 0;
+    if (!sc.out_multicast) {
+        cuda_ok(cudaMemsetAsync(img, 0, sizeof(float) * 3 * npix, st), "memset(img)");
+        if (ad && dimg) cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
+    }
     if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
         set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
@@ -628,7 +650,9 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
     const DCamera &cam = sc.dcameras[sensor];
     GradLayout gl = sc.grad_layout(sensor);
     gl.base = table;
-    cuda_ok(cudaMemsetAsync(table, 0, sizeof(float) * gl.total, st), "memset(grad table)");
+    for (auto &r : rp) r.out_multicast = sc.out_multicast ? 1 : 0;
+    if (sc.out_multicast && !grad_table_multicast_ok(gl)) throw std::runtime_error("gradient table too large for a multicast target (PSDR_Q_GRAD_TABLE_MULTICAST)");
+    if (!sc.out_multicast) cuda_ok(cudaMemsetAsync(table, 0, sizeof(float) * gl.total, st), "memset(grad table)");
     s->ev_used[0] = s->ev_used[1] = s->ev_used[2] = false;
     if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
         set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);

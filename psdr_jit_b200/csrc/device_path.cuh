@@ -21,6 +21,13 @@ struct Hit {
 };
 
 // local lane index of this rank -> global lane index of the term (RenderParams: block-cyclic deal of 32-lane blocks)
+// Output accumulation.  mc = 0: red.global into this GPU's buffer.  mc = 1: `p` is an NVLS multicast address of a buffer
+// that every rank of the node maps -- ONE multimem.red travels to the NVSwitch, which adds the value into the replica of
+// every GPU: the term kernels of the N ranks then build the complete image on all ranks with no reduction pass.
+__device__ __forceinline__ void out_add(float *p, float v, int mc) {
+    if (mc) asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    else atomicAdd(p, v);
+}
 __device__ __forceinline__ long long global_lane(const RenderParams &rp, long long j) {
     return rp.shard_world <= 1 ? rp.lane_begin + j : (((j >> 5) * rp.shard_world + rp.shard_rank) << 5) + (j & 31);
 }
@@ -1077,7 +1084,9 @@ __device__ __forceinline__ bool li_step(const DScene &sc, Pcg32 &rng, LiState<S>
 // the plain loop (`lanes` = 0) and re-converge at the caller's barrier, which measured 2-7 % faster for them.
 template <class S, int kCfg, bool kAD, class Rec>
 __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, Rec &R,
-                                    unsigned lanes = 0u, int mis = 2) {
+                                    unsigned lanes = 0u, int mis = 2, bool cta = false) {
+    // `cta`: every thread of the CTA calls Li together and the step loop is CTA-uniform (one block barrier per step), so
+    // that all warps of the CTA execute the same stretch of code at the same time (instruction-cache locality)
     LiState<S> st;
     li_begin<S>(st, ro, rd, active);
     if (lanes != 0u) {
@@ -1085,7 +1094,7 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
 #pragma unroll 1
         while (true) {
             if (!done) done = li_step<S, kCfg, kAD, Rec>(sc, rng, st, max_depth, hide_emitters, R, mis);
-            if (__all_sync(lanes, done)) break;
+            if (cta ? __syncthreads_and(done) != 0 : __all_sync(lanes, done)) break;
         }
     } else {
 #pragma unroll 1
@@ -1095,9 +1104,10 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
 }
 
 template <class S, int kCfg>
-__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, int mis = 2) {
+__device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, int max_depth, bool hide_emitters, int mis = 2,
+                                    bool cta = false) {
     NoRecord rec;
-    return Li<S, kCfg, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec, 0u, mis);
+    return Li<S, kCfg, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec, cta ? 0xffffffffu : 0u, mis, cta);
 }
 
 // ---- secondary (shadow) edges: reference src/scene/scene.cpp:1027-1068, src/integrator/path.cpp:172-270
@@ -1312,15 +1322,18 @@ __device__ __forceinline__ bool sec_edge_draw(const DScene &sc, const DCamera &c
 }
 // warp-uniform batch loop; `body(sample)` is called by the lanes that hold a candidate
 template <int kCfg, class F>
-__device__ __forceinline__ void sec_edge_batches(const DScene &sc, const DCamera &cam, const RenderParams &rp, int block, F body) {
+__device__ __forceinline__ void sec_edge_batches(const DScene &sc, const DCamera &cam, const RenderParams &rp, int block, F body, bool cta = false) {
     const long long span = rp.lane_end - rp.lane_begin;
     const unsigned lane = threadIdx.x & 31u;
     const long long n_warps = (long long) gridDim.x * (block / 32), warp = (long long) blockIdx.x * (block / 32) + (threadIdx.x >> 5);
     const long long per = ((span + n_warps - 1) / n_warps + 31) / 32 * 32;      // slice of this warp
     long long next = warp * per;
     const long long end = next + per < span ? next + per : span;
+    bool finished = false;      // (cta mode) this warp has drained its slice and only keeps the block barriers company
     while (true) {
-        __syncwarp();
+        if (cta) {
+            if (!__syncthreads_or(!finished)) break;
+        } else __syncwarp();
         bool have = false;
         SecSample smp;
         for (int round = 0; round < kSecFillRounds; ++round) {
@@ -1332,7 +1345,10 @@ __device__ __forceinline__ void sec_edge_batches(const DScene &sc, const DCamera
             }
             next += __popc(need);
         }
-        if (!__any_sync(0xffffffffu, have)) {
+        if (cta) {
+            if (!__any_sync(0xffffffffu, have) && next >= end) finished = true;
+            __syncthreads();        // fill phase | stage-1 phase
+        } else if (!__any_sync(0xffffffffu, have)) {
             if (next >= end) break;
             continue;
         }

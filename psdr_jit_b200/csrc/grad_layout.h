@@ -20,4 +20,10 @@ struct GradLayout {
     int total;
 };
 
+// The adjoint kernels keep a shared-memory copy of their section of the table when it fits (48 KB, no opt-in).
+constexpr int kGradSharedMaxFloats = 12 * 1024;
+// Multicast tables (psdr_scene_set_output_multicast) are written only by the flush of that shared copy (adjoint.cuh
+// grad_acc_end): every section must fit it and nothing may live outside it (environment-map / BSDF texel gradients do).
+inline bool grad_table_multicast_ok(const GradLayout &gl) { return gl.total == gl.off_env && gl.off_env <= kGradSharedMaxFloats; }
+
 }  // namespace psdr

@@ -9,28 +9,56 @@
 #include "device_path.cuh"
 #include "kernels.h"
 
-// resident CTAs per SM each kernel is compiled for (register cap = 65536 / (128 * n)); tuned on cfg 2, B200
+// ---- CTA shape of the three term kernels (tuned on cfg 2, B200; profiles/r02m, r02n) ---------------------------------
+// These kernels are 7-10 K SASS instructions (110-160 KB) against a 32 KB L1.5 instruction cache, and their warps walk
+// different paths: with 6-8 independent 128-thread CTAs per SM, 39 % of the stall samples of the interior and
+// secondary-edge kernels (16 % of the primary-edge kernel) were "no instruction" (profiles/r02a).  ONE large CTA per SM
+// with a block barrier where every path (edge side, batch) starts keeps all warps of the SM inside the same stretch of
+// code: interior 2.26 -> 1.76 ms, primary edges 6.52 -> 5.92 ms, secondary edges 1.26 -> 1.07 ms.  A barrier at every
+// path STEP (mode 2) costs more in idle warps than it saves (+10 %).
+// PSDR_LB_* = resident CTAs per SM each kernel is compiled for (register cap = 65536 / (block * n)).
 #ifndef PSDR_LB_INTERIOR
-#define PSDR_LB_INTERIOR 6
+#define PSDR_LB_INTERIOR 1
 #endif
 #ifndef PSDR_LB_INTERIOR_DUAL
-#define PSDR_LB_INTERIOR_DUAL 6
+#define PSDR_LB_INTERIOR_DUAL 1
 #endif
 #ifndef PSDR_LB_PRIMARY
-#define PSDR_LB_PRIMARY 8
+#define PSDR_LB_PRIMARY 1
 #endif
 #ifndef PSDR_LB_SECONDARY
-#define PSDR_LB_SECONDARY 8
+#define PSDR_LB_SECONDARY 1
+#endif
+// CTA-wide phase barriers: 0 = none; 1 = one block barrier per path (and per edge side / batch); 2 = additionally one
+// per path step.
+#ifndef PSDR_SYNC_I
+#define PSDR_SYNC_I 1
+#endif
+#ifndef PSDR_SYNC_P
+#define PSDR_SYNC_P 1
+#endif
+#ifndef PSDR_SYNC_S
+#define PSDR_SYNC_S 1
+#endif
+#ifndef PSDR_BLOCK_I
+#define PSDR_BLOCK_I 640
+#endif
+#ifndef PSDR_BLOCK_P
+#define PSDR_BLOCK_P 896
+#endif
+#ifndef PSDR_BLOCK_S
+#define PSDR_BLOCK_S 1024
 #endif
 
 namespace psdr {
 
 constexpr int kBlock = 128;
+constexpr int kBlockI = PSDR_BLOCK_I, kBlockP = PSDR_BLOCK_P, kBlockS = PSDR_BLOCK_S;
 
 // Reduce values over runs of consecutive lanes that share a pixel (lanes are pixel-major, so a
 // warp holds at most a few contiguous runs; with spp a multiple of 32 it is one run) and issue one
 // atomicAdd per run and channel.  Reference: scatter_reduce(Add) in integrator.cpp:128.
-__device__ __forceinline__ void splat_runs(float *img, int pix, float r, float g, float b, bool valid) {
+__device__ __forceinline__ void splat_runs(float *img, int pix, float r, float g, float b, bool valid, int mc) {
     const unsigned lane = threadIdx.x & 31u;
     const int key = valid ? pix : -1;
     if (!valid) { r = g = b = 0.f; }
@@ -43,9 +71,9 @@ __device__ __forceinline__ void splat_runs(float *img, int pix, float r, float g
     }
     const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
     if (valid && (lane == 0 || kprev != key)) {
-        atomicAdd(img + 3 * pix, r);
-        atomicAdd(img + 3 * pix + 1, g);
-        atomicAdd(img + 3 * pix + 2, b);
+        out_add(img + 3 * pix, r, mc);
+        out_add(img + 3 * pix + 1, g, mc);
+        out_add(img + 3 * pix + 2, b, mc);
     }
 }
 
@@ -54,21 +82,25 @@ __device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; 
 // ---- interior term: Integrator::__render / __render_batch ------------------------------------
 // kAD = use the formulas of the reference's renderD instantiation (the primary hit re-intersected
 // analytically, scene.cpp:772-801) -- <float, kBvh, true> is the primal image of renderD.
-template <class S, int kCfg, bool kAD>
-__global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? PSDR_LB_INTERIOR_DUAL : PSDR_LB_INTERIOR)) interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
-                                                           const __grid_constant__ RenderParams rp, float *__restrict__ img,
-                                                           float *__restrict__ dimg) {
-    brute_init<kCfg>(sc, kBlock);
-    const long long stride = (long long) gridDim.x * kBlock;
+// kBig: the one-CTA-per-SM shape with block barriers (above); else the 128-thread shape for launches too small to fill it.
+template <class S, int kCfg, bool kAD, bool kBig>
+__global__ void __launch_bounds__(kBig ? kBlockI : kBlock, kBig ? (IsDual<S>::value ? PSDR_LB_INTERIOR_DUAL : PSDR_LB_INTERIOR) : 6)
+    interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp, float *__restrict__ img,
+                    float *__restrict__ dimg) {
+    constexpr int kBlockI = kBig ? psdr::kBlockI : kBlock, kSync = kBig ? PSDR_SYNC_I : 0;
+    brute_init<kCfg>(sc, kBlockI);
+    const long long stride = (long long) gridDim.x * kBlockI;
     const long long span = rp.lane_end - rp.lane_begin;
-    const long long span_pad = (span + 31) / 32 * 32;   // keep warps converged for the shuffles
+    const long long span_pad = (span + kBlockI - 1) / kBlockI * kBlockI;   // keep warps converged for the shuffles (and the trip count CTA-uniform)
     const float inv_spp = sc.spp > 1 ? 1.f / (float) sc.spp : 1.f;
-    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
-        const long long i = global_lane(rp, j);
-        const bool live = j < span && i < rp.n_lanes;
+    for (long long j = (long long) blockIdx.x * kBlockI + threadIdx.x; j < span_pad; j += stride) {
+        if (kSync) __syncthreads();
+        const long long gi = global_lane(rp, j);
+        const bool live = j < span && gi < rp.n_lanes;
+        const long long i = live ? gi : 0;
         int idx = 0;
         V3<S> v(S(0.f));
-        if (live) {
+        if (kSync >= 2 || live) {
             idx = (int) (sc.spp > 1 ? i / sc.spp : i);
             const int pix = rp.pix_id ? __ldg(rp.pix_id + idx) : idx;
             const unsigned long long seed_value = rp.pix_id ? (unsigned long long) ((long long) pix + rp.seed) : (unsigned long long) (i + rp.seed);
@@ -81,38 +113,40 @@ __global__ void __launch_bounds__(kBlock, (IsDual<S>::value ? PSDR_LB_INTERIOR_D
             V3<S> o, d;
             sample_primary_ray<S>(cam, V2f(sx, sy), o, d);
             NoRecord rec;
-            v = Li<S, kCfg, kAD, NoRecord>(sc, rng, o, d, true, rp.max_depth, rp.hide_emitters != 0, rec, 0u, rp.mis);
+            v = Li<S, kCfg, kAD, NoRecord>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, rec, kSync >= 2 ? 0xffffffffu : 0u, rp.mis, kSync >= 2);
         }
         float r = val(v.x), g = val(v.y), b = val(v.z), dr = tang(v.x), dg = tang(v.y), db = tang(v.z);
         // masked(value, ~isfinite(value)) = 0 zeroes value and tangent (integrator.cpp:126)
         if (!isfinite(r)) { r = 0.f; dr = 0.f; }
         if (!isfinite(g)) { g = 0.f; dg = 0.f; }
         if (!isfinite(b)) { b = 0.f; db = 0.f; }
-        splat_runs(img, idx, r * inv_spp, g * inv_spp, b * inv_spp, live);
+        splat_runs(img, idx, r * inv_spp, g * inv_spp, b * inv_spp, live, rp.out_multicast);
         if (IsDual<S>::value) {
             const float ts = rp.tangent_scale * inv_spp;
-            splat_runs(dimg, idx, scrub(dr) * ts, scrub(dg) * ts, scrub(db) * ts, live);
+            splat_runs(dimg, idx, scrub(dr) * ts, scrub(dg) * ts, scrub(db) * ts, live, rp.out_multicast);
         }
     }
 }
 
 // ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges
-template <int kCfg>
-__global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+template <int kCfg, bool kBig>
+__global__ void __launch_bounds__(kBig ? kBlockP : kBlock, kBig ? PSDR_LB_PRIMARY : 8) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
-    brute_init<kCfg>(sc, kBlock);
-    const long long stride = (long long) gridDim.x * kBlock;
+    constexpr int kBlockP = kBig ? psdr::kBlockP : kBlock, kSync = kBig ? PSDR_SYNC_P : 0;
+    brute_init<kCfg>(sc, kBlockP);
+    const long long stride = (long long) gridDim.x * kBlockP;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
     // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
-    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
-    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
-        __syncwarp();
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + kBlockP - 1) / kBlockP * kBlockP;
+    for (long long j = (long long) blockIdx.x * kBlockP + threadIdx.x; j < span_pad; j += stride) {
+        if (kSync) __syncthreads();
+        else __syncwarp();
         const long long i = global_lane(rp, j);
         const bool live = j < span && i < rp.n_lanes;
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-        if (!live) continue;
+        if (!kSync && !live) continue;        // (with block barriers dead lanes ride along inactive)
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
@@ -124,18 +158,19 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(c
         const Dual px = fmadd(Dual(a.x, da.x), Dual(w0), Dual(a.z, da.z) * s1), py = fmadd(Dual(a.y, da.y), Dual(w0), Dual(a.w, da.w) * s1);
         const Dual x_dot_n = dot(V2d(px, py), V2d(Dual(bq.x), Dual(bq.y)));
         const int ix = (int) floorf(px.v * (float) sc.width), iy = (int) floorf(py.v * (float) sc.height);
-        const bool valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+        const bool valid = live && ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
         // Li(ray_n) - Li(ray_p): the reference binary evaluates Li(ray_p) first (verified on the
         // running reference, tests/golden/renderD_*: primary-only images).  One rolled loop over the two
         // sides keeps a single copy of Li in the kernel.
         V3f Lside[2];
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
-            __syncwarp(live_mask);
+            if (kSync) __syncthreads();
+            else __syncwarp(live_mask);
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px.v + sg * bq.x, py.v + sg * bq.y), ro, rd);
-            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis);
+            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis, kSync >= 2);
         }
         const V3f Lp = Lside[0], Ln = Lside[1];
         if (!valid) continue;
@@ -147,7 +182,7 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(c
             const float primal = x_dot_n.v * dl[c];
             if (!isfinite(primal)) continue;
             const float t = x_dot_n.d * dl[c] * inv_sppe;
-            if (t != 0.f && isfinite(t)) atomicAdd(dimg + 3 * pix + c, t);
+            if (t != 0.f && isfinite(t)) out_add(dimg + 3 * pix + c, t, rp.out_multicast);
         }
     }
 }
@@ -158,12 +193,13 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_PRIMARY) primary_edge_kernel(c
 // samples of the slice through stage 0 (cheap, ~30 % pass) until the warp is (nearly) full, then all candidates run
 // stage 1 -- the three closest-hit scans -- together.  One sample per lane per iteration ran those scans with
 // 12, 10 and 2.5 of 32 lanes (profiles/r01i).
-template <int kCfg>
-__global__ void __launch_bounds__(kBlock, PSDR_LB_SECONDARY) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+template <int kCfg, bool kBig>
+__global__ void __launch_bounds__(kBig ? kBlockS : kBlock, kBig ? PSDR_LB_SECONDARY : 8) secondary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                  const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
-    brute_init<kCfg>(sc, kBlock);
+    constexpr int kBlockS = kBig ? psdr::kBlockS : kBlock, kSync = kBig ? PSDR_SYNC_S : 0;
+    brute_init<kCfg>(sc, kBlockS);
     const float scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
-    sec_edge_batches<kCfg>(sc, cam, rp, kBlock, [&](const SecSample &smp) {
+    sec_edge_batches<kCfg>(sc, cam, rp, kBlockS, [&](const SecSample &smp) {
         V3f value0, tangent;
         const int pix = sec_edge_stage1<kCfg, NoSecAdjoint>(sc, cam, smp.cand, value0, tangent, NoSecAdjoint());
         if (pix < 0) return;
@@ -171,9 +207,9 @@ __global__ void __launch_bounds__(kBlock, PSDR_LB_SECONDARY) secondary_edge_kern
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             if (smp.pdf0 > kEpsilon) t[c] = t[c] / smp.pdf0;                 // masked(value, pdf0 > Epsilon) /= pdf0
-            if (isfinite(t[c]) && t[c] != 0.f) atomicAdd(dimg + 3 * pix + c, t[c] * scale);
+            if (isfinite(t[c]) && t[c] != 0.f) out_add(dimg + 3 * pix + c, t[c] * scale, rp.out_multicast);
         }
-    });
+    }, kSync != 0);
 }
 
 // ---- guiding pre-pass: PathTracer::preprocess_secondary_edges (reference src/integrator/path.cpp:130-168)
@@ -257,21 +293,37 @@ template <class K> inline int persistent_grid(K kernel, int block, size_t smem, 
     return (int) (need < cap ? (need > 0 ? need : 1) : cap);
 }
 
+// Launches with fewer lanes than ~4 per thread of the one-CTA-per-SM grid run the 128-thread shape (more CTAs, all SMs busy).
+// g_cta_policy (psdr_set_cta_policy): 0 = by size, 1 = always the 128-thread shape, 2 = always the large-CTA shape.
+extern int g_cta_policy;
+inline bool use_big_cta(long long lanes, int block) {
+    if (g_cta_policy == 1) return false;
+    if (g_cta_policy == 2) return true;
+    return lanes >= 4LL * 148 * block;
+}
+
 template <int kCfg> struct ForwardLaunch {
-    static cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st) {
+    template <class S, bool kAD> static void interior_as(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *img, float *dimg, cudaStream_t st) {
         const long long n = rp.lane_end - rp.lane_begin;
-        if (ad && dimg) interior_kernel<Dual, kCfg, true><<<persistent_grid(interior_kernel<Dual, kCfg, true>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
-        else if (ad)    // primal image of renderD
-            interior_kernel<float, kCfg, true><<<persistent_grid(interior_kernel<float, kCfg, true>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
-        else interior_kernel<float, kCfg, false><<<persistent_grid(interior_kernel<float, kCfg, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+        if (use_big_cta(n, kBlockI)) interior_kernel<S, kCfg, kAD, true><<<persistent_grid(interior_kernel<S, kCfg, kAD, true>, kBlockI, 0, n), kBlockI, 0, st>>>(sc, cam, rp, img, dimg);
+        else interior_kernel<S, kCfg, kAD, false><<<persistent_grid(interior_kernel<S, kCfg, kAD, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+    }
+    static cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st) {
+        if (ad && dimg) interior_as<Dual, true>(sc, cam, rp, img, dimg, st);
+        else if (ad) interior_as<float, true>(sc, cam, rp, img, dimg, st);     // primal image of renderD
+        else interior_as<float, false>(sc, cam, rp, img, dimg, st);
         return cudaGetLastError();
     }
     static cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) {
-        primary_edge_kernel<kCfg><<<persistent_grid(primary_edge_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, dimg);
+        const long long n = rp.lane_end - rp.lane_begin;
+        if (use_big_cta(n, kBlockP)) primary_edge_kernel<kCfg, true><<<persistent_grid(primary_edge_kernel<kCfg, true>, kBlockP, 0, n), kBlockP, 0, st>>>(sc, cam, rp, dimg);
+        else primary_edge_kernel<kCfg, false><<<persistent_grid(primary_edge_kernel<kCfg, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, dimg);
         return cudaGetLastError();
     }
     static cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) {
-        secondary_edge_kernel<kCfg><<<persistent_grid(secondary_edge_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, dimg);
+        const long long n = rp.lane_end - rp.lane_begin;
+        if (use_big_cta(n, kBlockS)) secondary_edge_kernel<kCfg, true><<<persistent_grid(secondary_edge_kernel<kCfg, true>, kBlockS, 0, n), kBlockS, 0, st>>>(sc, cam, rp, dimg);
+        else secondary_edge_kernel<kCfg, false><<<persistent_grid(secondary_edge_kernel<kCfg, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, dimg);
         return cudaGetLastError();
     }
     static cudaError_t guiding(const DScene &sc, const DCamera &cam, const int reso[4], int nrounds, long long seed, float *mass, cudaStream_t st) {

@@ -11,28 +11,60 @@
 namespace psdr {
 
 constexpr int kBlockV = 128;
+// CTA shapes + block barriers of the adjoint kernels, for the same reason as the forward kernels (kernels_impl.cuh):
+// keep the warps of an SM inside the same stretch of code.  The interior adjoint has two phases per path -- primal replay,
+// reverse sweep -- with a barrier in front of each (6.76 -> 5.28 ms at 2 x 256 threads); primary-edge adjoint 6.76 ->
+// 6.01 ms (1 x 1024); secondary-edge adjoint 1.68 -> 1.35 ms (2 x 384).  profiles/r02l, r02n.
 #ifndef PSDR_LB_IVJP
-#define PSDR_LB_IVJP 5          // resident CTAs per SM the interior adjoint is compiled for (96 registers)
+#define PSDR_LB_IVJP 2          // resident CTAs per SM the interior adjoint is compiled for
 #endif
+#ifndef PSDR_BLOCK_IVJP
+#define PSDR_BLOCK_IVJP 256
+#endif
+#ifndef PSDR_VJP_PHASE_SYNC
+#define PSDR_VJP_PHASE_SYNC 1   // 1: block barrier before the primal replay and before the reverse sweep; 2: + every replay step; 3: + every sweep step
+#endif
+#ifndef PSDR_BLOCK_PVJP
+#define PSDR_BLOCK_PVJP 1024
+#endif
+#ifndef PSDR_LB_PVJP
+#define PSDR_LB_PVJP 1
+#endif
+#ifndef PSDR_SYNC_PVJP
+#define PSDR_SYNC_PVJP 1
+#endif
+#ifndef PSDR_BLOCK_SVJP
+#define PSDR_BLOCK_SVJP 384
+#endif
+#ifndef PSDR_LB_SVJP
+#define PSDR_LB_SVJP 2
+#endif
+#ifndef PSDR_SYNC_SVJP
+#define PSDR_SYNC_SVJP 1
+#endif
+constexpr int kBlockIV = PSDR_BLOCK_IVJP, kBlockPV = PSDR_BLOCK_PVJP, kBlockSV = PSDR_BLOCK_SVJP;
 
-template <int kCfg, int kD>
-__global__ void __launch_bounds__(kBlockV, PSDR_LB_IVJP) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+// kBig: the large-CTA shape with block barriers (above); else 128 threads, for launches too small to fill it
+template <int kCfg, int kD, bool kBig>
+__global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP : 5) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                 const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                 const float *__restrict__ d_img) {
+    constexpr int kBlockIV = kBig ? psdr::kBlockIV : kBlockV, kSync = kBig ? PSDR_VJP_PHASE_SYNC : 0;
     extern __shared__ float smem[];
-    brute_init<kCfg>(sc, kBlockV);
-    const GradAcc acc = grad_acc_begin(gl, smem, 0, gl.off_pe, rp.smem_grad != 0, true);
-    const long long stride = (long long) gridDim.x * kBlockV;
+    brute_init<kCfg>(sc, kBlockIV);
+    const GradAcc acc = grad_acc_begin(gl, smem, 0, gl.off_pe, rp.smem_grad != 0, true, rp.out_multicast);
+    const long long stride = (long long) gridDim.x * kBlockIV;
     const float inv_spp = (sc.spp > 1 ? 1.f / (float) sc.spp : 1.f) * rp.tangent_scale;
     // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
-    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
-    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + kBlockIV - 1) / kBlockIV * kBlockIV;   // CTA-uniform trip count
+    for (long long j = (long long) blockIdx.x * kBlockIV + threadIdx.x; j < span_pad; j += stride) {
         // the whole body is warp-uniform control flow: lanes past the end of the span ride along inactive (the
         // span is padded to 32), so the barriers here and inside path_adjoint are full-mask barriers at the top
         // level -- the only form that really re-converges the warp (see path_adjoint)
-        __syncwarp();
+        if (kSync) __syncthreads();
+        else __syncwarp();
         const long long gi = global_lane(rp, j);
         const bool live = j < span && gi < rp.n_lanes;
         const long long i = live ? gi : 0;
@@ -49,38 +81,41 @@ __global__ void __launch_bounds__(kBlockV, PSDR_LB_IVJP) interior_vjp_kernel(con
         const V3f o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f)), d = xform_dir(cam.to_world, dc);
         PathRecord<kD> R;
         R.reset();
-        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, R, 0xffffffffu, rp.mis);
+        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, R, 0xffffffffu, rp.mis, kSync >= 2);
         // cotangent of this lane's value; channels the forward pass scrubbed (non-finite) carry none
         V3f g(__ldg(d_img + 3 * idx) * inv_spp, __ldg(d_img + 3 * idx + 1) * inv_spp, __ldg(d_img + 3 * idx + 2) * inv_spp);
         if (!isfinite(v.x)) g.x = 0.f;
         if (!isfinite(v.y)) g.y = 0.f;
         if (!isfinite(v.z)) g.z = 0.f;
         const bool has_cotangent = !(g.x == 0.f && g.y == 0.f && g.z == 0.f);
-        __syncwarp();
+        if (kSync) __syncthreads();
+        else __syncwarp();
         path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, live && has_cotangent);
     }
     grad_acc_end(acc);
 }
 
-template <int kCfg>
-__global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+template <int kCfg, bool kBig>
+__global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP : 8) primary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                     const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                     const float *__restrict__ d_img) {
+    constexpr int kBlockPV = kBig ? psdr::kBlockPV : kBlockV, kSync = kBig ? PSDR_SYNC_PVJP : 0;
     extern __shared__ float smem[];
-    brute_init<kCfg>(sc, kBlockV);
-    const GradAcc acc = grad_acc_begin(gl, smem, gl.off_pe, gl.off_se, rp.smem_grad != 0, false);
-    const long long stride = (long long) gridDim.x * kBlockV;
+    brute_init<kCfg>(sc, kBlockPV);
+    const GradAcc acc = grad_acc_begin(gl, smem, gl.off_pe, gl.off_se, rp.smem_grad != 0, false, rp.out_multicast);
+    const long long stride = (long long) gridDim.x * kBlockPV;
     const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
     // every lane of a warp runs the same number of iterations (the span is padded to 32) and the warp re-converges
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
-    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
-    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
-        __syncwarp();
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + kBlockPV - 1) / kBlockPV * kBlockPV;
+    for (long long j = (long long) blockIdx.x * kBlockPV + threadIdx.x; j < span_pad; j += stride) {
+        if (kSync) __syncthreads();
+        else __syncwarp();
         const long long i = global_lane(rp, j);
         const bool live = j < span && i < rp.n_lanes;
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-        if (!live) continue;
+        if (!kSync && !live) continue;
         Pcg32 rng;
         rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
         if (rp.skip) rng.advance(rp.skip);
@@ -92,11 +127,12 @@ __global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __gr
         const float px = fmaf(a.x, w0, a.z * s1), py = fmaf(a.y, w0, a.w * s1);
         const float x_dot_n = fmaf(py, bq.y, px * bq.x);
         const int ix = (int) floorf(px * (float) sc.width), iy = (int) floorf(py * (float) sc.height);
-        const bool valid = ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
+        const bool valid = live && ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height;
         V3f Lside[2];
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
-            __syncwarp(live_mask);
+            if (kSync) __syncthreads();
+            else __syncwarp(live_mask);
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px + sg * bq.x, py + sg * bq.y), ro, rd);
@@ -125,31 +161,32 @@ __global__ void __launch_bounds__(kBlockV, 8) primary_edge_vjp_kernel(const __gr
     grad_acc_end(acc);
 }
 
-template <int kCfg>
-__global__ void __launch_bounds__(kBlockV, 6) secondary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+template <int kCfg, bool kBig>
+__global__ void __launch_bounds__(kBig ? kBlockSV : kBlockV, kBig ? PSDR_LB_SVJP : 6) secondary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                       const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                       const float *__restrict__ d_img) {
+    constexpr int kBlockSV = kBig ? psdr::kBlockSV : kBlockV, kSync = kBig ? PSDR_SYNC_SVJP : 0;
     extern __shared__ float smem[];
-    brute_init<kCfg>(sc, kBlockV);
+    brute_init<kCfg>(sc, kBlockSV);
     SecEdgeAdjoint adj;
-    adj.acc = grad_acc_begin(gl, smem, 0, gl.off_env, rp.smem_grad != 0, false);
+    adj.acc = grad_acc_begin(gl, smem, 0, gl.off_env, rp.smem_grad != 0, false, rp.out_multicast);
     adj.gl = gl;
     adj.d_img = d_img;
     adj.scale = rp.tangent_scale * (sc.sppse > 1 ? 1.f / (float) sc.sppse : 1.f);
     // batches of stage-0 survivors, as in the forward kernel (kernels_impl.cuh sec_edge_batches); this kernel needs the
     // warp-uniform scan loop to keep its lanes together across the three traces of stage 1 (device_path.cuh trace())
     constexpr int kC = kCfg | kCfgUniformScan;
-    sec_edge_batches<kC>(sc, cam, rp, kBlockV, [&](const SecSample &smp) {
+    sec_edge_batches<kC>(sc, cam, rp, kBlockSV, [&](const SecSample &smp) {
         SecEdgeAdjoint a2 = adj;
         if (cam.guided && smp.pdf0 > kEpsilon) a2.scale = adj.scale / smp.pdf0;
         V3f value0, tangent;
         sec_edge_stage1<kC, SecEdgeAdjoint>(sc, cam, smp.cand, value0, tangent, a2);
-    });
+    }, kSync != 0);
     grad_acc_end(adj.acc);
 }
 
 // ---- per-configuration launchers (one translation unit per configuration: vjp_cfg*.cu) -----------------
-template <class K> inline int vjp_grid(K kernel, size_t smem, long long lanes) {   // resident CTAs only (see kernels_impl.cuh)
+template <class K> inline int vjp_grid(K kernel, size_t smem, long long lanes, int kBlockV = psdr::kBlockV) {   // resident CTAs only (see kernels_impl.cuh)
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -157,30 +194,47 @@ template <class K> inline int vjp_grid(K kernel, size_t smem, long long lanes) {
     const long long need = (lanes + kBlockV - 1) / kBlockV, cap = (long long) sms * per_sm;
     return (int) (need < cap ? (need > 0 ? need : 1) : cap);
 }
-constexpr int kSmemGradMaxFloats = 12 * 1024;   // 48 KB: no opt-in needed
+constexpr int kSmemGradMaxFloats = kGradSharedMaxFloats;   // 48 KB: no opt-in needed (grad_layout.h)
+
+extern int g_cta_policy;        // kernels_impl.cuh use_big_cta
+inline bool vjp_big_cta(long long lanes, int block) {
+    if (g_cta_policy == 1) return false;
+    if (g_cta_policy == 2) return true;
+    return lanes >= 4LL * 148 * block;
+}
 
 template <int kCfg> struct AdjointLaunch {
+    template <int kD> static void interior_as(const DScene &sc, const DCamera &cam, const RenderParams &rq, const GradLayout &gl, const float *d_img, size_t bytes, cudaStream_t st) {
+        const long long n = rq.lane_end - rq.lane_begin;
+        if (vjp_big_cta(n, 2 * kBlockIV)) interior_vjp_kernel<kCfg, kD, true><<<vjp_grid(interior_vjp_kernel<kCfg, kD, true>, bytes, n, kBlockIV), kBlockIV, bytes, st>>>(sc, cam, rq, gl, d_img);
+        else interior_vjp_kernel<kCfg, kD, false><<<vjp_grid(interior_vjp_kernel<kCfg, kD, false>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+    }
     static cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
         RenderParams rq = rp;
         rq.smem_grad = gl.off_pe <= kSmemGradMaxFloats ? 1 : 0;
         const size_t bytes = rq.smem_grad ? sizeof(float) * gl.off_pe : 0;
-        const long long n = rp.lane_end - rp.lane_begin;
-        if (rp.max_depth > 4) interior_vjp_kernel<kCfg, 8><<<vjp_grid(interior_vjp_kernel<kCfg, 8>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
-        else interior_vjp_kernel<kCfg, 4><<<vjp_grid(interior_vjp_kernel<kCfg, 4>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+        if (rp.max_depth > 4) interior_as<8>(sc, cam, rq, gl, d_img, bytes, st);
+        else interior_as<4>(sc, cam, rq, gl, d_img, bytes, st);
         return cudaGetLastError();
     }
     static cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
         RenderParams rq = rp;
         const int n = gl.off_se - gl.off_pe;
         rq.smem_grad = n <= kSmemGradMaxFloats ? 1 : 0;
-        primary_edge_vjp_kernel<kCfg><<<vjp_grid(primary_edge_vjp_kernel<kCfg>, rq.smem_grad ? sizeof(float) * n : 0, rp.lane_end - rp.lane_begin), kBlockV, rq.smem_grad ? sizeof(float) * n : 0, st>>>(sc, cam, rq, gl, d_img);
+        const size_t bytes = rq.smem_grad ? sizeof(float) * n : 0;
+        const long long lanes = rp.lane_end - rp.lane_begin;
+        if (vjp_big_cta(lanes, kBlockPV)) primary_edge_vjp_kernel<kCfg, true><<<vjp_grid(primary_edge_vjp_kernel<kCfg, true>, bytes, lanes, kBlockPV), kBlockPV, bytes, st>>>(sc, cam, rq, gl, d_img);
+        else primary_edge_vjp_kernel<kCfg, false><<<vjp_grid(primary_edge_vjp_kernel<kCfg, false>, bytes, lanes), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
         return cudaGetLastError();
     }
     static cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
         RenderParams rq = rp;
         const int n = gl.off_env;            // everything but the envmap texels
         rq.smem_grad = n <= kSmemGradMaxFloats ? 1 : 0;
-        secondary_edge_vjp_kernel<kCfg><<<vjp_grid(secondary_edge_vjp_kernel<kCfg>, rq.smem_grad ? sizeof(float) * n : 0, rp.lane_end - rp.lane_begin), kBlockV, rq.smem_grad ? sizeof(float) * n : 0, st>>>(sc, cam, rq, gl, d_img);
+        const size_t bytes = rq.smem_grad ? sizeof(float) * n : 0;
+        const long long lanes = rp.lane_end - rp.lane_begin;
+        if (vjp_big_cta(lanes, 2 * kBlockSV)) secondary_edge_vjp_kernel<kCfg, true><<<vjp_grid(secondary_edge_vjp_kernel<kCfg, true>, bytes, lanes, kBlockSV), kBlockSV, bytes, st>>>(sc, cam, rq, gl, d_img);
+        else secondary_edge_vjp_kernel<kCfg, false><<<vjp_grid(secondary_edge_vjp_kernel<kCfg, false>, bytes, lanes), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
         return cudaGetLastError();
     }
 };

@@ -45,3 +45,56 @@ def all_reduce_images(*tensors, group=None, dst=None):
         out.append(flat[o:o + t.numel()].view_as(t))
         o += t.numel()
     return tuple(out)
+
+
+class PeerBuffers:
+    """Fused render + reduction over NVLink (include/psdr_b200.h psdr_scene_set_output_multicast).
+
+    Two symmetric float32 buffers of `numel` entries, mapped by every rank of `group` and bound to an NVLS multicast
+    address (torch symmetric memory: cuMemCreate + cuMulticastBindMem underneath).  The term kernels of every rank
+    accumulate into the multicast address with `multimem.red.add.f32`: the NVSwitch adds each contribution into the
+    replica of EVERY GPU, so when the kernels of all ranks are done every rank holds the complete sum -- the all-reduce
+    pass (and its extra read + write of the frame on every GPU) does not exist.
+
+    Protocol of step k (b = k % 2), all stream-ordered, ONE device-side barrier per step:
+      target()  -> (multicast address, local replica) of buffer b, which is all zeros on every rank
+      ... the caller's kernels add into the multicast address ...
+      finish()  -> barrier over the ranks (everyone's adds have landed), copy buffer b out, zero it for step k + 2.
+    Buffer b is next written in step k + 2, i.e. after barrier k + 1, which every rank enters only after its zeroing
+    of step k; step k + 1 writes the OTHER buffer, so a fast rank never adds into a replica that is still being read
+    or cleared."""
+
+    def __init__(self, numel: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if not dist.is_initialized():
+            raise RuntimeError("PeerBuffers needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.numel = int(numel)
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm.empty(self.numel, dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, self.group)
+            if not getattr(h, "multicast_ptr", 0):
+                raise RuntimeError("this node has no NVLS multicast support (symmetric memory multicast_ptr = 0)")
+            t.zero_()
+            self.bufs.append(t)
+            self.handles.append(h)
+        self.k = 0
+        torch.cuda.synchronize(device)
+        self.handles[0].barrier(channel=0)
+        torch.cuda.synchronize(device)
+
+    def target(self):
+        b = self.k % 2
+        return int(self.handles[b].multicast_ptr), self.bufs[b]
+
+    def finish(self, n: int = None):
+        """Barrier, then the summed buffer (first n entries) as a fresh tensor; the slot is cleared for reuse."""
+        b = self.k % 2
+        self.handles[b].barrier(channel=0)
+        out = self.bufs[b][:n].clone() if n is not None else self.bufs[b].clone()
+        self.bufs[b].zero_()
+        self.k += 1
+        return out

@@ -82,3 +82,81 @@ def test_two_gpu_sharded_render_and_autograd():
     print(out)
     assert out["fwd_img"] < 1e-6 and out["fwd_dimg"] < 1e-4, out
     assert out["loss"] < 1e-5 and out["grad_transform"] < 2e-4 and out["grad_radiance"] < 2e-4, out
+
+
+def _worker_peer(rank, world, port, q):
+    """The fused path: kernels add through the NVLS multicast address (dist.PeerBuffers) -- no all-reduce anywhere."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import psdr_jit_b200 as psdr
+    from tests.common import build_product, scenes
+    kw = dict(move_mesh=0, axis_scale=(100.0, 0.0, 0.0))
+    integ = psdr.PathTracer(3)
+    part = build_product(scenes.cbox_meshes(), 96, 96, 8, 8, 8, shard=(rank, world), **kw)
+    out = {"multicast": bool(part.enable_peer_reduction())}
+    if out["multicast"]:
+        full = build_product(scenes.cbox_meshes(), 96, 96, 8, 8, 8, **kw)
+        # several steps: the double-buffer protocol (zeroing, reuse) must hold beyond the first use of each buffer
+        errs = []
+        for step in range(5):
+            img, dimg = integ.renderD_fwd(part, 0, seed=step)
+            assert integ.last_reduced
+            ref_img, ref_dimg = integ.renderD_fwd(full, 0, seed=step)
+            errs.append((float((img - ref_img).norm() / ref_img.norm()), float((dimg - ref_dimg).norm() / ref_dimg.norm())))
+        out["fwd_img"], out["fwd_dimg"] = max(e[0] for e in errs), max(e[1] for e in errs)
+        imgc = integ.renderC(part, 0, seed=3)
+        out["renderC"] = float((imgc - integ.renderC(full, 0, seed=3)).norm() / imgc.norm())
+
+        def grad_of_loss(shard, peer):
+            sc = build_product(scenes.cbox_meshes(), 96, 96, 8, 8, 8, shard=shard)
+            if peer:
+                assert sc.enable_peer_reduction()
+            t = torch.eye(4, dtype=torch.float32, requires_grad=True)
+            sc.param_map["Mesh[0]"].set_transform(t)
+            r = torch.tensor([20.0, 20.0, 8.0], requires_grad=True)
+            sc.param_map["Emitter[0]"].radiance = r
+            sc.configure([0])
+            res = []
+            for step in range(3):
+                if t.grad is not None:
+                    t.grad = None
+                    r.grad = None
+                img = integ.renderD(sc, 0, seed=2 + step)
+                loss = ((img - torch.full_like(img, 0.3)) ** 2).sum()
+                loss.backward()
+                res.append((float(loss), t.grad.clone(), r.grad.clone()))
+            return res
+        a = grad_of_loss((rank, world), True)
+        b = grad_of_loss(None, False)
+        out["loss"] = max(abs(x[0] - y[0]) / abs(y[0]) for x, y in zip(a, b))
+        out["grad_transform"] = max(float((x[1] - y[1]).norm() / y[1].norm()) for x, y in zip(a, b))
+        out["grad_radiance"] = max(float((x[2] - y[2]).norm() / y[2].norm()) for x, y in zip(a, b))
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_fused_multicast_reduction():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_peer, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    print(out)
+    if not out["multicast"]:
+        pytest.skip("no NVLS multicast support on this node")
+    assert out["fwd_img"] < 1e-6 and out["fwd_dimg"] < 1e-4 and out["renderC"] < 1e-6, out
+    assert out["loss"] < 1e-5 and out["grad_transform"] < 2e-4 and out["grad_radiance"] < 2e-4, out
