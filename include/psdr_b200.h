@@ -42,7 +42,9 @@ enum {
      * no reverse-mode gradient */
     PSDR_BSDF_REFLECTANCE_UV = 14,
     PSDR_BSDF_SPECULAR_UV = 15,
-    PSDR_BSDF_ROUGHNESS_UV = 16
+    PSDR_BSDF_ROUGHNESS_UV = 16,
+    PSDR_BSDF_ETA = 17,            /* RoughConductorBSDF.eta (1x1 Bitmap3fD), 3 floats */
+    PSDR_BSDF_K = 18               /* RoughConductorBSDF.k (1x1 Bitmap3fD), 3 floats */
 };
 
 /* Texture slots of a BSDF (psdr_scene_set_bsdf_texture_slot). */
@@ -128,6 +130,14 @@ int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float refle
  * include/psdr/bsdf/microfacet.h:12 (argument order: specular, diffuse, roughness), src/bsdf/microfacet.cpp. */
 int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float specular[3], const float diffuse[3], float roughness,
                                    int two_side);
+
+/* Scene.add_BSDF(RoughConductorBSDF(alpha, eta, k), name, twoSide) -- src/psdr.cpp:286-293,
+ * include/psdr/bsdf/roughconductor.h:10-17 (isotropic form: alpha_u = alpha_v = alpha; specular_reflectance defaults to 1),
+ * src/bsdf/roughconductor.cpp:38-122, conductor Fresnel include/psdr/utils.h:167-183.  eta, k and specular_reflectance
+ * are per-channel constants (1x1 Bitmap3fD) -- parameters PSDR_BSDF_ETA / PSDR_BSDF_K / PSDR_BSDF_SPECULAR; alpha is
+ * PSDR_BSDF_ROUGHNESS.  The anisotropic constructors (alpha_u != alpha_v) are not supported. */
+int psdr_scene_add_bsdf_roughconductor(psdr_scene *s, const char *id, float alpha, const float eta[3], const float k[3], const float specular[3],
+                                       int two_side);
 
 /* DiffuseBSDF.reflectance / MicrofacetBSDF.diffuseReflectance = Bitmap3fD(w, h, data) with more than one texel
  * (src/psdr.cpp:209-219, src/core/bitmap.cpp:46-131): declares the texture resolution of BSDF `index`; afterwards

@@ -121,10 +121,11 @@ struct Edge {  // reference src/shape/mesh.cpp:244-305 (m_edge_indices rows)
 };
 
 struct Bsdf {
-    int type = 0;  // 0 Diffuse, 1 Microfacet
+    int type = 0;  // 0 Diffuse, 1 Microfacet, 2 RoughConductor
     V3d reflectance;  // Diffuse reflectance / Microfacet diffuseReflectance
-    V3d specular;     // Microfacet specularReflectance
-    Dual roughness;   // Microfacet roughness
+    V3d specular;     // Microfacet specularReflectance / RoughConductor specular_reflectance
+    Dual roughness;   // Microfacet roughness / RoughConductor alpha (alpha_u = alpha_v)
+    V3d eta, k;       // RoughConductor eta + i k
     bool two_side = false;
     // bitmap slots with more than one texel (channels interleaved, pixel = y*w + x): 0 reflectance / diffuseReflectance
     // (Bitmap3fD), 1 specularReflectance (Bitmap3fD), 2 roughness (Bitmap1fD); each with the bitmap's uv transform
@@ -907,7 +908,41 @@ template <class S> static V3<S> microfacet_eval(const Bsdf &b, V3<S> wi, V3<S> w
     V3<S> specular = numerator / (denominator + S(1e-6f));
     return (diffuse + specular) * cos_nl;
 }
-// Microfacet::__pdf (microfacet.cpp:108-133), detached
+// fresnel<ad>(eta_r, eta_i, cos_theta_i) for conductors (reference include/psdr/utils.h:167-183), one channel
+template <class S> static S fresnel_conductor(S eta_r, S eta_i, S cos_theta_i) {
+    S cos_theta_i_2 = sqr(cos_theta_i), sin_theta_i_2 = S(1.f) - cos_theta_i_2, sin_theta_i_4 = sqr(sin_theta_i_2);
+    S temp_1 = sqr(eta_r) - sqr(eta_i) - sin_theta_i_2;
+    S a_2_pb_2 = safe_sqrt(sqr(temp_1) + S(4.f) * sqr(eta_i * eta_r));
+    S a = safe_sqrt(S(.5f) * (a_2_pb_2 + temp_1));
+    S term_1 = a_2_pb_2 + cos_theta_i_2, term_2 = S(2.f) * cos_theta_i * a;
+    S r_s = (term_1 - term_2) / (term_1 + term_2);
+    S term_3 = a_2_pb_2 * cos_theta_i_2 + sin_theta_i_4, term_4 = term_2 * sin_theta_i_2;
+    S r_p = r_s * (term_3 - term_4) / (term_3 + term_4);
+    return S(.5f) * (r_s + r_p);
+}
+template <class S> static V3<S> lift_v3(const V3d &v);
+template <> V3<Dual> lift_v3<Dual>(const V3d &v) { return v; }
+template <> V3<float> lift_v3<float>(const V3d &v) { return val(v); }
+// RoughConductor::__eval (reference src/bsdf/roughconductor.cpp:38-66), isotropic
+template <class S> static V3<S> conductor_eval(const Bsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
+    if (b.two_side) {
+        if (std::signbit(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
+    S alpha = rough_of<S>(b, uv);
+    V3<S> H = normalize(wo + wi);
+    S D = ggx_eval<S>(alpha, H);
+    if (val(D) == 0.f) return V3<S>(S(0.f));
+    S G = ggx_smith_g1<S>(alpha, wi, H) * ggx_smith_g1<S>(alpha, wo, H);
+    S result = D * G / (S(4.f) * wi.z);
+    S c = dot(wi, H);
+    V3<S> eta = lift_v3<S>(b.eta), k = lift_v3<S>(b.k);
+    V3<S> F(fresnel_conductor<S>(eta.x, k.x, c), fresnel_conductor<S>(eta.y, k.y, c), fresnel_conductor<S>(eta.z, k.z, c));
+    return F * result * spec_of<S>(b, uv);
+}
+// Microfacet::__pdf (microfacet.cpp:108-133), detached; RoughConductor::__pdf (roughconductor.cpp:70-95) is the same
+// expression with alpha given directly
 static float microfacet_pdf(const Bsdf &b, V3f wi, V3f wo, V2f uv) {
     if (b.two_side) {
         if (std::signbit(wi.z)) wo.z = -wo.z;
@@ -915,7 +950,7 @@ static float microfacet_pdf(const Bsdf &b, V3f wi, V3f wo, V2f uv) {
     }
     V3f m = normalize(wo + wi);
     if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
-    float alpha = sqr(rough_of<float>(b, uv));
+    float alpha = b.type == 2 ? rough_of<float>(b, uv) : sqr(rough_of<float>(b, uv));
     return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
 }
 
@@ -924,6 +959,7 @@ template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3
     if (sc.meshes[its.mesh].bsdf < 0) return V3<S>(S(0.f));   // bsdf == nullptr (envmap bounding mesh): a Dr.Jit vcall on null yields 0
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
     if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo, its.uv);
+    if (b.type == 2) return conductor_eval<S>(b, its.wi, wo, its.uv);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (std::signbit(val(wiz))) wo.z = -wo.z;
@@ -938,7 +974,7 @@ template <class S> static float bsdf_pdf(const Scene &sc, const Its<S> &its, V3<
     if (!active || !its.valid) return 0.f;
     if (sc.meshes[its.mesh].bsdf < 0) return 0.f;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type == 1) return microfacet_pdf(b, val(its.wi), val(wo), val(its.uv));
+    if (b.type != 0) return microfacet_pdf(b, val(its.wi), val(wo), val(its.uv));
     float wiz = val(its.wi.z), woz = val(wo.z);
     if (b.two_side) {
         if (std::signbit(wiz)) woz = -woz;
@@ -983,7 +1019,7 @@ static V2f ggx_sample_visible_11(float cos_theta_i, V2f sample) {
 static BsdfSample microfacet_sample(const Bsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
     BsdfSample bs;
     if (b.two_side) wi.z = std::fabs(wi.z);
-    float alpha = sqr(rough_of<float>(b, uv));
+    float alpha = b.type == 2 ? rough_of<float>(b, uv) : sqr(rough_of<float>(b, uv));   // RoughConductor::__sample (roughconductor.cpp:99-122)
     V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
     float sin_theta_2 = std::fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / std::sqrt(sin_theta_2);
     bool pole = std::fabs(sin_theta_2) <= 4.f * kEpsilon;
@@ -1005,7 +1041,7 @@ template <class S> static BsdfSample bsdf_sample(const Scene &sc, const Its<S> &
     if (!its.valid) return bs;
     if (sc.meshes[its.mesh].bsdf < 0) return bs;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type == 1) return microfacet_sample(b, val(its.wi), sample, active, val(its.uv));
+    if (b.type != 0) return microfacet_sample(b, val(its.wi), sample, active, val(its.uv));
     float wiz = val(its.wi.z);
     if (b.two_side) wiz = std::fabs(wiz);
     V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));  // tail<2>(sample)
@@ -1536,6 +1572,21 @@ int orc_add_microfacet(void *h, const float *spec, const float *diff, float roug
     b.specular = V3d(Dual(spec[0], d ? d[0] : 0.f), Dual(spec[1], d ? d[1] : 0.f), Dual(spec[2], d ? d[2] : 0.f));
     b.reflectance = V3d(Dual(diff[0], d ? d[3] : 0.f), Dual(diff[1], d ? d[4] : 0.f), Dual(diff[2], d ? d[5] : 0.f));
     b.roughness = Dual(rough, d ? d[6] : 0.f);
+    b.two_side = two_side != 0;
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+}
+
+// RoughConductorBSDF(alpha, eta, k[, specular_reflectance]); d = [d_alpha, d_eta(3), d_k(3), d_spec(3)] or NULL
+int orc_add_roughconductor(void *h, float alpha, const float *eta, const float *k, const float *spec, const float *d, int two_side) {
+    Scene *s = (Scene *) h;
+    Bsdf b;
+    b.type = 2;
+    b.roughness = Dual(alpha, d ? d[0] : 0.f);
+    b.eta = V3d(Dual(eta[0], d ? d[1] : 0.f), Dual(eta[1], d ? d[2] : 0.f), Dual(eta[2], d ? d[3] : 0.f));
+    b.k = V3d(Dual(k[0], d ? d[4] : 0.f), Dual(k[1], d ? d[5] : 0.f), Dual(k[2], d ? d[6] : 0.f));
+    b.specular = V3d(Dual(spec[0], d ? d[7] : 0.f), Dual(spec[1], d ? d[8] : 0.f), Dual(spec[2], d ? d[9] : 0.f));
+    b.reflectance = V3d(Dual(0.f), Dual(0.f), Dual(0.f));
     b.two_side = two_side != 0;
     s->bsdfs.push_back(b);
     return (int) s->bsdfs.size() - 1;

@@ -40,6 +40,7 @@ def lib():
         L.orc_set_mis.argtypes = [C.c_void_p, C.c_int]
         L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
         L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
+        L.orc_add_roughconductor.argtypes = [C.c_void_p, C.c_float, _f, _f, _f, _f, C.c_int]
         L.orc_add_envmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int, _f, _f, C.c_float, C.c_float]
         L.orc_set_bsdf_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f, _f]
         L.orc_set_bsdf_texture_slot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f, _f, _f, _f]
@@ -127,6 +128,13 @@ class OracleScene:
         """d = (d_spec[3], d_diff[3], d_rough) flattened to 7 floats, or None"""
         sp, df, dd = _f32(spec), _f32(diff), _f32(d)
         idx = self.L.orc_add_microfacet(self.h, _fp(sp), _fp(df), float(rough), _fp(dd), int(two_side))
+        self.bsdf_ids[name] = idx
+        return idx
+
+    def add_roughconductor(self, name, alpha, eta, k, spec=(1.0, 1.0, 1.0), d=None, two_side=False):
+        """RoughConductorBSDF(alpha, eta, k) (reference src/bsdf/roughconductor.cpp); d = (d_alpha, d_eta[3], d_k[3],
+        d_spec[3]) flattened to 10 floats, or None"""
+        idx = self.L.orc_add_roughconductor(self.h, float(alpha), _fp(_f32(eta)), _fp(_f32(k)), _fp(_f32(spec)), _fp(_f32(d)), int(two_side))
         self.bsdf_ids[name] = idx
         return idx
 

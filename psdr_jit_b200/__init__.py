@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib, scenes  # noqa: F401
 from . import loader as _loader
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "RoughConductorBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
@@ -206,6 +206,52 @@ class MicrofacetBSDF(BSDF):
         b.d_specularReflectance = _f32(self.d_specularReflectance, (3,)).copy()
         b.d_diffuseReflectance = _f32(self.d_diffuseReflectance).copy()
         b.d_roughness = np.float32(self.d_roughness)
+        b.twoSide = self.twoSide
+        return b
+
+
+class RoughConductorBSDF(BSDF):
+    """reference src/psdr.cpp:286-293, include/psdr/bsdf/roughconductor.h, src/bsdf/roughconductor.cpp: GGX conductor with
+    complex index of refraction eta + i k.  ``RoughConductorBSDF(alpha, eta, k)`` with Bitmap1fD / Bitmap3fD arguments as
+    in tutorials/batch_render.ipynb (plain numbers / triples are accepted too).  ``alpha_u`` (= ``alpha_v``: the isotropic
+    form) and ``specular_reflectance`` may be textures; ``eta`` and ``k`` are per-channel constants."""
+
+    def __init__(self, alpha=None, eta=None, k=None, specular_reflectance=None):
+        self.alpha_u = alpha if isinstance(alpha, Bitmap1fD) else (np.float32(0.1) if alpha is None else
+                                                                   (alpha if hasattr(alpha, "requires_grad") else np.float32(alpha)))
+        self.eta = self._const3(eta, 0.0)
+        self.k = self._const3(k, 1.0)
+        sr = specular_reflectance
+        self.specular_reflectance = sr if isinstance(sr, Bitmap3fD) and sr._textured() else self._const3(sr, 1.0)
+        self.d_alpha_u = np.float32(0.0)
+        self.d_eta, self.d_k, self.d_specular_reflectance = (np.zeros(3, dtype=np.float32) for _ in range(3))
+
+    @staticmethod
+    def _const3(v, default):
+        if v is None:
+            return np.full(3, default, dtype=np.float32)
+        if isinstance(v, _Bitmap):
+            if v._textured():
+                raise RuntimeError("RoughConductorBSDF: eta and k are constants (1x1 bitmaps) on this path")
+            v = v.data
+        if hasattr(v, "requires_grad"):
+            return v
+        return _f32(v, (3,)).copy()
+
+    @property
+    def alpha_v(self):
+        return self.alpha_u
+
+    @alpha_v.setter
+    def alpha_v(self, v):
+        self.alpha_u = v
+
+    def _clone(self):
+        cl = lambda x: x._clone() if isinstance(x, _Bitmap) else x      # noqa: E731
+        b = RoughConductorBSDF(cl(self.alpha_u), cl(self.eta), cl(self.k), cl(self.specular_reflectance))
+        b.d_alpha_u = np.float32(self.d_alpha_u)
+        b.d_eta, b.d_k = _f32(self.d_eta, (3,)).copy(), _f32(self.d_k, (3,)).copy()
+        b.d_specular_reflectance = _f32(self.d_specular_reflectance, (3,)).copy()
         b.twoSide = self.twoSide
         return b
 
@@ -452,7 +498,7 @@ class Scene(Object):
         self._register("Sensor", self._sensors)
 
     def add_BSDF(self, bsdf: BSDF, name: str, twoSide: bool = False):
-        if not isinstance(bsdf, (DiffuseBSDF, MicrofacetBSDF)):
+        if not isinstance(bsdf, (DiffuseBSDF, MicrofacetBSDF, RoughConductorBSDF)):
             raise RuntimeError("Unknown BSDF type!")
         if ("BSDF[id=%s]" % name) in self.param_map:
             raise RuntimeError("Duplicate BSDF id: " + name)
@@ -613,6 +659,10 @@ class Scene(Object):
                 s0 = np.full(3, 0.04, np.float32) if isinstance(b.specularReflectance, _Bitmap) else _f32(b.specularReflectance)
                 r0 = 0.8 if isinstance(b.roughness, _Bitmap) else float(_f32(b.roughness).ravel()[0])
                 rc = L.psdr_scene_add_bsdf_microfacet(self._h, b.id.encode(), _fp(s0), _fp(d0), r0, int(b.twoSide))
+            elif isinstance(b, RoughConductorBSDF):
+                a0 = 0.1 if isinstance(b.alpha_u, _Bitmap) else float(_f32(b.alpha_u).ravel()[0])
+                s0 = np.ones(3, np.float32) if isinstance(b.specular_reflectance, _Bitmap) else _f32(b.specular_reflectance, (3,))
+                rc = L.psdr_scene_add_bsdf_roughconductor(self._h, b.id.encode(), a0, _fp(_f32(b.eta, (3,))), _fp(_f32(b.k, (3,))), _fp(s0), int(b.twoSide))
             else:
                 r0 = np.full(3, 0.5, np.float32) if isinstance(b.reflectance, Bitmap3fD) else _f32(b.reflectance)
                 rc = L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(r0), int(b.twoSide))
@@ -698,6 +748,11 @@ class Scene(Object):
                 push_slot(i, _lib.TEX_REFLECTANCE, _lib.BSDF_REFLECTANCE, b.diffuseReflectance, b.d_diffuseReflectance)
                 push_slot(i, _lib.TEX_SPECULAR, _lib.BSDF_SPECULAR, b.specularReflectance, b.d_specularReflectance)
                 push_slot(i, _lib.TEX_ROUGHNESS, _lib.BSDF_ROUGHNESS, b.roughness, b.d_roughness)
+            elif isinstance(b, RoughConductorBSDF):
+                push_slot(i, _lib.TEX_SPECULAR, _lib.BSDF_SPECULAR, b.specular_reflectance, b.d_specular_reflectance)
+                push_slot(i, _lib.TEX_ROUGHNESS, _lib.BSDF_ROUGHNESS, b.alpha_u, b.d_alpha_u)
+                push(_lib.BSDF_ETA, i, np.reshape(_f32(b.eta), (-1,)), np.reshape(_f32(b.d_eta), (-1,)))
+                push(_lib.BSDF_K, i, np.reshape(_f32(b.k), (-1,)), np.reshape(_f32(b.d_k), (-1,)))
             else:
                 push_slot(i, _lib.TEX_REFLECTANCE, _lib.BSDF_REFLECTANCE, b.reflectance, b.d_reflectance)
         for i, e in enumerate(self._emitters):
@@ -723,7 +778,9 @@ class Scene(Object):
                     "BSDF": (("reflectance", _lib.BSDF_REFLECTANCE), ("diffuseReflectance", _lib.BSDF_REFLECTANCE),
                              ("reflectance.data", _lib.BSDF_REFLECTANCE), ("diffuseReflectance.data", _lib.BSDF_REFLECTANCE),
                              ("specularReflectance", _lib.BSDF_SPECULAR), ("roughness", _lib.BSDF_ROUGHNESS),
-                             ("specularReflectance.data", _lib.BSDF_SPECULAR), ("roughness.data", _lib.BSDF_ROUGHNESS)),
+                             ("specularReflectance.data", _lib.BSDF_SPECULAR), ("roughness.data", _lib.BSDF_ROUGHNESS),
+                             ("alpha_u", _lib.BSDF_ROUGHNESS), ("alpha_u.data", _lib.BSDF_ROUGHNESS), ("eta", _lib.BSDF_ETA), ("k", _lib.BSDF_K),
+                             ("specular_reflectance", _lib.BSDF_SPECULAR), ("specular_reflectance.data", _lib.BSDF_SPECULAR)),
                     "Emitter": (("radiance", _lib.EMITTER_RADIANCE),),
                     "EnvironmentMap": (("radiance.data", _lib.ENVMAP_RADIANCE), ("scale", _lib.ENVMAP_SCALE),
                                        ("to_world_left", _lib.ENVMAP_TO_WORLD_LEFT))}

@@ -184,6 +184,7 @@ template <class S> struct BsdfP {
     int type, two_side;
     V3<S> diff, spec;
     S rough;
+    V3<S> eta, k;       // RoughConductor
 };
 struct BsdfVals {       // the three parameter slots of a BSDF evaluated at a vertex (constants or texture lookups)
     V3f refl, spec;
@@ -196,6 +197,8 @@ template <class S> __device__ __forceinline__ BsdfP<S> bsdf_params(const DBsdf &
     p.diff = V3<S>(S(v.refl.x), S(v.refl.y), S(v.refl.z));
     p.spec = V3<S>(S(v.spec.x), S(v.spec.y), S(v.spec.z));
     p.rough = S(v.rough);
+    p.eta = V3<S>(S(b.eta[0]), S(b.eta[1]), S(b.eta[2]));
+    p.k = V3<S>(S(b.kk[0]), S(b.kk[1]), S(b.kk[2]));
     return p;
 }
 template <class S> __device__ __forceinline__ S iso_smith_g1(S alpha, S vz, S vdoth) {
@@ -218,6 +221,17 @@ template <class S> __device__ __forceinline__ void iso_specular(S rough, S ci, S
     e = exp2_(vh * (S(-5.55473f) * vh - S(6.8316f)));
     dg = ggx * iso_smith_g1<S>(alpha, ci, vh) * iso_smith_g1<S>(alpha, co, vh) / (S(4.f) * co * ci + S(1e-6f));
 }
+// RoughConductor (src/bsdf/roughconductor.cpp:38-66) in the same quantities: D G / (4 ci), and <wi, H>
+template <class S> __device__ __forceinline__ void iso_conductor(S alpha, S ci, S co, S cio, S &res, S &vh) {
+    const S L = sqrt_(S(2.f) + S(2.f) * cio);
+    const S hz = (ci + co) / L;
+    vh = (S(1.f) + cio) / L;
+    const S s2 = S(1.f) - sqr(hz);
+    const S t = (val(s2) > 0.f ? s2 : S(0.f)) / sqr(alpha) + sqr(hz);
+    S ggx = rcp_(S(kPi) * sqr(alpha) * sqr(t));
+    if (!(val(ggx) * val(hz) > 1e-20f)) ggx = S(0.f);
+    res = ggx * iso_smith_g1<S>(alpha, ci, vh) * iso_smith_g1<S>(alpha, co, vh) / (S(4.f) * ci);
+}
 template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_iso(const BsdfP<S> &b, S ci, S co, S cio) {
     if (b.two_side) {
         if (signbit_(val(ci))) co = -co;
@@ -229,6 +243,13 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_iso(const Bsd
         iso_specular<S>(b.rough, ci, co, cio, dg, e);
         const V3<S> fresnel = b.spec + (V3<S>(S(1.f)) - b.spec) * e;
         return (b.diff * S(kInvPi) + fresnel * dg) * co;
+    }
+    if ((kCfg & kCfgFull) && b.type == 2) {
+        S res, vh;
+        iso_conductor<S>(b.rough, ci, co, cio, res, vh);
+        if (val(res) == 0.f) return V3<S>(S(0.f));
+        const V3<S> F(fresnel_conductor<S>(b.eta.x, b.k.x, vh), fresnel_conductor<S>(b.eta.y, b.k.y, vh), fresnel_conductor<S>(b.eta.z, b.k.z, vh));
+        return F * res * b.spec;
     }
     return b.diff * S(kInvPi) * co;
 }
@@ -246,7 +267,7 @@ template <int kCfg> __device__ __forceinline__ BsdfJet bsdf_jet(const DBsdf &b, 
     j.d_ci = W.x * a.x.d + W.y * a.y.d + W.z * a.z.d;
     j.d_co = W.x * c.x.d + W.y * c.y.d + W.z * c.z.d;
     j.d_cio = 0.f;
-    if ((kCfg & kCfgFull) && b.type == 1) {
+    if ((kCfg & kCfgFull) && b.type != 0) {
         const V3d e = bsdf_iso<Dual, kCfg>(p, Dual(ci), Dual(co), Dual(cio, 1.f));
         j.d_cio = W.x * e.x.d + W.y * e.y.d + W.z * e.z.d;
     }
@@ -281,6 +302,33 @@ template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAc
     }
     if (!(ci > 0.f && co > 0.f)) return;
     const int base = gl.off_bsdf + kGradBsdf * bi;
+    if ((kCfg & kCfgFull) && b.type == 2) {
+        // f_c = F(eta_c, k_c, vh) res(alpha) spec_c
+        Dual res, vh;
+        iso_conductor<Dual>(Dual(bv.rough, 1.f), Dual(ci), Dual(co), Dual(cio), res, vh);
+        if (res.v == 0.f) return;
+        const float sp[3] = {bv.spec.x, bv.spec.y, bv.spec.z}, Wc[3] = {W.x, W.y, W.z};
+        float F[3], g_alpha = 0.f;
+        V3f g_eta, g_k;
+        float *ge = &g_eta.x, *gk = &g_k.x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const Dual fe = fresnel_conductor<Dual>(Dual(b.eta[c], 1.f), Dual(b.kk[c]), Dual(vh.v));
+            const Dual fk = fresnel_conductor<Dual>(Dual(b.eta[c]), Dual(b.kk[c], 1.f), Dual(vh.v));
+            F[c] = fe.v;
+            ge[c] = Wc[c] * fe.d * res.v * sp[c] * scale;
+            gk[c] = Wc[c] * fk.d * res.v * sp[c] * scale;
+            g_alpha += Wc[c] * F[c] * sp[c];
+        }
+        acc.add3(base + 8, g_eta);
+        acc.add3(base + 12, g_k);
+        const V3f g_spec(W.x * F[0] * res.v * scale, W.y * F[1] * res.v * scale, W.z * F[2] * res.v * scale);
+        if (b.tex[1].w > 0) tex_slot_grad(acc, gl, b.tex[1], uv, g_spec, uv_bar);
+        else acc.add3(base + 4, g_spec);
+        if (b.tex[2].w > 0) tex_slot_grad(acc, gl, b.tex[2], uv, V3f(g_alpha * res.d * scale, 0.f, 0.f), uv_bar);
+        else acc.add(base + 3, g_alpha * res.d * scale);
+        return;
+    }
     const float k = kInvPi * co * scale;
     if ((kCfg & kCfgFull) && b.tex[0].w > 0) tex_slot_grad(acc, gl, b.tex[0], uv, W * k, uv_bar);
     else acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));

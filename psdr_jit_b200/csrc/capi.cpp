@@ -188,12 +188,32 @@ int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float sp
     return (int) sc.bsdfs.size() - 1;
 }
 
+int psdr_scene_add_bsdf_roughconductor(psdr_scene *s, const char *id, float alpha, const float eta[3], const float k[3], const float specular[3],
+                                       int two_side) {
+    if (!s || !id || !eta || !k || !specular) { fail("null argument"); return -1; }
+    Scene &sc = s->sc;
+    if (sc.find_bsdf(id) >= 0) { fail(std::string("Duplicate BSDF id: ") + id); return -1; }
+    HBsdf b;
+    b.id = id;
+    b.type = 2;
+    b.reflectance = V3d(Dual(0.f), Dual(0.f), Dual(0.f));
+    b.specular = V3d(Dual(specular[0]), Dual(specular[1]), Dual(specular[2]));
+    b.roughness = Dual(alpha);
+    b.eta = V3d(Dual(eta[0]), Dual(eta[1]), Dual(eta[2]));
+    b.k = V3d(Dual(k[0]), Dual(k[1]), Dual(k[2]));
+    b.two_side = two_side != 0;
+    sc.bsdfs.push_back(b);
+    sc.configured = false;
+    return (int) sc.bsdfs.size() - 1;
+}
+
 int psdr_scene_set_bsdf_texture_slot(psdr_scene *s, int index, int slot, int w, int h) {
     if (!s) return fail("null scene");
     Scene &sc = s->sc;
     if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
     if (slot < 0 || slot > 2) return fail("invalid texture slot");
-    if (slot > 0 && sc.bsdfs[index].type != 1) return fail("specular / roughness textures need a MicrofacetBSDF");
+    if (slot > 0 && sc.bsdfs[index].type == 0) return fail("specular / roughness textures need a MicrofacetBSDF or a RoughConductorBSDF");
+    if (slot == 0 && sc.bsdfs[index].type == 2) return fail("a RoughConductorBSDF has no diffuse reflectance");
     if (w < 1 || h < 1 || (w * h > 1 && (w < 2 || h < 2))) return fail("Bitmap: invalid resolution!");
     HBsdf::Tex &t = sc.bsdfs[index].tex[slot];
     if (w * h == 1) { t.w = t.h = 0; t.data.clear(); t.ddata.clear(); }
@@ -343,6 +363,14 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
             if (rc == 0) break;
             if (n != 1) return fail("roughness is 1 float");
             put(sc.bsdfs[index].roughness, data[0]);
+            break;
+        }
+        case PSDR_BSDF_ETA: case PSDR_BSDF_K: {
+            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            if (sc.bsdfs[index].type != 2) return fail("eta / k belong to a RoughConductorBSDF");
+            if (n != 3) return fail("eta / k are 3 floats");
+            V3d &v = kind == PSDR_BSDF_ETA ? sc.bsdfs[index].eta : sc.bsdfs[index].k;
+            put(v.x, data[0]); put(v.y, data[1]); put(v.z, data[2]);
             break;
         }
         case PSDR_BSDF_REFLECTANCE_UV: case PSDR_BSDF_SPECULAR_UV: case PSDR_BSDF_ROUGHNESS_UV: {
@@ -793,6 +821,12 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
             if (index < 0 || index >= (int) g.bsdf_rough.size()) return fail("invalid BSDF index");
             if (index < (int) g.bsdf_tex[2].size() && !g.bsdf_tex[2][index].empty()) return copy_tex(g.bsdf_tex[2][index]);
             return copy(g.bsdf_rough.data() + index, 1);
+        case PSDR_BSDF_ETA:
+            if (index < 0 || 3 * index + 3 > (int) g.bsdf_eta.size()) return fail("invalid BSDF index");
+            return copy(g.bsdf_eta.data() + 3 * index, 3);
+        case PSDR_BSDF_K:
+            if (index < 0 || 3 * index + 3 > (int) g.bsdf_k.size()) return fail("invalid BSDF index");
+            return copy(g.bsdf_k.data() + 3 * index, 3);
         case PSDR_EMITTER_RADIANCE:
             if (index < 0 || 3 * index + 3 > (int) g.emitter_rad.size()) return fail("invalid emitter index");
             return copy(g.emitter_rad.data() + 3 * index, 3);

@@ -28,6 +28,19 @@ __device__ __forceinline__ void out_add(float *p, float v, int mc) {
     if (mc) asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
     else atomicAdd(p, v);
 }
+// Persistent-loop schedule of the interior kernels.  Iteration k covers local lanes [k G B, (k + 1) G B) (G CTAs of B
+// threads); CTA c takes chunk (c + k) mod G of it.  With the plain grid-stride loop (chunk c every time) a CTA revisits
+// the same image COLUMNS whenever G B / spp (x the number of ranks) shares a large factor with the image width: the
+// interior adjoint's 2368 pixels per iteration at 512 columns give 8 column sets, at 8 ranks every iteration of a CTA
+// lands on the same 64 columns, and the kernel ends with the CTAs that own the expensive columns -- the sharded
+// interior adjoint took 1.5x its share at 4 ranks and 1.65x at 8 (profiles/r02q).  Shifting by one chunk per iteration
+// walks every CTA across the row.
+__device__ __forceinline__ long long rotated_lane(long long k, int block) {
+    const unsigned G = gridDim.x;
+    unsigned chunk = blockIdx.x + (unsigned) (k % G);
+    if (chunk >= G) chunk -= G;
+    return (k * (long long) G + chunk) * block + threadIdx.x;
+}
 __device__ __forceinline__ long long global_lane(const RenderParams &rp, long long j) {
     return rp.shard_world <= 1 ? rp.lane_begin + j : (((j >> 5) * rp.shard_world + rp.shard_rank) << 5) + (j & 31);
 }
@@ -634,12 +647,52 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> microfacet_eval(co
     return (diffuse + specular) * cos_nl;
 }
 
+// Fresnel reflectance of a conductor with complex index eta + i k, unpolarised (reference include/psdr/utils.h:167-183)
+template <class S> __device__ __forceinline__ S fresnel_conductor(S eta, S k, S cos_theta_i) {
+    const S c2 = sqr(cos_theta_i), s2 = S(1.f) - c2, s4 = sqr(s2);
+    const S temp_1 = sqr(eta) - sqr(k) - s2;
+    const S a_2_pb_2 = safe_sqrt(sqr(temp_1) + S(4.f) * sqr(k * eta));
+    const S a = safe_sqrt(S(.5f) * (a_2_pb_2 + temp_1));
+    const S term_1 = a_2_pb_2 + c2, term_2 = S(2.f) * cos_theta_i * a;
+    const S r_s = (term_1 - term_2) / (term_1 + term_2);
+    const S term_3 = a_2_pb_2 * c2 + s4, term_4 = term_2 * s2;
+    const S r_p = r_s * (term_3 - term_4) / (term_3 + term_4);
+    return S(.5f) * (r_s + r_p);
+}
+template <class S> __device__ __forceinline__ V3<S> bsdf_eta(const DBsdf &b);
+template <> __device__ __forceinline__ V3f bsdf_eta<float>(const DBsdf &b) { return V3f(b.eta[0], b.eta[1], b.eta[2]); }
+template <> __device__ __forceinline__ V3d bsdf_eta<Dual>(const DBsdf &b) { return V3d(Dual(b.eta[0], b.d_eta[0]), Dual(b.eta[1], b.d_eta[1]), Dual(b.eta[2], b.d_eta[2])); }
+template <class S> __device__ __forceinline__ V3<S> bsdf_k(const DBsdf &b);
+template <> __device__ __forceinline__ V3f bsdf_k<float>(const DBsdf &b) { return V3f(b.kk[0], b.kk[1], b.kk[2]); }
+template <> __device__ __forceinline__ V3d bsdf_k<Dual>(const DBsdf &b) { return V3d(Dual(b.kk[0], b.d_kk[0]), Dual(b.kk[1], b.d_kk[1]), Dual(b.kk[2], b.d_kk[2])); }
+
+// RoughConductor::__eval (reference src/bsdf/roughconductor.cpp:38-66), isotropic (alpha_u = alpha_v):
+// F(eta, k, <wi, H>) D(H) G(wi, wo, H) / (4 cos_theta_i) * specular_reflectance
+template <class S, int kCfg> __device__ __forceinline__ V3<S> conductor_eval(const DBsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
+    if (b.two_side) {
+        if (signbit_(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
+    const S alpha = bsdf_roughness<S>(b, uv);
+    const V3<S> H = normalize(wo + wi);
+    const S D = ggx_eval<S>(alpha, H);
+    if (val(D) == 0.f) return V3<S>(S(0.f));
+    const S G = ggx_smith_g1<S>(alpha, wi, H) * ggx_smith_g1<S>(alpha, wo, H);
+    const S result = D * G / (S(4.f) * wi.z);
+    const S cos_ih = dot(wi, H);
+    const V3<S> eta = bsdf_eta<S>(b), k = bsdf_k<S>(b);
+    const V3<S> F(fresnel_conductor<S>(eta.x, k.x, cos_ih), fresnel_conductor<S>(eta.y, k.y, cos_ih), fresnel_conductor<S>(eta.z, k.z, cos_ih));
+    return F * result * bsdf_specular<S>(b, uv);
+}
+
 template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return V3<S>(S(0.f));
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return V3<S>(S(0.f));
     const DBsdf &b = sc.bsdfs[bi];
     if ((kCfg & kCfgFull) && b.type == 1) return microfacet_eval<S, kCfg>(b, its.wi, wo, its.uv);
+    if ((kCfg & kCfgFull) && b.type == 2) return conductor_eval<S, kCfg>(b, its.wi, wo, its.uv);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (signbit_(val(wiz))) wo.z = -wo.z;
@@ -657,7 +710,8 @@ __device__ __forceinline__ float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo, 
     }
     const V3f m = normalize(wo + wi);
     if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
-    const float alpha = sqr(bsdf_roughness<float>(b, uv));
+    // RoughConductor::__pdf (src/bsdf/roughconductor.cpp:70-95) is the same expression with alpha given directly
+    const float alpha = b.type == 2 ? bsdf_roughness<float>(b, uv) : sqr(bsdf_roughness<float>(b, uv));
     return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
 }
 
@@ -665,7 +719,7 @@ template <class S, int kCfg> __device__ __forceinline__ float bsdf_pdf(const DSc
     if (!active || !its.valid) return 0.f;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return 0.f;
-    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo), val(its.uv));
+    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type != 0) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo), val(its.uv));
     float wiz = val(its.wi.z), woz = val(wo.z);
     if (sc.bsdfs[bi].two_side) {
         if (signbit_(wiz)) woz = -woz;
@@ -709,7 +763,8 @@ __device__ __forceinline__ V2f ggx_sample_visible_11(float cos_theta_i, V2f samp
 __device__ __forceinline__ BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
     BsdfSample bs;
     if (b.two_side) wi.z = fabsf(wi.z);
-    const float alpha = sqr(bsdf_roughness<float>(b, uv));
+    // RoughConductor::__sample (src/bsdf/roughconductor.cpp:99-122): the same visible-normal sampling, alpha given directly
+    const float alpha = b.type == 2 ? bsdf_roughness<float>(b, uv) : sqr(bsdf_roughness<float>(b, uv));
     const V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
     const float sin_theta_2 = fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / sqrtf(sin_theta_2);
     const bool pole = fabsf(sin_theta_2) <= 4.f * kEpsilon;
@@ -734,7 +789,7 @@ template <class S, int kCfg> __device__ __forceinline__ BsdfSample bsdf_sample(c
     if (!its.valid) return bs;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return bs;
-    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type == 1) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active, val(its.uv));
+    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type != 0) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active, val(its.uv));
     float wiz = val(its.wi.z);
     if (sc.bsdfs[bi].two_side) wiz = fabsf(wiz);
     const V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));

@@ -155,6 +155,10 @@ void upload_scene(Scene &sc) {
         d.d_spec[0] = b.specular.x.d; d.d_spec[1] = b.specular.y.d; d.d_spec[2] = b.specular.z.d;
         d.rough = b.roughness.v;
         d.d_rough = b.roughness.d;
+        d.eta[0] = b.eta.x.v; d.eta[1] = b.eta.y.v; d.eta[2] = b.eta.z.v;
+        d.d_eta[0] = b.eta.x.d; d.d_eta[1] = b.eta.y.d; d.d_eta[2] = b.eta.z.d;
+        d.kk[0] = b.k.x.v; d.kk[1] = b.k.y.v; d.kk[2] = b.k.z.v;
+        d.d_kk[0] = b.k.x.d; d.d_kk[1] = b.k.y.d; d.d_kk[2] = b.k.z.d;
         dbsdf.push_back(d);
     }
     for (const HEmitter &e : sc.emitters) {

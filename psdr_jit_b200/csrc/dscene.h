@@ -77,11 +77,13 @@ struct DEnv {
 struct DBsdf {
     float refl[3];           // Diffuse: reflectance; Microfacet: diffuseReflectance
     float d_refl[3];
-    int type;                // 0 Diffuse, 1 Microfacet
+    int type;                // 0 Diffuse, 1 Microfacet, 2 RoughConductor
     int two_side;
-    float spec[3];           // Microfacet: specularReflectance (F0)
+    float spec[3];           // Microfacet: specularReflectance (F0); RoughConductor: specular_reflectance
     float d_spec[3];
-    float rough, d_rough;    // Microfacet: roughness (alpha = roughness^2)
+    float rough, d_rough;    // Microfacet: roughness (alpha = roughness^2); RoughConductor: alpha (alpha_u = alpha_v)
+    float eta[3], d_eta[3];  // RoughConductor: complex index of refraction eta + i k per channel
+    float kk[3], d_kk[3];
     // texture slots (texture.h DTex): 0 reflectance / diffuseReflectance (Bitmap3fD), 1 specularReflectance (Bitmap3fD),
     // 2 roughness (Bitmap1fD); w * h == 0: the constant above
     DTex tex[3];

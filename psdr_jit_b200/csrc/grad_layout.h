@@ -6,11 +6,11 @@ namespace psdr {
 // per triangle 24 floats: 0 p0 | 3 e1 | 6 e2 | 9 area | 10 n0 | 13 n1 | 16 n2 | 19 fn | 22,23 pad
 constexpr int kGradTri = 24;
 constexpr int kGradCam = 40;
-constexpr int kGradBsdf = 8;
+constexpr int kGradBsdf = 16;
 constexpr int kGradEnvHead = 16;
 struct GradLayout {
     float *base;      // global table (device)
-    int off_bsdf;     // kGradBsdf floats per BSDF: 0..2 d reflectance (diffuse) | 3 d roughness | 4..6 d specular
+    int off_bsdf;     // kGradBsdf floats per BSDF: 0..2 d reflectance (diffuse) | 3 d roughness / alpha | 4..6 d specular | 8..10 d eta | 12..14 d k
     int off_emit;     // 4 floats per emitter (d radiance rgb)
     int off_cam;      // 40 floats: 0..15 d to_world | 16..31 d world_to_sample | 32..34 d pos | 35..37 d dir
     int off_pe;       // 4 floats per primary edge of the rendered sensor (d p0.xy, d p1.xy)

@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(kBig ? kBlockI : kBlock, kBig ? (IsDual<S>::va
     const long long span = rp.lane_end - rp.lane_begin;
     const long long span_pad = (span + kBlockI - 1) / kBlockI * kBlockI;   // keep warps converged for the shuffles (and the trip count CTA-uniform)
     const float inv_spp = sc.spp > 1 ? 1.f / (float) sc.spp : 1.f;
+    // (plain grid-stride loop: the rotated schedule of the interior adjoint, device_path.cuh rotated_lane, measured 1-5 %
+    // slower here -- a 640-thread CTA already spans 20 pixels of a row)
     for (long long j = (long long) blockIdx.x * kBlockI + threadIdx.x; j < span_pad; j += stride) {
         if (kSync) __syncthreads();
         const long long gi = global_lane(rp, j);

@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + kBlockIV - 1) / kBlockIV * kBlockIV;   // CTA-uniform trip count
-    for (long long j = (long long) blockIdx.x * kBlockIV + threadIdx.x; j < span_pad; j += stride) {
+    const long long iters = (span_pad + stride - 1) / stride;
+    for (long long k = 0; k < iters; ++k) {
+        const long long j = rotated_lane(k, kBlockIV);     // (CTA-uniform: span_pad is a multiple of the CTA size)
+        if (j >= span_pad) continue;
         // the whole body is warp-uniform control flow: lanes past the end of the span ride along inactive (the
         // span is padded to 32), so the barriers here and inside path_adjoint are full-mask barriers at the top
         // level -- the only form that really re-converges the warp (see path_adjoint)

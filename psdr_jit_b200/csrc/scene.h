@@ -30,10 +30,11 @@ struct HEdge {
 
 struct HBsdf {
     std::string id;
-    int type = 0;             // 0 Diffuse, 1 Microfacet
+    int type = 0;             // 0 Diffuse, 1 Microfacet, 2 RoughConductor
     V3d reflectance;          // Diffuse reflectance / Microfacet diffuseReflectance
-    V3d specular;             // Microfacet specularReflectance
-    Dual roughness;           // Microfacet roughness
+    V3d specular;             // Microfacet specularReflectance / RoughConductor specular_reflectance
+    Dual roughness;           // Microfacet roughness / RoughConductor alpha
+    V3d eta, k;               // RoughConductor eta, k
     bool two_side = false;
     // texture slots (Bitmap with more than one texel; channels interleaved, pixel = y*w + x):
     // 0 reflectance / diffuseReflectance (3 channels), 1 specularReflectance (3), 2 roughness (1);
@@ -129,7 +130,7 @@ struct ParamGrads {
     struct CamG { double to_world[3][16]; };
     std::vector<MeshG> meshes;
     std::vector<CamG> cameras;
-    std::vector<double> bsdf_refl, emitter_rad, bsdf_spec;   // 3 per object
+    std::vector<double> bsdf_refl, emitter_rad, bsdf_spec, bsdf_eta, bsdf_k;   // 3 per object
     std::vector<double> bsdf_rough;                          // 1 per BSDF
     std::vector<float> env_radiance;                         // 3*w*h
     std::vector<std::vector<float>> bsdf_tex[3];             // per BSDF and texture slot: channels*w*h (empty: not textured)

@@ -251,10 +251,14 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
     }
     grads.bsdf_spec.assign(3 * bsdfs.size(), 0.0);
     grads.bsdf_rough.assign(bsdfs.size(), 0.0);
+    grads.bsdf_eta.assign(3 * bsdfs.size(), 0.0);
+    grads.bsdf_k.assign(3 * bsdfs.size(), 0.0);
     for (size_t i = 0; i < bsdfs.size(); ++i) {
         for (int c = 0; c < 3; ++c) {
             grads.bsdf_refl[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + c];
             grads.bsdf_spec[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + 4 + c];
+            grads.bsdf_eta[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + 8 + c];
+            grads.bsdf_k[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + 12 + c];
         }
         grads.bsdf_rough[i] = table[gl.off_bsdf + kGradBsdf * i + 3];
     }
