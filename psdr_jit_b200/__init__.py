@@ -791,6 +791,8 @@ class Scene(Object):
             o = getattr(o, part, None)
             if o is None:
                 return None
+        if isinstance(o, _Bitmap):        # a bitmap-valued field named without ".data": its texels are the parameter
+            o = o.data
         return o
 
     def _fields_of(self, kind_name, o):
@@ -801,12 +803,13 @@ class Scene(Object):
 
     def _grad_leaves(self):
         """[(tensor, kind, index)] for every parameter field that is a torch tensor requiring grad."""
-        out = []
+        out, seen = [], set()
         for kind_name, objs in self._objects():
             for i, o in enumerate(objs):
                 for field, kind in self._fields_of(kind_name, o):
                     t = self._field(o, field)
-                    if hasattr(t, "requires_grad") and t.requires_grad:
+                    if hasattr(t, "requires_grad") and t.requires_grad and id(t) not in seen:    # ("x" and "x.data" name the same texels)
+                        seen.add(id(t))
                         out.append((t, kind, i))
         return out
 

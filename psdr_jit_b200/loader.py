@@ -173,8 +173,11 @@ def load_scene_xml(scene, root, base_dir: str = "."):
             b = psdr.MicrofacetBSDF(texture(_child_by_name(node, {"specular_reflectance", "specularReflectance"}), 3),
                                     texture(_child_by_name(node, {"diffuse_reflectance", "diffuseReflectance"}), 3),
                                     texture(_child_by_name(node, {"roughness"}), 1))
-        elif t in ("roughconductor", "roughdielectric", "normalmap"):
-            raise RuntimeError("BSDF type '%s' is not implemented by this port (Diffuse and Microfacet are)" % t)
+        elif t == "roughconductor":      # scene_loader.cpp:334-345: alpha (-> alpha_u = alpha_v), eta, k
+            b = psdr.RoughConductorBSDF(texture(_child_by_name(node, {"alpha"}), 1), texture(_child_by_name(node, {"eta"}), 3),
+                                        texture(_child_by_name(node, {"k"}), 3))
+        elif t in ("roughdielectric", "normalmap"):
+            raise RuntimeError("BSDF type '%s' is not implemented by this port (Diffuse, Microfacet and RoughConductor are)" % t)
         else:
             raise RuntimeError("Unsupported BSDF: " + str(t))
         scene.add_BSDF(b, bid)

@@ -33,6 +33,11 @@ def is_microfacet(params):
     return len(params) == 3 and hasattr(params[0], "__len__")
 
 
+def is_conductor(params):
+    """("name", {"conductor": (alpha, eta[3], k[3])}) or with a 4th entry specular_reflectance[3]"""
+    return isinstance(params, dict) and "conductor" in params
+
+
 def test_envmap(w=32, h=16, seed=0):
     """synthetic lat-long environment map (BASELINE config 3 recipe: rng.random**4 * 4), [h*w, 3]"""
     rng = np.random.default_rng(seed)
@@ -61,7 +66,10 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
     sc = OracleScene(w, h, spp, sppe, sppse)
     for name, params in (bsdfs or scenes.CBOX_BSDFS):
         d = d_bsdf.get(name) if d_bsdf else None
-        if is_microfacet(params):
+        if is_conductor(params):        # d = (d_alpha, d_eta[3], d_k[3], d_spec[3])
+            c = params["conductor"]
+            sc.add_roughconductor(name, c[0], c[1], c[2], c[3] if len(c) > 3 else (1.0, 1.0, 1.0), d=d)
+        elif is_microfacet(params):
             sc.add_microfacet(name, params[0], params[1], params[2], d=d)
         else:
             sc.add_diffuse(name, params, d_refl=d)
@@ -95,7 +103,14 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
     sc.add_Sensor(sensor)
     for name, params in (bsdfs or scenes.CBOX_BSDFS):
         d = d_bsdf.get(name) if d_bsdf else None
-        if is_microfacet(params):
+        if is_conductor(params):
+            c = params["conductor"]
+            b = psdr.RoughConductorBSDF(psdr.Bitmap1fD(float(c[0])), psdr.Bitmap3fD(list(c[1])), psdr.Bitmap3fD(list(c[2])))
+            if len(c) > 3:
+                b.specular_reflectance = np.float32(c[3])
+            if d is not None:
+                b.d_alpha_u, b.d_eta, b.d_k, b.d_specular_reflectance = np.float32(d[0]), np.float32(d[1:4]), np.float32(d[4:7]), np.float32(d[7:10])
+        elif is_microfacet(params):
             b = psdr.MicrofacetBSDF(params[0], params[1], params[2])
             if d is not None:
                 b.d_specularReflectance, b.d_diffuseReflectance, b.d_roughness = np.float32(d[0:3]), np.float32(d[3:6]), np.float32(d[6])
@@ -112,7 +127,9 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
                     bm.scale, bm.rotate, bm.translate = np.float32(t["xform"][0]), np.float32(t["xform"][1]), np.float32(t["xform"][2:4])
                 if t.get("d_xform") is not None:
                     bm.d_scale, bm.d_rotate, bm.d_translate = np.float32(t["d_xform"][0]), np.float32(t["d_xform"][1]), np.float32(t["d_xform"][2:4])
-                if not is_microfacet(params):
+                if is_conductor(params):
+                    setattr(b, (None, "specular_reflectance", "alpha_u")[slot], bm)
+                elif not is_microfacet(params):
                     b.reflectance = bm
                 else:
                     setattr(b, ("diffuseReflectance", "specularReflectance", "roughness")[slot], bm)

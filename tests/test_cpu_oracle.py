@@ -351,3 +351,29 @@ def test_oracle_direct_integrator_vs_reference_golden(oracle):
         img, d = osc.render(1, seed=0, mode=1, terms=1)
         r, nbad, r_ex = compare_stats(2.0 * d, g["gradD_int_mis%d" % mis], flip_rel=1e-3)
         assert nbad < 250 and r_ex < 1e-4, (mis, r, nbad, r_ex)
+
+
+def test_oracle_roughconductor_vs_reference_golden(oracle):
+    """RoughConductorBSDF (tests/golden/conductor.npz, tools/ref_golden8.py: the RUNNING reference, gold eta / k of
+    tutorials/batch_render.ipynb on the two blocks).  The specular lobe amplifies the reference's approximate rcp / sqrt:
+    a few pixels flip a hit; the rest agrees to ~1e-4 (image) / ~2e-3 (derivative images, which the reference scales by 2)."""
+    g = np.load(os.path.join(GOLDEN, "conductor.npz"))
+    eta, k = g["eta"], g["k"]
+
+    def bs(alpha):
+        return [(n, {"conductor": (alpha, eta, k)}) if n == "cat" else (n, p) for n, p in scenes.CBOX_BSDFS]
+    for tag, alpha in (("a15", 0.15), ("a01", 0.01)):
+        img = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bs(alpha)).render(3, seed=0, mode=0)
+        r, nbad, r_ex = compare_stats(img, g["imgC_" + tag])
+        assert nbad <= 16 and r_ex < 5e-4, (tag, r, nbad, r_ex)
+    img, d = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bs(0.15), move_mesh=0, axis_scale=(100.0, 0.0, 0.0)).render(3, seed=0, mode=1, terms=1)
+    r, nbad, r_ex = compare_stats(img, g["imgD_geo"])
+    assert nbad <= 128 and r_ex < 2e-3, (r, nbad, r_ex)
+    r, nbad, r_ex = compare_stats(2.0 * d, g["gradD_geo"])
+    assert nbad <= 256 and r_ex < 5e-3, (r, nbad, r_ex)
+    for tag, j in (("alpha", 0), ("eta", 1), ("k", 5)):
+        dd = np.zeros(10, np.float32)
+        dd[j] = 1.0
+        _, d = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bs(0.15), d_bsdf={"cat": dd}).render(3, seed=0, mode=1, terms=1)
+        r, nbad, r_ex = compare_stats(2.0 * d, g["gradD_" + tag])
+        assert nbad <= 256 and r_ex < 5e-3, (tag, r, nbad, r_ex)
