@@ -167,7 +167,6 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # N > 1: the reduction over ranks is fused into the term kernels (multimem.red through the NVSwitch into every rank's
     # replica, psdr_jit_b200/dist.py PeerBuffers); without NVLS multicast on the node: one NCCL all-reduce per step
     peer = world > 1 and not args.no_peer and sc.enable_peer_reduction()
-    _lib.check(L.psdr_scene_enable_timing(sc._h, 1))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
     n_samples = W * H * (SPP + SPPE + SPPSE)
     st = torch.cuda.current_stream()
@@ -201,13 +200,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = psdr.kernel_launch_count() - launches0
-    # per-kernel device times from a few extra steps OUTSIDE the timed region: reading the library's events waits for the
-    # step, which would serialise host and device every step (at 8 GPUs a step is 1.4 ms and that wait cost 5 % of it)
+    # per-kernel device times from a few extra steps OUTSIDE the timed region, with the library's per-kernel events on:
+    # that mode runs the three term kernels back to back on one stream (the timed steps above overlap their tails on
+    # three streams, csrc/capi.cpp TermStreams), and reading the events waits for the step
+    _lib.check(L.psdr_scene_enable_timing(sc._h, 1))
     for it in range(min(args.steps, 5)):
         flush.fill_(it & 255)
         step(-1)
         for term in (1, 2, 4):
             kernel_ms[term].append(L.psdr_scene_kernel_ms(sc._h, term))
+    _lib.check(L.psdr_scene_enable_timing(sc._h, 0))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -239,8 +241,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             e1.record(st)
             e1.synchronize()
             vms += e0.elapsed_time(e1)
+        _lib.check(L.psdr_scene_enable_timing(sc._h, 1))          # per-kernel times: extra steps, serial launches (see above)
+        for it in range(min(args.steps, 5)):
+            flush.fill_(it & 255)
+            vjp_step(args.warmup + args.steps + it)
             for term in (1, 2, 4):
                 vk[term].append(L.psdr_scene_kernel_ms(sc._h, term))
+        _lib.check(L.psdr_scene_enable_timing(sc._h, 0))
         t = torch.tensor([vms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -475,7 +482,6 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
         integ.preprocess_secondary_edges(sc, 0, wl["guiding"], 1)
         torch.cuda.synchronize()
         prep_ms = (time.perf_counter() - t0) * 1e3
-    _lib.check(L.psdr_scene_enable_timing(sc._h, 1))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     mine = [k for k in wl["sensors"] if (k % world == rank or not per_sensor)]
     n_samples = wl["samples_per_call"] * len(wl["sensors"])
@@ -515,11 +521,13 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
         dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = psdr.kernel_launch_count() - launches0
+    _lib.check(L.psdr_scene_enable_timing(sc._h, 1))
     for it in range(min(args.steps, 3)):                  # per-kernel times outside the timed region (see run_ours)
         flush.fill_(it & 255)
         step(-1)
         for term in (1, 2, 4):
             kernel_ms[term].append(L.psdr_scene_kernel_ms(sc._h, term))
+    _lib.check(L.psdr_scene_enable_timing(sc._h, 0))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -99,13 +99,16 @@ int psdr_scene_set_shard(psdr_scene *s, int rank, int world);
  * sampling only, mis = 1 BSDF sampling only.  The sample streams consume only the draws the mode uses. */
 enum { PSDR_INTEGRATOR_PATH = 0, PSDR_INTEGRATOR_DIRECT = 1 };
 int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis);
-/* Multi-GPU output fusion (new: SURVEY.md 8e).  on = 1: the img / dimg pointers of psdr_render_c / psdr_render_d and the
+/* Multi-GPU output fusion (new: SURVEY.md 8e).  on = 1 or 2: the img / dimg pointers of psdr_render_c / psdr_render_d and the
  * grad_table pointer of psdr_render_vjp_device are NVLS MULTICAST addresses of a buffer that every rank of the node has
  * mapped (cuMulticast* / torch symmetric memory).  The term kernels then accumulate with multimem.red: the NVSwitch adds
  * every contribution into the replica of every GPU, so the complete image (or gradient table) is present on all ranks
  * when the kernels of all ranks have finished -- no all-reduce pass.  The calls do NOT zero the buffer in this mode: the
  * caller zeroes every replica and synchronises the ranks before, and synchronises them again before reading
- * (psdr_jit_b200/dist.py PeerBuffers does both with one device-side barrier per step). */
+ * (psdr_jit_b200/dist.py PeerBuffers does both with one device-side barrier per step).
+ * on = 2: additionally the multicast images are float32[npix][4] (rgb + one unused float, 16-byte aligned) and a pixel
+ * travels as ONE multimem.red.v4 -- a third of the packets, which is what the NVLink fabric is limited by when every
+ * GPU receives the adds of all ranks.  The gradient table keeps its layout in both modes. */
 int psdr_scene_set_output_multicast(psdr_scene *s, int on);
 /* CTA shape of the term kernels (process-wide; new).  Every term kernel exists in two shapes: large CTAs (one or two
  * per SM) with block barriers that keep the warps of an SM in the same stretch of code, and 128-thread CTAs for launches

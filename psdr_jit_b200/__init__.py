@@ -888,17 +888,17 @@ class Integrator(Object):
     last_reduced = False     # the last render already holds the sum over the ranks (fused NVLink reduction)
 
     @staticmethod
-    def _multicast(scene, pb, launch):
+    def _multicast(scene, pb, launch, mode=1, extract=None):
         """Run `launch(base address)` with the scene's outputs switched to the multicast address of `pb`, then barrier
-        and fetch the summed buffer (dist.PeerBuffers)."""
+        and fetch the summed buffer (dist.PeerBuffers).  mode 2: float4 pixels (include/psdr_b200.h)."""
         L = _lib.load()
         base, _ = pb.target()
-        _lib.check(L.psdr_scene_set_output_multicast(scene._h, 1))
+        _lib.check(L.psdr_scene_set_output_multicast(scene._h, mode))
         try:
             launch(base)
         finally:
             _lib.check(L.psdr_scene_set_output_multicast(scene._h, 0))
-        return pb.finish()
+        return pb.finish(extract)
 
     def renderC(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
         """Primal image, float32[H*W, 3] on the GPU (reference Integrator::renderC)."""
@@ -910,10 +910,10 @@ class Integrator(Object):
         L = _lib.load()
         args = (scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters),
                 None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel())
-        pb = scene._peer("img", 3 * n)
+        pb = scene._peer("img", 4 * n)
         self.last_reduced = pb is not None
         if pb is not None:
-            return self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_c(*args, base, st))).view(n, 3)
+            return self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_c(*args, base, st)), 2, lambda b: b.view(n, 4)[:, :3].contiguous())
         img = torch.empty((n, 3), dtype=torch.float32, device=dev)
         _lib.check(L.psdr_render_c(*args, img.data_ptr(), st))
         return img
@@ -928,10 +928,11 @@ class Integrator(Object):
         L = _lib.load()
         args = (scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), int(terms), int(self.reference_tangent_scaling),
                 None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel())
-        pb = scene._peer("img2", 6 * n)
+        pb = scene._peer("img2", 8 * n)
         self.last_reduced = pb is not None
-        if pb is not None:      # fused reduction: the kernels of all ranks add straight into every rank's replica
-            buf = self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_d(*args, base, base + 12 * n, st))).view(2, n, 3)
+        if pb is not None:      # fused reduction: the kernels of all ranks add straight into every rank's replica (float4 pixels)
+            buf = self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_d(*args, base, base + 16 * n, st)), 2,
+                                  lambda b: b.view(2, n, 4)[:, :, :3].contiguous())
         else:
             # ONE [2, n, 3] buffer: the NCCL path sums image and derivative image with a single all-reduce of it
             buf = torch.empty((2, n, 3), dtype=torch.float32, device=dev)
@@ -961,10 +962,10 @@ class Integrator(Object):
         L = _lib.load()
         args = (scene._h, sensor_id, self.max_depth, int(seed), int(self.hide_emitters), _lib.TERM_ALL, 0,
                 None if pix is None else pix.data_ptr(), 0 if pix is None else pix.numel())
-        pb = scene._peer("img", 3 * n)
+        pb = scene._peer("img", 4 * n)
         self.last_reduced = pb is not None
         if pb is not None:
-            return self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_d(*args, base, None, st))).view(n, 3)
+            return self._multicast(scene, pb, lambda base: _lib.check(L.psdr_render_d(*args, base, None, st)), 2, lambda b: b.view(n, 4)[:, :3].contiguous())
         img = torch.empty((n, 3), dtype=torch.float32, device=dev)
         _lib.check(L.psdr_render_d(*args, img.data_ptr(), None, st))
         return img

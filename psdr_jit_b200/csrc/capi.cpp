@@ -29,7 +29,13 @@ struct psdr_scene {
     bool timing = false;
     cudaEvent_t ev[3][2] = {};
     bool ev_used[3] = {false, false, false};
+    // the three term kernels of one call run on three streams (TermStreams below)
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     ~psdr_scene() {
+        for (auto &q : side) if (q) cudaStreamDestroy(q);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto &e : ev_join) if (e) cudaEventDestroy(e);
         for (auto &p : ev)
             for (auto &e : p)
                 if (e) cudaEventDestroy(e);
@@ -146,7 +152,8 @@ int psdr_set_cta_policy(int policy) {
 
 int psdr_scene_set_output_multicast(psdr_scene *s, int on) {
     if (!s) return fail("null scene");
-    s->sc.out_multicast = on != 0;
+    if (on < 0 || on > 2) return fail("mode >= 0 && mode <= 2");
+    s->sc.out_multicast = on;
     return 0;
 }
 
@@ -562,6 +569,43 @@ void tick(psdr_scene *s, int k, int which, cudaStream_t st) {
     if (which) s->ev_used[k] = true;
 }
 
+// The term kernels of one call are independent (they only ADD into the outputs), each is a persistent grid that fills
+// the GPU, and each ends with a tail in which the SMs whose CTA finished early sit idle.  Launched on three streams
+// the next kernel's CTAs move into those SMs as they free up, so only the LAST kernel's tail is exposed: the caller's
+// stream forks after the output memsets and joins behind the last kernel.  Order: interior, secondary edges, primary
+// edges -- the primary-edge kernel's lanes are statistically identical, its tail is the shortest.  With per-kernel
+// timing enabled (psdr_scene_enable_timing) everything stays on the caller's stream, back to back.
+struct TermStreams {
+    psdr_scene *s;
+    cudaStream_t main;
+    bool overlap;
+    int used = 0;
+    TermStreams(psdr_scene *s_, cudaStream_t st, int n_kernels) : s(s_), main(st), overlap(!s_->timing && n_kernels > 1) {
+        if (!overlap) return;
+        for (int i = 0; i < 2; ++i) {
+            if (!s->side[i]) cuda_ok(cudaStreamCreateWithFlags(&s->side[i], cudaStreamNonBlocking), "cudaStreamCreate");
+            if (!s->ev_join[i]) cuda_ok(cudaEventCreateWithFlags(&s->ev_join[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        if (!s->ev_fork) cuda_ok(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+        cuda_ok(cudaEventRecord(s->ev_fork, main), "cudaEventRecord(fork)");
+    }
+    // stream of the next kernel: the first runs on the caller's stream, the others on the side streams
+    cudaStream_t next() {
+        if (!overlap || used == 0) { ++used; return main; }
+        cudaStream_t q = s->side[used - 1];
+        ++used;
+        cuda_ok(cudaStreamWaitEvent(q, s->ev_fork, 0), "cudaStreamWaitEvent(fork)");
+        return q;
+    }
+    void join() {
+        if (!overlap) return;
+        for (int i = 0; i + 1 < used; ++i) {
+            cuda_ok(cudaEventRecord(s->ev_join[i], s->side[i]), "cudaEventRecord(join)");
+            cuda_ok(cudaStreamWaitEvent(main, s->ev_join[i], 0), "cudaStreamWaitEvent(join)");
+        }
+    }
+};
+
 int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hide_emitters, bool ad, int terms, int reference_scaling,
                 const int *pix_id, int npix_sel, float *img, float *dimg, cudaStream_t st) {
     Scene &sc = s->sc;
@@ -584,37 +628,44 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
     const bool primal_only = ad && !dimg;   // renderD's image without the forward-mode derivative image
     const DCamera &cam = sc.dcameras[sensor];
     // multicast outputs: the caller zeroed every rank's replica (and synchronised the ranks) before this call
-    for (auto &r : rp) r.out_multicast = sc.out_multicast ? 1 : 0;
+    for (auto &r : rp) r.out_multicast = sc.out_multicast;
     if (!sc.out_multicast) {
         cuda_ok(cudaMemsetAsync(img, 0, sizeof(float) * 3 * npix, st), "memset(img)");
         if (ad && dimg) cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
     }
-    if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
+    const bool do_int = sc.spp > 0 && (terms & PSDR_TERM_INTERIOR);
+    const bool do_pri = ad && !primal_only && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0;
+    const bool do_sec = ad && !primal_only && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0;
+    if ((do_pri || do_sec) && pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+    TermStreams ts(s, st, (int) do_int + (int) do_pri + (int) do_sec);
+    if (do_int) {
         set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
         rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
-        tick(s, 0, 0, st);
-        cuda_ok(launch_interior(sc.dscene, cam, rp[0], ad, img, dimg, st), "interior kernel");
-        tick(s, 0, 1, st);
+        cudaStream_t q = ts.next();
+        tick(s, 0, 0, q);
+        cuda_ok(launch_interior(sc.dscene, cam, rp[0], ad, img, dimg, q), "interior kernel");
+        tick(s, 0, 1, q);
         g_launches++;
     }
-    if (ad && !primal_only && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
-        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
-        set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
-        tick(s, 1, 0, st);
-        cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, st), "primary-edge kernel");
-        tick(s, 1, 1, st);
-        g_launches++;
-    }
-    if (ad && !primal_only && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
-        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+    if (do_sec) {
         set_shard(rp[2], npix_full * sc.sppse, sc.rank, sc.world);
         rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
-        tick(s, 2, 0, st);
-        cuda_ok(launch_secondary_edges(sc.dscene, cam, rp[2], dimg, st), "secondary-edge kernel");
-        tick(s, 2, 1, st);
+        cudaStream_t q = ts.next();
+        tick(s, 2, 0, q);
+        cuda_ok(launch_secondary_edges(sc.dscene, cam, rp[2], dimg, q), "secondary-edge kernel");
+        tick(s, 2, 1, q);
         g_launches++;
     }
+    if (do_pri) {
+        set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
+        cudaStream_t q = ts.next();
+        tick(s, 1, 0, q);
+        cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, q), "primary-edge kernel");
+        tick(s, 1, 1, q);
+        g_launches++;
+    }
+    ts.join();
     return 0;
 }
 
@@ -682,32 +733,39 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
     if (sc.out_multicast && !grad_table_multicast_ok(gl)) throw std::runtime_error("gradient table too large for a multicast target (PSDR_Q_GRAD_TABLE_MULTICAST)");
     if (!sc.out_multicast) cuda_ok(cudaMemsetAsync(table, 0, sizeof(float) * gl.total, st), "memset(grad table)");
     s->ev_used[0] = s->ev_used[1] = s->ev_used[2] = false;
-    if (sc.spp > 0 && (terms & PSDR_TERM_INTERIOR)) {
+    const bool do_int = sc.spp > 0 && (terms & PSDR_TERM_INTERIOR);
+    const bool do_pri = sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0;
+    const bool do_sec = sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0;
+    if ((do_pri || do_sec) && pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+    TermStreams ts(s, st, (int) do_int + (int) do_pri + (int) do_sec);      // see render_impl
+    if (do_int) {
         set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
         rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
-        tick(s, 0, 0, st);
-        cuda_ok(launch_interior_vjp(sc.dscene, cam, rp[0], gl, d_img, st), "interior adjoint kernel");
-        tick(s, 0, 1, st);
+        cudaStream_t q = ts.next();
+        tick(s, 0, 0, q);
+        cuda_ok(launch_interior_vjp(sc.dscene, cam, rp[0], gl, d_img, q), "interior adjoint kernel");
+        tick(s, 0, 1, q);
         g_launches++;
     }
-    if (sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0) {
-        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
-        set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
-        tick(s, 1, 0, st);
-        cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp[1], gl, d_img, st), "primary-edge adjoint kernel");
-        tick(s, 1, 1, st);
-        g_launches++;
-    }
-    if (sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0) {
-        if (pix_id) throw std::runtime_error("batch rendering supports the interior term only");
+    if (do_sec) {
         set_shard(rp[2], npix_full * sc.sppse, sc.rank, sc.world);
         rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
-        tick(s, 2, 0, st);
-        cuda_ok(launch_secondary_edges_vjp(sc.dscene, cam, rp[2], gl, d_img, st), "secondary-edge adjoint kernel");
-        tick(s, 2, 1, st);
+        cudaStream_t q = ts.next();
+        tick(s, 2, 0, q);
+        cuda_ok(launch_secondary_edges_vjp(sc.dscene, cam, rp[2], gl, d_img, q), "secondary-edge adjoint kernel");
+        tick(s, 2, 1, q);
         g_launches++;
     }
+    if (do_pri) {
+        set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
+        cudaStream_t q = ts.next();
+        tick(s, 1, 0, q);
+        cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp[1], gl, d_img, q), "primary-edge adjoint kernel");
+        tick(s, 1, 1, q);
+        g_launches++;
+    }
+    ts.join();
 }
 
 static void ensure_grad_table(psdr_scene *s, size_t total) {

@@ -28,6 +28,21 @@ __device__ __forceinline__ void out_add(float *p, float v, int mc) {
     if (mc) asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
     else atomicAdd(p, v);
 }
+// One pixel (rgb) of an image.  mc = 0 / 1: float32[npix][3], three adds (zero channels skipped).  mc = 2: the multicast
+// image is float32[npix][4] and the pixel travels as ONE 16-byte multimem.red.v4 -- every multimem.red is replicated by
+// the switch to all N GPUs, so each GPU receives the reds of ALL ranks and the packet count, not the byte count, is what
+// the links carry: three 4-byte reds per splat slowed the secondary-edge kernel by 1.5x at 8 GPUs (profiles/r02v).
+__device__ __forceinline__ void out_add_rgb(float *img, long long pix, float r, float g, float b, int mc) {
+    if (mc == 2) {
+        asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(img + 4 * pix), "f"(r), "f"(g), "f"(b), "f"(0.f)
+                     : "memory");
+        return;
+    }
+    float *p = img + 3 * pix;
+    if (r != 0.f) out_add(p, r, mc);
+    if (g != 0.f) out_add(p + 1, g, mc);
+    if (b != 0.f) out_add(p + 2, b, mc);
+}
 // Persistent-loop schedule of the interior kernels.  Iteration k covers local lanes [k G B, (k + 1) G B) (G CTAs of B
 // threads); CTA c takes chunk (c + k) mod G of it.  With the plain grid-stride loop (chunk c every time) a CTA revisits
 // the same image COLUMNS whenever G B / spp (x the number of ranks) shares a large factor with the image width: the

@@ -71,9 +71,12 @@ __device__ __forceinline__ void splat_runs(float *img, int pix, float r, float g
     }
     const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
     if (valid && (lane == 0 || kprev != key)) {
-        out_add(img + 3 * pix, r, mc);
-        out_add(img + 3 * pix + 1, g, mc);
-        out_add(img + 3 * pix + 2, b, mc);
+        if (mc == 2) out_add_rgb(img, pix, r, g, b, mc);
+        else {      // (zero channels are added too: the reference's scatter_reduce writes every lane)
+            out_add(img + 3 * pix, r, mc);
+            out_add(img + 3 * pix + 1, g, mc);
+            out_add(img + 3 * pix + 2, b, mc);
+        }
     }
 }
 
@@ -179,13 +182,14 @@ __global__ void __launch_bounds__(kBig ? kBlockP : kBlock, kBig ? PSDR_LB_PRIMAR
         const int pix = iy * sc.width + ix;
         const float inv_pdf = 1.f / pdf;
         const float dl[3] = {(Ln.x - Lp.x) * inv_pdf, (Ln.y - Lp.y) * inv_pdf, (Ln.z - Lp.z) * inv_pdf};
+        float t3[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float primal = x_dot_n.v * dl[c];
-            if (!isfinite(primal)) continue;
             const float t = x_dot_n.d * dl[c] * inv_sppe;
-            if (t != 0.f && isfinite(t)) out_add(dimg + 3 * pix + c, t, rp.out_multicast);
+            t3[c] = (isfinite(primal) && isfinite(t)) ? t : 0.f;
         }
+        if (t3[0] != 0.f || t3[1] != 0.f || t3[2] != 0.f) out_add_rgb(dimg, pix, t3[0], t3[1], t3[2], rp.out_multicast);
     }
 }
 
@@ -209,8 +213,9 @@ __global__ void __launch_bounds__(kBig ? kBlockS : kBlock, kBig ? PSDR_LB_SECOND
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             if (smp.pdf0 > kEpsilon) t[c] = t[c] / smp.pdf0;                 // masked(value, pdf0 > Epsilon) /= pdf0
-            if (isfinite(t[c]) && t[c] != 0.f) out_add(dimg + 3 * pix + c, t[c] * scale, rp.out_multicast);
+            t[c] = isfinite(t[c]) ? t[c] * scale : 0.f;
         }
+        if (t[0] != 0.f || t[1] != 0.f || t[2] != 0.f) out_add_rgb(dimg, pix, t[0], t[1], t[2], rp.out_multicast);
     }, kSync != 0);
 }
 

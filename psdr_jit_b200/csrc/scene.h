@@ -165,7 +165,7 @@ struct Scene {
     bool bvh_rebuild = false;  // force a topology rebuild at the next configure (psdr_scene_set_accel)
     int bvh_builds = 0, bvh_refits = 0;   // host topology builds / GPU refits so far (psdr_scene_query)
     int integrator_mis = 2;    // 2 PathTracer / Direct(2); 0, 1: Direct(0), Direct(1) (psdr_scene_set_integrator)
-    bool out_multicast = false;   // outputs are NVLS multicast addresses (psdr_scene_set_output_multicast)
+    int out_multicast = 0;        // outputs are NVLS multicast addresses: 1 = same layout, 2 = float4 pixels (psdr_scene_set_output_multicast)
     bool ref_rcp = false;      // reference arithmetic for the analytic primary hit (psdr_scene_set_reference_arithmetic)
     DeviceBuffers *dev = nullptr;
     DScene dscene{};

@@ -90,11 +90,12 @@ class PeerBuffers:
         b = self.k % 2
         return int(self.handles[b].multicast_ptr), self.bufs[b]
 
-    def finish(self, n: int = None):
-        """Barrier, then the summed buffer (first n entries) as a fresh tensor; the slot is cleared for reuse."""
+    def finish(self, extract=None):
+        """Barrier, then the summed buffer as a fresh tensor (`extract(buffer)` if given: the caller's own copy-out, e.g.
+        the rgb part of float4 pixels); the slot is cleared for reuse."""
         b = self.k % 2
         self.handles[b].barrier(channel=0)
-        out = self.bufs[b][:n].clone() if n is not None else self.bufs[b].clone()
+        out = extract(self.bufs[b]) if extract is not None else self.bufs[b].clone()
         self.bufs[b].zero_()
         self.k += 1
         return out
