@@ -30,9 +30,12 @@ struct psdr_scene {
     cudaEvent_t ev[3][2] = {};
     bool ev_used[3] = {false, false, false};
     // the three term kernels of one call run on three streams (TermStreams below)
+    int *d_sched = nullptr;               // chunk hand-out counters of the large-CTA interior kernels (ChunkSched): forward {0,1}, adjoint {2,3}
+    float *early_img_host = nullptr;      // psdr_render_d_host: copy the primal image out as soon as the interior kernel is done
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     ~psdr_scene() {
+        if (d_sched) cudaFree(d_sched);
         for (auto &q : side) if (q) cudaStreamDestroy(q);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto &e : ev_join) if (e) cudaEventDestroy(e);
@@ -563,6 +566,14 @@ void begin_render(Scene &sc, int sensor, long long seed, const int *pix_id, bool
     }
 }
 
+int *sched_counters(psdr_scene *s, int which) {
+    if (!s->d_sched) {
+        cuda_ok(cudaMalloc(&s->d_sched, sizeof(int) * 8), "cudaMalloc(sched)");
+        cuda_ok(cudaMemset(s->d_sched, 0, sizeof(int) * 8), "cudaMemset(sched)");
+    }
+    return s->d_sched + 2 * which;
+}
+
 void tick(psdr_scene *s, int k, int which, cudaStream_t st) {
     if (!s->timing) return;
     cuda_ok(cudaEventRecord(s->ev[k][which], st), "cudaEventRecord");
@@ -642,11 +653,14 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
         rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
+        rp[0].sched = sched_counters(s, 0);
         cudaStream_t q = ts.next();
         tick(s, 0, 0, q);
         cuda_ok(launch_interior(sc.dscene, cam, rp[0], ad, img, dimg, q), "interior kernel");
         tick(s, 0, 1, q);
         g_launches++;
+        // the primal image is final here (the edge kernels only add to the derivative image): its D2H overlaps them
+        if (s->early_img_host) cuda_ok(cudaMemcpyAsync(s->early_img_host, img, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, q), "D2H(img)");
     }
     if (do_sec) {
         set_shard(rp[2], npix_full * sc.sppse, sc.rank, sc.world);
@@ -742,6 +756,7 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
         set_shard(rp[0], npix * sc.spp, sc.rank, sc.world);
         rp[0].pix_id = pix_id; rp[0].npix = (int) npix;
         rp[0].tangent_scale = reference_scaling ? 2.f : 1.f;
+        rp[0].sched = sched_counters(s, 1);
         cudaStream_t q = ts.next();
         tick(s, 0, 0, q);
         cuda_ok(launch_interior_vjp(sc.dscene, cam, rp[0], gl, d_img, q), "interior adjoint kernel");
@@ -989,8 +1004,16 @@ int psdr_render_d_host(psdr_scene *s, int sensor, int max_depth, long long seed,
     const size_t n = pix_id_host ? (size_t) npix : (size_t) s->sc.width * s->sc.height;
     ensure_staging(s, n, pix_id_host ? n : 0);
     if (pix_id_host) cuda_ok(cudaMemcpyAsync(s->d_pix, pix_id_host, sizeof(int) * n, cudaMemcpyHostToDevice, s->stream), "H2D(pix)");
-    render_impl(s, sensor, max_depth, seed, hide_emitters, true, terms, reference_scaling, pix_id_host ? s->d_pix : nullptr, npix, s->d_img, s->d_dimg, s->stream);
-    cuda_ok(cudaMemcpyAsync(img_host, s->d_img, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream), "D2H(img)");
+    const bool early = s->sc.spp > 0 && (terms & PSDR_TERM_INTERIOR);
+    s->early_img_host = early ? img_host : nullptr;
+    try {
+        render_impl(s, sensor, max_depth, seed, hide_emitters, true, terms, reference_scaling, pix_id_host ? s->d_pix : nullptr, npix, s->d_img, s->d_dimg, s->stream);
+    } catch (...) {
+        s->early_img_host = nullptr;
+        throw;
+    }
+    s->early_img_host = nullptr;
+    if (!early) cuda_ok(cudaMemcpyAsync(img_host, s->d_img, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream), "D2H(img)");
     cuda_ok(cudaMemcpyAsync(dimg_host, s->d_dimg, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream), "D2H(dimg)");
     cuda_ok(cudaStreamSynchronize(s->stream), "stream sync");
     return 0;

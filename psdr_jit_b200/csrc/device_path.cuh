@@ -56,6 +56,30 @@ __device__ __forceinline__ long long rotated_lane(long long k, int block) {
     if (chunk >= G) chunk -= G;
     return (k * (long long) G + chunk) * block + threadIdx.x;
 }
+// Dynamic chunk hand-out for the large-CTA interior kernels: a chunk is one CTA-load of local lanes; thread 0 takes the
+// next chunk index from a global counter and the block barrier that starts every path broadcasts it.  The static
+// schedules end with the CTAs whose pixels were the expensive ones (the image is not uniform, and a CTA is 1/148 of the
+// machine): at 131 k pixels per rank the interior kernel took 1.27x its share.  Here the tail is bounded by one chunk.
+// The last CTA out re-arms the two counters, so consecutive launches need no memset.
+struct ChunkSched {
+    int *ctr;
+    __device__ __forceinline__ long long next(long long *slot) {      // every thread of the CTA calls it together
+        __syncthreads();        // everyone is done with the previous chunk (and has read *slot)
+        if (threadIdx.x == 0) *slot = (long long) atomicAdd(ctr, 1);
+        __syncthreads();
+        return *slot;
+    }
+    __device__ __forceinline__ void finish() {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(ctr + 1, 1) == (int) gridDim.x - 1) {     // every CTA has taken its terminating chunk
+                ctr[0] = 0;
+                ctr[1] = 0;
+                __threadfence();
+            }
+        }
+    }
+};
 __device__ __forceinline__ long long global_lane(const RenderParams &rp, long long j) {
     return rp.shard_world <= 1 ? rp.lane_begin + j : (((j >> 5) * rp.shard_world + rp.shard_rank) << 5) + (j & 31);
 }

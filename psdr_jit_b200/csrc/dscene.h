@@ -159,6 +159,7 @@ struct RenderParams {
     int npix;                // number of output pixels (W*H or len(pix_id))
     int smem_grad;           // adjoint kernels: 1 = accumulate into a shared-memory copy of the gradient table
     float tangent_scale;     // 1, or 2 to reproduce the reference's forward-mode scaling
+    int *sched;              // large-CTA interior kernels: {next chunk, CTAs done} of the dynamic chunk hand-out (device, zero between launches)
     int out_multicast;       // 1, 2 = the output pointers are NVLS multicast addresses: every add is a multimem.red that lands
                              // in the replica of EVERY rank; 2: images are float32[npix][4] (psdr_scene_set_output_multicast)
 };

@@ -96,10 +96,21 @@ __global__ void __launch_bounds__(kBig ? kBlockI : kBlock, kBig ? (IsDual<S>::va
     const long long span = rp.lane_end - rp.lane_begin;
     const long long span_pad = (span + kBlockI - 1) / kBlockI * kBlockI;   // keep warps converged for the shuffles (and the trip count CTA-uniform)
     const float inv_spp = sc.spp > 1 ? 1.f / (float) sc.spp : 1.f;
-    // (plain grid-stride loop: the rotated schedule of the interior adjoint, device_path.cuh rotated_lane, measured 1-5 %
-    // slower here -- a 640-thread CTA already spans 20 pixels of a row)
-    for (long long j = (long long) blockIdx.x * kBlockI + threadIdx.x; j < span_pad; j += stride) {
-        if (kSync) __syncthreads();
+    // large CTAs: chunks handed out dynamically (device_path.cuh ChunkSched; its barriers are the per-path block barrier);
+    // 128-thread CTAs: plain grid-stride loop
+    __shared__ long long s_chunk;
+    const bool dynamic = kSync != 0 && rp.sched != nullptr;
+    ChunkSched sched{rp.sched};
+    for (long long k = 0;; ++k) {
+        long long j;
+        if (dynamic) {
+            j = sched.next(&s_chunk) * kBlockI + threadIdx.x;
+            if (j >= span_pad) break;
+        } else {
+            j = (long long) blockIdx.x * kBlockI + threadIdx.x + k * stride;
+            if (j >= span_pad) break;
+            if (kSync) __syncthreads();
+        }
         const long long gi = global_lane(rp, j);
         const bool live = j < span && gi < rp.n_lanes;
         const long long i = live ? gi : 0;
@@ -131,6 +142,7 @@ __global__ void __launch_bounds__(kBig ? kBlockI : kBlock, kBig ? (IsDual<S>::va
             splat_runs(dimg, idx, scrub(dr) * ts, scrub(dg) * ts, scrub(db) * ts, live, rp.out_multicast);
         }
     }
+    if (dynamic) sched.finish();
 }
 
 // ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges

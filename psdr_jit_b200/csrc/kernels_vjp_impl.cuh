@@ -59,15 +59,26 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + kBlockIV - 1) / kBlockIV * kBlockIV;   // CTA-uniform trip count
+    // large CTAs: chunks handed out dynamically (device_path.cuh ChunkSched; its barriers are the block barrier in front
+    // of the replay phase); 128-thread CTAs: the rotated static schedule (rotated_lane)
+    __shared__ long long s_chunk;
+    const bool dynamic = kSync != 0 && rp.sched != nullptr;
+    ChunkSched sched{rp.sched};
     const long long iters = (span_pad + stride - 1) / stride;
-    for (long long k = 0; k < iters; ++k) {
-        const long long j = rotated_lane(k, kBlockIV);     // (CTA-uniform: span_pad is a multiple of the CTA size)
-        if (j >= span_pad) continue;
+    for (long long k = 0; dynamic || k < iters; ++k) {
+        long long j;
+        if (dynamic) {
+            j = sched.next(&s_chunk) * kBlockIV + threadIdx.x;
+            if (j >= span_pad) break;
+        } else {
+            j = rotated_lane(k, kBlockIV);     // (CTA-uniform: span_pad is a multiple of the CTA size)
+            if (j >= span_pad) continue;
+        }
         // the whole body is warp-uniform control flow: lanes past the end of the span ride along inactive (the
         // span is padded to 32), so the barriers here and inside path_adjoint are full-mask barriers at the top
         // level -- the only form that really re-converges the warp (see path_adjoint)
-        if (kSync) __syncthreads();
-        else __syncwarp();
+        if (kSync && !dynamic) __syncthreads();
+        else if (!kSync) __syncwarp();
         const long long gi = global_lane(rp, j);
         const bool live = j < span && gi < rp.n_lanes;
         const long long i = live ? gi : 0;
@@ -95,6 +106,7 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
         else __syncwarp();
         path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, live && has_cotangent);
     }
+    if (dynamic) sched.finish();
     grad_acc_end(acc);
 }
 

@@ -29,9 +29,9 @@ def test_full_size_properties(cfg):
     img, dimg = _render(psdr, wl, integ, sc)
     assert torch.isfinite(img).all() and torch.isfinite(dimg).all()
     assert float(img.abs().max()) > 0 and float(dimg.abs().max()) > 0
-    # determinism (primal: one writer per pixel -> bit exact; derivative image: float atomics of the edge terms)
+    # determinism up to the order of float atomics (a pixel's spp lanes span several warps above spp 32)
     img2, dimg2 = _render(psdr, wl, integ, sc)
-    assert torch.equal(img, img2)
+    assert rel_l2(img2.cpu().numpy(), img.cpu().numpy()) < 1e-6
     assert rel_l2(dimg2.cpu().numpy(), dimg.cpu().numpy()) < 1e-4
     # the CTA shape does not change a lane's value
     try:
@@ -39,7 +39,7 @@ def test_full_size_properties(cfg):
         img3, dimg3 = _render(psdr, wl, integ, sc)
     finally:
         psdr.set_cta_policy(0)
-    assert torch.equal(img, img3)
+    assert rel_l2(img3.cpu().numpy(), img.cpu().numpy()) < 1e-6
     assert rel_l2(dimg3.cpu().numpy(), dimg.cpu().numpy()) < 1e-4
     # lane shards: the partial images of 3 ranks add up to the image (what the multi-GPU reduction computes)
     acc = torch.zeros_like(integ.last_buffer)
