@@ -593,12 +593,20 @@ class Scene(Object):
             if strict:
                 raise RuntimeError("enable_peer_reduction needs a sharded scene and an initialised process group")
             return False
+        import torch
+        dev = torch.device("cuda", self._device_index())
+        probe, err = None, None
         try:
-            import torch
-            probe = _dist.PeerBuffers(32, torch.device("cuda", self._device_index()), group)
-        except Exception:
+            probe = _dist.PeerBuffers(32, dev, group)
+        except Exception as e:      # no symmetric memory / no multicast on this node
+            err = e
+        # the ranks must take the same path: one of them falling back to NCCL while the others wait in the device
+        # barrier would hang the job
+        ok = torch.tensor([1 if probe is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
             if strict:
-                raise
+                raise RuntimeError("no NVLS multicast path on every rank: %s" % (err,))
             return False
         self._peer_group = group if group is not None else dist.group.WORLD
         self._peer_bufs = {("probe", 32): probe}

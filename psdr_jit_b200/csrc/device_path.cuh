@@ -663,7 +663,18 @@ template <class S> __device__ __forceinline__ S ggx_smith_g1(S alpha, V3<S> v, V
 
 // Microfacet::__eval (reference src/bsdf/microfacet.cpp:22-68): Lambert + GGX specular with the
 // Schlick-Gaussian Fresnel fit; wi, wo in the shading frame
-template <class S, int kCfg> __device__ __forceinline__ V3<S> microfacet_eval(const DBsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
+// The full-feature kernels are 250 KB of code with everything inlined (each BSDF evaluation twice per path step, in
+// dual numbers) against a 32 KB instruction cache; PSDR_FULL_OUTLINE = 1 keeps ONE copy of the Microfacet / conductor /
+// environment-map routines per kernel (calls instead of inlining).
+#ifndef PSDR_FULL_OUTLINE
+#define PSDR_FULL_OUTLINE 0
+#endif
+#if PSDR_FULL_OUTLINE
+#define PSDR_FULL_FN __device__ __noinline__
+#else
+#define PSDR_FULL_FN __device__ __forceinline__
+#endif
+template <class S, int kCfg> PSDR_FULL_FN V3<S> microfacet_eval(const DBsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
     if (b.two_side) {
         if (signbit_(val(wi.z))) wo.z = -wo.z;
         wi.z = abs_(wi.z);
@@ -707,7 +718,7 @@ template <> __device__ __forceinline__ V3d bsdf_k<Dual>(const DBsdf &b) { return
 
 // RoughConductor::__eval (reference src/bsdf/roughconductor.cpp:38-66), isotropic (alpha_u = alpha_v):
 // F(eta, k, <wi, H>) D(H) G(wi, wo, H) / (4 cos_theta_i) * specular_reflectance
-template <class S, int kCfg> __device__ __forceinline__ V3<S> conductor_eval(const DBsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
+template <class S, int kCfg> PSDR_FULL_FN V3<S> conductor_eval(const DBsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
     if (b.two_side) {
         if (signbit_(val(wi.z))) wo.z = -wo.z;
         wi.z = abs_(wi.z);
@@ -742,7 +753,7 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DS
 }
 
 // Microfacet::__pdf (reference src/bsdf/microfacet.cpp:108-133), detached
-__device__ __forceinline__ float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo, V2f uv) {
+static PSDR_FULL_FN float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo, V2f uv) {
     if (b.two_side) {
         if (signbit_(wi.z)) wo.z = -wo.z;
         wi.z = fabsf(wi.z);
@@ -799,7 +810,7 @@ __device__ __forceinline__ V2f ggx_sample_visible_11(float cos_theta_i, V2f samp
 }
 
 // Microfacet::__sample (reference src/bsdf/microfacet.cpp:80-98) + GGXDistribution::sample (ggx.cpp:36-79)
-__device__ __forceinline__ BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
+static PSDR_FULL_FN BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
     BsdfSample bs;
     if (b.two_side) wi.z = fabsf(wi.z);
     // RoughConductor::__sample (src/bsdf/roughconductor.cpp:99-122): the same visible-normal sampling, alpha given directly
@@ -899,7 +910,7 @@ template <class S> struct PosSample {
 // EnvironmentMap::sample_direction + __sample_position (reference src/emitter/envmap.cpp:86-129) and
 // ray_intersect_scene_aabb (include/psdr/utils.h:144-164): a direction drawn from the cell distribution,
 // turned into the point where it leaves the scene bounding box.  Everything is detached.
-__device__ __forceinline__ void env_sample_position(const DEnv &e, V3f ref_p, V2f sample2, V3f &p, V3f &n, float &pdf_out) {
+static PSDR_FULL_FN void env_sample_position(const DEnv &e, V3f ref_p, V2f sample2, V3f &p, V3f &n, float &pdf_out) {
     const int ncells = e.cw * e.ch;
     float prob;
     const int idx = sample_reuse(e.cell_pmf, e.cell_cmf, ncells, e.cell_sum, sample2.y, prob);   // HyperCube<2>: last dimension

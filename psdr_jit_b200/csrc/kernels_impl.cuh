@@ -43,6 +43,9 @@
 #ifndef PSDR_BLOCK_I
 #define PSDR_BLOCK_I 640
 #endif
+#ifndef PSDR_BLOCK_I_FULL
+#define PSDR_BLOCK_I_FULL 896   // interior kernel of the full-feature family (Microfacet / envmap / textures): cfg 3 214.6 -> 209.2 ms (profiles/r03ab)
+#endif
 #ifndef PSDR_BLOCK_P
 #define PSDR_BLOCK_P 896
 #endif
@@ -54,6 +57,7 @@ namespace psdr {
 
 constexpr int kBlock = 128;
 constexpr int kBlockI = PSDR_BLOCK_I, kBlockP = PSDR_BLOCK_P, kBlockS = PSDR_BLOCK_S;
+template <int kCfg> struct InteriorBlock { static constexpr int value = (kCfg & kCfgFull) ? PSDR_BLOCK_I_FULL : PSDR_BLOCK_I; };
 
 // Reduce values over runs of consecutive lanes that share a pixel (lanes are pixel-major, so a
 // warp holds at most a few contiguous runs; with spp a multiple of 32 it is one run) and issue one
@@ -87,10 +91,10 @@ __device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; 
 // analytically, scene.cpp:772-801) -- <float, kBvh, true> is the primal image of renderD.
 // kBig: the one-CTA-per-SM shape with block barriers (above); else the 128-thread shape for launches too small to fill it.
 template <class S, int kCfg, bool kAD, bool kBig>
-__global__ void __launch_bounds__(kBig ? kBlockI : kBlock, kBig ? (IsDual<S>::value ? PSDR_LB_INTERIOR_DUAL : PSDR_LB_INTERIOR) : 6)
+__global__ void __launch_bounds__(kBig ? InteriorBlock<kCfg>::value : kBlock, kBig ? (IsDual<S>::value ? PSDR_LB_INTERIOR_DUAL : PSDR_LB_INTERIOR) : 6)
     interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp, float *__restrict__ img,
                     float *__restrict__ dimg) {
-    constexpr int kBlockI = kBig ? psdr::kBlockI : kBlock, kSync = kBig ? PSDR_SYNC_I : 0;
+    constexpr int kBlockI = kBig ? InteriorBlock<kCfg>::value : kBlock, kSync = kBig ? PSDR_SYNC_I : 0;
     brute_init<kCfg>(sc, kBlockI);
     const long long stride = (long long) gridDim.x * kBlockI;
     const long long span = rp.lane_end - rp.lane_begin;
@@ -324,6 +328,7 @@ inline bool use_big_cta(long long lanes, int block) {
 template <int kCfg> struct ForwardLaunch {
     template <class S, bool kAD> static void interior_as(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *img, float *dimg, cudaStream_t st) {
         const long long n = rp.lane_end - rp.lane_begin;
+        constexpr int kBlockI = InteriorBlock<kCfg>::value;
         if (use_big_cta(n, kBlockI)) interior_kernel<S, kCfg, kAD, true><<<persistent_grid(interior_kernel<S, kCfg, kAD, true>, kBlockI, 0, n), kBlockI, 0, st>>>(sc, cam, rp, img, dimg);
         else interior_kernel<S, kCfg, kAD, false><<<persistent_grid(interior_kernel<S, kCfg, kAD, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
     }
