@@ -254,6 +254,16 @@ int psdr_render_d_host(psdr_scene *s, int sensor, int max_depth, long long seed,
 /* FieldExtractionIntegrator taps (src/integrator/field.cpp:47-121) at the scene's spp: per lane 14 floats
  * (mesh id + 1, triangle id, position xyz, distance, geometric normal xyz, shading normal xyz, uv). */
 int psdr_render_aov(psdr_scene *s, int sensor, long long seed, float *out, void *cuda_stream);
+/* FieldExtractionIntegrator.renderD followed by drjit.forward_to (src/integrator/field.cpp:47-121 through
+ * Integrator::renderD, src/integrator/integrator.cpp:51-100,179-198), in two parts.
+ * psdr_render_aov_d: the interior part -- the same 14 taps from the AD instantiation of the primary hit (re-intersected
+ * analytically, src/scene/scene.cpp:772-801) in `out`, and their forward-mode tangents for the tangents set with
+ * psdr_scene_set_tangent in `dout` (both float32[lanes][14]).
+ * psdr_render_field_edges: the primary-edge part at the scene's sppe -- dimg (device, float32[W*H][3], zeroed by the call)
+ * receives jump-of-the-field x normal velocity of the sampled pixel-space edges.  field: 0 segmentation (mesh index),
+ * 1 silhouette, 2 position, 3 depth, 4 geoNormal, 5 shNormal, 6 uv; object >= 0 keeps that mesh only ("<field> <id>"). */
+int psdr_render_aov_d(psdr_scene *s, int sensor, long long seed, float *out, float *dout, void *cuda_stream);
+int psdr_render_field_edges(psdr_scene *s, int sensor, long long seed, int field, int object, float *dimg, void *cuda_stream);
 
 /* Sampler.seed / next_1d (src/psdr.cpp:181-185): out[ndraws][n], host memory, computed on the host. */
 int psdr_sampler_draws(long long seed, int n, int ndraws, float *out);

@@ -1800,6 +1800,78 @@ void orc_aov(void *h, int sensor, int seed, float *out) {
     }
 }
 
+// FieldExtractionIntegrator::renderD in forward mode (reference src/integrator/field.cpp:47-121 through Integrator::renderD,
+// src/integrator/integrator.cpp:51-100): interior part = the taps of orc_aov from ray_intersect<Dual> with tangents
+void orc_aov_d(void *h, int sensor, int seed, float *out, float *dout) {
+    Scene &sc = *(Scene *) h;
+    const Camera &cam = sc.cameras[sensor];
+    int64_t N = (int64_t) sc.width * sc.height * sc.spp;
+#pragma omp parallel for
+    for (int64_t i = 0; i < N; ++i) {
+        int64_t idx = sc.spp > 1 ? i / sc.spp : i;
+        Pcg32 rng = make_sampler((uint64_t) (i + seed), (uint64_t) i);
+        float jy = rng.next_1d(), jx = rng.next_1d();
+        float sx = ((float) (idx % sc.width) + jx) / (float) sc.width, sy = ((float) (idx / sc.width) + jy) / (float) sc.height;
+        V3d o, d;
+        sample_primary_ray<Dual>(cam, V2f(sx, sy), o, d);
+        Its<Dual> its = ray_intersect<Dual>(sc, o, d, true, false);
+        float *r = out + 14 * i, *t = dout + 14 * i;
+        for (int k = 0; k < 14; ++k) { r[k] = 0.f; t[k] = 0.f; }
+        if (!its.valid) { r[1] = -1.f; continue; }
+        r[0] = (float) (its.mesh + 1); r[1] = (float) its.tri;
+        const Dual f[12] = {its.p.x, its.p.y, its.p.z, its.t, its.n.x, its.n.y, its.n.z, its.sh_n.x, its.sh_n.y, its.sh_n.z, its.uv.x, its.uv.y};
+        for (int k = 0; k < 12; ++k) { r[2 + k] = f[k].v; t[2 + k] = std::isfinite(f[k].d) ? f[k].d : 0.f; }
+    }
+}
+
+static V3f field_value(const Its<float> &its, int field, int object) {
+    if (!its.valid || (object >= 0 && its.mesh != object)) return V3f(0.f, 0.f, 0.f);
+    switch (field) {
+        case 0: return V3f((float) its.mesh, (float) its.mesh, (float) its.mesh);
+        case 1: return V3f(1.f, 1.f, 1.f);
+        case 2: return its.p;
+        case 3: return V3f(its.t, its.t, its.t);
+        case 4: return its.n;
+        case 5: return its.sh_n;
+        default: return V3f(its.uv.x, its.uv.y, 0.f);
+    }
+}
+// primary-edge part (Integrator::render_primary_edges, integrator.cpp:179-198, with Li = the field): dimg[W*H*3], zeroed here
+void orc_field_edges(void *h, int sensor, int seed, int field, int object, float *dimg) {
+    Scene &sc = *(Scene *) h;
+    const Camera &cam = sc.cameras[sensor];
+    for (int64_t k = 0; k < (int64_t) sc.width * sc.height * 3; ++k) dimg[k] = 0.f;
+    if (!cam.enable_edges || sc.sppe <= 0) return;
+    int64_t N = (int64_t) sc.width * sc.height * sc.sppe;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < N; ++i) {
+        Pcg32 rng = make_sampler((uint64_t) (i + seed), (uint64_t) i);
+        float s1 = rng.next_1d();
+        auto r = cam.edge_distrb.sample_reuse(s1);
+        const PrimEdge &e = cam.edges[r.first];
+        float pdf = r.second / e.length;
+        V2d p_(fmadd(e.p0.x, Dual(1.0f - s1), e.p1.x * s1), fmadd(e.p0.y, Dual(1.0f - s1), e.p1.y * s1));
+        V2f p = val(p_);
+        Dual x_dot_n = dot(p_, lift<Dual>(e.normal));
+        int ix = (int) std::floor(p.x * (float) sc.width), iy = (int) std::floor(p.y * (float) sc.height);
+        if (!(ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height)) continue;
+        V3f op, dp, on, dn;
+        sample_primary_ray<float>(cam, V2f(p.x + kEdgeEpsilon * e.normal.x, p.y + kEdgeEpsilon * e.normal.y), op, dp);
+        sample_primary_ray<float>(cam, V2f(p.x - kEdgeEpsilon * e.normal.x, p.y - kEdgeEpsilon * e.normal.y), on, dn);
+        V3f Lp = field_value(ray_intersect<float>(sc, op, dp, true, false), field, object);
+        V3f Ln = field_value(ray_intersect<float>(sc, on, dn, true, false), field, object);
+        const float inv_pdf = 1.f / pdf;
+        for (int c = 0; c < 3; ++c) {
+            float dl = (Ln[c] - Lp[c]) * inv_pdf;
+            Dual value = x_dot_n * Dual(dl);
+            if (!std::isfinite(value.v)) continue;
+            float t = value.d;
+            if (sc.sppe > 1) t /= (float) sc.sppe;
+            splat(dimg, iy * sc.width + ix, c, t);
+        }
+    }
+}
+
 int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -40,6 +40,8 @@ def lib():
         L.orc_set_mis.argtypes = [C.c_void_p, C.c_int]
         L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
         L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
+        L.orc_aov_d.argtypes = [C.c_void_p, C.c_int, C.c_int, _f, _f]
+        L.orc_field_edges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f]
         L.orc_add_roughconductor.argtypes = [C.c_void_p, C.c_float, _f, _f, _f, _f, C.c_int]
         L.orc_add_envmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int, _f, _f, C.c_float, C.c_float]
         L.orc_set_bsdf_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f, _f]
@@ -241,6 +243,35 @@ class OracleScene:
         out = np.zeros((self.width * self.height * self.spp, 14), dtype=np.float32)
         self.L.orc_aov(self.h, sensor, seed, _fp(out))
         return out
+
+    FIELDS = ("segmentation", "silhouette", "position", "depth", "geoNormal", "shNormal", "uv")
+
+    def field_render_d(self, field, sensor=0, seed=0, obj=-1, terms=3):
+        """FieldExtractionIntegrator(field).renderD in forward mode (reference src/integrator/field.cpp through
+        Integrator::renderD): (field image, derivative image); terms bit 0 interior, bit 1 primary edges."""
+        n, spp = self.width * self.height, max(self.spp, 1)
+        a = np.zeros((n * spp, 14), dtype=np.float32)
+        da = np.zeros_like(a)
+        self.L.orc_aov_d(self.h, sensor, seed, _fp(a), _fp(da))
+        a, da = a.reshape(n, spp, 14), da.reshape(n, spp, 14)
+        valid = a[:, :, 0] > 0
+        if obj >= 0:
+            valid &= a[:, :, 0] == float(obj + 1)
+
+        def sel(x):
+            return {"segmentation": np.repeat(x[:, :, 0:1], 3, axis=2) - 1.0, "silhouette": np.ones_like(x[:, :, 2:5]), "position": x[:, :, 2:5],
+                    "depth": np.repeat(x[:, :, 5:6], 3, axis=2), "geoNormal": x[:, :, 6:9], "shNormal": x[:, :, 9:12],
+                    "uv": np.concatenate((x[:, :, 12:14], np.zeros_like(x[:, :, 0:1])), axis=2)}[field]
+        m = valid[:, :, None]
+        img = (sel(a) * m).sum(axis=1) / float(spp)
+        dimg = np.zeros_like(img)
+        if (terms & 1) and field not in ("segmentation", "silhouette"):
+            dimg += (sel(da) * m).sum(axis=1) / float(spp)
+        if (terms & 2) and self.sppe > 0:
+            e = np.zeros((n, 3), dtype=np.float32)
+            self.L.orc_field_edges(self.h, sensor, seed, self.FIELDS.index(field), obj, _fp(e))
+            dimg += e
+        return img.astype(np.float32), dimg.astype(np.float32)
 
 
 def sampler_draws(seed, n, ndraws):

@@ -1114,7 +1114,9 @@ class FieldExtractionIntegrator(Integrator):
     """reference src/psdr.cpp:423-425, src/integrator/field.cpp: the value of an intersection field at the primary hit,
     averaged over the pixel's samples.  Fields: silhouette, position, depth, geoNormal, shNormal, uv, segmentation
     (mesh index; the reference reports the id parsed from the mesh's name), optionally "<field> <mesh index>" to keep
-    one object only.  renderC only (the derivative of a field image is not part of this path)."""
+    one object only.  renderD: forward mode only -- interior part (the field at the analytically re-intersected primary
+    hit, differentiated) + primary-edge part (jump of the field across the pixel-space edges x their normal velocity);
+    the derivative image for the tangents configured on the scene is kept in ``grad_image``."""
     FIELDS = ("segmentation", "silhouette", "position", "depth", "geoNormal", "shNormal", "uv")
 
     def __init__(self, field: str):
@@ -1137,6 +1139,44 @@ class FieldExtractionIntegrator(Integrator):
              "depth": a[:, :, 5:6].expand(-1, -1, 3), "geoNormal": a[:, :, 6:9], "shNormal": a[:, :, 9:12],
              "uv": torch.cat((a[:, :, 12:14], torch.zeros_like(a[:, :, 0:1])), dim=2)}[self.field]
         return (f * valid.unsqueeze(-1)).sum(dim=1) / float(spp)
+
+    def _select(self, torch, a):
+        """field columns of a [npix, spp, 14] tap (or tangent-tap) array"""
+        return {"segmentation": a[:, :, 0:1].expand(-1, -1, 3) - 1.0, "silhouette": torch.ones_like(a[:, :, 2:5]), "position": a[:, :, 2:5],
+                "depth": a[:, :, 5:6].expand(-1, -1, 3), "geoNormal": a[:, :, 6:9], "shNormal": a[:, :, 9:12],
+                "uv": torch.cat((a[:, :, 12:14], torch.zeros_like(a[:, :, 0:1])), dim=2)}[self.field]
+
+    def renderD_fwd(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL):
+        """(field image, forward-mode derivative image) -- Integrator::renderD with Li = the field (field.cpp:47-121)."""
+        self._check(scene)
+        torch = self._torch()
+        dev, st = self._dev_stream(torch, scene)
+        L = _lib.load()
+        spp = max(scene.opts.spp, 1)
+        npix = scene.opts.width * scene.opts.height
+        sd = 0 if seed < 0 else int(seed)
+        a = torch.empty((npix * spp, 14), dtype=torch.float32, device=dev)
+        da = torch.empty_like(a)
+        _lib.check(L.psdr_render_aov_d(scene._h, sensor_id, sd, a.data_ptr(), da.data_ptr(), st))
+        a, da = a.view(-1, spp, 14), da.view(-1, spp, 14)
+        valid = a[:, :, 0] > 0
+        obj = int(self.object) if self.object else -1
+        if obj >= 0:
+            valid = valid & (a[:, :, 0] == float(obj + 1))
+        m = valid.unsqueeze(-1)
+        img = (self._select(torch, a) * m).sum(dim=1) / float(spp)
+        dimg = torch.zeros_like(img)
+        if (terms & _lib.TERM_INTERIOR) and self.field not in ("segmentation", "silhouette"):
+            dimg = dimg + (self._select(torch, da) * m).sum(dim=1) / float(spp)
+        if (terms & _lib.TERM_PRIMARY_EDGES) and scene.opts.sppe > 0:
+            e = torch.empty((npix, 3), dtype=torch.float32, device=dev)
+            _lib.check(L.psdr_render_field_edges(scene._h, sensor_id, sd, self.FIELDS.index(self.field), obj, e.data_ptr(), st))
+            dimg = dimg + e
+        return img, dimg
+
+    def renderD(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        img, self.grad_image = self.renderD_fwd(scene, sensor_id, seed, batch_pix)
+        return img
 
 
 def _render_d_autograd(integ: Integrator, scene: Scene, sensor_id: int, seed: int, batch_pix, leaves):

@@ -1036,6 +1036,45 @@ int psdr_render_aov(psdr_scene *s, int sensor, long long seed, float *out, void 
     PSDR_CATCH
 }
 
+int psdr_render_aov_d(psdr_scene *s, int sensor, long long seed, float *out, float *dout, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    if (!out || !dout) throw std::runtime_error("null output buffer");
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    RenderParams rp{};
+    rp.seed = seed < 0 ? 0 : seed;
+    set_shard(rp, (long long) sc.width * sc.height * std::max(sc.spp, 1), 0, 1);
+    cuda_ok(launch_aov_d(sc.dscene, sc.dcameras[sensor], rp, out, dout, (cudaStream_t) cuda_stream), "aov (forward mode) kernel");
+    g_launches++;
+    return 0;
+    PSDR_CATCH
+}
+
+int psdr_render_field_edges(psdr_scene *s, int sensor, long long seed, int field, int object, float *dimg, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    if (field < 0 || field > 6) throw std::runtime_error("Unsupported field");
+    if (!dimg) throw std::runtime_error("null output buffer");
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t) cuda_stream;
+    const long long npix = (long long) sc.width * sc.height;
+    cuda_ok(cudaMemsetAsync(dimg, 0, sizeof(float) * 3 * npix, st), "memset(dimg)");
+    if (sc.sppe <= 0 || sc.dcameras[sensor].n_edges <= 0) return 0;
+    RenderParams rp{};
+    rp.seed = seed < 0 ? 0 : seed;
+    set_shard(rp, npix * sc.sppe, 0, 1);
+    cuda_ok(launch_field_edges(sc.dscene, sc.dcameras[sensor], rp, field, object, dimg, st), "field edge kernel");
+    g_launches++;
+    return 0;
+    PSDR_CATCH
+}
+
 int psdr_sampler_draws(long long seed, int n, int ndraws, float *out) {
     if (!out || n < 0 || ndraws < 0) return fail("invalid arguments");
     for (int i = 0; i < n; ++i) {

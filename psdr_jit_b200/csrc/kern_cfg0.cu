@@ -14,5 +14,9 @@ cudaError_t guiding(const DScene &sc, const DCamera &cam, const int reso[4], int
     return ForwardLaunch<0>::guiding(sc, cam, reso, nrounds, seed, mass, st);
 }
 cudaError_t aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st) { return ForwardLaunch<0>::aov(sc, cam, rp, out, st); }
+cudaError_t aov_d(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, float *dout, cudaStream_t st) { return ForwardLaunch<0>::aov_d(sc, cam, rp, out, dout, st); }
+cudaError_t field_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, int field, int object, float *dimg, cudaStream_t st) {
+    return ForwardLaunch<0>::field_edges(sc, cam, rp, field, object, dimg, st);
+}
 }  // namespace fwd0
 }  // namespace psdr

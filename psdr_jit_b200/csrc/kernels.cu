@@ -37,6 +37,14 @@ cudaError_t launch_aov(const DScene &sc, const DCamera &cam, const RenderParams 
     if (rp.lane_end - rp.lane_begin <= 0) return cudaSuccess;
     PSDR_DISPATCH(aov(sc, cam, rp, out, st))
 }
+cudaError_t launch_aov_d(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, float *dout, cudaStream_t st) {
+    if (rp.lane_end - rp.lane_begin <= 0) return cudaSuccess;
+    PSDR_DISPATCH(aov_d(sc, cam, rp, out, dout, st))
+}
+cudaError_t launch_field_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, int field, int object, float *dimg, cudaStream_t st) {
+    if (rp.lane_end - rp.lane_begin <= 0 || cam.n_edges <= 0) return cudaSuccess;
+    PSDR_DISPATCH(field_edges(sc, cam, rp, field, object, dimg, st))
+}
 #undef PSDR_DISPATCH
 
 #define PSDR_DISPATCH_V(CALL)                 \

@@ -12,6 +12,8 @@ cudaError_t launch_primary_edges(const DScene &sc, const DCamera &cam, const Ren
 cudaError_t launch_secondary_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);
 cudaError_t launch_guiding(const DScene &sc, const DCamera &cam, const int reso[4], int nrounds, long long seed, float *mass, cudaStream_t st);
 cudaError_t launch_aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st);
+cudaError_t launch_aov_d(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, float *dout, cudaStream_t st);
+cudaError_t launch_field_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, int field, int object, float *dimg, cudaStream_t st);
 
 // reverse mode (kernels_vjp.cu); GradLayout = adjoint.cuh
 cudaError_t launch_interior_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st);

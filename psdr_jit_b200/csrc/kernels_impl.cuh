@@ -303,6 +303,94 @@ __global__ void __launch_bounds__(kBlock) aov_kernel(const __grid_constant__ DSc
     }
 }
 
+// ---- FieldExtractionIntegrator::renderD, forward mode (reference src/integrator/field.cpp:47-121 through
+// Integrator::renderD, src/integrator/integrator.cpp:51-100,179-198) ----------------------------------------------
+// Interior part: the taps of aov_kernel from the AD instantiation of ray_intersect (primary hit re-intersected
+// analytically, scene.cpp:772-801) with their forward tangents: 14 values + 14 tangents per lane.
+template <int kCfg>
+__global__ void __launch_bounds__(kBlock) aov_d_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+                                                        const __grid_constant__ RenderParams rp, float *__restrict__ out, float *__restrict__ dout) {
+    brute_init<kCfg>(sc, kBlock);
+    const long long stride = (long long) gridDim.x * kBlock;
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const long long i = global_lane(rp, j);
+        if (!(j < span && i < rp.n_lanes)) continue;
+        const int idx = (int) (sc.spp > 1 ? i / sc.spp : i);
+        Pcg32 rng;
+        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+        const float jy = rng.next_1d(), jx = rng.next_1d();
+        const float sx = ((float) (idx % sc.width) + jx) / (float) sc.width, sy = ((float) (idx / sc.width) + jy) / (float) sc.height;
+        V3d o, d;
+        sample_primary_ray<Dual>(cam, V2f(sx, sy), o, d);
+        const Its<Dual> its = ray_intersect<Dual, kCfg, true>(sc, o, d, true, false);
+        float *r = out + 14 * i, *t = dout + 14 * i;
+        for (int k = 0; k < 14; ++k) { r[k] = 0.f; t[k] = 0.f; }
+        if (!its.valid) { r[1] = -1.f; continue; }
+        r[0] = (float) (its.mesh + 1); r[1] = (float) its.tri;
+        const Dual f[12] = {its.p.x, its.p.y, its.p.z, its.t, its.n.x, its.n.y, its.n.z, its.sh_n.x, its.sh_n.y, its.sh_n.z, its.uv.x, its.uv.y};
+        for (int k = 0; k < 12; ++k) { r[2 + k] = f[k].v; t[2 + k] = isfinite(f[k].d) ? f[k].d : 0.f; }
+    }
+}
+
+// field ids of psdr_render_field_edges
+__device__ __forceinline__ V3f field_value(const Its<float> &its, int field, int object) {
+    if (!its.valid || (object >= 0 && its.mesh != object)) return V3f(0.f, 0.f, 0.f);
+    switch (field) {
+        case 0: return V3f((float) its.mesh, (float) its.mesh, (float) its.mesh);      // segmentation
+        case 1: return V3f(1.f, 1.f, 1.f);                                                // silhouette
+        case 2: return its.p;                                                             // position
+        case 3: return V3f(its.t, its.t, its.t);                                          // depth
+        case 4: return its.n;                                                             // geoNormal
+        case 5: return its.sh_n;                                                          // shNormal
+        default: return V3f(its.uv.x, its.uv.y, 0.f);                                     // uv
+    }
+}
+// Primary-edge part (Integrator::render_primary_edges with Li = the field at the primary hit): the jump of the field across
+// the sampled pixel-space edge times the edge's normal velocity.
+template <int kCfg>
+__global__ void __launch_bounds__(kBlock) field_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+                                                             const __grid_constant__ RenderParams rp, int field, int object, float *__restrict__ dimg) {
+    brute_init<kCfg>(sc, kBlock);
+    const long long stride = (long long) gridDim.x * kBlock;
+    const float inv_sppe = sc.sppe > 1 ? 1.f / (float) sc.sppe : 1.f;
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    for (long long j = (long long) blockIdx.x * kBlock + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const long long i = global_lane(rp, j);
+        if (!(j < span && i < rp.n_lanes)) continue;
+        Pcg32 rng;
+        rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
+        float s1 = rng.next_1d(), prob;
+        const int ei = sample_reuse(cam.pe_pmf, cam.pe_cmf, cam.n_edges, cam.edge_sum, s1, prob);
+        const float4 a = __ldg(cam.pe_a + ei), da = __ldg(cam.pe_da + ei), bq = __ldg(cam.pe_b + ei);
+        const float pdf = prob / bq.z;
+        const float w0 = 1.0f - s1;
+        const Dual px = fmadd(Dual(a.x, da.x), Dual(w0), Dual(a.z, da.z) * s1), py = fmadd(Dual(a.y, da.y), Dual(w0), Dual(a.w, da.w) * s1);
+        const Dual x_dot_n = dot(V2d(px, py), V2d(Dual(bq.x), Dual(bq.y)));
+        const int ix = (int) floorf(px.v * (float) sc.width), iy = (int) floorf(py.v * (float) sc.height);
+        if (!(ix >= 0 && ix < sc.width && iy >= 0 && iy < sc.height)) continue;
+        V3f side[2];
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            const float sg = k == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
+            V3f ro, rd;
+            sample_primary_ray<float>(cam, V2f(px.v + sg * bq.x, py.v + sg * bq.y), ro, rd);
+            side[k] = field_value(ray_intersect<float, kCfg>(sc, ro, rd, true, false), field, object);
+        }
+        const float inv_pdf = 1.f / pdf;
+        const float dl[3] = {(side[1].x - side[0].x) * inv_pdf, (side[1].y - side[0].y) * inv_pdf, (side[1].z - side[0].z) * inv_pdf};
+        float t3[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float primal = x_dot_n.v * dl[c], t = x_dot_n.d * dl[c] * inv_sppe;
+            t3[c] = (isfinite(primal) && isfinite(t)) ? t : 0.f;
+        }
+        if (t3[0] != 0.f || t3[1] != 0.f || t3[2] != 0.f) out_add_rgb(dimg, iy * sc.width + ix, t3[0], t3[1], t3[2], 0);
+    }
+}
+
 // ---- per-configuration launchers: one explicit instantiation of ForwardLaunch<kCfg> per translation unit
 // (kern_cfg*.cu) so that the four kernel families compile in parallel ----------------------------------------
 // Persistent grid = exactly the number of CTAs that are resident at once (occupancy API x SM count): a larger
@@ -357,6 +445,14 @@ template <int kCfg> struct ForwardLaunch {
     }
     static cudaError_t aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st) {
         aov_kernel<kCfg><<<persistent_grid(aov_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, out);
+        return cudaGetLastError();
+    }
+    static cudaError_t aov_d(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, float *dout, cudaStream_t st) {
+        aov_d_kernel<kCfg><<<persistent_grid(aov_d_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, out, dout);
+        return cudaGetLastError();
+    }
+    static cudaError_t field_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, int field, int object, float *dimg, cudaStream_t st) {
+        field_edge_kernel<kCfg><<<persistent_grid(field_edge_kernel<kCfg>, kBlock, 0, rp.lane_end - rp.lane_begin), kBlock, 0, st>>>(sc, cam, rp, field, object, dimg);
         return cudaGetLastError();
     }
 };

@@ -13,6 +13,8 @@ namespace psdr {
     cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st);                         \
     cudaError_t guiding(const DScene &sc, const DCamera &cam, const int reso[4], int nrounds, long long seed, float *mass, cudaStream_t st);   \
     cudaError_t aov(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, cudaStream_t st);                                \
+    cudaError_t aov_d(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, float *dout, cudaStream_t st);                 \
+    cudaError_t field_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, int field, int object, float *dimg, cudaStream_t st); \
     }
 PSDR_DECL_FWD(fwd0) PSDR_DECL_FWD(fwd1) PSDR_DECL_FWD(fwd2) PSDR_DECL_FWD(fwd3)
 #undef PSDR_DECL_FWD

@@ -377,3 +377,38 @@ def test_oracle_roughconductor_vs_reference_golden(oracle):
         _, d = build_oracle(scenes.cbox_meshes(), 128, 128, 4, 0, 0, bsdfs=bs(0.15), d_bsdf={"cat": dd}).render(3, seed=0, mode=1, terms=1)
         r, nbad, r_ex = compare_stats(2.0 * d, g["gradD_" + tag])
         assert nbad <= 256 and r_ex < 5e-3, (tag, r, nbad, r_ex)
+
+
+def test_oracle_field_integrator_vs_reference_golden(oracle):
+    """FieldExtractionIntegrator (tests/golden/fields.npz, tools/ref_golden9.py: the RUNNING reference).  Like Direct, the
+    reference binary returns exactly 2x the field (a fully covered pixel of "silhouette" reads 2) and 2x its interior
+    derivative; with that factor the images agree to 1e-6.  Its primary-edge part is NOT reproduced: it comes out at about a
+    sixth of the finite-difference-correct value (the covered area of the moving box changes by -56 pixels per unit P; the
+    reference's edge term sums to -9.9); ours matches finite differences (below, and tests/test_gpu_fields.py)."""
+    g = np.load(os.path.join(GOLDEN, "fields.npz"))
+    for tag, meshes in (("box", scenes.cbox_meshes()), ("open", scenes.cbox_meshes()[:3])):
+        osc = build_oracle(meshes, 128, 128, 4, 0, 0, move_mesh=1, axis_scale=(30.0, 10.0, 0.0))
+        for f in ("depth", "position", "shNormal", "geoNormal", "silhouette", "uv"):
+            img, d = osc.field_render_d(f, seed=0, terms=1)
+            r, nbad, r_ex = compare_stats(2.0 * img, g["%s_%s_C" % (tag, f)], flip_rel=1e-4)
+            assert nbad <= 4 and r_ex < 2e-6, (tag, f, r, nbad, r_ex)
+            gi = g["%s_%s_G_int" % (tag, f)]
+            if np.abs(gi).max() > 0:
+                r, nbad, r_ex = compare_stats(2.0 * d, gi, flip_rel=1e-4)
+                assert nbad <= 8 and r_ex < 1e-5, (tag, f, r, nbad, r_ex)
+            else:
+                assert np.abs(d).max() == 0
+    # the edge part against finite differences of the covered area
+    def area(P):
+        ms = scenes.cbox_meshes()[:3]
+        tw = ms[1].to_world.copy()
+        tw[0, 3] += 30 * P
+        tw[1, 3] += 10 * P
+        ms[1].to_world = tw
+        return float(build_oracle(ms, 128, 128, 64, 0, 0).field_render_d("silhouette", seed=1, terms=0)[0][:, 0].sum())
+    fd = (area(0.05) - area(-0.05)) / 0.1
+    osc = build_oracle(scenes.cbox_meshes()[:3], 128, 128, 4, 16, 0, move_mesh=1, axis_scale=(30.0, 10.0, 0.0))
+    est = float(osc.field_render_d("silhouette", seed=1, terms=2)[1][:, 0].sum())
+    assert abs(est - fd) < 0.03 * abs(fd), (est, fd)
+    ref_edges = float((g["open_silhouette_G_all"] - g["open_silhouette_G_int"])[:, 0].sum())
+    assert abs(ref_edges) < 0.3 * abs(fd)          # the reference's own edge term: not finite-difference consistent
