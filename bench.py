@@ -162,6 +162,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.load()
+    psdr.set_cta_policy(args.cta_policy)
     sc, tangent = build_scene(psdr, rank, world)
     integ = psdr.PathTracer(DEPTH)
     # N > 1: the reduction over ranks is fused into the term kernels (multimem.red through the NVSwitch into every rank's
@@ -471,6 +472,7 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.load()
+    psdr.set_cta_policy(args.cta_policy)
     wl = bench_scenes.workload(args.config)
     per_sensor = args.config == 5                        # one sensor per GPU: replicas, no image collective
     sc = bench_scenes.build_ours(psdr, wl, 0 if per_sensor else rank, 1 if per_sensor else world)
@@ -734,6 +736,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vjp", action="store_true")
+    ap.add_argument("--cta-policy", type=int, default=0, help="experiments: 1 = force 128-thread CTAs, 2 = force the large-CTA kernels (psdr_set_cta_policy)")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: sum the partial images with NCCL instead of the fused multimem.red path")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json workload (2 = the headline)")
     args = ap.parse_args()

@@ -899,6 +899,33 @@ __device__ __forceinline__ int sample_reuse(const float *pmf, const float *cmf, 
     return idx;
 }
 
+// The same search narrowed by a bucket table: lut[b] = first index whose CDF value is >= b * sum / n (n buckets, n + 1
+// entries, built in double precision by device_upload.cu build_cdf_lut), so the answer for a scaled sample in bucket b
+// lies in [lut[b - 1], lut[b + 2]] (one bucket of slack on either side absorbs the fp32 rounding of the bucket index)
+// and the bisection -- the same lower bound, hence the same index as sample_reuse -- takes 1-2 dependent loads instead
+// of log2(size): the 50 000-cell guiding grid and the 7 000-edge distribution of cfg 4 cost 16 and 13 (profiles/r02w:
+// a quarter of the secondary-edge kernel's stall samples sat on the search's load).
+__device__ __forceinline__ int sample_reuse_lut(const float *pmf, const float *cmf, int size, float sum, const int *lut, int n, float &s, float &prob) {
+    if (size == 1) { prob = 1.f; return 0; }
+    if (n <= 0) return sample_reuse(pmf, cmf, size, sum, s, prob);
+    s *= sum;
+    int b = (int) (s * ((float) n / sum));
+    b = min(max(b, 0), n - 1);
+    int start = __ldg(lut + max(b - 1, 0)), end = __ldg(lut + min(b + 2, n));
+    while (start < end) {
+        const int middle = (start + end) >> 1;
+        if (__ldg(cmf + middle) < s) start = middle + 1;
+        else end = middle;
+    }
+    const int idx = start;
+    if (idx > 0) s -= __ldg(cmf + idx - 1);
+    const float p = __ldg(pmf + idx);
+    if (p > 0.f) s /= p;
+    s = fminf(fmaxf(s, 0.f), 1.f);
+    prob = p / sum;
+    return idx;
+}
+
 template <class S> struct PosSample {
     V3<S> p, n;
     S J;
@@ -1286,7 +1313,7 @@ __device__ __forceinline__ SecEdgeGeo sec_edge_geo(const DScene &sc, int ei, flo
 template <int kCfg>
 __device__ __forceinline__ bool sec_edge_stage0(const DScene &sc, V3f sample3, SecCand &c) {
     float sample1 = sample3.x, pdf0;
-    const int ei = sample_reuse(sc.sec_pmf, sc.sec_cmf, sc.n_sec_edges, sc.sec_sum, sample1, pdf0);
+    const int ei = sample_reuse_lut(sc.sec_pmf, sc.sec_cmf, sc.n_sec_edges, sc.sec_sum, sc.sec_lut, sc.sec_lut_n, sample1, pdf0);
     V3f n0, n1;
     bool is_boundary;
     float e1_norm;
@@ -1389,7 +1416,7 @@ __device__ __forceinline__ int eval_secondary_edge(const DScene &sc, const DCame
 __device__ __forceinline__ float guide_sample_reuse(const DCamera &cam, V3f &s) {
     const int ncells = cam.greso[0] * cam.greso[1] * cam.greso[2];
     float prob;
-    const int idx = sample_reuse(cam.guide_pmf, cam.guide_cmf, ncells, cam.guide_sum, s.z, prob);
+    const int idx = sample_reuse_lut(cam.guide_pmf, cam.guide_cmf, ncells, cam.guide_sum, cam.guide_lut, cam.guide_lut_n, s.z, prob);
     const int r12 = cam.greso[1] * cam.greso[2];
     const int c0 = idx / r12, rem = idx - c0 * r12, c1 = rem / cam.greso[2], c2 = rem - c1 * cam.greso[2];
     s.x = (s.x + (float) c0) * (1.f / (float) cam.greso[0]);

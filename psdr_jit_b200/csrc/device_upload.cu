@@ -99,6 +99,23 @@ struct Packer {
         return off;
     }
 };
+// Bucket table of an unnormalised fp32 CDF for sample_reuse_lut (device_path.cuh): n = the power of two >= size (at most
+// 2^20) buckets; entry b = first index i with cmf[i] >= b * sum / n (clipped to size - 1), entry n = size - 1.  Appends
+// n + 1 ints to `out`, returns n (0 for distributions too small to bother).
+inline int build_cdf_lut(const std::vector<float> &cmf, float sum, std::vector<int> &out) {
+    const int size = (int) cmf.size();
+    if (size < 64 || !(sum > 0.f)) return 0;
+    int n = 64;
+    while (n < size && n < (1 << 20)) n <<= 1;
+    int i = 0;
+    for (int b = 0; b < n; ++b) {
+        const double v = (double) b * (double) sum / (double) n;
+        while (i < size - 1 && (double) cmf[i] < v) ++i;
+        out.push_back(i);
+    }
+    out.push_back(size - 1);
+    return n;
+}
 inline float as_float(int i) {
     float f;
     std::memcpy(&f, &i, 4);
@@ -214,15 +231,20 @@ void upload_scene(Scene &sc) {
     }
 
     std::vector<float> g_pmf, g_cmf;
-    std::vector<size_t> cam_guide_first(sc.cameras.size(), 0);
+    std::vector<int> g_lut, s_lut;
+    std::vector<size_t> cam_guide_first(sc.cameras.size(), 0), cam_lut_first(sc.cameras.size(), 0);
+    std::vector<int> cam_lut_n(sc.cameras.size(), 0);
     for (size_t ci = 0; ci < sc.cameras.size(); ++ci) {
         const HCamera &c = sc.cameras[ci];
         cam_guide_first[ci] = g_pmf.size();
+        cam_lut_first[ci] = g_lut.size();
         if (c.guide_ready) {
             g_pmf.insert(g_pmf.end(), c.guide.pmf.begin(), c.guide.pmf.end());
             g_cmf.insert(g_cmf.end(), c.guide.cmf.begin(), c.guide.cmf.end());
+            cam_lut_n[ci] = build_cdf_lut(c.guide.cmf, c.guide.sum, g_lut);
         }
     }
+    const int sec_lut_n = sc.sec_edges.empty() ? 0 : build_cdf_lut(sc.sec_edge_distrb.cmf, sc.sec_edge_distrb.sum, s_lut);
 
     const int ntris = (int) all_tris.size();
     const bool use_bvh = ntris > kMaxBruteTris || (sc.force_bvh < 0 ? false : sc.force_bvh != 0);
@@ -232,7 +254,7 @@ void upload_scene(Scene &sc) {
                  o_mesh = pk.add(dmeshes), o_emit = pk.add(demit), o_bsdf = pk.add(dbsdf), o_fp = pk.add(face_pmf), o_fc = pk.add(face_cmf),
                  o_ep = pk.add(em_pmf), o_ec = pk.add(em_cmf), o_sec = pk.add(sec), o_sp = pk.add(sec_pmf), o_scm = pk.add(sec_cmf),
                  o_pa = pk.add(pe_a), o_pda = pk.add(pe_da), o_pb = pk.add(pe_b), o_pp = pk.add(pe_pmf), o_pc = pk.add(pe_cmf),
-                 o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf),
+                 o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf), o_gl = pk.add(g_lut), o_sl = pk.add(s_lut),
                  o_small_end = 0;
     (void) o_small_end;
     std::vector<size_t> o_tex(3 * sc.bsdfs.size(), 0), o_dtex(3 * sc.bsdfs.size(), 0);
@@ -405,6 +427,8 @@ void upload_scene(Scene &sc) {
     d.sec_pmf = (const float *) (base + o_sp);
     d.sec_cmf = (const float *) (base + o_scm);
     d.sec_sum = sc.sec_edges.empty() ? 0.f : sc.sec_edge_distrb.sum;
+    d.sec_lut = (const int *) (base + o_sl);
+    d.sec_lut_n = sec_lut_n;
     d.nodes2 = use_bvh ? (const DBvhNode2 *) ((const unsigned char *) db.bvh + db.off_nodes2) : nullptr;
     d.leaf_tri = use_bvh ? (const float4 *) ((const unsigned char *) db.bvh + db.off_leaf_tri) : nullptr;
     if (!use_bvh) {
@@ -509,6 +533,8 @@ void upload_scene(Scene &sc) {
         dc.guide_sum = c.guide_ready ? c.guide.sum : 0.f;
         dc.guide_pmf = (const float *) (base + o_gp) + cam_guide_first[ci];
         dc.guide_cmf = (const float *) (base + o_gc) + cam_guide_first[ci];
+        dc.guide_lut = (const int *) (base + o_gl) + cam_lut_first[ci];
+        dc.guide_lut_n = cam_lut_n[ci];
     }
 }
 

@@ -106,6 +106,8 @@ struct DCamera {
     int greso[3];
     float guide_sum;
     const float *guide_pmf, *guide_cmf;
+    const int *guide_lut;    // bucket table of the grid's CDF (sample_reuse_lut, device_path.cuh); guide_lut_n buckets (0 = none)
+    int guide_lut_n;
 };
 
 struct DScene {
@@ -127,6 +129,8 @@ struct DScene {
     const float4 *sec_edges;
     const float *sec_pmf, *sec_cmf;
     float sec_sum;
+    const int *sec_lut;      // bucket table of the secondary-edge CDF; sec_lut_n buckets (0 = none)
+    int sec_lut_n;
     const DBvhNode2 *nodes2;                   // BVH mode: wide-fetch BVH2 (device_upload.cu builds / refits it)
     const float4 *leaf_tri;                    // 3 float4 per leaf slot: (p0.xyz, int_as_float(triangle id)), (e1.xyz, 0), (e2.xyz, 0)
     DEnv env;
