@@ -4,6 +4,10 @@
 // edge terms), Dual = value + forward tangent (renderD interior term; what the reference gets from
 // Dr.Jit's AD with detach() at the same places).  One thread = one lane of the reference wavefront.
 #pragma once
+// experiment knob (tools/gpu_cfg3_sweep.sh): 0 compiles the texture lookups and the conductor out of the full-feature family
+#ifndef PSDR_TEXCOND
+#define PSDR_TEXCOND 1
+#endif
 #include "dscene.h"
 #include "pmath.h"
 #include "texture.h"
@@ -624,7 +628,7 @@ template <> __device__ __forceinline__ V3d bsdf_reflectance_const<Dual>(const DB
 // Bitmap::eval(its.uv): 1x1 -> the constant, else transformed bilinear texture lookup (reference src/core/bitmap.cpp:46-131);
 // textures belong to the "full" kernel family
 template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_reflectance(const DBsdf &b, V2<S> uv) {
-    if ((kCfg & kCfgFull) && b.tex[0].w > 0) return tex_eval_uv<S>(b.tex[0], IsDual<S>::value, uv);
+    if (PSDR_TEXCOND && (kCfg & kCfgFull) && b.tex[0].w > 0) return tex_eval_uv<S>(b.tex[0], IsDual<S>::value, uv);
     return bsdf_reflectance_const<S>(b);
 }
 
@@ -634,14 +638,14 @@ template <> __device__ __forceinline__ V3d bsdf_specular_const<Dual>(const DBsdf
     return V3d(Dual(b.spec[0], b.d_spec[0]), Dual(b.spec[1], b.d_spec[1]), Dual(b.spec[2], b.d_spec[2]));
 }
 template <class S> __device__ __forceinline__ V3<S> bsdf_specular(const DBsdf &b, V2<S> uv) {     // Microfacet: full family only
-    if (b.tex[1].w > 0) return tex_eval_uv<S>(b.tex[1], IsDual<S>::value, uv);
+    if (PSDR_TEXCOND && b.tex[1].w > 0) return tex_eval_uv<S>(b.tex[1], IsDual<S>::value, uv);
     return bsdf_specular_const<S>(b);
 }
 template <class S> __device__ __forceinline__ S bsdf_roughness_const(const DBsdf &b);
 template <> __device__ __forceinline__ float bsdf_roughness_const<float>(const DBsdf &b) { return b.rough; }
 template <> __device__ __forceinline__ Dual bsdf_roughness_const<Dual>(const DBsdf &b) { return Dual(b.rough, b.d_rough); }
 template <class S> __device__ __forceinline__ S bsdf_roughness(const DBsdf &b, V2<S> uv) {
-    if (b.tex[2].w > 0) return tex_eval_uv<S>(b.tex[2], IsDual<S>::value, uv).x;
+    if (PSDR_TEXCOND && b.tex[2].w > 0) return tex_eval_uv<S>(b.tex[2], IsDual<S>::value, uv).x;
     return bsdf_roughness_const<S>(b);
 }
 
@@ -742,7 +746,7 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DS
     if (bi < 0) return V3<S>(S(0.f));
     const DBsdf &b = sc.bsdfs[bi];
     if ((kCfg & kCfgFull) && b.type == 1) return microfacet_eval<S, kCfg>(b, its.wi, wo, its.uv);
-    if ((kCfg & kCfgFull) && b.type == 2) return conductor_eval<S, kCfg>(b, its.wi, wo, its.uv);
+    if (PSDR_TEXCOND && (kCfg & kCfgFull) && b.type == 2) return conductor_eval<S, kCfg>(b, its.wi, wo, its.uv);
     S wiz = its.wi.z;
     if (b.two_side) {
         if (signbit_(val(wiz))) wo.z = -wo.z;
