@@ -44,7 +44,9 @@ enum {
     PSDR_BSDF_SPECULAR_UV = 15,
     PSDR_BSDF_ROUGHNESS_UV = 16,
     PSDR_BSDF_ETA = 17,            /* RoughConductorBSDF.eta (1x1 Bitmap3fD), 3 floats */
-    PSDR_BSDF_K = 18               /* RoughConductorBSDF.k (1x1 Bitmap3fD), 3 floats */
+    PSDR_BSDF_K = 18,              /* RoughConductorBSDF.k (1x1 Bitmap3fD), 3 floats */
+    PSDR_BSDF_PERVERTEX = 19       /* MicrofacetBSDFPerVertex tables, 7 floats per vertex: specularReflectance rgb,
+                                      diffuseReflectance rgb, roughness (src/psdr.cpp:306-310) */
 };
 
 /* Texture slots of a BSDF (psdr_scene_set_bsdf_texture_slot). */
@@ -67,8 +69,11 @@ enum {
     PSDR_Q_GUIDING_CELLS = 12,      /* index = sensor; cells of its secondary-edge guiding grid (0 = none) */
     PSDR_Q_BVH_BUILDS = 13,         /* host BVH topology builds so far (first configure, or after the set of meshes changed) */
     PSDR_Q_BVH_REFITS = 14,         /* GPU BVH refits so far (every configure of a scene above 64 triangles) */
-    PSDR_Q_GRAD_TABLE_MULTICAST = 15 /* index = sensor; 1 = psdr_render_vjp_device may target a multicast table
+    PSDR_Q_GRAD_TABLE_MULTICAST = 15, /* index = sensor; 1 = psdr_render_vjp_device may target a multicast table
                                       * (psdr_scene_set_output_multicast): the table fits the kernels' shared-memory copy */
+    PSDR_Q_KERNEL_FAMILY = 16        /* which kernel instantiation the configured scene runs: bit 0 BVH2 traversal, bit 1
+                                      * Microfacet / EnvironmentMap code, bit 3 extended materials (bitmaps, RoughConductor,
+                                      * RoughDielectric, MicrofacetPerVertex, NormalMap); -1 before configure() */
 };
 
 /* Terms of renderD (bit mask). */
@@ -141,6 +146,30 @@ int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float sp
  * PSDR_BSDF_ROUGHNESS.  The anisotropic constructors (alpha_u != alpha_v) are not supported. */
 int psdr_scene_add_bsdf_roughconductor(psdr_scene *s, const char *id, float alpha, const float eta[3], const float k[3], const float specular[3],
                                        int two_side);
+
+/* RoughDielectricBSDF(alpha, intIOR, extIOR) -- include/psdr/bsdf/roughdielectric.h:10-29, src/bsdf/roughdielectric.cpp:37-236
+ * (GGX reflection + refraction, Fresnel include/psdr/utils.h:185-215); the reference creates it from scene files only
+ * (src/scene/scene_loader.cpp:346-360; src/psdr.cpp:295 binds the class without a constructor).  alpha is PSDR_BSDF_ROUGHNESS
+ * (constant or Bitmap1fD through slot PSDR_TEX_ROUGHNESS); the indices of refraction are fixed at creation. */
+int psdr_scene_add_bsdf_roughdielectric(psdr_scene *s, const char *id, float alpha, float int_ior, float ext_ior, int two_side);
+
+/* Scene.add_BSDF(MicrofacetBSDFPerVertex(specular, diffuse, roughness), name, twoSide) -- src/psdr.cpp:306-310,
+ * src/bsdf/microfacet_pv.cpp: the three parameters are arrays over the VERTICES of the mesh the BSDF is attached to
+ * (specular / diffuse: n_vertices*3 floats, roughness: n_vertices floats), interpolated with the hit's barycentrics
+ * (microfacet_pv.cpp:146-160).  Afterwards PSDR_BSDF_PERVERTEX takes / returns all three as one 7*n_vertices table. */
+int psdr_scene_add_bsdf_microfacet_pervertex(psdr_scene *s, const char *id, const float *specular, const float *diffuse, const float *roughness,
+                                             int n_vertices, int two_side);
+
+/* Scene.add_normalmap_BSDF(NormalMapBSDF, MicrofacetBSDF, name, twoSide) -- src/psdr.cpp:273-277,402, src/scene/scene.cpp:128-145,
+ * src/bsdf/normalmap.cpp; scene files may nest a Diffuse, RoughConductor, RoughDielectric or Microfacet BSDF
+ * (src/scene/scene_loader.cpp:372-424).  The wrapped BSDF is created first: psdr_scene_begin_nested_bsdf() makes the NEXT
+ * psdr_scene_add_bsdf_* call create an un-numbered record and return its handle (>= PSDR_NESTED_BSDF_BASE), which is passed
+ * here as `nested` and accepted as `index` by psdr_scene_set_param / set_tangent / set_bsdf_texture_slot.  normal: the
+ * constant normal map (Scene.add_BSDF(NormalMapBSDF) uses (.499999, .499999, 1), scene.cpp:221); a bitmap goes through slot
+ * PSDR_TEX_REFLECTANCE + PSDR_BSDF_REFLECTANCE of the NormalMap's own index. */
+#define PSDR_NESTED_BSDF_BASE (1 << 20)
+int psdr_scene_begin_nested_bsdf(psdr_scene *s);
+int psdr_scene_add_bsdf_normalmap(psdr_scene *s, const char *id, const float normal[3], int nested, int two_side);
 
 /* DiffuseBSDF.reflectance / MicrofacetBSDF.diffuseReflectance = Bitmap3fD(w, h, data) with more than one texel
  * (src/psdr.cpp:209-219, src/core/bitmap.cpp:46-131): declares the texture resolution of BSDF `index`; afterwards

@@ -121,12 +121,14 @@ struct Edge {  // reference src/shape/mesh.cpp:244-305 (m_edge_indices rows)
 };
 
 struct Bsdf {
-    int type = 0;  // 0 Diffuse, 1 Microfacet, 2 RoughConductor
-    V3d reflectance;  // Diffuse reflectance / Microfacet diffuseReflectance
+    int type = 0;  // 0 Diffuse, 1 Microfacet, 2 RoughConductor, 3 RoughDielectric, 4 MicrofacetPerVertex, 5 NormalMap
+    V3d reflectance;  // Diffuse reflectance / Microfacet diffuseReflectance / NormalMap: constant normal map
     V3d specular;     // Microfacet specularReflectance / RoughConductor specular_reflectance
     Dual roughness;   // Microfacet roughness / RoughConductor alpha (alpha_u = alpha_v)
-    V3d eta, k;       // RoughConductor eta + i k
+    V3d eta, k;       // RoughConductor eta + i k; RoughDielectric: eta.x = intIOR / extIOR, eta.y = extIOR / intIOR
     bool two_side = false;
+    int nested = -1;                 // NormalMap: index (into Scene::bsdfs) of the BSDF it perturbs
+    std::vector<float> pv, d_pv;     // MicrofacetPerVertex: 7 floats per vertex (specular rgb, diffuse rgb, roughness) + tangents
     // bitmap slots with more than one texel (channels interleaved, pixel = y*w + x): 0 reflectance / diffuseReflectance
     // (Bitmap3fD), 1 specularReflectance (Bitmap3fD), 2 roughness (Bitmap1fD); each with the bitmap's uv transform
     // (reference include/psdr/core/bitmap.h:36-38)
@@ -217,6 +219,7 @@ struct Scene {
     std::vector<Tri<Dual>> tris;
     std::vector<int> tri_mesh;
     std::vector<V2f> tri_uv;  // 3 per triangle
+    std::vector<int> tri_fidx;  // 3 per triangle: mesh-local vertex indices (m_triangle_info.face_indices, mesh.cpp:28)
     // per triangle PAIR (2j, 2j+1): padded bounding box, centre / half extent (scenes of <= 64 triangles; see trace())
     std::vector<float> cull_c, cull_h;
     std::vector<SecEdge> sec_edges;
@@ -583,12 +586,14 @@ static bool configure_scene(Scene &sc, const int *active, int nactive) {
     sc.tris.clear();
     sc.tri_mesh.clear();
     sc.tri_uv.clear();
+    sc.tri_fidx.clear();
     for (size_t mi = 0; mi < sc.meshes.size(); ++mi) {
         auto &m = sc.meshes[mi];
         for (size_t i = 0; i < m.tris.size(); ++i) {
             sc.tris.push_back(m.tris[i]);
             sc.tri_mesh.push_back((int) mi);
             for (int k = 0; k < 3; ++k) sc.tri_uv.push_back(m.has_uv ? m.uv[m.fuv[3 * i + k]] : V2f(0.f, 0.f));
+            for (int k = 0; k < 3; ++k) sc.tri_fidx.push_back(3 * i + k < m.f.size() ? m.f[3 * i + k] : 0);
         }
     }
     build_cull_boxes(sc);
@@ -723,6 +728,8 @@ template <class S> struct Its {  // reference include/psdr/core/intersection.h:2
     S t = S(0.f), J = S(1.f);
     V2<S> uv;
     float bu = 0.f, bv = 0.f;
+    V2<S> bc;        // its.bc (scene.cpp:769,799)
+    V3<S> dp_du;     // its.dp_du (scene.cpp:760-763,789-792): zero without UVs
     V3<S> to_local(V3<S> v) const { return {dot(v, sh_s), dot(v, sh_t), dot(v, sh_n)}; }
     V3<S> to_world(V3<S> v) const { return sh_s * v.x + sh_t * v.y + sh_n * v.z; }
 };
@@ -787,6 +794,7 @@ template <class S> static Its<S> ray_intersect(const Scene &sc, V3<S> o, V3<S> d
         its.uv = bilinear2(uv0, duv0, duv1, uv);
         its.bu = h.u;
         its.bv = h.v;
+        its.bc = V2<S>(S(h.u), S(h.v));
         if (ad) its.J = T.area / detach(T.area);
     } else {
         S u, v, t;
@@ -799,12 +807,15 @@ template <class S> static Its<S> ray_intersect(const Scene &sc, V3<S> o, V3<S> d
         its.uv = bilinear2(uv0, duv0, duv1, uv);
         its.bu = val(u);
         its.bv = val(v);
+        its.bc = uv;
         dir = d;
     }
     its.sh_n = sh_n;
     coordinate_system(sh_n, its.sh_s, its.sh_t);
+    its.dp_du = V3<S>(S(0.f));
     if (valid_dp) {
         V3<S> dp_du = (T.e1 * duv1.y - T.e2 * duv0.y) * inv_det;
+        its.dp_du = dp_du;
         its.sh_s = normalize(dp_du - sh_n * dot(sh_n, dp_du));
         its.sh_t = cross(sh_n, its.sh_s);
     }
@@ -941,26 +952,92 @@ template <class S> static V3<S> conductor_eval(const Bsdf &b, V3<S> wi, V3<S> wo
     V3<S> F(fresnel_conductor<S>(eta.x, k.x, c), fresnel_conductor<S>(eta.y, k.y, c), fresnel_conductor<S>(eta.z, k.z, c));
     return F * result * spec_of<S>(b, uv);
 }
-// Microfacet::__pdf (microfacet.cpp:108-133), detached; RoughConductor::__pdf (roughconductor.cpp:70-95) is the same
-// expression with alpha given directly
-static float microfacet_pdf(const Bsdf &b, V3f wi, V3f wo, V2f uv) {
-    if (b.two_side) {
-        if (std::signbit(wi.z)) wo.z = -wo.z;
-        wi.z = std::fabs(wi.z);
-    }
-    V3f m = normalize(wo + wi);
-    if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
-    float alpha = b.type == 2 ? rough_of<float>(b, uv) : sqr(rough_of<float>(b, uv));
-    return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
+// fresnel_dielectric (reference include/psdr/utils.h:185-215)
+template <class S> struct FresnelDielectric {
+    S r, cos_theta_t, eta_it, eta_ti;
+};
+template <class S> static FresnelDielectric<S> fresnel_dielectric(S eta, S cos_theta_i) {
+    FresnelDielectric<S> f;
+    bool outside_mask = val(cos_theta_i) >= 0.f;
+    S rcp_eta = rcp_(eta);
+    f.eta_it = outside_mask ? eta : rcp_eta;
+    f.eta_ti = outside_mask ? rcp_eta : eta;
+    S cos_theta_t_sqr = fmadd(-fmadd(-cos_theta_i, cos_theta_i, S(1.f)), f.eta_ti * f.eta_ti, S(1.f));
+    S cos_theta_i_abs = abs_(cos_theta_i), cos_theta_t_abs = safe_sqrt(cos_theta_t_sqr);
+    bool index_matched = val(eta) == 1.f, special_case = index_matched || val(cos_theta_i_abs) == 0.f;
+    S a_s = fmadd(-f.eta_it, cos_theta_t_abs, cos_theta_i_abs) / fmadd(f.eta_it, cos_theta_t_abs, cos_theta_i_abs);
+    S a_p = fmadd(-f.eta_it, cos_theta_i_abs, cos_theta_t_abs) / fmadd(f.eta_it, cos_theta_i_abs, cos_theta_t_abs);
+    f.r = S(.5f) * (sqr(a_s) + sqr(a_p));
+    if (special_case) f.r = S(index_matched ? 0.f : 1.f);
+    f.cos_theta_t = std::signbit(val(cos_theta_i)) ? cos_theta_t_abs : -cos_theta_t_abs;   // mulsign_neg
+    return f;
 }
-
-template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
-    if (!active || !its.valid) return V3<S>(S(0.f));
-    if (sc.meshes[its.mesh].bsdf < 0) return V3<S>(S(0.f));   // bsdf == nullptr (envmap bounding mesh): a Dr.Jit vcall on null yields 0
-    const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type == 1) return microfacet_eval<S>(b, its.wi, wo, its.uv);
-    if (b.type == 2) return conductor_eval<S>(b, its.wi, wo, its.uv);
-    S wiz = its.wi.z;
+// RoughDielectric::__eval (reference src/bsdf/roughdielectric.cpp:37-122), alpha_u = alpha_v
+template <class S> static V3<S> dielectric_eval(const Bsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
+    if (b.two_side) {
+        if (std::signbit(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    S cos_theta_i = wi.z, cos_theta_o = wo.z;
+    if (val(cos_theta_i) == 0.f) return V3<S>(S(0.f));
+    bool reflect = val(cos_theta_i) * val(cos_theta_o) > 0.f;
+    S m_eta = lift_d<S>(b.eta.x), m_inv_eta = lift_d<S>(b.eta.y);
+    S eta = val(cos_theta_i) > 0.f ? m_eta : m_inv_eta, inv_eta = val(cos_theta_i) > 0.f ? m_inv_eta : m_eta;
+    V3<S> m = normalize(wi + wo * (reflect ? S(1.f) : eta));
+    if (std::signbit(val(m.z))) m = -m;
+    S alpha = rough_of<S>(b, uv);
+    S D = ggx_eval<S>(alpha, m);
+    S F = fresnel_dielectric<S>(m_eta, dot(wi, m)).r;
+    S G = ggx_smith_g1<S>(alpha, wi, m) * ggx_smith_g1<S>(alpha, wo, m);
+    if (reflect) return V3<S>(F * D * G / (S(4.f) * abs_(cos_theta_i)));
+    S scale = sqr(inv_eta);
+    S wi_m = dot(wi, m), wo_m = dot(wo, m);
+    S value = abs_((scale * (S(1.f) - F) * D * G * eta * eta * wi_m * wo_m) / (cos_theta_i * sqr(wi_m + eta * wo_m)));
+    return V3<S>(value);
+}
+// MicrofacetPerVertex::__interpolate (reference src/bsdf/microfacet_pv.cpp:146-160)
+template <class S> static S pv_interp(const Scene &sc, const Bsdf &b, const Its<S> &its, int c) {
+    auto at = [&](int vtx) -> S {
+        if (7 * vtx + c >= (int) b.pv.size()) return S(0.f);
+        return lift_d<S>(Dual(b.pv[7 * vtx + c], b.d_pv.empty() ? 0.f : b.d_pv[7 * vtx + c]));
+    };
+    S v0 = at(sc.tri_fidx[3 * its.tri]), v1 = at(sc.tri_fidx[3 * its.tri + 1]), v2 = at(sc.tri_fidx[3 * its.tri + 2]);
+    return fmadd(v1 - v0, its.bc.x, fmadd(v2 - v0, its.bc.y, v0));
+}
+// MicrofacetPerVertex::__eval (reference src/bsdf/microfacet_pv.cpp:20-68)
+template <class S> static V3<S> microfacet_pv_eval(const Scene &sc, const Bsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
+    if (b.two_side) {
+        if (std::signbit(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    S cos_nv = wi.z, cos_nl = wo.z;
+    if (!(val(cos_nv) > 0.f && val(cos_nl) > 0.f)) return V3<S>(S(0.f));
+    V3<S> F0(pv_interp<S>(sc, b, its, 0), pv_interp<S>(sc, b, its, 1), pv_interp<S>(sc, b, its, 2));
+    V3<S> diffuse = V3<S>(pv_interp<S>(sc, b, its, 3), pv_interp<S>(sc, b, its, 4), pv_interp<S>(sc, b, its, 5)) * S(kInvPi);
+    S roughness = pv_interp<S>(sc, b, its, 6);
+    V3<S> H = normalize(wi + wo);
+    S cos_nh = H.z, cos_vh = dot(H, wi);
+    S alpha = sqr(roughness);
+    S k = sqr(roughness + S(1.f)) / S(8.f);
+    S tmp = alpha / (cos_nh * cos_nh * (sqr(alpha) - S(1.f)) + S(1.f));
+    S ggx = tmp * tmp * S(kInvPi);
+    S coeff = cos_vh * (S(-5.55473f) * cos_vh - S(6.8316f));
+    V3<S> fresnel = F0 + (V3<S>(S(1.f)) - F0) * exp2_(coeff);
+    S smithG1 = cos_nv / (cos_nv * (S(1.f) - k) + k);
+    S smithG2 = cos_nl / (cos_nl * (S(1.f) - k) + k);
+    S smithG = smithG1 * smithG2;
+    V3<S> numerator = fresnel * (ggx * smithG);
+    S denominator = S(4.f) * cos_nl * cos_nv;
+    V3<S> specular = numerator / (denominator + S(1e-6f));
+    return (diffuse + specular) * cos_nl;
+}
+// BSDF::eval of a record that is not a NormalMap, incident direction given explicitly
+template <class S> static V3<S> bsdf_eval_leaf(const Scene &sc, const Bsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
+    if (b.type == 1) return microfacet_eval<S>(b, wi, wo, its.uv);
+    if (b.type == 2) return conductor_eval<S>(b, wi, wo, its.uv);
+    if (b.type == 3) return dielectric_eval<S>(b, wi, wo, its.uv);
+    if (b.type == 4) return microfacet_pv_eval<S>(sc, b, its, wi, wo);
+    S wiz = wi.z;
     if (b.two_side) {
         if (std::signbit(val(wiz))) wo.z = -wo.z;
         wiz = abs_(wiz);
@@ -969,19 +1046,154 @@ template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3
     V3<S> r = refl_of<S>(b, its.uv);
     return r * S(kInvPi) * wo.z;
 }
+// ---- NormalMap (reference src/bsdf/normalmap.cpp:17-40 helpers) ----
+template <class S> struct NmFrame {   // Frame(n, s), include/psdr/core/frame.h:42-45
+    V3<S> s, t, n;
+    V3<S> to_local(V3<S> v) const { return {dot(v, s), dot(v, t), dot(v, n)}; }
+    V3<S> to_world(V3<S> v) const { return s * v.x + t * v.y + n * v.z; }
+};
+template <class S> static S nm_pdot(V3<S> a, V3<S> b) {
+    S d = dot(a, b);
+    return val(d) > 0.f ? d : S(0.f);
+}
+template <class S> static S nm_sin_theta(V3<S> v) { return safe_sqrt(fmadd(v.x, v.x, sqr(v.y))); }
+template <class S> static V3<S> nm_wt(V3<S> wp) { return normalize(V3<S>(-wp.x, -wp.y, S(0.f))); }
+template <class S> static S nm_G1(V3<S> wp, V3<S> w) {
+    S cw = val(w.z) > 0.f ? w.z : S(0.f), cp = val(wp.z) > 0.f ? wp.z : S(0.f);
+    S g = cw * cp / (nm_pdot<S>(w, wp) + nm_pdot<S>(w, nm_wt<S>(wp)) * nm_sin_theta<S>(wp));
+    return val(g) < 1.f ? g : S(1.f);
+}
+template <class S> static S nm_lambda_p(V3<S> wp, V3<S> wi) {
+    S i_dot_p = nm_pdot<S>(wp, wi);
+    return i_dot_p / (i_dot_p + nm_pdot<S>(nm_wt<S>(wp), wi) * nm_sin_theta<S>(wp));
+}
+template <class S> static void nm_setup(const Bsdf &b, const Its<S> &its, V3<S> &wp, NmFrame<S> &fr) {
+    V3<S> c = refl_of<S>(b, its.uv);
+    wp = normalize(V3<S>(fmadd(c.x, S(2.f), S(-1.f)), fmadd(c.y, S(2.f), S(-1.f)), fmadd(c.z, S(2.f), S(-1.f))));
+    S d = dot(wp, its.dp_du);   // a shading-frame vector against a world-space one, as the reference writes it (normalmap.cpp:61)
+    V3<S> s0 = normalize(V3<S>(fmadd(-wp.x, d, its.dp_du.x), fmadd(-wp.y, d, its.dp_du.y), fmadd(-wp.z, d, its.dp_du.z)));
+    fr.n = wp;
+    fr.t = normalize(cross(wp, s0));
+    fr.s = normalize(cross(fr.t, wp));
+}
+template <class S> static V3<S> nm_reflect(V3<S> w, V3<S> wt) {
+    S k = S(2.f) * dot(w, wt);
+    return normalize(w - wt * k);
+}
+// NormalMap::__eval (normalmap.cpp:42-86)
+template <class S> static V3<S> normalmap_eval(const Scene &sc, const Bsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
+    if (b.two_side) {
+        if (std::signbit(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
+    const Bsdf &nb = sc.bsdfs[b.nested];
+    V3<S> wp;
+    NmFrame<S> fr;
+    nm_setup<S>(b, its, wp, fr);
+    V3<S> p_wo = fr.to_local(wo);
+    S shadowing = nm_G1<S>(wp, wo);
+    S lambda_p = nm_lambda_p<S>(wp, wi);
+    V3<S> wt = nm_wt<S>(wp);
+    V3<S> value = bsdf_eval_leaf<S>(sc, nb, its, fr.to_local(wi), p_wo) * lambda_p * shadowing;
+    if (val(dot(wi, wt)) > 0.f) {
+        V3<S> wi_r = nm_reflect<S>(wi, wt);
+        value = value + bsdf_eval_leaf<S>(sc, nb, its, fr.to_local(wi_r), p_wo) * ((S(1.f) - lambda_p) * shadowing);
+    }
+    return value;
+}
 
-template <class S> static float bsdf_pdf(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
-    if (!active || !its.valid) return 0.f;
-    if (sc.meshes[its.mesh].bsdf < 0) return 0.f;
+template <class S> static V3<S> bsdf_eval(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
+    if (!active || !its.valid) return V3<S>(S(0.f));
+    if (sc.meshes[its.mesh].bsdf < 0) return V3<S>(S(0.f));   // bsdf == nullptr (envmap bounding mesh): a Dr.Jit vcall on null yields 0
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type != 0) return microfacet_pdf(b, val(its.wi), val(wo), val(its.uv));
-    float wiz = val(its.wi.z), woz = val(wo.z);
+    if (b.type == 5) return normalmap_eval<S>(sc, b, its, its.wi, wo);
+    return bsdf_eval_leaf<S>(sc, b, its, its.wi, wo);
+}
+
+template <class S> static Its<float> its_detached(const Its<S> &its) {
+    Its<float> f;
+    f.valid = its.valid; f.mesh = its.mesh; f.tri = its.tri;
+    f.uv = V2f(val(its.uv.x), val(its.uv.y));
+    f.bc = V2f(val(its.bc.x), val(its.bc.y));
+    f.dp_du = val(its.dp_du);
+    return f;
+}
+// alpha of the GGX lobe used by __pdf / __sample (microfacet.cpp:92,123; microfacet_pv.cpp:93,135; roughconductor.cpp:83,107;
+// roughdielectric.cpp:158,191)
+static float bsdf_alpha(const Scene &sc, const Bsdf &b, const Its<float> &its) {
+    if (b.type == 4) return sqr(pv_interp<float>(sc, b, its, 6));
+    float r = rough_of<float>(b, its.uv);
+    return (b.type == 2 || b.type == 3) ? r : sqr(r);
+}
+// Microfacet::__pdf (microfacet.cpp:108-133), detached; RoughConductor::__pdf (roughconductor.cpp:70-95) and
+// MicrofacetPerVertex::__pdf (microfacet_pv.cpp:120-143) are the same expression with their own alpha
+static float ggx_reflect_pdf(float alpha, bool two_side, V3f wi, V3f wo) {
+    if (two_side) {
+        if (std::signbit(wi.z)) wo.z = -wo.z;
+        wi.z = std::fabs(wi.z);
+    }
+    V3f m = normalize(wo + wi);
+    if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
+    return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
+}
+// RoughDielectric::__pdf (roughdielectric.cpp:125-176)
+static float dielectric_pdf(const Bsdf &b, float alpha, V3f wi, V3f wo) {
+    if (b.two_side) {
+        if (std::signbit(wi.z)) wo.z = -wo.z;
+        wi.z = std::fabs(wi.z);
+    }
+    float cos_theta_i = wi.z, cos_theta_o = wo.z;
+    if (cos_theta_i == 0.f) return 0.f;
+    bool reflect = cos_theta_i * cos_theta_o > 0.f;
+    float eta = cos_theta_i > 0.f ? b.eta.x.v : b.eta.y.v;
+    V3f m = normalize(wi + wo * (reflect ? 1.f : eta));
+    if (std::signbit(m.z)) m = -m;
+    float wi_m = dot(wi, m), wo_m = dot(wo, m);
+    if (!(wi_m * wi.z > 0.f && wo_m * wo.z > 0.f)) return 0.f;
+    float dwh_dwo = reflect ? 1.f / (4.f * wo_m) : (eta * eta * wo_m) / sqr(wi_m + eta * wo_m);
+    V3f pwi = std::signbit(wi.z) ? -wi : wi;
+    float prob = ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, pwi, m) / pwi.z;
+    float F = fresnel_dielectric<float>(b.eta.x.v, wi_m).r;
+    prob *= reflect ? F : 1.f - F;
+    return prob * std::fabs(dwh_dwo);
+}
+static float bsdf_pdf_leaf(const Scene &sc, const Bsdf &b, const Its<float> &its, V3f wi, V3f wo) {
+    if (b.type == 3) return dielectric_pdf(b, bsdf_alpha(sc, b, its), wi, wo);
+    if (b.type != 0) return ggx_reflect_pdf(bsdf_alpha(sc, b, its), b.two_side, wi, wo);
+    float wiz = wi.z, woz = wo.z;
     if (b.two_side) {
         if (std::signbit(wiz)) woz = -woz;
         wiz = std::fabs(wiz);
     }
     if (!(wiz > 0.f && woz > 0.f)) return 0.f;
     return kInvPi * woz;
+}
+// NormalMap::__pdf (normalmap.cpp:109-144)
+static float normalmap_pdf(const Scene &sc, const Bsdf &b, const Its<float> &its, V3f wi, V3f wo) {
+    if (b.two_side) {
+        if (std::signbit(wi.z)) wo.z = -wo.z;
+        wi.z = std::fabs(wi.z);
+    }
+    if (!(wi.z > 0.f && wo.z > 0.f)) return 0.f;
+    const Bsdf &nb = sc.bsdfs[b.nested];
+    V3f wp;
+    NmFrame<float> fr;
+    nm_setup<float>(b, its, wp, fr);
+    V3f p_wo = fr.to_local(wo);
+    float probability_wp = nm_lambda_p<float>(wp, wi);
+    V3f wi_r = nm_reflect<float>(wi, nm_wt<float>(wp));
+    return probability_wp * bsdf_pdf_leaf(sc, nb, its, fr.to_local(wi), p_wo) +
+           (1.f - probability_wp) * bsdf_pdf_leaf(sc, nb, its, fr.to_local(wi_r), p_wo);
+}
+
+template <class S> static float bsdf_pdf(const Scene &sc, const Its<S> &its, V3<S> wo, bool active) {
+    if (!active || !its.valid) return 0.f;
+    if (sc.meshes[its.mesh].bsdf < 0) return 0.f;
+    const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
+    const Its<float> f = its_detached(its);
+    if (b.type == 5) return normalmap_pdf(sc, b, f, val(its.wi), val(wo));
+    return bsdf_pdf_leaf(sc, b, f, val(its.wi), val(wo));
 }
 
 struct BsdfSample {
@@ -1015,11 +1227,8 @@ static V2f ggx_sample_visible_11(float cos_theta_i, V2f sample) {
     float norm = 1.f / std::fmaf(sin_theta_i, y, cos_theta_i * z);
     return V2f(std::fmaf(cos_theta_i, y, -(sin_theta_i * z)) * norm, x * norm);
 }
-// Microfacet::__sample (microfacet.cpp:80-98) + GGXDistribution::sample (ggx.cpp:36-79); sin/cos phi: frame.h:104-122
-static BsdfSample microfacet_sample(const Bsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
-    BsdfSample bs;
-    if (b.two_side) wi.z = std::fabs(wi.z);
-    float alpha = b.type == 2 ? rough_of<float>(b, uv) : sqr(rough_of<float>(b, uv));   // RoughConductor::__sample (roughconductor.cpp:99-122)
+// GGXDistribution::sample (ggx.cpp:36-79); sin/cos phi: frame.h:104-122
+static void ggx_sample_m(float alpha, V3f wi, V3f sample, V3f &m, float &m_pdf) {
     V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
     float sin_theta_2 = std::fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / std::sqrt(sin_theta_2);
     bool pole = std::fabs(sin_theta_2) <= 4.f * kEpsilon;
@@ -1027,12 +1236,81 @@ static BsdfSample microfacet_sample(const Bsdf &b, V3f wi, V3f sample, bool acti
     float cos_phi = pole ? 1.f : std::fmin(std::fmax(wi_p.x * inv_sin_theta, -1.f), 1.f);
     V2f slope = ggx_sample_visible_11(wi_p.z, V2f(sample.x, sample.y));
     slope = V2f(std::fmaf(cos_phi, slope.x, -(sin_phi * slope.y)) * alpha, std::fmaf(sin_phi, slope.x, cos_phi * slope.y) * alpha);
-    V3f m = normalize(V3f(-slope.x, -slope.y, 1.f));
-    float m_pdf = ggx_smith_g1<float>(alpha, wi, m) * std::fabs(dot(wi, m)) * ggx_eval<float>(alpha, m) / std::fabs(wi.z);
+    m = normalize(V3f(-slope.x, -slope.y, 1.f));
+    m_pdf = ggx_smith_g1<float>(alpha, wi, m) * std::fabs(dot(wi, m)) * ggx_eval<float>(alpha, m) / std::fabs(wi.z);
+}
+// Microfacet::__sample (microfacet.cpp:80-98); RoughConductor::__sample (roughconductor.cpp:99-122) and
+// MicrofacetPerVertex::__sample (microfacet_pv.cpp:82-106) are the same with their own alpha
+static BsdfSample ggx_reflect_sample(float alpha, bool two_side, V3f wi, V3f sample, bool active) {
+    BsdfSample bs;
+    if (two_side) wi.z = std::fabs(wi.z);
+    V3f m;
+    float m_pdf;
+    ggx_sample_m(alpha, wi, sample, m, m_pdf);
     float k = 2.f * dot(wi, m);
     bs.wo = V3f(std::fmaf(m.x, k, -wi.x), std::fmaf(m.y, k, -wi.y), std::fmaf(m.z, k, -wi.z));
     bs.pdf = m_pdf / (4.f * dot(bs.wo, m));
     bs.valid = active && (wi.z > 0.f) && (bs.pdf != 0.f) && (bs.wo.z > 0.f);
+    return bs;
+}
+// RoughDielectric::__sample (roughdielectric.cpp:179-236)
+static BsdfSample dielectric_sample(const Bsdf &b, float alpha, V3f wi, V3f sample, bool active) {
+    BsdfSample bs;
+    if (b.two_side) wi.z = std::fabs(wi.z);
+    float cos_theta_i = wi.z;
+    active = active && cos_theta_i != 0.f;
+    V3f m;
+    ggx_sample_m(alpha, std::signbit(cos_theta_i) ? -wi : wi, sample, m, bs.pdf);
+    active = active && bs.pdf != 0.f;
+    float wi_m = dot(wi, m);
+    FresnelDielectric<float> f = fresnel_dielectric<float>(b.eta.x.v, wi_m);
+    bool selected_r = sample.z <= f.r && active, selected_t = !selected_r && active;
+    bs.pdf *= selected_r ? f.r : 1.f - f.r;
+    bs.eta = selected_r ? 1.f : f.eta_it;
+    bs.wo = V3f(0.f, 0.f, 0.f);
+    if (selected_r) {
+        float k = 2.f * wi_m;
+        bs.wo = V3f(std::fmaf(m.x, k, -wi.x), std::fmaf(m.y, k, -wi.y), std::fmaf(m.z, k, -wi.z));
+    }
+    float dwh_dwo = 1.f / (4.f * dot(bs.wo, m));   // assigned for every lane in the reference (:218), overwritten where refracting
+    if (selected_t) {
+        float k = std::fmaf(wi_m, f.eta_ti, f.cos_theta_t);
+        bs.wo = V3f(std::fmaf(m.x, k, -(wi.x * f.eta_ti)), std::fmaf(m.y, k, -(wi.y * f.eta_ti)), std::fmaf(m.z, k, -(wi.z * f.eta_ti)));
+        float wo_m = dot(bs.wo, m);
+        dwh_dwo = (sqr(bs.eta) * wo_m) / sqr(wi_m + bs.eta * wo_m);
+    }
+    bs.pdf *= std::fabs(dwh_dwo) * ggx_smith_g1<float>(alpha, bs.wo, m);
+    bs.valid = active && (selected_t || selected_r);
+    return bs;
+}
+static BsdfSample bsdf_sample_leaf(const Scene &sc, const Bsdf &b, const Its<float> &its, V3f wi, V3f sample, bool active) {
+    if (b.type == 3) return dielectric_sample(b, bsdf_alpha(sc, b, its), wi, sample, active);
+    if (b.type != 0) return ggx_reflect_sample(bsdf_alpha(sc, b, its), b.two_side, wi, sample, active);
+    BsdfSample bs;
+    float wiz = wi.z;
+    if (b.two_side) wiz = std::fabs(wiz);
+    V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));  // tail<2>(sample)
+    float z = safe_sqrt(1.f - (std::fmaf(p.y, p.y, p.x * p.x)));
+    bs.wo = V3f(p.x, p.y, z);
+    bs.pdf = kInvPi * z;
+    bs.valid = active && (wiz > 0.f);
+    return bs;
+}
+// NormalMap::__sample (normalmap.cpp:147-187)
+static BsdfSample normalmap_sample(const Scene &sc, const Bsdf &b, const Its<float> &its, V3f wi, V3f sample, bool active) {
+    if (b.two_side) wi.z = std::fabs(wi.z);
+    const Bsdf &nb = sc.bsdfs[b.nested];
+    V3f wp;
+    NmFrame<float> fr;
+    nm_setup<float>(b, its, wp, fr);
+    V3f p_wi = fr.to_local(wi);
+    float probability_wp = nm_lambda_p<float>(wp, wi);
+    bool itpo = sample.z >= probability_wp;
+    V3f r_wi = fr.to_local(nm_reflect<float>(wi, nm_wt<float>(wp)));
+    BsdfSample bs = bsdf_sample_leaf(sc, nb, its, itpo ? r_wi : p_wi, sample, active);
+    float pdf1 = bsdf_pdf_leaf(sc, nb, its, p_wi, bs.wo), pdf2 = bsdf_pdf_leaf(sc, nb, its, r_wi, bs.wo);
+    bs.pdf = probability_wp * pdf1 + (1.f - probability_wp) * pdf2;
+    bs.wo = fr.to_world(bs.wo);
     return bs;
 }
 
@@ -1041,15 +1319,9 @@ template <class S> static BsdfSample bsdf_sample(const Scene &sc, const Its<S> &
     if (!its.valid) return bs;
     if (sc.meshes[its.mesh].bsdf < 0) return bs;
     const Bsdf &b = sc.bsdfs[sc.meshes[its.mesh].bsdf];
-    if (b.type != 0) return microfacet_sample(b, val(its.wi), sample, active, val(its.uv));
-    float wiz = val(its.wi.z);
-    if (b.two_side) wiz = std::fabs(wiz);
-    V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));  // tail<2>(sample)
-    float z = safe_sqrt(1.f - (std::fmaf(p.y, p.y, p.x * p.x)));
-    bs.wo = V3f(p.x, p.y, z);
-    bs.pdf = kInvPi * z;
-    bs.valid = active && (wiz > 0.f);
-    return bs;
+    const Its<float> f = its_detached(its);
+    if (b.type == 5) return normalmap_sample(sc, b, f, val(its.wi), sample, active);
+    return bsdf_sample_leaf(sc, b, f, val(its.wi), sample, active);
 }
 
 // ---- emitters (reference src/emitter/area.cpp, src/shape/mesh.cpp:413-466) ---------------
@@ -1590,6 +1862,49 @@ int orc_add_roughconductor(void *h, float alpha, const float *eta, const float *
     b.two_side = two_side != 0;
     s->bsdfs.push_back(b);
     return (int) s->bsdfs.size() - 1;
+}
+
+// RoughDielectricBSDF(alpha, intIOR, extIOR) (roughdielectric.h:20-25: m_eta and m_inv_eta are two separate quotients)
+int orc_add_roughdielectric(void *h, float alpha, float d_alpha, float int_ior, float ext_ior, int two_side) {
+    Scene *s = (Scene *) h;
+    Bsdf b;
+    b.type = 3;
+    b.roughness = Dual(alpha, d_alpha);
+    b.eta = V3d(Dual(int_ior / ext_ior), Dual(ext_ior / int_ior), Dual(0.f));
+    b.two_side = two_side != 0;
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+}
+// MicrofacetBSDFPerVertex: pv / d_pv = n*7 floats (specular rgb, diffuse rgb, roughness per vertex); d_pv may be NULL
+int orc_add_microfacet_pervertex(void *h, const float *pv, const float *d_pv, int n, int two_side) {
+    Scene *s = (Scene *) h;
+    Bsdf b;
+    b.type = 4;
+    b.pv.assign(pv, pv + (size_t) 7 * n);
+    if (d_pv) b.d_pv.assign(d_pv, d_pv + (size_t) 7 * n);
+    b.two_side = two_side != 0;
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+}
+// NormalMapBSDF around BSDF `nested` (an index returned by an earlier orc_add_*; tests add the nested record LAST so that
+// the numbering of the visible BSDFs matches the product's); normal / d_normal: the constant normal map (a bitmap goes
+// through orc_set_bsdf_texture_slot, slot 0)
+int orc_add_normalmap(void *h, const float *normal, const float *d_normal, int nested, int two_side) {
+    Scene *s = (Scene *) h;
+    Bsdf b;
+    b.type = 5;
+    b.reflectance = V3d(Dual(normal[0], d_normal ? d_normal[0] : 0.f), Dual(normal[1], d_normal ? d_normal[1] : 0.f),
+                        Dual(normal[2], d_normal ? d_normal[2] : 0.f));
+    b.nested = nested;
+    b.two_side = two_side != 0;
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+}
+int orc_set_normalmap_nested(void *h, int bsdf, int nested) {
+    Scene *s = (Scene *) h;
+    if (bsdf < 0 || bsdf >= (int) s->bsdfs.size() || nested < 0 || nested >= (int) s->bsdfs.size()) return -1;
+    s->bsdfs[bsdf].nested = nested;
+    return 0;
 }
 
 // EnvironmentMap: radiance [h*w*3], optional tangents; to_world = (left, raw) 2x16 floats or NULL; returns emitter index

@@ -43,6 +43,9 @@ def lib():
         L.orc_aov_d.argtypes = [C.c_void_p, C.c_int, C.c_int, _f, _f]
         L.orc_field_edges.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f]
         L.orc_add_roughconductor.argtypes = [C.c_void_p, C.c_float, _f, _f, _f, _f, C.c_int]
+        L.orc_add_roughdielectric.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
+        L.orc_add_microfacet_pervertex.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int]
+        L.orc_add_normalmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int]
         L.orc_add_envmap.argtypes = [C.c_void_p, _f, _f, C.c_int, C.c_int, _f, _f, C.c_float, C.c_float]
         L.orc_set_bsdf_texture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f, _f]
         L.orc_set_bsdf_texture_slot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f, _f, _f, _f]
@@ -137,6 +140,29 @@ class OracleScene:
         """RoughConductorBSDF(alpha, eta, k) (reference src/bsdf/roughconductor.cpp); d = (d_alpha, d_eta[3], d_k[3],
         d_spec[3]) flattened to 10 floats, or None"""
         idx = self.L.orc_add_roughconductor(self.h, float(alpha), _fp(_f32(eta)), _fp(_f32(k)), _fp(_f32(spec)), _fp(_f32(d)), int(two_side))
+        self.bsdf_ids[name] = idx
+        return idx
+
+    def add_roughdielectric(self, name, alpha, int_ior, ext_ior, d_alpha=0.0, two_side=False):
+        """RoughDielectricBSDF(alpha, intIOR, extIOR) (reference src/bsdf/roughdielectric.cpp)"""
+        idx = self.L.orc_add_roughdielectric(self.h, float(alpha), float(d_alpha), float(int_ior), float(ext_ior), int(two_side))
+        self.bsdf_ids[name] = idx
+        return idx
+
+    def add_microfacet_pervertex(self, name, spec, diff, rough, d=None, two_side=False):
+        """MicrofacetBSDFPerVertex(spec[n,3], diff[n,3], rough[n]) (reference src/bsdf/microfacet_pv.cpp);
+        d = tangents as an [n,7] table (specular rgb, diffuse rgb, roughness) or None"""
+        sp, df, rg = _f32(spec).reshape(-1, 3), _f32(diff).reshape(-1, 3), _f32(rough).reshape(-1, 1)
+        pv = np.ascontiguousarray(np.concatenate([sp, df, rg], axis=1), np.float32)
+        dd = None if d is None else np.ascontiguousarray(_f32(d).reshape(-1, 7))
+        idx = self.L.orc_add_microfacet_pervertex(self.h, _fp(pv), _fp(dd), int(pv.shape[0]), int(two_side))
+        self.bsdf_ids[name] = idx
+        return idx
+
+    def add_normalmap(self, name, nested_name, normal=(0.499999, 0.499999, 1.0), d_normal=None, two_side=False):
+        """NormalMapBSDF around the BSDF added before under `nested_name` (reference src/bsdf/normalmap.cpp,
+        src/scene/scene.cpp:128-145); a normal-map bitmap goes through set_bsdf_texture(name, ..., slot=0)"""
+        idx = self.L.orc_add_normalmap(self.h, _fp(_f32(normal)), _fp(_f32(d_normal)), int(self.bsdf_ids[nested_name]), int(two_side))
         self.bsdf_ids[name] = idx
         return idx
 

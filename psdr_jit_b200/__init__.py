@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib, scenes  # noqa: F401
 from . import loader as _loader
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "RoughConductorBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "RoughConductorBSDF", "RoughDielectricBSDF", "MicrofacetBSDFPerVertex", "NormalMapBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
@@ -252,6 +252,89 @@ class RoughConductorBSDF(BSDF):
         b.d_alpha_u = np.float32(self.d_alpha_u)
         b.d_eta, b.d_k = _f32(self.d_eta, (3,)).copy(), _f32(self.d_k, (3,)).copy()
         b.d_specular_reflectance = _f32(self.d_specular_reflectance, (3,)).copy()
+        b.twoSide = self.twoSide
+        return b
+
+
+class RoughDielectricBSDF(BSDF):
+    """reference include/psdr/bsdf/roughdielectric.h, src/bsdf/roughdielectric.cpp: GGX reflection + refraction through an
+    interface with eta = intIOR / extIOR.  The reference binds the class without a constructor (src/psdr.cpp:295) and
+    creates it from scene files only (src/scene/scene_loader.cpp:346-360); ``RoughDielectricBSDF(alpha, intIOR, extIOR)``
+    mirrors the C++ constructors (roughdielectric.h:20-29) so that a scene can be built without XML as well.
+    ``alpha_u`` (= ``alpha_v``) may be a Bitmap1fD; the indices of refraction are fixed at add_BSDF time."""
+
+    def __init__(self, alpha=None, intIOR: float = 1.5, extIOR: float = 1.0):
+        self.alpha_u = alpha if isinstance(alpha, Bitmap1fD) else (np.float32(0.1) if alpha is None else np.float32(alpha))
+        self.intIOR, self.extIOR = float(intIOR), float(extIOR)
+        self.d_alpha_u = np.float32(0.0)
+
+    @property
+    def alpha_v(self):
+        return self.alpha_u
+
+    @alpha_v.setter
+    def alpha_v(self, v):
+        self.alpha_u = v
+
+    def _clone(self):
+        b = RoughDielectricBSDF(self.alpha_u._clone() if isinstance(self.alpha_u, _Bitmap) else self.alpha_u, self.intIOR, self.extIOR)
+        b.d_alpha_u = np.float32(self.d_alpha_u)
+        b.twoSide = self.twoSide
+        return b
+
+
+class MicrofacetBSDFPerVertex(BSDF):
+    """reference src/psdr.cpp:306-310, src/bsdf/microfacet_pv.cpp: Microfacet parameters given per VERTEX of the mesh the
+    BSDF is attached to -- ``MicrofacetBSDFPerVertex(specular[n,3], diffuse[n,3], roughness[n])`` -- and interpolated
+    with the hit's barycentrics.  Forward-mode tangents: d_specularReflectance, d_diffuseReflectance, d_roughness."""
+
+    def __init__(self, specular, diffuse, roughness):
+        self.specularReflectance = _f32(specular).reshape(-1, 3).copy()
+        self.diffuseReflectance = _f32(diffuse).reshape(-1, 3).copy()
+        self.roughness = _f32(roughness).reshape(-1).copy()
+        n = len(self.roughness)
+        if len(self.specularReflectance) != n or len(self.diffuseReflectance) != n:
+            raise RuntimeError("MicrofacetBSDFPerVertex: the three arrays must cover the same vertices")
+        self.d_specularReflectance = np.zeros((n, 3), np.float32)
+        self.d_diffuseReflectance = np.zeros((n, 3), np.float32)
+        self.d_roughness = np.zeros(n, np.float32)
+
+    def _table(self, tangent: bool):
+        p = "d_" if tangent else ""
+        return np.ascontiguousarray(np.concatenate([_f32(getattr(self, p + "specularReflectance")).reshape(-1, 3),
+                                                    _f32(getattr(self, p + "diffuseReflectance")).reshape(-1, 3),
+                                                    _f32(getattr(self, p + "roughness")).reshape(-1, 1)], axis=1), np.float32)
+
+    def _clone(self):
+        b = MicrofacetBSDFPerVertex(self.specularReflectance, self.diffuseReflectance, self.roughness)
+        b.d_specularReflectance = _f32(self.d_specularReflectance).reshape(-1, 3).copy()
+        b.d_diffuseReflectance = _f32(self.d_diffuseReflectance).reshape(-1, 3).copy()
+        b.d_roughness = _f32(self.d_roughness).reshape(-1).copy()
+        b.twoSide = self.twoSide
+        return b
+
+
+class NormalMapBSDF(BSDF):
+    """reference src/psdr.cpp:273-277, include/psdr/bsdf/normalmap.h, src/bsdf/normalmap.cpp: a nested BSDF evaluated on
+    the facet the normal map selects (+ one tangent facet).  ``NormalMapBSDF()`` / ``NormalMapBSDF([x, y, z])`` /
+    ``NormalMapBSDF(Bitmap3fD)``; fields ``normal_map`` and ``nested_bsdf`` as in the reference.  It enters a scene through
+    ``Scene.add_normalmap_BSDF(normalmap, microfacet, name)`` (src/scene/scene.cpp:128-145) or ``Scene.add_BSDF``, which --
+    as the reference does (scene.cpp:219-229) -- ignores the object's fields and installs the constant map
+    (.499999, .499999, 1) around a default MicrofacetBSDF."""
+
+    def __init__(self, normal_map=None):
+        if isinstance(normal_map, Bitmap3fD):
+            self.normal_map = normal_map
+        else:
+            self.normal_map = np.zeros(3, np.float32) if normal_map is None else _f32(normal_map, (3,)).copy()
+        self.d_normal_map = np.zeros(3, dtype=np.float32)
+        self.nested_bsdf = None
+
+    def _clone(self):
+        nm = self.normal_map
+        b = NormalMapBSDF(nm._clone() if isinstance(nm, _Bitmap) else nm)
+        b.d_normal_map = _f32(self.d_normal_map, (3,)).copy()
+        b.nested_bsdf = None if self.nested_bsdf is None else self.nested_bsdf._clone()
         b.twoSide = self.twoSide
         return b
 
@@ -498,11 +581,32 @@ class Scene(Object):
         self._register("Sensor", self._sensors)
 
     def add_BSDF(self, bsdf: BSDF, name: str, twoSide: bool = False):
-        if not isinstance(bsdf, (DiffuseBSDF, MicrofacetBSDF, RoughConductorBSDF)):
+        if not isinstance(bsdf, (DiffuseBSDF, MicrofacetBSDF, RoughConductorBSDF, RoughDielectricBSDF, MicrofacetBSDFPerVertex, NormalMapBSDF)):
             raise RuntimeError("Unknown BSDF type!")
         if ("BSDF[id=%s]" % name) in self.param_map:
             raise RuntimeError("Duplicate BSDF id: " + name)
-        b = bsdf._clone()
+        if isinstance(bsdf, NormalMapBSDF):
+            # scene.cpp:219-229: a fresh NormalMap((.499999, .499999, 1)) around Microfacet(), whatever was passed in
+            b = NormalMapBSDF([.499999, .499999, 1.0])
+            b.nested_bsdf = MicrofacetBSDF()
+        else:
+            b = bsdf._clone()
+        b.id = name
+        b.twoSide = bool(twoSide)
+        self._bsdfs.append(b)
+        self._register("BSDF", self._bsdfs)
+
+    def add_normalmap_BSDF(self, bsdf1: "NormalMapBSDF", bsdf2: BSDF, name: str, twoSide: bool = False):
+        """reference src/psdr.cpp:402, src/scene/scene.cpp:128-145: a NormalMap with bsdf1's normal map around a copy of the
+        MicrofacetBSDF bsdf2.  (The scene-file loader also nests Diffuse, RoughConductor and RoughDielectric BSDFs,
+        scene_loader.cpp:372-424; they are accepted here too.)"""
+        if not isinstance(bsdf1, NormalMapBSDF) or not isinstance(bsdf2, (MicrofacetBSDF, DiffuseBSDF, RoughConductorBSDF, RoughDielectricBSDF)):
+            raise RuntimeError("Unknown BSDF type!")
+        if ("BSDF[id=%s]" % name) in self.param_map:
+            raise RuntimeError("Duplicate BSDF id: " + name)
+        b = bsdf1._clone()
+        b.nested_bsdf = bsdf2._clone()
+        b.nested_bsdf.twoSide = False
         b.id = name
         b.twoSide = bool(twoSide)
         self._bsdfs.append(b)
@@ -661,21 +765,38 @@ class Scene(Object):
         _lib.check(L.psdr_scene_set_options(self._h, o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level))
         _lib.check(L.psdr_scene_set_seed(self._h, int(self.seed)))
         _lib.check(L.psdr_scene_set_reference_arithmetic(self._h, int(bool(self.reference_arithmetic))))
-        for b in self._bsdfs[self._pushed[0]:]:
+        def add_native_bsdf(b, name):
             if isinstance(b, MicrofacetBSDF):
                 d0 = np.full(3, 0.5, np.float32) if isinstance(b.diffuseReflectance, _Bitmap) else _f32(b.diffuseReflectance)
                 s0 = np.full(3, 0.04, np.float32) if isinstance(b.specularReflectance, _Bitmap) else _f32(b.specularReflectance)
                 r0 = 0.8 if isinstance(b.roughness, _Bitmap) else float(_f32(b.roughness).ravel()[0])
-                rc = L.psdr_scene_add_bsdf_microfacet(self._h, b.id.encode(), _fp(s0), _fp(d0), r0, int(b.twoSide))
+                rc = L.psdr_scene_add_bsdf_microfacet(self._h, name, _fp(s0), _fp(d0), r0, int(b.twoSide))
             elif isinstance(b, RoughConductorBSDF):
                 a0 = 0.1 if isinstance(b.alpha_u, _Bitmap) else float(_f32(b.alpha_u).ravel()[0])
                 s0 = np.ones(3, np.float32) if isinstance(b.specular_reflectance, _Bitmap) else _f32(b.specular_reflectance, (3,))
-                rc = L.psdr_scene_add_bsdf_roughconductor(self._h, b.id.encode(), a0, _fp(_f32(b.eta, (3,))), _fp(_f32(b.k, (3,))), _fp(s0), int(b.twoSide))
+                rc = L.psdr_scene_add_bsdf_roughconductor(self._h, name, a0, _fp(_f32(b.eta, (3,))), _fp(_f32(b.k, (3,))), _fp(s0), int(b.twoSide))
+            elif isinstance(b, RoughDielectricBSDF):
+                a0 = 0.1 if isinstance(b.alpha_u, _Bitmap) else float(_f32(b.alpha_u).ravel()[0])
+                rc = L.psdr_scene_add_bsdf_roughdielectric(self._h, name, a0, b.intIOR, b.extIOR, int(b.twoSide))
+            elif isinstance(b, MicrofacetBSDFPerVertex):
+                rc = L.psdr_scene_add_bsdf_microfacet_pervertex(self._h, name, _fp(_f32(b.specularReflectance).reshape(-1)), _fp(_f32(b.diffuseReflectance).reshape(-1)),
+                                                                _fp(_f32(b.roughness).reshape(-1)), len(_f32(b.roughness).reshape(-1)), int(b.twoSide))
+            elif isinstance(b, NormalMapBSDF):
+                if b.nested_bsdf is None:
+                    raise RuntimeError("NormalMapBSDF: nested_bsdf is not set")
+                _lib.check(L.psdr_scene_begin_nested_bsdf(self._h))
+                b._nested_handle = add_native_bsdf(b.nested_bsdf, b"")
+                n0 = np.array([.5, .5, 1.], np.float32) if isinstance(b.normal_map, _Bitmap) else _f32(b.normal_map, (3,))
+                rc = L.psdr_scene_add_bsdf_normalmap(self._h, name, _fp(n0), b._nested_handle, int(b.twoSide))
             else:
                 r0 = np.full(3, 0.5, np.float32) if isinstance(b.reflectance, Bitmap3fD) else _f32(b.reflectance)
-                rc = L.psdr_scene_add_bsdf_diffuse(self._h, b.id.encode(), _fp(r0), int(b.twoSide))
+                rc = L.psdr_scene_add_bsdf_diffuse(self._h, name, _fp(r0), int(b.twoSide))
             if rc < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
+            return rc
+
+        for b in self._bsdfs[self._pushed[0]:]:
+            add_native_bsdf(b, b.id.encode())
         self._pushed[0] = len(self._bsdfs)
         for kind, i in self._events[self._pushed[1]:]:
             if kind == "env":
@@ -751,7 +872,7 @@ class Scene(Object):
                 _lib.check(L.psdr_scene_set_bsdf_texture_slot(self._h, i, slot, 1, 1))
                 push(kind, i, r.data if isinstance(r, _Bitmap) else np.reshape(_f32(r), (-1,)), np.reshape(_f32(d_const), (-1,)))
 
-        for i, b in enumerate(self._bsdfs):
+        def push_bsdf(i, b):
             if isinstance(b, MicrofacetBSDF):
                 push_slot(i, _lib.TEX_REFLECTANCE, _lib.BSDF_REFLECTANCE, b.diffuseReflectance, b.d_diffuseReflectance)
                 push_slot(i, _lib.TEX_SPECULAR, _lib.BSDF_SPECULAR, b.specularReflectance, b.d_specularReflectance)
@@ -761,8 +882,18 @@ class Scene(Object):
                 push_slot(i, _lib.TEX_ROUGHNESS, _lib.BSDF_ROUGHNESS, b.alpha_u, b.d_alpha_u)
                 push(_lib.BSDF_ETA, i, np.reshape(_f32(b.eta), (-1,)), np.reshape(_f32(b.d_eta), (-1,)))
                 push(_lib.BSDF_K, i, np.reshape(_f32(b.k), (-1,)), np.reshape(_f32(b.d_k), (-1,)))
+            elif isinstance(b, RoughDielectricBSDF):
+                push_slot(i, _lib.TEX_ROUGHNESS, _lib.BSDF_ROUGHNESS, b.alpha_u, b.d_alpha_u)
+            elif isinstance(b, MicrofacetBSDFPerVertex):
+                push(_lib.BSDF_PERVERTEX, i, b._table(False), b._table(True))
+            elif isinstance(b, NormalMapBSDF):
+                push_slot(i, _lib.TEX_REFLECTANCE, _lib.BSDF_REFLECTANCE, b.normal_map, b.d_normal_map)
+                push_bsdf(b._nested_handle, b.nested_bsdf)
             else:
                 push_slot(i, _lib.TEX_REFLECTANCE, _lib.BSDF_REFLECTANCE, b.reflectance, b.d_reflectance)
+
+        for i, b in enumerate(self._bsdfs):
+            push_bsdf(i, b)
         for i, e in enumerate(self._emitters):
             if isinstance(e, EnvironmentMap):
                 push(_lib.ENVMAP_RADIANCE, i, e.radiance.data, e.radiance.d_data)
@@ -853,6 +984,11 @@ class Scene(Object):
 
     def num_secondary_edges(self) -> int:
         return _lib.load().psdr_scene_query(self._h, _lib.Q_NUM_SECONDARY_EDGES, 0)
+
+    def kernel_family(self) -> int:
+        """which kernel instantiation the configured scene runs (PSDR_Q_KERNEL_FAMILY): bit 0 BVH2, bit 1 Microfacet /
+        envmap code, bit 3 the extended material set"""
+        return _lib.load().psdr_scene_query(self._h, _lib.Q_KERNEL_FAMILY, 0)
 
     def last_configure_ms(self) -> float:
         return float(_lib.load().psdr_scene_last_configure_ms(self._h))

@@ -244,7 +244,7 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_iso(const Bsd
         const V3<S> fresnel = b.spec + (V3<S>(S(1.f)) - b.spec) * e;
         return (b.diff * S(kInvPi) + fresnel * dg) * co;
     }
-    if ((kCfg & kCfgFull) && b.type == 2) {
+    if ((kCfg & kCfgExt) && b.type == 2) {
         S res, vh;
         iso_conductor<S>(b.rough, ci, co, cio, res, vh);
         if (val(res) == 0.f) return V3<S>(S(0.f));
@@ -302,7 +302,7 @@ template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAc
     }
     if (!(ci > 0.f && co > 0.f)) return;
     const int base = gl.off_bsdf + kGradBsdf * bi;
-    if ((kCfg & kCfgFull) && b.type == 2) {
+    if ((kCfg & kCfgExt) && b.type == 2) {
         // f_c = F(eta_c, k_c, vh) res(alpha) spec_c
         Dual res, vh;
         iso_conductor<Dual>(Dual(bv.rough, 1.f), Dual(ci), Dual(co), Dual(cio), res, vh);
@@ -330,14 +330,14 @@ template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAc
         return;
     }
     const float k = kInvPi * co * scale;
-    if ((kCfg & kCfgFull) && b.tex[0].w > 0) tex_slot_grad(acc, gl, b.tex[0], uv, W * k, uv_bar);
+    if ((kCfg & kCfgExt) && b.tex[0].w > 0) tex_slot_grad(acc, gl, b.tex[0], uv, W * k, uv_bar);
     else acc.add3(base, V3f(W.x * k, W.y * k, W.z * k));
     if ((kCfg & kCfgFull) && b.type == 1) {
         Dual dg, e;
         iso_specular<Dual>(Dual(bv.rough, 1.f), Dual(ci), Dual(co), Dual(cio), dg, e);
         // f_spec,c = (F0_c + (1 - F0_c) e) dg co
         const float ks = (1.f - e.v) * dg.v * co * scale;
-        if (b.tex[1].w > 0) tex_slot_grad(acc, gl, b.tex[1], uv, W * ks, uv_bar);
+        if ((kCfg & kCfgExt) && b.tex[1].w > 0) tex_slot_grad(acc, gl, b.tex[1], uv, W * ks, uv_bar);
         else acc.add3(base + 4, V3f(W.x * ks, W.y * ks, W.z * ks));
         float gr = 0.f;
         const float F0[3] = {bv.spec.x, bv.spec.y, bv.spec.z}, Wc[3] = {W.x, W.y, W.z};
@@ -346,7 +346,7 @@ template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAc
             const Dual fr = Dual(F0[c]) + Dual(1.f - F0[c]) * e;
             gr += Wc[c] * (fr * dg).d;
         }
-        if (b.tex[2].w > 0) tex_slot_grad(acc, gl, b.tex[2], uv, V3f(gr * co * scale, 0.f, 0.f), uv_bar);
+        if ((kCfg & kCfgExt) && b.tex[2].w > 0) tex_slot_grad(acc, gl, b.tex[2], uv, V3f(gr * co * scale, 0.f, 0.f), uv_bar);
         else acc.add(base + 3, gr * co * scale);
     }
 }
@@ -365,9 +365,9 @@ struct VtxGeo {
 #define PSDR_VJP_GEO_NOINLINE 1     // out-of-line vertex_geo: interior adjoint 8.92 -> 8.63 ms (profiles/r02g vjp sweep)
 #endif
 #if PSDR_VJP_GEO_NOINLINE
-static __device__ __noinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
+template <int kCfg> static __device__ __noinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
 #else
-__device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
+template <int kCfg> __device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u, float v) {
 #endif
     VtxGeo g;
     const TriRec<float> T = load_tri<float>(sc, tri);
@@ -397,9 +397,10 @@ __device__ __forceinline__ VtxGeo vertex_geo(const DScene &sc, int tri, float u,
     g.bv.rough = 0.f;
     if (g.bsdf >= 0) {
         const DBsdf &b = sc.bsdfs[g.bsdf];
-        g.bv.refl = b.tex[0].w > 0 ? tex_eval_uv<float>(b.tex[0], false, g.uv) : V3f(b.refl[0], b.refl[1], b.refl[2]);
-        g.bv.spec = b.tex[1].w > 0 ? tex_eval_uv<float>(b.tex[1], false, g.uv) : V3f(b.spec[0], b.spec[1], b.spec[2]);
-        g.bv.rough = b.tex[2].w > 0 ? tex_eval_uv<float>(b.tex[2], false, g.uv).x : b.rough;
+        constexpr bool kTex = (kCfg & kCfgExt) != 0;      // bitmap-valued slots exist in the extended family only
+        g.bv.refl = kTex && b.tex[0].w > 0 ? tex_eval_uv<float>(b.tex[0], false, g.uv) : V3f(b.refl[0], b.refl[1], b.refl[2]);
+        g.bv.spec = kTex && b.tex[1].w > 0 ? tex_eval_uv<float>(b.tex[1], false, g.uv) : V3f(b.spec[0], b.spec[1], b.spec[2]);
+        g.bv.rough = kTex && b.tex[2].w > 0 ? tex_eval_uv<float>(b.tex[2], false, g.uv).x : b.rough;
     }
     return g;
 }
@@ -591,7 +592,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     if (has_v0) {
         T0 = load_tri<float>(sc, R.vtri[0]);
         ray_intersect_triangle<float>(T0.p0, T0.e1, T0.e2, o, d, u0, v0, t0);
-        v0geo = vertex_geo(sc, R.vtri[0], u0, v0);
+        v0geo = vertex_geo<kCfg>(sc, R.vtri[0], u0, v0);
         v0geo.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
         // Le at the primary hit
         if (!hide_emitters && v0geo.emitter >= 0) {
@@ -605,7 +606,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
 
     const VtxAdj zero_adj = {V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), 0.f, V2f(0.f, 0.f)};
     const int ktop = R.nsh - 1;
-    auto geo_of = [&](int k) { return k == 0 ? v0geo : vertex_geo(sc, R.vtri[k], R.vu[k], R.vv[k]); };
+    auto geo_of = [&](int k) { return k == 0 ? v0geo : vertex_geo<kCfg>(sc, R.vtri[k], R.vu[k], R.vv[k]); };
     VtxGeo y = v0geo, x = v0geo;
     if (sweep) {
         if (ktop + 1 < R.nv) y = geo_of(ktop + 1);      // only read when the bounce exists

@@ -22,6 +22,7 @@ struct psdr_scene {
     int *d_pix = nullptr;
     size_t img_cap = 0, pix_cap = 0;
     cudaStream_t stream = nullptr;
+    bool next_bsdf_nested = false;        // psdr_scene_begin_nested_bsdf: the next add_bsdf_* call creates a nested record
     // reverse mode: device gradient table + pinned host copy
     float *d_grad = nullptr, *h_grad = nullptr;
     size_t grad_cap = 0;
@@ -167,25 +168,53 @@ int psdr_scene_set_reference_arithmetic(psdr_scene *s, int on) {
     return 0;
 }
 
+// A BSDF record joins the numbered list ("BSDF[i]"), or -- right after psdr_scene_begin_nested_bsdf -- the un-numbered list of
+// BSDFs that NormalMap records wrap; the handle of a nested record is PSDR_NESTED_BSDF_BASE + its position.
+static bool bsdf_id_taken(psdr_scene *s, const char *id) {
+    if (s->next_bsdf_nested) return false;
+    if (s->sc.find_bsdf(id) >= 0) { fail(std::string("Duplicate BSDF id: ") + id); return true; }
+    return false;
+}
+static int push_bsdf(psdr_scene *s, const HBsdf &b) {
+    Scene &sc = s->sc;
+    sc.configured = false;
+    if (s->next_bsdf_nested) {
+        s->next_bsdf_nested = false;
+        sc.nested_bsdfs.push_back(b);
+        return PSDR_NESTED_BSDF_BASE + (int) sc.nested_bsdfs.size() - 1;
+    }
+    sc.bsdfs.push_back(b);
+    return (int) sc.bsdfs.size() - 1;
+}
+static HBsdf *bsdf_at(Scene &sc, int index) {
+    if (index >= PSDR_NESTED_BSDF_BASE) {
+        const int k = index - PSDR_NESTED_BSDF_BASE;
+        return k < (int) sc.nested_bsdfs.size() ? &sc.nested_bsdfs[k] : nullptr;
+    }
+    return (index >= 0 && index < (int) sc.bsdfs.size()) ? &sc.bsdfs[index] : nullptr;
+}
+
+int psdr_scene_begin_nested_bsdf(psdr_scene *s) {
+    if (!s) return fail("null scene");
+    s->next_bsdf_nested = true;
+    return 0;
+}
+
 int psdr_scene_add_bsdf_diffuse(psdr_scene *s, const char *id, const float reflectance[3], int two_side) {
     if (!s || !id || !reflectance) { fail("null argument"); return -1; }
-    Scene &sc = s->sc;
-    if (sc.find_bsdf(id) >= 0) { fail(std::string("Duplicate BSDF id: ") + id); return -1; }
+    if (bsdf_id_taken(s, id)) return -1;
     HBsdf b;
     b.id = id;
     b.type = 0;
     b.reflectance = V3d(Dual(reflectance[0]), Dual(reflectance[1]), Dual(reflectance[2]));
     b.two_side = two_side != 0;
-    sc.bsdfs.push_back(b);
-    sc.configured = false;
-    return (int) sc.bsdfs.size() - 1;
+    return push_bsdf(s, b);
 }
 
 int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float specular[3], const float diffuse[3], float roughness,
                                    int two_side) {
     if (!s || !id || !specular || !diffuse) { fail("null argument"); return -1; }
-    Scene &sc = s->sc;
-    if (sc.find_bsdf(id) >= 0) { fail(std::string("Duplicate BSDF id: ") + id); return -1; }
+    if (bsdf_id_taken(s, id)) return -1;
     HBsdf b;
     b.id = id;
     b.type = 1;
@@ -193,16 +222,13 @@ int psdr_scene_add_bsdf_microfacet(psdr_scene *s, const char *id, const float sp
     b.specular = V3d(Dual(specular[0]), Dual(specular[1]), Dual(specular[2]));
     b.roughness = Dual(roughness);
     b.two_side = two_side != 0;
-    sc.bsdfs.push_back(b);
-    sc.configured = false;
-    return (int) sc.bsdfs.size() - 1;
+    return push_bsdf(s, b);
 }
 
 int psdr_scene_add_bsdf_roughconductor(psdr_scene *s, const char *id, float alpha, const float eta[3], const float k[3], const float specular[3],
                                        int two_side) {
     if (!s || !id || !eta || !k || !specular) { fail("null argument"); return -1; }
-    Scene &sc = s->sc;
-    if (sc.find_bsdf(id) >= 0) { fail(std::string("Duplicate BSDF id: ") + id); return -1; }
+    if (bsdf_id_taken(s, id)) return -1;
     HBsdf b;
     b.id = id;
     b.type = 2;
@@ -212,20 +238,67 @@ int psdr_scene_add_bsdf_roughconductor(psdr_scene *s, const char *id, float alph
     b.eta = V3d(Dual(eta[0]), Dual(eta[1]), Dual(eta[2]));
     b.k = V3d(Dual(k[0]), Dual(k[1]), Dual(k[2]));
     b.two_side = two_side != 0;
-    sc.bsdfs.push_back(b);
-    sc.configured = false;
-    return (int) sc.bsdfs.size() - 1;
+    return push_bsdf(s, b);
+}
+
+int psdr_scene_add_bsdf_roughdielectric(psdr_scene *s, const char *id, float alpha, float int_ior, float ext_ior, int two_side) {
+    if (!s || !id) { fail("null argument"); return -1; }
+    if (bsdf_id_taken(s, id)) return -1;
+    HBsdf b;
+    b.id = id;
+    b.type = 3;
+    b.roughness = Dual(alpha);
+    // m_eta(intIOR / extIOR), m_inv_eta(extIOR / intIOR): two separately rounded quotients (roughdielectric.h:20-25)
+    b.eta = V3d(Dual(int_ior / ext_ior), Dual(ext_ior / int_ior), Dual(0.f));
+    b.two_side = two_side != 0;
+    return push_bsdf(s, b);
+}
+
+int psdr_scene_add_bsdf_microfacet_pervertex(psdr_scene *s, const char *id, const float *specular, const float *diffuse, const float *roughness,
+                                             int n_vertices, int two_side) {
+    if (!s || !id || !specular || !diffuse || !roughness || n_vertices <= 0) { fail("null argument"); return -1; }
+    if (bsdf_id_taken(s, id)) return -1;
+    HBsdf b;
+    b.id = id;
+    b.type = 4;
+    b.pv.resize((size_t) 7 * n_vertices);
+    for (int i = 0; i < n_vertices; ++i) {
+        for (int c = 0; c < 3; ++c) { b.pv[7 * i + c] = specular[3 * i + c]; b.pv[7 * i + 3 + c] = diffuse[3 * i + c]; }
+        b.pv[7 * i + 6] = roughness[i];
+    }
+    b.two_side = two_side != 0;
+    return push_bsdf(s, b);
+}
+
+int psdr_scene_add_bsdf_normalmap(psdr_scene *s, const char *id, const float normal[3], int nested, int two_side) {
+    if (!s || !id || !normal) { fail("null argument"); return -1; }
+    if (s->next_bsdf_nested) { s->next_bsdf_nested = false; fail("a NormalMap cannot be nested"); return -1; }
+    Scene &sc = s->sc;
+    if (nested < PSDR_NESTED_BSDF_BASE || nested - PSDR_NESTED_BSDF_BASE >= (int) sc.nested_bsdfs.size()) { fail("NormalMap: invalid nested BSDF handle"); return -1; }
+    if (bsdf_id_taken(s, id)) return -1;
+    HBsdf b;
+    b.id = id;
+    b.type = 5;
+    b.reflectance = V3d(Dual(normal[0]), Dual(normal[1]), Dual(normal[2]));
+    b.nested = nested - PSDR_NESTED_BSDF_BASE;
+    b.two_side = two_side != 0;
+    return push_bsdf(s, b);
 }
 
 int psdr_scene_set_bsdf_texture_slot(psdr_scene *s, int index, int slot, int w, int h) {
     if (!s) return fail("null scene");
     Scene &sc = s->sc;
-    if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+    HBsdf *bp = bsdf_at(sc, index);
+    if (!bp) return fail("invalid BSDF index");
     if (slot < 0 || slot > 2) return fail("invalid texture slot");
-    if (slot > 0 && sc.bsdfs[index].type == 0) return fail("specular / roughness textures need a MicrofacetBSDF or a RoughConductorBSDF");
-    if (slot == 0 && sc.bsdfs[index].type == 2) return fail("a RoughConductorBSDF has no diffuse reflectance");
+    const int type = bp->type;
+    if (slot > 0 && type == 0) return fail("specular / roughness textures need a MicrofacetBSDF or a RoughConductorBSDF");
+    if (slot == 0 && type == 2) return fail("a RoughConductorBSDF has no diffuse reflectance");
+    if (type == 3 && slot != 2) return fail("a RoughDielectricBSDF has an alpha bitmap only");
+    if (type == 4) return fail("a MicrofacetBSDFPerVertex has no bitmaps");
+    if (type == 5 && slot != 0) return fail("a NormalMapBSDF has one bitmap: the normal map");
     if (w < 1 || h < 1 || (w * h > 1 && (w < 2 || h < 2))) return fail("Bitmap: invalid resolution!");
-    HBsdf::Tex &t = sc.bsdfs[index].tex[slot];
+    HBsdf::Tex &t = bp->tex[slot];
     if (w * h == 1) { t.w = t.h = 0; t.data.clear(); t.ddata.clear(); }
     else if (t.w != w || t.h != h) {
         t.w = w; t.h = h;
@@ -349,44 +422,61 @@ static int set_param_impl(psdr_scene *s, int kind, int index, const float *data,
             break;
         }
         case PSDR_BSDF_REFLECTANCE: {
-            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
-            const int rc = put_texels(sc.bsdfs[index].tex[0], 3);
+            HBsdf *bp = bsdf_at(sc, index);
+            if (!bp) return fail("invalid BSDF index");
+            const int rc = put_texels(bp->tex[0], 3);
             if (rc > 0) return rc;
             if (rc == 0) break;
             if (n != 3) return fail("reflectance is 3 floats");
-            put(sc.bsdfs[index].reflectance.x, data[0]); put(sc.bsdfs[index].reflectance.y, data[1]); put(sc.bsdfs[index].reflectance.z, data[2]);
+            put(bp->reflectance.x, data[0]); put(bp->reflectance.y, data[1]); put(bp->reflectance.z, data[2]);
             break;
         }
         case PSDR_BSDF_SPECULAR: {
-            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
-            const int rc = put_texels(sc.bsdfs[index].tex[1], 3);
+            HBsdf *bp = bsdf_at(sc, index);
+            if (!bp) return fail("invalid BSDF index");
+            const int rc = put_texels(bp->tex[1], 3);
             if (rc > 0) return rc;
             if (rc == 0) break;
             if (n != 3) return fail("specular reflectance is 3 floats");
-            put(sc.bsdfs[index].specular.x, data[0]); put(sc.bsdfs[index].specular.y, data[1]); put(sc.bsdfs[index].specular.z, data[2]);
+            put(bp->specular.x, data[0]); put(bp->specular.y, data[1]); put(bp->specular.z, data[2]);
             break;
         }
         case PSDR_BSDF_ROUGHNESS: {
-            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
-            const int rc = put_texels(sc.bsdfs[index].tex[2], 1);
+            HBsdf *bp = bsdf_at(sc, index);
+            if (!bp) return fail("invalid BSDF index");
+            const int rc = put_texels(bp->tex[2], 1);
             if (rc > 0) return rc;
             if (rc == 0) break;
             if (n != 1) return fail("roughness is 1 float");
-            put(sc.bsdfs[index].roughness, data[0]);
+            put(bp->roughness, data[0]);
             break;
         }
         case PSDR_BSDF_ETA: case PSDR_BSDF_K: {
-            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
-            if (sc.bsdfs[index].type != 2) return fail("eta / k belong to a RoughConductorBSDF");
+            HBsdf *bp = bsdf_at(sc, index);
+            if (!bp) return fail("invalid BSDF index");
+            if (bp->type != 2) return fail("eta / k belong to a RoughConductorBSDF");
             if (n != 3) return fail("eta / k are 3 floats");
-            V3d &v = kind == PSDR_BSDF_ETA ? sc.bsdfs[index].eta : sc.bsdfs[index].k;
+            V3d &v = kind == PSDR_BSDF_ETA ? bp->eta : bp->k;
             put(v.x, data[0]); put(v.y, data[1]); put(v.z, data[2]);
             break;
         }
+        case PSDR_BSDF_PERVERTEX: {
+            HBsdf *bp = bsdf_at(sc, index);
+            if (!bp) return fail("invalid BSDF index");
+            if (bp->type != 4) return fail("per-vertex tables belong to a MicrofacetBSDFPerVertex");
+            if (n != (int) bp->pv.size()) return fail("per-vertex table size mismatch (7 floats per vertex: specular rgb, diffuse rgb, roughness)");
+            if (tangent) {
+                bool any = false;
+                for (int i = 0; i < n; ++i) any |= data[i] != 0.f;
+                if (any) bp->d_pv.assign(data, data + n); else bp->d_pv.clear();
+            } else bp->pv.assign(data, data + n);
+            break;
+        }
         case PSDR_BSDF_REFLECTANCE_UV: case PSDR_BSDF_SPECULAR_UV: case PSDR_BSDF_ROUGHNESS_UV: {
-            if (index < 0 || index >= (int) sc.bsdfs.size()) return fail("invalid BSDF index");
+            HBsdf *bp = bsdf_at(sc, index);
+            if (!bp) return fail("invalid BSDF index");
             if (n != 4) return fail("a uv transform is 4 floats (scale, rotate, translate.x, translate.y)");
-            HBsdf::Tex &t = sc.bsdfs[index].tex[kind - PSDR_BSDF_REFLECTANCE_UV];
+            HBsdf::Tex &t = bp->tex[kind - PSDR_BSDF_REFLECTANCE_UV];
             put(t.scale, data[0]); put(t.rot, data[1]); put(t.tx, data[2]); put(t.ty, data[3]);
             break;
         }
@@ -443,9 +533,13 @@ int psdr_scene_clear_tangents(psdr_scene *s) {
     for (HCamera &c : sc.cameras)
         for (auto &M : c.to_world)
             for (int i = 0; i < 16; ++i) M.m[i / 4][i % 4].d = 0.f;
-    for (HBsdf &b : sc.bsdfs) {
-        for (HBsdf::Tex &t : b.tex) { t.ddata.clear(); t.scale = detach(t.scale); t.rot = detach(t.rot); t.tx = detach(t.tx); t.ty = detach(t.ty); }
-        b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness); }
+    for (std::vector<HBsdf> *list : {&sc.bsdfs, &sc.nested_bsdfs})
+        for (HBsdf &b : *list) {
+            for (HBsdf::Tex &t : b.tex) { t.ddata.clear(); t.scale = detach(t.scale); t.rot = detach(t.rot); t.tx = detach(t.tx); t.ty = detach(t.ty); }
+            b.reflectance = detach(b.reflectance); b.specular = detach(b.specular); b.roughness = detach(b.roughness);
+            b.eta = detach(b.eta); b.k = detach(b.k);
+            b.d_pv.clear();
+        }
     for (HEmitter &e : sc.emitters) e.radiance = detach(e.radiance);
     if (!sc.env.ddata.empty()) sc.env.ddata_version++;
     sc.env.ddata.clear();
@@ -505,6 +599,7 @@ int psdr_scene_query(psdr_scene *s, int what, int index) {
         case PSDR_Q_UPLOAD_BYTES: return (int) sc.upload_bytes;
         case PSDR_Q_BVH_BUILDS: return sc.bvh_builds;
         case PSDR_Q_BVH_REFITS: return sc.bvh_refits;
+        case PSDR_Q_KERNEL_FAMILY: return sc.configured ? scene_cfg(sc.dscene) : -1;
         case PSDR_Q_GRAD_TABLE_MULTICAST: {
             if (index < 0 || index >= (int) sc.cameras.size()) { fail("sensor index out of range"); return -1; }
             const GradLayout gl = sc.grad_layout(index);
@@ -727,6 +822,10 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
     cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
     if (!d_img) throw std::runtime_error("null cotangent image");
     if (max_depth > 8) throw std::runtime_error("the adjoint supports max_depth <= 8");
+    for (const HBsdf &b : sc.bsdfs)
+        if (b.type >= 3)
+            throw std::runtime_error("reverse mode is not implemented for RoughDielectric / MicrofacetPerVertex / NormalMap BSDFs (BSDF '" + b.id +
+                                     "'): use the forward-mode derivative image (renderD with tangents)");
     RenderParams rp[3];
     for (auto &r : rp) {
         r = RenderParams{};

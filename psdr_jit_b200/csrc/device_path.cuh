@@ -4,10 +4,6 @@
 // edge terms), Dual = value + forward tangent (renderD interior term; what the reference gets from
 // Dr.Jit's AD with detach() at the same places).  One thread = one lane of the reference wavefront.
 #pragma once
-// experiment knob (tools/gpu_cfg3_sweep.sh): 0 compiles the texture lookups and the conductor out of the full-feature family
-#ifndef PSDR_TEXCOND
-#define PSDR_TEXCOND 1
-#endif
 #include "dscene.h"
 #include "pmath.h"
 #include "texture.h"
@@ -18,6 +14,11 @@ namespace psdr {
 constexpr int kCfgBvh = 1;    // BVH2 traversal instead of the parameter-space triangle scan
 constexpr int kCfgFull = 2;   // MicrofacetBSDF + EnvironmentMap code paths (otherwise Diffuse + AreaLight only)
 constexpr int kCfgUniformScan = 4;   // brute-force scan: warp-uniform trip count in the per-lane candidate loop (see trace())
+// Extended material set (implies kCfgFull): bitmap-valued BSDF slots, RoughConductor, RoughDielectric, MicrofacetPerVertex,
+// NormalMap.  A family of its own because code size is a first-order term for the full-feature kernels (32 KB instruction
+// cache): with the textures and the conductor compiled out, cfg 3 (constant Microfacet + envmap) runs 12 % faster
+// (profiles/r03g_cfg3_texcond.log), so scenes that use none of this do not carry it.
+constexpr int kCfgExt = 8;
 
 struct Hit {
     int tri;
@@ -510,6 +511,9 @@ template <class S> struct Its {   // reference include/psdr/core/intersection.h:
     S t, J;
     float bu, bv;   // detached barycentrics of the hit (p = p0 + bu e1 + bv e2)
     V2<S> uv;       // texture coordinate (differentiable at the primary hit of renderD, scene.cpp:755-788)
+    V2<S> bc;       // its.bc: the barycentrics as the reference keeps them (tangent-carrying at the analytic primary hit)
+    V3<S> dp_du;    // world-space position derivative along u (zero without UVs); bc and dp_du are read by the extended
+                    // material set only (MicrofacetPerVertex, NormalMap) and vanish from the other kernel families
     __device__ __forceinline__ V3<S> to_local(V3<S> v) const { return V3<S>(dot(v, sh_s), dot(v, sh_t), dot(v, sh_n)); }
     __device__ __forceinline__ V3<S> to_world(V3<S> v) const { return sh_s * v.x + sh_t * v.y + sh_n * v.z; }
 };
@@ -603,6 +607,8 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
     its.sh_n = sh_n;
     coordinate_system(sh_n, its.sh_s, its.sh_t);
     its.uv = V2<S>(S(0.f), S(0.f));
+    its.bc = V2<S>(bary_u, bary_v);
+    its.dp_du = V3<S>(S(0.f));
     if (mesh.flags & 2) {   // uv-derived tangent frame (scene.cpp:716-728, 757-765)
         const float2 t0 = __ldg(sc.uv + 3 * h.tri), t1 = __ldg(sc.uv + 3 * h.tri + 1), t2 = __ldg(sc.uv + 3 * h.tri + 2);
         const float du0x = t1.x - t0.x, du0y = t1.y - t0.y, du1x = t2.x - t0.x, du1y = t2.y - t0.y;
@@ -611,6 +617,7 @@ __device__ __forceinline__ Its<S> ray_intersect(const DScene &sc, V3<S> o, V3<S>
         if (det != 0.f) {
             const float inv_det = 1.f / det;
             const V3<S> dp_du = (T.e1 * S(du1y) - T.e2 * S(du0y)) * S(inv_det);
+            its.dp_du = dp_du;
             its.sh_s = normalize(dp_du - sh_n * dot(sh_n, dp_du));
             its.sh_t = cross(sh_n, its.sh_s);
         }
@@ -628,7 +635,7 @@ template <> __device__ __forceinline__ V3d bsdf_reflectance_const<Dual>(const DB
 // Bitmap::eval(its.uv): 1x1 -> the constant, else transformed bilinear texture lookup (reference src/core/bitmap.cpp:46-131);
 // textures belong to the "full" kernel family
 template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_reflectance(const DBsdf &b, V2<S> uv) {
-    if (PSDR_TEXCOND && (kCfg & kCfgFull) && b.tex[0].w > 0) return tex_eval_uv<S>(b.tex[0], IsDual<S>::value, uv);
+    if ((kCfg & kCfgExt) && b.tex[0].w > 0) return tex_eval_uv<S>(b.tex[0], IsDual<S>::value, uv);
     return bsdf_reflectance_const<S>(b);
 }
 
@@ -637,15 +644,15 @@ template <> __device__ __forceinline__ V3f bsdf_specular_const<float>(const DBsd
 template <> __device__ __forceinline__ V3d bsdf_specular_const<Dual>(const DBsdf &b) {
     return V3d(Dual(b.spec[0], b.d_spec[0]), Dual(b.spec[1], b.d_spec[1]), Dual(b.spec[2], b.d_spec[2]));
 }
-template <class S> __device__ __forceinline__ V3<S> bsdf_specular(const DBsdf &b, V2<S> uv) {     // Microfacet: full family only
-    if (PSDR_TEXCOND && b.tex[1].w > 0) return tex_eval_uv<S>(b.tex[1], IsDual<S>::value, uv);
+template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_specular(const DBsdf &b, V2<S> uv) {     // Microfacet: full family only
+    if ((kCfg & kCfgExt) && b.tex[1].w > 0) return tex_eval_uv<S>(b.tex[1], IsDual<S>::value, uv);
     return bsdf_specular_const<S>(b);
 }
 template <class S> __device__ __forceinline__ S bsdf_roughness_const(const DBsdf &b);
 template <> __device__ __forceinline__ float bsdf_roughness_const<float>(const DBsdf &b) { return b.rough; }
 template <> __device__ __forceinline__ Dual bsdf_roughness_const<Dual>(const DBsdf &b) { return Dual(b.rough, b.d_rough); }
-template <class S> __device__ __forceinline__ S bsdf_roughness(const DBsdf &b, V2<S> uv) {
-    if (PSDR_TEXCOND && b.tex[2].w > 0) return tex_eval_uv<S>(b.tex[2], IsDual<S>::value, uv).x;
+template <class S, int kCfg> __device__ __forceinline__ S bsdf_roughness(const DBsdf &b, V2<S> uv) {
+    if ((kCfg & kCfgExt) && b.tex[2].w > 0) return tex_eval_uv<S>(b.tex[2], IsDual<S>::value, uv).x;
     return bsdf_roughness_const<S>(b);
 }
 
@@ -688,8 +695,8 @@ template <class S, int kCfg> PSDR_FULL_FN V3<S> microfacet_eval(const DBsdf &b, 
     const V3<S> diffuse = bsdf_reflectance<S, kCfg>(b, uv) * S(kInvPi);
     const V3<S> H = normalize(wi + wo);
     const S cos_vh = dot(H, wi);
-    const V3<S> F0 = bsdf_specular<S>(b, uv);
-    const S alpha = sqr(bsdf_roughness<S>(b, uv));
+    const V3<S> F0 = bsdf_specular<S, kCfg>(b, uv);
+    const S alpha = sqr(bsdf_roughness<S, kCfg>(b, uv));
     const S ggx = ggx_eval<S>(alpha, H);
     const S coeff = cos_vh * (S(-5.55473f) * cos_vh - S(6.8316f));
     const S e = exp2_(coeff);
@@ -728,7 +735,7 @@ template <class S, int kCfg> PSDR_FULL_FN V3<S> conductor_eval(const DBsdf &b, V
         wi.z = abs_(wi.z);
     }
     if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
-    const S alpha = bsdf_roughness<S>(b, uv);
+    const S alpha = bsdf_roughness<S, kCfg>(b, uv);
     const V3<S> H = normalize(wo + wi);
     const S D = ggx_eval<S>(alpha, H);
     if (val(D) == 0.f) return V3<S>(S(0.f));
@@ -737,17 +744,115 @@ template <class S, int kCfg> PSDR_FULL_FN V3<S> conductor_eval(const DBsdf &b, V
     const S cos_ih = dot(wi, H);
     const V3<S> eta = bsdf_eta<S>(b), k = bsdf_k<S>(b);
     const V3<S> F(fresnel_conductor<S>(eta.x, k.x, cos_ih), fresnel_conductor<S>(eta.y, k.y, cos_ih), fresnel_conductor<S>(eta.z, k.z, cos_ih));
-    return F * result * bsdf_specular<S>(b, uv);
+    return F * result * bsdf_specular<S, kCfg>(b, uv);
 }
 
-template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
-    if (!active || !its.valid) return V3<S>(S(0.f));
-    const int bi = sc.meshes[its.mesh].bsdf;
-    if (bi < 0) return V3<S>(S(0.f));
-    const DBsdf &b = sc.bsdfs[bi];
-    if ((kCfg & kCfgFull) && b.type == 1) return microfacet_eval<S, kCfg>(b, its.wi, wo, its.uv);
-    if (PSDR_TEXCOND && (kCfg & kCfgFull) && b.type == 2) return conductor_eval<S, kCfg>(b, its.wi, wo, its.uv);
-    S wiz = its.wi.z;
+// ---- extended material set (kCfgExt) --------------------------------------------------------------
+// fresnel_dielectric (reference include/psdr/utils.h:185-215): unpolarised Fresnel reflectance of a dielectric interface
+// with relative index eta, plus the cosine of the transmitted direction and the two relative indices
+template <class S> struct FresnelDielectric {
+    S r, cos_theta_t, eta_it, eta_ti;
+};
+template <class S> __device__ __forceinline__ FresnelDielectric<S> fresnel_dielectric(S eta, S cos_theta_i) {
+    FresnelDielectric<S> f;
+    const bool outside = val(cos_theta_i) >= 0.f;
+    const S rcp_eta = rcp_(eta);
+    f.eta_it = outside ? eta : rcp_eta;
+    f.eta_ti = outside ? rcp_eta : eta;
+    const S sin_i_2 = fmadd(-cos_theta_i, cos_theta_i, S(1.f));
+    const S cos_theta_t_sqr = fmadd(-sin_i_2, f.eta_ti * f.eta_ti, S(1.f));
+    const S ci_abs = abs_(cos_theta_i), ct_abs = safe_sqrt(cos_theta_t_sqr);
+    const bool index_matched = val(eta) == 1.f, special_case = index_matched || val(ci_abs) == 0.f;
+    const S a_s = fmadd(-f.eta_it, ct_abs, ci_abs) / fmadd(f.eta_it, ct_abs, ci_abs);
+    const S a_p = fmadd(-f.eta_it, ci_abs, ct_abs) / fmadd(f.eta_it, ci_abs, ct_abs);
+    f.r = S(.5f) * (sqr(a_s) + sqr(a_p));
+    if (special_case) f.r = S(index_matched ? 0.f : 1.f);
+    f.cos_theta_t = signbit_(val(cos_theta_i)) ? ct_abs : -ct_abs;      // mulsign_neg(cos_theta_t_abs, cos_theta_i)
+    return f;
+}
+template <class S> __device__ __forceinline__ S bsdf_scalar(float v, float d);
+template <> __device__ __forceinline__ float bsdf_scalar<float>(float v, float) { return v; }
+template <> __device__ __forceinline__ Dual bsdf_scalar<Dual>(float v, float d) { return Dual(v, d); }
+
+// RoughDielectric::__eval (reference src/bsdf/roughdielectric.cpp:37-122): GGX reflection + refraction through an
+// interface with eta = intIOR / extIOR (DBsdf::eta[0]) and its separately rounded inverse extIOR / intIOR (eta[1]);
+// alpha_u = alpha_v = the roughness slot
+template <class S, int kCfg> PSDR_FULL_FN V3<S> dielectric_eval(const DBsdf &b, V3<S> wi, V3<S> wo, V2<S> uv) {
+    if (b.two_side) {
+        if (signbit_(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    const S cos_theta_i = wi.z, cos_theta_o = wo.z;
+    if (val(cos_theta_i) == 0.f) return V3<S>(S(0.f));
+    const bool reflect = val(cos_theta_i) * val(cos_theta_o) > 0.f;
+    const S m_eta = bsdf_scalar<S>(b.eta[0], b.d_eta[0]), m_inv_eta = bsdf_scalar<S>(b.eta[1], b.d_eta[1]);
+    const bool front = val(cos_theta_i) > 0.f;
+    const S eta = front ? m_eta : m_inv_eta, inv_eta = front ? m_inv_eta : m_eta;
+    V3<S> m = normalize(wi + wo * (reflect ? S(1.f) : eta));
+    if (signbit_(val(m.z))) m = -m;                                     // mulsign(m, cos_theta(m))
+    const S alpha = bsdf_roughness<S, kCfg>(b, uv);
+    const S D = ggx_eval<S>(alpha, m);
+    const S F = fresnel_dielectric<S>(m_eta, dot(wi, m)).r;
+    const S G = ggx_smith_g1<S>(alpha, wi, m) * ggx_smith_g1<S>(alpha, wo, m);
+    if (reflect) return V3<S>(F * D * G / (S(4.f) * abs_(cos_theta_i)));
+    const S scale = sqr(inv_eta);
+    const S wi_m = dot(wi, m), wo_m = dot(wo, m);
+    const S value = abs_((scale * (S(1.f) - F) * D * G * eta * eta * wi_m * wo_m) / (cos_theta_i * sqr(wi_m + eta * wo_m)));
+    return V3<S>(value);
+}
+
+// MicrofacetPerVertex::__interpolate (reference src/bsdf/microfacet_pv.cpp:146-160): channel c of the per-vertex table
+// (DBsdf::pv, 7 floats per vertex: specular rgb, diffuse rgb, roughness) at the hit's barycentrics; the vertex indices are
+// the mesh-local face indices of the triangle (DScene::face_idx)
+template <class S> __device__ __forceinline__ S pv_load(const DBsdf &b, int vtx, int c);
+template <> __device__ __forceinline__ float pv_load<float>(const DBsdf &b, int vtx, int c) { return __ldg(b.pv + 7 * vtx + c); }
+template <> __device__ __forceinline__ Dual pv_load<Dual>(const DBsdf &b, int vtx, int c) {
+    return Dual(__ldg(b.pv + 7 * vtx + c), b.d_pv ? __ldg(b.d_pv + 7 * vtx + c) : 0.f);
+}
+template <class S> __device__ __forceinline__ S pv_interp(const DScene &sc, const DBsdf &b, const Its<S> &its, int c) {
+    const int i0 = __ldg(sc.face_idx + 3 * its.tri), i1 = __ldg(sc.face_idx + 3 * its.tri + 1), i2 = __ldg(sc.face_idx + 3 * its.tri + 2);
+    // a table shorter than the mesh's vertex list reads as zeros (Dr.Jit gathers out of range are undefined; we define them)
+    const S v0 = i0 < b.pv_n ? pv_load<S>(b, i0, c) : S(0.f), v1 = i1 < b.pv_n ? pv_load<S>(b, i1, c) : S(0.f),
+            v2 = i2 < b.pv_n ? pv_load<S>(b, i2, c) : S(0.f);
+    return fmadd(v1 - v0, its.bc.x, fmadd(v2 - v0, its.bc.y, v0));
+}
+// MicrofacetPerVertex::__eval (reference src/bsdf/microfacet_pv.cpp:20-68): Lambert + GGX with the Schlick-Smith k form
+// (NOT GGXDistribution: its own NDF / geometry expressions)
+template <class S, int kCfg> PSDR_FULL_FN V3<S> microfacet_pv_eval(const DScene &sc, const DBsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
+    if (b.two_side) {
+        if (signbit_(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    const S cos_nv = wi.z, cos_nl = wo.z;
+    if (!(val(cos_nv) > 0.f && val(cos_nl) > 0.f)) return V3<S>(S(0.f));
+    const V3<S> F0(pv_interp<S>(sc, b, its, 0), pv_interp<S>(sc, b, its, 1), pv_interp<S>(sc, b, its, 2));
+    const V3<S> diffuse = V3<S>(pv_interp<S>(sc, b, its, 3), pv_interp<S>(sc, b, its, 4), pv_interp<S>(sc, b, its, 5)) * S(kInvPi);
+    const S roughness = pv_interp<S>(sc, b, its, 6);
+    const V3<S> H = normalize(wi + wo);
+    const S cos_nh = H.z, cos_vh = dot(H, wi);
+    const S alpha = sqr(roughness);
+    const S k = sqr(roughness + S(1.f)) / S(8.f);
+    const S tmp = alpha / (cos_nh * cos_nh * (sqr(alpha) - S(1.f)) + S(1.f));
+    const S ggx = tmp * tmp * S(kInvPi);
+    const S coeff = cos_vh * (S(-5.55473f) * cos_vh - S(6.8316f));
+    const V3<S> fresnel = F0 + (V3<S>(S(1.f)) - F0) * exp2_(coeff);
+    const S smithG1 = cos_nv / (cos_nv * (S(1.f) - k) + k);
+    const S smithG2 = cos_nl / (cos_nl * (S(1.f) - k) + k);
+    const S smithG = smithG1 * smithG2;
+    const V3<S> numerator = fresnel * (ggx * smithG);
+    const S denominator = S(4.f) * cos_nl * cos_nv;
+    const V3<S> specular = numerator / (denominator + S(1e-6f));
+    return (diffuse + specular) * cos_nl;
+}
+
+// BSDF::eval of a record that is not a NormalMap, with the incident direction given explicitly (NormalMap evaluates its
+// nested BSDF with perturbed directions); `its` supplies uv, barycentrics and the triangle
+template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval_leaf(const DScene &sc, const DBsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
+    if ((kCfg & kCfgFull) && b.type == 1) return microfacet_eval<S, kCfg>(b, wi, wo, its.uv);
+    if ((kCfg & kCfgExt) && b.type == 2) return conductor_eval<S, kCfg>(b, wi, wo, its.uv);
+    if ((kCfg & kCfgExt) && b.type == 3) return dielectric_eval<S, kCfg>(b, wi, wo, its.uv);
+    if ((kCfg & kCfgExt) && b.type == 4) return microfacet_pv_eval<S, kCfg>(sc, b, its, wi, wo);
+    S wiz = wi.z;
     if (b.two_side) {
         if (signbit_(val(wiz))) wo.z = -wo.z;
         wiz = abs_(wiz);
@@ -756,31 +861,160 @@ template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DS
     return bsdf_reflectance<S, kCfg>(b, its.uv) * S(kInvPi) * wo.z;
 }
 
-// Microfacet::__pdf (reference src/bsdf/microfacet.cpp:108-133), detached
-static PSDR_FULL_FN float microfacet_pdf(const DBsdf &b, V3f wi, V3f wo, V2f uv) {
+// ---- NormalMap (reference src/bsdf/normalmap.cpp): microfacet-based normal mapping, one tangent facet -----------------
+// The perturbed normal wp comes from the normal map (2 rgb - 1, normalised) in the SHADING frame; the reference then builds
+// the perturbed frame from wp and its.dp_du, a WORLD-space vector, as written (normalmap.cpp:61) -- reproduced, not fixed.
+template <class S> struct NmFrame {
+    V3<S> s, t, n;      // Frame(n, s) (include/psdr/core/frame.h:42-45)
+    __device__ __forceinline__ V3<S> to_local(V3<S> v) const { return V3<S>(dot(v, s), dot(v, t), dot(v, n)); }
+    __device__ __forceinline__ V3<S> to_world(V3<S> v) const { return s * v.x + t * v.y + n * v.z; }
+};
+template <class S> __device__ __forceinline__ S nm_pdot(V3<S> a, V3<S> b) {      // maximum(0, dot): a NaN dot gives 0, as max.f32 does
+    const S d = dot(a, b);
+    return val(d) > 0.f ? d : S(0.f);
+}
+template <class S> __device__ __forceinline__ S nm_sin_theta(V3<S> v) { return safe_sqrt(fmadd(v.x, v.x, sqr(v.y))); }
+template <class S> __device__ __forceinline__ V3<S> nm_wt(V3<S> wp) { return normalize(V3<S>(-wp.x, -wp.y, S(0.f))); }
+template <class S> __device__ __forceinline__ S nm_G1(V3<S> wp, V3<S> w) {
+    const S cw = val(w.z) > 0.f ? w.z : S(0.f), cp = val(wp.z) > 0.f ? wp.z : S(0.f);
+    const S g = cw * cp / (nm_pdot<S>(w, wp) + nm_pdot<S>(w, nm_wt<S>(wp)) * nm_sin_theta<S>(wp));
+    return val(g) < 1.f ? g : S(1.f);      // minimum(1, g): a NaN g gives 1
+}
+template <class S> __device__ __forceinline__ S nm_lambda_p(V3<S> wp, V3<S> wi) {
+    const S i_dot_p = nm_pdot<S>(wp, wi);
+    return i_dot_p / (i_dot_p + nm_pdot<S>(nm_wt<S>(wp), wi) * nm_sin_theta<S>(wp));
+}
+template <class S, int kCfg> __device__ __forceinline__ void nm_setup(const DBsdf &b, const Its<S> &its, V3<S> &wp, NmFrame<S> &fr) {
+    const V3<S> c = bsdf_reflectance<S, kCfg>(b, its.uv);                // the normal map lives in slot 0
+    wp = normalize(V3<S>(fmadd(c.x, S(2.f), S(-1.f)), fmadd(c.y, S(2.f), S(-1.f)), fmadd(c.z, S(2.f), S(-1.f))));
+    const S d = dot(wp, its.dp_du);
+    const V3<S> s0 = normalize(V3<S>(fmadd(-wp.x, d, its.dp_du.x), fmadd(-wp.y, d, its.dp_du.y), fmadd(-wp.z, d, its.dp_du.z)));
+    fr.n = wp;
+    fr.t = normalize(cross(wp, s0));
+    fr.s = normalize(cross(fr.t, wp));
+}
+template <class S> __device__ __forceinline__ V3<S> nm_reflect(V3<S> w, V3<S> wt) {      // normalize(w - 2 <w, wt> wt)
+    const S k = S(2.f) * dot(w, wt);
+    return normalize(w - wt * k);
+}
+// NormalMap::__eval (normalmap.cpp:42-86): i -> p -> o and i -> t -> p -> o
+template <class S, int kCfg> PSDR_FULL_FN V3<S> normalmap_eval(const DScene &sc, const DBsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
     if (b.two_side) {
+        if (signbit_(val(wi.z))) wo.z = -wo.z;
+        wi.z = abs_(wi.z);
+    }
+    if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
+    const DBsdf &nb = sc.bsdfs[b.nested];
+    V3<S> wp;
+    NmFrame<S> fr;
+    nm_setup<S, kCfg>(b, its, wp, fr);
+    const V3<S> p_wo = fr.to_local(wo);
+    const S shadowing = nm_G1<S>(wp, wo);
+    const S lambda_p = nm_lambda_p<S>(wp, wi);
+    const V3<S> wt = nm_wt<S>(wp);
+    V3<S> value = bsdf_eval_leaf<S, kCfg>(sc, nb, its, fr.to_local(wi), p_wo) * lambda_p * shadowing;
+    if (val(dot(wi, wt)) > 0.f) {
+        const V3<S> wi_r = nm_reflect<S>(wi, wt);
+        value = value + bsdf_eval_leaf<S, kCfg>(sc, nb, its, fr.to_local(wi_r), p_wo) * ((S(1.f) - lambda_p) * shadowing);
+    }
+    return value;
+}
+
+template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
+    if (!active || !its.valid) return V3<S>(S(0.f));
+    const int bi = sc.meshes[its.mesh].bsdf;
+    if (bi < 0) return V3<S>(S(0.f));
+    const DBsdf &b = sc.bsdfs[bi];
+    if ((kCfg & kCfgExt) && b.type == 5) return normalmap_eval<S, kCfg>(sc, b, its, its.wi, wo);
+    return bsdf_eval_leaf<S, kCfg>(sc, b, its, its.wi, wo);
+}
+
+// alpha of the GGX lobe that __pdf / __sample of a record use (detached): Microfacet and MicrofacetPerVertex square the
+// roughness (microfacet.cpp:92,123, microfacet_pv.cpp:93,135), RoughConductor and RoughDielectric store alpha itself
+template <class S, int kCfg> __device__ __forceinline__ float bsdf_alpha(const DScene &sc, const DBsdf &b, const Its<S> &its) {
+    if ((kCfg & kCfgExt) && b.type == 4) {
+        Its<float> f;
+        f.tri = its.tri;
+        f.bc = V2f(val(its.bc.x), val(its.bc.y));
+        return sqr(pv_interp<float>(sc, b, f, 6));
+    }
+    const float r = bsdf_roughness<float, kCfg>(b, val(its.uv));
+    return ((kCfg & kCfgExt) && (b.type == 2 || b.type == 3)) ? r : sqr(r);
+}
+
+// Microfacet::__pdf (reference src/bsdf/microfacet.cpp:108-133), detached; RoughConductor::__pdf
+// (src/bsdf/roughconductor.cpp:70-95) and MicrofacetPerVertex::__pdf (microfacet_pv.cpp:120-143) are the same expression
+static PSDR_FULL_FN float ggx_reflect_pdf(float alpha, bool two_side, V3f wi, V3f wo) {
+    if (two_side) {
         if (signbit_(wi.z)) wo.z = -wo.z;
         wi.z = fabsf(wi.z);
     }
     const V3f m = normalize(wo + wi);
     if (!(wi.z > 0.f && wo.z > 0.f && dot(wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
-    // RoughConductor::__pdf (src/bsdf/roughconductor.cpp:70-95) is the same expression with alpha given directly
-    const float alpha = b.type == 2 ? bsdf_roughness<float>(b, uv) : sqr(bsdf_roughness<float>(b, uv));
     return ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, wi, m) / (4.f * wi.z);
+}
+// RoughDielectric::__pdf (reference src/bsdf/roughdielectric.cpp:125-176)
+static PSDR_FULL_FN float dielectric_pdf(const DBsdf &b, float alpha, V3f wi, V3f wo) {
+    if (b.two_side) {
+        if (signbit_(wi.z)) wo.z = -wo.z;
+        wi.z = fabsf(wi.z);
+    }
+    const float cos_theta_i = wi.z, cos_theta_o = wo.z;
+    if (cos_theta_i == 0.f) return 0.f;
+    const bool reflect = cos_theta_i * cos_theta_o > 0.f;
+    const float eta = cos_theta_i > 0.f ? b.eta[0] : b.eta[1];
+    V3f m = normalize(wi + wo * (reflect ? 1.f : eta));
+    if (signbit_(m.z)) m = -m;
+    const float wi_m = dot(wi, m), wo_m = dot(wo, m);
+    if (!(wi_m * wi.z > 0.f && wo_m * wo.z > 0.f)) return 0.f;
+    const float dwh_dwo = reflect ? 1.f / (4.f * wo_m) : (eta * eta * wo_m) / sqr(wi_m + eta * wo_m);
+    const V3f pwi = signbit_(wi.z) ? -wi : wi;
+    float prob = ggx_eval<float>(alpha, m) * ggx_smith_g1<float>(alpha, pwi, m) / pwi.z;
+    const float F = fresnel_dielectric<float>(b.eta[0], wi_m).r;
+    prob *= reflect ? F : 1.f - F;
+    return prob * fabsf(dwh_dwo);
+}
+template <class S, int kCfg> __device__ __forceinline__ float bsdf_pdf_leaf(const DScene &sc, const DBsdf &b, const Its<S> &its, V3f wi, V3f wo) {
+    if ((kCfg & kCfgExt) && b.type == 3) return dielectric_pdf(b, bsdf_alpha<S, kCfg>(sc, b, its), wi, wo);
+    if ((kCfg & kCfgFull) && b.type != 0) return ggx_reflect_pdf(bsdf_alpha<S, kCfg>(sc, b, its), b.two_side != 0, wi, wo);
+    float wiz = wi.z, woz = wo.z;
+    if (b.two_side) {
+        if (signbit_(wiz)) woz = -woz;
+        wiz = fabsf(wiz);
+    }
+    if (!(wiz > 0.f && woz > 0.f)) return 0.f;
+    return kInvPi * woz;
+}
+// NormalMap::__pdf (normalmap.cpp:109-144), detached
+template <class S, int kCfg> PSDR_FULL_FN float normalmap_pdf(const DScene &sc, const DBsdf &b, const Its<S> &its, V3f wi, V3f wo) {
+    if (b.two_side) {
+        if (signbit_(wi.z)) wo.z = -wo.z;
+        wi.z = fabsf(wi.z);
+    }
+    if (!(wi.z > 0.f && wo.z > 0.f)) return 0.f;
+    const DBsdf &nb = sc.bsdfs[b.nested];
+    Its<float> f;
+    f.tri = its.tri;
+    f.uv = val(its.uv);
+    f.bc = V2f(val(its.bc.x), val(its.bc.y));
+    f.dp_du = val(its.dp_du);
+    V3f wp;
+    NmFrame<float> fr;
+    nm_setup<float, kCfg>(b, f, wp, fr);
+    const V3f p_wo = fr.to_local(wo);
+    const float probability_wp = nm_lambda_p<float>(wp, wi);
+    const V3f wi_r = nm_reflect<float>(wi, nm_wt<float>(wp));
+    return probability_wp * bsdf_pdf_leaf<float, kCfg>(sc, nb, f, fr.to_local(wi), p_wo) +
+           (1.f - probability_wp) * bsdf_pdf_leaf<float, kCfg>(sc, nb, f, fr.to_local(wi_r), p_wo);
 }
 
 template <class S, int kCfg> __device__ __forceinline__ float bsdf_pdf(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {
     if (!active || !its.valid) return 0.f;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return 0.f;
-    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type != 0) return microfacet_pdf(sc.bsdfs[bi], val(its.wi), val(wo), val(its.uv));
-    float wiz = val(its.wi.z), woz = val(wo.z);
-    if (sc.bsdfs[bi].two_side) {
-        if (signbit_(wiz)) woz = -woz;
-        wiz = fabsf(wiz);
-    }
-    if (!(wiz > 0.f && woz > 0.f)) return 0.f;
-    return kInvPi * woz;
+    const DBsdf &b = sc.bsdfs[bi];
+    if ((kCfg & kCfgExt) && b.type == 5) return normalmap_pdf<S, kCfg>(sc, b, its, val(its.wi), val(wo));
+    return bsdf_pdf_leaf<S, kCfg>(sc, b, its, val(its.wi), val(wo));
 }
 
 struct BsdfSample {
@@ -813,12 +1047,8 @@ __device__ __forceinline__ V2f ggx_sample_visible_11(float cos_theta_i, V2f samp
     return V2f(fmaf(cos_theta_i, y, -(sin_theta_i * z)) * norm, x * norm);
 }
 
-// Microfacet::__sample (reference src/bsdf/microfacet.cpp:80-98) + GGXDistribution::sample (ggx.cpp:36-79)
-static PSDR_FULL_FN BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sample, bool active, V2f uv) {
-    BsdfSample bs;
-    if (b.two_side) wi.z = fabsf(wi.z);
-    // RoughConductor::__sample (src/bsdf/roughconductor.cpp:99-122): the same visible-normal sampling, alpha given directly
-    const float alpha = b.type == 2 ? bsdf_roughness<float>(b, uv) : sqr(bsdf_roughness<float>(b, uv));
+// GGXDistribution::sample (reference src/bsdf/ggx.cpp:36-79): visible-normal sample m and its density
+__device__ __forceinline__ void ggx_sample_m(float alpha, V3f wi, V3f sample, V3f &m, float &m_pdf) {
     const V3f wi_p = normalize(V3f(alpha * wi.x, alpha * wi.y, wi.z));
     const float sin_theta_2 = fmaf(wi_p.x, wi_p.x, sqr(wi_p.y)), inv_sin_theta = 1.f / sqrtf(sin_theta_2);
     const bool pole = fabsf(sin_theta_2) <= 4.f * kEpsilon;
@@ -826,12 +1056,89 @@ static PSDR_FULL_FN BsdfSample microfacet_sample(const DBsdf &b, V3f wi, V3f sam
     const float cos_phi = pole ? 1.f : fminf(fmaxf(wi_p.x * inv_sin_theta, -1.f), 1.f);
     V2f slope = ggx_sample_visible_11(wi_p.z, V2f(sample.x, sample.y));
     slope = V2f(fmaf(cos_phi, slope.x, -(sin_phi * slope.y)) * alpha, fmaf(sin_phi, slope.x, cos_phi * slope.y) * alpha);
-    const V3f m = normalize(V3f(-slope.x, -slope.y, 1.f));
-    const float m_pdf = ggx_smith_g1<float>(alpha, wi, m) * fabsf(dot(wi, m)) * ggx_eval<float>(alpha, m) / fabsf(wi.z);
+    m = normalize(V3f(-slope.x, -slope.y, 1.f));
+    m_pdf = ggx_smith_g1<float>(alpha, wi, m) * fabsf(dot(wi, m)) * ggx_eval<float>(alpha, m) / fabsf(wi.z);
+}
+// Microfacet::__sample (reference src/bsdf/microfacet.cpp:80-98); RoughConductor::__sample (roughconductor.cpp:99-122) and
+// MicrofacetPerVertex::__sample (microfacet_pv.cpp:82-106) are the same with their own alpha
+static PSDR_FULL_FN BsdfSample ggx_reflect_sample(float alpha, bool two_side, V3f wi, V3f sample, bool active) {
+    BsdfSample bs;
+    if (two_side) wi.z = fabsf(wi.z);
+    V3f m;
+    float m_pdf;
+    ggx_sample_m(alpha, wi, sample, m, m_pdf);
     const float k = 2.f * dot(wi, m);
     bs.wo = V3f(fmaf(m.x, k, -wi.x), fmaf(m.y, k, -wi.y), fmaf(m.z, k, -wi.z));
     bs.pdf = m_pdf / (4.f * dot(bs.wo, m));
     bs.valid = active && (wi.z > 0.f) && (bs.pdf != 0.f) && (bs.wo.z > 0.f);
+    return bs;
+}
+// RoughDielectric::__sample (reference src/bsdf/roughdielectric.cpp:179-236): sample.z chooses reflection / refraction
+static PSDR_FULL_FN BsdfSample dielectric_sample(const DBsdf &b, float alpha, V3f wi, V3f sample, bool active) {
+    BsdfSample bs;
+    if (b.two_side) wi.z = fabsf(wi.z);
+    const float cos_theta_i = wi.z;
+    active = active && cos_theta_i != 0.f;
+    V3f m;
+    ggx_sample_m(alpha, signbit_(cos_theta_i) ? -wi : wi, sample, m, bs.pdf);
+    active = active && bs.pdf != 0.f;
+    const float wi_m = dot(wi, m);
+    const FresnelDielectric<float> f = fresnel_dielectric<float>(b.eta[0], wi_m);
+    const bool selected_r = sample.z <= f.r && active, selected_t = !selected_r && active;
+    bs.pdf *= selected_r ? f.r : 1.f - f.r;
+    const float bs_eta = selected_r ? 1.f : f.eta_it;
+    bs.wo = V3f(0.f, 0.f, 0.f);
+    float dwh_dwo = 0.f;
+    if (selected_r) {
+        const float k = 2.f * wi_m;
+        bs.wo = V3f(fmaf(m.x, k, -wi.x), fmaf(m.y, k, -wi.y), fmaf(m.z, k, -wi.z));
+    }
+    // the reflection Jacobian is evaluated for every lane (with wo = 0 where nothing was selected: rcp(0) = inf)
+    dwh_dwo = 1.f / (4.f * dot(bs.wo, m));
+    if (selected_t) {
+        const float k = fmaf(wi_m, f.eta_ti, f.cos_theta_t);
+        bs.wo = V3f(fmaf(m.x, k, -(wi.x * f.eta_ti)), fmaf(m.y, k, -(wi.y * f.eta_ti)), fmaf(m.z, k, -(wi.z * f.eta_ti)));
+        const float wo_m = dot(bs.wo, m);
+        dwh_dwo = (sqr(bs_eta) * wo_m) / sqr(wi_m + bs_eta * wo_m);
+    }
+    bs.pdf *= fabsf(dwh_dwo) * ggx_smith_g1<float>(alpha, bs.wo, m);
+    bs.valid = active && (selected_t || selected_r);
+    return bs;
+}
+template <class S, int kCfg> __device__ __forceinline__ BsdfSample bsdf_sample_leaf(const DScene &sc, const DBsdf &b, const Its<S> &its, V3f wi, V3f sample, bool active) {
+    if ((kCfg & kCfgExt) && b.type == 3) return dielectric_sample(b, bsdf_alpha<S, kCfg>(sc, b, its), wi, sample, active);
+    if ((kCfg & kCfgFull) && b.type != 0) return ggx_reflect_sample(bsdf_alpha<S, kCfg>(sc, b, its), b.two_side != 0, wi, sample, active);
+    BsdfSample bs;
+    float wiz = wi.z;
+    if (b.two_side) wiz = fabsf(wiz);
+    const V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));
+    const float z = safe_sqrt(1.f - fmaf(p.y, p.y, p.x * p.x));
+    bs.wo = V3f(p.x, p.y, z);
+    bs.pdf = kInvPi * z;
+    bs.valid = active && (wiz > 0.f);
+    return bs;
+}
+// NormalMap::__sample (normalmap.cpp:147-187): sample.z picks the facet the nested BSDF is sampled on
+template <class S, int kCfg> PSDR_FULL_FN BsdfSample normalmap_sample(const DScene &sc, const DBsdf &b, const Its<S> &its, V3f wi, V3f sample, bool active) {
+    if (b.two_side) wi.z = fabsf(wi.z);
+    const DBsdf &nb = sc.bsdfs[b.nested];
+    Its<float> f;
+    f.tri = its.tri;
+    f.uv = val(its.uv);
+    f.bc = V2f(val(its.bc.x), val(its.bc.y));
+    f.dp_du = val(its.dp_du);
+    V3f wp;
+    NmFrame<float> fr;
+    nm_setup<float, kCfg>(b, f, wp, fr);
+    const V3f p_wi = fr.to_local(wi);
+    const float probability_wp = nm_lambda_p<float>(wp, wi);
+    const bool itpo = sample.z >= probability_wp;
+    // i -> t -> p -> o: the reflected incident direction (the reference leaves its.wi.z of this copy as passed in)
+    const V3f r_wi = fr.to_local(nm_reflect<float>(wi, nm_wt<float>(wp)));
+    BsdfSample bs = bsdf_sample_leaf<float, kCfg>(sc, nb, f, itpo ? r_wi : p_wi, sample, active);
+    const float pdf1 = bsdf_pdf_leaf<float, kCfg>(sc, nb, f, p_wi, bs.wo), pdf2 = bsdf_pdf_leaf<float, kCfg>(sc, nb, f, r_wi, bs.wo);
+    bs.pdf = probability_wp * pdf1 + (1.f - probability_wp) * pdf2;
+    bs.wo = fr.to_world(bs.wo);
     return bs;
 }
 
@@ -843,15 +1150,9 @@ template <class S, int kCfg> __device__ __forceinline__ BsdfSample bsdf_sample(c
     if (!its.valid) return bs;
     const int bi = sc.meshes[its.mesh].bsdf;
     if (bi < 0) return bs;
-    if ((kCfg & kCfgFull) && sc.bsdfs[bi].type != 0) return microfacet_sample(sc.bsdfs[bi], val(its.wi), sample, active, val(its.uv));
-    float wiz = val(its.wi.z);
-    if (sc.bsdfs[bi].two_side) wiz = fabsf(wiz);
-    const V2f p = square_to_uniform_disk_concentric(V2f(sample.y, sample.z));
-    const float z = safe_sqrt(1.f - fmaf(p.y, p.y, p.x * p.x));
-    bs.wo = V3f(p.x, p.y, z);
-    bs.pdf = kInvPi * z;
-    bs.valid = active && (wiz > 0.f);
-    return bs;
+    const DBsdf &b = sc.bsdfs[bi];
+    if ((kCfg & kCfgExt) && b.type == 5) return normalmap_sample<S, kCfg>(sc, b, its, val(its.wi), sample, active);
+    return bsdf_sample_leaf<S, kCfg>(sc, b, its, val(its.wi), sample, active);
 }
 
 // ---- emitters (reference src/emitter/area.cpp, src/shape/mesh.cpp:413-466) --------------------

@@ -127,6 +127,7 @@ void upload_scene(Scene &sc) {
     check(cudaSetDevice(sc.device), "cudaSetDevice");
     std::vector<float4> geo, shade, dgeo, dshade, sec, pe_a, pe_da, pe_b;
     std::vector<float2> uv;
+    std::vector<int> face_idx;
     std::vector<DMesh> dmeshes;
     std::vector<DEmitter> demit;
     std::vector<DBsdf> dbsdf;
@@ -159,10 +160,17 @@ void upload_scene(Scene &sc) {
             for (int k = 0; k < 3; ++k) {
                 const V2f c = m.has_uv ? m.uv[m.fuv[3 * i + k]] : V2f(0.f, 0.f);
                 uv.push_back(make_float2(c.x, c.y));
+                face_idx.push_back(3 * i + k < m.f.size() ? m.f[3 * i + k] : 0);   // the envmap's bounding mesh has no index list of its own
             }
         }
     }
-    for (const HBsdf &b : sc.bsdfs) {
+    // numbered BSDFs first, then the records NormalMaps wrap (DBsdf::nested indexes the combined table)
+    std::vector<const HBsdf *> all_bsdfs;
+    for (const HBsdf &b : sc.bsdfs) all_bsdfs.push_back(&b);
+    for (const HBsdf &b : sc.nested_bsdfs) all_bsdfs.push_back(&b);
+    bool any_pv = false;
+    for (const HBsdf *bp : all_bsdfs) {
+        const HBsdf &b = *bp;
         DBsdf d{};
         d.refl[0] = b.reflectance.x.v; d.refl[1] = b.reflectance.y.v; d.refl[2] = b.reflectance.z.v;
         d.d_refl[0] = b.reflectance.x.d; d.d_refl[1] = b.reflectance.y.d; d.d_refl[2] = b.reflectance.z.d;
@@ -176,6 +184,9 @@ void upload_scene(Scene &sc) {
         d.d_eta[0] = b.eta.x.d; d.d_eta[1] = b.eta.y.d; d.d_eta[2] = b.eta.z.d;
         d.kk[0] = b.k.x.v; d.kk[1] = b.k.y.v; d.kk[2] = b.k.z.v;
         d.d_kk[0] = b.k.x.d; d.d_kk[1] = b.k.y.d; d.d_kk[2] = b.k.z.d;
+        d.nested = b.nested >= 0 ? (int) sc.bsdfs.size() + b.nested : -1;
+        d.pv_n = (int) b.pv.size() / 7;
+        any_pv |= b.type == 4;
         dbsdf.push_back(d);
     }
     for (const HEmitter &e : sc.emitters) {
@@ -257,12 +268,19 @@ void upload_scene(Scene &sc) {
                  o_gp = pk.add(g_pmf), o_gc = pk.add(g_cmf), o_gl = pk.add(g_lut), o_sl = pk.add(s_lut),
                  o_small_end = 0;
     (void) o_small_end;
-    std::vector<size_t> o_tex(3 * sc.bsdfs.size(), 0), o_dtex(3 * sc.bsdfs.size(), 0);
-    for (size_t i = 0; i < sc.bsdfs.size(); ++i)
-        for (int k = 0; k < 3; ++k) if (sc.bsdfs[i].tex[k].w > 0) {
-            o_tex[3 * i + k] = pk.add(sc.bsdfs[i].tex[k].data);
-            o_dtex[3 * i + k] = pk.add(sc.bsdfs[i].tex[k].ddata);
+    if (!any_pv) face_idx.clear();
+    const size_t o_fi = pk.add(face_idx);
+    std::vector<size_t> o_tex(3 * all_bsdfs.size(), 0), o_dtex(3 * all_bsdfs.size(), 0), o_pv(all_bsdfs.size(), 0), o_dpv(all_bsdfs.size(), 0);
+    for (size_t i = 0; i < all_bsdfs.size(); ++i) {
+        for (int k = 0; k < 3; ++k) if (all_bsdfs[i]->tex[k].w > 0) {
+            o_tex[3 * i + k] = pk.add(all_bsdfs[i]->tex[k].data);
+            o_dtex[3 * i + k] = pk.add(all_bsdfs[i]->tex[k].ddata);
         }
+        if (!all_bsdfs[i]->pv.empty()) {
+            o_pv[i] = pk.add(all_bsdfs[i]->pv);
+            o_dpv[i] = pk.add(all_bsdfs[i]->d_pv);
+        }
+    }
 
     if (!sc.dev) sc.dev = new DeviceBuffers();
     DeviceBuffers &db = *sc.dev;
@@ -299,14 +317,19 @@ void upload_scene(Scene &sc) {
         db.big_ddata_version = e.ddata_version;
     }
     // texture pointers of the BSDF records can only be filled in once the allocation is known
-    for (size_t i = 0; i < sc.bsdfs.size(); ++i) {
+    for (size_t i = 0; i < all_bsdfs.size(); ++i) {
         DBsdf *rec = reinterpret_cast<DBsdf *>(pk.bytes.data() + o_bsdf) + i;
+        if (!all_bsdfs[i]->pv.empty()) {
+            rec->pv = (const float *) ((const unsigned char *) db.dev + o_pv[i]);
+            rec->d_pv = all_bsdfs[i]->d_pv.empty() ? nullptr : (const float *) ((const unsigned char *) db.dev + o_dpv[i]);
+        }
         for (int k = 0; k < 3; ++k) {
-            const HBsdf::Tex &t = sc.bsdfs[i].tex[k];
+            const HBsdf::Tex &t = all_bsdfs[i]->tex[k];
             DTex &dt = rec->tex[k];
             dt = DTex{};
             dt.ch = HBsdf::tex_channels(k);
-            dt.goff = sc.texture_grad_offset((int) i, k);   // relative to the end of the gradient table
+            // relative to the end of the gradient table (nested records have no gradient blocks: reverse mode rejects NormalMap)
+            dt.goff = i < sc.bsdfs.size() ? sc.texture_grad_offset((int) i, k) : 0;
             // cos / sin of the rotation on the host (the reference evaluates them per lookup on the device)
             const float cr = std::cos(t.rot.v), sr = std::sin(t.rot.v);
             dt.cr = cr; dt.sr = sr; dt.d_cr = -sr * t.rot.d; dt.d_sr = cr * t.rot.d;
@@ -409,12 +432,17 @@ void upload_scene(Scene &sc) {
     d.use_bvh = use_bvh ? 1 : 0;
     d.ref_rcp = sc.ref_rcp ? 1 : 0;
     d.full_features = sc.env.present ? 1 : 0;
-    for (const HBsdf &b : sc.bsdfs) d.full_features |= (b.type != 0 || b.tex[0].w > 0 || b.tex[1].w > 0 || b.tex[2].w > 0) ? 1 : 0;
+    for (const HBsdf *b : all_bsdfs) {
+        d.ext_features |= (b->type >= 2 || b->tex[0].w > 0 || b->tex[1].w > 0 || b->tex[2].w > 0) ? 1 : 0;
+        d.full_features |= b->type != 0 ? 1 : 0;
+    }
+    d.full_features |= d.ext_features;
     d.geo = (const float4 *) (base + o_geo);
     d.shade = (const float4 *) (base + o_shade);
     d.dgeo = (const float4 *) (base + o_dgeo);
     d.dshade = (const float4 *) (base + o_dshade);
     d.uv = (const float2 *) (base + o_uv);
+    d.face_idx = face_idx.empty() ? nullptr : (const int *) (base + o_fi);
     d.meshes = (const DMesh *) (base + o_mesh);
     d.emitters = (const DEmitter *) (base + o_emit);
     d.bsdfs = (const DBsdf *) (base + o_bsdf);

@@ -77,16 +77,23 @@ struct DEnv {
 struct DBsdf {
     float refl[3];           // Diffuse: reflectance; Microfacet: diffuseReflectance
     float d_refl[3];
-    int type;                // 0 Diffuse, 1 Microfacet, 2 RoughConductor
+    int type;                // 0 Diffuse, 1 Microfacet, 2 RoughConductor, 3 RoughDielectric, 4 MicrofacetPerVertex, 5 NormalMap
     int two_side;
     float spec[3];           // Microfacet: specularReflectance (F0); RoughConductor: specular_reflectance
     float d_spec[3];
     float rough, d_rough;    // Microfacet: roughness (alpha = roughness^2); RoughConductor: alpha (alpha_u = alpha_v)
-    float eta[3], d_eta[3];  // RoughConductor: complex index of refraction eta + i k per channel
+    float eta[3], d_eta[3];  // RoughConductor: complex index of refraction eta + i k per channel;
+                             // RoughDielectric: eta[0] = intIOR / extIOR, eta[1] = extIOR / intIOR (rounded separately, as the reference does)
     float kk[3], d_kk[3];
     // texture slots (texture.h DTex): 0 reflectance / diffuseReflectance (Bitmap3fD), 1 specularReflectance (Bitmap3fD),
     // 2 roughness (Bitmap1fD); w * h == 0: the constant above
+    // NormalMap: slot 0 (refl / tex[0]) is the normal map, `nested` the record of the BSDF it perturbs (nested records
+    // follow the n_bsdfs user-visible ones in DScene::bsdfs)
     DTex tex[3];
+    int nested;
+    // MicrofacetPerVertex: pv_n vertices x 7 floats (specular rgb, diffuse rgb, roughness) and their forward tangents
+    int pv_n;
+    const float *pv, *d_pv;
 };
 
 struct DCamera {
@@ -116,8 +123,10 @@ struct DScene {
     int use_bvh;             // 0: brute force over all triangles (tiny scenes)
     int ref_rcp;             // 1: the analytic primary hit of renderD uses Dr.Jit's approximate rcp (device_path.cuh rcp_approx)
     int full_features;       // 1: some BSDF is a Microfacet or an EnvironmentMap exists (selects the kernel variant)
+    int ext_features;        // 1: bitmap-valued BSDF slots or a BSDF of type >= 2 (kCfgExt kernel family; implies full_features)
     const float4 *geo, *shade, *dgeo, *dshade;
     const float2 *uv;
+    const int *face_idx;     // 3 mesh-local vertex indices per triangle (MicrofacetPerVertex gathers through them); nullptr if unused
     const DMesh *meshes;
     const DEmitter *emitters;
     const DBsdf *bsdfs;

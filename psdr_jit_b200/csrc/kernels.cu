@@ -1,5 +1,6 @@
 // Host-callable launchers (kernels.h): pick the kernel family a scene needs -- bit 0 BVH2 traversal, bit 1
-// Microfacet / EnvironmentMap code -- and forward to its translation unit (kern_cfg*.cu, vjp_cfg*.cu).
+// Microfacet / EnvironmentMap code, bit 3 the extended material set (bitmaps, conductor, dielectric, per-vertex, normal
+// map; implies bit 1) -- and forward to its translation unit (kern_cfg*.cu, vjp_cfg*.cu).
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -7,14 +8,16 @@
 
 namespace psdr {
 
-int scene_cfg(const DScene &sc) { return (sc.use_bvh ? 1 : 0) | (sc.full_features ? 2 : 0); }
+int scene_cfg(const DScene &sc) { return (sc.use_bvh ? 1 : 0) | (sc.full_features ? 2 : 0) | (sc.ext_features ? 10 : 0); }
 
 #define PSDR_DISPATCH(CALL)                   \
     switch (scene_cfg(sc)) {                  \
         case 0: return fwd0::CALL;            \
         case 1: return fwd1::CALL;            \
         case 2: return fwd2::CALL;            \
-        default: return fwd3::CALL;           \
+        case 3: return fwd3::CALL;            \
+        case 10: return fwd10::CALL;          \
+        default: return fwd11::CALL;          \
     }
 
 cudaError_t launch_interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st) {
@@ -52,7 +55,9 @@ cudaError_t launch_field_edges(const DScene &sc, const DCamera &cam, const Rende
         case 0: return vjp0::CALL;            \
         case 1: return vjp1::CALL;            \
         case 2: return vjp2::CALL;            \
-        default: return vjp3::CALL;           \
+        case 3: return vjp3::CALL;            \
+        case 10: return vjp10::CALL;          \
+        default: return vjp11::CALL;          \
     }
 cudaError_t launch_interior_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
     if (rp.lane_end - rp.lane_begin <= 0) return cudaSuccess;

@@ -16,7 +16,7 @@ namespace psdr {
     cudaError_t aov_d(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, float *dout, cudaStream_t st);                 \
     cudaError_t field_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, int field, int object, float *dimg, cudaStream_t st); \
     }
-PSDR_DECL_FWD(fwd0) PSDR_DECL_FWD(fwd1) PSDR_DECL_FWD(fwd2) PSDR_DECL_FWD(fwd3)
+PSDR_DECL_FWD(fwd0) PSDR_DECL_FWD(fwd1) PSDR_DECL_FWD(fwd2) PSDR_DECL_FWD(fwd3) PSDR_DECL_FWD(fwd10) PSDR_DECL_FWD(fwd11)
 #undef PSDR_DECL_FWD
 #define PSDR_DECL_VJP(NS)                                                                                                                              \
     namespace NS {                                                                                                                                     \
@@ -24,6 +24,6 @@ PSDR_DECL_FWD(fwd0) PSDR_DECL_FWD(fwd1) PSDR_DECL_FWD(fwd2) PSDR_DECL_FWD(fwd3)
     cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st);      \
     cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st);    \
     }
-PSDR_DECL_VJP(vjp0) PSDR_DECL_VJP(vjp1) PSDR_DECL_VJP(vjp2) PSDR_DECL_VJP(vjp3)
+PSDR_DECL_VJP(vjp0) PSDR_DECL_VJP(vjp1) PSDR_DECL_VJP(vjp2) PSDR_DECL_VJP(vjp3) PSDR_DECL_VJP(vjp10) PSDR_DECL_VJP(vjp11)
 #undef PSDR_DECL_VJP
 }  // namespace psdr

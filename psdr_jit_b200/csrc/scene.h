@@ -30,12 +30,14 @@ struct HEdge {
 
 struct HBsdf {
     std::string id;
-    int type = 0;             // 0 Diffuse, 1 Microfacet, 2 RoughConductor
-    V3d reflectance;          // Diffuse reflectance / Microfacet diffuseReflectance
+    int type = 0;             // 0 Diffuse, 1 Microfacet, 2 RoughConductor, 3 RoughDielectric, 4 MicrofacetPerVertex, 5 NormalMap
+    V3d reflectance;          // Diffuse reflectance / Microfacet diffuseReflectance / NormalMap: the (constant) normal map
     V3d specular;             // Microfacet specularReflectance / RoughConductor specular_reflectance
     Dual roughness;           // Microfacet roughness / RoughConductor alpha
-    V3d eta, k;               // RoughConductor eta, k
+    V3d eta, k;               // RoughConductor eta, k; RoughDielectric: eta.x = intIOR / extIOR, eta.y = extIOR / intIOR
     bool two_side = false;
+    int nested = -1;          // NormalMap: index into Scene::nested_bsdfs of the BSDF it perturbs
+    std::vector<float> pv, d_pv;   // MicrofacetPerVertex: 7 floats per vertex (specular rgb, diffuse rgb, roughness) + tangents
     // texture slots (Bitmap with more than one texel; channels interleaved, pixel = y*w + x):
     // 0 reflectance / diffuseReflectance (3 channels), 1 specularReflectance (3), 2 roughness (1);
     // each with the bitmap's uv transform (reference include/psdr/core/bitmap.h:36-38: m_scale, m_rot, m_trans)
@@ -151,6 +153,7 @@ struct Scene {
     int width = 128, height = 128, spp = 1, sppe = 0, sppse = 0, log_level = 1;  // RenderOption defaults (types.h:217-228)
     long long seed = 0;
     std::vector<HBsdf> bsdfs;
+    std::vector<HBsdf> nested_bsdfs;   // the BSDFs NormalMap records wrap: not numbered, not in param_map (scene.cpp:128-145)
     std::vector<HMesh> meshes;
     std::vector<HEmitter> emitters;
     std::vector<HCamera> cameras;

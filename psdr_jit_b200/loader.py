@@ -167,19 +167,30 @@ def load_scene_xml(scene, root, base_dir: str = "."):
         if not bid:
             raise RuntimeError("BSDF must have an id")
         t = node.get("type")
-        if t == "diffuse":
-            b = psdr.DiffuseBSDF(texture(_child_by_name(node, {"reflectance"}), 3))
-        elif t == "microfacet":
-            b = psdr.MicrofacetBSDF(texture(_child_by_name(node, {"specular_reflectance", "specularReflectance"}), 3),
-                                    texture(_child_by_name(node, {"diffuse_reflectance", "diffuseReflectance"}), 3),
-                                    texture(_child_by_name(node, {"roughness"}), 1))
-        elif t == "roughconductor":      # scene_loader.cpp:334-345: alpha (-> alpha_u = alpha_v), eta, k
-            b = psdr.RoughConductorBSDF(texture(_child_by_name(node, {"alpha"}), 1), texture(_child_by_name(node, {"eta"}), 3),
-                                        texture(_child_by_name(node, {"k"}), 3))
-        elif t in ("roughdielectric", "normalmap"):
-            raise RuntimeError("BSDF type '%s' is not implemented by this port (Diffuse, Microfacet and RoughConductor are)" % t)
-        else:
-            raise RuntimeError("Unsupported BSDF: " + str(t))
+
+        def leaf(n, t, what="Unsupported BSDF: "):
+            if t == "diffuse":
+                return psdr.DiffuseBSDF(texture(_child_by_name(n, {"reflectance"}), 3))
+            if t == "microfacet":
+                return psdr.MicrofacetBSDF(texture(_child_by_name(n, {"specular_reflectance", "specularReflectance"}), 3),
+                                           texture(_child_by_name(n, {"diffuse_reflectance", "diffuseReflectance"}), 3),
+                                           texture(_child_by_name(n, {"roughness"}), 1))
+            if t == "roughconductor":      # scene_loader.cpp:334-345: alpha (-> alpha_u = alpha_v), eta, k
+                return psdr.RoughConductorBSDF(texture(_child_by_name(n, {"alpha"}), 1), texture(_child_by_name(n, {"eta"}), 3),
+                                               texture(_child_by_name(n, {"k"}), 3))
+            if t == "roughdielectric":     # scene_loader.cpp:346-360: alpha, intIOR, extIOR
+                return psdr.RoughDielectricBSDF(texture(_child_by_name(n, {"alpha"}), 1), float(_child_by_name(n, {"intIOR"}).get("value")),
+                                                float(_child_by_name(n, {"extIOR"}).get("value")))
+            raise RuntimeError(what + str(t))
+
+        if t == "normalmap":               # scene_loader.cpp:372-424: <normalmap> texture + one nested <bsdf>
+            inner = node.find("bsdf")
+            if inner is None:
+                raise RuntimeError("Unsupported normal map nested BSDF: ")
+            nm = psdr.NormalMapBSDF(texture(_child_by_name(node, {"normalmap"}), 3))
+            scene.add_normalmap_BSDF(nm, leaf(inner, inner.get("type"), "Unsupported normal map nested BSDF: "), bid)
+            continue
+        b = leaf(node, t)
         scene.add_BSDF(b, bid)
     for node in root.findall("emitter"):
         if node.get("type") != "envmap":

@@ -38,6 +38,16 @@ def is_conductor(params):
     return isinstance(params, dict) and "conductor" in params
 
 
+def ext_kind(params):
+    """extended material set: {"dielectric": (alpha, intIOR, extIOR)}, {"pervertex": (spec[n,3], diff[n,3], rough[n])},
+    {"normalmap": {"normal": (x, y, z), "nested": <any non-normalmap spec>, "d_nested": tangent of the nested spec}}"""
+    if isinstance(params, dict):
+        for k in ("dielectric", "pervertex", "normalmap"):
+            if k in params:
+                return k
+    return None
+
+
 def test_envmap(w=32, h=16, seed=0):
     """synthetic lat-long environment map (BASELINE config 3 recipe: rng.random**4 * 4), [h*w, 3]"""
     rng = np.random.default_rng(seed)
@@ -64,15 +74,28 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
     from oracle.psdr_oracle import OracleScene
     cam = cam or scenes.CBOX_CAMERA
     sc = OracleScene(w, h, spp, sppe, sppse)
-    for name, params in (bsdfs or scenes.CBOX_BSDFS):
-        d = d_bsdf.get(name) if d_bsdf else None
-        if is_conductor(params):        # d = (d_alpha, d_eta[3], d_k[3], d_spec[3])
+    def add_oracle_bsdf(name, params, d):
+        kind = ext_kind(params)
+        if kind == "dielectric":        # d = (d_alpha,)
+            c = params["dielectric"]
+            sc.add_roughdielectric(name, c[0], c[1], c[2], d_alpha=0.0 if d is None else float(np.ravel(d)[0]))
+        elif kind == "pervertex":       # d = [n, 7] table
+            c = params["pervertex"]
+            sc.add_microfacet_pervertex(name, c[0], c[1], c[2], d=d)
+        elif kind == "normalmap":       # d = d_normal[3]; the nested BSDF gets a name of its own in the oracle
+            c = params["normalmap"]
+            add_oracle_bsdf(name + "/nested", c["nested"], c.get("d_nested"))
+            sc.add_normalmap(name, name + "/nested", c.get("normal", (0.499999, 0.499999, 1.0)), d_normal=d)
+        elif is_conductor(params):      # d = (d_alpha, d_eta[3], d_k[3], d_spec[3])
             c = params["conductor"]
             sc.add_roughconductor(name, c[0], c[1], c[2], c[3] if len(c) > 3 else (1.0, 1.0, 1.0), d=d)
         elif is_microfacet(params):
             sc.add_microfacet(name, params[0], params[1], params[2], d=d)
         else:
             sc.add_diffuse(name, params, d_refl=d)
+
+    for name, params in (bsdfs or scenes.CBOX_BSDFS):
+        add_oracle_bsdf(name, params, d_bsdf.get(name) if d_bsdf else None)
         if textures and name in textures:
             for slot, t in tex_slots(textures[name]).items():
                 sc.set_bsdf_texture(name, t["data"], t["w"], t["h"], t.get("d_data"), slot=slot, xform=t.get("xform"), d_xform=t.get("d_xform"))
@@ -101,8 +124,60 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
     sensor = psdr.PerspectiveCamera(cam["fov"], cam["near"], cam["far"])
     sensor.to_world = cam["to_world"]
     sc.add_Sensor(sensor)
+    def make_bsdf(params, d):
+        kind = ext_kind(params)
+        if kind == "dielectric":
+            c = params["dielectric"]
+            b = psdr.RoughDielectricBSDF(float(c[0]), float(c[1]), float(c[2]))
+            if d is not None:
+                b.d_alpha_u = np.float32(np.ravel(d)[0])
+            return b
+        if kind == "pervertex":
+            c = params["pervertex"]
+            b = psdr.MicrofacetBSDFPerVertex(c[0], c[1], c[2])
+            if d is not None:
+                t = np.float32(d).reshape(-1, 7)
+                b.d_specularReflectance, b.d_diffuseReflectance, b.d_roughness = t[:, 0:3].copy(), t[:, 3:6].copy(), t[:, 6].copy()
+            return b
+        if is_conductor(params):
+            c = params["conductor"]
+            b = psdr.RoughConductorBSDF(psdr.Bitmap1fD(float(c[0])), psdr.Bitmap3fD(list(c[1])), psdr.Bitmap3fD(list(c[2])))
+            if len(c) > 3:
+                b.specular_reflectance = np.float32(c[3])
+            if d is not None:
+                b.d_alpha_u, b.d_eta, b.d_k, b.d_specular_reflectance = np.float32(d[0]), np.float32(d[1:4]), np.float32(d[4:7]), np.float32(d[7:10])
+            return b
+        if is_microfacet(params):
+            b = psdr.MicrofacetBSDF(params[0], params[1], params[2])
+            if d is not None:
+                b.d_specularReflectance, b.d_diffuseReflectance, b.d_roughness = np.float32(d[0:3]), np.float32(d[3:6]), np.float32(d[6])
+            return b
+        b = psdr.DiffuseBSDF(params)
+        if d is not None:
+            b.d_reflectance = np.float32(d)
+        return b
+
     for name, params in (bsdfs or scenes.CBOX_BSDFS):
         d = d_bsdf.get(name) if d_bsdf else None
+        if ext_kind(params) == "normalmap":
+            c = params["normalmap"]
+            nm = psdr.NormalMapBSDF(c.get("normal", (0.499999, 0.499999, 1.0)))
+            if d is not None:
+                nm.d_normal_map = np.float32(d)
+            if textures and name in textures:
+                t = tex_slots(textures[name])[0]
+                nm.normal_map = psdr.Bitmap3fD(t["w"], t["h"], t["data"])
+                if t.get("d_data") is not None:
+                    nm.normal_map.d_data = np.asarray(t["d_data"], dtype=np.float32)
+            sc.add_normalmap_BSDF(nm, make_bsdf(c["nested"], c.get("d_nested")), name, twoSide=two_side)
+            continue
+        if ext_kind(params) in ("dielectric", "pervertex"):
+            b = make_bsdf(params, d)
+            if textures and name in textures and ext_kind(params) == "dielectric":
+                t = tex_slots(textures[name])[2]
+                b.alpha_u = psdr.Bitmap1fD(t["w"], t["h"], t["data"])
+            sc.add_BSDF(b, name, twoSide=two_side)
+            continue
         if is_conductor(params):
             c = params["conductor"]
             b = psdr.RoughConductorBSDF(psdr.Bitmap1fD(float(c[0])), psdr.Bitmap3fD(list(c[1])), psdr.Bitmap3fD(list(c[2])))

@@ -379,6 +379,71 @@ def test_oracle_roughconductor_vs_reference_golden(oracle):
         assert nbad <= 256 and r_ex < 5e-3, (tag, r, nbad, r_ex)
 
 
+def test_oracle_ext_bsdfs_vs_reference_golden(oracle):
+    """MicrofacetBSDFPerVertex, NormalMapBSDF (add_normalmap_BSDF and add_BSDF's defaults) and RoughDielectricBSDF (through
+    a scene file) on the tall block: tests/golden/ext_bsdfs.npz, tools/ref_golden10.py -- the RUNNING reference.  As for the
+    other glossy BSDFs a few pixels of 16 384 flip a hit or a lobe choice under the reference's approximate arithmetic
+    (8-15 in renderC, up to ~160 in the derivative images, where single samples reach 1e2-1e4); the rest agrees to 2-4e-4
+    (images) / 1-5e-3 (derivative images, which the reference scales by 2)."""
+    import copy
+    g = np.load(os.path.join(GOLDEN, "ext_bsdfs.npz"))
+    spp = int(g["spp"])
+
+    def meshes():
+        ms = copy.deepcopy(scenes.cbox_meshes())
+        for m in ms:
+            if m.name == "largebox":
+                m.bsdf = "ext"
+        return ms
+
+    def bs(spec):
+        return list(scenes.CBOX_BSDFS) + [("ext", spec)]
+    nm = {"normalmap": {"normal": tuple(g["nm_normal"]), "nested": (list(g["nm_spec"]), list(g["nm_diff"]), float(g["nm_rough"]))}}
+    cases = {"pervertex": {"pervertex": (g["pv_spec"], g["pv_diff"], g["pv_rough"])}, "normalmap": nm,
+             "normalmap_default": {"normalmap": {"normal": (0.499999, 0.499999, 1.0), "nested": ([0.04] * 3, [0.5] * 3, 0.8)}},
+             "dielectric": {"dielectric": (0.2, 1.5, 1.0)}}
+    for tag, spec in cases.items():
+        img = build_oracle(meshes(), 128, 128, spp, 0, 0, bsdfs=bs(spec)).render(3, seed=0, mode=0)
+        r, nbad, r_ex = compare_stats(img, g["imgC_" + tag])
+        assert nbad <= 32 and r_ex < 6e-4, (tag, r, nbad, r_ex)
+    for tag in ("normalmap", "dielectric"):
+        img, d = build_oracle(meshes(), 128, 128, spp, 0, 0, bsdfs=bs(cases[tag]), move_mesh=0, axis_scale=(100.0, 0.0, 0.0)).render(3, seed=0, mode=1, terms=1)
+        r, nbad, r_ex = compare_stats(img, g["imgD_" + tag])
+        assert nbad <= 128 and r_ex < 1e-3, (tag, r, nbad, r_ex)
+        r, nbad, r_ex = compare_stats(2.0 * d, g["gradD_" + tag])
+        assert nbad <= 256 and r_ex < 5e-3, (tag, r, nbad, r_ex)
+    d_pv = np.zeros((8, 7), np.float32)
+    d_pv[:, 6] = 1.0
+    for tag, spec, dd in (("pervertex_rough", cases["pervertex"], d_pv), ("normalmap_normal", nm, np.float32([1, 0, 0]))):
+        _, d = build_oracle(meshes(), 128, 128, spp, 0, 0, bsdfs=bs(spec), d_bsdf={"ext": dd}).render(3, seed=0, mode=1, terms=1)
+        r, nbad, r_ex = compare_stats(2.0 * d, g["gradD_" + tag])
+        assert nbad <= 256 and r_ex < 7e-3, (tag, r, nbad, r_ex)
+
+
+def test_oracle_pervertex_tangent_matches_finite_differences(oracle):
+    """d/d(per-vertex diffuse colour): the oracle's forward-mode image against central differences (a parameter outside the
+    detached sampling densities, so the two agree per seed)"""
+    import copy
+    rng = np.random.default_rng(5)
+    sp, df, rg = rng.uniform(0.02, 0.9, (8, 3)).astype(np.float32), rng.uniform(0.05, 0.8, (8, 3)).astype(np.float32), rng.uniform(0.15, 0.9, 8).astype(np.float32)
+    ms = copy.deepcopy(scenes.cbox_meshes())
+    for m in ms:
+        if m.name == "largebox":
+            m.bsdf = "ext"
+
+    def render(eps, tangent):
+        d2 = df.copy()
+        d2[:, 1] += np.float32(eps)
+        d = np.zeros((8, 7), np.float32)
+        d[:, 4] = 1.0
+        sc = build_oracle(ms, 48, 48, 16, 0, 0, bsdfs=list(scenes.CBOX_BSDFS) + [("ext", {"pervertex": (sp, d2, rg)})], d_bsdf={"ext": d} if tangent else None)
+        return sc.render(2, seed=4, mode=1, terms=1)[1 if tangent else 0]
+    h = 1e-2
+    fd = (render(h, False) - render(-h, False)) / (2 * h)
+    ad = render(0.0, True)
+    assert np.abs(ad).max() > 0 and rel_l2(ad, fd) < 1e-3
+
+
 def test_oracle_field_integrator_vs_reference_golden(oracle):
     """FieldExtractionIntegrator (tests/golden/fields.npz, tools/ref_golden9.py: the RUNNING reference).  Like Direct, the
     reference binary returns exactly 2x the field (a fully covered pixel of "silhouette" reads 2) and 2x its interior
