@@ -957,6 +957,11 @@ class Scene(Object):
         obj = self.param_map[name]
         for kind_name, objs in self._objects():
             for i, o in enumerate(objs):
+                if o is obj and isinstance(o, MicrofacetBSDFPerVertex):
+                    cols = {"specularReflectance": slice(0, 3), "diffuseReflectance": slice(3, 6), "roughness": 6}
+                    if field not in cols:
+                        break
+                    return self._read_grad(_lib.BSDF_PERVERTEX, i, (len(o.roughness), 7))[:, cols[field]].copy()
                 if o is obj:
                     for f, kind in self._fields_of(kind_name, o):
                         if f == field:

@@ -49,7 +49,8 @@ def load():
     if _LIB is not None:
         return _LIB
     # raises if nvcc / sources are missing; PSDR_REFERENCE_ARITHMETIC=1 selects the approximate-division variant (build.py)
-    path = _build.build_native(variant="refarith" if os.environ.get("PSDR_REFERENCE_ARITHMETIC") == "1" else "")
+    # PSDR_B200_LIB: load exactly this library (A/B runs of kernel variants built beforehand, tools/build_variant.py)
+    path = os.environ.get("PSDR_B200_LIB") or _build.build_native(variant="refarith" if os.environ.get("PSDR_REFERENCE_ARITHMETIC") == "1" else "")
     L = C.CDLL(path)
     vp, ll, i, f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
     L.psdr_last_error.restype = C.c_char_p

@@ -232,12 +232,50 @@ template <class S> __device__ __forceinline__ void iso_conductor(S alpha, S ci, 
     if (!(val(ggx) * val(hz) > 1e-20f)) ggx = S(0.f);
     res = ggx * iso_smith_g1<S>(alpha, ci, vh) * iso_smith_g1<S>(alpha, co, vh) / (S(4.f) * ci);
 }
+// RoughDielectric (src/bsdf/roughdielectric.cpp:37-122) in the same quantities; with e = 1 (reflection) or eta (refraction):
+// |wi + e wo|^2 = 1 + e^2 + 2 e cio, m.z = (ci + e co)/|.|, <wi, m> = (1 + e cio)/|.|, <wo, m> = (cio + e)/|.|
+template <class S> __device__ __forceinline__ S iso_dielectric(S alpha, S m_eta, S m_inv_eta, S ci, S co, S cio) {
+    if (val(ci) == 0.f) return S(0.f);
+    const bool reflect = val(ci) * val(co) > 0.f, front = val(ci) > 0.f;
+    const S eta = front ? m_eta : m_inv_eta, inv_eta = front ? m_inv_eta : m_eta;
+    const S e = reflect ? S(1.f) : eta;
+    const S L = sqrt_(S(1.f) + sqr(e) + S(2.f) * e * cio);
+    S mz = (ci + e * co) / L, wim = (S(1.f) + e * cio) / L, wom = (cio + e) / L;
+    if (signbit_(val(mz))) { mz = -mz; wim = -wim; wom = -wom; }
+    const S s2 = S(1.f) - sqr(mz);
+    const S t = (val(s2) > 0.f ? s2 : S(0.f)) / sqr(alpha) + sqr(mz);
+    S D = rcp_(S(kPi) * sqr(alpha) * sqr(t));
+    if (!(val(D) * val(mz) > 1e-20f)) D = S(0.f);
+    const S F = fresnel_dielectric<S>(m_eta, wim).r;
+    const S G = iso_smith_g1<S>(alpha, ci, wim) * iso_smith_g1<S>(alpha, co, wom);
+    if (reflect) return F * D * G / (S(4.f) * abs_(ci));
+    return abs_((sqr(inv_eta) * (S(1.f) - F) * D * G * eta * eta * wim * wom) / (ci * sqr(wim + eta * wom)));
+}
+// MicrofacetPerVertex (src/bsdf/microfacet_pv.cpp:20-68): specular lobe without the Fresnel colour,
+// ggx smithG / (4 ci co + 1e-6) in its own NDF / Schlick-Smith form, and the Fresnel blend weight e
+template <class S> __device__ __forceinline__ void iso_specular_pv(S rough, S ci, S co, S cio, S &dg, S &e) {
+    const S L = sqrt_(S(2.f) + S(2.f) * cio);
+    const S hz = (ci + co) / L, vh = (S(1.f) + cio) / L;
+    const S alpha = sqr(rough), k = sqr(rough + S(1.f)) / S(8.f);
+    const S tmp = alpha / (hz * hz * (sqr(alpha) - S(1.f)) + S(1.f));
+    const S ggx = tmp * tmp * S(kInvPi);
+    e = exp2_(vh * (S(-5.55473f) * vh - S(6.8316f)));
+    const S smithG = (ci / (ci * (S(1.f) - k) + k)) * (co / (co * (S(1.f) - k) + k));
+    dg = ggx * smithG / (S(4.f) * co * ci + S(1e-6f));
+}
 template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_iso(const BsdfP<S> &b, S ci, S co, S cio) {
     if (b.two_side) {
         if (signbit_(val(ci))) co = -co;
         ci = abs_(ci);
     }
+    if ((kCfg & kCfgExt) && b.type == 3) return V3<S>(iso_dielectric<S>(b.rough, b.eta.x, b.eta.y, ci, co, cio));
     if (!(val(ci) > 0.f && val(co) > 0.f)) return V3<S>(S(0.f));
+    if ((kCfg & kCfgExt) && b.type == 4) {
+        S dg, e;
+        iso_specular_pv<S>(b.rough, ci, co, cio, dg, e);
+        const V3<S> fresnel = b.spec + (V3<S>(S(1.f)) - b.spec) * e;
+        return (b.diff * S(kInvPi) + fresnel * dg) * co;
+    }
     if ((kCfg & kCfgFull) && b.type == 1) {
         S dg, e;
         iso_specular<S>(b.rough, ci, co, cio, dg, e);
@@ -294,14 +332,58 @@ __device__ __forceinline__ void tex_slot_grad(const GradAcc &acc, const GradLayo
 // d(sum_c W_c f_c * scale)/d(params): reflectance (Diffuse / Microfacet diffuse), Microfacet specular + roughness;
 // constants go to the BSDF block of the table, textured slots to their texel blocks.
 // uv_bar: d(contribution)/d(texture coordinate) through textured slots (used at the primary hit only)
-template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, int bi, const DBsdf &b, const BsdfVals &bv,
-                                                float ci, float co, float cio, V3f W, float scale, V2f uv, V2f &uv_bar) {
+// (tri, bu, bv2): the vertex's triangle and barycentrics -- MicrofacetPerVertex scatters through them into the per-vertex
+// gradient block, and bc_bar receives d(contribution)/d(barycentrics) (used at the primary hit only, like uv_bar)
+template <int kCfg> __device__ __forceinline__ void bsdf_param_grad(const GradAcc &acc, const GradLayout &gl, const DScene &sc, int bi, const DBsdf &b, const BsdfVals &bv,
+                                                float ci, float co, float cio, V3f W, float scale, V2f uv, V2f &uv_bar, int tri, float bu, float bv2, V2f &bc_bar) {
     if (b.two_side) {
         if (signbit_(ci)) co = -co;
         ci = fabsf(ci);
     }
-    if (!(ci > 0.f && co > 0.f)) return;
     const int base = gl.off_bsdf + kGradBsdf * bi;
+    if ((kCfg & kCfgExt) && b.type == 3) {
+        // f_c = iso_dielectric(alpha): one value for the three channels; eta is fixed at creation
+        const Dual f = iso_dielectric<Dual>(Dual(bv.rough, 1.f), Dual(b.eta[0]), Dual(b.eta[1]), Dual(ci), Dual(co), Dual(cio));
+        const float g_alpha = (W.x + W.y + W.z) * f.d * scale;
+        if (b.tex[2].w > 0) tex_slot_grad(acc, gl, b.tex[2], uv, V3f(g_alpha, 0.f, 0.f), uv_bar);
+        else acc.add(base + 3, g_alpha);
+        return;
+    }
+    if (!(ci > 0.f && co > 0.f)) return;
+    if ((kCfg & kCfgExt) && b.type == 4) {
+        // f_c = (diff_c / pi + (F0_c + (1 - F0_c) e) dg(rough)) co with the three parameters interpolated from the corners
+        Dual dg, e;
+        iso_specular_pv<Dual>(Dual(bv.rough, 1.f), Dual(ci), Dual(co), Dual(cio), dg, e);
+        const float kd = kInvPi * co * scale, ks = (1.f - e.v) * dg.v * co * scale;
+        const float F0[3] = {bv.spec.x, bv.spec.y, bv.spec.z}, Wc[3] = {W.x, W.y, W.z};
+        float vbar[7];
+        float gr = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            vbar[c] = Wc[c] * ks;
+            vbar[3 + c] = Wc[c] * kd;
+            gr += Wc[c] * (F0[c] + (1.f - F0[c]) * e.v) * dg.d;
+        }
+        vbar[6] = gr * co * scale;
+        const int i0 = __ldg(sc.face_idx + 3 * tri), i1 = __ldg(sc.face_idx + 3 * tri + 1), i2 = __ldg(sc.face_idx + 3 * tri + 2);
+        const int pbase = gl.total + b.pv_goff;
+        const float w0 = 1.f - bu - bv2;
+        float dbu = 0.f, dbv = 0.f;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+            if (vbar[c] == 0.f) continue;
+            const float a0 = i0 < b.pv_n ? __ldg(b.pv + 7 * i0 + c) : 0.f, a1 = i1 < b.pv_n ? __ldg(b.pv + 7 * i1 + c) : 0.f,
+                        a2 = i2 < b.pv_n ? __ldg(b.pv + 7 * i2 + c) : 0.f;
+            if (i0 < b.pv_n) acc.add(pbase + 7 * i0 + c, vbar[c] * w0);
+            if (i1 < b.pv_n) acc.add(pbase + 7 * i1 + c, vbar[c] * bu);
+            if (i2 < b.pv_n) acc.add(pbase + 7 * i2 + c, vbar[c] * bv2);
+            dbu += vbar[c] * (a1 - a0);
+            dbv += vbar[c] * (a2 - a0);
+        }
+        bc_bar.x += dbu;
+        bc_bar.y += dbv;
+        return;
+    }
     if ((kCfg & kCfgExt) && b.type == 2) {
         // f_c = F(eta_c, k_c, vh) res(alpha) spec_c
         Dual res, vh;
@@ -401,6 +483,14 @@ template <int kCfg> __device__ __forceinline__ VtxGeo vertex_geo(const DScene &s
         g.bv.refl = kTex && b.tex[0].w > 0 ? tex_eval_uv<float>(b.tex[0], false, g.uv) : V3f(b.refl[0], b.refl[1], b.refl[2]);
         g.bv.spec = kTex && b.tex[1].w > 0 ? tex_eval_uv<float>(b.tex[1], false, g.uv) : V3f(b.spec[0], b.spec[1], b.spec[2]);
         g.bv.rough = kTex && b.tex[2].w > 0 ? tex_eval_uv<float>(b.tex[2], false, g.uv).x : b.rough;
+        if (kTex && b.type == 4) {      // MicrofacetPerVertex: the three parameters interpolated from the triangle's corners
+            Its<float> f;
+            f.tri = tri;
+            f.bc = V2f(u, v);
+            g.bv.spec = V3f(pv_interp<float>(sc, b, f, 0), pv_interp<float>(sc, b, f, 1), pv_interp<float>(sc, b, f, 2));
+            g.bv.refl = V3f(pv_interp<float>(sc, b, f, 3), pv_interp<float>(sc, b, f, 4), pv_interp<float>(sc, b, f, 5));
+            g.bv.rough = pv_interp<float>(sc, b, f, 6);
+        }
     }
     return g;
 }
@@ -409,6 +499,7 @@ struct VtxAdj {
     V3f p, shn, fn;
     float area;
     V2f uv;
+    V2f bc;       // d/d(barycentrics) through per-vertex BSDF tables (consumed at the primary hit, where (u, v) are differentiable)
 };
 
 // adjoint of v -> (w = v / |v|, t = |v|):  v_bar = (w_bar - w <w, w_bar>)/t + t_bar w
@@ -539,7 +630,7 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const float phi = W.x * j.f.x + W.y * j.f.y + W.z * j.f.z;          // sum_c W_c f_c
     // C = phi * G * J * scale
     const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
-    bsdf_param_grad<kCfg>(acc, gl, x.bsdf, b, x.bv, ci, co, cio, W, G * scale, x.uv, xa.uv);
+    bsdf_param_grad<kCfg>(acc, gl, sc, x.bsdf, b, x.bv, ci, co, cio, W, G * scale, x.uv, xa.uv, x.tri, x.u, x.v, xa.bc);
     const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
     // adjoints are often exactly 0 (W = 0): multiply by reciprocals, a zero numerator sends div.rn.f32 down its slow path
     const float inv_t = 1.f / t, inv_t2 = 1.f / (t * t);
@@ -604,7 +695,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         }
     }
 
-    const VtxAdj zero_adj = {V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), 0.f, V2f(0.f, 0.f)};
+    const VtxAdj zero_adj = {V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), V3f(0.f, 0.f, 0.f), 0.f, V2f(0.f, 0.f), V2f(0.f, 0.f)};
     const int ktop = R.nsh - 1;
     auto geo_of = [&](int k) { return k == 0 ? v0geo : vertex_geo<kCfg>(sc, R.vtri[k], R.vu[k], R.vv[k]); };
     VtxGeo y = v0geo, x = v0geo;
@@ -774,7 +865,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         if (sweep) {
             const ShadeRec<float> N = load_shade<float>(sc, y.tri);
             // uv = uv0 + u duv0 + v duv1 is differentiable at the primary hit (scene.cpp:785-788)
-            const float u_bar = dot(N.n1 - N.n0, m_bar) + dot(y.duv0, a0.uv), v_bar = dot(N.n2 - N.n0, m_bar) + dot(y.duv1, a0.uv);
+            const float u_bar = dot(N.n1 - N.n0, m_bar) + dot(y.duv0, a0.uv) + a0.bc.x, v_bar = dot(N.n2 - N.n0, m_bar) + dot(y.duv1, a0.uv) + a0.bc.y;
             o_bar = o_bar + a0.p;
             d_bar = d_bar + a0.p * t0;
             const float t_bar = dot(d, a0.p);

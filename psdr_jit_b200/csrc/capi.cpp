@@ -823,8 +823,8 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
     if (!d_img) throw std::runtime_error("null cotangent image");
     if (max_depth > 8) throw std::runtime_error("the adjoint supports max_depth <= 8");
     for (const HBsdf &b : sc.bsdfs)
-        if (b.type >= 3)
-            throw std::runtime_error("reverse mode is not implemented for RoughDielectric / MicrofacetPerVertex / NormalMap BSDFs (BSDF '" + b.id +
+        if (b.type == 5)
+            throw std::runtime_error("reverse mode is not implemented for NormalMap BSDFs (BSDF '" + b.id +
                                      "'): use the forward-mode derivative image (renderD with tangents)");
     RenderParams rp[3];
     for (auto &r : rp) {
@@ -999,6 +999,9 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
         case PSDR_BSDF_K:
             if (index < 0 || 3 * index + 3 > (int) g.bsdf_k.size()) return fail("invalid BSDF index");
             return copy(g.bsdf_k.data() + 3 * index, 3);
+        case PSDR_BSDF_PERVERTEX:
+            if (index < 0 || index >= (int) g.bsdf_pv.size() || g.bsdf_pv[index].empty()) return fail("not a MicrofacetBSDFPerVertex");
+            return copy_tex(g.bsdf_pv[index]);
         case PSDR_EMITTER_RADIANCE:
             if (index < 0 || 3 * index + 3 > (int) g.emitter_rad.size()) return fail("invalid emitter index");
             return copy(g.emitter_rad.data() + 3 * index, 3);

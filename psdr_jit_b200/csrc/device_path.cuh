@@ -1245,7 +1245,7 @@ template <class S> struct PosSample {
 static PSDR_FULL_FN void env_sample_position(const DEnv &e, V3f ref_p, V2f sample2, V3f &p, V3f &n, float &pdf_out) {
     const int ncells = e.cw * e.ch;
     float prob;
-    const int idx = sample_reuse(e.cell_pmf, e.cell_cmf, ncells, e.cell_sum, sample2.y, prob);   // HyperCube<2>: last dimension
+    const int idx = sample_reuse_lut(e.cell_pmf, e.cell_cmf, ncells, e.cell_sum, e.cell_lut, e.cell_lut_n, sample2.y, prob);   // HyperCube<2>: last dimension
     const int cx = idx / e.ch, cy = idx - cx * e.ch;
     const float u = (sample2.x + (float) cx) * (1.f / (float) e.cw), v = (sample2.y + (float) cy) * (1.f / (float) e.ch);
     float pdf = prob * (float) ncells;

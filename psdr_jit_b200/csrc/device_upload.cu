@@ -20,7 +20,9 @@ struct DeviceBuffers {
     // the environment map's big tables (texels, texel tangents, cell pmf / cdf: 22 MB for a 1024 x 512 map) live in their
     // own allocation and are re-uploaded only when their versions change (HEnvmap::data_version / ddata_version)
     void *big = nullptr;
-    size_t big_capacity = 0, big_off[4] = {0, 0, 0, 0};
+    size_t big_capacity = 0, big_off[5] = {0, 0, 0, 0, 0};
+    std::vector<int> env_lut;           // bucket table of the envmap cell CDF (rebuilt with the cell table)
+    int env_lut_n = 0;
     unsigned big_data_version = 0, big_ddata_version = 0;
     // BVH (scenes above 64 triangles): the TOPOLOGY (node links, leaf slots -> triangle ids) is built on the host (binned
     // SAH) when the set of meshes / face counts changes and stays on the device; every configure() after that only
@@ -297,8 +299,13 @@ void upload_scene(Scene &sc) {
     if (sc.env.present) {
         const HEnvmap &e = sc.env;
         const std::vector<float> *tabs[4] = {&e.data, &e.ddata, &e.cell.pmf, &e.cell.cmf};
-        size_t need = 0, off[4];
+        size_t need = 0, off[5];
         for (int k = 0; k < 4; ++k) { off[k] = need; need += (std::max<size_t>(tabs[k]->size() * sizeof(float), 16) + 255) / 256 * 256; }
+        // bucket table of the cell CDF (sample_reuse_lut): at most 2^20 + 1 ints
+        int lut_cap = 64;
+        while (lut_cap < e.cell.size && lut_cap < (1 << 20)) lut_cap <<= 1;
+        off[4] = need;
+        need += ((size_t) (lut_cap + 1) * sizeof(int) + 255) / 256 * 256;
         const bool realloc = need > db.big_capacity;
         if (realloc) {
             if (db.big) cudaFree(db.big);
@@ -312,6 +319,14 @@ void upload_scene(Scene &sc) {
             check(cudaMemcpy((unsigned char *) db.big + off[k], tabs[k]->data(), tabs[k]->size() * sizeof(float), cudaMemcpyHostToDevice), "cudaMemcpy(envmap tables)");
             big_uploaded += tabs[k]->size() * sizeof(float);
         }
+        if (data_changed) {
+            db.env_lut.clear();
+            db.env_lut_n = build_cdf_lut(e.cell.cmf, e.cell.sum, db.env_lut);
+            if (db.env_lut_n > 0) {
+                check(cudaMemcpy((unsigned char *) db.big + off[4], db.env_lut.data(), db.env_lut.size() * sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy(envmap cell table)");
+                big_uploaded += db.env_lut.size() * sizeof(int);
+            }
+        }
         std::memcpy(db.big_off, off, sizeof(off));
         db.big_data_version = e.data_version;
         db.big_ddata_version = e.ddata_version;
@@ -322,6 +337,7 @@ void upload_scene(Scene &sc) {
         if (!all_bsdfs[i]->pv.empty()) {
             rec->pv = (const float *) ((const unsigned char *) db.dev + o_pv[i]);
             rec->d_pv = all_bsdfs[i]->d_pv.empty() ? nullptr : (const float *) ((const unsigned char *) db.dev + o_dpv[i]);
+            rec->pv_goff = i < sc.bsdfs.size() ? sc.pervertex_grad_offset((int) i) : 0;
         }
         for (int k = 0; k < 3; ++k) {
             const HBsdf::Tex &t = all_bsdfs[i]->tex[k];
@@ -528,6 +544,8 @@ void upload_scene(Scene &sc) {
         de.cell_sum = e.cell.sum;
         de.cell_pmf = (const float *) (big + db.big_off[2]);
         de.cell_cmf = (const float *) (big + db.big_off[3]);
+        de.cell_lut = (const int *) (big + db.big_off[4]);
+        de.cell_lut_n = db.env_lut_n;
     }
 
     sc.dcameras.assign(sc.cameras.size(), DCamera{});

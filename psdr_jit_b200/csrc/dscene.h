@@ -72,6 +72,8 @@ struct DEnv {
     int cw, ch;                        // cell grid 2(w-1) x 2(h-1)
     float cell_sum;
     const float *cell_pmf, *cell_cmf;
+    const int *cell_lut;               // bucket table of the cell CDF (sample_reuse_lut; cell_lut_n buckets, 0 = none):
+    int cell_lut_n;                    // 21 dependent loads of the bisection over 2 M cells become ~4
 };
 
 struct DBsdf {
@@ -94,6 +96,7 @@ struct DBsdf {
     // MicrofacetPerVertex: pv_n vertices x 7 floats (specular rgb, diffuse rgb, roughness) and their forward tangents
     int pv_n;
     const float *pv, *d_pv;
+    int pv_goff;             // offset of the table's gradients, relative to the END of the adjoint's gradient table
 };
 
 struct DCamera {

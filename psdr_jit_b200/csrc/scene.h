@@ -136,6 +136,7 @@ struct ParamGrads {
     std::vector<double> bsdf_rough;                          // 1 per BSDF
     std::vector<float> env_radiance;                         // 3*w*h
     std::vector<std::vector<float>> bsdf_tex[3];             // per BSDF and texture slot: channels*w*h (empty: not textured)
+    std::vector<std::vector<float>> bsdf_pv;                 // per BSDF: 7 floats per vertex (MicrofacetPerVertex; empty otherwise)
     double env_scale = 0.0, env_to_world_left[16] = {};
     bool valid = false;
 };
@@ -181,6 +182,7 @@ struct Scene {
     // table gradients -> world vertices -> raw vertices / to_world / camera matrices (scene_grad.cpp)
     GradLayout grad_layout(int sensor) const;
     int texture_grad_offset(int bsdf, int slot) const;   // relative to GradLayout::total (negative)
+    int pervertex_grad_offset(int bsdf) const;           // MicrofacetPerVertex tables: the last blocks of the table (negative)
     void backprop(const float *table, const GradLayout &gl, int sensor);
 
     Scene();

@@ -113,10 +113,17 @@ void transform_pos_adj(const Mat &M, D3 p, D3 gq, D3 &gp, Mat &gM) {
 
 }  // namespace
 
-int Scene::texture_grad_offset(int bsdf, int slot) const {
-    // tail of the table: [.. secondary edges | envmap block | textures of BSDF 0 (slots 0, 1, 2), BSDF 1, ...]; the
-    // sensor-dependent primary-edge block sits before, so the offset is taken relative to the END of the table
+int Scene::pervertex_grad_offset(int bsdf) const {
     int back = 0;
+    for (int i = (int) bsdfs.size() - 1; i >= bsdf; --i) back += (int) bsdfs[i].pv.size();
+    return -back;
+}
+
+int Scene::texture_grad_offset(int bsdf, int slot) const {
+    // tail of the table: [.. secondary edges | envmap block | textures of BSDF 0 (slots 0, 1, 2), BSDF 1, ... | per-vertex
+    // tables of BSDF 0, 1, ...]; the sensor-dependent primary-edge block sits before, so the offset is taken relative to
+    // the END of the table
+    int back = -pervertex_grad_offset(0);
     for (int i = (int) bsdfs.size() - 1; i >= bsdf; --i)
         for (int k = 2; k >= (i == bsdf ? slot : 0); --k) back += HBsdf::tex_channels(k) * bsdfs[i].tex[k].w * bsdfs[i].tex[k].h;
     return -back;   // negative: relative to GradLayout::total
@@ -137,6 +144,7 @@ GradLayout Scene::grad_layout(int sensor) const {
     gl.total = gl.off_env + (env.present ? kGradEnvHead + 3 * env.w * env.h : 0);
     for (const HBsdf &b : bsdfs)
         for (int k = 0; k < 3; ++k) gl.total += HBsdf::tex_channels(k) * b.tex[k].w * b.tex[k].h;      // same order as texture_grad_offset()
+    for (const HBsdf &b : bsdfs) gl.total += (int) b.pv.size();
     return gl;
 }
 
@@ -249,6 +257,12 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
                 grads.bsdf_tex[k][i].assign(g, g + (size_t) HBsdf::tex_channels(k) * bsdfs[i].tex[k].w * bsdfs[i].tex[k].h);
             }
     }
+    grads.bsdf_pv.assign(bsdfs.size(), std::vector<float>());
+    for (size_t i = 0; i < bsdfs.size(); ++i)
+        if (!bsdfs[i].pv.empty()) {
+            const float *g = table + gl.total + pervertex_grad_offset((int) i);
+            grads.bsdf_pv[i].assign(g, g + bsdfs[i].pv.size());
+        }
     grads.bsdf_spec.assign(3 * bsdfs.size(), 0.0);
     grads.bsdf_rough.assign(bsdfs.size(), 0.0);
     grads.bsdf_eta.assign(3 * bsdfs.size(), 0.0);

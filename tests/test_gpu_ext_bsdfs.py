@@ -1,8 +1,8 @@
 """The rest of the reference's BSDF set on the CUDA path: RoughDielectricBSDF
 (src/bsdf/roughdielectric.cpp), MicrofacetBSDFPerVertex (src/bsdf/microfacet_pv.cpp) and NormalMapBSDF
 (src/bsdf/normalmap.cpp) -- against the oracle (values and forward-mode tangents, all three terms), against the reference's
-own output (tests/golden/ext_bsdfs.npz, tools/ref_golden10.py), through the scene-file loader, and the error behaviour of
-reverse mode (not implemented for these three)."""
+own output (tests/golden/ext_bsdfs.npz, tools/ref_golden10.py), through the scene-file loader; reverse mode of the
+dielectric and the per-vertex BSDF against forward mode (NormalMap is forward-mode only and says so)."""
 import copy
 import os
 
@@ -239,11 +239,85 @@ def test_add_BSDF_normalmap_installs_the_reference_defaults():
 
 
 def test_reverse_mode_reports_unsupported_bsdfs():
+    """NormalMap has no adjoint (its perturbed frame is not a function of the three cosines the adjoint differentiates)"""
     import torch
     import psdr_jit_b200 as psdr
-    sc = build_product(box_meshes(), 32, 32, 2, 0, 0, bsdfs=with_ext(SPECS["dielectric"]))
+    sc = build_product(box_meshes(), 32, 32, 2, 0, 0, bsdfs=with_ext(SPECS["normalmap_mf"]))
     with pytest.raises(RuntimeError, match="reverse mode is not implemented"):
         psdr.PathTracer(2).render_vjp(sc, torch.ones(32 * 32, 3, device="cuda"), 0, seed=0, terms=1)
+
+
+def test_vjp_per_parameter_dielectric_and_pervertex():
+    """one JVP per parameter against the matching entry of a single VJP: alpha of the dielectric, entries of the per-vertex
+    tables (roughness, a diffuse and a specular channel at several vertices)"""
+    import torch
+    import psdr_jit_b200 as psdr
+    rng = np.random.default_rng(4)
+    w = h = 48
+    integ = psdr.PathTracer(3)
+    cot = torch.as_tensor(rng.normal(size=(w * h, 3)).astype(np.float32), device="cuda")
+
+    def check(lhs_dimg, grad):
+        lhs = float((cot.double() * lhs_dimg.double()).sum())
+        ref = float(torch.linalg.norm(cot.double()) * torch.linalg.norm(lhs_dimg.double()))
+        assert abs(lhs - float(grad)) < 5e-4 * max(abs(lhs), 1e-2 * ref), (lhs, float(grad))
+
+    bs = with_ext(SPECS["dielectric"])
+    sc = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs)
+    integ.render_vjp(sc, cot, 0, seed=2, terms=1)
+    g_alpha = sc.grad_of("BSDF[id=ext]", "alpha_u").ravel()
+    assert g_alpha.size == 1 and abs(g_alpha[0]) > 0
+    sc2 = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs, d_bsdf={"ext": np.float32([1.0])})
+    check(integ.renderD_fwd(sc2, 0, seed=2, terms=1)[1], g_alpha[0])
+
+    bs = with_ext(SPECS["pervertex"])
+    sc = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs)
+    integ.render_vjp(sc, cot, 0, seed=2, terms=1)
+    g = np.concatenate([sc.grad_of("BSDF[id=ext]", "specularReflectance"), sc.grad_of("BSDF[id=ext]", "diffuseReflectance"),
+                        sc.grad_of("BSDF[id=ext]", "roughness").reshape(-1, 1)], axis=1)
+    assert g.shape == (8, 7) and np.abs(g).max() > 0
+    for vtx, col in ((0, 6), (3, 6), (5, 4), (2, 0), (7, 2)):
+        d = np.zeros((8, 7), np.float32)
+        d[vtx, col] = 1.0
+        sc2 = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs, d_bsdf={"ext": d})
+        check(integ.renderD_fwd(sc2, 0, seed=2, terms=1)[1], g[vtx, col])
+
+
+@pytest.mark.parametrize("kind", ["dielectric", "pervertex"])
+def test_vjp_is_transpose_with_geometry_and_edges(kind):
+    """<cotangent, J t> == <J^T cotangent, t> with t = (translation of the luminaire and of the tall box, material tangent),
+    all three terms: the box moves under the camera, so the per-vertex tables are also reached through the differentiable
+    barycentrics of the primary hit"""
+    import torch
+    import psdr_jit_b200 as psdr
+    rng = np.random.default_rng(8)
+    w = h = 64
+    mt = material_tangent(kind)["d_bsdf"]["ext"]
+    sc = build_product(box_meshes(), w, h, 8, 8, 8, bsdfs=with_ext(SPECS[kind]), d_bsdf={"ext": mt})
+    t = np.zeros((4, 4), np.float32)
+    t[:3, 3] = rng.normal(size=3) * 30
+    tang = {}
+    for name in ("Mesh[0]", "Mesh[2]"):
+        sc.param_map[name].d_to_world_left = t.copy()
+        tang[(name, "to_world_left")] = t.copy()
+    if kind == "dielectric":
+        tang[("BSDF[id=ext]", "alpha_u")] = np.float32(mt).reshape(1)
+    else:
+        m = np.float32(mt).reshape(8, 7)
+        tang[("BSDF[id=ext]", "specularReflectance")] = m[:, 0:3]
+        tang[("BSDF[id=ext]", "diffuseReflectance")] = m[:, 3:6]
+        tang[("BSDF[id=ext]", "roughness")] = m[:, 6]
+    sc.configure()
+    sc.configure([0])
+    integ = psdr.PathTracer(3)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=3)
+    cot = torch.as_tensor(rng.normal(size=(w * h, 3)).astype(np.float32), device=img.device)
+    lhs = float((cot.double() * dimg.double()).sum())
+    integ.render_vjp(sc, cot, 0, seed=3)
+    parts = {k: float((sc.grad_of(*k).reshape(np.shape(v)).astype(np.float64) * v.astype(np.float64)).sum()) for k, v in tang.items()}
+    rhs = sum(parts.values())
+    mag = max(abs(lhs), sum(abs(v) for v in parts.values()))
+    assert mag > 0 and abs(lhs - rhs) < 5e-4 * mag, (lhs, rhs, parts)
 
 
 def test_constant_microfacet_scene_uses_the_small_family():
