@@ -270,14 +270,33 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     mesh0 = sc.param_map["Mesh[0]"]
 
     pinned = torch.empty((2, W * H, 3), dtype=torch.float32, pin_memory=True) if world > 1 else None
+    # fused reduction: every rank ends a step holding the complete [2, npix, 3] result, so the device->host copy is split
+    # N ways into ONE page-locked buffer all ranks map (psdr_jit_b200.dist.SharedHostBuffer) -- rank r moves slice r over
+    # its own PCIe link; --no-shared-d2h keeps the single 6.3 MB copy on rank 0
+    shared = None
+    if peer and not args.no_shared_d2h:
+        try:
+            shared = psdr_dist.SharedHostBuffer(2 * W * H * 3, rank, world, "e2e")
+        except Exception as e:      # e.g. no /dev/shm: fall back to the one-rank copy (all ranks take the same branch)
+            print("bench: shared host buffer unavailable (%s)" % e, file=sys.stderr)
+        ok = torch.tensor([1 if shared is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            shared = None
+    e2e_no = [0]
 
     def e2e_step(seed):
         mesh0.set_transform(np.eye(4, dtype=np.float32), tangent=tangent)
         sc.configure([0])
         if world > 1:
-            # N ranks: each renders its lane shard on the device, ONE NCCL reduce sums the partial images on rank 0
-            # (psdr_jit_b200.dist.all_reduce_images), one D2H into pinned host memory there
+            # N ranks: each renders its lane shard on the device; the partial images are summed inside the kernels
+            # (multimem.red) or by ONE NCCL reduce to rank 0 (psdr_jit_b200.dist.all_reduce_images)
             integ.renderD_fwd(sc, 0, seed=seed)
+            if integ.last_reduced and shared is not None:
+                # the step's device barrier (PeerBuffers.finish) orders this write behind rank 0's read of the previous step
+                e2e_no[0] += 1
+                shared.gather(integ.last_buffer, e2e_no[0])
+                return float(shared.wait_all(e2e_no[0])[0]) if rank == 0 else 0.0
             if not integ.last_reduced:
                 psdr_dist.all_reduce_images(integ.last_buffer, dst=0)      # the result is needed on the host of rank 0 only
             if rank == 0:
@@ -333,7 +352,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
                     "path": ("set_transform + Scene.configure + psdr_render_d_host (pinned host image buffers)" if world == 1 else
                              "set_transform + Scene.configure + renderD_fwd on each rank's lane shard + " +
-                             ("in-kernel multimem.red into every rank's replica" if peer else "one NCCL reduce to rank 0") + " + one D2H into pinned host memory on rank 0")},
+                             ("in-kernel multimem.red into every rank's replica" if peer else "one NCCL reduce to rank 0") +
+                             (" + D2H split over the ranks into one shared page-locked host buffer (each rank copies 1/%d of the frame)" % world if shared is not None
+                              else " + one D2H into pinned host memory on rank 0"))},
             "gpu_launches": int(launches),
             "kernel_ms": {"interior": round(means[1], 4), "primary_edges": round(means[2], 4), "secondary_edges": round(means[4], 4)},
             "roofline": {"bound": "hbm", "kernel": {1: "interior_kernel<Dual>", 2: "primary_edge_kernel", 4: "secondary_edge_kernel"}[dom],
@@ -737,6 +758,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vjp", action="store_true")
     ap.add_argument("--cta-policy", type=int, default=0, help="experiments: 1 = force 128-thread CTAs, 2 = force the large-CTA kernels (psdr_set_cta_policy)")
+    ap.add_argument("--no-shared-d2h", action="store_true", help="N > 1, fused path: rank 0 copies the whole result to the host instead of every rank 1/N of it")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: sum the partial images with NCCL instead of the fused multimem.red path")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json workload (2 = the headline)")
     args = ap.parse_args()

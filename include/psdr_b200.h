@@ -198,6 +198,10 @@ int psdr_scene_add_envmap(psdr_scene *s, const float *radiance, int w, int h, co
 
 /* Scene.add_Sensor(PerspectiveCamera(fov, near, far)) with sensor.to_world -- src/psdr.cpp:365-375,396 */
 int psdr_scene_add_perspective(psdr_scene *s, float fov_x, float near_clip, float far_clip, const float *to_world);
+/* Scene.add_Sensor(PerspectiveCamera(fx, fy, cx, cy, near, far)) -- src/psdr.cpp:366, include/psdr/sensor/perspective.h:11-12,
+ * src/sensor/perspective.cpp:15-20, include/psdr/core/transform.h:63-71: pinhole intrinsics in units of the image size
+ * (focal lengths fx, fy and principal point cx, cy as fractions of width / height). */
+int psdr_scene_add_perspective_intrinsic(psdr_scene *s, float fx, float fy, float cx, float cy, float near_clip, float far_clip, const float *to_world);
 
 /* Writes through Scene.param_map[...] (README.md:87-90): new primal value of a parameter ... */
 int psdr_scene_set_param(psdr_scene *s, int kind, int index, const float *value, int n);

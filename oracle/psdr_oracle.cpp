@@ -194,6 +194,8 @@ struct SecEdge {  // edge.h:49-66
 
 struct Camera {
     float fov, near_, far_;
+    bool use_intrinsic = false;   // PerspectiveCamera(fx, fy, cx, cy, near, far) (include/psdr/sensor/perspective.h:11-12)
+    float fx = 0.f, fy = 0.f, cx = 0.f, cy = 0.f;
     M4<Dual> to_world[3];
     // configured (reference src/sensor/perspective.cpp:10-46)
     M4<Dual> to_world_full, world_to_sample, sample_to_camera;
@@ -357,6 +359,22 @@ static M4<float> perspective(float fov, float near_, float far_) {
     return t;
 }
 
+// reference include/psdr/core/transform.h:63-71
+static M4<float> perspective_intrinsic(float fx, float fy, float cx, float cy, float near_, float far_) {
+    float recip = 1.f / (far_ - near_);
+    M4<float> t = M4<float>::identity();
+    t.m[2][2] = far_ * recip;
+    t.m[3][3] = 0.f;
+    t.m[2][3] = -near_ * far_ * recip;
+    t.m[3][2] = 1.f;
+    M4<float> tr = M4<float>::identity(), sc_ = M4<float>::identity();
+    tr.m[0][3] = 1.f - 2.f * cx;
+    tr.m[1][3] = 1.f - 2.f * cy;
+    sc_.m[0][0] = 2.f * fx;
+    sc_.m[1][1] = 2.f * fy;
+    return (tr * sc_) * t;
+}
+
 // reference src/shape/mesh.cpp:317-382
 static void configure_mesh(MeshRec &m) {
     M4<Dual> tw = (m.to_world[0] * m.to_world[1]) * m.to_world[2];
@@ -378,7 +396,12 @@ static bool configure_camera(Scene &sc, Camera &cam, bool build_primary_edges) {
     sc_.m[1][1] = -0.5f * aspect;
     tr.m[0][3] = -1.f;
     tr.m[1][3] = -1.f / aspect;
-    M4<float> c2s = (sc_ * tr) * perspective(cam.fov, cam.near_, cam.far_);
+    if (cam.use_intrinsic) {   // perspective.cpp:15-20
+        sc_.m[1][1] = -0.5f;
+        tr.m[1][3] = -1.f;
+    }
+    M4<float> c2s = (sc_ * tr) * (cam.use_intrinsic ? perspective_intrinsic(cam.fx, cam.fy, cam.cx, cam.cy, cam.near_, cam.far_)
+                                                    : perspective(cam.fov, cam.near_, cam.far_));
     M4<Dual> camera_to_sample = lift<Dual>(c2s);
     cam.sample_to_camera = lift<Dual>(inverse(c2s));
     cam.to_world_full = (cam.to_world[0] * cam.to_world[1]) * cam.to_world[2];
@@ -1967,6 +1990,14 @@ int orc_add_camera(void *h, float fov, float near_, float far_, const float *to_
     s->cameras.push_back(c);
     s->configured = false;
     return (int) s->cameras.size() - 1;
+}
+
+int orc_add_camera_intrinsic(void *h, float fx, float fy, float cx, float cy, float near_, float far_, const float *to_world, const float *d_to_world) {
+    int i = orc_add_camera(h, 0.f, near_, far_, to_world, d_to_world);
+    Camera &c = ((Scene *) h)->cameras[i];
+    c.use_intrinsic = true;
+    c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy;
+    return i;
 }
 
 int orc_configure(void *h, const int *active, int nactive) { return configure_scene(*(Scene *) h, active, nactive) ? 0 : 1; }

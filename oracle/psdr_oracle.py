@@ -51,6 +51,7 @@ def lib():
         L.orc_set_bsdf_texture_slot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _f, _f, _f, _f]
         L.orc_add_mesh.argtypes = [C.c_void_p, _f, _f, C.c_int, _i, C.c_int, _f, C.c_int, _i, _f, _f, C.c_int, _f, _f, C.c_int, C.c_int]
         L.orc_add_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f, _f]
+        L.orc_add_camera_intrinsic.argtypes = [C.c_void_p] + [C.c_float] * 6 + [_f, _f]
         L.orc_configure.argtypes = [C.c_void_p, _i, C.c_int]
         L.orc_num_primary_edges.argtypes = [C.c_void_p, C.c_int]
         L.orc_num_secondary_edges.argtypes = [C.c_void_p]
@@ -201,6 +202,11 @@ class OracleScene:
     def add_camera(self, fov, near, far, to_world, d_to_world=None):
         tw, dtw = _mats(to_world), _dmats(d_to_world)
         return self.L.orc_add_camera(self.h, fov, near, far, _fp(tw), _fp(dtw))
+
+    def add_camera_intrinsic(self, fx, fy, cx, cy, near, far, to_world, d_to_world=None):
+        """PerspectiveCamera(fx, fy, cx, cy, near, far) (reference include/psdr/sensor/perspective.h:11-12)"""
+        tw, dtw = _mats(to_world), _dmats(d_to_world)
+        return self.L.orc_add_camera_intrinsic(self.h, fx, fy, cx, cy, near, far, _fp(tw), _fp(dtw))
 
     def configure(self, active=(0,)):
         a = np.asarray(list(active), dtype=np.int32)

@@ -137,14 +137,21 @@ class _Transformable(Object):
 class PerspectiveCamera(_Transformable):
     """reference src/psdr.cpp:365-375, src/sensor/perspective.cpp"""
 
-    def __init__(self, fov: float, near: float, far: float, *intrinsics):
+    def __init__(self, *args):
+        """PerspectiveCamera(fov_x, near, far) | PerspectiveCamera(fx, fy, cx, cy, near, far): the second form takes pinhole
+        intrinsics in units of the image size (include/psdr/sensor/perspective.h:10-12, src/sensor/perspective.cpp:15-20)."""
         super().__init__()
-        if intrinsics:
-            raise NotImplementedError("PerspectiveCamera(fx, fy, cx, cy, near, far) is outside the north-star path")
-        self.fov, self.near, self.far = float(fov), float(near), float(far)
+        if len(args) == 3:
+            self.intrinsics = None
+            self.fov, self.near, self.far = (float(a) for a in args)
+        elif len(args) == 6:
+            self.intrinsics = tuple(float(a) for a in args[:4])
+            self.fov, self.near, self.far = 0.0, float(args[4]), float(args[5])
+        else:
+            raise TypeError("PerspectiveCamera(): expected (fov_x, near, far) or (fx, fy, cx, cy, near, far)")
 
     def _clone(self):
-        c = PerspectiveCamera(self.fov, self.near, self.far)
+        c = PerspectiveCamera(self.fov, self.near, self.far) if self.intrinsics is None else PerspectiveCamera(*self.intrinsics, self.near, self.far)
         c._copy_transform_from(self)
         return c
 
@@ -816,7 +823,9 @@ class Scene(Object):
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[1] = len(self._events)
         for s in self._sensors[self._pushed[2]:]:
-            if L.psdr_scene_add_perspective(self._h, s.fov, s.near, s.far, _fp(_mat4(s.to_world))) < 0:
+            rc = (L.psdr_scene_add_perspective(self._h, s.fov, s.near, s.far, _fp(_mat4(s.to_world))) if s.intrinsics is None else
+                  L.psdr_scene_add_perspective_intrinsic(self._h, *s.intrinsics, s.near, s.far, _fp(_mat4(s.to_world))))
+            if rc < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[2] = len(self._sensors)
 

@@ -384,6 +384,15 @@ int psdr_scene_add_perspective(psdr_scene *s, float fov_x, float near_clip, floa
     return (int) s->sc.cameras.size() - 1;
 }
 
+int psdr_scene_add_perspective_intrinsic(psdr_scene *s, float fx, float fy, float cx, float cy, float near_clip, float far_clip, const float *to_world) {
+    const int i = psdr_scene_add_perspective(s, 0.f, near_clip, far_clip, to_world);
+    if (i < 0) return i;
+    HCamera &c = s->sc.cameras[i];
+    c.use_intrinsic = true;
+    c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy;
+    return i;
+}
+
 static int set_param_impl(psdr_scene *s, int kind, int index, const float *data, int n, bool tangent) {
     if (!s || !data) return fail("null argument");
     Scene &sc = s->sc;

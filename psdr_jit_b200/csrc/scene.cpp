@@ -181,6 +181,22 @@ static M4<float> perspective_matrix(float fov, float near_, float far_) {
     return t;
 }
 
+// reference include/psdr/core/transform.h:63-71: translate(1 - 2cx, 1 - 2cy, 0) * scale(2fx, 2fy, 1) * trafo
+static M4<float> perspective_intrinsic_matrix(float fx, float fy, float cx, float cy, float near_, float far_) {
+    const float recip = 1.f / (far_ - near_);
+    M4<float> t = M4<float>::identity();
+    t.m[2][2] = far_ * recip;
+    t.m[3][3] = 0.f;
+    t.m[2][3] = -near_ * far_ * recip;
+    t.m[3][2] = 1.f;
+    M4<float> trn = M4<float>::identity(), scl = M4<float>::identity();
+    trn.m[0][3] = 1.f - 2.f * cx;
+    trn.m[1][3] = 1.f - 2.f * cy;
+    scl.m[0][0] = 2.f * fx;
+    scl.m[1][1] = 2.f * fy;
+    return (trn * scl) * t;
+}
+
 static void configure_mesh(HMesh &m) {
     if (m.edges_dirty) make_edge_list(m);
     const M4<Dual> tw = (m.to_world[0] * m.to_world[1]) * m.to_world[2];
@@ -201,7 +217,12 @@ static void configure_camera(const Scene &sc, HCamera &cam, bool with_primary_ed
     scl.m[1][1] = -0.5f * aspect;
     trn.m[0][3] = -1.f;
     trn.m[1][3] = -1.f / aspect;
-    const M4<float> c2s = (scl * trn) * perspective_matrix(cam.fov, cam.near_, cam.far_);
+    if (cam.use_intrinsic) {      // perspective.cpp:15-20: no aspect ratio in this branch
+        scl.m[1][1] = -0.5f;
+        trn.m[1][3] = -1.f;
+    }
+    const M4<float> c2s = (scl * trn) * (cam.use_intrinsic ? perspective_intrinsic_matrix(cam.fx, cam.fy, cam.cx, cam.cy, cam.near_, cam.far_)
+                                                           : perspective_matrix(cam.fov, cam.near_, cam.far_));
     cam.sample_to_camera = invert(c2s);
     cam.camera_to_sample = c2s;
     cam.to_world_full = (cam.to_world[0] * cam.to_world[1]) * cam.to_world[2];

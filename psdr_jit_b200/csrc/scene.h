@@ -106,6 +106,8 @@ struct HPrimEdge {
 
 struct HCamera {
     float fov = 60.f, near_ = 1e-6f, far_ = 1e7f;
+    bool use_intrinsic = false;          // PerspectiveCamera(fx, fy, cx, cy, near, far) (perspective.h:11-12)
+    float fx = 0.f, fy = 0.f, cx = 0.f, cy = 0.f;
     M4<Dual> to_world[3];
     M4<Dual> to_world_full, world_to_sample;
     M4<float> sample_to_camera, camera_to_sample;

@@ -54,6 +54,45 @@ def test_lane_shards_allreduce_to_full_image(oracle):
     assert rng == (0, 64, 2048)
 
 
+def _worker_shared(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from psdr_jit_b200.dist import SharedHostBuffer
+    n = 1001
+    buf = SharedHostBuffer(n, rank, world, "t")
+    ok = True
+    for step in (1, 2, 3):
+        src = torch.arange(n, dtype=torch.float32) * step          # every rank holds the complete result
+        buf.gather(src, step)
+        if rank == 0:
+            full = buf.wait_all(step)
+            ok = ok and bool(torch.equal(full, src))
+        dist.barrier()                                             # the next step overwrites the buffer
+    if rank == 0:
+        q.put((ok, list(buf.bounds)))
+    buf.close()
+    dist.destroy_process_group()
+
+
+def test_shared_host_buffer_gathers_slices_of_every_rank():
+    """the N-way split of the device->host copy (psdr_jit_b200.dist.SharedHostBuffer): each rank writes its slice of a
+    result all ranks hold, rank 0 sees the whole buffer once every rank has published the step"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shared, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, bounds = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and bounds == [0, 504, 1001]
+
+
 def test_shard_lanes_properties():
     from psdr_jit_b200.dist import shard_lanes
     for n in (0, 31, 32, 1000, 65536, 123457):

@@ -107,6 +107,20 @@ def _worker_peer(rank, world, port, q):
             ref_img, ref_dimg = integ.renderD_fwd(full, 0, seed=step)
             errs.append((float((img - ref_img).norm() / ref_img.norm()), float((dimg - ref_dimg).norm() / ref_dimg.norm())))
         out["fwd_img"], out["fwd_dimg"] = max(e[0] for e in errs), max(e[1] for e in errs)
+        # the device->host copy split over the ranks (dist.SharedHostBuffer): every rank holds the summed result, each
+        # copies its slice into ONE page-locked buffer all ranks map, rank 0 reads the whole frame
+        from psdr_jit_b200.dist import SharedHostBuffer
+        shared = SharedHostBuffer(2 * 96 * 96 * 3, rank, world, "t2")
+        bad = 0.0
+        for step in range(1, 4):
+            img, dimg = integ.renderD_fwd(part, 0, seed=10 + step)
+            shared.gather(integ.last_buffer, step)
+            if rank == 0:
+                host = shared.wait_all(step).view(2, -1, 3)
+                bad = max(bad, float((host[0] - img.cpu()).abs().max()), float((host[1] - dimg.cpu()).abs().max()))
+        out["shared_host"] = bad
+        out["shared_registered"] = bool(shared.registered)
+        shared.close()
         imgc = integ.renderC(part, 0, seed=3)
         out["renderC"] = float((imgc - integ.renderC(full, 0, seed=3)).norm() / imgc.norm())
 
@@ -159,4 +173,5 @@ def test_two_gpu_fused_multicast_reduction():
     if not out["multicast"]:
         pytest.skip("no NVLS multicast support on this node")
     assert out["fwd_img"] < 1e-6 and out["fwd_dimg"] < 1e-4 and out["renderC"] < 1e-6, out
+    assert out["shared_host"] == 0.0 and out["shared_registered"], out
     assert out["loss"] < 1e-5 and out["grad_transform"] < 2e-4 and out["grad_radiance"] < 2e-4, out

@@ -714,3 +714,38 @@ def test_bvh_gpu_refit_matches_fresh_build(oracle):
     osc = build_oracle(moved, 96, 96, 2, 0, 0)
     assert np.array_equal(aov_refit[:, 1], osc.aov(0, seed=0)[:, 1])       # triangle ids vs the brute-force oracle
     assert rel_l2(img_refit, osc.render(3, seed=2, mode=0)) < TOL
+
+
+INTRINSIC_CAM = dict(scenes.CBOX_CAMERA, intrinsics=(0.9, 1.1, 0.45, 0.55))
+
+
+def test_intrinsics_camera_vs_oracle():
+    """PerspectiveCamera(fx, fy, cx, cy, near, far) (reference perspective.h:11-12, perspective.cpp:15-20): image and forward
+    derivative image, all three terms, off-centre principal point and fx != fy"""
+    import psdr_jit_b200 as psdr
+    kw = dict(move_mesh=1, axis_scale=(30.0, 10.0, 0.0), cam=INTRINSIC_CAM)
+    img_ref, dimg_ref = build_oracle(scenes.cbox_meshes(), 96, 96, 4, 4, 4, **kw).render(2, seed=5, mode=1, terms=7)
+    sc = build_product(scenes.cbox_meshes(), 96, 96, 4, 4, 4, **kw)
+    img, dimg = psdr.PathTracer(2).renderD_fwd(sc, 0, seed=5)
+    assert rel_l2(img.cpu().numpy(), img_ref) < 1e-6
+    assert np.abs(dimg_ref).max() > 0 and rel_l2(dimg.cpu().numpy(), dimg_ref) < 1e-4
+
+
+def test_intrinsics_camera_vs_reference_golden():
+    """the same camera against the RUNNING reference (tests/golden/intrinsics.npz, tools/ref_golden11.py), term by term"""
+    import psdr_jit_b200 as psdr
+    path = os.path.join(GOLDEN, "intrinsics.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/intrinsics.npz not generated yet")
+    g = np.load(path)
+    cam = dict(scenes.CBOX_CAMERA, intrinsics=tuple(float(x) for x in g["intrinsics"]))
+    integ = psdr.PathTracer(2)
+    integ.reference_tangent_scaling = True
+    got = integ.renderC(build_product(scenes.cbox_meshes(), 128, 128, 4, 0, 0, cam=cam), 0, seed=0).cpu().numpy()
+    r, nbad, r_ex = compare_stats(got, g["imgC"])
+    assert nbad <= 16 and r_ex < 3e-4, (r, nbad, r_ex)      # measured: 4 flipped pixels, 1.2e-4 on the rest
+    for tag, (spp, sppe, sppse), term in (("int", (4, 0, 0), 1), ("pri", (0, 4, 0), 2), ("sec", (0, 0, 4), 4)):
+        sc = build_product(scenes.cbox_meshes(), 128, 128, spp, sppe, sppse, move_mesh=1, axis_scale=(30.0, 10.0, 0.0), cam=cam)
+        dimg = integ.renderD_fwd(sc, 0, seed=0, terms=term)[1].cpu().numpy()
+        r, nbad, r_ex = compare_stats(dimg, g["gradD_" + tag])
+        assert nbad <= 256 and r_ex < 5e-3, (tag, r, nbad, r_ex)
