@@ -270,11 +270,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     mesh0 = sc.param_map["Mesh[0]"]
 
     pinned = torch.empty((2, W * H, 3), dtype=torch.float32, pin_memory=True) if world > 1 else None
-    # fused reduction: every rank ends a step holding the complete [2, npix, 3] result, so the device->host copy is split
-    # N ways into ONE page-locked buffer all ranks map (psdr_jit_b200.dist.SharedHostBuffer) -- rank r moves slice r over
-    # its own PCIe link; --no-shared-d2h keeps the single 6.3 MB copy on rank 0
+    # fused reduction: every rank ends a step holding the complete [2, npix, 3] result, so the device->host copy CAN be
+    # split N ways into ONE page-locked buffer all ranks map (psdr_jit_b200.dist.SharedHostBuffer, --shared-d2h).  Off by
+    # default: the whole 6.3 MB frame takes 125 us over one link (50 GB/s, profiles/r04f_probe_d2h.log), a 1/8 slice
+    # 31 us, and making rank 0 wait for the host side of every other rank costs more than that saves (N = 2: 4.90 ms per
+    # step with the split, 4.71 ms without, profiles/r04e_*).
     shared = None
-    if peer and not args.no_shared_d2h:
+    if peer and args.shared_d2h:
         try:
             shared = psdr_dist.SharedHostBuffer(2 * W * H * 3, rank, world, "e2e")
         except Exception as e:      # e.g. no /dev/shm: fall back to the one-rank copy (all ranks take the same branch)
@@ -758,7 +760,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vjp", action="store_true")
     ap.add_argument("--cta-policy", type=int, default=0, help="experiments: 1 = force 128-thread CTAs, 2 = force the large-CTA kernels (psdr_set_cta_policy)")
-    ap.add_argument("--no-shared-d2h", action="store_true", help="N > 1, fused path: rank 0 copies the whole result to the host instead of every rank 1/N of it")
+    ap.add_argument("--shared-d2h", action="store_true", help="N > 1, fused path: every rank copies 1/N of the result into one shared page-locked host buffer instead of rank 0 copying all of it (measured slower, see the comment in run_ours)")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: sum the partial images with NCCL instead of the fused multimem.red path")
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json workload (2 = the headline)")
     args = ap.parse_args()
