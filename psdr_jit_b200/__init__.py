@@ -928,7 +928,8 @@ class Scene(Object):
                              ("specularReflectance", _lib.BSDF_SPECULAR), ("roughness", _lib.BSDF_ROUGHNESS),
                              ("specularReflectance.data", _lib.BSDF_SPECULAR), ("roughness.data", _lib.BSDF_ROUGHNESS),
                              ("alpha_u", _lib.BSDF_ROUGHNESS), ("alpha_u.data", _lib.BSDF_ROUGHNESS), ("eta", _lib.BSDF_ETA), ("k", _lib.BSDF_K),
-                             ("specular_reflectance", _lib.BSDF_SPECULAR), ("specular_reflectance.data", _lib.BSDF_SPECULAR)),
+                             ("specular_reflectance", _lib.BSDF_SPECULAR), ("specular_reflectance.data", _lib.BSDF_SPECULAR),
+                             ("normal_map", _lib.BSDF_REFLECTANCE), ("normal_map.data", _lib.BSDF_REFLECTANCE)),
                     "Emitter": (("radiance", _lib.EMITTER_RADIANCE),),
                     "EnvironmentMap": (("radiance.data", _lib.ENVMAP_RADIANCE), ("scale", _lib.ENVMAP_SCALE),
                                        ("to_world_left", _lib.ENVMAP_TO_WORLD_LEFT))}
@@ -959,6 +960,12 @@ class Scene(Object):
                     if hasattr(t, "requires_grad") and t.requires_grad and id(t) not in seen:    # ("x" and "x.data" name the same texels)
                         seen.add(id(t))
                         out.append((t, kind, i))
+                if isinstance(o, NormalMapBSDF) and o.nested_bsdf is not None and hasattr(o, "_nested_handle"):
+                    for field, kind in self._GRAD_FIELDS["BSDF"]:      # the wrapped BSDF: addressed by its nested handle
+                        t = self._field(o.nested_bsdf, field)
+                        if hasattr(t, "requires_grad") and t.requires_grad and id(t) not in seen:
+                            seen.add(id(t))
+                            out.append((t, kind, o._nested_handle))
         return out
 
     def grad_of(self, name: str, field: str) -> np.ndarray:
@@ -971,6 +978,12 @@ class Scene(Object):
                     if field not in cols:
                         break
                     return self._read_grad(_lib.BSDF_PERVERTEX, i, (len(o.roughness), 7))[:, cols[field]].copy()
+                if o is obj and isinstance(o, NormalMapBSDF) and field.startswith("nested_bsdf."):
+                    sub = field[len("nested_bsdf."):]
+                    for f, kind in self._GRAD_FIELDS["BSDF"]:
+                        if f == sub and self._field(o.nested_bsdf, f) is not None:
+                            return self._read_grad(kind, o._nested_handle, np.asarray(_f32(self._field(o.nested_bsdf, f))).shape)
+                    break
                 if o is obj:
                     for f, kind in self._fields_of(kind_name, o):
                         if f == field:

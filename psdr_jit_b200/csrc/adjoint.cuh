@@ -495,6 +495,84 @@ template <int kCfg> __device__ __forceinline__ VtxGeo vertex_geo(const DScene &s
     return g;
 }
 
+// the three parameter slots of a record at a texture coordinate (constants or bitmap lookups)
+template <int kCfg> __device__ __forceinline__ BsdfVals bsdf_vals_at(const DBsdf &b, V2f uv) {
+    constexpr bool kTex = (kCfg & kCfgExt) != 0;
+    BsdfVals v;
+    v.refl = kTex && b.tex[0].w > 0 ? tex_eval_uv<float>(b.tex[0], false, uv) : V3f(b.refl[0], b.refl[1], b.refl[2]);
+    v.spec = kTex && b.tex[1].w > 0 ? tex_eval_uv<float>(b.tex[1], false, uv) : V3f(b.spec[0], b.spec[1], b.spec[2]);
+    v.rough = kTex && b.tex[2].w > 0 ? tex_eval_uv<float>(b.tex[2], false, uv).x : b.rough;
+    return v;
+}
+
+// ---- NormalMap in reverse mode ---------------------------------------------------------------------------------------
+// Its value is not a function of the three cosines: the perturbed frame is built from the normal map (shading frame) and
+// dp_du (world frame).  The adjoint therefore differentiates the forward code itself, written as a function of
+// world-space quantities -- wi, wo, the shading normal, dp_du and the normal-map value -- by forward mode: fifteen dual
+// evaluations per event in ONE rolled loop (one copy of the code).  Both records are local copies without the
+// forward-mode tangents a user may have set on the scene (psdr_scene_set_tangent), which would leak into the duals.
+__device__ __forceinline__ void strip_tangents(DBsdf &b) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) b.d_refl[c] = b.d_spec[c] = b.d_eta[c] = b.d_kk[c] = 0.f;
+    b.d_rough = 0.f;
+    b.d_pv = nullptr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b.tex[k].ddata = nullptr;
+        b.tex[k].d_cr = b.tex[k].d_sr = b.tex[k].d_scale = b.tex[k].d_tx = b.tex[k].d_ty = 0.f;
+    }
+}
+template <class S> struct NmVertex {      // what Scene::ray_intersect leaves in the intersection record, as arguments
+    int tri;
+    V2f bc, uv;
+    bool valid_dp;
+};
+template <class S, int kCfg>
+__device__ __forceinline__ Its<S> nm_its(const NmVertex<S> &v, V3<S> shn, V3<S> dp_du) {
+    Its<S> its;
+    its.valid = true;
+    its.tri = v.tri;
+    its.mesh = -1;
+    its.bc = V2<S>(S(v.bc.x), S(v.bc.y));
+    its.uv = V2<S>(S(v.uv.x), S(v.uv.y));
+    its.dp_du = dp_du;
+    its.sh_n = shn;
+    coordinate_system(shn, its.sh_s, its.sh_t);
+    if (v.valid_dp) {      // scene.cpp:764-765
+        its.sh_s = normalize(dp_du - shn * dot(shn, dp_du));
+        its.sh_t = cross(shn, its.sh_s);
+    }
+    return its;
+}
+struct NmJet {
+    V3f f;            // BSDF value
+    float g[15];      // d(sum_c W_c f_c) / d(wi, wo, shn, dp_du, normal-map value)
+    bool ok;          // all of it finite
+};
+template <int kCfg>
+static __device__ __noinline__ NmJet normalmap_jet(const DScene &sc, DBsdf &bl, const DBsdf &nbl, const NmVertex<Dual> &v, V3f shn, V3f dp_du, V3f wi, V3f wo, V3f W) {
+    NmJet j;
+    j.ok = true;
+    j.f = V3f(0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int a = 0; a < 15; ++a) {
+        const int grp = a / 3, c = a - 3 * grp;
+        auto seed = [&](V3f x, int gsel) {
+            return V3d(Dual(x.x, (grp == gsel && c == 0) ? 1.f : 0.f), Dual(x.y, (grp == gsel && c == 1) ? 1.f : 0.f), Dual(x.z, (grp == gsel && c == 2) ? 1.f : 0.f));
+        };
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bl.d_refl[k] = (grp == 4 && c == k) ? 1.f : 0.f;
+        const Its<Dual> its = nm_its<Dual, kCfg>(v, seed(shn, 2), seed(dp_du, 3));
+        const V3d r = normalmap_eval_nb<Dual, kCfg>(sc, bl, nbl, its, its.to_local(seed(wi, 0)), its.to_local(seed(wo, 1)));
+        j.g[a] = W.x * r.x.d + W.y * r.y.d + W.z * r.z.d;
+        j.f = val(r);
+        j.ok = j.ok && isfinite(j.g[a]) && isfinite(r.x.v) && isfinite(r.y.v) && isfinite(r.z.v);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bl.d_refl[k] = 0.f;
+    return j;
+}
+
 struct VtxAdj {
     V3f p, shn, fn;
     float area;
@@ -623,24 +701,88 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
     const V3f wo = vec / t;
     const float cy = -dot(ny, wo);
     const float G = fabsf(cy) / (t * t);
-    const float ci = dot(wi, x.shn), co = dot(wo, x.shn), cio = dot(wi, wo);
-    const BsdfJet j = bsdf_jet<kCfg>(b, x.bv, ci, co, cio, W);
-    r.f = j.f;
+    // adjoints of wi, wo, sh_n (d(sum_c W_c f_c)/d(.) times phi_bar = G scale): through the three cosines, or (NormalMap)
+    // from the world-space jet
+    V3f f, wi_bar_v, wo_bar_v, shn_bar_v;
+    if ((kCfg & kCfgExt) && b.type == 5) {
+        DBsdf bl = b, nbl = sc.bsdfs[b.nested];
+        strip_tangents(bl);
+        strip_tangents(nbl);
+        const V3f nm_value = bsdf_vals_at<kCfg>(b, x.uv).refl;       // the map at this vertex: constant or bitmap lookup
+        bl.tex[0].w = bl.tex[0].h = 0;                                // the duals differentiate w.r.t. the VALUE; the texel
+        bl.refl[0] = nm_value.x; bl.refl[1] = nm_value.y; bl.refl[2] = nm_value.z;     // scatter follows below
+        const TriRec<float> T = load_tri<float>(sc, x.tri);
+        const float det = x.duv0.x * x.duv1.y - x.duv0.y * x.duv1.x;
+        NmVertex<Dual> nv;
+        nv.tri = x.tri;
+        nv.bc = V2f(x.u, x.v);
+        nv.uv = x.uv;
+        nv.valid_dp = det != 0.f;
+        const float inv_det = nv.valid_dp ? 1.f / det : 0.f;
+        const V3f dp_du = nv.valid_dp ? (T.e1 * x.duv1.y - T.e2 * x.duv0.y) * inv_det : V3f(0.f, 0.f, 0.f);
+        const NmJet j = normalmap_jet<kCfg>(sc, bl, nbl, nv, x.shn, dp_du, wi, wo, W);
+        if (!j.ok) return r;                                          // a NaN value is scrubbed by the forward pass: no gradient
+        f = j.f;
+        const float ps = G * scale;                                   // = phi_bar below
+        wi_bar_v = V3f(j.g[0], j.g[1], j.g[2]) * ps;
+        wo_bar_v = V3f(j.g[3], j.g[4], j.g[5]) * ps;
+        shn_bar_v = V3f(j.g[6], j.g[7], j.g[8]) * ps;
+        // dp_du = (e1 duv1.y - e2 duv0.y) / det
+        const V3f dpdu_bar = V3f(j.g[9], j.g[10], j.g[11]) * ps;
+        acc.add3(kGradTri * x.tri + 3, dpdu_bar * (x.duv1.y * inv_det));
+        acc.add3(kGradTri * x.tri + 6, dpdu_bar * (-x.duv0.y * inv_det));
+        // the normal map itself
+        const V3f nm_bar = V3f(j.g[12], j.g[13], j.g[14]) * ps;
+        if (b.tex[0].w > 0) tex_slot_grad(acc, gl, b.tex[0], x.uv, nm_bar, xa.uv);
+        else acc.add3(gl.off_bsdf + kGradBsdf * x.bsdf, nm_bar);
+        // parameters of the nested BSDF: f = N(pwi, pwo) lp sh + [<wi, wt> > 0] N(rwi, pwo) (1 - lp) sh
+        {
+            const Its<float> itf = nm_its<float, kCfg>(NmVertex<float>{x.tri, V2f(x.u, x.v), x.uv, nv.valid_dp}, x.shn, dp_du);
+            V3f wil = itf.to_local(wi), wol = itf.to_local(wo);
+            if (b.two_side) {
+                if (signbit_(wil.z)) wol.z = -wol.z;
+                wil.z = fabsf(wil.z);
+            }
+            if (wil.z > 0.f && wol.z > 0.f) {
+                V3f wp;
+                NmFrame<float> fr;
+                nm_setup<float, kCfg>(bl, itf, wp, fr);
+                const V3f p_wo = fr.to_local(wol), p_wi = fr.to_local(wil), wt = nm_wt<float>(wp);
+                const float sh = nm_G1<float>(wp, wol), lp = nm_lambda_p<float>(wp, wil);
+                const BsdfVals nbv = bsdf_vals_at<kCfg>(nbl, x.uv);
+                V2f bc_unused(0.f, 0.f);
+                bsdf_param_grad<kCfg>(acc, gl, sc, b.nested, nbl, nbv, p_wi.z, p_wo.z, dot(p_wi, p_wo), W, ps * lp * sh, x.uv, xa.uv, x.tri, x.u, x.v, bc_unused);
+                if (dot(wil, wt) > 0.f) {
+                    const V3f r_wi = fr.to_local(nm_reflect<float>(wil, wt));
+                    bsdf_param_grad<kCfg>(acc, gl, sc, b.nested, nbl, nbv, r_wi.z, p_wo.z, dot(r_wi, p_wo), W, ps * (1.f - lp) * sh, x.uv, xa.uv, x.tri, x.u, x.v, bc_unused);
+                }
+            }
+        }
+    } else {
+        const float ci = dot(wi, x.shn), co = dot(wo, x.shn), cio = dot(wi, wo);
+        const BsdfJet j = bsdf_jet<kCfg>(b, x.bv, ci, co, cio, W);
+        f = j.f;
+        bsdf_param_grad<kCfg>(acc, gl, sc, x.bsdf, b, x.bv, ci, co, cio, W, G * scale, x.uv, xa.uv, x.tri, x.u, x.v, xa.bc);
+        const float phi_bar0 = G * scale;
+        const float ci_bar = phi_bar0 * j.d_ci, co_bar = phi_bar0 * j.d_co, cio_bar = phi_bar0 * j.d_cio;
+        wo_bar_v = x.shn * co_bar + wi * cio_bar;
+        wi_bar_v = wo * cio_bar + x.shn * ci_bar;
+        shn_bar_v = wo * co_bar + wi * ci_bar;
+    }
+    r.f = f;
     r.geo = G * scale;
-    const float phi = W.x * j.f.x + W.y * j.f.y + W.z * j.f.z;          // sum_c W_c f_c
+    const float phi = W.x * f.x + W.y * f.y + W.z * f.z;          // sum_c W_c f_c
     // C = phi * G * J * scale
-    const float phi_bar = G * scale, G_bar = phi * scale, J_bar = phi * G * scale;
-    bsdf_param_grad<kCfg>(acc, gl, sc, x.bsdf, b, x.bv, ci, co, cio, W, G * scale, x.uv, xa.uv, x.tri, x.u, x.v, xa.bc);
-    const float ci_bar = phi_bar * j.d_ci, co_bar = phi_bar * j.d_co, cio_bar = phi_bar * j.d_cio;
+    const float G_bar = phi * scale, J_bar = phi * G * scale;
     // adjoints are often exactly 0 (W = 0): multiply by reciprocals, a zero numerator sends div.rn.f32 down its slow path
     const float inv_t = 1.f / t, inv_t2 = 1.f / (t * t);
     const float cy_bar = G_bar * (cy < 0.f ? -1.f : 1.f) * inv_t2;
     const float t_bar = G_bar * (-2.f * fabsf(cy) * (inv_t2 * inv_t));
-    V3f wo_bar = ny * (-cy_bar) + x.shn * co_bar + wi * cio_bar;
-    wo_bar = wo_bar + wo_extra(wo, j.f * (G * scale));
+    V3f wo_bar = ny * (-cy_bar) + wo_bar_v;
+    wo_bar = wo_bar + wo_extra(wo, f * (G * scale));
     r.ny = wo * (-cy_bar);
-    r.wi_bar = wo * cio_bar + x.shn * ci_bar;
-    xa.shn = xa.shn + wo * co_bar + wi * ci_bar;
+    r.wi_bar = wi_bar_v;
+    xa.shn = xa.shn + shn_bar_v;
     const V3f vec_bar = unit_adj(wo, t, wo_bar, t_bar);
     r.py = vec_bar;
     xa.p = xa.p - vec_bar;

@@ -831,10 +831,6 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
     cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
     if (!d_img) throw std::runtime_error("null cotangent image");
     if (max_depth > 8) throw std::runtime_error("the adjoint supports max_depth <= 8");
-    for (const HBsdf &b : sc.bsdfs)
-        if (b.type == 5)
-            throw std::runtime_error("reverse mode is not implemented for NormalMap BSDFs (BSDF '" + b.id +
-                                     "'): use the forward-mode derivative image (renderD with tangents)");
     RenderParams rp[3];
     for (auto &r : rp) {
         r = RenderParams{};
@@ -960,6 +956,12 @@ int psdr_scene_backprop_table(psdr_scene *s, int sensor, const float *grad_table
 }
 
 int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
+    if (s && index >= PSDR_NESTED_BSDF_BASE && kind != PSDR_MESH_VERTICES) {
+        // a nested BSDF (psdr_scene_begin_nested_bsdf): its gradients follow those of the numbered records
+        const int k = index - PSDR_NESTED_BSDF_BASE;
+        if (k >= (int) s->sc.nested_bsdfs.size()) return fail("invalid BSDF index");
+        index = (int) s->sc.bsdfs.size() + k;
+    }
     if (!s || !out) return fail("null argument");
     const Scene &sc = s->sc;
     const ParamGrads &g = sc.grads;

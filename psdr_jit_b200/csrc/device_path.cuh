@@ -898,13 +898,13 @@ template <class S> __device__ __forceinline__ V3<S> nm_reflect(V3<S> w, V3<S> wt
     return normalize(w - wt * k);
 }
 // NormalMap::__eval (normalmap.cpp:42-86): i -> p -> o and i -> t -> p -> o
-template <class S, int kCfg> PSDR_FULL_FN V3<S> normalmap_eval(const DScene &sc, const DBsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
+// (nb = the nested record, passed explicitly: the adjoint evaluates this with tangent-free local copies of both records)
+template <class S, int kCfg> PSDR_FULL_FN V3<S> normalmap_eval_nb(const DScene &sc, const DBsdf &b, const DBsdf &nb, const Its<S> &its, V3<S> wi, V3<S> wo) {
     if (b.two_side) {
         if (signbit_(val(wi.z))) wo.z = -wo.z;
         wi.z = abs_(wi.z);
     }
     if (!(val(wi.z) > 0.f && val(wo.z) > 0.f)) return V3<S>(S(0.f));
-    const DBsdf &nb = sc.bsdfs[b.nested];
     V3<S> wp;
     NmFrame<S> fr;
     nm_setup<S, kCfg>(b, its, wp, fr);
@@ -918,6 +918,10 @@ template <class S, int kCfg> PSDR_FULL_FN V3<S> normalmap_eval(const DScene &sc,
         value = value + bsdf_eval_leaf<S, kCfg>(sc, nb, its, fr.to_local(wi_r), p_wo) * ((S(1.f) - lambda_p) * shadowing);
     }
     return value;
+}
+
+template <class S, int kCfg> PSDR_FULL_FN V3<S> normalmap_eval(const DScene &sc, const DBsdf &b, const Its<S> &its, V3<S> wi, V3<S> wo) {
+    return normalmap_eval_nb<S, kCfg>(sc, b, sc.bsdfs[b.nested], its, wi, wo);
 }
 
 template <class S, int kCfg> __device__ __forceinline__ V3<S> bsdf_eval(const DScene &sc, const Its<S> &its, V3<S> wo, bool active) {

@@ -337,15 +337,14 @@ void upload_scene(Scene &sc) {
         if (!all_bsdfs[i]->pv.empty()) {
             rec->pv = (const float *) ((const unsigned char *) db.dev + o_pv[i]);
             rec->d_pv = all_bsdfs[i]->d_pv.empty() ? nullptr : (const float *) ((const unsigned char *) db.dev + o_dpv[i]);
-            rec->pv_goff = i < sc.bsdfs.size() ? sc.pervertex_grad_offset((int) i) : 0;
+            rec->pv_goff = sc.pervertex_grad_offset((int) i);
         }
         for (int k = 0; k < 3; ++k) {
             const HBsdf::Tex &t = all_bsdfs[i]->tex[k];
             DTex &dt = rec->tex[k];
             dt = DTex{};
             dt.ch = HBsdf::tex_channels(k);
-            // relative to the end of the gradient table (nested records have no gradient blocks: reverse mode rejects NormalMap)
-            dt.goff = i < sc.bsdfs.size() ? sc.texture_grad_offset((int) i, k) : 0;
+            dt.goff = sc.texture_grad_offset((int) i, k);   // relative to the end of the gradient table (nested records included)
             // cos / sin of the rotation on the host (the reference evaluates them per lookup on the device)
             const float cr = std::cos(t.rot.v), sr = std::sin(t.rot.v);
             dt.cr = cr; dt.sr = sr; dt.d_cr = -sr * t.rot.d; dt.d_sr = cr * t.rot.d;

@@ -183,6 +183,9 @@ struct Scene {
     // reverse mode: table layout for `sensor` (base = nullptr) and the host chain
     // table gradients -> world vertices -> raw vertices / to_world / camera matrices (scene_grad.cpp)
     GradLayout grad_layout(int sensor) const;
+    // reverse mode numbers the BSDF records as the device does: the numbered ones, then the nested ones
+    int num_bsdf_records() const { return (int) (bsdfs.size() + nested_bsdfs.size()); }
+    const HBsdf &bsdf_record(int i) const { return i < (int) bsdfs.size() ? bsdfs[i] : nested_bsdfs[i - (int) bsdfs.size()]; }
     int texture_grad_offset(int bsdf, int slot) const;   // relative to GradLayout::total (negative)
     int pervertex_grad_offset(int bsdf) const;           // MicrofacetPerVertex tables: the last blocks of the table (negative)
     void backprop(const float *table, const GradLayout &gl, int sensor);

@@ -115,7 +115,7 @@ void transform_pos_adj(const Mat &M, D3 p, D3 gq, D3 &gp, Mat &gM) {
 
 int Scene::pervertex_grad_offset(int bsdf) const {
     int back = 0;
-    for (int i = (int) bsdfs.size() - 1; i >= bsdf; --i) back += (int) bsdfs[i].pv.size();
+    for (int i = num_bsdf_records() - 1; i >= bsdf; --i) back += (int) bsdf_record(i).pv.size();
     return -back;
 }
 
@@ -124,8 +124,8 @@ int Scene::texture_grad_offset(int bsdf, int slot) const {
     // tables of BSDF 0, 1, ...]; the sensor-dependent primary-edge block sits before, so the offset is taken relative to
     // the END of the table
     int back = -pervertex_grad_offset(0);
-    for (int i = (int) bsdfs.size() - 1; i >= bsdf; --i)
-        for (int k = 2; k >= (i == bsdf ? slot : 0); --k) back += HBsdf::tex_channels(k) * bsdfs[i].tex[k].w * bsdfs[i].tex[k].h;
+    for (int i = num_bsdf_records() - 1; i >= bsdf; --i)
+        for (int k = 2; k >= (i == bsdf ? slot : 0); --k) back += HBsdf::tex_channels(k) * bsdf_record(i).tex[k].w * bsdf_record(i).tex[k].h;
     return -back;   // negative: relative to GradLayout::total
 }
 
@@ -135,16 +135,16 @@ GradLayout Scene::grad_layout(int sensor) const {
     for (const HMesh &m : meshes) ntris += (int) m.tris.size();
     gl.base = nullptr;
     gl.off_bsdf = kGradTri * ntris;
-    gl.off_emit = gl.off_bsdf + kGradBsdf * (int) bsdfs.size();
+    gl.off_emit = gl.off_bsdf + kGradBsdf * num_bsdf_records();
     gl.off_cam = gl.off_emit + 4 * (int) emitters.size();
     gl.off_pe = gl.off_cam + kGradCam;
     const int npe = (sensor >= 0 && sensor < (int) cameras.size()) ? (int) cameras[sensor].edges.size() : 0;
     gl.off_se = gl.off_pe + 4 * npe;
     gl.off_env = gl.off_se + 6 * (int) sec_edges.size();
     gl.total = gl.off_env + (env.present ? kGradEnvHead + 3 * env.w * env.h : 0);
-    for (const HBsdf &b : bsdfs)
-        for (int k = 0; k < 3; ++k) gl.total += HBsdf::tex_channels(k) * b.tex[k].w * b.tex[k].h;      // same order as texture_grad_offset()
-    for (const HBsdf &b : bsdfs) gl.total += (int) b.pv.size();
+    for (int i = 0; i < num_bsdf_records(); ++i)
+        for (int k = 0; k < 3; ++k) gl.total += HBsdf::tex_channels(k) * bsdf_record(i).tex[k].w * bsdf_record(i).tex[k].h;      // same order as texture_grad_offset()
+    for (int i = 0; i < num_bsdf_records(); ++i) gl.total += (int) bsdf_record(i).pv.size();
     return gl;
 }
 
@@ -152,7 +152,7 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
     grads = ParamGrads{};
     grads.meshes.resize(meshes.size());
     grads.cameras.resize(cameras.size());
-    grads.bsdf_refl.assign(3 * bsdfs.size(), 0.0);
+    grads.bsdf_refl.assign(3 * (size_t) num_bsdf_records(), 0.0);
     grads.emitter_rad.assign(3 * emitters.size(), 0.0);
     for (auto &c : grads.cameras) std::memset(c.to_world, 0, sizeof(c.to_world));
 
@@ -250,24 +250,24 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
         split_product(m.to_world, gtw, out.to_world);
     }
     for (int k = 0; k < 3; ++k) {
-        grads.bsdf_tex[k].assign(bsdfs.size(), std::vector<float>());
-        for (size_t i = 0; i < bsdfs.size(); ++i)
-            if (bsdfs[i].tex[k].w > 0) {
+        grads.bsdf_tex[k].assign((size_t) num_bsdf_records(), std::vector<float>());
+        for (size_t i = 0; i < (size_t) num_bsdf_records(); ++i)
+            if (bsdf_record((int) i).tex[k].w > 0) {
                 const float *g = table + gl.total + texture_grad_offset((int) i, k);
-                grads.bsdf_tex[k][i].assign(g, g + (size_t) HBsdf::tex_channels(k) * bsdfs[i].tex[k].w * bsdfs[i].tex[k].h);
+                grads.bsdf_tex[k][i].assign(g, g + (size_t) HBsdf::tex_channels(k) * bsdf_record((int) i).tex[k].w * bsdf_record((int) i).tex[k].h);
             }
     }
-    grads.bsdf_pv.assign(bsdfs.size(), std::vector<float>());
-    for (size_t i = 0; i < bsdfs.size(); ++i)
-        if (!bsdfs[i].pv.empty()) {
+    grads.bsdf_pv.assign((size_t) num_bsdf_records(), std::vector<float>());
+    for (size_t i = 0; i < (size_t) num_bsdf_records(); ++i)
+        if (!bsdf_record((int) i).pv.empty()) {
             const float *g = table + gl.total + pervertex_grad_offset((int) i);
-            grads.bsdf_pv[i].assign(g, g + bsdfs[i].pv.size());
+            grads.bsdf_pv[i].assign(g, g + bsdf_record((int) i).pv.size());
         }
-    grads.bsdf_spec.assign(3 * bsdfs.size(), 0.0);
-    grads.bsdf_rough.assign(bsdfs.size(), 0.0);
-    grads.bsdf_eta.assign(3 * bsdfs.size(), 0.0);
-    grads.bsdf_k.assign(3 * bsdfs.size(), 0.0);
-    for (size_t i = 0; i < bsdfs.size(); ++i) {
+    grads.bsdf_spec.assign(3 * (size_t) num_bsdf_records(), 0.0);
+    grads.bsdf_rough.assign((size_t) num_bsdf_records(), 0.0);
+    grads.bsdf_eta.assign(3 * (size_t) num_bsdf_records(), 0.0);
+    grads.bsdf_k.assign(3 * (size_t) num_bsdf_records(), 0.0);
+    for (size_t i = 0; i < (size_t) num_bsdf_records(); ++i) {
         for (int c = 0; c < 3; ++c) {
             grads.bsdf_refl[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + c];
             grads.bsdf_spec[3 * i + c] = table[gl.off_bsdf + kGradBsdf * i + 4 + c];

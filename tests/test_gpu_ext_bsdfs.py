@@ -2,7 +2,7 @@
 (src/bsdf/roughdielectric.cpp), MicrofacetBSDFPerVertex (src/bsdf/microfacet_pv.cpp) and NormalMapBSDF
 (src/bsdf/normalmap.cpp) -- against the oracle (values and forward-mode tangents, all three terms), against the reference's
 own output (tests/golden/ext_bsdfs.npz, tools/ref_golden10.py), through the scene-file loader; reverse mode of the
-dielectric and the per-vertex BSDF against forward mode (NormalMap is forward-mode only and says so)."""
+three against forward mode."""
 import copy
 import os
 
@@ -238,13 +238,53 @@ def test_add_BSDF_normalmap_installs_the_reference_defaults():
     assert np.allclose(b.nested_bsdf.roughness, 0.8) and np.allclose(b.nested_bsdf.specularReflectance, 0.04)
 
 
-def test_reverse_mode_reports_unsupported_bsdfs():
-    """NormalMap has no adjoint (its perturbed frame is not a function of the three cosines the adjoint differentiates)"""
+def test_vjp_per_parameter_normalmap():
+    """NormalMap in reverse mode (the adjoint differentiates the forward code as a function of world-space quantities,
+    adjoint.cuh normalmap_jet): one JVP per parameter against the matching entry of a single VJP -- the constant normal map,
+    the nested Microfacet's three parameters, and texels of a bitmap normal map"""
     import torch
     import psdr_jit_b200 as psdr
-    sc = build_product(box_meshes(), 32, 32, 2, 0, 0, bsdfs=with_ext(SPECS["normalmap_mf"]))
-    with pytest.raises(RuntimeError, match="reverse mode is not implemented"):
-        psdr.PathTracer(2).render_vjp(sc, torch.ones(32 * 32, 3, device="cuda"), 0, seed=0, terms=1)
+    rng = np.random.default_rng(4)
+    w = h = 48
+    integ = psdr.PathTracer(3)
+    cot = torch.as_tensor(rng.normal(size=(w * h, 3)).astype(np.float32), device="cuda")
+
+    def check(dimg, grad, what):
+        lhs = float((cot.double() * dimg.double()).sum())
+        ref = float(torch.linalg.norm(cot.double()) * torch.linalg.norm(dimg.double()))
+        assert abs(lhs - float(grad)) < 1e-3 * max(abs(lhs), 1e-2 * ref), (what, lhs, float(grad))
+
+    bs = with_ext(SPECS["normalmap_mf"])
+    sc = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs)
+    integ.render_vjp(sc, cot, 0, seed=2, terms=1)
+    g_nm = sc.grad_of("BSDF[id=ext]", "normal_map").ravel().copy()
+    g_nested = np.concatenate([sc.grad_of("BSDF[id=ext]", "nested_bsdf.specularReflectance").ravel(), sc.grad_of("BSDF[id=ext]", "nested_bsdf.diffuseReflectance").ravel(),
+                               sc.grad_of("BSDF[id=ext]", "nested_bsdf.roughness").ravel()])
+    assert g_nm.size == 3 and g_nested.size == 7 and np.abs(g_nm).max() > 0 and np.abs(g_nested).max() > 0
+    for k in range(3):
+        d = np.zeros(3, np.float32)
+        d[k] = 1.0
+        sc2 = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs, d_bsdf={"ext": d})
+        check(integ.renderD_fwd(sc2, 0, seed=2, terms=1)[1], g_nm[k], ("normal", k))
+    for k in (0, 4, 6):
+        spec = copy.deepcopy(SPECS["normalmap_mf"])
+        d = np.zeros(7, np.float32)
+        d[k] = 1.0
+        spec["normalmap"]["d_nested"] = d
+        sc2 = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=with_ext(spec))
+        check(integ.renderD_fwd(sc2, 0, seed=2, terms=1)[1], g_nested[k], ("nested", k))
+    # bitmap normal map: texel gradients
+    tex = normal_texture()
+    sc = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs, textures={"ext": {0: tex}})
+    integ.render_vjp(sc, cot, 0, seed=2, terms=1)
+    g_tex = sc.grad_of("BSDF[id=ext]", "normal_map").reshape(-1, 3)
+    assert g_tex.shape == (tex["w"] * tex["h"], 3) and np.abs(g_tex).max() > 0
+    hot = np.argsort(-np.abs(g_tex).sum(axis=1))[:3]
+    for t in hot:
+        d = np.zeros_like(tex["data"])
+        d[t, 1] = 1.0
+        sc2 = build_product(box_meshes(), w, h, 16, 0, 0, bsdfs=bs, textures={"ext": {0: dict(tex, d_data=d)}})
+        check(integ.renderD_fwd(sc2, 0, seed=2, terms=1)[1], g_tex[t, 1], ("texel", int(t)))
 
 
 def test_vjp_per_parameter_dielectric_and_pervertex():
@@ -283,7 +323,7 @@ def test_vjp_per_parameter_dielectric_and_pervertex():
         check(integ.renderD_fwd(sc2, 0, seed=2, terms=1)[1], g[vtx, col])
 
 
-@pytest.mark.parametrize("kind", ["dielectric", "pervertex"])
+@pytest.mark.parametrize("kind", ["dielectric", "pervertex", "normalmap_mf"])
 def test_vjp_is_transpose_with_geometry_and_edges(kind):
     """<cotangent, J t> == <J^T cotangent, t> with t = (translation of the luminaire and of the tall box, material tangent),
     all three terms: the box moves under the camera, so the per-vertex tables are also reached through the differentiable
@@ -302,6 +342,8 @@ def test_vjp_is_transpose_with_geometry_and_edges(kind):
         tang[(name, "to_world_left")] = t.copy()
     if kind == "dielectric":
         tang[("BSDF[id=ext]", "alpha_u")] = np.float32(mt).reshape(1)
+    elif kind == "normalmap_mf":
+        tang[("BSDF[id=ext]", "normal_map")] = np.float32(mt).reshape(3)
     else:
         m = np.float32(mt).reshape(8, 7)
         tang[("BSDF[id=ext]", "specularReflectance")] = m[:, 0:3]
