@@ -45,8 +45,9 @@ enum {
     PSDR_BSDF_ROUGHNESS_UV = 16,
     PSDR_BSDF_ETA = 17,            /* RoughConductorBSDF.eta (1x1 Bitmap3fD), 3 floats */
     PSDR_BSDF_K = 18,              /* RoughConductorBSDF.k (1x1 Bitmap3fD), 3 floats */
-    PSDR_BSDF_PERVERTEX = 19       /* MicrofacetBSDFPerVertex tables, 7 floats per vertex: specularReflectance rgb,
+    PSDR_BSDF_PERVERTEX = 19,      /* MicrofacetBSDFPerVertex tables, 7 floats per vertex: specularReflectance rgb,
                                       diffuseReflectance rgb, roughness (src/psdr.cpp:306-310) */
+    PSDR_INTEGRATOR_INTENSITY = 20 /* psdr_scene_get_grad only: d/d CollocatedIntegrator.m_intensity of the last adjoint pass */
 };
 
 /* Texture slots of a BSDF (psdr_scene_set_bsdf_texture_slot). */
@@ -104,6 +105,11 @@ int psdr_scene_set_shard(psdr_scene *s, int rank, int world);
  * sampling only, mis = 1 BSDF sampling only.  The sample streams consume only the draws the mode uses. */
 enum { PSDR_INTEGRATOR_PATH = 0, PSDR_INTEGRATOR_DIRECT = 1 };
 int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis);
+/* CollocatedIntegrator(intensity) -- src/psdr.cpp:427-429, src/integrator/collocated.cpp:21-53: a point light at the camera;
+ * Li = BSDF(wi, wo = wi) * intensity / t^2 at the primary hit, no emitters, no random numbers in Li, no secondary-edge
+ * term (Integrator::render_secondary_edges is empty, include/psdr/integrator/integrator.h:22).  d_intensity: forward-mode
+ * tangent of m_intensity.  The following render calls (max_depth ignored) evaluate it until psdr_scene_set_integrator. */
+int psdr_scene_set_integrator_collocated(psdr_scene *s, float intensity, float d_intensity);
 /* Multi-GPU output fusion (new: SURVEY.md 8e).  on = 1 or 2: the img / dimg pointers of psdr_render_c / psdr_render_d and the
  * grad_table pointer of psdr_render_vjp_device are NVLS MULTICAST addresses of a buffer that every rank of the node has
  * mapped (cuMulticast* / torch symmetric memory).  The term kernels then accumulate with multimem.red: the NVSwitch adds

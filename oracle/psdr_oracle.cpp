@@ -230,7 +230,9 @@ struct Scene {
     std::string error;
     // options
     bool li_p_first = true;  // evaluation order of Li(ray_n) - Li(ray_p), integrator.cpp:185-186
-    int mis = 2;             // 2: PathTracer / Direct(2); 0 / 1: Direct(0) / Direct(1) (reference src/integrator/direct.cpp)
+    int mis = 2;             // 2: PathTracer / Direct(2); 0 / 1: Direct(0) / Direct(1) (reference src/integrator/direct.cpp);
+                             // 3: CollocatedIntegrator (reference src/integrator/collocated.cpp)
+    Dual colloc_intensity = Dual(0.f);
 };
 
 // The product's closest-hit query (psdr_jit_b200/csrc/device_path.cuh trace<brute>, the replacement of OptiX) tests a
@@ -1512,6 +1514,10 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
     // primary hit: ray_intersect<ad> (path_space = false)
     Its<S> its = ray_intersect<S>(sc, ro, rd, active, false);
     active = active && its.valid;
+    if (sc.mis == 3) {   // CollocatedIntegrator::__Li (collocated.cpp:21-53): evalD(its, its.wi) / sqr(its.t) * m_intensity
+        if (!active) return V3<S>(S(0.f));
+        return bsdf_eval<S>(sc, its, its.wi, true) / sqr(its.t) * lift_d<S>(sc.colloc_intensity);
+    }
     V3<S> throughput(S(1.f));
     V3<S> result = hide_emitters ? V3<S>(S(0.f)) : Le(sc, its, active);
     for (int depth = 0; depth < max_depth; ++depth) {
@@ -1829,6 +1835,10 @@ void orc_destroy(void *h) { delete (Scene *) h; }
 const char *orc_error(void *h) { return ((Scene *) h)->error.c_str(); }
 void orc_set_li_order(void *h, int p_first) { ((Scene *) h)->li_p_first = p_first != 0; }
 void orc_set_mis(void *h, int mis) { ((Scene *) h)->mis = mis; }
+void orc_set_collocated(void *h, float intensity, float d_intensity) {
+    ((Scene *) h)->mis = 3;
+    ((Scene *) h)->colloc_intensity = Dual(intensity, d_intensity);
+}
 
 int orc_add_diffuse(void *h, const float *refl, const float *d_refl, int two_side) {
     Scene *s = (Scene *) h;
@@ -2032,7 +2042,7 @@ int orc_render(void *h, int sensor, int max_depth, int seed, int mode, int terms
     }
     if (mode == 1 && dimg) {
         if ((terms & 2) && sc.sppe > 0) render_primary_edges(sc, ra, dimg);
-        if ((terms & 4) && sc.sppse > 0) render_secondary_edges(sc, ra, dimg);
+        if ((terms & 4) && sc.sppse > 0 && sc.mis != 3) render_secondary_edges(sc, ra, dimg);   // (Integrator::render_secondary_edges is empty)
     }
     return 0;
 }

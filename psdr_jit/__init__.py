@@ -95,6 +95,13 @@ class Direct(_IntegratorMixin, _b.Direct):
     pass
 
 
+class CollocatedIntegrator(_IntegratorMixin, _b.CollocatedIntegrator):
+    """psdr.CollocatedIntegrator(intensity) (reference src/psdr.cpp:427-429); a Dr.Jit (stand-in) float is accepted"""
+
+    def __init__(self, intensity):
+        _b.CollocatedIntegrator.__init__(self, float(np.asarray(intensity.numpy() if hasattr(intensity, "numpy") else intensity).ravel()[0]))
+
+
 class FieldExtractionIntegrator(_b.FieldExtractionIntegrator):
     def renderC(self, scene, sensor_id=0, seed=-1, batch_pix=-1):
         return ArrayXf(super().renderC(scene, sensor_id, seed, batch_pix))

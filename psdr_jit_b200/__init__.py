@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib, scenes  # noqa: F401
 from . import loader as _loader
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "RoughConductorBSDF", "RoughDielectricBSDF", "MicrofacetBSDFPerVertex", "NormalMapBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "RoughConductorBSDF", "RoughDielectricBSDF", "MicrofacetBSDFPerVertex", "NormalMapBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "CollocatedIntegrator", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
@@ -1117,11 +1117,15 @@ class Integrator(Object):
         adjoint kernels (``psdr_render_vjp``) -- ``loss(img).backward()`` then fills ``param.grad`` like
         ``drjit.backward`` does in the reference.  Otherwise: primal image, and the forward-mode derivative
         image for the configured tangents is kept in ``self.grad_image``."""
-        leaves = scene._grad_leaves()
+        leaves = scene._grad_leaves() + self._own_leaves()
         if leaves:
             return _render_d_autograd(self, scene, sensor_id, int(seed), batch_pix, leaves)
         img, self.grad_image = self.renderD_fwd(scene, sensor_id, seed, batch_pix)
         return img
+
+    def _own_leaves(self):
+        """[(tensor, kind, index)] for differentiable parameters of the integrator itself (CollocatedIntegrator.m_intensity)"""
+        return []
 
     def renderD_primal(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
         """Image of renderD without any derivative (psdr_render_d with dimg = NULL)."""
@@ -1271,6 +1275,38 @@ class Direct(PathTracer):
 
 
 DirectIntegrator = Direct
+
+
+class CollocatedIntegrator(Integrator):
+    """reference src/psdr.cpp:427-429, src/integrator/collocated.cpp: a point light of ``m_intensity`` at the camera --
+    Li = BSDF(wi, wo = wi) * intensity / t^2 at the primary hit (flash photography); no emitters are used, Li draws no
+    random numbers, and there is no secondary-edge term.  renderC / renderD / forward mode (``d_m_intensity`` is the
+    tangent of the intensity) / reverse mode (``grad_intensity(scene)``, or a torch tensor with requires_grad as
+    ``m_intensity``) as for PathTracer."""
+
+    def __init__(self, intensity):
+        self.m_intensity = intensity if hasattr(intensity, "requires_grad") else np.float32(intensity)
+        self.d_m_intensity = np.float32(0.0)
+        self.max_depth = 1
+
+    def _check(self, scene: Scene):
+        if scene._h is None or not scene.is_ready():
+            raise RuntimeError("Input scene must be configured!")
+        _lib.check(_lib.load().psdr_scene_set_integrator_collocated(scene._h, float(_f32(self.m_intensity).ravel()[0]), float(_f32(self.d_m_intensity).ravel()[0])))
+
+    def _own_leaves(self):
+        t = self.m_intensity
+        return [(t, _lib.INTEGRATOR_INTENSITY, 0)] if hasattr(t, "requires_grad") and t.requires_grad else []
+
+    def grad_intensity(self, scene: Scene) -> float:
+        """d<d_img, img>/d(m_intensity) of the last ``render_vjp``"""
+        return float(scene._read_grad(_lib.INTEGRATOR_INTENSITY, 0, (1,))[0])
+
+    def renderD_fwd(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL):
+        return super().renderD_fwd(scene, sensor_id, seed, batch_pix, terms & ~_lib.TERM_SECONDARY_EDGES)
+
+    def render_vjp(self, scene: Scene, d_img, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL, group=None):
+        return super().render_vjp(scene, d_img, sensor_id, seed, batch_pix, terms & ~_lib.TERM_SECONDARY_EDGES, group)
 
 
 class FieldExtractionIntegrator(Integrator):

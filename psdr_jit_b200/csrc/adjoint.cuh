@@ -795,7 +795,9 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
 // direction, camera-space direction).  The loop runs k = nsh-1 .. 0 with a rolling window of three vertices
 // (previous, x = vertex k, y = vertex k+1) held in registers; a vertex's adjoint is complete -- and scattered
 // -- one iteration after it was x.
-template <int kD, int kCfg>
+// kColloc: CollocatedIntegrator -- the lane's value is ONE event at the primary hit, written as an event towards the camera
+// position with "normal" wo there: sum_c g_c f_c(wi, wo = wi) |cos_y| / t^2 * intensity with |cos_y| = 1.
+template <int kD, int kCfg, bool kColloc = false>
 __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout &gl, const GradAcc &acc, const PathRecord<kD> &R, V3f o, V3f d,
                                              V3f dc, V3f g, bool hide_emitters, bool enabled) {
     // Called by ALL 32 lanes of the warp from warp-uniform control flow (`enabled` = this lane has a path and a
@@ -805,7 +807,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     // groups through one by one without merging them -- profiles/r01g: 3 of 32 lanes active in the sweep.)
     constexpr bool kFull = (kCfg & kCfgFull) != 0;
     const bool has_v0 = enabled && R.nv > 0;
-    const bool sweep = has_v0 && R.nsh > 0;
+    const bool sweep = has_v0 && (kColloc || R.nsh > 0);
     // Emitter-radiance gradients are summed per lane in registers and scattered ONCE, from the warp-uniform epilogue:
     // every event of every lane of the warp adds to the same few entries (one emitter in most scenes), and inside the
     // divergent event code that was a same-target add with a partial lane mask -- the slow path of grad_add3_impl
@@ -828,7 +830,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         v0geo = vertex_geo<kCfg>(sc, R.vtri[0], u0, v0);
         v0geo.p = V3f(fmaf(d.x, t0, o.x), fmaf(d.y, t0, o.y), fmaf(d.z, t0, o.z));
         // Le at the primary hit
-        if (!hide_emitters && v0geo.emitter >= 0) {
+        if (!kColloc && !hide_emitters && v0geo.emitter >= 0) {
             if (kFull && sc.emitters[v0geo.emitter].type == 1) {
                 V3f le;
                 d_bar = d_bar + env_le_adjoint(acc, gl, sc.env, d, g, le);
@@ -841,14 +843,25 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
     const int ktop = R.nsh - 1;
     auto geo_of = [&](int k) { return k == 0 ? v0geo : vertex_geo<kCfg>(sc, R.vtri[k], R.vu[k], R.vv[k]); };
     VtxGeo y = v0geo, x = v0geo;
-    if (sweep) {
+    if (sweep && !kColloc) {
         if (ktop + 1 < R.nv) y = geo_of(ktop + 1);      // only read when the bounce exists
         x = geo_of(ktop);
     }
     VtxAdj ya = zero_adj, xa = zero_adj, pa = zero_adj;
+    if (kColloc && sweep) {
+        const V3f wi = -d;
+        auto none = [](V3f, V3f) { return V3f(0.f, 0.f, 0.f); };
+        const EventAdj ev = event_adjoint<kCfg>(acc, gl, sc, v0geo, wi, o, wi, 0.f, g, sc.colloc_intensity, ya, none);
+        // wo = (o - p)/|o - p| and wi = -d: ev.py is d/d(o), ev.wi_bar d/d(wi); ya.p (= -ev.py) follows p = o + t d in the epilogue
+        o_bar = o_bar + ev.py;
+        d_bar = d_bar - ev.wi_bar;
+        // d/d(intensity): the lane's value over the intensity
+        const V3f fb = ev.f * ev.geo;
+        if (sc.colloc_intensity != 0.f) acc.add(gl.off_cam + 38, (g.x * fb.x + g.y * fb.y + g.z * fb.z) / sc.colloc_intensity);
+    }
     V3f Lnext(0.f, 0.f, 0.f);     // R_{k+1}: radiance gathered after vertex k+1 (without E_{k+1})
     // every lane executes iteration kk together, whatever its own k is
-    const int iters = __reduce_max_sync(0xffffffffu, sweep ? R.nsh : 0);
+    const int iters = __reduce_max_sync(0xffffffffu, (sweep && !kColloc) ? R.nsh : 0);
 #pragma unroll 1
     for (int kk = 0;; ++kk) {
 #if defined(PSDR_VJP_PHASE_SYNC) && PSDR_VJP_PHASE_SYNC >= 3

@@ -148,6 +148,13 @@ int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis) {
     return 0;
 }
 
+int psdr_scene_set_integrator_collocated(psdr_scene *s, float intensity, float d_intensity) {
+    if (!s) return fail("null scene");
+    s->sc.integrator_mis = 3;
+    s->sc.colloc_intensity = Dual(intensity, d_intensity);
+    return 0;
+}
+
 int psdr_set_cta_policy(int policy) {
     if (policy < 0 || policy > 2) return fail("policy >= 0 && policy <= 2");
     psdr::g_cta_policy = policy;
@@ -651,8 +658,11 @@ void set_shard(RenderParams &rp, long long n, int rank, int world) {
 // sampler (re)seeding; returns the per-sampler (seed, skip) pair of this call.
 void begin_render(Scene &sc, int sensor, long long seed, const int *pix_id, bool ad, int terms, int max_depth, RenderParams rp[3]) {
     const int mis = sc.integrator_mis;
-    const unsigned long long per_bounce = mis == 0 ? 2ull : mis == 1 ? 3ull : 5ull;      // draws per bounce (device_path.cuh li_step)
+    // draws per bounce (device_path.cuh li_step); the CollocatedIntegrator's Li draws nothing
+    const unsigned long long per_bounce = mis == 3 ? 0ull : mis == 0 ? 2ull : mis == 1 ? 3ull : 5ull;
     for (int k = 0; k < 3; ++k) rp[k].mis = mis;
+    sc.dscene.colloc_intensity = sc.colloc_intensity.v;
+    sc.dscene.d_colloc_intensity = sc.colloc_intensity.d;
     if (pix_id && seed == -1) throw std::runtime_error("While using batch rendering, seed must be set!");
     if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
     if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
@@ -750,7 +760,8 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
     }
     const bool do_int = sc.spp > 0 && (terms & PSDR_TERM_INTERIOR);
     const bool do_pri = ad && !primal_only && sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0;
-    const bool do_sec = ad && !primal_only && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0;
+    // (the CollocatedIntegrator has no secondary-edge term: Integrator::render_secondary_edges is empty, integrator.h:22)
+    const bool do_sec = ad && !primal_only && sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0 && sc.integrator_mis != 3;
     if ((do_pri || do_sec) && pix_id) throw std::runtime_error("batch rendering supports the interior term only");
     TermStreams ts(s, st, (int) do_int + (int) do_pri + (int) do_sec);
     if (do_int) {
@@ -853,7 +864,7 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
     s->ev_used[0] = s->ev_used[1] = s->ev_used[2] = false;
     const bool do_int = sc.spp > 0 && (terms & PSDR_TERM_INTERIOR);
     const bool do_pri = sc.sppe > 0 && (terms & PSDR_TERM_PRIMARY_EDGES) && cam.n_edges > 0;
-    const bool do_sec = sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0;
+    const bool do_sec = sc.sppse > 0 && (terms & PSDR_TERM_SECONDARY_EDGES) && sc.dscene.n_sec_edges > 0 && sc.integrator_mis != 3;
     if ((do_pri || do_sec) && pix_id) throw std::runtime_error("batch rendering supports the interior term only");
     TermStreams ts(s, st, (int) do_int + (int) do_pri + (int) do_sec);      // see render_impl
     if (do_int) {
@@ -1013,6 +1024,7 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
         case PSDR_BSDF_PERVERTEX:
             if (index < 0 || index >= (int) g.bsdf_pv.size() || g.bsdf_pv[index].empty()) return fail("not a MicrofacetBSDFPerVertex");
             return copy_tex(g.bsdf_pv[index]);
+        case PSDR_INTEGRATOR_INTENSITY: return copy(&g.colloc_intensity, 1);
         case PSDR_EMITTER_RADIANCE:
             if (index < 0 || 3 * index + 3 > (int) g.emitter_rad.size()) return fail("invalid emitter index");
             return copy(g.emitter_rad.data() + 3 * index, 3);

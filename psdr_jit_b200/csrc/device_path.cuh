@@ -1551,6 +1551,17 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
     return Li<S, kCfg, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec, cta ? 0xffffffffu : 0u, mis, cta);
 }
 
+// CollocatedIntegrator::__Li (reference src/integrator/collocated.cpp:21-53): a point light at the camera -- the BSDF towards
+// the viewer for light arriving from the viewer, times intensity / t^2; no emitters, no sampling, no random numbers.
+// Kept out of li_step (its own small kernel instantiations, kernels_impl.cuh kColloc): the path tracer's kernels do not
+// carry a second inlined copy of the BSDF code for it.
+template <class S, int kCfg, bool kAD>
+__device__ __forceinline__ V3<S> Li_collocated(const DScene &sc, V3<S> ro, V3<S> rd, bool active) {
+    const Its<S> its = ray_intersect<S, kCfg, kAD>(sc, ro, rd, active, false);
+    if (!(active && its.valid)) return V3<S>(S(0.f));
+    return bsdf_eval<S, kCfg>(sc, its, its.wi, true) / sqr(its.t) * bsdf_scalar<S>(sc.colloc_intensity, sc.d_colloc_intensity);
+}
+
 // ---- secondary (shadow) edges: reference src/scene/scene.cpp:1027-1068, src/integrator/path.cpp:172-270
 struct SensorDirect {
     V2f q;

@@ -127,6 +127,7 @@ struct DScene {
     int ref_rcp;             // 1: the analytic primary hit of renderD uses Dr.Jit's approximate rcp (device_path.cuh rcp_approx)
     int full_features;       // 1: some BSDF is a Microfacet or an EnvironmentMap exists (selects the kernel variant)
     int ext_features;        // 1: bitmap-valued BSDF slots or a BSDF of type >= 2 (kCfgExt kernel family; implies full_features)
+    float colloc_intensity, d_colloc_intensity;   // CollocatedIntegrator::m_intensity and its forward tangent (RenderParams::mis == 3)
     const float4 *geo, *shade, *dgeo, *dshade;
     const float2 *uv;
     const int *face_idx;     // 3 mesh-local vertex indices per triangle (MicrofacetPerVertex gathers through them); nullptr if unused
@@ -161,7 +162,8 @@ struct DScene {
 struct RenderParams {
     int max_depth;
     int hide_emitters;
-    int mis;                 // 2: PathTracer / Direct(2) (both strategies, power heuristic); 0 / 1: Direct(0) / Direct(1)
+    int mis;                 // 2: PathTracer / Direct(2) (both strategies, power heuristic); 0 / 1: Direct(0) / Direct(1);
+                             // 3: CollocatedIntegrator (Li = BSDF(wi, wi) intensity / t^2 at the primary hit, no sampling)
     long long seed;          // >= 0
     unsigned long long skip; // draws already consumed per lane of this sampler (seed = -1 continuation)
     long long lane_begin, lane_end;   // LOCAL lane index range of this call: [0, 32 * owned blocks)

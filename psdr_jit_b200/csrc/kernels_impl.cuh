@@ -90,7 +90,8 @@ __device__ __forceinline__ float scrub(float x) { return isfinite(x) ? x : 0.f; 
 // kAD = use the formulas of the reference's renderD instantiation (the primary hit re-intersected
 // analytically, scene.cpp:772-801) -- <float, kBvh, true> is the primal image of renderD.
 // kBig: the one-CTA-per-SM shape with block barriers (above); else the 128-thread shape for launches too small to fill it.
-template <class S, int kCfg, bool kAD, bool kBig>
+// kColloc: Li = CollocatedIntegrator (device_path.cuh Li_collocated) instead of the path tracer; 128-thread shape only.
+template <class S, int kCfg, bool kAD, bool kBig, bool kColloc = false>
 __global__ void __launch_bounds__(kBig ? InteriorBlock<kCfg>::value : kBlock, kBig ? (IsDual<S>::value ? PSDR_LB_INTERIOR_DUAL : PSDR_LB_INTERIOR) : 6)
     interior_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ RenderParams rp, float *__restrict__ img,
                     float *__restrict__ dimg) {
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(kBig ? InteriorBlock<kCfg>::value : kBlock, kB
             V3<S> o, d;
             sample_primary_ray<S>(cam, V2f(sx, sy), o, d);
             NoRecord rec;
-            v = Li<S, kCfg, kAD, NoRecord>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, rec, kSync >= 2 ? 0xffffffffu : 0u, rp.mis, kSync >= 2);
+            if (kColloc) v = Li_collocated<S, kCfg, kAD>(sc, o, d, live);
+            else v = Li<S, kCfg, kAD, NoRecord>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, rec, kSync >= 2 ? 0xffffffffu : 0u, rp.mis, kSync >= 2);
         }
         float r = val(v.x), g = val(v.y), b = val(v.z), dr = tang(v.x), dg = tang(v.y), db = tang(v.z);
         // masked(value, ~isfinite(value)) = 0 zeroes value and tangent (integrator.cpp:126)
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kBig ? InteriorBlock<kCfg>::value : kBlock, kB
 }
 
 // ---- primary (pixel) edges: PerspectiveCamera::sample_primary_edge + Integrator::render_primary_edges
-template <int kCfg, bool kBig>
+template <int kCfg, bool kBig, bool kColloc = false>
 __global__ void __launch_bounds__(kBig ? kBlockP : kBlock, kBig ? PSDR_LB_PRIMARY : 8) primary_edge_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                const __grid_constant__ RenderParams rp, float *__restrict__ dimg) {
     constexpr int kBlockP = kBig ? psdr::kBlockP : kBlock, kSync = kBig ? PSDR_SYNC_P : 0;
@@ -191,7 +193,8 @@ __global__ void __launch_bounds__(kBig ? kBlockP : kBlock, kBig ? PSDR_LB_PRIMAR
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px.v + sg * bq.x, py.v + sg * bq.y), ro, rd);
-            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis, kSync >= 2);
+            if (kColloc) Lside[side] = Li_collocated<float, kCfg, false>(sc, ro, rd, valid);
+            else Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis, kSync >= 2);
         }
         const V3f Lp = Lside[0], Ln = Lside[1];
         if (!valid) continue;
@@ -417,6 +420,10 @@ template <int kCfg> struct ForwardLaunch {
     template <class S, bool kAD> static void interior_as(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *img, float *dimg, cudaStream_t st) {
         const long long n = rp.lane_end - rp.lane_begin;
         constexpr int kBlockI = InteriorBlock<kCfg>::value;
+        if (rp.mis == 3) {      // CollocatedIntegrator
+            interior_kernel<S, kCfg, kAD, false, true><<<persistent_grid(interior_kernel<S, kCfg, kAD, false, true>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
+            return;
+        }
         if (use_big_cta(n, kBlockI)) interior_kernel<S, kCfg, kAD, true><<<persistent_grid(interior_kernel<S, kCfg, kAD, true>, kBlockI, 0, n), kBlockI, 0, st>>>(sc, cam, rp, img, dimg);
         else interior_kernel<S, kCfg, kAD, false><<<persistent_grid(interior_kernel<S, kCfg, kAD, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, img, dimg);
     }
@@ -428,6 +435,10 @@ template <int kCfg> struct ForwardLaunch {
     }
     static cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) {
         const long long n = rp.lane_end - rp.lane_begin;
+        if (rp.mis == 3) {      // CollocatedIntegrator
+            primary_edge_kernel<kCfg, false, true><<<persistent_grid(primary_edge_kernel<kCfg, false, true>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, dimg);
+            return cudaGetLastError();
+        }
         if (use_big_cta(n, kBlockP)) primary_edge_kernel<kCfg, true><<<persistent_grid(primary_edge_kernel<kCfg, true>, kBlockP, 0, n), kBlockP, 0, st>>>(sc, cam, rp, dimg);
         else primary_edge_kernel<kCfg, false><<<persistent_grid(primary_edge_kernel<kCfg, false>, kBlock, 0, n), kBlock, 0, st>>>(sc, cam, rp, dimg);
         return cudaGetLastError();

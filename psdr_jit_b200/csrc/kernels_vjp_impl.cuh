@@ -45,7 +45,8 @@ constexpr int kBlockV = 128;
 constexpr int kBlockIV = PSDR_BLOCK_IVJP, kBlockPV = PSDR_BLOCK_PVJP, kBlockSV = PSDR_BLOCK_SVJP;
 
 // kBig: the large-CTA shape with block barriers (above); else 128 threads, for launches too small to fill it
-template <int kCfg, int kD, bool kBig>
+// kColloc: CollocatedIntegrator (device_path.cuh Li_collocated): the "path" is the primary hit alone; 128-thread shape only
+template <int kCfg, int kD, bool kBig, bool kColloc = false>
 __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP : 5) interior_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                 const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                 const float *__restrict__ d_img) {
@@ -95,7 +96,14 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
         const V3f o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f)), d = xform_dir(cam.to_world, dc);
         PathRecord<kD> R;
         R.reset();
-        const V3f v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, R, 0xffffffffu, rp.mis, kSync >= 2);
+        V3f v(0.f, 0.f, 0.f);
+        if (kColloc) {
+            const Its<float> its = ray_intersect<float, kCfg, true>(sc, o, d, live, false);
+            if (its.valid) {
+                R.vertex(0, its.tri, its.bu, its.bv);
+                v = bsdf_eval<float, kCfg>(sc, its, its.wi, true) / sqr(its.t) * sc.colloc_intensity;
+            }
+        } else v = Li<float, kCfg, true, PathRecord<kD>>(sc, rng, o, d, live, rp.max_depth, rp.hide_emitters != 0, R, 0xffffffffu, rp.mis, kSync >= 2);
         // cotangent of this lane's value; channels the forward pass scrubbed (non-finite) carry none
         V3f g(__ldg(d_img + 3 * idx) * inv_spp, __ldg(d_img + 3 * idx + 1) * inv_spp, __ldg(d_img + 3 * idx + 2) * inv_spp);
         if (!isfinite(v.x)) g.x = 0.f;
@@ -104,13 +112,13 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
         const bool has_cotangent = !(g.x == 0.f && g.y == 0.f && g.z == 0.f);
         if (kSync) __syncthreads();
         else __syncwarp();
-        path_adjoint<kD, kCfg>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, live && has_cotangent);
+        path_adjoint<kD, kCfg, kColloc>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, live && has_cotangent);
     }
     if (dynamic) sched.finish();
     grad_acc_end(acc);
 }
 
-template <int kCfg, bool kBig>
+template <int kCfg, bool kBig, bool kColloc = false>
 __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP : 8) primary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                     const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                     const float *__restrict__ d_img) {
@@ -151,7 +159,8 @@ __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px + sg * bq.x, py + sg * bq.y), ro, rd);
-            Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis);
+            if (kColloc) Lside[side] = Li_collocated<float, kCfg, false>(sc, ro, rd, valid);
+            else Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis);
         }
         if (!valid) continue;
         const int pix = iy * sc.width + ix;
@@ -228,6 +237,11 @@ template <int kCfg> struct AdjointLaunch {
         RenderParams rq = rp;
         rq.smem_grad = gl.off_pe <= kSmemGradMaxFloats ? 1 : 0;
         const size_t bytes = rq.smem_grad ? sizeof(float) * gl.off_pe : 0;
+        if (rp.mis == 3) {      // CollocatedIntegrator
+            const long long n = rq.lane_end - rq.lane_begin;
+            interior_vjp_kernel<kCfg, 1, false, true><<<vjp_grid(interior_vjp_kernel<kCfg, 1, false, true>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+            return cudaGetLastError();
+        }
         if (rp.max_depth > 4) interior_as<8>(sc, cam, rq, gl, d_img, bytes, st);
         else interior_as<4>(sc, cam, rq, gl, d_img, bytes, st);
         return cudaGetLastError();
@@ -238,6 +252,10 @@ template <int kCfg> struct AdjointLaunch {
         rq.smem_grad = n <= kSmemGradMaxFloats ? 1 : 0;
         const size_t bytes = rq.smem_grad ? sizeof(float) * n : 0;
         const long long lanes = rp.lane_end - rp.lane_begin;
+        if (rp.mis == 3) {      // CollocatedIntegrator
+            primary_edge_vjp_kernel<kCfg, false, true><<<vjp_grid(primary_edge_vjp_kernel<kCfg, false, true>, bytes, lanes), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+            return cudaGetLastError();
+        }
         if (vjp_big_cta(lanes, kBlockPV)) primary_edge_vjp_kernel<kCfg, true><<<vjp_grid(primary_edge_vjp_kernel<kCfg, true>, bytes, lanes, kBlockPV), kBlockPV, bytes, st>>>(sc, cam, rq, gl, d_img);
         else primary_edge_vjp_kernel<kCfg, false><<<vjp_grid(primary_edge_vjp_kernel<kCfg, false>, bytes, lanes), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
         return cudaGetLastError();

@@ -278,6 +278,7 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
     }
     for (size_t i = 0; i < emitters.size(); ++i)
         for (int c = 0; c < 3; ++c) grads.emitter_rad[3 * i + c] = table[gl.off_emit + 4 * i + c];
+    grads.colloc_intensity = table[gl.off_cam + 38];
     grads.env_radiance.clear();
     grads.env_scale = 0.0;
     std::memset(grads.env_to_world_left, 0, sizeof(grads.env_to_world_left));
