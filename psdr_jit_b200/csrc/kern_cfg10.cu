@@ -5,9 +5,6 @@
 
 namespace psdr {
 namespace fwd10 {
-cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, bool ad, float *img, float *dimg, cudaStream_t st) {
-    return ForwardLaunch<10>::interior(sc, cam, rp, ad, img, dimg, st);
-}
 cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) { return ForwardLaunch<10>::primary(sc, cam, rp, dimg, st); }
 cudaError_t secondary(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *dimg, cudaStream_t st) { return ForwardLaunch<10>::secondary(sc, cam, rp, dimg, st); }
 cudaError_t guiding(const DScene &sc, const DCamera &cam, const int reso[4], int nrounds, long long seed, float *mass, cudaStream_t st) {

@@ -4,9 +4,6 @@
 
 namespace psdr {
 namespace vjp11 {
-cudaError_t interior(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
-    return AdjointLaunch<11>::interior(sc, cam, rp, gl, d_img, st);
-}
 cudaError_t primary(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st) {
     return AdjointLaunch<11>::primary(sc, cam, rp, gl, d_img, st);
 }
