@@ -108,8 +108,10 @@ int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis);
 /* CollocatedIntegrator(intensity) -- src/psdr.cpp:427-429, src/integrator/collocated.cpp:21-53: a point light at the camera;
  * Li = BSDF(wi, wo = wi) * intensity / t^2 at the primary hit, no emitters, no random numbers in Li, no secondary-edge
  * term (Integrator::render_secondary_edges is empty, include/psdr/integrator/integrator.h:22).  d_intensity: forward-mode
- * tangent of m_intensity.  The following render calls (max_depth ignored) evaluate it until psdr_scene_set_integrator. */
-int psdr_scene_set_integrator_collocated(psdr_scene *s, float intensity, float d_intensity);
+ * tangent of m_intensity.  The following render calls (max_depth ignored) evaluate it until psdr_scene_set_integrator.
+ * bsdf_field = 1: the "bsdf" field of FieldExtractionIntegrator (src/integrator/field.cpp:72-92) -- the BSDF term alone,
+ * without intensity / t^2 (forward mode only). */
+int psdr_scene_set_integrator_collocated(psdr_scene *s, float intensity, float d_intensity, int bsdf_field);
 /* Multi-GPU output fusion (new: SURVEY.md 8e).  on = 1 or 2: the img / dimg pointers of psdr_render_c / psdr_render_d and the
  * grad_table pointer of psdr_render_vjp_device are NVLS MULTICAST addresses of a buffer that every rank of the node has
  * mapped (cuMulticast* / torch symmetric memory).  The term kernels then accumulate with multimem.red: the NVSwitch adds

@@ -233,6 +233,7 @@ struct Scene {
     int mis = 2;             // 2: PathTracer / Direct(2); 0 / 1: Direct(0) / Direct(1) (reference src/integrator/direct.cpp);
                              // 3: CollocatedIntegrator (reference src/integrator/collocated.cpp)
     Dual colloc_intensity = Dual(0.f);
+    bool colloc_field = false;   // FieldExtractionIntegrator("bsdf") (field.cpp:72-92): the BSDF term alone
 };
 
 // The product's closest-hit query (psdr_jit_b200/csrc/device_path.cuh trace<brute>, the replacement of OptiX) tests a
@@ -1516,6 +1517,7 @@ static V3<S> Li(const Scene &sc, Pcg32 &rng, V3<S> ro, V3<S> rd, bool active, in
     active = active && its.valid;
     if (sc.mis == 3) {   // CollocatedIntegrator::__Li (collocated.cpp:21-53): evalD(its, its.wi) / sqr(its.t) * m_intensity
         if (!active) return V3<S>(S(0.f));
+        if (sc.colloc_field) return bsdf_eval<S>(sc, its, its.wi, true);
         return bsdf_eval<S>(sc, its, its.wi, true) / sqr(its.t) * lift_d<S>(sc.colloc_intensity);
     }
     V3<S> throughput(S(1.f));
@@ -1835,9 +1837,10 @@ void orc_destroy(void *h) { delete (Scene *) h; }
 const char *orc_error(void *h) { return ((Scene *) h)->error.c_str(); }
 void orc_set_li_order(void *h, int p_first) { ((Scene *) h)->li_p_first = p_first != 0; }
 void orc_set_mis(void *h, int mis) { ((Scene *) h)->mis = mis; }
-void orc_set_collocated(void *h, float intensity, float d_intensity) {
+void orc_set_collocated(void *h, float intensity, float d_intensity, int bsdf_field) {
     ((Scene *) h)->mis = 3;
     ((Scene *) h)->colloc_intensity = Dual(intensity, d_intensity);
+    ((Scene *) h)->colloc_field = bsdf_field != 0;
 }
 
 int orc_add_diffuse(void *h, const float *refl, const float *d_refl, int two_side) {

@@ -38,7 +38,7 @@ def lib():
         L.orc_error.argtypes = [C.c_void_p]
         L.orc_set_li_order.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_mis.argtypes = [C.c_void_p, C.c_int]
-        L.orc_set_collocated.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.orc_set_collocated.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int]
         L.orc_add_diffuse.argtypes = [C.c_void_p, _f, _f, C.c_int]
         L.orc_add_microfacet.argtypes = [C.c_void_p, _f, _f, C.c_float, _f, C.c_int]
         L.orc_aov_d.argtypes = [C.c_void_p, C.c_int, C.c_int, _f, _f]
@@ -215,9 +215,10 @@ class OracleScene:
         if rc:
             raise RuntimeError(self.L.orc_error(self.h).decode())
 
-    def set_collocated(self, intensity, d_intensity=0.0):
-        """CollocatedIntegrator(intensity) (reference src/integrator/collocated.cpp); render with any depth"""
-        self.L.orc_set_collocated(self.h, float(intensity), float(d_intensity))
+    def set_collocated(self, intensity, d_intensity=0.0, bsdf_field=False):
+        """CollocatedIntegrator(intensity) (reference src/integrator/collocated.cpp); render with any depth.
+        bsdf_field: FieldExtractionIntegrator("bsdf") (src/integrator/field.cpp:72-92), the BSDF term alone"""
+        self.L.orc_set_collocated(self.h, float(intensity), float(d_intensity), int(bool(bsdf_field)))
 
     def set_mis(self, mis=2):
         """2: PathTracer / Direct(2); 0 / 1: Direct(0) / Direct(1) -- render with depth 1"""

@@ -971,6 +971,16 @@ class Scene(Object):
     def grad_of(self, name: str, field: str) -> np.ndarray:
         """Gradient of the last adjoint pass for ``scene.param_map[name].<field>`` (drjit.grad in the reference)."""
         obj = self.param_map[name]
+        if "." in field and field.rsplit(".", 1)[1] in ("scale", "rotate", "translate") and isinstance(obj, BSDF):
+            # the uv transform of a bitmap-valued slot (reference include/psdr/core/bitmap.h:36-38)
+            attr, what = field.rsplit(".", 1)
+            slots = {"reflectance": 0, "diffuseReflectance": 0, "normal_map": 0, "specularReflectance": 1, "specular_reflectance": 1,
+                     "roughness": 2, "alpha_u": 2}
+            bm = getattr(obj, attr, None)
+            if attr in slots and isinstance(bm, _Bitmap) and bm._textured():
+                g = self._read_grad(_lib.BSDF_REFLECTANCE_UV + slots[attr], self._bsdfs.index(obj), (4,))
+                return {"scale": g[0:1], "rotate": g[1:2], "translate": g[2:4]}[what].copy()
+            raise RuntimeError("no bitmap-valued field %s on %s" % (attr, name))
         for kind_name, objs in self._objects():
             for i, o in enumerate(objs):
                 if o is obj and isinstance(o, MicrofacetBSDFPerVertex):
@@ -1292,7 +1302,7 @@ class CollocatedIntegrator(Integrator):
     def _check(self, scene: Scene):
         if scene._h is None or not scene.is_ready():
             raise RuntimeError("Input scene must be configured!")
-        _lib.check(_lib.load().psdr_scene_set_integrator_collocated(scene._h, float(_f32(self.m_intensity).ravel()[0]), float(_f32(self.d_m_intensity).ravel()[0])))
+        _lib.check(_lib.load().psdr_scene_set_integrator_collocated(scene._h, float(_f32(self.m_intensity).ravel()[0]), float(_f32(self.d_m_intensity).ravel()[0]), 0))
 
     def _own_leaves(self):
         t = self.m_intensity
@@ -1322,12 +1332,23 @@ class FieldExtractionIntegrator(Integrator):
         tok = field.split()
         if not tok or tok[0] not in self.FIELDS + ("bsdf",):
             raise RuntimeError("Unsupported field: " + (tok[0] if tok else ""))
-        if tok[0] == "bsdf":
-            raise NotImplementedError("FieldExtractionIntegrator('bsdf') is not implemented")
+        if tok[0] == "bsdf" and len(tok) > 1:
+            raise NotImplementedError("FieldExtractionIntegrator('bsdf <object>'): the object filter is not implemented for this field")
         self.field, self.object = tok[0], (tok[1] if len(tok) > 1 else "")
         self.max_depth = 0
 
+    def _check(self, scene: Scene):
+        if self.field != "bsdf":
+            return super()._check(scene)
+        # the "bsdf" field (field.cpp:72-92) is BSDF(wi, wi) at the primary hit: the CollocatedIntegrator's kernels without
+        # intensity / t^2
+        if scene._h is None or not scene.is_ready():
+            raise RuntimeError("Input scene must be configured!")
+        _lib.check(_lib.load().psdr_scene_set_integrator_collocated(scene._h, 1.0, 0.0, 1))
+
     def renderC(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        if self.field == "bsdf":
+            return Integrator.renderC(self, scene, sensor_id, seed, batch_pix)
         torch = self._torch()
         spp = max(scene.opts.spp, 1)
         a = self.render_aov(scene, sensor_id, 0 if seed < 0 else seed).view(-1, spp, 14)
@@ -1347,6 +1368,8 @@ class FieldExtractionIntegrator(Integrator):
 
     def renderD_fwd(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL):
         """(field image, forward-mode derivative image) -- Integrator::renderD with Li = the field (field.cpp:47-121)."""
+        if self.field == "bsdf":
+            return Integrator.renderD_fwd(self, scene, sensor_id, seed, batch_pix, terms & ~_lib.TERM_SECONDARY_EDGES)
         self._check(scene)
         torch = self._torch()
         dev, st = self._dev_stream(torch, scene)

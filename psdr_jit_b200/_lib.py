@@ -64,7 +64,7 @@ def load():
     L.psdr_scene_set_accel.argtypes = [vp, i]
     L.psdr_scene_set_reference_arithmetic.argtypes = [vp, i]
     L.psdr_scene_set_integrator.argtypes = [vp, i, i]
-    L.psdr_scene_set_integrator_collocated.argtypes = [vp, f, f]
+    L.psdr_scene_set_integrator_collocated.argtypes = [vp, f, f, i]
     L.psdr_scene_set_output_multicast.argtypes = [vp, i]
     L.psdr_set_cta_policy.argtypes = [i]
     L.psdr_scene_add_bsdf_diffuse.argtypes = [vp, C.c_char_p, P_F, i]

@@ -324,10 +324,27 @@ __device__ __forceinline__ void tex_slot_grad(const GradAcc &acc, const GradLayo
         if (t.ch == 1) acc.add(tbase + idx[k], value_bar.x * bw[k]);
         else acc.add3(tbase + 3 * idx[k], value_bar * bw[k]);
     }
-    const V3d ru = tex_eval_uv<Dual>(t, false, V2d(Dual(uv.x, 1.f), Dual(uv.y)));
-    const V3d rv = tex_eval_uv<Dual>(t, false, V2d(Dual(uv.x), Dual(uv.y, 1.f)));
+    // derivatives of the lookup w.r.t. the texture coordinate and w.r.t. the bitmap's uv transform (scale, rotation,
+    // translation: bitmap.cpp:64-72): six dual evaluations on a copy of the slot WITHOUT the forward-mode tangents a user
+    // may have set on the transform.  The four transform gradients follow the slot's texels in the table.
+    DTex q = t;
+    q.d_cr = q.d_sr = q.d_scale = q.d_tx = q.d_ty = 0.f;
+    q.ddata = nullptr;
+    const V3d ru = tex_eval_uv<Dual>(q, false, V2d(Dual(uv.x, 1.f), Dual(uv.y)));
+    const V3d rv = tex_eval_uv<Dual>(q, false, V2d(Dual(uv.x), Dual(uv.y, 1.f)));
     uv_bar.x += value_bar.x * ru.x.d + value_bar.y * ru.y.d + value_bar.z * ru.z.d;
     uv_bar.y += value_bar.x * rv.x.d + value_bar.y * rv.y.d + value_bar.z * rv.z.d;
+    const int ubase = tbase + t.ch * t.w * t.h;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        DTex qk = q;
+        if (k == 0) qk.d_scale = 1.f;
+        else if (k == 1) { qk.d_cr = -q.sr; qk.d_sr = q.cr; }      // d cos(rot), d sin(rot)
+        else if (k == 2) qk.d_tx = 1.f;
+        else qk.d_ty = 1.f;
+        const V3d r = tex_eval_uv<Dual>(qk, false, V2d(Dual(uv.x), Dual(uv.y)));
+        acc.add(ubase + k, value_bar.x * r.x.d + value_bar.y * r.y.d + value_bar.z * r.z.d);
+    }
 }
 // d(sum_c W_c f_c * scale)/d(params): reflectance (Diffuse / Microfacet diffuse), Microfacet specular + roughness;
 // constants go to the BSDF block of the table, textured slots to their texel blocks.

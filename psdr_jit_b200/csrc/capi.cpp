@@ -148,10 +148,11 @@ int psdr_scene_set_integrator(psdr_scene *s, int kind, int mis) {
     return 0;
 }
 
-int psdr_scene_set_integrator_collocated(psdr_scene *s, float intensity, float d_intensity) {
+int psdr_scene_set_integrator_collocated(psdr_scene *s, float intensity, float d_intensity, int bsdf_field) {
     if (!s) return fail("null scene");
     s->sc.integrator_mis = 3;
     s->sc.colloc_intensity = Dual(intensity, d_intensity);
+    s->sc.colloc_field = bsdf_field != 0;
     return 0;
 }
 
@@ -663,6 +664,7 @@ void begin_render(Scene &sc, int sensor, long long seed, const int *pix_id, bool
     for (int k = 0; k < 3; ++k) rp[k].mis = mis;
     sc.dscene.colloc_intensity = sc.colloc_intensity.v;
     sc.dscene.d_colloc_intensity = sc.colloc_intensity.d;
+    sc.dscene.colloc_field = sc.colloc_field ? 1 : 0;
     if (pix_id && seed == -1) throw std::runtime_error("While using batch rendering, seed must be set!");
     if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
     if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
@@ -842,6 +844,7 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
     cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
     if (!d_img) throw std::runtime_error("null cotangent image");
     if (max_depth > 8) throw std::runtime_error("the adjoint supports max_depth <= 8");
+    if (sc.integrator_mis == 3 && sc.colloc_field) throw std::runtime_error("FieldExtractionIntegrator has no reverse mode: use the forward-mode derivative image");
     RenderParams rp[3];
     for (auto &r : rp) {
         r = RenderParams{};
@@ -1025,6 +1028,11 @@ int psdr_scene_get_grad(psdr_scene *s, int kind, int index, float *out, int n) {
             if (index < 0 || index >= (int) g.bsdf_pv.size() || g.bsdf_pv[index].empty()) return fail("not a MicrofacetBSDFPerVertex");
             return copy_tex(g.bsdf_pv[index]);
         case PSDR_INTEGRATOR_INTENSITY: return copy(&g.colloc_intensity, 1);
+        case PSDR_BSDF_REFLECTANCE_UV: case PSDR_BSDF_SPECULAR_UV: case PSDR_BSDF_ROUGHNESS_UV: {
+            const int k = kind - PSDR_BSDF_REFLECTANCE_UV;
+            if (index < 0 || index >= (int) g.bsdf_tex_uv[k].size() || g.bsdf_tex_uv[k][index].empty()) return fail("the slot holds a constant: no uv transform");
+            return copy_tex(g.bsdf_tex_uv[k][index]);
+        }
         case PSDR_EMITTER_RADIANCE:
             if (index < 0 || 3 * index + 3 > (int) g.emitter_rad.size()) return fail("invalid emitter index");
             return copy(g.emitter_rad.data() + 3 * index, 3);

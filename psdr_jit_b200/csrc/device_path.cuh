@@ -1559,7 +1559,9 @@ template <class S, int kCfg, bool kAD>
 __device__ __forceinline__ V3<S> Li_collocated(const DScene &sc, V3<S> ro, V3<S> rd, bool active) {
     const Its<S> its = ray_intersect<S, kCfg, kAD>(sc, ro, rd, active, false);
     if (!(active && its.valid)) return V3<S>(S(0.f));
-    return bsdf_eval<S, kCfg>(sc, its, its.wi, true) / sqr(its.t) * bsdf_scalar<S>(sc.colloc_intensity, sc.d_colloc_intensity);
+    const V3<S> f = bsdf_eval<S, kCfg>(sc, its, its.wi, true);
+    if (sc.colloc_field) return f;      // FieldExtractionIntegrator("bsdf") (reference src/integrator/field.cpp:72-92)
+    return f / sqr(its.t) * bsdf_scalar<S>(sc.colloc_intensity, sc.d_colloc_intensity);
 }
 
 // ---- secondary (shadow) edges: reference src/scene/scene.cpp:1027-1068, src/integrator/path.cpp:172-270

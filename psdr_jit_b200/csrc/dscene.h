@@ -128,6 +128,7 @@ struct DScene {
     int full_features;       // 1: some BSDF is a Microfacet or an EnvironmentMap exists (selects the kernel variant)
     int ext_features;        // 1: bitmap-valued BSDF slots or a BSDF of type >= 2 (kCfgExt kernel family; implies full_features)
     float colloc_intensity, d_colloc_intensity;   // CollocatedIntegrator::m_intensity and its forward tangent (RenderParams::mis == 3)
+    int colloc_field;        // 1: the "bsdf" field of FieldExtractionIntegrator -- BSDF(wi, wi) alone, no intensity / t^2 (field.cpp:72-92)
     const float4 *geo, *shade, *dgeo, *dshade;
     const float2 *uv;
     const int *face_idx;     // 3 mesh-local vertex indices per triangle (MicrofacetPerVertex gathers through them); nullptr if unused

@@ -138,6 +138,7 @@ struct ParamGrads {
     std::vector<double> bsdf_rough;                          // 1 per BSDF
     std::vector<float> env_radiance;                         // 3*w*h
     std::vector<std::vector<float>> bsdf_tex[3];             // per BSDF and texture slot: channels*w*h (empty: not textured)
+    std::vector<std::vector<float>> bsdf_tex_uv[3];          // per BSDF and textured slot: d/d(scale, rotation, translate.x, translate.y)
     std::vector<std::vector<float>> bsdf_pv;                 // per BSDF: 7 floats per vertex (MicrofacetPerVertex; empty otherwise)
     double env_scale = 0.0, env_to_world_left[16] = {};
     double colloc_intensity = 0.0;                           // CollocatedIntegrator::m_intensity
@@ -173,6 +174,7 @@ struct Scene {
     int bvh_builds = 0, bvh_refits = 0;   // host topology builds / GPU refits so far (psdr_scene_query)
     int integrator_mis = 2;    // 2 PathTracer / Direct(2); 0, 1: Direct(0), Direct(1); 3: CollocatedIntegrator (psdr_scene_set_integrator)
     Dual colloc_intensity = Dual(0.f);   // CollocatedIntegrator::m_intensity
+    bool colloc_field = false;           // FieldExtractionIntegrator("bsdf"): the BSDF term alone
     int out_multicast = 0;        // outputs are NVLS multicast addresses: 1 = same layout, 2 = float4 pixels (psdr_scene_set_output_multicast)
     bool ref_rcp = false;      // reference arithmetic for the analytic primary hit (psdr_scene_set_reference_arithmetic)
     DeviceBuffers *dev = nullptr;

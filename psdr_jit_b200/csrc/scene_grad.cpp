@@ -113,6 +113,12 @@ void transform_pos_adj(const Mat &M, D3 p, D3 gq, D3 &gp, Mat &gM) {
 
 }  // namespace
 
+// gradient block of a textured slot: its texels, then 4 floats for the bitmap's uv transform (scale, rotation, translation)
+static int tex_block_floats(const HBsdf &b, int slot) {
+    const HBsdf::Tex &t = b.tex[slot];
+    return t.w > 0 ? HBsdf::tex_channels(slot) * t.w * t.h + 4 : 0;
+}
+
 int Scene::pervertex_grad_offset(int bsdf) const {
     int back = 0;
     for (int i = num_bsdf_records() - 1; i >= bsdf; --i) back += (int) bsdf_record(i).pv.size();
@@ -125,7 +131,7 @@ int Scene::texture_grad_offset(int bsdf, int slot) const {
     // the END of the table
     int back = -pervertex_grad_offset(0);
     for (int i = num_bsdf_records() - 1; i >= bsdf; --i)
-        for (int k = 2; k >= (i == bsdf ? slot : 0); --k) back += HBsdf::tex_channels(k) * bsdf_record(i).tex[k].w * bsdf_record(i).tex[k].h;
+        for (int k = 2; k >= (i == bsdf ? slot : 0); --k) back += tex_block_floats(bsdf_record(i), k);
     return -back;   // negative: relative to GradLayout::total
 }
 
@@ -143,7 +149,7 @@ GradLayout Scene::grad_layout(int sensor) const {
     gl.off_env = gl.off_se + 6 * (int) sec_edges.size();
     gl.total = gl.off_env + (env.present ? kGradEnvHead + 3 * env.w * env.h : 0);
     for (int i = 0; i < num_bsdf_records(); ++i)
-        for (int k = 0; k < 3; ++k) gl.total += HBsdf::tex_channels(k) * bsdf_record(i).tex[k].w * bsdf_record(i).tex[k].h;      // same order as texture_grad_offset()
+        for (int k = 0; k < 3; ++k) gl.total += tex_block_floats(bsdf_record(i), k);      // same order as texture_grad_offset()
     for (int i = 0; i < num_bsdf_records(); ++i) gl.total += (int) bsdf_record(i).pv.size();
     return gl;
 }
@@ -251,10 +257,13 @@ void Scene::backprop(const float *table, const GradLayout &gl, int sensor) {
     }
     for (int k = 0; k < 3; ++k) {
         grads.bsdf_tex[k].assign((size_t) num_bsdf_records(), std::vector<float>());
+        grads.bsdf_tex_uv[k].assign((size_t) num_bsdf_records(), std::vector<float>());
         for (size_t i = 0; i < (size_t) num_bsdf_records(); ++i)
             if (bsdf_record((int) i).tex[k].w > 0) {
                 const float *g = table + gl.total + texture_grad_offset((int) i, k);
-                grads.bsdf_tex[k][i].assign(g, g + (size_t) HBsdf::tex_channels(k) * bsdf_record((int) i).tex[k].w * bsdf_record((int) i).tex[k].h);
+                const size_t nt = (size_t) HBsdf::tex_channels(k) * bsdf_record((int) i).tex[k].w * bsdf_record((int) i).tex[k].h;
+                grads.bsdf_tex[k][i].assign(g, g + nt);
+                grads.bsdf_tex_uv[k][i].assign(g + nt, g + nt + 4);
             }
     }
     grads.bsdf_pv.assign((size_t) num_bsdf_records(), std::vector<float>());

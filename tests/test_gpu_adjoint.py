@@ -25,9 +25,10 @@ def _scene_with_tangents(psdr, meshes, w, h, spps, rng, what):
     if "slots" in what:        # all three bitmap slots of the Microfacet BSDFs textured, with uv transforms (no transform tangents)
         from tests.test_gpu_parity import _slot_textures
         slot_tex = _slot_textures(with_tangent=True)
-        for n in slot_tex:
-            for k in slot_tex[n]:
-                slot_tex[n][k].pop("d_xform", None)
+        if "xform" not in what:      # "slots xform": the tangents of the bitmaps' uv transforms stay in
+            for n in slot_tex:
+                for k in slot_tex[n]:
+                    slot_tex[n][k].pop("d_xform", None)
         textures, mf = slot_tex, True
     sc = build_product(meshes, w, h, *spps, bsdfs=scenes.CBOX_MF_BSDFS if mf else None, envmap=envmap, textures=textures)
     tang = {}
@@ -35,7 +36,13 @@ def _scene_with_tangents(psdr, meshes, w, h, spps, rng, what):
         for n in slot_tex:
             for k, field in ((0, "diffuseReflectance.data"), (1, "specularReflectance.data"), (2, "roughness.data")):
                 tang[("BSDF[id=%s]" % n, field)] = slot_tex[n][k]["d_data"]
-        what = [x for x in what if x != "slots"]
+                dx = slot_tex[n][k].get("d_xform")
+                if dx is not None:      # (scale, rotate, translate.x, translate.y) of the slot's bitmap
+                    base = field[:-len(".data")]
+                    tang[("BSDF[id=%s]" % n, base + ".scale")] = np.float32(dx[0:1])
+                    tang[("BSDF[id=%s]" % n, base + ".rotate")] = np.float32(dx[1:2])
+                    tang[("BSDF[id=%s]" % n, base + ".translate")] = np.float32(dx[2:4])
+        what = [x for x in what if x not in ("slots", "xform")]
         textures = None
     if textures is not None:
         for n in textures:
@@ -106,7 +113,7 @@ CASES = [
     ("microfacet", 1, 3, "cbox"), ("microfacet mesh_left vertices camera", 1, 2, "cbox"),
     ("microfacet mesh_left vertices camera", 7, 2, "sphere"),
     ("textures", 1, 2, "cbox"), ("textures camera mesh_left", 7, 2, "cbox"), ("textures microfacet camera", 1, 3, "cbox"),
-    ("slots", 1, 2, "cbox"), ("slots camera mesh_left", 7, 3, "cbox"),
+    ("slots", 1, 2, "cbox"), ("slots camera mesh_left", 7, 3, "cbox"), ("slots xform", 1, 2, "cbox"), ("slots xform camera mesh_left", 7, 2, "cbox"),
     ("envmap", 1, 2, "cbox"), ("envmap microfacet", 1, 3, "cbox"), ("envmap microfacet mesh_left vertices camera", 7, 3, "cbox"),
 ]
 

@@ -142,3 +142,18 @@ def test_autograd_intensity_leaf():
     img = integ.renderD(sc, 0, seed=1)
     img.sum().backward()
     assert inten.grad is not None and abs(float(inten.grad) - float(img.sum()) / 5e5) < 1e-4 * abs(float(inten.grad))
+
+
+def test_bsdf_field_vs_oracle():
+    """FieldExtractionIntegrator("bsdf") (reference src/integrator/field.cpp:72-92): BSDF(wi, wi) at the primary hit"""
+    import psdr_jit_b200 as psdr
+    kw = dict(move_mesh=1, axis_scale=(30.0, 10.0, 0.0), bsdfs=MF)
+    osc = build_oracle(scenes.cbox_meshes(), 96, 96, 4, 4, 0, **kw)
+    osc.set_collocated(1.0, 0.0, bsdf_field=True)
+    img_ref, dimg_ref = osc.render(1, seed=5, mode=1, terms=3)
+    sc = build_product(scenes.cbox_meshes(), 96, 96, 4, 4, 0, **kw)
+    integ = psdr.FieldExtractionIntegrator("bsdf")
+    img = integ.renderD(sc, 0, seed=5)
+    assert rel_l2(img.cpu().numpy(), img_ref) < 1e-5
+    assert np.abs(dimg_ref).max() > 0 and rel_l2(integ.grad_image.cpu().numpy(), dimg_ref) < 1e-4
+    assert float(img.max()) < 2.0          # a BSDF value, not a radiance
