@@ -210,6 +210,11 @@ int psdr_scene_add_perspective(psdr_scene *s, float fov_x, float near_clip, floa
  * src/sensor/perspective.cpp:15-20, include/psdr/core/transform.h:63-71: pinhole intrinsics in units of the image size
  * (focal lengths fx, fy and principal point cx, cy as fractions of width / height). */
 int psdr_scene_add_perspective_intrinsic(psdr_scene *s, float fx, float fy, float cx, float cy, float near_clip, float far_clip, const float *to_world);
+/* Scene.add_Sensor(OrthographicCamera(near, far)) -- src/psdr.cpp:375-383, src/sensor/orthographic.cpp: rays leave the
+ * sample's point on the near plane along the camera's +z; the view volume is 2 x 2/aspect camera units (the sensor transform
+ * may not scale, sensor.cpp:12-13).  Everything else -- sample_direct, the primary-edge list -- is the perspective camera's
+ * code in the reference (orthographic.cpp:46-104,134-175) and here. */
+int psdr_scene_add_orthographic(psdr_scene *s, float near_clip, float far_clip, const float *to_world);
 
 /* Writes through Scene.param_map[...] (README.md:87-90): new primal value of a parameter ... */
 int psdr_scene_set_param(psdr_scene *s, int kind, int index, const float *value, int n);

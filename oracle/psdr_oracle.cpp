@@ -194,6 +194,7 @@ struct SecEdge {  // edge.h:49-66
 
 struct Camera {
     float fov, near_, far_;
+    bool ortho = false;           // OrthographicCamera(near, far) (src/sensor/orthographic.cpp)
     bool use_intrinsic = false;   // PerspectiveCamera(fx, fy, cx, cy, near, far) (include/psdr/sensor/perspective.h:11-12)
     float fx = 0.f, fy = 0.f, cx = 0.f, cy = 0.f;
     M4<Dual> to_world[3];
@@ -403,8 +404,14 @@ static bool configure_camera(Scene &sc, Camera &cam, bool build_primary_edges) {
         sc_.m[1][1] = -0.5f;
         tr.m[1][3] = -1.f;
     }
-    M4<float> c2s = (sc_ * tr) * (cam.use_intrinsic ? perspective_intrinsic(cam.fx, cam.fy, cam.cx, cam.cy, cam.near_, cam.far_)
-                                                    : perspective(cam.fov, cam.near_, cam.far_));
+    M4<float> proj;
+    if (cam.ortho) {   // transform::orthographic (transform.h:73-76), orthographic.cpp:17-20
+        M4<float> os = M4<float>::identity(), ot = M4<float>::identity();
+        os.m[2][2] = 1.f / (cam.far_ - cam.near_);
+        ot.m[2][3] = -cam.near_;
+        proj = os * ot;
+    } else proj = cam.use_intrinsic ? perspective_intrinsic(cam.fx, cam.fy, cam.cx, cam.cy, cam.near_, cam.far_) : perspective(cam.fov, cam.near_, cam.far_);
+    M4<float> c2s = (sc_ * tr) * proj;
     M4<Dual> camera_to_sample = lift<Dual>(c2s);
     cam.sample_to_camera = lift<Dual>(inverse(c2s));
     cam.to_world_full = (cam.to_world[0] * cam.to_world[1]) * cam.to_world[2];
@@ -1472,12 +1479,22 @@ static inline float mis_weight(float a, float b) {
 template <class S> static void sample_primary_ray(const Camera &cam, V2f s, V3<S> &o, V3<S> &d);
 template <> void sample_primary_ray<float>(const Camera &cam, V2f s, V3f &o, V3f &d) {
     M4<float> s2c = val(cam.sample_to_camera), tw = val(cam.to_world_full);
+    if (cam.ortho) {   // OrthographicCamera::sample_primary_ray (orthographic.cpp:109-119)
+        o = transform_pos(tw, transform_pos(s2c, V3f(s.x, s.y, 0.f)));
+        d = transform_dir(tw, V3f(0.f, 0.f, 1.f));
+        return;
+    }
     V3f dc = normalize(transform_pos(s2c, V3f(s.x, s.y, 0.f)));
     o = transform_pos(tw, V3f(0.f, 0.f, 0.f));
     d = transform_dir(tw, dc);
 }
 template <> void sample_primary_ray<Dual>(const Camera &cam, V2f s, V3d &o, V3d &d) {
     M4<float> s2c = val(cam.sample_to_camera);
+    if (cam.ortho) {   // orthographic.cpp:122-131
+        o = transform_pos(cam.to_world_full, lift<Dual>(transform_pos(s2c, V3f(s.x, s.y, 0.f))));
+        d = transform_dir(cam.to_world_full, V3d(Dual(0.f), Dual(0.f), Dual(1.f)));
+        return;
+    }
     V3f dc = normalize(transform_pos(s2c, V3f(s.x, s.y, 0.f)));
     o = transform_pos(cam.to_world_full, V3d(Dual(0.f), Dual(0.f), Dual(0.f)));
     d = transform_dir(cam.to_world_full, lift<Dual>(dc));
@@ -2010,6 +2027,12 @@ int orc_add_camera_intrinsic(void *h, float fx, float fy, float cx, float cy, fl
     Camera &c = ((Scene *) h)->cameras[i];
     c.use_intrinsic = true;
     c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy;
+    return i;
+}
+
+int orc_add_camera_orthographic(void *h, float near_, float far_, const float *to_world, const float *d_to_world) {
+    int i = orc_add_camera(h, 0.f, near_, far_, to_world, d_to_world);
+    ((Scene *) h)->cameras[i].ortho = true;
     return i;
 }
 

@@ -53,6 +53,7 @@ def lib():
         L.orc_add_mesh.argtypes = [C.c_void_p, _f, _f, C.c_int, _i, C.c_int, _f, C.c_int, _i, _f, _f, C.c_int, _f, _f, C.c_int, C.c_int]
         L.orc_add_camera.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f, _f]
         L.orc_add_camera_intrinsic.argtypes = [C.c_void_p] + [C.c_float] * 6 + [_f, _f]
+        L.orc_add_camera_orthographic.argtypes = [C.c_void_p, C.c_float, C.c_float, _f, _f]
         L.orc_configure.argtypes = [C.c_void_p, _i, C.c_int]
         L.orc_num_primary_edges.argtypes = [C.c_void_p, C.c_int]
         L.orc_num_secondary_edges.argtypes = [C.c_void_p]
@@ -208,6 +209,11 @@ class OracleScene:
         """PerspectiveCamera(fx, fy, cx, cy, near, far) (reference include/psdr/sensor/perspective.h:11-12)"""
         tw, dtw = _mats(to_world), _dmats(d_to_world)
         return self.L.orc_add_camera_intrinsic(self.h, fx, fy, cx, cy, near, far, _fp(tw), _fp(dtw))
+
+    def add_camera_orthographic(self, near, far, to_world, d_to_world=None):
+        """OrthographicCamera(near, far) (reference src/sensor/orthographic.cpp)"""
+        tw, dtw = _mats(to_world), _dmats(d_to_world)
+        return self.L.orc_add_camera_orthographic(self.h, near, far, _fp(tw), _fp(dtw))
 
     def configure(self, active=(0,)):
         a = np.asarray(list(active), dtype=np.int32)

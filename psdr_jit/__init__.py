@@ -11,7 +11,7 @@ import psdr_jit_b200 as _b
 from psdr_jit_b200 import compat as _compat
 from psdr_jit_b200 import (AreaLight, Bitmap1fD, Bitmap3fD, DiffuseBSDF, EnvironmentMap, Mesh, MicrofacetBSDF, Object,  # noqa: F401
                            RoughConductorBSDF, RoughDielectricBSDF, MicrofacetBSDFPerVertex, NormalMapBSDF,
-                           PerspectiveCamera, RenderOption, Sampler, Scene)
+                           OrthographicCamera, PerspectiveCamera, RenderOption, Sampler, Scene)
 
 STAND_IN_DRJIT = _compat.install()
 __version__ = "0.2.1+b200"

@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib, scenes  # noqa: F401
 from . import loader as _loader
 
-__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "DiffuseBSDF", "MicrofacetBSDF", "RoughConductorBSDF", "RoughDielectricBSDF", "MicrofacetBSDFPerVertex", "NormalMapBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "CollocatedIntegrator", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
+__all__ = ["Scene", "RenderOption", "PerspectiveCamera", "OrthographicCamera", "DiffuseBSDF", "MicrofacetBSDF", "RoughConductorBSDF", "RoughDielectricBSDF", "MicrofacetBSDFPerVertex", "NormalMapBSDF", "AreaLight", "EnvironmentMap", "Bitmap3fD", "Bitmap1fD", "Mesh", "PathTracer", "CollocatedIntegrator", "Direct", "DirectIntegrator", "FieldExtractionIntegrator", "Sampler",
            "Integrator", "Object", "scenes", "kernel_launch_count"]
 
 
@@ -152,6 +152,21 @@ class PerspectiveCamera(_Transformable):
 
     def _clone(self):
         c = PerspectiveCamera(self.fov, self.near, self.far) if self.intrinsics is None else PerspectiveCamera(*self.intrinsics, self.near, self.far)
+        c._copy_transform_from(self)
+        return c
+
+
+class OrthographicCamera(PerspectiveCamera):
+    """reference src/psdr.cpp:375-383, src/sensor/orthographic.cpp: ``OrthographicCamera(near, far)``; rays leave the near
+    plane along the camera's +z, the view volume is 2 x 2/aspect camera units."""
+
+    def __init__(self, near: float, far: float):
+        _Transformable.__init__(self)
+        self.intrinsics = None
+        self.fov, self.near, self.far = 0.0, float(near), float(far)
+
+    def _clone(self):
+        c = OrthographicCamera(self.near, self.far)
         c._copy_transform_from(self)
         return c
 
@@ -823,8 +838,11 @@ class Scene(Object):
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[1] = len(self._events)
         for s in self._sensors[self._pushed[2]:]:
-            rc = (L.psdr_scene_add_perspective(self._h, s.fov, s.near, s.far, _fp(_mat4(s.to_world))) if s.intrinsics is None else
-                  L.psdr_scene_add_perspective_intrinsic(self._h, *s.intrinsics, s.near, s.far, _fp(_mat4(s.to_world))))
+            if isinstance(s, OrthographicCamera):
+                rc = L.psdr_scene_add_orthographic(self._h, s.near, s.far, _fp(_mat4(s.to_world)))
+            else:
+                rc = (L.psdr_scene_add_perspective(self._h, s.fov, s.near, s.far, _fp(_mat4(s.to_world))) if s.intrinsics is None else
+                      L.psdr_scene_add_perspective_intrinsic(self._h, *s.intrinsics, s.near, s.far, _fp(_mat4(s.to_world))))
             if rc < 0:
                 raise RuntimeError(L.psdr_last_error().decode())
         self._pushed[2] = len(self._sensors)

@@ -644,14 +644,15 @@ __device__ __forceinline__ void scatter_isect_tri(const GradAcc &acc, int tri, f
     acc.add3(b + 6, r_bar * (-v));
 }
 // camera ray o = to_world * (0,0,0,1), d = to_world[:3,:3] * d_cam
-__device__ __forceinline__ void scatter_camera_ray(const GradAcc &acc, const GradLayout &gl, V3f dc, V3f o_bar, V3f d_bar) {
+// (oc = camera-space origin: zero for the perspective camera, the near-plane point of the orthographic one)
+__device__ __forceinline__ void scatter_camera_ray(const GradAcc &acc, const GradLayout &gl, V3f dc, V3f o_bar, V3f d_bar, V3f oc = V3f(0.f, 0.f, 0.f)) {
     const int b = gl.off_cam;
-    const float ob[3] = {o_bar.x, o_bar.y, o_bar.z}, db[3] = {d_bar.x, d_bar.y, d_bar.z}, c[3] = {dc.x, dc.y, dc.z};
-    float f[12];      // rows 0..2 of d to_world: (d_bar_i * dc, o_bar_i); twelve consecutive entries = four vector adds
+    const float ob[3] = {o_bar.x, o_bar.y, o_bar.z}, db[3] = {d_bar.x, d_bar.y, d_bar.z}, c[3] = {dc.x, dc.y, dc.z}, q[3] = {oc.x, oc.y, oc.z};
+    float f[12];      // rows 0..2 of d to_world: (d_bar_i * dc + o_bar_i * oc, o_bar_i); twelve consecutive entries = four vector adds
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) f[4 * i + j] = db[i] * c[j];
+        for (int j = 0; j < 3; ++j) f[4 * i + j] = fmaf(ob[i], q[j], db[i] * c[j]);
         f[4 * i + 3] = ob[i];
     }
 #pragma unroll
@@ -816,7 +817,7 @@ __device__ __forceinline__ EventAdj event_adjoint(const GradAcc &acc, const Grad
 // position with "normal" wo there: sum_c g_c f_c(wi, wo = wi) |cos_y| / t^2 * intensity with |cos_y| = 1.
 template <int kD, int kCfg, bool kColloc = false>
 __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout &gl, const GradAcc &acc, const PathRecord<kD> &R, V3f o, V3f d,
-                                             V3f dc, V3f g, bool hide_emitters, bool enabled) {
+                                             V3f dc, V3f g, bool hide_emitters, bool enabled, V3f oc = V3f(0.f, 0.f, 0.f)) {
     // Called by ALL 32 lanes of the warp from warp-uniform control flow (`enabled` = this lane has a path and a
     // cotangent).  The sweep loop below therefore sits at the top level, runs the warp's maximum trip count and
     // re-converges with a full-mask barrier every iteration; everything lane-specific hangs off plain `if`s.
@@ -851,7 +852,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
             if (kFull && sc.emitters[v0geo.emitter].type == 1) {
                 V3f le;
                 d_bar = d_bar + env_le_adjoint(acc, gl, sc.env, d, g, le);
-                if (R.nsh <= 0) scatter_camera_ray(acc, gl, dc, o_bar, d_bar);
+                if (R.nsh <= 0) scatter_camera_ray(acc, gl, dc, o_bar, d_bar, oc);
             } else if (dot(-d, v0geo.shn) > 0.f) add_emitter(v0geo.emitter, g);
         }
     }
@@ -1048,7 +1049,7 @@ __device__ __forceinline__ void path_adjoint(const DScene &sc, const GradLayout 
         acc.add3(b, -r_bar);                                    // scatter_isect_tri
         acc.add3(b + 3, r_bar * (-(sweep ? u0 : 0.f)));
         acc.add3(b + 6, r_bar * (-(sweep ? v0 : 0.f)));
-        scatter_camera_ray(acc, gl, dc, sweep ? o_bar : V3f(0.f, 0.f, 0.f), sweep ? d_bar : V3f(0.f, 0.f, 0.f));
+        scatter_camera_ray(acc, gl, dc, sweep ? o_bar : V3f(0.f, 0.f, 0.f), sweep ? d_bar : V3f(0.f, 0.f, 0.f), oc);
     }
     if (ew != 0u) {
         const int leader = __ffs((int) ew) - 1;
@@ -1107,8 +1108,9 @@ struct SecEdgeAdjoint {
     scatter_isect_tri(acc, its1.tri, its1.bu, its1.bv, r1);
     o_bar = o_bar + r1;
     d_bar = d_bar + r1 * t1;
-    const V3f dc = normalize(xform_pos(cam.sample_to_camera, V3f(q.x, q.y, 0.f)));
-    scatter_camera_ray(acc, adj->gl, dc, o_bar, d_bar);
+    V3f oc, dc;
+    camera_ray_local(cam, q, oc, dc);
+    scatter_camera_ray(acc, adj->gl, dc, o_bar, d_bar, oc);
     }
 };
 

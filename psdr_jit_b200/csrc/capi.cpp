@@ -401,6 +401,13 @@ int psdr_scene_add_perspective_intrinsic(psdr_scene *s, float fx, float fy, floa
     return i;
 }
 
+int psdr_scene_add_orthographic(psdr_scene *s, float near_clip, float far_clip, const float *to_world) {
+    const int i = psdr_scene_add_perspective(s, 0.f, near_clip, far_clip, to_world);
+    if (i < 0) return i;
+    s->sc.cameras[i].ortho = true;
+    return i;
+}
+
 static int set_param_impl(psdr_scene *s, int kind, int index, const float *data, int n, bool tangent) {
     if (!s || !data) return fail("null argument");
     Scene &sc = s->sc;

@@ -1378,14 +1378,23 @@ __device__ __forceinline__ V3d xform_dir_d(const float *M, const float *dM, V3d 
 }
 
 template <class S> __device__ __forceinline__ void sample_primary_ray(const DCamera &cam, V2f s, V3<S> &o, V3<S> &d);
+// the ray in CAMERA space: perspective -- origin 0, direction through the sample on the near plane; orthographic
+// (reference src/sensor/orthographic.cpp:109-131) -- origin = the sample on the near plane, direction +z
+__device__ __forceinline__ void camera_ray_local(const DCamera &cam, V2f s, V3f &oc, V3f &dc) {
+    const V3f q = xform_pos(cam.sample_to_camera, V3f(s.x, s.y, 0.f));
+    if (cam.ortho) { oc = q; dc = V3f(0.f, 0.f, 1.f); }
+    else { oc = V3f(0.f, 0.f, 0.f); dc = normalize(q); }
+}
 template <> __device__ __forceinline__ void sample_primary_ray<float>(const DCamera &cam, V2f s, V3f &o, V3f &d) {
-    const V3f dc = normalize(xform_pos(cam.sample_to_camera, V3f(s.x, s.y, 0.f)));
-    o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f));
+    V3f oc, dc;
+    camera_ray_local(cam, s, oc, dc);
+    o = xform_pos(cam.to_world, oc);
     d = xform_dir(cam.to_world, dc);
 }
 template <> __device__ __forceinline__ void sample_primary_ray<Dual>(const DCamera &cam, V2f s, V3d &o, V3d &d) {
-    const V3f dc = normalize(xform_pos(cam.sample_to_camera, V3f(s.x, s.y, 0.f)));   // detached direction
-    o = xform_pos_d(cam.to_world, cam.d_to_world, V3d(Dual(0.f), Dual(0.f), Dual(0.f)));
+    V3f oc, dc;
+    camera_ray_local(cam, s, oc, dc);                                               // detached in camera space
+    o = xform_pos_d(cam.to_world, cam.d_to_world, lift3<Dual>(oc));
     d = xform_dir_d(cam.to_world, cam.d_to_world, lift3<Dual>(dc));
 }
 

@@ -565,6 +565,7 @@ void upload_scene(Scene &sc) {
         dc.dir[0] = c.dir.x.v; dc.dir[1] = c.dir.y.v; dc.dir[2] = c.dir.z.v;
         dc.d_dir[0] = c.dir.x.d; dc.d_dir[1] = c.dir.y.d; dc.d_dir[2] = c.dir.z.d;
         dc.inv_area = c.inv_area;
+        dc.ortho = c.ortho ? 1 : 0;
         dc.n_edges = (int) c.edges.size();
         dc.edge_sum = c.edges.empty() ? 0.f : c.edge_distrb.sum;
         dc.pe_a = (const float4 *) (base + o_pa) + cam_edge_first[ci];

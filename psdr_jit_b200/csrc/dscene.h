@@ -107,7 +107,7 @@ struct DCamera {
     float inv_area;
     int n_edges;             // primary edges (0 = none / not an active sensor)
     float edge_sum;
-    int pad;
+    int ortho;               // 1: OrthographicCamera -- rays leave the near plane along +z of the camera (orthographic.cpp:109-131)
     // primary edges: pe_a = (p0.x,p0.y,p1.x,p1.y), pe_da = tangents, pe_b = (nx,ny,len,0)
     const float4 *pe_a, *pe_da, *pe_b;
     const float *pe_pmf, *pe_cmf;

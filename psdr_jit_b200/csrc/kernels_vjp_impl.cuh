@@ -92,8 +92,9 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
         const float jy = rng.next_1d(), jx = rng.next_1d();
         const float sx = ((float) (pix % sc.width) + jx) / (float) sc.width;
         const float sy = ((float) (pix / sc.width) + jy) / (float) sc.height;
-        const V3f dc = normalize(xform_pos(cam.sample_to_camera, V3f(sx, sy, 0.f)));
-        const V3f o = xform_pos(cam.to_world, V3f(0.f, 0.f, 0.f)), d = xform_dir(cam.to_world, dc);
+        V3f oc, dc;
+        camera_ray_local(cam, V2f(sx, sy), oc, dc);
+        const V3f o = xform_pos(cam.to_world, oc), d = xform_dir(cam.to_world, dc);
         PathRecord<kD> R;
         R.reset();
         V3f v(0.f, 0.f, 0.f);
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
         const bool has_cotangent = !(g.x == 0.f && g.y == 0.f && g.z == 0.f);
         if (kSync) __syncthreads();
         else __syncwarp();
-        path_adjoint<kD, kCfg, kColloc>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, live && has_cotangent);
+        path_adjoint<kD, kCfg, kColloc>(sc, gl, acc, R, o, d, dc, g, rp.hide_emitters != 0, live && has_cotangent, oc);
     }
     if (dynamic) sched.finish();
     grad_acc_end(acc);

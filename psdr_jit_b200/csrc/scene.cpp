@@ -221,8 +221,15 @@ static void configure_camera(const Scene &sc, HCamera &cam, bool with_primary_ed
         scl.m[1][1] = -0.5f;
         trn.m[1][3] = -1.f;
     }
-    const M4<float> c2s = (scl * trn) * (cam.use_intrinsic ? perspective_intrinsic_matrix(cam.fx, cam.fy, cam.cx, cam.cy, cam.near_, cam.far_)
-                                                           : perspective_matrix(cam.fov, cam.near_, cam.far_));
+    M4<float> proj;
+    if (cam.ortho) {          // transform::orthographic (transform.h:73-76): scale(1, 1, 1 / (far - near)) * translate(0, 0, -near)
+        M4<float> os = M4<float>::identity(), ot = M4<float>::identity();
+        os.m[2][2] = 1.f / (cam.far_ - cam.near_);
+        ot.m[2][3] = -cam.near_;
+        proj = os * ot;
+    } else proj = cam.use_intrinsic ? perspective_intrinsic_matrix(cam.fx, cam.fy, cam.cx, cam.cy, cam.near_, cam.far_)
+                                    : perspective_matrix(cam.fov, cam.near_, cam.far_);
+    const M4<float> c2s = (scl * trn) * proj;
     cam.sample_to_camera = invert(c2s);
     cam.camera_to_sample = c2s;
     cam.to_world_full = (cam.to_world[0] * cam.to_world[1]) * cam.to_world[2];

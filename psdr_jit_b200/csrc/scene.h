@@ -106,6 +106,7 @@ struct HPrimEdge {
 
 struct HCamera {
     float fov = 60.f, near_ = 1e-6f, far_ = 1e7f;
+    bool ortho = false;                  // OrthographicCamera(near, far) (include/psdr/sensor/orthographic.h, src/sensor/orthographic.cpp)
     bool use_intrinsic = false;          // PerspectiveCamera(fx, fy, cx, cy, near, far) (perspective.h:11-12)
     float fx = 0.f, fy = 0.f, cx = 0.f, cy = 0.f;
     M4<Dual> to_world[3];

@@ -107,7 +107,9 @@ def build_oracle(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=None
         if move_mesh is not None and i == move_mesh:
             dtw = {"left": translation_tangent(axis_scale)}
         sc.add_mesh(m.v, m.f, m.bsdf, uv=m.uv, fuv=m.fuv, to_world={"raw": m.to_world}, d_to_world=dtw, radiance=m.emitter)
-    if cam.get("intrinsics") is not None:      # PerspectiveCamera(fx, fy, cx, cy, near, far)
+    if cam.get("ortho"):                       # OrthographicCamera(near, far)
+        sc.add_camera_orthographic(cam["near"], cam["far"], {"raw": cam["to_world"]})
+    elif cam.get("intrinsics") is not None:    # PerspectiveCamera(fx, fy, cx, cy, near, far)
         sc.add_camera_intrinsic(*cam["intrinsics"], cam["near"], cam["far"], {"raw": cam["to_world"]})
     else:
         sc.add_camera(cam["fov"], cam["near"], cam["far"], {"raw": cam["to_world"]})
@@ -124,7 +126,9 @@ def build_product(meshes, w, h, spp, sppe, sppse, move_mesh=None, axis_scale=Non
     sc = psdr.Scene()
     o = sc.opts
     o.width, o.height, o.spp, o.sppe, o.sppse, o.log_level = w, h, spp, sppe, sppse, log_level
-    if cam.get("intrinsics") is not None:
+    if cam.get("ortho"):
+        sensor = psdr.OrthographicCamera(cam["near"], cam["far"])
+    elif cam.get("intrinsics") is not None:
         sensor = psdr.PerspectiveCamera(*cam["intrinsics"], cam["near"], cam["far"])
     else:
         sensor = psdr.PerspectiveCamera(cam["fov"], cam["near"], cam["far"])

@@ -516,3 +516,17 @@ def test_oracle_collocated_vs_reference_golden(oracle):
     osc.set_collocated(float(g["intensity"]))
     d = osc.render(1, seed=0, mode=1, terms=2)[1]
     assert ((np.abs(d).max(axis=1) > 0) == (np.abs(g["gradD_pri"]).max(axis=1) > 0)).all()
+
+
+def test_oracle_orthographic_camera_vs_reference_golden(oracle):
+    """OrthographicCamera (tests/golden/ortho.npz, tools/ref_golden13.py: the RUNNING reference on the Cornell box shrunk by
+    300): image 2.4e-7, primary-edge derivative 1.6e-7, interior derivative 3.9e-4 (which the reference scales by 2)"""
+    g = np.load(os.path.join(GOLDEN, "ortho.npz"))
+    ms, cam = scenes.scaled_cbox(1.0 / 300.0)
+    cam = dict(cam, ortho=True, near=1e-3, far=1e3)
+    r, nbad, r_ex = compare_stats(build_oracle(ms, 128, 128, 4, 0, 0, cam=cam).render(2, seed=0, mode=0), g["imgC"])
+    assert nbad <= 4 and r_ex < 1e-5, (r, nbad, r_ex)
+    for tag, (spp, sppe), term, f, tol in (("int", (4, 0), 1, 2.0, 2e-3), ("pri", (0, 4), 2, 1.0, 1e-5)):
+        _, d = build_oracle(ms, 128, 128, spp, sppe, 0, cam=cam, move_mesh=1, axis_scale=(0.1, 0.03, 0.0)).render(2, seed=0, mode=1, terms=term)
+        r, nbad, r_ex = compare_stats(f * d, g["gradD_" + tag])
+        assert nbad <= 8 and r_ex < tol, (tag, r, nbad, r_ex)
