@@ -530,3 +530,43 @@ def test_oracle_orthographic_camera_vs_reference_golden(oracle):
         _, d = build_oracle(ms, 128, 128, spp, sppe, 0, cam=cam, move_mesh=1, axis_scale=(0.1, 0.03, 0.0)).render(2, seed=0, mode=1, terms=term)
         r, nbad, r_ex = compare_stats(f * d, g["gradD_" + tag])
         assert nbad <= 8 and r_ex < tol, (tag, r, nbad, r_ex)
+
+
+def test_oracle_scaled_cfg2_vs_reference_golden(oracle):
+    """BASELINE config 2's scene and derivative at a scene scale of 1/300 (tests/golden/scaled_cfg2.npz, tools/ref_golden14.py:
+    the RUNNING reference).  With coordinates ~2 no decision sits on the reference's fixed epsilon bands any more: the image
+    agrees to 3.7e-5 with no flipped pixel (north-star bar 1e-4), the primary-edge derivative to 7e-7, the interior
+    derivative to 2e-6 outside ONE pixel.  The secondary-edge term is the subject of the next test."""
+    g = np.load(os.path.join(GOLDEN, "scaled_cfg2.npz"))
+    s, ax = float(g["scale"]), float(g["axis"])
+    ms, cam = scenes.scaled_cbox(s)
+    img = build_oracle(ms, 128, 128, 4, 0, 0, cam=cam).render(3, seed=0, mode=0)
+    assert rel_l2(img, g["imgC"]) < 1e-4
+    for tag, (spp, sppe), term, f, tol in (("int", (4, 0), 1, 2.0, 1e-5), ("pri", (0, 4), 2, 1.0, 1e-5)):
+        im, d = build_oracle(ms, 128, 128, spp, sppe, 0, cam=cam, move_mesh=0, axis_scale=(ax, 0.0, 0.0)).render(3, seed=0, mode=1, terms=term)
+        assert rel_l2(im, g["imgD_" + tag]) < 1e-4
+        r, nbad, r_ex = compare_stats(f * d, g["gradD_" + tag])
+        assert nbad <= 2 and r_ex < tol, (tag, r, nbad, r_ex)
+
+
+def test_reference_secondary_edge_derivative_is_not_deterministic(oracle):
+    """tests/golden/ref_determinism_sec.npz (tools/ref_probe5.py): the reference's forward-mode secondary-edge derivative image
+    rendered FOUR times with identical scene, seed and parameters, at full scale and at scale 1/300.  The four images
+    differ from each other in two thirds of their non-zero pixels (rel-L2 between two runs 0.13 - 0.18; interior and
+    primary-edge terms are reproducible): individual (pixel, channel) sums come out lower by a different amount in every
+    run -- lost updates in the reference's accumulation under forward-mode AD.  Ours is the complete sum: it exceeds every
+    run's total, bounds 98 % of the entries in magnitude, and coincides with at least one of the four runs in three
+    quarters of the entries.  This is the floor of the gradient-image parity; no implementation can
+    agree with a moving target more closely than it agrees with itself."""
+    D = np.load(os.path.join(GOLDEN, "ref_determinism_sec.npz"))
+    for tag, (ms, cam), ax in (("scaled", scenes.scaled_cbox(1.0 / 300.0), 100.0 / 300.0), ("full", (scenes.cbox_meshes(), scenes.CBOX_CAMERA), 100.0)):
+        a = D[tag].astype(np.float64)                      # [4 runs, npix, 3]
+        d = 2.0 * build_oracle(ms, 128, 128, 0, 0, 4, cam=cam, move_mesh=0, axis_scale=(ax, 0.0, 0.0)).render(3, seed=0, mode=1, terms=4)[1]
+        self_spread = min(rel_l2(a[i], a[j]) for i in range(4) for j in range(i))
+        assert self_spread > 0.08, (tag, self_spread)      # the reference does not reproduce itself
+        assert max(rel_l2(d, a[i]) for i in range(4)) < 2.0 * max(rel_l2(a[i], a[j]) for i in range(4) for j in range(i)), tag
+        nz = np.abs(d) > 0
+        tol = 2e-4 * np.abs(d).max()
+        assert (np.abs(a - d[None]) < tol).any(axis=0)[nz].mean() > 0.7, tag          # equal to ours in some run
+        assert (np.abs(d)[None] >= np.abs(a) - tol)[:, nz].mean() > 0.97, tag         # lost updates only lower a sum
+        assert all(np.abs(d).sum() > np.abs(a[i]).sum() * 1.05 for i in range(4)), tag

@@ -749,3 +749,36 @@ def test_intrinsics_camera_vs_reference_golden():
         dimg = integ.renderD_fwd(sc, 0, seed=0, terms=term)[1].cpu().numpy()
         r, nbad, r_ex = compare_stats(dimg, g["gradD_" + tag])
         assert nbad <= 256 and r_ex < 5e-3, (tag, r, nbad, r_ex)
+
+
+def test_scaled_cfg2_vs_reference_golden_and_reference_nondeterminism():
+    """The CUDA path on BASELINE config 2's scene at scale 1/300 against the running reference (tests/golden/scaled_cfg2.npz):
+    image 3.7e-5 (no flipped pixel; north-star bar 1e-4), primary-edge derivative 7e-7, interior derivative 2e-6 outside one
+    pixel.  The secondary-edge derivative of the reference is NOT reproducible between identical runs
+    (tests/golden/ref_determinism_sec.npz, tools/ref_probe5.py: two runs of the reference differ by rel-L2 0.13 - 0.18, lost
+    updates in its accumulation); ours is the complete sum -- above every run's total, equal to some run in most entries."""
+    import psdr_jit_b200 as psdr
+    g = np.load(os.path.join(GOLDEN, "scaled_cfg2.npz"))
+    s, ax = float(g["scale"]), float(g["axis"])
+    ms, cam = scenes.scaled_cbox(s)
+    integ = psdr.PathTracer(3)
+    integ.reference_tangent_scaling = True
+    img = integ.renderC(build_product(ms, 128, 128, 4, 0, 0, cam=cam), 0, seed=0).cpu().numpy()
+    assert rel_l2(img, g["imgC"]) < 1e-4
+    for tag, (spp, sppe), term, tol in (("int", (4, 0), 1, 1e-5), ("pri", (0, 4), 2, 1e-5)):
+        sc = build_product(ms, 128, 128, spp, sppe, 0, cam=cam, move_mesh=0, axis_scale=(ax, 0.0, 0.0))
+        im, d = integ.renderD_fwd(sc, 0, seed=0, terms=term)
+        assert rel_l2(im.cpu().numpy(), g["imgD_" + tag]) < 1e-4
+        r, nbad, r_ex = compare_stats(d.cpu().numpy(), g["gradD_" + tag])
+        assert nbad <= 2 and r_ex < tol, (tag, r, nbad, r_ex)
+    D = np.load(os.path.join(GOLDEN, "ref_determinism_sec.npz"))
+    for tag, (ms2, cam2), ax2 in (("scaled", (ms, cam), ax), ("full", (scenes.cbox_meshes(), scenes.CBOX_CAMERA), 100.0)):
+        a = D[tag].astype(np.float64)
+        sc = build_product(ms2, 128, 128, 0, 0, 4, cam=cam2, move_mesh=0, axis_scale=(ax2, 0.0, 0.0))
+        d = integ.renderD_fwd(sc, 0, seed=0, terms=4)[1].cpu().numpy().astype(np.float64)
+        assert min(rel_l2(a[i], a[j]) for i in range(4) for j in range(i)) > 0.08
+        nz = np.abs(d) > 0
+        tol = 2e-4 * np.abs(d).max()
+        assert (np.abs(a - d[None]) < tol).any(axis=0)[nz].mean() > 0.7, tag
+        assert (np.abs(d)[None] >= np.abs(a) - tol)[:, nz].mean() > 0.97, tag
+        assert all(np.abs(d).sum() > np.abs(a[i]).sum() * 1.05 for i in range(4)), tag
