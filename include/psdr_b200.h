@@ -310,6 +310,12 @@ int psdr_render_aov(psdr_scene *s, int sensor, long long seed, float *out, void 
  * 1 silhouette, 2 position, 3 depth, 4 geoNormal, 5 shNormal, 6 uv; object >= 0 keeps that mesh only ("<field> <id>"). */
 int psdr_render_aov_d(psdr_scene *s, int sensor, long long seed, float *out, float *dout, void *cuda_stream);
 int psdr_render_field_edges(psdr_scene *s, int sensor, long long seed, int field, int object, float *dimg, void *cuda_stream);
+/* Reverse mode of FieldExtractionIntegrator::renderD: gradients of <d_img, field image> with respect to every parameter
+ * (read with psdr_scene_get_grad) -- the interior part (the adjoint of the analytically re-intersected primary hit: position,
+ * depth, normals, uv; zero for silhouette / segmentation) and the primary-edge part (the jump of the field across the
+ * pixel-space edges).  d_img: width*height*3 floats on the device. */
+int psdr_render_field_vjp(psdr_scene *s, int sensor, long long seed, int field, int object, int terms, int reference_scaling,
+                          const float *d_img, void *cuda_stream);
 
 /* Sampler.seed / next_1d (src/psdr.cpp:181-185): out[ndraws][n], host memory, computed on the host. */
 int psdr_sampler_draws(long long seed, int n, int ndraws, float *out);

@@ -1415,8 +1415,36 @@ class FieldExtractionIntegrator(Integrator):
         return img, dimg
 
     def renderD(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        """The field image; with torch parameters that require grad (``scene.param_map``) it carries an autograd node whose
+        backward runs the adjoint (``render_vjp``) -- e.g. a silhouette / mask loss in an optimisation loop.  Otherwise the
+        forward-mode derivative image for the configured tangents is kept in ``grad_image``."""
+        leaves = scene._grad_leaves() if self.field != "bsdf" else []
+        if leaves:
+            return _render_d_autograd(self, scene, sensor_id, int(seed), batch_pix, leaves)
         img, self.grad_image = self.renderD_fwd(scene, sensor_id, seed, batch_pix)
         return img
+
+    last_reduced = True          # (autograd node: nothing to all-reduce, the field integrator runs unsharded)
+
+    def renderD_primal(self, scene: Scene, sensor_id: int = 0, seed: int = -1, batch_pix=-1):
+        return self.renderC(scene, sensor_id, seed, batch_pix)
+
+    def render_vjp(self, scene: Scene, d_img, sensor_id: int = 0, seed: int = -1, batch_pix=-1, terms: int = _lib.TERM_ALL, group=None):
+        """Adjoint of the field image: accumulates d<d_img, field image>/d(parameter) for every scene parameter (read with
+        ``scene.grad_of``): the interior part through the analytically re-intersected primary hit (position, depth, normals,
+        uv) and the primary-edge part (every field; the only part of a silhouette)."""
+        if self.field == "bsdf":
+            raise RuntimeError("FieldExtractionIntegrator('bsdf') has no reverse mode: use the forward-mode derivative image")
+        self._check(scene)
+        torch = self._torch()
+        dev, st = self._dev_stream(torch, scene)
+        n = scene.opts.width * scene.opts.height
+        d_img = torch.as_tensor(d_img, dtype=torch.float32, device=dev).contiguous()
+        if d_img.numel() != 3 * n:
+            raise RuntimeError("cotangent image must have %d x 3 entries" % n)
+        obj = int(self.object) if self.object else -1
+        _lib.check(_lib.load().psdr_render_field_vjp(scene._h, sensor_id, 0 if seed < 0 else int(seed), self.FIELDS.index(self.field), obj, int(terms),
+                                                      0, d_img.data_ptr(), st))      # (the forward image carries no reference scaling either)
 
 
 def _render_d_autograd(integ: Integrator, scene: Scene, sensor_id: int, seed: int, batch_pix, leaves):

@@ -35,7 +35,7 @@ EXPORTS = [
     "psdr_scene_add_bsdf_diffuse", "psdr_scene_add_bsdf_microfacet", "psdr_scene_add_bsdf_roughconductor", "psdr_scene_add_bsdf_roughdielectric", "psdr_scene_add_bsdf_microfacet_pervertex", "psdr_scene_begin_nested_bsdf", "psdr_scene_add_bsdf_normalmap", "psdr_scene_add_envmap", "psdr_scene_set_bsdf_texture", "psdr_scene_set_bsdf_texture_slot", "psdr_scene_add_mesh", "psdr_scene_add_perspective", "psdr_scene_add_perspective_intrinsic", "psdr_scene_add_orthographic", "psdr_scene_set_param",
     "psdr_scene_set_tangent", "psdr_scene_clear_tangents", "psdr_scene_configure", "psdr_scene_last_configure_ms",
     "psdr_scene_query", "psdr_scene_mesh_edges", "psdr_render_c", "psdr_render_d", "psdr_render_c_host",
-    "psdr_render_d_host", "psdr_render_aov", "psdr_render_aov_d", "psdr_render_field_edges", "psdr_sampler_draws", "psdr_scene_enable_timing", "psdr_scene_kernel_ms",
+    "psdr_render_d_host", "psdr_render_aov", "psdr_render_aov_d", "psdr_render_field_edges", "psdr_render_field_vjp", "psdr_sampler_draws", "psdr_scene_enable_timing", "psdr_scene_kernel_ms",
     "psdr_preprocess_secondary_edges", "psdr_scene_set_guiding", "psdr_scene_guiding_mass", "psdr_render_vjp", "psdr_grad_table_size", "psdr_render_vjp_device", "psdr_scene_backprop_table", "psdr_scene_get_grad", "psdr_scene_get_sampler_state", "psdr_scene_set_sampler_state",
 ]
 
@@ -99,6 +99,7 @@ def load():
     L.psdr_render_aov.argtypes = [vp, i, ll, vp, vp]
     L.psdr_render_aov_d.argtypes = [vp, i, ll, vp, vp, vp]
     L.psdr_render_field_edges.argtypes = [vp, i, ll, i, i, vp, vp]
+    L.psdr_render_field_vjp.argtypes = [vp, i, ll, i, i, i, i, vp, vp]
     L.psdr_sampler_draws.argtypes = [ll, i, i, P_F]
     L.psdr_preprocess_secondary_edges.argtypes = [vp, i, P_I, i, ll, vp]
     L.psdr_scene_set_guiding.argtypes = [vp, i, i]

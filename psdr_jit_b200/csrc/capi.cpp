@@ -1215,6 +1215,47 @@ int psdr_render_field_edges(psdr_scene *s, int sensor, long long seed, int field
     PSDR_CATCH
 }
 
+int psdr_render_field_vjp(psdr_scene *s, int sensor, long long seed, int field, int object, int terms, int reference_scaling,
+                          const float *d_img, void *cuda_stream) {
+    if (!s) return fail("null scene");
+    PSDR_TRY
+    Scene &sc = s->sc;
+    if (!sc.configured) throw std::runtime_error("Input scene must be configured!");
+    if (sensor < 0 || sensor >= (int) sc.cameras.size()) throw std::runtime_error("Invalid sensor id!");
+    if (field < 0 || field > 6) throw std::runtime_error("Unsupported field");
+    if (!d_img) throw std::runtime_error("null cotangent image");
+    if (sc.world > 1) throw std::runtime_error("FieldExtractionIntegrator: reverse mode runs unsharded");
+    cuda_ok(cudaSetDevice(sc.device), "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t) cuda_stream;
+    GradLayout gl = sc.grad_layout(sensor);
+    ensure_grad_table(s, (size_t) gl.total);
+    gl.base = s->d_grad;
+    cuda_ok(cudaMemsetAsync(s->d_grad, 0, sizeof(float) * gl.total, st), "memset(grad table)");
+    const long long npix = (long long) sc.width * sc.height;
+    const DCamera &cam = sc.dcameras[sensor];
+    RenderParams rp{};
+    rp.seed = seed < 0 ? 0 : seed;
+    rp.use_field = 1;
+    rp.field = field;
+    rp.field_object = object;
+    // the reference's field images and their interior derivatives come out 2x; its edge term is 1x
+    if ((terms & PSDR_TERM_INTERIOR) && sc.spp > 0 && field >= 2) {
+        rp.tangent_scale = reference_scaling ? 2.f : 1.f;
+        set_shard(rp, npix * sc.spp, 0, 1);
+        cuda_ok(launch_interior_vjp(sc.dscene, cam, rp, gl, d_img, st), "field adjoint kernel");
+        g_launches++;
+    }
+    if ((terms & PSDR_TERM_PRIMARY_EDGES) && sc.sppe > 0 && cam.n_edges > 0) {
+        rp.tangent_scale = 1.f;
+        set_shard(rp, npix * sc.sppe, 0, 1);
+        cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp, gl, d_img, st), "field edge adjoint kernel");
+        g_launches++;
+    }
+    vjp_finish(s, sensor, s->d_grad, st);
+    return 0;
+    PSDR_CATCH
+}
+
 int psdr_sampler_draws(long long seed, int n, int ndraws, float *out) {
     if (!out || n < 0 || ndraws < 0) return fail("invalid arguments");
     for (int i = 0; i < n; ++i) {

@@ -1560,6 +1560,20 @@ __device__ __forceinline__ V3<S> Li(const DScene &sc, Pcg32 &rng, V3<S> ro, V3<S
     return Li<S, kCfg, IsDual<S>::value, NoRecord>(sc, rng, ro, rd, active, max_depth, hide_emitters, rec, cta ? 0xffffffffu : 0u, mis, cta);
 }
 
+// field ids of psdr_render_field_edges
+__device__ __forceinline__ V3f field_value(const Its<float> &its, int field, int object) {
+    if (!its.valid || (object >= 0 && its.mesh != object)) return V3f(0.f, 0.f, 0.f);
+    switch (field) {
+        case 0: return V3f((float) its.mesh, (float) its.mesh, (float) its.mesh);      // segmentation
+        case 1: return V3f(1.f, 1.f, 1.f);                                                // silhouette
+        case 2: return its.p;                                                             // position
+        case 3: return V3f(its.t, its.t, its.t);                                          // depth
+        case 4: return its.n;                                                             // geoNormal
+        case 5: return its.sh_n;                                                          // shNormal
+        default: return V3f(its.uv.x, its.uv.y, 0.f);                                     // uv
+    }
+}
+
 // CollocatedIntegrator::__Li (reference src/integrator/collocated.cpp:21-53): a point light at the camera -- the BSDF towards
 // the viewer for light arriving from the viewer, times intensity / t^2; no emitters, no sampling, no random numbers.
 // Kept out of li_step (its own small kernel instantiations, kernels_impl.cuh kColloc): the path tracer's kernels do not

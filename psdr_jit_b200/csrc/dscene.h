@@ -179,6 +179,9 @@ struct RenderParams {
     int smem_grad;           // adjoint kernels: 1 = accumulate into a shared-memory copy of the gradient table
     float tangent_scale;     // 1, or 2 to reproduce the reference's forward-mode scaling
     int *sched;              // large-CTA interior kernels: {next chunk, CTAs done} of the dynamic chunk hand-out (device, zero between launches)
+    int use_field;           // 1: the adjoint launches evaluate FieldExtractionIntegrator (field, field_object) instead of an Li
+    int field, field_object; // FieldExtractionIntegrator in reverse mode (kernels_vjp_impl.cuh kField): field id (device_path.cuh
+                             // field_value) and the mesh to keep (-1 = all)
     int out_multicast;       // 1, 2 = the output pointers are NVLS multicast addresses: every add is a multimem.red that lands
                              // in the replica of EVERY rank; 2: images are float32[npix][4] (psdr_scene_set_output_multicast)
 };

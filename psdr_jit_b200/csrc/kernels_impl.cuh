@@ -337,19 +337,6 @@ __global__ void __launch_bounds__(kBlock) aov_d_kernel(const __grid_constant__ D
     }
 }
 
-// field ids of psdr_render_field_edges
-__device__ __forceinline__ V3f field_value(const Its<float> &its, int field, int object) {
-    if (!its.valid || (object >= 0 && its.mesh != object)) return V3f(0.f, 0.f, 0.f);
-    switch (field) {
-        case 0: return V3f((float) its.mesh, (float) its.mesh, (float) its.mesh);      // segmentation
-        case 1: return V3f(1.f, 1.f, 1.f);                                                // silhouette
-        case 2: return its.p;                                                             // position
-        case 3: return V3f(its.t, its.t, its.t);                                          // depth
-        case 4: return its.n;                                                             // geoNormal
-        case 5: return its.sh_n;                                                          // shNormal
-        default: return V3f(its.uv.x, its.uv.y, 0.f);                                     // uv
-    }
-}
 // Primary-edge part (Integrator::render_primary_edges with Li = the field at the primary hit): the jump of the field across
 // the sampled pixel-space edge times the edge's normal velocity.
 template <int kCfg>

@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(kBig ? kBlockIV : kBlockV, kBig ? PSDR_LB_IVJP
     grad_acc_end(acc);
 }
 
-template <int kCfg, bool kBig, bool kColloc = false>
+// kField: Li = the field of FieldExtractionIntegrator at the primary hit (rp.field, rp.field_object); 128-thread shape only
+template <int kCfg, bool kBig, bool kColloc = false, bool kField = false>
 __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP : 8) primary_edge_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
                                                                     const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
                                                                     const float *__restrict__ d_img) {
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP
             const float sg = side == 0 ? kEdgeEpsilon : -kEdgeEpsilon;
             V3f ro, rd;
             sample_primary_ray<float>(cam, V2f(px + sg * bq.x, py + sg * bq.y), ro, rd);
-            if (kColloc) Lside[side] = Li_collocated<float, kCfg, false>(sc, ro, rd, valid);
+            if (kField) Lside[side] = field_value(ray_intersect<float, kCfg>(sc, ro, rd, valid, false), rp.field, rp.field_object);
+            else if (kColloc) Lside[side] = Li_collocated<float, kCfg, false>(sc, ro, rd, valid);
             else Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis);
         }
         if (!valid) continue;
@@ -182,6 +184,76 @@ __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP
         acc.add(b + 1, gsum * w0 * bq.y);
         acc.add(b + 2, gsum * s1 * bq.x);
         acc.add(b + 3, gsum * s1 * bq.y);
+    }
+    grad_acc_end(acc);
+}
+
+// ---- FieldExtractionIntegrator, interior part in reverse mode: the adjoint of the analytically re-intersected primary hit
+// (aov_d_kernel's taps: p = o + t d, t, face normal, shading normal at the differentiable (u, v), uv) for the cotangent of the
+// field image.  Same sample positions as aov_kernel (seed + lane, no stream continuation).
+template <int kCfg>
+__global__ void __launch_bounds__(kBlockV, 5) field_vjp_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam,
+                                                               const __grid_constant__ RenderParams rp, const __grid_constant__ GradLayout gl,
+                                                               const float *__restrict__ d_img) {
+    extern __shared__ float smem[];
+    brute_init<kCfg>(sc, kBlockV);
+    const GradAcc acc = grad_acc_begin(gl, smem, 0, gl.off_pe, rp.smem_grad != 0, true, 0);
+    const long long stride = (long long) gridDim.x * kBlockV;
+    const float inv_spp = (sc.spp > 1 ? 1.f / (float) sc.spp : 1.f) * rp.tangent_scale;
+    const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + 31) / 32 * 32;
+    const int field = rp.field;
+    for (long long j = (long long) blockIdx.x * kBlockV + threadIdx.x; j < span_pad; j += stride) {
+        __syncwarp();
+        const long long i = global_lane(rp, j);
+        const bool live = j < span && i < rp.n_lanes;
+        const long long il = live ? i : 0;
+        const int idx = (int) (sc.spp > 1 ? il / sc.spp : il);
+        Pcg32 rng;
+        rng.seed((unsigned long long) (il + rp.seed), (unsigned long long) il);
+        const float jy = rng.next_1d(), jx = rng.next_1d();
+        const float sx = ((float) (idx % sc.width) + jx) / (float) sc.width, sy = ((float) (idx / sc.width) + jy) / (float) sc.height;
+        V3f oc, dc;
+        camera_ray_local(cam, V2f(sx, sy), oc, dc);
+        const V3f o = xform_pos(cam.to_world, oc), d = xform_dir(cam.to_world, dc);
+        const Its<float> its = ray_intersect<float, kCfg, true>(sc, o, d, live, false);
+        const V3f g(__ldg(d_img + 3 * idx) * inv_spp, __ldg(d_img + 3 * idx + 1) * inv_spp, __ldg(d_img + 3 * idx + 2) * inv_spp);
+        const bool on = live && its.valid && (rp.field_object < 0 || its.mesh == rp.field_object) && field >= 2 &&
+                        !(g.x == 0.f && g.y == 0.f && g.z == 0.f);
+        // lanes without work ride along with zeros: the camera-ray scatter below is warp-uniform
+        V3f o_bar(0.f, 0.f, 0.f), d_bar(0.f, 0.f, 0.f);
+        if (on) {
+            const TriRec<float> T = load_tri<float>(sc, its.tri);
+            float u, v, t;
+            ray_intersect_triangle<float>(T.p0, T.e1, T.e2, o, d, u, v, t);
+            float u_bar = 0.f, v_bar = 0.f, t_bar = 0.f;
+            const int b = kGradTri * its.tri;
+            if (field == 2) {                                   // position: p = o + t d
+                o_bar = g;
+                d_bar = g * t;
+                t_bar = dot(d, g);
+            } else if (field == 3) t_bar = g.x + g.y + g.z;     // depth, replicated to the three channels
+            else if (field == 4) acc.add3(b + 19, g);           // geoNormal: the face normal record
+            else if (field == 5) {                              // shNormal: normalised interpolated normal at (u, v)
+                const VtxGeo geo = vertex_geo<kCfg>(sc, its.tri, u, v);
+                V3f m_bar;
+                scatter_shading_normal(acc, geo, g, m_bar);
+                if (!geo.face_normals) {
+                    const ShadeRec<float> N = load_shade<float>(sc, its.tri);
+                    u_bar = dot(N.n1 - N.n0, m_bar);
+                    v_bar = dot(N.n2 - N.n0, m_bar);
+                }
+            } else if (field == 6 && (sc.meshes[its.mesh].flags & 2)) {      // uv = uv0 + u duv0 + v duv1
+                const float2 t0 = __ldg(sc.uv + 3 * its.tri), t1 = __ldg(sc.uv + 3 * its.tri + 1), t2 = __ldg(sc.uv + 3 * its.tri + 2);
+                u_bar = g.x * (t1.x - t0.x) + g.y * (t1.y - t0.y);
+                v_bar = g.x * (t2.x - t0.x) + g.y * (t2.y - t0.y);
+            }
+            const V3f r_bar = isect_adj(T.e1, T.e2, d, u_bar, v_bar, t_bar);
+            scatter_isect_tri(acc, its.tri, u, v, r_bar);
+            o_bar = o_bar + r_bar;
+            d_bar = d_bar + r_bar * t;
+        }
+        __syncwarp();
+        scatter_camera_ray(acc, gl, dc, o_bar, d_bar, oc);
     }
     grad_acc_end(acc);
 }
@@ -238,6 +310,11 @@ template <int kCfg> struct AdjointLaunch {
         RenderParams rq = rp;
         rq.smem_grad = gl.off_pe <= kSmemGradMaxFloats ? 1 : 0;
         const size_t bytes = rq.smem_grad ? sizeof(float) * gl.off_pe : 0;
+        if (rp.use_field) {     // FieldExtractionIntegrator: the adjoint of the primary hit alone
+            const long long n = rq.lane_end - rq.lane_begin;
+            field_vjp_kernel<kCfg><<<vjp_grid(field_vjp_kernel<kCfg>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+            return cudaGetLastError();
+        }
         if (rp.mis == 3) {      // CollocatedIntegrator
             const long long n = rq.lane_end - rq.lane_begin;
             interior_vjp_kernel<kCfg, 1, false, true><<<vjp_grid(interior_vjp_kernel<kCfg, 1, false, true>, bytes, n), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
@@ -253,6 +330,10 @@ template <int kCfg> struct AdjointLaunch {
         rq.smem_grad = n <= kSmemGradMaxFloats ? 1 : 0;
         const size_t bytes = rq.smem_grad ? sizeof(float) * n : 0;
         const long long lanes = rp.lane_end - rp.lane_begin;
+        if (rp.use_field) {     // FieldExtractionIntegrator
+            primary_edge_vjp_kernel<kCfg, false, false, true><<<vjp_grid(primary_edge_vjp_kernel<kCfg, false, false, true>, bytes, lanes), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
+            return cudaGetLastError();
+        }
         if (rp.mis == 3) {      // CollocatedIntegrator
             primary_edge_vjp_kernel<kCfg, false, true><<<vjp_grid(primary_edge_vjp_kernel<kCfg, false, true>, bytes, lanes), kBlockV, bytes, st>>>(sc, cam, rq, gl, d_img);
             return cudaGetLastError();

@@ -68,3 +68,73 @@ def test_field_vs_reference_golden_and_finite_differences():
     integ.renderD(sc, 0, seed=1)
     est = float(integ.grad_image[:, 0].sum())
     assert abs(est - fd) < 0.04 * abs(fd), (est, fd)      # (the finite difference of a 64-spp coverage image carries ~2 % noise itself)
+
+
+@pytest.mark.parametrize("field", ["silhouette", "depth", "position", "shNormal", "geoNormal", "uv", "silhouette 1"])
+def test_field_vjp_is_transpose_of_forward_mode(field):
+    """reverse mode of FieldExtractionIntegrator (psdr_render_field_vjp): <cot, J t> == <J^T cot, t> for t = translations /
+    a small rotation of two meshes, a vertex field and the camera; interior + primary-edge parts"""
+    import torch
+    import psdr_jit_b200 as psdr
+    rng = np.random.default_rng(11)
+    w = h = 64
+    sc = build_product(scenes.cbox_meshes(), w, h, 8, 8, 0)
+    tang = {}
+    t = np.zeros((4, 4), np.float32)
+    t[:3, 3] = rng.normal(size=3) * 30
+    t[:3, :3] = rng.normal(size=(3, 3)) * 0.05
+    for name in ("Mesh[1]", "Mesh[2]"):
+        sc.param_map[name].d_to_world_left = t.copy()
+        tang[(name, "to_world_left")] = t.copy()
+    m = sc.param_map["Mesh[2]"]
+    tv = (rng.normal(size=m.vertex_positions.shape) * 3).astype(np.float32)
+    m.d_vertex_positions = tv
+    tang[("Mesh[2]", "vertex_positions")] = tv
+    tc = np.zeros((4, 4), np.float32)
+    tc[:3, 3] = rng.normal(size=3) * 5
+    sc.param_map["Sensor[0]"].d_to_world_left = tc
+    tang[("Sensor[0]", "to_world_left")] = tc
+    sc.configure()
+    sc.configure([0])
+    integ = psdr.FieldExtractionIntegrator(field)
+    img, dimg = integ.renderD_fwd(sc, 0, seed=3)
+    cot = torch.as_tensor(rng.normal(size=(w * h, 3)).astype(np.float32), device=img.device)
+    lhs = float((cot.double() * dimg.double()).sum())
+    integ.render_vjp(sc, cot, 0, seed=3)
+    parts = {k: float((sc.grad_of(*k).reshape(np.shape(v)).astype(np.float64) * v.astype(np.float64)).sum()) for k, v in tang.items()}
+    rhs = sum(parts.values())
+    mag = max(abs(lhs), sum(abs(v) for v in parts.values()))
+    assert mag > 0 and abs(lhs - rhs) < 5e-4 * mag, (field, lhs, rhs, parts)
+
+
+def test_silhouette_loss_gradient_through_autograd():
+    """a mask loss in an optimisation loop: d/dP ||silhouette(P) - silhouette(P*)||^2 for a box translated by P along x has
+    the sign that moves P towards P*, on both sides of it, and vanishes at P*"""
+    import torch
+    import psdr_jit_b200 as psdr
+    integ = psdr.FieldExtractionIntegrator("silhouette 1")
+
+    def scene_at(p):
+        sc = build_product(scenes.cbox_meshes(), 96, 96, 16, 16, 0)
+        T = torch.eye(4)
+        T[0, 3] = p
+        return sc, T
+
+    sc, T = scene_at(0.0)
+    sc.param_map["Mesh[1]"].set_transform(T.numpy())
+    sc.configure([0])
+    target = integ.renderC(sc, 0, seed=1).clone()
+    grads = {}
+    for p0 in (-25.0, 0.0, 25.0):
+        sc, _ = scene_at(p0)
+        p = torch.tensor(p0, requires_grad=True)
+        M = torch.eye(4)
+        M[0, 3] = p                      # (in place on a fresh tensor: M joins p's graph)
+        sc.param_map["Mesh[1]"].set_transform(M)
+        sc.configure([0])
+        img = integ.renderD(sc, 0, seed=1)
+        loss = ((img - target) ** 2).sum()
+        loss.backward()
+        grads[p0] = float(p.grad)
+    assert grads[-25.0] < 0 < grads[25.0], grads            # descent moves P back to 0 from either side
+    assert abs(grads[0.0]) < 0.05 * min(abs(grads[-25.0]), abs(grads[25.0])), grads
