@@ -305,6 +305,10 @@ template <int kCfg> __device__ __forceinline__ void brute_init(const DScene &sc,
 //   the strict "closer" keep the lowest triangle id on ties, as a full ascending scan would.
 // The box test is part of the definition of the closest hit (the CPU checker used by the tests applies the identical
 // test), so hit ids agree bit for bit whether or not a pad was generous enough.
+#ifndef PSDR_BVH_LOOP
+#define PSDR_BVH_LOOP 0     // 1: one unit of work per traversal iteration + distance-tagged stack (see trace(), BVH branch);
+                            // measured SLOWER on cfg 4: 21.6 vs 20.55 ms (profiles/r04q_cfg4_bvh_loop_variants.log), kept as a switch
+#endif
 #ifndef PSDR_TRACE_NOINLINE
 #define PSDR_TRACE_NOINLINE 0   // 1: one out-of-line copy of the closest-hit query per kernel (instruction-cache experiments)
 #endif
@@ -433,6 +437,72 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
         // soon as their box is hit.  The slab test is conservative (padded boxes, slack on the comparison), candidates
         // pass the same numerator test as the brute-force scan and ties go to the lowest id whatever the visiting order.
         const float ix = 1.f / d.x, iy = 1.f / d.y, iz = 1.f / d.z;
+#if PSDR_BVH_LOOP == 1
+        // ONE unit of work per loop iteration -- a triangle test of the pending leaf, or a node visit -- so that lanes in
+        // a leaf and lanes descending stay in the same loop instead of one group waiting for the other's inner loop
+        // (profiles/r02w: 9 - 11 of 32 lanes active in the kernels of cfg 4 with the leaf loop inline); entries popped from the
+        // stack carry their entry distance and are skipped when a closer hit has been found since they were pushed.
+        int stack[32];
+        float stack_t[32];
+        int sp = 0;
+        int node = 0;
+        float best_t = kTraceTMax;          // conservative bound for the box pruning only
+        int lf0 = 0, ln0 = 0, lf1 = 0, ln1 = 0;          // pending leaf slots: [lf0, lf0 + ln0) first, then [lf1, lf1 + ln1)
+        float lt1 = 0.f;                                 // entry distance of the second pending leaf
+        while (true) {
+            if (ln0 > 0) {
+                const float4 a = __ldg(sc.leaf_tri + 3 * lf0), b = __ldg(sc.leaf_tri + 3 * lf0 + 1), c2 = __ldg(sc.leaf_tri + 3 * lf0 + 2);
+                tri_test<false>(V3f(a.x, a.y, a.z), V3f(b.x, b.y, b.z), V3f(c2.x, c2.y, c2.z), __float_as_int(a.w), o, d, best);
+                ++lf0;
+                if (--ln0 == 0) {
+                    best_t = best.ts / best.adet * 1.000001f;
+                    lf0 = lf1; ln0 = (ln1 > 0 && lt1 <= best_t) ? ln1 : 0; ln1 = 0;      // the nearer leaf may have pruned the other
+                }
+                continue;
+            }
+            if (node < 0) {
+                if (sp == 0) break;
+                --sp;
+                if (stack_t[sp] > best_t) continue;          // pruned by a hit found after the push
+                node = stack[sp];
+            }
+            const float4 *nd = reinterpret_cast<const float4 *>(sc.nodes2 + node);
+            const float4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2);
+            const int4 lk = __ldg(reinterpret_cast<const int4 *>(nd + 3));
+            float tn[2], tf[2];
+            {
+                const float x0 = (n0.x - o.x) * ix, x1 = (n0.w - o.x) * ix, y0 = (n0.y - o.y) * iy, y1 = (n1.x - o.y) * iy;
+                const float z0 = (n0.z - o.z) * iz, z1 = (n1.y - o.z) * iz;
+                tn[0] = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                tf[0] = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best_t));
+            }
+            {
+                const float x0 = (n1.z - o.x) * ix, x1 = (n2.y - o.x) * ix, y0 = (n1.w - o.y) * iy, y1 = (n2.z - o.y) * iy;
+                const float z0 = (n2.x - o.z) * iz, z1 = (n2.w - o.z) * iz;
+                tn[1] = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+                tf[1] = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best_t));
+            }
+            bool h0 = tn[0] <= tf[0] * 1.0000005f + 1e-6f, h1 = tn[1] <= tf[1] * 1.0000005f + 1e-6f;
+            int c0 = lk.x, c1 = lk.y;
+            if (h0 && h1 && tn[1] < tn[0]) {      // nearer child first
+                const int t = c0; c0 = c1; c1 = t;
+                const float q = tn[0]; tn[0] = tn[1]; tn[1] = q;
+            } else if (!h0) { c0 = c1; tn[0] = tn[1]; h0 = h1; h1 = false; }
+            node = -1;
+            if (h0) {
+                if (c0 < 0) { const int code = ~c0; lf0 = code >> 3; ln0 = code & 7; }
+                else node = c0;
+            }
+            if (h1) {
+                if (c1 < 0) {
+                    const int code = ~c1;
+                    if (ln0 > 0) { lf1 = code >> 3; ln1 = code & 7; lt1 = tn[1]; }
+                    else { lf0 = code >> 3; ln0 = code & 7; }
+                } else if (node < 0) node = c1;
+                else if (sp < 31) { stack[sp] = c1; stack_t[sp] = tn[1]; ++sp; }
+            }
+        }
+#else
         int stack[32];
         int sp = 0;
         int node = 0;
@@ -486,6 +556,7 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
             }
             node = next;
         }
+#endif
         if (best.tri < 0) return miss;
         const float4 a = __ldg(sc.geo + 3 * best.tri), b = __ldg(sc.geo + 3 * best.tri + 1);
         const float c = __ldg(&sc.geo[3 * best.tri + 2].x);
