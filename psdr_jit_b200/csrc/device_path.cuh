@@ -307,7 +307,8 @@ template <int kCfg> __device__ __forceinline__ void brute_init(const DScene &sc,
 // test), so hit ids agree bit for bit whether or not a pad was generous enough.
 #ifndef PSDR_BVH_LOOP
 #define PSDR_BVH_LOOP 0     // 1: one unit of work per traversal iteration + distance-tagged stack (see trace(), BVH branch);
-                            // measured SLOWER on cfg 4: 21.6 vs 20.55 ms (profiles/r04q_cfg4_bvh_loop_variants.log), kept as a switch
+                            // 2: the shipped loop + distance-tagged stack only.  Both bit-identical and both measured SLOWER on
+                            // cfg 4: 21.6 / 21.2 vs 20.55 ms (profiles/r04q_cfg4_bvh_loop_variants.log), kept as switches
 #endif
 #ifndef PSDR_TRACE_NOINLINE
 #define PSDR_TRACE_NOINLINE 0   // 1: one out-of-line copy of the closest-hit query per kernel (instruction-cache experiments)
@@ -504,6 +505,9 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
         }
 #else
         int stack[32];
+#if PSDR_BVH_LOOP == 2
+        float stack_t[32];      // entry distance of a pushed node: skipped when a closer hit has been found since (variant 2)
+#endif
         int sp = 0;
         int node = 0;
         float best_t = kTraceTMax;          // conservative bound for the box pruning only
@@ -548,9 +552,17 @@ template <int kCfg> __device__ __forceinline__ Hit trace(const DScene &sc, V3f o
             if (h1 && tn[1] <= best_t) {          // the nearer leaf may have pruned it
                 if (c1 < 0) leaf(c1);
                 else if (next < 0) next = c1;
-                else if (sp < 31) stack[sp++] = c1;
+                else if (sp < 31) {
+#if PSDR_BVH_LOOP == 2
+                    stack_t[sp] = tn[1];
+#endif
+                    stack[sp++] = c1;
+                }
             }
             if (next < 0) {
+#if PSDR_BVH_LOOP == 2
+                while (sp > 0 && stack_t[sp - 1] > best_t) --sp;
+#endif
                 if (sp == 0) break;
                 next = stack[--sp];
             }
