@@ -163,6 +163,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.load()
     psdr.set_cta_policy(args.cta_policy)
+    psdr.set_edge_sort(args.edge_sort)
     sc, tangent = build_scene(psdr, rank, world)
     integ = psdr.PathTracer(DEPTH)
     # N > 1: the reduction over ranks is fused into the term kernels (multimem.red through the NVSwitch into every rank's
@@ -496,6 +497,7 @@ def run_ours_config(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.load()
     psdr.set_cta_policy(args.cta_policy)
+    psdr.set_edge_sort(args.edge_sort)
     wl = bench_scenes.workload(args.config)
     per_sensor = args.config == 5                        # one sensor per GPU: replicas, no image collective
     sc = bench_scenes.build_ours(psdr, wl, 0 if per_sensor else rank, 1 if per_sensor else world)
@@ -759,6 +761,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vjp", action="store_true")
+    ap.add_argument("--edge-sort", type=int, default=512, help="experiments: buckets of the primary-edge lane ordering, 0 = lane order (psdr_set_edge_sort)")
     ap.add_argument("--cta-policy", type=int, default=0, help="experiments: 1 = force 128-thread CTAs, 2 = force the large-CTA kernels (psdr_set_cta_policy)")
     ap.add_argument("--shared-d2h", action="store_true", help="N > 1, fused path: every rank copies 1/N of the result into one shared page-locked host buffer instead of rank 0 copying all of it (measured slower, see the comment in run_ours)")
     ap.add_argument("--no-peer", action="store_true", help="N > 1: sum the partial images with NCCL instead of the fused multimem.red path")

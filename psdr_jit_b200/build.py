@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libpsdr_b200.so")
 # against the running reference is rounding mode.  Selected with PSDR_REFERENCE_ARITHMETIC=1 (psdr_jit_b200/_lib.py).
 LIB_REFARITH = os.path.join(HERE, "libpsdr_b200_refarith.so")
 SOURCES = ["kern_cfg11a.cu", "kern_cfg10a.cu", "vjp_cfg11a.cu", "vjp_cfg10a.cu", "vjp_cfg11.cu", "vjp_cfg10.cu", "kern_cfg11.cu", "kern_cfg10.cu", "vjp_cfg3.cu", "vjp_cfg2.cu", "vjp_cfg1.cu", "vjp_cfg0.cu", "kern_cfg3.cu", "kern_cfg2.cu", "kern_cfg1.cu", "kern_cfg0.cu",
-           "capi.cpp", "scene.cpp", "scene_grad.cpp", "device_upload.cu", "kernels.cu"]
+           "capi.cpp", "scene.cpp", "scene_grad.cpp", "device_upload.cu", "kernels.cu", "edge_sort.cu"]
 HEADERS = ["pmath.h", "dscene.h", "scene.h", "kernels.h", "device_path.cuh", "adjoint.cuh", "grad_layout.h", "texture.h", "kernels_impl.cuh", "kernels_vjp_impl.cuh", "launch_decl.h", os.path.join("..", "..", "include", "psdr_b200.h")]
 
 

@@ -32,11 +32,18 @@ struct psdr_scene {
     bool ev_used[3] = {false, false, false};
     // the three term kernels of one call run on three streams (TermStreams below)
     int *d_sched = nullptr;               // chunk hand-out counters of the large-CTA interior kernels (ChunkSched): forward {0,1}, adjoint {2,3}
+    // primary-edge lane ordering (edge_sort.cu): one set of buffers for the forward launch, one for the adjoint launch
+    struct EdgeSort { unsigned short *key = nullptr; int *perm = nullptr, *work = nullptr; size_t cap = 0; } edge_sort[2];
     float *early_img_host = nullptr;      // psdr_render_d_host: copy the primal image out as soon as the interior kernel is done
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     ~psdr_scene() {
         if (d_sched) cudaFree(d_sched);
+        for (auto &e : edge_sort) {
+            if (e.key) cudaFree(e.key);
+            if (e.perm) cudaFree(e.perm);
+            if (e.work) cudaFree(e.work);
+        }
         for (auto &q : side) if (q) cudaStreamDestroy(q);
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto &e : ev_join) if (e) cudaEventDestroy(e);
@@ -54,6 +61,7 @@ struct psdr_scene {
 
 static thread_local std::string g_error;
 static std::atomic<long long> g_launches{0};
+static int g_edge_sort_bins = 512;          // psdr_set_edge_sort
 namespace psdr { int g_cta_policy = 0; }      // psdr_set_cta_policy; read by the launchers (kernels_impl.cuh use_big_cta)
 
 static int fail(const std::string &msg) {
@@ -159,6 +167,12 @@ int psdr_scene_set_integrator_collocated(psdr_scene *s, float intensity, float d
 int psdr_set_cta_policy(int policy) {
     if (policy < 0 || policy > 2) return fail("policy >= 0 && policy <= 2");
     psdr::g_cta_policy = policy;
+    return 0;
+}
+
+int psdr_set_edge_sort(int bins) {
+    if (bins < 0 || bins == 1 || bins > psdr::kEdgeSortMaxBins) return fail("bins == 0 || (bins >= 2 && bins <= 2048)");
+    g_edge_sort_bins = bins;
     return 0;
 }
 
@@ -697,6 +711,30 @@ int *sched_counters(psdr_scene *s, int which) {
     return s->d_sched + 2 * which;
 }
 
+// Primary-edge launches of at least kEdgeSortMinLanes local lanes walk their lanes in the order of edge_sort.cu (three small
+// kernels on the term's stream, counted as launches); smaller ones keep the lane order.
+constexpr long long kEdgeSortMinLanes = 32768;
+void order_edge_lanes(psdr_scene *s, int which, RenderParams &rp, cudaStream_t q) {
+    const long long span = rp.lane_end - rp.lane_begin;
+    if (g_edge_sort_bins < 2 || span < kEdgeSortMinLanes || span > 2147483647LL) return;
+    auto &e = s->edge_sort[which];
+    if ((size_t) span > e.cap) {
+        if (e.key) cudaFree(e.key);
+        if (e.perm) cudaFree(e.perm);
+        e.key = nullptr; e.perm = nullptr; e.cap = 0;
+        cuda_ok(cudaMalloc(&e.key, sizeof(unsigned short) * span), "cudaMalloc(edge sort keys)");
+        cuda_ok(cudaMalloc(&e.perm, sizeof(int) * span), "cudaMalloc(edge sort order)");
+        e.cap = (size_t) span;
+    }
+    if (!e.work) {
+        cuda_ok(cudaMalloc(&e.work, sizeof(int) * 2 * kEdgeSortMaxBins), "cudaMalloc(edge sort counters)");
+        cuda_ok(cudaMemsetAsync(e.work, 0, sizeof(int) * 2 * kEdgeSortMaxBins, q), "memset(edge sort counters)");
+    }
+    cuda_ok(launch_edge_sort(rp, g_edge_sort_bins, e.key, e.work, e.perm, q), "edge sort kernels");
+    g_launches += 3;
+    rp.perm = e.perm;
+}
+
 void tick(psdr_scene *s, int k, int which, cudaStream_t st) {
     if (!s->timing) return;
     cuda_ok(cudaEventRecord(s->ev[k][which], st), "cudaEventRecord");
@@ -799,6 +837,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
         cudaStream_t q = ts.next();
         tick(s, 1, 0, q);
+        order_edge_lanes(s, 0, rp[1], q);
         cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, q), "primary-edge kernel");
         tick(s, 1, 1, q);
         g_launches++;
@@ -901,6 +940,7 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
         set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
         cudaStream_t q = ts.next();
         tick(s, 1, 0, q);
+        order_edge_lanes(s, 1, rp[1], q);
         cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp[1], gl, d_img, q), "primary-edge adjoint kernel");
         tick(s, 1, 1, q);
         g_launches++;

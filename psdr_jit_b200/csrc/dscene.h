@@ -184,6 +184,8 @@ struct RenderParams {
                              // field_value) and the mesh to keep (-1 = all)
     int out_multicast;       // 1, 2 = the output pointers are NVLS multicast addresses: every add is a multimem.red that lands
                              // in the replica of EVERY rank; 2: images are float32[npix][4] (psdr_scene_set_output_multicast)
+    const int *perm;         // primary-edge kernels: thread j evaluates local lane perm[j] (edge_sort.cu: the lanes bucketed by
+                             // their position along the edge list, so that a warp's rays start next to each other); nullptr = j
 };
 
 }  // namespace psdr

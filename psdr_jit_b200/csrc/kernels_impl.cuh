@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kBig ? kBlockP : kBlock, kBig ? PSDR_LB_PRIMAR
     for (long long j = (long long) blockIdx.x * kBlockP + threadIdx.x; j < span_pad; j += stride) {
         if (kSync) __syncthreads();
         else __syncwarp();
-        const long long i = global_lane(rp, j);
+        const long long i = global_lane(rp, rp.perm && j < span ? (long long) __ldg(rp.perm + j) : j);
         const bool live = j < span && i < rp.n_lanes;
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
         if (!kSync && !live) continue;        // (with block barriers dead lanes ride along inactive)
