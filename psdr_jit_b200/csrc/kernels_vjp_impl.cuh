@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP
     for (long long j = (long long) blockIdx.x * kBlockPV + threadIdx.x; j < span_pad; j += stride) {
         if (kSync) __syncthreads();
         else __syncwarp();
-        const long long i = global_lane(rp, j);
+        const long long i = global_lane(rp, rp.perm && j < span ? (long long) __ldg(rp.perm + j) : j);
         const bool live = j < span && i < rp.n_lanes;
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
         if (!kSync && !live) continue;
@@ -165,20 +165,47 @@ __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP
             else if (kColloc) Lside[side] = Li_collocated<float, kCfg, false>(sc, ro, rd, valid);
             else Lside[side] = Li<float, kCfg>(sc, rng, ro, rd, valid, rp.max_depth, rp.hide_emitters != 0, rp.mis);
         }
-        if (!valid) continue;
-        const int pix = iy * sc.width + ix;
-        const float inv_pdf = 1.f / pdf;
-        const float dl[3] = {(Lside[1].x - Lside[0].x) * inv_pdf, (Lside[1].y - Lside[0].y) * inv_pdf, (Lside[1].z - Lside[0].z) * inv_pdf};
         float gsum = 0.f;
+        if (valid) {
+            const int pix = iy * sc.width + ix;
+            const float inv_pdf = 1.f / pdf;
+            const float dl[3] = {(Lside[1].x - Lside[0].x) * inv_pdf, (Lside[1].y - Lside[0].y) * inv_pdf, (Lside[1].z - Lside[0].z) * inv_pdf};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float primal = x_dot_n * dl[c];
-            if (!isfinite(primal)) continue;
-            gsum += __ldg(d_img + 3 * pix + c) * dl[c];
+            for (int c = 0; c < 3; ++c) {
+                const float primal = x_dot_n * dl[c];
+                if (!isfinite(primal)) continue;
+                gsum += __ldg(d_img + 3 * pix + c) * dl[c];
+            }
+            gsum *= inv_sppe;
         }
-        gsum *= inv_sppe;
-        if (gsum == 0.f || !isfinite(gsum)) continue;
-        // x_dot_n = <lerp(p0, p1, s), n>
+        const bool ok = valid && gsum != 0.f && isfinite(gsum);
+        // x_dot_n = <lerp(p0, p1, s), n>: four table entries per edge.  With the lanes ordered along the edge list (rp.perm) a
+        // warp usually holds ONE edge, and 32 lanes adding into the same four shared-memory words is a 32-way conflict of
+        // compare-and-swap loops: such warps add once, after a shuffle reduction.
+        __syncwarp(live_mask);
+        bool merged = false;
+        if (kSync || live_mask == 0xffffffffu) {        // all 32 lanes are here
+            const unsigned okm = __ballot_sync(0xffffffffu, ok);
+            const int e0 = __shfl_sync(0xffffffffu, ei, okm ? __ffs(okm) - 1 : 0);
+            if (okm != 0u && __popc(okm) > 2 && __all_sync(0xffffffffu, !ok || ei == e0)) {
+                float ga = ok ? gsum * w0 : 0.f, gb = ok ? gsum * s1 : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                    gb += __shfl_xor_sync(0xffffffffu, gb, o);
+                }
+                if ((threadIdx.x & 31) == 0) {
+                    const float4 be = __ldg(cam.pe_b + e0);
+                    const int b = gl.off_pe + 4 * e0;
+                    acc.add(b, ga * be.x);
+                    acc.add(b + 1, ga * be.y);
+                    acc.add(b + 2, gb * be.x);
+                    acc.add(b + 3, gb * be.y);
+                }
+                merged = true;
+            }
+        }
+        if (merged || !ok) continue;
         const int b = gl.off_pe + 4 * ei;
         acc.add(b, gsum * w0 * bq.x);
         acc.add(b + 1, gsum * w0 * bq.y);
