@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -31,7 +32,7 @@ struct psdr_scene {
     cudaEvent_t ev[3][2] = {};
     bool ev_used[3] = {false, false, false};
     // the three term kernels of one call run on three streams (TermStreams below)
-    int *d_sched = nullptr;               // chunk hand-out counters of the large-CTA interior kernels (ChunkSched): forward {0,1}, adjoint {2,3}
+    int *d_sched = nullptr;               // chunk hand-out counters of the large-CTA kernels (ChunkSched), two ints each: interior forward, interior adjoint, primary edges forward, primary edges adjoint
     // primary-edge lane ordering (edge_sort.cu): one set of buffers for the forward launch, one for the adjoint launch
     struct EdgeSort { unsigned short *key = nullptr; int *perm = nullptr, *work = nullptr; size_t cap = 0; } edge_sort[2];
     float *early_img_host = nullptr;      // psdr_render_d_host: copy the primal image out as soon as the interior kernel is done
@@ -703,6 +704,12 @@ void begin_render(Scene &sc, int sensor, long long seed, const int *pix_id, bool
     }
 }
 
+// PSDR_EDGE_DYNAMIC=0: static slices in the large-CTA primary-edge kernels (A/B switch; default: dynamic chunk hand-out)
+bool edge_dynamic() {
+    static const bool on = [] { const char *e = getenv("PSDR_EDGE_DYNAMIC"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 int *sched_counters(psdr_scene *s, int which) {
     if (!s->d_sched) {
         cuda_ok(cudaMalloc(&s->d_sched, sizeof(int) * 8), "cudaMalloc(sched)");
@@ -838,6 +845,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         cudaStream_t q = ts.next();
         tick(s, 1, 0, q);
         order_edge_lanes(s, 0, rp[1], q);
+        if (edge_dynamic()) rp[1].sched = sched_counters(s, 2);
         cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, q), "primary-edge kernel");
         tick(s, 1, 1, q);
         g_launches++;
@@ -941,6 +949,7 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
         cudaStream_t q = ts.next();
         tick(s, 1, 0, q);
         order_edge_lanes(s, 1, rp[1], q);
+        if (edge_dynamic()) rp[1].sched = sched_counters(s, 3);
         cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp[1], gl, d_img, q), "primary-edge adjoint kernel");
         tick(s, 1, 1, q);
         g_launches++;

@@ -163,9 +163,24 @@ __global__ void __launch_bounds__(kBig ? kBlockP : kBlock, kBig ? PSDR_LB_PRIMAR
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + kBlockP - 1) / kBlockP * kBlockP;
-    for (long long j = (long long) blockIdx.x * kBlockP + threadIdx.x; j < span_pad; j += stride) {
-        if (kSync) __syncthreads();
-        else __syncwarp();
+    // large CTAs: chunks (one CTA-load of lanes) handed out dynamically, as in the interior kernel (device_path.cuh ChunkSched;
+    // its barriers are the per-path block barrier).  With the lanes ordered along the edge list (rp.perm) a chunk lies inside
+    // one bucket and chunks differ in cost -- off-screen stretches are free, a stretch in front of the light is not -- so a
+    // static slice per CTA ends with the CTAs that drew the expensive stretches.
+    __shared__ long long s_chunk;
+    const bool dynamic = kSync != 0 && rp.sched != nullptr;
+    ChunkSched sched{rp.sched};
+    for (long long k = 0;; ++k) {
+        long long j;
+        if (dynamic) {
+            j = sched.next(&s_chunk) * kBlockP + threadIdx.x;
+            if (j >= span_pad) break;
+        } else {
+            j = (long long) blockIdx.x * kBlockP + threadIdx.x + k * stride;
+            if (j >= span_pad) break;
+            if (kSync) __syncthreads();
+            else __syncwarp();
+        }
         const long long i = global_lane(rp, rp.perm && j < span ? (long long) __ldg(rp.perm + j) : j);
         const bool live = j < span && i < rp.n_lanes;
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
@@ -210,6 +225,7 @@ __global__ void __launch_bounds__(kBig ? kBlockP : kBlock, kBig ? PSDR_LB_PRIMAR
         }
         if (t3[0] != 0.f || t3[1] != 0.f || t3[2] != 0.f) out_add_rgb(dimg, pix, t3[0], t3[1], t3[2], rp.out_multicast);
     }
+    if (dynamic) sched.finish();
 }
 
 // ---- secondary (shadow) edges: PathTracer::render_secondary_edges -----------------------------

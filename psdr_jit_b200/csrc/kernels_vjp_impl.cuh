@@ -134,9 +134,21 @@ __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP
     // at the top of each one: without the barrier lanes that finish a path early run ahead into the next lane's
     // closest-hit scans and the warp stays split (profiles/r01d: 5 of 32 lanes active in the adjoint kernel)
     const long long span = rp.lane_end - rp.lane_begin, span_pad = (span + kBlockPV - 1) / kBlockPV * kBlockPV;
-    for (long long j = (long long) blockIdx.x * kBlockPV + threadIdx.x; j < span_pad; j += stride) {
-        if (kSync) __syncthreads();
-        else __syncwarp();
+    // large CTAs: dynamic chunk hand-out, as in the forward kernel (kernels_impl.cuh primary_edge_kernel)
+    __shared__ long long s_chunk;
+    const bool dynamic = kSync != 0 && rp.sched != nullptr;
+    ChunkSched sched{rp.sched};
+    for (long long k = 0;; ++k) {
+        long long j;
+        if (dynamic) {
+            j = sched.next(&s_chunk) * kBlockPV + threadIdx.x;
+            if (j >= span_pad) break;
+        } else {
+            j = (long long) blockIdx.x * kBlockPV + threadIdx.x + k * stride;
+            if (j >= span_pad) break;
+            if (kSync) __syncthreads();
+            else __syncwarp();
+        }
         const long long i = global_lane(rp, rp.perm && j < span ? (long long) __ldg(rp.perm + j) : j);
         const bool live = j < span && i < rp.n_lanes;
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
@@ -212,6 +224,7 @@ __global__ void __launch_bounds__(kBig ? kBlockPV : kBlockV, kBig ? PSDR_LB_PVJP
         acc.add(b + 2, gsum * s1 * bq.x);
         acc.add(b + 3, gsum * s1 * bq.y);
     }
+    if (dynamic) sched.finish();
     grad_acc_end(acc);
 }
 
