@@ -128,11 +128,13 @@ int psdr_scene_set_output_multicast(psdr_scene *s, int on);
  * too small to fill the large shape.  0 = choose by launch size (default), 1 = always 128 threads, 2 = always large.
  * Results do not depend on the shape (a lane's value is a function of its global index and the seed). */
 int psdr_set_cta_policy(int policy);
-/* Lane order of the primary-edge kernels (process-wide; new).  Sample i of Integrator::render_primary_edges
+/* Lane order of the primary- and secondary-edge kernels (process-wide; new).  Sample i of Integrator::render_primary_edges
  * (src/integrator/integrator.cpp:144-189) is a function of (seed, i) alone; its first draw selects the edge and the point on
  * it (src/sensor/perspective.cpp:117-141).  bins >= 2 (default 512, at most 2048): launches of 32768 lanes or more bucket
  * their lanes by that draw first (one counting-sort pass on the GPU) so that the rays of a warp start on the same stretch
- * of the same edge; 0 = lane order.  Values do not depend on it, only the order of the atomic adds into the image. */
+ * of the same edge; 0 = lane order.  PathTracer::render_secondary_edges (src/integrator/path.cpp:268-302) likewise, by the
+ * sample dimension that Scene::sample_boundary_segment_direct uses for the edge (after the guiding distribution's warp).
+ * Values do not depend on it, only the order of the atomic adds into the image. */
 int psdr_set_edge_sort(int bins);
 /* New.  on != 0: the analytic re-intersection of the primary hit in renderD (src/scene/scene.cpp:772-801,
  * include/psdr/utils.h:82-93) takes its reciprocal with rcp.approx.ftz.f32, the instruction Dr.Jit emits for rcp()

@@ -68,8 +68,8 @@ def set_cta_policy(policy: int = 0):
 
 
 def set_edge_sort(bins: int = 512):
-    """Lane order of the primary-edge kernels: launches of 32768 lanes or more bucket their samples by position along the
-    pixel-space edge list (``bins`` buckets, 2..2048) so that a warp's rays start next to each other; 0 = lane order
+    """Lane order of the primary- and secondary-edge kernels: launches of 32768 lanes or more bucket their samples by position
+    along the edge list (``bins`` buckets, 2..2048) so that a warp's rays start next to each other; 0 = lane order
     (include/psdr_b200.h psdr_set_edge_sort).  Results do not depend on it."""
     _lib.check(_lib.load().psdr_set_edge_sort(int(bins)))
 

@@ -33,8 +33,8 @@ struct psdr_scene {
     bool ev_used[3] = {false, false, false};
     // the three term kernels of one call run on three streams (TermStreams below)
     int *d_sched = nullptr;               // chunk hand-out counters of the large-CTA kernels (ChunkSched), two ints each: interior forward, interior adjoint, primary edges forward, primary edges adjoint
-    // primary-edge lane ordering (edge_sort.cu): one set of buffers for the forward launch, one for the adjoint launch
-    struct EdgeSort { unsigned short *key = nullptr; int *perm = nullptr, *work = nullptr; size_t cap = 0; } edge_sort[2];
+    // primary- and secondary-edge lane ordering (edge_sort.cu): one set of buffers per kernel that can be in flight
+    struct EdgeSort { unsigned short *key = nullptr; int *perm = nullptr, *work = nullptr; size_t cap = 0; } edge_sort[4];   // primary fwd / adjoint, secondary fwd / adjoint
     float *early_img_host = nullptr;      // psdr_render_d_host: copy the primal image out as soon as the interior kernel is done
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -710,6 +710,12 @@ bool edge_dynamic() {
     return on;
 }
 
+// PSDR_SEC_EDGE_SORT=0: the secondary-edge kernels keep the lane order whatever psdr_set_edge_sort says (A/B switch)
+bool sec_edge_sort() {
+    static const bool on = [] { const char *e = getenv("PSDR_SEC_EDGE_SORT"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 int *sched_counters(psdr_scene *s, int which) {
     if (!s->d_sched) {
         cuda_ok(cudaMalloc(&s->d_sched, sizeof(int) * 8), "cudaMalloc(sched)");
@@ -721,7 +727,7 @@ int *sched_counters(psdr_scene *s, int which) {
 // Primary-edge launches of at least kEdgeSortMinLanes local lanes walk their lanes in the order of edge_sort.cu (three small
 // kernels on the term's stream, counted as launches); smaller ones keep the lane order.
 constexpr long long kEdgeSortMinLanes = 32768;
-void order_edge_lanes(psdr_scene *s, int which, RenderParams &rp, cudaStream_t q) {
+void order_edge_lanes(psdr_scene *s, int which, RenderParams &rp, const DCamera &cam, cudaStream_t q) {
     const long long span = rp.lane_end - rp.lane_begin;
     if (g_edge_sort_bins < 2 || span < kEdgeSortMinLanes || span > 2147483647LL) return;
     auto &e = s->edge_sort[which];
@@ -737,7 +743,7 @@ void order_edge_lanes(psdr_scene *s, int which, RenderParams &rp, cudaStream_t q
         cuda_ok(cudaMalloc(&e.work, sizeof(int) * 2 * kEdgeSortMaxBins), "cudaMalloc(edge sort counters)");
         cuda_ok(cudaMemsetAsync(e.work, 0, sizeof(int) * 2 * kEdgeSortMaxBins, q), "memset(edge sort counters)");
     }
-    cuda_ok(launch_edge_sort(rp, g_edge_sort_bins, e.key, e.work, e.perm, q), "edge sort kernels");
+    cuda_ok(launch_edge_sort(rp, cam, which >= 2, g_edge_sort_bins, e.key, e.work, e.perm, q), "edge sort kernels");
     g_launches += 3;
     rp.perm = e.perm;
 }
@@ -836,6 +842,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
         cudaStream_t q = ts.next();
         tick(s, 2, 0, q);
+        if (sec_edge_sort()) order_edge_lanes(s, 2, rp[2], cam, q);
         cuda_ok(launch_secondary_edges(sc.dscene, cam, rp[2], dimg, q), "secondary-edge kernel");
         tick(s, 2, 1, q);
         g_launches++;
@@ -844,7 +851,7 @@ int render_impl(psdr_scene *s, int sensor, int max_depth, long long seed, int hi
         set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
         cudaStream_t q = ts.next();
         tick(s, 1, 0, q);
-        order_edge_lanes(s, 0, rp[1], q);
+        order_edge_lanes(s, 0, rp[1], cam, q);
         if (edge_dynamic()) rp[1].sched = sched_counters(s, 2);
         cuda_ok(launch_primary_edges(sc.dscene, cam, rp[1], dimg, q), "primary-edge kernel");
         tick(s, 1, 1, q);
@@ -940,6 +947,7 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
         rp[2].tangent_scale = reference_scaling ? 2.f : 1.f;
         cudaStream_t q = ts.next();
         tick(s, 2, 0, q);
+        if (sec_edge_sort()) order_edge_lanes(s, 3, rp[2], cam, q);
         cuda_ok(launch_secondary_edges_vjp(sc.dscene, cam, rp[2], gl, d_img, q), "secondary-edge adjoint kernel");
         tick(s, 2, 1, q);
         g_launches++;
@@ -948,7 +956,7 @@ static void vjp_launch(psdr_scene *s, int sensor, int max_depth, long long seed,
         set_shard(rp[1], npix_full * sc.sppe, sc.rank, sc.world);
         cudaStream_t q = ts.next();
         tick(s, 1, 0, q);
-        order_edge_lanes(s, 1, rp[1], q);
+        order_edge_lanes(s, 1, rp[1], cam, q);
         if (edge_dynamic()) rp[1].sched = sched_counters(s, 3);
         cuda_ok(launch_primary_edges_vjp(sc.dscene, cam, rp[1], gl, d_img, q), "primary-edge adjoint kernel");
         tick(s, 1, 1, q);

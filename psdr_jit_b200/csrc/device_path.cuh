@@ -1869,7 +1869,7 @@ struct SecSample {      // what the fill loop hands to stage 1
 };
 template <int kCfg>
 __device__ __forceinline__ bool sec_edge_draw(const DScene &sc, const DCamera &cam, const RenderParams &rp, long long j, SecSample &out) {
-    const long long i = global_lane(rp, j);
+    const long long i = global_lane(rp, rp.perm ? (long long) __ldg(rp.perm + j) : j);
     if (i >= rp.n_lanes) return false;
     Pcg32 rng;
     rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
@@ -1886,9 +1886,17 @@ __device__ __forceinline__ void sec_edge_batches(const DScene &sc, const DCamera
     const long long span = rp.lane_end - rp.lane_begin;
     const unsigned lane = threadIdx.x & 31u;
     const long long n_warps = (long long) gridDim.x * (block / 32), warp = (long long) blockIdx.x * (block / 32) + (threadIdx.x >> 5);
-    const long long per = ((span + n_warps - 1) / n_warps + 31) / 32 * 32;      // slice of this warp
-    long long next = warp * per;
-    const long long end = next + per < span ? next + per : span;
+    // Lane order (rp.perm == nullptr): warp w owns the contiguous slice [w per, (w + 1) per) -- all slices are statistically
+    // alike.  Samples ordered along the edge list (rp.perm, edge_sort.cu): consecutive samples sit on the same stretch of
+    // the same edge, whole stretches fail stage 0 (edges facing away from the light) and others pass it three times as
+    // often as the average, so a warp takes every n_warps-th block of kSecBlock ordered samples instead -- coherent inside
+    // a block, and every warp walks the whole edge list.
+    constexpr long long kSecBlock = 256;
+    const bool ordered = rp.perm != nullptr;
+    const long long per = ordered ? (span + n_warps * kSecBlock - 1) / (n_warps * kSecBlock) * kSecBlock
+                                  : ((span + n_warps - 1) / n_warps + 31) / 32 * 32;      // samples of this warp
+    long long next = ordered ? 0 : warp * per;
+    const long long end = ordered ? per : (next + per < span ? next + per : span);
     bool finished = false;      // (cta mode) this warp has drained its slice and only keeps the block barriers company
     while (true) {
         if (cta) {
@@ -1900,8 +1908,9 @@ __device__ __forceinline__ void sec_edge_batches(const DScene &sc, const DCamera
             const unsigned need = __ballot_sync(0xffffffffu, !have);
             if (need == 0u || next >= end) break;
             if (!have) {
-                const long long j = next + __popc(need & ((1u << lane) - 1u));
-                if (j < end) have = sec_edge_draw<kCfg>(sc, cam, rp, j, smp);
+                const long long t = next + __popc(need & ((1u << lane) - 1u));
+                const long long j = ordered ? ((t / kSecBlock) * n_warps + warp) * kSecBlock + (t % kSecBlock) : t;
+                if (t < end && j < span) have = sec_edge_draw<kCfg>(sc, cam, rp, j, smp);
             }
             next += __popc(need);
         }

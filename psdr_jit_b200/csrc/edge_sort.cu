@@ -7,8 +7,13 @@
 // one counting-sort pass: histogram, exclusive scan, scatter -- and the kernels walk the buckets: a warp's rays start on
 // the same stretch of the same edge, hit the same two surfaces and take the same branches.  Which thread evaluates a sample
 // does not change its value; only the (already unordered) order of the atomic adds into the image changes.
+// The secondary-edge kernels (PathTracer::render_secondary_edges, src/integrator/path.cpp:268-302) get the same treatment: the
+// first dimension of a sample -- after the guiding distribution has warped it, if there is one -- selects the edge and the
+// point on it (Scene::sample_boundary_segment_direct, src/scene/scene.cpp), so bucketing by it puts the three traces of a
+// warp's candidates next to each other; device_path.cuh sec_edge_batches deals the ordered samples to the warps in blocks.
 #include <cuda_runtime.h>
 
+#include "device_path.cuh"
 #include "kernels.h"
 #include "pmath.h"
 
@@ -17,26 +22,30 @@ namespace {
 
 constexpr int kSortBlock = 1024, kSortPerThread = 8, kSortChunk = kSortBlock * kSortPerThread;
 
-// device_path.cuh global_lane
-__device__ __forceinline__ long long sort_global_lane(const RenderParams &rp, long long j) {
-    return rp.shard_world <= 1 ? rp.lane_begin + j : (((j >> 5) * rp.shard_world + rp.shard_rank) << 5) + (j & 31);
-}
-
 // pass 1: bucket of every local lane (dead lanes of the last 32-block go to the last bucket) + histogram
-__global__ void __launch_bounds__(kSortBlock) edge_bucket_kernel(const __grid_constant__ RenderParams rp, int nb, unsigned short *__restrict__ key,
-                                                                  int *__restrict__ hist) {
+// kSecondary: the key is the first dimension of the secondary-edge sample (device_path.cuh sec_edge_draw), else the first draw
+template <bool kSecondary>
+__global__ void __launch_bounds__(kSortBlock) edge_bucket_kernel(const __grid_constant__ RenderParams rp, const __grid_constant__ DCamera cam, int nb,
+                                                                  unsigned short *__restrict__ key, int *__restrict__ hist) {
     extern __shared__ int s_hist[];
     for (int t = threadIdx.x; t < nb; t += kSortBlock) s_hist[t] = 0;
     __syncthreads();
     const long long span = rp.lane_end - rp.lane_begin, stride = (long long) gridDim.x * kSortBlock;
     for (long long j = (long long) blockIdx.x * kSortBlock + threadIdx.x; j < span; j += stride) {
-        const long long i = sort_global_lane(rp, j);
+        const long long i = global_lane(rp, j);
         int b = nb - 1;
         if (i < rp.n_lanes) {
             Pcg32 rng;
             rng.seed((unsigned long long) (i + rp.seed), (unsigned long long) i);
             if (rp.skip) rng.advance(rp.skip);
-            b = min((int) (rng.next_1d() * (float) nb), nb - 1);
+            float x = rng.next_1d();
+            if (kSecondary) {
+                const float d2 = rng.next_1d(), d3 = rng.next_1d();
+                V3f sample3(d3, d2, x);
+                if (cam.guided) guide_sample_reuse(cam, sample3);
+                x = sample3.x;
+            }
+            b = max(min((int) (x * (float) nb), nb - 1), 0);
         }
         key[j] = (unsigned short) b;
         atomicAdd(&s_hist[b], 1);
@@ -101,7 +110,7 @@ __global__ void __launch_bounds__(kSortBlock) edge_scatter_kernel(long long span
 }  // namespace
 
 // key: span uint16, work: 2 * bins ints (zero before the first call; left zeroed), perm: span ints
-cudaError_t launch_edge_sort(const RenderParams &rp, int bins, unsigned short *key, int *work, int *perm, cudaStream_t st) {
+cudaError_t launch_edge_sort(const RenderParams &rp, const DCamera &cam, bool secondary, int bins, unsigned short *key, int *work, int *perm, cudaStream_t st) {
     const long long span = rp.lane_end - rp.lane_begin;
     if (span <= 0 || bins < 2 || bins > kEdgeSortMaxBins || span > 2147483647LL) return cudaErrorInvalidValue;
     int dev = 0, sms = 148;
@@ -110,7 +119,8 @@ cudaError_t launch_edge_sort(const RenderParams &rp, int bins, unsigned short *k
     const size_t smem = sizeof(int) * bins;
     const long long need = (span + kSortChunk - 1) / kSortChunk;
     const int grid = (int) (need < 2LL * sms ? need : 2LL * sms);
-    edge_bucket_kernel<<<grid, kSortBlock, smem, st>>>(rp, bins, key, work);
+    if (secondary) edge_bucket_kernel<true><<<grid, kSortBlock, smem, st>>>(rp, cam, bins, key, work);
+    else edge_bucket_kernel<false><<<grid, kSortBlock, smem, st>>>(rp, cam, bins, key, work);
     edge_scan_kernel<<<1, kSortBlock, 0, st>>>(bins, work, work + bins);
     edge_scatter_kernel<<<grid, kSortBlock, smem, st>>>(span, bins, key, work + bins, perm);
     return cudaGetLastError();

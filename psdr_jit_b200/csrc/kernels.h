@@ -15,9 +15,10 @@ cudaError_t launch_aov(const DScene &sc, const DCamera &cam, const RenderParams 
 cudaError_t launch_aov_d(const DScene &sc, const DCamera &cam, const RenderParams &rp, float *out, float *dout, cudaStream_t st);
 cudaError_t launch_field_edges(const DScene &sc, const DCamera &cam, const RenderParams &rp, int field, int object, float *dimg, cudaStream_t st);
 
-// edge_sort.cu: perm = the local lanes of a primary-edge launch bucketed by their first draw (= position along the edge list)
+// edge_sort.cu: perm = the local lanes of a primary-edge (secondary-edge) launch bucketed by the sample dimension that
+// selects the edge and the point on it (= position along the edge list)
 constexpr int kEdgeSortMaxBins = 2048;
-cudaError_t launch_edge_sort(const RenderParams &rp, int bins, unsigned short *key, int *work, int *perm, cudaStream_t st);
+cudaError_t launch_edge_sort(const RenderParams &rp, const DCamera &cam, bool secondary, int bins, unsigned short *key, int *work, int *perm, cudaStream_t st);
 
 // reverse mode (kernels_vjp.cu); GradLayout = adjoint.cuh
 cudaError_t launch_interior_vjp(const DScene &sc, const DCamera &cam, const RenderParams &rp, const GradLayout &gl, const float *d_img, cudaStream_t st);
