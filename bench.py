@@ -365,7 +365,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "frac": None if ach is None else round(ach / peak, 4), "traffic": load_traffic(dom),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
                          "note": "achieved = SURVEY 8(d) wavefront bytes (88 B/ray + splats) / CUDA-event kernel time; the fused kernel keeps "
-                                 "rays and hits in registers, so DRAM traffic is far below the algorithmic figure and frac may exceed 1"},
+                                 "rays and hits in registers, so DRAM traffic is far below the algorithmic figure and frac may exceed 1; "
+                                 "kernel time includes the sample-ordering pass of the edge terms (edge_sort.cu)",
+                         # what actually bounds the kernel, from the committed ncu capture of this kernel (not measured in this run)
+                         "limiter": ({"kind": "instruction issue x active lanes", "issue_active_pct": 75.5, "active_lanes_of_32": 22.3,
+                                      "fma_pipe_pct": 51.4, "source": "profiles/r05b_ncu_summary.txt"} if dom == 2 else None)},
             "cpu_baseline": cpu,
             "vjp": vjp,
         }
