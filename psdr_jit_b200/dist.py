@@ -22,6 +22,17 @@ def shard_lanes(n: int, rank: int, world: int):
     return lanes[lanes < n]
 
 
+def ordered_deal(span: int, n_warps: int, warp: int, block: int = 256):
+    """Positions (in the bucketed sample order of csrc/edge_sort.cu) that warp `warp` of `n_warps` evaluates in the
+    secondary-edge kernels -- the deal of csrc/device_path.cuh sec_edge_batches for ordered samples: every n_warps-th block of
+    `block` consecutive positions, so that each warp walks the whole edge list and a block stays on one stretch of it."""
+    import numpy as np
+    per = (span + n_warps * block - 1) // (n_warps * block) * block
+    t = np.arange(per, dtype=np.int64)
+    j = ((t // block) * n_warps + warp) * block + t % block
+    return j[j < span]
+
+
 def all_reduce_images(*tensors, group=None, dst=None):
     """Sum partial full-frame images over ranks in ONE collective (NCCL on GPUs, gloo in the CPU tests).  A single
     contiguous tensor (e.g. the [2, npix, 3] image + derivative-image buffer of renderD_fwd) is reduced in place;

@@ -106,3 +106,22 @@ def test_shard_lanes_properties():
                 assert np.all((p // 32) % world == r)                      # block b belongs to rank b % world
     with pytest.raises(ValueError):
         shard_lanes(10, 2, 2)
+
+
+def test_ordered_deal_properties():
+    """the deal of bucket-ordered secondary-edge samples to warps (csrc/device_path.cuh sec_edge_batches, mirrored by
+    dist.ordered_deal): a partition of the positions, whole 256-blocks, every warp spread over the whole order"""
+    from psdr_jit_b200.dist import ordered_deal
+    for span in (1, 255, 256, 40255, 32768, 1048576 + 77):
+        for n_warps in (4, 1260, 148 * 32):
+            parts = [ordered_deal(span, n_warps, w) for w in range(n_warps)]
+            allv = np.sort(np.concatenate(parts))
+            assert np.array_equal(allv, np.arange(span))
+            for w in (0, n_warps // 2, n_warps - 1):
+                p = parts[w]
+                if len(p) == 0:
+                    continue
+                assert np.all((p // 256) % n_warps == w)                   # block b belongs to warp b % n_warps
+                assert np.all(np.diff(p) > 0)                              # walked front to back
+            sizes = np.array([len(p) for p in parts])
+            assert sizes.max() - sizes.min() <= 256 or span < n_warps * 256
