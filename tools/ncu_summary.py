@@ -33,6 +33,18 @@ for f in files:
 open(out, 'w').write('\n'.join(lines) + '\n')
 tj = os.path.join(os.path.dirname(out), 'traffic.json')
 pick = lambda s: next((v for k, v in traffic.items() if k.startswith(s)), None)
-json.dump({'interior': pick('interior_kernel<Dual'), 'primary_edges': pick('primary_edge_kernel'), 'secondary_edges': pick('secondary_edge_kernel'),
-           'source': '%s (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, cfg 2)' % out, 'all': traffic}, open(tj, 'w'), indent=1)
+# merge into the existing record: a capture of one kernel must not drop the entries of the others
+try:
+    old = json.load(open(tj))
+except Exception:
+    old = {}
+rec = {'interior': pick('interior_kernel<Dual'), 'primary_edges': pick('primary_edge_kernel'), 'secondary_edges': pick('secondary_edge_kernel')}
+for k in rec:
+    if rec[k] is None:
+        rec[k] = old.get(k)
+allk = dict(old.get('all', {}))
+allk.update({'%s (%s)' % (k, os.path.basename(out).split('_')[0]): v for k, v in traffic.items()})
+rec['source'] = '%s for the kernels it holds, earlier captures otherwise (see the tags in "all"); dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full' % out
+rec['all'] = allk
+json.dump(rec, open(tj, 'w'), indent=1)
 print(open(out).read()[:600])
